@@ -1,0 +1,359 @@
+"""Host-side mirror of the reference rasterizer interface over the C ABI.
+
+Same names, argument meaning and error behaviour as /root/reference/src/rasterizer:
+`Framebuffer` (render.rs:10-45), `Camera` (camera.rs:9-91), `RasterSettings` (types.rs:1392-1495),
+`Light` (types.rs:1307-1373), `Texture15` (types.rs:532-539), `render_mesh_15` (render.rs:2302-2310).
+Where the reference panics (bad vertex index, NaN sort key) `render_mesh_15` raises `B32Error`.
+
+Vertices and faces are numpy record arrays (`abi.VERTEX_DTYPE`, `abi.FACE_DTYPE`) — the POD layout
+the Rust shim marshals `&[Vertex]` / `&[Face]` into.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import abi
+from .abi import (BLEND_OPAQUE, SHADE_GOURAUD, LIGHT_DIRECTIONAL, LIGHT_POINT, LIGHT_SPOT,
+                  TEX_RGB555, TEX_IDX8, TEX_IDX4, B32Error)
+
+F32 = np.float32
+
+
+def _v3(x, y, z):
+    return np.array([x, y, z], dtype=F32)
+
+
+def _normalize(v):
+    """Vec3::normalize, math.rs:39-49 (sqrt and / are IEEE-exact, so host == reference)."""
+    l = np.sqrt(F32(F32(F32(v[0] * v[0]) + F32(v[1] * v[1])) + F32(v[2] * v[2])))
+    if l == 0:
+        return _v3(0, 0, 0)
+    return np.array([v[0] / l, v[1] / l, v[2] / l], dtype=F32)
+
+
+def _cross(a, b):
+    """Vec3::cross, math.rs:27-33."""
+    return np.array([F32(a[1] * b[2]) - F32(a[2] * b[1]),
+                     F32(a[2] * b[0]) - F32(a[0] * b[2]),
+                     F32(a[0] * b[1]) - F32(a[1] * b[0])], dtype=F32)
+
+
+class Camera:
+    """camera.rs:9-91. Basis vectors are computed on the host (libm sin/cos) and passed as data."""
+
+    def __init__(self):
+        self.position = _v3(0, 0, 0)
+        self.rotation_x = F32(0.0)
+        self.rotation_y = F32(0.0)
+        self.basis_x = _v3(1, 0, 0)
+        self.basis_y = _v3(0, 1, 0)
+        self.basis_z = _v3(0, 0, 1)
+        self.update_basis()
+
+    def update_basis(self):  # camera.rs:76-91
+        upward = _v3(0.0, -1.0, 0.0)
+        rx, ry = F32(self.rotation_x), F32(self.rotation_y)
+        self.basis_z = np.array([F32(np.cos(rx) * np.sin(ry)), F32(-np.sin(rx)), F32(np.cos(rx) * np.cos(ry))], dtype=F32)
+        self.basis_x = _normalize(_cross(upward, self.basis_z))
+        self.basis_y = _cross(self.basis_z, self.basis_x)
+
+    def to_abi(self) -> abi.Camera:
+        c = abi.Camera()
+        for name in ("position", "basis_x", "basis_y", "basis_z"):
+            getattr(c, name)[:] = [float(x) for x in getattr(self, name)]
+        return c
+
+
+@dataclass
+class Light:
+    """types.rs:1307-1373."""
+    type: int = LIGHT_DIRECTIONAL
+    position: np.ndarray = field(default_factory=lambda: _v3(0, 0, 0))
+    direction: np.ndarray = field(default_factory=lambda: _v3(0, 0, 0))
+    radius: float = 0.0
+    angle: float = 0.0
+    intensity: float = 1.0
+    color: tuple = (255, 255, 255)
+    enabled: bool = True
+
+    @staticmethod
+    def directional(direction, intensity):           # types.rs:1317-1325
+        return Light(type=LIGHT_DIRECTIONAL, direction=_normalize(np.asarray(direction, dtype=F32)), intensity=intensity)
+
+    @staticmethod
+    def point(position, radius, intensity):          # types.rs:1328-1336
+        return Light(type=LIGHT_POINT, position=np.asarray(position, dtype=F32), radius=radius, intensity=intensity)
+
+    @staticmethod
+    def point_colored(position, radius, intensity, r, g, b):   # types.rs:1339-1352 (`as u8` saturates)
+        col = tuple(int(min(max(np.trunc(F32(F32(c) * F32(255.0))), 0), 255)) for c in (r, g, b))
+        return Light(type=LIGHT_POINT, position=np.asarray(position, dtype=F32), radius=radius, intensity=intensity, color=col)
+
+    @staticmethod
+    def spot(position, direction, angle, radius, intensity):   # types.rs:1355-1368
+        return Light(type=LIGHT_SPOT, position=np.asarray(position, dtype=F32),
+                     direction=_normalize(np.asarray(direction, dtype=F32)), angle=angle, radius=radius, intensity=intensity)
+
+    def to_abi(self) -> abi.Light:
+        l = abi.Light()
+        l.type = self.type
+        l.position[:] = [float(x) for x in self.position]
+        l.direction[:] = [float(x) for x in self.direction]
+        l.radius, l.angle, l.intensity = self.radius, self.angle, self.intensity
+        l.r, l.g, l.b = self.color
+        l.enabled = 1 if self.enabled else 0
+        return l
+
+
+@dataclass
+class RasterSettings:
+    """types.rs:1392-1428, defaults :1475-1495."""
+    affine_textures: bool = True
+    use_zbuffer: bool = True
+    shading: int = SHADE_GOURAUD
+    backface_cull: bool = True
+    backface_wireframe: bool = True
+    lights: list = field(default_factory=lambda: [Light.directional((-1.0, -1.0, -1.0), 0.7)])
+    ambient: float = 0.3
+    dithering: bool = True
+    wireframe_overlay: bool = False
+    ortho_projection: Optional[tuple] = None     # (zoom, center_x, center_y)
+    use_rgb555: bool = True
+    use_fixed_point: bool = True
+    xray_mode: bool = False
+
+    @staticmethod
+    def game():                                   # types.rs:1455-1460
+        return RasterSettings(backface_wireframe=False)
+
+    @staticmethod
+    def modeler():                                # types.rs:1465-1472
+        return RasterSettings(backface_wireframe=False, lights=[], ambient=0.7)
+
+    def to_abi(self):
+        """Returns (abi.Settings, keepalive)."""
+        s = abi.Settings()
+        s.affine_textures = self.affine_textures
+        s.use_zbuffer = self.use_zbuffer
+        s.shading = self.shading
+        s.backface_cull = self.backface_cull
+        s.backface_wireframe = self.backface_wireframe
+        s.dithering = self.dithering
+        s.wireframe_overlay = self.wireframe_overlay
+        s.use_rgb555 = self.use_rgb555
+        s.use_fixed_point = self.use_fixed_point
+        s.xray_mode = self.xray_mode
+        s.ortho_enabled = self.ortho_projection is not None
+        if self.ortho_projection is not None:
+            s.ortho_zoom, s.ortho_center_x, s.ortho_center_y = self.ortho_projection
+        s.ambient = self.ambient
+        arr = (abi.Light * max(1, len(self.lights)))(*[l.to_abi() for l in self.lights])
+        s.n_lights = len(self.lights)
+        s.lights = C.cast(arr, C.POINTER(abi.Light))
+        return s, arr
+
+
+@dataclass
+class Texture15:
+    """types.rs:532-539, or an indexed texture + CLUT (types.rs:438; mesh_editor.rs:669-682)."""
+    width: int
+    height: int
+    pixels: np.ndarray                      # u16[h*w] | u8[h*w] | u8[(h*w+1)//2]
+    blend_mode: int = BLEND_OPAQUE
+    format: int = TEX_RGB555
+    clut: Optional[np.ndarray] = None       # u16[clut_len]
+
+    def to_abi(self):
+        d = abi.TexDesc()
+        d.width, d.height, d.format, d.blend_mode = self.width, self.height, self.format, self.blend_mode
+        want = np.uint16 if self.format == TEX_RGB555 else np.uint8
+        px = np.ascontiguousarray(self.pixels, dtype=want)
+        d.pixels = px.ctypes.data
+        keep = [px]
+        if self.clut is not None:
+            cl = np.ascontiguousarray(self.clut, dtype=np.uint16)
+            d.clut = cl.ctypes.data_as(C.POINTER(C.c_uint16))
+            d.clut_len = cl.size
+            keep.append(cl)
+        return d, keep
+
+
+def tex_descs(textures: Sequence[Texture15]):
+    keep = []
+    arr = (abi.TexDesc * max(1, len(textures)))()
+    for i, t in enumerate(textures):
+        d, k = t.to_abi()
+        arr[i] = d
+        keep.append(k)
+    return arr, keep
+
+
+def fog_to_abi(fog):
+    """fog: None or (start, falloff, cull_distance, (r, g, b[, blend]))."""
+    if fog is None:
+        return None
+    f = abi.Fog()
+    f.start, f.falloff, f.cull_distance = fog[0], fog[1], fog[2]
+    col = tuple(fog[3])
+    f.r, f.g, f.b = col[:3]
+    f.blend = col[3] if len(col) > 3 else BLEND_OPAQUE
+    return f
+
+
+class Context:
+    """One GPU, one stream, one device-resident framebuffer (b32_ctx)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = abi.load_library()
+        h = C.c_void_p()
+        rc = self.lib.b32_ctx_create(device, C.byref(h))
+        if rc != abi.B32_OK:
+            raise B32Error(rc, "b32_ctx_create failed (no CPU fallback exists)")
+        self.h = h
+        self._tex_key = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.b32_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc != abi.B32_OK:
+            msg = self.lib.b32_last_error(self.h)
+            raise B32Error(rc, msg.decode() if msg else "")
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.b32_ctx_stream(self.h) or 0)
+
+    def sync(self):
+        self.check(self.lib.b32_sync(self.h))
+
+    def kernel_launches(self) -> int:
+        return int(self.lib.b32_kernel_launches(self.h))
+
+    def set_textures(self, textures: Sequence[Texture15]):
+        arr, keep = tex_descs(textures)
+        self.check(self.lib.b32_textures_set(self.h, arr, len(textures)))
+        self._tex_key = id(textures)
+
+
+_default_ctx: Optional[Context] = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+class Framebuffer:
+    """render.rs:10-45. `pixels` (RGBA8) and `zbuffer` (f32) live on the device; the numpy views
+    returned by `.pixels` / `.zbuffer` are downloads (the frame-end sync point)."""
+
+    def __init__(self, width: int, height: int, ctx: Optional[Context] = None):
+        self.ctx = ctx or default_context()
+        self.width, self.height = 0, 0
+        self.resize(width, height)
+        self.clear_transparent()                    # Framebuffer::new: pixels 0, zbuffer f32::MAX
+
+    def resize(self, width: int, height: int):      # render.rs:27-34 (no-op when the size is unchanged)
+        self.ctx.check(self.ctx.lib.b32_fb_resize(self.ctx.h, width, height))
+        self.width, self.height = width, height
+
+    def clear(self, color):                         # render.rs:36-45; color = (r, g, b[, blend])
+        r, g, b = color[:3]
+        a = 0 if (len(color) > 3 and color[3] == abi.BLEND_ERASE) else 255   # Color::to_bytes
+        self.ctx.check(self.ctx.lib.b32_fb_clear(self.ctx.h, r, g, b, a))
+
+    def clear_transparent(self):                    # render.rs:48-56
+        self.ctx.check(self.ctx.lib.b32_fb_clear(self.ctx.h, 0, 0, 0, 0))
+
+    def upload(self, pixels: np.ndarray, zbuffer: Optional[np.ndarray] = None):
+        px = np.ascontiguousarray(pixels, dtype=np.uint8)
+        assert px.size == self.width * self.height * 4
+        zp = None
+        if zbuffer is not None:
+            zb = np.ascontiguousarray(zbuffer, dtype=np.float32)
+            assert zb.size == self.width * self.height
+            zp = zb.ctypes.data
+        self.ctx.check(self.ctx.lib.b32_fb_upload(self.ctx.h, px.ctypes.data, zp))
+
+    def download(self, want_z: bool = True):
+        px = np.empty((self.height, self.width, 4), dtype=np.uint8)
+        zb = np.empty((self.height, self.width), dtype=np.float32) if want_z else None
+        self.ctx.check(self.ctx.lib.b32_fb_download(self.ctx.h, px.ctypes.data, zb.ctypes.data if want_z else None))
+        return px, zb
+
+    @property
+    def pixels(self) -> np.ndarray:
+        return self.download(False)[0]
+
+    @property
+    def zbuffer(self) -> np.ndarray:
+        return self.download(True)[1]
+
+
+def _check_geometry(vertices, faces):
+    v = np.ascontiguousarray(vertices, dtype=abi.VERTEX_DTYPE)
+    f = np.ascontiguousarray(faces, dtype=abi.FACE_DTYPE)
+    return v, f
+
+
+def render_mesh_15(fb: Framebuffer, vertices: np.ndarray, faces: np.ndarray,
+                   textures: Sequence[Texture15], camera: Camera, settings: RasterSettings,
+                   fog=None) -> dict:
+    """render.rs:2302-2310. Returns RasterTimings as a dict (types.rs:1499-1514)."""
+    ctx = fb.ctx
+    v, f = _check_geometry(vertices, faces)
+    if ctx._tex_key != id(textures):
+        ctx.set_textures(textures)
+    cam = camera.to_abi()
+    s, keep = settings.to_abi()
+    fg = fog_to_abi(fog)
+    tm = abi.Timings()
+    rc = ctx.lib.b32_render_mesh_15(ctx.h, v.ctypes.data, len(v), f.ctypes.data, len(f),
+                                    C.byref(cam), C.byref(s), C.byref(fg) if fg is not None else None, C.byref(tm))
+    del keep
+    ctx.check(rc)
+    return tm.as_dict()
+
+
+class Mesh:
+    """Device-resident geometry (b32_mesh): upload once, render many times."""
+
+    def __init__(self, ctx: Context, vertices: np.ndarray, faces: np.ndarray):
+        self.ctx = ctx
+        v, f = _check_geometry(vertices, faces)
+        h = C.c_void_p()
+        ctx.check(ctx.lib.b32_mesh_upload(ctx.h, v.ctypes.data, len(v), f.ctypes.data, len(f), C.byref(h)))
+        self.h = h
+        self.nv, self.nf = len(v), len(f)
+
+    def free(self):
+        if self.h:
+            self.ctx.lib.b32_mesh_free(self.ctx.h, self.h)
+            self.h = None
+
+    def render(self, camera: Camera, settings: RasterSettings, fog=None, enqueue_only=False):
+        cam = camera.to_abi()
+        s, keep = settings.to_abi()
+        fg = fog_to_abi(fog)
+        fgp = C.byref(fg) if fg is not None else None
+        if enqueue_only:
+            self.ctx.check(self.ctx.lib.b32_render_mesh_15_enqueue(self.ctx.h, self.h, C.byref(cam), C.byref(s), fgp))
+            return None
+        tm = abi.Timings()
+        self.ctx.check(self.ctx.lib.b32_render_mesh_15_resident(self.ctx.h, self.h, C.byref(cam), C.byref(s), fgp, C.byref(tm)))
+        return tm.as_dict()

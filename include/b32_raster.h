@@ -1,0 +1,210 @@
+/*
+ * b32_raster.h — C ABI of the B200-native BONNIE-32 rasterizer hot path.
+ *
+ * The reference (EBonura/bonnie-32) has no FFI around its rasterizer: the boundary is the
+ * in-process Rust signature
+ *
+ *     pub fn render_mesh_15(fb: &mut Framebuffer, vertices: &[Vertex], faces: &[Face],
+ *                           textures: &[Texture15], camera: &Camera, settings: &RasterSettings,
+ *                           fog: Option<(f32, f32, f32, Color)>) -> RasterTimings
+ *                                                   (src/rasterizer/render.rs:2302-2310)
+ *
+ * plus `struct Framebuffer` (src/rasterizer/render.rs:10-45).  This header is what a Rust
+ * `extern "C"` shim keeping those signatures binds (see INTEGRATION.md for the shim).
+ * Plain pointers and sizes only; no CUDA or torch types appear in any signature.
+ *
+ * Threading: a context is not thread-safe; use one context per host thread / GPU.
+ * Ownership: the caller owns every buffer it passes; the library borrows it for the call only.
+ */
+#ifndef B32_RASTER_H
+#define B32_RASTER_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- return codes (the reference panics where these are returned) --------------------- */
+#define B32_OK               0
+#define B32_ERR_INVALID      1  /* null pointer / zero-sized framebuffer / bad enum            */
+#define B32_ERR_OOB_INDEX    2  /* face.v* >= nv: reference panics on slice index              */
+#define B32_ERR_NAN_DEPTH    3  /* NaN sort key: reference `partial_cmp().unwrap()` panics,    */
+                                /* src/rasterizer/render.rs:2531                                */
+#define B32_ERR_UNSUPPORTED  4  /* Spot light (libm acos is not bit-reproducible on device)    */
+#define B32_ERR_CUDA         5  /* a CUDA runtime call failed; see b32_last_error()            */
+#define B32_ERR_NO_DEVICE    6  /* no CUDA device: there is NO CPU fallback                    */
+
+/* ---- enums (values = declaration order of the Rust enums) ----------------------------- */
+/* BlendMode, src/rasterizer/types.rs:1378-1388 */
+enum { B32_BLEND_OPAQUE = 0, B32_BLEND_AVERAGE = 1, B32_BLEND_ADD = 2,
+       B32_BLEND_SUBTRACT = 3, B32_BLEND_ADD_QUARTER = 4, B32_BLEND_ERASE = 5 };
+/* ShadingMode, src/rasterizer/types.rs:1288-1293 */
+enum { B32_SHADE_NONE = 0, B32_SHADE_FLAT = 1, B32_SHADE_GOURAUD = 2 };
+/* LightType, src/rasterizer/types.rs:1296-1304 */
+enum { B32_LIGHT_DIRECTIONAL = 0, B32_LIGHT_POINT = 1, B32_LIGHT_SPOT = 2 };
+/* texture storage formats accepted by b32_textures_set */
+enum { B32_TEX_RGB555 = 0,   /* Texture15.pixels: u16 sRRRRRGGGGGBBBBB  (types.rs:532-539)     */
+       B32_TEX_IDX8   = 1,   /* one u8 palette index per texel + CLUT   (types.rs:438, 390-397) */
+       B32_TEX_IDX4   = 2 }; /* two texels per byte, low nibble = even x, + CLUT               */
+
+/* ---- POD records ---------------------------------------------------------------------- */
+
+/* struct Vertex, src/rasterizer/types.rs:947-959 (bone_index is ignored by the rasterizer).
+ * `blend` is Color.blend: it takes part in the `vc1 != vc2` test of needs_dither
+ * (render.rs:1487-1492) and is therefore carried.  36 bytes. */
+typedef struct b32_vertex {
+    float   pos[3];
+    float   uv[2];
+    float   normal[3];
+    uint8_t r, g, b, blend;
+} b32_vertex;
+
+/* struct Face, src/rasterizer/types.rs:984-1002.  16 bytes.
+ * flags: bits 0-15 texture_id (0xFFFF = None), bits 16-18 blend_mode, bit 19 black_transparent,
+ *        bits 24-31 editor_alpha. */
+typedef struct b32_face {
+    uint32_t v0, v1, v2;
+    uint32_t flags;
+} b32_face;
+#define B32_FACE_TEX_NONE 0xFFFFu
+#define B32_FACE_FLAGS(tex_id, blend, black_transparent, editor_alpha)                      \
+    (((uint32_t)(tex_id) & 0xFFFFu) | (((uint32_t)(blend) & 7u) << 16) |                    \
+     (((uint32_t)((black_transparent) ? 1u : 0u)) << 19) | (((uint32_t)(editor_alpha) & 0xFFu) << 24))
+
+/* struct Camera, src/rasterizer/camera.rs:9-18 (basis vectors are computed on the host by
+ * Camera::update_basis, camera.rs:76-91, and passed as data). 48 bytes. */
+typedef struct b32_camera {
+    float position[3];
+    float basis_x[3];
+    float basis_y[3];
+    float basis_z[3];
+} b32_camera;
+
+/* struct Light / enum LightType, src/rasterizer/types.rs:1296-1314.
+ * direction must already be normalised (Light::directional does it, types.rs:1319). */
+typedef struct b32_light {
+    uint32_t type;           /* B32_LIGHT_*                                   */
+    float    position[3];    /* Point, Spot                                   */
+    float    direction[3];   /* Directional, Spot                             */
+    float    radius;         /* Point, Spot                                   */
+    float    angle;          /* Spot                                          */
+    float    intensity;
+    uint8_t  r, g, b;        /* Light.color                                   */
+    uint8_t  enabled;
+} b32_light;
+
+/* struct RasterSettings, src/rasterizer/types.rs:1392-1428 (low_resolution and stretch_to_fill
+ * are UI-only and not carried). */
+typedef struct b32_settings {
+    uint8_t affine_textures;
+    uint8_t use_zbuffer;
+    uint8_t shading;             /* B32_SHADE_*                               */
+    uint8_t backface_cull;
+    uint8_t backface_wireframe;
+    uint8_t dithering;
+    uint8_t wireframe_overlay;
+    uint8_t use_rgb555;          /* informational: callers pick render_mesh vs render_mesh_15 */
+    uint8_t use_fixed_point;
+    uint8_t xray_mode;
+    uint8_t ortho_enabled;       /* ortho_projection.is_some()                */
+    uint8_t _pad;
+    float   ambient;
+    float   ortho_zoom, ortho_center_x, ortho_center_y;
+    uint32_t        n_lights;
+    const b32_light* lights;     /* n_lights entries, may be NULL when 0      */
+} b32_settings;
+
+/* fog: Option<(start, falloff, cull_distance, Color)>, render.rs:2309 */
+typedef struct b32_fog {
+    float   start, falloff, cull_distance;
+    uint8_t r, g, b, blend;
+} b32_fog;
+
+/* struct RasterTimings, src/rasterizer/types.rs:1499-1514.  Phase times are device times
+ * (CUDA events) of the kernels that replace each reference phase. */
+typedef struct b32_timings {
+    float    transform_ms, fog_ms, cull_ms, sort_ms, draw_ms, wireframe_ms;
+    uint32_t triangles_drawn;
+} b32_timings;
+
+/* struct Texture15 (types.rs:532-539) or an indexed texture + CLUT (types.rs:438, 328-397;
+ * IndexedAtlas::to_texture15, src/modeler/mesh_editor.rs:669-682). */
+typedef struct b32_tex_desc {
+    uint32_t        width, height;
+    uint32_t        format;      /* B32_TEX_*                                 */
+    uint32_t        blend_mode;  /* Texture15.blend_mode                      */
+    const void*     pixels;      /* u16[w*h] | u8[w*h] | u8[(w*h+1)/2]        */
+    const uint16_t* clut;        /* indexed formats: clut_len Color15 entries */
+    uint32_t        clut_len;    /* index >= clut_len samples 0x0000 (Clut::lookup, types.rs:390-397) */
+} b32_tex_desc;
+
+typedef struct b32_ctx  b32_ctx;   /* one GPU, one stream, one device-resident Framebuffer   */
+typedef struct b32_mesh b32_mesh;  /* device-resident vertex/face buffers                    */
+
+/* ---- context -------------------------------------------------------------------------- */
+int         b32_ctx_create(int device, b32_ctx** out);
+void        b32_ctx_destroy(b32_ctx* ctx);
+const char* b32_last_error(const b32_ctx* ctx);
+/* The cudaStream_t all work of this context is enqueued on (for external event timing). */
+void*       b32_ctx_stream(b32_ctx* ctx);
+/* Block until everything enqueued so far has finished; returns the first deferred error. */
+int         b32_sync(b32_ctx* ctx);
+/* Number of kernels of this library launched on this context so far. */
+uint64_t    b32_kernel_launches(const b32_ctx* ctx);
+
+/* ---- Framebuffer (src/rasterizer/render.rs:10-77) -------------------------------------- */
+/* Framebuffer::new / resize: pixels zeroed, zbuffer = f32::MAX (render.rs:18-34). */
+int b32_fb_resize(b32_ctx* ctx, uint32_t width, uint32_t height);
+/* Framebuffer::clear(color): every pixel = (r,g,b,a), zbuffer = f32::MAX (render.rs:36-45). */
+int b32_fb_clear(b32_ctx* ctx, uint8_t r, uint8_t g, uint8_t b, uint8_t a);
+/* Host access to Framebuffer.pixels / .zbuffer (host overlays, present). z may be NULL. */
+int b32_fb_upload(b32_ctx* ctx, const uint8_t* rgba, const float* z);
+int b32_fb_download(b32_ctx* ctx, uint8_t* rgba, float* z);
+int b32_fb_size(const b32_ctx* ctx, uint32_t* width, uint32_t* height);
+
+/* ---- textures (&[Texture15] argument of render_mesh_15) -------------------------------- */
+/* Replaces the context's texture table; face.texture_id indexes it. Cached across calls. */
+int b32_textures_set(b32_ctx* ctx, const b32_tex_desc* descs, uint32_t n);
+
+/* ---- the hot path ---------------------------------------------------------------------- */
+/* render_mesh_15 (render.rs:2302-2638) on host buffers: copies vertices/faces to the device,
+ * renders into the context's framebuffer, waits, fills *timings (may be NULL). */
+int b32_render_mesh_15(b32_ctx* ctx,
+                       const b32_vertex* vertices, uint32_t nv,
+                       const b32_face* faces, uint32_t nf,
+                       const b32_camera* camera, const b32_settings* settings,
+                       const b32_fog* fog_or_null, b32_timings* timings);
+
+/* Device-resident geometry: upload once, render many times (static level geometry; this is
+ * also how `value` is measured with inputs already in HBM). */
+int  b32_mesh_upload(b32_ctx* ctx, const b32_vertex* vertices, uint32_t nv,
+                     const b32_face* faces, uint32_t nf, b32_mesh** out);
+void b32_mesh_free(b32_ctx* ctx, b32_mesh* mesh);
+int  b32_render_mesh_15_resident(b32_ctx* ctx, const b32_mesh* mesh,
+                                 const b32_camera* camera, const b32_settings* settings,
+                                 const b32_fog* fog_or_null, b32_timings* timings);
+/* Same, but only enqueues (no wait, no timings); errors surface at b32_sync/b32_fb_download. */
+int  b32_render_mesh_15_enqueue(b32_ctx* ctx, const b32_mesh* mesh,
+                                const b32_camera* camera, const b32_settings* settings,
+                                const b32_fog* fog_or_null);
+
+/* ---- pinned host memory for callers that want zero-copy DMA of their Vec buffers -------- */
+void* b32_host_alloc(size_t bytes);
+void  b32_host_free(void* p);
+
+/* ---- per-stage device outputs, for parity tests of the individual kernels --------------- */
+/* Transform + snap only (render.rs:2321-2360): out_screen[nv*3] = projected (x,y,z),
+ * out_cam[nv*3] = cam_space_positions. */
+int b32_debug_transform(b32_ctx* ctx, const b32_vertex* vertices, uint32_t nv,
+                        const b32_camera* camera, const b32_settings* settings,
+                        float* out_screen, float* out_cam);
+/* Draw order of the last render call: out_face_idx[i] = Surface.face_idx of the i-th surface
+ * drawn (opaque pass then transparent pass). Returns count via *n (<= cap written). */
+int b32_debug_draw_order(b32_ctx* ctx, uint32_t* out_face_idx, uint32_t cap, uint32_t* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B32_RASTER_H */

@@ -1,0 +1,132 @@
+"""Named parity scenes shared by the CPU tests (oracle vs pymodel vs golden) and the GPU tests
+(CUDA vs oracle).  Each covers one feature of render_mesh_15 / rasterize_triangle_15."""
+from __future__ import annotations
+
+import copy
+
+import numpy as np
+
+from bonnie32_b200 import abi, scenes
+from bonnie32_b200.raster import Camera, Light, RasterSettings, Texture15
+
+
+def _rng_texture(seed, w, h, blend=abi.BLEND_OPAQUE, semi_fraction=0.0, zero_fraction=0.05):
+    u = scenes.splitmix64_u01(seed, w * h * 3)
+    px = np.floor(u[: w * h] * 32768.0).astype(np.uint16)
+    px[u[w * h: 2 * w * h] < zero_fraction] = 0
+    semi = u[2 * w * h:] < semi_fraction
+    px[semi] |= 0x8000
+    return Texture15(w, h, px, blend_mode=blend)
+
+
+def _with(scene, name, **kw):
+    s = copy.copy(scene)
+    s.settings = copy.copy(scene.settings)
+    s.name = name
+    for k, v in kw.items():
+        if hasattr(s.settings, k):
+            setattr(s.settings, k, v)
+        else:
+            setattr(s, k, v)
+    return s
+
+
+def _rotated_camera(rx, ry, pos):
+    c = Camera()
+    c.rotation_x = np.float32(rx)
+    c.rotation_y = np.float32(ry)
+    c.update_basis()
+    c.position = np.asarray(pos, dtype=np.float32)
+    return c
+
+
+def _mixed_faces(scene, seed):
+    """Give the faces a mix of blend modes / black_transparent / editor_alpha / texture ids."""
+    n = len(scene.faces)
+    u = scenes.splitmix64_u01(seed, n * 4).reshape(n, 4)
+    blend = np.where(u[:, 0] < 0.5, 0, np.floor(u[:, 0] * 10).astype(np.int64) - 4)   # 0 or 1..5
+    blend = np.clip(blend, 0, 5)
+    black_tr = u[:, 1] < 0.6
+    ea = np.where(u[:, 2] < 0.7, 255, np.floor(u[:, 2] * 256).astype(np.int64))
+    ea = np.where(u[:, 2] > 0.98, 0, ea)
+    tex = np.floor(u[:, 3] * 4).astype(np.int64)          # 0..3 ; 3 = out of range -> untextured
+    tex = np.where(u[:, 3] > 0.9, abi.FACE_TEX_NONE, tex)
+    f = scene.faces.copy()
+    f["flags"] = abi.face_flags(tex, blend, black_tr, ea)
+    return f
+
+
+def feature_scenes(n_tris=160):
+    """A list of small scenes, one per feature; all 320x240 unless stated."""
+    out = []
+    base = scenes.scene_c2(n_tris=n_tris)
+    out.append(_with(base, "painter_idx8"))
+    out.append(_with(base, "zbuffer_idx8", use_zbuffer=True))
+    out.append(_with(base, "nodither", dithering=False))
+    out.append(_with(base, "float_projection", use_fixed_point=False))
+    out.append(_with(base, "perspective_correct", affine_textures=False))
+    out.append(_with(base, "nocull_painter", backface_cull=False))
+    out.append(_with(base, "nocull_zbuffer", backface_cull=False, use_zbuffer=True))
+    out.append(_with(base, "xray", xray_mode=True, use_zbuffer=True))
+    out.append(_with(base, "ortho", ortho_projection=(6.0, 0.5, -0.25), use_zbuffer=True))
+    out.append(_with(base, "fb_200x150", width=200, height=150))
+    out.append(_with(base, "fb_640x480_zbuffer", width=640, height=480, use_zbuffer=True))
+
+    lights = [Light.directional((-1.0, -1.0, -1.0), 0.7),
+              Light.point_colored((0.5, 0.5, 4.0), 30.0, 1.5, 1.0, 0.5, 0.25),
+              Light.point((-3.0, 2.0, 20.0), 25.0, 0.9)]
+    off = Light.point((0.0, 0.0, 10.0), 50.0, 2.0)
+    off.enabled = False
+    # random (non-unit) normals so that lighting varies per vertex
+    g = copy.copy(base)
+    g.vertices = base.vertices.copy()
+    un = scenes.splitmix64_u01(77, len(g.vertices) * 3).reshape(-1, 3)
+    g.vertices["normal"] = (2.0 * un - 1.0).astype(np.float32)
+    out.append(_with(g, "gouraud_lights", shading=abi.SHADE_GOURAUD, lights=lights + [off], ambient=0.3, use_zbuffer=True))
+    out.append(_with(g, "flat_lights", shading=abi.SHADE_FLAT, lights=lights, ambient=0.2))
+    out.append(_with(g, "gouraud_default_nocull", shading=abi.SHADE_GOURAUD,
+                     lights=[Light.directional((-1.0, -1.0, -1.0), 0.7)], ambient=0.3, backface_cull=False, use_zbuffer=True))
+
+    out.append(_with(base, "fog", fog=(10.0, 30.0, 50.0, (90, 110, 130)), use_zbuffer=True))
+    out.append(_with(base, "fog_nofalloff", fog=(20.0, 0.0, 45.0, (10, 200, 30, abi.BLEND_ADD))))
+
+    # several textures, mixed face flags: transparent pass, all blend modes, editor alpha
+    m = copy.copy(base)
+    m.textures = [_rng_texture(11, 64, 64, semi_fraction=0.5),
+                  _rng_texture(12, 32, 64, blend=abi.BLEND_AVERAGE, semi_fraction=0.5),
+                  _rng_texture(13, 16, 8, blend=abi.BLEND_ADD, semi_fraction=0.9, zero_fraction=0.3)]
+    m.faces = _mixed_faces(base, 99)
+    out.append(_with(m, "mixed_painter"))
+    out.append(_with(m, "mixed_zbuffer", use_zbuffer=True))
+    out.append(_with(m, "mixed_zbuffer_nocull_gouraud", use_zbuffer=True, backface_cull=False,
+                     shading=abi.SHADE_GOURAUD, lights=lights, ambient=0.4))
+    out.append(_with(m, "mixed_xray", xray_mode=True))
+
+    # untextured vertex-coloured triangles (needs_dither from colour inequality)
+    ut = copy.copy(base)
+    ut.faces = base.faces.copy()
+    ut.faces["flags"] = abi.face_flags(abi.FACE_TEX_NONE)
+    out.append(_with(ut, "untextured_vertex_colours"))
+
+    # camera inside the cloud, rotated: near-plane rejects, huge off-screen coordinates (slow edge path)
+    big = scenes.scene_c2(n_tris=n_tris, seed=0xB32000AA)
+    big.vertices = big.vertices.copy()
+    big.vertices["pos"] *= np.float32(40.0)
+    out.append(_with(big, "rotated_camera_large_world", camera=_rotated_camera(0.3, 0.7, (10.0, -20.0, 300.0)), use_zbuffer=True))
+    out.append(_with(big, "rotated_camera_large_world_float", camera=_rotated_camera(-0.2, 2.4, (-30.0, 15.0, 900.0)),
+                     use_fixed_point=False))
+    return out
+
+
+def big_triangle_scene():
+    """Few very large triangles that cover the whole screen with vertices far off-screen."""
+    pos = [(-4000.0, -3000.0, 60.0), (5000.0, -2500.0, 30.0), (100.0, 4000.0, 2.0),
+           (-30.0, -20.0, 8.0), (40.0, -25.0, 9.0), (5.0, 35.0, 1.0),
+           (-900.5, 700.25, 3.0), (800.75, 650.5, 2.5), (10.25, -1200.125, 40.0)]
+    uv = [(0, 0), (3, 0), (0, 3)] * 3
+    rgba = [(255, 128, 64, 0), (64, 255, 128, 0), (128, 64, 255, 0)] * 3
+    v = scenes.make_vertices(pos, uv=uv, normal=[(0, 0, -1)] * 9, rgba=rgba)
+    f = scenes.make_faces([(0, 1, 2), (0, 2, 1), (3, 4, 5), (3, 5, 4), (6, 7, 8), (6, 8, 7)], tex_id=0)
+    tex = _rng_texture(5, 64, 64)
+    s = scenes.common_settings(use_zbuffer=True, backface_cull=False)
+    return scenes.Scene("big_triangles", v, f, [tex], Camera(), s)
