@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py — Mtriangles/s of the rasterizer hot path at 320x240 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A step = one render_mesh_15 pass (transform -> cull -> sort -> fill) of one 100 000-triangle frame
+per GPU into a cleared 320x240 framebuffer.  N=1 renders BASELINE config 4 (seed 0xB3200004);
+N>1 renders the C5 frames (rank r renders frame r, seed 0xB3200500+r): frames shard over GPUs with
+no data-path collective (weak scaling).  `value` = submitted triangles of all ranks / device time
+with geometry resident in HBM; `e2e` = same through b32_render_mesh_15 with pinned HOST buffers
+(H2D of vertices+faces and D2H of the framebuffer inside the timed region, wall clock).
+
+--impl reference times the CPU oracle (oracle/, a line-by-line C++ restatement of the reference's
+Rust rasterizer; the Rust itself cannot be built here: no rustc) on the host cores, rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as entry  # noqa: E402
+
+N_TRIS = 100_000
+METRIC = "Mtriangles/s at 320x240 (render_mesh_15, 100k-triangle scene, framebuffer bit-exact vs oracle)"
+UNIT = "Mtriangles/s"
+
+
+def frame_scene(pkg, n_gpus: int, rank: int):
+    if n_gpus == 1:
+        return pkg.scenes.scene_c4(n_tris=N_TRIS)
+    return pkg.scenes.scene_c5(rank, n_tris=N_TRIS)
+
+
+def workload_config(n_gpus: int):
+    return {
+        "workload": ("BASELINE configs[3]: 100k-triangle synthetic stress scene, 256x256 4-bit atlas, 320x240"
+                     if n_gpus == 1 else
+                     f"BASELINE configs[4]: {n_gpus} independent 100k-triangle frames (C5 seeds), one per GPU, 320x240"),
+        "triangles_per_frame": N_TRIS, "vertices_per_frame": 3 * N_TRIS, "framebuffer": "320x240 RGBA8 + f32 z",
+        "settings": "painter's sort (use_zbuffer=false), affine, fixed-point snap, RGB555 + dither, backface cull",
+        "parallelism": f"frames sharded over {n_gpus} GPU(s), no data-path collective",
+        "l2": "256 MiB device memset between timed steps (flushes the 126 MB L2); excluded from the step time",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.idx = device_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower() == "active":
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def _oracle_worker_init(n_gpus):
+    global _W_PKG, _W_ORC, _W_SCENES, _W_NG
+    _W_PKG = entry.load_package()
+    from oracle import oracle as orc
+    _W_ORC = orc
+    _W_SCENES = {}
+    _W_NG = n_gpus
+
+
+def _oracle_worker_frame(rank):
+    sc = _W_SCENES.get(rank)
+    if sc is None:
+        sc = _W_SCENES[rank] = frame_scene(_W_PKG, _W_NG, rank)
+    t = time.perf_counter()
+    rgba, z, tm, rc = _W_ORC.render_scene(sc)
+    assert rc == 0
+    return time.perf_counter() - t, tm["triangles_drawn"]
+
+
+def time_oracle(n_gpus: int, steps: int, warmup: int):
+    """Frames of the same workload through the CPU oracle. One thread per frame (the reference is
+    single-threaded); with N frames per step, up to N processes run side by side."""
+    import multiprocessing as mp
+    entry.build_oracle()
+    cores = min(n_gpus, os.cpu_count() or 1)
+    if cores == 1:
+        _oracle_worker_init(n_gpus)
+        for _ in range(warmup):
+            _oracle_worker_frame(0)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            for r in range(n_gpus):
+                _oracle_worker_frame(r)
+        dt = time.perf_counter() - t0
+    else:
+        with mp.get_context("fork").Pool(cores, initializer=_oracle_worker_init, initargs=(n_gpus,)) as pool:
+            for _ in range(warmup):
+                pool.map(_oracle_worker_frame, range(n_gpus))
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                pool.map(_oracle_worker_frame, range(n_gpus))
+            dt = time.perf_counter() - t0
+    return dt, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    dt, cores = time_oracle(args.gpus, args.steps, args.warmup)
+    ms = dt * 1000.0 / args.steps
+    value = args.gpus * N_TRIS / (dt / args.steps) / 1e6
+    sample = f"{args.steps} steps x {args.gpus} full 100k-triangle frame(s), {cores} process(es), 1 thread per frame"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32+i32/i64 fixed-point", "data": "synthetic", "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "note": "Rust reference not executable here (no rustc); CPU figure is the line-by-line C++ restatement in oracle/"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "frames_per_s": args.gpus / (dt / args.steps),
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    pkg = entry.load_package()
+    import ctypes as C
+    abi = pkg.abi
+    sc = frame_scene(pkg, world, rank)
+    ctx = pkg.Context(local_rank)
+    lib = ctx.lib
+    fb = pkg.Framebuffer(sc.width, sc.height, ctx)
+    ctx.set_textures(sc.textures)
+    mesh = pkg.Mesh(ctx, sc.vertices, sc.faces)
+    cam = sc.camera.to_abi()
+    st, keep = sc.settings.to_abi()
+    tm = abi.Timings()
+    ktimes = (C.c_float * 16)()
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    r, g, b = sc.clear
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        ctx.check(lib.b32_fb_clear(ctx.h, r, g, b, 255))
+        ctx.check(lib.b32_render_mesh_15_resident(ctx.h, mesh.h, C.byref(cam), C.byref(st), None, C.byref(tm)))
+
+    # ---- device-resident value -----------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    drawn = tm.triangles_drawn
+    launches0 = ctx.kernel_launches()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    step_ms, phase = [], {"transform_ms": 0.0, "cull_ms": 0.0, "sort_ms": 0.0, "draw_ms": 0.0}
+    kern = np.zeros(16)
+    with torch.cuda.stream(stream):
+        for _ in range(args.steps):
+            flush.fill_(1)                                   # evict the L2 (not timed)
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            step_resident()
+            e1.record(stream)
+            e1.synchronize()
+            step_ms.append(e0.elapsed_time(e1))
+            for k in phase:
+                phase[k] += getattr(tm, k)
+            n = lib.b32_debug_kernel_times(ctx.h, ktimes, 16)
+            kern[:n] += np.array(ktimes[:n])
+    barrier()
+    clocks = sampler.stop()
+    launches = ctx.kernel_launches() - launches0
+    total_ms = float(sum(step_ms))
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)            # max over ranks; NCCL only gathers timing
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * N_TRIS / (ms_per_step * 1e-3) / 1e6
+
+    # ---- end to end through the host-buffer ABI ----------------------------------------------------
+    nvb, nfb = sc.vertices.nbytes, sc.faces.nbytes
+    hv = lib.b32_host_alloc(nvb); hf = lib.b32_host_alloc(nfb); hp = lib.b32_host_alloc(sc.width * sc.height * 4)
+    C.memmove(hv, sc.vertices.ctypes.data, nvb); C.memmove(hf, sc.faces.ctypes.data, nfb)
+
+    def step_e2e():
+        ctx.check(lib.b32_fb_clear(ctx.h, r, g, b, 255))
+        ctx.check(lib.b32_render_mesh_15(ctx.h, hv, len(sc.vertices), hf, len(sc.faces), C.byref(cam), C.byref(st), None, C.byref(tm)))
+        ctx.check(lib.b32_fb_download(ctx.h, hp, None))
+
+    for _ in range(max(args.warmup, 3)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_value = world * N_TRIS / (e2e_s / args.steps) / 1e6
+    got = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_uint8)), shape=(sc.height, sc.width, 4)).copy()
+
+    # ---- parity of the frame just timed, against the committed golden hash -------------------------
+    import hashlib
+    parity = None
+    try:
+        hashes = json.load(open(os.path.join(ROOT, "tests", "golden", "hashes.json")))
+        parity = hashes[sc.name]["rgba_sha256"] == hashlib.sha256(got.tobytes()).hexdigest()
+    except Exception:
+        pass
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        names = ["k_transform", "k_setup", "sort_faces(cub)", "bin_count+scan", "bin_emit+tile_scan", "sort_entries(cub)", "k_fill"]
+        kavg = {n: float(kern[i] / args.steps) for i, n in enumerate(names)}
+        dom = max(kavg, key=kavg.get)
+        alg_bytes = sc.algorithmic_bytes
+        ach = alg_bytes / (kavg[dom] * 1e-3) / 1e9 if kavg[dom] > 0 else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32+i32/i64 fixed-point", "data": "synthetic", "config": workload_config(world),
+            "frames_per_s": world / (ms_per_step * 1e-3), "triangles_drawn": int(drawn), "bit_exact_vs_golden": parity,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nvb + nfb, "d2h_bytes_per_step": sc.width * sc.height * 4,
+                    "ms_per_step": e2e_s * 1e3 / args.steps, "frames_per_s": world / (e2e_s / args.steps)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": (ach / peak) if ach else None, "traffic": None,
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                         "kernel_ms": kavg, "phase_ms": {k: v / args.steps for k, v in phase.items()},
+                         "whole_frame_frac": alg_bytes / (ms_per_step * 1e-3) / 1e9 / peak},
+        }
+        if world == 1 and not args.no_cpu:
+            n_cpu = 20
+            dt, cores = time_oracle(1, n_cpu, 2)
+            line["cpu_baseline"] = {"value": N_TRIS / (dt / n_cpu) / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{n_cpu} full 100k-triangle frames of the same scene, single thread, oracle -O3",
+                                    "note": "Rust reference not executable here (no rustc); C++ restatement in oracle/"}
+        print(json.dumps(line))
+    lib.b32_host_free(hv); lib.b32_host_free(hf); lib.b32_host_free(hp)
+    mesh.free()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -106,6 +106,7 @@ SYMBOLS = {
     "b32_host_free": (None, [_P]),
     "b32_debug_transform": (C.c_int, [_P, _P, C.c_uint32, C.POINTER(Camera), C.POINTER(Settings), _P, _P]),
     "b32_debug_draw_order": (C.c_int, [_P, _P, C.c_uint32, C.POINTER(C.c_uint32)]),
+    "b32_debug_kernel_times": (C.c_int, [_P, C.POINTER(C.c_float), C.c_uint32]),
 }
 
 _lib = None

@@ -1,0 +1,532 @@
+// b32_api.cu — the C ABI of include/b32_raster.h: context, device memory, streams, and the
+// orchestration of one render_mesh_15 call (render.rs:2302-2638) as a sequence of kernels on the
+// context's stream.  There is no CPU fallback: without a CUDA device b32_ctx_create fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "b32_launch.h"
+#include "b32_raster.h"
+
+using namespace b32;
+
+namespace {
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;     // elements
+    cudaError_t reserve(size_t n, bool keep = false, cudaStream_t s = 0) {
+        if (n <= cap) return cudaSuccess;
+        size_t ncap = std::max(n, cap + cap / 2);
+        T* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, ncap * sizeof(T));
+        if (e != cudaSuccess) return e;
+        if (keep && p && cap) cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, s);
+        if (p) { cudaStreamSynchronize(s); cudaFree(p); }
+        p = q; cap = ncap;
+        return cudaSuccess;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct b32_mesh {
+    b32_vertex* verts = nullptr;
+    b32_face* faces = nullptr;
+    uint32_t nv = 0, nf = 0;
+};
+
+struct b32_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaDeviceProp prop{};
+    std::string err;
+    int deferred = B32_OK;
+    uint64_t launches = 0;
+
+    // framebuffer (render.rs:10-15)
+    uint32_t width = 0, height = 0;
+    DevBuf<uint32_t> fb_rgba;
+    DevBuf<float> fb_z;
+
+    // textures
+    DevBuf<uint16_t> texels;
+    DevBuf<TexDev> texdesc;
+    std::vector<TexDev> texdesc_h;
+    uint32_t ntex = 0;
+
+    // staging geometry for host-buffer calls
+    DevBuf<b32_vertex> verts;
+    DevBuf<b32_face> faces;
+
+    // per-call work buffers
+    DevBuf<TVert> tv;
+    DevBuf<SurfRec> recs;
+    DevBuf<uint64_t> keys, keys_sorted;
+    DevBuf<uint32_t> vals, order, counts, offsets;
+    DevBuf<uint32_t> ent_tile, ent_surf, ent_tile_sorted, ent_surf_sorted;
+    DevBuf<uint32_t> tile_count, tile_start;
+    DevBuf<uint8_t> temp;
+    DevBuf<LightDev> lights;
+    DevBuf<float> dbg;
+    uint8_t* unr_table = nullptr;
+    CallState* state = nullptr;        // device
+    CallState* state_h = nullptr;      // pinned host
+    uint8_t* pinned = nullptr;         // pinned staging ring for pageable host buffers
+    size_t pinned_bytes = 0;
+    uint32_t last_nf = 0;
+
+    cudaEvent_t ev[8] = {};
+    float kernel_ms[7] = {};
+    float emit_ms = 0.0f;
+
+    LaunchCtx L() { return LaunchCtx{stream, (uint32_t)prop.multiProcessorCount, unr_table, &launches}; }
+};
+
+namespace {
+
+int fail(b32_ctx* c, int code, const std::string& msg) { if (c) c->err = msg; return code; }
+int cuda_fail(b32_ctx* c, cudaError_t e, const char* what) {
+    return fail(c, B32_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return cuda_fail(ctx, _e, #call); } while (0)
+
+int32_t host_fx_from_f32(float f) {                 // Fixed32::from_f32, fixed.rs:125-127 (saturating `as i32`)
+    float s = f * 4096.0f;
+    if (s != s) return 0;
+    if (s >= 2147483648.0f) return INT32_MAX;
+    if (s <= -2147483648.0f) return INT32_MIN;
+    return (int32_t)s;
+}
+
+int fill_params(b32_ctx* ctx, CallParams& p, const b32_camera* cam, const b32_settings* s, const b32_fog* fog,
+                uint32_t nv, uint32_t nf, std::vector<LightDev>& lights) {
+    std::memset(&p, 0, sizeof(p));
+    for (int i = 0; i < 3; ++i) {
+        p.cam_pos[i] = cam->position[i]; p.bx[i] = cam->basis_x[i]; p.by[i] = cam->basis_y[i]; p.bz[i] = cam->basis_z[i];
+        p.fcam_pos[i] = host_fx_from_f32(cam->position[i]);
+        p.fbx[i] = host_fx_from_f32(cam->basis_x[i]); p.fby[i] = host_fx_from_f32(cam->basis_y[i]); p.fbz[i] = host_fx_from_f32(cam->basis_z[i]);
+    }
+    p.width = ctx->width; p.height = ctx->height;
+    p.tiles_x = (ctx->width + TILE_W - 1) / TILE_W; p.tiles_y = (ctx->height + TILE_H - 1) / TILE_H;
+    p.viewport_scale = host_fx_from_f32(((float)std::min(ctx->width, ctx->height) / 2.0f) * 0.75f);   // fixed.rs:398
+    p.half_w = (int32_t)(((uint32_t)((int32_t)ctx->width / 2)) << 12);                                // fixed.rs:399-400
+    p.half_h = (int32_t)(((uint32_t)((int32_t)ctx->height / 2)) << 12);
+    p.nv = nv; p.nf = nf; p.ntex = ctx->ntex;
+    p.affine_textures = s->affine_textures != 0; p.use_zbuffer = s->use_zbuffer != 0; p.shading = s->shading;
+    p.backface_cull = s->backface_cull != 0; p.dithering = s->dithering != 0; p.use_fixed_point = s->use_fixed_point != 0;
+    p.xray_mode = s->xray_mode != 0; p.ortho = s->ortho_enabled != 0;
+    p.ambient = s->ambient; p.ortho_zoom = s->ortho_zoom; p.ortho_cx = s->ortho_center_x; p.ortho_cy = s->ortho_center_y;
+    if (fog) {
+        p.fog_enabled = 1; p.fog_start = fog->start; p.fog_falloff = fog->falloff; p.fog_cull = fog->cull_distance;
+        p.fog_r = fog->r; p.fog_g = fog->g; p.fog_b = fog->b; p.fog_blend = fog->blend;
+    }
+    if (s->shading > B32_SHADE_GOURAUD) return fail(ctx, B32_ERR_INVALID, "settings.shading out of range");
+    lights.clear();
+    if (s->n_lights && !s->lights) return fail(ctx, B32_ERR_INVALID, "settings.lights is NULL");
+    for (uint32_t i = 0; i < s->n_lights; ++i) {
+        const b32_light& l = s->lights[i];
+        if (l.type > B32_LIGHT_SPOT) return fail(ctx, B32_ERR_INVALID, "light type out of range");
+        // Spot lights use libm acos (render.rs:1047), not bit-reproducible on the device.  The app never
+        // constructs them (scene.rs:62 only makes point lights); only enabled lights matter (:1018).
+        if (l.type == B32_LIGHT_SPOT && l.enabled && s->shading != B32_SHADE_NONE)
+            return fail(ctx, B32_ERR_UNSUPPORTED, "enabled Spot light: libm acos is not reproducible on the device");
+        LightDev d{};
+        d.type = l.type; d.px = l.position[0]; d.py = l.position[1]; d.pz = l.position[2];
+        d.dx = l.direction[0]; d.dy = l.direction[1]; d.dz = l.direction[2];
+        d.radius = l.radius; d.angle = l.angle; d.intensity = l.intensity;
+        d.cr = (float)l.r / 255.0f; d.cg = (float)l.g / 255.0f; d.cb = (float)l.b / 255.0f;   // render.rs:1062-1064
+        d.enabled = l.enabled && l.type != B32_LIGHT_SPOT;
+        lights.push_back(d);
+    }
+    p.n_lights = (uint32_t)lights.size();
+    return B32_OK;
+}
+
+// copy a host buffer to the device on the context stream; pageable memory goes through the pinned ring
+int h2d(b32_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!bytes) return B32_OK;
+    cudaPointerAttributes a{};
+    bool pinned_src = cudaPointerGetAttributes(&a, src) == cudaSuccess && (a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged);
+    cudaGetLastError();
+    if (pinned_src) { CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream)); return B32_OK; }
+    // two-slot ring: memcpy into slot k overlaps the DMA of slot k^1
+    const size_t slot = ctx->pinned_bytes / 2;
+    cudaEvent_t done[2]; CK(cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming));
+    bool used[2] = {false, false};
+    size_t off = 0; int k = 0;
+    while (off < bytes) {
+        size_t n = std::min(slot, bytes - off);
+        if (used[k]) CK(cudaEventSynchronize(done[k]));
+        std::memcpy(ctx->pinned + k * slot, (const uint8_t*)src + off, n);
+        CK(cudaMemcpyAsync((uint8_t*)dst + off, ctx->pinned + k * slot, n, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaEventRecord(done[k], ctx->stream)); used[k] = true;
+        off += n; k ^= 1;
+    }
+    for (int i = 0; i < 2; ++i) { if (used[i]) cudaEventSynchronize(done[i]); cudaEventDestroy(done[i]); }
+    return B32_OK;
+}
+
+int ensure_work(b32_ctx* ctx, uint32_t nv, uint32_t nf) {
+    CK(ctx->tv.reserve(std::max<uint32_t>(nv, 1)));
+    CK(ctx->recs.reserve(std::max<uint32_t>(nf, 1)));
+    CK(ctx->keys.reserve(std::max<uint32_t>(nf, 1)));
+    CK(ctx->keys_sorted.reserve(std::max<uint32_t>(nf, 1)));
+    CK(ctx->vals.reserve(std::max<uint32_t>(nf, 1)));
+    CK(ctx->order.reserve(std::max<uint32_t>(nf, 1)));
+    CK(ctx->counts.reserve(std::max<uint32_t>(nf, 1)));
+    CK(ctx->offsets.reserve(std::max<uint32_t>(nf, 1)));
+    uint32_t ntiles = ((ctx->width + TILE_W - 1) / TILE_W) * ((ctx->height + TILE_H - 1) / TILE_H);
+    CK(ctx->tile_count.reserve(std::max<uint32_t>(ntiles, 1)));
+    CK(ctx->tile_start.reserve(std::max<uint32_t>(ntiles, 1)));
+    return B32_OK;
+}
+
+int ensure_entries(b32_ctx* ctx, size_t n) {
+    n = std::max<size_t>(n, 1 << 16);
+    CK(ctx->ent_tile.reserve(n)); CK(ctx->ent_surf.reserve(n));
+    CK(ctx->ent_tile_sorted.reserve(n)); CK(ctx->ent_surf_sorted.reserve(n));
+    return B32_OK;
+}
+
+int ensure_temp(b32_ctx* ctx, uint32_t nf, size_t entries) {
+    size_t need = sort_temp_bytes(std::max<uint32_t>(nf, 1), (uint32_t)std::max<size_t>(entries, 1));
+    CK(ctx->temp.reserve(need));
+    return B32_OK;
+}
+
+// One render_mesh_15 on device-resident geometry. sync=false only enqueues.
+int render_device(b32_ctx* ctx, const b32_vertex* d_verts, uint32_t nv, const b32_face* d_faces, uint32_t nf,
+                  const b32_camera* cam, const b32_settings* s, const b32_fog* fog, b32_timings* tm) {
+    if (!cam || !s) return fail(ctx, B32_ERR_INVALID, "camera/settings is NULL");
+    if (ctx->width == 0 || ctx->height == 0) return fail(ctx, B32_ERR_INVALID, "framebuffer has zero size (call b32_fb_resize)");
+    if (ctx->width > 65535 || ctx->height > 65535) return fail(ctx, B32_ERR_UNSUPPORTED, "framebuffer dimension > 65535");
+    CallParams p;
+    std::vector<LightDev> lights;
+    int rc = fill_params(ctx, p, cam, s, fog, nv, nf, lights);
+    if (rc != B32_OK) return rc;
+    if (tm) std::memset(tm, 0, sizeof(*tm));
+    ctx->last_nf = nf;
+    if (nf == 0) return B32_OK;
+
+    rc = ensure_work(ctx, nv, nf); if (rc) return rc;
+    rc = ensure_entries(ctx, (size_t)nf * 8); if (rc) return rc;
+    rc = ensure_temp(ctx, nf, ctx->ent_tile.cap); if (rc) return rc;
+    if (!lights.empty()) {
+        CK(ctx->lights.reserve(lights.size()));
+        CK(cudaMemcpyAsync(ctx->lights.p, lights.data(), lights.size() * sizeof(LightDev), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));   // `lights` is a host temporary
+    }
+    LaunchCtx L = ctx->L();
+    cudaStream_t st = ctx->stream;
+    const uint32_t ntiles = p.tiles_x * p.tiles_y;
+
+    CK(cudaMemsetAsync(ctx->state, 0, sizeof(CallState), st));
+    CK(cudaEventRecord(ctx->ev[0], st));
+    launch_transform(L, d_verts, ctx->tv.p, nullptr, p);                                     // TRANSFORM
+    CK(cudaEventRecord(ctx->ev[1], st));
+    launch_setup(L, d_verts, d_faces, ctx->tv.p, ctx->texdesc.p, ctx->lights.p, ctx->recs.p, ctx->keys.p, ctx->vals.p, ctx->state, p);   // CULL
+    CK(cudaEventRecord(ctx->ev[2], st));
+    launch_sort_faces(L, ctx->temp.p, ctx->temp.cap, ctx->keys.p, ctx->keys_sorted.p, ctx->vals.p, ctx->order.p, nf);   // SORT
+    CK(cudaEventRecord(ctx->ev[3], st));
+    launch_binning(L, ctx->temp.p, ctx->temp.cap, ctx->recs.p, ctx->order.p, ctx->counts.p, ctx->offsets.p, ctx->ent_tile.p, ctx->ent_surf.p,
+                   ctx->ent_tile_sorted.p, ctx->ent_surf_sorted.p, ctx->tile_count.p, ctx->tile_start.p, ctx->state, p,
+                   (uint32_t)std::min<size_t>(ctx->ent_tile.cap, 0xFFFFFFFFu), true, false);
+    CK(cudaEventRecord(ctx->ev[4], st));
+    launch_binning(L, ctx->temp.p, ctx->temp.cap, ctx->recs.p, ctx->order.p, ctx->counts.p, ctx->offsets.p, ctx->ent_tile.p, ctx->ent_surf.p,
+                   ctx->ent_tile_sorted.p, ctx->ent_surf_sorted.p, ctx->tile_count.p, ctx->tile_start.p, ctx->state, p,
+                   (uint32_t)std::min<size_t>(ctx->ent_tile.cap, 0xFFFFFFFFu), false, true);
+    CK(cudaEventRecord(ctx->ev[5], st));
+    // the entry sort needs the entry count on the host
+    CK(cudaMemcpyAsync(ctx->state_h, ctx->state, sizeof(CallState), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CallState hs = *ctx->state_h;
+    cudaEventElapsedTime(&ctx->emit_ms, ctx->ev[4], ctx->ev[5]);
+    if (hs.oob) { ctx->deferred = B32_OK; return fail(ctx, B32_ERR_OOB_INDEX, "face vertex index out of range (reference: slice index panic)"); }
+    if (hs.abort) return fail(ctx, B32_ERR_NAN_DEPTH, "NaN depth key in a sorted pass (reference: partial_cmp().unwrap() panic, render.rs:2531)");
+    if (hs.overflow) {      // grow the entry buffers and redo the emit
+        rc = ensure_entries(ctx, (size_t)hs.n_entries + hs.n_entries / 4); if (rc) return rc;
+        rc = ensure_temp(ctx, nf, ctx->ent_tile.cap); if (rc) return rc;
+        launch_binning(L, ctx->temp.p, ctx->temp.cap, ctx->recs.p, ctx->order.p, ctx->counts.p, ctx->offsets.p, ctx->ent_tile.p, ctx->ent_surf.p,
+                       ctx->ent_tile_sorted.p, ctx->ent_surf_sorted.p, ctx->tile_count.p, ctx->tile_start.p, ctx->state, p,
+                       (uint32_t)std::min<size_t>(ctx->ent_tile.cap, 0xFFFFFFFFu), false, true);
+    }
+    CK(cudaEventRecord(ctx->ev[5], st));     // (re-recorded: excludes the host round trip above)
+    launch_sort_entries(L, ctx->temp.p, ctx->temp.cap, ctx->ent_tile.p, ctx->ent_tile_sorted.p, ctx->ent_surf.p, ctx->ent_surf_sorted.p, hs.n_entries, ntiles);
+    CK(cudaEventRecord(ctx->ev[6], st));
+    launch_fill(L, ctx->recs.p, ctx->ent_surf_sorted.p, ctx->tile_start.p, ctx->tile_count.p, ctx->texdesc.p, ctx->texels.p,
+                ctx->fb_rgba.p, ctx->fb_z.p, ctx->state, p);                                 // DRAW
+    CK(cudaEventRecord(ctx->ev[7], st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    // ev: 0 start | 1 transform | 2 setup | 3 face sort | 4 bin count+scan | [emit, host round trip] 5 | 6 entry sort | 7 fill
+    float* k = ctx->kernel_ms;
+    cudaEventElapsedTime(&k[0], ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&k[1], ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&k[2], ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&k[3], ctx->ev[3], ctx->ev[4]);
+    k[4] = ctx->emit_ms;
+    cudaEventElapsedTime(&k[5], ctx->ev[5], ctx->ev[6]);
+    cudaEventElapsedTime(&k[6], ctx->ev[6], ctx->ev[7]);
+    if (tm) {
+        tm->transform_ms = k[0];
+        tm->cull_ms = k[1];                      // fog is fused into the cull kernel (fog_ms stays 0)
+        tm->sort_ms = k[2];
+        tm->draw_ms = k[3] + k[4] + k[5] + k[6]; // binning + fill
+        tm->triangles_drawn = hs.n_opaque + hs.n_transp;                           // render.rs:2545
+    }
+    return B32_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int b32_ctx_create(int device, b32_ctx** out) {
+    if (!out) return B32_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) { cudaGetLastError(); return B32_ERR_NO_DEVICE; }
+    b32_ctx* ctx = new b32_ctx();
+    ctx->device = device;
+    auto bail = [&](cudaError_t e, const char* what) { fprintf(stderr, "b32_ctx_create: %s: %s\n", what, cudaGetErrorString(e)); delete ctx; return B32_ERR_CUDA; };
+    cudaError_t e;
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e, "cudaSetDevice");
+    if ((e = cudaGetDeviceProperties(&ctx->prop, device)) != cudaSuccess) return bail(e, "cudaGetDeviceProperties");
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    for (auto& ev : ctx->ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = cudaMalloc(&ctx->state, sizeof(CallState))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMallocHost(&ctx->state_h, sizeof(CallState))) != cudaSuccess) return bail(e, "cudaMallocHost");
+    ctx->pinned_bytes = 8u << 20;
+    if ((e = cudaMallocHost(&ctx->pinned, ctx->pinned_bytes)) != cudaSuccess) return bail(e, "cudaMallocHost");
+    // UNR table, fixed.rs:20-31: table[i] = max(0, (0x40000 / (i + 0x100) + 1) / 2 - 0x101)
+    uint8_t table[257];
+    for (uint32_t i = 0; i < 257; ++i) { int32_t v = (int32_t)((0x40000u / (i + 0x100u) + 1) / 2) - 0x101; table[i] = v > 0 ? (uint8_t)v : 0; }
+    if ((e = cudaMalloc(&ctx->unr_table, 260)) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMemcpy(ctx->unr_table, table, 257, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "cudaMemcpy");
+    ctx->texdesc.reserve(1); ctx->texels.reserve(1); ctx->lights.reserve(1);
+    *out = ctx;
+    return B32_OK;
+}
+
+void b32_ctx_destroy(b32_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->fb_rgba.release(); ctx->fb_z.release(); ctx->texels.release(); ctx->texdesc.release(); ctx->verts.release(); ctx->faces.release();
+    ctx->tv.release(); ctx->recs.release(); ctx->keys.release(); ctx->keys_sorted.release(); ctx->vals.release(); ctx->order.release();
+    ctx->counts.release(); ctx->offsets.release(); ctx->ent_tile.release(); ctx->ent_surf.release(); ctx->ent_tile_sorted.release();
+    ctx->ent_surf_sorted.release(); ctx->tile_count.release(); ctx->tile_start.release(); ctx->temp.release(); ctx->lights.release(); ctx->dbg.release();
+    if (ctx->unr_table) cudaFree(ctx->unr_table);
+    if (ctx->state) cudaFree(ctx->state);
+    if (ctx->state_h) cudaFreeHost(ctx->state_h);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* b32_last_error(const b32_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+void* b32_ctx_stream(b32_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+uint64_t b32_kernel_launches(const b32_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int b32_sync(b32_ctx* ctx) {
+    if (!ctx) return B32_ERR_INVALID;
+    CK(cudaStreamSynchronize(ctx->stream));
+    int d = ctx->deferred; ctx->deferred = B32_OK;
+    return d;
+}
+
+int b32_fb_resize(b32_ctx* ctx, uint32_t width, uint32_t height) {
+    if (!ctx) return B32_ERR_INVALID;
+    if (width == ctx->width && height == ctx->height) return B32_OK;          // render.rs:28
+    if (width > 65535 || height > 65535) return fail(ctx, B32_ERR_UNSUPPORTED, "framebuffer dimension > 65535");
+    CK(cudaStreamSynchronize(ctx->stream));
+    size_t n = (size_t)width * height;
+    CK(ctx->fb_rgba.reserve(std::max<size_t>(n, 1)));
+    CK(ctx->fb_z.reserve(std::max<size_t>(n, 1)));
+    ctx->width = width; ctx->height = height;
+    launch_fb_clear(ctx->L(), ctx->fb_rgba.p, ctx->fb_z.p, (uint32_t)n, 0u);   // pixels 0, zbuffer f32::MAX (render.rs:31-32)
+    return B32_OK;
+}
+
+int b32_fb_clear(b32_ctx* ctx, uint8_t r, uint8_t g, uint8_t b, uint8_t a) {
+    if (!ctx) return B32_ERR_INVALID;
+    uint32_t c = (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16) | ((uint32_t)a << 24);
+    launch_fb_clear(ctx->L(), ctx->fb_rgba.p, ctx->fb_z.p, ctx->width * ctx->height, c);
+    CK(cudaGetLastError());
+    return B32_OK;
+}
+
+int b32_fb_upload(b32_ctx* ctx, const uint8_t* rgba, const float* z) {
+    if (!ctx || !rgba) return B32_ERR_INVALID;
+    size_t n = (size_t)ctx->width * ctx->height;
+    int rc = h2d(ctx, ctx->fb_rgba.p, rgba, n * 4); if (rc) return rc;
+    if (z) { rc = h2d(ctx, ctx->fb_z.p, z, n * 4); if (rc) return rc; }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B32_OK;
+}
+
+int b32_fb_download(b32_ctx* ctx, uint8_t* rgba, float* z) {
+    if (!ctx) return B32_ERR_INVALID;
+    size_t n = (size_t)ctx->width * ctx->height;
+    if (rgba) CK(cudaMemcpyAsync(rgba, ctx->fb_rgba.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (z) CK(cudaMemcpyAsync(z, ctx->fb_z.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    int d = ctx->deferred; ctx->deferred = B32_OK;
+    return d;
+}
+
+int b32_fb_size(const b32_ctx* ctx, uint32_t* width, uint32_t* height) {
+    if (!ctx) return B32_ERR_INVALID;
+    if (width) *width = ctx->width;
+    if (height) *height = ctx->height;
+    return B32_OK;
+}
+
+int b32_textures_set(b32_ctx* ctx, const b32_tex_desc* descs, uint32_t n) {
+    if (!ctx || (n && !descs)) return B32_ERR_INVALID;
+    if (n > 0xFFFF) return fail(ctx, B32_ERR_UNSUPPORTED, "more than 65535 textures (face.flags carries a 16-bit texture id)");
+    CK(cudaStreamSynchronize(ctx->stream));
+    size_t total = 0, max_idx_bytes = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const b32_tex_desc& d = descs[i];
+        if (d.format > B32_TEX_IDX4 || d.blend_mode > B32_BLEND_ERASE) return fail(ctx, B32_ERR_INVALID, "texture format/blend out of range");
+        size_t px = (size_t)d.width * d.height;
+        if (px && !d.pixels) return fail(ctx, B32_ERR_INVALID, "texture pixels is NULL");
+        if (d.format != B32_TEX_RGB555 && d.clut_len && !d.clut) return fail(ctx, B32_ERR_INVALID, "texture clut is NULL");
+        total += px;
+        if (d.format == B32_TEX_IDX8) max_idx_bytes = std::max(max_idx_bytes, px);
+        if (d.format == B32_TEX_IDX4) max_idx_bytes = std::max(max_idx_bytes, (px + 1) / 2);
+    }
+    if (total > 0xFFFFFFFFull) return fail(ctx, B32_ERR_UNSUPPORTED, "texel pool exceeds 2^32 texels");
+    CK(ctx->texels.reserve(std::max<size_t>(total, 1)));
+    CK(ctx->texdesc.reserve(std::max<uint32_t>(n, 1)));
+    ctx->texdesc_h.resize(n);
+    DevBuf<uint8_t> idx; DevBuf<uint16_t> clut;
+    if (max_idx_bytes) { CK(idx.reserve(max_idx_bytes)); CK(clut.reserve(256)); }
+    size_t off = 0;
+    int rc = B32_OK;
+    for (uint32_t i = 0; i < n && rc == B32_OK; ++i) {
+        const b32_tex_desc& d = descs[i];
+        size_t px = (size_t)d.width * d.height;
+        ctx->texdesc_h[i] = TexDev{(uint32_t)off, d.width, d.height, d.blend_mode};
+        if (px) {
+            if (d.format == B32_TEX_RGB555) {
+                rc = h2d(ctx, ctx->texels.p + off, d.pixels, px * 2);
+            } else {
+                size_t bytes = d.format == B32_TEX_IDX8 ? px : (px + 1) / 2;
+                uint32_t clen = std::min<uint32_t>(d.clut_len, 256);
+                rc = h2d(ctx, idx.p, d.pixels, bytes);
+                if (rc == B32_OK && clen) rc = h2d(ctx, clut.p, d.clut, clen * 2);
+                if (rc == B32_OK) launch_tex_expand(ctx->L(), idx.p, clut.p, clen, d.format, (uint32_t)px, ctx->texels.p + off);
+                cudaStreamSynchronize(ctx->stream);      // idx/clut staging is reused by the next texture
+            }
+        }
+        off += px;
+    }
+    idx.release(); clut.release();
+    if (rc) return rc;
+    if (n) CK(cudaMemcpyAsync(ctx->texdesc.p, ctx->texdesc_h.data(), n * sizeof(TexDev), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->ntex = n;
+    return B32_OK;
+}
+
+int b32_render_mesh_15(b32_ctx* ctx, const b32_vertex* vertices, uint32_t nv, const b32_face* faces, uint32_t nf,
+                       const b32_camera* camera, const b32_settings* settings, const b32_fog* fog, b32_timings* timings) {
+    if (!ctx) return B32_ERR_INVALID;
+    if ((nv && !vertices) || (nf && !faces)) return fail(ctx, B32_ERR_INVALID, "vertices/faces is NULL");
+    CK(ctx->verts.reserve(std::max<uint32_t>(nv, 1)));
+    CK(ctx->faces.reserve(std::max<uint32_t>(nf, 1)));
+    int rc = h2d(ctx, ctx->verts.p, vertices, (size_t)nv * sizeof(b32_vertex)); if (rc) return rc;
+    rc = h2d(ctx, ctx->faces.p, faces, (size_t)nf * sizeof(b32_face)); if (rc) return rc;
+    return render_device(ctx, ctx->verts.p, nv, ctx->faces.p, nf, camera, settings, fog, timings);
+}
+
+int b32_mesh_upload(b32_ctx* ctx, const b32_vertex* vertices, uint32_t nv, const b32_face* faces, uint32_t nf, b32_mesh** out) {
+    if (!ctx || !out) return B32_ERR_INVALID;
+    if ((nv && !vertices) || (nf && !faces)) return fail(ctx, B32_ERR_INVALID, "vertices/faces is NULL");
+    b32_mesh* m = new b32_mesh();
+    m->nv = nv; m->nf = nf;
+    cudaError_t e = cudaMalloc(&m->verts, std::max<size_t>((size_t)nv * sizeof(b32_vertex), 16));
+    if (e == cudaSuccess) e = cudaMalloc(&m->faces, std::max<size_t>((size_t)nf * sizeof(b32_face), 16));
+    if (e != cudaSuccess) { if (m->verts) cudaFree(m->verts); delete m; return cuda_fail(ctx, e, "cudaMalloc(mesh)"); }
+    int rc = h2d(ctx, m->verts, vertices, (size_t)nv * sizeof(b32_vertex));
+    if (rc == B32_OK) rc = h2d(ctx, m->faces, faces, (size_t)nf * sizeof(b32_face));
+    cudaStreamSynchronize(ctx->stream);
+    if (rc) { cudaFree(m->verts); cudaFree(m->faces); delete m; return rc; }
+    *out = m;
+    return B32_OK;
+}
+
+void b32_mesh_free(b32_ctx* ctx, b32_mesh* mesh) {
+    if (!mesh) return;
+    if (ctx) cudaStreamSynchronize(ctx->stream);
+    cudaFree(mesh->verts); cudaFree(mesh->faces);
+    delete mesh;
+}
+
+int b32_render_mesh_15_resident(b32_ctx* ctx, const b32_mesh* mesh, const b32_camera* camera, const b32_settings* settings,
+                                const b32_fog* fog, b32_timings* timings) {
+    if (!ctx || !mesh) return B32_ERR_INVALID;
+    return render_device(ctx, mesh->verts, mesh->nv, mesh->faces, mesh->nf, camera, settings, fog, timings);
+}
+
+int b32_render_mesh_15_enqueue(b32_ctx* ctx, const b32_mesh* mesh, const b32_camera* camera, const b32_settings* settings, const b32_fog* fog) {
+    // v1: the binning still needs one host round trip per call, so "enqueue" completes the call.
+    if (!ctx || !mesh) return B32_ERR_INVALID;
+    return render_device(ctx, mesh->verts, mesh->nv, mesh->faces, mesh->nf, camera, settings, fog, nullptr);
+}
+
+void* b32_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void b32_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int b32_debug_transform(b32_ctx* ctx, const b32_vertex* vertices, uint32_t nv, const b32_camera* camera, const b32_settings* settings,
+                        float* out_screen, float* out_cam) {
+    if (!ctx || !camera || !settings || (nv && (!vertices || !out_screen || !out_cam))) return B32_ERR_INVALID;
+    if (nv == 0) return B32_OK;
+    CallParams p; std::vector<LightDev> lights;
+    int rc = fill_params(ctx, p, camera, settings, nullptr, nv, 0, lights); if (rc) return rc;
+    CK(ctx->verts.reserve(nv)); CK(ctx->tv.reserve(nv)); CK(ctx->dbg.reserve((size_t)nv * 3));
+    rc = h2d(ctx, ctx->verts.p, vertices, (size_t)nv * sizeof(b32_vertex)); if (rc) return rc;
+    launch_transform(ctx->L(), ctx->verts.p, ctx->tv.p, ctx->dbg.p, p);
+    std::vector<float4> tv(nv);
+    CK(cudaMemcpyAsync(tv.data(), ctx->tv.p, (size_t)nv * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(out_cam, ctx->dbg.p, (size_t)nv * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (uint32_t i = 0; i < nv; ++i) { out_screen[i * 3] = tv[i].x; out_screen[i * 3 + 1] = tv[i].y; out_screen[i * 3 + 2] = tv[i].z; }
+    return B32_OK;
+}
+
+int b32_debug_kernel_times(b32_ctx* ctx, float* out_ms, uint32_t cap) {
+    if (!ctx || !out_ms) return 0;
+    uint32_t n = std::min<uint32_t>(cap, 7);
+    for (uint32_t i = 0; i < n; ++i) out_ms[i] = ctx->kernel_ms[i];
+    return (int)n;
+}
+
+int b32_debug_draw_order(b32_ctx* ctx, uint32_t* out_face_idx, uint32_t cap, uint32_t* n) {
+    if (!ctx || !n) return B32_ERR_INVALID;
+    CK(cudaMemcpyAsync(ctx->state_h, ctx->state, sizeof(CallState), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    uint32_t drawn = ctx->state_h->n_opaque + ctx->state_h->n_transp;
+    *n = drawn;
+    uint32_t m = std::min(drawn, cap);
+    if (m && out_face_idx) CK(cudaMemcpy(out_face_idx, ctx->order.p, (size_t)m * 4, cudaMemcpyDeviceToHost));
+    return B32_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,145 @@
+// b32_device.cuh — device-side records and exact-arithmetic helpers shared by the kernels.
+//
+// Bit-exactness contract: every f32 expression is evaluated left to right with one
+// rounding per operator and never fused.  The translation unit is compiled with
+//   -fmad=false -prec-div=true -prec-sqrt=true -ftz=false
+// and the helpers below restate the Rust cast / min / max / rem_euclid semantics.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "b32_raster.h"
+
+namespace b32 {
+
+constexpr int TILE_W = 16;            // screen tile owned by one CTA of k_fill
+constexpr int TILE_H = 16;
+constexpr int FILL_THREADS = TILE_W * TILE_H;
+constexpr float NEAR_PLANE = 0.1f;    // math.rs:155
+
+// ---- per-vertex output of k_transform (render.rs:2321-2360) ------------------------------------
+// x,y,z = projected[i]; w = cam_space_positions[i].z (the only camera-space value the path reads:
+// near-plane test :2381-2385 and fog :2419-2436; cam x/y only feed the dead `normal`).
+typedef float4 TVert;
+
+// ---- one drawable surface, ready for the fill (struct Surface render.rs:975-1000 after the
+//      per-triangle preamble of rasterize_triangle_15, render.rs:1450-1527) -----------------------
+struct __align__(16) SurfRec {
+    float a0, b0, a1, b1;                 // edge-function steps, render.rs:1507-1510
+    float w0s, w1s, inv_area;             // row-start values at (min_x,min_y) :1517-1518, 1/area :1504
+    uint32_t flags;                       // SF_* below | editor_alpha << 8 | tex_id << 16
+    uint32_t bbox_x, bbox_y;              // min | max << 16 (max exclusive), render.rs:1455-1458
+    float iz1, iz2, iz3;                  // 1/v.z, render.rs:1546-1548 (pure function of the vertices)
+    float u1, v1, u2, v2, u3, v3;         // Surface.uv1..3
+    uint32_t vc1, vc2, vc3;               // Surface.vc1..3 as r | g<<8 | b<<16
+    float sh[9];                          // Gouraud: 3 vertices x rgb (:1475-1483); Flat: sh[0..2] (:1466-1472)
+    uint32_t _pad;
+};
+static_assert(sizeof(SurfRec) == 128, "SurfRec must be 128 bytes");
+
+enum : uint32_t {
+    SF_BLEND_MASK   = 0x7,        // blend_mode the fill uses: texture's if textured else face's (:1450-1452)
+    SF_BLACK_TR     = 1u << 3,    // Face.black_transparent
+    SF_DITHER       = 1u << 4,    // needs_dither, render.rs:1487-1492
+    SF_TEXTURED     = 1u << 5,    // texture.is_some()
+    SF_FAST_EDGE    = 1u << 6,    // edge stepping provably exact => closed form allowed
+    SF_TRANSPARENT  = 1u << 7,    // has_transparency: drawn in pass 2 with skip_z_write (:2561-2569)
+};
+
+struct TexDev { uint32_t off, w, h, blend; };   // texel pool offset (u16 units), size, Texture15.blend_mode
+
+struct LightDev {                     // b32_light without padding surprises
+    uint32_t type; float px, py, pz, dx, dy, dz, radius, angle, intensity, cr, cg, cb; uint32_t enabled;
+};
+
+// device-side counters / flags of one render call
+struct CallState {
+    uint32_t n_opaque, n_transp;          // drawn surfaces per pass
+    uint32_t nan_opaque, nan_transp;      // a NaN sort key was seen in the pass
+    uint32_t oob;                         // a face index >= nv was seen
+    uint32_t n_entries;                   // sum of tile counts (bin entries needed)
+    uint32_t overflow;                    // n_entries > capacity: fill skipped, host grows + retries
+    uint32_t abort;                       // reference would have panicked: nothing is drawn
+};
+
+// kernel parameters of one render call (passed by value => constant bank)
+struct CallParams {
+    float cam_pos[3], bx[3], by[3], bz[3];
+    int32_t fcam_pos[3], fbx[3], fby[3], fbz[3];      // Fixed32::from_f32 of the above (fixed.rs:370-373)
+    int32_t viewport_scale, half_w, half_h;           // fixed.rs:398-400
+    uint32_t width, height, tiles_x, tiles_y;
+    uint32_t nv, nf, ntex, n_lights;
+    uint8_t affine_textures, use_zbuffer, shading, backface_cull, dithering, use_fixed_point, xray_mode, ortho;
+    uint8_t fog_enabled, fog_r, fog_g, fog_b, fog_blend, _p0, _p1, _p2;
+    float ambient, ortho_zoom, ortho_cx, ortho_cy;
+    float fog_start, fog_falloff, fog_cull;
+};
+
+// ---- Rust scalar semantics -------------------------------------------------------------------
+// `f as i32` / `f as u32-ish`: cvt.rzi saturates and maps NaN to 0, exactly like Rust's `as`.
+__device__ __forceinline__ int32_t f2i32(float f) { return __float2int_rz(f); }
+__device__ __forceinline__ uint32_t f2u32sat(float f) { return __float2uint_rz(f); }   // usize, clipped to u32
+__device__ __forceinline__ uint32_t f2u8(float f) { return min(__float2uint_rz(f), 255u); }
+// f32::min/max = IEEE minNum/maxNum = fminf/fmaxf.  f32::clamp keeps NaN:
+__device__ __forceinline__ float rclamp(float x, float lo, float hi) { if (x < lo) x = lo; if (x > hi) x = hi; return x; }
+// f32::rem_euclid(1.0): r = fmod(u,1); if r < 0 { r + 1 }.  fmod(u,1) = u - trunc(u) exactly.
+__device__ __forceinline__ float rem_euclid1(float u) {
+    float r = u - truncf(u);                 // inf - inf = NaN, NaN stays NaN: same as fmodf
+    return r < 0.0f ? r + 1.0f : r;
+}
+
+// ---- fixed.rs -------------------------------------------------------------------------------
+__device__ __forceinline__ int32_t fx_from_f32(float f) { return f2i32(f * 4096.0f); }                 // :125-127
+__device__ __forceinline__ int32_t fx_mul(int32_t a, int32_t b) { return (int32_t)(((int64_t)a * (int64_t)b) >> 12); }  // :161-165
+__device__ __forceinline__ int32_t fx_add(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
+__device__ __forceinline__ int32_t fx_sub(int32_t a, int32_t b) { return (int32_t)((uint32_t)a - (uint32_t)b); }
+
+// UNR reciprocal of a non-zero divisor (fixed.rs:183-205): returns nr2 and the final shift.
+__device__ __forceinline__ void unr_recip(int32_t divisor, const uint8_t* __restrict__ table, uint64_t* nr2, uint32_t* shift) {
+    uint32_t den = divisor < 0 ? 0u - (uint32_t)divisor : (uint32_t)divisor;
+    uint32_t z = __clz(den);
+    uint64_t d16 = ((uint64_t)den << z) >> 16;
+    unsigned long long idx = min((unsigned long long)((d16 - 0x7FC0ull) >> 7), 256ull);
+    uint64_t u = (uint64_t)table[idx] + 0x101;
+    uint64_t nr1 = (0x2000080ull - d16 * u) >> 8;
+    *nr2 = (0x80ull + nr1 * u) >> 8;
+    *shift = 36u - z;
+}
+// fixed.rs:207-230 given the reciprocal
+__device__ __forceinline__ int32_t unr_apply(int32_t num, int32_t divisor, uint64_t nr2, uint32_t shift) {
+    bool neg = (num < 0) != (divisor < 0);
+    uint64_t n = num < 0 ? (uint64_t)(0u - (uint32_t)num) : (uint64_t)(uint32_t)num;
+    uint64_t raw = n * nr2;
+    uint64_t mag = (raw + (1ull << (shift - 1))) >> shift;       // shift in 5..36
+    int32_t c = (int32_t)min((unsigned long long)mag, 0x7FFFFFFFull);
+    return neg ? -c : c;
+}
+
+// ---- colour helpers --------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t expand5(uint32_t v) { return ((v << 3) | (v >> 2)) & 0xFF; }   // render.rs:1161-1163
+
+// blend_rgb555 for one channel (render.rs:1093-1145): 8-bit in, 5-bit math, result << 3
+__device__ __forceinline__ uint32_t blend5(uint32_t f8, uint32_t b8, uint32_t mode) {
+    uint32_t f5 = f8 >> 3, b5 = b8 >> 3, r;
+    switch (mode) {
+        case B32_BLEND_OPAQUE:      r = f5; break;
+        case B32_BLEND_AVERAGE:     r = min((b5 + f5) >> 1, 31u); break;
+        case B32_BLEND_ADD:         r = min(b5 + f5, 31u); break;
+        case B32_BLEND_SUBTRACT:    r = b5 > f5 ? b5 - f5 : 0u; break;
+        case B32_BLEND_ADD_QUARTER: r = min(b5 + (f5 >> 2), 31u); break;
+        default:                    r = b5; break;     // Erase
+    }
+    return r << 3;
+}
+
+// order-preserving key for a stable ASCENDING radix sort that yields back-to-front order:
+// descending center_z, +0 == -0 (render.rs:2527-2532)
+__device__ __forceinline__ uint32_t depth_key_desc(float z) {
+    uint32_t b = __float_as_uint(z);
+    if (z == 0.0f) b = 0;
+    uint32_t asc = b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+    return ~asc;
+}
+
+}  // namespace b32

@@ -1,0 +1,631 @@
+// b32_kernels.cu — sm_100a kernels of the BONNIE-32 rasterizer hot path.
+//
+//   k_transform   render.rs:2321-2360 + fixed.rs:362-441     vertex transform + snap
+//   k_setup       render.rs:2373-2513 + :1450-1527 + :1013-1071   cull / surface build / lighting /
+//                 triangle setup, sort key (:2527-2532)
+//   (sort)        render.rs:2522-2542   stable back-to-front radix sort, opaque | transparent
+//   k_bin_count / k_bin_emit            per-surface screen-tile lists in draw order
+//   k_fill        render.rs:1530-1713   in-order per-pixel emulation of rasterize_triangle_15
+//
+// Pixel-order semantics: the reference draws surfaces one after the other into one
+// framebuffer, so the value of a pixel is a fold over the surfaces that cover it, in draw order.
+// Pixels are independent of each other, so k_fill gives every pixel to one thread, which walks the
+// pixel's surfaces in draw order and applies the reference's z-test / blend / write rules to a
+// colour + depth held in registers.  No atomics, deterministic, exact for every blend mode.
+#include "b32_device.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "b32_launch.h"
+
+namespace b32 {
+
+// =================================================================================================
+// k_transform
+// =================================================================================================
+__global__ void __launch_bounds__(256)
+k_transform(const b32_vertex* __restrict__ verts, TVert* __restrict__ out, float* __restrict__ dbg_cam,
+            const uint8_t* __restrict__ unr_table_g, CallParams p) {
+    __shared__ uint8_t unr[260];
+    for (int i = threadIdx.x; i < 257; i += blockDim.x) unr[i] = unr_table_g[i];
+    __syncthreads();
+
+    const int32_t distance = 5 * 4096, scale = 4 * 4096;     // Fixed32::from_f32(5.0), (4.0): fixed.rs:396-397
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < p.nv; i += gridDim.x * blockDim.x) {
+        const float* vp = reinterpret_cast<const float*>(verts + i);
+        float px = vp[0], py = vp[1], pz = vp[2];
+        // rel_pos = v.pos - camera.position; cam_pos = perspective_transform(...)   (math.rs:103-109)
+        float rx = px - p.cam_pos[0], ry = py - p.cam_pos[1], rz = pz - p.cam_pos[2];
+        float cx = rx * p.bx[0] + ry * p.bx[1] + rz * p.bx[2];
+        float cy = rx * p.by[0] + ry * p.by[1] + rz * p.by[2];
+        float cz = rx * p.bz[0] + ry * p.bz[1] + rz * p.bz[2];
+        float sx, sy, sz;
+        if (p.ortho) {                                       // math.rs:140-148
+            sx = (cx - p.ortho_cx) * p.ortho_zoom + ((float)p.width / 2.0f);
+            sy = -(cy - p.ortho_cy) * p.ortho_zoom + ((float)p.height / 2.0f);
+            sz = cz;
+        } else if (p.use_fixed_point) {                      // fixed.rs:362-441
+            int32_t wx = fx_from_f32(px), wy = fx_from_f32(py), wz = fx_from_f32(pz);
+            int32_t ex = fx_sub(wx, p.fcam_pos[0]), ey = fx_sub(wy, p.fcam_pos[1]), ez = fx_sub(wz, p.fcam_pos[2]);
+            int32_t fcx = fx_add(fx_add(fx_mul(ex, p.fbx[0]), fx_mul(ey, p.fbx[1])), fx_mul(ez, p.fbx[2]));
+            int32_t fcy = fx_add(fx_add(fx_mul(ex, p.fby[0]), fx_mul(ey, p.fby[1])), fx_mul(ez, p.fby[2]));
+            int32_t fcz = fx_add(fx_add(fx_mul(ex, p.fbz[0]), fx_mul(ey, p.fbz[1])), fx_mul(ez, p.fbz[2]));
+            int32_t denom = fx_add(fcz, distance);
+            int32_t adenom = denom < 0 ? (int32_t)(0u - (uint32_t)denom) : denom;   // release-mode i32::abs
+            int32_t isx, isy;
+            if (adenom < 256) {                              // fixed.rs:406-408
+                isx = p.half_w >> 12; isy = p.half_h >> 12;
+            } else {
+                uint64_t nr2; uint32_t shift;
+                unr_recip(denom, unr, &nr2, &shift);         // one reciprocal serves x and y
+                int32_t proj_x = unr_apply(fx_mul(fcx, scale), denom, nr2, shift);
+                int32_t proj_y = unr_apply(fx_mul(fcy, scale), denom, nr2, shift);
+                isx = fx_add(fx_mul(proj_x, p.viewport_scale), p.half_w) >> 12;
+                isy = fx_add(fx_mul(proj_y, p.viewport_scale), p.half_h) >> 12;
+            }
+            sx = (float)isx; sy = (float)isy;
+            sz = cz + 5.0f;                                  // render.rs:2342-2345
+        } else {                                             // math.rs:117-136
+            const float us = 4.0f;
+            float vs = ((float)min(p.width, p.height) / 2.0f) * 0.75f;
+            float denom = cz + 5.0f;
+            if (fabsf(denom) < 0.001f) {
+                sx = (float)p.width / 2.0f; sy = (float)p.height / 2.0f; sz = cz;
+            } else {
+                sx = (cx * us) / denom * vs + ((float)p.width / 2.0f);
+                sy = (cy * us) / denom * vs + ((float)p.height / 2.0f);
+                sz = denom;
+            }
+        }
+        out[i] = make_float4(sx, sy, sz, cz);
+        if (dbg_cam) { dbg_cam[i * 3] = cx; dbg_cam[i * 3 + 1] = cy; dbg_cam[i * 3 + 2] = cz; }
+    }
+}
+
+// =================================================================================================
+// k_setup
+// =================================================================================================
+struct V3 { float x, y, z; };
+__device__ __forceinline__ float dot3(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ V3 normalize3(V3 a) {                      // math.rs:39-49
+    float l = sqrtf(dot3(a, a));
+    if (l == 0.0f) return V3{0.0f, 0.0f, 0.0f};
+    return V3{a.x / l, a.y / l, a.z / l};
+}
+
+// render.rs:1013-1071 (Directional + Point; Spot is rejected on the host with B32_ERR_UNSUPPORTED)
+__device__ void shade_multi_light_color(V3 n, V3 wp, const LightDev* __restrict__ lights, uint32_t nl, float ambient, float* out) {
+    float tr = ambient, tg = ambient, tb = ambient;
+    for (uint32_t i = 0; i < nl; ++i) {
+        LightDev L = lights[i];
+        if (!L.enabled) continue;
+        float contribution;
+        if (L.type == B32_LIGHT_DIRECTIONAL) {
+            V3 neg{L.dx * -1.0f, L.dy * -1.0f, L.dz * -1.0f};
+            float ndl = fmaxf(dot3(n, neg), 0.0f);
+            contribution = ndl * L.intensity;
+        } else {
+            V3 to_light{L.px - wp.x, L.py - wp.y, L.pz - wp.z};
+            float dist = sqrtf(dot3(to_light, to_light));
+            if (dist > L.radius || dist < 0.001f) {
+                contribution = 0.0f;
+            } else {
+                float att = 1.0f - (dist / L.radius);
+                float ndl = fmaxf(dot3(n, normalize3(to_light)), 0.0f);
+                contribution = ndl * L.intensity * att * att;
+            }
+        }
+        tr += contribution * L.cr; tg += contribution * L.cg; tb += contribution * L.cb;
+    }
+    out[0] = fminf(tr, 1.0f); out[1] = fminf(tg, 1.0f); out[2] = fminf(tb, 1.0f);
+}
+
+// render.rs:2266-2293
+__device__ __forceinline__ uint32_t fog_color(uint32_t c, float z, const CallParams& p) {
+    float f;
+    if (z <= p.fog_start) f = 0.0f;
+    else if (p.fog_falloff <= 0.0f) f = 1.0f;
+    else f = fminf((z - p.fog_start) / p.fog_falloff, 1.0f);
+    if (f <= 0.0f) return c;
+    if (f >= 1.0f) return (uint32_t)p.fog_r | ((uint32_t)p.fog_g << 8) | ((uint32_t)p.fog_b << 16) | ((uint32_t)p.fog_blend << 24);
+    float inv = 1.0f - f;
+    uint32_t r = f2u8((float)(c & 0xFF) * inv + (float)p.fog_r * f);
+    uint32_t g = f2u8((float)((c >> 8) & 0xFF) * inv + (float)p.fog_g * f);
+    uint32_t b = f2u8((float)((c >> 16) & 0xFF) * inv + (float)p.fog_b * f);
+    return r | (g << 8) | (b << 16);             // Color::new => blend Opaque (0)
+}
+
+__device__ __forceinline__ bool is_integral(float x) { return truncf(x) == x; }   // false for NaN/inf? inf==inf: guarded by bound
+
+__global__ void __launch_bounds__(128)
+k_setup(const b32_vertex* __restrict__ verts, const b32_face* __restrict__ faces, const TVert* __restrict__ tv,
+        const TexDev* __restrict__ tex, const LightDev* __restrict__ lights,
+        SurfRec* __restrict__ recs, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
+        CallState* __restrict__ st, CallParams p) {
+    uint32_t n_op = 0, n_tr = 0;
+    for (uint32_t fi = blockIdx.x * blockDim.x + threadIdx.x; fi < p.nf; fi += gridDim.x * blockDim.x) {
+        uint4 fc = *reinterpret_cast<const uint4*>(faces + fi);
+        uint32_t cls = 2;                 // 0 opaque pass, 1 transparent pass, 2 not drawn
+        uint32_t dkey = 0;
+        do {
+            if (fc.x >= p.nv || fc.y >= p.nv || fc.z >= p.nv) { st->oob = 1; break; }
+            uint32_t tex_id = fc.w & 0xFFFFu, face_blend = (fc.w >> 16) & 7u, editor_alpha = fc.w >> 24;
+            bool black_tr = (fc.w >> 19) & 1u;
+            bool textured = tex_id != B32_FACE_TEX_NONE && tex_id < p.ntex;
+            uint32_t tex_blend = 0;
+            if (textured) tex_blend = tex[tex_id].blend;
+
+            TVert t1 = tv[fc.x], t2 = tv[fc.y], t3 = tv[fc.z];
+            if (!p.ortho) {                                                       // :2380-2385
+                if (t1.w <= NEAR_PLANE || t2.w <= NEAR_PLANE || t3.w <= NEAR_PLANE) break;
+            }
+            float signed_area = (t2.x - t1.x) * (t3.y - t1.y) - (t3.x - t1.x) * (t2.y - t1.y);   // :2393
+            bool backface = signed_area <= 0.0f;
+            bool transparent;                                                     // :2403-2415
+            if (textured && tex_blend != B32_BLEND_OPAQUE) transparent = true;
+            else if (face_blend != B32_BLEND_OPAQUE) transparent = true;
+            else transparent = editor_alpha < 255;
+            if (p.fog_enabled && t1.w > p.fog_cull && t2.w > p.fog_cull && t3.w > p.fog_cull) break;   // :2421-2424
+            if (backface && !(!p.backface_cull || p.xray_mode)) break;            // :2445-2453
+
+            // vertex attributes (36-byte records: pos 0, uv 12, normal 20, rgba 32)
+            const uint32_t ia = fc.x, ib = backface ? fc.z : fc.y, ic = backface ? fc.y : fc.z;   // v2/v3 swap :2455-2457
+            TVert s1 = t1, s2 = backface ? t3 : t2, s3 = backface ? t2 : t3;
+            const float* va = reinterpret_cast<const float*>(verts + ia);
+            const float* vb = reinterpret_cast<const float*>(verts + ib);
+            const float* vc = reinterpret_cast<const float*>(verts + ic);
+            uint32_t c1 = reinterpret_cast<const uint32_t*>(va)[8], c2 = reinterpret_cast<const uint32_t*>(vb)[8], c3 = reinterpret_cast<const uint32_t*>(vc)[8];
+            if (p.fog_enabled) {                                                  // :2427-2436 (cam z of the same vertex)
+                c1 = fog_color(c1, s1.w, p); c2 = fog_color(c2, s2.w, p); c3 = fog_color(c3, s3.w, p);
+            }
+
+            SurfRec r;
+            uint32_t blend_mode = textured ? tex_blend : face_blend;               // :1450-1452
+            uint32_t flags = blend_mode | (black_tr ? SF_BLACK_TR : 0) | (textured ? SF_TEXTURED : 0) |
+                             (transparent ? SF_TRANSPARENT : 0) | (editor_alpha << 8) | ((textured ? tex_id : 0xFFFFu) << 16);
+            bool needs_dither = p.dithering && (p.shading == B32_SHADE_GOURAUD || textured || c1 != c2 || c2 != c3);   // :1487-1492
+            if (needs_dither) flags |= SF_DITHER;
+
+            // bounding box, render.rs:1455-1463
+            uint32_t min_x = f2u32sat(fmaxf(fminf(fminf(s1.x, s2.x), s3.x), 0.0f));
+            uint32_t max_x = f2u32sat(fminf(fmaxf(fmaxf(s1.x, s2.x), s3.x) + 1.0f, (float)p.width));
+            uint32_t min_y = f2u32sat(fmaxf(fminf(fminf(s1.y, s2.y), s3.y), 0.0f));
+            uint32_t max_y = f2u32sat(fminf(fmaxf(fmaxf(s1.y, s2.y), s3.y) + 1.0f, (float)p.height));
+            bool empty = min_x >= max_x || min_y >= max_y;
+            float area = (s2.y - s3.y) * (s1.x - s3.x) + (s3.x - s2.x) * (s1.y - s3.y);     // :1500
+            if (fabsf(area) < 0.00001f) empty = true;                                      // :1501-1503
+            if (empty) { min_x = max_x = min_y = max_y = 0; }
+            r.inv_area = 1.0f / area;
+            r.a0 = s2.y - s3.y; r.b0 = s3.x - s2.x; r.a1 = s3.y - s1.y; r.b1 = s1.x - s3.x;   // :1507-1510
+            float start_x = (float)min_x, start_y = (float)min_y;
+            r.w0s = r.a0 * (start_x - s3.x) + r.b0 * (start_y - s3.y);                      // :1517-1518
+            r.w1s = r.a1 * (start_x - s3.x) + r.b1 * (start_y - s3.y);
+            r.bbox_x = min_x | (max_x << 16);
+            r.bbox_y = min_y | (max_y << 16);
+            // incremental stepping == closed form when everything is an integer below 2^24
+            {
+                float nx = (float)(max_x - min_x), ny = (float)(max_y - min_y);
+                float m0 = fabsf(r.w0s) + ny * fabsf(r.b0) + nx * fabsf(r.a0);
+                float m1 = fabsf(r.w1s) + ny * fabsf(r.b1) + nx * fabsf(r.a1);
+                bool ints = is_integral(r.a0) && is_integral(r.b0) && is_integral(r.a1) && is_integral(r.b1) &&
+                            is_integral(r.w0s) && is_integral(r.w1s);
+                if (ints && m0 < 8388608.0f && m1 < 8388608.0f) flags |= SF_FAST_EDGE;
+            }
+            r.iz1 = 1.0f / s1.z; r.iz2 = 1.0f / s2.z; r.iz3 = 1.0f / s3.z;                  // :1546-1548
+            r.u1 = va[3]; r.v1 = va[4]; r.u2 = vb[3]; r.v2 = vb[4]; r.u3 = vc[3]; r.v3 = vc[4];
+            r.vc1 = c1 & 0xFFFFFF; r.vc2 = c2 & 0xFFFFFF; r.vc3 = c3 & 0xFFFFFF;
+            for (int k = 0; k < 9; ++k) r.sh[k] = 1.0f;
+            if (!empty && p.shading != B32_SHADE_NONE) {
+                float sgn = backface ? -1.0f : 1.0f;                                        // wn.scale(-1.0) :2464-2466
+                V3 w1{va[0], va[1], va[2]}, w2{vb[0], vb[1], vb[2]}, w3{vc[0], vc[1], vc[2]};
+                V3 n1{va[5], va[6], va[7]}, n2{vb[5], vb[6], vb[7]}, n3{vc[5], vc[6], vc[7]};
+                if (backface) { n1 = V3{n1.x * sgn, n1.y * sgn, n1.z * sgn}; n2 = V3{n2.x * sgn, n2.y * sgn, n2.z * sgn}; n3 = V3{n3.x * sgn, n3.y * sgn, n3.z * sgn}; }
+                if (p.shading == B32_SHADE_FLAT) {                                          // :1466-1472
+                    const float third = 1.0f / 3.0f;
+                    V3 c{((w1.x + w2.x) + w3.x) * third, ((w1.y + w2.y) + w3.y) * third, ((w1.z + w2.z) + w3.z) * third};
+                    V3 n = normalize3(V3{((n1.x + n2.x) + n3.x) * third, ((n1.y + n2.y) + n3.y) * third, ((n1.z + n2.z) + n3.z) * third});
+                    shade_multi_light_color(n, c, lights, p.n_lights, p.ambient, r.sh);
+                } else {                                                                    // :1475-1483
+                    shade_multi_light_color(n1, w1, lights, p.n_lights, p.ambient, r.sh);
+                    shade_multi_light_color(n2, w2, lights, p.n_lights, p.ambient, r.sh + 3);
+                    shade_multi_light_color(n3, w3, lights, p.n_lights, p.ambient, r.sh + 6);
+                }
+            }
+            r.flags = flags;
+            r._pad = 0;
+            recs[fi] = r;
+
+            cls = transparent ? 1u : 0u;
+            float center_z = (s1.z + s2.z + s3.z) / 3.0f;                                   // :2529
+            bool sorted = transparent || !p.use_zbuffer;                                    // :2527, :2536
+            if (sorted) {
+                if (center_z != center_z) { if (transparent) st->nan_transp = 1; else st->nan_opaque = 1; }
+                dkey = depth_key_desc(center_z);
+            }
+            if (transparent) ++n_tr; else ++n_op;
+        } while (0);
+        keys[fi] = ((uint64_t)cls << 32) | dkey;
+        vals[fi] = fi;
+    }
+    // per-warp aggregated counters
+    for (int o = 16; o > 0; o >>= 1) { n_op += __shfl_xor_sync(0xFFFFFFFFu, n_op, o); n_tr += __shfl_xor_sync(0xFFFFFFFFu, n_tr, o); }
+    if ((threadIdx.x & 31) == 0) {
+        if (n_op) atomicAdd(&st->n_opaque, n_op);
+        if (n_tr) atomicAdd(&st->n_transp, n_tr);
+    }
+}
+
+// =================================================================================================
+// binning: per-surface tile counts -> scan -> (tile, surface) pairs in draw order -> stable sort by tile
+// =================================================================================================
+// The reference panics (nothing drawn) on an out-of-range index or on a NaN key in a sorted slice of
+// length >= 2 (render.rs:2531).  Decide once, on the device, so the fill can be skipped without a
+// host round trip.
+__global__ void k_decide(CallState* st, uint32_t use_zbuffer) {
+    bool abort = st->oob != 0;
+    if (st->nan_transp && st->n_transp >= 2) abort = true;
+    if (!use_zbuffer && st->nan_opaque && st->n_opaque >= 2) abort = true;
+    st->abort = abort ? 1 : 0;
+}
+
+__device__ __forceinline__ void tile_range(const SurfRec& r, uint32_t& tx0, uint32_t& tx1, uint32_t& ty0, uint32_t& ty1) {
+    uint32_t min_x = r.bbox_x & 0xFFFF, max_x = r.bbox_x >> 16, min_y = r.bbox_y & 0xFFFF, max_y = r.bbox_y >> 16;
+    if (min_x >= max_x || min_y >= max_y) { tx0 = tx1 = ty0 = ty1 = 0; return; }
+    tx0 = min_x / TILE_W; tx1 = (max_x - 1) / TILE_W + 1;
+    ty0 = min_y / TILE_H; ty1 = (max_y - 1) / TILE_H + 1;
+}
+
+__global__ void __launch_bounds__(256)
+k_bin_count(const SurfRec* __restrict__ recs, const uint32_t* __restrict__ order, uint32_t* __restrict__ counts,
+            const CallState* __restrict__ st, uint32_t nf) {
+    uint32_t n_drawn = st->abort ? 0 : st->n_opaque + st->n_transp;
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nf; r += gridDim.x * blockDim.x) {
+        uint32_t c = 0;
+        if (r < n_drawn) {
+            const SurfRec& rec = recs[order[r]];
+            uint32_t bx = rec.bbox_x, by = rec.bbox_y;
+            uint32_t min_x = bx & 0xFFFF, max_x = bx >> 16, min_y = by & 0xFFFF, max_y = by >> 16;
+            if (min_x < max_x && min_y < max_y)
+                c = ((max_x - 1) / TILE_W - min_x / TILE_W + 1) * ((max_y - 1) / TILE_H - min_y / TILE_H + 1);
+        }
+        counts[r] = c;
+    }
+}
+
+// offsets = exclusive scan of counts; total = offsets[nf-1] + counts[nf-1]
+__global__ void __launch_bounds__(256)
+k_bin_emit(const SurfRec* __restrict__ recs, const uint32_t* __restrict__ order, const uint32_t* __restrict__ counts,
+           const uint32_t* __restrict__ offsets, uint32_t* __restrict__ ent_tile, uint32_t* __restrict__ ent_surf,
+           uint32_t* __restrict__ tile_count, CallState* __restrict__ st, uint32_t nf, uint32_t tiles_x, uint32_t capacity) {
+    uint32_t total = offsets[nf - 1] + counts[nf - 1];
+    if (blockIdx.x == 0 && threadIdx.x == 0) { st->n_entries = total; st->overflow = total > capacity ? 1 : 0; }
+    if (total > capacity || st->abort) return;
+    uint32_t n_drawn = st->n_opaque + st->n_transp;
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_drawn; r += gridDim.x * blockDim.x) {
+        if (counts[r] == 0) continue;
+        uint32_t f = order[r];
+        const SurfRec& rec = recs[f];
+        uint32_t tx0, tx1, ty0, ty1;
+        tile_range(rec, tx0, tx1, ty0, ty1);
+        uint32_t o = offsets[r];
+        for (uint32_t ty = ty0; ty < ty1; ++ty)
+            for (uint32_t tx = tx0; tx < tx1; ++tx) {
+                uint32_t t = ty * tiles_x + tx;
+                ent_tile[o] = t;
+                ent_surf[o] = f;
+                ++o;
+                atomicAdd(&tile_count[t], 1u);
+            }
+    }
+}
+
+// single-block exclusive scan of tile_count -> tile_start (ntiles is small: 300 at 320x240)
+__global__ void __launch_bounds__(1024)
+k_tile_scan(const uint32_t* __restrict__ tile_count, uint32_t* __restrict__ tile_start, uint32_t ntiles) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < ntiles; base += blockDim.x) {
+        uint32_t i = base + threadIdx.x;
+        uint32_t v = i < ntiles ? tile_count[i] : 0;
+        uint32_t x = v;
+        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
+        if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t w = threadIdx.x < (blockDim.x >> 5) ? warp_sums[threadIdx.x] : 0;
+            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, w, o); if (threadIdx.x >= o) w += y; }
+            warp_sums[threadIdx.x] = w;
+        }
+        __syncthreads();
+        uint32_t prefix = carry + (threadIdx.x >= 32 ? warp_sums[(threadIdx.x >> 5) - 1] : 0);
+        if (i < ntiles) tile_start[i] = prefix + x - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = prefix + x;
+        __syncthreads();
+    }
+}
+
+// =================================================================================================
+// k_fill
+// =================================================================================================
+struct Pixel { uint32_t rgba; float z; };
+
+// One fragment of rasterize_triangle_15 (render.rs:1534-1703) for pixel (x,y) against surface r.
+// `px` is the pixel's current framebuffer colour/depth, updated in place.
+__device__ __forceinline__ void fragment(const SurfRec& r, uint32_t x, uint32_t y, Pixel& px,
+                                         const TexDev* __restrict__ tex, const uint16_t* __restrict__ texels,
+                                         const CallParams& p) {
+    uint32_t min_x = r.bbox_x & 0xFFFF, min_y = r.bbox_y & 0xFFFF;
+    float w0, w1;
+    if (r.flags & SF_FAST_EDGE) {
+        // all terms are integers below 2^23: every rounded add of the reference is exact, so the
+        // stepped value equals the closed form
+        float dx = (float)(x - min_x), dy = (float)(y - min_y);
+        w0 = r.w0s + dy * r.b0 + dx * r.a0;
+        w1 = r.w1s + dy * r.b1 + dx * r.a1;
+    } else {
+        // replay the reference's rounded additions: (y-min_y) row steps, then (x-min_x) pixel steps
+        w0 = r.w0s; w1 = r.w1s;
+        for (uint32_t i = min_y; i < y; ++i) { w0 = __fadd_rn(w0, r.b0); w1 = __fadd_rn(w1, r.b1); }
+        for (uint32_t i = min_x; i < x; ++i) { w0 = __fadd_rn(w0, r.a0); w1 = __fadd_rn(w1, r.a1); }
+    }
+    float bc_x = w0 * r.inv_area;
+    float bc_y = w1 * r.inv_area;
+    float bc_z = 1.0f - bc_x - bc_y;
+    const float ERR = -0.0001f;
+    if (!(bc_x >= ERR && bc_y >= ERR && bc_z >= ERR)) return;                      // :1541-1542
+
+    float inv_z = bc_x * r.iz1 + bc_y * r.iz2 + bc_z * r.iz3;                      // :1549
+    float z = 1.0f / inv_z;
+    if (p.use_zbuffer && !p.xray_mode) { if (z >= px.z) return; }                   // :1553-1560
+
+    uint32_t color = 0x7FFF;                                                       // Color15::WHITE
+    if (r.flags & SF_TEXTURED) {
+        float u, v;
+        if (p.affine_textures) {                                                   // :1563-1567
+            u = bc_x * r.u1 + bc_y * r.u2 + bc_z * r.u3;
+            v = bc_x * r.v1 + bc_y * r.v2 + bc_z * r.v3;
+        } else {                                                                   // :1568-1578
+            float uo = bc_x * r.u1 * r.iz1 + bc_y * r.u2 * r.iz2 + bc_z * r.u3 * r.iz3;
+            float vo = bc_x * r.v1 * r.iz1 + bc_y * r.v2 * r.iz2 + bc_z * r.v3 * r.iz3;
+            u = uo / inv_z;
+            v = vo / inv_z;
+        }
+        TexDev t = tex[r.flags >> 16];
+        if (t.w == 0 || t.h == 0) {                                                // types.rs:673-675
+            color = 0;
+        } else {
+            float uw = rem_euclid1(u), vw = rem_euclid1(1.0f - v);                 // :1583, types.rs:676-677
+            uint32_t tx = min(f2u32sat(uw * (float)t.w), t.w - 1);
+            uint32_t ty = min(f2u32sat(vw * (float)t.h), t.h - 1);
+            color = __ldg(texels + t.off + ty * t.w + tx);
+        }
+    }
+    bool is_black = (color & 0x7FFF) == 0;                                         // :1591-1607
+    if (color == 0) {
+        if (!(r.flags & SF_BLACK_TR)) color = 0x8000; else return;
+    } else if ((r.flags & SF_BLACK_TR) && is_black) {
+        return;
+    }
+    uint32_t tr8 = expand5((color >> 10) & 31), tg8 = expand5((color >> 5) & 31), tb8 = expand5(color & 31);
+    uint32_t vr = f2u8(bc_x * (float)(r.vc1 & 0xFF) + bc_y * (float)(r.vc2 & 0xFF) + bc_z * (float)(r.vc3 & 0xFF));          // :1618-1620
+    uint32_t vg = f2u8(bc_x * (float)((r.vc1 >> 8) & 0xFF) + bc_y * (float)((r.vc2 >> 8) & 0xFF) + bc_z * (float)((r.vc3 >> 8) & 0xFF));
+    uint32_t vb = f2u8(bc_x * (float)(r.vc1 >> 16) + bc_y * (float)(r.vc2 >> 16) + bc_z * (float)(r.vc3 >> 16));
+    uint32_t mr = min((tr8 * vr) >> 7, 255u), mg = min((tg8 * vg) >> 7, 255u), mb = min((tb8 * vb) >> 7, 255u);   // :1624-1626
+    float sr, sg, sb;                                                              // :1629-1640
+    if (p.shading == B32_SHADE_NONE) { sr = sg = sb = 1.0f; }
+    else if (p.shading == B32_SHADE_FLAT) { sr = r.sh[0]; sg = r.sh[1]; sb = r.sh[2]; }
+    else {
+        sr = bc_x * r.sh[0] + bc_y * r.sh[3] + bc_z * r.sh[6];
+        sg = bc_x * r.sh[1] + bc_y * r.sh[4] + bc_z * r.sh[7];
+        sb = bc_x * r.sh[2] + bc_y * r.sh[5] + bc_z * r.sh[8];
+    }
+    uint32_t r8 = f2u8(fminf((float)mr * rclamp(sr, 0.0f, 2.0f), 255.0f));          // :1643-1645
+    uint32_t g8 = f2u8(fminf((float)mg * rclamp(sg, 0.0f, 2.0f), 255.0f));
+    uint32_t b8 = f2u8(fminf((float)mb * rclamp(sb, 0.0f, 2.0f), 255.0f));
+    uint32_t r5, g5, b5;
+    if (r.flags & SF_DITHER) {                                                     // :1173-1182
+        // PS1_DITHER_MATRIX rows packed as signed nibbles, :1150-1155
+        const int32_t M[4] = {(int32_t)0x1D0C, (int32_t)0xF3E2, (int32_t)0x0C1D, (int32_t)0xE2F3};
+        int32_t row = M[y & 3];
+        int32_t off = ((row >> ((x & 3) * 4)) & 0xF);
+        off = (off ^ 8) - 8;                                                       // sign-extend the nibble
+        r5 = (uint32_t)min(max(((int32_t)r8 + off) >> 3, 0), 31);
+        g5 = (uint32_t)min(max(((int32_t)g8 + off) >> 3, 0), 31);
+        b5 = (uint32_t)min(max(((int32_t)b8 + off) >> 3, 0), 31);
+    } else {
+        r5 = r8 >> 3; g5 = g8 >> 3; b5 = b8 >> 3;
+    }
+    bool semi = (color & 0x8000) || (r5 == 0 && g5 == 0 && b5 == 0);               // :1659-1661
+    uint32_t o_r = expand5(r5), o_g = expand5(g5), o_b = expand5(b5);              // Color15::r8/g8/b8
+
+    uint32_t editor_alpha = (r.flags >> 8) & 0xFF;
+    if (editor_alpha == 0) return;                                                 // :1664-1669
+    uint32_t br = px.rgba & 0xFF, bg = (px.rgba >> 8) & 0xFF, bb = (px.rgba >> 16) & 0xFF;
+    uint32_t blend_mode = r.flags & SF_BLEND_MASK;
+    if (p.xray_mode) {                                                             // :507-526
+        px.rgba = ((o_r + br) >> 1) | (((o_g + bg) >> 1) << 8) | (((o_b + bb) >> 1) << 16) | 0xFF000000u;
+        return;
+    }
+    bool skip_z_write = (r.flags & SF_TRANSPARENT) != 0;                           // pass 2, :2561-2569
+    if (p.use_zbuffer) {
+        if (editor_alpha < 255) { /* rejected only on z >= zbuffer (:604), already tested above */ }
+        else if (!(z < px.z)) return;                                              // :1684
+        if (!skip_z_write) px.z = z;
+    }
+    if (semi && blend_mode != B32_BLEND_OPAQUE) {                                  // :1686 / :578 / :1697
+        o_r = blend5(o_r, br, blend_mode); o_g = blend5(o_g, bg, blend_mode); o_b = blend5(o_b, bb, blend_mode);
+    }
+    if (editor_alpha < 255) {                                                      // :587-593
+        uint32_t a = editor_alpha, ia = 255 - a;
+        o_r = (o_r * a + br * ia) / 255; o_g = (o_g * a + bg * ia) / 255; o_b = (o_b * a + bb * ia) / 255;
+    }
+    px.rgba = o_r | (o_g << 8) | (o_b << 16) | 0xFF000000u;
+}
+
+constexpr int FILL_CHUNK = 32;      // surfaces staged in shared memory per step (32 x 128 B = 4 KB)
+
+__global__ void __launch_bounds__(FILL_THREADS)
+k_fill(const SurfRec* __restrict__ recs, const uint32_t* __restrict__ ent_surf,
+       const uint32_t* __restrict__ tile_start, const uint32_t* __restrict__ tile_count,
+       const TexDev* __restrict__ tex, const uint16_t* __restrict__ texels,
+       uint32_t* __restrict__ fb_rgba, float* __restrict__ fb_z, const CallState* __restrict__ st, CallParams p) {
+    __shared__ SurfRec s_rec[FILL_CHUNK];
+    if (st->abort || st->overflow) return;
+    const uint32_t tile = blockIdx.x;
+    const uint32_t n = tile_count[tile];
+    if (n == 0) return;
+    const uint32_t start = tile_start[tile];
+    const uint32_t tx = tile % p.tiles_x, ty = tile / p.tiles_x;
+    // thread -> pixel: each warp owns an 8x4 block of the 16x16 tile
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bx0 = tx * TILE_W + (warp & 1) * 8, by0 = ty * TILE_H + (warp >> 1) * 4;
+    const uint32_t x = bx0 + (lane & 7), y = by0 + (lane >> 3);
+    const bool valid = x < p.width && y < p.height;
+    Pixel px{0, 0.0f};
+    Pixel px0 = px;
+    if (valid) { px.rgba = fb_rgba[y * p.width + x]; px.z = fb_z[y * p.width + x]; px0 = px; }
+
+    for (uint32_t base = 0; base < n; base += FILL_CHUNK) {
+        uint32_t cnt = min((uint32_t)FILL_CHUNK, n - base);
+        __syncthreads();
+        {   // stage cnt records: 8 threads x 16 B per record
+            uint32_t rec_i = threadIdx.x >> 3, part = threadIdx.x & 7;
+            if (rec_i < cnt) {
+                uint32_t f = ent_surf[start + base + rec_i];
+                reinterpret_cast<uint4*>(&s_rec[rec_i])[part] = reinterpret_cast<const uint4*>(&recs[f])[part];
+            }
+        }
+        __syncthreads();
+        for (uint32_t i = 0; i < cnt; ++i) {
+            const SurfRec& r = s_rec[i];
+            uint32_t min_x = r.bbox_x & 0xFFFF, max_x = r.bbox_x >> 16, min_y = r.bbox_y & 0xFFFF, max_y = r.bbox_y >> 16;
+            // warp-uniform reject of surfaces that miss this warp's 8x4 block
+            if (max_x <= bx0 || min_x >= bx0 + 8 || max_y <= by0 || min_y >= by0 + 4) continue;
+            if (valid && x >= min_x && x < max_x && y >= min_y && y < max_y) fragment(r, x, y, px, tex, texels, p);
+        }
+    }
+    if (valid) {
+        if (px.rgba != px0.rgba) fb_rgba[y * p.width + x] = px.rgba;
+        if (__float_as_uint(px.z) != __float_as_uint(px0.z)) fb_z[y * p.width + x] = px.z;
+    }
+}
+
+// =================================================================================================
+// small utility kernels
+// =================================================================================================
+__global__ void k_fb_clear(uint32_t* __restrict__ rgba, float* __restrict__ z, uint32_t n, uint32_t color) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { rgba[i] = color; z[i] = 3.40282347e+38f; }
+}
+
+// index -> CLUT expansion of a texture into the RGB555 texel pool (Clut::lookup, types.rs:390-397;
+// IndexedAtlas::to_texture15, mesh_editor.rs:669-682)
+__global__ void k_tex_expand(const uint8_t* __restrict__ idx, const uint16_t* __restrict__ clut, uint32_t clut_len,
+                             uint32_t format, uint32_t n, uint16_t* __restrict__ out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t k = format == B32_TEX_IDX8 ? idx[i] : ((idx[i >> 1] >> ((i & 1) * 4)) & 0xF);
+        out[i] = k < clut_len ? clut[k] : (uint16_t)0;
+    }
+}
+
+__global__ void k_gather_order(const uint32_t* __restrict__ order, const CallState* __restrict__ st, uint32_t* __restrict__ out, uint32_t cap) {
+    uint32_t n = st->n_opaque + st->n_transp;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n && i < cap; i += gridDim.x * blockDim.x) out[i] = order[i];
+}
+
+// =================================================================================================
+// launchers (host)
+// =================================================================================================
+static inline uint32_t grid_for(uint32_t n, uint32_t block, uint32_t sms) {
+    uint32_t g = (n + block - 1) / block;
+    uint32_t cap = sms * 8;
+    return g < 1 ? 1 : (g > cap ? cap : g);
+}
+
+size_t sort_temp_bytes(uint32_t max_faces, uint32_t max_entries) {
+    size_t a = 0, b = 0, c = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, a, (uint64_t*)nullptr, (uint64_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)max_faces, 0, 34);
+    cub::DeviceRadixSort::SortPairs(nullptr, b, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)max_entries, 0, 32);
+    cub::DeviceScan::ExclusiveSum(nullptr, c, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)max_faces);
+    size_t m = a > b ? a : b;
+    return (m > c ? m : c) + 256;
+}
+
+void launch_transform(const LaunchCtx& L, const b32_vertex* verts, TVert* out, float* dbg_cam, const CallParams& p) {
+    if (p.nv == 0) return;
+    k_transform<<<grid_for(p.nv, 256, L.sms), 256, 0, L.stream>>>(verts, out, dbg_cam, L.unr_table, p);
+    ++*L.launches;
+}
+
+void launch_setup(const LaunchCtx& L, const b32_vertex* verts, const b32_face* faces, const TVert* tv, const TexDev* tex,
+                  const LightDev* lights, SurfRec* recs, uint64_t* keys, uint32_t* vals, CallState* st, const CallParams& p) {
+    if (p.nf == 0) return;
+    k_setup<<<grid_for(p.nf, 128, L.sms), 128, 0, L.stream>>>(verts, faces, tv, tex, lights, recs, keys, vals, st, p);
+    ++*L.launches;
+}
+
+void launch_sort_faces(const LaunchCtx& L, void* temp, size_t temp_bytes, const uint64_t* keys_in, uint64_t* keys_out,
+                       const uint32_t* vals_in, uint32_t* vals_out, uint32_t nf) {
+    if (nf == 0) return;
+    cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, (int)nf, 0, 34, L.stream);
+}
+
+void launch_binning(const LaunchCtx& L, void* temp, size_t temp_bytes, const SurfRec* recs, const uint32_t* order,
+                    uint32_t* counts, uint32_t* offsets, uint32_t* ent_tile, uint32_t* ent_surf,
+                    uint32_t* ent_tile_sorted, uint32_t* ent_surf_sorted, uint32_t* tile_count, uint32_t* tile_start,
+                    CallState* st, const CallParams& p, uint32_t capacity, bool count_phase, bool emit_phase) {
+    if (p.nf == 0) return;
+    uint32_t ntiles = p.tiles_x * p.tiles_y;
+    if (count_phase) {
+        k_decide<<<1, 1, 0, L.stream>>>(st, p.use_zbuffer);
+        k_bin_count<<<grid_for(p.nf, 256, L.sms), 256, 0, L.stream>>>(recs, order, counts, st, p.nf);
+        *L.launches += 2;
+        cub::DeviceScan::ExclusiveSum(temp, temp_bytes, counts, offsets, (int)p.nf, L.stream);
+    }
+    if (emit_phase) {
+        cudaMemsetAsync(tile_count, 0, ntiles * sizeof(uint32_t), L.stream);
+        k_bin_emit<<<grid_for(p.nf, 256, L.sms), 256, 0, L.stream>>>(recs, order, counts, offsets, ent_tile, ent_surf, tile_count, st, p.nf, p.tiles_x, capacity);
+        k_tile_scan<<<1, 1024, 0, L.stream>>>(tile_count, tile_start, ntiles);
+        *L.launches += 2;
+    }
+}
+
+void launch_sort_entries(const LaunchCtx& L, void* temp, size_t temp_bytes, const uint32_t* ent_tile, uint32_t* ent_tile_sorted,
+                         const uint32_t* ent_surf, uint32_t* ent_surf_sorted, uint32_t n_entries, uint32_t ntiles) {
+    if (n_entries == 0) return;
+    int bits = 1;
+    while ((1u << bits) < ntiles) ++bits;
+    cub::DeviceRadixSort::SortPairs(temp, temp_bytes, ent_tile, ent_tile_sorted, ent_surf, ent_surf_sorted, (int)n_entries, 0, bits, L.stream);
+}
+
+void launch_fill(const LaunchCtx& L, const SurfRec* recs, const uint32_t* ent_surf_sorted, const uint32_t* tile_start,
+                 const uint32_t* tile_count, const TexDev* tex, const uint16_t* texels, uint32_t* fb_rgba, float* fb_z,
+                 const CallState* st, const CallParams& p) {
+    uint32_t ntiles = p.tiles_x * p.tiles_y;
+    if (ntiles == 0 || p.nf == 0) return;
+    k_fill<<<ntiles, FILL_THREADS, 0, L.stream>>>(recs, ent_surf_sorted, tile_start, tile_count, tex, texels, fb_rgba, fb_z, st, p);
+    ++*L.launches;
+}
+
+void launch_fb_clear(const LaunchCtx& L, uint32_t* rgba, float* z, uint32_t n, uint32_t color) {
+    if (n == 0) return;
+    k_fb_clear<<<grid_for(n, 256, L.sms), 256, 0, L.stream>>>(rgba, z, n, color);
+    ++*L.launches;
+}
+
+void launch_tex_expand(const LaunchCtx& L, const uint8_t* idx, const uint16_t* clut, uint32_t clut_len, uint32_t format, uint32_t n, uint16_t* out) {
+    if (n == 0) return;
+    k_tex_expand<<<grid_for(n, 256, L.sms), 256, 0, L.stream>>>(idx, clut, clut_len, format, n, out);
+    ++*L.launches;
+}
+
+void launch_gather_order(const LaunchCtx& L, const uint32_t* order, const CallState* st, uint32_t* out, uint32_t cap) {
+    if (cap == 0) return;
+    k_gather_order<<<grid_for(cap, 256, L.sms), 256, 0, L.stream>>>(order, st, out, cap);
+    ++*L.launches;
+}
+
+}  // namespace b32

@@ -214,7 +214,7 @@ class Context:
         if rc != abi.B32_OK:
             raise B32Error(rc, "b32_ctx_create failed (no CPU fallback exists)")
         self.h = h
-        self._tex_key = None
+        self._tex_ref = None      # the list last uploaded (kept alive so identity stays meaningful)
 
     def close(self):
         if getattr(self, "h", None):
@@ -245,7 +245,7 @@ class Context:
     def set_textures(self, textures: Sequence[Texture15]):
         arr, keep = tex_descs(textures)
         self.check(self.lib.b32_textures_set(self.h, arr, len(textures)))
-        self._tex_key = id(textures)
+        self._tex_ref = textures
 
 
 _default_ctx: Optional[Context] = None
@@ -317,7 +317,7 @@ def render_mesh_15(fb: Framebuffer, vertices: np.ndarray, faces: np.ndarray,
     """render.rs:2302-2310. Returns RasterTimings as a dict (types.rs:1499-1514)."""
     ctx = fb.ctx
     v, f = _check_geometry(vertices, faces)
-    if ctx._tex_key != id(textures):
+    if ctx._tex_ref is not textures:     # cf. textures_15_cache_generation, src/editor/viewport_3d.rs:3459
         ctx.set_textures(textures)
     cam = camera.to_abi()
     s, keep = settings.to_abi()

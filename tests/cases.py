@@ -130,3 +130,16 @@ def big_triangle_scene():
     tex = _rng_texture(5, 64, 64)
     s = scenes.common_settings(use_zbuffer=True, backface_cull=False)
     return scenes.Scene("big_triangles", v, f, [tex], Camera(), s)
+
+
+def nan_depth_vertices(scene, oracle):
+    """A copy of scene.vertices where one drawn face got a NaN depth that survives culling, so the
+    reference's `partial_cmp().unwrap()` (render.rs:2531) panics in painter's mode."""
+    import dataclasses
+    from bonnie32_b200 import abi
+    for fi in range(len(scene.faces)):
+        v = scene.vertices.copy()
+        v["pos"][scene.faces["v"][fi, 0], 2] = np.nan
+        if oracle.render_scene(dataclasses.replace(scene, vertices=v))[3] == abi.B32_ERR_NAN_DEPTH:
+            return v
+    raise AssertionError("no face produces a NaN sort key")

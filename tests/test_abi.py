@@ -1,0 +1,108 @@
+"""CPU tests of the boundary: the C-ABI library loads, exports every symbol include/b32_raster.h
+declares, the POD layouts match the header, and the product has no CPU fallback."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import __graft_entry__ as entry
+import bonnie32_b200 as pkg
+from bonnie32_b200 import abi
+
+ROOT = entry.ROOT
+HEADER = os.path.join(ROOT, "include", "b32_raster.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(b32_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    entry.build_cuda()
+    lib = abi.load_library()
+    names = declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"libb32raster.so does not export {n}"
+    assert sorted(abi.SYMBOLS) == names, "abi.py and include/b32_raster.h disagree on the symbol list"
+
+
+def test_pod_layouts_match_header(tmp_path):
+    """sizeof/offsetof as the C compiler sees them == the ctypes / numpy mirrors."""
+    prog = tmp_path / "sizes.c"
+    prog.write_text(r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "b32_raster.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(b32_vertex), sizeof(b32_face), sizeof(b32_camera), sizeof(b32_light),
+         sizeof(b32_settings), sizeof(b32_fog), sizeof(b32_timings), sizeof(b32_tex_desc));
+  printf("%zu %zu %zu %zu %zu\n", offsetof(b32_vertex, uv), offsetof(b32_vertex, normal), offsetof(b32_vertex, r),
+         offsetof(b32_settings, ambient), offsetof(b32_settings, lights));
+  return 0; }''')
+    exe = tmp_path / "sizes"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(prog)])
+    out = subprocess.check_output([str(exe)], text=True).split()
+    sizes = [int(x) for x in out]
+    assert sizes[:8] == [36, 16, 48, C.sizeof(abi.Light), C.sizeof(abi.Settings), C.sizeof(abi.Fog), C.sizeof(abi.Timings), C.sizeof(abi.TexDesc)]
+    assert abi.VERTEX_DTYPE.itemsize == 36 and abi.FACE_DTYPE.itemsize == 16 and C.sizeof(abi.Camera) == 48
+    assert sizes[8:] == [12, 20, 32, abi.Settings.ambient.offset, abi.Settings.lights.offset]
+    assert abi.VERTEX_DTYPE.fields["uv"][1] == 12 and abi.VERTEX_DTYPE.fields["normal"][1] == 20 and abi.VERTEX_DTYPE.fields["rgba"][1] == 32
+
+
+def test_face_flags_packing():
+    f = abi.face_flags(7, abi.BLEND_ADD, True, 200)
+    assert int(f) == 7 | (2 << 16) | (1 << 19) | (200 << 24)
+    assert int(abi.face_flags()) == 0xFFFF | (1 << 19) | (255 << 24)
+
+
+def test_no_cpu_fallback_without_gpu():
+    """Without a CUDA device context creation fails loudly; nothing renders on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(pkg.B32Error) as e:
+        pkg.Context(0)
+    assert e.value.code == abi.B32_ERR_NO_DEVICE
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    saved = abi._lib
+    abi._lib = None
+    try:
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            abi.load_library(str(tmp_path / "nope.so"))
+    finally:
+        abi._lib = saved
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under bonnie-32_b200/ or include/ may reference it."""
+    bad = []
+    for base in (entry.PKG_DIR, os.path.join(ROOT, "include")):
+        for dp, _, files in os.walk(base):
+            for fn in files:
+                if fn.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                    txt = open(os.path.join(dp, fn), errors="ignore").read()
+                    if re.search(r"\boracle\b|b32o_|pymodel", txt):
+                        bad.append(os.path.join(dp, fn))
+    assert not bad, bad
+
+
+def test_built_for_sm100a_with_exact_arithmetic_flags():
+    """The cubin targets sm_100a and is compiled without FMA contraction / with IEEE div+sqrt, no FTZ.
+    (FFMA still appears in SASS inside the correctly-rounded division sequences, so the flags — and
+    the GPU parity tests — are what is checked.)"""
+    for flag in ("-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false", "arch=compute_100a,code=sm_100a", "-lineinfo"):
+        assert flag in entry.NVCC_FLAGS
+    entry.build_cuda()
+    out = subprocess.run(["cuobjdump", "-lelf", entry.LIB], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in out.stdout

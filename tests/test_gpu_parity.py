@@ -1,0 +1,219 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle, bit for bit."""
+import copy
+import dataclasses
+
+import numpy as np
+import pytest
+
+import bonnie32_b200 as pkg
+from bonnie32_b200 import abi, scenes
+import cases
+
+pytestmark = pytest.mark.gpu
+
+
+def render_gpu(ctx, sc, resident=False):
+    fb = pkg.Framebuffer(sc.width, sc.height, ctx)
+    fb.clear(sc.clear)
+    if resident:
+        ctx.set_textures(sc.textures)
+        mesh = pkg.Mesh(ctx, sc.vertices, sc.faces)
+        tm = mesh.render(sc.camera, sc.settings, sc.fog)
+        mesh.free()
+    else:
+        tm = pkg.render_mesh_15(fb, sc.vertices, sc.faces, sc.textures, sc.camera, sc.settings, sc.fog)
+    rgba, z = fb.download()
+    return rgba, z, tm
+
+
+def assert_same(sc, got, got_z, tm, want, want_z, otm):
+    assert tm["triangles_drawn"] == otm["triangles_drawn"], sc.name
+    if not np.array_equal(got, want):
+        bad = (got != want).any(axis=-1)
+        ys, xs = np.nonzero(bad)
+        raise AssertionError(f"{sc.name}: {bad.sum()} pixels differ, first at (x={xs[0]}, y={ys[0]}): "
+                             f"got {got[ys[0], xs[0]]} want {want[ys[0], xs[0]]}")
+    zb = got_z.view(np.uint32) != want_z.view(np.uint32)
+    assert not zb.any(), f"{sc.name}: {zb.sum()} z-buffer values differ"
+
+
+FEATURES = cases.feature_scenes()
+
+
+@pytest.mark.parametrize("sc", FEATURES, ids=[s.name for s in FEATURES])
+def test_feature_scene(ctx, oracle, sc):
+    want, want_z, otm, rc, order = oracle.render_scene(sc, want_order=True)
+    assert rc == 0
+    got, got_z, tm = render_gpu(ctx, sc)
+    # draw order (opaque pass then transparent pass) must be the reference's
+    n = np.zeros(1, dtype=np.uint32)
+    buf = np.zeros(max(len(sc.faces), 1), dtype=np.uint32)
+    import ctypes as C
+    ctx.check(ctx.lib.b32_debug_draw_order(ctx.h, buf.ctypes.data, len(buf), n.ctypes.data_as(C.POINTER(C.c_uint32))))
+    assert n[0] == len(order)
+    assert np.array_equal(buf[: n[0]], order), sc.name
+    assert_same(sc, got, got_z, tm, want, want_z, otm)
+
+
+@pytest.mark.parametrize("fixed", [True, False])
+def test_c1_single_triangle(ctx, oracle, fixed):
+    sc = scenes.scene_c1(fixed)
+    want, want_z, otm, rc = oracle.render_scene(sc)
+    got, got_z, tm = render_gpu(ctx, sc)
+    assert tm["triangles_drawn"] == 1          # the reversed copy is culled
+    assert_same(sc, got, got_z, tm, want, want_z, otm)
+
+
+def test_big_triangles_slow_edge_path(ctx, oracle):
+    sc = cases.big_triangle_scene()
+    want, want_z, otm, rc = oracle.render_scene(sc)
+    got, got_z, tm = render_gpu(ctx, sc)
+    assert_same(sc, got, got_z, tm, want, want_z, otm)
+
+
+@pytest.mark.parametrize("zbuf", [False, True])
+def test_c2_full(ctx, oracle, zbuf):
+    sc = scenes.scene_c2(use_zbuffer=zbuf)
+    want, want_z, otm, rc = oracle.render_scene(sc)
+    got, got_z, tm = render_gpu(ctx, sc)
+    assert_same(sc, got, got_z, tm, want, want_z, otm)
+
+
+@pytest.mark.parametrize("zbuf", [False, True])
+def test_c4_full_size(ctx, oracle, zbuf):
+    """BASELINE config 4 at full size (100k triangles): byte-identical to the oracle."""
+    sc = scenes.scene_c4(use_zbuffer=zbuf)
+    want, want_z, otm, rc = oracle.render_scene(sc)
+    got, got_z, tm = render_gpu(ctx, sc, resident=True)
+    assert_same(sc, got, got_z, tm, want, want_z, otm)
+
+
+def test_indexed_equals_expanded(ctx):
+    """Sampling index->CLUT on the device == expanding to Texture15 on the host first."""
+    sc = scenes.scene_c4(n_tris=5000)
+    a, az, _ = render_gpu(ctx, sc)
+    sc2 = copy.copy(sc)
+    sc2.textures = [scenes.expand_texture(t) for t in sc.textures]
+    b, bz, _ = render_gpu(ctx, sc2)
+    assert np.array_equal(a, b) and np.array_equal(az.view(np.uint32), bz.view(np.uint32))
+
+
+def test_multiple_calls_compose(ctx, oracle):
+    """Several render_mesh_15 calls into one framebuffer, in call order (scene.rs:196-259)."""
+    parts = [scenes.scene_c2(n_tris=200, seed=s, use_zbuffer=True) for s in (1, 2, 3)]
+    fb = pkg.Framebuffer(320, 240, ctx)
+    fb.clear(parts[0].clear)
+    want = np.empty((240, 320, 4), np.uint8); want_z = np.empty((240, 320), np.float32)
+    want[...] = np.array(list(parts[0].clear) + [255], np.uint8); want_z[...] = np.finfo(np.float32).max
+    for sc in parts:
+        pkg.render_mesh_15(fb, sc.vertices, sc.faces, sc.textures, sc.camera, sc.settings, sc.fog)
+        rc, _, _ = oracle.render_mesh_15(want, want_z, sc.vertices, sc.faces, sc.textures, sc.camera, sc.settings, sc.fog)
+        assert rc == 0
+    got, got_z = fb.download()
+    assert np.array_equal(got, want) and np.array_equal(got_z.view(np.uint32), want_z.view(np.uint32))
+
+
+def test_fb_upload_roundtrip(ctx):
+    fb = pkg.Framebuffer(64, 48, ctx)
+    rng = np.random.default_rng(3)
+    px = rng.integers(0, 256, (48, 64, 4), dtype=np.uint8)
+    z = rng.random((48, 64), dtype=np.float32)
+    fb.upload(px, z)
+    a, b = fb.download()
+    assert np.array_equal(a, px) and np.array_equal(b, z)
+    fb.clear((1, 2, 3))
+    a, b = fb.download()
+    assert (a == np.array([1, 2, 3, 255], np.uint8)).all() and (b == np.finfo(np.float32).max).all()
+
+
+def test_transform_parity_random_and_adversarial(ctx, oracle):
+    """k_transform vs the oracle on 1M vertices incl. denormals, signed zeros, huge values, NaN/inf,
+    and denominators near the |denom|<256 early-out (fixed.rs:406-408)."""
+    import ctypes as C
+    n = 1_000_000
+    u = scenes.splitmix64_u01(42, n * 3).reshape(n, 3)
+    pos = ((u - 0.5) * np.array([200.0, 200.0, 120.0])).astype(np.float32)
+    special = np.array([0.0, -0.0, 1e-40, -1e-40, 1e5, -1e5, 524287.9, -524288.0, 1e9, -1e9, 3.4e38, np.inf, -np.inf, np.nan,
+                        -5.0, -5.05, -4.95, -4.9375, -5.0625, 0.1, 0.0999], dtype=np.float32)
+    k = len(special)
+    grid = np.stack(np.meshgrid(special, special, special, indexing="ij"), axis=-1).reshape(-1, 3)
+    pos[: len(grid)] = grid
+    v = scenes.make_vertices(pos)
+    cam = cases._rotated_camera(0.37, -1.2, (3.0, -2.0, 1.5))
+    for kw in (dict(), dict(use_fixed_point=False), dict(ortho_projection=(7.5, 1.0, -2.0))):
+        s = scenes.common_settings(**kw)
+        for w, h in ((320, 240), (640, 480), (201, 333)):
+            fb = pkg.Framebuffer(w, h, ctx)
+            want_s, want_c = oracle.transform(v, cam, s, w, h)
+            got_s = np.empty((n, 3), np.float32); got_c = np.empty((n, 3), np.float32)
+            ca = cam.to_abi(); sa, keep = s.to_abi()
+            ctx.check(ctx.lib.b32_debug_transform(ctx.h, v.ctypes.data, n, C.byref(ca), C.byref(sa), got_s.ctypes.data, got_c.ctypes.data))
+            # compare bit patterns; NaN payloads may differ, so canonicalise NaNs
+            def canon(a):
+                b = a.view(np.uint32).copy(); b[np.isnan(a)] = 0x7FC00000; return b
+            assert np.array_equal(canon(got_s), canon(want_s)), (kw, w, h)
+            assert np.array_equal(canon(got_c), canon(want_c)), (kw, w, h)
+
+
+def test_error_codes(ctx, oracle):
+    sc = scenes.scene_c2(n_tris=50)
+    fb = pkg.Framebuffer(320, 240, ctx)
+    fb.clear(sc.clear)
+    before, _ = fb.download()
+    # out-of-range vertex index: reference panics -> B32_ERR_OOB_INDEX, framebuffer untouched
+    f = sc.faces.copy(); f["v"][7, 1] = len(sc.vertices)
+    with pytest.raises(pkg.B32Error) as e:
+        pkg.render_mesh_15(fb, sc.vertices, f, sc.textures, sc.camera, sc.settings)
+    assert e.value.code == abi.B32_ERR_OOB_INDEX
+    assert np.array_equal(fb.download()[0], before)
+    # NaN depth in a sorted pass: reference unwrap() panics -> B32_ERR_NAN_DEPTH
+    v = cases.nan_depth_vertices(sc, oracle)
+    with pytest.raises(pkg.B32Error) as e:
+        pkg.render_mesh_15(fb, v, sc.faces, sc.textures, sc.camera, sc.settings)
+    assert e.value.code == abi.B32_ERR_NAN_DEPTH
+    assert np.array_equal(fb.download()[0], before)
+    rc = oracle.render_scene(dataclasses.replace(sc, vertices=v))[3]
+    assert rc == abi.B32_ERR_NAN_DEPTH
+    # with the z-buffer on, the opaque pass is not sorted: NaN is legal and must match the oracle
+    s2 = copy.copy(sc); s2.vertices = v; s2.settings = scenes.common_settings(use_zbuffer=True)
+    want, want_z, otm, rc = oracle.render_scene(s2)
+    assert rc == 0
+    got, got_z, tm = render_gpu(ctx, s2)
+    assert_same(s2, got, got_z, tm, want, want_z, otm)
+    # spot light is unsupported on the device
+    s3 = copy.copy(sc); s3.settings = scenes.common_settings(shading=abi.SHADE_GOURAUD, lights=[pkg.Light.spot((0, 0, 0), (0, 0, 1), 0.5, 10.0, 1.0)])
+    with pytest.raises(pkg.B32Error) as e:
+        pkg.render_mesh_15(fb, sc.vertices, sc.faces, sc.textures, sc.camera, s3.settings)
+    assert e.value.code == abi.B32_ERR_UNSUPPORTED
+
+
+def test_empty_inputs(ctx):
+    fb = pkg.Framebuffer(320, 240, ctx)
+    fb.clear((9, 8, 7))
+    s = scenes.common_settings()
+    v0 = np.zeros(0, abi.VERTEX_DTYPE); f0 = np.zeros(0, abi.FACE_DTYPE)
+    tm = pkg.render_mesh_15(fb, v0, f0, [], pkg.Camera(), s)
+    assert tm["triangles_drawn"] == 0
+    sc = scenes.scene_c1()
+    tm = pkg.render_mesh_15(fb, sc.vertices, f0, [], pkg.Camera(), s)
+    assert tm["triangles_drawn"] == 0
+    assert (fb.download()[0] == np.array([9, 8, 7, 255], np.uint8)).all()
+
+
+def test_properties_full_size(ctx):
+    """Size-independent properties at BASELINE size (100k triangles)."""
+    sc = scenes.scene_c4()
+    a, az, tm = render_gpu(ctx, sc, resident=True)
+    # determinism: same inputs, same bytes
+    b, bz, _ = render_gpu(ctx, sc, resident=True)
+    assert np.array_equal(a, b) and np.array_equal(az.view(np.uint32), bz.view(np.uint32))
+    # painter's mode never touches the z-buffer
+    assert (az == np.finfo(np.float32).max).all()
+    # every written pixel is 5-bit expanded with A=255: (v<<3)|(v>>2)
+    written = (a[..., :3] != np.array(sc.clear, np.uint8)).any(-1)
+    c = a[written][:, :3].astype(np.int32)
+    assert ((((c >> 3) << 3) | (c >> 5)) == c).all() and (a[written][:, 3] == 255).all()
+    # painter's order == reversing the face list reverses ties only: drawing the scene twice is idempotent
+    fb = pkg.Framebuffer(sc.width, sc.height, ctx); fb.upload(a, az)
+    pkg.render_mesh_15(fb, sc.vertices, sc.faces, sc.textures, sc.camera, sc.settings)
+    assert np.array_equal(fb.download()[0], a)

@@ -1,0 +1,227 @@
+"""CPU tests of the oracle: the reference's own exact unit-test facts (fixed.rs:477-548), spec
+constants, agreement with the independent numpy model (oracle/pymodel.py) and with the committed
+golden fixtures (tests/golden, produced by the numpy model)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import bonnie32_b200 as pkg
+from bonnie32_b200 import abi, scenes
+from oracle import pymodel
+import cases
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+HASHES = json.load(open(os.path.join(GOLDEN, "hashes.json")))
+
+
+# ---- fixed.rs:477-548: the only exact facts the reference's tests pin --------------------------
+def test_fixed32_precision(oracle):                    # fixed.rs:478-489
+    L = oracle.lib()
+    assert L.b32o_fixed_from_f32(1.0) == 4096
+    assert L.b32o_fixed_from_f32(0.5) == 2048
+    assert L.b32o_fixed_from_f32(0.001) > 0
+
+
+def test_fixed32_mul(oracle):                          # fixed.rs:492-497
+    L = oracle.lib()
+    r = L.b32o_fixed_mul(L.b32o_fixed_from_f32(2.0), L.b32o_fixed_from_f32(3.0))
+    assert abs(r / 4096.0 - 6.0) < 0.01
+
+
+def test_unr_division(oracle):                         # fixed.rs:500-531 (tolerances) + survey transcription values
+    L = oracle.lib()
+    fx = L.b32o_fixed_from_f32
+    assert abs(L.b32o_div_unr(fx(10.0), fx(3.0)) / 4096.0 - 10.0 / 3.0) < 0.1
+    assert abs(L.b32o_div_unr(fx(10.0), fx(2.0)) / 4096.0 - 5.0) < 0.01
+    assert abs(L.b32o_div_unr(fx(-6.0), fx(2.0)) / 4096.0 + 3.0) < 0.01
+    assert abs(L.b32o_div_unr(fx(7.5), fx(1.0)) / 4096.0 - 7.5) < 0.1
+    assert L.b32o_div_unr(40960, 12288) == 13653
+    assert L.b32o_div_unr(40960, 8192) == 20480
+    assert L.b32o_div_unr(-24576, 8192) == -12288
+    assert L.b32o_div_unr(30720, 4096) == 30720
+    assert L.b32o_div_unr(123, 0) == 0
+
+
+def test_projection_outputs_integers(oracle):          # fixed.rs:534-548
+    import ctypes as C
+    cam = abi.Camera()
+    cam.basis_x[:] = [1, 0, 0]; cam.basis_y[:] = [0, 1, 0]; cam.basis_z[:] = [0, 0, 1]
+    w = (C.c_float * 3)(1.234, 2.567, 5.0)
+    sx, sy, d = C.c_int32(), C.c_int32(), C.c_float()
+    oracle.lib().b32o_project_fixed(w, C.byref(cam), C.c_uint32(320), C.c_uint32(240), C.byref(sx), C.byref(sy), C.byref(d))
+    assert -1000 < sx.value < 1000 and -1000 < sy.value < 1000
+    # hand computation: x = 160 + floor(1.234*4/10*90) region
+    assert (sx.value, sy.value) == (204, 212)
+
+
+def test_unr_table_formula(oracle):                    # fixed.rs:18-31
+    L = oracle.lib()
+    t = [L.b32o_unr_table(i) for i in range(257)]
+    assert t[:4] == [255, 253, 251, 249] and t[256] == 0
+    assert t == [max(0, ((0x40000 // (i + 0x100)) + 1) // 2 - 0x101) for i in range(257)]
+    assert t == list(pymodel.UNR_TABLE)
+
+
+def test_div_unr_matches_numpy_model(oracle):
+    L = oracle.lib()
+    rng = np.random.default_rng(7)
+    num = rng.integers(-2**31, 2**31, 20000, dtype=np.int64)
+    den = rng.integers(-2**31, 2**31, 20000, dtype=np.int64)
+    den[:2000] = rng.integers(-5000, 5000, 2000)
+    num[2000:4000] = rng.integers(-5000, 5000, 2000)
+    edge = np.array([0, 1, -1, 255, 256, 257, -256, 2**31 - 1, -2**31, 0x7FC0, 0x8000, 0xFFFF, 0x10000], dtype=np.int64)
+    num = np.concatenate([num, np.repeat(edge, len(edge))]); den = np.concatenate([den, np.tile(edge, len(edge))])
+    want = pymodel.div_unr(num, den)
+    got = np.array([L.b32o_div_unr(int(a), int(b)) for a, b in zip(num, den)], dtype=np.int32)
+    assert np.array_equal(got, want)
+
+
+def test_dither_truth_table(oracle):                   # render.rs:1150-1182, exhaustive 256 x 16
+    import ctypes as C
+    out = (C.c_uint8 * 3)()
+    M = [[-4, 0, -3, 1], [2, -2, 3, -1], [-3, 1, -4, 0], [3, -1, 2, -2]]
+    for c in range(256):
+        for y in range(4):
+            for x in range(4):
+                oracle.lib().b32o_dither_and_quantize(C.c_uint8(c), C.c_uint8(255 - c), C.c_uint8(c ^ 0x55), C.c_uint32(x + 4), C.c_uint32(y + 8), out)
+                exp = [min(max((v + M[y][x]) >> 3, 0), 31) for v in (c, 255 - c, c ^ 0x55)]
+                assert list(out) == exp
+
+
+def test_blend_truth_table(oracle):                    # render.rs:1093-1145, all 6 modes x 32 x 32 five-bit pairs
+    import ctypes as C
+    out = (C.c_uint8 * 3)()
+    for mode in range(6):
+        for f in range(0, 256, 8):
+            for b in range(0, 256, 8):
+                oracle.lib().b32o_blend_rgb555(C.c_uint8(f), C.c_uint8(f | 7), C.c_uint8(f), C.c_uint8(b), C.c_uint8(b), C.c_uint8(b | 5),
+                                               C.c_uint32(mode), out)
+                want = pymodel.blend555(np.array([f, f | 7, f]), np.array([b, b, b | 5]), mode)
+                assert list(out) == list(want), (mode, f, b)
+                f5, b5 = f >> 3, b >> 3
+                exp = {0: f5, 1: (b5 + f5) // 2, 2: min(b5 + f5, 31), 3: max(b5 - f5, 0), 4: min(b5 + f5 // 4, 31), 5: b5}[mode] << 3
+                assert out[0] == exp
+
+
+def test_texture_sample_wrap(oracle):                  # types.rs:671-681, X6: tiny negative u wraps to exactly 1.0
+    import ctypes as C
+    px = np.arange(8 * 4, dtype=np.uint16) + 1
+    t = pkg.Texture15(8, 4, px)
+    d, keep = t.to_abi()
+    f = oracle.lib().b32o_texture_sample
+    f.argtypes = [C.POINTER(abi.TexDesc), C.c_float, C.c_float]
+    assert f(C.byref(d), 0.0, 0.0) == 1
+    assert f(C.byref(d), -1e-9, 0.0) == 8            # rem_euclid -> 1.0 -> clamped to w-1
+    assert f(C.byref(d), 0.999, 0.999) == 32
+    assert f(C.byref(d), 1.5, -0.25) == px[3 * 8 + 4]
+    assert f(C.byref(d), float("nan"), float("inf")) == 1
+    got = [f(C.byref(d), float(u), float(v)) for u in np.linspace(-3, 3, 41) for v in np.linspace(-2, 2, 17)]
+    uu, vv = np.meshgrid(np.linspace(-3, 3, 41).astype(np.float32), np.linspace(-2, 2, 17).astype(np.float32), indexing="ij")
+    want = pymodel.sample(px.reshape(4, 8), uu.reshape(-1), vv.reshape(-1))
+    assert got == list(want)
+
+
+def test_camera_new_basis():                           # camera.rs:21-32, 76-91 and SURVEY §8d
+    c = pkg.Camera()
+    assert list(c.basis_x) == [-1.0, 0.0, 0.0] and list(c.basis_y) == [0.0, -1.0, 0.0] and list(c.basis_z) == [0.0, 0.0, 1.0]
+
+
+def test_c1_screen_coordinates(oracle):                # (205,165) (115,165) (160,75)
+    for fixed in (True, False):
+        sc = scenes.scene_c1(fixed)
+        scr, cam = oracle.transform(sc.vertices, sc.camera, sc.settings, 320, 240)
+        assert scr.tolist() == [[205.0, 165.0, 8.0], [115.0, 165.0, 8.0], [160.0, 75.0, 8.0]]
+
+
+# ---- oracle vs the independent numpy model, and vs the committed golden fixtures -----------------
+def _digest(rgba, z, order):
+    return {"rgba_sha256": hashlib.sha256(np.ascontiguousarray(rgba).tobytes()).hexdigest(),
+            "z_sha256": hashlib.sha256(np.ascontiguousarray(z).tobytes()).hexdigest(),
+            "triangles_drawn": len(order),
+            "order_sha256": hashlib.sha256(np.asarray(order, dtype=np.uint32).tobytes()).hexdigest()}
+
+
+SMALL = [scenes.scene_c1(True), scenes.scene_c1(False)] + cases.feature_scenes() + [cases.big_triangle_scene()]
+
+
+@pytest.mark.parametrize("sc", SMALL, ids=[s.name for s in SMALL])
+def test_oracle_equals_numpy_model_and_golden(oracle, sc):
+    want, want_z, tm, rc, order = oracle.render_scene(sc, want_order=True)
+    assert rc == 0
+    rgba, z = pymodel.fb_clear(sc.width, sc.height, sc.clear)
+    order2 = pymodel.render_mesh_15(rgba, z, sc.vertices, sc.faces, sc.textures, sc.camera, sc.settings, sc.fog)
+    assert list(order) == order2
+    assert np.array_equal(rgba, want)
+    assert np.array_equal(z.view(np.uint32), want_z.view(np.uint32))
+    assert _digest(want, want_z, order) == HASHES[sc.name]
+
+
+def test_scenes_exercise_their_feature(oracle):
+    """Guards against vacuous parity: the feature scenes must really hit the code they name."""
+    by = {s.name: s for s in cases.feature_scenes()}
+    base, _, _, _ = oracle.render_scene(by["painter_idx8"])
+    for name in ("nodither", "float_projection", "perspective_correct", "nocull_painter", "xray", "fog",
+                 "gouraud_lights", "flat_lights", "mixed_painter", "untextured_vertex_colours"):
+        img, _, _, _ = oracle.render_scene(by[name])
+        assert not np.array_equal(img, base), name
+    # the mixed scene has both passes
+    m = by["mixed_zbuffer"]
+    blends = (m.faces["flags"] >> 16) & 7
+    assert (blends != 0).any() and (blends == 0).any()
+    # the large-world scene produces edge values beyond 2^24 (forces the exact incremental path)
+    big = by["rotated_camera_large_world"]
+    scr, cam = oracle.transform(big.vertices, big.camera, big.settings, 320, 240)
+    assert np.abs(scr[:, :2]).max() > 5000
+
+
+@pytest.mark.parametrize("name", ["c2_1000_tris_64x64_idx8", "c2_1000_tris_64x64_idx8_zbuffer"])
+def test_c2_golden_full_framebuffer(oracle, name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    sc = scenes.scene_c2(use_zbuffer=name.endswith("zbuffer"))
+    want, want_z, tm, rc, order = oracle.render_scene(sc, want_order=True)
+    assert rc == 0 and tm["triangles_drawn"] == len(g["order"])
+    assert np.array_equal(order, g["order"])
+    assert np.array_equal(want, g["rgba"]) and np.array_equal(want_z.view(np.uint32), g["z"].view(np.uint32))
+    # the fixture and the hash file agree
+    assert hashlib.sha256(g["rgba"].tobytes()).hexdigest() == HASHES[name]["rgba_sha256"]
+
+
+@pytest.mark.parametrize("name,zbuf", [("c4_100000_tris_256x256_idx4", False), ("c4_100000_tris_256x256_idx4_zbuffer", True)])
+def test_c4_golden_hash(oracle, name, zbuf):
+    """BASELINE config 4 at full size: the oracle reproduces the numpy model's framebuffer."""
+    sc = scenes.scene_c4(use_zbuffer=zbuf)
+    want, want_z, tm, rc, order = oracle.render_scene(sc, want_order=True)
+    assert rc == 0
+    assert _digest(want, want_z, order) == HASHES[name]
+
+
+def test_oracle_panics_map_to_error_codes(oracle):
+    sc = scenes.scene_c2(n_tris=50)
+    f = sc.faces.copy(); f["v"][7, 1] = len(sc.vertices)
+    rgba, z = pymodel.fb_clear(320, 240, sc.clear)
+    rc, _, _ = oracle.render_mesh_15(rgba, z, sc.vertices, f, sc.textures, sc.camera, sc.settings)
+    assert rc == abi.B32_ERR_OOB_INDEX
+    with pytest.raises(pymodel.ReferencePanic):
+        pymodel.render_mesh_15(rgba, z, sc.vertices, f, sc.textures, sc.camera, sc.settings)
+    v = cases.nan_depth_vertices(sc, oracle)
+    rc, _, _ = oracle.render_mesh_15(rgba, z, v, sc.faces, sc.textures, sc.camera, sc.settings)
+    assert rc == abi.B32_ERR_NAN_DEPTH
+    with pytest.raises(pymodel.ReferencePanic):
+        pymodel.render_mesh_15(rgba, z, v, sc.faces, sc.textures, sc.camera, sc.settings)
+
+
+def test_splitmix64_reference_values():
+    """SplitMix64 known answers (seed 0: first outputs of the published algorithm)."""
+    z = []
+    x = 0
+    for _ in range(3):
+        x = (x + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+        t = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+        t = ((t ^ (t >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+        z.append(t ^ (t >> 31))
+    assert z[0] == 0xE220A8397B1DCDAF and z[1] == 0x6E789E6AA1B965F4
+    u = scenes.splitmix64_u01(0, 3)
+    assert [int(v * 2**24) for v in u] == [v >> 40 for v in z]
