@@ -41,6 +41,7 @@ struct b32_mesh {
     b32_vertex* verts = nullptr;
     b32_face* faces = nullptr;
     uint32_t nv = 0, nf = 0;
+    bool has_nonopaque = false;     // some face has blend != Opaque or editor_alpha < 255
 };
 
 struct b32_ctx {
@@ -73,11 +74,18 @@ struct b32_ctx {
     DevBuf<uint32_t> vals, order, counts, offsets;
     DevBuf<uint32_t> ent_tile, ent_surf, ent_tile_sorted, ent_surf_sorted;
     DevBuf<uint32_t> tile_count, tile_start;
+    DevBuf<BinHead> bins;
+    uint32_t bin_cap_hint = 0;
+    std::vector<LightDev> lights_h;
+    bool order_valid = false;
+    bool async_pending = false;
+    CallParams last_params{};
     DevBuf<uint8_t> temp;
     DevBuf<LightDev> lights;
     DevBuf<float> dbg;
     uint8_t* unr_table = nullptr;
     CallState* state = nullptr;        // device
+    uint32_t* sticky = nullptr;        // device: error bits of enqueue-only calls
     CallState* state_h = nullptr;      // pinned host
     uint8_t* pinned = nullptr;         // pinned staging ring for pageable host buffers
     size_t pinned_bytes = 0;
@@ -175,112 +183,156 @@ int h2d(b32_ctx* ctx, void* dst, const void* src, size_t bytes) {
 }
 
 int ensure_work(b32_ctx* ctx, uint32_t nv, uint32_t nf) {
-    CK(ctx->tv.reserve(std::max<uint32_t>(nv, 1)));
-    CK(ctx->recs.reserve(std::max<uint32_t>(nf, 1)));
-    CK(ctx->keys.reserve(std::max<uint32_t>(nf, 1)));
-    CK(ctx->keys_sorted.reserve(std::max<uint32_t>(nf, 1)));
-    CK(ctx->vals.reserve(std::max<uint32_t>(nf, 1)));
-    CK(ctx->order.reserve(std::max<uint32_t>(nf, 1)));
-    CK(ctx->counts.reserve(std::max<uint32_t>(nf, 1)));
-    CK(ctx->offsets.reserve(std::max<uint32_t>(nf, 1)));
+    uint32_t m = std::max<uint32_t>(nf, 1);
+    CK(ctx->recs.reserve(m));
+    CK(ctx->keys.reserve(m));
+    CK(ctx->vals.reserve(m));
     uint32_t ntiles = ((ctx->width + TILE_W - 1) / TILE_W) * ((ctx->height + TILE_H - 1) / TILE_H);
     CK(ctx->tile_count.reserve(std::max<uint32_t>(ntiles, 1)));
     CK(ctx->tile_start.reserve(std::max<uint32_t>(ntiles, 1)));
     return B32_OK;
 }
 
-int ensure_entries(b32_ctx* ctx, size_t n) {
-    n = std::max<size_t>(n, 1 << 16);
-    CK(ctx->ent_tile.reserve(n)); CK(ctx->ent_surf.reserve(n));
-    CK(ctx->ent_tile_sorted.reserve(n)); CK(ctx->ent_surf_sorted.reserve(n));
-    return B32_OK;
-}
-
-int ensure_temp(b32_ctx* ctx, uint32_t nf, size_t entries) {
-    size_t need = sort_temp_bytes(std::max<uint32_t>(nf, 1), (uint32_t)std::max<size_t>(entries, 1));
+int ensure_ordered(b32_ctx* ctx, uint32_t nf, size_t entries) {
+    uint32_t m = std::max<uint32_t>(nf, 1);
+    CK(ctx->keys_sorted.reserve(m));
+    CK(ctx->order.reserve(m));
+    CK(ctx->counts.reserve(m));
+    CK(ctx->offsets.reserve(m));
+    entries = std::max<size_t>(entries, 1 << 16);
+    CK(ctx->ent_tile.reserve(entries)); CK(ctx->ent_surf.reserve(entries));
+    CK(ctx->ent_tile_sorted.reserve(entries)); CK(ctx->ent_surf_sorted.reserve(entries));
+    size_t need = sort_temp_bytes(m, (uint32_t)std::min<size_t>(ctx->ent_tile.cap, 0x7FFFFFFFu));
     CK(ctx->temp.reserve(need));
     return B32_OK;
 }
 
-// One render_mesh_15 on device-resident geometry. sync=false only enqueues.
-int render_device(b32_ctx* ctx, const b32_vertex* d_verts, uint32_t nv, const b32_face* d_faces, uint32_t nf,
-                  const b32_camera* cam, const b32_settings* s, const b32_fog* fog, b32_timings* tm) {
-    if (!cam || !s) return fail(ctx, B32_ERR_INVALID, "camera/settings is NULL");
-    if (ctx->width == 0 || ctx->height == 0) return fail(ctx, B32_ERR_INVALID, "framebuffer has zero size (call b32_fb_resize)");
-    if (ctx->width > 65535 || ctx->height > 65535) return fail(ctx, B32_ERR_UNSUPPORTED, "framebuffer dimension > 65535");
-    CallParams p;
-    std::vector<LightDev> lights;
-    int rc = fill_params(ctx, p, cam, s, fog, nv, nf, lights);
-    if (rc != B32_OK) return rc;
-    if (tm) std::memset(tm, 0, sizeof(*tm));
-    ctx->last_nf = nf;
-    if (nf == 0) return B32_OK;
+// capacity (entries) of one tile bin of the opaque pass; a surface adds at most one entry per tile
+uint32_t pick_bin_cap(b32_ctx* ctx, uint32_t nf, uint32_t ntiles, bool worst_case) {
+    uint32_t cap = worst_case ? nf : std::max<uint32_t>(ctx->bin_cap_hint, std::max<uint32_t>(1024, (uint32_t)(16ull * nf / std::max<uint32_t>(ntiles, 1))));
+    cap = std::min<uint32_t>(cap, std::max<uint32_t>(nf, 1));
+    return (cap + 31u) & ~31u;
+}
 
-    rc = ensure_work(ctx, nv, nf); if (rc) return rc;
-    rc = ensure_entries(ctx, (size_t)nf * 8); if (rc) return rc;
-    rc = ensure_temp(ctx, nf, ctx->ent_tile.cap); if (rc) return rc;
-    if (!lights.empty()) {
-        CK(ctx->lights.reserve(lights.size()));
-        CK(cudaMemcpyAsync(ctx->lights.p, lights.data(), lights.size() * sizeof(LightDev), cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));   // `lights` is a host temporary
-    }
+int upload_lights(b32_ctx* ctx, const std::vector<LightDev>& lights) {
+    if (lights.empty()) return B32_OK;
+    // lights change rarely: skip the copy (and its sync) when the bytes are the ones already on the device
+    size_t bytes = lights.size() * sizeof(LightDev);
+    if (ctx->lights_h.size() == lights.size() && std::memcmp(ctx->lights_h.data(), lights.data(), bytes) == 0) return B32_OK;
+    CK(ctx->lights.reserve(lights.size()));
+    CK(cudaStreamSynchronize(ctx->stream));       // earlier calls may still read the old lights
+    CK(cudaMemcpyAsync(ctx->lights.p, lights.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));       // `lights` is a host temporary
+    ctx->lights_h = lights;
+    return B32_OK;
+}
+
+// Pass 2 (semi-transparent surfaces, back to front) and x-ray mode: strict draw-order replay.
+int render_ordered(b32_ctx* ctx, const CallParams& p) {
     LaunchCtx L = ctx->L();
     cudaStream_t st = ctx->stream;
-    const uint32_t ntiles = p.tiles_x * p.tiles_y;
-
-    CK(cudaMemsetAsync(ctx->state, 0, sizeof(CallState), st));
-    CK(cudaEventRecord(ctx->ev[0], st));
-    launch_transform(L, d_verts, ctx->tv.p, nullptr, p);                                     // TRANSFORM
-    CK(cudaEventRecord(ctx->ev[1], st));
-    launch_setup(L, d_verts, d_faces, ctx->tv.p, ctx->texdesc.p, ctx->lights.p, ctx->recs.p, ctx->keys.p, ctx->vals.p, ctx->state, p);   // CULL
+    const uint32_t nf = p.nf, ntiles = p.tiles_x * p.tiles_y;
+    int rc = ensure_ordered(ctx, nf, (size_t)nf * 4); if (rc) return rc;
     CK(cudaEventRecord(ctx->ev[2], st));
-    launch_sort_faces(L, ctx->temp.p, ctx->temp.cap, ctx->keys.p, ctx->keys_sorted.p, ctx->vals.p, ctx->order.p, nf);   // SORT
+    launch_sort_faces(L, ctx->temp.p, ctx->temp.cap, ctx->keys.p, ctx->keys_sorted.p, ctx->vals.p, ctx->order.p, nf);
+    ctx->order_valid = true;
     CK(cudaEventRecord(ctx->ev[3], st));
-    launch_binning(L, ctx->temp.p, ctx->temp.cap, ctx->recs.p, ctx->order.p, ctx->counts.p, ctx->offsets.p, ctx->ent_tile.p, ctx->ent_surf.p,
-                   ctx->ent_tile_sorted.p, ctx->ent_surf_sorted.p, ctx->tile_count.p, ctx->tile_start.p, ctx->state, p,
-                   (uint32_t)std::min<size_t>(ctx->ent_tile.cap, 0xFFFFFFFFu), true, false);
+    launch_bin_count(L, ctx->temp.p, ctx->temp.cap, ctx->recs.p, ctx->order.p, ctx->counts.p, ctx->offsets.p, ctx->state, p);
     CK(cudaEventRecord(ctx->ev[4], st));
-    launch_binning(L, ctx->temp.p, ctx->temp.cap, ctx->recs.p, ctx->order.p, ctx->counts.p, ctx->offsets.p, ctx->ent_tile.p, ctx->ent_surf.p,
-                   ctx->ent_tile_sorted.p, ctx->ent_surf_sorted.p, ctx->tile_count.p, ctx->tile_start.p, ctx->state, p,
-                   (uint32_t)std::min<size_t>(ctx->ent_tile.cap, 0xFFFFFFFFu), false, true);
+    launch_bin_emit(L, ctx->recs.p, ctx->order.p, ctx->counts.p, ctx->offsets.p, ctx->ent_tile.p, ctx->ent_surf.p,
+                    ctx->tile_count.p, ctx->tile_start.p, ctx->state, p, (uint32_t)std::min<size_t>(ctx->ent_tile.cap, 0xFFFFFFFFu));
     CK(cudaEventRecord(ctx->ev[5], st));
     // the entry sort needs the entry count on the host
     CK(cudaMemcpyAsync(ctx->state_h, ctx->state, sizeof(CallState), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CallState hs = *ctx->state_h;
-    cudaEventElapsedTime(&ctx->emit_ms, ctx->ev[4], ctx->ev[5]);
-    if (hs.oob) { ctx->deferred = B32_OK; return fail(ctx, B32_ERR_OOB_INDEX, "face vertex index out of range (reference: slice index panic)"); }
-    if (hs.abort) return fail(ctx, B32_ERR_NAN_DEPTH, "NaN depth key in a sorted pass (reference: partial_cmp().unwrap() panic, render.rs:2531)");
+    cudaEventElapsedTime(&ctx->kernel_ms[4], ctx->ev[4], ctx->ev[5]);
     if (hs.overflow) {      // grow the entry buffers and redo the emit
-        rc = ensure_entries(ctx, (size_t)hs.n_entries + hs.n_entries / 4); if (rc) return rc;
-        rc = ensure_temp(ctx, nf, ctx->ent_tile.cap); if (rc) return rc;
-        launch_binning(L, ctx->temp.p, ctx->temp.cap, ctx->recs.p, ctx->order.p, ctx->counts.p, ctx->offsets.p, ctx->ent_tile.p, ctx->ent_surf.p,
-                       ctx->ent_tile_sorted.p, ctx->ent_surf_sorted.p, ctx->tile_count.p, ctx->tile_start.p, ctx->state, p,
-                       (uint32_t)std::min<size_t>(ctx->ent_tile.cap, 0xFFFFFFFFu), false, true);
+        rc = ensure_ordered(ctx, nf, (size_t)hs.n_entries + hs.n_entries / 4); if (rc) return rc;
+        launch_bin_emit(L, ctx->recs.p, ctx->order.p, ctx->counts.p, ctx->offsets.p, ctx->ent_tile.p, ctx->ent_surf.p,
+                        ctx->tile_count.p, ctx->tile_start.p, ctx->state, p, (uint32_t)std::min<size_t>(ctx->ent_tile.cap, 0xFFFFFFFFu));
     }
-    CK(cudaEventRecord(ctx->ev[5], st));     // (re-recorded: excludes the host round trip above)
+    CK(cudaEventRecord(ctx->ev[5], st));
     launch_sort_entries(L, ctx->temp.p, ctx->temp.cap, ctx->ent_tile.p, ctx->ent_tile_sorted.p, ctx->ent_surf.p, ctx->ent_surf_sorted.p, hs.n_entries, ntiles);
     CK(cudaEventRecord(ctx->ev[6], st));
-    launch_fill(L, ctx->recs.p, ctx->ent_surf_sorted.p, ctx->tile_start.p, ctx->tile_count.p, ctx->texdesc.p, ctx->texels.p,
-                ctx->fb_rgba.p, ctx->fb_z.p, ctx->state, p);                                 // DRAW
+    launch_fill_ordered(L, ctx->recs.p, ctx->ent_surf_sorted.p, ctx->tile_start.p, ctx->tile_count.p, ctx->texdesc.p, ctx->texels.p,
+                        ctx->fb_rgba.p, ctx->fb_z.p, ctx->state, p);
     CK(cudaEventRecord(ctx->ev[7], st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
-    // ev: 0 start | 1 transform | 2 setup | 3 face sort | 4 bin count+scan | [emit, host round trip] 5 | 6 entry sort | 7 fill
-    float* k = ctx->kernel_ms;
-    cudaEventElapsedTime(&k[0], ctx->ev[0], ctx->ev[1]);
-    cudaEventElapsedTime(&k[1], ctx->ev[1], ctx->ev[2]);
-    cudaEventElapsedTime(&k[2], ctx->ev[2], ctx->ev[3]);
-    cudaEventElapsedTime(&k[3], ctx->ev[3], ctx->ev[4]);
-    k[4] = ctx->emit_ms;
-    cudaEventElapsedTime(&k[5], ctx->ev[5], ctx->ev[6]);
-    cudaEventElapsedTime(&k[6], ctx->ev[6], ctx->ev[7]);
+    cudaEventElapsedTime(&ctx->kernel_ms[2], ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&ctx->kernel_ms[3], ctx->ev[3], ctx->ev[4]);
+    cudaEventElapsedTime(&ctx->kernel_ms[5], ctx->ev[5], ctx->ev[6]);
+    cudaEventElapsedTime(&ctx->kernel_ms[6], ctx->ev[6], ctx->ev[7]);
+    return B32_OK;
+}
+
+// One render_mesh_15 (render.rs:2302-2572) on device-resident geometry.
+//   wait=true : returns when the frame is in the framebuffer; fills *tm.
+//   wait=false: only enqueues pass 1 (no host round trip); the caller guarantees there is no pass 2.
+int render_device(b32_ctx* ctx, const b32_vertex* d_verts, uint32_t nv, const b32_face* d_faces, uint32_t nf,
+                  const b32_camera* cam, const b32_settings* s, const b32_fog* fog, b32_timings* tm, bool wait) {
+    if (!cam || !s) return fail(ctx, B32_ERR_INVALID, "camera/settings is NULL");
+    if (ctx->width == 0 || ctx->height == 0) return fail(ctx, B32_ERR_INVALID, "framebuffer has zero size (call b32_fb_resize)");
+    CallParams p;
+    std::vector<LightDev> lights;
+    int rc = fill_params(ctx, p, cam, s, fog, nv, nf, lights);
+    if (rc != B32_OK) return rc;
+    if (tm) std::memset(tm, 0, sizeof(*tm));
+    for (float& k : ctx->kernel_ms) k = 0.0f;
+    ctx->last_nf = nf;
+    ctx->order_valid = false;
+    ctx->last_params = p;
+    if (nf == 0) return B32_OK;
+
+    const uint32_t ntiles = p.tiles_x * p.tiles_y;
+    rc = ensure_work(ctx, nv, nf); if (rc) return rc;
+    rc = upload_lights(ctx, lights); if (rc) return rc;
+    LaunchCtx L = ctx->L();
+    cudaStream_t st = ctx->stream;
+    CallState hs{};
+    for (int attempt = 0;; ++attempt) {
+        p.bin_cap = pick_bin_cap(ctx, nf, ntiles, !wait);
+        p.async_call = wait ? 0 : 1;
+        CK(ctx->bins.reserve((size_t)ntiles * p.bin_cap));
+        ctx->last_params = p;
+        CK(cudaMemsetAsync(ctx->state, 0, sizeof(CallState), st));
+        CK(cudaMemsetAsync(ctx->tile_count.p, 0, ntiles * sizeof(uint32_t), st));
+        if (wait) CK(cudaEventRecord(ctx->ev[0], st));
+        launch_setup(L, d_verts, d_faces, nullptr, ctx->texdesc.p, ctx->lights.p, ctx->recs.p, ctx->keys.p, ctx->vals.p,
+                     ctx->bins.p, ctx->tile_count.p, ctx->state, p);                          // TRANSFORM + CULL + setup + binning
+        if (wait) CK(cudaEventRecord(ctx->ev[1], st));
+        launch_fill_opaque(L, ctx->recs.p, ctx->bins.p, ctx->tile_count.p, ctx->texdesc.p, ctx->texels.p,
+                           ctx->fb_rgba.p, ctx->fb_z.p, ctx->state, ctx->sticky, p);          // DRAW, pass 1
+        if (!wait) { ctx->async_pending = true; return B32_OK; }
+        CK(cudaEventRecord(ctx->ev[2], st));
+        CK(cudaMemcpyAsync(ctx->state_h, ctx->state, sizeof(CallState), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        hs = *ctx->state_h;
+        if (hs.oob) return fail(ctx, B32_ERR_OOB_INDEX, "face vertex index out of range (reference: slice index panic)");
+        if (hs.bin_overflow && attempt < 4) {       // a tile bin was too small: nothing was drawn; grow and redo
+            ctx->bin_cap_hint = hs.bin_max + hs.bin_max / 4;
+            continue;
+        }
+        if (hs.bin_overflow) return fail(ctx, B32_ERR_CUDA, "tile bin overflow persists");
+        break;
+    }
+    {   // the reference panics on a NaN key in a sorted slice of length >= 2 (render.rs:2531)
+        bool nan_abort = (hs.nan_transp && hs.n_transp >= 2) || (!p.use_zbuffer && hs.nan_opaque && hs.n_opaque >= 2);
+        if (nan_abort) return fail(ctx, B32_ERR_NAN_DEPTH, "NaN depth key in a sorted pass (reference: partial_cmp().unwrap() panic, render.rs:2531)");
+    }
+    cudaEventElapsedTime(&ctx->kernel_ms[0], ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&ctx->kernel_ms[1], ctx->ev[1], ctx->ev[2]);
+    bool need_ordered = p.xray_mode ? (hs.n_opaque + hs.n_transp) > 0 : hs.n_transp > 0;
+    if (need_ordered) { rc = render_ordered(ctx, p); if (rc) return rc; }
     if (tm) {
-        tm->transform_ms = k[0];
-        tm->cull_ms = k[1];                      // fog is fused into the cull kernel (fog_ms stays 0)
-        tm->sort_ms = k[2];
-        tm->draw_ms = k[3] + k[4] + k[5] + k[6]; // binning + fill
-        tm->triangles_drawn = hs.n_opaque + hs.n_transp;                           // render.rs:2545
+        const float* k = ctx->kernel_ms;
+        tm->transform_ms = 0.0f;                    // the transform is fused into the cull/setup kernel
+        tm->cull_ms = k[0];                         // ... as is fog (fog_ms stays 0)
+        tm->sort_ms = k[2];                         // only pass 2 / x-ray sort; pass 1 needs no sort
+        tm->draw_ms = k[1] + k[3] + k[4] + k[5] + k[6];
+        tm->triangles_drawn = hs.n_opaque + hs.n_transp;                            // render.rs:2545
     }
     return B32_OK;
 }
@@ -304,6 +356,8 @@ int b32_ctx_create(int device, b32_ctx** out) {
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     for (auto& ev : ctx->ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaMalloc(&ctx->state, sizeof(CallState))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMalloc(&ctx->sticky, sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMemset(ctx->sticky, 0, sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMemset");
     if ((e = cudaMallocHost(&ctx->state_h, sizeof(CallState))) != cudaSuccess) return bail(e, "cudaMallocHost");
     ctx->pinned_bytes = 8u << 20;
     if ((e = cudaMallocHost(&ctx->pinned, ctx->pinned_bytes)) != cudaSuccess) return bail(e, "cudaMallocHost");
@@ -324,9 +378,10 @@ void b32_ctx_destroy(b32_ctx* ctx) {
     ctx->fb_rgba.release(); ctx->fb_z.release(); ctx->texels.release(); ctx->texdesc.release(); ctx->verts.release(); ctx->faces.release();
     ctx->tv.release(); ctx->recs.release(); ctx->keys.release(); ctx->keys_sorted.release(); ctx->vals.release(); ctx->order.release();
     ctx->counts.release(); ctx->offsets.release(); ctx->ent_tile.release(); ctx->ent_surf.release(); ctx->ent_tile_sorted.release();
-    ctx->ent_surf_sorted.release(); ctx->tile_count.release(); ctx->tile_start.release(); ctx->temp.release(); ctx->lights.release(); ctx->dbg.release();
+    ctx->ent_surf_sorted.release(); ctx->tile_count.release(); ctx->tile_start.release(); ctx->bins.release(); ctx->temp.release(); ctx->lights.release(); ctx->dbg.release();
     if (ctx->unr_table) cudaFree(ctx->unr_table);
     if (ctx->state) cudaFree(ctx->state);
+    if (ctx->sticky) cudaFree(ctx->sticky);
     if (ctx->state_h) cudaFreeHost(ctx->state_h);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -338,11 +393,27 @@ const char* b32_last_error(const b32_ctx* ctx) { return ctx ? ctx->err.c_str() :
 void* b32_ctx_stream(b32_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 uint64_t b32_kernel_launches(const b32_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+// errors of calls that were only enqueued surface here (the device kept a sticky error word)
+static int collect_async(b32_ctx* ctx) {
+    if (!ctx->async_pending) return B32_OK;
+    ctx->async_pending = false;
+    uint32_t sticky = 0;
+    CK(cudaMemcpyAsync(ctx->state_h, ctx->sticky, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    sticky = *reinterpret_cast<uint32_t*>(ctx->state_h);
+    if (!sticky) return B32_OK;
+    CK(cudaMemsetAsync(ctx->sticky, 0, sizeof(uint32_t), ctx->stream));
+    if (sticky & 1u) return fail(ctx, B32_ERR_OOB_INDEX, "an enqueued call had a face vertex index out of range");
+    if (sticky & 2u) return fail(ctx, B32_ERR_NAN_DEPTH, "an enqueued call had a NaN depth key in a sorted pass");
+    return fail(ctx, B32_ERR_CUDA, "an enqueued call overflowed its tile bins");
+}
+
 int b32_sync(b32_ctx* ctx) {
     if (!ctx) return B32_ERR_INVALID;
+    int rc = collect_async(ctx);
     CK(cudaStreamSynchronize(ctx->stream));
-    int d = ctx->deferred; ctx->deferred = B32_OK;
-    return d;
+    CK(cudaGetLastError());
+    return rc;
 }
 
 int b32_fb_resize(b32_ctx* ctx, uint32_t width, uint32_t height) {
@@ -381,8 +452,7 @@ int b32_fb_download(b32_ctx* ctx, uint8_t* rgba, float* z) {
     if (rgba) CK(cudaMemcpyAsync(rgba, ctx->fb_rgba.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (z) CK(cudaMemcpyAsync(z, ctx->fb_z.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    int d = ctx->deferred; ctx->deferred = B32_OK;
-    return d;
+    return collect_async(ctx);
 }
 
 int b32_fb_size(const b32_ctx* ctx, uint32_t* width, uint32_t* height) {
@@ -449,7 +519,7 @@ int b32_render_mesh_15(b32_ctx* ctx, const b32_vertex* vertices, uint32_t nv, co
     CK(ctx->faces.reserve(std::max<uint32_t>(nf, 1)));
     int rc = h2d(ctx, ctx->verts.p, vertices, (size_t)nv * sizeof(b32_vertex)); if (rc) return rc;
     rc = h2d(ctx, ctx->faces.p, faces, (size_t)nf * sizeof(b32_face)); if (rc) return rc;
-    return render_device(ctx, ctx->verts.p, nv, ctx->faces.p, nf, camera, settings, fog, timings);
+    return render_device(ctx, ctx->verts.p, nv, ctx->faces.p, nf, camera, settings, fog, timings, true);
 }
 
 int b32_mesh_upload(b32_ctx* ctx, const b32_vertex* vertices, uint32_t nv, const b32_face* faces, uint32_t nf, b32_mesh** out) {
@@ -457,6 +527,10 @@ int b32_mesh_upload(b32_ctx* ctx, const b32_vertex* vertices, uint32_t nv, const
     if ((nv && !vertices) || (nf && !faces)) return fail(ctx, B32_ERR_INVALID, "vertices/faces is NULL");
     b32_mesh* m = new b32_mesh();
     m->nv = nv; m->nf = nf;
+    for (uint32_t i = 0; i < nf; ++i) {
+        uint32_t fl = faces[i].flags;
+        if (((fl >> 16) & 7u) != B32_BLEND_OPAQUE || (fl >> 24) != 255u) { m->has_nonopaque = true; break; }
+    }
     cudaError_t e = cudaMalloc(&m->verts, std::max<size_t>((size_t)nv * sizeof(b32_vertex), 16));
     if (e == cudaSuccess) e = cudaMalloc(&m->faces, std::max<size_t>((size_t)nf * sizeof(b32_face), 16));
     if (e != cudaSuccess) { if (m->verts) cudaFree(m->verts); delete m; return cuda_fail(ctx, e, "cudaMalloc(mesh)"); }
@@ -478,13 +552,18 @@ void b32_mesh_free(b32_ctx* ctx, b32_mesh* mesh) {
 int b32_render_mesh_15_resident(b32_ctx* ctx, const b32_mesh* mesh, const b32_camera* camera, const b32_settings* settings,
                                 const b32_fog* fog, b32_timings* timings) {
     if (!ctx || !mesh) return B32_ERR_INVALID;
-    return render_device(ctx, mesh->verts, mesh->nv, mesh->faces, mesh->nf, camera, settings, fog, timings);
+    return render_device(ctx, mesh->verts, mesh->nv, mesh->faces, mesh->nf, camera, settings, fog, timings, true);
 }
 
 int b32_render_mesh_15_enqueue(b32_ctx* ctx, const b32_mesh* mesh, const b32_camera* camera, const b32_settings* settings, const b32_fog* fog) {
-    // v1: the binning still needs one host round trip per call, so "enqueue" completes the call.
-    if (!ctx || !mesh) return B32_ERR_INVALID;
-    return render_device(ctx, mesh->verts, mesh->nv, mesh->faces, mesh->nf, camera, settings, fog, nullptr);
+    if (!ctx || !mesh || !settings) return B32_ERR_INVALID;
+    // Pass 1 needs no host round trip.  Pass 2 (any semi-transparent surface) and x-ray mode do, so a
+    // mesh/texture set that can produce them is rendered synchronously instead.
+    bool may_blend = mesh->has_nonopaque || settings->xray_mode;
+    for (const TexDev& t : ctx->texdesc_h) may_blend = may_blend || t.blend != B32_BLEND_OPAQUE;
+    uint32_t ntiles = ((ctx->width + TILE_W - 1) / TILE_W) * ((ctx->height + TILE_H - 1) / TILE_H);
+    bool bins_fit = (size_t)ntiles * mesh->nf * sizeof(BinHead) <= ((size_t)4 << 30);   // worst-case bins (no overflow possible)
+    return render_device(ctx, mesh->verts, mesh->nv, mesh->faces, mesh->nf, camera, settings, fog, nullptr, may_blend || !bins_fit);
 }
 
 void* b32_host_alloc(size_t bytes) {
@@ -524,6 +603,12 @@ int b32_debug_draw_order(b32_ctx* ctx, uint32_t* out_face_idx, uint32_t cap, uin
     CK(cudaStreamSynchronize(ctx->stream));
     uint32_t drawn = ctx->state_h->n_opaque + ctx->state_h->n_transp;
     *n = drawn;
+    if (!ctx->order_valid && ctx->last_nf) {      // pass 1 is order-free: sort on demand for the test API
+        int rc = ensure_ordered(ctx, ctx->last_nf, 1); if (rc) return rc;
+        launch_sort_faces(ctx->L(), ctx->temp.p, ctx->temp.cap, ctx->keys.p, ctx->keys_sorted.p, ctx->vals.p, ctx->order.p, ctx->last_nf);
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->order_valid = true;
+    }
     uint32_t m = std::min(drawn, cap);
     if (m && out_face_idx) CK(cudaMemcpy(out_face_idx, ctx->order.p, (size_t)m * 4, cudaMemcpyDeviceToHost));
     return B32_OK;

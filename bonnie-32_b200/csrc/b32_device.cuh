@@ -47,6 +47,15 @@ enum : uint32_t {
     SF_TRANSPARENT  = 1u << 7,    // has_transparency: drawn in pass 2 with skip_z_write (:2561-2569)
 };
 
+// 16-byte bin entry of the unordered (opaque) pass: what a warp needs to reject a surface without
+// touching its 128-byte record.
+struct __align__(16) BinHead {
+    uint32_t bbox_x, bbox_y;              // as in SurfRec
+    uint32_t key;                         // depth_key_desc(center_z) (painter's priority), 0 in z-buffer mode
+    uint32_t face;                        // Surface.face_idx == index of the SurfRec
+};
+static_assert(sizeof(BinHead) == 16, "BinHead must be 16 bytes");
+
 struct TexDev { uint32_t off, w, h, blend; };   // texel pool offset (u16 units), size, Texture15.blend_mode
 
 struct LightDev {                     // b32_light without padding surprises
@@ -58,10 +67,21 @@ struct CallState {
     uint32_t n_opaque, n_transp;          // drawn surfaces per pass
     uint32_t nan_opaque, nan_transp;      // a NaN sort key was seen in the pass
     uint32_t oob;                         // a face index >= nv was seen
-    uint32_t n_entries;                   // sum of tile counts (bin entries needed)
-    uint32_t overflow;                    // n_entries > capacity: fill skipped, host grows + retries
+    uint32_t n_entries;                   // ordered pass: sum of tile counts (bin entries needed)
+    uint32_t overflow;                    // ordered pass: n_entries > capacity: fill skipped, host grows + retries
     uint32_t abort;                       // reference would have panicked: nothing is drawn
+    uint32_t bin_overflow;                // opaque pass: a tile bin exceeded its capacity (fill skipped, host grows + retries)
+    uint32_t bin_max;                     // opaque pass: largest tile count seen
 };
+
+// The reference panics (and draws nothing) on an out-of-range vertex index, or when a NaN key is
+// compared by the sort, i.e. in any sorted slice of length >= 2 (render.rs:2531).
+__device__ __forceinline__ bool call_aborts(const CallState& st, bool use_zbuffer) {
+    if (st.oob) return true;
+    if (st.nan_transp && st.n_transp >= 2) return true;
+    if (!use_zbuffer && st.nan_opaque && st.n_opaque >= 2) return true;
+    return false;
+}
 
 // kernel parameters of one render call (passed by value => constant bank)
 struct CallParams {
@@ -70,8 +90,9 @@ struct CallParams {
     int32_t viewport_scale, half_w, half_h;           // fixed.rs:398-400
     uint32_t width, height, tiles_x, tiles_y;
     uint32_t nv, nf, ntex, n_lights;
+    uint32_t bin_cap;                                 // capacity (entries) of one tile bin of the opaque pass
     uint8_t affine_textures, use_zbuffer, shading, backface_cull, dithering, use_fixed_point, xray_mode, ortho;
-    uint8_t fog_enabled, fog_r, fog_g, fog_b, fog_blend, _p0, _p1, _p2;
+    uint8_t fog_enabled, fog_r, fog_g, fog_b, fog_blend, async_call, _p1, _p2;
     float ambient, ortho_zoom, ortho_cx, ortho_cy;
     float fog_start, fog_falloff, fog_cull;
 };

@@ -1,17 +1,26 @@
 // b32_kernels.cu — sm_100a kernels of the BONNIE-32 rasterizer hot path.
 //
-//   k_transform   render.rs:2321-2360 + fixed.rs:362-441     vertex transform + snap
-//   k_setup       render.rs:2373-2513 + :1450-1527 + :1013-1071   cull / surface build / lighting /
-//                 triangle setup, sort key (:2527-2532)
-//   (sort)        render.rs:2522-2542   stable back-to-front radix sort, opaque | transparent
-//   k_bin_count / k_bin_emit            per-surface screen-tile lists in draw order
-//   k_fill        render.rs:1530-1713   in-order per-pixel emulation of rasterize_triangle_15
+//   k_transform    render.rs:2321-2360 + fixed.rs:362-441   vertex transform + snap (stand-alone form)
+//   k_setup        the same transform fused with render.rs:2373-2513 (cull / surface build / fog),
+//                  :1450-1527 (triangle setup), :1013-1071 (lighting), the sort key (:2527-2532) and
+//                  the screen-tile binning of the opaque pass
+//   k_fill_opaque  render.rs:1530-1713 for pass 1 (opaque surfaces), order-free (see below)
+//   k_bin_* + k_fill_ordered   pass 2 (semi-transparent surfaces, sorted back to front) and x-ray
+//                  mode: strict draw-order emulation
 //
-// Pixel-order semantics: the reference draws surfaces one after the other into one
-// framebuffer, so the value of a pixel is a fold over the surfaces that cover it, in draw order.
-// Pixels are independent of each other, so k_fill gives every pixel to one thread, which walks the
-// pixel's surfaces in draw order and applies the reference's z-test / blend / write rules to a
-// colour + depth held in registers.  No atomics, deterministic, exact for every blend mode.
+// Pixel-order semantics.  The reference draws surfaces one after the other, so a
+// pixel's final value is a fold over the surfaces covering it, in draw order; pixels are independent.
+// Every fill kernel therefore gives each pixel to one thread that keeps colour + depth in registers.
+//   * Pass 1 never blends (has_transparency == false  =>  blend Opaque, editor_alpha 255), so its
+//     fold has a closed form that needs NO sort:
+//       painter's mode : the winner is the writing fragment drawn last = max (sort key, face index)
+//       z-buffer mode  : the winner is the writing fragment with min (z, face index); `z < zbuf` is
+//                        strict, so among equal depths the first-drawn (lowest index) wins, and the
+//                        framebuffer's incoming depth wins every tie.
+//     k_fill_opaque walks a tile's surfaces in whatever order the binning produced and keeps the
+//     winner; the result is the reference's, bit for bit, and deterministic.
+//   * Pass 2 blends against the running colour, so it is replayed in exact draw order from lists
+//     that a stable radix sort and a stable tile binning produce.
 #include "b32_device.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
@@ -22,64 +31,70 @@
 namespace b32 {
 
 // =================================================================================================
-// k_transform
+// vertex transform + snap (render.rs:2321-2360)
 // =================================================================================================
+__device__ __forceinline__ TVert transform_vertex(float px, float py, float pz, const CallParams& p,
+                                                  const uint8_t* __restrict__ unr, float* cam_xy) {
+    // rel_pos = v.pos - camera.position; cam_pos = perspective_transform(...)   (math.rs:103-109)
+    float rx = px - p.cam_pos[0], ry = py - p.cam_pos[1], rz = pz - p.cam_pos[2];
+    float cx = rx * p.bx[0] + ry * p.bx[1] + rz * p.bx[2];
+    float cy = rx * p.by[0] + ry * p.by[1] + rz * p.by[2];
+    float cz = rx * p.bz[0] + ry * p.bz[1] + rz * p.bz[2];
+    if (cam_xy) { cam_xy[0] = cx; cam_xy[1] = cy; }
+    float sx, sy, sz;
+    if (p.ortho) {                                       // math.rs:140-148
+        sx = (cx - p.ortho_cx) * p.ortho_zoom + ((float)p.width / 2.0f);
+        sy = -(cy - p.ortho_cy) * p.ortho_zoom + ((float)p.height / 2.0f);
+        sz = cz;
+    } else if (p.use_fixed_point) {                      // fixed.rs:362-441
+        const int32_t distance = 5 * 4096, scale = 4 * 4096;     // Fixed32::from_f32(5.0), (4.0): fixed.rs:396-397
+        int32_t wx = fx_from_f32(px), wy = fx_from_f32(py), wz = fx_from_f32(pz);
+        int32_t ex = fx_sub(wx, p.fcam_pos[0]), ey = fx_sub(wy, p.fcam_pos[1]), ez = fx_sub(wz, p.fcam_pos[2]);
+        int32_t fcx = fx_add(fx_add(fx_mul(ex, p.fbx[0]), fx_mul(ey, p.fbx[1])), fx_mul(ez, p.fbx[2]));
+        int32_t fcy = fx_add(fx_add(fx_mul(ex, p.fby[0]), fx_mul(ey, p.fby[1])), fx_mul(ez, p.fby[2]));
+        int32_t fcz = fx_add(fx_add(fx_mul(ex, p.fbz[0]), fx_mul(ey, p.fbz[1])), fx_mul(ez, p.fbz[2]));
+        int32_t denom = fx_add(fcz, distance);
+        int32_t adenom = denom < 0 ? (int32_t)(0u - (uint32_t)denom) : denom;   // release-mode i32::abs
+        int32_t isx, isy;
+        if (adenom < 256) {                              // fixed.rs:406-408
+            isx = p.half_w >> 12; isy = p.half_h >> 12;
+        } else {
+            uint64_t nr2; uint32_t shift;
+            unr_recip(denom, unr, &nr2, &shift);         // one reciprocal serves x and y
+            int32_t proj_x = unr_apply(fx_mul(fcx, scale), denom, nr2, shift);
+            int32_t proj_y = unr_apply(fx_mul(fcy, scale), denom, nr2, shift);
+            isx = fx_add(fx_mul(proj_x, p.viewport_scale), p.half_w) >> 12;
+            isy = fx_add(fx_mul(proj_y, p.viewport_scale), p.half_h) >> 12;
+        }
+        sx = (float)isx; sy = (float)isy;
+        sz = cz + 5.0f;                                  // render.rs:2342-2345
+    } else {                                             // math.rs:117-136
+        const float us = 4.0f;
+        float vs = ((float)min(p.width, p.height) / 2.0f) * 0.75f;
+        float denom = cz + 5.0f;
+        if (fabsf(denom) < 0.001f) {
+            sx = (float)p.width / 2.0f; sy = (float)p.height / 2.0f; sz = cz;
+        } else {
+            sx = (cx * us) / denom * vs + ((float)p.width / 2.0f);
+            sy = (cy * us) / denom * vs + ((float)p.height / 2.0f);
+            sz = denom;
+        }
+    }
+    return make_float4(sx, sy, sz, cz);
+}
+
 __global__ void __launch_bounds__(256)
 k_transform(const b32_vertex* __restrict__ verts, TVert* __restrict__ out, float* __restrict__ dbg_cam,
             const uint8_t* __restrict__ unr_table_g, CallParams p) {
     __shared__ uint8_t unr[260];
     for (int i = threadIdx.x; i < 257; i += blockDim.x) unr[i] = unr_table_g[i];
     __syncthreads();
-
-    const int32_t distance = 5 * 4096, scale = 4 * 4096;     // Fixed32::from_f32(5.0), (4.0): fixed.rs:396-397
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < p.nv; i += gridDim.x * blockDim.x) {
         const float* vp = reinterpret_cast<const float*>(verts + i);
-        float px = vp[0], py = vp[1], pz = vp[2];
-        // rel_pos = v.pos - camera.position; cam_pos = perspective_transform(...)   (math.rs:103-109)
-        float rx = px - p.cam_pos[0], ry = py - p.cam_pos[1], rz = pz - p.cam_pos[2];
-        float cx = rx * p.bx[0] + ry * p.bx[1] + rz * p.bx[2];
-        float cy = rx * p.by[0] + ry * p.by[1] + rz * p.by[2];
-        float cz = rx * p.bz[0] + ry * p.bz[1] + rz * p.bz[2];
-        float sx, sy, sz;
-        if (p.ortho) {                                       // math.rs:140-148
-            sx = (cx - p.ortho_cx) * p.ortho_zoom + ((float)p.width / 2.0f);
-            sy = -(cy - p.ortho_cy) * p.ortho_zoom + ((float)p.height / 2.0f);
-            sz = cz;
-        } else if (p.use_fixed_point) {                      // fixed.rs:362-441
-            int32_t wx = fx_from_f32(px), wy = fx_from_f32(py), wz = fx_from_f32(pz);
-            int32_t ex = fx_sub(wx, p.fcam_pos[0]), ey = fx_sub(wy, p.fcam_pos[1]), ez = fx_sub(wz, p.fcam_pos[2]);
-            int32_t fcx = fx_add(fx_add(fx_mul(ex, p.fbx[0]), fx_mul(ey, p.fbx[1])), fx_mul(ez, p.fbx[2]));
-            int32_t fcy = fx_add(fx_add(fx_mul(ex, p.fby[0]), fx_mul(ey, p.fby[1])), fx_mul(ez, p.fby[2]));
-            int32_t fcz = fx_add(fx_add(fx_mul(ex, p.fbz[0]), fx_mul(ey, p.fbz[1])), fx_mul(ez, p.fbz[2]));
-            int32_t denom = fx_add(fcz, distance);
-            int32_t adenom = denom < 0 ? (int32_t)(0u - (uint32_t)denom) : denom;   // release-mode i32::abs
-            int32_t isx, isy;
-            if (adenom < 256) {                              // fixed.rs:406-408
-                isx = p.half_w >> 12; isy = p.half_h >> 12;
-            } else {
-                uint64_t nr2; uint32_t shift;
-                unr_recip(denom, unr, &nr2, &shift);         // one reciprocal serves x and y
-                int32_t proj_x = unr_apply(fx_mul(fcx, scale), denom, nr2, shift);
-                int32_t proj_y = unr_apply(fx_mul(fcy, scale), denom, nr2, shift);
-                isx = fx_add(fx_mul(proj_x, p.viewport_scale), p.half_w) >> 12;
-                isy = fx_add(fx_mul(proj_y, p.viewport_scale), p.half_h) >> 12;
-            }
-            sx = (float)isx; sy = (float)isy;
-            sz = cz + 5.0f;                                  // render.rs:2342-2345
-        } else {                                             // math.rs:117-136
-            const float us = 4.0f;
-            float vs = ((float)min(p.width, p.height) / 2.0f) * 0.75f;
-            float denom = cz + 5.0f;
-            if (fabsf(denom) < 0.001f) {
-                sx = (float)p.width / 2.0f; sy = (float)p.height / 2.0f; sz = cz;
-            } else {
-                sx = (cx * us) / denom * vs + ((float)p.width / 2.0f);
-                sy = (cy * us) / denom * vs + ((float)p.height / 2.0f);
-                sz = denom;
-            }
-        }
-        out[i] = make_float4(sx, sy, sz, cz);
-        if (dbg_cam) { dbg_cam[i * 3] = cx; dbg_cam[i * 3 + 1] = cy; dbg_cam[i * 3 + 2] = cz; }
+        float cxy[2];
+        TVert t = transform_vertex(vp[0], vp[1], vp[2], p, unr, cxy);
+        out[i] = t;
+        if (dbg_cam) { dbg_cam[i * 3] = cxy[0]; dbg_cam[i * 3 + 1] = cxy[1]; dbg_cam[i * 3 + 2] = t.w; }
     }
 }
 
@@ -136,14 +151,21 @@ __device__ __forceinline__ uint32_t fog_color(uint32_t c, float z, const CallPar
     return r | (g << 8) | (b << 16);             // Color::new => blend Opaque (0)
 }
 
-__device__ __forceinline__ bool is_integral(float x) { return truncf(x) == x; }   // false for NaN/inf? inf==inf: guarded by bound
+__device__ __forceinline__ bool is_integral(float x) { return truncf(x) == x; }
 
+// One thread per face.  `tv` (pre-transformed vertices) may be NULL: then the three vertices are
+// transformed here (no intermediate vertex buffer: each vertex record is read exactly once per use).
 __global__ void __launch_bounds__(128)
 k_setup(const b32_vertex* __restrict__ verts, const b32_face* __restrict__ faces, const TVert* __restrict__ tv,
-        const TexDev* __restrict__ tex, const LightDev* __restrict__ lights,
+        const TexDev* __restrict__ tex, const LightDev* __restrict__ lights, const uint8_t* __restrict__ unr_table_g,
         SurfRec* __restrict__ recs, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
+        BinHead* __restrict__ bins, uint32_t* __restrict__ tile_count,
         CallState* __restrict__ st, CallParams p) {
-    uint32_t n_op = 0, n_tr = 0;
+    __shared__ uint8_t unr[260];
+    for (int i = threadIdx.x; i < 257; i += blockDim.x) unr[i] = unr_table_g[i];
+    __syncthreads();
+
+    uint32_t n_op = 0, n_tr = 0, bmax = 0;
     for (uint32_t fi = blockIdx.x * blockDim.x + threadIdx.x; fi < p.nf; fi += gridDim.x * blockDim.x) {
         uint4 fc = *reinterpret_cast<const uint4*>(faces + fi);
         uint32_t cls = 2;                 // 0 opaque pass, 1 transparent pass, 2 not drawn
@@ -156,7 +178,16 @@ k_setup(const b32_vertex* __restrict__ verts, const b32_face* __restrict__ faces
             uint32_t tex_blend = 0;
             if (textured) tex_blend = tex[tex_id].blend;
 
-            TVert t1 = tv[fc.x], t2 = tv[fc.y], t3 = tv[fc.z];
+            const float* v0 = reinterpret_cast<const float*>(verts + fc.x);
+            const float* v1 = reinterpret_cast<const float*>(verts + fc.y);
+            const float* v2 = reinterpret_cast<const float*>(verts + fc.z);
+            TVert t1, t2, t3;
+            if (tv) { t1 = tv[fc.x]; t2 = tv[fc.y]; t3 = tv[fc.z]; }
+            else {
+                t1 = transform_vertex(v0[0], v0[1], v0[2], p, unr, nullptr);
+                t2 = transform_vertex(v1[0], v1[1], v1[2], p, unr, nullptr);
+                t3 = transform_vertex(v2[0], v2[1], v2[2], p, unr, nullptr);
+            }
             if (!p.ortho) {                                                       // :2380-2385
                 if (t1.w <= NEAR_PLANE || t2.w <= NEAR_PLANE || t3.w <= NEAR_PLANE) break;
             }
@@ -169,12 +200,11 @@ k_setup(const b32_vertex* __restrict__ verts, const b32_face* __restrict__ faces
             if (p.fog_enabled && t1.w > p.fog_cull && t2.w > p.fog_cull && t3.w > p.fog_cull) break;   // :2421-2424
             if (backface && !(!p.backface_cull || p.xray_mode)) break;            // :2445-2453
 
-            // vertex attributes (36-byte records: pos 0, uv 12, normal 20, rgba 32)
-            const uint32_t ia = fc.x, ib = backface ? fc.z : fc.y, ic = backface ? fc.y : fc.z;   // v2/v3 swap :2455-2457
+            // vertex attributes (36-byte records: pos 0, uv 12, normal 20, rgba 32); v2/v3 swap :2455-2457
             TVert s1 = t1, s2 = backface ? t3 : t2, s3 = backface ? t2 : t3;
-            const float* va = reinterpret_cast<const float*>(verts + ia);
-            const float* vb = reinterpret_cast<const float*>(verts + ib);
-            const float* vc = reinterpret_cast<const float*>(verts + ic);
+            const float* va = v0;
+            const float* vb = backface ? v2 : v1;
+            const float* vc = backface ? v1 : v2;
             uint32_t c1 = reinterpret_cast<const uint32_t*>(va)[8], c2 = reinterpret_cast<const uint32_t*>(vb)[8], c3 = reinterpret_cast<const uint32_t*>(vc)[8];
             if (p.fog_enabled) {                                                  // :2427-2436 (cam z of the same vertex)
                 c1 = fog_color(c1, s1.w, p); c2 = fog_color(c2, s2.w, p); c3 = fog_color(c3, s3.w, p);
@@ -203,7 +233,7 @@ k_setup(const b32_vertex* __restrict__ verts, const b32_face* __restrict__ faces
             r.w1s = r.a1 * (start_x - s3.x) + r.b1 * (start_y - s3.y);
             r.bbox_x = min_x | (max_x << 16);
             r.bbox_y = min_y | (max_y << 16);
-            // incremental stepping == closed form when everything is an integer below 2^24
+            // incremental stepping == closed form when everything is an integer below 2^23
             {
                 float nx = (float)(max_x - min_x), ny = (float)(max_y - min_y);
                 float m0 = fabsf(r.w0s) + ny * fabsf(r.b0) + nx * fabsf(r.a0);
@@ -217,10 +247,12 @@ k_setup(const b32_vertex* __restrict__ verts, const b32_face* __restrict__ faces
             r.vc1 = c1 & 0xFFFFFF; r.vc2 = c2 & 0xFFFFFF; r.vc3 = c3 & 0xFFFFFF;
             for (int k = 0; k < 9; ++k) r.sh[k] = 1.0f;
             if (!empty && p.shading != B32_SHADE_NONE) {
-                float sgn = backface ? -1.0f : 1.0f;                                        // wn.scale(-1.0) :2464-2466
                 V3 w1{va[0], va[1], va[2]}, w2{vb[0], vb[1], vb[2]}, w3{vc[0], vc[1], vc[2]};
                 V3 n1{va[5], va[6], va[7]}, n2{vb[5], vb[6], vb[7]}, n3{vc[5], vc[6], vc[7]};
-                if (backface) { n1 = V3{n1.x * sgn, n1.y * sgn, n1.z * sgn}; n2 = V3{n2.x * sgn, n2.y * sgn, n2.z * sgn}; n3 = V3{n3.x * sgn, n3.y * sgn, n3.z * sgn}; }
+                if (backface) {                                                             // wn.scale(-1.0) :2464-2466
+                    n1 = V3{n1.x * -1.0f, n1.y * -1.0f, n1.z * -1.0f}; n2 = V3{n2.x * -1.0f, n2.y * -1.0f, n2.z * -1.0f};
+                    n3 = V3{n3.x * -1.0f, n3.y * -1.0f, n3.z * -1.0f};
+                }
                 if (p.shading == B32_SHADE_FLAT) {                                          // :1466-1472
                     const float third = 1.0f / 3.0f;
                     V3 c{((w1.x + w2.x) + w3.x) * third, ((w1.y + w2.y) + w3.y) * third, ((w1.z + w2.z) + w3.z) * third};
@@ -244,46 +276,254 @@ k_setup(const b32_vertex* __restrict__ verts, const b32_face* __restrict__ faces
                 dkey = depth_key_desc(center_z);
             }
             if (transparent) ++n_tr; else ++n_op;
+
+            // pass-1 surfaces go straight into their screen tiles' bins (any order; see file header)
+            if (!transparent && !p.xray_mode && !empty) {
+                BinHead h{r.bbox_x, r.bbox_y, dkey, fi};
+                uint32_t tx0 = min_x / TILE_W, tx1 = (max_x - 1) / TILE_W, ty0 = min_y / TILE_H, ty1 = (max_y - 1) / TILE_H;
+                for (uint32_t ty = ty0; ty <= ty1; ++ty)
+                    for (uint32_t tx = tx0; tx <= tx1; ++tx) {
+                        uint32_t t = ty * p.tiles_x + tx;
+                        uint32_t slot = atomicAdd(&tile_count[t], 1u);
+                        if (slot < p.bin_cap) bins[(size_t)t * p.bin_cap + slot] = h;
+                        bmax = max(bmax, slot + 1);
+                    }
+            }
         } while (0);
         keys[fi] = ((uint64_t)cls << 32) | dkey;
         vals[fi] = fi;
     }
     // per-warp aggregated counters
-    for (int o = 16; o > 0; o >>= 1) { n_op += __shfl_xor_sync(0xFFFFFFFFu, n_op, o); n_tr += __shfl_xor_sync(0xFFFFFFFFu, n_tr, o); }
+    for (int o = 16; o > 0; o >>= 1) {
+        n_op += __shfl_xor_sync(0xFFFFFFFFu, n_op, o); n_tr += __shfl_xor_sync(0xFFFFFFFFu, n_tr, o);
+        bmax = max(bmax, __shfl_xor_sync(0xFFFFFFFFu, bmax, o));
+    }
     if ((threadIdx.x & 31) == 0) {
         if (n_op) atomicAdd(&st->n_opaque, n_op);
         if (n_tr) atomicAdd(&st->n_transp, n_tr);
+        if (bmax) { atomicMax(&st->bin_max, bmax); if (bmax > p.bin_cap) st->bin_overflow = 1; }
     }
 }
 
 // =================================================================================================
-// binning: per-surface tile counts -> scan -> (tile, surface) pairs in draw order -> stable sort by tile
+// fragment evaluation shared by both fill kernels (render.rs:1534-1661)
 // =================================================================================================
-// The reference panics (nothing drawn) on an out-of-range index or on a NaN key in a sorted slice of
-// length >= 2 (render.rs:2531).  Decide once, on the device, so the fill can be skipped without a
-// host round trip.
-__global__ void k_decide(CallState* st, uint32_t use_zbuffer) {
-    bool abort = st->oob != 0;
-    if (st->nan_transp && st->n_transp >= 2) abort = true;
-    if (!use_zbuffer && st->nan_opaque && st->n_opaque >= 2) abort = true;
-    st->abort = abort ? 1 : 0;
+struct Pixel { uint32_t rgba; float z; };
+
+// Edge functions + barycentrics at pixel (x,y): render.rs:1517-1542, 1706-1712.
+__device__ __forceinline__ bool inside_test(const SurfRec& r, uint32_t x, uint32_t y, float& bc_x, float& bc_y, float& bc_z) {
+    uint32_t min_x = r.bbox_x & 0xFFFF, min_y = r.bbox_y & 0xFFFF;
+    float w0, w1;
+    if (r.flags & SF_FAST_EDGE) {
+        // all terms are integers below 2^23: every rounded add of the reference is exact, so the
+        // stepped value equals the closed form
+        float dx = (float)(x - min_x), dy = (float)(y - min_y);
+        w0 = r.w0s + dy * r.b0 + dx * r.a0;
+        w1 = r.w1s + dy * r.b1 + dx * r.a1;
+    } else {
+        // replay the reference's rounded additions: (y-min_y) row steps, then (x-min_x) pixel steps
+        w0 = r.w0s; w1 = r.w1s;
+        for (uint32_t i = min_y; i < y; ++i) { w0 = __fadd_rn(w0, r.b0); w1 = __fadd_rn(w1, r.b1); }
+        for (uint32_t i = min_x; i < x; ++i) { w0 = __fadd_rn(w0, r.a0); w1 = __fadd_rn(w1, r.a1); }
+    }
+    bc_x = w0 * r.inv_area;
+    bc_y = w1 * r.inv_area;
+    bc_z = 1.0f - bc_x - bc_y;
+    const float ERR = -0.0001f;
+    return bc_x >= ERR && bc_y >= ERR && bc_z >= ERR;                              // :1541-1542
 }
 
-__device__ __forceinline__ void tile_range(const SurfRec& r, uint32_t& tx0, uint32_t& tx1, uint32_t& ty0, uint32_t& ty1) {
-    uint32_t min_x = r.bbox_x & 0xFFFF, max_x = r.bbox_x >> 16, min_y = r.bbox_y & 0xFFFF, max_y = r.bbox_y >> 16;
-    if (min_x >= max_x || min_y >= max_y) { tx0 = tx1 = ty0 = ty1 = 0; return; }
-    tx0 = min_x / TILE_W; tx1 = (max_x - 1) / TILE_W + 1;
-    ty0 = min_y / TILE_H; ty1 = (max_y - 1) / TILE_H + 1;
+// Texture sample + transparency rules + colour pipeline (render.rs:1563-1661).  Returns false when the
+// texel is skipped; otherwise rgb = Color15::r8/g8/b8 of the final colour, semi = its bit 15.
+__device__ __forceinline__ bool shade(const SurfRec& r, uint32_t x, uint32_t y, float bc_x, float bc_y, float bc_z, float inv_z,
+                                      const TexDev* __restrict__ tex, const uint16_t* __restrict__ texels, const CallParams& p,
+                                      uint32_t& o_r, uint32_t& o_g, uint32_t& o_b, bool& semi) {
+    uint32_t color = 0x7FFF;                                                       // Color15::WHITE
+    if (r.flags & SF_TEXTURED) {
+        float u, v;
+        if (p.affine_textures) {                                                   // :1563-1567
+            u = bc_x * r.u1 + bc_y * r.u2 + bc_z * r.u3;
+            v = bc_x * r.v1 + bc_y * r.v2 + bc_z * r.v3;
+        } else {                                                                   // :1568-1578
+            float uo = bc_x * r.u1 * r.iz1 + bc_y * r.u2 * r.iz2 + bc_z * r.u3 * r.iz3;
+            float vo = bc_x * r.v1 * r.iz1 + bc_y * r.v2 * r.iz2 + bc_z * r.v3 * r.iz3;
+            u = uo / inv_z;
+            v = vo / inv_z;
+        }
+        TexDev t = tex[r.flags >> 16];
+        if (t.w == 0 || t.h == 0) {                                                // types.rs:673-675
+            color = 0;
+        } else {
+            float uw = rem_euclid1(u), vw = rem_euclid1(1.0f - v);                 // :1583, types.rs:676-677
+            uint32_t tx = min(f2u32sat(uw * (float)t.w), t.w - 1);
+            uint32_t ty = min(f2u32sat(vw * (float)t.h), t.h - 1);
+            color = __ldg(texels + t.off + ty * t.w + tx);
+        }
+    }
+    bool is_black = (color & 0x7FFF) == 0;                                         // :1591-1607
+    if (color == 0) {
+        if (!(r.flags & SF_BLACK_TR)) color = 0x8000; else return false;
+    } else if ((r.flags & SF_BLACK_TR) && is_black) {
+        return false;
+    }
+    uint32_t tr8 = expand5((color >> 10) & 31), tg8 = expand5((color >> 5) & 31), tb8 = expand5(color & 31);
+    uint32_t vr = f2u8(bc_x * (float)(r.vc1 & 0xFF) + bc_y * (float)(r.vc2 & 0xFF) + bc_z * (float)(r.vc3 & 0xFF));          // :1618-1620
+    uint32_t vg = f2u8(bc_x * (float)((r.vc1 >> 8) & 0xFF) + bc_y * (float)((r.vc2 >> 8) & 0xFF) + bc_z * (float)((r.vc3 >> 8) & 0xFF));
+    uint32_t vb = f2u8(bc_x * (float)(r.vc1 >> 16) + bc_y * (float)(r.vc2 >> 16) + bc_z * (float)(r.vc3 >> 16));
+    uint32_t mr = min((tr8 * vr) >> 7, 255u), mg = min((tg8 * vg) >> 7, 255u), mb = min((tb8 * vb) >> 7, 255u);   // :1624-1626
+    float sr, sg, sb;                                                              // :1629-1640
+    if (p.shading == B32_SHADE_NONE) { sr = sg = sb = 1.0f; }
+    else if (p.shading == B32_SHADE_FLAT) { sr = r.sh[0]; sg = r.sh[1]; sb = r.sh[2]; }
+    else {
+        sr = bc_x * r.sh[0] + bc_y * r.sh[3] + bc_z * r.sh[6];
+        sg = bc_x * r.sh[1] + bc_y * r.sh[4] + bc_z * r.sh[7];
+        sb = bc_x * r.sh[2] + bc_y * r.sh[5] + bc_z * r.sh[8];
+    }
+    uint32_t r8 = f2u8(fminf((float)mr * rclamp(sr, 0.0f, 2.0f), 255.0f));          // :1643-1645
+    uint32_t g8 = f2u8(fminf((float)mg * rclamp(sg, 0.0f, 2.0f), 255.0f));
+    uint32_t b8 = f2u8(fminf((float)mb * rclamp(sb, 0.0f, 2.0f), 255.0f));
+    uint32_t r5, g5, b5;
+    if (r.flags & SF_DITHER) {                                                     // :1173-1182
+        // PS1_DITHER_MATRIX rows packed as signed nibbles, :1150-1155
+        const uint32_t rows = (y & 2) ? ((y & 1) ? 0xE2F3u : 0x0C1Du) : ((y & 1) ? 0xF3E2u : 0x1D0Cu);
+        int32_t off = (int32_t)((rows >> ((x & 3) * 4)) & 0xF);
+        off = (off ^ 8) - 8;                                                       // sign-extend the nibble
+        r5 = (uint32_t)min(max(((int32_t)r8 + off) >> 3, 0), 31);
+        g5 = (uint32_t)min(max(((int32_t)g8 + off) >> 3, 0), 31);
+        b5 = (uint32_t)min(max(((int32_t)b8 + off) >> 3, 0), 31);
+    } else {
+        r5 = r8 >> 3; g5 = g8 >> 3; b5 = b8 >> 3;
+    }
+    semi = (color & 0x8000) || (r5 == 0 && g5 == 0 && b5 == 0);                    // :1659-1661
+    o_r = expand5(r5); o_g = expand5(g5); o_b = expand5(b5);                       // Color15::r8/g8/b8
+    return true;
+}
+
+// =================================================================================================
+// k_fill_opaque — pass 1, order-free
+// =================================================================================================
+constexpr int OP_STAGE = 8;     // surface records staged per warp per step (8 x 128 B)
+
+__global__ void __launch_bounds__(FILL_THREADS)
+k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins, const uint32_t* __restrict__ tile_count,
+              const TexDev* __restrict__ tex, const uint16_t* __restrict__ texels,
+              uint32_t* __restrict__ fb_rgba, float* __restrict__ fb_z, const CallState* __restrict__ st,
+              uint32_t* __restrict__ sticky, CallParams p) {
+    __shared__ BinHead s_head[FILL_THREADS / 32][32];
+    __shared__ SurfRec s_rec[FILL_THREADS / 32][OP_STAGE];
+    {
+        CallState s = *st;
+        bool aborts = call_aborts(s, p.use_zbuffer);
+        if (p.async_call && blockIdx.x == 0 && threadIdx.x == 0 && (aborts || s.bin_overflow))   // enqueue-only callers
+            atomicOr(sticky, s.oob ? 1u : (aborts ? 2u : 4u));
+        if (s.bin_overflow || aborts || p.xray_mode) return;
+    }
+    const uint32_t tile = blockIdx.x;
+    const uint32_t n = tile_count[tile];
+    if (n == 0) return;
+    const BinHead* bin = bins + (size_t)tile * p.bin_cap;
+    const uint32_t tx = tile % p.tiles_x, ty = tile / p.tiles_x;
+    // thread -> pixel: each warp owns an 8x4 block of the 16x16 tile
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bx0 = tx * TILE_W + (warp & 1) * 8, by0 = ty * TILE_H + (warp >> 1) * 4;
+    const uint32_t x = bx0 + (lane & 7), y = by0 + (lane >> 3);
+    const bool valid = x < p.width && y < p.height;
+    if (bx0 >= p.width || by0 >= p.height) return;        // whole warp off-screen (warps never sync with each other)
+    Pixel px{0, 0.0f};
+    if (valid) { px.rgba = fb_rgba[y * p.width + x]; px.z = fb_z[y * p.width + x]; }
+    const Pixel px0 = px;
+    // painter's: best = (key << 32 | face) + 1 of the winner so far (0 = framebuffer content)
+    // z-buffer : best_face = face + 1 of the winner so far (0 = framebuffer content), depth in px.z
+    uint64_t best = valid ? 0ull : ~0ull;
+    uint32_t best_face = 0;
+    BinHead* my_heads = s_head[warp];
+    SurfRec* my_recs = s_rec[warp];
+
+    for (uint32_t base = 0; base < n; base += 32) {
+        // ---- filter 32 bin entries, one per lane -------------------------------------------------
+        BinHead h{0, 0, 0, 0};
+        bool cand = false;
+        if (base + lane < n) {
+            h = bin[base + lane];
+            uint32_t min_x = h.bbox_x & 0xFFFF, max_x = h.bbox_x >> 16, min_y = h.bbox_y & 0xFFFF, max_y = h.bbox_y >> 16;
+            cand = !(max_x <= bx0 || min_x >= bx0 + 8 || max_y <= by0 || min_y >= by0 + 4);
+        }
+        if (!p.use_zbuffer) {
+            // a surface that cannot beat the weakest pixel of this block cannot change anything
+            uint64_t wmin = best;
+            for (int o = 16; o > 0; o >>= 1) { uint64_t t = __shfl_xor_sync(0xFFFFFFFFu, wmin, o); wmin = t < wmin ? t : wmin; }
+            uint64_t prio = (((uint64_t)h.key << 32) | h.face) + 1;
+            cand = cand && prio > wmin;
+        }
+        uint32_t mask = __ballot_sync(0xFFFFFFFFu, cand);
+        if (mask == 0) continue;
+        uint32_t cnt = __popc(mask);
+        __syncwarp();
+        if (cand) my_heads[__popc(mask & ((1u << lane) - 1))] = h;
+        __syncwarp();
+        // ---- survivors, OP_STAGE records at a time -------------------------------------------------
+        for (uint32_t s0 = 0; s0 < cnt; s0 += OP_STAGE) {
+            uint32_t m = min((uint32_t)OP_STAGE, cnt - s0);
+            __syncwarp();
+            #pragma unroll
+            for (int g = 0; g < OP_STAGE / 4; ++g) {          // 32 lanes x 16 B = 4 records per round
+                uint32_t ri = g * 4 + (lane >> 3);
+                if (ri < m) reinterpret_cast<uint4*>(&my_recs[ri])[lane & 7] =
+                    reinterpret_cast<const uint4*>(&recs[my_heads[s0 + ri].face])[lane & 7];
+            }
+            __syncwarp();
+            for (uint32_t i = 0; i < m; ++i) {
+                const SurfRec& r = my_recs[i];
+                const uint32_t face = my_heads[s0 + i].face;
+                uint32_t min_x = r.bbox_x & 0xFFFF, max_x = r.bbox_x >> 16, min_y = r.bbox_y & 0xFFFF, max_y = r.bbox_y >> 16;
+                if (!(valid && x >= min_x && x < max_x && y >= min_y && y < max_y)) continue;
+                uint64_t prio = 0;
+                if (!p.use_zbuffer) {
+                    prio = (((uint64_t)my_heads[s0 + i].key << 32) | face) + 1;
+                    if (prio <= best) continue;                   // drawn earlier than the current winner
+                }
+                float bc_x, bc_y, bc_z;
+                if (!inside_test(r, x, y, bc_x, bc_y, bc_z)) continue;
+                float inv_z = bc_x * r.iz1 + bc_y * r.iz2 + bc_z * r.iz3;              // :1549
+                float z = 1.0f / inv_z;
+                if (p.use_zbuffer) {
+                    // lexicographic (z, face) minimum == sequential `z < zbuffer` in face order (:1553-1560, :1684)
+                    if (!(z < px.z || (z == px.z && face + 1 < best_face))) continue;
+                }
+                uint32_t o_r, o_g, o_b; bool semi;
+                if (!shade(r, x, y, bc_x, bc_y, bc_z, inv_z, tex, texels, p, o_r, o_g, o_b, semi)) continue;
+                // pass 1: blend mode Opaque and editor_alpha 255 => set_pixel_15 (:445-454)
+                px.rgba = o_r | (o_g << 8) | (o_b << 16) | 0xFF000000u;
+                if (p.use_zbuffer) { px.z = z; best_face = face + 1; }
+                else best = prio;
+            }
+        }
+    }
+    if (valid) {
+        if (px.rgba != px0.rgba) fb_rgba[y * p.width + x] = px.rgba;
+        if (__float_as_uint(px.z) != __float_as_uint(px0.z)) fb_z[y * p.width + x] = px.z;
+    }
+}
+
+// =================================================================================================
+// ordered pass (pass 2 + x-ray): stable binning in draw order, then strict in-order replay
+// =================================================================================================
+// ranks [first, first+count) of the sorted surface list are drawn in order.
+__device__ __forceinline__ void ordered_range(const CallState& s, const CallParams& p, uint32_t& first, uint32_t& count) {
+    if (call_aborts(s, p.use_zbuffer)) { first = 0; count = 0; return; }
+    if (p.xray_mode) { first = 0; count = s.n_opaque + s.n_transp; }      // everything blends at 50% (:1671-1673)
+    else { first = s.n_opaque; count = s.n_transp; }                      // pass 2 only
 }
 
 __global__ void __launch_bounds__(256)
 k_bin_count(const SurfRec* __restrict__ recs, const uint32_t* __restrict__ order, uint32_t* __restrict__ counts,
-            const CallState* __restrict__ st, uint32_t nf) {
-    uint32_t n_drawn = st->abort ? 0 : st->n_opaque + st->n_transp;
-    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nf; r += gridDim.x * blockDim.x) {
+            const CallState* __restrict__ st, CallParams p) {
+    uint32_t first, count;
+    ordered_range(*st, p, first, count);
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < p.nf; r += gridDim.x * blockDim.x) {
         uint32_t c = 0;
-        if (r < n_drawn) {
-            const SurfRec& rec = recs[order[r]];
+        if (r < count) {
+            const SurfRec& rec = recs[order[first + r]];
             uint32_t bx = rec.bbox_x, by = rec.bbox_y;
             uint32_t min_x = bx & 0xFFFF, max_x = bx >> 16, min_y = by & 0xFFFF, max_y = by >> 16;
             if (min_x < max_x && min_y < max_y)
@@ -297,21 +537,22 @@ k_bin_count(const SurfRec* __restrict__ recs, const uint32_t* __restrict__ order
 __global__ void __launch_bounds__(256)
 k_bin_emit(const SurfRec* __restrict__ recs, const uint32_t* __restrict__ order, const uint32_t* __restrict__ counts,
            const uint32_t* __restrict__ offsets, uint32_t* __restrict__ ent_tile, uint32_t* __restrict__ ent_surf,
-           uint32_t* __restrict__ tile_count, CallState* __restrict__ st, uint32_t nf, uint32_t tiles_x, uint32_t capacity) {
-    uint32_t total = offsets[nf - 1] + counts[nf - 1];
+           uint32_t* __restrict__ tile_count, CallState* __restrict__ st, CallParams p, uint32_t capacity) {
+    uint32_t total = offsets[p.nf - 1] + counts[p.nf - 1];
     if (blockIdx.x == 0 && threadIdx.x == 0) { st->n_entries = total; st->overflow = total > capacity ? 1 : 0; }
-    if (total > capacity || st->abort) return;
-    uint32_t n_drawn = st->n_opaque + st->n_transp;
-    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_drawn; r += gridDim.x * blockDim.x) {
+    if (total > capacity) return;
+    uint32_t first, count;
+    ordered_range(*st, p, first, count);
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < count; r += gridDim.x * blockDim.x) {
         if (counts[r] == 0) continue;
-        uint32_t f = order[r];
+        uint32_t f = order[first + r];
         const SurfRec& rec = recs[f];
-        uint32_t tx0, tx1, ty0, ty1;
-        tile_range(rec, tx0, tx1, ty0, ty1);
+        uint32_t min_x = rec.bbox_x & 0xFFFF, max_x = rec.bbox_x >> 16, min_y = rec.bbox_y & 0xFFFF, max_y = rec.bbox_y >> 16;
+        uint32_t tx0 = min_x / TILE_W, tx1 = (max_x - 1) / TILE_W, ty0 = min_y / TILE_H, ty1 = (max_y - 1) / TILE_H;
         uint32_t o = offsets[r];
-        for (uint32_t ty = ty0; ty < ty1; ++ty)
-            for (uint32_t tx = tx0; tx < tx1; ++tx) {
-                uint32_t t = ty * tiles_x + tx;
+        for (uint32_t ty = ty0; ty <= ty1; ++ty)
+            for (uint32_t tx = tx0; tx <= tx1; ++tx) {
+                uint32_t t = ty * p.tiles_x + tx;
                 ent_tile[o] = t;
                 ent_surf[o] = f;
                 ++o;
@@ -320,7 +561,7 @@ k_bin_emit(const SurfRec* __restrict__ recs, const uint32_t* __restrict__ order,
     }
 }
 
-// single-block exclusive scan of tile_count -> tile_start (ntiles is small: 300 at 320x240)
+// single-block exclusive scan of tile_count -> tile_start
 __global__ void __launch_bounds__(1024)
 k_tile_scan(const uint32_t* __restrict__ tile_count, uint32_t* __restrict__ tile_start, uint32_t ntiles) {
     __shared__ uint32_t warp_sums[32];
@@ -348,100 +589,9 @@ k_tile_scan(const uint32_t* __restrict__ tile_count, uint32_t* __restrict__ tile
     }
 }
 
-// =================================================================================================
-// k_fill
-// =================================================================================================
-struct Pixel { uint32_t rgba; float z; };
-
-// One fragment of rasterize_triangle_15 (render.rs:1534-1703) for pixel (x,y) against surface r.
-// `px` is the pixel's current framebuffer colour/depth, updated in place.
-__device__ __forceinline__ void fragment(const SurfRec& r, uint32_t x, uint32_t y, Pixel& px,
-                                         const TexDev* __restrict__ tex, const uint16_t* __restrict__ texels,
-                                         const CallParams& p) {
-    uint32_t min_x = r.bbox_x & 0xFFFF, min_y = r.bbox_y & 0xFFFF;
-    float w0, w1;
-    if (r.flags & SF_FAST_EDGE) {
-        // all terms are integers below 2^23: every rounded add of the reference is exact, so the
-        // stepped value equals the closed form
-        float dx = (float)(x - min_x), dy = (float)(y - min_y);
-        w0 = r.w0s + dy * r.b0 + dx * r.a0;
-        w1 = r.w1s + dy * r.b1 + dx * r.a1;
-    } else {
-        // replay the reference's rounded additions: (y-min_y) row steps, then (x-min_x) pixel steps
-        w0 = r.w0s; w1 = r.w1s;
-        for (uint32_t i = min_y; i < y; ++i) { w0 = __fadd_rn(w0, r.b0); w1 = __fadd_rn(w1, r.b1); }
-        for (uint32_t i = min_x; i < x; ++i) { w0 = __fadd_rn(w0, r.a0); w1 = __fadd_rn(w1, r.a1); }
-    }
-    float bc_x = w0 * r.inv_area;
-    float bc_y = w1 * r.inv_area;
-    float bc_z = 1.0f - bc_x - bc_y;
-    const float ERR = -0.0001f;
-    if (!(bc_x >= ERR && bc_y >= ERR && bc_z >= ERR)) return;                      // :1541-1542
-
-    float inv_z = bc_x * r.iz1 + bc_y * r.iz2 + bc_z * r.iz3;                      // :1549
-    float z = 1.0f / inv_z;
-    if (p.use_zbuffer && !p.xray_mode) { if (z >= px.z) return; }                   // :1553-1560
-
-    uint32_t color = 0x7FFF;                                                       // Color15::WHITE
-    if (r.flags & SF_TEXTURED) {
-        float u, v;
-        if (p.affine_textures) {                                                   // :1563-1567
-            u = bc_x * r.u1 + bc_y * r.u2 + bc_z * r.u3;
-            v = bc_x * r.v1 + bc_y * r.v2 + bc_z * r.v3;
-        } else {                                                                   // :1568-1578
-            float uo = bc_x * r.u1 * r.iz1 + bc_y * r.u2 * r.iz2 + bc_z * r.u3 * r.iz3;
-            float vo = bc_x * r.v1 * r.iz1 + bc_y * r.v2 * r.iz2 + bc_z * r.v3 * r.iz3;
-            u = uo / inv_z;
-            v = vo / inv_z;
-        }
-        TexDev t = tex[r.flags >> 16];
-        if (t.w == 0 || t.h == 0) {                                                // types.rs:673-675
-            color = 0;
-        } else {
-            float uw = rem_euclid1(u), vw = rem_euclid1(1.0f - v);                 // :1583, types.rs:676-677
-            uint32_t tx = min(f2u32sat(uw * (float)t.w), t.w - 1);
-            uint32_t ty = min(f2u32sat(vw * (float)t.h), t.h - 1);
-            color = __ldg(texels + t.off + ty * t.w + tx);
-        }
-    }
-    bool is_black = (color & 0x7FFF) == 0;                                         // :1591-1607
-    if (color == 0) {
-        if (!(r.flags & SF_BLACK_TR)) color = 0x8000; else return;
-    } else if ((r.flags & SF_BLACK_TR) && is_black) {
-        return;
-    }
-    uint32_t tr8 = expand5((color >> 10) & 31), tg8 = expand5((color >> 5) & 31), tb8 = expand5(color & 31);
-    uint32_t vr = f2u8(bc_x * (float)(r.vc1 & 0xFF) + bc_y * (float)(r.vc2 & 0xFF) + bc_z * (float)(r.vc3 & 0xFF));          // :1618-1620
-    uint32_t vg = f2u8(bc_x * (float)((r.vc1 >> 8) & 0xFF) + bc_y * (float)((r.vc2 >> 8) & 0xFF) + bc_z * (float)((r.vc3 >> 8) & 0xFF));
-    uint32_t vb = f2u8(bc_x * (float)(r.vc1 >> 16) + bc_y * (float)(r.vc2 >> 16) + bc_z * (float)(r.vc3 >> 16));
-    uint32_t mr = min((tr8 * vr) >> 7, 255u), mg = min((tg8 * vg) >> 7, 255u), mb = min((tb8 * vb) >> 7, 255u);   // :1624-1626
-    float sr, sg, sb;                                                              // :1629-1640
-    if (p.shading == B32_SHADE_NONE) { sr = sg = sb = 1.0f; }
-    else if (p.shading == B32_SHADE_FLAT) { sr = r.sh[0]; sg = r.sh[1]; sb = r.sh[2]; }
-    else {
-        sr = bc_x * r.sh[0] + bc_y * r.sh[3] + bc_z * r.sh[6];
-        sg = bc_x * r.sh[1] + bc_y * r.sh[4] + bc_z * r.sh[7];
-        sb = bc_x * r.sh[2] + bc_y * r.sh[5] + bc_z * r.sh[8];
-    }
-    uint32_t r8 = f2u8(fminf((float)mr * rclamp(sr, 0.0f, 2.0f), 255.0f));          // :1643-1645
-    uint32_t g8 = f2u8(fminf((float)mg * rclamp(sg, 0.0f, 2.0f), 255.0f));
-    uint32_t b8 = f2u8(fminf((float)mb * rclamp(sb, 0.0f, 2.0f), 255.0f));
-    uint32_t r5, g5, b5;
-    if (r.flags & SF_DITHER) {                                                     // :1173-1182
-        // PS1_DITHER_MATRIX rows packed as signed nibbles, :1150-1155
-        const int32_t M[4] = {(int32_t)0x1D0C, (int32_t)0xF3E2, (int32_t)0x0C1D, (int32_t)0xE2F3};
-        int32_t row = M[y & 3];
-        int32_t off = ((row >> ((x & 3) * 4)) & 0xF);
-        off = (off ^ 8) - 8;                                                       // sign-extend the nibble
-        r5 = (uint32_t)min(max(((int32_t)r8 + off) >> 3, 0), 31);
-        g5 = (uint32_t)min(max(((int32_t)g8 + off) >> 3, 0), 31);
-        b5 = (uint32_t)min(max(((int32_t)b8 + off) >> 3, 0), 31);
-    } else {
-        r5 = r8 >> 3; g5 = g8 >> 3; b5 = b8 >> 3;
-    }
-    bool semi = (color & 0x8000) || (r5 == 0 && g5 == 0 && b5 == 0);               // :1659-1661
-    uint32_t o_r = expand5(r5), o_g = expand5(g5), o_b = expand5(b5);              // Color15::r8/g8/b8
-
+// The write stage of rasterize_triangle_15 (render.rs:1664-1702) against a pixel held in registers.
+__device__ __forceinline__ void write_ordered(const SurfRec& r, Pixel& px, float z, uint32_t o_r, uint32_t o_g, uint32_t o_b, bool semi,
+                                              const CallParams& p) {
     uint32_t editor_alpha = (r.flags >> 8) & 0xFF;
     if (editor_alpha == 0) return;                                                 // :1664-1669
     uint32_t br = px.rgba & 0xFF, bg = (px.rgba >> 8) & 0xFF, bb = (px.rgba >> 16) & 0xFF;
@@ -452,7 +602,7 @@ __device__ __forceinline__ void fragment(const SurfRec& r, uint32_t x, uint32_t 
     }
     bool skip_z_write = (r.flags & SF_TRANSPARENT) != 0;                           // pass 2, :2561-2569
     if (p.use_zbuffer) {
-        if (editor_alpha < 255) { /* rejected only on z >= zbuffer (:604), already tested above */ }
+        if (editor_alpha < 255) { /* rejected only on z >= zbuffer (:604), already tested by the caller */ }
         else if (!(z < px.z)) return;                                              // :1684
         if (!skip_z_write) px.z = z;
     }
@@ -469,25 +619,27 @@ __device__ __forceinline__ void fragment(const SurfRec& r, uint32_t x, uint32_t 
 constexpr int FILL_CHUNK = 32;      // surfaces staged in shared memory per step (32 x 128 B = 4 KB)
 
 __global__ void __launch_bounds__(FILL_THREADS)
-k_fill(const SurfRec* __restrict__ recs, const uint32_t* __restrict__ ent_surf,
-       const uint32_t* __restrict__ tile_start, const uint32_t* __restrict__ tile_count,
-       const TexDev* __restrict__ tex, const uint16_t* __restrict__ texels,
-       uint32_t* __restrict__ fb_rgba, float* __restrict__ fb_z, const CallState* __restrict__ st, CallParams p) {
+k_fill_ordered(const SurfRec* __restrict__ recs, const uint32_t* __restrict__ ent_surf,
+               const uint32_t* __restrict__ tile_start, const uint32_t* __restrict__ tile_count,
+               const TexDev* __restrict__ tex, const uint16_t* __restrict__ texels,
+               uint32_t* __restrict__ fb_rgba, float* __restrict__ fb_z, const CallState* __restrict__ st, CallParams p) {
     __shared__ SurfRec s_rec[FILL_CHUNK];
-    if (st->abort || st->overflow) return;
+    {
+        CallState s = *st;
+        if (s.overflow || call_aborts(s, p.use_zbuffer)) return;
+    }
     const uint32_t tile = blockIdx.x;
     const uint32_t n = tile_count[tile];
     if (n == 0) return;
     const uint32_t start = tile_start[tile];
     const uint32_t tx = tile % p.tiles_x, ty = tile / p.tiles_x;
-    // thread -> pixel: each warp owns an 8x4 block of the 16x16 tile
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bx0 = tx * TILE_W + (warp & 1) * 8, by0 = ty * TILE_H + (warp >> 1) * 4;
     const uint32_t x = bx0 + (lane & 7), y = by0 + (lane >> 3);
     const bool valid = x < p.width && y < p.height;
     Pixel px{0, 0.0f};
-    Pixel px0 = px;
-    if (valid) { px.rgba = fb_rgba[y * p.width + x]; px.z = fb_z[y * p.width + x]; px0 = px; }
+    if (valid) { px.rgba = fb_rgba[y * p.width + x]; px.z = fb_z[y * p.width + x]; }
+    const Pixel px0 = px;
 
     for (uint32_t base = 0; base < n; base += FILL_CHUNK) {
         uint32_t cnt = min((uint32_t)FILL_CHUNK, n - base);
@@ -505,7 +657,15 @@ k_fill(const SurfRec* __restrict__ recs, const uint32_t* __restrict__ ent_surf,
             uint32_t min_x = r.bbox_x & 0xFFFF, max_x = r.bbox_x >> 16, min_y = r.bbox_y & 0xFFFF, max_y = r.bbox_y >> 16;
             // warp-uniform reject of surfaces that miss this warp's 8x4 block
             if (max_x <= bx0 || min_x >= bx0 + 8 || max_y <= by0 || min_y >= by0 + 4) continue;
-            if (valid && x >= min_x && x < max_x && y >= min_y && y < max_y) fragment(r, x, y, px, tex, texels, p);
+            if (!(valid && x >= min_x && x < max_x && y >= min_y && y < max_y)) continue;
+            float bc_x, bc_y, bc_z;
+            if (!inside_test(r, x, y, bc_x, bc_y, bc_z)) continue;
+            float inv_z = bc_x * r.iz1 + bc_y * r.iz2 + bc_z * r.iz3;              // :1549
+            float z = 1.0f / inv_z;
+            if (p.use_zbuffer && !p.xray_mode) { if (z >= px.z) continue; }         // :1553-1560
+            uint32_t o_r, o_g, o_b; bool semi;
+            if (!shade(r, x, y, bc_x, bc_y, bc_z, inv_z, tex, texels, p, o_r, o_g, o_b, semi)) continue;
+            write_ordered(r, px, z, o_r, o_g, o_b, semi, p);
         }
     }
     if (valid) {
@@ -531,17 +691,12 @@ __global__ void k_tex_expand(const uint8_t* __restrict__ idx, const uint16_t* __
     }
 }
 
-__global__ void k_gather_order(const uint32_t* __restrict__ order, const CallState* __restrict__ st, uint32_t* __restrict__ out, uint32_t cap) {
-    uint32_t n = st->n_opaque + st->n_transp;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n && i < cap; i += gridDim.x * blockDim.x) out[i] = order[i];
-}
-
 // =================================================================================================
 // launchers (host)
 // =================================================================================================
-static inline uint32_t grid_for(uint32_t n, uint32_t block, uint32_t sms) {
+static inline uint32_t grid_for(uint32_t n, uint32_t block, uint32_t sms, uint32_t per_sm = 8) {
     uint32_t g = (n + block - 1) / block;
-    uint32_t cap = sms * 8;
+    uint32_t cap = sms * per_sm;
     return g < 1 ? 1 : (g > cap ? cap : g);
 }
 
@@ -561,9 +716,19 @@ void launch_transform(const LaunchCtx& L, const b32_vertex* verts, TVert* out, f
 }
 
 void launch_setup(const LaunchCtx& L, const b32_vertex* verts, const b32_face* faces, const TVert* tv, const TexDev* tex,
-                  const LightDev* lights, SurfRec* recs, uint64_t* keys, uint32_t* vals, CallState* st, const CallParams& p) {
+                  const LightDev* lights, SurfRec* recs, uint64_t* keys, uint32_t* vals, BinHead* bins, uint32_t* tile_count,
+                  CallState* st, const CallParams& p) {
     if (p.nf == 0) return;
-    k_setup<<<grid_for(p.nf, 128, L.sms), 128, 0, L.stream>>>(verts, faces, tv, tex, lights, recs, keys, vals, st, p);
+    k_setup<<<grid_for(p.nf, 128, L.sms, 16), 128, 0, L.stream>>>(verts, faces, tv, tex, lights, L.unr_table, recs, keys, vals, bins, tile_count, st, p);
+    ++*L.launches;
+}
+
+void launch_fill_opaque(const LaunchCtx& L, const SurfRec* recs, const BinHead* bins, const uint32_t* tile_count,
+                        const TexDev* tex, const uint16_t* texels, uint32_t* fb_rgba, float* fb_z, const CallState* st,
+                        uint32_t* sticky, const CallParams& p) {
+    uint32_t ntiles = p.tiles_x * p.tiles_y;
+    if (ntiles == 0 || p.nf == 0) return;
+    k_fill_opaque<<<ntiles, FILL_THREADS, 0, L.stream>>>(recs, bins, tile_count, tex, texels, fb_rgba, fb_z, st, sticky, p);
     ++*L.launches;
 }
 
@@ -573,24 +738,23 @@ void launch_sort_faces(const LaunchCtx& L, void* temp, size_t temp_bytes, const 
     cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, (int)nf, 0, 34, L.stream);
 }
 
-void launch_binning(const LaunchCtx& L, void* temp, size_t temp_bytes, const SurfRec* recs, const uint32_t* order,
-                    uint32_t* counts, uint32_t* offsets, uint32_t* ent_tile, uint32_t* ent_surf,
-                    uint32_t* ent_tile_sorted, uint32_t* ent_surf_sorted, uint32_t* tile_count, uint32_t* tile_start,
-                    CallState* st, const CallParams& p, uint32_t capacity, bool count_phase, bool emit_phase) {
+void launch_bin_count(const LaunchCtx& L, void* temp, size_t temp_bytes, const SurfRec* recs, const uint32_t* order,
+                      uint32_t* counts, uint32_t* offsets, const CallState* st, const CallParams& p) {
+    if (p.nf == 0) return;
+    k_bin_count<<<grid_for(p.nf, 256, L.sms), 256, 0, L.stream>>>(recs, order, counts, st, p);
+    ++*L.launches;
+    cub::DeviceScan::ExclusiveSum(temp, temp_bytes, counts, offsets, (int)p.nf, L.stream);
+}
+
+void launch_bin_emit(const LaunchCtx& L, const SurfRec* recs, const uint32_t* order, const uint32_t* counts, const uint32_t* offsets,
+                     uint32_t* ent_tile, uint32_t* ent_surf, uint32_t* tile_count, uint32_t* tile_start, CallState* st,
+                     const CallParams& p, uint32_t capacity) {
     if (p.nf == 0) return;
     uint32_t ntiles = p.tiles_x * p.tiles_y;
-    if (count_phase) {
-        k_decide<<<1, 1, 0, L.stream>>>(st, p.use_zbuffer);
-        k_bin_count<<<grid_for(p.nf, 256, L.sms), 256, 0, L.stream>>>(recs, order, counts, st, p.nf);
-        *L.launches += 2;
-        cub::DeviceScan::ExclusiveSum(temp, temp_bytes, counts, offsets, (int)p.nf, L.stream);
-    }
-    if (emit_phase) {
-        cudaMemsetAsync(tile_count, 0, ntiles * sizeof(uint32_t), L.stream);
-        k_bin_emit<<<grid_for(p.nf, 256, L.sms), 256, 0, L.stream>>>(recs, order, counts, offsets, ent_tile, ent_surf, tile_count, st, p.nf, p.tiles_x, capacity);
-        k_tile_scan<<<1, 1024, 0, L.stream>>>(tile_count, tile_start, ntiles);
-        *L.launches += 2;
-    }
+    cudaMemsetAsync(tile_count, 0, ntiles * sizeof(uint32_t), L.stream);
+    k_bin_emit<<<grid_for(p.nf, 256, L.sms), 256, 0, L.stream>>>(recs, order, counts, offsets, ent_tile, ent_surf, tile_count, st, p, capacity);
+    k_tile_scan<<<1, 1024, 0, L.stream>>>(tile_count, tile_start, ntiles);
+    *L.launches += 2;
 }
 
 void launch_sort_entries(const LaunchCtx& L, void* temp, size_t temp_bytes, const uint32_t* ent_tile, uint32_t* ent_tile_sorted,
@@ -601,12 +765,12 @@ void launch_sort_entries(const LaunchCtx& L, void* temp, size_t temp_bytes, cons
     cub::DeviceRadixSort::SortPairs(temp, temp_bytes, ent_tile, ent_tile_sorted, ent_surf, ent_surf_sorted, (int)n_entries, 0, bits, L.stream);
 }
 
-void launch_fill(const LaunchCtx& L, const SurfRec* recs, const uint32_t* ent_surf_sorted, const uint32_t* tile_start,
-                 const uint32_t* tile_count, const TexDev* tex, const uint16_t* texels, uint32_t* fb_rgba, float* fb_z,
-                 const CallState* st, const CallParams& p) {
+void launch_fill_ordered(const LaunchCtx& L, const SurfRec* recs, const uint32_t* ent_surf_sorted, const uint32_t* tile_start,
+                         const uint32_t* tile_count, const TexDev* tex, const uint16_t* texels, uint32_t* fb_rgba, float* fb_z,
+                         const CallState* st, const CallParams& p) {
     uint32_t ntiles = p.tiles_x * p.tiles_y;
     if (ntiles == 0 || p.nf == 0) return;
-    k_fill<<<ntiles, FILL_THREADS, 0, L.stream>>>(recs, ent_surf_sorted, tile_start, tile_count, tex, texels, fb_rgba, fb_z, st, p);
+    k_fill_ordered<<<ntiles, FILL_THREADS, 0, L.stream>>>(recs, ent_surf_sorted, tile_start, tile_count, tex, texels, fb_rgba, fb_z, st, p);
     ++*L.launches;
 }
 
@@ -619,12 +783,6 @@ void launch_fb_clear(const LaunchCtx& L, uint32_t* rgba, float* z, uint32_t n, u
 void launch_tex_expand(const LaunchCtx& L, const uint8_t* idx, const uint16_t* clut, uint32_t clut_len, uint32_t format, uint32_t n, uint16_t* out) {
     if (n == 0) return;
     k_tex_expand<<<grid_for(n, 256, L.sms), 256, 0, L.stream>>>(idx, clut, clut_len, format, n, out);
-    ++*L.launches;
-}
-
-void launch_gather_order(const LaunchCtx& L, const uint32_t* order, const CallState* st, uint32_t* out, uint32_t cap) {
-    if (cap == 0) return;
-    k_gather_order<<<grid_for(cap, 256, L.sms), 256, 0, L.stream>>>(order, st, out, cap);
     ++*L.launches;
 }
 

@@ -204,9 +204,10 @@ int b32_debug_transform(b32_ctx* ctx, const b32_vertex* vertices, uint32_t nv,
  * drawn (opaque pass then transparent pass). Returns count via *n (<= cap written). */
 int b32_debug_draw_order(b32_ctx* ctx, uint32_t* out_face_idx, uint32_t cap, uint32_t* n);
 
-/* Device time (ms, CUDA events on the context stream) of each kernel group of the last render call:
- * [0] k_transform [1] k_setup [2] face sort [3] bin count + scan [4] bin emit + tile scan
- * [5] entry sort [6] k_fill.  Returns the number of values written (<= cap). */
+/* Device time (ms, CUDA events on the context stream) of each kernel group of the last synchronous
+ * render call: [0] k_setup (transform + cull + setup + binning) [1] k_fill_opaque (pass 1), and for
+ * pass 2 / x-ray: [2] face sort [3] bin count + scan [4] bin emit + tile scan [5] entry sort
+ * [6] k_fill_ordered.  Returns the number of values written (<= cap). */
 int b32_debug_kernel_times(b32_ctx* ctx, float* out_ms, uint32_t cap);
 
 #ifdef __cplusplus

@@ -217,3 +217,54 @@ def test_properties_full_size(ctx):
     fb = pkg.Framebuffer(sc.width, sc.height, ctx); fb.upload(a, az)
     pkg.render_mesh_15(fb, sc.vertices, sc.faces, sc.textures, sc.camera, sc.settings)
     assert np.array_equal(fb.download()[0], a)
+
+
+def test_enqueue_only_path(ctx, oracle):
+    """b32_render_mesh_15_enqueue: pass 1 without any host round trip; same bytes as the oracle."""
+    for zbuf in (False, True):
+        sc = scenes.scene_c4(n_tris=20000, use_zbuffer=zbuf)
+        want, want_z, otm, rc = oracle.render_scene(sc)
+        fb = pkg.Framebuffer(sc.width, sc.height, ctx)
+        ctx.set_textures(sc.textures)
+        mesh = pkg.Mesh(ctx, sc.vertices, sc.faces)
+        for _ in range(3):                       # several frames in flight
+            fb.clear(sc.clear)
+            mesh.render(sc.camera, sc.settings, sc.fog, enqueue_only=True)
+        got, got_z = fb.download()
+        mesh.free()
+        assert np.array_equal(got, want) and np.array_equal(got_z.view(np.uint32), want_z.view(np.uint32))
+
+
+def test_enqueue_only_errors_surface_at_sync(ctx):
+    sc = scenes.scene_c2(n_tris=50)
+    f = sc.faces.copy(); f["v"][7, 1] = len(sc.vertices)
+    fb = pkg.Framebuffer(320, 240, ctx); fb.clear(sc.clear)
+    before = fb.download()[0]
+    ctx.set_textures(sc.textures)
+    mesh = pkg.Mesh(ctx, sc.vertices, f)
+    mesh.render(sc.camera, sc.settings, None, enqueue_only=True)
+    with pytest.raises(pkg.B32Error) as e:
+        ctx.sync()
+    assert e.value.code == abi.B32_ERR_OOB_INDEX
+    assert np.array_equal(fb.download()[0], before)
+    mesh.free()
+
+
+def test_crowded_tile_bin_growth(ctx, oracle):
+    """Thousands of surfaces in one screen tile: the per-tile bins overflow once, grow, and the frame is redone."""
+    n = 6000
+    u = scenes.splitmix64_u01(5150, n * 9).reshape(n, 3, 3)
+    pos = np.empty((n, 3, 3))
+    pos[..., 0] = (u[..., 0] - 0.5) * 0.9          # all inside a few pixels around the screen centre
+    pos[..., 1] = (u[..., 1] - 0.5) * 0.9
+    pos[..., 2] = 10.0 + 30.0 * u[..., 2]
+    v = scenes.make_vertices(pos.reshape(-1, 3), uv=u[..., :2].reshape(-1, 2),
+                             rgba=np.concatenate([np.floor(u * 255).reshape(-1, 3), np.zeros((n * 3, 1))], axis=1))
+    f = scenes.make_faces(np.arange(n * 3).reshape(n, 3), tex_id=abi.FACE_TEX_NONE)
+    for zbuf in (False, True):
+        sc = scenes.Scene("crowded_tile", v, f, [], pkg.Camera(), scenes.common_settings(use_zbuffer=zbuf, backface_cull=False))
+        want, want_z, otm, rc = oracle.render_scene(sc)
+        ctx2 = pkg.Context(0)                     # fresh context: no learned bin capacity
+        got, got_z, tm = render_gpu(ctx2, sc)
+        ctx2.close()
+        assert_same(sc, got, got_z, tm, want, want_z, otm)
