@@ -153,145 +153,229 @@ __device__ __forceinline__ uint32_t fog_color(uint32_t c, float z, const CallPar
 
 __device__ __forceinline__ bool is_integral(float x) { return truncf(x) == x; }
 
-// One thread per face.  `tv` (pre-transformed vertices) may be NULL: then the three vertices are
-// transformed here (no intermediate vertex buffer: each vertex record is read exactly once per use).
-__global__ void __launch_bounds__(128)
+// Up to SETUP_FPT faces per thread and round.  `tv` (pre-transformed vertices) may be NULL: then the
+// three vertices are transformed here (no intermediate vertex buffer: each vertex record is read
+// once per use).
+//
+// Binning of pass-1 surfaces into per-tile bins is aggregated per block: same-address global atomics
+// serialise in the L2 (hot tiles get hundreds of hits), so a block first counts its surfaces per tile
+// in shared memory, reserves one contiguous range per touched tile with ONE global atomic, and then
+// hands out slots from shared memory.
+constexpr int SETUP_THREADS = 256;
+constexpr int SETUP_FPT = 4;                 // faces per thread per round  => 1024 faces per block round
+constexpr int SETUP_MAX_TILES = 4096;        // shared-memory aggregation up to this many tiles (2 x 16 KB)
+
+__device__ __forceinline__ void setup_face(uint32_t fi, const b32_vertex* __restrict__ verts, const b32_face* __restrict__ faces,
+                                           const TVert* __restrict__ tv, const TexDev* __restrict__ tex,
+                                           const LightDev* __restrict__ lights, const uint8_t* __restrict__ unr,
+                                           SurfRec* __restrict__ recs, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                           CallState* __restrict__ st, const CallParams& p,
+                                           uint32_t& n_op, uint32_t& n_tr, BinHead& head, bool& binned) {
+    binned = false;
+    uint4 fc = *reinterpret_cast<const uint4*>(faces + fi);
+    uint32_t cls = 2;                 // 0 opaque pass, 1 transparent pass, 2 not drawn
+    uint32_t dkey = 0;
+    do {
+        if (fc.x >= p.nv || fc.y >= p.nv || fc.z >= p.nv) { st->oob = 1; break; }
+        uint32_t tex_id = fc.w & 0xFFFFu, face_blend = (fc.w >> 16) & 7u, editor_alpha = fc.w >> 24;
+        bool black_tr = (fc.w >> 19) & 1u;
+        bool textured = tex_id != B32_FACE_TEX_NONE && tex_id < p.ntex;
+        uint32_t tex_blend = 0;
+        if (textured) tex_blend = tex[tex_id].blend;
+
+        const float* v0 = reinterpret_cast<const float*>(verts + fc.x);
+        const float* v1 = reinterpret_cast<const float*>(verts + fc.y);
+        const float* v2 = reinterpret_cast<const float*>(verts + fc.z);
+        TVert t1, t2, t3;
+        if (tv) { t1 = tv[fc.x]; t2 = tv[fc.y]; t3 = tv[fc.z]; }
+        else {
+            t1 = transform_vertex(v0[0], v0[1], v0[2], p, unr, nullptr);
+            t2 = transform_vertex(v1[0], v1[1], v1[2], p, unr, nullptr);
+            t3 = transform_vertex(v2[0], v2[1], v2[2], p, unr, nullptr);
+        }
+        if (!p.ortho) {                                                       // :2380-2385
+            if (t1.w <= NEAR_PLANE || t2.w <= NEAR_PLANE || t3.w <= NEAR_PLANE) break;
+        }
+        float signed_area = (t2.x - t1.x) * (t3.y - t1.y) - (t3.x - t1.x) * (t2.y - t1.y);   // :2393
+        bool backface = signed_area <= 0.0f;
+        bool transparent;                                                     // :2403-2415
+        if (textured && tex_blend != B32_BLEND_OPAQUE) transparent = true;
+        else if (face_blend != B32_BLEND_OPAQUE) transparent = true;
+        else transparent = editor_alpha < 255;
+        if (p.fog_enabled && t1.w > p.fog_cull && t2.w > p.fog_cull && t3.w > p.fog_cull) break;   // :2421-2424
+        if (backface && !(!p.backface_cull || p.xray_mode)) break;            // :2445-2453
+
+        // vertex attributes (36-byte records: pos 0, uv 12, normal 20, rgba 32); v2/v3 swap :2455-2457
+        TVert s1 = t1, s2 = backface ? t3 : t2, s3 = backface ? t2 : t3;
+        const float* va = v0;
+        const float* vb = backface ? v2 : v1;
+        const float* vc = backface ? v1 : v2;
+        uint32_t c1 = reinterpret_cast<const uint32_t*>(va)[8], c2 = reinterpret_cast<const uint32_t*>(vb)[8], c3 = reinterpret_cast<const uint32_t*>(vc)[8];
+        if (p.fog_enabled) {                                                  // :2427-2436 (cam z of the same vertex)
+            c1 = fog_color(c1, s1.w, p); c2 = fog_color(c2, s2.w, p); c3 = fog_color(c3, s3.w, p);
+        }
+
+        SurfRec r;
+        uint32_t blend_mode = textured ? tex_blend : face_blend;               // :1450-1452
+        uint32_t flags = blend_mode | (black_tr ? SF_BLACK_TR : 0) | (textured ? SF_TEXTURED : 0) |
+                         (transparent ? SF_TRANSPARENT : 0) | (editor_alpha << 8) | ((textured ? tex_id : 0xFFFFu) << 16);
+        bool needs_dither = p.dithering && (p.shading == B32_SHADE_GOURAUD || textured || c1 != c2 || c2 != c3);   // :1487-1492
+        if (needs_dither) flags |= SF_DITHER;
+
+        // bounding box, render.rs:1455-1463
+        uint32_t min_x = f2u32sat(fmaxf(fminf(fminf(s1.x, s2.x), s3.x), 0.0f));
+        uint32_t max_x = f2u32sat(fminf(fmaxf(fmaxf(s1.x, s2.x), s3.x) + 1.0f, (float)p.width));
+        uint32_t min_y = f2u32sat(fmaxf(fminf(fminf(s1.y, s2.y), s3.y), 0.0f));
+        uint32_t max_y = f2u32sat(fminf(fmaxf(fmaxf(s1.y, s2.y), s3.y) + 1.0f, (float)p.height));
+        bool empty = min_x >= max_x || min_y >= max_y;
+        float area = (s2.y - s3.y) * (s1.x - s3.x) + (s3.x - s2.x) * (s1.y - s3.y);     // :1500
+        if (fabsf(area) < 0.00001f) empty = true;                                      // :1501-1503
+        if (empty) { min_x = max_x = min_y = max_y = 0; }
+        r.inv_area = 1.0f / area;
+        r.a0 = s2.y - s3.y; r.b0 = s3.x - s2.x; r.a1 = s3.y - s1.y; r.b1 = s1.x - s3.x;   // :1507-1510
+        float start_x = (float)min_x, start_y = (float)min_y;
+        r.w0s = r.a0 * (start_x - s3.x) + r.b0 * (start_y - s3.y);                      // :1517-1518
+        r.w1s = r.a1 * (start_x - s3.x) + r.b1 * (start_y - s3.y);
+        r.bbox_x = min_x | (max_x << 16);
+        r.bbox_y = min_y | (max_y << 16);
+        // incremental stepping == closed form when everything is an integer below 2^23
+        {
+            float nx = (float)(max_x - min_x), ny = (float)(max_y - min_y);
+            float m0 = fabsf(r.w0s) + ny * fabsf(r.b0) + nx * fabsf(r.a0);
+            float m1 = fabsf(r.w1s) + ny * fabsf(r.b1) + nx * fabsf(r.a1);
+            bool ints = is_integral(r.a0) && is_integral(r.b0) && is_integral(r.a1) && is_integral(r.b1) &&
+                        is_integral(r.w0s) && is_integral(r.w1s);
+            if (ints && m0 < 8388608.0f && m1 < 8388608.0f) flags |= SF_FAST_EDGE;
+        }
+        r.iz1 = 1.0f / s1.z; r.iz2 = 1.0f / s2.z; r.iz3 = 1.0f / s3.z;                  // :1546-1548
+        r.u1 = va[3]; r.v1 = va[4]; r.u2 = vb[3]; r.v2 = vb[4]; r.u3 = vc[3]; r.v3 = vc[4];
+        r.vc1 = c1 & 0xFFFFFF; r.vc2 = c2 & 0xFFFFFF; r.vc3 = c3 & 0xFFFFFF;
+        for (int k = 0; k < 9; ++k) r.sh[k] = 1.0f;
+        if (!empty && p.shading != B32_SHADE_NONE) {
+            V3 w1{va[0], va[1], va[2]}, w2{vb[0], vb[1], vb[2]}, w3{vc[0], vc[1], vc[2]};
+            V3 n1{va[5], va[6], va[7]}, n2{vb[5], vb[6], vb[7]}, n3{vc[5], vc[6], vc[7]};
+            if (backface) {                                                             // wn.scale(-1.0) :2464-2466
+                n1 = V3{n1.x * -1.0f, n1.y * -1.0f, n1.z * -1.0f}; n2 = V3{n2.x * -1.0f, n2.y * -1.0f, n2.z * -1.0f};
+                n3 = V3{n3.x * -1.0f, n3.y * -1.0f, n3.z * -1.0f};
+            }
+            if (p.shading == B32_SHADE_FLAT) {                                          // :1466-1472
+                const float third = 1.0f / 3.0f;
+                V3 c{((w1.x + w2.x) + w3.x) * third, ((w1.y + w2.y) + w3.y) * third, ((w1.z + w2.z) + w3.z) * third};
+                V3 n = normalize3(V3{((n1.x + n2.x) + n3.x) * third, ((n1.y + n2.y) + n3.y) * third, ((n1.z + n2.z) + n3.z) * third});
+                shade_multi_light_color(n, c, lights, p.n_lights, p.ambient, r.sh);
+            } else {                                                                    // :1475-1483
+                shade_multi_light_color(n1, w1, lights, p.n_lights, p.ambient, r.sh);
+                shade_multi_light_color(n2, w2, lights, p.n_lights, p.ambient, r.sh + 3);
+                shade_multi_light_color(n3, w3, lights, p.n_lights, p.ambient, r.sh + 6);
+            }
+        }
+        r.flags = flags;
+        r._pad = 0;
+        recs[fi] = r;
+
+        cls = transparent ? 1u : 0u;
+        float center_z = (s1.z + s2.z + s3.z) / 3.0f;                                   // :2529
+        bool sorted = transparent || !p.use_zbuffer;                                    // :2527, :2536
+        if (sorted) {
+            if (center_z != center_z) { if (transparent) st->nan_transp = 1; else st->nan_opaque = 1; }
+            dkey = depth_key_desc(center_z);
+        }
+        if (transparent) ++n_tr; else ++n_op;
+
+        // pass-1 surfaces go into their screen tiles' bins (any order; see file header)
+        if (!transparent && !p.xray_mode && !empty) {
+            uint32_t hkey = dkey;
+            if (p.use_zbuffer) {
+                // front-to-back walk key: a lower bound of every depth this surface can produce.
+                // 1/z = sum(bc_i / z_i) with bc_i >= -1e-4 and sum(bc) = 1.  If all z_i > 0 and
+                // zmax <= 1000 * zmin then 0 < 1/z <= (1 + 2e-4) / zmin, so z >= 0.9997 * zmin; the bound
+                // 0.999 * zmin also absorbs rounding.  Otherwise (ortho depths <= 0, NaN, extreme depth
+                // ratios where 1/z can change sign) no bound is claimed: key 0xFFFFFFFF = "never cull".
+                float zmin = fminf(fminf(s1.z, s2.z), s3.z), zmax = fmaxf(fmaxf(s1.z, s2.z), s3.z);
+                bool ok = s1.z > 0.0f && s2.z > 0.0f && s3.z > 0.0f && zmax <= 1000.0f * zmin && zmax <= 3.0e38f;
+                float lb = ok ? zmin * 0.999f : 0.0f;
+                hkey = ~__float_as_uint(lb);           // lb >= 0: bits are monotone; inverted so "descending key" = front first
+            }
+            head = BinHead{r.bbox_x, r.bbox_y, hkey, fi};
+            binned = true;
+        }
+    } while (0);
+    keys[fi] = ((uint64_t)cls << 32) | dkey;
+    vals[fi] = fi;
+}
+
+__global__ void __launch_bounds__(SETUP_THREADS)
 k_setup(const b32_vertex* __restrict__ verts, const b32_face* __restrict__ faces, const TVert* __restrict__ tv,
         const TexDev* __restrict__ tex, const LightDev* __restrict__ lights, const uint8_t* __restrict__ unr_table_g,
         SurfRec* __restrict__ recs, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
         BinHead* __restrict__ bins, uint32_t* __restrict__ tile_count,
         CallState* __restrict__ st, CallParams p) {
     __shared__ uint8_t unr[260];
+    extern __shared__ uint32_t s_tiles[];            // [ntiles] counts/cursors, [ntiles] bases (when ntiles <= SETUP_MAX_TILES)
+    const uint32_t ntiles = p.tiles_x * p.tiles_y;
+    const bool aggregate = ntiles <= SETUP_MAX_TILES;
+    uint32_t* s_cnt = s_tiles;
+    uint32_t* s_base = s_tiles + ntiles;
     for (int i = threadIdx.x; i < 257; i += blockDim.x) unr[i] = unr_table_g[i];
+    if (aggregate) for (uint32_t i = threadIdx.x; i < ntiles; i += blockDim.x) s_cnt[i] = 0;
     __syncthreads();
 
     uint32_t n_op = 0, n_tr = 0, bmax = 0;
-    for (uint32_t fi = blockIdx.x * blockDim.x + threadIdx.x; fi < p.nf; fi += gridDim.x * blockDim.x) {
-        uint4 fc = *reinterpret_cast<const uint4*>(faces + fi);
-        uint32_t cls = 2;                 // 0 opaque pass, 1 transparent pass, 2 not drawn
-        uint32_t dkey = 0;
-        do {
-            if (fc.x >= p.nv || fc.y >= p.nv || fc.z >= p.nv) { st->oob = 1; break; }
-            uint32_t tex_id = fc.w & 0xFFFFu, face_blend = (fc.w >> 16) & 7u, editor_alpha = fc.w >> 24;
-            bool black_tr = (fc.w >> 19) & 1u;
-            bool textured = tex_id != B32_FACE_TEX_NONE && tex_id < p.ntex;
-            uint32_t tex_blend = 0;
-            if (textured) tex_blend = tex[tex_id].blend;
-
-            const float* v0 = reinterpret_cast<const float*>(verts + fc.x);
-            const float* v1 = reinterpret_cast<const float*>(verts + fc.y);
-            const float* v2 = reinterpret_cast<const float*>(verts + fc.z);
-            TVert t1, t2, t3;
-            if (tv) { t1 = tv[fc.x]; t2 = tv[fc.y]; t3 = tv[fc.z]; }
-            else {
-                t1 = transform_vertex(v0[0], v0[1], v0[2], p, unr, nullptr);
-                t2 = transform_vertex(v1[0], v1[1], v1[2], p, unr, nullptr);
-                t3 = transform_vertex(v2[0], v2[1], v2[2], p, unr, nullptr);
+    const uint32_t per_round = SETUP_THREADS * SETUP_FPT;
+    for (uint32_t base = blockIdx.x * per_round; base < p.nf; base += gridDim.x * per_round) {
+        BinHead head[SETUP_FPT];
+        bool binned[SETUP_FPT];
+        #pragma unroll
+        for (int k = 0; k < SETUP_FPT; ++k) {
+            uint32_t fi = base + k * SETUP_THREADS + threadIdx.x;
+            binned[k] = false;
+            if (fi < p.nf) setup_face(fi, verts, faces, tv, tex, lights, unr, recs, keys, vals, st, p, n_op, n_tr, head[k], binned[k]);
+        }
+        if (aggregate) {
+            // 1) count this round's surfaces per tile
+            #pragma unroll
+            for (int k = 0; k < SETUP_FPT; ++k) if (binned[k]) {
+                uint32_t min_x = head[k].bbox_x & 0xFFFF, max_x = head[k].bbox_x >> 16, min_y = head[k].bbox_y & 0xFFFF, max_y = head[k].bbox_y >> 16;
+                uint32_t tx0 = min_x / TILE_W, tx1 = (max_x - 1) / TILE_W, ty0 = min_y / TILE_H, ty1 = (max_y - 1) / TILE_H;
+                for (uint32_t ty = ty0; ty <= ty1; ++ty)
+                    for (uint32_t tx = tx0; tx <= tx1; ++tx) atomicAdd(&s_cnt[ty * p.tiles_x + tx], 1u);
             }
-            if (!p.ortho) {                                                       // :2380-2385
-                if (t1.w <= NEAR_PLANE || t2.w <= NEAR_PLANE || t3.w <= NEAR_PLANE) break;
+            __syncthreads();
+            // 2) one global atomic per touched tile reserves a contiguous slot range
+            for (uint32_t t = threadIdx.x; t < ntiles; t += blockDim.x) {
+                uint32_t c = s_cnt[t];
+                if (c) { uint32_t b = atomicAdd(&tile_count[t], c); s_base[t] = b; s_cnt[t] = 0; bmax = max(bmax, b + c); }
             }
-            float signed_area = (t2.x - t1.x) * (t3.y - t1.y) - (t3.x - t1.x) * (t2.y - t1.y);   // :2393
-            bool backface = signed_area <= 0.0f;
-            bool transparent;                                                     // :2403-2415
-            if (textured && tex_blend != B32_BLEND_OPAQUE) transparent = true;
-            else if (face_blend != B32_BLEND_OPAQUE) transparent = true;
-            else transparent = editor_alpha < 255;
-            if (p.fog_enabled && t1.w > p.fog_cull && t2.w > p.fog_cull && t3.w > p.fog_cull) break;   // :2421-2424
-            if (backface && !(!p.backface_cull || p.xray_mode)) break;            // :2445-2453
-
-            // vertex attributes (36-byte records: pos 0, uv 12, normal 20, rgba 32); v2/v3 swap :2455-2457
-            TVert s1 = t1, s2 = backface ? t3 : t2, s3 = backface ? t2 : t3;
-            const float* va = v0;
-            const float* vb = backface ? v2 : v1;
-            const float* vc = backface ? v1 : v2;
-            uint32_t c1 = reinterpret_cast<const uint32_t*>(va)[8], c2 = reinterpret_cast<const uint32_t*>(vb)[8], c3 = reinterpret_cast<const uint32_t*>(vc)[8];
-            if (p.fog_enabled) {                                                  // :2427-2436 (cam z of the same vertex)
-                c1 = fog_color(c1, s1.w, p); c2 = fog_color(c2, s2.w, p); c3 = fog_color(c3, s3.w, p);
+            __syncthreads();
+            // 3) hand out the slots
+            #pragma unroll
+            for (int k = 0; k < SETUP_FPT; ++k) if (binned[k]) {
+                uint32_t min_x = head[k].bbox_x & 0xFFFF, max_x = head[k].bbox_x >> 16, min_y = head[k].bbox_y & 0xFFFF, max_y = head[k].bbox_y >> 16;
+                uint32_t tx0 = min_x / TILE_W, tx1 = (max_x - 1) / TILE_W, ty0 = min_y / TILE_H, ty1 = (max_y - 1) / TILE_H;
+                for (uint32_t ty = ty0; ty <= ty1; ++ty)
+                    for (uint32_t tx = tx0; tx <= tx1; ++tx) {
+                        uint32_t t = ty * p.tiles_x + tx;
+                        uint32_t slot = s_base[t] + atomicAdd(&s_cnt[t], 1u);
+                        if (slot < p.bin_cap) bins[(size_t)t * p.bin_cap + slot] = head[k];
+                    }
             }
-
-            SurfRec r;
-            uint32_t blend_mode = textured ? tex_blend : face_blend;               // :1450-1452
-            uint32_t flags = blend_mode | (black_tr ? SF_BLACK_TR : 0) | (textured ? SF_TEXTURED : 0) |
-                             (transparent ? SF_TRANSPARENT : 0) | (editor_alpha << 8) | ((textured ? tex_id : 0xFFFFu) << 16);
-            bool needs_dither = p.dithering && (p.shading == B32_SHADE_GOURAUD || textured || c1 != c2 || c2 != c3);   // :1487-1492
-            if (needs_dither) flags |= SF_DITHER;
-
-            // bounding box, render.rs:1455-1463
-            uint32_t min_x = f2u32sat(fmaxf(fminf(fminf(s1.x, s2.x), s3.x), 0.0f));
-            uint32_t max_x = f2u32sat(fminf(fmaxf(fmaxf(s1.x, s2.x), s3.x) + 1.0f, (float)p.width));
-            uint32_t min_y = f2u32sat(fmaxf(fminf(fminf(s1.y, s2.y), s3.y), 0.0f));
-            uint32_t max_y = f2u32sat(fminf(fmaxf(fmaxf(s1.y, s2.y), s3.y) + 1.0f, (float)p.height));
-            bool empty = min_x >= max_x || min_y >= max_y;
-            float area = (s2.y - s3.y) * (s1.x - s3.x) + (s3.x - s2.x) * (s1.y - s3.y);     // :1500
-            if (fabsf(area) < 0.00001f) empty = true;                                      // :1501-1503
-            if (empty) { min_x = max_x = min_y = max_y = 0; }
-            r.inv_area = 1.0f / area;
-            r.a0 = s2.y - s3.y; r.b0 = s3.x - s2.x; r.a1 = s3.y - s1.y; r.b1 = s1.x - s3.x;   // :1507-1510
-            float start_x = (float)min_x, start_y = (float)min_y;
-            r.w0s = r.a0 * (start_x - s3.x) + r.b0 * (start_y - s3.y);                      // :1517-1518
-            r.w1s = r.a1 * (start_x - s3.x) + r.b1 * (start_y - s3.y);
-            r.bbox_x = min_x | (max_x << 16);
-            r.bbox_y = min_y | (max_y << 16);
-            // incremental stepping == closed form when everything is an integer below 2^23
-            {
-                float nx = (float)(max_x - min_x), ny = (float)(max_y - min_y);
-                float m0 = fabsf(r.w0s) + ny * fabsf(r.b0) + nx * fabsf(r.a0);
-                float m1 = fabsf(r.w1s) + ny * fabsf(r.b1) + nx * fabsf(r.a1);
-                bool ints = is_integral(r.a0) && is_integral(r.b0) && is_integral(r.a1) && is_integral(r.b1) &&
-                            is_integral(r.w0s) && is_integral(r.w1s);
-                if (ints && m0 < 8388608.0f && m1 < 8388608.0f) flags |= SF_FAST_EDGE;
-            }
-            r.iz1 = 1.0f / s1.z; r.iz2 = 1.0f / s2.z; r.iz3 = 1.0f / s3.z;                  // :1546-1548
-            r.u1 = va[3]; r.v1 = va[4]; r.u2 = vb[3]; r.v2 = vb[4]; r.u3 = vc[3]; r.v3 = vc[4];
-            r.vc1 = c1 & 0xFFFFFF; r.vc2 = c2 & 0xFFFFFF; r.vc3 = c3 & 0xFFFFFF;
-            for (int k = 0; k < 9; ++k) r.sh[k] = 1.0f;
-            if (!empty && p.shading != B32_SHADE_NONE) {
-                V3 w1{va[0], va[1], va[2]}, w2{vb[0], vb[1], vb[2]}, w3{vc[0], vc[1], vc[2]};
-                V3 n1{va[5], va[6], va[7]}, n2{vb[5], vb[6], vb[7]}, n3{vc[5], vc[6], vc[7]};
-                if (backface) {                                                             // wn.scale(-1.0) :2464-2466
-                    n1 = V3{n1.x * -1.0f, n1.y * -1.0f, n1.z * -1.0f}; n2 = V3{n2.x * -1.0f, n2.y * -1.0f, n2.z * -1.0f};
-                    n3 = V3{n3.x * -1.0f, n3.y * -1.0f, n3.z * -1.0f};
-                }
-                if (p.shading == B32_SHADE_FLAT) {                                          // :1466-1472
-                    const float third = 1.0f / 3.0f;
-                    V3 c{((w1.x + w2.x) + w3.x) * third, ((w1.y + w2.y) + w3.y) * third, ((w1.z + w2.z) + w3.z) * third};
-                    V3 n = normalize3(V3{((n1.x + n2.x) + n3.x) * third, ((n1.y + n2.y) + n3.y) * third, ((n1.z + n2.z) + n3.z) * third});
-                    shade_multi_light_color(n, c, lights, p.n_lights, p.ambient, r.sh);
-                } else {                                                                    // :1475-1483
-                    shade_multi_light_color(n1, w1, lights, p.n_lights, p.ambient, r.sh);
-                    shade_multi_light_color(n2, w2, lights, p.n_lights, p.ambient, r.sh + 3);
-                    shade_multi_light_color(n3, w3, lights, p.n_lights, p.ambient, r.sh + 6);
-                }
-            }
-            r.flags = flags;
-            r._pad = 0;
-            recs[fi] = r;
-
-            cls = transparent ? 1u : 0u;
-            float center_z = (s1.z + s2.z + s3.z) / 3.0f;                                   // :2529
-            bool sorted = transparent || !p.use_zbuffer;                                    // :2527, :2536
-            if (sorted) {
-                if (center_z != center_z) { if (transparent) st->nan_transp = 1; else st->nan_opaque = 1; }
-                dkey = depth_key_desc(center_z);
-            }
-            if (transparent) ++n_tr; else ++n_op;
-
-            // pass-1 surfaces go straight into their screen tiles' bins (any order; see file header)
-            if (!transparent && !p.xray_mode && !empty) {
-                BinHead h{r.bbox_x, r.bbox_y, dkey, fi};
+            __syncthreads();
+            for (uint32_t t = threadIdx.x; t < ntiles; t += blockDim.x) s_cnt[t] = 0;
+            __syncthreads();
+        } else {
+            #pragma unroll
+            for (int k = 0; k < SETUP_FPT; ++k) if (binned[k]) {
+                uint32_t min_x = head[k].bbox_x & 0xFFFF, max_x = head[k].bbox_x >> 16, min_y = head[k].bbox_y & 0xFFFF, max_y = head[k].bbox_y >> 16;
                 uint32_t tx0 = min_x / TILE_W, tx1 = (max_x - 1) / TILE_W, ty0 = min_y / TILE_H, ty1 = (max_y - 1) / TILE_H;
                 for (uint32_t ty = ty0; ty <= ty1; ++ty)
                     for (uint32_t tx = tx0; tx <= tx1; ++tx) {
                         uint32_t t = ty * p.tiles_x + tx;
                         uint32_t slot = atomicAdd(&tile_count[t], 1u);
-                        if (slot < p.bin_cap) bins[(size_t)t * p.bin_cap + slot] = h;
+                        if (slot < p.bin_cap) bins[(size_t)t * p.bin_cap + slot] = head[k];
                         bmax = max(bmax, slot + 1);
                     }
             }
-        } while (0);
-        keys[fi] = ((uint64_t)cls << 32) | dkey;
-        vals[fi] = fi;
+        }
     }
     // per-warp aggregated counters
     for (int o = 16; o > 0; o >>= 1) {
@@ -402,13 +486,24 @@ __device__ __forceinline__ bool shade(const SurfRec& r, uint32_t x, uint32_t y, 
 // =================================================================================================
 // k_fill_opaque — pass 1, order-free
 // =================================================================================================
-constexpr int OP_STAGE = 8;     // surface records staged per warp per step (8 x 128 B)
+// One CTA per 16x16 screen tile, one warp per 8x4 pixel block, one lane per pixel.
+//   1. the tile's bin (<= OP_SORT_MAX entries) is sorted in shared memory by the walk key: painter's
+//      mode = nearest (last drawn) first, z-buffer mode = smallest depth lower bound first.  The sort
+//      is an efficiency device only: the per-pixel winner rule below is exact for ANY order, ties and
+//      all, so bins larger than OP_SORT_MAX are simply walked unsorted.
+//   2. every warp walks the list 32 entries at a time: lanes first act as entry filters (bbox vs the
+//      warp's block, priority / depth bound vs the block's weakest pixel), survivors are compacted,
+//      their 128-byte records staged in shared memory, then lanes act as pixels.
+//   3. the walk stops as soon as no later entry can change any pixel of the block.
+constexpr int OP_STAGE = 8;          // surface records staged per warp per step (8 x 128 B)
+constexpr int OP_SORT_MAX = 2048;    // bin entries sortable in shared memory (16 KB of keys)
 
 __global__ void __launch_bounds__(FILL_THREADS)
 k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins, const uint32_t* __restrict__ tile_count,
               const TexDev* __restrict__ tex, const uint16_t* __restrict__ texels,
               uint32_t* __restrict__ fb_rgba, float* __restrict__ fb_z, const CallState* __restrict__ st,
               uint32_t* __restrict__ sticky, CallParams p) {
+    __shared__ uint64_t s_key[OP_SORT_MAX];                 // (walk key << 32) | slot in the bin
     __shared__ BinHead s_head[FILL_THREADS / 32][32];
     __shared__ SurfRec s_rec[FILL_THREADS / 32][OP_STAGE];
     {
@@ -422,13 +517,36 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
     const uint32_t n = tile_count[tile];
     if (n == 0) return;
     const BinHead* bin = bins + (size_t)tile * p.bin_cap;
+
+    // ---- 1. sort the bin by walk key, descending (bitonic, all 256 threads) -------------------------
+    const bool sorted = n <= OP_SORT_MAX;
+    if (sorted) {
+        uint32_t m = 32;
+        while (m < n) m <<= 1;
+        for (uint32_t i = threadIdx.x; i < m; i += FILL_THREADS)
+            s_key[i] = i < n ? (((uint64_t)bin[i].key << 32) | i) : 0ull;       // padding sorts last
+        __syncthreads();
+        for (uint32_t k = 2; k <= m; k <<= 1)
+            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                for (uint32_t i = threadIdx.x; i < m; i += FILL_THREADS) {
+                    uint32_t l = i ^ j;
+                    if (l > i) {
+                        uint64_t a = s_key[i], b = s_key[l];
+                        bool desc = (i & k) == 0;
+                        if ((a < b) == desc) { s_key[i] = b; s_key[l] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+    }
+
     const uint32_t tx = tile % p.tiles_x, ty = tile / p.tiles_x;
     // thread -> pixel: each warp owns an 8x4 block of the 16x16 tile
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bx0 = tx * TILE_W + (warp & 1) * 8, by0 = ty * TILE_H + (warp >> 1) * 4;
     const uint32_t x = bx0 + (lane & 7), y = by0 + (lane >> 3);
     const bool valid = x < p.width && y < p.height;
-    if (bx0 >= p.width || by0 >= p.height) return;        // whole warp off-screen (warps never sync with each other)
+    if (bx0 >= p.width || by0 >= p.height) return;        // whole warp off-screen (no CTA-wide sync below)
     Pixel px{0, 0.0f};
     if (valid) { px.rgba = fb_rgba[y * p.width + x]; px.z = fb_z[y * p.width + x]; }
     const Pixel px0 = px;
@@ -440,20 +558,28 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
     SurfRec* my_recs = s_rec[warp];
 
     for (uint32_t base = 0; base < n; base += 32) {
-        // ---- filter 32 bin entries, one per lane -------------------------------------------------
+        // ---- what the weakest pixel of this block still accepts ----------------------------------------
+        uint64_t wmin = best;                              // painter's: smallest winner priority in the block
+        float wz = valid ? px.z : -INFINITY;               // z-buffer: largest depth in the block
+        for (int o = 16; o > 0; o >>= 1) {
+            uint64_t t = __shfl_xor_sync(0xFFFFFFFFu, wmin, o); wmin = t < wmin ? t : wmin;
+            wz = fmaxf(wz, __shfl_xor_sync(0xFFFFFFFFu, wz, o));
+        }
+        // ---- 3. early out: entries are in descending key order ------------------------------------------
+        if (sorted) {
+            uint32_t k0 = (uint32_t)(s_key[base] >> 32);                     // largest key still to come
+            if (!p.use_zbuffer) { if (wmin != 0 && k0 < (uint32_t)((wmin - 1) >> 32)) break; }
+            else if (k0 != 0xFFFFFFFFu && __uint_as_float(~k0) > wz) break;     // every later surface is behind every pixel
+        }
+        // ---- 2a. filter 32 bin entries, one per lane ------------------------------------------------------
         BinHead h{0, 0, 0, 0};
         bool cand = false;
         if (base + lane < n) {
-            h = bin[base + lane];
+            h = bin[sorted ? (uint32_t)s_key[base + lane] : base + lane];
             uint32_t min_x = h.bbox_x & 0xFFFF, max_x = h.bbox_x >> 16, min_y = h.bbox_y & 0xFFFF, max_y = h.bbox_y >> 16;
             cand = !(max_x <= bx0 || min_x >= bx0 + 8 || max_y <= by0 || min_y >= by0 + 4);
-        }
-        if (!p.use_zbuffer) {
-            // a surface that cannot beat the weakest pixel of this block cannot change anything
-            uint64_t wmin = best;
-            for (int o = 16; o > 0; o >>= 1) { uint64_t t = __shfl_xor_sync(0xFFFFFFFFu, wmin, o); wmin = t < wmin ? t : wmin; }
-            uint64_t prio = (((uint64_t)h.key << 32) | h.face) + 1;
-            cand = cand && prio > wmin;
+            if (!p.use_zbuffer) cand = cand && ((((uint64_t)h.key << 32) | h.face) + 1) > wmin;
+            else cand = cand && (h.key == 0xFFFFFFFFu || !(__uint_as_float(~h.key) > wz));
         }
         uint32_t mask = __ballot_sync(0xFFFFFFFFu, cand);
         if (mask == 0) continue;
@@ -461,7 +587,7 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
         __syncwarp();
         if (cand) my_heads[__popc(mask & ((1u << lane) - 1))] = h;
         __syncwarp();
-        // ---- survivors, OP_STAGE records at a time -------------------------------------------------
+        // ---- 2b. survivors, OP_STAGE records at a time --------------------------------------------------
         for (uint32_t s0 = 0; s0 < cnt; s0 += OP_STAGE) {
             uint32_t m = min((uint32_t)OP_STAGE, cnt - s0);
             __syncwarp();
@@ -719,7 +845,12 @@ void launch_setup(const LaunchCtx& L, const b32_vertex* verts, const b32_face* f
                   const LightDev* lights, SurfRec* recs, uint64_t* keys, uint32_t* vals, BinHead* bins, uint32_t* tile_count,
                   CallState* st, const CallParams& p) {
     if (p.nf == 0) return;
-    k_setup<<<grid_for(p.nf, 128, L.sms, 16), 128, 0, L.stream>>>(verts, faces, tv, tex, lights, L.unr_table, recs, keys, vals, bins, tile_count, st, p);
+    uint32_t ntiles = p.tiles_x * p.tiles_y;
+    size_t smem = ntiles <= (uint32_t)SETUP_MAX_TILES ? (size_t)ntiles * 8 : 0;
+    uint32_t per_round = SETUP_THREADS * SETUP_FPT;
+    uint32_t grid = (p.nf + per_round - 1) / per_round;
+    if (grid > L.sms * 4) grid = L.sms * 4;
+    k_setup<<<grid, SETUP_THREADS, smem, L.stream>>>(verts, faces, tv, tex, lights, L.unr_table, recs, keys, vals, bins, tile_count, st, p);
     ++*L.launches;
 }
 
