@@ -74,7 +74,7 @@ struct b32_ctx {
     DevBuf<uint32_t> vals, order, counts, offsets;
     DevBuf<uint32_t> ent_tile, ent_surf, ent_tile_sorted, ent_surf_sorted;
     DevBuf<uint32_t> tile_count, tile_start;
-    DevBuf<BinHead> bins;
+    DevBuf<BinHead> bins, heads;
     uint32_t bin_cap_hint = 0;
     std::vector<LightDev> lights_h;
     bool order_valid = false;
@@ -187,6 +187,7 @@ int ensure_work(b32_ctx* ctx, uint32_t nv, uint32_t nf) {
     CK(ctx->recs.reserve(m));
     CK(ctx->keys.reserve(m));
     CK(ctx->vals.reserve(m));
+    CK(ctx->heads.reserve(m));
     uint32_t ntiles = ((ctx->width + TILE_W - 1) / TILE_W) * ((ctx->height + TILE_H - 1) / TILE_H);
     CK(ctx->tile_count.reserve(std::max<uint32_t>(ntiles, 1)));
     CK(ctx->tile_start.reserve(std::max<uint32_t>(ntiles, 1)));
@@ -300,7 +301,7 @@ int render_device(b32_ctx* ctx, const b32_vertex* d_verts, uint32_t nv, const b3
         CK(cudaMemsetAsync(ctx->tile_count.p, 0, ntiles * sizeof(uint32_t), st));
         if (wait) CK(cudaEventRecord(ctx->ev[0], st));
         launch_setup(L, d_verts, d_faces, nullptr, ctx->texdesc.p, ctx->lights.p, ctx->recs.p, ctx->keys.p, ctx->vals.p,
-                     ctx->bins.p, ctx->tile_count.p, ctx->state, p);                          // TRANSFORM + CULL + setup + binning
+                     ctx->heads.p, ctx->bins.p, ctx->tile_count.p, ctx->state, p);                          // TRANSFORM + CULL + setup + binning
         if (wait) CK(cudaEventRecord(ctx->ev[1], st));
         launch_fill_opaque(L, ctx->recs.p, ctx->bins.p, ctx->tile_count.p, ctx->texdesc.p, ctx->texels.p,
                            ctx->fb_rgba.p, ctx->fb_z.p, ctx->state, ctx->sticky, p);          // DRAW, pass 1
@@ -378,7 +379,7 @@ void b32_ctx_destroy(b32_ctx* ctx) {
     ctx->fb_rgba.release(); ctx->fb_z.release(); ctx->texels.release(); ctx->texdesc.release(); ctx->verts.release(); ctx->faces.release();
     ctx->tv.release(); ctx->recs.release(); ctx->keys.release(); ctx->keys_sorted.release(); ctx->vals.release(); ctx->order.release();
     ctx->counts.release(); ctx->offsets.release(); ctx->ent_tile.release(); ctx->ent_surf.release(); ctx->ent_tile_sorted.release();
-    ctx->ent_surf_sorted.release(); ctx->tile_count.release(); ctx->tile_start.release(); ctx->bins.release(); ctx->temp.release(); ctx->lights.release(); ctx->dbg.release();
+    ctx->ent_surf_sorted.release(); ctx->tile_count.release(); ctx->tile_start.release(); ctx->bins.release(); ctx->heads.release(); ctx->temp.release(); ctx->lights.release(); ctx->dbg.release();
     if (ctx->unr_table) cudaFree(ctx->unr_table);
     if (ctx->state) cudaFree(ctx->state);
     if (ctx->sticky) cudaFree(ctx->sticky);

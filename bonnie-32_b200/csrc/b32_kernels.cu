@@ -153,17 +153,10 @@ __device__ __forceinline__ uint32_t fog_color(uint32_t c, float z, const CallPar
 
 __device__ __forceinline__ bool is_integral(float x) { return truncf(x) == x; }
 
-// Up to SETUP_FPT faces per thread and round.  `tv` (pre-transformed vertices) may be NULL: then the
-// three vertices are transformed here (no intermediate vertex buffer: each vertex record is read
-// once per use).
-//
-// Binning of pass-1 surfaces into per-tile bins is aggregated per block: same-address global atomics
-// serialise in the L2 (hot tiles get hundreds of hits), so a block first counts its surfaces per tile
-// in shared memory, reserves one contiguous range per touched tile with ONE global atomic, and then
-// hands out slots from shared memory.
-constexpr int SETUP_THREADS = 256;
-constexpr int SETUP_FPT = 4;                 // faces per thread per round  => 1024 faces per block round
-constexpr int SETUP_MAX_TILES = 4096;        // shared-memory aggregation up to this many tiles (2 x 16 KB)
+// One thread per face.  `tv` (pre-transformed vertices) may be NULL: then the three vertices are
+// transformed here (no intermediate vertex buffer: each vertex record is read once per use).
+// Pass-1 surfaces also emit a 16-byte BinHead (heads[face]); k_bin_opaque scatters those to tiles.
+constexpr int SETUP_THREADS = 128;
 
 __device__ __forceinline__ void setup_face(uint32_t fi, const b32_vertex* __restrict__ verts, const b32_face* __restrict__ faces,
                                            const TVert* __restrict__ tv, const TexDev* __restrict__ tex,
@@ -308,50 +301,77 @@ __global__ void __launch_bounds__(SETUP_THREADS)
 k_setup(const b32_vertex* __restrict__ verts, const b32_face* __restrict__ faces, const TVert* __restrict__ tv,
         const TexDev* __restrict__ tex, const LightDev* __restrict__ lights, const uint8_t* __restrict__ unr_table_g,
         SurfRec* __restrict__ recs, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
-        BinHead* __restrict__ bins, uint32_t* __restrict__ tile_count,
-        CallState* __restrict__ st, CallParams p) {
+        BinHead* __restrict__ heads, CallState* __restrict__ st, CallParams p) {
     __shared__ uint8_t unr[260];
-    extern __shared__ uint32_t s_tiles[];            // [ntiles] counts/cursors, [ntiles] bases (when ntiles <= SETUP_MAX_TILES)
+    for (int i = threadIdx.x; i < 257; i += blockDim.x) unr[i] = unr_table_g[i];
+    __syncthreads();
+    uint32_t n_op = 0, n_tr = 0;
+    for (uint32_t fi = blockIdx.x * blockDim.x + threadIdx.x; fi < p.nf; fi += gridDim.x * blockDim.x) {
+        BinHead head{0, 0, 0, fi};            // bbox 0 = not binned
+        bool binned;
+        setup_face(fi, verts, faces, tv, tex, lights, unr, recs, keys, vals, st, p, n_op, n_tr, head, binned);
+        heads[fi] = head;
+    }
+    for (int o = 16; o > 0; o >>= 1) { n_op += __shfl_xor_sync(0xFFFFFFFFu, n_op, o); n_tr += __shfl_xor_sync(0xFFFFFFFFu, n_tr, o); }
+    if ((threadIdx.x & 31) == 0) {
+        if (n_op) atomicAdd(&st->n_opaque, n_op);
+        if (n_tr) atomicAdd(&st->n_transp, n_tr);
+    }
+}
+
+// =================================================================================================
+// k_bin_opaque — scatter pass-1 surfaces into per-tile bins (any order)
+// =================================================================================================
+// Same-address global atomics from different warps are serviced one by one in the L2, and a hot tile
+// receives hundreds of surfaces, so the binning is aggregated: a block takes BIN_FPB consecutive
+// faces, counts them per tile in shared memory, reserves one contiguous slot range per touched tile
+// with ONE global atomic, then hands out slots from shared memory.
+constexpr int BIN_THREADS = 256;
+constexpr int BIN_FPT = 4;                      // faces per thread  => 1024 faces per block
+constexpr int BIN_MAX_TILES = 4096;             // shared-memory aggregation up to this many tiles (2 x 16 KB)
+
+__device__ __forceinline__ void head_tiles(const BinHead& h, uint32_t& tx0, uint32_t& tx1, uint32_t& ty0, uint32_t& ty1) {
+    uint32_t min_x = h.bbox_x & 0xFFFF, max_x = h.bbox_x >> 16, min_y = h.bbox_y & 0xFFFF, max_y = h.bbox_y >> 16;
+    tx0 = min_x / TILE_W; tx1 = (max_x - 1) / TILE_W; ty0 = min_y / TILE_H; ty1 = (max_y - 1) / TILE_H;
+}
+
+__global__ void __launch_bounds__(BIN_THREADS)
+k_bin_opaque(const BinHead* __restrict__ heads, BinHead* __restrict__ bins, uint32_t* __restrict__ tile_count,
+             CallState* __restrict__ st, CallParams p) {
+    extern __shared__ uint32_t s_tiles[];            // [ntiles] counts/cursors, [ntiles] bases (when ntiles <= BIN_MAX_TILES)
     const uint32_t ntiles = p.tiles_x * p.tiles_y;
-    const bool aggregate = ntiles <= SETUP_MAX_TILES;
+    const bool aggregate = ntiles <= BIN_MAX_TILES;
     uint32_t* s_cnt = s_tiles;
     uint32_t* s_base = s_tiles + ntiles;
-    for (int i = threadIdx.x; i < 257; i += blockDim.x) unr[i] = unr_table_g[i];
+    if (p.xray_mode) return;
     if (aggregate) for (uint32_t i = threadIdx.x; i < ntiles; i += blockDim.x) s_cnt[i] = 0;
     __syncthreads();
 
-    uint32_t n_op = 0, n_tr = 0, bmax = 0;
-    const uint32_t per_round = SETUP_THREADS * SETUP_FPT;
+    uint32_t bmax = 0;
+    const uint32_t per_round = BIN_THREADS * BIN_FPT;
     for (uint32_t base = blockIdx.x * per_round; base < p.nf; base += gridDim.x * per_round) {
-        BinHead head[SETUP_FPT];
-        bool binned[SETUP_FPT];
+        BinHead head[BIN_FPT];
         #pragma unroll
-        for (int k = 0; k < SETUP_FPT; ++k) {
-            uint32_t fi = base + k * SETUP_THREADS + threadIdx.x;
-            binned[k] = false;
-            if (fi < p.nf) setup_face(fi, verts, faces, tv, tex, lights, unr, recs, keys, vals, st, p, n_op, n_tr, head[k], binned[k]);
+        for (int k = 0; k < BIN_FPT; ++k) {
+            uint32_t fi = base + k * BIN_THREADS + threadIdx.x;
+            head[k] = fi < p.nf ? heads[fi] : BinHead{0, 0, 0, 0};
         }
         if (aggregate) {
-            // 1) count this round's surfaces per tile
             #pragma unroll
-            for (int k = 0; k < SETUP_FPT; ++k) if (binned[k]) {
-                uint32_t min_x = head[k].bbox_x & 0xFFFF, max_x = head[k].bbox_x >> 16, min_y = head[k].bbox_y & 0xFFFF, max_y = head[k].bbox_y >> 16;
-                uint32_t tx0 = min_x / TILE_W, tx1 = (max_x - 1) / TILE_W, ty0 = min_y / TILE_H, ty1 = (max_y - 1) / TILE_H;
+            for (int k = 0; k < BIN_FPT; ++k) if (head[k].bbox_x) {                      // 1) count per tile
+                uint32_t tx0, tx1, ty0, ty1; head_tiles(head[k], tx0, tx1, ty0, ty1);
                 for (uint32_t ty = ty0; ty <= ty1; ++ty)
                     for (uint32_t tx = tx0; tx <= tx1; ++tx) atomicAdd(&s_cnt[ty * p.tiles_x + tx], 1u);
             }
             __syncthreads();
-            // 2) one global atomic per touched tile reserves a contiguous slot range
-            for (uint32_t t = threadIdx.x; t < ntiles; t += blockDim.x) {
+            for (uint32_t t = threadIdx.x; t < ntiles; t += blockDim.x) {             // 2) reserve ranges
                 uint32_t c = s_cnt[t];
                 if (c) { uint32_t b = atomicAdd(&tile_count[t], c); s_base[t] = b; s_cnt[t] = 0; bmax = max(bmax, b + c); }
             }
             __syncthreads();
-            // 3) hand out the slots
             #pragma unroll
-            for (int k = 0; k < SETUP_FPT; ++k) if (binned[k]) {
-                uint32_t min_x = head[k].bbox_x & 0xFFFF, max_x = head[k].bbox_x >> 16, min_y = head[k].bbox_y & 0xFFFF, max_y = head[k].bbox_y >> 16;
-                uint32_t tx0 = min_x / TILE_W, tx1 = (max_x - 1) / TILE_W, ty0 = min_y / TILE_H, ty1 = (max_y - 1) / TILE_H;
+            for (int k = 0; k < BIN_FPT; ++k) if (head[k].bbox_x) {                      // 3) hand out slots
+                uint32_t tx0, tx1, ty0, ty1; head_tiles(head[k], tx0, tx1, ty0, ty1);
                 for (uint32_t ty = ty0; ty <= ty1; ++ty)
                     for (uint32_t tx = tx0; tx <= tx1; ++tx) {
                         uint32_t t = ty * p.tiles_x + tx;
@@ -364,9 +384,8 @@ k_setup(const b32_vertex* __restrict__ verts, const b32_face* __restrict__ faces
             __syncthreads();
         } else {
             #pragma unroll
-            for (int k = 0; k < SETUP_FPT; ++k) if (binned[k]) {
-                uint32_t min_x = head[k].bbox_x & 0xFFFF, max_x = head[k].bbox_x >> 16, min_y = head[k].bbox_y & 0xFFFF, max_y = head[k].bbox_y >> 16;
-                uint32_t tx0 = min_x / TILE_W, tx1 = (max_x - 1) / TILE_W, ty0 = min_y / TILE_H, ty1 = (max_y - 1) / TILE_H;
+            for (int k = 0; k < BIN_FPT; ++k) if (head[k].bbox_x) {
+                uint32_t tx0, tx1, ty0, ty1; head_tiles(head[k], tx0, tx1, ty0, ty1);
                 for (uint32_t ty = ty0; ty <= ty1; ++ty)
                     for (uint32_t tx = tx0; tx <= tx1; ++tx) {
                         uint32_t t = ty * p.tiles_x + tx;
@@ -377,16 +396,8 @@ k_setup(const b32_vertex* __restrict__ verts, const b32_face* __restrict__ faces
             }
         }
     }
-    // per-warp aggregated counters
-    for (int o = 16; o > 0; o >>= 1) {
-        n_op += __shfl_xor_sync(0xFFFFFFFFu, n_op, o); n_tr += __shfl_xor_sync(0xFFFFFFFFu, n_tr, o);
-        bmax = max(bmax, __shfl_xor_sync(0xFFFFFFFFu, bmax, o));
-    }
-    if ((threadIdx.x & 31) == 0) {
-        if (n_op) atomicAdd(&st->n_opaque, n_op);
-        if (n_tr) atomicAdd(&st->n_transp, n_tr);
-        if (bmax) { atomicMax(&st->bin_max, bmax); if (bmax > p.bin_cap) st->bin_overflow = 1; }
-    }
+    for (int o = 16; o > 0; o >>= 1) bmax = max(bmax, __shfl_xor_sync(0xFFFFFFFFu, bmax, o));
+    if ((threadIdx.x & 31) == 0 && bmax) { atomicMax(&st->bin_max, bmax); if (bmax > p.bin_cap) st->bin_overflow = 1; }
 }
 
 // =================================================================================================
@@ -503,7 +514,10 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
               const TexDev* __restrict__ tex, const uint16_t* __restrict__ texels,
               uint32_t* __restrict__ fb_rgba, float* __restrict__ fb_z, const CallState* __restrict__ st,
               uint32_t* __restrict__ sticky, CallParams p) {
-    __shared__ uint64_t s_key[OP_SORT_MAX];                 // (walk key << 32) | slot in the bin
+    __shared__ uint64_t s_key[OP_SORT_MAX];                 // (walk key << 32) | slot in the bin, bucket-ordered
+    __shared__ uint32_t s_hist[256];
+    __shared__ uint32_t s_wsum[FILL_THREADS / 32];
+    __shared__ uint32_t s_minmax[2];
     __shared__ BinHead s_head[FILL_THREADS / 32][32];
     __shared__ SurfRec s_rec[FILL_THREADS / 32][OP_STAGE];
     {
@@ -518,26 +532,56 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
     if (n == 0) return;
     const BinHead* bin = bins + (size_t)tile * p.bin_cap;
 
-    // ---- 1. sort the bin by walk key, descending (bitonic, all 256 threads) -------------------------
+    // ---- 1. order the bin by walk key, descending: one counting-sort pass into 256 key buckets ---------
+    // (within a bucket the order is arbitrary; the early-out below uses the bucket's upper key bound)
     const bool sorted = n <= OP_SORT_MAX;
+    uint32_t kmin = 0, shift = 0;
     if (sorted) {
-        uint32_t m = 32;
-        while (m < n) m <<= 1;
-        for (uint32_t i = threadIdx.x; i < m; i += FILL_THREADS)
-            s_key[i] = i < n ? (((uint64_t)bin[i].key << 32) | i) : 0ull;       // padding sorts last
+        constexpr int KPT = OP_SORT_MAX / FILL_THREADS;            // keys per thread
+        uint32_t kk[KPT];
+        uint32_t lo = 0xFFFFFFFFu, hi = 0;
+        #pragma unroll
+        for (int q = 0; q < KPT; ++q) {
+            uint32_t i = q * FILL_THREADS + threadIdx.x;
+            kk[q] = i < n ? bin[i].key : 0xFFFFFFFFu;
+            if (kk[q] != 0xFFFFFFFFu) { lo = min(lo, kk[q]); hi = max(hi, kk[q]); }   // 0xFFFFFFFF = "never cull": bucket 0
+        }
+        if (threadIdx.x < 256) s_hist[threadIdx.x] = 0;
+        if (threadIdx.x == 0) { s_minmax[0] = 0xFFFFFFFFu; s_minmax[1] = 0; }
+        for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, o)); hi = max(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, o)); }
         __syncthreads();
-        for (uint32_t k = 2; k <= m; k <<= 1)
-            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-                for (uint32_t i = threadIdx.x; i < m; i += FILL_THREADS) {
-                    uint32_t l = i ^ j;
-                    if (l > i) {
-                        uint64_t a = s_key[i], b = s_key[l];
-                        bool desc = (i & k) == 0;
-                        if ((a < b) == desc) { s_key[i] = b; s_key[l] = a; }
-                    }
-                }
-                __syncthreads();
+        if ((threadIdx.x & 31) == 0) { atomicMin(&s_minmax[0], lo); atomicMax(&s_minmax[1], hi); }
+        __syncthreads();
+        kmin = s_minmax[0];
+        uint32_t kmax = s_minmax[1];
+        if (kmin > kmax) { kmin = 0; kmax = 0; }
+        uint32_t range = kmax - kmin;
+        shift = range >= 256 ? (32 - __clz(range)) - 8 : 0;         // (range >> shift) <= 255
+        #pragma unroll
+        for (int q = 0; q < KPT; ++q) {
+            uint32_t i = q * FILL_THREADS + threadIdx.x;
+            if (i < n) atomicAdd(&s_hist[kk[q] == 0xFFFFFFFFu ? 0 : 255 - ((kk[q] - kmin) >> shift)], 1u);
+        }
+        __syncthreads();
+        {   // exclusive scan of the 256 bucket counts
+            uint32_t v = s_hist[threadIdx.x], xs = v;
+            for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, xs, o); if ((threadIdx.x & 31) >= o) xs += t; }
+            if ((threadIdx.x & 31) == 31) s_wsum[threadIdx.x >> 5] = xs;
+            __syncthreads();
+            uint32_t pre = 0;
+            for (uint32_t w = 0; w < (threadIdx.x >> 5); ++w) pre += s_wsum[w];
+            s_hist[threadIdx.x] = pre + xs - v;
+        }
+        __syncthreads();
+        #pragma unroll
+        for (int q = 0; q < KPT; ++q) {
+            uint32_t i = q * FILL_THREADS + threadIdx.x;
+            if (i < n) {
+                uint32_t pos = atomicAdd(&s_hist[kk[q] == 0xFFFFFFFFu ? 0 : 255 - ((kk[q] - kmin) >> shift)], 1u);
+                s_key[pos] = ((uint64_t)kk[q] << 32) | i;
             }
+        }
+        __syncthreads();
     }
 
     const uint32_t tx = tile % p.tiles_x, ty = tile / p.tiles_x;
@@ -567,9 +611,14 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
         }
         // ---- 3. early out: entries are in descending key order ------------------------------------------
         if (sorted) {
-            uint32_t k0 = (uint32_t)(s_key[base] >> 32);                     // largest key still to come
-            if (!p.use_zbuffer) { if (wmin != 0 && k0 < (uint32_t)((wmin - 1) >> 32)) break; }
-            else if (k0 != 0xFFFFFFFFu && __uint_as_float(~k0) > wz) break;     // every later surface is behind every pixel
+            uint32_t k0 = (uint32_t)(s_key[base] >> 32);
+            if (k0 != 0xFFFFFFFFu) {
+                // upper bound of every key still to come = top of k0's bucket
+                uint64_t ub64 = (uint64_t)kmin + (((uint64_t)((k0 - kmin) >> shift) + 1) << shift) - 1;
+                uint32_t ub = ub64 > 0xFFFFFFFEull ? 0xFFFFFFFEu : (uint32_t)ub64;
+                if (!p.use_zbuffer) { if (wmin != 0 && ub < (uint32_t)((wmin - 1) >> 32)) break; }
+                else if (__uint_as_float(~ub) > wz) break;                   // every later surface is behind every pixel
+            }
         }
         // ---- 2a. filter 32 bin entries, one per lane ------------------------------------------------------
         BinHead h{0, 0, 0, 0};
@@ -842,15 +891,18 @@ void launch_transform(const LaunchCtx& L, const b32_vertex* verts, TVert* out, f
 }
 
 void launch_setup(const LaunchCtx& L, const b32_vertex* verts, const b32_face* faces, const TVert* tv, const TexDev* tex,
-                  const LightDev* lights, SurfRec* recs, uint64_t* keys, uint32_t* vals, BinHead* bins, uint32_t* tile_count,
-                  CallState* st, const CallParams& p) {
+                  const LightDev* lights, SurfRec* recs, uint64_t* keys, uint32_t* vals, BinHead* heads, BinHead* bins,
+                  uint32_t* tile_count, CallState* st, const CallParams& p) {
     if (p.nf == 0) return;
+    k_setup<<<grid_for(p.nf, SETUP_THREADS, L.sms, 16), SETUP_THREADS, 0, L.stream>>>(verts, faces, tv, tex, lights, L.unr_table, recs, keys, vals, heads, st, p);
+    ++*L.launches;
+    if (p.xray_mode) return;
     uint32_t ntiles = p.tiles_x * p.tiles_y;
-    size_t smem = ntiles <= (uint32_t)SETUP_MAX_TILES ? (size_t)ntiles * 8 : 0;
-    uint32_t per_round = SETUP_THREADS * SETUP_FPT;
+    size_t smem = ntiles <= (uint32_t)BIN_MAX_TILES ? (size_t)ntiles * 8 : 0;
+    uint32_t per_round = BIN_THREADS * BIN_FPT;
     uint32_t grid = (p.nf + per_round - 1) / per_round;
     if (grid > L.sms * 4) grid = L.sms * 4;
-    k_setup<<<grid, SETUP_THREADS, smem, L.stream>>>(verts, faces, tv, tex, lights, L.unr_table, recs, keys, vals, bins, tile_count, st, p);
+    k_bin_opaque<<<grid, BIN_THREADS, smem, L.stream>>>(heads, bins, tile_count, st, p);
     ++*L.launches;
 }
 

@@ -22,8 +22,8 @@ size_t sort_temp_bytes(uint32_t max_faces, uint32_t max_entries);
 void launch_transform(const LaunchCtx& L, const b32_vertex* verts, TVert* out, float* dbg_cam, const CallParams& p);
 // tv == nullptr: vertices are transformed inside k_setup (fused path)
 void launch_setup(const LaunchCtx& L, const b32_vertex* verts, const b32_face* faces, const TVert* tv, const TexDev* tex,
-                  const LightDev* lights, SurfRec* recs, uint64_t* keys, uint32_t* vals, BinHead* bins, uint32_t* tile_count,
-                  CallState* st, const CallParams& p);
+                  const LightDev* lights, SurfRec* recs, uint64_t* keys, uint32_t* vals, BinHead* heads, BinHead* bins,
+                  uint32_t* tile_count, CallState* st, const CallParams& p);
 void launch_fill_opaque(const LaunchCtx& L, const SurfRec* recs, const BinHead* bins, const uint32_t* tile_count,
                         const TexDev* tex, const uint16_t* texels, uint32_t* fb_rgba, float* fb_z, const CallState* st,
                         uint32_t* sticky, const CallParams& p);
