@@ -1,0 +1,122 @@
+//! b32_shim.rs — drop-in replacement body for `render_mesh_15` that forwards to the CUDA library.
+//!
+//! NOT compiled in this repository's environment (no rustc); it is the reference-side binding a
+//! BONNIE-32 maintainer adds.  Put it at `src/rasterizer/b32_shim.rs`, add `mod b32_shim;` to
+//! `src/rasterizer/mod.rs`, and re-export `b32_shim::render_mesh_15` instead of
+//! `render::render_mesh_15` (mod.rs:63).  Link with `-lb32raster` (build.rs:
+//! `println!("cargo:rustc-link-lib=dylib=b32raster")`).
+//!
+//! Signature and semantics are those of `src/rasterizer/render.rs:2302-2310`.  Where the reference
+//! panics (bad vertex index, NaN sort key) this shim panics with the library's message.
+#![allow(non_camel_case_types)]
+use super::camera::Camera;
+use super::render::Framebuffer;
+use super::types::{BlendMode, Color, Face, LightType, RasterSettings, RasterTimings, ShadingMode, Texture15, Vertex};
+use std::os::raw::{c_char, c_int, c_void};
+
+#[repr(C)] #[derive(Clone, Copy)]
+pub struct b32_vertex { pos: [f32; 3], uv: [f32; 2], normal: [f32; 3], r: u8, g: u8, b: u8, blend: u8 }
+#[repr(C)] #[derive(Clone, Copy)]
+pub struct b32_face { v0: u32, v1: u32, v2: u32, flags: u32 }
+#[repr(C)] pub struct b32_camera { position: [f32; 3], basis_x: [f32; 3], basis_y: [f32; 3], basis_z: [f32; 3] }
+#[repr(C)] #[derive(Clone, Copy)]
+pub struct b32_light { kind: u32, position: [f32; 3], direction: [f32; 3], radius: f32, angle: f32, intensity: f32,
+                       r: u8, g: u8, b: u8, enabled: u8 }
+#[repr(C)] pub struct b32_settings {
+    affine_textures: u8, use_zbuffer: u8, shading: u8, backface_cull: u8, backface_wireframe: u8, dithering: u8,
+    wireframe_overlay: u8, use_rgb555: u8, use_fixed_point: u8, xray_mode: u8, ortho_enabled: u8, _pad: u8,
+    ambient: f32, ortho_zoom: f32, ortho_center_x: f32, ortho_center_y: f32, n_lights: u32, lights: *const b32_light }
+#[repr(C)] pub struct b32_fog { start: f32, falloff: f32, cull_distance: f32, r: u8, g: u8, b: u8, blend: u8 }
+#[repr(C)] #[derive(Default)]
+pub struct b32_timings { transform_ms: f32, fog_ms: f32, cull_ms: f32, sort_ms: f32, draw_ms: f32, wireframe_ms: f32,
+                         triangles_drawn: u32 }
+#[repr(C)] pub struct b32_tex_desc { width: u32, height: u32, format: u32, blend_mode: u32, pixels: *const c_void,
+                                     clut: *const u16, clut_len: u32 }
+pub enum b32_ctx {}
+
+extern "C" {
+    fn b32_ctx_create(device: c_int, out: *mut *mut b32_ctx) -> c_int;
+    fn b32_last_error(ctx: *const b32_ctx) -> *const c_char;
+    fn b32_fb_resize(ctx: *mut b32_ctx, w: u32, h: u32) -> c_int;
+    fn b32_fb_upload(ctx: *mut b32_ctx, rgba: *const u8, z: *const f32) -> c_int;
+    fn b32_fb_download(ctx: *mut b32_ctx, rgba: *mut u8, z: *mut f32) -> c_int;
+    fn b32_textures_set(ctx: *mut b32_ctx, descs: *const b32_tex_desc, n: u32) -> c_int;
+    fn b32_render_mesh_15(ctx: *mut b32_ctx, v: *const b32_vertex, nv: u32, f: *const b32_face, nf: u32,
+                          cam: *const b32_camera, s: *const b32_settings, fog: *const b32_fog,
+                          out: *mut b32_timings) -> c_int;
+}
+
+fn blend_u8(b: BlendMode) -> u8 { b as u8 }   // declaration order = B32_BLEND_* (types.rs:1378-1388)
+
+thread_local! {
+    // one context per (main) thread: the reference renders on the macroquad main thread only
+    static CTX: *mut b32_ctx = unsafe {
+        let mut c = std::ptr::null_mut();
+        assert_eq!(b32_ctx_create(0, &mut c), 0, "b32_ctx_create failed: no CUDA device (there is no CPU fallback)");
+        c
+    };
+    static TEX_GEN: std::cell::Cell<(usize, usize)> = std::cell::Cell::new((0, 0));
+}
+
+fn check(ctx: *mut b32_ctx, rc: c_int) {
+    if rc != 0 {
+        let msg = unsafe { std::ffi::CStr::from_ptr(b32_last_error(ctx)) }.to_string_lossy().into_owned();
+        panic!("b32 rasterizer error {}: {}", rc, msg);   // the reference panics in the same situations
+    }
+}
+
+pub fn render_mesh_15(fb: &mut Framebuffer, vertices: &[Vertex], faces: &[Face], textures: &[Texture15],
+                      camera: &Camera, settings: &RasterSettings, fog: Option<(f32, f32, f32, Color)>) -> RasterTimings {
+    CTX.with(|&ctx| unsafe {
+        // --- marshal &[Vertex] / &[Face] into the 36 B / 16 B POD records (include/b32_raster.h) ---
+        let v: Vec<b32_vertex> = vertices.iter().map(|v| b32_vertex {
+            pos: [v.pos.x, v.pos.y, v.pos.z], uv: [v.uv.x, v.uv.y], normal: [v.normal.x, v.normal.y, v.normal.z],
+            r: v.color.r, g: v.color.g, b: v.color.b, blend: blend_u8(v.color.blend) }).collect();
+        let f: Vec<b32_face> = faces.iter().map(|f| {
+            let tex = match f.texture_id { Some(id) if id < 0xFFFF => id as u32, _ => 0xFFFF };
+            b32_face { v0: f.v0.min(u32::MAX as usize) as u32, v1: f.v1.min(u32::MAX as usize) as u32,
+                       v2: f.v2.min(u32::MAX as usize) as u32,
+                       flags: tex | ((blend_u8(f.blend_mode) as u32) << 16) | ((f.black_transparent as u32) << 19)
+                              | ((f.editor_alpha as u32) << 24) } }).collect();
+        // --- textures: re-upload only when the slice changed (cf. textures_15_cache_generation) ---
+        let key = (textures.as_ptr() as usize, textures.len());
+        if TEX_GEN.with(|g| g.replace(key)) != key {
+            let d: Vec<b32_tex_desc> = textures.iter().map(|t| b32_tex_desc {
+                width: t.width as u32, height: t.height as u32, format: 0, blend_mode: blend_u8(t.blend_mode) as u32,
+                pixels: t.pixels.as_ptr() as *const c_void, clut: std::ptr::null(), clut_len: 0 }).collect();
+            check(ctx, b32_textures_set(ctx, d.as_ptr(), d.len() as u32));
+        }
+        // --- settings ---
+        let lights: Vec<b32_light> = settings.lights.iter().map(|l| {
+            let (kind, position, direction, radius, angle) = match l.light_type {
+                LightType::Directional { direction: d } => (0, [0.0; 3], [d.x, d.y, d.z], 0.0, 0.0),
+                LightType::Point { position: p, radius } => (1, [p.x, p.y, p.z], [0.0; 3], radius, 0.0),
+                LightType::Spot { position: p, direction: d, angle, radius } => (2, [p.x, p.y, p.z], [d.x, d.y, d.z], radius, angle),
+            };
+            b32_light { kind, position, direction, radius, angle, intensity: l.intensity,
+                        r: l.color.r, g: l.color.g, b: l.color.b, enabled: l.enabled as u8 } }).collect();
+        let (oe, oz, ox, oy) = match &settings.ortho_projection { Some(o) => (1, o.zoom, o.center_x, o.center_y), None => (0, 0.0, 0.0, 0.0) };
+        let s = b32_settings {
+            affine_textures: settings.affine_textures as u8, use_zbuffer: settings.use_zbuffer as u8,
+            shading: match settings.shading { ShadingMode::None => 0, ShadingMode::Flat => 1, ShadingMode::Gouraud => 2 },
+            backface_cull: settings.backface_cull as u8, backface_wireframe: settings.backface_wireframe as u8,
+            dithering: settings.dithering as u8, wireframe_overlay: settings.wireframe_overlay as u8,
+            use_rgb555: settings.use_rgb555 as u8, use_fixed_point: settings.use_fixed_point as u8,
+            xray_mode: settings.xray_mode as u8, ortho_enabled: oe, _pad: 0, ambient: settings.ambient,
+            ortho_zoom: oz, ortho_center_x: ox, ortho_center_y: oy, n_lights: lights.len() as u32, lights: lights.as_ptr() };
+        let cam = b32_camera { position: [camera.position.x, camera.position.y, camera.position.z],
+            basis_x: [camera.basis_x.x, camera.basis_x.y, camera.basis_x.z],
+            basis_y: [camera.basis_y.x, camera.basis_y.y, camera.basis_y.z],
+            basis_z: [camera.basis_z.x, camera.basis_z.y, camera.basis_z.z] };
+        let fogc = fog.map(|(start, falloff, cull_distance, c)| b32_fog { start, falloff, cull_distance, r: c.r, g: c.g, b: c.b, blend: blend_u8(c.blend) });
+        // --- framebuffer: the host owns fb.pixels / fb.zbuffer between calls (clear, skybox, overlays) ---
+        check(ctx, b32_fb_resize(ctx, fb.width as u32, fb.height as u32));
+        check(ctx, b32_fb_upload(ctx, fb.pixels.as_ptr(), fb.zbuffer.as_ptr()));
+        let mut tm = b32_timings::default();
+        check(ctx, b32_render_mesh_15(ctx, v.as_ptr(), v.len() as u32, f.as_ptr(), f.len() as u32, &cam, &s,
+                                      fogc.as_ref().map_or(std::ptr::null(), |f| f as *const _), &mut tm));
+        check(ctx, b32_fb_download(ctx, fb.pixels.as_mut_ptr(), fb.zbuffer.as_mut_ptr()));
+        RasterTimings { transform_ms: tm.transform_ms, fog_ms: tm.fog_ms, cull_ms: tm.cull_ms, sort_ms: tm.sort_ms,
+                        draw_ms: tm.draw_ms, wireframe_ms: tm.wireframe_ms, triangles_drawn: tm.triangles_drawn }
+    })
+}
