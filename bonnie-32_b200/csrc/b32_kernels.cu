@@ -497,29 +497,35 @@ __device__ __forceinline__ bool shade(const SurfRec& r, uint32_t x, uint32_t y, 
 // =================================================================================================
 // k_fill_opaque — pass 1, order-free
 // =================================================================================================
-// One CTA per 16x16 screen tile, one warp per 8x4 pixel block, one lane per pixel.
-//   1. the tile's bin (<= OP_SORT_MAX entries) is sorted in shared memory by the walk key: painter's
-//      mode = nearest (last drawn) first, z-buffer mode = smallest depth lower bound first.  The sort
-//      is an efficiency device only: the per-pixel winner rule below is exact for ANY order, ties and
-//      all, so bins larger than OP_SORT_MAX are simply walked unsorted.
+// One CTA per 16x16 screen tile; one warp per 4x4 pixel block; a pixel is owned by TWO lanes (lane
+// and lane+16) that evaluate two different surfaces at the same time and merge their winners — the
+// winner rule is associative, so the merge is exact.  The kernel is latency-bound (long dependent
+// f32 chains, few warps per tile), hence small blocks (more warps, shorter walks) and two surfaces
+// in flight per warp.
+//   1. the tile's bin (<= OP_SORT_MAX entries) is ordered in shared memory by the walk key with one
+//      counting-sort pass: painter's mode = nearest (last drawn) first, z-buffer mode = smallest depth
+//      lower bound first.  The order is an efficiency device only: the per-pixel winner rule is exact
+//      for ANY order, ties and all, so bins larger than OP_SORT_MAX are simply walked unordered.
 //   2. every warp walks the list 32 entries at a time: lanes first act as entry filters (bbox vs the
 //      warp's block, priority / depth bound vs the block's weakest pixel), survivors are compacted,
 //      their 128-byte records staged in shared memory, then lanes act as pixels.
 //   3. the walk stops as soon as no later entry can change any pixel of the block.
+constexpr int OP_THREADS = 512;      // 16 warps = 16 blocks of 4x4 pixels
+constexpr int OP_WARPS = OP_THREADS / 32;
 constexpr int OP_STAGE = 8;          // surface records staged per warp per step (8 x 128 B)
-constexpr int OP_SORT_MAX = 2048;    // bin entries sortable in shared memory (16 KB of keys)
+constexpr int OP_SORT_MAX = 2048;    // bin entries orderable in shared memory (16 KB of keys)
 
-__global__ void __launch_bounds__(FILL_THREADS)
+__global__ void __launch_bounds__(OP_THREADS)
 k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins, const uint32_t* __restrict__ tile_count,
               const TexDev* __restrict__ tex, const uint16_t* __restrict__ texels,
               uint32_t* __restrict__ fb_rgba, float* __restrict__ fb_z, const CallState* __restrict__ st,
               uint32_t* __restrict__ sticky, CallParams p) {
     __shared__ uint64_t s_key[OP_SORT_MAX];                 // (walk key << 32) | slot in the bin, bucket-ordered
     __shared__ uint32_t s_hist[256];
-    __shared__ uint32_t s_wsum[FILL_THREADS / 32];
+    __shared__ uint32_t s_wsum[8];
     __shared__ uint32_t s_minmax[2];
-    __shared__ BinHead s_head[FILL_THREADS / 32][32];
-    __shared__ SurfRec s_rec[FILL_THREADS / 32][OP_STAGE];
+    __shared__ BinHead s_head[OP_WARPS][32];
+    __shared__ SurfRec s_rec[OP_WARPS][OP_STAGE];
     {
         CallState s = *st;
         bool aborts = call_aborts(s, p.use_zbuffer);
@@ -537,12 +543,12 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
     const bool sorted = n <= OP_SORT_MAX;
     uint32_t kmin = 0, shift = 0;
     if (sorted) {
-        constexpr int KPT = OP_SORT_MAX / FILL_THREADS;            // keys per thread
+        constexpr int KPT = OP_SORT_MAX / OP_THREADS;              // keys per thread
         uint32_t kk[KPT];
         uint32_t lo = 0xFFFFFFFFu, hi = 0;
         #pragma unroll
         for (int q = 0; q < KPT; ++q) {
-            uint32_t i = q * FILL_THREADS + threadIdx.x;
+            uint32_t i = q * OP_THREADS + threadIdx.x;
             kk[q] = i < n ? bin[i].key : 0xFFFFFFFFu;
             if (kk[q] != 0xFFFFFFFFu) { lo = min(lo, kk[q]); hi = max(hi, kk[q]); }   // 0xFFFFFFFF = "never cull": bucket 0
         }
@@ -559,15 +565,18 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
         shift = range >= 256 ? (32 - __clz(range)) - 8 : 0;         // (range >> shift) <= 255
         #pragma unroll
         for (int q = 0; q < KPT; ++q) {
-            uint32_t i = q * FILL_THREADS + threadIdx.x;
+            uint32_t i = q * OP_THREADS + threadIdx.x;
             if (i < n) atomicAdd(&s_hist[kk[q] == 0xFFFFFFFFu ? 0 : 255 - ((kk[q] - kmin) >> shift)], 1u);
         }
         __syncthreads();
-        {   // exclusive scan of the 256 bucket counts
-            uint32_t v = s_hist[threadIdx.x], xs = v;
+        uint32_t v = 0, xs = 0;                              // exclusive scan of the 256 bucket counts (threads 0..255)
+        if (threadIdx.x < 256) {
+            v = s_hist[threadIdx.x]; xs = v;
             for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, xs, o); if ((threadIdx.x & 31) >= o) xs += t; }
             if ((threadIdx.x & 31) == 31) s_wsum[threadIdx.x >> 5] = xs;
-            __syncthreads();
+        }
+        __syncthreads();
+        if (threadIdx.x < 256) {
             uint32_t pre = 0;
             for (uint32_t w = 0; w < (threadIdx.x >> 5); ++w) pre += s_wsum[w];
             s_hist[threadIdx.x] = pre + xs - v;
@@ -575,7 +584,7 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
         __syncthreads();
         #pragma unroll
         for (int q = 0; q < KPT; ++q) {
-            uint32_t i = q * FILL_THREADS + threadIdx.x;
+            uint32_t i = q * OP_THREADS + threadIdx.x;
             if (i < n) {
                 uint32_t pos = atomicAdd(&s_hist[kk[q] == 0xFFFFFFFFu ? 0 : 255 - ((kk[q] - kmin) >> shift)], 1u);
                 s_key[pos] = ((uint64_t)kk[q] << 32) | i;
@@ -585,10 +594,11 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
     }
 
     const uint32_t tx = tile % p.tiles_x, ty = tile / p.tiles_x;
-    // thread -> pixel: each warp owns an 8x4 block of the 16x16 tile
+    // thread -> pixel: each warp owns a 4x4 block of the 16x16 tile; lanes l and l+16 share a pixel
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t bx0 = tx * TILE_W + (warp & 1) * 8, by0 = ty * TILE_H + (warp >> 1) * 4;
-    const uint32_t x = bx0 + (lane & 7), y = by0 + (lane >> 3);
+    const uint32_t pix = lane & 15, sub = lane >> 4;
+    const uint32_t bx0 = tx * TILE_W + (warp & 3) * 4, by0 = ty * TILE_H + (warp >> 2) * 4;
+    const uint32_t x = bx0 + (pix & 3), y = by0 + (pix >> 2);
     const bool valid = x < p.width && y < p.height;
     if (bx0 >= p.width || by0 >= p.height) return;        // whole warp off-screen (no CTA-wide sync below)
     Pixel px{0, 0.0f};
@@ -605,11 +615,11 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
         // ---- what the weakest pixel of this block still accepts ----------------------------------------
         uint64_t wmin = best;                              // painter's: smallest winner priority in the block
         float wz = valid ? px.z : -INFINITY;               // z-buffer: largest depth in the block
-        for (int o = 16; o > 0; o >>= 1) {
+        for (int o = 8; o > 0; o >>= 1) {                  // (both halves hold the same merged state)
             uint64_t t = __shfl_xor_sync(0xFFFFFFFFu, wmin, o); wmin = t < wmin ? t : wmin;
             wz = fmaxf(wz, __shfl_xor_sync(0xFFFFFFFFu, wz, o));
         }
-        // ---- 3. early out: entries are in descending key order ------------------------------------------
+        // ---- 3. early out: entries are in descending key-bucket order ------------------------------------
         if (sorted) {
             uint32_t k0 = (uint32_t)(s_key[base] >> 32);
             if (k0 != 0xFFFFFFFFu) {
@@ -626,7 +636,7 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
         if (base + lane < n) {
             h = bin[sorted ? (uint32_t)s_key[base + lane] : base + lane];
             uint32_t min_x = h.bbox_x & 0xFFFF, max_x = h.bbox_x >> 16, min_y = h.bbox_y & 0xFFFF, max_y = h.bbox_y >> 16;
-            cand = !(max_x <= bx0 || min_x >= bx0 + 8 || max_y <= by0 || min_y >= by0 + 4);
+            cand = !(max_x <= bx0 || min_x >= bx0 + 4 || max_y <= by0 || min_y >= by0 + 4);
             if (!p.use_zbuffer) cand = cand && ((((uint64_t)h.key << 32) | h.face) + 1) > wmin;
             else cand = cand && (h.key == 0xFFFFFFFFu || !(__uint_as_float(~h.key) > wz));
         }
@@ -636,7 +646,7 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
         __syncwarp();
         if (cand) my_heads[__popc(mask & ((1u << lane) - 1))] = h;
         __syncwarp();
-        // ---- 2b. survivors, OP_STAGE records at a time --------------------------------------------------
+        // ---- 2b. survivors, OP_STAGE records at a time, two per step (one per half-warp) -----------------
         for (uint32_t s0 = 0; s0 < cnt; s0 += OP_STAGE) {
             uint32_t m = min((uint32_t)OP_STAGE, cnt - s0);
             __syncwarp();
@@ -647,14 +657,15 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
                     reinterpret_cast<const uint4*>(&recs[my_heads[s0 + ri].face])[lane & 7];
             }
             __syncwarp();
-            for (uint32_t i = 0; i < m; ++i) {
+            for (uint32_t i = sub; i < m; i += 2) {
                 const SurfRec& r = my_recs[i];
-                const uint32_t face = my_heads[s0 + i].face;
-                uint32_t min_x = r.bbox_x & 0xFFFF, max_x = r.bbox_x >> 16, min_y = r.bbox_y & 0xFFFF, max_y = r.bbox_y >> 16;
+                const BinHead hd = my_heads[s0 + i];
+                uint32_t min_x = hd.bbox_x & 0xFFFF, max_x = hd.bbox_x >> 16, min_y = hd.bbox_y & 0xFFFF, max_y = hd.bbox_y >> 16;
                 if (!(valid && x >= min_x && x < max_x && y >= min_y && y < max_y)) continue;
+                const uint32_t face = hd.face;
                 uint64_t prio = 0;
                 if (!p.use_zbuffer) {
-                    prio = (((uint64_t)my_heads[s0 + i].key << 32) | face) + 1;
+                    prio = (((uint64_t)hd.key << 32) | face) + 1;
                     if (prio <= best) continue;                   // drawn earlier than the current winner
                 }
                 float bc_x, bc_y, bc_z;
@@ -672,9 +683,19 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
                 if (p.use_zbuffer) { px.z = z; best_face = face + 1; }
                 else best = prio;
             }
+            __syncwarp();
+            {   // merge the two half-warps' winners for each pixel (exact: max / lexicographic min are associative)
+                uint64_t ob = __shfl_xor_sync(0xFFFFFFFFu, best, 16);
+                uint32_t orgba = __shfl_xor_sync(0xFFFFFFFFu, px.rgba, 16);
+                float oz = __shfl_xor_sync(0xFFFFFFFFu, px.z, 16);
+                uint32_t of = __shfl_xor_sync(0xFFFFFFFFu, best_face, 16);
+                // z-buffer: lexicographic (z, face+1) minimum, 0 = framebuffer content wins ties; painter's: max priority
+                bool take = p.use_zbuffer ? (oz < px.z || (oz == px.z && of < best_face)) : (ob > best);
+                if (take) { best = ob; px.rgba = orgba; px.z = oz; best_face = of; }
+            }
         }
     }
-    if (valid) {
+    if (valid && sub == 0) {
         if (px.rgba != px0.rgba) fb_rgba[y * p.width + x] = px.rgba;
         if (__float_as_uint(px.z) != __float_as_uint(px0.z)) fb_z[y * p.width + x] = px.z;
     }
@@ -911,7 +932,7 @@ void launch_fill_opaque(const LaunchCtx& L, const SurfRec* recs, const BinHead* 
                         uint32_t* sticky, const CallParams& p) {
     uint32_t ntiles = p.tiles_x * p.tiles_y;
     if (ntiles == 0 || p.nf == 0) return;
-    k_fill_opaque<<<ntiles, FILL_THREADS, 0, L.stream>>>(recs, bins, tile_count, tex, texels, fb_rgba, fb_z, st, sticky, p);
+    k_fill_opaque<<<ntiles, OP_THREADS, 0, L.stream>>>(recs, bins, tile_count, tex, texels, fb_rgba, fb_z, st, sticky, p);
     ++*L.launches;
 }
 
