@@ -495,37 +495,71 @@ __device__ __forceinline__ bool shade(const SurfRec& r, uint32_t x, uint32_t y, 
 }
 
 // =================================================================================================
-// k_fill_opaque — pass 1, order-free
+// k_fill_opaque — pass 1, order-free, visibility first
 // =================================================================================================
 // One CTA per 16x16 screen tile; one warp per 4x4 pixel block; a pixel is owned by TWO lanes (lane
-// and lane+16) that evaluate two different surfaces at the same time and merge their winners — the
-// winner rule is associative, so the merge is exact.  The kernel is latency-bound (long dependent
-// f32 chains, few warps per tile), hence small blocks (more warps, shorter walks) and two surfaces
-// in flight per warp.
-//   1. the tile's bin (<= OP_SORT_MAX entries) is ordered in shared memory by the walk key with one
-//      counting-sort pass: painter's mode = nearest (last drawn) first, z-buffer mode = smallest depth
-//      lower bound first.  The order is an efficiency device only: the per-pixel winner rule is exact
-//      for ANY order, ties and all, so bins larger than OP_SORT_MAX are simply walked unordered.
+// and lane+16) that evaluate different surfaces at the same time and merge their winners — the
+// winner rule is associative, so the merge is exact.
+//   1. the tile's bin (<= OP_SORT_MAX entries) is copied into shared memory in walk-key order with
+//      one counting-sort pass: painter's mode = nearest (last drawn) first, z-buffer mode = smallest
+//      depth lower bound first.  The order is an efficiency device only: the per-pixel winner rule is
+//      exact for ANY order, ties and all, so larger bins are simply walked unordered from global memory.
 //   2. every warp walks the list 32 entries at a time: lanes first act as entry filters (bbox vs the
 //      warp's block, priority / depth bound vs the block's weakest pixel), survivors are compacted,
-//      their 128-byte records staged in shared memory, then lanes act as pixels.
+//      their records staged in shared memory, then lanes act as pixels.  The walk only decides WHO
+//      wins each pixel: inside test, depth, and — for black-keyed textured surfaces — the texel
+//      transparency test, whose loads are issued for a whole staged group before any is consumed.
 //   3. the walk stops as soon as no later entry can change any pixel of the block.
+//   4. each pixel shades its winner once (texture, modulate, lighting, dither), at the end.
+// Measured (profiles/): the kernel is bound by dependent latency (L2 round trips + f32 chains), not by
+// instruction issue or DRAM, so the structure minimises the number of dependent global round trips.
 constexpr int OP_THREADS = 512;      // 16 warps = 16 blocks of 4x4 pixels
 constexpr int OP_WARPS = OP_THREADS / 32;
 constexpr int OP_STAGE = 8;          // surface records staged per warp per step (8 x 128 B)
-constexpr int OP_SORT_MAX = 2048;    // bin entries orderable in shared memory (16 KB of keys)
+constexpr int OP_SORT_MAX = 2048;    // bin entries orderable in shared memory (32 KB of heads)
+constexpr int OP_TEX_SMEM = 256;     // texture descriptors cached in shared memory
+constexpr size_t OP_SMEM = (size_t)OP_SORT_MAX * sizeof(BinHead) + (size_t)OP_WARPS * 32 * sizeof(BinHead) +
+                           (size_t)OP_WARPS * OP_STAGE * sizeof(SurfRec) + (size_t)OP_TEX_SMEM * sizeof(TexDev);
+#ifdef B32_FILL_STATS
+__device__ uint32_t g_fill_stats[4096 * 16 * 8];     // [tile][warp][8]: t_start, t_sorted, t_end, batches, survivors, inside, shaded, smid
+__device__ __forceinline__ uint32_t smid() { uint32_t r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t gtime() { uint64_t t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return (uint32_t)t; }
+#endif
+
+// texel of the surface at barycentric (bc): render.rs:1563-1586, types.rs:671-681.  Returns its address
+// in the texel pool, or nullptr for a zero-sized texture (sample() = TRANSPARENT).
+__device__ __forceinline__ const uint16_t* texel_addr(const SurfRec& r, float bc_x, float bc_y, float bc_z, float inv_z,
+                                                      const TexDev& t, const uint16_t* __restrict__ texels, const CallParams& p) {
+    float u, v;
+    if (p.affine_textures) {                                                   // :1563-1567
+        u = bc_x * r.u1 + bc_y * r.u2 + bc_z * r.u3;
+        v = bc_x * r.v1 + bc_y * r.v2 + bc_z * r.v3;
+    } else {                                                                   // :1568-1578
+        float uo = bc_x * r.u1 * r.iz1 + bc_y * r.u2 * r.iz2 + bc_z * r.u3 * r.iz3;
+        float vo = bc_x * r.v1 * r.iz1 + bc_y * r.v2 * r.iz2 + bc_z * r.v3 * r.iz3;
+        u = uo / inv_z;
+        v = vo / inv_z;
+    }
+    if (t.w == 0 || t.h == 0) return nullptr;                                  // types.rs:673-675
+    float uw = rem_euclid1(u), vw = rem_euclid1(1.0f - v);                     // :1583, types.rs:676-677
+    uint32_t tx = min(f2u32sat(uw * (float)t.w), t.w - 1);
+    uint32_t ty = min(f2u32sat(vw * (float)t.h), t.h - 1);
+    return texels + t.off + ty * t.w + tx;
+}
 
 __global__ void __launch_bounds__(OP_THREADS)
 k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins, const uint32_t* __restrict__ tile_count,
               const TexDev* __restrict__ tex, const uint16_t* __restrict__ texels,
               uint32_t* __restrict__ fb_rgba, float* __restrict__ fb_z, const CallState* __restrict__ st,
               uint32_t* __restrict__ sticky, CallParams p) {
-    __shared__ uint64_t s_key[OP_SORT_MAX];                 // (walk key << 32) | slot in the bin, bucket-ordered
+    extern __shared__ __align__(16) uint8_t op_smem[];
+    BinHead* s_sh = reinterpret_cast<BinHead*>(op_smem);                               // [OP_SORT_MAX] bin in walk order
+    BinHead* s_head = s_sh + OP_SORT_MAX;                                               // [OP_WARPS][32] survivors
+    SurfRec* s_rec = reinterpret_cast<SurfRec*>(s_head + OP_WARPS * 32);                // [OP_WARPS][OP_STAGE]
+    TexDev* s_tex = reinterpret_cast<TexDev*>(s_rec + OP_WARPS * OP_STAGE);             // [OP_TEX_SMEM]
     __shared__ uint32_t s_hist[256];
     __shared__ uint32_t s_wsum[8];
     __shared__ uint32_t s_minmax[2];
-    __shared__ BinHead s_head[OP_WARPS][32];
-    __shared__ SurfRec s_rec[OP_WARPS][OP_STAGE];
     {
         CallState s = *st;
         bool aborts = call_aborts(s, p.use_zbuffer);
@@ -537,26 +571,42 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
     const uint32_t n = tile_count[tile];
     if (n == 0) return;
     const BinHead* bin = bins + (size_t)tile * p.bin_cap;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t pix = lane & 15, sub = lane >> 4;
+    const uint32_t tx = tile % p.tiles_x, ty = tile / p.tiles_x;
+    // thread -> pixel: each warp owns a 4x4 block of the 16x16 tile; lanes l and l+16 share a pixel
+    const uint32_t bx0 = tx * TILE_W + (warp & 3) * 4, by0 = ty * TILE_H + (warp >> 2) * 4;
+    const uint32_t x = bx0 + (pix & 3), y = by0 + (pix >> 2);
+    const bool valid = x < p.width && y < p.height;
+    // the pixel's framebuffer content is requested now and consumed after the sort
+    Pixel px{0, 0.0f};
+    if (valid) { px.rgba = fb_rgba[y * p.width + x]; px.z = fb_z[y * p.width + x]; }
+    const bool tex_cached = p.ntex <= OP_TEX_SMEM;
+    if (tex_cached) for (uint32_t i = threadIdx.x; i < p.ntex; i += OP_THREADS) s_tex[i] = tex[i];
+    const TexDev* texd = tex_cached ? s_tex : tex;
+#ifdef B32_FILL_STATS
+    uint32_t st_t0 = gtime(), st_batches = 0, st_surv = 0, st_inside = 0, st_shaded = 0;
+#endif
 
-    // ---- 1. order the bin by walk key, descending: one counting-sort pass into 256 key buckets ---------
-    // (within a bucket the order is arbitrary; the early-out below uses the bucket's upper key bound)
+    // ---- 1. copy the bin to shared memory ordered by walk key, descending: one counting-sort pass into
+    //         256 key buckets (within a bucket the order is arbitrary; the early-out uses bucket bounds)
     const bool sorted = n <= OP_SORT_MAX;
     uint32_t kmin = 0, shift = 0;
     if (sorted) {
-        constexpr int KPT = OP_SORT_MAX / OP_THREADS;              // keys per thread
-        uint32_t kk[KPT];
+        constexpr int KPT = OP_SORT_MAX / OP_THREADS;              // entries per thread
+        BinHead hh[KPT];
         uint32_t lo = 0xFFFFFFFFu, hi = 0;
         #pragma unroll
         for (int q = 0; q < KPT; ++q) {
             uint32_t i = q * OP_THREADS + threadIdx.x;
-            kk[q] = i < n ? bin[i].key : 0xFFFFFFFFu;
-            if (kk[q] != 0xFFFFFFFFu) { lo = min(lo, kk[q]); hi = max(hi, kk[q]); }   // 0xFFFFFFFF = "never cull": bucket 0
+            if (i < n) hh[q] = bin[i]; else hh[q] = BinHead{0, 0, 0xFFFFFFFFu, 0};
+            if (hh[q].key != 0xFFFFFFFFu) { lo = min(lo, hh[q].key); hi = max(hi, hh[q].key); }   // 0xFFFFFFFF = "never cull": bucket 0
         }
         if (threadIdx.x < 256) s_hist[threadIdx.x] = 0;
         if (threadIdx.x == 0) { s_minmax[0] = 0xFFFFFFFFu; s_minmax[1] = 0; }
         for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, o)); hi = max(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, o)); }
         __syncthreads();
-        if ((threadIdx.x & 31) == 0) { atomicMin(&s_minmax[0], lo); atomicMax(&s_minmax[1], hi); }
+        if (lane == 0) { atomicMin(&s_minmax[0], lo); atomicMax(&s_minmax[1], hi); }
         __syncthreads();
         kmin = s_minmax[0];
         uint32_t kmax = s_minmax[1];
@@ -566,52 +616,46 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
         #pragma unroll
         for (int q = 0; q < KPT; ++q) {
             uint32_t i = q * OP_THREADS + threadIdx.x;
-            if (i < n) atomicAdd(&s_hist[kk[q] == 0xFFFFFFFFu ? 0 : 255 - ((kk[q] - kmin) >> shift)], 1u);
+            if (i < n) atomicAdd(&s_hist[hh[q].key == 0xFFFFFFFFu ? 0 : 255 - ((hh[q].key - kmin) >> shift)], 1u);
         }
         __syncthreads();
         uint32_t v = 0, xs = 0;                              // exclusive scan of the 256 bucket counts (threads 0..255)
         if (threadIdx.x < 256) {
             v = s_hist[threadIdx.x]; xs = v;
-            for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, xs, o); if ((threadIdx.x & 31) >= o) xs += t; }
-            if ((threadIdx.x & 31) == 31) s_wsum[threadIdx.x >> 5] = xs;
+            for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, xs, o); if (lane >= (uint32_t)o) xs += t; }
+            if (lane == 31) s_wsum[warp] = xs;
         }
         __syncthreads();
         if (threadIdx.x < 256) {
             uint32_t pre = 0;
-            for (uint32_t w = 0; w < (threadIdx.x >> 5); ++w) pre += s_wsum[w];
+            for (uint32_t w = 0; w < warp; ++w) pre += s_wsum[w];
             s_hist[threadIdx.x] = pre + xs - v;
         }
         __syncthreads();
         #pragma unroll
         for (int q = 0; q < KPT; ++q) {
             uint32_t i = q * OP_THREADS + threadIdx.x;
-            if (i < n) {
-                uint32_t pos = atomicAdd(&s_hist[kk[q] == 0xFFFFFFFFu ? 0 : 255 - ((kk[q] - kmin) >> shift)], 1u);
-                s_key[pos] = ((uint64_t)kk[q] << 32) | i;
-            }
+            if (i < n) s_sh[atomicAdd(&s_hist[hh[q].key == 0xFFFFFFFFu ? 0 : 255 - ((hh[q].key - kmin) >> shift)], 1u)] = hh[q];
         }
-        __syncthreads();
     }
+    __syncthreads();                                      // s_sh and s_tex are ready
 
-    const uint32_t tx = tile % p.tiles_x, ty = tile / p.tiles_x;
-    // thread -> pixel: each warp owns a 4x4 block of the 16x16 tile; lanes l and l+16 share a pixel
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t pix = lane & 15, sub = lane >> 4;
-    const uint32_t bx0 = tx * TILE_W + (warp & 3) * 4, by0 = ty * TILE_H + (warp >> 2) * 4;
-    const uint32_t x = bx0 + (pix & 3), y = by0 + (pix >> 2);
-    const bool valid = x < p.width && y < p.height;
     if (bx0 >= p.width || by0 >= p.height) return;        // whole warp off-screen (no CTA-wide sync below)
-    Pixel px{0, 0.0f};
-    if (valid) { px.rgba = fb_rgba[y * p.width + x]; px.z = fb_z[y * p.width + x]; }
     const Pixel px0 = px;
     // painter's: best = (key << 32 | face) + 1 of the winner so far (0 = framebuffer content)
-    // z-buffer : best_face = face + 1 of the winner so far (0 = framebuffer content), depth in px.z
+    // z-buffer : best_face = face + 1 of the winner so far (0 = framebuffer content), its depth in px.z
     uint64_t best = valid ? 0ull : ~0ull;
     uint32_t best_face = 0;
-    BinHead* my_heads = s_head[warp];
-    SurfRec* my_recs = s_rec[warp];
+    BinHead* my_heads = s_head + warp * 32;
+    SurfRec* my_recs = s_rec + warp * OP_STAGE;
+#ifdef B32_FILL_STATS
+    uint32_t st_t1 = gtime();
+#endif
 
     for (uint32_t base = 0; base < n; base += 32) {
+#ifdef B32_FILL_STATS
+        ++st_batches;
+#endif
         // ---- what the weakest pixel of this block still accepts ----------------------------------------
         uint64_t wmin = best;                              // painter's: smallest winner priority in the block
         float wz = valid ? px.z : -INFINITY;               // z-buffer: largest depth in the block
@@ -621,7 +665,7 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
         }
         // ---- 3. early out: entries are in descending key-bucket order ------------------------------------
         if (sorted) {
-            uint32_t k0 = (uint32_t)(s_key[base] >> 32);
+            uint32_t k0 = s_sh[base].key;
             if (k0 != 0xFFFFFFFFu) {
                 // upper bound of every key still to come = top of k0's bucket
                 uint64_t ub64 = (uint64_t)kmin + (((uint64_t)((k0 - kmin) >> shift) + 1) << shift) - 1;
@@ -634,7 +678,7 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
         BinHead h{0, 0, 0, 0};
         bool cand = false;
         if (base + lane < n) {
-            h = bin[sorted ? (uint32_t)s_key[base + lane] : base + lane];
+            h = sorted ? s_sh[base + lane] : bin[base + lane];
             uint32_t min_x = h.bbox_x & 0xFFFF, max_x = h.bbox_x >> 16, min_y = h.bbox_y & 0xFFFF, max_y = h.bbox_y >> 16;
             cand = !(max_x <= bx0 || min_x >= bx0 + 4 || max_y <= by0 || min_y >= by0 + 4);
             if (!p.use_zbuffer) cand = cand && ((((uint64_t)h.key << 32) | h.face) + 1) > wmin;
@@ -643,10 +687,13 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
         uint32_t mask = __ballot_sync(0xFFFFFFFFu, cand);
         if (mask == 0) continue;
         uint32_t cnt = __popc(mask);
+#ifdef B32_FILL_STATS
+        st_surv += cnt;
+#endif
         __syncwarp();
         if (cand) my_heads[__popc(mask & ((1u << lane) - 1))] = h;
         __syncwarp();
-        // ---- 2b. survivors, OP_STAGE records at a time, two per step (one per half-warp) -----------------
+        // ---- 2b. survivors, OP_STAGE records at a time; each half-warp takes every other record -----------
         for (uint32_t s0 = 0; s0 < cnt; s0 += OP_STAGE) {
             uint32_t m = min((uint32_t)OP_STAGE, cnt - s0);
             __syncwarp();
@@ -657,49 +704,93 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
                     reinterpret_cast<const uint4*>(&recs[my_heads[s0 + ri].face])[lane & 7];
             }
             __syncwarp();
-            for (uint32_t i = sub; i < m; i += 2) {
+            // visibility of this half-warp's records: all inside tests and texel requests first ...
+            constexpr int PER = OP_STAGE / 2;
+            uint64_t c_prio[PER]; float c_z[PER]; uint32_t c_face[PER]; uint32_t c_tex[PER]; bool c_ok[PER];
+            #pragma unroll
+            for (int k = 0; k < PER; ++k) {
+                c_ok[k] = false; c_tex[k] = 1; c_prio[k] = 0; c_z[k] = 0.0f; c_face[k] = 0;
+                uint32_t i = sub + 2 * k;
+                if (i >= m) continue;
                 const SurfRec& r = my_recs[i];
                 const BinHead hd = my_heads[s0 + i];
                 uint32_t min_x = hd.bbox_x & 0xFFFF, max_x = hd.bbox_x >> 16, min_y = hd.bbox_y & 0xFFFF, max_y = hd.bbox_y >> 16;
                 if (!(valid && x >= min_x && x < max_x && y >= min_y && y < max_y)) continue;
-                const uint32_t face = hd.face;
-                uint64_t prio = 0;
+                c_face[k] = hd.face + 1;
                 if (!p.use_zbuffer) {
-                    prio = (((uint64_t)hd.key << 32) | face) + 1;
-                    if (prio <= best) continue;                   // drawn earlier than the current winner
+                    c_prio[k] = (((uint64_t)hd.key << 32) | hd.face) + 1;
+                    if (c_prio[k] <= best) continue;              // drawn earlier than the current winner
                 }
                 float bc_x, bc_y, bc_z;
                 if (!inside_test(r, x, y, bc_x, bc_y, bc_z)) continue;
-                float inv_z = bc_x * r.iz1 + bc_y * r.iz2 + bc_z * r.iz3;              // :1549
-                float z = 1.0f / inv_z;
+                float inv_z = 0.0f;
+                if (p.use_zbuffer || !p.affine_textures) inv_z = bc_x * r.iz1 + bc_y * r.iz2 + bc_z * r.iz3;   // :1549
                 if (p.use_zbuffer) {
                     // lexicographic (z, face) minimum == sequential `z < zbuffer` in face order (:1553-1560, :1684)
-                    if (!(z < px.z || (z == px.z && face + 1 < best_face))) continue;
+                    c_z[k] = 1.0f / inv_z;
+                    if (!(c_z[k] < px.z || (c_z[k] == px.z && c_face[k] < best_face))) continue;
                 }
-                uint32_t o_r, o_g, o_b; bool semi;
-                if (!shade(r, x, y, bc_x, bc_y, bc_z, inv_z, tex, texels, p, o_r, o_g, o_b, semi)) continue;
-                // pass 1: blend mode Opaque and editor_alpha 255 => set_pixel_15 (:445-454)
-                px.rgba = o_r | (o_g << 8) | (o_b << 16) | 0xFF000000u;
-                if (p.use_zbuffer) { px.z = z; best_face = face + 1; }
-                else best = prio;
+                c_ok[k] = true;
+#ifdef B32_FILL_STATS
+                ++st_inside;
+#endif
+                // black-keyed textured surface: the texel decides whether this fragment writes (:1591-1607)
+                if ((r.flags & (SF_TEXTURED | SF_BLACK_TR)) == (SF_TEXTURED | SF_BLACK_TR)) {
+                    const uint16_t* a = texel_addr(r, bc_x, bc_y, bc_z, inv_z, texd[r.flags >> 16], texels, p);
+                    c_tex[k] = a ? __ldg(a) : 0u;
+                }
             }
-            __syncwarp();
+            // ... then the winners
+            #pragma unroll
+            for (int k = 0; k < PER; ++k) {
+                if (!c_ok[k] || (c_tex[k] & 0x7FFF) == 0) continue;       // transparent key / black-keyed texel: no write
+                if (!p.use_zbuffer) { if (c_prio[k] > best) best = c_prio[k]; }
+                else if (c_z[k] < px.z || (c_z[k] == px.z && c_face[k] < best_face)) { px.z = c_z[k]; best_face = c_face[k]; }
+            }
             {   // merge the two half-warps' winners for each pixel (exact: max / lexicographic min are associative)
                 uint64_t ob = __shfl_xor_sync(0xFFFFFFFFu, best, 16);
-                uint32_t orgba = __shfl_xor_sync(0xFFFFFFFFu, px.rgba, 16);
                 float oz = __shfl_xor_sync(0xFFFFFFFFu, px.z, 16);
                 uint32_t of = __shfl_xor_sync(0xFFFFFFFFu, best_face, 16);
                 // z-buffer: lexicographic (z, face+1) minimum, 0 = framebuffer content wins ties; painter's: max priority
                 bool take = p.use_zbuffer ? (oz < px.z || (oz == px.z && of < best_face)) : (ob > best);
-                if (take) { best = ob; px.rgba = orgba; px.z = oz; best_face = of; }
+                if (take) { best = ob; px.z = oz; best_face = of; }
             }
         }
     }
+    // ---- 4. shade each pixel's winner once (lanes 0..15 of the warp) ------------------------------------------
     if (valid && sub == 0) {
+        uint32_t winner = p.use_zbuffer ? best_face : (best ? (uint32_t)((best - 1) & 0xFFFFFFFFu) + 1 : 0);
+        if (winner) {
+            const SurfRec& r = recs[winner - 1];
+            float bc_x, bc_y, bc_z;
+            inside_test(r, x, y, bc_x, bc_y, bc_z);                        // same arithmetic as in the walk
+            float inv_z = bc_x * r.iz1 + bc_y * r.iz2 + bc_z * r.iz3;      // :1549
+            uint32_t o_r, o_g, o_b; bool semi;
+            if (shade(r, x, y, bc_x, bc_y, bc_z, inv_z, texd, texels, p, o_r, o_g, o_b, semi))
+                px.rgba = o_r | (o_g << 8) | (o_b << 16) | 0xFF000000u;    // pass 1: set_pixel_15 (:445-454)
+#ifdef B32_FILL_STATS
+            ++st_shaded;
+#endif
+        }
         if (px.rgba != px0.rgba) fb_rgba[y * p.width + x] = px.rgba;
         if (__float_as_uint(px.z) != __float_as_uint(px0.z)) fb_z[y * p.width + x] = px.z;
     }
+#ifdef B32_FILL_STATS
+    {
+        for (int o = 16; o > 0; o >>= 1) { st_inside += __shfl_xor_sync(0xFFFFFFFFu, st_inside, o); st_shaded += __shfl_xor_sync(0xFFFFFFFFu, st_shaded, o); }
+        if (lane == 0 && tile < 4096) {
+            uint32_t* o = g_fill_stats + (tile * 16 + warp) * 8;
+            o[0] = st_t0; o[1] = st_t1; o[2] = gtime(); o[3] = st_batches; o[4] = st_surv; o[5] = st_inside; o[6] = st_shaded; o[7] = smid();
+        }
+    }
+#endif
 }
+
+#ifdef B32_FILL_STATS
+extern "C" int b32_debug_fill_stats(uint32_t* out, uint32_t n_words) {
+    return (int)cudaMemcpyFromSymbol(out, g_fill_stats, (size_t)n_words * 4);
+}
+#endif
 
 // =================================================================================================
 // ordered pass (pass 2 + x-ray): stable binning in draw order, then strict in-order replay
@@ -932,7 +1023,9 @@ void launch_fill_opaque(const LaunchCtx& L, const SurfRec* recs, const BinHead* 
                         uint32_t* sticky, const CallParams& p) {
     uint32_t ntiles = p.tiles_x * p.tiles_y;
     if (ntiles == 0 || p.nf == 0) return;
-    k_fill_opaque<<<ntiles, OP_THREADS, 0, L.stream>>>(recs, bins, tile_count, tex, texels, fb_rgba, fb_z, st, sticky, p);
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(k_fill_opaque, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OP_SMEM); attr_set = true; }
+    k_fill_opaque<<<ntiles, OP_THREADS, OP_SMEM, L.stream>>>(recs, bins, tile_count, tex, texels, fb_rgba, fb_z, st, sticky, p);
     ++*L.launches;
 }
 
