@@ -513,10 +513,10 @@ __device__ __forceinline__ bool shade(const SurfRec& r, uint32_t x, uint32_t y, 
 //   4. each pixel shades its winner once (texture, modulate, lighting, dither), at the end.
 // Measured (profiles/): the kernel is bound by dependent latency (L2 round trips + f32 chains), not by
 // instruction issue or DRAM, so the structure minimises the number of dependent global round trips.
-constexpr int OP_THREADS = 512;      // 16 warps = 16 blocks of 4x4 pixels
+constexpr int OP_THREADS = 256;      // 8 warps = 8 blocks of 4x4 pixels = half a tile (16x8); two CTAs per tile
 constexpr int OP_WARPS = OP_THREADS / 32;
 constexpr int OP_STAGE = 8;          // surface records staged per warp per step (8 x 128 B)
-constexpr int OP_SORT_MAX = 2048;    // bin entries orderable in shared memory (32 KB of heads)
+constexpr int OP_SORT_MAX = 1024;    // bin entries orderable in shared memory (16 KB of heads)
 constexpr int OP_TEX_SMEM = 256;     // texture descriptors cached in shared memory
 constexpr size_t OP_SMEM = (size_t)OP_SORT_MAX * sizeof(BinHead) + (size_t)OP_WARPS * 32 * sizeof(BinHead) +
                            (size_t)OP_WARPS * OP_STAGE * sizeof(SurfRec) + (size_t)OP_TEX_SMEM * sizeof(TexDev);
@@ -547,7 +547,7 @@ __device__ __forceinline__ const uint16_t* texel_addr(const SurfRec& r, float bc
     return texels + t.off + ty * t.w + tx;
 }
 
-__global__ void __launch_bounds__(OP_THREADS)
+__global__ void __launch_bounds__(OP_THREADS, 5)
 k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins, const uint32_t* __restrict__ tile_count,
               const TexDev* __restrict__ tex, const uint16_t* __restrict__ texels,
               uint32_t* __restrict__ fb_rgba, float* __restrict__ fb_z, const CallState* __restrict__ st,
@@ -567,15 +567,15 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
             atomicOr(sticky, s.oob ? 1u : (aborts ? 2u : 4u));
         if (s.bin_overflow || aborts || p.xray_mode) return;
     }
-    const uint32_t tile = blockIdx.x;
+    const uint32_t tile = blockIdx.x >> 1, half = blockIdx.x & 1;
     const uint32_t n = tile_count[tile];
     if (n == 0) return;
     const BinHead* bin = bins + (size_t)tile * p.bin_cap;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t pix = lane & 15, sub = lane >> 4;
     const uint32_t tx = tile % p.tiles_x, ty = tile / p.tiles_x;
-    // thread -> pixel: each warp owns a 4x4 block of the 16x16 tile; lanes l and l+16 share a pixel
-    const uint32_t bx0 = tx * TILE_W + (warp & 3) * 4, by0 = ty * TILE_H + (warp >> 2) * 4;
+    // thread -> pixel: each warp owns a 4x4 block of its half tile; lanes l and l+16 share a pixel
+    const uint32_t bx0 = tx * TILE_W + (warp & 3) * 4, by0 = ty * TILE_H + half * 8 + (warp >> 2) * 4;
     const uint32_t x = bx0 + (pix & 3), y = by0 + (pix >> 2);
     const bool valid = x < p.width && y < p.height;
     // the pixel's framebuffer content is requested now and consumed after the sort
@@ -664,6 +664,9 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
             wz = fmaxf(wz, __shfl_xor_sync(0xFFFFFFFFu, wz, o));
         }
         // ---- 3. early out: entries are in descending key-bucket order ------------------------------------
+        // `open` pixels are those some entry of this batch or a later one could still change; only their
+        // bounding box [ox0,ox1) x [oy0,oy1) needs to be met by a surface's bbox.
+        uint32_t ox0 = bx0, ox1 = bx0 + 4, oy0 = by0, oy1 = by0 + 4;
         if (sorted) {
             uint32_t k0 = s_sh[base].key;
             if (k0 != 0xFFFFFFFFu) {
@@ -672,6 +675,14 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
                 uint32_t ub = ub64 > 0xFFFFFFFEull ? 0xFFFFFFFEu : (uint32_t)ub64;
                 if (!p.use_zbuffer) { if (wmin != 0 && ub < (uint32_t)((wmin - 1) >> 32)) break; }
                 else if (__uint_as_float(~ub) > wz) break;                   // every later surface is behind every pixel
+                bool open = valid && (!p.use_zbuffer ? (best == 0 || (uint32_t)((best - 1) >> 32) <= ub)
+                                                     : !(__uint_as_float(~ub) > px.z));
+                uint32_t om = __ballot_sync(0xFFFFFFFFu, open) & 0xFFFFu;     // bit q = pixel q (row-major 4x4) is open
+                if (om == 0) break;
+                uint32_t cols = (om | (om >> 4) | (om >> 8) | (om >> 12)) & 0xFu;
+                uint32_t rows = ((om & 0x000Fu) ? 1u : 0u) | ((om & 0x00F0u) ? 2u : 0u) | ((om & 0x0F00u) ? 4u : 0u) | ((om & 0xF000u) ? 8u : 0u);
+                ox0 = bx0 + (__ffs(cols) - 1); ox1 = bx0 + (32 - __clz(cols));
+                oy0 = by0 + (__ffs(rows) - 1); oy1 = by0 + (32 - __clz(rows));
             }
         }
         // ---- 2a. filter 32 bin entries, one per lane ------------------------------------------------------
@@ -680,7 +691,7 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
         if (base + lane < n) {
             h = sorted ? s_sh[base + lane] : bin[base + lane];
             uint32_t min_x = h.bbox_x & 0xFFFF, max_x = h.bbox_x >> 16, min_y = h.bbox_y & 0xFFFF, max_y = h.bbox_y >> 16;
-            cand = !(max_x <= bx0 || min_x >= bx0 + 4 || max_y <= by0 || min_y >= by0 + 4);
+            cand = !(max_x <= ox0 || min_x >= ox1 || max_y <= oy0 || min_y >= oy1);
             if (!p.use_zbuffer) cand = cand && ((((uint64_t)h.key << 32) | h.face) + 1) > wmin;
             else cand = cand && (h.key == 0xFFFFFFFFu || !(__uint_as_float(~h.key) > wz));
         }
@@ -779,7 +790,7 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
     {
         for (int o = 16; o > 0; o >>= 1) { st_inside += __shfl_xor_sync(0xFFFFFFFFu, st_inside, o); st_shaded += __shfl_xor_sync(0xFFFFFFFFu, st_shaded, o); }
         if (lane == 0 && tile < 4096) {
-            uint32_t* o = g_fill_stats + (tile * 16 + warp) * 8;
+            uint32_t* o = g_fill_stats + (tile * 16 + half * 8 + warp) * 8;
             o[0] = st_t0; o[1] = st_t1; o[2] = gtime(); o[3] = st_batches; o[4] = st_surv; o[5] = st_inside; o[6] = st_shaded; o[7] = smid();
         }
     }
@@ -1025,7 +1036,7 @@ void launch_fill_opaque(const LaunchCtx& L, const SurfRec* recs, const BinHead* 
     if (ntiles == 0 || p.nf == 0) return;
     static bool attr_set = false;
     if (!attr_set) { cudaFuncSetAttribute(k_fill_opaque, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OP_SMEM); attr_set = true; }
-    k_fill_opaque<<<ntiles, OP_THREADS, OP_SMEM, L.stream>>>(recs, bins, tile_count, tex, texels, fb_rgba, fb_z, st, sticky, p);
+    k_fill_opaque<<<ntiles * 2, OP_THREADS, OP_SMEM, L.stream>>>(recs, bins, tile_count, tex, texels, fb_rgba, fb_z, st, sticky, p);
     ++*L.launches;
 }
 
