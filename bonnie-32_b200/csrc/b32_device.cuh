@@ -129,13 +129,20 @@ __device__ __forceinline__ int32_t fx_mul(int32_t a, int32_t b) { return (int32_
 __device__ __forceinline__ int32_t fx_add(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
 __device__ __forceinline__ int32_t fx_sub(int32_t a, int32_t b) { return (int32_t)((uint32_t)a - (uint32_t)b); }
 
+// UNR_TABLE[i] (fixed.rs:18-31), computed instead of looked up: one u32 division is cheaper here than a
+// per-block table load + barrier in front of every thread's first global load.
+__device__ __forceinline__ uint32_t unr_entry(uint32_t i) {
+    int32_t v = (int32_t)((0x40000u / (i + 0x100u) + 1u) >> 1) - 0x101;
+    return v > 0 ? (uint32_t)v : 0u;
+}
+
 // UNR reciprocal of a non-zero divisor (fixed.rs:183-205): returns nr2 and the final shift.
-__device__ __forceinline__ void unr_recip(int32_t divisor, const uint8_t* __restrict__ table, uint64_t* nr2, uint32_t* shift) {
+__device__ __forceinline__ void unr_recip(int32_t divisor, uint64_t* nr2, uint32_t* shift) {
     uint32_t den = divisor < 0 ? 0u - (uint32_t)divisor : (uint32_t)divisor;
     uint32_t z = __clz(den);
-    uint64_t d16 = ((uint64_t)den << z) >> 16;
-    unsigned long long idx = min((unsigned long long)((d16 - 0x7FC0ull) >> 7), 256ull);
-    uint64_t u = (uint64_t)table[idx] + 0x101;
+    uint64_t d16 = ((uint64_t)den << z) >> 16;                    // 0x8000..0xFFFF
+    uint32_t idx = min((uint32_t)((d16 - 0x7FC0ull) >> 7), 256u);
+    uint64_t u = (uint64_t)unr_entry(idx) + 0x101;
     uint64_t nr1 = (0x2000080ull - d16 * u) >> 8;
     *nr2 = (0x80ull + nr1 * u) >> 8;
     *shift = 36u - z;

@@ -33,8 +33,7 @@ namespace b32 {
 // =================================================================================================
 // vertex transform + snap (render.rs:2321-2360)
 // =================================================================================================
-__device__ __forceinline__ TVert transform_vertex(float px, float py, float pz, const CallParams& p,
-                                                  const uint8_t* __restrict__ unr, float* cam_xy) {
+__device__ __forceinline__ TVert transform_vertex(float px, float py, float pz, const CallParams& p, float* cam_xy) {
     // rel_pos = v.pos - camera.position; cam_pos = perspective_transform(...)   (math.rs:103-109)
     float rx = px - p.cam_pos[0], ry = py - p.cam_pos[1], rz = pz - p.cam_pos[2];
     float cx = rx * p.bx[0] + ry * p.bx[1] + rz * p.bx[2];
@@ -60,7 +59,7 @@ __device__ __forceinline__ TVert transform_vertex(float px, float py, float pz, 
             isx = p.half_w >> 12; isy = p.half_h >> 12;
         } else {
             uint64_t nr2; uint32_t shift;
-            unr_recip(denom, unr, &nr2, &shift);         // one reciprocal serves x and y
+            unr_recip(denom, &nr2, &shift);              // one reciprocal serves x and y
             int32_t proj_x = unr_apply(fx_mul(fcx, scale), denom, nr2, shift);
             int32_t proj_y = unr_apply(fx_mul(fcy, scale), denom, nr2, shift);
             isx = fx_add(fx_mul(proj_x, p.viewport_scale), p.half_w) >> 12;
@@ -84,15 +83,11 @@ __device__ __forceinline__ TVert transform_vertex(float px, float py, float pz, 
 }
 
 __global__ void __launch_bounds__(256)
-k_transform(const b32_vertex* __restrict__ verts, TVert* __restrict__ out, float* __restrict__ dbg_cam,
-            const uint8_t* __restrict__ unr_table_g, CallParams p) {
-    __shared__ uint8_t unr[260];
-    for (int i = threadIdx.x; i < 257; i += blockDim.x) unr[i] = unr_table_g[i];
-    __syncthreads();
+k_transform(const b32_vertex* __restrict__ verts, TVert* __restrict__ out, float* __restrict__ dbg_cam, CallParams p) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < p.nv; i += gridDim.x * blockDim.x) {
         const float* vp = reinterpret_cast<const float*>(verts + i);
         float cxy[2];
-        TVert t = transform_vertex(vp[0], vp[1], vp[2], p, unr, cxy);
+        TVert t = transform_vertex(vp[0], vp[1], vp[2], p, cxy);
         out[i] = t;
         if (dbg_cam) { dbg_cam[i * 3] = cxy[0]; dbg_cam[i * 3 + 1] = cxy[1]; dbg_cam[i * 3 + 2] = t.w; }
     }
@@ -160,7 +155,7 @@ constexpr int SETUP_THREADS = 128;
 
 __device__ __forceinline__ void setup_face(uint32_t fi, const b32_vertex* __restrict__ verts, const b32_face* __restrict__ faces,
                                            const TVert* __restrict__ tv, const TexDev* __restrict__ tex,
-                                           const LightDev* __restrict__ lights, const uint8_t* __restrict__ unr,
+                                           const LightDev* __restrict__ lights,
                                            SurfRec* __restrict__ recs, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
                                            CallState* __restrict__ st, const CallParams& p,
                                            uint32_t& n_op, uint32_t& n_tr, BinHead& head, bool& binned) {
@@ -182,9 +177,9 @@ __device__ __forceinline__ void setup_face(uint32_t fi, const b32_vertex* __rest
         TVert t1, t2, t3;
         if (tv) { t1 = tv[fc.x]; t2 = tv[fc.y]; t3 = tv[fc.z]; }
         else {
-            t1 = transform_vertex(v0[0], v0[1], v0[2], p, unr, nullptr);
-            t2 = transform_vertex(v1[0], v1[1], v1[2], p, unr, nullptr);
-            t3 = transform_vertex(v2[0], v2[1], v2[2], p, unr, nullptr);
+            t1 = transform_vertex(v0[0], v0[1], v0[2], p, nullptr);
+            t2 = transform_vertex(v1[0], v1[1], v1[2], p, nullptr);
+            t3 = transform_vertex(v2[0], v2[1], v2[2], p, nullptr);
         }
         if (!p.ortho) {                                                       // :2380-2385
             if (t1.w <= NEAR_PLANE || t2.w <= NEAR_PLANE || t3.w <= NEAR_PLANE) break;
@@ -299,24 +294,24 @@ __device__ __forceinline__ void setup_face(uint32_t fi, const b32_vertex* __rest
 
 __global__ void __launch_bounds__(SETUP_THREADS)
 k_setup(const b32_vertex* __restrict__ verts, const b32_face* __restrict__ faces, const TVert* __restrict__ tv,
-        const TexDev* __restrict__ tex, const LightDev* __restrict__ lights, const uint8_t* __restrict__ unr_table_g,
+        const TexDev* __restrict__ tex, const LightDev* __restrict__ lights,
         SurfRec* __restrict__ recs, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
         BinHead* __restrict__ heads, CallState* __restrict__ st, CallParams p) {
-    __shared__ uint8_t unr[260];
-    for (int i = threadIdx.x; i < 257; i += blockDim.x) unr[i] = unr_table_g[i];
-    __syncthreads();
+    __shared__ uint32_t s_cnt[2];
+    if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
     uint32_t n_op = 0, n_tr = 0;
     for (uint32_t fi = blockIdx.x * blockDim.x + threadIdx.x; fi < p.nf; fi += gridDim.x * blockDim.x) {
         BinHead head{0, 0, 0, fi};            // bbox 0 = not binned
         bool binned;
-        setup_face(fi, verts, faces, tv, tex, lights, unr, recs, keys, vals, st, p, n_op, n_tr, head, binned);
+        setup_face(fi, verts, faces, tv, tex, lights, recs, keys, vals, st, p, n_op, n_tr, head, binned);
         heads[fi] = head;
     }
+    // one pair of global atomics per block
     for (int o = 16; o > 0; o >>= 1) { n_op += __shfl_xor_sync(0xFFFFFFFFu, n_op, o); n_tr += __shfl_xor_sync(0xFFFFFFFFu, n_tr, o); }
-    if ((threadIdx.x & 31) == 0) {
-        if (n_op) atomicAdd(&st->n_opaque, n_op);
-        if (n_tr) atomicAdd(&st->n_transp, n_tr);
-    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { if (n_op) atomicAdd(&s_cnt[0], n_op); if (n_tr) atomicAdd(&s_cnt[1], n_tr); }
+    __syncthreads();
+    if (threadIdx.x == 0) { if (s_cnt[0]) atomicAdd(&st->n_opaque, s_cnt[0]); if (s_cnt[1]) atomicAdd(&st->n_transp, s_cnt[1]); }
 }
 
 // =================================================================================================
@@ -326,8 +321,8 @@ k_setup(const b32_vertex* __restrict__ verts, const b32_face* __restrict__ faces
 // receives hundreds of surfaces, so the binning is aggregated: a block takes BIN_FPB consecutive
 // faces, counts them per tile in shared memory, reserves one contiguous slot range per touched tile
 // with ONE global atomic, then hands out slots from shared memory.
-constexpr int BIN_THREADS = 256;
-constexpr int BIN_FPT = 4;                      // faces per thread  => 1024 faces per block
+constexpr int BIN_THREADS = 1024;
+constexpr int BIN_FPT = 1;                      // faces per thread  => 1024 faces per block
 constexpr int BIN_MAX_TILES = 4096;             // shared-memory aggregation up to this many tiles (2 x 16 KB)
 
 __device__ __forceinline__ void head_tiles(const BinHead& h, uint32_t& tx0, uint32_t& tx1, uint32_t& ty0, uint32_t& ty1) {
@@ -1009,7 +1004,7 @@ size_t sort_temp_bytes(uint32_t max_faces, uint32_t max_entries) {
 
 void launch_transform(const LaunchCtx& L, const b32_vertex* verts, TVert* out, float* dbg_cam, const CallParams& p) {
     if (p.nv == 0) return;
-    k_transform<<<grid_for(p.nv, 256, L.sms), 256, 0, L.stream>>>(verts, out, dbg_cam, L.unr_table, p);
+    k_transform<<<grid_for(p.nv, 256, L.sms), 256, 0, L.stream>>>(verts, out, dbg_cam, p);
     ++*L.launches;
 }
 
@@ -1017,7 +1012,7 @@ void launch_setup(const LaunchCtx& L, const b32_vertex* verts, const b32_face* f
                   const LightDev* lights, SurfRec* recs, uint64_t* keys, uint32_t* vals, BinHead* heads, BinHead* bins,
                   uint32_t* tile_count, CallState* st, const CallParams& p) {
     if (p.nf == 0) return;
-    k_setup<<<grid_for(p.nf, SETUP_THREADS, L.sms, 16), SETUP_THREADS, 0, L.stream>>>(verts, faces, tv, tex, lights, L.unr_table, recs, keys, vals, heads, st, p);
+    k_setup<<<grid_for(p.nf, SETUP_THREADS, L.sms, 16), SETUP_THREADS, 0, L.stream>>>(verts, faces, tv, tex, lights, recs, keys, vals, heads, st, p);
     ++*L.launches;
     if (p.xray_mode) return;
     uint32_t ntiles = p.tiles_x * p.tiles_y;
