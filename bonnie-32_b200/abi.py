@@ -25,6 +25,7 @@ SHADE_NONE, SHADE_FLAT, SHADE_GOURAUD = range(3)
 LIGHT_DIRECTIONAL, LIGHT_POINT, LIGHT_SPOT = range(3)
 TEX_RGB555, TEX_IDX8, TEX_IDX4 = range(3)
 FACE_TEX_NONE = 0xFFFF
+RENDER_ASYNC, RENDER_ALL_OPAQUE = 1, 2
 
 # ---- POD records as numpy dtypes (b32_vertex 36 B, b32_face 16 B) ---------------------------
 VERTEX_DTYPE = np.dtype([("pos", "<f4", 3), ("uv", "<f4", 2), ("normal", "<f4", 3), ("rgba", "u1", 4)])
@@ -97,6 +98,9 @@ SYMBOLS = {
     "b32_textures_set": (C.c_int, [_P, C.POINTER(TexDesc), C.c_uint32]),
     "b32_render_mesh_15": (C.c_int, [_P, _P, C.c_uint32, _P, C.c_uint32, C.POINTER(Camera),
                                      C.POINTER(Settings), C.POINTER(Fog), C.POINTER(Timings)]),
+    "b32_render_mesh_15_ex": (C.c_int, [_P, _P, C.c_uint32, _P, C.c_uint32, C.POINTER(Camera),
+                                        C.POINTER(Settings), C.POINTER(Fog), C.c_uint32, C.POINTER(Timings)]),
+    "b32_fb_download_async": (C.c_int, [_P, _P, _P]),
     "b32_mesh_upload": (C.c_int, [_P, _P, C.c_uint32, _P, C.c_uint32, C.POINTER(_P)]),
     "b32_mesh_free": (None, [_P, _P]),
     "b32_render_mesh_15_resident": (C.c_int, [_P, _P, C.POINTER(Camera), C.POINTER(Settings),

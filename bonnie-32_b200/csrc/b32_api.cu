@@ -406,6 +406,7 @@ static int collect_async(b32_ctx* ctx) {
     CK(cudaMemsetAsync(ctx->sticky, 0, sizeof(uint32_t), ctx->stream));
     if (sticky & 1u) return fail(ctx, B32_ERR_OOB_INDEX, "an enqueued call had a face vertex index out of range");
     if (sticky & 2u) return fail(ctx, B32_ERR_NAN_DEPTH, "an enqueued call had a NaN depth key in a sorted pass");
+    if (sticky & 8u) return fail(ctx, B32_ERR_INVALID, "an enqueued call had semi-transparent surfaces (pass 2 was not drawn): B32_RENDER_ALL_OPAQUE was wrong");
     return fail(ctx, B32_ERR_CUDA, "an enqueued call overflowed its tile bins");
 }
 
@@ -521,6 +522,31 @@ int b32_render_mesh_15(b32_ctx* ctx, const b32_vertex* vertices, uint32_t nv, co
     int rc = h2d(ctx, ctx->verts.p, vertices, (size_t)nv * sizeof(b32_vertex)); if (rc) return rc;
     rc = h2d(ctx, ctx->faces.p, faces, (size_t)nf * sizeof(b32_face)); if (rc) return rc;
     return render_device(ctx, ctx->verts.p, nv, ctx->faces.p, nf, camera, settings, fog, timings, true);
+}
+
+int b32_render_mesh_15_ex(b32_ctx* ctx, const b32_vertex* vertices, uint32_t nv, const b32_face* faces, uint32_t nf,
+                          const b32_camera* camera, const b32_settings* settings, const b32_fog* fog, uint32_t flags, b32_timings* timings) {
+    if (!ctx) return B32_ERR_INVALID;
+    if (!(flags & B32_RENDER_ASYNC)) return b32_render_mesh_15(ctx, vertices, nv, faces, nf, camera, settings, fog, timings);
+    if (!(flags & B32_RENDER_ALL_OPAQUE)) return fail(ctx, B32_ERR_INVALID, "B32_RENDER_ASYNC needs B32_RENDER_ALL_OPAQUE (pass 2 needs a host round trip)");
+    if ((nv && !vertices) || (nf && !faces) || !settings) return fail(ctx, B32_ERR_INVALID, "vertices/faces/settings is NULL");
+    if (settings->xray_mode) return fail(ctx, B32_ERR_INVALID, "x-ray mode cannot be enqueued");
+    for (const TexDev& t : ctx->texdesc_h) if (t.blend != B32_BLEND_OPAQUE) return fail(ctx, B32_ERR_INVALID, "a bound texture has a blend mode: cannot be enqueued");
+    uint32_t ntiles = ((ctx->width + TILE_W - 1) / TILE_W) * ((ctx->height + TILE_H - 1) / TILE_H);
+    if ((size_t)ntiles * nf * sizeof(BinHead) > ((size_t)4 << 30)) return fail(ctx, B32_ERR_UNSUPPORTED, "mesh too large to enqueue without a host round trip");
+    CK(ctx->verts.reserve(std::max<uint32_t>(nv, 1)));
+    CK(ctx->faces.reserve(std::max<uint32_t>(nf, 1)));
+    int rc = h2d(ctx, ctx->verts.p, vertices, (size_t)nv * sizeof(b32_vertex)); if (rc) return rc;
+    rc = h2d(ctx, ctx->faces.p, faces, (size_t)nf * sizeof(b32_face)); if (rc) return rc;
+    return render_device(ctx, ctx->verts.p, nv, ctx->faces.p, nf, camera, settings, fog, nullptr, false);
+}
+
+int b32_fb_download_async(b32_ctx* ctx, uint8_t* rgba, float* z) {
+    if (!ctx) return B32_ERR_INVALID;
+    size_t n = (size_t)ctx->width * ctx->height;
+    if (rgba) CK(cudaMemcpyAsync(rgba, ctx->fb_rgba.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (z) CK(cudaMemcpyAsync(z, ctx->fb_z.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    return B32_OK;
 }
 
 int b32_mesh_upload(b32_ctx* ctx, const b32_vertex* vertices, uint32_t nv, const b32_face* faces, uint32_t nf, b32_mesh** out) {

@@ -558,8 +558,10 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
     {
         CallState s = *st;
         bool aborts = call_aborts(s, p.use_zbuffer);
-        if (p.async_call && blockIdx.x == 0 && threadIdx.x == 0 && (aborts || s.bin_overflow))   // enqueue-only callers
-            atomicOr(sticky, s.oob ? 1u : (aborts ? 2u : 4u));
+        if (p.async_call && blockIdx.x == 0 && threadIdx.x == 0) {                                // enqueue-only callers
+            if (aborts || s.bin_overflow) atomicOr(sticky, s.oob ? 1u : (aborts ? 2u : 4u));
+            else if (s.n_transp) atomicOr(sticky, 8u);                                           // pass 2 exists but was not enqueued
+        }
         if (s.bin_overflow || aborts || p.xray_mode) return;
     }
     const uint32_t tile = blockIdx.x >> 1, half = blockIdx.x & 1;

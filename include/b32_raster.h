@@ -177,6 +177,22 @@ int b32_render_mesh_15(b32_ctx* ctx,
                        const b32_camera* camera, const b32_settings* settings,
                        const b32_fog* fog_or_null, b32_timings* timings);
 
+/* Same call with control flags.  B32_RENDER_ASYNC: copy + render are only enqueued on the context's
+ * stream (the host buffers must stay valid and unchanged until b32_sync / b32_fb_download returns);
+ * no timings; errors surface at b32_sync / b32_fb_download.  Only pass 1 can be enqueued, so the caller
+ * must also assert B32_RENDER_ALL_OPAQUE: no face has blend_mode != Opaque or editor_alpha < 255, no
+ * bound texture has blend_mode != Opaque, and x-ray mode is off (a marshalling shim knows this for
+ * free); the device checks the assertion and reports B32_ERR_INVALID at the next sync if it was wrong. */
+#define B32_RENDER_ASYNC       1u
+#define B32_RENDER_ALL_OPAQUE  2u
+int b32_render_mesh_15_ex(b32_ctx* ctx,
+                          const b32_vertex* vertices, uint32_t nv,
+                          const b32_face* faces, uint32_t nf,
+                          const b32_camera* camera, const b32_settings* settings,
+                          const b32_fog* fog_or_null, uint32_t flags, b32_timings* timings);
+/* Enqueue the framebuffer read-back (pinned destination recommended); complete after b32_sync. */
+int b32_fb_download_async(b32_ctx* ctx, uint8_t* rgba, float* z);
+
 /* Device-resident geometry: upload once, render many times (static level geometry; this is
  * also how `value` is measured with inputs already in HBM). */
 int  b32_mesh_upload(b32_ctx* ctx, const b32_vertex* vertices, uint32_t nv,

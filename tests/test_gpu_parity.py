@@ -268,3 +268,37 @@ def test_crowded_tile_bin_growth(ctx, oracle):
         got, got_z, tm = render_gpu(ctx2, sc)
         ctx2.close()
         assert_same(sc, got, got_z, tm, want, want_z, otm)
+
+
+def test_async_host_buffer_path(ctx, oracle):
+    """b32_render_mesh_15_ex(ASYNC|ALL_OPAQUE) + b32_fb_download_async from pinned memory == oracle;
+    a wrong ALL_OPAQUE assertion is reported at the next sync."""
+    import ctypes as C
+    sc = scenes.scene_c4(n_tris=20000)
+    want, want_z, otm, rc = oracle.render_scene(sc)
+    fb = pkg.Framebuffer(sc.width, sc.height, ctx)
+    ctx.set_textures(sc.textures)
+    lib = ctx.lib
+    nvb, nfb, npx = sc.vertices.nbytes, sc.faces.nbytes, sc.width * sc.height * 4
+    hv, hf, hp = lib.b32_host_alloc(nvb), lib.b32_host_alloc(nfb), lib.b32_host_alloc(npx)
+    C.memmove(hv, sc.vertices.ctypes.data, nvb); C.memmove(hf, sc.faces.ctypes.data, nfb)
+    cam = sc.camera.to_abi(); st, keep = sc.settings.to_abi()
+    flags = abi.RENDER_ASYNC | abi.RENDER_ALL_OPAQUE
+    for _ in range(2):
+        fb.clear(sc.clear)
+        ctx.check(lib.b32_render_mesh_15_ex(ctx.h, hv, len(sc.vertices), hf, len(sc.faces), C.byref(cam), C.byref(st), None, flags, None))
+        ctx.check(lib.b32_fb_download_async(ctx.h, hp, None))
+    ctx.sync()
+    got = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_uint8)), shape=(sc.height, sc.width, 4)).copy()
+    assert np.array_equal(got, want)
+    # wrong assertion: a face with a blend mode
+    f = sc.faces.copy(); f["flags"][:] = abi.face_flags(0, abi.BLEND_ADD, True, 255)
+    C.memmove(hf, f.ctypes.data, nfb)
+    ctx.check(lib.b32_render_mesh_15_ex(ctx.h, hv, len(sc.vertices), hf, len(sc.faces), C.byref(cam), C.byref(st), None, flags, None))
+    with pytest.raises(pkg.B32Error) as e:
+        ctx.sync()
+    assert e.value.code == abi.B32_ERR_INVALID
+    # ASYNC without ALL_OPAQUE is refused up front
+    assert lib.b32_render_mesh_15_ex(ctx.h, hv, len(sc.vertices), hf, len(sc.faces), C.byref(cam), C.byref(st), None, abi.RENDER_ASYNC, None) == abi.B32_ERR_INVALID
+    for h in (hv, hf, hp):
+        lib.b32_host_free(h)
