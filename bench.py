@@ -50,7 +50,7 @@ def workload_config(n_gpus: int):
         "settings": "painter's sort (use_zbuffer=false), affine, fixed-point snap, RGB555 + dither, backface cull",
         "parallelism": f"frames sharded over {n_gpus} GPU(s), no data-path collective",
         "l2": "inputs larger than L2: successive steps read 16 distinct resident copies of the scene (198 MB > 126 MB L2), "
-              "2 frames in flight on 2 streams; per-kernel times use a 256 MiB memset between steps instead",
+              "frames in flight on separate streams (see inflight); per-kernel times use a 256 MiB memset between steps instead",
     }
 
 
@@ -190,7 +190,7 @@ def run_b200(args):
     import ctypes as C
     abi = pkg.abi
     sc = frame_scene(pkg, world, rank)
-    N_CTX, N_COPIES = 2, 16          # frames in flight; resident copies of the scene (16 x 12.4 MB > 126 MB L2)
+    N_CTX, N_COPIES = args.inflight, 16     # frames in flight; resident copies of the scene (16 x 12.4 MB > 126 MB L2)
     ctxs = [pkg.Context(local_rank) for _ in range(N_CTX)]
     ctx = ctxs[0]
     lib = ctx.lib
@@ -346,11 +346,18 @@ def run_b200(args):
         dom = max(kavg, key=kavg.get)
         alg_bytes = sc.algorithmic_bytes
         ach = alg_bytes / (kavg[dom] * 1e-3) / 1e9 if kavg[dom] > 0 else None
+        traffic = None                      # dram__bytes_read+write of that kernel from the committed ncu --set full capture
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_kernels.json")))
+            traffic = prof[dom.split("(")[0]]["dram_bytes"]
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32+i32/i64 fixed-point", "data": "synthetic", "config": workload_config(world),
             "frames_per_s": world / (ms_per_step * 1e-3), "triangles_drawn": int(drawn), "bit_exact_vs_golden": parity,
+            "inflight": N_CTX,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nvb + nfb, "d2h_bytes_per_step": sc.width * sc.height * 4,
                     "ms_per_step": e2e_s * 1e3 / args.steps, "frames_per_s": world / (e2e_s / args.steps),
                     "how": f"b32_render_mesh_15_ex(ASYNC) + b32_fb_download_async from/to pinned host memory, {N_CTX} frames in flight "
@@ -361,7 +368,7 @@ def run_b200(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": (ach / peak) if ach else None, "traffic": None,
+                         "frac": (ach / peak) if ach else None, "traffic": traffic,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                          "kernel_ms": kavg, "phase_ms": {k: v / n_sync for k, v in phase.items()},
@@ -392,6 +399,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--inflight", type=int, default=4, help="frames in flight (contexts/streams) for value and e2e")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
