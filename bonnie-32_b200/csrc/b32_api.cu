@@ -75,6 +75,7 @@ struct b32_ctx {
     DevBuf<uint32_t> ent_tile, ent_surf, ent_tile_sorted, ent_surf_sorted;
     DevBuf<uint32_t> tile_count, tile_start;
     DevBuf<BinHead> bins, heads;
+    DevBuf<WireTri> wire;
     uint32_t bin_cap_hint = 0;
     std::vector<LightDev> lights_h;
     bool order_valid = false;
@@ -94,6 +95,7 @@ struct b32_ctx {
     cudaEvent_t ev[8] = {};
     float kernel_ms[7] = {};
     float emit_ms = 0.0f;
+    float wire_ms = 0.0f;
 
     LaunchCtx L() { return LaunchCtx{stream, (uint32_t)prop.multiProcessorCount, unr_table, &launches}; }
 };
@@ -131,6 +133,8 @@ int fill_params(b32_ctx* ctx, CallParams& p, const b32_camera* cam, const b32_se
     p.affine_textures = s->affine_textures != 0; p.use_zbuffer = s->use_zbuffer != 0; p.shading = s->shading;
     p.backface_cull = s->backface_cull != 0; p.dithering = s->dithering != 0; p.use_fixed_point = s->use_fixed_point != 0;
     p.xray_mode = s->xray_mode != 0; p.ortho = s->ortho_enabled != 0;
+    p.wire_back = (s->backface_cull && s->backface_wireframe) ? 1 : 0;      // render.rs:2576
+    p.wire_front = s->wireframe_overlay ? 1 : 0;                            // render.rs:2606, :2550
     p.ambient = s->ambient; p.ortho_zoom = s->ortho_zoom; p.ortho_cx = s->ortho_center_x; p.ortho_cy = s->ortho_center_y;
     if (fog) {
         p.fog_enabled = 1; p.fog_start = fog->start; p.fog_falloff = fog->falloff; p.fog_cull = fog->cull_distance;
@@ -300,11 +304,14 @@ int render_device(b32_ctx* ctx, const b32_vertex* d_verts, uint32_t nv, const b3
         CK(cudaMemsetAsync(ctx->state, 0, sizeof(CallState), st));
         CK(cudaMemsetAsync(ctx->tile_count.p, 0, ntiles * sizeof(uint32_t), st));
         if (wait) CK(cudaEventRecord(ctx->ev[0], st));
+        const bool wire_on = p.wire_back || p.wire_front;
+        if (wire_on) CK(ctx->wire.reserve(nf));
         launch_setup(L, d_verts, d_faces, nullptr, ctx->texdesc.p, ctx->lights.p, ctx->recs.p, ctx->keys.p, ctx->vals.p,
-                     ctx->heads.p, ctx->bins.p, ctx->tile_count.p, ctx->state, p);                          // TRANSFORM + CULL + setup + binning
+                     ctx->heads.p, ctx->bins.p, ctx->tile_count.p, wire_on ? ctx->wire.p : nullptr, ctx->state, p);                          // TRANSFORM + CULL + setup + binning
         if (wait) CK(cudaEventRecord(ctx->ev[1], st));
-        launch_fill_opaque(L, ctx->recs.p, ctx->bins.p, ctx->tile_count.p, ctx->texdesc.p, ctx->texels.p,
-                           ctx->fb_rgba.p, ctx->fb_z.p, ctx->state, ctx->sticky, p);          // DRAW, pass 1
+        if (!p.wire_front)
+            launch_fill_opaque(L, ctx->recs.p, ctx->bins.p, ctx->tile_count.p, ctx->texdesc.p, ctx->texels.p,
+                               ctx->fb_rgba.p, ctx->fb_z.p, ctx->state, ctx->sticky, p);      // DRAW, pass 1
         if (!wait) { ctx->async_pending = true; return B32_OK; }
         CK(cudaEventRecord(ctx->ev[2], st));
         CK(cudaMemcpyAsync(ctx->state_h, ctx->state, sizeof(CallState), cudaMemcpyDeviceToHost, st));
@@ -326,13 +333,23 @@ int render_device(b32_ctx* ctx, const b32_vertex* d_verts, uint32_t nv, const b3
     cudaEventElapsedTime(&ctx->kernel_ms[0], ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&ctx->kernel_ms[1], ctx->ev[1], ctx->ev[2]);
     bool need_ordered = p.xray_mode ? (hs.n_opaque + hs.n_transp) > 0 : hs.n_transp > 0;
-    if (need_ordered) { rc = render_ordered(ctx, p); if (rc) return rc; }
+    if (need_ordered && !p.wire_front) { rc = render_ordered(ctx, p); if (rc) return rc; }
+    if (p.wire_back || p.wire_front) {          // WIREFRAME phase, render.rs:2574-2635
+        CK(cudaEventRecord(ctx->ev[0], st));
+        if (p.wire_back) launch_wire(L, ctx->wire.p, 1, 80u | (80u << 8) | (100u << 16) | 0xFF000000u, true, ctx->fb_rgba.p, ctx->fb_z.p, ctx->state, p);
+        if (p.wire_front) launch_wire(L, ctx->wire.p, 2, 200u | (200u << 8) | (220u << 16) | 0xFF000000u, false, ctx->fb_rgba.p, ctx->fb_z.p, ctx->state, p);
+        CK(cudaEventRecord(ctx->ev[1], st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        cudaEventElapsedTime(&ctx->wire_ms, ctx->ev[0], ctx->ev[1]);
+    } else ctx->wire_ms = 0.0f;
     if (tm) {
         const float* k = ctx->kernel_ms;
         tm->transform_ms = 0.0f;                    // the transform is fused into the cull/setup kernel
         tm->cull_ms = k[0];                         // ... as is fog (fog_ms stays 0)
         tm->sort_ms = k[2];                         // only pass 2 / x-ray sort; pass 1 needs no sort
         tm->draw_ms = k[1] + k[3] + k[4] + k[5] + k[6];
+        tm->wireframe_ms = ctx->wire_ms;
         tm->triangles_drawn = hs.n_opaque + hs.n_transp;                            // render.rs:2545
     }
     return B32_OK;
@@ -379,7 +396,7 @@ void b32_ctx_destroy(b32_ctx* ctx) {
     ctx->fb_rgba.release(); ctx->fb_z.release(); ctx->texels.release(); ctx->texdesc.release(); ctx->verts.release(); ctx->faces.release();
     ctx->tv.release(); ctx->recs.release(); ctx->keys.release(); ctx->keys_sorted.release(); ctx->vals.release(); ctx->order.release();
     ctx->counts.release(); ctx->offsets.release(); ctx->ent_tile.release(); ctx->ent_surf.release(); ctx->ent_tile_sorted.release();
-    ctx->ent_surf_sorted.release(); ctx->tile_count.release(); ctx->tile_start.release(); ctx->bins.release(); ctx->heads.release(); ctx->temp.release(); ctx->lights.release(); ctx->dbg.release();
+    ctx->ent_surf_sorted.release(); ctx->tile_count.release(); ctx->tile_start.release(); ctx->bins.release(); ctx->heads.release(); ctx->wire.release(); ctx->temp.release(); ctx->lights.release(); ctx->dbg.release();
     if (ctx->unr_table) cudaFree(ctx->unr_table);
     if (ctx->state) cudaFree(ctx->state);
     if (ctx->sticky) cudaFree(ctx->sticky);
@@ -531,6 +548,8 @@ int b32_render_mesh_15_ex(b32_ctx* ctx, const b32_vertex* vertices, uint32_t nv,
     if (!(flags & B32_RENDER_ALL_OPAQUE)) return fail(ctx, B32_ERR_INVALID, "B32_RENDER_ASYNC needs B32_RENDER_ALL_OPAQUE (pass 2 needs a host round trip)");
     if ((nv && !vertices) || (nf && !faces) || !settings) return fail(ctx, B32_ERR_INVALID, "vertices/faces/settings is NULL");
     if (settings->xray_mode) return fail(ctx, B32_ERR_INVALID, "x-ray mode cannot be enqueued");
+    if ((settings->backface_cull && settings->backface_wireframe) || settings->wireframe_overlay)
+        return fail(ctx, B32_ERR_INVALID, "the wireframe phase cannot be enqueued");
     for (const TexDev& t : ctx->texdesc_h) if (t.blend != B32_BLEND_OPAQUE) return fail(ctx, B32_ERR_INVALID, "a bound texture has a blend mode: cannot be enqueued");
     uint32_t ntiles = ((ctx->width + TILE_W - 1) / TILE_W) * ((ctx->height + TILE_H - 1) / TILE_H);
     if ((size_t)ntiles * nf * sizeof(BinHead) > ((size_t)4 << 30)) return fail(ctx, B32_ERR_UNSUPPORTED, "mesh too large to enqueue without a host round trip");
@@ -586,7 +605,7 @@ int b32_render_mesh_15_enqueue(b32_ctx* ctx, const b32_mesh* mesh, const b32_cam
     if (!ctx || !mesh || !settings) return B32_ERR_INVALID;
     // Pass 1 needs no host round trip.  Pass 2 (any semi-transparent surface) and x-ray mode do, so a
     // mesh/texture set that can produce them is rendered synchronously instead.
-    bool may_blend = mesh->has_nonopaque || settings->xray_mode;
+    bool may_blend = mesh->has_nonopaque || settings->xray_mode || (settings->backface_cull && settings->backface_wireframe) || settings->wireframe_overlay;
     for (const TexDev& t : ctx->texdesc_h) may_blend = may_blend || t.blend != B32_BLEND_OPAQUE;
     uint32_t ntiles = ((ctx->width + TILE_W - 1) / TILE_W) * ((ctx->height + TILE_H - 1) / TILE_H);
     bool bins_fit = (size_t)ntiles * mesh->nf * sizeof(BinHead) <= ((size_t)4 << 30);   // worst-case bins (no overflow possible)

@@ -69,6 +69,10 @@ struct __align__(16) BinHead {
 };
 static_assert(sizeof(BinHead) == 16, "BinHead must be 16 bytes");
 
+// A triangle collected for the wireframe phase (render.rs:2448-2450, :2509-2511): projected x, y, z of
+// the ORIGINAL (unswapped) v1, v2, v3.  kind: 0 none, 1 back face, 2 front face.
+struct WireTri { float x[3], y[3], z[3]; uint32_t kind; };
+
 struct TexDev { uint32_t off, w, h, blend; };   // texel pool offset (u16 units), size, Texture15.blend_mode
 
 struct LightDev {                     // b32_light without padding surprises
@@ -105,7 +109,7 @@ struct CallParams {
     uint32_t nv, nf, ntex, n_lights;
     uint32_t bin_cap;                                 // capacity (entries) of one tile bin of the opaque pass
     uint8_t affine_textures, use_zbuffer, shading, backface_cull, dithering, use_fixed_point, xray_mode, ortho;
-    uint8_t fog_enabled, fog_r, fog_g, fog_b, fog_blend, async_call, _p1, _p2;
+    uint8_t fog_enabled, fog_r, fog_g, fog_b, fog_blend, async_call, wire_back, wire_front;   // wire_*: render.rs:2576, :2606
     float ambient, ortho_zoom, ortho_cx, ortho_cy;
     float fog_start, fog_falloff, fog_cull;
 };

@@ -158,8 +158,9 @@ __device__ __forceinline__ void setup_face(uint32_t fi, const b32_vertex* __rest
                                            const LightDev* __restrict__ lights,
                                            SurfRec* __restrict__ recs, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
                                            CallState* __restrict__ st, const CallParams& p,
-                                           uint32_t& n_op, uint32_t& n_tr, BinHead& head, bool& binned) {
+                                           uint32_t& n_op, uint32_t& n_tr, BinHead& head, bool& binned, WireTri* __restrict__ wire) {
     binned = false;
+    if (wire) wire[fi].kind = 0;
     uint4 fc = *reinterpret_cast<const uint4*>(faces + fi);
     uint32_t cls = 2;                 // 0 opaque pass, 1 transparent pass, 2 not drawn
     uint32_t dkey = 0;
@@ -191,6 +192,10 @@ __device__ __forceinline__ void setup_face(uint32_t fi, const b32_vertex* __rest
         else if (face_blend != B32_BLEND_OPAQUE) transparent = true;
         else transparent = editor_alpha < 255;
         if (p.fog_enabled && t1.w > p.fog_cull && t2.w > p.fog_cull && t3.w > p.fog_cull) break;   // :2421-2424
+        if (wire) {       // wireframe phase inputs: back faces unless x-ray (:2446-2450), front faces in overlay mode (:2509-2511)
+            uint32_t kind = backface ? ((p.wire_back && !p.xray_mode) ? 1u : 0u) : (p.wire_front ? 2u : 0u);
+            if (kind) wire[fi] = WireTri{{t1.x, t2.x, t3.x}, {t1.y, t2.y, t3.y}, {t1.z, t2.z, t3.z}, kind};
+        }
         if (backface && !(!p.backface_cull || p.xray_mode)) break;            // :2445-2453
 
         // vertex attributes (36-byte records: pos 0, uv 12, normal 20, rgba 32); v2/v3 swap :2455-2457
@@ -296,14 +301,14 @@ __global__ void __launch_bounds__(SETUP_THREADS)
 k_setup(const b32_vertex* __restrict__ verts, const b32_face* __restrict__ faces, const TVert* __restrict__ tv,
         const TexDev* __restrict__ tex, const LightDev* __restrict__ lights,
         SurfRec* __restrict__ recs, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
-        BinHead* __restrict__ heads, CallState* __restrict__ st, CallParams p) {
+        BinHead* __restrict__ heads, WireTri* __restrict__ wire, CallState* __restrict__ st, CallParams p) {
     __shared__ uint32_t s_cnt[2];
     if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
     uint32_t n_op = 0, n_tr = 0;
     for (uint32_t fi = blockIdx.x * blockDim.x + threadIdx.x; fi < p.nf; fi += gridDim.x * blockDim.x) {
         BinHead head{0, 0, 0, fi};            // bbox 0 = not binned
         bool binned;
-        setup_face(fi, verts, faces, tv, tex, lights, recs, keys, vals, st, p, n_op, n_tr, head, binned);
+        setup_face(fi, verts, faces, tv, tex, lights, recs, keys, vals, st, p, n_op, n_tr, head, binned, wire);
         heads[fi] = head;
     }
     // one pair of global atomics per block
@@ -970,6 +975,72 @@ k_fill_ordered(const SurfRec* __restrict__ recs, const uint32_t* __restrict__ en
 }
 
 // =================================================================================================
+// wireframe phase (render.rs:2574-2635): editor feature, off in RasterSettings::game()
+// =================================================================================================
+// Every line of one wireframe pass has the same colour and only READS the z-buffer, so the order of the
+// lines does not matter and each unique edge can be walked by its own thread.  What does matter is the
+// reference's de-duplication: edges are compared by their integer end points only and the FIRST
+// occurrence (in face order) keeps its depths (:2589-2591), so edge e is drawn iff no earlier edge of
+// the same kind has the same end points.  The reference does this search in O(n^2) too.
+struct WireEdge { int32_t x0, y0, x1, y1; float z0, z1; };
+
+__device__ __forceinline__ bool wire_edge(const WireTri& t, uint32_t k, WireEdge& e) {
+    uint32_t a = k, b = (k + 1) % 3;
+    int32_t ax = f2i32(t.x[a]), ay = f2i32(t.y[a]), bx = f2i32(t.x[b]), by = f2i32(t.y[b]);      // `as i32` (:2581-2585)
+    bool lt = ax < bx || (ax == bx && ay < by);                                                   // (x0,y0) < (x1,y1)
+    e = lt ? WireEdge{ax, ay, bx, by, t.z[a], t.z[b]} : WireEdge{bx, by, ax, ay, t.z[b], t.z[a]};
+    return true;
+}
+
+// draw_line_3d (depth_test = true, :768-817) / draw_line (:714-751); colour via set_pixel (:301-310)
+__global__ void __launch_bounds__(128)
+k_wire(const WireTri* __restrict__ wire, uint32_t nf, uint32_t kind, uint32_t color, bool depth_test,
+       uint32_t* __restrict__ fb_rgba, const float* __restrict__ fb_z, const CallState* __restrict__ st, CallParams p) {
+    if (call_aborts(*st, p.use_zbuffer)) return;
+    const int32_t W = (int32_t)p.width, H = (int32_t)p.height;
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < nf * 3; e += gridDim.x * blockDim.x) {
+        const WireTri& t = wire[e / 3];
+        if (t.kind != kind) continue;
+        WireEdge me;
+        wire_edge(t, e % 3, me);
+        bool dup = false;                                                   // unique_edges.iter().any(...)  (:2589)
+        for (uint32_t j = 0; j < e && !dup; ++j) {
+            const WireTri& o = wire[j / 3];
+            if (o.kind != kind) { j += 2 - (j % 3); continue; }
+            WireEdge oe;
+            wire_edge(o, j % 3, oe);
+            dup = oe.x0 == me.x0 && oe.y0 == me.y0 && oe.x1 == me.x1 && oe.y1 == me.y1;
+        }
+        if (dup) continue;
+        // Bresenham with wrapping i32 arithmetic (release-mode Rust)
+        int32_t x0 = me.x0, y0 = me.y0, x1 = me.x1, y1 = me.y1;
+        int32_t ddx = (int32_t)((uint32_t)x1 - (uint32_t)x0), ddy = (int32_t)((uint32_t)y1 - (uint32_t)y0);
+        int32_t dx = ddx < 0 ? (int32_t)(0u - (uint32_t)ddx) : ddx;
+        int32_t dy = -(ddy < 0 ? (int32_t)(0u - (uint32_t)ddy) : ddy);
+        int32_t sx = x0 < x1 ? 1 : -1, sy = y0 < y1 ? 1 : -1;
+        int32_t err = (int32_t)((uint32_t)dx + (uint32_t)dy), x = x0, y = y0;
+        float total_steps = (float)max(dx, max(-dy, 1));
+        float step = 0.0f;
+        for (;;) {
+            if (x >= 0 && x < W && y >= 0 && y < H) {
+                uint32_t idx = (uint32_t)y * p.width + (uint32_t)x;
+                bool pass = true;
+                if (depth_test) {
+                    float tt = step / total_steps;
+                    float z = me.z0 + tt * (me.z1 - me.z0);
+                    pass = z < fb_z[idx];
+                }
+                if (pass) fb_rgba[idx] = color;
+            }
+            if (x == x1 && y == y1) break;
+            int32_t e2 = (int32_t)(2u * (uint32_t)err);
+            if (e2 >= dy) { err = (int32_t)((uint32_t)err + (uint32_t)dy); x += sx; if (depth_test) step += 1.0f; }
+            if (e2 <= dx) { err = (int32_t)((uint32_t)err + (uint32_t)dx); y += sy; if (depth_test && e2 < dy) step += 1.0f; }
+        }
+    }
+}
+
+// =================================================================================================
 // small utility kernels
 // =================================================================================================
 __global__ void k_fb_clear(uint32_t* __restrict__ rgba, float* __restrict__ z, uint32_t n, uint32_t color) {
@@ -1012,11 +1083,11 @@ void launch_transform(const LaunchCtx& L, const b32_vertex* verts, TVert* out, f
 
 void launch_setup(const LaunchCtx& L, const b32_vertex* verts, const b32_face* faces, const TVert* tv, const TexDev* tex,
                   const LightDev* lights, SurfRec* recs, uint64_t* keys, uint32_t* vals, BinHead* heads, BinHead* bins,
-                  uint32_t* tile_count, CallState* st, const CallParams& p) {
+                  uint32_t* tile_count, WireTri* wire, CallState* st, const CallParams& p) {
     if (p.nf == 0) return;
-    k_setup<<<grid_for(p.nf, SETUP_THREADS, L.sms, 16), SETUP_THREADS, 0, L.stream>>>(verts, faces, tv, tex, lights, recs, keys, vals, heads, st, p);
+    k_setup<<<grid_for(p.nf, SETUP_THREADS, L.sms, 16), SETUP_THREADS, 0, L.stream>>>(verts, faces, tv, tex, lights, recs, keys, vals, heads, wire, st, p);
     ++*L.launches;
-    if (p.xray_mode) return;
+    if (p.xray_mode || p.wire_front) return;        // wireframe_overlay draws no solid surfaces (:2550)
     uint32_t ntiles = p.tiles_x * p.tiles_y;
     size_t smem = ntiles <= (uint32_t)BIN_MAX_TILES ? (size_t)ntiles * 8 : 0;
     uint32_t per_round = BIN_THREADS * BIN_FPT;
@@ -1076,6 +1147,13 @@ void launch_fill_ordered(const LaunchCtx& L, const SurfRec* recs, const uint32_t
     uint32_t ntiles = p.tiles_x * p.tiles_y;
     if (ntiles == 0 || p.nf == 0) return;
     k_fill_ordered<<<ntiles, FILL_THREADS, 0, L.stream>>>(recs, ent_surf_sorted, tile_start, tile_count, tex, texels, fb_rgba, fb_z, st, p);
+    ++*L.launches;
+}
+
+void launch_wire(const LaunchCtx& L, const WireTri* wire, uint32_t kind, uint32_t color, bool depth_test,
+                 uint32_t* fb_rgba, const float* fb_z, const CallState* st, const CallParams& p) {
+    if (p.nf == 0) return;
+    k_wire<<<grid_for(p.nf * 3, 128, L.sms, 16), 128, 0, L.stream>>>(wire, p.nf, kind, color, depth_test, fb_rgba, fb_z, st, p);
     ++*L.launches;
 }
 

@@ -23,7 +23,10 @@ void launch_transform(const LaunchCtx& L, const b32_vertex* verts, TVert* out, f
 // tv == nullptr: vertices are transformed inside k_setup (fused path)
 void launch_setup(const LaunchCtx& L, const b32_vertex* verts, const b32_face* faces, const TVert* tv, const TexDev* tex,
                   const LightDev* lights, SurfRec* recs, uint64_t* keys, uint32_t* vals, BinHead* heads, BinHead* bins,
-                  uint32_t* tile_count, CallState* st, const CallParams& p);
+                  uint32_t* tile_count, WireTri* wire, CallState* st, const CallParams& p);
+// wireframe phase: kind 1 = back-face edges (depth tested), 2 = front-face overlay edges
+void launch_wire(const LaunchCtx& L, const WireTri* wire, uint32_t kind, uint32_t color, bool depth_test,
+                 uint32_t* fb_rgba, const float* fb_z, const CallState* st, const CallParams& p);
 void launch_fill_opaque(const LaunchCtx& L, const SurfRec* recs, const BinHead* bins, const uint32_t* tile_count,
                         const TexDev* tex, const uint16_t* texels, uint32_t* fb_rgba, float* fb_z, const CallState* st,
                         uint32_t* sticky, const CallParams& p);

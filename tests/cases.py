@@ -143,3 +143,21 @@ def nan_depth_vertices(scene, oracle):
         if oracle.render_scene(dataclasses.replace(scene, vertices=v))[3] == abi.B32_ERR_NAN_DEPTH:
             return v
     raise AssertionError("no face produces a NaN sort key")
+
+
+def wireframe_scenes(n_tris=160):
+    """Editor wireframe phase (render.rs:2574-2635): back-face edges with depth test, front-face overlay."""
+    base = scenes.scene_c2(n_tris=n_tris)
+    big = scenes.scene_c2(n_tris=n_tris, seed=0xB32000AA)
+    big.vertices = big.vertices.copy()
+    big.vertices["pos"] *= np.float32(40.0)
+    cam = _rotated_camera(0.3, 0.7, (10.0, -20.0, 300.0))
+    return [
+        _with(base, "wire_backface_zbuffer", backface_wireframe=True, use_zbuffer=True),
+        _with(base, "wire_backface_painter", backface_wireframe=True),
+        _with(base, "wire_overlay", wireframe_overlay=True),
+        _with(base, "wire_overlay_and_backface", wireframe_overlay=True, backface_wireframe=True, use_zbuffer=True),
+        _with(base, "wire_backface_nocull_is_off", backface_wireframe=True, backface_cull=False, use_zbuffer=True),
+        _with(base, "wire_backface_xray", backface_wireframe=True, xray_mode=True),
+        _with(big, "wire_backface_large_world", camera=cam, backface_wireframe=True, use_zbuffer=True),
+    ]

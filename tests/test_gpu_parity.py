@@ -302,3 +302,26 @@ def test_async_host_buffer_path(ctx, oracle):
     assert lib.b32_render_mesh_15_ex(ctx.h, hv, len(sc.vertices), hf, len(sc.faces), C.byref(cam), C.byref(st), None, abi.RENDER_ASYNC, None) == abi.B32_ERR_INVALID
     for h in (hv, hf, hp):
         lib.b32_host_free(h)
+
+
+WIRE = cases.wireframe_scenes()
+
+
+@pytest.mark.parametrize("sc", WIRE, ids=[s.name for s in WIRE])
+def test_wireframe_phase(ctx, oracle, sc):
+    """render.rs:2574-2635 on the device vs the oracle (first-occurrence edge de-duplication, depth-tested
+    Bresenham lines, overlay mode draws no solid surfaces)."""
+    want, want_z, otm, rc = oracle.render_scene(sc)
+    assert rc == 0
+    got, got_z, tm = render_gpu(ctx, sc)
+    assert_same(sc, got, got_z, tm, want, want_z, otm)
+
+
+def test_wireframe_scenes_draw_lines(oracle):
+    by = {s.name: s for s in WIRE}
+    plain = copy.copy(by["wire_backface_zbuffer"]); plain.settings = copy.copy(plain.settings); plain.settings.backface_wireframe = False
+    a = oracle.render_scene(plain)[0]; b = oracle.render_scene(by["wire_backface_zbuffer"])[0]
+    diff = (a != b).any(-1)
+    assert diff.sum() > 100 and (b[diff][:, :3] == np.array([80, 80, 100], np.uint8)).all()
+    c = oracle.render_scene(by["wire_overlay"])[0]
+    assert ((c[..., :3] == np.array([200, 200, 220], np.uint8)).all(-1)).sum() > 100
