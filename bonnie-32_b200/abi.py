@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libb32raster.so")
+LIB_PATH = os.environ.get("B32_LIB") or os.path.join(HERE, "libb32raster.so")   # B32_LIB: experiment builds only
 
 # ---- return codes -------------------------------------------------------------------------
 B32_OK, B32_ERR_INVALID, B32_ERR_OOB_INDEX, B32_ERR_NAN_DEPTH = 0, 1, 2, 3

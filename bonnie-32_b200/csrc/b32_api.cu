@@ -84,7 +84,6 @@ struct b32_ctx {
     DevBuf<uint8_t> temp;
     DevBuf<LightDev> lights;
     DevBuf<float> dbg;
-    uint8_t* unr_table = nullptr;
     CallState* state = nullptr;        // device
     uint32_t* sticky = nullptr;        // device: error bits of enqueue-only calls
     CallState* state_h = nullptr;      // pinned host
@@ -97,7 +96,7 @@ struct b32_ctx {
     float emit_ms = 0.0f;
     float wire_ms = 0.0f;
 
-    LaunchCtx L() { return LaunchCtx{stream, (uint32_t)prop.multiProcessorCount, unr_table, &launches}; }
+    LaunchCtx L() { return LaunchCtx{stream, (uint32_t)prop.multiProcessorCount, &launches}; }
 };
 
 namespace {
@@ -379,11 +378,6 @@ int b32_ctx_create(int device, b32_ctx** out) {
     if ((e = cudaMallocHost(&ctx->state_h, sizeof(CallState))) != cudaSuccess) return bail(e, "cudaMallocHost");
     ctx->pinned_bytes = 8u << 20;
     if ((e = cudaMallocHost(&ctx->pinned, ctx->pinned_bytes)) != cudaSuccess) return bail(e, "cudaMallocHost");
-    // UNR table, fixed.rs:20-31: table[i] = max(0, (0x40000 / (i + 0x100) + 1) / 2 - 0x101)
-    uint8_t table[257];
-    for (uint32_t i = 0; i < 257; ++i) { int32_t v = (int32_t)((0x40000u / (i + 0x100u) + 1) / 2) - 0x101; table[i] = v > 0 ? (uint8_t)v : 0; }
-    if ((e = cudaMalloc(&ctx->unr_table, 260)) != cudaSuccess) return bail(e, "cudaMalloc");
-    if ((e = cudaMemcpy(ctx->unr_table, table, 257, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "cudaMemcpy");
     ctx->texdesc.reserve(1); ctx->texels.reserve(1); ctx->lights.reserve(1);
     *out = ctx;
     return B32_OK;
@@ -397,7 +391,6 @@ void b32_ctx_destroy(b32_ctx* ctx) {
     ctx->tv.release(); ctx->recs.release(); ctx->keys.release(); ctx->keys_sorted.release(); ctx->vals.release(); ctx->order.release();
     ctx->counts.release(); ctx->offsets.release(); ctx->ent_tile.release(); ctx->ent_surf.release(); ctx->ent_tile_sorted.release();
     ctx->ent_surf_sorted.release(); ctx->tile_count.release(); ctx->tile_start.release(); ctx->bins.release(); ctx->heads.release(); ctx->wire.release(); ctx->temp.release(); ctx->lights.release(); ctx->dbg.release();
-    if (ctx->unr_table) cudaFree(ctx->unr_table);
     if (ctx->state) cudaFree(ctx->state);
     if (ctx->sticky) cudaFree(ctx->sticky);
     if (ctx->state_h) cudaFreeHost(ctx->state_h);

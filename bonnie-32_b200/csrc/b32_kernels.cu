@@ -513,7 +513,11 @@ __device__ __forceinline__ bool shade(const SurfRec& r, uint32_t x, uint32_t y, 
 //   4. each pixel shades its winner once (texture, modulate, lighting, dither), at the end.
 // Measured (profiles/): the kernel is bound by dependent latency (L2 round trips + f32 chains), not by
 // instruction issue or DRAM, so the structure minimises the number of dependent global round trips.
-constexpr int OP_THREADS = 256;      // 8 warps = 8 blocks of 4x4 pixels = half a tile (16x8); two CTAs per tile
+#ifndef B32_OP_THREADS
+#define B32_OP_THREADS 256
+#endif
+constexpr int OP_THREADS = B32_OP_THREADS;   // 256: 8 warps = half a tile (16x8 px), two CTAs per tile; 512: one CTA per tile
+constexpr int OP_SPLIT = 512 / OP_THREADS;   // CTAs per tile
 constexpr int OP_WARPS = OP_THREADS / 32;
 constexpr int OP_STAGE = 8;          // surface records staged per warp per step (8 x 128 B)
 constexpr int OP_SORT_MAX = 1024;    // bin entries orderable in shared memory (16 KB of heads)
@@ -547,7 +551,7 @@ __device__ __forceinline__ const uint16_t* texel_addr(const SurfRec& r, float bc
     return texels + t.off + ty * t.w + tx;
 }
 
-__global__ void __launch_bounds__(OP_THREADS, 5)
+__global__ void __launch_bounds__(OP_THREADS, OP_THREADS == 256 ? 5 : 2)
 k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins, const uint32_t* __restrict__ tile_count,
               const TexDev* __restrict__ tex, const uint16_t* __restrict__ texels,
               uint32_t* __restrict__ fb_rgba, float* __restrict__ fb_z, const CallState* __restrict__ st,
@@ -569,7 +573,7 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
         }
         if (s.bin_overflow || aborts || p.xray_mode) return;
     }
-    const uint32_t tile = blockIdx.x >> 1, half = blockIdx.x & 1;
+    const uint32_t tile = blockIdx.x / OP_SPLIT, half = blockIdx.x % OP_SPLIT;
     const uint32_t n = tile_count[tile];
     if (n == 0) return;
     const BinHead* bin = bins + (size_t)tile * p.bin_cap;
@@ -577,7 +581,7 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
     const uint32_t pix = lane & 15, sub = lane >> 4;
     const uint32_t tx = tile % p.tiles_x, ty = tile / p.tiles_x;
     // thread -> pixel: each warp owns a 4x4 block of its half tile; lanes l and l+16 share a pixel
-    const uint32_t bx0 = tx * TILE_W + (warp & 3) * 4, by0 = ty * TILE_H + half * 8 + (warp >> 2) * 4;
+    const uint32_t bx0 = tx * TILE_W + (warp & 3) * 4, by0 = ty * TILE_H + half * (OP_WARPS / 4) * 4 + (warp >> 2) * 4;
     const uint32_t x = bx0 + (pix & 3), y = by0 + (pix >> 2);
     const bool valid = x < p.width && y < p.height;
     // the pixel's framebuffer content is requested now and consumed after the sort
@@ -792,7 +796,7 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
     {
         for (int o = 16; o > 0; o >>= 1) { st_inside += __shfl_xor_sync(0xFFFFFFFFu, st_inside, o); st_shaded += __shfl_xor_sync(0xFFFFFFFFu, st_shaded, o); }
         if (lane == 0 && tile < 4096) {
-            uint32_t* o = g_fill_stats + (tile * 16 + half * 8 + warp) * 8;
+            uint32_t* o = g_fill_stats + (tile * 16 + half * OP_WARPS + warp) * 8;
             o[0] = st_t0; o[1] = st_t1; o[2] = gtime(); o[3] = st_batches; o[4] = st_surv; o[5] = st_inside; o[6] = st_shaded; o[7] = smid();
         }
     }
@@ -1104,7 +1108,7 @@ void launch_fill_opaque(const LaunchCtx& L, const SurfRec* recs, const BinHead* 
     if (ntiles == 0 || p.nf == 0) return;
     static bool attr_set = false;
     if (!attr_set) { cudaFuncSetAttribute(k_fill_opaque, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OP_SMEM); attr_set = true; }
-    k_fill_opaque<<<ntiles * 2, OP_THREADS, OP_SMEM, L.stream>>>(recs, bins, tile_count, tex, texels, fb_rgba, fb_z, st, sticky, p);
+    k_fill_opaque<<<ntiles * OP_SPLIT, OP_THREADS, OP_SMEM, L.stream>>>(recs, bins, tile_count, tex, texels, fb_rgba, fb_z, st, sticky, p);
     ++*L.launches;
 }
 

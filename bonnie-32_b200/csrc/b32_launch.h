@@ -13,7 +13,6 @@ namespace b32 {
 struct LaunchCtx {
     cudaStream_t stream;
     uint32_t sms;                 // SM count of the device: grids are sized in multiples of it
-    const uint8_t* unr_table;     // device copy of the 257-entry UNR table (fixed.rs:20-31)
     uint64_t* launches;           // counter of this library's own kernel launches
 };
 
