@@ -340,8 +340,7 @@ def run_b200(args):
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        names = ["k_setup(transform+cull+setup+bin)", "k_fill_opaque", "pass2:sort_faces", "pass2:bin_count+scan",
-                 "pass2:bin_emit", "pass2:sort_entries", "pass2:k_fill_ordered"]
+        names = ["k_setup+k_bin_opaque", "k_fill_opaque", "pass2:k_bin", "pass2:k_fill_ordered"]
         kavg = {n: float(kern[i]) for i, n in enumerate(names)}
         dom = max(kavg, key=kavg.get)
         alg_bytes = sc.algorithmic_bytes
@@ -349,7 +348,7 @@ def run_b200(args):
         traffic = None                      # dram__bytes_read+write of that kernel from the committed ncu --set full capture
         try:
             prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_kernels.json")))
-            traffic = prof[dom.split("(")[0]]["dram_bytes"]
+            traffic = prof[dom.split("+")[0]]["dram_bytes"]
         except Exception:
             pass
         line = {

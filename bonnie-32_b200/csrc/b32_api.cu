@@ -70,18 +70,15 @@ struct b32_ctx {
     // per-call work buffers
     DevBuf<TVert> tv;
     DevBuf<SurfRec> recs;
-    DevBuf<uint64_t> keys, keys_sorted;
-    DevBuf<uint32_t> vals, order, counts, offsets;
-    DevBuf<uint32_t> ent_tile, ent_surf, ent_tile_sorted, ent_surf_sorted;
-    DevBuf<uint32_t> tile_count, tile_start;
-    DevBuf<BinHead> bins, heads;
+    DevBuf<uint64_t> keys;
+    DevBuf<uint32_t> tile_count, otile_count;
+    DevBuf<BinHead> bins, heads, obins, oheads;
+    uint32_t obin_cap_hint = 0;
     DevBuf<WireTri> wire;
     uint32_t bin_cap_hint = 0;
     std::vector<LightDev> lights_h;
-    bool order_valid = false;
     bool async_pending = false;
     CallParams last_params{};
-    DevBuf<uint8_t> temp;
     DevBuf<LightDev> lights;
     DevBuf<float> dbg;
     CallState* state = nullptr;        // device
@@ -189,25 +186,11 @@ int ensure_work(b32_ctx* ctx, uint32_t nv, uint32_t nf) {
     uint32_t m = std::max<uint32_t>(nf, 1);
     CK(ctx->recs.reserve(m));
     CK(ctx->keys.reserve(m));
-    CK(ctx->vals.reserve(m));
     CK(ctx->heads.reserve(m));
+    CK(ctx->oheads.reserve(m));
     uint32_t ntiles = ((ctx->width + TILE_W - 1) / TILE_W) * ((ctx->height + TILE_H - 1) / TILE_H);
     CK(ctx->tile_count.reserve(std::max<uint32_t>(ntiles, 1)));
-    CK(ctx->tile_start.reserve(std::max<uint32_t>(ntiles, 1)));
-    return B32_OK;
-}
-
-int ensure_ordered(b32_ctx* ctx, uint32_t nf, size_t entries) {
-    uint32_t m = std::max<uint32_t>(nf, 1);
-    CK(ctx->keys_sorted.reserve(m));
-    CK(ctx->order.reserve(m));
-    CK(ctx->counts.reserve(m));
-    CK(ctx->offsets.reserve(m));
-    entries = std::max<size_t>(entries, 1 << 16);
-    CK(ctx->ent_tile.reserve(entries)); CK(ctx->ent_surf.reserve(entries));
-    CK(ctx->ent_tile_sorted.reserve(entries)); CK(ctx->ent_surf_sorted.reserve(entries));
-    size_t need = sort_temp_bytes(m, (uint32_t)std::min<size_t>(ctx->ent_tile.cap, 0x7FFFFFFFu));
-    CK(ctx->temp.reserve(need));
+    CK(ctx->otile_count.reserve(std::max<uint32_t>(ntiles, 1)));
     return B32_OK;
 }
 
@@ -232,42 +215,38 @@ int upload_lights(b32_ctx* ctx, const std::vector<LightDev>& lights) {
 }
 
 // Pass 2 (semi-transparent surfaces, back to front) and x-ray mode: strict draw-order replay.
-int render_ordered(b32_ctx* ctx, const CallParams& p) {
+// The surfaces' draw-order keys were written by k_setup; bin them per tile (any order), then every
+// tile sorts its bin by key and replays it (k_fill_ordered).
+int render_ordered(b32_ctx* ctx, const CallParams& p, uint32_t n_ordered) {
     LaunchCtx L = ctx->L();
     cudaStream_t st = ctx->stream;
-    const uint32_t nf = p.nf, ntiles = p.tiles_x * p.tiles_y;
-    int rc = ensure_ordered(ctx, nf, (size_t)nf * 4); if (rc) return rc;
-    CK(cudaEventRecord(ctx->ev[2], st));
-    launch_sort_faces(L, ctx->temp.p, ctx->temp.cap, ctx->keys.p, ctx->keys_sorted.p, ctx->vals.p, ctx->order.p, nf);
-    ctx->order_valid = true;
-    CK(cudaEventRecord(ctx->ev[3], st));
-    launch_bin_count(L, ctx->temp.p, ctx->temp.cap, ctx->recs.p, ctx->order.p, ctx->counts.p, ctx->offsets.p, ctx->state, p);
-    CK(cudaEventRecord(ctx->ev[4], st));
-    launch_bin_emit(L, ctx->recs.p, ctx->order.p, ctx->counts.p, ctx->offsets.p, ctx->ent_tile.p, ctx->ent_surf.p,
-                    ctx->tile_count.p, ctx->tile_start.p, ctx->state, p, (uint32_t)std::min<size_t>(ctx->ent_tile.cap, 0xFFFFFFFFu));
-    CK(cudaEventRecord(ctx->ev[5], st));
-    // the entry sort needs the entry count on the host
-    CK(cudaMemcpyAsync(ctx->state_h, ctx->state, sizeof(CallState), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    CallState hs = *ctx->state_h;
-    cudaEventElapsedTime(&ctx->kernel_ms[4], ctx->ev[4], ctx->ev[5]);
-    if (hs.overflow) {      // grow the entry buffers and redo the emit
-        rc = ensure_ordered(ctx, nf, (size_t)hs.n_entries + hs.n_entries / 4); if (rc) return rc;
-        launch_bin_emit(L, ctx->recs.p, ctx->order.p, ctx->counts.p, ctx->offsets.p, ctx->ent_tile.p, ctx->ent_surf.p,
-                        ctx->tile_count.p, ctx->tile_start.p, ctx->state, p, (uint32_t)std::min<size_t>(ctx->ent_tile.cap, 0xFFFFFFFFu));
+    const uint32_t ntiles = p.tiles_x * p.tiles_y;
+    for (int attempt = 0;; ++attempt) {
+        uint32_t cap = std::max<uint32_t>(ctx->obin_cap_hint, 256);
+        cap = std::min<uint32_t>(cap, std::max<uint32_t>(n_ordered, 2));
+        uint32_t cap2 = 2; while (cap2 < cap) cap2 <<= 1;                 // power of two: the tile sort pads in place
+        CK(ctx->obins.reserve((size_t)ntiles * cap2));
+        CK(cudaMemsetAsync(ctx->otile_count.p, 0, ntiles * sizeof(uint32_t), st));
+        CK(cudaEventRecord(ctx->ev[2], st));
+        launch_bin(L, ctx->oheads.p, ctx->obins.p, ctx->otile_count.p, ctx->state, p, cap2, true);
+        CK(cudaEventRecord(ctx->ev[3], st));
+        launch_fill_ordered(L, ctx->recs.p, ctx->obins.p, ctx->otile_count.p, ctx->texdesc.p, ctx->texels.p,
+                            ctx->fb_rgba.p, ctx->fb_z.p, ctx->state, p, cap2);
+        CK(cudaEventRecord(ctx->ev[4], st));
+        CK(cudaMemcpyAsync(ctx->state_h, ctx->state, sizeof(CallState), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        CallState hs = *ctx->state_h;
+        if (hs.obin_overflow && attempt < 4) {      // a tile bin was too small: the fill was skipped; grow and redo
+            ctx->obin_cap_hint = hs.obin_max;
+            CK(cudaMemsetAsync(&ctx->state->obin_overflow, 0, 2 * sizeof(uint32_t), st));
+            continue;
+        }
+        if (hs.obin_overflow) return fail(ctx, B32_ERR_CUDA, "ordered tile bin overflow persists");
+        break;
     }
-    CK(cudaEventRecord(ctx->ev[5], st));
-    launch_sort_entries(L, ctx->temp.p, ctx->temp.cap, ctx->ent_tile.p, ctx->ent_tile_sorted.p, ctx->ent_surf.p, ctx->ent_surf_sorted.p, hs.n_entries, ntiles);
-    CK(cudaEventRecord(ctx->ev[6], st));
-    launch_fill_ordered(L, ctx->recs.p, ctx->ent_surf_sorted.p, ctx->tile_start.p, ctx->tile_count.p, ctx->texdesc.p, ctx->texels.p,
-                        ctx->fb_rgba.p, ctx->fb_z.p, ctx->state, p);
-    CK(cudaEventRecord(ctx->ev[7], st));
-    CK(cudaStreamSynchronize(st));
-    CK(cudaGetLastError());
     cudaEventElapsedTime(&ctx->kernel_ms[2], ctx->ev[2], ctx->ev[3]);
     cudaEventElapsedTime(&ctx->kernel_ms[3], ctx->ev[3], ctx->ev[4]);
-    cudaEventElapsedTime(&ctx->kernel_ms[5], ctx->ev[5], ctx->ev[6]);
-    cudaEventElapsedTime(&ctx->kernel_ms[6], ctx->ev[6], ctx->ev[7]);
     return B32_OK;
 }
 
@@ -285,7 +264,6 @@ int render_device(b32_ctx* ctx, const b32_vertex* d_verts, uint32_t nv, const b3
     if (tm) std::memset(tm, 0, sizeof(*tm));
     for (float& k : ctx->kernel_ms) k = 0.0f;
     ctx->last_nf = nf;
-    ctx->order_valid = false;
     ctx->last_params = p;
     if (nf == 0) return B32_OK;
 
@@ -305,8 +283,8 @@ int render_device(b32_ctx* ctx, const b32_vertex* d_verts, uint32_t nv, const b3
         if (wait) CK(cudaEventRecord(ctx->ev[0], st));
         const bool wire_on = p.wire_back || p.wire_front;
         if (wire_on) CK(ctx->wire.reserve(nf));
-        launch_setup(L, d_verts, d_faces, nullptr, ctx->texdesc.p, ctx->lights.p, ctx->recs.p, ctx->keys.p, ctx->vals.p,
-                     ctx->heads.p, ctx->bins.p, ctx->tile_count.p, wire_on ? ctx->wire.p : nullptr, ctx->state, p);                          // TRANSFORM + CULL + setup + binning
+        launch_setup(L, d_verts, d_faces, nullptr, ctx->texdesc.p, ctx->lights.p, ctx->recs.p, ctx->keys.p,
+                     ctx->heads.p, ctx->oheads.p, ctx->bins.p, ctx->tile_count.p, wire_on ? ctx->wire.p : nullptr, ctx->state, p);                          // TRANSFORM + CULL + setup + binning
         if (wait) CK(cudaEventRecord(ctx->ev[1], st));
         if (!p.wire_front)
             launch_fill_opaque(L, ctx->recs.p, ctx->bins.p, ctx->tile_count.p, ctx->texdesc.p, ctx->texels.p,
@@ -332,7 +310,7 @@ int render_device(b32_ctx* ctx, const b32_vertex* d_verts, uint32_t nv, const b3
     cudaEventElapsedTime(&ctx->kernel_ms[0], ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&ctx->kernel_ms[1], ctx->ev[1], ctx->ev[2]);
     bool need_ordered = p.xray_mode ? (hs.n_opaque + hs.n_transp) > 0 : hs.n_transp > 0;
-    if (need_ordered && !p.wire_front) { rc = render_ordered(ctx, p); if (rc) return rc; }
+    if (need_ordered && !p.wire_front) { rc = render_ordered(ctx, p, p.xray_mode ? hs.n_opaque + hs.n_transp : hs.n_transp); if (rc) return rc; }
     if (p.wire_back || p.wire_front) {          // WIREFRAME phase, render.rs:2574-2635
         CK(cudaEventRecord(ctx->ev[0], st));
         if (p.wire_back) launch_wire(L, ctx->wire.p, 1, 80u | (80u << 8) | (100u << 16) | 0xFF000000u, true, ctx->fb_rgba.p, ctx->fb_z.p, ctx->state, p);
@@ -346,8 +324,8 @@ int render_device(b32_ctx* ctx, const b32_vertex* d_verts, uint32_t nv, const b3
         const float* k = ctx->kernel_ms;
         tm->transform_ms = 0.0f;                    // the transform is fused into the cull/setup kernel
         tm->cull_ms = k[0];                         // ... as is fog (fog_ms stays 0)
-        tm->sort_ms = k[2];                         // only pass 2 / x-ray sort; pass 1 needs no sort
-        tm->draw_ms = k[1] + k[3] + k[4] + k[5] + k[6];
+        tm->sort_ms = 0.0f;                         // pass 1 needs no sort; pass 2 sorts per tile inside its fill kernel
+        tm->draw_ms = k[1] + k[2] + k[3];
         tm->wireframe_ms = ctx->wire_ms;
         tm->triangles_drawn = hs.n_opaque + hs.n_transp;                            // render.rs:2545
     }
@@ -388,9 +366,9 @@ void b32_ctx_destroy(b32_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     ctx->fb_rgba.release(); ctx->fb_z.release(); ctx->texels.release(); ctx->texdesc.release(); ctx->verts.release(); ctx->faces.release();
-    ctx->tv.release(); ctx->recs.release(); ctx->keys.release(); ctx->keys_sorted.release(); ctx->vals.release(); ctx->order.release();
-    ctx->counts.release(); ctx->offsets.release(); ctx->ent_tile.release(); ctx->ent_surf.release(); ctx->ent_tile_sorted.release();
-    ctx->ent_surf_sorted.release(); ctx->tile_count.release(); ctx->tile_start.release(); ctx->bins.release(); ctx->heads.release(); ctx->wire.release(); ctx->temp.release(); ctx->lights.release(); ctx->dbg.release();
+    ctx->tv.release(); ctx->recs.release(); ctx->keys.release(); ctx->tile_count.release(); ctx->otile_count.release();
+    ctx->bins.release(); ctx->heads.release(); ctx->obins.release(); ctx->oheads.release(); ctx->wire.release();
+    ctx->lights.release(); ctx->dbg.release();
     if (ctx->state) cudaFree(ctx->state);
     if (ctx->sticky) cudaFree(ctx->sticky);
     if (ctx->state_h) cudaFreeHost(ctx->state_h);
@@ -637,19 +615,18 @@ int b32_debug_kernel_times(b32_ctx* ctx, float* out_ms, uint32_t cap) {
 }
 
 int b32_debug_draw_order(b32_ctx* ctx, uint32_t* out_face_idx, uint32_t cap, uint32_t* n) {
+    // Test hook: the draw order of the last call = stable sort of (pass, depth key) over the drawn faces
+    // (render.rs:2522-2542).  Pass 1 is order-free on the device and pass 2 sorts per tile, so the global
+    // order only exists here, computed on the host from the device's keys.
     if (!ctx || !n) return B32_ERR_INVALID;
-    CK(cudaMemcpyAsync(ctx->state_h, ctx->state, sizeof(CallState), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    uint32_t drawn = ctx->state_h->n_opaque + ctx->state_h->n_transp;
-    *n = drawn;
-    if (!ctx->order_valid && ctx->last_nf) {      // pass 1 is order-free: sort on demand for the test API
-        int rc = ensure_ordered(ctx, ctx->last_nf, 1); if (rc) return rc;
-        launch_sort_faces(ctx->L(), ctx->temp.p, ctx->temp.cap, ctx->keys.p, ctx->keys_sorted.p, ctx->vals.p, ctx->order.p, ctx->last_nf);
-        CK(cudaStreamSynchronize(ctx->stream));
-        ctx->order_valid = true;
-    }
-    uint32_t m = std::min(drawn, cap);
-    if (m && out_face_idx) CK(cudaMemcpy(out_face_idx, ctx->order.p, (size_t)m * 4, cudaMemcpyDeviceToHost));
+    std::vector<uint64_t> keys(ctx->last_nf);
+    if (ctx->last_nf) CK(cudaMemcpy(keys.data(), ctx->keys.p, (size_t)ctx->last_nf * 8, cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> idx;
+    for (uint32_t i = 0; i < ctx->last_nf; ++i) if ((keys[i] >> 32) < 2) idx.push_back(i);
+    std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+    *n = (uint32_t)idx.size();
+    for (uint32_t i = 0; i < idx.size() && i < cap && out_face_idx; ++i) out_face_idx[i] = idx[i];
     return B32_OK;
 }
 

@@ -84,9 +84,9 @@ struct CallState {
     uint32_t n_opaque, n_transp;          // drawn surfaces per pass
     uint32_t nan_opaque, nan_transp;      // a NaN sort key was seen in the pass
     uint32_t oob;                         // a face index >= nv was seen
-    uint32_t n_entries;                   // ordered pass: sum of tile counts (bin entries needed)
-    uint32_t overflow;                    // ordered pass: n_entries > capacity: fill skipped, host grows + retries
-    uint32_t abort;                       // reference would have panicked: nothing is drawn
+    uint32_t obin_overflow;               // ordered pass: a tile bin exceeded its capacity (fill skipped, host grows + retries)
+    uint32_t obin_max;                    // ordered pass: largest tile count seen
+    uint32_t _unused;
     uint32_t bin_overflow;                // opaque pass: a tile bin exceeded its capacity (fill skipped, host grows + retries)
     uint32_t bin_max;                     // opaque pass: largest tile count seen
 };

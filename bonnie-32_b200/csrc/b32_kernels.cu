@@ -23,9 +23,6 @@
 //     that a stable radix sort and a stable tile binning produce.
 #include "b32_device.cuh"
 
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
-
 #include "b32_launch.h"
 
 namespace b32 {
@@ -156,9 +153,10 @@ constexpr int SETUP_THREADS = 128;
 __device__ __forceinline__ void setup_face(uint32_t fi, const b32_vertex* __restrict__ verts, const b32_face* __restrict__ faces,
                                            const TVert* __restrict__ tv, const TexDev* __restrict__ tex,
                                            const LightDev* __restrict__ lights,
-                                           SurfRec* __restrict__ recs, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                           SurfRec* __restrict__ recs, uint64_t* __restrict__ keys,
                                            CallState* __restrict__ st, const CallParams& p,
-                                           uint32_t& n_op, uint32_t& n_tr, BinHead& head, bool& binned, WireTri* __restrict__ wire) {
+                                           uint32_t& n_op, uint32_t& n_tr, BinHead& head, bool& binned, BinHead& ohead,
+                                           WireTri* __restrict__ wire) {
     binned = false;
     if (wire) wire[fi].kind = 0;
     uint4 fc = *reinterpret_cast<const uint4*>(faces + fi);
@@ -292,24 +290,31 @@ __device__ __forceinline__ void setup_face(uint32_t fi, const b32_vertex* __rest
             head = BinHead{r.bbox_x, r.bbox_y, hkey, fi};
             binned = true;
         }
+        // pass-2 surfaces (and every surface in x-ray mode) are replayed in draw order: their bin entry
+        // carries the unique 64-bit draw-order key (pass, depth key, face): opaque list first (sorted only
+        // in painter's mode), then the transparent list, ties by face index = stable sort (:2522-2542)
+        if ((transparent || p.xray_mode) && !empty) {
+            uint64_t okey = ((uint64_t)cls << 62) | ((uint64_t)dkey << 30) | fi;
+            ohead = BinHead{r.bbox_x, r.bbox_y, (uint32_t)(okey >> 32), (uint32_t)okey};
+        }
     } while (0);
     keys[fi] = ((uint64_t)cls << 32) | dkey;
-    vals[fi] = fi;
 }
 
 __global__ void __launch_bounds__(SETUP_THREADS)
 k_setup(const b32_vertex* __restrict__ verts, const b32_face* __restrict__ faces, const TVert* __restrict__ tv,
         const TexDev* __restrict__ tex, const LightDev* __restrict__ lights,
-        SurfRec* __restrict__ recs, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
-        BinHead* __restrict__ heads, WireTri* __restrict__ wire, CallState* __restrict__ st, CallParams p) {
+        SurfRec* __restrict__ recs, uint64_t* __restrict__ keys,
+        BinHead* __restrict__ heads, BinHead* __restrict__ oheads, WireTri* __restrict__ wire, CallState* __restrict__ st, CallParams p) {
     __shared__ uint32_t s_cnt[2];
     if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
     uint32_t n_op = 0, n_tr = 0;
     for (uint32_t fi = blockIdx.x * blockDim.x + threadIdx.x; fi < p.nf; fi += gridDim.x * blockDim.x) {
-        BinHead head{0, 0, 0, fi};            // bbox 0 = not binned
+        BinHead head{0, 0, 0, fi}, ohead{0, 0, 0, 0};            // bbox 0 = not binned
         bool binned;
-        setup_face(fi, verts, faces, tv, tex, lights, recs, keys, vals, st, p, n_op, n_tr, head, binned, wire);
+        setup_face(fi, verts, faces, tv, tex, lights, recs, keys, st, p, n_op, n_tr, head, binned, ohead, wire);
         heads[fi] = head;
+        oheads[fi] = ohead;
     }
     // one pair of global atomics per block
     for (int o = 16; o > 0; o >>= 1) { n_op += __shfl_xor_sync(0xFFFFFFFFu, n_op, o); n_tr += __shfl_xor_sync(0xFFFFFFFFu, n_tr, o); }
@@ -337,13 +342,12 @@ __device__ __forceinline__ void head_tiles(const BinHead& h, uint32_t& tx0, uint
 
 __global__ void __launch_bounds__(BIN_THREADS)
 k_bin_opaque(const BinHead* __restrict__ heads, BinHead* __restrict__ bins, uint32_t* __restrict__ tile_count,
-             CallState* __restrict__ st, CallParams p) {
+             CallState* __restrict__ st, CallParams p, uint32_t bin_cap, bool ordered) {
     extern __shared__ uint32_t s_tiles[];            // [ntiles] counts/cursors, [ntiles] bases (when ntiles <= BIN_MAX_TILES)
     const uint32_t ntiles = p.tiles_x * p.tiles_y;
     const bool aggregate = ntiles <= BIN_MAX_TILES;
     uint32_t* s_cnt = s_tiles;
     uint32_t* s_base = s_tiles + ntiles;
-    if (p.xray_mode) return;
     if (aggregate) for (uint32_t i = threadIdx.x; i < ntiles; i += blockDim.x) s_cnt[i] = 0;
     __syncthreads();
 
@@ -376,7 +380,7 @@ k_bin_opaque(const BinHead* __restrict__ heads, BinHead* __restrict__ bins, uint
                     for (uint32_t tx = tx0; tx <= tx1; ++tx) {
                         uint32_t t = ty * p.tiles_x + tx;
                         uint32_t slot = s_base[t] + atomicAdd(&s_cnt[t], 1u);
-                        if (slot < p.bin_cap) bins[(size_t)t * p.bin_cap + slot] = head[k];
+                        if (slot < bin_cap) bins[(size_t)t * bin_cap + slot] = head[k];
                     }
             }
             __syncthreads();
@@ -390,14 +394,17 @@ k_bin_opaque(const BinHead* __restrict__ heads, BinHead* __restrict__ bins, uint
                     for (uint32_t tx = tx0; tx <= tx1; ++tx) {
                         uint32_t t = ty * p.tiles_x + tx;
                         uint32_t slot = atomicAdd(&tile_count[t], 1u);
-                        if (slot < p.bin_cap) bins[(size_t)t * p.bin_cap + slot] = head[k];
+                        if (slot < bin_cap) bins[(size_t)t * bin_cap + slot] = head[k];
                         bmax = max(bmax, slot + 1);
                     }
             }
         }
     }
     for (int o = 16; o > 0; o >>= 1) bmax = max(bmax, __shfl_xor_sync(0xFFFFFFFFu, bmax, o));
-    if ((threadIdx.x & 31) == 0 && bmax) { atomicMax(&st->bin_max, bmax); if (bmax > p.bin_cap) st->bin_overflow = 1; }
+    if ((threadIdx.x & 31) == 0 && bmax) {
+        if (ordered) { atomicMax(&st->obin_max, bmax); if (bmax > bin_cap) st->obin_overflow = 1; }
+        else { atomicMax(&st->bin_max, bmax); if (bmax > bin_cap) st->bin_overflow = 1; }
+    }
 }
 
 // =================================================================================================
@@ -810,89 +817,8 @@ extern "C" int b32_debug_fill_stats(uint32_t* out, uint32_t n_words) {
 #endif
 
 // =================================================================================================
-// ordered pass (pass 2 + x-ray): stable binning in draw order, then strict in-order replay
+// ordered pass (pass 2 + x-ray): per-tile sort by the unique draw-order key, then strict in-order replay
 // =================================================================================================
-// ranks [first, first+count) of the sorted surface list are drawn in order.
-__device__ __forceinline__ void ordered_range(const CallState& s, const CallParams& p, uint32_t& first, uint32_t& count) {
-    if (call_aborts(s, p.use_zbuffer)) { first = 0; count = 0; return; }
-    if (p.xray_mode) { first = 0; count = s.n_opaque + s.n_transp; }      // everything blends at 50% (:1671-1673)
-    else { first = s.n_opaque; count = s.n_transp; }                      // pass 2 only
-}
-
-__global__ void __launch_bounds__(256)
-k_bin_count(const SurfRec* __restrict__ recs, const uint32_t* __restrict__ order, uint32_t* __restrict__ counts,
-            const CallState* __restrict__ st, CallParams p) {
-    uint32_t first, count;
-    ordered_range(*st, p, first, count);
-    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < p.nf; r += gridDim.x * blockDim.x) {
-        uint32_t c = 0;
-        if (r < count) {
-            const SurfRec& rec = recs[order[first + r]];
-            uint32_t bx = rec.bbox_x, by = rec.bbox_y;
-            uint32_t min_x = bx & 0xFFFF, max_x = bx >> 16, min_y = by & 0xFFFF, max_y = by >> 16;
-            if (min_x < max_x && min_y < max_y)
-                c = ((max_x - 1) / TILE_W - min_x / TILE_W + 1) * ((max_y - 1) / TILE_H - min_y / TILE_H + 1);
-        }
-        counts[r] = c;
-    }
-}
-
-// offsets = exclusive scan of counts; total = offsets[nf-1] + counts[nf-1]
-__global__ void __launch_bounds__(256)
-k_bin_emit(const SurfRec* __restrict__ recs, const uint32_t* __restrict__ order, const uint32_t* __restrict__ counts,
-           const uint32_t* __restrict__ offsets, uint32_t* __restrict__ ent_tile, uint32_t* __restrict__ ent_surf,
-           uint32_t* __restrict__ tile_count, CallState* __restrict__ st, CallParams p, uint32_t capacity) {
-    uint32_t total = offsets[p.nf - 1] + counts[p.nf - 1];
-    if (blockIdx.x == 0 && threadIdx.x == 0) { st->n_entries = total; st->overflow = total > capacity ? 1 : 0; }
-    if (total > capacity) return;
-    uint32_t first, count;
-    ordered_range(*st, p, first, count);
-    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < count; r += gridDim.x * blockDim.x) {
-        if (counts[r] == 0) continue;
-        uint32_t f = order[first + r];
-        const SurfRec& rec = recs[f];
-        uint32_t min_x = rec.bbox_x & 0xFFFF, max_x = rec.bbox_x >> 16, min_y = rec.bbox_y & 0xFFFF, max_y = rec.bbox_y >> 16;
-        uint32_t tx0 = min_x / TILE_W, tx1 = (max_x - 1) / TILE_W, ty0 = min_y / TILE_H, ty1 = (max_y - 1) / TILE_H;
-        uint32_t o = offsets[r];
-        for (uint32_t ty = ty0; ty <= ty1; ++ty)
-            for (uint32_t tx = tx0; tx <= tx1; ++tx) {
-                uint32_t t = ty * p.tiles_x + tx;
-                ent_tile[o] = t;
-                ent_surf[o] = f;
-                ++o;
-                atomicAdd(&tile_count[t], 1u);
-            }
-    }
-}
-
-// single-block exclusive scan of tile_count -> tile_start
-__global__ void __launch_bounds__(1024)
-k_tile_scan(const uint32_t* __restrict__ tile_count, uint32_t* __restrict__ tile_start, uint32_t ntiles) {
-    __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    for (uint32_t base = 0; base < ntiles; base += blockDim.x) {
-        uint32_t i = base + threadIdx.x;
-        uint32_t v = i < ntiles ? tile_count[i] : 0;
-        uint32_t x = v;
-        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
-        if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = x;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            uint32_t w = threadIdx.x < (blockDim.x >> 5) ? warp_sums[threadIdx.x] : 0;
-            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, w, o); if (threadIdx.x >= o) w += y; }
-            warp_sums[threadIdx.x] = w;
-        }
-        __syncthreads();
-        uint32_t prefix = carry + (threadIdx.x >= 32 ? warp_sums[(threadIdx.x >> 5) - 1] : 0);
-        if (i < ntiles) tile_start[i] = prefix + x - v;
-        __syncthreads();
-        if (threadIdx.x == blockDim.x - 1) carry = prefix + x;
-        __syncthreads();
-    }
-}
-
 // The write stage of rasterize_triangle_15 (render.rs:1664-1702) against a pixel held in registers.
 __device__ __forceinline__ void write_ordered(const SurfRec& r, Pixel& px, float z, uint32_t o_r, uint32_t o_g, uint32_t o_b, bool semi,
                                               const CallParams& p) {
@@ -920,22 +846,58 @@ __device__ __forceinline__ void write_ordered(const SurfRec& r, Pixel& px, float
     px.rgba = o_r | (o_g << 8) | (o_b << 16) | 0xFF000000u;
 }
 
-constexpr int FILL_CHUNK = 32;      // surfaces staged in shared memory per step (32 x 128 B = 4 KB)
+constexpr int FILL_CHUNK = 32;       // surfaces staged in shared memory per step (32 x 128 B = 4 KB)
+constexpr int ORD_SORT_MAX = 2048;   // bin entries sortable in shared memory (32 KB); larger bins are sorted in place in global memory
 
+__device__ __forceinline__ uint64_t ord_key(const BinHead& h) { return ((uint64_t)h.key << 32) | h.face; }
+
+// CTA-wide bitonic sort (ascending by draw-order key) of m = 2^k entries; works on shared or global memory.
+__device__ void bitonic_sort_heads(BinHead* a, uint32_t m) {
+    for (uint32_t k = 2; k <= m; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
+                uint32_t l = i ^ j;
+                if (l > i) {
+                    BinHead x = a[i], y = a[l];
+                    bool asc = (i & k) == 0;
+                    if ((ord_key(x) > ord_key(y)) == asc) { a[i] = y; a[l] = x; }
+                }
+            }
+            __syncthreads();
+        }
+}
+
+// One CTA per 16x16 tile, one warp per 8x4 block, one lane per pixel.  The tile's bin is sorted by the
+// unique draw-order key, then every pixel replays its surfaces one after the other, applying the
+// reference's z-test / blend / write rules (render.rs:1664-1702) to a colour + depth held in registers.
 __global__ void __launch_bounds__(FILL_THREADS)
-k_fill_ordered(const SurfRec* __restrict__ recs, const uint32_t* __restrict__ ent_surf,
-               const uint32_t* __restrict__ tile_start, const uint32_t* __restrict__ tile_count,
+k_fill_ordered(const SurfRec* __restrict__ recs, BinHead* __restrict__ bins, const uint32_t* __restrict__ tile_count,
                const TexDev* __restrict__ tex, const uint16_t* __restrict__ texels,
-               uint32_t* __restrict__ fb_rgba, float* __restrict__ fb_z, const CallState* __restrict__ st, CallParams p) {
+               uint32_t* __restrict__ fb_rgba, float* __restrict__ fb_z, const CallState* __restrict__ st, CallParams p, uint32_t bin_cap) {
+    extern __shared__ __align__(16) uint8_t ord_smem[];
+    BinHead* s_sorted = reinterpret_cast<BinHead*>(ord_smem);                          // [ORD_SORT_MAX]
     __shared__ SurfRec s_rec[FILL_CHUNK];
     {
         CallState s = *st;
-        if (s.overflow || call_aborts(s, p.use_zbuffer)) return;
+        if (s.obin_overflow || call_aborts(s, p.use_zbuffer)) return;
     }
     const uint32_t tile = blockIdx.x;
     const uint32_t n = tile_count[tile];
     if (n == 0) return;
-    const uint32_t start = tile_start[tile];
+    BinHead* bin = bins + (size_t)tile * bin_cap;
+    uint32_t m = 2;
+    while (m < n) m <<= 1;                              // bin_cap is a power of two >= n
+    BinHead* sorted;
+    if (m <= ORD_SORT_MAX) {
+        for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) s_sorted[i] = i < n ? bin[i] : BinHead{0, 0, 0xFFFFFFFFu, 0xFFFFFFFFu};
+        sorted = s_sorted;
+    } else {
+        for (uint32_t i = n + threadIdx.x; i < m; i += blockDim.x) bin[i] = BinHead{0, 0, 0xFFFFFFFFu, 0xFFFFFFFFu};
+        sorted = bin;
+    }
+    __syncthreads();
+    bitonic_sort_heads(sorted, m);
+
     const uint32_t tx = tile % p.tiles_x, ty = tile / p.tiles_x;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bx0 = tx * TILE_W + (warp & 1) * 8, by0 = ty * TILE_H + (warp >> 1) * 4;
@@ -951,7 +913,7 @@ k_fill_ordered(const SurfRec* __restrict__ recs, const uint32_t* __restrict__ en
         {   // stage cnt records: 8 threads x 16 B per record
             uint32_t rec_i = threadIdx.x >> 3, part = threadIdx.x & 7;
             if (rec_i < cnt) {
-                uint32_t f = ent_surf[start + base + rec_i];
+                uint32_t f = sorted[base + rec_i].face & 0x3FFFFFFFu;
                 reinterpret_cast<uint4*>(&s_rec[rec_i])[part] = reinterpret_cast<const uint4*>(&recs[f])[part];
             }
         }
@@ -1070,15 +1032,6 @@ static inline uint32_t grid_for(uint32_t n, uint32_t block, uint32_t sms, uint32
     return g < 1 ? 1 : (g > cap ? cap : g);
 }
 
-size_t sort_temp_bytes(uint32_t max_faces, uint32_t max_entries) {
-    size_t a = 0, b = 0, c = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, a, (uint64_t*)nullptr, (uint64_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)max_faces, 0, 34);
-    cub::DeviceRadixSort::SortPairs(nullptr, b, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)max_entries, 0, 32);
-    cub::DeviceScan::ExclusiveSum(nullptr, c, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)max_faces);
-    size_t m = a > b ? a : b;
-    return (m > c ? m : c) + 256;
-}
-
 void launch_transform(const LaunchCtx& L, const b32_vertex* verts, TVert* out, float* dbg_cam, const CallParams& p) {
     if (p.nv == 0) return;
     k_transform<<<grid_for(p.nv, 256, L.sms), 256, 0, L.stream>>>(verts, out, dbg_cam, p);
@@ -1086,18 +1039,24 @@ void launch_transform(const LaunchCtx& L, const b32_vertex* verts, TVert* out, f
 }
 
 void launch_setup(const LaunchCtx& L, const b32_vertex* verts, const b32_face* faces, const TVert* tv, const TexDev* tex,
-                  const LightDev* lights, SurfRec* recs, uint64_t* keys, uint32_t* vals, BinHead* heads, BinHead* bins,
+                  const LightDev* lights, SurfRec* recs, uint64_t* keys, BinHead* heads, BinHead* oheads, BinHead* bins,
                   uint32_t* tile_count, WireTri* wire, CallState* st, const CallParams& p) {
     if (p.nf == 0) return;
-    k_setup<<<grid_for(p.nf, SETUP_THREADS, L.sms, 16), SETUP_THREADS, 0, L.stream>>>(verts, faces, tv, tex, lights, recs, keys, vals, heads, wire, st, p);
+    k_setup<<<grid_for(p.nf, SETUP_THREADS, L.sms, 16), SETUP_THREADS, 0, L.stream>>>(verts, faces, tv, tex, lights, recs, keys, heads, oheads, wire, st, p);
     ++*L.launches;
     if (p.xray_mode || p.wire_front) return;        // wireframe_overlay draws no solid surfaces (:2550)
+    launch_bin(L, heads, bins, tile_count, st, p, p.bin_cap, false);
+}
+
+void launch_bin(const LaunchCtx& L, const BinHead* heads, BinHead* bins, uint32_t* tile_count, CallState* st, const CallParams& p,
+                uint32_t bin_cap, bool ordered) {
+    if (p.nf == 0) return;
     uint32_t ntiles = p.tiles_x * p.tiles_y;
     size_t smem = ntiles <= (uint32_t)BIN_MAX_TILES ? (size_t)ntiles * 8 : 0;
     uint32_t per_round = BIN_THREADS * BIN_FPT;
     uint32_t grid = (p.nf + per_round - 1) / per_round;
     if (grid > L.sms * 4) grid = L.sms * 4;
-    k_bin_opaque<<<grid, BIN_THREADS, smem, L.stream>>>(heads, bins, tile_count, st, p);
+    k_bin_opaque<<<grid, BIN_THREADS, smem, L.stream>>>(heads, bins, tile_count, st, p, bin_cap, ordered);
     ++*L.launches;
 }
 
@@ -1112,45 +1071,15 @@ void launch_fill_opaque(const LaunchCtx& L, const SurfRec* recs, const BinHead* 
     ++*L.launches;
 }
 
-void launch_sort_faces(const LaunchCtx& L, void* temp, size_t temp_bytes, const uint64_t* keys_in, uint64_t* keys_out,
-                       const uint32_t* vals_in, uint32_t* vals_out, uint32_t nf) {
-    if (nf == 0) return;
-    cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, (int)nf, 0, 34, L.stream);
-}
-
-void launch_bin_count(const LaunchCtx& L, void* temp, size_t temp_bytes, const SurfRec* recs, const uint32_t* order,
-                      uint32_t* counts, uint32_t* offsets, const CallState* st, const CallParams& p) {
-    if (p.nf == 0) return;
-    k_bin_count<<<grid_for(p.nf, 256, L.sms), 256, 0, L.stream>>>(recs, order, counts, st, p);
-    ++*L.launches;
-    cub::DeviceScan::ExclusiveSum(temp, temp_bytes, counts, offsets, (int)p.nf, L.stream);
-}
-
-void launch_bin_emit(const LaunchCtx& L, const SurfRec* recs, const uint32_t* order, const uint32_t* counts, const uint32_t* offsets,
-                     uint32_t* ent_tile, uint32_t* ent_surf, uint32_t* tile_count, uint32_t* tile_start, CallState* st,
-                     const CallParams& p, uint32_t capacity) {
-    if (p.nf == 0) return;
-    uint32_t ntiles = p.tiles_x * p.tiles_y;
-    cudaMemsetAsync(tile_count, 0, ntiles * sizeof(uint32_t), L.stream);
-    k_bin_emit<<<grid_for(p.nf, 256, L.sms), 256, 0, L.stream>>>(recs, order, counts, offsets, ent_tile, ent_surf, tile_count, st, p, capacity);
-    k_tile_scan<<<1, 1024, 0, L.stream>>>(tile_count, tile_start, ntiles);
-    *L.launches += 2;
-}
-
-void launch_sort_entries(const LaunchCtx& L, void* temp, size_t temp_bytes, const uint32_t* ent_tile, uint32_t* ent_tile_sorted,
-                         const uint32_t* ent_surf, uint32_t* ent_surf_sorted, uint32_t n_entries, uint32_t ntiles) {
-    if (n_entries == 0) return;
-    int bits = 1;
-    while ((1u << bits) < ntiles) ++bits;
-    cub::DeviceRadixSort::SortPairs(temp, temp_bytes, ent_tile, ent_tile_sorted, ent_surf, ent_surf_sorted, (int)n_entries, 0, bits, L.stream);
-}
-
-void launch_fill_ordered(const LaunchCtx& L, const SurfRec* recs, const uint32_t* ent_surf_sorted, const uint32_t* tile_start,
-                         const uint32_t* tile_count, const TexDev* tex, const uint16_t* texels, uint32_t* fb_rgba, float* fb_z,
-                         const CallState* st, const CallParams& p) {
+void launch_fill_ordered(const LaunchCtx& L, const SurfRec* recs, BinHead* obins, const uint32_t* otile_count,
+                         const TexDev* tex, const uint16_t* texels, uint32_t* fb_rgba, float* fb_z,
+                         const CallState* st, const CallParams& p, uint32_t obin_cap) {
     uint32_t ntiles = p.tiles_x * p.tiles_y;
     if (ntiles == 0 || p.nf == 0) return;
-    k_fill_ordered<<<ntiles, FILL_THREADS, 0, L.stream>>>(recs, ent_surf_sorted, tile_start, tile_count, tex, texels, fb_rgba, fb_z, st, p);
+    static bool attr_set = false;
+    const int smem = ORD_SORT_MAX * (int)sizeof(BinHead);
+    if (!attr_set) { cudaFuncSetAttribute(k_fill_ordered, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
+    k_fill_ordered<<<ntiles, FILL_THREADS, smem, L.stream>>>(recs, obins, otile_count, tex, texels, fb_rgba, fb_z, st, p, obin_cap);
     ++*L.launches;
 }
 

@@ -16,32 +16,23 @@ struct LaunchCtx {
     uint64_t* launches;           // counter of this library's own kernel launches
 };
 
-size_t sort_temp_bytes(uint32_t max_faces, uint32_t max_entries);
-
 void launch_transform(const LaunchCtx& L, const b32_vertex* verts, TVert* out, float* dbg_cam, const CallParams& p);
-// tv == nullptr: vertices are transformed inside k_setup (fused path)
+// tv == nullptr: vertices are transformed inside k_setup (fused path). Also bins the pass-1 surfaces.
 void launch_setup(const LaunchCtx& L, const b32_vertex* verts, const b32_face* faces, const TVert* tv, const TexDev* tex,
-                  const LightDev* lights, SurfRec* recs, uint64_t* keys, uint32_t* vals, BinHead* heads, BinHead* bins,
+                  const LightDev* lights, SurfRec* recs, uint64_t* keys, BinHead* heads, BinHead* oheads, BinHead* bins,
                   uint32_t* tile_count, WireTri* wire, CallState* st, const CallParams& p);
-// wireframe phase: kind 1 = back-face edges (depth tested), 2 = front-face overlay edges
-void launch_wire(const LaunchCtx& L, const WireTri* wire, uint32_t kind, uint32_t color, bool depth_test,
-                 uint32_t* fb_rgba, const float* fb_z, const CallState* st, const CallParams& p);
+void launch_bin(const LaunchCtx& L, const BinHead* heads, BinHead* bins, uint32_t* tile_count, CallState* st, const CallParams& p,
+                uint32_t bin_cap, bool ordered);
 void launch_fill_opaque(const LaunchCtx& L, const SurfRec* recs, const BinHead* bins, const uint32_t* tile_count,
                         const TexDev* tex, const uint16_t* texels, uint32_t* fb_rgba, float* fb_z, const CallState* st,
                         uint32_t* sticky, const CallParams& p);
-// ordered pass (pass 2 / x-ray)
-void launch_sort_faces(const LaunchCtx& L, void* temp, size_t temp_bytes, const uint64_t* keys_in, uint64_t* keys_out,
-                       const uint32_t* vals_in, uint32_t* vals_out, uint32_t nf);
-void launch_bin_count(const LaunchCtx& L, void* temp, size_t temp_bytes, const SurfRec* recs, const uint32_t* order,
-                      uint32_t* counts, uint32_t* offsets, const CallState* st, const CallParams& p);
-void launch_bin_emit(const LaunchCtx& L, const SurfRec* recs, const uint32_t* order, const uint32_t* counts, const uint32_t* offsets,
-                     uint32_t* ent_tile, uint32_t* ent_surf, uint32_t* tile_count, uint32_t* tile_start, CallState* st,
-                     const CallParams& p, uint32_t capacity);
-void launch_sort_entries(const LaunchCtx& L, void* temp, size_t temp_bytes, const uint32_t* ent_tile, uint32_t* ent_tile_sorted,
-                         const uint32_t* ent_surf, uint32_t* ent_surf_sorted, uint32_t n_entries, uint32_t ntiles);
-void launch_fill_ordered(const LaunchCtx& L, const SurfRec* recs, const uint32_t* ent_surf_sorted, const uint32_t* tile_start,
-                         const uint32_t* tile_count, const TexDev* tex, const uint16_t* texels, uint32_t* fb_rgba, float* fb_z,
-                         const CallState* st, const CallParams& p);
+// ordered pass (pass 2 / x-ray): bins of draw-order keys, sorted per tile, replayed in order
+void launch_fill_ordered(const LaunchCtx& L, const SurfRec* recs, BinHead* obins, const uint32_t* otile_count,
+                         const TexDev* tex, const uint16_t* texels, uint32_t* fb_rgba, float* fb_z,
+                         const CallState* st, const CallParams& p, uint32_t obin_cap);
+// wireframe phase: kind 1 = back-face edges (depth tested), 2 = front-face overlay edges
+void launch_wire(const LaunchCtx& L, const WireTri* wire, uint32_t kind, uint32_t color, bool depth_test,
+                 uint32_t* fb_rgba, const float* fb_z, const CallState* st, const CallParams& p);
 void launch_fb_clear(const LaunchCtx& L, uint32_t* rgba, float* z, uint32_t n, uint32_t color);
 void launch_tex_expand(const LaunchCtx& L, const uint8_t* idx, const uint16_t* clut, uint32_t clut_len, uint32_t format, uint32_t n, uint16_t* out);
 

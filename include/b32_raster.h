@@ -221,9 +221,9 @@ int b32_debug_transform(b32_ctx* ctx, const b32_vertex* vertices, uint32_t nv,
 int b32_debug_draw_order(b32_ctx* ctx, uint32_t* out_face_idx, uint32_t cap, uint32_t* n);
 
 /* Device time (ms, CUDA events on the context stream) of each kernel group of the last synchronous
- * render call: [0] k_setup (transform + cull + setup + binning) [1] k_fill_opaque (pass 1), and for
- * pass 2 / x-ray: [2] face sort [3] bin count + scan [4] bin emit + tile scan [5] entry sort
- * [6] k_fill_ordered.  Returns the number of values written (<= cap). */
+ * render call: [0] k_setup + k_bin_opaque (transform + cull + setup + binning) [1] k_fill_opaque (pass 1),
+ * and for pass 2 / x-ray: [2] binning of the draw-order keys [3] k_fill_ordered (per-tile sort + replay).
+ * Returns the number of values written (<= cap). */
 int b32_debug_kernel_times(b32_ctx* ctx, float* out_ms, uint32_t cap);
 
 #ifdef __cplusplus

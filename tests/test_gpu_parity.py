@@ -261,13 +261,20 @@ def test_crowded_tile_bin_growth(ctx, oracle):
     v = scenes.make_vertices(pos.reshape(-1, 3), uv=u[..., :2].reshape(-1, 2),
                              rgba=np.concatenate([np.floor(u * 255).reshape(-1, 3), np.zeros((n * 3, 1))], axis=1))
     f = scenes.make_faces(np.arange(n * 3).reshape(n, 3), tex_id=abi.FACE_TEX_NONE)
-    for zbuf in (False, True):
-        sc = scenes.Scene("crowded_tile", v, f, [], pkg.Camera(), scenes.common_settings(use_zbuffer=zbuf, backface_cull=False))
-        want, want_z, otm, rc = oracle.render_scene(sc)
-        ctx2 = pkg.Context(0)                     # fresh context: no learned bin capacity
-        got, got_z, tm = render_gpu(ctx2, sc)
-        ctx2.close()
-        assert_same(sc, got, got_z, tm, want, want_z, otm)
+    # second variant: every other face semi-transparent (pass 2): > 2048 entries in one tile exercises the
+    # in-place global-memory tile sort and the growth of the ordered bins
+    f2 = f.copy()
+    f2["flags"][::2] = abi.face_flags(abi.FACE_TEX_NONE, abi.BLEND_AVERAGE, True, 200)
+    f2["flags"][1::4] = abi.face_flags(abi.FACE_TEX_NONE, abi.BLEND_ADD, False, 255)
+    for faces_, xray in ((f, False), (f2, False), (f2, True)):
+        for zbuf in (False, True):
+            sc = scenes.Scene("crowded_tile", v, faces_, [], pkg.Camera(),
+                              scenes.common_settings(use_zbuffer=zbuf, backface_cull=False, xray_mode=xray))
+            want, want_z, otm, rc = oracle.render_scene(sc)
+            ctx2 = pkg.Context(0)                     # fresh context: no learned bin capacity
+            got, got_z, tm = render_gpu(ctx2, sc)
+            ctx2.close()
+            assert_same(sc, got, got_z, tm, want, want_z, otm)
 
 
 def test_async_host_buffer_path(ctx, oracle):
