@@ -59,6 +59,8 @@ struct b32_ctx {
 
     // textures
     DevBuf<uint16_t> texels;
+    DevBuf<uint32_t> texmask;          // 1 bit per texel of the pool: the texel writes on a black-keyed surface
+    uint32_t texmask_words = 0;        // multiple of 4 (16-byte bulk copies)
     DevBuf<TexDev> texdesc;
     std::vector<TexDev> texdesc_h;
     uint32_t ntex = 0;
@@ -71,8 +73,14 @@ struct b32_ctx {
     DevBuf<TVert> tv;
     DevBuf<SurfRec> recs;
     DevBuf<uint64_t> keys;
-    DevBuf<uint32_t> tile_count, otile_count;
-    DevBuf<BinHead> bins, heads, obins, oheads;
+    // CallState + pass-1 tile counters live together in one of two sets used alternately: k_setup of call i
+    // zeroes the set of call i+1, so no memset sits in front of a call on the stream
+    DevBuf<uint32_t> state_ring;
+    uint32_t state_stride = 0;         // words per set
+    int state_cur = 0;
+    uint32_t* tile_count = nullptr;    // current set's tile counters
+    DevBuf<uint32_t> otile_count;
+    DevBuf<BinHead> bins, heads, obins;
     uint32_t obin_cap_hint = 0;
     DevBuf<WireTri> wire;
     uint32_t bin_cap_hint = 0;
@@ -81,7 +89,7 @@ struct b32_ctx {
     CallParams last_params{};
     DevBuf<LightDev> lights;
     DevBuf<float> dbg;
-    CallState* state = nullptr;        // device
+    CallState* state = nullptr;        // device: current set's CallState
     uint32_t* sticky = nullptr;        // device: error bits of enqueue-only calls
     CallState* state_h = nullptr;      // pinned host
     uint8_t* pinned = nullptr;         // pinned staging ring for pageable host buffers
@@ -103,6 +111,9 @@ int cuda_fail(b32_ctx* c, cudaError_t e, const char* what) {
     return fail(c, B32_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
 #define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return cuda_fail(ctx, _e, #call); } while (0)
+
+constexpr uint32_t STATE_WORDS = 16;    // CallState padded to 64 bytes; the tile counters follow
+static_assert(sizeof(CallState) <= STATE_WORDS * 4, "CallState must fit its slot");
 
 int32_t host_fx_from_f32(float f) {                 // Fixed32::from_f32, fixed.rs:125-127 (saturating `as i32`)
     float s = f * 4096.0f;
@@ -126,6 +137,7 @@ int fill_params(b32_ctx* ctx, CallParams& p, const b32_camera* cam, const b32_se
     p.half_w = (int32_t)(((uint32_t)((int32_t)ctx->width / 2)) << 12);                                // fixed.rs:399-400
     p.half_h = (int32_t)(((uint32_t)((int32_t)ctx->height / 2)) << 12);
     p.nv = nv; p.nf = nf; p.ntex = ctx->ntex;
+    p.mask_smem_words = ctx->texmask_words <= (uint32_t)OP_MASK_SMEM_WORDS ? ctx->texmask_words : 0;
     p.affine_textures = s->affine_textures != 0; p.use_zbuffer = s->use_zbuffer != 0; p.shading = s->shading;
     p.backface_cull = s->backface_cull != 0; p.dithering = s->dithering != 0; p.use_fixed_point = s->use_fixed_point != 0;
     p.xray_mode = s->xray_mode != 0; p.ortho = s->ortho_enabled != 0;
@@ -187,10 +199,19 @@ int ensure_work(b32_ctx* ctx, uint32_t nv, uint32_t nf) {
     CK(ctx->recs.reserve(m));
     CK(ctx->keys.reserve(m));
     CK(ctx->heads.reserve(m));
-    CK(ctx->oheads.reserve(m));
     uint32_t ntiles = ((ctx->width + TILE_W - 1) / TILE_W) * ((ctx->height + TILE_H - 1) / TILE_H);
-    CK(ctx->tile_count.reserve(std::max<uint32_t>(ntiles, 1)));
     CK(ctx->otile_count.reserve(std::max<uint32_t>(ntiles, 1)));
+    uint32_t need = STATE_WORDS + ((std::max<uint32_t>(ntiles, 1) + 3u) & ~3u);
+    if (need > ctx->state_stride) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->state_ring.release();
+        CK(ctx->state_ring.reserve((size_t)need * 2));
+        CK(cudaMemsetAsync(ctx->state_ring.p, 0, (size_t)need * 2 * sizeof(uint32_t), ctx->stream));
+        ctx->state_stride = need;
+        ctx->state_cur = 0;
+        ctx->state = reinterpret_cast<CallState*>(ctx->state_ring.p);
+        ctx->tile_count = ctx->state_ring.p + STATE_WORDS;
+    }
     return B32_OK;
 }
 
@@ -228,7 +249,7 @@ int render_ordered(b32_ctx* ctx, const CallParams& p, uint32_t n_ordered) {
         CK(ctx->obins.reserve((size_t)ntiles * cap2));
         CK(cudaMemsetAsync(ctx->otile_count.p, 0, ntiles * sizeof(uint32_t), st));
         CK(cudaEventRecord(ctx->ev[2], st));
-        launch_bin(L, ctx->oheads.p, ctx->obins.p, ctx->otile_count.p, ctx->state, p, cap2, true);
+        launch_bin(L, nullptr, ctx->keys.p, ctx->recs.p, ctx->obins.p, ctx->otile_count.p, ctx->state, p, cap2, true);
         CK(cudaEventRecord(ctx->ev[3], st));
         launch_fill_ordered(L, ctx->recs.p, ctx->obins.p, ctx->otile_count.p, ctx->texdesc.p, ctx->texels.p,
                             ctx->fb_rgba.p, ctx->fb_z.p, ctx->state, p, cap2);
@@ -278,16 +299,21 @@ int render_device(b32_ctx* ctx, const b32_vertex* d_verts, uint32_t nv, const b3
         p.async_call = wait ? 0 : 1;
         CK(ctx->bins.reserve((size_t)ntiles * p.bin_cap));
         ctx->last_params = p;
-        CK(cudaMemsetAsync(ctx->state, 0, sizeof(CallState), st));
-        CK(cudaMemsetAsync(ctx->tile_count.p, 0, ntiles * sizeof(uint32_t), st));
-        if (wait) CK(cudaEventRecord(ctx->ev[0], st));
         const bool wire_on = p.wire_back || p.wire_front;
         if (wire_on) CK(ctx->wire.reserve(nf));
+        if (wait) CK(cudaEventRecord(ctx->ev[0], st));
+        // take the set the previous call's k_setup zeroed; this call's k_setup zeroes the other one
+        // (nothing between here and the launch can fail, so the two sets never get out of step)
+        ctx->state_cur ^= 1;
+        ctx->state = reinterpret_cast<CallState*>(ctx->state_ring.p + (size_t)ctx->state_cur * ctx->state_stride);
+        ctx->tile_count = ctx->state_ring.p + (size_t)ctx->state_cur * ctx->state_stride + STATE_WORDS;
+        uint32_t* zero_next = ctx->state_ring.p + (size_t)(ctx->state_cur ^ 1) * ctx->state_stride;
         launch_setup(L, d_verts, d_faces, nullptr, ctx->texdesc.p, ctx->lights.p, ctx->recs.p, ctx->keys.p,
-                     ctx->heads.p, ctx->oheads.p, ctx->bins.p, ctx->tile_count.p, wire_on ? ctx->wire.p : nullptr, ctx->state, p);                          // TRANSFORM + CULL + setup + binning
+                     ctx->heads.p, ctx->bins.p, ctx->tile_count, wire_on ? ctx->wire.p : nullptr, ctx->state,
+                     zero_next, ctx->state_stride, p);                          // TRANSFORM + CULL + setup + binning
         if (wait) CK(cudaEventRecord(ctx->ev[1], st));
         if (!p.wire_front)
-            launch_fill_opaque(L, ctx->recs.p, ctx->bins.p, ctx->tile_count.p, ctx->texdesc.p, ctx->texels.p,
+            launch_fill_opaque(L, ctx->recs.p, ctx->bins.p, ctx->tile_count, ctx->texdesc.p, ctx->texels.p, ctx->texmask.p,
                                ctx->fb_rgba.p, ctx->fb_z.p, ctx->state, ctx->sticky, p);      // DRAW, pass 1
         if (!wait) { ctx->async_pending = true; return B32_OK; }
         CK(cudaEventRecord(ctx->ev[2], st));
@@ -350,13 +376,12 @@ int b32_ctx_create(int device, b32_ctx** out) {
     if ((e = cudaGetDeviceProperties(&ctx->prop, device)) != cudaSuccess) return bail(e, "cudaGetDeviceProperties");
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     for (auto& ev : ctx->ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(e, "cudaEventCreate");
-    if ((e = cudaMalloc(&ctx->state, sizeof(CallState))) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMalloc(&ctx->sticky, sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMemset(ctx->sticky, 0, sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMemset");
     if ((e = cudaMallocHost(&ctx->state_h, sizeof(CallState))) != cudaSuccess) return bail(e, "cudaMallocHost");
     ctx->pinned_bytes = 8u << 20;
     if ((e = cudaMallocHost(&ctx->pinned, ctx->pinned_bytes)) != cudaSuccess) return bail(e, "cudaMallocHost");
-    ctx->texdesc.reserve(1); ctx->texels.reserve(1); ctx->lights.reserve(1);
+    ctx->texdesc.reserve(1); ctx->texels.reserve(1); ctx->texmask.reserve(4); ctx->lights.reserve(1);
     *out = ctx;
     return B32_OK;
 }
@@ -365,11 +390,10 @@ void b32_ctx_destroy(b32_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    ctx->fb_rgba.release(); ctx->fb_z.release(); ctx->texels.release(); ctx->texdesc.release(); ctx->verts.release(); ctx->faces.release();
-    ctx->tv.release(); ctx->recs.release(); ctx->keys.release(); ctx->tile_count.release(); ctx->otile_count.release();
-    ctx->bins.release(); ctx->heads.release(); ctx->obins.release(); ctx->oheads.release(); ctx->wire.release();
+    ctx->fb_rgba.release(); ctx->fb_z.release(); ctx->texels.release(); ctx->texmask.release(); ctx->texdesc.release(); ctx->verts.release(); ctx->faces.release();
+    ctx->tv.release(); ctx->recs.release(); ctx->keys.release(); ctx->state_ring.release(); ctx->otile_count.release();
+    ctx->bins.release(); ctx->heads.release(); ctx->obins.release(); ctx->wire.release();
     ctx->lights.release(); ctx->dbg.release();
-    if (ctx->state) cudaFree(ctx->state);
     if (ctx->sticky) cudaFree(ctx->sticky);
     if (ctx->state_h) cudaFreeHost(ctx->state_h);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -495,6 +519,12 @@ int b32_textures_set(b32_ctx* ctx, const b32_tex_desc* descs, uint32_t n) {
     }
     idx.release(); clut.release();
     if (rc) return rc;
+    {   // the visibility walk of k_fill_opaque asks "does this texel write?" of a 1-bit mask, not of the texel
+        uint32_t words = (uint32_t)(((total + 31) / 32 + 3) & ~(size_t)3);
+        CK(ctx->texmask.reserve(std::max<uint32_t>(words, 4)));
+        launch_tex_mask(ctx->L(), ctx->texels.p, (uint32_t)total, words, ctx->texmask.p);
+        ctx->texmask_words = words;
+    }
     if (n) CK(cudaMemcpyAsync(ctx->texdesc.p, ctx->texdesc_h.data(), n * sizeof(TexDev), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->ntex = n;

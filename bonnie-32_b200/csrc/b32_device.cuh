@@ -17,6 +17,7 @@ constexpr int TILE_W = 16;            // screen tile owned by one CTA of k_fill
 constexpr int TILE_H = 16;
 constexpr int FILL_THREADS = TILE_W * TILE_H;
 constexpr float NEAR_PLANE = 0.1f;    // math.rs:155
+constexpr int OP_MASK_SMEM_WORDS = 2048;   // k_fill_opaque keeps the "texel writes" mask in shared memory up to 65536 texels (8 KB)
 
 // ---- per-vertex output of k_transform (render.rs:2321-2360) ------------------------------------
 // x,y,z = projected[i]; w = cam_space_positions[i].z (the only camera-space value the path reads:
@@ -108,6 +109,7 @@ struct CallParams {
     uint32_t width, height, tiles_x, tiles_y;
     uint32_t nv, nf, ntex, n_lights;
     uint32_t bin_cap;                                 // capacity (entries) of one tile bin of the opaque pass
+    uint32_t mask_smem_words;                         // words of the "texel writes" mask to stage in shared memory (0: read it from global)
     uint8_t affine_textures, use_zbuffer, shading, backface_cull, dithering, use_fixed_point, xray_mode, ortho;
     uint8_t fog_enabled, fog_r, fog_g, fog_b, fog_blend, async_call, wire_back, wire_front;   // wire_*: render.rs:2576, :2606
     float ambient, ortho_zoom, ortho_cx, ortho_cy;

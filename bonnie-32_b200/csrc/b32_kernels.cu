@@ -155,7 +155,7 @@ __device__ __forceinline__ void setup_face(uint32_t fi, const b32_vertex* __rest
                                            const LightDev* __restrict__ lights,
                                            SurfRec* __restrict__ recs, uint64_t* __restrict__ keys,
                                            CallState* __restrict__ st, const CallParams& p,
-                                           uint32_t& n_op, uint32_t& n_tr, BinHead& head, bool& binned, BinHead& ohead,
+                                           uint32_t& n_op, uint32_t& n_tr, BinHead& head, bool& binned,
                                            WireTri* __restrict__ wire) {
     binned = false;
     if (wire) wire[fi].kind = 0;
@@ -290,13 +290,8 @@ __device__ __forceinline__ void setup_face(uint32_t fi, const b32_vertex* __rest
             head = BinHead{r.bbox_x, r.bbox_y, hkey, fi};
             binned = true;
         }
-        // pass-2 surfaces (and every surface in x-ray mode) are replayed in draw order: their bin entry
-        // carries the unique 64-bit draw-order key (pass, depth key, face): opaque list first (sorted only
-        // in painter's mode), then the transparent list, ties by face index = stable sort (:2522-2542)
-        if ((transparent || p.xray_mode) && !empty) {
-            uint64_t okey = ((uint64_t)cls << 62) | ((uint64_t)dkey << 30) | fi;
-            ohead = BinHead{r.bbox_x, r.bbox_y, (uint32_t)(okey >> 32), (uint32_t)okey};
-        }
+        // pass-2 surfaces (and every surface in x-ray mode) are replayed in draw order: k_bin_opaque(ordered)
+        // rebuilds their bin entry from keys[fi] (pass, depth key) and this record's bbox.
     } while (0);
     keys[fi] = ((uint64_t)cls << 32) | dkey;
 }
@@ -305,16 +300,18 @@ __global__ void __launch_bounds__(SETUP_THREADS)
 k_setup(const b32_vertex* __restrict__ verts, const b32_face* __restrict__ faces, const TVert* __restrict__ tv,
         const TexDev* __restrict__ tex, const LightDev* __restrict__ lights,
         SurfRec* __restrict__ recs, uint64_t* __restrict__ keys,
-        BinHead* __restrict__ heads, BinHead* __restrict__ oheads, WireTri* __restrict__ wire, CallState* __restrict__ st, CallParams p) {
+        BinHead* __restrict__ heads, WireTri* __restrict__ wire, CallState* __restrict__ st,
+        uint32_t* __restrict__ zero_next, uint32_t zero_words, CallParams p) {
     __shared__ uint32_t s_cnt[2];
+    // the call after this one finds its CallState + tile counters zeroed (two sets, used alternately)
+    if (blockIdx.x == 0) for (uint32_t i = threadIdx.x; i < zero_words; i += blockDim.x) zero_next[i] = 0;
     if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
     uint32_t n_op = 0, n_tr = 0;
     for (uint32_t fi = blockIdx.x * blockDim.x + threadIdx.x; fi < p.nf; fi += gridDim.x * blockDim.x) {
-        BinHead head{0, 0, 0, fi}, ohead{0, 0, 0, 0};            // bbox 0 = not binned
+        BinHead head{0, 0, 0, fi};                               // bbox 0 = not binned
         bool binned;
-        setup_face(fi, verts, faces, tv, tex, lights, recs, keys, st, p, n_op, n_tr, head, binned, ohead, wire);
+        setup_face(fi, verts, faces, tv, tex, lights, recs, keys, st, p, n_op, n_tr, head, binned, wire);
         heads[fi] = head;
-        oheads[fi] = ohead;
     }
     // one pair of global atomics per block
     for (int o = 16; o > 0; o >>= 1) { n_op += __shfl_xor_sync(0xFFFFFFFFu, n_op, o); n_tr += __shfl_xor_sync(0xFFFFFFFFu, n_tr, o); }
@@ -341,7 +338,8 @@ __device__ __forceinline__ void head_tiles(const BinHead& h, uint32_t& tx0, uint
 }
 
 __global__ void __launch_bounds__(BIN_THREADS)
-k_bin_opaque(const BinHead* __restrict__ heads, BinHead* __restrict__ bins, uint32_t* __restrict__ tile_count,
+k_bin_opaque(const BinHead* __restrict__ heads, const uint64_t* __restrict__ keys, const SurfRec* __restrict__ recs,
+             BinHead* __restrict__ bins, uint32_t* __restrict__ tile_count,
              CallState* __restrict__ st, CallParams p, uint32_t bin_cap, bool ordered) {
     extern __shared__ uint32_t s_tiles[];            // [ntiles] counts/cursors, [ntiles] bases (when ntiles <= BIN_MAX_TILES)
     const uint32_t ntiles = p.tiles_x * p.tiles_y;
@@ -358,7 +356,22 @@ k_bin_opaque(const BinHead* __restrict__ heads, BinHead* __restrict__ bins, uint
         #pragma unroll
         for (int k = 0; k < BIN_FPT; ++k) {
             uint32_t fi = base + k * BIN_THREADS + threadIdx.x;
-            head[k] = fi < p.nf ? heads[fi] : BinHead{0, 0, 0, 0};
+            head[k] = BinHead{0, 0, 0, 0};
+            if (fi < p.nf) {
+                if (!ordered) head[k] = heads[fi];
+                else {
+                    // draw-order entry of a pass-2 surface (or of any surface in x-ray mode): the unique 64-bit key
+                    // (pass:2 | depth key:32 | face:30) = opaque list first (sorted only in painter's mode), then the
+                    // transparent list, ties by face index = stable sort (render.rs:2522-2542)
+                    uint64_t k64 = keys[fi];
+                    uint32_t cls = (uint32_t)(k64 >> 32);
+                    if (cls < 2 && (cls == 1 || p.xray_mode)) {
+                        uint2 bb = *reinterpret_cast<const uint2*>(&recs[fi].bbox_x);      // all zero = empty surface
+                        uint64_t okey = ((uint64_t)cls << 62) | ((uint64_t)(uint32_t)k64 << 30) | fi;
+                        if (bb.x) head[k] = BinHead{bb.x, bb.y, (uint32_t)(okey >> 32), (uint32_t)okey};
+                    }
+                }
+            }
         }
         if (aggregate) {
             #pragma unroll
@@ -504,43 +517,75 @@ __device__ __forceinline__ bool shade(const SurfRec& r, uint32_t x, uint32_t y, 
 // =================================================================================================
 // k_fill_opaque — pass 1, order-free, visibility first
 // =================================================================================================
-// One CTA per 16x16 screen tile; one warp per 4x4 pixel block; a pixel is owned by TWO lanes (lane
-// and lane+16) that evaluate different surfaces at the same time and merge their winners — the
-// winner rule is associative, so the merge is exact.
+// One CTA per 16x8 half of a 16x16 screen tile (all CTAs of a 320x240 frame are resident at once); one
+// warp per 4x4 pixel block; a pixel is owned by TWO lanes (lane and lane+16) that evaluate different
+// surfaces at the same time and merge their winners — the winner rule is associative, so the merge is
+// exact.
 //   1. the tile's bin (<= OP_SORT_MAX entries) is copied into shared memory in walk-key order with
 //      one counting-sort pass: painter's mode = nearest (last drawn) first, z-buffer mode = smallest
 //      depth lower bound first.  The order is an efficiency device only: the per-pixel winner rule is
 //      exact for ANY order, ties and all, so larger bins are simply walked unordered from global memory.
-//   2. every warp walks the list 32 entries at a time: lanes first act as entry filters (bbox vs the
-//      warp's block, priority / depth bound vs the block's weakest pixel), survivors are compacted,
-//      their records staged in shared memory, then lanes act as pixels.  The walk only decides WHO
-//      wins each pixel: inside test, depth, and — for black-keyed textured surfaces — the texel
-//      transparency test, whose loads are issued for a whole staged group before any is consumed.
-//   3. the walk stops as soon as no later entry can change any pixel of the block.
-//   4. each pixel shades its winner once (texture, modulate, lighting, dither), at the end.
-// Measured (profiles/): the kernel is bound by dependent latency (L2 round trips + f32 chains), not by
-// instruction issue or DRAM, so the structure minimises the number of dependent global round trips.
+//   2. the CTA streams the surface records of the walk order through a 3-deep shared-memory ring,
+//      OP_CHUNK records per step, one 16-byte cp.async per thread: the loads of steps c+1 and c+2 are in
+//      flight while the warps work on step c, so no warp ever waits for an L2 round trip of its own.
+//   3. every warp filters the step's entries one per lane (bbox vs the block's still-open pixels,
+//      priority / depth bound vs the block's weakest pixel); survivors are evaluated two per half-warp at
+//      a time.  The walk only decides WHO wins each pixel: inside test, depth, and — for black-keyed
+//      textured surfaces — whether the texel writes at all, answered by a 1-bit-per-texel mask of the
+//      texel pool that a TMA bulk copy (cp.async.bulk + mbarrier) put into shared memory at CTA start
+//      (8 KB for a 256x256 atlas; larger pools read the mask through L1).
+//   4. a warp stops as soon as no later entry can change any pixel of its block; the CTA stops when all
+//      its warps have.
+//   5. each pixel shades its winner once (texture, modulate, lighting, dither), at the end.
 #ifndef B32_OP_THREADS
 #define B32_OP_THREADS 256
 #endif
 constexpr int OP_THREADS = B32_OP_THREADS;   // 256: 8 warps = half a tile (16x8 px), two CTAs per tile; 512: one CTA per tile
 constexpr int OP_SPLIT = 512 / OP_THREADS;   // CTAs per tile
 constexpr int OP_WARPS = OP_THREADS / 32;
-constexpr int OP_STAGE = 8;          // surface records staged per warp per step (8 x 128 B)
-constexpr int OP_SORT_MAX = 1024;    // bin entries orderable in shared memory (16 KB of heads)
-constexpr int OP_TEX_SMEM = 256;     // texture descriptors cached in shared memory
-constexpr size_t OP_SMEM = (size_t)OP_SORT_MAX * sizeof(BinHead) + (size_t)OP_WARPS * 32 * sizeof(BinHead) +
-                           (size_t)OP_WARPS * OP_STAGE * sizeof(SurfRec) + (size_t)OP_TEX_SMEM * sizeof(TexDev);
+constexpr int OP_CHUNK = OP_THREADS / 8;     // surface records staged per step (8 x 16 B each => one piece per thread)
+constexpr int OP_RING = 3;                   // ring depth: steps c, c+1, c+2
+constexpr int OP_SORT_MAX = 1024;            // bin entries orderable in shared memory (16 KB of heads)
+constexpr int OP_TEX_SMEM = 256;             // texture descriptors cached in shared memory
+constexpr size_t OP_SMEM = (size_t)OP_SORT_MAX * sizeof(BinHead) + (size_t)OP_RING * OP_CHUNK * sizeof(SurfRec) +
+                           (size_t)OP_TEX_SMEM * sizeof(TexDev) + (size_t)OP_MASK_SMEM_WORDS * 4 +
+                           (size_t)OP_WARPS * 32 * sizeof(uint2) + (size_t)OP_WARPS * 32;
 #ifdef B32_FILL_STATS
 __device__ uint32_t g_fill_stats[4096 * 16 * 8];     // [tile][warp][8]: t_start, t_sorted, t_end, batches, survivors, inside, shaded, smid
 __device__ __forceinline__ uint32_t smid() { uint32_t r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t gtime() { uint64_t t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return (uint32_t)t; }
 #endif
 
-// texel of the surface at barycentric (bc): render.rs:1563-1586, types.rs:671-681.  Returns its address
-// in the texel pool, or nullptr for a zero-sized texture (sample() = TRANSPARENT).
-__device__ __forceinline__ const uint16_t* texel_addr(const SurfRec& r, float bc_x, float bc_y, float bc_z, float inv_z,
-                                                      const TexDev& t, const uint16_t* __restrict__ texels, const CallParams& p) {
+// ---- asynchronous copies ----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+// texel of the surface at barycentric (bc): render.rs:1563-1586, types.rs:671-681.  Returns its index
+// in the texel pool, or TEXEL_NONE for a zero-sized texture (sample() = TRANSPARENT).
+constexpr uint32_t TEXEL_NONE = 0xFFFFFFFFu;
+template <typename Rec>
+__device__ __forceinline__ uint32_t texel_index(const Rec& r, float bc_x, float bc_y, float bc_z, float inv_z,
+                                                const TexDev& t, const CallParams& p) {
     float u, v;
     if (p.affine_textures) {                                                   // :1563-1567
         u = bc_x * r.u1 + bc_y * r.u2 + bc_z * r.u3;
@@ -551,26 +596,29 @@ __device__ __forceinline__ const uint16_t* texel_addr(const SurfRec& r, float bc
         u = uo / inv_z;
         v = vo / inv_z;
     }
-    if (t.w == 0 || t.h == 0) return nullptr;                                  // types.rs:673-675
+    if (t.w == 0 || t.h == 0) return TEXEL_NONE;                               // types.rs:673-675
     float uw = rem_euclid1(u), vw = rem_euclid1(1.0f - v);                     // :1583, types.rs:676-677
     uint32_t tx = min(f2u32sat(uw * (float)t.w), t.w - 1);
     uint32_t ty = min(f2u32sat(vw * (float)t.h), t.h - 1);
-    return texels + t.off + ty * t.w + tx;
+    return t.off + ty * t.w + tx;
 }
 
 __global__ void __launch_bounds__(OP_THREADS, OP_THREADS == 256 ? 5 : 2)
 k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins, const uint32_t* __restrict__ tile_count,
-              const TexDev* __restrict__ tex, const uint16_t* __restrict__ texels,
+              const TexDev* __restrict__ tex, const uint16_t* __restrict__ texels, const uint32_t* __restrict__ texmask,
               uint32_t* __restrict__ fb_rgba, float* __restrict__ fb_z, const CallState* __restrict__ st,
               uint32_t* __restrict__ sticky, CallParams p) {
-    extern __shared__ __align__(16) uint8_t op_smem[];
-    BinHead* s_sh = reinterpret_cast<BinHead*>(op_smem);                               // [OP_SORT_MAX] bin in walk order
-    BinHead* s_head = s_sh + OP_SORT_MAX;                                               // [OP_WARPS][32] survivors
-    SurfRec* s_rec = reinterpret_cast<SurfRec*>(s_head + OP_WARPS * 32);                // [OP_WARPS][OP_STAGE]
-    TexDev* s_tex = reinterpret_cast<TexDev*>(s_rec + OP_WARPS * OP_STAGE);             // [OP_TEX_SMEM]
+    extern __shared__ __align__(128) uint8_t op_smem[];
+    SurfRec* s_rec = reinterpret_cast<SurfRec*>(op_smem);                               // [OP_RING][OP_CHUNK] record ring
+    BinHead* s_sh = reinterpret_cast<BinHead*>(s_rec + OP_RING * OP_CHUNK);             // [OP_SORT_MAX] bin in walk order
+    TexDev* s_tex = reinterpret_cast<TexDev*>(s_sh + OP_SORT_MAX);                      // [OP_TEX_SMEM]
+    uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_tex + OP_TEX_SMEM);                // [OP_MASK_SMEM_WORDS] "texel writes" bits
+    uint2* s_surv = reinterpret_cast<uint2*>(s_mask + OP_MASK_SMEM_WORDS);              // [OP_WARPS][32] survivors: (key, face)
+    uint8_t* s_sidx = reinterpret_cast<uint8_t*>(s_surv + OP_WARPS * 32);               // [OP_WARPS][32] ... and their slot in the ring step
     __shared__ uint32_t s_hist[256];
     __shared__ uint32_t s_wsum[8];
     __shared__ uint32_t s_minmax[2];
+    __shared__ __align__(8) uint64_t s_mbar;
     {
         CallState s = *st;
         bool aborts = call_aborts(s, p.use_zbuffer);
@@ -583,6 +631,10 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
     const uint32_t tile = blockIdx.x / OP_SPLIT, half = blockIdx.x % OP_SPLIT;
     const uint32_t n = tile_count[tile];
     if (n == 0) return;
+    // the "texel writes" mask of the whole texel pool travels by TMA while the bin is sorted
+    const bool mask_staged = p.mask_smem_words != 0;
+    if (mask_staged && threadIdx.x == 0) { mbar_init(&s_mbar, 1); bulk_g2s(s_mask, texmask, p.mask_smem_words * 4, &s_mbar); }
+    const uint32_t* maskw = mask_staged ? s_mask : texmask;
     const BinHead* bin = bins + (size_t)tile * p.bin_cap;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t pix = lane & 15, sub = lane >> 4;
@@ -651,125 +703,161 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
             if (i < n) s_sh[atomicAdd(&s_hist[hh[q].key == 0xFFFFFFFFu ? 0 : 255 - ((hh[q].key - kmin) >> shift)], 1u)] = hh[q];
         }
     }
-    __syncthreads();                                      // s_sh and s_tex are ready
+    __syncthreads();                                      // s_sh, s_tex and the mbarrier are ready
 
-    if (bx0 >= p.width || by0 >= p.height) return;        // whole warp off-screen (no CTA-wide sync below)
+    // ---- 2. the record ring: step c -> slot c % OP_RING; thread t moves piece (t & 7) of entry (t >> 3)
+    auto stage = [&](uint32_t c) {
+        uint32_t e = c * OP_CHUNK + (threadIdx.x >> 3);
+        if (e < n) {
+            uint32_t f = sorted ? s_sh[e].face : bin[e].face;
+            cp_async16(reinterpret_cast<uint4*>(&s_rec[(c % OP_RING) * OP_CHUNK + (threadIdx.x >> 3)]) + (threadIdx.x & 7),
+                       reinterpret_cast<const uint4*>(&recs[f]) + (threadIdx.x & 7));
+        }
+        cp_async_commit();
+    };
+    stage(0);
+    stage(1);
+
+    bool done = bx0 >= p.width || by0 >= p.height;        // whole warp off-screen
     const Pixel px0 = px;
     // painter's: best = (key << 32 | face) + 1 of the winner so far (0 = framebuffer content)
     // z-buffer : best_face = face + 1 of the winner so far (0 = framebuffer content), its depth in px.z
     uint64_t best = valid ? 0ull : ~0ull;
     uint32_t best_face = 0;
-    BinHead* my_heads = s_head + warp * 32;
-    SurfRec* my_recs = s_rec + warp * OP_STAGE;
+    uint2* my_surv = s_surv + warp * 32;
+    uint8_t* my_sidx = s_sidx + warp * 32;
 #ifdef B32_FILL_STATS
     uint32_t st_t1 = gtime();
 #endif
+    if (mask_staged) while (!mbar_try_wait(&s_mbar, 0)) {}
+#ifdef B32_FILL_STATS
+    uint32_t st_tm = gtime(), st_tl = 0;
+#endif
 
-    for (uint32_t base = 0; base < n; base += 32) {
+    const uint32_t nchunks = (n + OP_CHUNK - 1) / OP_CHUNK;
+    for (uint32_t c = 0; c < nchunks; ++c) {
+        cp_async_wait<1>();                               // this thread's pieces of step c have landed ...
+        if (__syncthreads_and(done)) break;               // ... and so have everybody else's; slot (c+2) % 3 is free again
+        stage(c + 2);
+        if (done) continue;
+        const SurfRec* crec = s_rec + (c % OP_RING) * OP_CHUNK;
+        for (uint32_t sb = 0; sb < (uint32_t)OP_CHUNK; sb += 32) {
+            const uint32_t base = c * OP_CHUNK + sb;
+            if (base >= n) break;
 #ifdef B32_FILL_STATS
-        ++st_batches;
+            ++st_batches;
 #endif
-        // ---- what the weakest pixel of this block still accepts ----------------------------------------
-        uint64_t wmin = best;                              // painter's: smallest winner priority in the block
-        float wz = valid ? px.z : -INFINITY;               // z-buffer: largest depth in the block
-        for (int o = 8; o > 0; o >>= 1) {                  // (both halves hold the same merged state)
-            uint64_t t = __shfl_xor_sync(0xFFFFFFFFu, wmin, o); wmin = t < wmin ? t : wmin;
-            wz = fmaxf(wz, __shfl_xor_sync(0xFFFFFFFFu, wz, o));
-        }
-        // ---- 3. early out: entries are in descending key-bucket order ------------------------------------
-        // `open` pixels are those some entry of this batch or a later one could still change; only their
-        // bounding box [ox0,ox1) x [oy0,oy1) needs to be met by a surface's bbox.
-        uint32_t ox0 = bx0, ox1 = bx0 + 4, oy0 = by0, oy1 = by0 + 4;
-        if (sorted) {
-            uint32_t k0 = s_sh[base].key;
-            if (k0 != 0xFFFFFFFFu) {
-                // upper bound of every key still to come = top of k0's bucket
-                uint64_t ub64 = (uint64_t)kmin + (((uint64_t)((k0 - kmin) >> shift) + 1) << shift) - 1;
-                uint32_t ub = ub64 > 0xFFFFFFFEull ? 0xFFFFFFFEu : (uint32_t)ub64;
-                if (!p.use_zbuffer) { if (wmin != 0 && ub < (uint32_t)((wmin - 1) >> 32)) break; }
-                else if (__uint_as_float(~ub) > wz) break;                   // every later surface is behind every pixel
-                bool open = valid && (!p.use_zbuffer ? (best == 0 || (uint32_t)((best - 1) >> 32) <= ub)
-                                                     : !(__uint_as_float(~ub) > px.z));
-                uint32_t om = __ballot_sync(0xFFFFFFFFu, open) & 0xFFFFu;     // bit q = pixel q (row-major 4x4) is open
-                if (om == 0) break;
-                uint32_t cols = (om | (om >> 4) | (om >> 8) | (om >> 12)) & 0xFu;
-                uint32_t rows = ((om & 0x000Fu) ? 1u : 0u) | ((om & 0x00F0u) ? 2u : 0u) | ((om & 0x0F00u) ? 4u : 0u) | ((om & 0xF000u) ? 8u : 0u);
-                ox0 = bx0 + (__ffs(cols) - 1); ox1 = bx0 + (32 - __clz(cols));
-                oy0 = by0 + (__ffs(rows) - 1); oy1 = by0 + (32 - __clz(rows));
+            // ---- what the weakest pixel of this block still accepts ----------------------------------------
+            // painter's: wkey = smallest winner KEY in the block (0 while some pixel has no winner); z-buffer: wz =
+            // largest depth in the block.  One warp reduction (REDUX) each; both halves hold the same merged state.
+            uint32_t wkey = 0;
+            float wz = 0.0f;
+            if (!p.use_zbuffer) {
+                bool allw = __all_sync(0xFFFFFFFFu, best != 0);                          // invalid lanes carry ~0
+                wkey = allw ? __reduce_min_sync(0xFFFFFFFFu, (uint32_t)((best - 1) >> 32)) : 0u;
+            } else {
+                // order-preserving image of the depth (NaN never occurs in px.z: only `z < px.z` winners are stored)
+                uint32_t zb = __float_as_uint(valid ? px.z : -INFINITY);
+                zb ^= (zb >> 31) ? 0xFFFFFFFFu : 0x80000000u;
+                zb = __reduce_max_sync(0xFFFFFFFFu, zb);
+                zb ^= (zb >> 31) ? 0x80000000u : 0xFFFFFFFFu;
+                wz = __uint_as_float(zb);
             }
-        }
-        // ---- 2a. filter 32 bin entries, one per lane ------------------------------------------------------
-        BinHead h{0, 0, 0, 0};
-        bool cand = false;
-        if (base + lane < n) {
-            h = sorted ? s_sh[base + lane] : bin[base + lane];
-            uint32_t min_x = h.bbox_x & 0xFFFF, max_x = h.bbox_x >> 16, min_y = h.bbox_y & 0xFFFF, max_y = h.bbox_y >> 16;
-            cand = !(max_x <= ox0 || min_x >= ox1 || max_y <= oy0 || min_y >= oy1);
-            if (!p.use_zbuffer) cand = cand && ((((uint64_t)h.key << 32) | h.face) + 1) > wmin;
-            else cand = cand && (h.key == 0xFFFFFFFFu || !(__uint_as_float(~h.key) > wz));
-        }
-        uint32_t mask = __ballot_sync(0xFFFFFFFFu, cand);
-        if (mask == 0) continue;
-        uint32_t cnt = __popc(mask);
+            // ---- 4. early out: entries are in descending key-bucket order ------------------------------------
+            // `open` pixels are those some entry of this batch or a later one could still change; only their
+            // bounding box [ox0,ox1) x [oy0,oy1) needs to be met by a surface's bbox.
+            uint32_t ox0 = bx0, ox1 = bx0 + 4, oy0 = by0, oy1 = by0 + 4;
+            if (sorted) {
+                uint32_t k0 = s_sh[base].key;
+                if (k0 != 0xFFFFFFFFu) {
+                    // upper bound of every key still to come = top of k0's bucket
+                    uint64_t ub64 = (uint64_t)kmin + (((uint64_t)((k0 - kmin) >> shift) + 1) << shift) - 1;
+                    uint32_t ub = ub64 > 0xFFFFFFFEull ? 0xFFFFFFFEu : (uint32_t)ub64;
+                    if (!p.use_zbuffer) { if (ub < wkey) { done = true; break; } }    // every later surface was drawn before every winner
+                    else if (__uint_as_float(~ub) > wz) { done = true; break; }   // every later surface is behind every pixel
+                    bool open = valid && (!p.use_zbuffer ? (best == 0 || (uint32_t)((best - 1) >> 32) <= ub)
+                                                         : !(__uint_as_float(~ub) > px.z));
+                    uint32_t om = __ballot_sync(0xFFFFFFFFu, open) & 0xFFFFu;     // bit q = pixel q (row-major 4x4) is open
+                    if (om == 0) { done = true; break; }
+                    uint32_t cols = (om | (om >> 4) | (om >> 8) | (om >> 12)) & 0xFu;
+                    uint32_t rows = ((om & 0x000Fu) ? 1u : 0u) | ((om & 0x00F0u) ? 2u : 0u) | ((om & 0x0F00u) ? 4u : 0u) | ((om & 0xF000u) ? 8u : 0u);
+                    ox0 = bx0 + (__ffs(cols) - 1); ox1 = bx0 + (32 - __clz(cols));
+                    oy0 = by0 + (__ffs(rows) - 1); oy1 = by0 + (32 - __clz(rows));
+                }
+            }
+            // ---- 3a. filter 32 bin entries, one per lane ------------------------------------------------------
+            BinHead h{0, 0, 0, 0};
+            bool cand = false;
+            if (base + lane < n) {
+                h = sorted ? s_sh[base + lane] : bin[base + lane];
+                uint32_t min_x = h.bbox_x & 0xFFFF, max_x = h.bbox_x >> 16, min_y = h.bbox_y & 0xFFFF, max_y = h.bbox_y >> 16;
+                cand = !(max_x <= ox0 || min_x >= ox1 || max_y <= oy0 || min_y >= oy1);
+                if (!p.use_zbuffer) cand = cand && h.key >= wkey;
+                else cand = cand && (h.key == 0xFFFFFFFFu || !(__uint_as_float(~h.key) > wz));
+                if (cand) {
+                    // trivial reject against the open box (clipped to the bbox).  For SF_FAST_EDGE surfaces the edge
+                    // values are exact integers, linear in (x, y), and bc = fl(w * inv_area) is monotone in w, so
+                    // each barycentric's extreme over the box is at a corner; bc_z = fl(fl(1 - bc_x) - bc_y) is
+                    // monotone non-increasing in both.  A surface whose upper bounds fail `>= -0.0001` (:1541)
+                    // has no inside pixel in the box.
+                    const SurfRec& r = crec[sb + lane];
+                    if (r.flags & SF_FAST_EDGE) {
+                        float dx0 = (float)(max(ox0, min_x) - min_x), dx1 = (float)(min(ox1, max_x) - 1 - min_x);
+                        float dy0 = (float)(max(oy0, min_y) - min_y), dy1 = (float)(min(oy1, max_y) - 1 - min_y);
+                        float r0 = r.w0s + dy0 * r.b0, r1 = r.w0s + dy1 * r.b0, q0 = r.w1s + dy0 * r.b1, q1 = r.w1s + dy1 * r.b1;
+                        float ax0 = dx0 * r.a0, ax1 = dx1 * r.a0, cx0 = dx0 * r.a1, cx1 = dx1 * r.a1;
+                        float x00 = (r0 + ax0) * r.inv_area, x01 = (r0 + ax1) * r.inv_area, x10 = (r1 + ax0) * r.inv_area, x11 = (r1 + ax1) * r.inv_area;
+                        float y00 = (q0 + cx0) * r.inv_area, y01 = (q0 + cx1) * r.inv_area, y10 = (q1 + cx0) * r.inv_area, y11 = (q1 + cx1) * r.inv_area;
+                        float xmax = fmaxf(fmaxf(x00, x01), fmaxf(x10, x11)), xmin = fminf(fminf(x00, x01), fminf(x10, x11));
+                        float ymax = fmaxf(fmaxf(y00, y01), fmaxf(y10, y11)), ymin = fminf(fminf(y00, y01), fminf(y10, y11));
+                        const float ERR = -0.0001f;
+                        float zub = 1.0f - xmin - ymin;
+                        if (xmax < ERR || ymax < ERR || zub < ERR) cand = false;
+                    }
+                }
+            }
+            uint32_t mask = __ballot_sync(0xFFFFFFFFu, cand);
+            if (mask == 0) continue;
+            uint32_t cnt = __popc(mask);
 #ifdef B32_FILL_STATS
-        st_surv += cnt;
+            st_surv += cnt;
 #endif
-        __syncwarp();
-        if (cand) my_heads[__popc(mask & ((1u << lane) - 1))] = h;
-        __syncwarp();
-        // ---- 2b. survivors, OP_STAGE records at a time; each half-warp takes every other record -----------
-        for (uint32_t s0 = 0; s0 < cnt; s0 += OP_STAGE) {
-            uint32_t m = min((uint32_t)OP_STAGE, cnt - s0);
             __syncwarp();
-            #pragma unroll
-            for (int g = 0; g < OP_STAGE / 4; ++g) {          // 32 lanes x 16 B = 4 records per round
-                uint32_t ri = g * 4 + (lane >> 3);
-                if (ri < m) reinterpret_cast<uint4*>(&my_recs[ri])[lane & 7] =
-                    reinterpret_cast<const uint4*>(&recs[my_heads[s0 + ri].face])[lane & 7];
-            }
+            if (cand) { uint32_t pos = __popc(mask & ((1u << lane) - 1)); my_surv[pos] = make_uint2(h.key, h.face); my_sidx[pos] = (uint8_t)(sb + lane); }
             __syncwarp();
-            // visibility of this half-warp's records: all inside tests and texel requests first ...
-            constexpr int PER = OP_STAGE / 2;
-            uint64_t c_prio[PER]; float c_z[PER]; uint32_t c_face[PER]; uint32_t c_tex[PER]; bool c_ok[PER];
-            #pragma unroll
-            for (int k = 0; k < PER; ++k) {
-                c_ok[k] = false; c_tex[k] = 1; c_prio[k] = 0; c_z[k] = 0.0f; c_face[k] = 0;
-                uint32_t i = sub + 2 * k;
-                if (i >= m) continue;
-                const SurfRec& r = my_recs[i];
-                const BinHead hd = my_heads[s0 + i];
-                uint32_t min_x = hd.bbox_x & 0xFFFF, max_x = hd.bbox_x >> 16, min_y = hd.bbox_y & 0xFFFF, max_y = hd.bbox_y >> 16;
-                if (!(valid && x >= min_x && x < max_x && y >= min_y && y < max_y)) continue;
-                c_face[k] = hd.face + 1;
-                if (!p.use_zbuffer) {
-                    c_prio[k] = (((uint64_t)hd.key << 32) | hd.face) + 1;
-                    if (c_prio[k] <= best) continue;              // drawn earlier than the current winner
-                }
-                float bc_x, bc_y, bc_z;
-                if (!inside_test(r, x, y, bc_x, bc_y, bc_z)) continue;
-                float inv_z = 0.0f;
-                if (p.use_zbuffer || !p.affine_textures) inv_z = bc_x * r.iz1 + bc_y * r.iz2 + bc_z * r.iz3;   // :1549
-                if (p.use_zbuffer) {
-                    // lexicographic (z, face) minimum == sequential `z < zbuffer` in face order (:1553-1560, :1684)
-                    c_z[k] = 1.0f / inv_z;
-                    if (!(c_z[k] < px.z || (c_z[k] == px.z && c_face[k] < best_face))) continue;
-                }
-                c_ok[k] = true;
+            // ---- 3b. survivors: each half-warp takes every other one, two at a time ----------------------------
+            for (uint32_t j0 = 0; j0 < cnt; j0 += 4) {
+                #pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    uint32_t j = j0 + 2 * k + sub;
+                    if (j >= cnt) continue;
+                    const SurfRec& r = crec[my_sidx[j]];
+                    const uint2 kf = my_surv[j];
+                    uint32_t min_x = r.bbox_x & 0xFFFF, max_x = r.bbox_x >> 16, min_y = r.bbox_y & 0xFFFF, max_y = r.bbox_y >> 16;
+                    if (!(valid && x >= min_x && x < max_x && y >= min_y && y < max_y)) continue;
+                    uint32_t c_face = kf.y + 1;
+                    uint64_t c_prio = (((uint64_t)kf.x << 32) | kf.y) + 1;
+                    if (!p.use_zbuffer && c_prio <= best) continue;               // drawn earlier than the current winner
+                    float bc_x, bc_y, bc_z;
+                    if (!inside_test(r, x, y, bc_x, bc_y, bc_z)) continue;
+                    float inv_z = 0.0f, c_z = 0.0f;
+                    if (p.use_zbuffer || !p.affine_textures) inv_z = bc_x * r.iz1 + bc_y * r.iz2 + bc_z * r.iz3;   // :1549
+                    if (p.use_zbuffer) {
+                        // lexicographic (z, face) minimum == sequential `z < zbuffer` in face order (:1553-1560, :1684)
+                        c_z = 1.0f / inv_z;
+                        if (!(c_z < px.z || (c_z == px.z && c_face < best_face))) continue;
+                    }
 #ifdef B32_FILL_STATS
-                ++st_inside;
+                    ++st_inside;
 #endif
-                // black-keyed textured surface: the texel decides whether this fragment writes (:1591-1607)
-                if ((r.flags & (SF_TEXTURED | SF_BLACK_TR)) == (SF_TEXTURED | SF_BLACK_TR)) {
-                    const uint16_t* a = texel_addr(r, bc_x, bc_y, bc_z, inv_z, texd[r.flags >> 16], texels, p);
-                    c_tex[k] = a ? __ldg(a) : 0u;
+                    // black-keyed textured surface: the texel decides whether this fragment writes (:1591-1607)
+                    if ((r.flags & (SF_TEXTURED | SF_BLACK_TR)) == (SF_TEXTURED | SF_BLACK_TR)) {
+                        uint32_t ti = texel_index(r, bc_x, bc_y, bc_z, inv_z, texd[r.flags >> 16], p);
+                        if (ti == TEXEL_NONE || !((maskw[ti >> 5] >> (ti & 31)) & 1u)) continue;    // transparent key / black-keyed texel
+                    }
+                    if (!p.use_zbuffer) best = c_prio;
+                    else { px.z = c_z; best_face = c_face; }
                 }
-            }
-            // ... then the winners
-            #pragma unroll
-            for (int k = 0; k < PER; ++k) {
-                if (!c_ok[k] || (c_tex[k] & 0x7FFF) == 0) continue;       // transparent key / black-keyed texel: no write
-                if (!p.use_zbuffer) { if (c_prio[k] > best) best = c_prio[k]; }
-                else if (c_z[k] < px.z || (c_z[k] == px.z && c_face[k] < best_face)) { px.z = c_z[k]; best_face = c_face[k]; }
             }
             {   // merge the two half-warps' winners for each pixel (exact: max / lexicographic min are associative)
                 uint64_t ob = __shfl_xor_sync(0xFFFFFFFFu, best, 16);
@@ -781,7 +869,11 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
             }
         }
     }
-    // ---- 4. shade each pixel's winner once (lanes 0..15 of the warp) ------------------------------------------
+    cp_async_wait<0>();
+#ifdef B32_FILL_STATS
+    st_tl = gtime();
+#endif
+    // ---- 5. shade each pixel's winner once (lanes 0..15 of the warp) ------------------------------------------
     if (valid && sub == 0) {
         uint32_t winner = p.use_zbuffer ? best_face : (best ? (uint32_t)((best - 1) & 0xFFFFFFFFu) + 1 : 0);
         if (winner) {
@@ -804,7 +896,7 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
         for (int o = 16; o > 0; o >>= 1) { st_inside += __shfl_xor_sync(0xFFFFFFFFu, st_inside, o); st_shaded += __shfl_xor_sync(0xFFFFFFFFu, st_shaded, o); }
         if (lane == 0 && tile < 4096) {
             uint32_t* o = g_fill_stats + (tile * 16 + half * OP_WARPS + warp) * 8;
-            o[0] = st_t0; o[1] = st_t1; o[2] = gtime(); o[3] = st_batches; o[4] = st_surv; o[5] = st_inside; o[6] = st_shaded; o[7] = smid();
+            o[0] = st_t0; o[1] = st_t1; o[2] = gtime(); o[3] = st_batches; o[4] = st_surv; o[5] = st_tm; o[6] = st_tl; o[7] = smid();
         }
     }
 #endif
@@ -1023,6 +1115,19 @@ __global__ void k_tex_expand(const uint8_t* __restrict__ idx, const uint16_t* __
     }
 }
 
+// "texel writes" mask of the texel pool: bit i = (texel i & 0x7FFF) != 0, i.e. the texel of a black-keyed
+// surface is neither the transparent key 0x0000 nor black (render.rs:1591-1607).  One thread per word.
+__global__ void k_tex_mask(const uint16_t* __restrict__ texels, uint32_t n_texels, uint32_t n_words, uint32_t* __restrict__ mask) {
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += gridDim.x * blockDim.x) {
+        uint32_t m = 0;
+        for (uint32_t b = 0; b < 32; ++b) {
+            uint32_t i = w * 32 + b;
+            if (i < n_texels && (texels[i] & 0x7FFFu)) m |= 1u << b;
+        }
+        mask[w] = m;
+    }
+}
+
 // =================================================================================================
 // launchers (host)
 // =================================================================================================
@@ -1039,35 +1144,36 @@ void launch_transform(const LaunchCtx& L, const b32_vertex* verts, TVert* out, f
 }
 
 void launch_setup(const LaunchCtx& L, const b32_vertex* verts, const b32_face* faces, const TVert* tv, const TexDev* tex,
-                  const LightDev* lights, SurfRec* recs, uint64_t* keys, BinHead* heads, BinHead* oheads, BinHead* bins,
-                  uint32_t* tile_count, WireTri* wire, CallState* st, const CallParams& p) {
+                  const LightDev* lights, SurfRec* recs, uint64_t* keys, BinHead* heads, BinHead* bins,
+                  uint32_t* tile_count, WireTri* wire, CallState* st, uint32_t* zero_next, uint32_t zero_words, const CallParams& p) {
     if (p.nf == 0) return;
-    k_setup<<<grid_for(p.nf, SETUP_THREADS, L.sms, 16), SETUP_THREADS, 0, L.stream>>>(verts, faces, tv, tex, lights, recs, keys, heads, oheads, wire, st, p);
+    k_setup<<<grid_for(p.nf, SETUP_THREADS, L.sms, 16), SETUP_THREADS, 0, L.stream>>>(verts, faces, tv, tex, lights, recs, keys, heads, wire, st,
+                                                                                      zero_next, zero_words, p);
     ++*L.launches;
     if (p.xray_mode || p.wire_front) return;        // wireframe_overlay draws no solid surfaces (:2550)
-    launch_bin(L, heads, bins, tile_count, st, p, p.bin_cap, false);
+    launch_bin(L, heads, keys, recs, bins, tile_count, st, p, p.bin_cap, false);
 }
 
-void launch_bin(const LaunchCtx& L, const BinHead* heads, BinHead* bins, uint32_t* tile_count, CallState* st, const CallParams& p,
-                uint32_t bin_cap, bool ordered) {
+void launch_bin(const LaunchCtx& L, const BinHead* heads, const uint64_t* keys, const SurfRec* recs, BinHead* bins, uint32_t* tile_count,
+                CallState* st, const CallParams& p, uint32_t bin_cap, bool ordered) {
     if (p.nf == 0) return;
     uint32_t ntiles = p.tiles_x * p.tiles_y;
     size_t smem = ntiles <= (uint32_t)BIN_MAX_TILES ? (size_t)ntiles * 8 : 0;
     uint32_t per_round = BIN_THREADS * BIN_FPT;
     uint32_t grid = (p.nf + per_round - 1) / per_round;
     if (grid > L.sms * 4) grid = L.sms * 4;
-    k_bin_opaque<<<grid, BIN_THREADS, smem, L.stream>>>(heads, bins, tile_count, st, p, bin_cap, ordered);
+    k_bin_opaque<<<grid, BIN_THREADS, smem, L.stream>>>(heads, keys, recs, bins, tile_count, st, p, bin_cap, ordered);
     ++*L.launches;
 }
 
 void launch_fill_opaque(const LaunchCtx& L, const SurfRec* recs, const BinHead* bins, const uint32_t* tile_count,
-                        const TexDev* tex, const uint16_t* texels, uint32_t* fb_rgba, float* fb_z, const CallState* st,
-                        uint32_t* sticky, const CallParams& p) {
+                        const TexDev* tex, const uint16_t* texels, const uint32_t* texmask, uint32_t* fb_rgba, float* fb_z,
+                        const CallState* st, uint32_t* sticky, const CallParams& p) {
     uint32_t ntiles = p.tiles_x * p.tiles_y;
     if (ntiles == 0 || p.nf == 0) return;
     static bool attr_set = false;
     if (!attr_set) { cudaFuncSetAttribute(k_fill_opaque, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OP_SMEM); attr_set = true; }
-    k_fill_opaque<<<ntiles * OP_SPLIT, OP_THREADS, OP_SMEM, L.stream>>>(recs, bins, tile_count, tex, texels, fb_rgba, fb_z, st, sticky, p);
+    k_fill_opaque<<<ntiles * OP_SPLIT, OP_THREADS, OP_SMEM, L.stream>>>(recs, bins, tile_count, tex, texels, texmask, fb_rgba, fb_z, st, sticky, p);
     ++*L.launches;
 }
 
@@ -1099,6 +1205,12 @@ void launch_fb_clear(const LaunchCtx& L, uint32_t* rgba, float* z, uint32_t n, u
 void launch_tex_expand(const LaunchCtx& L, const uint8_t* idx, const uint16_t* clut, uint32_t clut_len, uint32_t format, uint32_t n, uint16_t* out) {
     if (n == 0) return;
     k_tex_expand<<<grid_for(n, 256, L.sms), 256, 0, L.stream>>>(idx, clut, clut_len, format, n, out);
+    ++*L.launches;
+}
+
+void launch_tex_mask(const LaunchCtx& L, const uint16_t* texels, uint32_t n_texels, uint32_t n_words, uint32_t* mask) {
+    if (n_words == 0) return;
+    k_tex_mask<<<grid_for(n_words, 256, L.sms), 256, 0, L.stream>>>(texels, n_texels, n_words, mask);
     ++*L.launches;
 }
 

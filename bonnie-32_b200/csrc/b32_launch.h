@@ -19,13 +19,14 @@ struct LaunchCtx {
 void launch_transform(const LaunchCtx& L, const b32_vertex* verts, TVert* out, float* dbg_cam, const CallParams& p);
 // tv == nullptr: vertices are transformed inside k_setup (fused path). Also bins the pass-1 surfaces.
 void launch_setup(const LaunchCtx& L, const b32_vertex* verts, const b32_face* faces, const TVert* tv, const TexDev* tex,
-                  const LightDev* lights, SurfRec* recs, uint64_t* keys, BinHead* heads, BinHead* oheads, BinHead* bins,
-                  uint32_t* tile_count, WireTri* wire, CallState* st, const CallParams& p);
-void launch_bin(const LaunchCtx& L, const BinHead* heads, BinHead* bins, uint32_t* tile_count, CallState* st, const CallParams& p,
-                uint32_t bin_cap, bool ordered);
+                  const LightDev* lights, SurfRec* recs, uint64_t* keys, BinHead* heads, BinHead* bins,
+                  uint32_t* tile_count, WireTri* wire, CallState* st, uint32_t* zero_next, uint32_t zero_words, const CallParams& p);
+// ordered = false: scatter heads[] (pass 1); true: scatter the draw-order entries rebuilt from keys[] + recs[] (pass 2 / x-ray)
+void launch_bin(const LaunchCtx& L, const BinHead* heads, const uint64_t* keys, const SurfRec* recs, BinHead* bins, uint32_t* tile_count,
+                CallState* st, const CallParams& p, uint32_t bin_cap, bool ordered);
 void launch_fill_opaque(const LaunchCtx& L, const SurfRec* recs, const BinHead* bins, const uint32_t* tile_count,
-                        const TexDev* tex, const uint16_t* texels, uint32_t* fb_rgba, float* fb_z, const CallState* st,
-                        uint32_t* sticky, const CallParams& p);
+                        const TexDev* tex, const uint16_t* texels, const uint32_t* texmask, uint32_t* fb_rgba, float* fb_z,
+                        const CallState* st, uint32_t* sticky, const CallParams& p);
 // ordered pass (pass 2 / x-ray): bins of draw-order keys, sorted per tile, replayed in order
 void launch_fill_ordered(const LaunchCtx& L, const SurfRec* recs, BinHead* obins, const uint32_t* otile_count,
                          const TexDev* tex, const uint16_t* texels, uint32_t* fb_rgba, float* fb_z,
@@ -35,5 +36,8 @@ void launch_wire(const LaunchCtx& L, const WireTri* wire, uint32_t kind, uint32_
                  uint32_t* fb_rgba, const float* fb_z, const CallState* st, const CallParams& p);
 void launch_fb_clear(const LaunchCtx& L, uint32_t* rgba, float* z, uint32_t n, uint32_t color);
 void launch_tex_expand(const LaunchCtx& L, const uint8_t* idx, const uint16_t* clut, uint32_t clut_len, uint32_t format, uint32_t n, uint16_t* out);
+
+// bit i of mask = texel i of the pool writes when its surface is black-keyed; n_words covers n_texels, zero padded
+void launch_tex_mask(const LaunchCtx& L, const uint16_t* texels, uint32_t n_texels, uint32_t n_words, uint32_t* mask);
 
 }  // namespace b32

@@ -25,7 +25,8 @@ print('sort ns per tile mean/max', sort_ns.max(1).mean(), sort_ns.max(1).max())
 print('walk ns per warp mean/median/p90/max', walk_ns.mean(), np.median(walk_ns), np.percentile(walk_ns,90), walk_ns.max())
 print('tile total ns (max warp end - start) mean/max', (t2.max(1)-t0.min(1)).mean(), (t2.max(1)-t0.min(1)).max())
 print('batches per warp mean/max', st[:,:,3].mean(), st[:,:,3].max(), ' survivors per warp mean/max', st[:,:,4].mean(), st[:,:,4].max())
-print('inside-lane-tests per warp mean', st[:,:,5].mean(), 'shaded per warp mean', st[:,:,6].mean())
+tm=st[:,:,5]; tl=st[:,:,6]
+print('mask wait ns mean/max', (tm-t1).mean(), (tm-t1).max(), ' loop ns mean/max', (tl-tm).mean(), (tl-tm).max(), ' shade ns mean/max', (t2-tl).mean(), (t2-tl).max())
 end_by_sm={}
 for t in range(300):
     sm=st[t,0,7]; end_by_sm.setdefault(sm,[]).append((t0[t].min()-base, t2[t].max()-base))
