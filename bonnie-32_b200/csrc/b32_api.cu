@@ -249,7 +249,7 @@ int render_ordered(b32_ctx* ctx, const CallParams& p, uint32_t n_ordered) {
         CK(ctx->obins.reserve((size_t)ntiles * cap2));
         CK(cudaMemsetAsync(ctx->otile_count.p, 0, ntiles * sizeof(uint32_t), st));
         CK(cudaEventRecord(ctx->ev[2], st));
-        launch_bin(L, nullptr, ctx->keys.p, ctx->recs.p, ctx->obins.p, ctx->otile_count.p, ctx->state, p, cap2, true);
+        launch_bin(L, nullptr, ctx->keys.p, ctx->recs.p, ctx->obins.p, ctx->otile_count.p, ctx->state, p, cap2, true, false);
         CK(cudaEventRecord(ctx->ev[3], st));
         launch_fill_ordered(L, ctx->recs.p, ctx->obins.p, ctx->otile_count.p, ctx->texdesc.p, ctx->texels.p,
                             ctx->fb_rgba.p, ctx->fb_z.p, ctx->state, p, cap2);

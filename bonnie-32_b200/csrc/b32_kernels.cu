@@ -27,6 +27,12 @@
 
 namespace b32 {
 
+// Programmatic dependent launch: k_setup -> k_bin_opaque -> k_fill_opaque are chained on one stream; a
+// dependent kernel is launched while its predecessor still runs, does the part of its prologue that reads
+// nothing the predecessor writes, then waits here until the predecessor has completed and flushed.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // =================================================================================================
 // vertex transform + snap (render.rs:2321-2360)
 // =================================================================================================
@@ -303,6 +309,7 @@ k_setup(const b32_vertex* __restrict__ verts, const b32_face* __restrict__ faces
         BinHead* __restrict__ heads, WireTri* __restrict__ wire, CallState* __restrict__ st,
         uint32_t* __restrict__ zero_next, uint32_t zero_words, CallParams p) {
     __shared__ uint32_t s_cnt[2];
+    pdl_launch_dependents();           // k_bin_opaque may be scheduled as SM resources free up; it waits for this grid's completion
     // the call after this one finds its CallState + tile counters zeroed (two sets, used alternately)
     if (blockIdx.x == 0) for (uint32_t i = threadIdx.x; i < zero_words; i += blockDim.x) zero_next[i] = 0;
     if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
@@ -347,6 +354,8 @@ k_bin_opaque(const BinHead* __restrict__ heads, const uint64_t* __restrict__ key
     uint32_t* s_cnt = s_tiles;
     uint32_t* s_base = s_tiles + ntiles;
     if (aggregate) for (uint32_t i = threadIdx.x; i < ntiles; i += blockDim.x) s_cnt[i] = 0;
+    pdl_wait();                        // k_setup has completed: heads / keys / recs / counters are visible
+    pdl_launch_dependents();           // k_fill_opaque may start its prologue
     __syncthreads();
 
     uint32_t bmax = 0;
@@ -540,10 +549,21 @@ __device__ __forceinline__ bool shade(const SurfRec& r, uint32_t x, uint32_t y, 
 #ifndef B32_OP_THREADS
 #define B32_OP_THREADS 256
 #endif
-constexpr int OP_THREADS = B32_OP_THREADS;   // 256: 8 warps = half a tile (16x8 px), two CTAs per tile; 512: one CTA per tile
-constexpr int OP_SPLIT = 512 / OP_THREADS;   // CTAs per tile
+#ifndef B32_OP_DUAL
+#define B32_OP_DUAL 1
+#endif
+constexpr int OP_THREADS = B32_OP_THREADS;
+constexpr bool OP_DUAL = B32_OP_DUAL != 0;   // true: a warp owns 4x4 pixels, two lanes per pixel; false: 8x4 pixels, one lane per pixel
 constexpr int OP_WARPS = OP_THREADS / 32;
-constexpr int OP_CHUNK = OP_THREADS / 8;     // surface records staged per step (8 x 16 B each => one piece per thread)
+constexpr int OP_BW = OP_DUAL ? 4 : 8, OP_BH = 4;                     // pixel block of one warp
+constexpr int OP_WPT = (TILE_W / OP_BW) * (TILE_H / OP_BH);            // warps per 16x16 tile
+constexpr int OP_SPLIT = OP_WPT / OP_WARPS;  // CTAs per tile (256 threads, dual: 2 = half tiles of 16x8 px)
+static_assert(OP_SPLIT >= 1 && OP_SPLIT * OP_WARPS == OP_WPT, "a CTA covers a whole number of block rows of one tile");
+constexpr int OP_CHUNK = 32;                 // surface records staged per step: 256 x 16 B, OP_PIECES per thread
+constexpr int OP_PIECES = OP_CHUNK * 8 / OP_THREADS;
+static_assert(OP_PIECES >= 1 && OP_PIECES * OP_THREADS == OP_CHUNK * 8, "OP_THREADS must divide 256");
+constexpr int OP_BUCKETS = OP_THREADS < 256 ? OP_THREADS : 256;       // key buckets of the counting sort (one scan thread each)
+constexpr int OP_BUCKET_BITS = OP_BUCKETS == 256 ? 8 : (OP_BUCKETS == 128 ? 7 : 6);
 constexpr int OP_RING = 3;                   // ring depth: steps c, c+1, c+2
 constexpr int OP_SORT_MAX = 1024;            // bin entries orderable in shared memory (16 KB of heads)
 constexpr int OP_TEX_SMEM = 256;             // texture descriptors cached in shared memory
@@ -603,7 +623,10 @@ __device__ __forceinline__ uint32_t texel_index(const Rec& r, float bc_x, float 
     return t.off + ty * t.w + tx;
 }
 
-__global__ void __launch_bounds__(OP_THREADS, OP_THREADS == 256 ? 5 : 2)
+#ifndef B32_OP_MINB
+#define B32_OP_MINB (OP_THREADS == 256 ? 5 : (OP_THREADS == 128 ? 5 : 2))
+#endif
+__global__ void __launch_bounds__(OP_THREADS, B32_OP_MINB)
 k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins, const uint32_t* __restrict__ tile_count,
               const TexDev* __restrict__ tex, const uint16_t* __restrict__ texels, const uint32_t* __restrict__ texmask,
               uint32_t* __restrict__ fb_rgba, float* __restrict__ fb_z, const CallState* __restrict__ st,
@@ -615,10 +638,34 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
     uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_tex + OP_TEX_SMEM);                // [OP_MASK_SMEM_WORDS] "texel writes" bits
     uint2* s_surv = reinterpret_cast<uint2*>(s_mask + OP_MASK_SMEM_WORDS);              // [OP_WARPS][32] survivors: (key, face)
     uint8_t* s_sidx = reinterpret_cast<uint8_t*>(s_surv + OP_WARPS * 32);               // [OP_WARPS][32] ... and their slot in the ring step
-    __shared__ uint32_t s_hist[256];
-    __shared__ uint32_t s_wsum[8];
+    __shared__ uint32_t s_hist[OP_BUCKETS];
+    __shared__ uint32_t s_wsum[OP_BUCKETS / 32];
     __shared__ uint32_t s_minmax[2];
     __shared__ __align__(8) uint64_t s_mbar;
+    // ---- prologue: nothing here reads what k_setup / k_bin_opaque write, so it runs while they finish -----
+    const uint32_t tile = blockIdx.x / OP_SPLIT, half = blockIdx.x % OP_SPLIT;
+    // the "texel writes" mask of the whole texel pool travels by TMA while the bin is sorted
+    const bool mask_staged = p.mask_smem_words != 0;
+    if (mask_staged && threadIdx.x == 0) { mbar_init(&s_mbar, 1); bulk_g2s(s_mask, texmask, p.mask_smem_words * 4, &s_mbar); }
+    const uint32_t* maskw = mask_staged ? s_mask : texmask;
+    const BinHead* bin = bins + (size_t)tile * p.bin_cap;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t pix = OP_DUAL ? (lane & 15) : lane, sub = OP_DUAL ? (lane >> 4) : 0;
+    const uint32_t tx = tile % p.tiles_x, ty = tile / p.tiles_x;
+    // thread -> pixel: each warp owns a 4x4 block of its half tile; lanes l and l+16 share a pixel
+    constexpr uint32_t BPR = TILE_W / OP_BW;               // warp blocks per tile row
+    const uint32_t wt = half * OP_WARPS + warp;            // this warp's block within the tile
+    const uint32_t bx0 = tx * TILE_W + (wt % BPR) * OP_BW, by0 = ty * TILE_H + (wt / BPR) * OP_BH;
+    const uint32_t x = bx0 + (pix % OP_BW), y = by0 + (pix / OP_BW);
+    const bool valid = x < p.width && y < p.height;
+    // the pixel's framebuffer content (written by earlier stream work, complete before k_setup started)
+    Pixel px{0, 0.0f};
+    if (valid) { px.rgba = fb_rgba[y * p.width + x]; px.z = fb_z[y * p.width + x]; }
+    const bool tex_cached = p.ntex <= OP_TEX_SMEM;
+    if (tex_cached) for (uint32_t i = threadIdx.x; i < p.ntex; i += OP_THREADS) s_tex[i] = tex[i];
+    const TexDev* texd = tex_cached ? s_tex : tex;
+    pdl_wait();                                            // k_bin_opaque (and k_setup before it) have completed
+    bool skip;
     {
         CallState s = *st;
         bool aborts = call_aborts(s, p.use_zbuffer);
@@ -626,29 +673,13 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
             if (aborts || s.bin_overflow) atomicOr(sticky, s.oob ? 1u : (aborts ? 2u : 4u));
             else if (s.n_transp) atomicOr(sticky, 8u);                                           // pass 2 exists but was not enqueued
         }
-        if (s.bin_overflow || aborts || p.xray_mode) return;
+        skip = s.bin_overflow || aborts || p.xray_mode;
     }
-    const uint32_t tile = blockIdx.x / OP_SPLIT, half = blockIdx.x % OP_SPLIT;
-    const uint32_t n = tile_count[tile];
-    if (n == 0) return;
-    // the "texel writes" mask of the whole texel pool travels by TMA while the bin is sorted
-    const bool mask_staged = p.mask_smem_words != 0;
-    if (mask_staged && threadIdx.x == 0) { mbar_init(&s_mbar, 1); bulk_g2s(s_mask, texmask, p.mask_smem_words * 4, &s_mbar); }
-    const uint32_t* maskw = mask_staged ? s_mask : texmask;
-    const BinHead* bin = bins + (size_t)tile * p.bin_cap;
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t pix = lane & 15, sub = lane >> 4;
-    const uint32_t tx = tile % p.tiles_x, ty = tile / p.tiles_x;
-    // thread -> pixel: each warp owns a 4x4 block of its half tile; lanes l and l+16 share a pixel
-    const uint32_t bx0 = tx * TILE_W + (warp & 3) * 4, by0 = ty * TILE_H + half * (OP_WARPS / 4) * 4 + (warp >> 2) * 4;
-    const uint32_t x = bx0 + (pix & 3), y = by0 + (pix >> 2);
-    const bool valid = x < p.width && y < p.height;
-    // the pixel's framebuffer content is requested now and consumed after the sort
-    Pixel px{0, 0.0f};
-    if (valid) { px.rgba = fb_rgba[y * p.width + x]; px.z = fb_z[y * p.width + x]; }
-    const bool tex_cached = p.ntex <= OP_TEX_SMEM;
-    if (tex_cached) for (uint32_t i = threadIdx.x; i < p.ntex; i += OP_THREADS) s_tex[i] = tex[i];
-    const TexDev* texd = tex_cached ? s_tex : tex;
+    const uint32_t n = skip ? 0u : tile_count[tile];
+    if (n == 0) {                                          // nothing to draw here; the mask copy must land before the CTA exits
+        if (mask_staged && threadIdx.x == 0) while (!mbar_try_wait(&s_mbar, 0)) {}
+        return;
+    }
 #ifdef B32_FILL_STATS
     uint32_t st_t0 = gtime(), st_batches = 0, st_surv = 0, st_inside = 0, st_shaded = 0;
 #endif
@@ -667,7 +698,7 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
             if (i < n) hh[q] = bin[i]; else hh[q] = BinHead{0, 0, 0xFFFFFFFFu, 0};
             if (hh[q].key != 0xFFFFFFFFu) { lo = min(lo, hh[q].key); hi = max(hi, hh[q].key); }   // 0xFFFFFFFF = "never cull": bucket 0
         }
-        if (threadIdx.x < 256) s_hist[threadIdx.x] = 0;
+        if (threadIdx.x < OP_BUCKETS) s_hist[threadIdx.x] = 0;
         if (threadIdx.x == 0) { s_minmax[0] = 0xFFFFFFFFu; s_minmax[1] = 0; }
         for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, o)); hi = max(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, o)); }
         __syncthreads();
@@ -677,21 +708,21 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
         uint32_t kmax = s_minmax[1];
         if (kmin > kmax) { kmin = 0; kmax = 0; }
         uint32_t range = kmax - kmin;
-        shift = range >= 256 ? (32 - __clz(range)) - 8 : 0;         // (range >> shift) <= 255
+        shift = range >= OP_BUCKETS ? (32 - __clz(range)) - OP_BUCKET_BITS : 0;         // (range >> shift) <= OP_BUCKETS - 1
         #pragma unroll
         for (int q = 0; q < KPT; ++q) {
             uint32_t i = q * OP_THREADS + threadIdx.x;
-            if (i < n) atomicAdd(&s_hist[hh[q].key == 0xFFFFFFFFu ? 0 : 255 - ((hh[q].key - kmin) >> shift)], 1u);
+            if (i < n) atomicAdd(&s_hist[hh[q].key == 0xFFFFFFFFu ? 0 : (OP_BUCKETS - 1) - ((hh[q].key - kmin) >> shift)], 1u);
         }
         __syncthreads();
-        uint32_t v = 0, xs = 0;                              // exclusive scan of the 256 bucket counts (threads 0..255)
-        if (threadIdx.x < 256) {
+        uint32_t v = 0, xs = 0;                              // exclusive scan of the bucket counts (threads 0..OP_BUCKETS-1)
+        if (threadIdx.x < OP_BUCKETS) {
             v = s_hist[threadIdx.x]; xs = v;
             for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, xs, o); if (lane >= (uint32_t)o) xs += t; }
             if (lane == 31) s_wsum[warp] = xs;
         }
         __syncthreads();
-        if (threadIdx.x < 256) {
+        if (threadIdx.x < OP_BUCKETS) {
             uint32_t pre = 0;
             for (uint32_t w = 0; w < warp; ++w) pre += s_wsum[w];
             s_hist[threadIdx.x] = pre + xs - v;
@@ -700,18 +731,22 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
         #pragma unroll
         for (int q = 0; q < KPT; ++q) {
             uint32_t i = q * OP_THREADS + threadIdx.x;
-            if (i < n) s_sh[atomicAdd(&s_hist[hh[q].key == 0xFFFFFFFFu ? 0 : 255 - ((hh[q].key - kmin) >> shift)], 1u)] = hh[q];
+            if (i < n) s_sh[atomicAdd(&s_hist[hh[q].key == 0xFFFFFFFFu ? 0 : (OP_BUCKETS - 1) - ((hh[q].key - kmin) >> shift)], 1u)] = hh[q];
         }
     }
     __syncthreads();                                      // s_sh, s_tex and the mbarrier are ready
 
     // ---- 2. the record ring: step c -> slot c % OP_RING; thread t moves piece (t & 7) of entry (t >> 3)
     auto stage = [&](uint32_t c) {
-        uint32_t e = c * OP_CHUNK + (threadIdx.x >> 3);
-        if (e < n) {
-            uint32_t f = sorted ? s_sh[e].face : bin[e].face;
-            cp_async16(reinterpret_cast<uint4*>(&s_rec[(c % OP_RING) * OP_CHUNK + (threadIdx.x >> 3)]) + (threadIdx.x & 7),
-                       reinterpret_cast<const uint4*>(&recs[f]) + (threadIdx.x & 7));
+        #pragma unroll
+        for (int q = 0; q < OP_PIECES; ++q) {
+            uint32_t piece = q * OP_THREADS + threadIdx.x;
+            uint32_t e = c * OP_CHUNK + (piece >> 3);
+            if (e < n) {
+                uint32_t f = sorted ? s_sh[e].face : bin[e].face;
+                cp_async16(reinterpret_cast<uint4*>(&s_rec[(c % OP_RING) * OP_CHUNK + (piece >> 3)]) + (piece & 7),
+                           reinterpret_cast<const uint4*>(&recs[f]) + (piece & 7));
+            }
         }
         cp_async_commit();
     };
@@ -766,7 +801,7 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
             // ---- 4. early out: entries are in descending key-bucket order ------------------------------------
             // `open` pixels are those some entry of this batch or a later one could still change; only their
             // bounding box [ox0,ox1) x [oy0,oy1) needs to be met by a surface's bbox.
-            uint32_t ox0 = bx0, ox1 = bx0 + 4, oy0 = by0, oy1 = by0 + 4;
+            uint32_t ox0 = bx0, ox1 = bx0 + OP_BW, oy0 = by0, oy1 = by0 + OP_BH;
             if (sorted) {
                 uint32_t k0 = s_sh[base].key;
                 if (k0 != 0xFFFFFFFFu) {
@@ -777,10 +812,13 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
                     else if (__uint_as_float(~ub) > wz) { done = true; break; }   // every later surface is behind every pixel
                     bool open = valid && (!p.use_zbuffer ? (best == 0 || (uint32_t)((best - 1) >> 32) <= ub)
                                                          : !(__uint_as_float(~ub) > px.z));
-                    uint32_t om = __ballot_sync(0xFFFFFFFFu, open) & 0xFFFFu;     // bit q = pixel q (row-major 4x4) is open
+                    uint32_t om = __ballot_sync(0xFFFFFFFFu, open);                // bit q = pixel q (row-major in the block) is open
+                    if (OP_DUAL) om &= 0xFFFFu;
                     if (om == 0) { done = true; break; }
-                    uint32_t cols = (om | (om >> 4) | (om >> 8) | (om >> 12)) & 0xFu;
-                    uint32_t rows = ((om & 0x000Fu) ? 1u : 0u) | ((om & 0x00F0u) ? 2u : 0u) | ((om & 0x0F00u) ? 4u : 0u) | ((om & 0xF000u) ? 8u : 0u);
+                    constexpr uint32_t RM = (1u << OP_BW) - 1;                      // one block row of `om`
+                    uint32_t cols = (om | (om >> OP_BW) | (om >> (2 * OP_BW)) | (om >> (3 * OP_BW))) & RM;
+                    uint32_t rows = ((om & RM) ? 1u : 0u) | ((om & (RM << OP_BW)) ? 2u : 0u) | ((om & (RM << (2 * OP_BW))) ? 4u : 0u) |
+                                    ((om & (RM << (3 * OP_BW))) ? 8u : 0u);
                     ox0 = bx0 + (__ffs(cols) - 1); ox1 = bx0 + (32 - __clz(cols));
                     oy0 = by0 + (__ffs(rows) - 1); oy1 = by0 + (32 - __clz(rows));
                 }
@@ -825,11 +863,12 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
             __syncwarp();
             if (cand) { uint32_t pos = __popc(mask & ((1u << lane) - 1)); my_surv[pos] = make_uint2(h.key, h.face); my_sidx[pos] = (uint8_t)(sb + lane); }
             __syncwarp();
-            // ---- 3b. survivors: each half-warp takes every other one, two at a time ----------------------------
-            for (uint32_t j0 = 0; j0 < cnt; j0 += 4) {
+            // ---- 3b. survivors, two at a time per pixel lane (dual: each half-warp takes every other one) -----------
+            constexpr uint32_t NSUB = OP_DUAL ? 2 : 1;
+            for (uint32_t j0 = 0; j0 < cnt; j0 += 2 * NSUB) {
                 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
-                    uint32_t j = j0 + 2 * k + sub;
+                    uint32_t j = j0 + NSUB * k + sub;
                     if (j >= cnt) continue;
                     const SurfRec& r = crec[my_sidx[j]];
                     const uint2 kf = my_surv[j];
@@ -859,7 +898,7 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
                     else { px.z = c_z; best_face = c_face; }
                 }
             }
-            {   // merge the two half-warps' winners for each pixel (exact: max / lexicographic min are associative)
+            if (OP_DUAL) {   // merge the two half-warps' winners for each pixel (exact: max / lexicographic min are associative)
                 uint64_t ob = __shfl_xor_sync(0xFFFFFFFFu, best, 16);
                 float oz = __shfl_xor_sync(0xFFFFFFFFu, px.z, 16);
                 uint32_t of = __shfl_xor_sync(0xFFFFFFFFu, best_face, 16);
@@ -895,7 +934,7 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
     {
         for (int o = 16; o > 0; o >>= 1) { st_inside += __shfl_xor_sync(0xFFFFFFFFu, st_inside, o); st_shaded += __shfl_xor_sync(0xFFFFFFFFu, st_shaded, o); }
         if (lane == 0 && tile < 4096) {
-            uint32_t* o = g_fill_stats + (tile * 16 + half * OP_WARPS + warp) * 8;
+            uint32_t* o = g_fill_stats + (tile * 16 + wt) * 8;
             o[0] = st_t0; o[1] = st_t1; o[2] = gtime(); o[3] = st_batches; o[4] = st_surv; o[5] = st_tm; o[6] = st_tl; o[7] = smid();
         }
     }
@@ -1131,6 +1170,19 @@ __global__ void k_tex_mask(const uint16_t* __restrict__ texels, uint32_t n_texel
 // =================================================================================================
 // launchers (host)
 // =================================================================================================
+// launch with (optionally) the programmatic-stream-serialization attribute: the kernel may start before the
+// previous kernel on the stream has finished; it orders itself with pdl_wait()
+template <typename... KArgs, typename... Args>
+static void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1u : 0u;
+    cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 static inline uint32_t grid_for(uint32_t n, uint32_t block, uint32_t sms, uint32_t per_sm = 8) {
     uint32_t g = (n + block - 1) / block;
     uint32_t cap = sms * per_sm;
@@ -1151,18 +1203,18 @@ void launch_setup(const LaunchCtx& L, const b32_vertex* verts, const b32_face* f
                                                                                       zero_next, zero_words, p);
     ++*L.launches;
     if (p.xray_mode || p.wire_front) return;        // wireframe_overlay draws no solid surfaces (:2550)
-    launch_bin(L, heads, keys, recs, bins, tile_count, st, p, p.bin_cap, false);
+    launch_bin(L, heads, keys, recs, bins, tile_count, st, p, p.bin_cap, false, true);
 }
 
 void launch_bin(const LaunchCtx& L, const BinHead* heads, const uint64_t* keys, const SurfRec* recs, BinHead* bins, uint32_t* tile_count,
-                CallState* st, const CallParams& p, uint32_t bin_cap, bool ordered) {
+                CallState* st, const CallParams& p, uint32_t bin_cap, bool ordered, bool after_setup) {
     if (p.nf == 0) return;
     uint32_t ntiles = p.tiles_x * p.tiles_y;
     size_t smem = ntiles <= (uint32_t)BIN_MAX_TILES ? (size_t)ntiles * 8 : 0;
     uint32_t per_round = BIN_THREADS * BIN_FPT;
     uint32_t grid = (p.nf + per_round - 1) / per_round;
     if (grid > L.sms * 4) grid = L.sms * 4;
-    k_bin_opaque<<<grid, BIN_THREADS, smem, L.stream>>>(heads, keys, recs, bins, tile_count, st, p, bin_cap, ordered);
+    launch_k(k_bin_opaque, grid, BIN_THREADS, smem, L.stream, after_setup, heads, keys, recs, bins, tile_count, st, p, bin_cap, ordered);
     ++*L.launches;
 }
 
@@ -1173,7 +1225,9 @@ void launch_fill_opaque(const LaunchCtx& L, const SurfRec* recs, const BinHead* 
     if (ntiles == 0 || p.nf == 0) return;
     static bool attr_set = false;
     if (!attr_set) { cudaFuncSetAttribute(k_fill_opaque, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OP_SMEM); attr_set = true; }
-    k_fill_opaque<<<ntiles * OP_SPLIT, OP_THREADS, OP_SMEM, L.stream>>>(recs, bins, tile_count, tex, texels, texmask, fb_rgba, fb_z, st, sticky, p);
+    // launched right behind k_bin_opaque except in x-ray mode (no pass-1 binning: then it is an ordinary launch)
+    launch_k(k_fill_opaque, ntiles * OP_SPLIT, OP_THREADS, OP_SMEM, L.stream, !p.xray_mode, recs, bins, tile_count, tex, texels, texmask,
+             fb_rgba, fb_z, st, sticky, p);
     ++*L.launches;
 }
 
