@@ -7,5 +7,5 @@ identifier; import it as `bonnie32_b200` through `__graft_entry__.load_package()
 """
 from . import abi, raster, scenes  # noqa: F401
 from .abi import B32Error  # noqa: F401
-from .raster import (Camera, Context, Framebuffer, Light, Mesh, RasterSettings, Texture15,  # noqa: F401
-                     render_mesh_15)
+from .raster import (Camera, Context, Framebuffer, Light, Mesh, RasterSettings, Texture, Texture15,  # noqa: F401
+                     render_mesh, render_mesh_15)

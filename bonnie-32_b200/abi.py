@@ -81,6 +81,11 @@ class TexDesc(C.Structure):
                 ("clut_len", C.c_uint32)]
 
 
+class Tex8Desc(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("blend_mode", C.c_uint32), ("_pad", C.c_uint32),
+                ("pixels", C.c_void_p)]
+
+
 # Every symbol include/b32_raster.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -106,6 +111,9 @@ SYMBOLS = {
     "b32_render_mesh_15_resident": (C.c_int, [_P, _P, C.POINTER(Camera), C.POINTER(Settings),
                                               C.POINTER(Fog), C.POINTER(Timings)]),
     "b32_render_mesh_15_enqueue": (C.c_int, [_P, _P, C.POINTER(Camera), C.POINTER(Settings), C.POINTER(Fog)]),
+    "b32_textures_set_rgb888": (C.c_int, [_P, C.POINTER(Tex8Desc), C.c_uint32]),
+    "b32_render_mesh": (C.c_int, [_P, _P, C.c_uint32, _P, C.c_uint32, C.POINTER(Camera), C.POINTER(Settings), C.POINTER(Timings)]),
+    "b32_render_mesh_resident": (C.c_int, [_P, _P, C.POINTER(Camera), C.POINTER(Settings), C.POINTER(Timings)]),
     "b32_host_alloc": (_P, [C.c_size_t]),
     "b32_host_free": (None, [_P]),
     "b32_debug_transform": (C.c_int, [_P, _P, C.c_uint32, C.POINTER(Camera), C.POINTER(Settings), _P, _P]),

@@ -65,6 +65,13 @@ struct b32_ctx {
     std::vector<TexDev> texdesc_h;
     uint32_t ntex = 0;
 
+    // textures of the RGB888 sibling (render_mesh): one Color (r, g, b, blend) = u32 per texel
+    DevBuf<uint32_t> texels8;
+    DevBuf<uint32_t> tex8mask;         // 1 bit per texel: tag != Erase
+    uint32_t tex8mask_words = 0;
+    DevBuf<TexDev> tex8desc;           // TexDev.blend = 1 iff the texture holds texels with a PS1 blend tag
+    uint32_t ntex8 = 0;
+
     // staging geometry for host-buffer calls
     DevBuf<b32_vertex> verts;
     DevBuf<b32_face> faces;
@@ -124,7 +131,7 @@ int32_t host_fx_from_f32(float f) {                 // Fixed32::from_f32, fixed.
 }
 
 int fill_params(b32_ctx* ctx, CallParams& p, const b32_camera* cam, const b32_settings* s, const b32_fog* fog,
-                uint32_t nv, uint32_t nf, std::vector<LightDev>& lights) {
+                uint32_t nv, uint32_t nf, std::vector<LightDev>& lights, bool rgb888 = false) {
     std::memset(&p, 0, sizeof(p));
     for (int i = 0; i < 3; ++i) {
         p.cam_pos[i] = cam->position[i]; p.bx[i] = cam->basis_x[i]; p.by[i] = cam->basis_y[i]; p.bz[i] = cam->basis_z[i];
@@ -136,8 +143,10 @@ int fill_params(b32_ctx* ctx, CallParams& p, const b32_camera* cam, const b32_se
     p.viewport_scale = host_fx_from_f32(((float)std::min(ctx->width, ctx->height) / 2.0f) * 0.75f);   // fixed.rs:398
     p.half_w = (int32_t)(((uint32_t)((int32_t)ctx->width / 2)) << 12);                                // fixed.rs:399-400
     p.half_h = (int32_t)(((uint32_t)((int32_t)ctx->height / 2)) << 12);
-    p.nv = nv; p.nf = nf; p.ntex = ctx->ntex;
-    p.mask_smem_words = ctx->texmask_words <= (uint32_t)OP_MASK_SMEM_WORDS ? ctx->texmask_words : 0;
+    p.nv = nv; p.nf = nf; p.ntex = rgb888 ? ctx->ntex8 : ctx->ntex;
+    p.rgb888 = rgb888 ? 1 : 0;
+    const uint32_t mask_words = rgb888 ? ctx->tex8mask_words : ctx->texmask_words;
+    p.mask_smem_words = mask_words <= (uint32_t)OP_MASK_SMEM_WORDS ? mask_words : 0;
     p.affine_textures = s->affine_textures != 0; p.use_zbuffer = s->use_zbuffer != 0; p.shading = s->shading;
     p.backface_cull = s->backface_cull != 0; p.dithering = s->dithering != 0; p.use_fixed_point = s->use_fixed_point != 0;
     p.xray_mode = s->xray_mode != 0; p.ortho = s->ortho_enabled != 0;
@@ -251,7 +260,8 @@ int render_ordered(b32_ctx* ctx, const CallParams& p, uint32_t n_ordered) {
         CK(cudaEventRecord(ctx->ev[2], st));
         launch_bin(L, nullptr, ctx->keys.p, ctx->recs.p, ctx->obins.p, ctx->otile_count.p, ctx->state, p, cap2, true, false);
         CK(cudaEventRecord(ctx->ev[3], st));
-        launch_fill_ordered(L, ctx->recs.p, ctx->obins.p, ctx->otile_count.p, ctx->texdesc.p, ctx->texels.p,
+        launch_fill_ordered(L, ctx->recs.p, ctx->obins.p, ctx->otile_count.p, p.rgb888 ? ctx->tex8desc.p : ctx->texdesc.p,
+                            p.rgb888 ? reinterpret_cast<const uint16_t*>(ctx->texels8.p) : ctx->texels.p,
                             ctx->fb_rgba.p, ctx->fb_z.p, ctx->state, p, cap2);
         CK(cudaEventRecord(ctx->ev[4], st));
         CK(cudaMemcpyAsync(ctx->state_h, ctx->state, sizeof(CallState), cudaMemcpyDeviceToHost, st));
@@ -275,14 +285,17 @@ int render_ordered(b32_ctx* ctx, const CallParams& p, uint32_t n_ordered) {
 //   wait=true : returns when the frame is in the framebuffer; fills *tm.
 //   wait=false: only enqueues pass 1 (no host round trip); the caller guarantees there is no pass 2.
 int render_device(b32_ctx* ctx, const b32_vertex* d_verts, uint32_t nv, const b32_face* d_faces, uint32_t nf,
-                  const b32_camera* cam, const b32_settings* s, const b32_fog* fog, b32_timings* tm, bool wait) {
+                  const b32_camera* cam, const b32_settings* s, const b32_fog* fog, b32_timings* tm, bool wait, bool rgb888 = false) {
     if (!cam || !s) return fail(ctx, B32_ERR_INVALID, "camera/settings is NULL");
     if (ctx->width == 0 || ctx->height == 0) return fail(ctx, B32_ERR_INVALID, "framebuffer has zero size (call b32_fb_resize)");
     CallParams p;
     std::vector<LightDev> lights;
-    int rc = fill_params(ctx, p, cam, s, fog, nv, nf, lights);
+    int rc = fill_params(ctx, p, cam, s, fog, nv, nf, lights, rgb888);
     if (rc != B32_OK) return rc;
     if (tm) std::memset(tm, 0, sizeof(*tm));
+    const TexDev* texdesc = rgb888 ? ctx->tex8desc.p : ctx->texdesc.p;
+    const uint16_t* texels = rgb888 ? reinterpret_cast<const uint16_t*>(ctx->texels8.p) : ctx->texels.p;
+    const uint32_t* texmask = rgb888 ? ctx->tex8mask.p : ctx->texmask.p;
     for (float& k : ctx->kernel_ms) k = 0.0f;
     ctx->last_nf = nf;
     ctx->last_params = p;
@@ -308,12 +321,12 @@ int render_device(b32_ctx* ctx, const b32_vertex* d_verts, uint32_t nv, const b3
         ctx->state = reinterpret_cast<CallState*>(ctx->state_ring.p + (size_t)ctx->state_cur * ctx->state_stride);
         ctx->tile_count = ctx->state_ring.p + (size_t)ctx->state_cur * ctx->state_stride + STATE_WORDS;
         uint32_t* zero_next = ctx->state_ring.p + (size_t)(ctx->state_cur ^ 1) * ctx->state_stride;
-        launch_setup(L, d_verts, d_faces, nullptr, ctx->texdesc.p, ctx->lights.p, ctx->recs.p, ctx->keys.p,
+        launch_setup(L, d_verts, d_faces, nullptr, texdesc, ctx->lights.p, ctx->recs.p, ctx->keys.p,
                      ctx->heads.p, ctx->bins.p, ctx->tile_count, wire_on ? ctx->wire.p : nullptr, ctx->state,
                      zero_next, ctx->state_stride, p);                          // TRANSFORM + CULL + setup + binning
         if (wait) CK(cudaEventRecord(ctx->ev[1], st));
         if (!p.wire_front)
-            launch_fill_opaque(L, ctx->recs.p, ctx->bins.p, ctx->tile_count, ctx->texdesc.p, ctx->texels.p, ctx->texmask.p,
+            launch_fill_opaque(L, ctx->recs.p, ctx->bins.p, ctx->tile_count, texdesc, texels, texmask,
                                ctx->fb_rgba.p, ctx->fb_z.p, ctx->state, ctx->sticky, p);      // DRAW, pass 1
         if (!wait) { ctx->async_pending = true; return B32_OK; }
         CK(cudaEventRecord(ctx->ev[2], st));
@@ -329,14 +342,17 @@ int render_device(b32_ctx* ctx, const b32_vertex* d_verts, uint32_t nv, const b3
         if (hs.bin_overflow) return fail(ctx, B32_ERR_CUDA, "tile bin overflow persists");
         break;
     }
-    {   // the reference panics on a NaN key in a sorted slice of length >= 2 (render.rs:2531)
-        bool nan_abort = (hs.nan_transp && hs.n_transp >= 2) || (!p.use_zbuffer && hs.nan_opaque && hs.n_opaque >= 2);
+    {   // the reference panics on a NaN key in a sorted slice of length >= 2 (render.rs:2531; RGB888: one list, :2161)
+        bool nan_abort = rgb888 ? (!p.use_zbuffer && hs.nan_opaque && hs.n_opaque + hs.n_transp >= 2)
+                                : (hs.nan_transp && hs.n_transp >= 2) || (!p.use_zbuffer && hs.nan_opaque && hs.n_opaque >= 2);
         if (nan_abort) return fail(ctx, B32_ERR_NAN_DEPTH, "NaN depth key in a sorted pass (reference: partial_cmp().unwrap() panic, render.rs:2531)");
     }
     cudaEventElapsedTime(&ctx->kernel_ms[0], ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&ctx->kernel_ms[1], ctx->ev[1], ctx->ev[2]);
-    bool need_ordered = p.xray_mode ? (hs.n_opaque + hs.n_transp) > 0 : hs.n_transp > 0;
-    if (need_ordered && !p.wire_front) { rc = render_ordered(ctx, p, p.xray_mode ? hs.n_opaque + hs.n_transp : hs.n_transp); if (rc) return rc; }
+    // RGB888: one surface that may read the framebuffer sends the whole list through the ordered replay (pass 1 was skipped)
+    const bool all_ordered = rgb888 ? hs.n_transp > 0 : p.xray_mode != 0;
+    bool need_ordered = all_ordered ? (hs.n_opaque + hs.n_transp) > 0 : (!rgb888 && hs.n_transp > 0);
+    if (need_ordered && !p.wire_front) { rc = render_ordered(ctx, p, all_ordered ? hs.n_opaque + hs.n_transp : hs.n_transp); if (rc) return rc; }
     if (p.wire_back || p.wire_front) {          // WIREFRAME phase, render.rs:2574-2635
         CK(cudaEventRecord(ctx->ev[0], st));
         if (p.wire_back) launch_wire(L, ctx->wire.p, 1, 80u | (80u << 8) | (100u << 16) | 0xFF000000u, true, ctx->fb_rgba.p, ctx->fb_z.p, ctx->state, p);
@@ -382,6 +398,7 @@ int b32_ctx_create(int device, b32_ctx** out) {
     ctx->pinned_bytes = 8u << 20;
     if ((e = cudaMallocHost(&ctx->pinned, ctx->pinned_bytes)) != cudaSuccess) return bail(e, "cudaMallocHost");
     ctx->texdesc.reserve(1); ctx->texels.reserve(1); ctx->texmask.reserve(4); ctx->lights.reserve(1);
+    ctx->tex8desc.reserve(1); ctx->texels8.reserve(1); ctx->tex8mask.reserve(4);
     *out = ctx;
     return B32_OK;
 }
@@ -390,7 +407,8 @@ void b32_ctx_destroy(b32_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    ctx->fb_rgba.release(); ctx->fb_z.release(); ctx->texels.release(); ctx->texmask.release(); ctx->texdesc.release(); ctx->verts.release(); ctx->faces.release();
+    ctx->fb_rgba.release(); ctx->fb_z.release(); ctx->texels.release(); ctx->texmask.release(); ctx->texdesc.release();
+    ctx->texels8.release(); ctx->tex8mask.release(); ctx->tex8desc.release(); ctx->verts.release(); ctx->faces.release();
     ctx->tv.release(); ctx->recs.release(); ctx->keys.release(); ctx->state_ring.release(); ctx->otile_count.release();
     ctx->bins.release(); ctx->heads.release(); ctx->obins.release(); ctx->wire.release();
     ctx->lights.release(); ctx->dbg.release();
@@ -529,6 +547,55 @@ int b32_textures_set(b32_ctx* ctx, const b32_tex_desc* descs, uint32_t n) {
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->ntex = n;
     return B32_OK;
+}
+
+int b32_textures_set_rgb888(b32_ctx* ctx, const b32_tex8_desc* descs, uint32_t n) {
+    if (!ctx || (n && !descs)) return B32_ERR_INVALID;
+    if (n > 0xFFFF) return fail(ctx, B32_ERR_UNSUPPORTED, "more than 65535 textures (face.flags carries a 16-bit texture id)");
+    CK(cudaStreamSynchronize(ctx->stream));
+    size_t total = 0, max_px = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        size_t px = (size_t)descs[i].width * descs[i].height;
+        if (descs[i].blend_mode > B32_BLEND_ERASE) return fail(ctx, B32_ERR_INVALID, "texture blend out of range");
+        if (px && !descs[i].pixels) return fail(ctx, B32_ERR_INVALID, "texture pixels is NULL");
+        total += px; max_px = std::max(max_px, px);
+    }
+    if (total > 0xFFFFFFFFull) return fail(ctx, B32_ERR_UNSUPPORTED, "texel pool exceeds 2^32 texels");
+    CK(ctx->texels8.reserve(std::max<size_t>(total, 1)));
+    CK(ctx->tex8desc.reserve(std::max<uint32_t>(n, 1)));
+    std::vector<TexDev> desc_h(n);
+    size_t off = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        size_t px = (size_t)descs[i].width * descs[i].height;
+        desc_h[i] = TexDev{(uint32_t)off, descs[i].width, descs[i].height, 0u};       // .blend is computed on the device below
+        int rc = h2d(ctx, ctx->texels8.p + off, descs[i].pixels, px * 4); if (rc) return rc;
+        off += px;
+    }
+    if (n) CK(cudaMemcpyAsync(ctx->tex8desc.p, desc_h.data(), n * sizeof(TexDev), cudaMemcpyHostToDevice, ctx->stream));
+    uint32_t words = (uint32_t)(((total + 31) / 32 + 3) & ~(size_t)3);
+    CK(ctx->tex8mask.reserve(std::max<uint32_t>(words, 4)));
+    launch_tex8_scan(ctx->L(), ctx->texels8.p, (uint32_t)total, words, ctx->tex8mask.p, ctx->tex8desc.p, n, (uint32_t)std::min<size_t>(max_px, 0xFFFFFFFFu));
+    CK(cudaStreamSynchronize(ctx->stream));      // desc_h is a host temporary
+    CK(cudaGetLastError());
+    ctx->tex8mask_words = words;
+    ctx->ntex8 = n;
+    return B32_OK;
+}
+
+int b32_render_mesh(b32_ctx* ctx, const b32_vertex* vertices, uint32_t nv, const b32_face* faces, uint32_t nf,
+                    const b32_camera* camera, const b32_settings* settings, b32_timings* timings) {
+    if (!ctx) return B32_ERR_INVALID;
+    if ((nv && !vertices) || (nf && !faces)) return fail(ctx, B32_ERR_INVALID, "vertices/faces is NULL");
+    CK(ctx->verts.reserve(std::max<uint32_t>(nv, 1)));
+    CK(ctx->faces.reserve(std::max<uint32_t>(nf, 1)));
+    int rc = h2d(ctx, ctx->verts.p, vertices, (size_t)nv * sizeof(b32_vertex)); if (rc) return rc;
+    rc = h2d(ctx, ctx->faces.p, faces, (size_t)nf * sizeof(b32_face)); if (rc) return rc;
+    return render_device(ctx, ctx->verts.p, nv, ctx->faces.p, nf, camera, settings, nullptr, timings, true, true);
+}
+
+int b32_render_mesh_resident(b32_ctx* ctx, const b32_mesh* mesh, const b32_camera* camera, const b32_settings* settings, b32_timings* timings) {
+    if (!ctx || !mesh) return B32_ERR_INVALID;
+    return render_device(ctx, mesh->verts, mesh->nv, mesh->faces, mesh->nf, camera, settings, nullptr, timings, true, true);
 }
 
 int b32_render_mesh_15(b32_ctx* ctx, const b32_vertex* vertices, uint32_t nv, const b32_face* faces, uint32_t nf,

@@ -94,8 +94,11 @@ struct CallState {
 
 // The reference panics (and draws nothing) on an out-of-range vertex index, or when a NaN key is
 // compared by the sort, i.e. in any sorted slice of length >= 2 (render.rs:2531).
-__device__ __forceinline__ bool call_aborts(const CallState& st, bool use_zbuffer) {
+// render_mesh (RGB888) sorts ONE list and only in painter's mode (render.rs:2155-2162): k_setup then reports
+// every NaN key in nan_opaque and the list length is n_opaque + n_transp.
+__device__ __forceinline__ bool call_aborts(const CallState& st, bool use_zbuffer, bool rgb888) {
     if (st.oob) return true;
+    if (rgb888) return !use_zbuffer && st.nan_opaque && st.n_opaque + st.n_transp >= 2;
     if (st.nan_transp && st.n_transp >= 2) return true;
     if (!use_zbuffer && st.nan_opaque && st.n_opaque >= 2) return true;
     return false;
@@ -112,6 +115,7 @@ struct CallParams {
     uint32_t mask_smem_words;                         // words of the "texel writes" mask to stage in shared memory (0: read it from global)
     uint8_t affine_textures, use_zbuffer, shading, backface_cull, dithering, use_fixed_point, xray_mode, ortho;
     uint8_t fog_enabled, fog_r, fog_g, fog_b, fog_blend, async_call, wire_back, wire_front;   // wire_*: render.rs:2576, :2606
+    uint8_t rgb888, _padb[3];                         // 1: render_mesh / rasterize_triangle (render.rs:1971-2259, 1202-1433)
     float ambient, ortho_zoom, ortho_cx, ortho_cy;
     float fog_start, fog_falloff, fog_cull;
 };
@@ -178,6 +182,17 @@ __device__ __forceinline__ uint32_t blend5(uint32_t f8, uint32_t b8, uint32_t mo
         default:                    r = b5; break;     // Erase
     }
     return r << 3;
+}
+
+// Color::blend_with for one channel (types.rs:886-930): 8-bit math; Erase never reaches a writer
+__device__ __forceinline__ uint32_t blend8(uint32_t f8, uint32_t b8, uint32_t mode) {
+    switch (mode) {
+        case B32_BLEND_AVERAGE:     return (b8 + f8) >> 1;
+        case B32_BLEND_ADD:         return min(b8 + f8, 255u);
+        case B32_BLEND_SUBTRACT:    return b8 > f8 ? b8 - f8 : 0u;
+        case B32_BLEND_ADD_QUARTER: return min(b8 + (f8 >> 2), 255u);
+        default:                    return f8;         // Opaque
+    }
 }
 
 // order-preserving key for a stable ASCENDING radix sort that yields back-to-front order:

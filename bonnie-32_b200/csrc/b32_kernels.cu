@@ -21,6 +21,8 @@
 //     winner; the result is the reference's, bit for bit, and deterministic.
 //   * Pass 2 blends against the running colour, so it is replayed in exact draw order from lists
 //     that a stable radix sort and a stable tile binning produce.
+#include <algorithm>
+
 #include "b32_device.cuh"
 
 #include "b32_launch.h"
@@ -191,8 +193,13 @@ __device__ __forceinline__ void setup_face(uint32_t fi, const b32_vertex* __rest
         }
         float signed_area = (t2.x - t1.x) * (t3.y - t1.y) - (t3.x - t1.x) * (t2.y - t1.y);   // :2393
         bool backface = signed_area <= 0.0f;
-        bool transparent;                                                     // :2403-2415
-        if (textured && tex_blend != B32_BLEND_OPAQUE) transparent = true;
+        // render_mesh_15: has_transparency (:2403-2415) = drawn in pass 2.  render_mesh (RGB888) has ONE list and a blend
+        // tag per texel, so here the flag means "this surface may read the framebuffer" (its texture holds blended
+        // texels — TexDev.blend of the RGB888 table — or editor_alpha < 255): any such surface sends the whole call
+        // through the strict draw-order replay.
+        bool transparent;
+        if (p.rgb888) transparent = (textured && tex_blend != 0) || editor_alpha < 255;
+        else if (textured && tex_blend != B32_BLEND_OPAQUE) transparent = true;
         else if (face_blend != B32_BLEND_OPAQUE) transparent = true;
         else transparent = editor_alpha < 255;
         if (p.fog_enabled && t1.w > p.fog_cull && t2.w > p.fog_cull && t3.w > p.fog_cull) break;   // :2421-2424
@@ -214,6 +221,7 @@ __device__ __forceinline__ void setup_face(uint32_t fi, const b32_vertex* __rest
 
         SurfRec r;
         uint32_t blend_mode = textured ? tex_blend : face_blend;               // :1450-1452
+        if (p.rgb888) { blend_mode = 0; black_tr = textured; }                 // RGB888: blend tags are per texel; Erase texels skip (:1350)
         uint32_t flags = blend_mode | (black_tr ? SF_BLACK_TR : 0) | (textured ? SF_TEXTURED : 0) |
                          (transparent ? SF_TRANSPARENT : 0) | (editor_alpha << 8) | ((textured ? tex_id : 0xFFFFu) << 16);
         bool needs_dither = p.dithering && (p.shading == B32_SHADE_GOURAUD || textured || c1 != c2 || c2 != c3);   // :1487-1492
@@ -272,15 +280,15 @@ __device__ __forceinline__ void setup_face(uint32_t fi, const b32_vertex* __rest
 
         cls = transparent ? 1u : 0u;
         float center_z = (s1.z + s2.z + s3.z) / 3.0f;                                   // :2529
-        bool sorted = transparent || !p.use_zbuffer;                                    // :2527, :2536
+        bool sorted = (transparent && !p.rgb888) || !p.use_zbuffer;                     // :2527, :2536; RGB888: :2155
         if (sorted) {
-            if (center_z != center_z) { if (transparent) st->nan_transp = 1; else st->nan_opaque = 1; }
+            if (center_z != center_z) { if (transparent && !p.rgb888) st->nan_transp = 1; else st->nan_opaque = 1; }
             dkey = depth_key_desc(center_z);
         }
         if (transparent) ++n_tr; else ++n_op;
 
         // pass-1 surfaces go into their screen tiles' bins (any order; see file header)
-        if (!transparent && !p.xray_mode && !empty) {
+        if (!transparent && !(p.xray_mode && !p.rgb888) && !empty) {
             uint32_t hkey = dkey;
             if (p.use_zbuffer) {
                 // front-to-back walk key: a lower bound of every depth this surface can produce.
@@ -374,9 +382,10 @@ k_bin_opaque(const BinHead* __restrict__ heads, const uint64_t* __restrict__ key
                     // transparent list, ties by face index = stable sort (render.rs:2522-2542)
                     uint64_t k64 = keys[fi];
                     uint32_t cls = (uint32_t)(k64 >> 32);
-                    if (cls < 2 && (cls == 1 || p.xray_mode)) {
+                    // (RGB888: one list, so every drawn surface and no pass bit)
+                    if (cls < 2 && (cls == 1 || p.xray_mode || p.rgb888)) {
                         uint2 bb = *reinterpret_cast<const uint2*>(&recs[fi].bbox_x);      // all zero = empty surface
-                        uint64_t okey = ((uint64_t)cls << 62) | ((uint64_t)(uint32_t)k64 << 30) | fi;
+                        uint64_t okey = ((uint64_t)(p.rgb888 ? 0u : cls) << 62) | ((uint64_t)(uint32_t)k64 << 30) | fi;
                         if (bb.x) head[k] = BinHead{bb.x, bb.y, (uint32_t)(okey >> 32), (uint32_t)okey};
                     }
                 }
@@ -520,6 +529,60 @@ __device__ __forceinline__ bool shade(const SurfRec& r, uint32_t x, uint32_t y, 
     }
     semi = (color & 0x8000) || (r5 == 0 && g5 == 0 && b5 == 0);                    // :1659-1661
     o_r = expand5(r5); o_g = expand5(g5); o_b = expand5(b5);                       // Color15::r8/g8/b8
+    return true;
+}
+
+// RGB888 colour pipeline of rasterize_triangle (render.rs:1343-1389): Texture::sample (types.rs:1242-1253),
+// Erase texels skip, Color::modulate (types.rs:801-808), shade_color_rgb WITHOUT a clamp of the factor
+// (render.rs:1074-1081), apply_dither re-expanded with `<< 3` (render.rs:1186-1197).  blend = the texel's tag.
+__device__ __forceinline__ bool shade888(const SurfRec& r, uint32_t x, uint32_t y, float bc_x, float bc_y, float bc_z, float inv_z,
+                                         const TexDev* __restrict__ tex, const uint32_t* __restrict__ texels, const CallParams& p,
+                                         uint32_t& o_r, uint32_t& o_g, uint32_t& o_b, uint32_t& o_blend) {
+    uint32_t cr = 255, cg = 255, cb = 255, blend = B32_BLEND_OPAQUE;               // Color::WHITE
+    if (r.flags & SF_TEXTURED) {
+        float u, v;
+        if (p.affine_textures) {
+            u = bc_x * r.u1 + bc_y * r.u2 + bc_z * r.u3;
+            v = bc_x * r.v1 + bc_y * r.v2 + bc_z * r.v3;
+        } else {
+            float uo = bc_x * r.u1 * r.iz1 + bc_y * r.u2 * r.iz2 + bc_z * r.u3 * r.iz3;
+            float vo = bc_x * r.v1 * r.iz1 + bc_y * r.v2 * r.iz2 + bc_z * r.v3 * r.iz3;
+            u = uo / inv_z;
+            v = vo / inv_z;
+        }
+        TexDev t = tex[r.flags >> 16];
+        if (t.w == 0 || t.h == 0) return false;                                    // Color::TRANSPARENT
+        float uw = rem_euclid1(u), vw = rem_euclid1(1.0f - v);
+        uint32_t tx = min(f2u32sat(uw * (float)t.w), t.w - 1);
+        uint32_t ty = min(f2u32sat(vw * (float)t.h), t.h - 1);
+        uint32_t c = __ldg(texels + t.off + ty * t.w + tx);
+        cr = c & 0xFF; cg = (c >> 8) & 0xFF; cb = (c >> 16) & 0xFF; blend = c >> 24;
+    }
+    if (blend == B32_BLEND_ERASE) return false;                                    // :1350-1354
+    uint32_t vr = f2u8(bc_x * (float)(r.vc1 & 0xFF) + bc_y * (float)(r.vc2 & 0xFF) + bc_z * (float)(r.vc3 & 0xFF));          // :1357-1362
+    uint32_t vg = f2u8(bc_x * (float)((r.vc1 >> 8) & 0xFF) + bc_y * (float)((r.vc2 >> 8) & 0xFF) + bc_z * (float)((r.vc3 >> 8) & 0xFF));
+    uint32_t vb = f2u8(bc_x * (float)(r.vc1 >> 16) + bc_y * (float)(r.vc2 >> 16) + bc_z * (float)(r.vc3 >> 16));
+    uint32_t mr = min((cr * vr) >> 7, 255u), mg = min((cg * vg) >> 7, 255u), mb = min((cb * vb) >> 7, 255u);   // :1365
+    float sr, sg, sb;                                                              // :1368-1381
+    if (p.shading == B32_SHADE_NONE) { sr = sg = sb = 1.0f; }
+    else if (p.shading == B32_SHADE_FLAT) { sr = r.sh[0]; sg = r.sh[1]; sb = r.sh[2]; }
+    else {
+        sr = bc_x * r.sh[0] + bc_y * r.sh[3] + bc_z * r.sh[6];
+        sg = bc_x * r.sh[1] + bc_y * r.sh[4] + bc_z * r.sh[7];
+        sb = bc_x * r.sh[2] + bc_y * r.sh[5] + bc_z * r.sh[8];
+    }
+    uint32_t r8 = f2u8(fminf((float)mr * sr, 255.0f));                             // :1383
+    uint32_t g8 = f2u8(fminf((float)mg * sg, 255.0f));
+    uint32_t b8 = f2u8(fminf((float)mb * sb, 255.0f));
+    if (r.flags & SF_DITHER) {                                                     // :1387-1389
+        const uint32_t rows = (y & 2) ? ((y & 1) ? 0xE2F3u : 0x0C1Du) : ((y & 1) ? 0xF3E2u : 0x1D0Cu);
+        int32_t off = (int32_t)((rows >> ((x & 3) * 4)) & 0xF);
+        off = (off ^ 8) - 8;
+        r8 = (uint32_t)min(max(((int32_t)r8 + off) >> 3, 0), 31) << 3;
+        g8 = (uint32_t)min(max(((int32_t)g8 + off) >> 3, 0), 31) << 3;
+        b8 = (uint32_t)min(max(((int32_t)b8 + off) >> 3, 0), 31) << 3;
+    }
+    o_r = r8; o_g = g8; o_b = b8; o_blend = blend;
     return true;
 }
 
@@ -668,12 +731,13 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
     bool skip;
     {
         CallState s = *st;
-        bool aborts = call_aborts(s, p.use_zbuffer);
+        bool aborts = call_aborts(s, p.use_zbuffer, p.rgb888);
         if (p.async_call && blockIdx.x == 0 && threadIdx.x == 0) {                                // enqueue-only callers
             if (aborts || s.bin_overflow) atomicOr(sticky, s.oob ? 1u : (aborts ? 2u : 4u));
             else if (s.n_transp) atomicOr(sticky, 8u);                                           // pass 2 exists but was not enqueued
         }
-        skip = s.bin_overflow || aborts || p.xray_mode;
+        // x-ray (render_mesh_15) and any framebuffer-reading surface (render_mesh) go through the ordered replay instead
+        skip = s.bin_overflow || aborts || (p.xray_mode && !p.rgb888) || (p.rgb888 && s.n_transp);
     }
     const uint32_t n = skip ? 0u : tile_count[tile];
     if (n == 0) {                                          // nothing to draw here; the mask copy must land before the CTA exits
@@ -920,9 +984,10 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
             float bc_x, bc_y, bc_z;
             inside_test(r, x, y, bc_x, bc_y, bc_z);                        // same arithmetic as in the walk
             float inv_z = bc_x * r.iz1 + bc_y * r.iz2 + bc_z * r.iz3;      // :1549
-            uint32_t o_r, o_g, o_b; bool semi;
-            if (shade(r, x, y, bc_x, bc_y, bc_z, inv_z, texd, texels, p, o_r, o_g, o_b, semi))
-                px.rgba = o_r | (o_g << 8) | (o_b << 16) | 0xFF000000u;    // pass 1: set_pixel_15 (:445-454)
+            uint32_t o_r, o_g, o_b, o_blend; bool semi;
+            bool wrote = p.rgb888 ? shade888(r, x, y, bc_x, bc_y, bc_z, inv_z, texd, reinterpret_cast<const uint32_t*>(texels), p, o_r, o_g, o_b, o_blend)
+                                  : shade(r, x, y, bc_x, bc_y, bc_z, inv_z, texd, texels, p, o_r, o_g, o_b, semi);
+            if (wrote) px.rgba = o_r | (o_g << 8) | (o_b << 16) | 0xFF000000u;    // pass 1: set_pixel_15 (:445-454) / set_pixel (:301-310)
 #ifdef B32_FILL_STATS
             ++st_shaded;
 #endif
@@ -977,6 +1042,29 @@ __device__ __forceinline__ void write_ordered(const SurfRec& r, Pixel& px, float
     px.rgba = o_r | (o_g << 8) | (o_b << 16) | 0xFF000000u;
 }
 
+// The write stage of rasterize_triangle (RGB888, render.rs:1392-1424) against a pixel held in registers:
+// set_pixel / set_pixel_blended / set_pixel_with_depth / the two editor-alpha writers (render.rs:301-437).
+__device__ __forceinline__ void write_ordered888(const SurfRec& r, Pixel& px, float z, uint32_t o_r, uint32_t o_g, uint32_t o_b, uint32_t blend,
+                                                 const CallParams& p) {
+    uint32_t editor_alpha = (r.flags >> 8) & 0xFF;
+    if (editor_alpha == 0) return;                                                 // :1392-1398
+    uint32_t br = px.rgba & 0xFF, bg = (px.rgba >> 8) & 0xFF, bb = (px.rgba >> 16) & 0xFF;
+    if (p.use_zbuffer) {
+        if (editor_alpha < 255) { if (z >= px.z) return; }                         // :393
+        else if (!(z < px.z)) return;                                              // :425, :1408
+        px.z = z;
+    }
+    if (blend != B32_BLEND_OPAQUE) { o_r = blend8(o_r, br, blend); o_g = blend8(o_g, bg, blend); o_b = blend8(o_b, bb, blend); }
+    if (editor_alpha < 255) {                                                      // :362-371: float lerp, `as u8`
+        float a = (float)editor_alpha / 255.0f;
+        float inv_a = 1.0f - a;
+        o_r = f2u8((float)o_r * a + (float)br * inv_a);
+        o_g = f2u8((float)o_g * a + (float)bg * inv_a);
+        o_b = f2u8((float)o_b * a + (float)bb * inv_a);
+    }
+    px.rgba = o_r | (o_g << 8) | (o_b << 16) | 0xFF000000u;
+}
+
 constexpr int FILL_CHUNK = 32;       // surfaces staged in shared memory per step (32 x 128 B = 4 KB)
 constexpr int ORD_SORT_MAX = 2048;   // bin entries sortable in shared memory (32 KB); larger bins are sorted in place in global memory
 
@@ -1010,7 +1098,7 @@ k_fill_ordered(const SurfRec* __restrict__ recs, BinHead* __restrict__ bins, con
     __shared__ SurfRec s_rec[FILL_CHUNK];
     {
         CallState s = *st;
-        if (s.obin_overflow || call_aborts(s, p.use_zbuffer)) return;
+        if (s.obin_overflow || call_aborts(s, p.use_zbuffer, p.rgb888)) return;
     }
     const uint32_t tile = blockIdx.x;
     const uint32_t n = tile_count[tile];
@@ -1060,9 +1148,16 @@ k_fill_ordered(const SurfRec* __restrict__ recs, BinHead* __restrict__ bins, con
             float inv_z = bc_x * r.iz1 + bc_y * r.iz2 + bc_z * r.iz3;              // :1549
             float z = 1.0f / inv_z;
             if (p.use_zbuffer && !p.xray_mode) { if (z >= px.z) continue; }         // :1553-1560
-            uint32_t o_r, o_g, o_b; bool semi;
-            if (!shade(r, x, y, bc_x, bc_y, bc_z, inv_z, tex, texels, p, o_r, o_g, o_b, semi)) continue;
-            write_ordered(r, px, z, o_r, o_g, o_b, semi, p);
+            uint32_t o_r, o_g, o_b;
+            if (p.rgb888) {
+                uint32_t blend;
+                if (!shade888(r, x, y, bc_x, bc_y, bc_z, inv_z, tex, reinterpret_cast<const uint32_t*>(texels), p, o_r, o_g, o_b, blend)) continue;
+                write_ordered888(r, px, z, o_r, o_g, o_b, blend, p);
+            } else {
+                bool semi;
+                if (!shade(r, x, y, bc_x, bc_y, bc_z, inv_z, tex, texels, p, o_r, o_g, o_b, semi)) continue;
+                write_ordered(r, px, z, o_r, o_g, o_b, semi, p);
+            }
         }
     }
     if (valid) {
@@ -1093,7 +1188,7 @@ __device__ __forceinline__ bool wire_edge(const WireTri& t, uint32_t k, WireEdge
 __global__ void __launch_bounds__(128)
 k_wire(const WireTri* __restrict__ wire, uint32_t nf, uint32_t kind, uint32_t color, bool depth_test,
        uint32_t* __restrict__ fb_rgba, const float* __restrict__ fb_z, const CallState* __restrict__ st, CallParams p) {
-    if (call_aborts(*st, p.use_zbuffer)) return;
+    if (call_aborts(*st, p.use_zbuffer, p.rgb888)) return;
     const int32_t W = (int32_t)p.width, H = (int32_t)p.height;
     for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < nf * 3; e += gridDim.x * blockDim.x) {
         const WireTri& t = wire[e / 3];
@@ -1167,6 +1262,32 @@ __global__ void k_tex_mask(const uint16_t* __restrict__ texels, uint32_t n_texel
     }
 }
 
+// The same for the RGB888 texel pool (one Color = r | g << 8 | b << 16 | blend << 24 per texel): a texel writes
+// unless its tag is Erase (Color::is_transparent, types.rs:783-785).
+__global__ void k_tex8_mask(const uint32_t* __restrict__ texels, uint32_t n_texels, uint32_t n_words, uint32_t* __restrict__ mask) {
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += gridDim.x * blockDim.x) {
+        uint32_t m = 0;
+        for (uint32_t b = 0; b < 32; ++b) {
+            uint32_t i = w * 32 + b;
+            if (i < n_texels && (texels[i] >> 24) != B32_BLEND_ERASE) m |= 1u << b;
+        }
+        mask[w] = m;
+    }
+}
+
+// TexDev.blend of an RGB888 texture = 1 iff some texel carries a PS1 blend tag (neither Opaque nor Erase): only
+// surfaces of such textures (or with editor alpha) ever read the framebuffer.  blockIdx.y = texture.
+__global__ void k_tex8_flags(const uint32_t* __restrict__ texels, TexDev* __restrict__ desc) {
+    TexDev d = desc[blockIdx.y];
+    uint32_t n = d.w * d.h;
+    bool any = false;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t tag = texels[d.off + i] >> 24;
+        any = any || (tag != B32_BLEND_OPAQUE && tag != B32_BLEND_ERASE);
+    }
+    if (__any_sync(0xFFFFFFFFu, any) && (threadIdx.x & 31) == 0) atomicOr(&desc[blockIdx.y].blend, 1u);
+}
+
 // =================================================================================================
 // launchers (host)
 // =================================================================================================
@@ -1202,7 +1323,7 @@ void launch_setup(const LaunchCtx& L, const b32_vertex* verts, const b32_face* f
     k_setup<<<grid_for(p.nf, SETUP_THREADS, L.sms, 16), SETUP_THREADS, 0, L.stream>>>(verts, faces, tv, tex, lights, recs, keys, heads, wire, st,
                                                                                       zero_next, zero_words, p);
     ++*L.launches;
-    if (p.xray_mode || p.wire_front) return;        // wireframe_overlay draws no solid surfaces (:2550)
+    if ((p.xray_mode && !p.rgb888) || p.wire_front) return;        // wireframe_overlay draws no solid surfaces (:2550)
     launch_bin(L, heads, keys, recs, bins, tile_count, st, p, p.bin_cap, false, true);
 }
 
@@ -1226,7 +1347,7 @@ void launch_fill_opaque(const LaunchCtx& L, const SurfRec* recs, const BinHead* 
     static bool attr_set = false;
     if (!attr_set) { cudaFuncSetAttribute(k_fill_opaque, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OP_SMEM); attr_set = true; }
     // launched right behind k_bin_opaque except in x-ray mode (no pass-1 binning: then it is an ordinary launch)
-    launch_k(k_fill_opaque, ntiles * OP_SPLIT, OP_THREADS, OP_SMEM, L.stream, !p.xray_mode, recs, bins, tile_count, tex, texels, texmask,
+    launch_k(k_fill_opaque, ntiles * OP_SPLIT, OP_THREADS, OP_SMEM, L.stream, !(p.xray_mode && !p.rgb888), recs, bins, tile_count, tex, texels, texmask,
              fb_rgba, fb_z, st, sticky, p);
     ++*L.launches;
 }
@@ -1266,6 +1387,16 @@ void launch_tex_mask(const LaunchCtx& L, const uint16_t* texels, uint32_t n_texe
     if (n_words == 0) return;
     k_tex_mask<<<grid_for(n_words, 256, L.sms), 256, 0, L.stream>>>(texels, n_texels, n_words, mask);
     ++*L.launches;
+}
+
+void launch_tex8_scan(const LaunchCtx& L, const uint32_t* texels, uint32_t n_texels, uint32_t n_words, uint32_t* mask,
+                      TexDev* desc, uint32_t ntex, uint32_t max_texels) {
+    if (n_words) { k_tex8_mask<<<grid_for(n_words, 256, L.sms), 256, 0, L.stream>>>(texels, n_texels, n_words, mask); ++*L.launches; }
+    if (ntex && max_texels) {
+        dim3 grid(std::min<uint32_t>((max_texels + 255) / 256, 64), ntex);
+        k_tex8_flags<<<grid, 256, 0, L.stream>>>(texels, desc);
+        ++*L.launches;
+    }
 }
 
 }  // namespace b32

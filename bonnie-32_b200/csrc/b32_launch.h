@@ -40,4 +40,8 @@ void launch_tex_expand(const LaunchCtx& L, const uint8_t* idx, const uint16_t* c
 // bit i of mask = texel i of the pool writes when its surface is black-keyed; n_words covers n_texels, zero padded
 void launch_tex_mask(const LaunchCtx& L, const uint16_t* texels, uint32_t n_texels, uint32_t n_words, uint32_t* mask);
 
+// RGB888 texel pool: the "texel writes" mask (tag != Erase) and, per texture, TexDev.blend = "has blended texels"
+void launch_tex8_scan(const LaunchCtx& L, const uint32_t* texels, uint32_t n_texels, uint32_t n_words, uint32_t* mask,
+                      TexDev* desc, uint32_t ntex, uint32_t max_texels);
+
 }  // namespace b32

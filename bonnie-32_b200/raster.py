@@ -2,8 +2,9 @@
 
 Same names, argument meaning and error behaviour as /root/reference/src/rasterizer:
 `Framebuffer` (render.rs:10-45), `Camera` (camera.rs:9-91), `RasterSettings` (types.rs:1392-1495),
-`Light` (types.rs:1307-1373), `Texture15` (types.rs:532-539), `render_mesh_15` (render.rs:2302-2310).
-Where the reference panics (bad vertex index, NaN sort key) `render_mesh_15` raises `B32Error`.
+`Light` (types.rs:1307-1373), `Texture15` (types.rs:532-539), `render_mesh_15` (render.rs:2302-2310),
+and the RGB888 siblings `Texture` (types.rs:1058-1066) / `render_mesh` (render.rs:1971-1978).
+Where the reference panics (bad vertex index, NaN sort key) the render calls raise `B32Error`.
 
 Vertices and faces are numpy record arrays (`abi.VERTEX_DTYPE`, `abi.FACE_DTYPE`) — the POD layout
 the Rust shim marshals `&[Vertex]` / `&[Face]` into.
@@ -192,6 +193,34 @@ def tex_descs(textures: Sequence[Texture15]):
     return arr, keep
 
 
+@dataclass
+class Texture:
+    """RGB888 texture, types.rs:1058-1066: one Color (r, g, b, blend) per texel, blend == Erase = transparent."""
+    width: int
+    height: int
+    pixels: np.ndarray                      # u8[h*w*4]
+    blend_mode: int = BLEND_OPAQUE
+    name: str = ""
+
+    def to_abi(self):
+        d = abi.Tex8Desc()
+        d.width, d.height, d.blend_mode = self.width, self.height, self.blend_mode
+        px = np.ascontiguousarray(self.pixels, dtype=np.uint8)
+        assert px.size == self.width * self.height * 4
+        d.pixels = px.ctypes.data
+        return d, [px]
+
+
+def tex8_descs(textures: Sequence[Texture]):
+    keep = []
+    arr = (abi.Tex8Desc * max(1, len(textures)))()
+    for i, t in enumerate(textures):
+        d, k = t.to_abi()
+        arr[i] = d
+        keep.append(k)
+    return arr, keep
+
+
 def fog_to_abi(fog):
     """fog: None or (start, falloff, cull_distance, (r, g, b[, blend]))."""
     if fog is None:
@@ -215,6 +244,7 @@ class Context:
             raise B32Error(rc, "b32_ctx_create failed (no CPU fallback exists)")
         self.h = h
         self._tex_ref = None      # the list last uploaded (kept alive so identity stays meaningful)
+        self._tex8_ref = None
 
     def close(self):
         if getattr(self, "h", None):
@@ -246,6 +276,12 @@ class Context:
         arr, keep = tex_descs(textures)
         self.check(self.lib.b32_textures_set(self.h, arr, len(textures)))
         self._tex_ref = textures
+
+
+    def set_textures_rgb888(self, textures: Sequence[Texture]):
+        arr, keep = tex8_descs(textures)
+        self.check(self.lib.b32_textures_set_rgb888(self.h, arr, len(textures)))
+        self._tex8_ref = textures
 
 
 _default_ctx: Optional[Context] = None
@@ -330,6 +366,22 @@ def render_mesh_15(fb: Framebuffer, vertices: np.ndarray, faces: np.ndarray,
     return tm.as_dict()
 
 
+def render_mesh(fb: Framebuffer, vertices: np.ndarray, faces: np.ndarray, textures: Sequence[Texture],
+                camera: Camera, settings: RasterSettings) -> dict:
+    """render.rs:1971-1978, the RGB888 sibling (RasterSettings.use_rgb555 == false)."""
+    ctx = fb.ctx
+    v, f = _check_geometry(vertices, faces)
+    if ctx._tex8_ref is not textures:
+        ctx.set_textures_rgb888(textures)
+    cam = camera.to_abi()
+    s, keep = settings.to_abi()
+    tm = abi.Timings()
+    rc = ctx.lib.b32_render_mesh(ctx.h, v.ctypes.data, len(v), f.ctypes.data, len(f), C.byref(cam), C.byref(s), C.byref(tm))
+    del keep
+    ctx.check(rc)
+    return tm.as_dict()
+
+
 class Mesh:
     """Device-resident geometry (b32_mesh): upload once, render many times."""
 
@@ -356,4 +408,12 @@ class Mesh:
             return None
         tm = abi.Timings()
         self.ctx.check(self.ctx.lib.b32_render_mesh_15_resident(self.ctx.h, self.h, C.byref(cam), C.byref(s), fgp, C.byref(tm)))
+        return tm.as_dict()
+
+    def render_rgb888(self, camera: Camera, settings: RasterSettings):
+        """render_mesh (RGB888) on the resident geometry; textures come from Context.set_textures_rgb888."""
+        cam = camera.to_abi()
+        s, keep = settings.to_abi()
+        tm = abi.Timings()
+        self.ctx.check(self.ctx.lib.b32_render_mesh_resident(self.ctx.h, self.h, C.byref(cam), C.byref(s), C.byref(tm)))
         return tm.as_dict()

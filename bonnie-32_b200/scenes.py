@@ -51,6 +51,7 @@ class Scene:
     width: int = 320
     height: int = 240
     clear: tuple = CLEAR_COLOR
+    textures8: Optional[list] = None        # RGB888 scenes: raster.Texture list for render_mesh
 
     @property
     def algorithmic_bytes(self) -> int:

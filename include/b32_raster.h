@@ -140,6 +140,16 @@ typedef struct b32_tex_desc {
     uint32_t        clut_len;    /* index >= clut_len samples 0x0000 (Clut::lookup, types.rs:390-397) */
 } b32_tex_desc;
 
+/* struct Texture of the RGB888 path (types.rs:1058-1066): `pixels: Vec<Color>`, one Color per texel
+ * marshalled as 4 bytes r, g, b, blend (struct Color, types.rs:721-726; blend = B32_BLEND_*, Erase =
+ * transparent texel, types.rs:783-785). */
+typedef struct b32_tex8_desc {
+    uint32_t       width, height;
+    uint32_t       blend_mode;   /* Texture.blend_mode: only feeds the unused has_transparency (render.rs:2074-2078) */
+    uint32_t       _pad;
+    const uint8_t* pixels;       /* 4 * w * h bytes                          */
+} b32_tex8_desc;
+
 typedef struct b32_ctx  b32_ctx;   /* one GPU, one stream, one device-resident Framebuffer   */
 typedef struct b32_mesh b32_mesh;  /* device-resident vertex/face buffers                    */
 
@@ -205,6 +215,19 @@ int  b32_render_mesh_15_resident(b32_ctx* ctx, const b32_mesh* mesh,
 int  b32_render_mesh_15_enqueue(b32_ctx* ctx, const b32_mesh* mesh,
                                 const b32_camera* camera, const b32_settings* settings,
                                 const b32_fog* fog_or_null);
+
+/* ---- the RGB888 sibling (RasterSettings.use_rgb555 == false) ----------------------------- */
+/* `textures: &[Texture]` of render_mesh: a second texture table, independent of b32_textures_set's. */
+int b32_textures_set_rgb888(b32_ctx* ctx, const b32_tex8_desc* descs, uint32_t n);
+/* render_mesh (render.rs:1971-2259) -> rasterize_triangle (render.rs:1202-1433): no fog, ONE surface list
+ * (sorted back to front only when !use_zbuffer), 8-bit colour pipeline, per-texel blend tags, 8-bit blends
+ * (Color::blend_with, types.rs:886-930), dither re-expanded with `<< 3` (render.rs:1186-1197). */
+int b32_render_mesh(b32_ctx* ctx,
+                    const b32_vertex* vertices, uint32_t nv,
+                    const b32_face* faces, uint32_t nf,
+                    const b32_camera* camera, const b32_settings* settings, b32_timings* timings);
+int b32_render_mesh_resident(b32_ctx* ctx, const b32_mesh* mesh,
+                             const b32_camera* camera, const b32_settings* settings, b32_timings* timings);
 
 /* ---- pinned host memory for callers that want zero-copy DMA of their Vec buffers -------- */
 void* b32_host_alloc(size_t bytes);

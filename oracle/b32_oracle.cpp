@@ -557,6 +557,218 @@ void rasterize_triangle_15(Fb& fb, const Surface& surface, const Tex15* texture,
     }
 }
 
+// =============================================================================================
+// RGB888 path: struct Texture (types.rs:1058-1066), Color ops (types.rs:783-934), writers
+// (render.rs:301-437), rasterize_triangle (render.rs:1202-1433)
+// =============================================================================================
+struct Tex8 {
+    uint32_t width = 0, height = 0;
+    const Col* pixels = nullptr;       // width * height Colors (r, g, b, blend)
+    uint32_t blend_mode = 0;
+};
+// Texture::sample, types.rs:1242-1253
+inline Col tex8_sample(const Tex8& t, float u, float v) {
+    if (t.width == 0 || t.height == 0 || t.pixels == nullptr) return Col{0, 0, 0, B32_BLEND_ERASE};   // Color::TRANSPARENT
+    float u_wrapped = rem_euclid(u, 1.0f);
+    float v_wrapped = rem_euclid(v, 1.0f);
+    uint64_t tx = std::min<uint64_t>(f2usize(u_wrapped * (float)t.width), t.width - 1);
+    uint64_t ty = std::min<uint64_t>(f2usize(v_wrapped * (float)t.height), t.height - 1);
+    return t.pixels[ty * t.width + tx];
+}
+// Color::modulate, types.rs:801-808
+inline Col col_modulate(Col c, Col vc) {
+    return Col{(uint8_t)std::min<uint16_t>((uint16_t)((uint16_t)c.r * (uint16_t)vc.r / 128), 255),
+               (uint8_t)std::min<uint16_t>((uint16_t)((uint16_t)c.g * (uint16_t)vc.g / 128), 255),
+               (uint8_t)std::min<uint16_t>((uint16_t)((uint16_t)c.b * (uint16_t)vc.b / 128), 255), c.blend};
+}
+// shade_color_rgb, render.rs:1074-1081 (no clamp of the shade factor; `as u8` saturates, NaN -> 0)
+inline Col shade_color_rgb(Col c, float sr, float sg, float sb) {
+    return Col{f2u8(rmin((float)c.r * sr, 255.0f)), f2u8(rmin((float)c.g * sg, 255.0f)), f2u8(rmin((float)c.b * sb, 255.0f)), c.blend};
+}
+// apply_dither, render.rs:1186-1197
+inline Col apply_dither(Col c, uint64_t x, uint64_t y) {
+    int32_t offset = PS1_DITHER_MATRIX[y & 3][x & 3];
+    uint8_t r5 = (uint8_t)std::clamp(((int32_t)c.r + offset) >> 3, 0, 31);
+    uint8_t g5 = (uint8_t)std::clamp(((int32_t)c.g + offset) >> 3, 0, 31);
+    uint8_t b5 = (uint8_t)std::clamp(((int32_t)c.b + offset) >> 3, 0, 31);
+    return Col{(uint8_t)(r5 << 3), (uint8_t)(g5 << 3), (uint8_t)(b5 << 3), c.blend};
+}
+// Color::blend(back, mode) = with_blend(.., mode).blend_with(back), types.rs:886-936
+inline Col col_blend(Col f, Col back, uint32_t mode) {
+    switch (mode) {
+        case B32_BLEND_OPAQUE: return Col{f.r, f.g, f.b, B32_BLEND_OPAQUE};
+        case B32_BLEND_AVERAGE:
+            return Col{(uint8_t)(((uint16_t)back.r + f.r) / 2), (uint8_t)(((uint16_t)back.g + f.g) / 2), (uint8_t)(((uint16_t)back.b + f.b) / 2), B32_BLEND_OPAQUE};
+        case B32_BLEND_ADD:
+            return Col{(uint8_t)std::min<uint16_t>((uint16_t)back.r + f.r, 255), (uint8_t)std::min<uint16_t>((uint16_t)back.g + f.g, 255),
+                       (uint8_t)std::min<uint16_t>((uint16_t)back.b + f.b, 255), B32_BLEND_OPAQUE};
+        case B32_BLEND_SUBTRACT:
+            return Col{(uint8_t)std::max<int16_t>((int16_t)((int16_t)back.r - (int16_t)f.r), 0), (uint8_t)std::max<int16_t>((int16_t)((int16_t)back.g - (int16_t)f.g), 0),
+                       (uint8_t)std::max<int16_t>((int16_t)((int16_t)back.b - (int16_t)f.b), 0), B32_BLEND_OPAQUE};
+        case B32_BLEND_ADD_QUARTER:
+            return Col{(uint8_t)std::min<uint16_t>((uint16_t)back.r + (uint16_t)f.r / 4, 255), (uint8_t)std::min<uint16_t>((uint16_t)back.g + (uint16_t)f.g / 4, 255),
+                       (uint8_t)std::min<uint16_t>((uint16_t)back.b + (uint16_t)f.b / 4, 255), B32_BLEND_OPAQUE};
+        default: return Col{0, 0, 0, B32_BLEND_ERASE};                                 // Color::TRANSPARENT
+    }
+}
+inline Col fb_back(const Fb& fb, uint64_t idx) { return Col{fb.pixels[idx], fb.pixels[idx + 1], fb.pixels[idx + 2], B32_BLEND_OPAQUE}; }
+inline void fb_put(Fb& fb, uint64_t idx, Col c) {                                        // Color::to_bytes, types.rs:829-832
+    fb.pixels[idx] = c.r; fb.pixels[idx + 1] = c.g; fb.pixels[idx + 2] = c.b; fb.pixels[idx + 3] = c.blend == B32_BLEND_ERASE ? 0 : 255;
+}
+inline void fb_set_pixel_blended(Fb& fb, uint64_t x, uint64_t y, Col c, uint32_t mode) {   // render.rs:312-333
+    if (x < fb.width && y < fb.height) {
+        uint64_t idx = (y * fb.width + x) * 4;
+        fb_put(fb, idx, col_blend(c, fb_back(fb, idx), mode));
+    }
+}
+// shared tail of the two editor-alpha writers (render.rs:349-373 / 395-419): PS1 blend, then a float lerp
+inline void editor_alpha_write8(Fb& fb, uint64_t idx, Col c, uint32_t mode, uint8_t editor_alpha) {
+    Col back = fb_back(fb, idx);
+    Col ps1 = col_blend(c, back, mode);
+    Col fin = ps1;
+    if (editor_alpha < 255) {
+        float a = (float)editor_alpha / 255.0f;
+        float inv_a = 1.0f - a;
+        fin = Col{f2u8((float)ps1.r * a + (float)back.r * inv_a), f2u8((float)ps1.g * a + (float)back.g * inv_a),
+                  f2u8((float)ps1.b * a + (float)back.b * inv_a), B32_BLEND_OPAQUE};
+    }
+    fb_put(fb, idx, fin);
+}
+inline void fb_set_pixel_with_editor_alpha(Fb& fb, uint64_t x, uint64_t y, Col c, uint32_t mode, uint8_t ea) {   // render.rs:338-380
+    if (ea == 0) return;
+    if (x >= fb.width || y >= fb.height) return;
+    editor_alpha_write8(fb, (y * fb.width + x) * 4, c, mode, ea);
+}
+inline bool fb_set_pixel_with_depth_and_editor_alpha(Fb& fb, uint64_t x, uint64_t y, float z, Col c, uint32_t mode, uint8_t ea) {  // :383-420
+    if (ea == 0) return false;
+    if (x >= fb.width || y >= fb.height) return false;
+    uint64_t depth_idx = y * fb.width + x;
+    if (z >= fb.zbuffer[depth_idx]) return false;
+    fb.zbuffer[depth_idx] = z;
+    editor_alpha_write8(fb, depth_idx * 4, c, mode, ea);
+    return true;
+}
+inline bool fb_set_pixel_with_depth(Fb& fb, uint64_t x, uint64_t y, float z, Col c) {      // render.rs:422-437
+    if (x < fb.width && y < fb.height) {
+        uint64_t idx = y * fb.width + x;
+        if (z < fb.zbuffer[idx]) {
+            fb.zbuffer[idx] = z;
+            fb_put(fb, idx * 4, c);
+            return true;
+        }
+    }
+    return false;
+}
+
+// render.rs:1202-1433
+void rasterize_triangle(Fb& fb, const Surface& surface, const Tex8* texture, const b32_settings& settings) {
+    uint64_t min_x = f2usize(rmax(rmin(rmin(surface.v1.x, surface.v2.x), surface.v3.x), 0.0f));            // :1209-1212
+    uint64_t max_x = f2usize(rmin(rmax(rmax(surface.v1.x, surface.v2.x), surface.v3.x) + 1.0f, (float)fb.width));
+    uint64_t min_y = f2usize(rmax(rmin(rmin(surface.v1.y, surface.v2.y), surface.v3.y), 0.0f));
+    uint64_t max_y = f2usize(rmin(rmax(rmax(surface.v1.y, surface.v2.y), surface.v3.y) + 1.0f, (float)fb.height));
+    if (min_x >= max_x || min_y >= max_y) return;                                              // :1215-1217
+
+    float flat_shade[3] = {1.0f, 1.0f, 1.0f};
+    if (settings.shading == B32_SHADE_FLAT) {                                                  // :1220-1226
+        V3 center_pos = scale(add(add(surface.w1, surface.w2), surface.w3), 1.0f / 3.0f);
+        V3 world_normal = normalize(scale(add(add(surface.wn1, surface.wn2), surface.wn3), 1.0f / 3.0f));
+        shade_multi_light_color(world_normal, center_pos, settings.lights, settings.n_lights, settings.ambient, flat_shade);
+    }
+    float gs1[3], gs2[3], gs3[3];
+    bool gouraud = settings.shading == B32_SHADE_GOURAUD;
+    if (gouraud) {                                                                             // :1229-1237
+        shade_multi_light_color(surface.wn1, surface.w1, settings.lights, settings.n_lights, settings.ambient, gs1);
+        shade_multi_light_color(surface.wn2, surface.w2, settings.lights, settings.n_lights, settings.ambient, gs2);
+        shade_multi_light_color(surface.wn3, surface.w3, settings.lights, settings.n_lights, settings.ambient, gs3);
+    }
+    bool needs_dither = settings.dithering && (gouraud || texture != nullptr ||               // :1241-1246
+                                               !col_eq(surface.vc1, surface.vc2) || !col_eq(surface.vc2, surface.vc3));
+
+    V3 v1 = surface.v1, v2 = surface.v2, v3 = surface.v3;
+    float area = (v2.y - v3.y) * (v1.x - v3.x) + (v3.x - v2.x) * (v1.y - v3.y);              // :1257
+    if (std::fabs(area) < 0.00001f) return;
+    float inv_area = 1.0f / area;
+    float a0 = v2.y - v3.y, b0 = v3.x - v2.x, a1 = v3.y - v1.y, b1 = v1.x - v3.x;            // :1265-1270
+    float start_x = (float)min_x, start_y = (float)min_y;
+    float w0_row = a0 * (start_x - v3.x) + b0 * (start_y - v3.y);                             // :1278-1279
+    float w1_row = a1 * (start_x - v3.x) + b1 * (start_y - v3.y);
+
+    for (uint64_t y = min_y; y < max_y; ++y) {                                                 // :1291
+        float w0 = w0_row, w1 = w1_row;
+        for (uint64_t x = min_x; x < max_x; ++x) {
+            float bc_x = w0 * inv_area;
+            float bc_y = w1 * inv_area;
+            float bc_z = 1.0f - bc_x - bc_y;
+            const float ERR = -0.0001f;
+            if (bc_x >= ERR && bc_y >= ERR && bc_z >= ERR) {                                   // :1303
+                float inv_z1 = 1.0f / v1.z, inv_z2 = 1.0f / v2.z, inv_z3 = 1.0f / v3.z;
+                float inv_z_interp = bc_x * inv_z1 + bc_y * inv_z2 + bc_z * inv_z3;
+                float z = 1.0f / inv_z_interp;
+
+                if (settings.use_zbuffer && !settings.xray_mode) {                             // :1313-1320
+                    uint64_t idx = y * fb.width + x;
+                    if (z >= fb.zbuffer[idx]) { w0 += a0; w1 += a1; continue; }
+                }
+
+                float u, v;
+                if (settings.affine_textures) {                                                // :1323-1340
+                    u = bc_x * surface.uv1[0] + bc_y * surface.uv2[0] + bc_z * surface.uv3[0];
+                    v = bc_x * surface.uv1[1] + bc_y * surface.uv2[1] + bc_z * surface.uv3[1];
+                } else {
+                    float u_over_z = bc_x * surface.uv1[0] * inv_z1 + bc_y * surface.uv2[0] * inv_z2 + bc_z * surface.uv3[0] * inv_z3;
+                    float v_over_z = bc_x * surface.uv1[1] * inv_z1 + bc_y * surface.uv2[1] * inv_z2 + bc_z * surface.uv3[1] * inv_z3;
+                    u = u_over_z / inv_z_interp;
+                    v = v_over_z / inv_z_interp;
+                }
+
+                Col color = texture ? tex8_sample(*texture, u, 1.0f - v) : Col{255, 255, 255, B32_BLEND_OPAQUE};   // :1343-1347
+                if (color.blend == B32_BLEND_ERASE) { w0 += a0; w1 += a1; continue; }          // :1350-1354
+
+                Col vertex_color{                                                              // :1357-1362
+                    f2u8(bc_x * (float)surface.vc1.r + bc_y * (float)surface.vc2.r + bc_z * (float)surface.vc3.r),
+                    f2u8(bc_x * (float)surface.vc1.g + bc_y * (float)surface.vc2.g + bc_z * (float)surface.vc3.g),
+                    f2u8(bc_x * (float)surface.vc1.b + bc_y * (float)surface.vc2.b + bc_z * (float)surface.vc3.b),
+                    B32_BLEND_OPAQUE};
+                color = col_modulate(color, vertex_color);                                     // :1365
+
+                float shade_r, shade_g, shade_b;                                               // :1368-1381
+                if (settings.shading == B32_SHADE_NONE) { shade_r = shade_g = shade_b = 1.0f; }
+                else if (settings.shading == B32_SHADE_FLAT) { shade_r = flat_shade[0]; shade_g = flat_shade[1]; shade_b = flat_shade[2]; }
+                else {
+                    shade_r = bc_x * gs1[0] + bc_y * gs2[0] + bc_z * gs3[0];
+                    shade_g = bc_x * gs1[1] + bc_y * gs2[1] + bc_z * gs3[1];
+                    shade_b = bc_x * gs1[2] + bc_y * gs2[2] + bc_z * gs3[2];
+                }
+                color = shade_color_rgb(color, shade_r, shade_g, shade_b);                     // :1383
+                if (needs_dither) color = apply_dither(color, x, y);                           // :1387-1389
+
+                uint8_t editor_alpha = surface.editor_alpha;                                   // :1392-1398
+                if (editor_alpha == 0) { w0 += a0; w1 += a1; continue; }
+
+                if (settings.use_zbuffer) {                                                    // :1400-1413
+                    if (editor_alpha < 255) {
+                        fb_set_pixel_with_depth_and_editor_alpha(fb, x, y, z, color, color.blend, editor_alpha);
+                    } else if (color.blend == B32_BLEND_OPAQUE) {
+                        fb_set_pixel_with_depth(fb, x, y, z, color);
+                    } else {
+                        uint64_t idx = y * fb.width + x;
+                        if (z < fb.zbuffer[idx]) {
+                            fb.zbuffer[idx] = z;
+                            fb_set_pixel_blended(fb, x, y, color, color.blend);
+                        }
+                    }
+                } else {                                                                       // :1414-1423
+                    if (editor_alpha < 255) fb_set_pixel_with_editor_alpha(fb, x, y, color, color.blend, editor_alpha);
+                    else if (color.blend == B32_BLEND_OPAQUE) fb_set_pixel(fb, x, y, color);
+                    else fb_set_pixel_blended(fb, x, y, color, color.blend);
+                }
+            }
+            w0 += a0; w1 += a1;                                                                // :1427-1428
+        }
+        w0_row += b0; w1_row += b1;                                                            // :1432-1433
+    }
+}
+
 // render.rs:2266-2275
 inline float calculate_fog_factor(float z, float fog_start, float fog_falloff) {
     if (z <= fog_start) return 0.0f;
@@ -607,6 +819,37 @@ void transform_phase(const b32_vertex* vertices, uint32_t nv, const b32_camera* 
         out.projected.push_back(screen_pos);
         V3 cam_normal = perspective_transform(mk3(v.normal), bx, by, bz);
         out.cam_normals.push_back(normalize(cam_normal));
+    }
+}
+
+struct Tri3 { V3 a, b, c; };
+// WIREFRAME PHASE, identical in render_mesh_15 (render.rs:2574-2635) and render_mesh (render.rs:2195-2256)
+void wireframe_phase(Fb& fb, const b32_settings& st, const std::vector<Tri3>& backface_wireframes, const std::vector<Tri3>& frontface_wireframes) {
+    const b32_settings* settings = &st;
+    struct Edge { int32_t x0, y0; float z0; int32_t x1, y1; float z1; };
+    auto collect = [](const std::vector<Tri3>& tris, std::vector<Edge>& unique_edges) {
+        for (const Tri3& t : tris) {
+            Edge es[3] = {{f2i32(t.a.x), f2i32(t.a.y), t.a.z, f2i32(t.b.x), f2i32(t.b.y), t.b.z},
+                          {f2i32(t.b.x), f2i32(t.b.y), t.b.z, f2i32(t.c.x), f2i32(t.c.y), t.c.z},
+                          {f2i32(t.c.x), f2i32(t.c.y), t.c.z, f2i32(t.a.x), f2i32(t.a.y), t.a.z}};
+            for (const Edge& e0 : es) {
+                bool lt = (e0.x0 < e0.x1) || (e0.x0 == e0.x1 && e0.y0 < e0.y1);      // tuple `<`
+                Edge e = lt ? e0 : Edge{e0.x1, e0.y1, e0.z1, e0.x0, e0.y0, e0.z0};
+                bool found = false;
+                for (const Edge& u : unique_edges) if (u.x0 == e.x0 && u.y0 == e.y0 && u.x1 == e.x1 && u.y1 == e.y1) { found = true; break; }
+                if (!found) unique_edges.push_back(e);
+            }
+        }
+    };
+    if (settings->backface_cull && settings->backface_wireframe) {
+        std::vector<Edge> ue; collect(backface_wireframes, ue);
+        Col wc{80, 80, 100, B32_BLEND_OPAQUE};
+        for (const Edge& e : ue) fb_draw_line_3d(fb, e.x0, e.y0, e.z0, e.x1, e.y1, e.z1, wc);
+    }
+    if (settings->wireframe_overlay && !frontface_wireframes.empty()) {
+        std::vector<Edge> ue; collect(frontface_wireframes, ue);
+        Col wc{200, 200, 220, B32_BLEND_OPAQUE};
+        for (const Edge& e : ue) fb_draw_line(fb, e.x0, e.y0, e.x1, e.y1, wc);
     }
 }
 
@@ -683,7 +926,6 @@ int b32o_render_mesh_15(uint8_t* fb_rgba, float* fb_z, uint32_t w, uint32_t h,
     double fog_total = 0.0;
     std::vector<Surface> surfaces;
     surfaces.reserve(nf);
-    struct Tri3 { V3 a, b, c; };
     std::vector<Tri3> backface_wireframes, frontface_wireframes;
 
     for (uint32_t face_idx = 0; face_idx < nf; ++face_idx) {
@@ -806,31 +1048,118 @@ int b32o_render_mesh_15(uint8_t* fb_rgba, float* fb_z, uint32_t w, uint32_t h,
 
     // === WIREFRAME PHASE === render.rs:2574-2635
     double wire_start = now_s();
-    struct Edge { int32_t x0, y0; float z0; int32_t x1, y1; float z1; };
-    auto collect = [](const std::vector<Tri3>& tris, std::vector<Edge>& unique_edges) {
-        for (const Tri3& t : tris) {
-            Edge es[3] = {{f2i32(t.a.x), f2i32(t.a.y), t.a.z, f2i32(t.b.x), f2i32(t.b.y), t.b.z},
-                          {f2i32(t.b.x), f2i32(t.b.y), t.b.z, f2i32(t.c.x), f2i32(t.c.y), t.c.z},
-                          {f2i32(t.c.x), f2i32(t.c.y), t.c.z, f2i32(t.a.x), f2i32(t.a.y), t.a.z}};
-            for (const Edge& e0 : es) {
-                bool lt = (e0.x0 < e0.x1) || (e0.x0 == e0.x1 && e0.y0 < e0.y1);      // tuple `<`
-                Edge e = lt ? e0 : Edge{e0.x1, e0.y1, e0.z1, e0.x0, e0.y0, e0.z0};
-                bool found = false;
-                for (const Edge& u : unique_edges) if (u.x0 == e.x0 && u.y0 == e.y0 && u.x1 == e.x1 && u.y1 == e.y1) { found = true; break; }
-                if (!found) unique_edges.push_back(e);
-            }
+    wireframe_phase(fb, *settings, backface_wireframes, frontface_wireframes);
+    tm.wireframe_ms = (float)((now_s() - wire_start) * 1000.0);
+
+    if (timings) *timings = tm;
+    return B32_OK;
+}
+
+// render_mesh, render.rs:1971-2259
+int b32o_render_mesh(uint8_t* fb_rgba, float* fb_z, uint32_t w, uint32_t h,
+                     const b32_vertex* vertices, uint32_t nv, const b32_face* faces, uint32_t nf,
+                     const b32_tex8_desc* textures, uint32_t ntex, const b32_camera* camera,
+                     const b32_settings* settings, b32_timings* timings,
+                     uint32_t* draw_order, uint32_t cap, uint32_t* n_drawn) {
+    Fb fb{fb_rgba, fb_z, w, h};
+    b32_timings tm{};
+    std::vector<Tex8> tex8(ntex);
+    for (uint32_t i = 0; i < ntex; ++i)
+        tex8[i] = Tex8{textures[i].width, textures[i].height, reinterpret_cast<const Col*>(textures[i].pixels), textures[i].blend_mode};
+
+    // === TRANSFORM PHASE === render.rs:1981-2028 (the same loop as render_mesh_15's)
+    double t0 = now_s();
+    Projected P;
+    transform_phase(vertices, nv, camera, settings, w, h, P);
+    tm.transform_ms = (float)((now_s() - t0) * 1000.0);
+
+    // === CULL PHASE === render.rs:2030-2151
+    double cull_start = now_s();
+    std::vector<Surface> surfaces;
+    surfaces.reserve(nf);
+    std::vector<Tri3> backface_wireframes, frontface_wireframes;
+    for (uint32_t face_idx = 0; face_idx < nf; ++face_idx) {
+        const b32_face& face = faces[face_idx];
+        if (face.v0 >= nv || face.v1 >= nv || face.v2 >= nv) return B32_ERR_OOB_INDEX;  // Rust: index panic
+        uint32_t tex_id = face.flags & 0xFFFFu;
+        uint32_t face_blend = (face.flags >> 16) & 7u;
+        bool black_transparent = ((face.flags >> 19) & 1u) != 0;
+        uint8_t editor_alpha = (uint8_t)(face.flags >> 24);
+        const Tex8* tex = (tex_id != B32_FACE_TEX_NONE && tex_id < ntex) ? &tex8[tex_id] : nullptr;
+
+        V3 cv1 = P.cam_pos[face.v0], cv2 = P.cam_pos[face.v1], cv3 = P.cam_pos[face.v2];
+        if (!settings->ortho_enabled) {                                                  // :2049-2053
+            if (cv1.z <= NEAR_PLANE || cv2.z <= NEAR_PLANE || cv3.z <= NEAR_PLANE) continue;
         }
-    };
-    if (settings->backface_cull && settings->backface_wireframe) {
-        std::vector<Edge> ue; collect(backface_wireframes, ue);
-        Col wc{80, 80, 100, B32_BLEND_OPAQUE};
-        for (const Edge& e : ue) fb_draw_line_3d(fb, e.x0, e.y0, e.z0, e.x1, e.y1, e.z1, wc);
+        V3 v1 = P.projected[face.v0], v2 = P.projected[face.v1], v3 = P.projected[face.v2];
+        float signed_area = (v2.x - v1.x) * (v3.y - v1.y) - (v3.x - v1.x) * (v2.y - v1.y);  // :2061
+        bool is_backface = signed_area <= 0.0f;
+
+        V3 edge1 = sub(cv2, cv1), edge2 = sub(cv3, cv1);                                 // :2065-2067 (dead value)
+        V3 cr{edge1.y * edge2.z - edge1.z * edge2.y, edge1.z * edge2.x - edge1.x * edge2.z, edge1.x * edge2.y - edge1.y * edge2.x};
+        V3 normal = normalize(cr);
+
+        bool has_transparency = (tex && tex->blend_mode != B32_BLEND_OPAQUE) || editor_alpha < 255;   // :2070-2075 (never read again)
+
+        const b32_vertex &A = vertices[face.v0], &B = vertices[face.v1], &C = vertices[face.v2];
+        if (is_backface) {                                                               // :2077-2113
+            if (!settings->xray_mode) backface_wireframes.push_back(Tri3{v1, v2, v3});
+            if (!settings->backface_cull || settings->xray_mode) {
+                Surface s;
+                s.v1 = v1; s.v2 = v3; s.v3 = v2;
+                s.w1 = mk3(A.pos); s.w2 = mk3(C.pos); s.w3 = mk3(B.pos);
+                s.vn1 = scale(P.cam_normals[face.v0], -1.0f); s.vn2 = scale(P.cam_normals[face.v2], -1.0f); s.vn3 = scale(P.cam_normals[face.v1], -1.0f);
+                s.wn1 = scale(mk3(A.normal), -1.0f); s.wn2 = scale(mk3(C.normal), -1.0f); s.wn3 = scale(mk3(B.normal), -1.0f);
+                s.uv1[0] = A.uv[0]; s.uv1[1] = A.uv[1]; s.uv2[0] = C.uv[0]; s.uv2[1] = C.uv[1]; s.uv3[0] = B.uv[0]; s.uv3[1] = B.uv[1];
+                s.vc1 = vcol(A); s.vc2 = vcol(C); s.vc3 = vcol(B);
+                s.normal = scale(normal, -1.0f);
+                s.face_idx = face_idx; s.black_transparent = black_transparent; s.has_transparency = has_transparency;
+                s.blend_mode = face_blend; s.editor_alpha = editor_alpha;
+                surfaces.push_back(s);
+            }
+        } else {                                                                         // :2114-2148
+            Surface s;
+            s.v1 = v1; s.v2 = v2; s.v3 = v3;
+            s.w1 = mk3(A.pos); s.w2 = mk3(B.pos); s.w3 = mk3(C.pos);
+            s.vn1 = P.cam_normals[face.v0]; s.vn2 = P.cam_normals[face.v1]; s.vn3 = P.cam_normals[face.v2];
+            s.wn1 = mk3(A.normal); s.wn2 = mk3(B.normal); s.wn3 = mk3(C.normal);
+            s.uv1[0] = A.uv[0]; s.uv1[1] = A.uv[1]; s.uv2[0] = B.uv[0]; s.uv2[1] = B.uv[1]; s.uv3[0] = C.uv[0]; s.uv3[1] = C.uv[1];
+            s.vc1 = vcol(A); s.vc2 = vcol(B); s.vc3 = vcol(C);
+            s.normal = normal;
+            s.face_idx = face_idx; s.black_transparent = black_transparent; s.has_transparency = has_transparency;
+            s.blend_mode = face_blend; s.editor_alpha = editor_alpha;
+            surfaces.push_back(s);
+            if (settings->wireframe_overlay) frontface_wireframes.push_back(Tri3{v1, v2, v3});
+        }
     }
-    if (settings->wireframe_overlay && !frontface_wireframes.empty()) {
-        std::vector<Edge> ue; collect(frontface_wireframes, ue);
-        Col wc{200, 200, 220, B32_BLEND_OPAQUE};
-        for (const Edge& e : ue) fb_draw_line(fb, e.x0, e.y0, e.x1, e.y1, wc);
+    tm.cull_ms = (float)((now_s() - cull_start) * 1000.0);
+
+    // === SORT PHASE === render.rs:2153-2168: ONE list, sorted only for the painter's algorithm
+    double sort_start = now_s();
+    auto center_z = [](const Surface& s) { return (s.v1.z + s.v2.z + s.v3.z) / 3.0f; };
+    if (!settings->use_zbuffer) {
+        if (surfaces.size() >= 2) for (const Surface& s : surfaces) { float k = center_z(s); if (k != k) return B32_ERR_NAN_DEPTH; }   // unwrap() panic
+        std::stable_sort(surfaces.begin(), surfaces.end(), [&](const Surface& a, const Surface& b) { return center_z(a) > center_z(b); });
     }
+    tm.sort_ms = (float)((now_s() - sort_start) * 1000.0);
+    tm.triangles_drawn = (uint32_t)surfaces.size();
+    if (n_drawn) *n_drawn = tm.triangles_drawn;
+    if (draw_order) { uint32_t k = 0; for (const Surface& s : surfaces) { if (k < cap) draw_order[k] = (uint32_t)s.face_idx; ++k; } }
+
+    // === DRAW PHASE === render.rs:2170-2186
+    double draw_start = now_s();
+    if (!settings->wireframe_overlay) {
+        for (const Surface& s : surfaces) {
+            uint32_t id = faces[s.face_idx].flags & 0xFFFFu;
+            const Tex8* tex = (id != B32_FACE_TEX_NONE && id < ntex) ? &tex8[id] : nullptr;
+            rasterize_triangle(fb, s, tex, *settings);
+        }
+    }
+    tm.draw_ms = (float)((now_s() - draw_start) * 1000.0);
+
+    // === WIREFRAME PHASE === render.rs:2188-2256
+    double wire_start = now_s();
+    wireframe_phase(fb, *settings, backface_wireframes, frontface_wireframes);
     tm.wireframe_ms = (float)((now_s() - wire_start) * 1000.0);
 
     if (timings) *timings = tm;

@@ -60,6 +60,15 @@ int b32o_render_mesh_15(uint8_t* fb_rgba, float* fb_z, uint32_t w, uint32_t h,
                         const b32_fog* fog_or_null, b32_timings* timings,
                         uint32_t* draw_order, uint32_t cap, uint32_t* n_drawn);
 
+/* render_mesh, render.rs:1971-2259 (RGB888 path: rasterize_triangle render.rs:1202-1433, Color ops
+ * types.rs:783-934, Texture::sample types.rs:1242-1253).  Same conventions as b32o_render_mesh_15. */
+int b32o_render_mesh(uint8_t* fb_rgba, float* fb_z, uint32_t w, uint32_t h,
+                     const b32_vertex* vertices, uint32_t nv,
+                     const b32_face* faces, uint32_t nf,
+                     const b32_tex8_desc* textures, uint32_t ntex,
+                     const b32_camera* camera, const b32_settings* settings, b32_timings* timings,
+                     uint32_t* draw_order, uint32_t cap, uint32_t* n_drawn);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,6 +41,7 @@ def lib():
         _lib.b32o_div_unr.argtypes = [C.c_int32, C.c_int32]
         _lib.b32o_texture_sample.restype = C.c_uint16
         _lib.b32o_render_mesh_15.restype = C.c_int
+        _lib.b32o_render_mesh.restype = C.c_int
     return _lib
 
 
@@ -89,6 +90,43 @@ def render_mesh_15(fb_rgba, fb_z, vertices, faces, textures, camera, settings, f
         C.byref(tm), C.c_void_p(order.ctypes.data) if want_order else None, C.c_uint32(cap), C.byref(n))
     del keep_t, keep_s
     return rc, tm.as_dict(), order[: n.value] if want_order else None
+
+
+def render_mesh(fb_rgba, fb_z, vertices, faces, textures8, camera, settings, want_order=False):
+    """Oracle render_mesh (RGB888, render.rs:1971-2259) into caller-owned numpy framebuffer arrays."""
+    abi = _abi()
+    from bonnie32_b200.raster import tex8_descs
+    h, w = fb_z.shape
+    v = np.ascontiguousarray(vertices, dtype=abi.VERTEX_DTYPE)
+    f = np.ascontiguousarray(faces, dtype=abi.FACE_DTYPE)
+    tex, keep_t = tex8_descs(textures8)
+    cam = camera.to_abi()
+    s, keep_s = settings.to_abi()
+    tm = abi.Timings()
+    cap = len(f) if want_order else 0
+    order = np.zeros(max(cap, 1), dtype=np.uint32)
+    n = C.c_uint32(0)
+    rc = lib().b32o_render_mesh(
+        C.c_void_p(fb_rgba.ctypes.data), C.c_void_p(fb_z.ctypes.data), C.c_uint32(w), C.c_uint32(h),
+        C.c_void_p(v.ctypes.data), C.c_uint32(len(v)), C.c_void_p(f.ctypes.data), C.c_uint32(len(f)),
+        tex, C.c_uint32(len(textures8)), C.byref(cam), C.byref(s),
+        C.byref(tm), C.c_void_p(order.ctypes.data) if want_order else None, C.c_uint32(cap), C.byref(n))
+    del keep_t, keep_s
+    return rc, tm.as_dict(), order[: n.value] if want_order else None
+
+
+def render_scene888(scene, want_order=False):
+    """Oracle render_mesh on a Scene with `textures8`. Returns (rgba, z, timings, rc[, order])."""
+    w, h = scene.width, scene.height
+    fb_rgba = np.empty((h, w, 4), dtype=np.uint8)
+    fb_z = np.empty((h, w), dtype=np.float32)
+    r, g, b = scene.clear[:3]
+    lib().b32o_fb_clear(fb_rgba.ctypes.data_as(C.c_void_p), fb_z.ctypes.data_as(C.c_void_p), C.c_uint32(w), C.c_uint32(h),
+                        C.c_uint8(r), C.c_uint8(g), C.c_uint8(b), C.c_uint8(255))
+    rc, tm, order = render_mesh(fb_rgba, fb_z, scene.vertices, scene.faces, scene.textures8, scene.camera, scene.settings, want_order=True)
+    if want_order:
+        return fb_rgba, fb_z, tm, rc, order
+    return fb_rgba, fb_z, tm, rc
 
 
 def transform(vertices, camera, settings, w, h):

@@ -275,7 +275,40 @@ def blend555(f8, b8, mode):                                   # render.rs:1093-1
 # ------------------------------------------------------------------------------------------
 def render_mesh_15(fb_rgba, fb_z, vertices, faces, textures, camera, settings, fog=None):
     """fb_rgba u8[h,w,4], fb_z f32[h,w] are updated in place. Returns list of face_idx in draw order."""
-    H, W = fb_z.shape
+    tex_px = [texels_u16(t) for t in textures]
+    surfaces = _build_surfaces(fb_z.shape, vertices, faces, textures, camera, settings, fog, rgb888=False)
+
+    # ---- SORT (render.rs:2518-2545) ----
+    opaque = [s for s in surfaces if not s["has_tr"]]
+    transp = [s for s in surfaces if s["has_tr"]]
+    transp = _back_to_front(transp)
+    if not settings.use_zbuffer:
+        opaque = _back_to_front(opaque)
+
+    # ---- DRAW (render.rs:2547-2572) ----
+    if not settings.wireframe_overlay:
+        for s in opaque:
+            _fill(fb_rgba, fb_z, s, textures, tex_px, settings, skip_z_write=False)
+        for s in transp:
+            _fill(fb_rgba, fb_z, s, textures, tex_px, settings, skip_z_write=True)
+    return [s["face_idx"] for s in opaque + transp]
+
+
+def _back_to_front(lst):
+    """stable `sort_by(b.partial_cmp(a).unwrap())` on the centre depth (render.rs:2527-2532 / :2157-2162)."""
+    if len(lst) < 2:
+        return lst
+    keys = np.array([(s["v"][0][2] + s["v"][1][2] + s["v"][2][2]) / F(3.0) for s in lst], dtype=F)
+    if np.isnan(keys).any():
+        raise ReferencePanic("partial_cmp().unwrap() on NaN")
+    order = np.argsort(-keys, kind="stable")                   # descending, ties keep order
+    return [lst[i] for i in order]
+
+
+def _build_surfaces(shape, vertices, faces, textures, camera, settings, fog, rgb888):
+    """TRANSFORM + CULL phases shared by render_mesh_15 (render.rs:2313-2516) and render_mesh
+    (render.rs:1981-2149; no fog, has_transparency = texture blend or editor alpha)."""
+    H, W = shape
     pos = np.asarray(vertices["pos"], dtype=F)
     nv = len(pos)
     cpos = np.asarray(camera.position, dtype=F)
@@ -308,7 +341,6 @@ def render_mesh_15(fb_rgba, fb_z, vertices, faces, textures, camera, settings, f
     if len(fv) and fv.max() >= nv:
         raise ReferencePanic("vertex index out of bounds")
     flags = np.asarray(faces["flags"], dtype=I64)
-    tex_px = [texels_u16(t) for t in textures]
     rgba = np.asarray(vertices["rgba"], dtype=I64)
     uvs = np.asarray(vertices["uv"], dtype=F)
     nrm = np.asarray(vertices["normal"], dtype=F)
@@ -328,9 +360,9 @@ def render_mesh_15(fb_rgba, fb_z, vertices, faces, textures, camera, settings, f
         signed_area = (v2[0] - v1[0]) * (v3[1] - v1[1]) - (v3[0] - v1[0]) * (v2[1] - v1[1])   # :2393
         backface = bool(signed_area <= 0)
         tex_blend = textures[tex].blend_mode if tex is not None else None
-        if tex_blend is not None and tex_blend != OPAQUE:                               # :2403-2415
+        if tex_blend is not None and tex_blend != OPAQUE:                               # :2403-2415 / :2071-2075
             has_tr = True
-        elif face_blend != OPAQUE:
+        elif face_blend != OPAQUE and not rgb888:
             has_tr = True
         else:
             has_tr = editor_alpha < 255
@@ -373,30 +405,7 @@ def render_mesh_15(fb_rgba, fb_z, vertices, faces, textures, camera, settings, f
             vc=[cols[k] for k in order],
             face_idx=fi, tex=tex, black_tr=black_tr, has_tr=has_tr, blend=face_blend, editor_alpha=editor_alpha))
 
-    # ---- SORT (render.rs:2518-2545) ----
-    opaque = [s for s in surfaces if not s["has_tr"]]
-    transp = [s for s in surfaces if s["has_tr"]]
-
-    def back_to_front(lst):
-        if len(lst) < 2:
-            return lst
-        keys = np.array([(s["v"][0][2] + s["v"][1][2] + s["v"][2][2]) / F(3.0) for s in lst], dtype=F)
-        if np.isnan(keys).any():
-            raise ReferencePanic("partial_cmp().unwrap() on NaN")
-        order = np.argsort(-keys, kind="stable")                   # descending, ties keep order
-        return [lst[i] for i in order]
-
-    transp = back_to_front(transp)
-    if not settings.use_zbuffer:
-        opaque = back_to_front(opaque)
-
-    # ---- DRAW (render.rs:2547-2572) ----
-    if not settings.wireframe_overlay:
-        for s in opaque:
-            _fill(fb_rgba, fb_z, s, textures, tex_px, settings, skip_z_write=False)
-        for s in transp:
-            _fill(fb_rgba, fb_z, s, textures, tex_px, settings, skip_z_write=True)
-    return [s["face_idx"] for s in opaque + transp]
+    return surfaces
 
 
 def _fill(fb_rgba, fb_z, s, textures, tex_px, settings, skip_z_write):
@@ -528,6 +537,147 @@ def _fill(fb_rgba, fb_z, s, textures, tex_px, settings, skip_z_write):
                 new = ps1
             if settings.use_zbuffer and not skip_z_write:
                 zb[wmask] = z[wmask]
+        px[wmask, 0] = new[wmask, 0]
+        px[wmask, 1] = new[wmask, 1]
+        px[wmask, 2] = new[wmask, 2]
+        px[wmask, 3] = 255
+
+
+# ------------------------------------------------------------------------------------------
+# render_mesh, render.rs:1971-2259 (RGB888 path) — textures: objects with width, height, blend_mode and
+# pixels = u8[h*w*4] (r, g, b, blend per texel: struct Color, types.rs:721-726)
+# ------------------------------------------------------------------------------------------
+def render_mesh(fb_rgba, fb_z, vertices, faces, textures, camera, settings):
+    tex_px = [np.asarray(t.pixels, dtype=np.uint8).reshape(t.height, t.width, 4).astype(I64) if t.width * t.height
+              else np.zeros((t.height, t.width, 4), dtype=I64) for t in textures]
+    surfaces = _build_surfaces(fb_z.shape, vertices, faces, textures, camera, settings, None, rgb888=True)
+    if not settings.use_zbuffer:                                   # :2155-2162, one list
+        surfaces = _back_to_front(surfaces)
+    if not settings.wireframe_overlay:                             # :2172-2181
+        for s in surfaces:
+            _fill888(fb_rgba, fb_z, s, tex_px, settings)
+    return [s["face_idx"] for s in surfaces]
+
+
+def blend888(f, b, mode):                                      # Color::blend_with, types.rs:886-930; int arrays [n,3]
+    if mode == OPAQUE:
+        return f
+    if mode == AVERAGE:
+        return (b + f) // 2
+    if mode == ADD:
+        return np.minimum(b + f, 255)
+    if mode == SUBTRACT:
+        return np.maximum(b - f, 0)
+    if mode == ADD_QUARTER:
+        return np.minimum(b + f // 4, 255)
+    raise AssertionError("Erase never reaches a writer (skipped at render.rs:1350)")
+
+
+def _fill888(fb_rgba, fb_z, s, tex_px, settings):
+    """rasterize_triangle, render.rs:1202-1433, vectorised over the bounding box.  A surface never covers
+    a pixel twice, so per-pixel reads of the framebuffer see the state before this surface."""
+    H, W = fb_z.shape
+    v1, v2, v3 = s["v"]
+    tex = s["tex"]
+    min_x = int(as_usize(fmax(fmin(fmin(v1[0], v2[0]), v3[0]), F(0.0))))                # :1209-1212
+    max_x = int(as_usize(fmin(fmax(fmax(v1[0], v2[0]), v3[0]) + F(1.0), F(W))))
+    min_y = int(as_usize(fmax(fmin(fmin(v1[1], v2[1]), v3[1]), F(0.0))))
+    max_y = int(as_usize(fmin(fmax(fmax(v1[1], v2[1]), v3[1]) + F(1.0), F(H))))
+    if min_x >= max_x or min_y >= max_y:
+        return
+    third = F(1.0) / F(3.0)
+    flat = gour = None
+    if settings.shading == SH_FLAT:                                                     # :1220-1226
+        center = ((s["w"][0] + s["w"][1]) + s["w"][2]) * third
+        wn = normalize3((((s["wn"][0] + s["wn"][1]) + s["wn"][2]) * third)[None, :])[0]
+        flat = shade_multi_light_color(wn, center, settings.lights, settings.ambient)
+    elif settings.shading == SH_GOURAUD:                                                # :1229-1237
+        gour = [shade_multi_light_color(s["wn"][k], s["w"][k], settings.lights, settings.ambient) for k in range(3)]
+    vc = s["vc"]
+    needs_dither = settings.dithering and (settings.shading == SH_GOURAUD or tex is not None
+                                           or vc[0] != vc[1] or vc[1] != vc[2])          # :1241-1246
+    with np.errstate(all="ignore"):
+        area = (v2[1] - v3[1]) * (v1[0] - v3[0]) + (v3[0] - v2[0]) * (v1[1] - v3[1])     # :1257
+        if np.abs(area) < F(0.00001):
+            return
+        inv_area = F(1.0) / area
+        a0 = v2[1] - v3[1]; b0 = v3[0] - v2[0]; a1 = v3[1] - v1[1]; b1 = v1[0] - v3[0]
+        w0s = a0 * (F(min_x) - v3[0]) + b0 * (F(min_y) - v3[1])                          # :1278-1279
+        w1s = a1 * (F(min_x) - v3[0]) + b1 * (F(min_y) - v3[1])
+        ny, nx = max_y - min_y, max_x - min_x
+
+        def grid(ws, a, b):                                                               # incremental stepping :1427-1433
+            col = np.add.accumulate(np.concatenate([[ws], np.full(ny - 1, b, dtype=F)]).astype(F), dtype=F)
+            g = np.empty((ny, nx), dtype=F)
+            g[:, 0] = col
+            if nx > 1:
+                g[:, 1:] = a
+            return np.add.accumulate(g, axis=1, dtype=F)
+
+        bc_x = grid(w0s, a0, b0) * inv_area
+        bc_y = grid(w1s, a1, b1) * inv_area
+        bc_z = F(1.0) - bc_x - bc_y
+        ERR = F(-0.0001)
+        live = (bc_x >= ERR) & (bc_y >= ERR) & (bc_z >= ERR)                              # :1303
+        inv_z1 = F(1.0) / v1[2]; inv_z2 = F(1.0) / v2[2]; inv_z3 = F(1.0) / v3[2]
+        inv_z = bc_x * inv_z1 + bc_y * inv_z2 + bc_z * inv_z3
+        z = F(1.0) / inv_z
+        zb = fb_z[min_y:max_y, min_x:max_x]
+        px = fb_rgba[min_y:max_y, min_x:max_x]
+        if settings.use_zbuffer and not settings.xray_mode:
+            live &= ~(z >= zb)                                                            # :1313-1320
+        uv1, uv2, uv3 = s["uv"]
+        if settings.affine_textures:                                                      # :1323-1340
+            u = bc_x * uv1[0] + bc_y * uv2[0] + bc_z * uv3[0]
+            v = bc_x * uv1[1] + bc_y * uv2[1] + bc_z * uv3[1]
+        else:
+            uo = bc_x * uv1[0] * inv_z1 + bc_y * uv2[0] * inv_z2 + bc_z * uv3[0] * inv_z3
+            vo = bc_x * uv1[1] * inv_z1 + bc_y * uv2[1] * inv_z2 + bc_z * uv3[1] * inv_z3
+            u = uo / inv_z
+            v = vo / inv_z
+        if tex is not None:                                                               # :1343-1347, types.rs:1242-1253
+            tp = tex_px[tex]
+            th, tw = tp.shape[:2]
+            if tw == 0 or th == 0:
+                return                                                                    # every sample is TRANSPARENT
+            tx = np.minimum(as_usize(rem_euclid_1(u) * F(tw)), tw - 1)
+            ty = np.minimum(as_usize(rem_euclid_1(F(1.0) - v) * F(th)), th - 1)
+            color = tp[ty, tx]
+        else:
+            color = np.broadcast_to(np.array([255, 255, 255, OPAQUE], dtype=I64), (ny, nx, 4))
+        cblend = color[..., 3]
+        live &= cblend != ERASE                                                           # :1350-1354
+        vcol = np.stack([as_u8(bc_x * F(vc[0][k]) + bc_y * F(vc[1][k]) + bc_z * F(vc[2][k])) for k in range(3)], axis=-1)
+        mod8 = np.minimum((color[..., :3] * vcol) // 128, 255)                             # Color::modulate
+        if settings.shading == SH_NONE:
+            shade = [np.full((ny, nx), F(1.0), dtype=F)] * 3
+        elif settings.shading == SH_FLAT:
+            shade = [np.full((ny, nx), flat[k], dtype=F) for k in range(3)]
+        else:
+            shade = [bc_x * gour[0][k] + bc_y * gour[1][k] + bc_z * gour[2][k] for k in range(3)]
+        c8 = np.stack([as_u8(fmin(mod8[..., k].astype(F) * shade[k].astype(F), F(255.0))) for k in range(3)], axis=-1)   # :1074-1081
+        if needs_dither:                                                                  # :1186-1197
+            yy, xx = np.meshgrid(np.arange(min_y, max_y), np.arange(min_x, max_x), indexing="ij")
+            c8 = np.clip((c8 + DITHER[yy & 3, xx & 3][..., None]) >> 3, 0, 31) << 3
+        ea = s["editor_alpha"]
+        if ea == 0:                                                                       # :1392-1398
+            return
+        back = px[..., :3].astype(I64)
+        ps1 = c8.copy()
+        for mode in (AVERAGE, ADD, SUBTRACT, ADD_QUARTER):                                # per-texel blend tag
+            m = cblend == mode
+            if m.any():
+                ps1[m] = blend888(c8[m], back[m], mode)
+        if ea < 255:                                                                      # :338-420
+            a = F(ea) / F(255.0)
+            inv_a = F(1.0) - a
+            new = np.stack([as_u8(ps1[..., k].astype(F) * a + back[..., k].astype(F) * inv_a) for k in range(3)], axis=-1)
+            wmask = live & ~(z >= zb) if settings.use_zbuffer else live                   # :393
+        else:
+            new = ps1
+            wmask = live & (z < zb) if settings.use_zbuffer else live                     # :425 / :1408
+        if settings.use_zbuffer:
+            zb[wmask] = z[wmask]
         px[wmask, 0] = new[wmask, 0]
         px[wmask, 1] = new[wmask, 1]
         px[wmask, 2] = new[wmask, 2]

@@ -7,7 +7,7 @@ import copy
 import numpy as np
 
 from bonnie32_b200 import abi, scenes
-from bonnie32_b200.raster import Camera, Light, RasterSettings, Texture15
+from bonnie32_b200.raster import Camera, Light, RasterSettings, Texture, Texture15
 
 
 def _rng_texture(seed, w, h, blend=abi.BLEND_OPAQUE, semi_fraction=0.0, zero_fraction=0.05):
@@ -161,3 +161,64 @@ def wireframe_scenes(n_tris=160):
         _with(base, "wire_backface_xray", backface_wireframe=True, xray_mode=True),
         _with(big, "wire_backface_large_world", camera=cam, backface_wireframe=True, use_zbuffer=True),
     ]
+
+
+# ---- RGB888 sibling: render_mesh / rasterize_triangle (render.rs:1971-2259, 1202-1433) --------------------
+def _rng_texture8(seed, w, h, erase_fraction=0.1, blend_fraction=0.0, name=""):
+    """Random Color texels; blend tag Opaque, Erase (transparent) or one of the four PS1 blend modes."""
+    u = scenes.splitmix64_u01(seed, w * h * 5).reshape(5, w * h)
+    px = np.zeros((w * h, 4), dtype=np.uint8)
+    px[:, :3] = np.floor(u[:3].T * 256.0).astype(np.uint8)
+    tag = np.zeros(w * h, dtype=np.uint8)
+    tag[u[3] < erase_fraction] = abi.BLEND_ERASE
+    blended = u[3] > 1.0 - blend_fraction
+    tag[blended] = (1 + np.floor(u[4][blended] * 4.0)).astype(np.uint8)      # Average, Add, Subtract, AddQuarter
+    px[:, 3] = tag
+    return Texture(w, h, px.reshape(-1), name=name)
+
+
+def rgb888_scenes(n_tris=160):
+    """Scenes for render_mesh: opaque-only texels (order-free on the device) and per-texel blend tags /
+    editor alpha (strict draw-order replay), painter's and z-buffer, lights, x-ray, ortho, no-cull."""
+    out = []
+    base = scenes.scene_c2(n_tris=n_tris)
+    base.settings = copy.copy(base.settings)
+    base.settings.use_rgb555 = False
+    opaque_tex = [_rng_texture8(21, 64, 64)]
+    blend_tex = [_rng_texture8(22, 64, 64, blend_fraction=0.4), _rng_texture8(23, 32, 16, erase_fraction=0.3, blend_fraction=0.6),
+                 _rng_texture8(24, 8, 8, erase_fraction=0.0)]
+    o = _with(base, "rgb888_opaque_painter", textures8=opaque_tex)
+    out.append(o)
+    out.append(_with(o, "rgb888_opaque_zbuffer", use_zbuffer=True))
+    out.append(_with(o, "rgb888_opaque_nodither", dithering=False))
+    out.append(_with(o, "rgb888_opaque_float_perspective", use_fixed_point=False, affine_textures=False, use_zbuffer=True))
+    out.append(_with(o, "rgb888_opaque_nocull_xray_zbuffer", backface_cull=False, xray_mode=True, use_zbuffer=True))
+    out.append(_with(o, "rgb888_opaque_xray_painter", xray_mode=True))
+    out.append(_with(o, "rgb888_opaque_ortho", ortho_projection=(6.0, 0.5, -0.25), use_zbuffer=True))
+    out.append(_with(o, "rgb888_opaque_fb_200x150", width=200, height=150))
+    lights = [Light.directional((-1.0, -1.0, -1.0), 0.7), Light.point_colored((0.5, 0.5, 4.0), 30.0, 1.5, 1.0, 0.5, 0.25),
+              Light.point((-3.0, 2.0, 20.0), 25.0, 2.9)]
+    g = copy.copy(o)
+    g.vertices = base.vertices.copy()
+    un = scenes.splitmix64_u01(78, len(g.vertices) * 3).reshape(-1, 3)
+    g.vertices["normal"] = (2.0 * un - 1.0).astype(np.float32)
+    out.append(_with(g, "rgb888_gouraud_lights", shading=abi.SHADE_GOURAUD, lights=lights, ambient=0.3, use_zbuffer=True))
+    out.append(_with(g, "rgb888_flat_lights", shading=abi.SHADE_FLAT, lights=lights, ambient=0.2))
+    ut = copy.copy(o)
+    ut.faces = base.faces.copy()
+    ut.faces["flags"] = abi.face_flags(abi.FACE_TEX_NONE)
+    out.append(_with(ut, "rgb888_untextured_vertex_colours"))
+    # ordered replay: blended texels, editor alpha, several textures (id 3 is out of range -> untextured)
+    m = copy.copy(base)
+    m.faces = _mixed_faces(base, 101)
+    m = _with(m, "rgb888_mixed_painter", textures8=blend_tex)
+    out.append(m)
+    out.append(_with(m, "rgb888_mixed_zbuffer", use_zbuffer=True))
+    out.append(_with(m, "rgb888_mixed_zbuffer_xray_nocull", use_zbuffer=True, xray_mode=True, backface_cull=False))
+    out.append(_with(m, "rgb888_mixed_gouraud", shading=abi.SHADE_GOURAUD, lights=lights, ambient=0.4, use_zbuffer=True))
+    ea = copy.copy(o)                      # opaque texels, but some faces have editor alpha < 255
+    ea.faces = _mixed_faces(base, 102)
+    ea.faces["flags"] = (ea.faces["flags"] & ~np.uint32(0xFFFF)) | np.uint32(0)
+    out.append(_with(ea, "rgb888_editor_alpha_zbuffer", use_zbuffer=True))
+    out.append(_with(m, "rgb888_wire_backface", backface_wireframe=True, use_zbuffer=True))
+    return out

@@ -48,7 +48,23 @@ def golden_scenes(full=True):
     return out
 
 
+def main_rgb888():
+    """hashes_rgb888.json: the RGB888 sibling (render_mesh) on cases.rgb888_scenes(), numpy model."""
+    hashes = {}
+    for sc in cases.rgb888_scenes():
+        if sc.settings.backface_wireframe or sc.settings.wireframe_overlay:
+            continue                                  # the numpy model does not restate the wireframe phase
+        rgba, z = pymodel.fb_clear(sc.width, sc.height, sc.clear)
+        order = pymodel.render_mesh(rgba, z, sc.vertices, sc.faces, sc.textures8, sc.camera, sc.settings)
+        hashes[sc.name] = digest(rgba, z, order)
+        print(f"{sc.name:45s} drawn={len(order)}")
+    with open(os.path.join(HERE, "hashes_rgb888.json"), "w") as f:
+        json.dump(hashes, f, indent=1, sort_keys=True)
+
+
 def main():
+    if "--rgb888" in sys.argv:
+        return main_rgb888()
     hashes = {}
     for sc in golden_scenes():
         t = time.time()

@@ -332,3 +332,77 @@ def test_wireframe_scenes_draw_lines(oracle):
     assert diff.sum() > 100 and (b[diff][:, :3] == np.array([80, 80, 100], np.uint8)).all()
     c = oracle.render_scene(by["wire_overlay"])[0]
     assert ((c[..., :3] == np.array([200, 200, 220], np.uint8)).all(-1)).sum() > 100
+
+
+# ---- RGB888 sibling: b32_render_mesh vs the oracle's render_mesh (render.rs:1971-2259) -------------------
+RGB888 = cases.rgb888_scenes()
+
+
+def render_gpu888(ctx, sc, resident=False):
+    fb = pkg.Framebuffer(sc.width, sc.height, ctx)
+    fb.clear(sc.clear)
+    if resident:
+        ctx.set_textures_rgb888(sc.textures8)
+        mesh = pkg.Mesh(ctx, sc.vertices, sc.faces)
+        tm = mesh.render_rgb888(sc.camera, sc.settings)
+        mesh.free()
+    else:
+        tm = pkg.render_mesh(fb, sc.vertices, sc.faces, sc.textures8, sc.camera, sc.settings)
+    rgba, z = fb.download()
+    return rgba, z, tm
+
+
+@pytest.mark.parametrize("sc", RGB888, ids=[s.name for s in RGB888])
+def test_rgb888_scene(ctx, oracle, sc):
+    want, want_z, otm, rc, order = oracle.render_scene888(sc, want_order=True)
+    assert rc == 0
+    got, got_z, tm = render_gpu888(ctx, sc)
+    assert_same(sc, got, got_z, tm, want, want_z, otm)
+
+
+@pytest.mark.parametrize("zbuf,blended", [(False, False), (True, False), (True, True), (False, True)])
+def test_rgb888_c2_full(ctx, oracle, zbuf, blended):
+    """1 000 triangles through render_mesh: order-free pass (opaque texels) and ordered replay (blend tags)."""
+    sc = scenes.scene_c2(use_zbuffer=zbuf)
+    sc.settings.use_rgb555 = False
+    sc.textures8 = [cases._rng_texture8(31, 64, 64, blend_fraction=0.3 if blended else 0.0)]
+    want, want_z, otm, rc = oracle.render_scene888(sc)
+    got, got_z, tm = render_gpu888(ctx, sc, resident=True)
+    assert_same(sc, got, got_z, tm, want, want_z, otm)
+
+
+def test_rgb888_and_rgb555_tables_are_independent(ctx, oracle):
+    """Both texture tables stay bound: alternating render_mesh / render_mesh_15 calls (the editor's RGB555 toggle)."""
+    a = next(s for s in RGB888 if s.name == "rgb888_opaque_zbuffer")
+    b = next(s for s in FEATURES if s.name == "zbuffer_idx8")
+    for _ in range(2):
+        got, got_z, tm = render_gpu888(ctx, a)
+        want, want_z, otm, rc = oracle.render_scene888(a)
+        assert_same(a, got, got_z, tm, want, want_z, otm)
+        got, got_z, tm = render_gpu(ctx, b)
+        want, want_z, otm, rc = oracle.render_scene(b)
+        assert_same(b, got, got_z, tm, want, want_z, otm)
+
+
+def test_rgb888_error_codes(ctx, oracle):
+    sc = next(s for s in RGB888 if s.name == "rgb888_opaque_painter")
+    fb = pkg.Framebuffer(sc.width, sc.height, ctx)
+    fb.clear(sc.clear)
+    before, _ = fb.download()
+    f = sc.faces.copy(); f["v"][3, 1] = len(sc.vertices)
+    with pytest.raises(pkg.B32Error) as e:
+        pkg.render_mesh(fb, sc.vertices, f, sc.textures8, sc.camera, sc.settings)
+    assert e.value.code == abi.B32_ERR_OOB_INDEX
+    for fi in range(len(sc.faces)):
+        v = sc.vertices.copy()
+        v["pos"][sc.faces["v"][fi, 0], 2] = np.nan
+        if oracle.render_scene888(dataclasses.replace(sc, vertices=v))[3] == abi.B32_ERR_NAN_DEPTH:
+            break
+    with pytest.raises(pkg.B32Error) as e:
+        pkg.render_mesh(fb, v, sc.faces, sc.textures8, sc.camera, sc.settings)
+    assert e.value.code == abi.B32_ERR_NAN_DEPTH
+    assert np.array_equal(fb.download()[0], before)           # the reference panics before drawing
+    zs = dataclasses.replace(sc.settings, use_zbuffer=True)   # no sort in z-buffer mode: the NaN face just draws nothing
+    pkg.render_mesh(fb, v, sc.faces, sc.textures8, sc.camera, zs)
+    want, want_z, otm, rc = oracle.render_scene888(dataclasses.replace(sc, vertices=v, settings=zs))
+    assert rc == 0 and np.array_equal(fb.download()[0], want)

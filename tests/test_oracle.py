@@ -225,3 +225,60 @@ def test_splitmix64_reference_values():
     assert z[0] == 0xE220A8397B1DCDAF and z[1] == 0x6E789E6AA1B965F4
     u = scenes.splitmix64_u01(0, 3)
     assert [int(v * 2**24) for v in u] == [v >> 40 for v in z]
+
+
+# ---- RGB888 sibling: render_mesh / rasterize_triangle (render.rs:1971-2259, 1202-1433) ---------------------
+RGB888 = cases.rgb888_scenes()
+with open(os.path.join(GOLDEN, "hashes_rgb888.json")) as _f:
+    HASHES888 = json.load(_f)
+
+
+@pytest.mark.parametrize("sc", RGB888, ids=[s.name for s in RGB888])
+def test_rgb888_oracle_equals_numpy_model_and_golden(oracle, sc):
+    want, want_z, tm, rc, order = oracle.render_scene888(sc, want_order=True)
+    assert rc == 0 and tm["triangles_drawn"] == len(order)
+    if sc.settings.backface_wireframe or sc.settings.wireframe_overlay:
+        return                                        # wireframe phase: C++ oracle only
+    rgba, z = pymodel.fb_clear(sc.width, sc.height, sc.clear)
+    order2 = pymodel.render_mesh(rgba, z, sc.vertices, sc.faces, sc.textures8, sc.camera, sc.settings)
+    assert list(order) == order2
+    assert np.array_equal(rgba, want)
+    assert np.array_equal(z.view(np.uint32), want_z.view(np.uint32))
+    assert _digest(want, want_z, order) == HASHES888[sc.name]
+
+
+def test_rgb888_scenes_exercise_their_feature(oracle):
+    by = {s.name: s for s in RGB888}
+    base = oracle.render_scene888(by["rgb888_opaque_painter"])[0]
+    # RGB888 without dithering keeps all 8 bits; with dithering every written channel is a multiple of 8
+    nd = oracle.render_scene888(by["rgb888_opaque_nodither"])[0]
+    clear = np.array(list(by["rgb888_opaque_painter"].clear) + [255], np.uint8)
+    drawn = (base != clear).any(-1)
+    assert (base[drawn][:, :3] % 8 == 0).all() and (nd[(nd != clear).any(-1)][:, :3] % 8 != 0).any()
+    for name in ("rgb888_gouraud_lights", "rgb888_flat_lights", "rgb888_mixed_painter",
+                 "rgb888_editor_alpha_zbuffer", "rgb888_untextured_vertex_colours"):
+        assert not np.array_equal(oracle.render_scene888(by[name])[0], base), name
+    # per-texel blend tags really blend: the mixed scene differs from itself with every tag forced to Opaque
+    m = by["rgb888_mixed_painter"]
+    forced = []
+    for t in m.textures8:
+        px = np.array(t.pixels, dtype=np.uint8).reshape(-1, 4).copy()
+        px[(px[:, 3] != abi.BLEND_ERASE), 3] = abi.BLEND_OPAQUE
+        forced.append(type(t)(t.width, t.height, px.reshape(-1)))
+    import copy as _copy
+    m2 = _copy.copy(m); m2.textures8 = forced
+    assert not np.array_equal(oracle.render_scene888(m2)[0], oracle.render_scene888(m)[0])
+
+
+def test_rgb888_nan_key_panics_only_in_painters_mode(oracle):
+    sc = next(s for s in RGB888 if s.name == "rgb888_opaque_painter")
+    import dataclasses
+    for fi in range(len(sc.faces)):
+        v = sc.vertices.copy()
+        v["pos"][sc.faces["v"][fi, 0], 2] = np.nan
+        bad = dataclasses.replace(sc, vertices=v)
+        if oracle.render_scene888(bad)[3] == abi.B32_ERR_NAN_DEPTH:
+            zb = dataclasses.replace(bad, settings=dataclasses.replace(bad.settings, use_zbuffer=True))
+            assert oracle.render_scene888(zb)[3] == 0          # no sort in z-buffer mode (render.rs:2155)
+            return
+    raise AssertionError("no face produces a NaN sort key")
