@@ -310,6 +310,38 @@ __device__ __forceinline__ void setup_face(uint32_t fi, const b32_vertex* __rest
     keys[fi] = ((uint64_t)cls << 32) | dkey;
 }
 
+// ---- tile binning helpers -------------------------------------------------------------------------
+__device__ __forceinline__ void head_tiles(const BinHead& h, uint32_t& tx0, uint32_t& tx1, uint32_t& ty0, uint32_t& ty1) {
+    uint32_t min_x = h.bbox_x & 0xFFFF, max_x = h.bbox_x >> 16, min_y = h.bbox_y & 0xFFFF, max_y = h.bbox_y >> 16;
+    tx0 = min_x / TILE_W; tx1 = (max_x - 1) / TILE_W; ty0 = min_y / TILE_H; ty1 = (max_y - 1) / TILE_H;
+}
+
+// f(tile, head) for every screen tile the bounding box of each lane's head touches.  Must be called by all 32
+// lanes of a warp (has = this lane holds a head).  A head that touches few tiles is walked by its own lane; one
+// that touches many (a wall close to the camera covers hundreds of tiles) is walked by the whole warp, 32 tiles
+// at a time, so no lane ever runs a long serial loop while the other 31 wait.
+constexpr uint32_t COOP_TILES = 16;
+template <typename F>
+__device__ __forceinline__ void for_each_tile(const BinHead& h, bool has, uint32_t tiles_x, F f) {
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t tx0 = 0, tx1 = 0, ty0 = 0, ty1 = 0, nt = 0;
+    if (has) { head_tiles(h, tx0, tx1, ty0, ty1); nt = (tx1 - tx0 + 1) * (ty1 - ty0 + 1); }
+    const bool big = nt > COOP_TILES;
+    if (has && !big)
+        for (uint32_t ty = ty0; ty <= ty1; ++ty)
+            for (uint32_t tx = tx0; tx <= tx1; ++tx) f(ty * tiles_x + tx, h);
+    uint32_t bigmask = __ballot_sync(0xFFFFFFFFu, big);
+    while (bigmask) {
+        const int src = __ffs(bigmask) - 1;
+        bigmask &= bigmask - 1;
+        BinHead hb{__shfl_sync(0xFFFFFFFFu, h.bbox_x, src), __shfl_sync(0xFFFFFFFFu, h.bbox_y, src),
+                   __shfl_sync(0xFFFFFFFFu, h.key, src), __shfl_sync(0xFFFFFFFFu, h.face, src)};
+        const uint32_t bx0 = __shfl_sync(0xFFFFFFFFu, tx0, src), by0 = __shfl_sync(0xFFFFFFFFu, ty0, src);
+        const uint32_t bw = __shfl_sync(0xFFFFFFFFu, tx1, src) - bx0 + 1, total = __shfl_sync(0xFFFFFFFFu, nt, src);
+        for (uint32_t i = lane; i < total; i += 32) f((by0 + i / bw) * tiles_x + bx0 + i % bw, hb);
+    }
+}
+
 __global__ void __launch_bounds__(SETUP_THREADS)
 k_setup(const b32_vertex* __restrict__ verts, const b32_face* __restrict__ faces, const TVert* __restrict__ tv,
         const TexDev* __restrict__ tex, const LightDev* __restrict__ lights,
@@ -340,19 +372,13 @@ k_setup(const b32_vertex* __restrict__ verts, const b32_face* __restrict__ faces
 // k_bin_opaque — scatter pass-1 surfaces into per-tile bins (any order)
 // =================================================================================================
 // Same-address global atomics from different warps are serviced one by one in the L2, and a hot tile
-// receives hundreds of surfaces, so the binning is aggregated: a block takes BIN_FPB consecutive
+// receives hundreds of surfaces, so the binning is aggregated: a block takes BIN_THREADS consecutive
 // faces, counts them per tile in shared memory, reserves one contiguous slot range per touched tile
 // with ONE global atomic, then hands out slots from shared memory.
 constexpr int BIN_THREADS = 1024;
-constexpr int BIN_FPT = 1;                      // faces per thread  => 1024 faces per block
-constexpr int BIN_MAX_TILES = 4096;             // shared-memory aggregation up to this many tiles (2 x 16 KB)
+constexpr int BIN_MAX_TILES = 16384;            // shared-memory aggregation up to this many tiles (2 x 64 KB: 2560x1440 has 14 400)
 
-__device__ __forceinline__ void head_tiles(const BinHead& h, uint32_t& tx0, uint32_t& tx1, uint32_t& ty0, uint32_t& ty1) {
-    uint32_t min_x = h.bbox_x & 0xFFFF, max_x = h.bbox_x >> 16, min_y = h.bbox_y & 0xFFFF, max_y = h.bbox_y >> 16;
-    tx0 = min_x / TILE_W; tx1 = (max_x - 1) / TILE_W; ty0 = min_y / TILE_H; ty1 = (max_y - 1) / TILE_H;
-}
-
-__global__ void __launch_bounds__(BIN_THREADS)
+__global__ void __launch_bounds__(BIN_THREADS, 2)
 k_bin_opaque(const BinHead* __restrict__ heads, const uint64_t* __restrict__ keys, const SurfRec* __restrict__ recs,
              BinHead* __restrict__ bins, uint32_t* __restrict__ tile_count,
              CallState* __restrict__ st, CallParams p, uint32_t bin_cap, bool ordered) {
@@ -367,68 +393,47 @@ k_bin_opaque(const BinHead* __restrict__ heads, const uint64_t* __restrict__ key
     __syncthreads();
 
     uint32_t bmax = 0;
-    const uint32_t per_round = BIN_THREADS * BIN_FPT;
-    for (uint32_t base = blockIdx.x * per_round; base < p.nf; base += gridDim.x * per_round) {
-        BinHead head[BIN_FPT];
-        #pragma unroll
-        for (int k = 0; k < BIN_FPT; ++k) {
-            uint32_t fi = base + k * BIN_THREADS + threadIdx.x;
-            head[k] = BinHead{0, 0, 0, 0};
-            if (fi < p.nf) {
-                if (!ordered) head[k] = heads[fi];
-                else {
-                    // draw-order entry of a pass-2 surface (or of any surface in x-ray mode): the unique 64-bit key
-                    // (pass:2 | depth key:32 | face:30) = opaque list first (sorted only in painter's mode), then the
-                    // transparent list, ties by face index = stable sort (render.rs:2522-2542)
-                    uint64_t k64 = keys[fi];
-                    uint32_t cls = (uint32_t)(k64 >> 32);
-                    // (RGB888: one list, so every drawn surface and no pass bit)
-                    if (cls < 2 && (cls == 1 || p.xray_mode || p.rgb888)) {
-                        uint2 bb = *reinterpret_cast<const uint2*>(&recs[fi].bbox_x);      // all zero = empty surface
-                        uint64_t okey = ((uint64_t)(p.rgb888 ? 0u : cls) << 62) | ((uint64_t)(uint32_t)k64 << 30) | fi;
-                        if (bb.x) head[k] = BinHead{bb.x, bb.y, (uint32_t)(okey >> 32), (uint32_t)okey};
-                    }
+    for (uint32_t base = blockIdx.x * BIN_THREADS; base < p.nf; base += gridDim.x * BIN_THREADS) {
+        const uint32_t fi = base + threadIdx.x;
+        BinHead head{0, 0, 0, 0};
+        if (fi < p.nf) {
+            if (!ordered) head = heads[fi];
+            else {
+                // draw-order entry of a pass-2 surface (or of any surface in x-ray mode): the unique 64-bit key
+                // (pass:2 | depth key:32 | face:30) = opaque list first (sorted only in painter's mode), then the
+                // transparent list, ties by face index = stable sort (render.rs:2522-2542)
+                // (RGB888: one list, so every drawn surface and no pass bit)
+                uint64_t k64 = keys[fi];
+                uint32_t cls = (uint32_t)(k64 >> 32);
+                if (cls < 2 && (cls == 1 || p.xray_mode || p.rgb888)) {
+                    uint2 bb = *reinterpret_cast<const uint2*>(&recs[fi].bbox_x);      // all zero = empty surface
+                    uint64_t okey = ((uint64_t)(p.rgb888 ? 0u : cls) << 62) | ((uint64_t)(uint32_t)k64 << 30) | fi;
+                    if (bb.x) head = BinHead{bb.x, bb.y, (uint32_t)(okey >> 32), (uint32_t)okey};
                 }
             }
         }
+        const bool has = head.bbox_x != 0;
         if (aggregate) {
-            #pragma unroll
-            for (int k = 0; k < BIN_FPT; ++k) if (head[k].bbox_x) {                      // 1) count per tile
-                uint32_t tx0, tx1, ty0, ty1; head_tiles(head[k], tx0, tx1, ty0, ty1);
-                for (uint32_t ty = ty0; ty <= ty1; ++ty)
-                    for (uint32_t tx = tx0; tx <= tx1; ++tx) atomicAdd(&s_cnt[ty * p.tiles_x + tx], 1u);
-            }
+            for_each_tile(head, has, p.tiles_x, [&](uint32_t t, const BinHead&) { atomicAdd(&s_cnt[t], 1u); });     // 1) count per tile
             __syncthreads();
             for (uint32_t t = threadIdx.x; t < ntiles; t += blockDim.x) {             // 2) reserve ranges
                 uint32_t c = s_cnt[t];
                 if (c) { uint32_t b = atomicAdd(&tile_count[t], c); s_base[t] = b; s_cnt[t] = 0; bmax = max(bmax, b + c); }
             }
             __syncthreads();
-            #pragma unroll
-            for (int k = 0; k < BIN_FPT; ++k) if (head[k].bbox_x) {                      // 3) hand out slots
-                uint32_t tx0, tx1, ty0, ty1; head_tiles(head[k], tx0, tx1, ty0, ty1);
-                for (uint32_t ty = ty0; ty <= ty1; ++ty)
-                    for (uint32_t tx = tx0; tx <= tx1; ++tx) {
-                        uint32_t t = ty * p.tiles_x + tx;
-                        uint32_t slot = s_base[t] + atomicAdd(&s_cnt[t], 1u);
-                        if (slot < bin_cap) bins[(size_t)t * bin_cap + slot] = head[k];
-                    }
-            }
+            for_each_tile(head, has, p.tiles_x, [&](uint32_t t, const BinHead& h) {                                 // 3) hand out slots
+                uint32_t slot = s_base[t] + atomicAdd(&s_cnt[t], 1u);
+                if (slot < bin_cap) bins[(size_t)t * bin_cap + slot] = h;
+            });
             __syncthreads();
             for (uint32_t t = threadIdx.x; t < ntiles; t += blockDim.x) s_cnt[t] = 0;
             __syncthreads();
         } else {
-            #pragma unroll
-            for (int k = 0; k < BIN_FPT; ++k) if (head[k].bbox_x) {
-                uint32_t tx0, tx1, ty0, ty1; head_tiles(head[k], tx0, tx1, ty0, ty1);
-                for (uint32_t ty = ty0; ty <= ty1; ++ty)
-                    for (uint32_t tx = tx0; tx <= tx1; ++tx) {
-                        uint32_t t = ty * p.tiles_x + tx;
-                        uint32_t slot = atomicAdd(&tile_count[t], 1u);
-                        if (slot < bin_cap) bins[(size_t)t * bin_cap + slot] = head[k];
-                        bmax = max(bmax, slot + 1);
-                    }
-            }
+            for_each_tile(head, has, p.tiles_x, [&](uint32_t t, const BinHead& h) {
+                uint32_t slot = atomicAdd(&tile_count[t], 1u);
+                if (slot < bin_cap) bins[(size_t)t * bin_cap + slot] = h;
+                bmax = max(bmax, slot + 1);
+            });
         }
     }
     for (int o = 16; o > 0; o >>= 1) bmax = max(bmax, __shfl_xor_sync(0xFFFFFFFFu, bmax, o));
@@ -689,6 +694,8 @@ __device__ __forceinline__ uint32_t texel_index(const Rec& r, float bc_x, float 
 #ifndef B32_OP_MINB
 #define B32_OP_MINB (OP_THREADS == 256 ? 5 : (OP_THREADS == 128 ? 5 : 2))
 #endif
+// RGB888 = the render_mesh instantiation (8-bit colour pipeline in step 5; everything else is shared)
+template <bool RGB888>
 __global__ void __launch_bounds__(OP_THREADS, B32_OP_MINB)
 k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins, const uint32_t* __restrict__ tile_count,
               const TexDev* __restrict__ tex, const uint16_t* __restrict__ texels, const uint32_t* __restrict__ texmask,
@@ -731,13 +738,13 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
     bool skip;
     {
         CallState s = *st;
-        bool aborts = call_aborts(s, p.use_zbuffer, p.rgb888);
+        bool aborts = call_aborts(s, p.use_zbuffer, RGB888);
         if (p.async_call && blockIdx.x == 0 && threadIdx.x == 0) {                                // enqueue-only callers
             if (aborts || s.bin_overflow) atomicOr(sticky, s.oob ? 1u : (aborts ? 2u : 4u));
             else if (s.n_transp) atomicOr(sticky, 8u);                                           // pass 2 exists but was not enqueued
         }
         // x-ray (render_mesh_15) and any framebuffer-reading surface (render_mesh) go through the ordered replay instead
-        skip = s.bin_overflow || aborts || (p.xray_mode && !p.rgb888) || (p.rgb888 && s.n_transp);
+        skip = s.bin_overflow || aborts || (p.xray_mode && !RGB888) || (RGB888 && s.n_transp);
     }
     const uint32_t n = skip ? 0u : tile_count[tile];
     if (n == 0) {                                          // nothing to draw here; the mask copy must land before the CTA exits
@@ -985,7 +992,7 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
             inside_test(r, x, y, bc_x, bc_y, bc_z);                        // same arithmetic as in the walk
             float inv_z = bc_x * r.iz1 + bc_y * r.iz2 + bc_z * r.iz3;      // :1549
             uint32_t o_r, o_g, o_b, o_blend; bool semi;
-            bool wrote = p.rgb888 ? shade888(r, x, y, bc_x, bc_y, bc_z, inv_z, texd, reinterpret_cast<const uint32_t*>(texels), p, o_r, o_g, o_b, o_blend)
+            bool wrote = RGB888 ? shade888(r, x, y, bc_x, bc_y, bc_z, inv_z, texd, reinterpret_cast<const uint32_t*>(texels), p, o_r, o_g, o_b, o_blend)
                                   : shade(r, x, y, bc_x, bc_y, bc_z, inv_z, texd, texels, p, o_r, o_g, o_b, semi);
             if (wrote) px.rgba = o_r | (o_g << 8) | (o_b << 16) | 0xFF000000u;    // pass 1: set_pixel_15 (:445-454) / set_pixel (:301-310)
 #ifdef B32_FILL_STATS
@@ -1320,10 +1327,11 @@ void launch_setup(const LaunchCtx& L, const b32_vertex* verts, const b32_face* f
                   const LightDev* lights, SurfRec* recs, uint64_t* keys, BinHead* heads, BinHead* bins,
                   uint32_t* tile_count, WireTri* wire, CallState* st, uint32_t* zero_next, uint32_t zero_words, const CallParams& p) {
     if (p.nf == 0) return;
+    const bool pass1 = !((p.xray_mode && !p.rgb888) || p.wire_front);        // wireframe_overlay draws no solid surfaces (:2550)
     k_setup<<<grid_for(p.nf, SETUP_THREADS, L.sms, 16), SETUP_THREADS, 0, L.stream>>>(verts, faces, tv, tex, lights, recs, keys, heads, wire, st,
                                                                                       zero_next, zero_words, p);
     ++*L.launches;
-    if ((p.xray_mode && !p.rgb888) || p.wire_front) return;        // wireframe_overlay draws no solid surfaces (:2550)
+    if (!pass1) return;
     launch_bin(L, heads, keys, recs, bins, tile_count, st, p, p.bin_cap, false, true);
 }
 
@@ -1332,7 +1340,9 @@ void launch_bin(const LaunchCtx& L, const BinHead* heads, const uint64_t* keys, 
     if (p.nf == 0) return;
     uint32_t ntiles = p.tiles_x * p.tiles_y;
     size_t smem = ntiles <= (uint32_t)BIN_MAX_TILES ? (size_t)ntiles * 8 : 0;
-    uint32_t per_round = BIN_THREADS * BIN_FPT;
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(k_bin_opaque, cudaFuncAttributeMaxDynamicSharedMemorySize, BIN_MAX_TILES * 8); attr_set = true; }
+    uint32_t per_round = BIN_THREADS;
     uint32_t grid = (p.nf + per_round - 1) / per_round;
     if (grid > L.sms * 4) grid = L.sms * 4;
     launch_k(k_bin_opaque, grid, BIN_THREADS, smem, L.stream, after_setup, heads, keys, recs, bins, tile_count, st, p, bin_cap, ordered);
@@ -1345,10 +1355,14 @@ void launch_fill_opaque(const LaunchCtx& L, const SurfRec* recs, const BinHead* 
     uint32_t ntiles = p.tiles_x * p.tiles_y;
     if (ntiles == 0 || p.nf == 0) return;
     static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k_fill_opaque, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OP_SMEM); attr_set = true; }
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_fill_opaque<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OP_SMEM);
+        cudaFuncSetAttribute(k_fill_opaque<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OP_SMEM);
+        attr_set = true;
+    }
     // launched right behind k_bin_opaque except in x-ray mode (no pass-1 binning: then it is an ordinary launch)
-    launch_k(k_fill_opaque, ntiles * OP_SPLIT, OP_THREADS, OP_SMEM, L.stream, !(p.xray_mode && !p.rgb888), recs, bins, tile_count, tex, texels, texmask,
-             fb_rgba, fb_z, st, sticky, p);
+    launch_k(p.rgb888 ? k_fill_opaque<true> : k_fill_opaque<false>, ntiles * OP_SPLIT, OP_THREADS, OP_SMEM, L.stream, !(p.xray_mode && !p.rgb888),
+             recs, bins, tile_count, tex, texels, texmask, fb_rgba, fb_z, st, sticky, p);
     ++*L.launches;
 }
 
