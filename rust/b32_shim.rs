@@ -120,3 +120,40 @@ pub fn render_mesh_15(fb: &mut Framebuffer, vertices: &[Vertex], faces: &[Face],
                         draw_ms: tm.draw_ms, wireframe_ms: tm.wireframe_ms, triangles_drawn: tm.triangles_drawn }
     })
 }
+
+// ---------------------------------------------------------------------------------------------------
+// RGB888 sibling: `render_mesh` (src/rasterizer/render.rs:1971-1978), picked by callers when
+// `settings.use_rgb555` is false.  Same marshalling; `Texture.pixels: Vec<Color>` becomes 4 bytes per texel.
+// ---------------------------------------------------------------------------------------------------
+#[repr(C)] pub struct b32_tex8_desc { width: u32, height: u32, blend_mode: u32, _pad: u32, pixels: *const u8 }
+extern "C" {
+    fn b32_textures_set_rgb888(ctx: *mut b32_ctx, descs: *const b32_tex8_desc, n: u32) -> c_int;
+    fn b32_render_mesh(ctx: *mut b32_ctx, v: *const b32_vertex, nv: u32, f: *const b32_face, nf: u32,
+                       cam: *const b32_camera, s: *const b32_settings, out: *mut b32_timings) -> c_int;
+}
+thread_local! { static TEX8_GEN: std::cell::Cell<(usize, usize)> = std::cell::Cell::new((0, 0)); }
+
+pub fn render_mesh(fb: &mut Framebuffer, vertices: &[Vertex], faces: &[Face], textures: &[super::types::Texture],
+                   camera: &Camera, settings: &RasterSettings) -> RasterTimings {
+    CTX.with(|&ctx| unsafe {
+        let (v, f) = marshal_geometry(vertices, faces);          // the two `map` expressions of render_mesh_15 above
+        let key = (textures.as_ptr() as usize, textures.len());
+        if TEX8_GEN.with(|g| g.replace(key)) != key {
+            let texels: Vec<Vec<u8>> = textures.iter().map(|t| t.pixels.iter()
+                .flat_map(|c| [c.r, c.g, c.b, blend_u8(c.blend)]).collect()).collect();
+            let d: Vec<b32_tex8_desc> = textures.iter().zip(&texels).map(|(t, px)| b32_tex8_desc {
+                width: t.width as u32, height: t.height as u32, blend_mode: blend_u8(t.blend_mode) as u32, _pad: 0,
+                pixels: px.as_ptr() }).collect();
+            check(ctx, b32_textures_set_rgb888(ctx, d.as_ptr(), d.len() as u32));
+        }
+        let (s, _lights) = marshal_settings(settings);           // as in render_mesh_15 above
+        let cam = marshal_camera(camera);
+        check(ctx, b32_fb_resize(ctx, fb.width as u32, fb.height as u32));
+        check(ctx, b32_fb_upload(ctx, fb.pixels.as_ptr(), fb.zbuffer.as_ptr()));
+        let mut tm = b32_timings::default();
+        check(ctx, b32_render_mesh(ctx, v.as_ptr(), v.len() as u32, f.as_ptr(), f.len() as u32, &cam, &s, &mut tm));
+        check(ctx, b32_fb_download(ctx, fb.pixels.as_mut_ptr(), fb.zbuffer.as_mut_ptr()));
+        RasterTimings { transform_ms: tm.transform_ms, fog_ms: tm.fog_ms, cull_ms: tm.cull_ms, sort_ms: tm.sort_ms,
+                        draw_ms: tm.draw_ms, wireframe_ms: tm.wireframe_ms, triangles_drawn: tm.triangles_drawn }
+    })
+}
