@@ -65,19 +65,58 @@ fn check(ctx: *mut b32_ctx, rc: c_int) {
     }
 }
 
+// --- marshal &[Vertex] / &[Face] into the 36 B / 16 B POD records (include/b32_raster.h) ---
+fn marshal_geometry(vertices: &[Vertex], faces: &[Face]) -> (Vec<b32_vertex>, Vec<b32_face>) {
+    let v = vertices.iter().map(|v| b32_vertex {
+        pos: [v.pos.x, v.pos.y, v.pos.z], uv: [v.uv.x, v.uv.y], normal: [v.normal.x, v.normal.y, v.normal.z],
+        r: v.color.r, g: v.color.g, b: v.color.b, blend: blend_u8(v.color.blend) }).collect();
+    let f = faces.iter().map(|f| {
+        let tex = match f.texture_id { Some(id) if id < 0xFFFF => id as u32, _ => 0xFFFF };
+        b32_face { v0: f.v0.min(u32::MAX as usize) as u32, v1: f.v1.min(u32::MAX as usize) as u32,
+                   v2: f.v2.min(u32::MAX as usize) as u32,
+                   flags: tex | ((blend_u8(f.blend_mode) as u32) << 16) | ((f.black_transparent as u32) << 19)
+                          | ((f.editor_alpha as u32) << 24) } }).collect();
+    (v, f)
+}
+
+/// The returned Vec owns the lights `b32_settings.lights` points at: keep it alive across the call.
+fn marshal_settings(settings: &RasterSettings) -> (b32_settings, Vec<b32_light>) {
+    let lights: Vec<b32_light> = settings.lights.iter().map(|l| {
+        let (kind, position, direction, radius, angle) = match l.light_type {
+            LightType::Directional { direction: d } => (0, [0.0; 3], [d.x, d.y, d.z], 0.0, 0.0),
+            LightType::Point { position: p, radius } => (1, [p.x, p.y, p.z], [0.0; 3], radius, 0.0),
+            LightType::Spot { position: p, direction: d, angle, radius } => (2, [p.x, p.y, p.z], [d.x, d.y, d.z], radius, angle),
+        };
+        b32_light { kind, position, direction, radius, angle, intensity: l.intensity,
+                    r: l.color.r, g: l.color.g, b: l.color.b, enabled: l.enabled as u8 } }).collect();
+    let (oe, oz, ox, oy) = match &settings.ortho_projection { Some(o) => (1, o.zoom, o.center_x, o.center_y), None => (0, 0.0, 0.0, 0.0) };
+    let s = b32_settings {
+        affine_textures: settings.affine_textures as u8, use_zbuffer: settings.use_zbuffer as u8,
+        shading: match settings.shading { ShadingMode::None => 0, ShadingMode::Flat => 1, ShadingMode::Gouraud => 2 },
+        backface_cull: settings.backface_cull as u8, backface_wireframe: settings.backface_wireframe as u8,
+        dithering: settings.dithering as u8, wireframe_overlay: settings.wireframe_overlay as u8,
+        use_rgb555: settings.use_rgb555 as u8, use_fixed_point: settings.use_fixed_point as u8,
+        xray_mode: settings.xray_mode as u8, ortho_enabled: oe, _pad: 0, ambient: settings.ambient,
+        ortho_zoom: oz, ortho_center_x: ox, ortho_center_y: oy, n_lights: lights.len() as u32, lights: lights.as_ptr() };
+    (s, lights)
+}
+
+fn marshal_camera(camera: &Camera) -> b32_camera {
+    b32_camera { position: [camera.position.x, camera.position.y, camera.position.z],
+        basis_x: [camera.basis_x.x, camera.basis_x.y, camera.basis_x.z],
+        basis_y: [camera.basis_y.x, camera.basis_y.y, camera.basis_y.z],
+        basis_z: [camera.basis_z.x, camera.basis_z.y, camera.basis_z.z] }
+}
+
+fn timings(tm: &b32_timings) -> RasterTimings {
+    RasterTimings { transform_ms: tm.transform_ms, fog_ms: tm.fog_ms, cull_ms: tm.cull_ms, sort_ms: tm.sort_ms,
+                    draw_ms: tm.draw_ms, wireframe_ms: tm.wireframe_ms, triangles_drawn: tm.triangles_drawn }
+}
+
 pub fn render_mesh_15(fb: &mut Framebuffer, vertices: &[Vertex], faces: &[Face], textures: &[Texture15],
                       camera: &Camera, settings: &RasterSettings, fog: Option<(f32, f32, f32, Color)>) -> RasterTimings {
     CTX.with(|&ctx| unsafe {
-        // --- marshal &[Vertex] / &[Face] into the 36 B / 16 B POD records (include/b32_raster.h) ---
-        let v: Vec<b32_vertex> = vertices.iter().map(|v| b32_vertex {
-            pos: [v.pos.x, v.pos.y, v.pos.z], uv: [v.uv.x, v.uv.y], normal: [v.normal.x, v.normal.y, v.normal.z],
-            r: v.color.r, g: v.color.g, b: v.color.b, blend: blend_u8(v.color.blend) }).collect();
-        let f: Vec<b32_face> = faces.iter().map(|f| {
-            let tex = match f.texture_id { Some(id) if id < 0xFFFF => id as u32, _ => 0xFFFF };
-            b32_face { v0: f.v0.min(u32::MAX as usize) as u32, v1: f.v1.min(u32::MAX as usize) as u32,
-                       v2: f.v2.min(u32::MAX as usize) as u32,
-                       flags: tex | ((blend_u8(f.blend_mode) as u32) << 16) | ((f.black_transparent as u32) << 19)
-                              | ((f.editor_alpha as u32) << 24) } }).collect();
+        let (v, f) = marshal_geometry(vertices, faces);
         // --- textures: re-upload only when the slice changed (cf. textures_15_cache_generation) ---
         let key = (textures.as_ptr() as usize, textures.len());
         if TEX_GEN.with(|g| g.replace(key)) != key {
@@ -86,28 +125,8 @@ pub fn render_mesh_15(fb: &mut Framebuffer, vertices: &[Vertex], faces: &[Face],
                 pixels: t.pixels.as_ptr() as *const c_void, clut: std::ptr::null(), clut_len: 0 }).collect();
             check(ctx, b32_textures_set(ctx, d.as_ptr(), d.len() as u32));
         }
-        // --- settings ---
-        let lights: Vec<b32_light> = settings.lights.iter().map(|l| {
-            let (kind, position, direction, radius, angle) = match l.light_type {
-                LightType::Directional { direction: d } => (0, [0.0; 3], [d.x, d.y, d.z], 0.0, 0.0),
-                LightType::Point { position: p, radius } => (1, [p.x, p.y, p.z], [0.0; 3], radius, 0.0),
-                LightType::Spot { position: p, direction: d, angle, radius } => (2, [p.x, p.y, p.z], [d.x, d.y, d.z], radius, angle),
-            };
-            b32_light { kind, position, direction, radius, angle, intensity: l.intensity,
-                        r: l.color.r, g: l.color.g, b: l.color.b, enabled: l.enabled as u8 } }).collect();
-        let (oe, oz, ox, oy) = match &settings.ortho_projection { Some(o) => (1, o.zoom, o.center_x, o.center_y), None => (0, 0.0, 0.0, 0.0) };
-        let s = b32_settings {
-            affine_textures: settings.affine_textures as u8, use_zbuffer: settings.use_zbuffer as u8,
-            shading: match settings.shading { ShadingMode::None => 0, ShadingMode::Flat => 1, ShadingMode::Gouraud => 2 },
-            backface_cull: settings.backface_cull as u8, backface_wireframe: settings.backface_wireframe as u8,
-            dithering: settings.dithering as u8, wireframe_overlay: settings.wireframe_overlay as u8,
-            use_rgb555: settings.use_rgb555 as u8, use_fixed_point: settings.use_fixed_point as u8,
-            xray_mode: settings.xray_mode as u8, ortho_enabled: oe, _pad: 0, ambient: settings.ambient,
-            ortho_zoom: oz, ortho_center_x: ox, ortho_center_y: oy, n_lights: lights.len() as u32, lights: lights.as_ptr() };
-        let cam = b32_camera { position: [camera.position.x, camera.position.y, camera.position.z],
-            basis_x: [camera.basis_x.x, camera.basis_x.y, camera.basis_x.z],
-            basis_y: [camera.basis_y.x, camera.basis_y.y, camera.basis_y.z],
-            basis_z: [camera.basis_z.x, camera.basis_z.y, camera.basis_z.z] };
+        let (s, _lights) = marshal_settings(settings);
+        let cam = marshal_camera(camera);
         let fogc = fog.map(|(start, falloff, cull_distance, c)| b32_fog { start, falloff, cull_distance, r: c.r, g: c.g, b: c.b, blend: blend_u8(c.blend) });
         // --- framebuffer: the host owns fb.pixels / fb.zbuffer between calls (clear, skybox, overlays) ---
         check(ctx, b32_fb_resize(ctx, fb.width as u32, fb.height as u32));
@@ -116,8 +135,7 @@ pub fn render_mesh_15(fb: &mut Framebuffer, vertices: &[Vertex], faces: &[Face],
         check(ctx, b32_render_mesh_15(ctx, v.as_ptr(), v.len() as u32, f.as_ptr(), f.len() as u32, &cam, &s,
                                       fogc.as_ref().map_or(std::ptr::null(), |f| f as *const _), &mut tm));
         check(ctx, b32_fb_download(ctx, fb.pixels.as_mut_ptr(), fb.zbuffer.as_mut_ptr()));
-        RasterTimings { transform_ms: tm.transform_ms, fog_ms: tm.fog_ms, cull_ms: tm.cull_ms, sort_ms: tm.sort_ms,
-                        draw_ms: tm.draw_ms, wireframe_ms: tm.wireframe_ms, triangles_drawn: tm.triangles_drawn }
+        timings(&tm)
     })
 }
 
@@ -136,7 +154,7 @@ thread_local! { static TEX8_GEN: std::cell::Cell<(usize, usize)> = std::cell::Ce
 pub fn render_mesh(fb: &mut Framebuffer, vertices: &[Vertex], faces: &[Face], textures: &[super::types::Texture],
                    camera: &Camera, settings: &RasterSettings) -> RasterTimings {
     CTX.with(|&ctx| unsafe {
-        let (v, f) = marshal_geometry(vertices, faces);          // the two `map` expressions of render_mesh_15 above
+        let (v, f) = marshal_geometry(vertices, faces);
         let key = (textures.as_ptr() as usize, textures.len());
         if TEX8_GEN.with(|g| g.replace(key)) != key {
             let texels: Vec<Vec<u8>> = textures.iter().map(|t| t.pixels.iter()
@@ -146,14 +164,13 @@ pub fn render_mesh(fb: &mut Framebuffer, vertices: &[Vertex], faces: &[Face], te
                 pixels: px.as_ptr() }).collect();
             check(ctx, b32_textures_set_rgb888(ctx, d.as_ptr(), d.len() as u32));
         }
-        let (s, _lights) = marshal_settings(settings);           // as in render_mesh_15 above
+        let (s, _lights) = marshal_settings(settings);
         let cam = marshal_camera(camera);
         check(ctx, b32_fb_resize(ctx, fb.width as u32, fb.height as u32));
         check(ctx, b32_fb_upload(ctx, fb.pixels.as_ptr(), fb.zbuffer.as_ptr()));
         let mut tm = b32_timings::default();
         check(ctx, b32_render_mesh(ctx, v.as_ptr(), v.len() as u32, f.as_ptr(), f.len() as u32, &cam, &s, &mut tm));
         check(ctx, b32_fb_download(ctx, fb.pixels.as_mut_ptr(), fb.zbuffer.as_mut_ptr()));
-        RasterTimings { transform_ms: tm.transform_ms, fog_ms: tm.fog_ms, cull_ms: tm.cull_ms, sort_ms: tm.sort_ms,
-                        draw_ms: tm.draw_ms, wireframe_ms: tm.wireframe_ms, triangles_drawn: tm.triangles_drawn }
+        timings(&tm)
     })
 }
