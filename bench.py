@@ -220,13 +220,19 @@ def run_b200(args):
 
     # ---- device-resident value: frames enqueued back to back on N_CTX contexts (streams) ---------------
     # Successive steps read different resident copies of the scene, so inputs never come from L2.
+    # One ABI call per frame (Framebuffer::clear + render_mesh_15); from its third frame on a (context, mesh) pair
+    # replays as a CUDA graph with re-parameterised kernel nodes, so the host submits one driver call per frame.
+    clear4 = (C.c_uint8 * 4)(r, g, b, 255)
+
     def step_enqueue(k):
         c = ctxs[k % N_CTX]
-        c.check(lib.b32_fb_clear(c.h, r, g, b, 255))
-        c.check(lib.b32_render_mesh_15_enqueue(c.h, meshes[k % N_COPIES].h, C.byref(cam), C.byref(st), None))
+        c.check(lib.b32_frame_15_enqueue(c.h, clear4, meshes[k % N_COPIES].h, C.byref(cam), C.byref(st), None))
 
     for k in range(max(args.warmup, 3) * N_CTX):
         step_resident(k)
+    # every (context, scene copy) pair the timed loop uses is warmed up at least 3 times (its CUDA graph exists)
+    import math
+    for k in range(max(args.warmup, 3) * (N_CTX * N_COPIES // math.gcd(N_CTX, N_COPIES))):
         step_enqueue(k)
     for c in ctxs:
         c.sync()

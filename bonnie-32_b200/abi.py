@@ -114,6 +114,8 @@ SYMBOLS = {
     "b32_textures_set_rgb888": (C.c_int, [_P, C.POINTER(Tex8Desc), C.c_uint32]),
     "b32_render_mesh": (C.c_int, [_P, _P, C.c_uint32, _P, C.c_uint32, C.POINTER(Camera), C.POINTER(Settings), C.POINTER(Timings)]),
     "b32_render_mesh_resident": (C.c_int, [_P, _P, C.POINTER(Camera), C.POINTER(Settings), C.POINTER(Timings)]),
+    "b32_frame_15_enqueue": (C.c_int, [_P, _P, _P, C.POINTER(Camera), C.POINTER(Settings), C.POINTER(Fog)]),
+    "b32_graph_launches": (C.c_uint64, [_P]),
     "b32_host_alloc": (_P, [C.c_size_t]),
     "b32_host_free": (None, [_P]),
     "b32_debug_transform": (C.c_int, [_P, _P, C.c_uint32, C.POINTER(Camera), C.POINTER(Settings), _P, _P]),

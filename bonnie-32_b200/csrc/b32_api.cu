@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -42,6 +43,27 @@ struct b32_mesh {
     b32_face* faces = nullptr;
     uint32_t nv = 0, nf = 0;
     bool has_nonopaque = false;     // some face has blend != Opaque or editor_alpha < 255
+};
+
+// What fixes the topology (kernels, grids) of an enqueued frame; everything else is a kernel argument.
+struct FrameKey {
+    const void* verts = nullptr; const void* faces = nullptr;
+    uint32_t nv = 0, nf = 0, width = 0, height = 0;
+    uint8_t rgb888 = 0, pass1 = 0, clear = 0, valid = 0;
+    bool operator==(const FrameKey& o) const {
+        return verts == o.verts && faces == o.faces && nv == o.nv && nf == o.nf && width == o.width && height == o.height &&
+               rgb888 == o.rgb888 && pass1 == o.pass1 && clear == o.clear && valid == o.valid;
+    }
+};
+struct FrameGraph {
+    cudaGraph_t graph = nullptr;
+    GraphPatch patch;
+    FrameKey key, seen;
+    void destroy() {
+        if (patch.exec) cudaGraphExecDestroy(patch.exec);
+        if (graph) cudaGraphDestroy(graph);
+        patch = GraphPatch{}; graph = nullptr; key = FrameKey{};
+    }
 };
 
 struct b32_ctx {
@@ -108,7 +130,14 @@ struct b32_ctx {
     float emit_ms = 0.0f;
     float wire_ms = 0.0f;
 
-    LaunchCtx L() { return LaunchCtx{stream, (uint32_t)prop.multiProcessorCount, &launches}; }
+    // enqueued frames of one mesh replay as a CUDA graph (see render_device); a few topologies are kept (round robin)
+    static constexpr int N_FRAME_GRAPHS = 32;
+    FrameGraph fgs[N_FRAME_GRAPHS];
+    FrameKey fg_seen[N_FRAME_GRAPHS];  // topologies seen once, not captured yet
+    int fg_next = 0, fg_seen_next = 0;
+    uint64_t graph_launches = 0, graph_captures = 0;
+
+    LaunchCtx L() { return LaunchCtx{stream, (uint32_t)prop.multiProcessorCount, &launches, nullptr}; }
 };
 
 namespace {
@@ -284,8 +313,31 @@ int render_ordered(b32_ctx* ctx, const CallParams& p, uint32_t n_ordered) {
 // One render_mesh_15 (render.rs:2302-2572) on device-resident geometry.
 //   wait=true : returns when the frame is in the framebuffer; fills *tm.
 //   wait=false: only enqueues pass 1 (no host round trip); the caller guarantees there is no pass 2.
+// Turn the frame just captured on the context's stream into an executable graph and remember its kernel nodes.
+bool finish_capture(b32_ctx* ctx, FrameGraph& fg, const FrameKey& key) {
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamEndCapture(ctx->stream, &graph) != cudaSuccess || !graph) { cudaGetLastError(); return false; }
+    fg.destroy();
+    fg.graph = graph;
+    if (cudaGraphInstantiate(&fg.patch.exec, graph, 0) != cudaSuccess) { cudaGetLastError(); fg.destroy(); return false; }
+    cudaGraphNode_t nodes[16]; size_t n = 16;
+    if (cudaGraphGetNodes(graph, nodes, &n) != cudaSuccess || n > 8) { cudaGetLastError(); fg.destroy(); return false; }
+    fg.patch.n = 0;
+    for (size_t i = 0; i < n; ++i) {
+        cudaGraphNodeType t;
+        cudaKernelNodeParams np{};
+        if (cudaGraphNodeGetType(nodes[i], &t) != cudaSuccess || t != cudaGraphNodeTypeKernel ||
+            cudaGraphKernelNodeGetParams(nodes[i], &np) != cudaSuccess) { cudaGetLastError(); fg.destroy(); return false; }
+        fg.patch.node[fg.patch.n] = nodes[i]; fg.patch.func[fg.patch.n] = np.func; ++fg.patch.n;
+    }
+    fg.key = key;
+    return true;
+}
+
+// clear_rgba (nullable): Framebuffer::clear first, as part of the same frame.
 int render_device(b32_ctx* ctx, const b32_vertex* d_verts, uint32_t nv, const b32_face* d_faces, uint32_t nf,
-                  const b32_camera* cam, const b32_settings* s, const b32_fog* fog, b32_timings* tm, bool wait, bool rgb888 = false) {
+                  const b32_camera* cam, const b32_settings* s, const b32_fog* fog, b32_timings* tm, bool wait, bool rgb888 = false,
+                  const uint8_t* clear_rgba = nullptr) {
     if (!cam || !s) return fail(ctx, B32_ERR_INVALID, "camera/settings is NULL");
     if (ctx->width == 0 || ctx->height == 0) return fail(ctx, B32_ERR_INVALID, "framebuffer has zero size (call b32_fb_resize)");
     CallParams p;
@@ -299,7 +351,12 @@ int render_device(b32_ctx* ctx, const b32_vertex* d_verts, uint32_t nv, const b3
     for (float& k : ctx->kernel_ms) k = 0.0f;
     ctx->last_nf = nf;
     ctx->last_params = p;
-    if (nf == 0) return B32_OK;
+    const uint32_t clear_color = clear_rgba ? ((uint32_t)clear_rgba[0] | ((uint32_t)clear_rgba[1] << 8) | ((uint32_t)clear_rgba[2] << 16) |
+                                               ((uint32_t)clear_rgba[3] << 24)) : 0u;
+    if (nf == 0) {
+        if (clear_rgba) launch_fb_clear(ctx->L(), ctx->fb_rgba.p, ctx->fb_z.p, ctx->width * ctx->height, clear_color);
+        return B32_OK;
+    }
 
     const uint32_t ntiles = p.tiles_x * p.tiles_y;
     rc = ensure_work(ctx, nv, nf); if (rc) return rc;
@@ -314,6 +371,29 @@ int render_device(b32_ctx* ctx, const b32_vertex* d_verts, uint32_t nv, const b3
         ctx->last_params = p;
         const bool wire_on = p.wire_back || p.wire_front;
         if (wire_on) CK(ctx->wire.reserve(nf));
+        // Enqueue-only frames: the second frame of one topology is captured into a CUDA graph, later ones re-parameterise
+        // its kernel nodes in place and launch it — one driver call per frame instead of one per kernel.
+        enum { PLAIN, CAPTURE, PATCH } mode = PLAIN;
+        FrameKey key;
+        FrameGraph* fg = nullptr;
+        static const bool no_graph = std::getenv("B32_NO_GRAPH") != nullptr;      // experiments: plain launches only
+        if (!wait && !no_graph) {
+            key.verts = d_verts; key.faces = d_faces; key.nv = nv; key.nf = nf; key.width = ctx->width; key.height = ctx->height;
+            key.rgb888 = rgb888; key.pass1 = !((p.xray_mode && !rgb888) || p.wire_front); key.clear = clear_rgba != nullptr; key.valid = 1;
+            for (FrameGraph& g : ctx->fgs) if (g.patch.exec && g.key == key) { fg = &g; mode = PATCH; break; }
+            if (!fg) {
+                bool seen = false;
+                for (const FrameKey& k : ctx->fg_seen) seen = seen || k == key;
+                // a caller that cycles through more topologies than the cache holds would capture forever: stop building
+                // graphs once captures stop paying for themselves (plain launches are always correct)
+                const bool thrashing = ctx->graph_captures > 2 * b32_ctx::N_FRAME_GRAPHS && ctx->graph_launches < 4 * ctx->graph_captures;
+                if (seen && !thrashing) { mode = CAPTURE; fg = &ctx->fgs[ctx->fg_next]; ctx->fg_next = (ctx->fg_next + 1) % b32_ctx::N_FRAME_GRAPHS; ++ctx->graph_captures; }
+                else { ctx->fg_seen[ctx->fg_seen_next] = key; ctx->fg_seen_next = (ctx->fg_seen_next + 1) % b32_ctx::N_FRAME_GRAPHS; }
+            }
+        }
+        if (mode == CAPTURE && cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); mode = PLAIN; }
+        if (mode == PATCH) { L.patch = &fg->patch; L.patch->err = cudaSuccess; for (bool& u : L.patch->used) u = false; }
+        if (clear_rgba) launch_fb_clear(L, ctx->fb_rgba.p, ctx->fb_z.p, ctx->width * ctx->height, clear_color);
         if (wait) CK(cudaEventRecord(ctx->ev[0], st));
         // take the set the previous call's k_setup zeroed; this call's k_setup zeroes the other one
         // (nothing between here and the launch can fail, so the two sets never get out of step)
@@ -328,7 +408,27 @@ int render_device(b32_ctx* ctx, const b32_vertex* d_verts, uint32_t nv, const b3
         if (!p.wire_front)
             launch_fill_opaque(L, ctx->recs.p, ctx->bins.p, ctx->tile_count, texdesc, texels, texmask,
                                ctx->fb_rgba.p, ctx->fb_z.p, ctx->state, ctx->sticky, p);      // DRAW, pass 1
-        if (!wait) { ctx->async_pending = true; return B32_OK; }
+        if (!wait) {
+            ctx->async_pending = true;
+            if (mode == CAPTURE) {
+                if (finish_capture(ctx, *fg, key)) { CK(cudaGraphLaunch(fg->patch.exec, st)); ++ctx->graph_launches; return B32_OK; }
+                mode = PLAIN;                              // could not build the graph: launch this frame the ordinary way
+                L.patch = nullptr;
+            } else if (mode == PATCH) {
+                if (L.patch->err == cudaSuccess) { CK(cudaGraphLaunch(fg->patch.exec, st)); ++ctx->graph_launches; return B32_OK; }
+                fg->destroy(); cudaGetLastError();
+                mode = PLAIN; L.patch = nullptr;
+            } else return B32_OK;
+            // fallback: nothing of this frame has been launched yet
+            if (clear_rgba) launch_fb_clear(L, ctx->fb_rgba.p, ctx->fb_z.p, ctx->width * ctx->height, clear_color);
+            launch_setup(L, d_verts, d_faces, nullptr, texdesc, ctx->lights.p, ctx->recs.p, ctx->keys.p,
+                         ctx->heads.p, ctx->bins.p, ctx->tile_count, wire_on ? ctx->wire.p : nullptr, ctx->state,
+                         zero_next, ctx->state_stride, p);
+            if (!p.wire_front)
+                launch_fill_opaque(L, ctx->recs.p, ctx->bins.p, ctx->tile_count, texdesc, texels, texmask,
+                                   ctx->fb_rgba.p, ctx->fb_z.p, ctx->state, ctx->sticky, p);
+            return B32_OK;
+        }
         CK(cudaEventRecord(ctx->ev[2], st));
         CK(cudaMemcpyAsync(ctx->state_h, ctx->state, sizeof(CallState), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -412,6 +512,7 @@ void b32_ctx_destroy(b32_ctx* ctx) {
     ctx->tv.release(); ctx->recs.release(); ctx->keys.release(); ctx->state_ring.release(); ctx->otile_count.release();
     ctx->bins.release(); ctx->heads.release(); ctx->obins.release(); ctx->wire.release();
     ctx->lights.release(); ctx->dbg.release();
+    for (FrameGraph& g : ctx->fgs) g.destroy();
     if (ctx->sticky) cudaFree(ctx->sticky);
     if (ctx->state_h) cudaFreeHost(ctx->state_h);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -627,6 +728,18 @@ int b32_render_mesh_15_ex(b32_ctx* ctx, const b32_vertex* vertices, uint32_t nv,
     rc = h2d(ctx, ctx->faces.p, faces, (size_t)nf * sizeof(b32_face)); if (rc) return rc;
     return render_device(ctx, ctx->verts.p, nv, ctx->faces.p, nf, camera, settings, fog, nullptr, false);
 }
+
+int b32_frame_15_enqueue(b32_ctx* ctx, const uint8_t* clear_rgba, const b32_mesh* mesh, const b32_camera* camera,
+                         const b32_settings* settings, const b32_fog* fog) {
+    if (!ctx || !mesh || !settings) return B32_ERR_INVALID;
+    bool may_blend = mesh->has_nonopaque || settings->xray_mode || (settings->backface_cull && settings->backface_wireframe) || settings->wireframe_overlay;
+    for (const TexDev& t : ctx->texdesc_h) may_blend = may_blend || t.blend != B32_BLEND_OPAQUE;
+    uint32_t ntiles = ((ctx->width + TILE_W - 1) / TILE_W) * ((ctx->height + TILE_H - 1) / TILE_H);
+    bool bins_fit = (size_t)ntiles * mesh->nf * sizeof(BinHead) <= ((size_t)4 << 30);
+    return render_device(ctx, mesh->verts, mesh->nv, mesh->faces, mesh->nf, camera, settings, fog, nullptr, may_blend || !bins_fit, false, clear_rgba);
+}
+
+uint64_t b32_graph_launches(const b32_ctx* ctx) { return ctx ? ctx->graph_launches : 0; }
 
 int b32_fb_download_async(b32_ctx* ctx, uint8_t* rgba, float* z) {
     if (!ctx) return B32_ERR_INVALID;

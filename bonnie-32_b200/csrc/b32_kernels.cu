@@ -22,6 +22,8 @@
 //   * Pass 2 blends against the running colour, so it is replayed in exact draw order from lists
 //     that a stable radix sort and a stable tile binning produce.
 #include <algorithm>
+#include <tuple>
+#include <utility>
 
 #include "b32_device.cuh"
 
@@ -1298,17 +1300,41 @@ __global__ void k_tex8_flags(const uint32_t* __restrict__ texels, TexDev* __rest
 // =================================================================================================
 // launchers (host)
 // =================================================================================================
-// launch with (optionally) the programmatic-stream-serialization attribute: the kernel may start before the
-// previous kernel on the stream has finished; it orders itself with pdl_wait()
-template <typename... KArgs, typename... Args>
-static void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl, Args&&... args) {
+// Launch a frame kernel, optionally with the programmatic-stream-serialization attribute (the kernel may start
+// before the previous kernel on the stream has finished; it orders itself with pdl_wait()).  With L.patch set
+// the arguments go into the matching kernel node of an instantiated graph instead (see GraphPatch).
+template <typename... KArgs, typename... Args, size_t... I>
+static void launch_k_impl(const LaunchCtx& L, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, bool pdl,
+                          std::index_sequence<I...>, Args&&... args) {
+    std::tuple<KArgs...> vals(static_cast<KArgs>(args)...);
+    void* ptrs[] = {static_cast<void*>(&std::get<I>(vals))...};
+    ++*L.launches;
+    if (L.patch) {
+        GraphPatch& g = *L.patch;
+        for (int i = 0; i < g.n; ++i)
+            if (g.func[i] == reinterpret_cast<void*>(kern) && !g.used[i]) {
+                cudaKernelNodeParams np{};
+                np.func = reinterpret_cast<void*>(kern); np.gridDim = grid; np.blockDim = block;
+                np.sharedMemBytes = (unsigned)smem; np.kernelParams = ptrs; np.extra = nullptr;
+                cudaError_t e = cudaGraphExecKernelNodeSetParams(g.exec, g.node[i], &np);
+                if (e != cudaSuccess) g.err = e;
+                g.used[i] = true;
+                return;
+            }
+        g.err = cudaErrorInvalidValue;           // the graph has no node for this kernel: topology changed
+        return;
+    }
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = L.stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = pdl ? 1u : 0u;
-    cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+    cudaLaunchKernelExC(&cfg, reinterpret_cast<const void*>(kern), ptrs);
+}
+template <typename... KArgs, typename... Args>
+static void launch_k(const LaunchCtx& L, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, bool pdl, Args&&... args) {
+    launch_k_impl(L, kern, grid, block, smem, pdl, std::index_sequence_for<KArgs...>{}, std::forward<Args>(args)...);
 }
 
 static inline uint32_t grid_for(uint32_t n, uint32_t block, uint32_t sms, uint32_t per_sm = 8) {
@@ -1328,9 +1354,8 @@ void launch_setup(const LaunchCtx& L, const b32_vertex* verts, const b32_face* f
                   uint32_t* tile_count, WireTri* wire, CallState* st, uint32_t* zero_next, uint32_t zero_words, const CallParams& p) {
     if (p.nf == 0) return;
     const bool pass1 = !((p.xray_mode && !p.rgb888) || p.wire_front);        // wireframe_overlay draws no solid surfaces (:2550)
-    k_setup<<<grid_for(p.nf, SETUP_THREADS, L.sms, 16), SETUP_THREADS, 0, L.stream>>>(verts, faces, tv, tex, lights, recs, keys, heads, wire, st,
-                                                                                      zero_next, zero_words, p);
-    ++*L.launches;
+    launch_k(L, k_setup, grid_for(p.nf, SETUP_THREADS, L.sms, 16), SETUP_THREADS, 0, false, verts, faces, tv, tex, lights, recs, keys, heads, wire, st,
+             zero_next, zero_words, p);
     if (!pass1) return;
     launch_bin(L, heads, keys, recs, bins, tile_count, st, p, p.bin_cap, false, true);
 }
@@ -1345,8 +1370,7 @@ void launch_bin(const LaunchCtx& L, const BinHead* heads, const uint64_t* keys, 
     uint32_t per_round = BIN_THREADS;
     uint32_t grid = (p.nf + per_round - 1) / per_round;
     if (grid > L.sms * 4) grid = L.sms * 4;
-    launch_k(k_bin_opaque, grid, BIN_THREADS, smem, L.stream, after_setup, heads, keys, recs, bins, tile_count, st, p, bin_cap, ordered);
-    ++*L.launches;
+    launch_k(L, k_bin_opaque, grid, BIN_THREADS, smem, after_setup, heads, keys, recs, bins, tile_count, st, p, bin_cap, ordered);
 }
 
 void launch_fill_opaque(const LaunchCtx& L, const SurfRec* recs, const BinHead* bins, const uint32_t* tile_count,
@@ -1361,9 +1385,8 @@ void launch_fill_opaque(const LaunchCtx& L, const SurfRec* recs, const BinHead* 
         attr_set = true;
     }
     // launched right behind k_bin_opaque except in x-ray mode (no pass-1 binning: then it is an ordinary launch)
-    launch_k(p.rgb888 ? k_fill_opaque<true> : k_fill_opaque<false>, ntiles * OP_SPLIT, OP_THREADS, OP_SMEM, L.stream, !(p.xray_mode && !p.rgb888),
+    launch_k(L, p.rgb888 ? k_fill_opaque<true> : k_fill_opaque<false>, ntiles * OP_SPLIT, OP_THREADS, OP_SMEM, !(p.xray_mode && !p.rgb888),
              recs, bins, tile_count, tex, texels, texmask, fb_rgba, fb_z, st, sticky, p);
-    ++*L.launches;
 }
 
 void launch_fill_ordered(const LaunchCtx& L, const SurfRec* recs, BinHead* obins, const uint32_t* otile_count,
@@ -1387,8 +1410,7 @@ void launch_wire(const LaunchCtx& L, const WireTri* wire, uint32_t kind, uint32_
 
 void launch_fb_clear(const LaunchCtx& L, uint32_t* rgba, float* z, uint32_t n, uint32_t color) {
     if (n == 0) return;
-    k_fb_clear<<<grid_for(n, 256, L.sms), 256, 0, L.stream>>>(rgba, z, n, color);
-    ++*L.launches;
+    launch_k(L, k_fb_clear, grid_for(n, 256, L.sms), 256, 0, false, rgba, z, n, color);
 }
 
 void launch_tex_expand(const LaunchCtx& L, const uint8_t* idx, const uint16_t* clut, uint32_t clut_len, uint32_t format, uint32_t n, uint16_t* out) {

@@ -10,10 +10,23 @@
 
 namespace b32 {
 
+// An instantiated CUDA graph of one enqueued frame (k_fb_clear, k_setup, k_bin_opaque, k_fill_opaque) whose
+// kernel nodes are re-parameterised in place: when LaunchCtx.patch is set, the frame kernels' launchers write
+// their arguments into the graph's nodes instead of launching, and the caller launches the graph once.
+struct GraphPatch {
+    cudaGraphExec_t exec = nullptr;
+    int n = 0;
+    cudaGraphNode_t node[8];
+    void* func[8];
+    bool used[8];
+    cudaError_t err = cudaSuccess;
+};
+
 struct LaunchCtx {
     cudaStream_t stream;
     uint32_t sms;                 // SM count of the device: grids are sized in multiples of it
     uint64_t* launches;           // counter of this library's own kernel launches
+    GraphPatch* patch = nullptr;  // non-null: patch graph nodes instead of launching
 };
 
 void launch_transform(const LaunchCtx& L, const b32_vertex* verts, TVert* out, float* dbg_cam, const CallParams& p);

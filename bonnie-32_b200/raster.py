@@ -272,6 +272,9 @@ class Context:
     def kernel_launches(self) -> int:
         return int(self.lib.b32_kernel_launches(self.h))
 
+    def graph_launches(self) -> int:
+        return int(self.lib.b32_graph_launches(self.h))
+
     def set_textures(self, textures: Sequence[Texture15]):
         arr, keep = tex_descs(textures)
         self.check(self.lib.b32_textures_set(self.h, arr, len(textures)))
@@ -409,6 +412,19 @@ class Mesh:
         tm = abi.Timings()
         self.ctx.check(self.ctx.lib.b32_render_mesh_15_resident(self.ctx.h, self.h, C.byref(cam), C.byref(s), fgp, C.byref(tm)))
         return tm.as_dict()
+
+    def frame_enqueue(self, clear, camera: Camera, settings: RasterSettings, fog=None):
+        """b32_frame_15_enqueue: Framebuffer::clear(clear) (None = keep) + render_mesh_15 as one enqueued frame
+        (a CUDA graph launch from the third frame of this mesh on).  Errors surface at sync / download."""
+        cam = camera.to_abi()
+        s, keep = settings.to_abi()
+        fg = fog_to_abi(fog)
+        col = None
+        if clear is not None:
+            a = 0 if (len(clear) > 3 and clear[3] == abi.BLEND_ERASE) else 255
+            col = (C.c_uint8 * 4)(clear[0], clear[1], clear[2], a)
+        self.ctx.check(self.ctx.lib.b32_frame_15_enqueue(self.ctx.h, col, self.h, C.byref(cam), C.byref(s),
+                                                         C.byref(fg) if fg is not None else None))
 
     def render_rgb888(self, camera: Camera, settings: RasterSettings):
         """render_mesh (RGB888) on the resident geometry; textures come from Context.set_textures_rgb888."""

@@ -216,6 +216,15 @@ int  b32_render_mesh_15_enqueue(b32_ctx* ctx, const b32_mesh* mesh,
                                 const b32_camera* camera, const b32_settings* settings,
                                 const b32_fog* fog_or_null);
 
+/* Framebuffer::clear(color) + render_mesh_15 on resident geometry as ONE enqueued frame (clear_rgba = 4 bytes
+ * r, g, b, a; NULL = no clear).  From the third frame of one mesh / framebuffer size on, the frame is replayed as
+ * a CUDA graph whose kernel nodes are re-parameterised in place (camera, settings, lights, fog change freely):
+ * one driver call per frame instead of one per kernel.  b32_render_mesh_15_enqueue takes the same path. */
+int  b32_frame_15_enqueue(b32_ctx* ctx, const uint8_t* clear_rgba, const b32_mesh* mesh,
+                          const b32_camera* camera, const b32_settings* settings, const b32_fog* fog_or_null);
+/* Number of frames launched as graphs on this context so far. */
+uint64_t b32_graph_launches(const b32_ctx* ctx);
+
 /* ---- the RGB888 sibling (RasterSettings.use_rgb555 == false) ----------------------------- */
 /* `textures: &[Texture]` of render_mesh: a second texture table, independent of b32_textures_set's. */
 int b32_textures_set_rgb888(b32_ctx* ctx, const b32_tex8_desc* descs, uint32_t n);

@@ -406,3 +406,56 @@ def test_rgb888_error_codes(ctx, oracle):
     pkg.render_mesh(fb, v, sc.faces, sc.textures8, sc.camera, zs)
     want, want_z, otm, rc = oracle.render_scene888(dataclasses.replace(sc, vertices=v, settings=zs))
     assert rc == 0 and np.array_equal(fb.download()[0], want)
+
+
+# ---- enqueued frames replayed as a CUDA graph with re-parameterised kernel nodes --------------------------
+def test_frame_graph_replay_matches_oracle(ctx, oracle):
+    """b32_frame_15_enqueue: frames 3.. of one mesh are graph launches; camera / settings / fog / lights / clear colour
+    change every frame and every frame must still equal the oracle.  A second mesh and a resize rebuild the graph."""
+    base = cases.feature_scenes(300)
+    a = next(s for s in base if s.name == "gouraud_lights")
+    b = scenes.scene_c2(n_tris=500, seed=77)
+    fb = pkg.Framebuffer(a.width, a.height, ctx)
+    ctx.set_textures(a.textures)
+    g0 = ctx.graph_launches()
+    variants = [dict(), dict(use_zbuffer=False), dict(dithering=False, shading=abi.SHADE_FLAT), dict(affine_textures=False),
+                dict(use_fixed_point=False), dict(ambient=0.9), dict(backface_cull=False)]
+    for sc, size in ((a, (320, 240)), (b, (320, 240)), (b, (200, 150)), (a, (320, 240))):
+        fb.resize(*size)
+        ctx.set_textures(sc.textures)
+        mesh = pkg.Mesh(ctx, sc.vertices, sc.faces)
+        for i, kw in enumerate(variants):
+            st = dataclasses.replace(sc.settings, **kw)
+            cam = cases._rotated_camera(0.02 * i, -0.03 * i, (0.1 * i, -0.05 * i, -0.2 * i))
+            fog = (10.0, 30.0, 50.0 + i, (90, 110, 130)) if i % 3 == 2 else None
+            clear = (20 + i, 22, 28 + 2 * i)
+            mesh.frame_enqueue(clear, cam, st, fog)
+            got, got_z = fb.download()
+            want = np.empty((size[1], size[0], 4), np.uint8); want_z = np.empty((size[1], size[0]), np.float32)
+            want[...] = np.array(list(clear) + [255], np.uint8); want_z[...] = np.finfo(np.float32).max
+            rc, otm, _ = oracle.render_mesh_15(want, want_z, sc.vertices, sc.faces, sc.textures, cam, st, fog)
+            assert rc == 0
+            assert np.array_equal(got, want), (sc.name, size, i)
+            assert np.array_equal(got_z.view(np.uint32), want_z.view(np.uint32)), (sc.name, size, i)
+        mesh.free()
+    assert ctx.graph_launches() - g0 >= 4 * (len(variants) - 1) - 4      # all but the first frame(s) of each topology
+
+
+def test_frame_graph_reports_errors_at_sync(ctx):
+    """A NaN sort key in an enqueued (graph) frame surfaces at the next sync, as for plain enqueues."""
+    sc = scenes.scene_c2(n_tris=300)
+    fb = pkg.Framebuffer(sc.width, sc.height, ctx)
+    ctx.set_textures(sc.textures)
+    v = sc.vertices.copy()
+    mesh = pkg.Mesh(ctx, v, sc.faces)
+    for _ in range(3):
+        mesh.frame_enqueue(sc.clear, sc.camera, sc.settings)
+    ctx.sync()
+    f = sc.faces.copy(); f["v"][5, 2] = len(v) + 7
+    bad = pkg.Mesh(ctx, v, f)
+    for _ in range(4):
+        bad.frame_enqueue(sc.clear, sc.camera, sc.settings)
+    with pytest.raises(pkg.B32Error) as e:
+        ctx.sync()
+    assert e.value.code == abi.B32_ERR_OOB_INDEX
+    mesh.free(); bad.free()
