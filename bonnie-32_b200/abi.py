@@ -30,7 +30,8 @@ RENDER_ASYNC, RENDER_ALL_OPAQUE = 1, 2
 # ---- POD records as numpy dtypes (b32_vertex 36 B, b32_face 16 B) ---------------------------
 VERTEX_DTYPE = np.dtype([("pos", "<f4", 3), ("uv", "<f4", 2), ("normal", "<f4", 3), ("rgba", "u1", 4)])
 FACE_DTYPE = np.dtype([("v", "<u4", 3), ("flags", "<u4")])
-assert VERTEX_DTYPE.itemsize == 36 and FACE_DTYPE.itemsize == 16
+SKY_VERTEX_DTYPE = np.dtype([("pos", "<f4", 3), ("rgb", "u1", 3), ("_pad", "u1")])     # b32_sky_vertex
+assert VERTEX_DTYPE.itemsize == 36 and FACE_DTYPE.itemsize == 16 and SKY_VERTEX_DTYPE.itemsize == 16
 
 
 def face_flags(tex_id=FACE_TEX_NONE, blend=BLEND_OPAQUE, black_transparent=True, editor_alpha=255):
@@ -116,6 +117,7 @@ SYMBOLS = {
     "b32_render_mesh_resident": (C.c_int, [_P, _P, C.POINTER(Camera), C.POINTER(Settings), C.POINTER(Timings)]),
     "b32_frame_15_enqueue": (C.c_int, [_P, _P, _P, C.POINTER(Camera), C.POINTER(Settings), C.POINTER(Fog)]),
     "b32_graph_launches": (C.c_uint64, [_P]),
+    "b32_render_skybox_mesh": (C.c_int, [_P, _P, C.c_uint32, _P, C.c_uint32, C.POINTER(Camera)]),
     "b32_host_alloc": (_P, [C.c_size_t]),
     "b32_host_free": (None, [_P]),
     "b32_debug_transform": (C.c_int, [_P, _P, C.c_uint32, C.POINTER(Camera), C.POINTER(Settings), _P, _P]),

@@ -793,6 +793,45 @@ int b32_render_mesh_15_enqueue(b32_ctx* ctx, const b32_mesh* mesh, const b32_cam
     return render_device(ctx, mesh->verts, mesh->nv, mesh->faces, mesh->nf, camera, settings, fog, nullptr, may_blend || !bins_fit);
 }
 
+int b32_render_skybox_mesh(b32_ctx* ctx, const b32_sky_vertex* vertices, uint32_t nv, const uint32_t* faces, uint32_t nf, const b32_camera* camera) {
+    if (!ctx || !camera) return B32_ERR_INVALID;
+    if ((nv && !vertices) || (nf && !faces)) return fail(ctx, B32_ERR_INVALID, "vertices/faces is NULL");
+    if (ctx->width == 0 || ctx->height == 0) return fail(ctx, B32_ERR_INVALID, "framebuffer has zero size (call b32_fb_resize)");
+    if (nf == 0) return B32_OK;
+    b32_settings s{};                     // project(): the float path, no ortho (render.rs:89, :107)
+    CallParams p; std::vector<LightDev> lights;
+    int rc = fill_params(ctx, p, camera, &s, nullptr, nv, nf, lights); if (rc) return rc;
+    rc = ensure_work(ctx, nv, nf); if (rc) return rc;
+    // the sky mesh reuses the mesh staging and record buffers (a SkyRec is smaller than a SurfRec)
+    static_assert(sizeof(SkyRec) <= sizeof(SurfRec) && sizeof(b32_sky_vertex) <= sizeof(b32_vertex), "staging reuse");
+    CK(ctx->verts.reserve(std::max<uint32_t>(nv, 1)));
+    CK(ctx->faces.reserve(std::max<uint32_t>(nf, 1)));      // 3 x u32 per face fits the 16-byte b32_face slots
+    rc = h2d(ctx, ctx->verts.p, vertices, (size_t)nv * sizeof(b32_sky_vertex)); if (rc) return rc;
+    rc = h2d(ctx, ctx->faces.p, faces, (size_t)nf * 12); if (rc) return rc;
+    const uint32_t ntiles = p.tiles_x * p.tiles_y;
+    cudaStream_t st = ctx->stream;
+    for (int attempt = 0;; ++attempt) {
+        p.bin_cap = pick_bin_cap(ctx, nf, ntiles, false);
+        CK(ctx->bins.reserve((size_t)ntiles * p.bin_cap));
+        ctx->state_cur ^= 1;
+        ctx->state = reinterpret_cast<CallState*>(ctx->state_ring.p + (size_t)ctx->state_cur * ctx->state_stride);
+        ctx->tile_count = ctx->state_ring.p + (size_t)ctx->state_cur * ctx->state_stride + STATE_WORDS;
+        uint32_t* zero_next = ctx->state_ring.p + (size_t)(ctx->state_cur ^ 1) * ctx->state_stride;
+        launch_sky(ctx->L(), reinterpret_cast<const b32_sky_vertex*>(ctx->verts.p), reinterpret_cast<const uint32_t*>(ctx->faces.p),
+                   reinterpret_cast<SkyRec*>(ctx->recs.p), ctx->heads.p, ctx->bins.p, ctx->tile_count, ctx->fb_rgba.p, ctx->state,
+                   zero_next, ctx->state_stride, p);
+        CK(cudaMemcpyAsync(ctx->state_h, ctx->state, sizeof(CallState), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        CallState hs = *ctx->state_h;
+        if (hs.oob) return fail(ctx, B32_ERR_OOB_INDEX, "skybox face vertex index out of range (reference: slice index panic)");
+        if (hs.bin_overflow && attempt < 4) { ctx->bin_cap_hint = hs.bin_max + hs.bin_max / 4; continue; }
+        if (hs.bin_overflow) return fail(ctx, B32_ERR_CUDA, "tile bin overflow persists");
+        break;
+    }
+    return B32_OK;
+}
+
 void* b32_host_alloc(size_t bytes) {
     void* p = nullptr;
     if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }

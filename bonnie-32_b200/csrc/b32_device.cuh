@@ -70,6 +70,14 @@ struct __align__(16) BinHead {
 };
 static_assert(sizeof(BinHead) == 16, "BinHead must be 16 bytes");
 
+// One drawable triangle of the skybox sphere pass (rasterize_skybox_triangle's arguments, render.rs:242-250)
+struct __align__(16) SkyRec {
+    float p0x, p0y, p1x, p1y, p2x, p2y, inv_denom;
+    uint32_t c0, c1, c2;                  // vertex colours r | g<<8 | b<<16
+    uint32_t _pad0, _pad1;
+};
+static_assert(sizeof(SkyRec) == 48, "SkyRec must be 48 bytes");
+
 // A triangle collected for the wireframe phase (render.rs:2448-2450, :2509-2511): projected x, y, z of
 // the ORIGINAL (unswapped) v1, v2, v3.  kind: 0 none, 1 back face, 2 front face.
 struct WireTri { float x[3], y[3], z[3]; uint32_t kind; };

@@ -1242,6 +1242,98 @@ k_wire(const WireTri* __restrict__ wire, uint32_t nf, uint32_t kind, uint32_t co
 }
 
 // =================================================================================================
+// skybox sphere pass: Framebuffer::render_skybox step 1 (render.rs:89-139) + rasterize_skybox_triangle (:242-299)
+// =================================================================================================
+// Faces are drawn in order into pixels nothing else reads (no depth, no blending), so a pixel's final colour is that
+// of the LAST face covering its centre: order-free like pass 1, with the face index as priority.  k_sky_setup
+// projects + culls one face per thread and emits a bin head (walked into the tile bins by k_bin_opaque);
+// k_sky_fill gives each pixel of a tile to one thread.
+__global__ void __launch_bounds__(128)
+k_sky_setup(const b32_sky_vertex* __restrict__ verts, const uint32_t* __restrict__ faces, SkyRec* __restrict__ recs,
+            BinHead* __restrict__ heads, CallState* __restrict__ st, uint32_t* __restrict__ zero_next, uint32_t zero_words, CallParams p) {
+    pdl_launch_dependents();
+    if (blockIdx.x == 0) for (uint32_t i = threadIdx.x; i < zero_words; i += blockDim.x) zero_next[i] = 0;
+    for (uint32_t fi = blockIdx.x * blockDim.x + threadIdx.x; fi < p.nf; fi += gridDim.x * blockDim.x) {
+        BinHead head{0, 0, 0, fi};
+        do {
+            uint32_t i0 = faces[fi * 3], i1 = faces[fi * 3 + 1], i2 = faces[fi * 3 + 2];
+            if (i0 >= p.nv || i1 >= p.nv || i2 >= p.nv) { st->oob = 1; break; }
+            const b32_sky_vertex a = verts[i0], b = verts[i1], c = verts[i2];
+            // rel_pos, perspective_transform, `cam_space.z <= 0.1` => NaN marker, project (:96-108): the float path
+            TVert t0 = transform_vertex(a.pos[0], a.pos[1], a.pos[2], p, nullptr);
+            TVert t1 = transform_vertex(b.pos[0], b.pos[1], b.pos[2], p, nullptr);
+            TVert t2 = transform_vertex(c.pos[0], c.pos[1], c.pos[2], p, nullptr);
+            if (t0.w <= 0.1f || t1.w <= 0.1f || t2.w <= 0.1f) break;                              // :118-120
+            if (t0.x != t0.x || t1.x != t1.x || t2.x != t2.x) break;                              // a NaN x also drops the face
+            float signed_area = (t1.x - t0.x) * (t2.y - t0.y) - (t2.x - t0.x) * (t1.y - t0.y);    // :124
+            if (signed_area >= 0.0f) break;
+            // rasterize_skybox_triangle: inclusive bbox (:252-259), degenerate test (:262-266)
+            uint32_t min_x = f2u32sat(fmaxf(fminf(fminf(t0.x, t1.x), t2.x), 0.0f));
+            uint32_t max_x = f2u32sat(fminf(fmaxf(fmaxf(t0.x, t1.x), t2.x), (float)p.width - 1.0f));
+            uint32_t min_y = f2u32sat(fmaxf(fminf(fminf(t0.y, t1.y), t2.y), 0.0f));
+            uint32_t max_y = f2u32sat(fminf(fmaxf(fmaxf(t0.y, t1.y), t2.y), (float)p.height - 1.0f));
+            if (min_x > max_x || min_y > max_y) break;
+            if (max_x >= p.width || max_y >= p.height) break;      // only for NaN-free garbage (w or h = 0 never reaches here)
+            float denom = (t1.y - t2.y) * (t0.x - t2.x) + (t2.x - t1.x) * (t0.y - t2.y);
+            if (fabsf(denom) < 0.0001f) break;
+            SkyRec r;
+            r.p0x = t0.x; r.p0y = t0.y; r.p1x = t1.x; r.p1y = t1.y; r.p2x = t2.x; r.p2y = t2.y;
+            r.inv_denom = 1.0f / denom;
+            r.c0 = a.r | (a.g << 8) | (a.b << 16); r.c1 = b.r | (b.g << 8) | (b.b << 16); r.c2 = c.r | (c.g << 8) | (c.b << 16);
+            r._pad0 = r._pad1 = 0;
+            recs[fi] = r;
+            head = BinHead{min_x | ((max_x + 1) << 16), min_y | ((max_y + 1) << 16), 0u, fi};   // exclusive max, as the mesh bins
+        } while (0);
+        heads[fi] = head;
+    }
+}
+
+__global__ void __launch_bounds__(FILL_THREADS)
+k_sky_fill(const SkyRec* __restrict__ recs, const BinHead* __restrict__ bins, const uint32_t* __restrict__ tile_count,
+           uint32_t* __restrict__ fb_rgba, const CallState* __restrict__ st, CallParams p) {
+    __shared__ BinHead s_head[FILL_THREADS];
+    pdl_wait();
+    {
+        CallState s = *st;
+        if (s.oob || s.bin_overflow) return;
+    }
+    const uint32_t tile = blockIdx.x;
+    const uint32_t n = tile_count[tile];
+    if (n == 0) return;
+    const BinHead* bin = bins + (size_t)tile * p.bin_cap;
+    const uint32_t x = (tile % p.tiles_x) * TILE_W + (threadIdx.x % TILE_W), y = (tile / p.tiles_x) * TILE_H + (threadIdx.x / TILE_W);
+    const bool valid = x < p.width && y < p.height;
+    const float px = (float)x + 0.5f, py = (float)y + 0.5f;                                      // :270-271
+    uint32_t best = 0;                                       // face + 1 of the last face covering this pixel centre
+    for (uint32_t base = 0; base < n; base += FILL_THREADS) {
+        __syncthreads();
+        if (base + threadIdx.x < n) s_head[threadIdx.x] = bin[base + threadIdx.x];
+        __syncthreads();
+        const uint32_t cnt = min((uint32_t)FILL_THREADS, n - base);
+        for (uint32_t i = 0; i < cnt; ++i) {
+            const BinHead h = s_head[i];
+            if (h.face + 1 <= best) continue;
+            if (!(valid && x >= (h.bbox_x & 0xFFFF) && x < (h.bbox_x >> 16) && y >= (h.bbox_y & 0xFFFF) && y < (h.bbox_y >> 16))) continue;
+            const SkyRec r = recs[h.face];
+            float w0 = ((r.p1y - r.p2y) * (px - r.p2x) + (r.p2x - r.p1x) * (py - r.p2y)) * r.inv_denom;   // :274-276
+            float w1 = ((r.p2y - r.p0y) * (px - r.p2x) + (r.p0x - r.p2x) * (py - r.p2y)) * r.inv_denom;
+            float w2 = 1.0f - w0 - w1;
+            if (w0 >= 0.0f && w1 >= 0.0f && w2 >= 0.0f) best = h.face + 1;
+        }
+    }
+    if (best) {
+        const SkyRec r = recs[best - 1];
+        float w0 = ((r.p1y - r.p2y) * (px - r.p2x) + (r.p2x - r.p1x) * (py - r.p2y)) * r.inv_denom;
+        float w1 = ((r.p2y - r.p0y) * (px - r.p2x) + (r.p0x - r.p2x) * (py - r.p2y)) * r.inv_denom;
+        float w2 = 1.0f - w0 - w1;
+        uint32_t cr = f2u8((float)(r.c0 & 0xFF) * w0 + (float)(r.c1 & 0xFF) * w1 + (float)(r.c2 & 0xFF) * w2);          // :281-283
+        uint32_t cg = f2u8((float)((r.c0 >> 8) & 0xFF) * w0 + (float)((r.c1 >> 8) & 0xFF) * w1 + (float)((r.c2 >> 8) & 0xFF) * w2);
+        uint32_t cb = f2u8((float)(r.c0 >> 16) * w0 + (float)(r.c1 >> 16) * w1 + (float)(r.c2 >> 16) * w2);
+        fb_rgba[y * p.width + x] = cr | (cg << 8) | (cb << 16) | 0xFF000000u;
+    }
+}
+
+// =================================================================================================
 // small utility kernels
 // =================================================================================================
 __global__ void k_fb_clear(uint32_t* __restrict__ rgba, float* __restrict__ z, uint32_t n, uint32_t color) {
@@ -1417,6 +1509,14 @@ void launch_tex_expand(const LaunchCtx& L, const uint8_t* idx, const uint16_t* c
     if (n == 0) return;
     k_tex_expand<<<grid_for(n, 256, L.sms), 256, 0, L.stream>>>(idx, clut, clut_len, format, n, out);
     ++*L.launches;
+}
+
+void launch_sky(const LaunchCtx& L, const b32_sky_vertex* verts, const uint32_t* faces, SkyRec* recs, BinHead* heads, BinHead* bins,
+                uint32_t* tile_count, uint32_t* fb_rgba, CallState* st, uint32_t* zero_next, uint32_t zero_words, const CallParams& p) {
+    if (p.nf == 0) return;
+    launch_k(L, k_sky_setup, grid_for(p.nf, 128, L.sms, 16), 128, 0, false, verts, faces, recs, heads, st, zero_next, zero_words, p);
+    launch_bin(L, heads, nullptr, nullptr, bins, tile_count, st, p, p.bin_cap, false, true);
+    launch_k(L, k_sky_fill, p.tiles_x * p.tiles_y, FILL_THREADS, 0, true, recs, bins, tile_count, fb_rgba, st, p);
 }
 
 void launch_tex_mask(const LaunchCtx& L, const uint16_t* texels, uint32_t n_texels, uint32_t n_words, uint32_t* mask) {

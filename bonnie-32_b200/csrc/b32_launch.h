@@ -50,6 +50,10 @@ void launch_wire(const LaunchCtx& L, const WireTri* wire, uint32_t kind, uint32_
 void launch_fb_clear(const LaunchCtx& L, uint32_t* rgba, float* z, uint32_t n, uint32_t color);
 void launch_tex_expand(const LaunchCtx& L, const uint8_t* idx, const uint16_t* clut, uint32_t clut_len, uint32_t format, uint32_t n, uint16_t* out);
 
+// skybox sphere pass (render.rs:81-139, :242-299): setup -> tile binning (k_bin_opaque) -> fill
+void launch_sky(const LaunchCtx& L, const b32_sky_vertex* verts, const uint32_t* faces, SkyRec* recs, BinHead* heads, BinHead* bins,
+                uint32_t* tile_count, uint32_t* fb_rgba, CallState* st, uint32_t* zero_next, uint32_t zero_words, const CallParams& p);
+
 // bit i of mask = texel i of the pool writes when its surface is black-keyed; n_words covers n_texels, zero padded
 void launch_tex_mask(const LaunchCtx& L, const uint16_t* texels, uint32_t n_texels, uint32_t n_words, uint32_t* mask);
 

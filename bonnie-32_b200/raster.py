@@ -335,6 +335,14 @@ class Framebuffer:
         self.ctx.check(self.ctx.lib.b32_fb_download(self.ctx.h, px.ctypes.data, zb.ctypes.data if want_z else None))
         return px, zb
 
+    def render_skybox_mesh(self, sky_vertices: np.ndarray, faces: np.ndarray, camera: "Camera"):
+        """Sphere pass of Framebuffer::render_skybox (render.rs:81-139): `sky_vertices` (abi.SKY_VERTEX_DTYPE) and
+        `faces` (int[nf,3]) are what Skybox::generate_mesh returns; stars stay a host pass."""
+        v = np.ascontiguousarray(sky_vertices, dtype=abi.SKY_VERTEX_DTYPE)
+        f = np.ascontiguousarray(faces, dtype=np.uint32).reshape(-1)
+        cam = camera.to_abi()
+        self.ctx.check(self.ctx.lib.b32_render_skybox_mesh(self.ctx.h, v.ctypes.data, len(v), f.ctypes.data, len(f) // 3, C.byref(cam)))
+
     @property
     def pixels(self) -> np.ndarray:
         return self.download(False)[0]

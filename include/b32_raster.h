@@ -238,6 +238,20 @@ int b32_render_mesh(b32_ctx* ctx,
 int b32_render_mesh_resident(b32_ctx* ctx, const b32_mesh* mesh,
                              const b32_camera* camera, const b32_settings* settings, b32_timings* timings);
 
+/* ---- skybox sphere pass (Framebuffer::render_skybox, render.rs:81-139) -------------------------------- */
+/* One vertex of Skybox::generate_mesh (src/world/geometry.rs:529-, struct SkyboxVertex :1027-1030): world position
+ * + colour.  The mesh (sphere + mountains, libm sin/cos/powf) is generated on the host as in the reference. */
+typedef struct b32_sky_vertex {
+    float   pos[3];
+    uint8_t r, g, b, _pad;
+} b32_sky_vertex;
+/* Step 1 of render_skybox: float transform + `project` of every vertex (behind-camera vertices drop their faces),
+ * inward-facing triangles only (signed area < 0), rasterize_skybox_triangle (render.rs:242-299): pixel centres,
+ * Gouraud vertex colours, no depth test or write, faces drawn in order (later ones overwrite).  faces = 3*nf
+ * vertex indices.  Step 2 (render_stars, libm sin/cos) stays on the host. */
+int b32_render_skybox_mesh(b32_ctx* ctx, const b32_sky_vertex* vertices, uint32_t nv,
+                           const uint32_t* faces, uint32_t nf, const b32_camera* camera);
+
 /* ---- pinned host memory for callers that want zero-copy DMA of their Vec buffers -------- */
 void* b32_host_alloc(size_t bytes);
 void  b32_host_free(void* p);

@@ -1166,4 +1166,56 @@ int b32o_render_mesh(uint8_t* fb_rgba, float* fb_z, uint32_t w, uint32_t h,
     return B32_OK;
 }
 
+// Framebuffer::render_skybox, step 1 (render.rs:89-139), with rasterize_skybox_triangle (render.rs:242-299) inlined
+int b32o_render_skybox_mesh(uint8_t* fb_rgba, uint32_t w, uint32_t h, const b32_sky_vertex* vertices, uint32_t nv,
+                            const uint32_t* faces, uint32_t nf, const b32_camera* camera) {
+    V3 cpos = mk3(camera->position), bx = mk3(camera->basis_x), by = mk3(camera->basis_y), bz = mk3(camera->basis_z);
+    struct P3 { float x, y, z; };
+    std::vector<P3> projected;
+    projected.reserve(nv);
+    const float nan = std::numeric_limits<float>::quiet_NaN();
+    for (uint32_t i = 0; i < nv; ++i) {                                              // :96-108
+        V3 world_pos = mk3(vertices[i].pos);
+        V3 rel_pos = sub(world_pos, cpos);
+        V3 cam_space = perspective_transform(rel_pos, bx, by, bz);
+        if (cam_space.z <= 0.1f) { projected.push_back(P3{nan, nan, nan}); continue; }
+        V3 screen = project(cam_space, w, h);
+        projected.push_back(P3{screen.x, screen.y, cam_space.z});
+    }
+    for (uint32_t fi = 0; fi < nf; ++fi) {                                           // :111-139
+        uint32_t i0 = faces[fi * 3], i1 = faces[fi * 3 + 1], i2 = faces[fi * 3 + 2];
+        if (i0 >= nv || i1 >= nv || i2 >= nv) return B32_ERR_OOB_INDEX;
+        P3 p0 = projected[i0], p1 = projected[i1], p2 = projected[i2];
+        if (p0.x != p0.x || p1.x != p1.x || p2.x != p2.x) continue;
+        float signed_area = (p1.x - p0.x) * (p2.y - p0.y) - (p2.x - p0.x) * (p1.y - p0.y);
+        if (signed_area >= 0.0f) continue;
+        const b32_sky_vertex &c0 = vertices[i0], &c1 = vertices[i1], &c2 = vertices[i2];
+        // rasterize_skybox_triangle, :242-299
+        uint64_t min_x = f2usize(rmax(rmin(rmin(p0.x, p1.x), p2.x), 0.0f));
+        uint64_t max_x = f2usize(rmin(rmax(rmax(p0.x, p1.x), p2.x), (float)w - 1.0f));
+        uint64_t min_y = f2usize(rmax(rmin(rmin(p0.y, p1.y), p2.y), 0.0f));
+        uint64_t max_y = f2usize(rmin(rmax(rmax(p0.y, p1.y), p2.y), (float)h - 1.0f));
+        if (min_x > max_x || min_y > max_y) continue;
+        float denom = (p1.y - p2.y) * (p0.x - p2.x) + (p2.x - p1.x) * (p0.y - p2.y);
+        if (std::fabs(denom) < 0.0001f) continue;
+        float inv_denom = 1.0f / denom;
+        for (uint64_t y = min_y; y <= max_y; ++y) {
+            for (uint64_t x = min_x; x <= max_x; ++x) {
+                float px = (float)x + 0.5f, py = (float)y + 0.5f;
+                float w0 = ((p1.y - p2.y) * (px - p2.x) + (p2.x - p1.x) * (py - p2.y)) * inv_denom;
+                float w1 = ((p2.y - p0.y) * (px - p2.x) + (p0.x - p2.x) * (py - p2.y)) * inv_denom;
+                float w2 = 1.0f - w0 - w1;
+                if (w0 >= 0.0f && w1 >= 0.0f && w2 >= 0.0f) {
+                    uint64_t idx = (y * w + x) * 4;
+                    fb_rgba[idx]     = f2u8((float)c0.r * w0 + (float)c1.r * w1 + (float)c2.r * w2);
+                    fb_rgba[idx + 1] = f2u8((float)c0.g * w0 + (float)c1.g * w1 + (float)c2.g * w2);
+                    fb_rgba[idx + 2] = f2u8((float)c0.b * w0 + (float)c1.b * w1 + (float)c2.b * w2);
+                    fb_rgba[idx + 3] = 255;
+                }
+            }
+        }
+    }
+    return B32_OK;
+}
+
 }  // extern "C"

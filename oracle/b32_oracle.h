@@ -69,6 +69,11 @@ int b32o_render_mesh(uint8_t* fb_rgba, float* fb_z, uint32_t w, uint32_t h,
                      const b32_camera* camera, const b32_settings* settings, b32_timings* timings,
                      uint32_t* draw_order, uint32_t cap, uint32_t* n_drawn);
 
+/* Framebuffer::render_skybox step 1 (sphere pass), render.rs:89-139 + rasterize_skybox_triangle :242-299. */
+int b32o_render_skybox_mesh(uint8_t* fb_rgba, uint32_t w, uint32_t h,
+                            const b32_sky_vertex* vertices, uint32_t nv, const uint32_t* faces, uint32_t nf,
+                            const b32_camera* camera);
+
 #ifdef __cplusplus
 }
 #endif

@@ -129,6 +129,18 @@ def render_scene888(scene, want_order=False):
     return fb_rgba, fb_z, tm, rc
 
 
+def render_skybox_mesh(fb_rgba, sky_vertices, faces, camera):
+    """Oracle sphere pass of Framebuffer::render_skybox into a caller-owned u8[h,w,4] array."""
+    abi = _abi()
+    h, w = fb_rgba.shape[:2]
+    v = np.ascontiguousarray(sky_vertices, dtype=abi.SKY_VERTEX_DTYPE)
+    f = np.ascontiguousarray(faces, dtype=np.uint32).reshape(-1)
+    cam = camera.to_abi()
+    lib().b32o_render_skybox_mesh.restype = C.c_int
+    return lib().b32o_render_skybox_mesh(C.c_void_p(fb_rgba.ctypes.data), C.c_uint32(w), C.c_uint32(h), C.c_void_p(v.ctypes.data),
+                                         C.c_uint32(len(v)), C.c_void_p(f.ctypes.data), C.c_uint32(len(f) // 3), C.byref(cam))
+
+
 def transform(vertices, camera, settings, w, h):
     abi = _abi()
     v = np.ascontiguousarray(vertices, dtype=abi.VERTEX_DTYPE)

@@ -684,6 +684,53 @@ def _fill888(fb_rgba, fb_z, s, tex_px, settings):
         px[wmask, 3] = 255
 
 
+# ------------------------------------------------------------------------------------------
+# Framebuffer::render_skybox step 1 (sphere pass): render.rs:89-139, rasterize_skybox_triangle :242-299
+# ------------------------------------------------------------------------------------------
+def render_skybox_mesh(fb_rgba, sky_vertices, faces, camera):
+    """sky_vertices: record array with pos f32[3], rgb u8[3]; faces int[nf,3]. No depth; faces in order."""
+    H, W = fb_rgba.shape[:2]
+    pos = np.asarray(sky_vertices["pos"], dtype=F)
+    col = np.asarray(sky_vertices["rgb"], dtype=I64)
+    cam_space = perspective_transform(pos - np.asarray(camera.position, dtype=F)[None, :], camera)
+    with np.errstate(all="ignore"):
+        vs = (F(min(W, H)) / F(2.0)) * F(0.75)                                       # math.rs:117-136
+        denom = cam_space[:, 2] + F(5.0)
+        tiny = np.abs(denom) < F(0.001)
+        sx = np.where(tiny, F(W) / F(2.0), (cam_space[:, 0] * F(4.0)) / denom * vs + (F(W) / F(2.0)))
+        sy = np.where(tiny, F(H) / F(2.0), (cam_space[:, 1] * F(4.0)) / denom * vs + (F(H) / F(2.0)))
+    behind = cam_space[:, 2] <= F(0.1)
+    for i0, i1, i2 in np.asarray(faces, dtype=I64).reshape(-1, 3):
+        if behind[i0] or behind[i1] or behind[i2]:
+            continue
+        p0 = (sx[i0], sy[i0]); p1 = (sx[i1], sy[i1]); p2 = (sx[i2], sy[i2])
+        with np.errstate(all="ignore"):
+            signed_area = (p1[0] - p0[0]) * (p2[1] - p0[1]) - (p2[0] - p0[0]) * (p1[1] - p0[1])
+            if signed_area >= 0:
+                continue
+            min_x = int(as_usize(fmax(fmin(fmin(p0[0], p1[0]), p2[0]), F(0.0))))
+            max_x = int(as_usize(fmin(fmax(fmax(p0[0], p1[0]), p2[0]), F(W) - F(1.0))))
+            min_y = int(as_usize(fmax(fmin(fmin(p0[1], p1[1]), p2[1]), F(0.0))))
+            max_y = int(as_usize(fmin(fmax(fmax(p0[1], p1[1]), p2[1]), F(H) - F(1.0))))
+            if min_x > max_x or min_y > max_y:
+                continue
+            den = (p1[1] - p2[1]) * (p0[0] - p2[0]) + (p2[0] - p1[0]) * (p0[1] - p2[1])
+            if np.abs(den) < F(0.0001):
+                continue
+            inv = F(1.0) / den
+            yy, xx = np.meshgrid(np.arange(min_y, max_y + 1), np.arange(min_x, max_x + 1), indexing="ij")
+            px = xx.astype(F) + F(0.5); py = yy.astype(F) + F(0.5)
+            w0 = ((p1[1] - p2[1]) * (px - p2[0]) + (p2[0] - p1[0]) * (py - p2[1])) * inv
+            w1 = ((p2[1] - p0[1]) * (px - p2[0]) + (p0[0] - p2[0]) * (py - p2[1])) * inv
+            w2 = F(1.0) - w0 - w1
+            m = (w0 >= 0) & (w1 >= 0) & (w2 >= 0)
+            out = fb_rgba[min_y:max_y + 1, min_x:max_x + 1]
+            for k in range(3):
+                v = as_u8(F(col[i0, k]) * w0 + F(col[i1, k]) * w1 + F(col[i2, k]) * w2)
+                out[..., k][m] = v[m]
+            out[..., 3][m] = 255
+
+
 def fb_clear(w, h, color):
     rgba = np.empty((h, w, 4), dtype=np.uint8)
     rgba[...] = np.array(list(color[:3]) + [255], dtype=np.uint8)

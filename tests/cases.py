@@ -222,3 +222,51 @@ def rgb888_scenes(n_tris=160):
     out.append(_with(ea, "rgb888_editor_alpha_zbuffer", use_zbuffer=True))
     out.append(_with(m, "rgb888_wire_backface", backface_wireframe=True, use_zbuffer=True))
     return out
+
+
+# ---- skybox sphere pass (Framebuffer::render_skybox step 1, render.rs:81-139) ------------------------------
+def sky_mesh(center, seed=5, h_segments=48, v_segments=32, radius=10000.0, n_mountains=40):
+    """A mesh shaped like Skybox::generate_mesh's (src/world/geometry.rs:529-): a vertex-coloured sphere around `center`
+    wound for inside viewing, plus a ring of peaked 'mountain' triangles slightly inside it, drawn after the sphere."""
+    u = scenes.splitmix64_u01(seed, (v_segments + 1) * (h_segments + 1) * 3 + n_mountains * 16)
+    k = 0
+    verts = []
+    for v in range(v_segments + 1):
+        phi = np.pi * v / v_segments
+        for h in range(h_segments + 1):
+            theta = 2.0 * np.pi * h / h_segments
+            d = (np.sin(phi) * np.cos(theta), np.cos(phi), np.sin(phi) * np.sin(theta))
+            col = tuple(int(u[k + c] * 256.0) for c in range(3)); k += 3
+            verts.append((tuple(center[c] + d[c] * radius for c in range(3)), col))
+    faces = []
+    rw = h_segments + 1
+    for v in range(v_segments):
+        for h in range(h_segments):
+            i0, i1, i2, i3 = v * rw + h, v * rw + h + 1, (v + 1) * rw + h, (v + 1) * rw + h + 1
+            faces += [(i0, i2, i1), (i1, i2, i3)]
+    r2 = radius * 0.97
+    for m in range(n_mountains):
+        t0 = 2.0 * np.pi * (m + u[k]) / n_mountains; wdt = 0.05 + 0.1 * u[k + 1]; hgt = 0.05 + 0.25 * u[k + 2]
+        base_phi = np.pi * 0.5 + 0.08
+        pts = [(t0 - wdt, base_phi), (t0 + wdt, base_phi), (t0, base_phi - hgt)]
+        b = len(verts)
+        for j, (th, ph) in enumerate(pts):
+            d = (np.sin(ph) * np.cos(th), np.cos(ph), np.sin(ph) * np.sin(th))
+            col = tuple(int(u[k + 3 + 3 * j + c] * 200.0) for c in range(3))
+            verts.append((tuple(center[c] + d[c] * r2 for c in range(3)), col))
+        k += 16
+        faces += [(b, b + 2, b + 1), (b, b + 1, b + 2)]          # both windings: one of them faces inward
+    sv = np.zeros(len(verts), dtype=abi.SKY_VERTEX_DTYPE)
+    sv["pos"] = np.array([p for p, _ in verts], dtype=np.float32)
+    sv["rgb"] = np.array([c for _, c in verts], dtype=np.uint8)
+    return sv, np.array(faces, dtype=np.uint32)
+
+
+def sky_cases():
+    """(name, width, height, camera) for the skybox pass; the mesh is centred on the camera as in the reference."""
+    out = []
+    for name, w, h, rx, ry, pos in [("sky_level", 320, 240, 0.0, 0.0, (0.0, 0.0, 0.0)), ("sky_look_up", 320, 240, -0.9, 0.4, (3.0, 2.0, -1.0)),
+                                    ("sky_look_down_turned", 320, 240, 0.7, 2.5, (100.0, -30.0, 250.0)), ("sky_640x480", 640, 480, 0.2, -1.3, (0.0, 5.0, 0.0)),
+                                    ("sky_straight_up", 200, 150, -1.5707964, 0.0, (0.0, 0.0, 0.0))]:
+        out.append((name, w, h, _rotated_camera(rx, ry, pos)))
+    return out

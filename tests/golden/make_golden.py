@@ -62,9 +62,24 @@ def main_rgb888():
         json.dump(hashes, f, indent=1, sort_keys=True)
 
 
+def main_sky():
+    """hashes_sky.json: the skybox sphere pass on cases.sky_cases(), numpy model."""
+    hashes = {}
+    for name, w, h, cam in cases.sky_cases():
+        sv, f = cases.sky_mesh(cam.position)
+        rgba, _ = pymodel.fb_clear(w, h, (0, 0, 0))
+        pymodel.render_skybox_mesh(rgba, sv, f, cam)
+        hashes[name] = hashlib.sha256(rgba.tobytes()).hexdigest()
+        print(name, hashes[name][:16])
+    with open(os.path.join(HERE, "hashes_sky.json"), "w") as f_:
+        json.dump(hashes, f_, indent=1, sort_keys=True)
+
+
 def main():
     if "--rgb888" in sys.argv:
         return main_rgb888()
+    if "--sky" in sys.argv:
+        return main_sky()
     hashes = {}
     for sc in golden_scenes():
         t = time.time()

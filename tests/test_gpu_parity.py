@@ -459,3 +459,42 @@ def test_frame_graph_reports_errors_at_sync(ctx):
         ctx.sync()
     assert e.value.code == abi.B32_ERR_OOB_INDEX
     mesh.free(); bad.free()
+
+
+# ---- skybox sphere pass ---------------------------------------------------------------------------------------
+SKY = cases.sky_cases()
+
+
+@pytest.mark.parametrize("name,w,h,cam", SKY, ids=[c[0] for c in SKY])
+def test_skybox_mesh(ctx, oracle, name, w, h, cam):
+    sv, f = cases.sky_mesh(cam.position)
+    fb = pkg.Framebuffer(w, h, ctx)
+    fb.clear((0, 0, 0))
+    _, z0 = fb.download()
+    fb.render_skybox_mesh(sv, f, cam)
+    got, got_z = fb.download()
+    want = np.zeros((h, w, 4), np.uint8); want[..., 3] = 255
+    assert oracle.render_skybox_mesh(want, sv, f, cam) == 0
+    bad = (got != want).any(-1)
+    assert not bad.any(), f"{name}: {bad.sum()} pixels differ"
+    assert np.array_equal(got_z.view(np.uint32), z0.view(np.uint32))     # the sky never touches the z-buffer
+
+
+def test_skybox_then_scene_composes(ctx, oracle):
+    """Game frame order (src/game/renderer.rs:91-137): clear, skybox, then the rooms over it."""
+    name, w, h, cam = SKY[1]
+    sv, f = cases.sky_mesh(cam.position)
+    sc = scenes.scene_c2(n_tris=400, use_zbuffer=True)
+    fb = pkg.Framebuffer(w, h, ctx)
+    fb.clear((0, 0, 0))
+    fb.render_skybox_mesh(sv, f, cam)
+    pkg.render_mesh_15(fb, sc.vertices, sc.faces, sc.textures, sc.camera, sc.settings)
+    got, got_z = fb.download()
+    want = np.zeros((h, w, 4), np.uint8); want[..., 3] = 255
+    want_z = np.full((h, w), np.finfo(np.float32).max, np.float32)
+    oracle.render_skybox_mesh(want, sv, f, cam)
+    rc, _, _ = oracle.render_mesh_15(want, want_z, sc.vertices, sc.faces, sc.textures, sc.camera, sc.settings)
+    assert rc == 0 and np.array_equal(got, want) and np.array_equal(got_z.view(np.uint32), want_z.view(np.uint32))
+    with pytest.raises(pkg.B32Error) as e:
+        fb.render_skybox_mesh(sv, np.array([[0, 1, len(sv)]], np.uint32), cam)
+    assert e.value.code == abi.B32_ERR_OOB_INDEX

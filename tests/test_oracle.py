@@ -282,3 +282,22 @@ def test_rgb888_nan_key_panics_only_in_painters_mode(oracle):
             assert oracle.render_scene888(zb)[3] == 0          # no sort in z-buffer mode (render.rs:2155)
             return
     raise AssertionError("no face produces a NaN sort key")
+
+
+# ---- skybox sphere pass (Framebuffer::render_skybox step 1, render.rs:81-139, :242-299) -------------------
+SKY = cases.sky_cases()
+with open(os.path.join(GOLDEN, "hashes_sky.json")) as _f:
+    HASHES_SKY = json.load(_f)
+
+
+@pytest.mark.parametrize("name,w,h,cam", SKY, ids=[c[0] for c in SKY])
+def test_skybox_oracle_equals_numpy_model_and_golden(oracle, name, w, h, cam):
+    sv, f = cases.sky_mesh(cam.position)
+    want, _ = pymodel.fb_clear(w, h, (0, 0, 0))
+    assert oracle.render_skybox_mesh(want, sv, f, cam) == 0
+    rgba, _ = pymodel.fb_clear(w, h, (0, 0, 0))
+    pymodel.render_skybox_mesh(rgba, sv, f, cam)
+    assert np.array_equal(rgba, want)
+    assert hashlib.sha256(want.tobytes()).hexdigest() == HASHES_SKY[name]
+    covered = (want[..., :3] != 0).any(-1).mean()
+    assert covered > 0.95, covered                 # inside the sphere the whole screen is sky
