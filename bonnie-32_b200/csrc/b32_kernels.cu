@@ -596,7 +596,7 @@ __device__ __forceinline__ bool shade888(const SurfRec& r, uint32_t x, uint32_t 
 // =================================================================================================
 // k_fill_opaque — pass 1, order-free, visibility first
 // =================================================================================================
-// One CTA per 16x8 half of a 16x16 screen tile (all CTAs of a 320x240 frame are resident at once); one
+// One CTA per 16x16 screen tile (all CTAs of a 320x240 frame are resident at once); one
 // warp per 4x4 pixel block; a pixel is owned by TWO lanes (lane and lane+16) that evaluate different
 // surfaces at the same time and merge their winners — the winner rule is associative, so the merge is
 // exact.
@@ -617,7 +617,7 @@ __device__ __forceinline__ bool shade888(const SurfRec& r, uint32_t x, uint32_t 
 //      its warps have.
 //   5. each pixel shades its winner once (texture, modulate, lighting, dither), at the end.
 #ifndef B32_OP_THREADS
-#define B32_OP_THREADS 256
+#define B32_OP_THREADS 512        // one CTA per 16x16 tile: the tile's sort and record staging are done once, not per half
 #endif
 #ifndef B32_OP_DUAL
 #define B32_OP_DUAL 1
@@ -629,9 +629,9 @@ constexpr int OP_BW = OP_DUAL ? 4 : 8, OP_BH = 4;                     // pixel b
 constexpr int OP_WPT = (TILE_W / OP_BW) * (TILE_H / OP_BH);            // warps per 16x16 tile
 constexpr int OP_SPLIT = OP_WPT / OP_WARPS;  // CTAs per tile (256 threads, dual: 2 = half tiles of 16x8 px)
 static_assert(OP_SPLIT >= 1 && OP_SPLIT * OP_WARPS == OP_WPT, "a CTA covers a whole number of block rows of one tile");
-constexpr int OP_CHUNK = 32;                 // surface records staged per step: 256 x 16 B, OP_PIECES per thread
+constexpr int OP_CHUNK = OP_THREADS > 256 ? OP_THREADS / 8 : 32;   // surface records staged per step (8 x 16 B each), OP_PIECES per thread
 constexpr int OP_PIECES = OP_CHUNK * 8 / OP_THREADS;
-static_assert(OP_PIECES >= 1 && OP_PIECES * OP_THREADS == OP_CHUNK * 8, "OP_THREADS must divide 256");
+static_assert(OP_PIECES >= 1 && OP_PIECES * OP_THREADS == OP_CHUNK * 8, "OP_THREADS must divide 256 or be a multiple of it");
 constexpr int OP_BUCKETS = OP_THREADS < 256 ? OP_THREADS : 256;       // key buckets of the counting sort (one scan thread each)
 constexpr int OP_BUCKET_BITS = OP_BUCKETS == 256 ? 8 : (OP_BUCKETS == 128 ? 7 : 6);
 constexpr int OP_RING = 3;                   // ring depth: steps c, c+1, c+2
@@ -694,7 +694,7 @@ __device__ __forceinline__ uint32_t texel_index(const Rec& r, float bc_x, float 
 }
 
 #ifndef B32_OP_MINB
-#define B32_OP_MINB (OP_THREADS == 256 ? 5 : (OP_THREADS == 128 ? 5 : 2))
+#define B32_OP_MINB (OP_THREADS == 512 ? 3 : 5)   // 512 threads: 3 CTAs per SM (444 slots >= the 300 tiles of a 320x240 frame: one wave)
 #endif
 // RGB888 = the render_mesh instantiation (8-bit colour pipeline in step 5; everything else is shared)
 template <bool RGB888>
