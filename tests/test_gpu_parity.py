@@ -498,3 +498,34 @@ def test_skybox_then_scene_composes(ctx, oracle):
     with pytest.raises(pkg.B32Error) as e:
         fb.render_skybox_mesh(sv, np.array([[0, 1, len(sv)]], np.uint32), cam)
     assert e.value.code == abi.B32_ERR_OOB_INDEX
+
+
+# ---- fuzz: random settings x adversarial geometry (indexed meshes, degenerate / huge / near-plane / non-finite triangles,
+#      zero-sized and out-of-range textures, odd framebuffer sizes) ----------------------------------------------------
+import fuzz
+
+
+@pytest.mark.parametrize("rgb888", [False, True], ids=["rgb555", "rgb888"])
+def test_fuzz_gpu_equals_oracle(ctx, oracle, rgb888):
+    ok = panics = 0
+    for seed in range(60):
+        sc = fuzz.fuzz_scene(seed, rgb888)
+        want, want_z, otm, rc = (oracle.render_scene888 if rgb888 else oracle.render_scene)(sc)
+        fb = pkg.Framebuffer(sc.width, sc.height, ctx)
+        fb.clear(sc.clear)
+        before = fb.download()[0]
+        try:
+            if rgb888:
+                tm = pkg.render_mesh(fb, sc.vertices, sc.faces, sc.textures8, sc.camera, sc.settings)
+            else:
+                tm = pkg.render_mesh_15(fb, sc.vertices, sc.faces, sc.textures, sc.camera, sc.settings, sc.fog)
+        except pkg.B32Error as e:
+            assert e.code == rc, (sc.name, e.code, rc)
+            assert np.array_equal(fb.download()[0], before), sc.name       # the reference panics before it draws
+            panics += 1
+            continue
+        assert rc == 0, sc.name
+        got, got_z = fb.download()
+        assert_same(sc, got, got_z, tm, want, want_z, otm)
+        ok += 1
+    assert ok >= 30 and ok + panics == 60

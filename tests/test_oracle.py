@@ -301,3 +301,32 @@ def test_skybox_oracle_equals_numpy_model_and_golden(oracle, name, w, h, cam):
     assert hashlib.sha256(want.tobytes()).hexdigest() == HASHES_SKY[name]
     covered = (want[..., :3] != 0).any(-1).mean()
     assert covered > 0.95, covered                 # inside the sphere the whole screen is sky
+
+
+# ---- fuzz: random settings x adversarial geometry; both restatements must agree (incl. on where the reference panics) ----
+import fuzz
+
+
+@pytest.mark.parametrize("rgb888", [False, True], ids=["rgb555", "rgb888"])
+def test_fuzz_oracle_equals_numpy_model(oracle, rgb888):
+    ok = panics = 0
+    for seed in range(24):
+        sc = fuzz.fuzz_scene(seed, rgb888)
+        want, want_z, tm, rc, order = (oracle.render_scene888 if rgb888 else oracle.render_scene)(sc, want_order=True)
+        rgba, z = pymodel.fb_clear(sc.width, sc.height, sc.clear)
+        try:
+            with np.errstate(all="ignore"):
+                if rgb888:
+                    order2 = pymodel.render_mesh(rgba, z, sc.vertices, sc.faces, sc.textures8, sc.camera, sc.settings)
+                else:
+                    order2 = pymodel.render_mesh_15(rgba, z, sc.vertices, sc.faces, sc.textures, sc.camera, sc.settings, sc.fog)
+        except pymodel.ReferencePanic:
+            assert rc in (abi.B32_ERR_NAN_DEPTH, abi.B32_ERR_OOB_INDEX), sc.name
+            panics += 1
+            continue
+        assert rc == 0, sc.name
+        assert list(order) == order2, sc.name
+        assert np.array_equal(rgba, want), sc.name
+        assert np.array_equal(z.view(np.uint32), want_z.view(np.uint32)), sc.name
+        ok += 1
+    assert ok >= 12
