@@ -310,9 +310,6 @@ int render_ordered(b32_ctx* ctx, const CallParams& p, uint32_t n_ordered) {
     return B32_OK;
 }
 
-// One render_mesh_15 (render.rs:2302-2572) on device-resident geometry.
-//   wait=true : returns when the frame is in the framebuffer; fills *tm.
-//   wait=false: only enqueues pass 1 (no host round trip); the caller guarantees there is no pass 2.
 // Turn the frame just captured on the context's stream into an executable graph and remember its kernel nodes.
 bool finish_capture(b32_ctx* ctx, FrameGraph& fg, const FrameKey& key) {
     cudaGraph_t graph = nullptr;
@@ -334,27 +331,107 @@ bool finish_capture(b32_ctx* ctx, FrameGraph& fg, const FrameKey& key) {
     return true;
 }
 
+// Everything the kernels of one frame need besides the context's own buffers.
+struct FrameArgs {
+    const b32_vertex* verts; const b32_face* faces;
+    const TexDev* texdesc; const uint16_t* texels; const uint32_t* texmask;
+    bool clear; uint32_t clear_color;
+    uint32_t* zero_next;             // the CallState + tile-counter set this frame's k_setup zeroes for the next call
+    CallParams p;
+};
+
+// The kernels of one frame on L: Framebuffer::clear (optional), TRANSFORM + CULL + setup + binning, DRAW pass 1.
+// L decides how: direct launches, launches into a capturing stream, or patches of an instantiated graph's nodes.
+// ev_setup / ev_fill (nullable) are recorded in front of the two kernel groups (synchronous calls time them).
+int launch_frame(b32_ctx* ctx, const LaunchCtx& L, const FrameArgs& a, cudaEvent_t ev_setup, cudaEvent_t ev_fill) {
+    const CallParams& p = a.p;
+    if (a.clear) launch_fb_clear(L, ctx->fb_rgba.p, ctx->fb_z.p, ctx->width * ctx->height, a.clear_color);
+    if (ev_setup) CK(cudaEventRecord(ev_setup, L.stream));
+    const bool wire_on = p.wire_back || p.wire_front;
+    launch_setup(L, a.verts, a.faces, nullptr, a.texdesc, ctx->lights.p, ctx->recs.p, ctx->keys.p, ctx->heads.p, ctx->bins.p,
+                 ctx->tile_count, wire_on ? ctx->wire.p : nullptr, ctx->state, a.zero_next, ctx->state_stride, p);
+    if (ev_fill) CK(cudaEventRecord(ev_fill, L.stream));
+    if (!p.wire_front)
+        launch_fill_opaque(L, ctx->recs.p, ctx->bins.p, ctx->tile_count, a.texdesc, a.texels, a.texmask,
+                           ctx->fb_rgba.p, ctx->fb_z.p, ctx->state, ctx->sticky, p);
+    return B32_OK;
+}
+
+// Enqueue-only frames: the second frame of one topology is captured into a CUDA graph, later ones re-parameterise
+// its kernel nodes in place and launch it — one driver call per frame instead of one per kernel.
+enum class Submit { PLAIN, CAPTURE, PATCH };
+
+Submit pick_submit_mode(b32_ctx* ctx, const FrameKey& key, FrameGraph*& fg) {
+    static const bool no_graph = std::getenv("B32_NO_GRAPH") != nullptr;      // experiments: plain launches only
+    fg = nullptr;
+    if (no_graph) return Submit::PLAIN;
+    for (FrameGraph& g : ctx->fgs) if (g.patch.exec && g.key == key) { fg = &g; return Submit::PATCH; }
+    bool seen = false;
+    for (const FrameKey& k : ctx->fg_seen) seen = seen || k == key;
+    // a caller that cycles through more topologies than the cache holds would capture forever: stop building
+    // graphs once captures stop paying for themselves (plain launches are always correct)
+    const bool thrashing = ctx->graph_captures > 2 * b32_ctx::N_FRAME_GRAPHS && ctx->graph_launches < 4 * ctx->graph_captures;
+    if (seen && !thrashing) {
+        fg = &ctx->fgs[ctx->fg_next];
+        ctx->fg_next = (ctx->fg_next + 1) % b32_ctx::N_FRAME_GRAPHS;
+        ++ctx->graph_captures;
+        return Submit::CAPTURE;
+    }
+    ctx->fg_seen[ctx->fg_seen_next] = key;
+    ctx->fg_seen_next = (ctx->fg_seen_next + 1) % b32_ctx::N_FRAME_GRAPHS;
+    return Submit::PLAIN;
+}
+
+int enqueue_frame(b32_ctx* ctx, const FrameArgs& a, const FrameKey& key) {
+    cudaStream_t st = ctx->stream;
+    LaunchCtx L = ctx->L();
+    FrameGraph* fg = nullptr;
+    Submit mode = pick_submit_mode(ctx, key, fg);
+    ctx->async_pending = true;
+    if (mode == Submit::CAPTURE) {
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+            launch_frame(ctx, L, a, nullptr, nullptr);
+            if (finish_capture(ctx, *fg, key)) { CK(cudaGraphLaunch(fg->patch.exec, st)); ++ctx->graph_launches; return B32_OK; }
+        }
+        cudaGetLastError();                                // could not build the graph: launch this frame the ordinary way
+    } else if (mode == Submit::PATCH) {
+        LaunchCtx P = L;
+        P.patch = &fg->patch; fg->patch.err = cudaSuccess;
+        for (bool& u : fg->patch.used) u = false;
+        launch_frame(ctx, P, a, nullptr, nullptr);
+        if (fg->patch.err == cudaSuccess) { CK(cudaGraphLaunch(fg->patch.exec, st)); ++ctx->graph_launches; return B32_OK; }
+        fg->destroy(); cudaGetLastError();                 // topology changed under the key: fall back to plain launches
+    }
+    return launch_frame(ctx, L, a, nullptr, nullptr);
+}
+
+// One render_mesh_15 / render_mesh (render.rs:2302-2572 / :1971-2259) on device-resident geometry.
+//   wait=true : returns when the frame is in the framebuffer; fills *tm.
+//   wait=false: only enqueues pass 1 (no host round trip); the caller guarantees there is no pass 2.
 // clear_rgba (nullable): Framebuffer::clear first, as part of the same frame.
 int render_device(b32_ctx* ctx, const b32_vertex* d_verts, uint32_t nv, const b32_face* d_faces, uint32_t nf,
                   const b32_camera* cam, const b32_settings* s, const b32_fog* fog, b32_timings* tm, bool wait, bool rgb888 = false,
                   const uint8_t* clear_rgba = nullptr) {
     if (!cam || !s) return fail(ctx, B32_ERR_INVALID, "camera/settings is NULL");
     if (ctx->width == 0 || ctx->height == 0) return fail(ctx, B32_ERR_INVALID, "framebuffer has zero size (call b32_fb_resize)");
-    CallParams p;
+    FrameArgs a{};
+    CallParams& p = a.p;
     std::vector<LightDev> lights;
     int rc = fill_params(ctx, p, cam, s, fog, nv, nf, lights, rgb888);
     if (rc != B32_OK) return rc;
     if (tm) std::memset(tm, 0, sizeof(*tm));
-    const TexDev* texdesc = rgb888 ? ctx->tex8desc.p : ctx->texdesc.p;
-    const uint16_t* texels = rgb888 ? reinterpret_cast<const uint16_t*>(ctx->texels8.p) : ctx->texels.p;
-    const uint32_t* texmask = rgb888 ? ctx->tex8mask.p : ctx->texmask.p;
+    a.verts = d_verts; a.faces = d_faces;
+    a.texdesc = rgb888 ? ctx->tex8desc.p : ctx->texdesc.p;
+    a.texels = rgb888 ? reinterpret_cast<const uint16_t*>(ctx->texels8.p) : ctx->texels.p;
+    a.texmask = rgb888 ? ctx->tex8mask.p : ctx->texmask.p;
+    a.clear = clear_rgba != nullptr;
+    a.clear_color = clear_rgba ? ((uint32_t)clear_rgba[0] | ((uint32_t)clear_rgba[1] << 8) | ((uint32_t)clear_rgba[2] << 16) |
+                                  ((uint32_t)clear_rgba[3] << 24)) : 0u;
     for (float& k : ctx->kernel_ms) k = 0.0f;
     ctx->last_nf = nf;
     ctx->last_params = p;
-    const uint32_t clear_color = clear_rgba ? ((uint32_t)clear_rgba[0] | ((uint32_t)clear_rgba[1] << 8) | ((uint32_t)clear_rgba[2] << 16) |
-                                               ((uint32_t)clear_rgba[3] << 24)) : 0u;
     if (nf == 0) {
-        if (clear_rgba) launch_fb_clear(ctx->L(), ctx->fb_rgba.p, ctx->fb_z.p, ctx->width * ctx->height, clear_color);
+        if (a.clear) launch_fb_clear(ctx->L(), ctx->fb_rgba.p, ctx->fb_z.p, ctx->width * ctx->height, a.clear_color);
         return B32_OK;
     }
 
@@ -369,66 +446,20 @@ int render_device(b32_ctx* ctx, const b32_vertex* d_verts, uint32_t nv, const b3
         p.async_call = wait ? 0 : 1;
         CK(ctx->bins.reserve((size_t)ntiles * p.bin_cap));
         ctx->last_params = p;
-        const bool wire_on = p.wire_back || p.wire_front;
-        if (wire_on) CK(ctx->wire.reserve(nf));
-        // Enqueue-only frames: the second frame of one topology is captured into a CUDA graph, later ones re-parameterise
-        // its kernel nodes in place and launch it — one driver call per frame instead of one per kernel.
-        enum { PLAIN, CAPTURE, PATCH } mode = PLAIN;
-        FrameKey key;
-        FrameGraph* fg = nullptr;
-        static const bool no_graph = std::getenv("B32_NO_GRAPH") != nullptr;      // experiments: plain launches only
-        if (!wait && !no_graph) {
-            key.verts = d_verts; key.faces = d_faces; key.nv = nv; key.nf = nf; key.width = ctx->width; key.height = ctx->height;
-            key.rgb888 = rgb888; key.pass1 = !((p.xray_mode && !rgb888) || p.wire_front); key.clear = clear_rgba != nullptr; key.valid = 1;
-            for (FrameGraph& g : ctx->fgs) if (g.patch.exec && g.key == key) { fg = &g; mode = PATCH; break; }
-            if (!fg) {
-                bool seen = false;
-                for (const FrameKey& k : ctx->fg_seen) seen = seen || k == key;
-                // a caller that cycles through more topologies than the cache holds would capture forever: stop building
-                // graphs once captures stop paying for themselves (plain launches are always correct)
-                const bool thrashing = ctx->graph_captures > 2 * b32_ctx::N_FRAME_GRAPHS && ctx->graph_launches < 4 * ctx->graph_captures;
-                if (seen && !thrashing) { mode = CAPTURE; fg = &ctx->fgs[ctx->fg_next]; ctx->fg_next = (ctx->fg_next + 1) % b32_ctx::N_FRAME_GRAPHS; ++ctx->graph_captures; }
-                else { ctx->fg_seen[ctx->fg_seen_next] = key; ctx->fg_seen_next = (ctx->fg_seen_next + 1) % b32_ctx::N_FRAME_GRAPHS; }
-            }
-        }
-        if (mode == CAPTURE && cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); mode = PLAIN; }
-        if (mode == PATCH) { L.patch = &fg->patch; L.patch->err = cudaSuccess; for (bool& u : L.patch->used) u = false; }
-        if (clear_rgba) launch_fb_clear(L, ctx->fb_rgba.p, ctx->fb_z.p, ctx->width * ctx->height, clear_color);
-        if (wait) CK(cudaEventRecord(ctx->ev[0], st));
+        if (p.wire_back || p.wire_front) CK(ctx->wire.reserve(nf));
         // take the set the previous call's k_setup zeroed; this call's k_setup zeroes the other one
         // (nothing between here and the launch can fail, so the two sets never get out of step)
         ctx->state_cur ^= 1;
         ctx->state = reinterpret_cast<CallState*>(ctx->state_ring.p + (size_t)ctx->state_cur * ctx->state_stride);
         ctx->tile_count = ctx->state_ring.p + (size_t)ctx->state_cur * ctx->state_stride + STATE_WORDS;
-        uint32_t* zero_next = ctx->state_ring.p + (size_t)(ctx->state_cur ^ 1) * ctx->state_stride;
-        launch_setup(L, d_verts, d_faces, nullptr, texdesc, ctx->lights.p, ctx->recs.p, ctx->keys.p,
-                     ctx->heads.p, ctx->bins.p, ctx->tile_count, wire_on ? ctx->wire.p : nullptr, ctx->state,
-                     zero_next, ctx->state_stride, p);                          // TRANSFORM + CULL + setup + binning
-        if (wait) CK(cudaEventRecord(ctx->ev[1], st));
-        if (!p.wire_front)
-            launch_fill_opaque(L, ctx->recs.p, ctx->bins.p, ctx->tile_count, texdesc, texels, texmask,
-                               ctx->fb_rgba.p, ctx->fb_z.p, ctx->state, ctx->sticky, p);      // DRAW, pass 1
+        a.zero_next = ctx->state_ring.p + (size_t)(ctx->state_cur ^ 1) * ctx->state_stride;
         if (!wait) {
-            ctx->async_pending = true;
-            if (mode == CAPTURE) {
-                if (finish_capture(ctx, *fg, key)) { CK(cudaGraphLaunch(fg->patch.exec, st)); ++ctx->graph_launches; return B32_OK; }
-                mode = PLAIN;                              // could not build the graph: launch this frame the ordinary way
-                L.patch = nullptr;
-            } else if (mode == PATCH) {
-                if (L.patch->err == cudaSuccess) { CK(cudaGraphLaunch(fg->patch.exec, st)); ++ctx->graph_launches; return B32_OK; }
-                fg->destroy(); cudaGetLastError();
-                mode = PLAIN; L.patch = nullptr;
-            } else return B32_OK;
-            // fallback: nothing of this frame has been launched yet
-            if (clear_rgba) launch_fb_clear(L, ctx->fb_rgba.p, ctx->fb_z.p, ctx->width * ctx->height, clear_color);
-            launch_setup(L, d_verts, d_faces, nullptr, texdesc, ctx->lights.p, ctx->recs.p, ctx->keys.p,
-                         ctx->heads.p, ctx->bins.p, ctx->tile_count, wire_on ? ctx->wire.p : nullptr, ctx->state,
-                         zero_next, ctx->state_stride, p);
-            if (!p.wire_front)
-                launch_fill_opaque(L, ctx->recs.p, ctx->bins.p, ctx->tile_count, texdesc, texels, texmask,
-                                   ctx->fb_rgba.p, ctx->fb_z.p, ctx->state, ctx->sticky, p);
-            return B32_OK;
+            FrameKey key;
+            key.verts = d_verts; key.faces = d_faces; key.nv = nv; key.nf = nf; key.width = ctx->width; key.height = ctx->height;
+            key.rgb888 = rgb888; key.pass1 = !((p.xray_mode && !rgb888) || p.wire_front); key.clear = a.clear; key.valid = 1;
+            return enqueue_frame(ctx, a, key);
         }
+        rc = launch_frame(ctx, L, a, ctx->ev[0], ctx->ev[1]); if (rc) return rc;
         CK(cudaEventRecord(ctx->ev[2], st));
         CK(cudaMemcpyAsync(ctx->state_h, ctx->state, sizeof(CallState), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));

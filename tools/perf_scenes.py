@@ -56,6 +56,18 @@ def main():
     run(ctx, "c4_1M_tris", one(sc), 320, 240, sc.clear, reps=5)
     sc = scenes.scene_c4(n_tris=1_000_000, use_zbuffer=True)
     run(ctx, "c4_1M_tris_z", one(sc), 320, 240, sc.clear, reps=5)
+    # ordered replay at scale: x-ray (every surface in draw order), all faces semi-transparent (pass 2 only)
+    import copy
+    sc = scenes.scene_c4(); ctx.set_textures(sc.textures)
+    x = copy.copy(sc); x.settings = copy.copy(sc.settings); x.settings.xray_mode = True
+    run(ctx, "c4_xray", one(x), 320, 240, sc.clear, reps=5)
+    t = copy.copy(sc); t.faces = sc.faces.copy(); t.faces["flags"] = abi.face_flags(0, abi.BLEND_AVERAGE, True, 255)
+    run(ctx, "c4_all_transparent_painter", one(t), 320, 240, sc.clear, reps=5)
+    t2 = copy.copy(t); t2.settings = copy.copy(sc.settings); t2.settings.use_zbuffer = True
+    run(ctx, "c4_all_transparent_zbuffer", one(t2), 320, 240, sc.clear, reps=5)
+    sc10 = scenes.scene_c4(n_tris=10_000); ctx.set_textures(sc10.textures)
+    t3 = copy.copy(sc10); t3.faces = sc10.faces.copy(); t3.faces["flags"] = abi.face_flags(0, abi.BLEND_ADD, True, 255)
+    run(ctx, "c4_10k_all_transparent", one(t3), 320, 240, sc.clear, reps=5)
     sc = cases.big_triangle_scene(); ctx.set_textures(sc.textures)
     run(ctx, "big_triangles", one(sc), 320, 240, sc.clear)
     run(ctx, "big_triangles_1920x1080", one(sc), 1920, 1080, sc.clear)
