@@ -473,33 +473,44 @@ __device__ __forceinline__ bool inside_test(const SurfRec& r, uint32_t x, uint32
     return bc_x >= ERR && bc_y >= ERR && bc_z >= ERR;                              // :1541-1542
 }
 
-// Texture sample + transparency rules + colour pipeline (render.rs:1563-1661).  Returns false when the
-// texel is skipped; otherwise rgb = Color15::r8/g8/b8 of the final colour, semi = its bit 15.
-__device__ __forceinline__ bool shade(const SurfRec& r, uint32_t x, uint32_t y, float bc_x, float bc_y, float bc_z, float inv_z,
-                                      const TexDev* __restrict__ tex, const uint16_t* __restrict__ texels, const CallParams& p,
-                                      uint32_t& o_r, uint32_t& o_g, uint32_t& o_b, bool& semi) {
-    uint32_t color = 0x7FFF;                                                       // Color15::WHITE
-    if (r.flags & SF_TEXTURED) {
-        float u, v;
-        if (p.affine_textures) {                                                   // :1563-1567
-            u = bc_x * r.u1 + bc_y * r.u2 + bc_z * r.u3;
-            v = bc_x * r.v1 + bc_y * r.v2 + bc_z * r.v3;
-        } else {                                                                   // :1568-1578
-            float uo = bc_x * r.u1 * r.iz1 + bc_y * r.u2 * r.iz2 + bc_z * r.u3 * r.iz3;
-            float vo = bc_x * r.v1 * r.iz1 + bc_y * r.v2 * r.iz2 + bc_z * r.v3 * r.iz3;
-            u = uo / inv_z;
-            v = vo / inv_z;
-        }
-        TexDev t = tex[r.flags >> 16];
-        if (t.w == 0 || t.h == 0) {                                                // types.rs:673-675
-            color = 0;
-        } else {
-            float uw = rem_euclid1(u), vw = rem_euclid1(1.0f - v);                 // :1583, types.rs:676-677
-            uint32_t tx = min(f2u32sat(uw * (float)t.w), t.w - 1);
-            uint32_t ty = min(f2u32sat(vw * (float)t.h), t.h - 1);
-            color = __ldg(texels + t.off + ty * t.w + tx);
-        }
+// texel of the surface at barycentric (bc): render.rs:1563-1586, types.rs:671-681.  Returns its index
+// in the texel pool, or TEXEL_NONE for a zero-sized texture (sample() = TRANSPARENT).
+constexpr uint32_t TEXEL_NONE = 0xFFFFFFFFu;
+template <typename Rec>
+__device__ __forceinline__ uint32_t texel_index(const Rec& r, float bc_x, float bc_y, float bc_z, float inv_z,
+                                                const TexDev& t, const CallParams& p) {
+    float u, v;
+    if (p.affine_textures) {                                                   // :1563-1567
+        u = bc_x * r.u1 + bc_y * r.u2 + bc_z * r.u3;
+        v = bc_x * r.v1 + bc_y * r.v2 + bc_z * r.v3;
+    } else {                                                                   // :1568-1578
+        float uo = bc_x * r.u1 * r.iz1 + bc_y * r.u2 * r.iz2 + bc_z * r.u3 * r.iz3;
+        float vo = bc_x * r.v1 * r.iz1 + bc_y * r.v2 * r.iz2 + bc_z * r.v3 * r.iz3;
+        u = uo / inv_z;
+        v = vo / inv_z;
     }
+    if (t.w == 0 || t.h == 0) return TEXEL_NONE;                               // types.rs:673-675
+    float uw = rem_euclid1(u), vw = rem_euclid1(1.0f - v);                     // :1583, types.rs:676-677
+    uint32_t tx = min(f2u32sat(uw * (float)t.w), t.w - 1);
+    uint32_t ty = min(f2u32sat(vw * (float)t.h), t.h - 1);
+    return t.off + ty * t.w + tx;
+}
+
+// The sampled texel of a fragment as one word: RGB555 path = the Color15 (0x7FFF = WHITE for untextured surfaces, 0x0000 =
+// TRANSPARENT for zero-sized textures); RGB888 path = r | g<<8 | b<<16 | blend<<24 (WHITE/Opaque, or Erase for zero-sized).
+template <bool RGB888>
+__device__ __forceinline__ uint32_t sample_texel(const SurfRec& r, float bc_x, float bc_y, float bc_z, float inv_z,
+                                                 const TexDev* __restrict__ tex, const void* __restrict__ texels, const CallParams& p) {
+    if (!(r.flags & SF_TEXTURED)) return RGB888 ? 0x00FFFFFFu : 0x7FFFu;
+    uint32_t ti = texel_index(r, bc_x, bc_y, bc_z, inv_z, tex[r.flags >> 16], p);
+    if (ti == TEXEL_NONE) return RGB888 ? ((uint32_t)B32_BLEND_ERASE << 24) : 0u;
+    return RGB888 ? __ldg(reinterpret_cast<const uint32_t*>(texels) + ti) : (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(texels) + ti);
+}
+
+// Transparency rules + colour pipeline of rasterize_triangle_15 (render.rs:1591-1661) on a sampled Color15.  Returns
+// false when the texel is skipped; otherwise rgb = Color15::r8/g8/b8 of the final colour, semi = its bit 15.
+__device__ __forceinline__ bool shade_color(const SurfRec& r, uint32_t x, uint32_t y, float bc_x, float bc_y, float bc_z, uint32_t color,
+                                            const CallParams& p, uint32_t& o_r, uint32_t& o_g, uint32_t& o_b, bool& semi) {
     bool is_black = (color & 0x7FFF) == 0;                                         // :1591-1607
     if (color == 0) {
         if (!(r.flags & SF_BLACK_TR)) color = 0x8000; else return false;
@@ -539,32 +550,19 @@ __device__ __forceinline__ bool shade(const SurfRec& r, uint32_t x, uint32_t y, 
     return true;
 }
 
-// RGB888 colour pipeline of rasterize_triangle (render.rs:1343-1389): Texture::sample (types.rs:1242-1253),
-// Erase texels skip, Color::modulate (types.rs:801-808), shade_color_rgb WITHOUT a clamp of the factor
-// (render.rs:1074-1081), apply_dither re-expanded with `<< 3` (render.rs:1186-1197).  blend = the texel's tag.
-__device__ __forceinline__ bool shade888(const SurfRec& r, uint32_t x, uint32_t y, float bc_x, float bc_y, float bc_z, float inv_z,
-                                         const TexDev* __restrict__ tex, const uint32_t* __restrict__ texels, const CallParams& p,
-                                         uint32_t& o_r, uint32_t& o_g, uint32_t& o_b, uint32_t& o_blend) {
-    uint32_t cr = 255, cg = 255, cb = 255, blend = B32_BLEND_OPAQUE;               // Color::WHITE
-    if (r.flags & SF_TEXTURED) {
-        float u, v;
-        if (p.affine_textures) {
-            u = bc_x * r.u1 + bc_y * r.u2 + bc_z * r.u3;
-            v = bc_x * r.v1 + bc_y * r.v2 + bc_z * r.v3;
-        } else {
-            float uo = bc_x * r.u1 * r.iz1 + bc_y * r.u2 * r.iz2 + bc_z * r.u3 * r.iz3;
-            float vo = bc_x * r.v1 * r.iz1 + bc_y * r.v2 * r.iz2 + bc_z * r.v3 * r.iz3;
-            u = uo / inv_z;
-            v = vo / inv_z;
-        }
-        TexDev t = tex[r.flags >> 16];
-        if (t.w == 0 || t.h == 0) return false;                                    // Color::TRANSPARENT
-        float uw = rem_euclid1(u), vw = rem_euclid1(1.0f - v);
-        uint32_t tx = min(f2u32sat(uw * (float)t.w), t.w - 1);
-        uint32_t ty = min(f2u32sat(vw * (float)t.h), t.h - 1);
-        uint32_t c = __ldg(texels + t.off + ty * t.w + tx);
-        cr = c & 0xFF; cg = (c >> 8) & 0xFF; cb = (c >> 16) & 0xFF; blend = c >> 24;
-    }
+// Texture sample (render.rs:1563-1586) + shade_color.
+__device__ __forceinline__ bool shade(const SurfRec& r, uint32_t x, uint32_t y, float bc_x, float bc_y, float bc_z, float inv_z,
+                                      const TexDev* __restrict__ tex, const uint16_t* __restrict__ texels, const CallParams& p,
+                                      uint32_t& o_r, uint32_t& o_g, uint32_t& o_b, bool& semi) {
+    return shade_color(r, x, y, bc_x, bc_y, bc_z, sample_texel<false>(r, bc_x, bc_y, bc_z, inv_z, tex, texels, p), p, o_r, o_g, o_b, semi);
+}
+
+// RGB888 colour pipeline of rasterize_triangle (render.rs:1350-1389) on a sampled Color word: Erase texels skip,
+// Color::modulate (types.rs:801-808), shade_color_rgb WITHOUT a clamp of the factor (render.rs:1074-1081),
+// apply_dither re-expanded with `<< 3` (render.rs:1186-1197).  blend = the texel's tag.
+__device__ __forceinline__ bool shade_color888(const SurfRec& r, uint32_t x, uint32_t y, float bc_x, float bc_y, float bc_z, uint32_t c,
+                                               const CallParams& p, uint32_t& o_r, uint32_t& o_g, uint32_t& o_b, uint32_t& o_blend) {
+    uint32_t cr = c & 0xFF, cg = (c >> 8) & 0xFF, cb = (c >> 16) & 0xFF, blend = c >> 24;
     if (blend == B32_BLEND_ERASE) return false;                                    // :1350-1354
     uint32_t vr = f2u8(bc_x * (float)(r.vc1 & 0xFF) + bc_y * (float)(r.vc2 & 0xFF) + bc_z * (float)(r.vc3 & 0xFF));          // :1357-1362
     uint32_t vg = f2u8(bc_x * (float)((r.vc1 >> 8) & 0xFF) + bc_y * (float)((r.vc2 >> 8) & 0xFF) + bc_z * (float)((r.vc3 >> 8) & 0xFF));
@@ -591,6 +589,13 @@ __device__ __forceinline__ bool shade888(const SurfRec& r, uint32_t x, uint32_t 
     }
     o_r = r8; o_g = g8; o_b = b8; o_blend = blend;
     return true;
+}
+
+// Texture::sample (types.rs:1242-1253) + shade_color888.
+__device__ __forceinline__ bool shade888(const SurfRec& r, uint32_t x, uint32_t y, float bc_x, float bc_y, float bc_z, float inv_z,
+                                         const TexDev* __restrict__ tex, const uint32_t* __restrict__ texels, const CallParams& p,
+                                         uint32_t& o_r, uint32_t& o_g, uint32_t& o_b, uint32_t& o_blend) {
+    return shade_color888(r, x, y, bc_x, bc_y, bc_z, sample_texel<true>(r, bc_x, bc_y, bc_z, inv_z, tex, texels, p), p, o_r, o_g, o_b, o_blend);
 }
 
 // =================================================================================================
@@ -668,29 +673,6 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
                  : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
-}
-
-// texel of the surface at barycentric (bc): render.rs:1563-1586, types.rs:671-681.  Returns its index
-// in the texel pool, or TEXEL_NONE for a zero-sized texture (sample() = TRANSPARENT).
-constexpr uint32_t TEXEL_NONE = 0xFFFFFFFFu;
-template <typename Rec>
-__device__ __forceinline__ uint32_t texel_index(const Rec& r, float bc_x, float bc_y, float bc_z, float inv_z,
-                                                const TexDev& t, const CallParams& p) {
-    float u, v;
-    if (p.affine_textures) {                                                   // :1563-1567
-        u = bc_x * r.u1 + bc_y * r.u2 + bc_z * r.u3;
-        v = bc_x * r.v1 + bc_y * r.v2 + bc_z * r.v3;
-    } else {                                                                   // :1568-1578
-        float uo = bc_x * r.u1 * r.iz1 + bc_y * r.u2 * r.iz2 + bc_z * r.u3 * r.iz3;
-        float vo = bc_x * r.v1 * r.iz1 + bc_y * r.v2 * r.iz2 + bc_z * r.v3 * r.iz3;
-        u = uo / inv_z;
-        v = vo / inv_z;
-    }
-    if (t.w == 0 || t.h == 0) return TEXEL_NONE;                               // types.rs:673-675
-    float uw = rem_euclid1(u), vw = rem_euclid1(1.0f - v);                     // :1583, types.rs:676-677
-    uint32_t tx = min(f2u32sat(uw * (float)t.w), t.w - 1);
-    uint32_t ty = min(f2u32sat(vw * (float)t.h), t.h - 1);
-    return t.off + ty * t.w + tx;
 }
 
 #ifndef B32_OP_MINB
@@ -1074,8 +1056,12 @@ __device__ __forceinline__ void write_ordered888(const SurfRec& r, Pixel& px, fl
     px.rgba = o_r | (o_g << 8) | (o_b << 16) | 0xFF000000u;
 }
 
-constexpr int FILL_CHUNK = 32;       // surfaces staged in shared memory per step (32 x 128 B = 4 KB)
+constexpr int ORD_CHUNK = 32;        // surfaces staged in shared memory per step (32 x 128 B = 4 KB), one 16-byte piece per thread
+constexpr int ORD_RING = 3;          // steps c, c+1, c+2 in flight
+constexpr int ORD_GROUP = 4;         // fragments of one pixel whose texels are requested together
 constexpr int ORD_SORT_MAX = 2048;   // bin entries sortable in shared memory (32 KB); larger bins are sorted in place in global memory
+constexpr size_t ORD_SMEM = (size_t)ORD_SORT_MAX * sizeof(BinHead) + (size_t)ORD_RING * ORD_CHUNK * sizeof(SurfRec) + (FILL_THREADS / 32) * 32;
+static_assert(FILL_THREADS == ORD_CHUNK * 8, "one 16-byte piece of the staged records per thread");
 
 __device__ __forceinline__ uint64_t ord_key(const BinHead& h) { return ((uint64_t)h.key << 32) | h.face; }
 
@@ -1095,19 +1081,25 @@ __device__ void bitonic_sort_heads(BinHead* a, uint32_t m) {
         }
 }
 
-// One CTA per 16x16 tile, one warp per 8x4 block, one lane per pixel.  The tile's bin is sorted by the
-// unique draw-order key, then every pixel replays its surfaces one after the other, applying the
-// reference's z-test / blend / write rules (render.rs:1664-1702) to a colour + depth held in registers.
+// One CTA per 16x16 tile, one warp per 8x4 block, one lane per pixel.  The tile's bin is sorted by the unique
+// draw-order key; the records stream through a 3-deep cp.async ring in that order; every pixel replays the surfaces
+// covering it one after the other, applying the reference's z-test / blend / write rules (render.rs:1664-1702 and, for
+// RGB888, :1392-1424) to a colour + depth held in registers.  Per step each lane first filters one of the 32 staged
+// surfaces against the warp's block (bbox, exact corner trivial reject); the survivors are then taken in order,
+// ORD_GROUP at a time: the inside tests, depths and texel requests of a group are issued together (they do not depend
+// on the pixel's running colour), and only then are its fragments shaded and written one after the other.
+template <bool RGB888>
 __global__ void __launch_bounds__(FILL_THREADS)
 k_fill_ordered(const SurfRec* __restrict__ recs, BinHead* __restrict__ bins, const uint32_t* __restrict__ tile_count,
-               const TexDev* __restrict__ tex, const uint16_t* __restrict__ texels,
+               const TexDev* __restrict__ tex, const void* __restrict__ texels,
                uint32_t* __restrict__ fb_rgba, float* __restrict__ fb_z, const CallState* __restrict__ st, CallParams p, uint32_t bin_cap) {
-    extern __shared__ __align__(16) uint8_t ord_smem[];
-    BinHead* s_sorted = reinterpret_cast<BinHead*>(ord_smem);                          // [ORD_SORT_MAX]
-    __shared__ SurfRec s_rec[FILL_CHUNK];
+    extern __shared__ __align__(128) uint8_t ord_smem[];
+    SurfRec* s_rec = reinterpret_cast<SurfRec*>(ord_smem);                              // [ORD_RING][ORD_CHUNK]
+    BinHead* s_sorted = reinterpret_cast<BinHead*>(s_rec + ORD_RING * ORD_CHUNK);       // [ORD_SORT_MAX]
+    uint8_t* s_sidx = reinterpret_cast<uint8_t*>(s_sorted + ORD_SORT_MAX);              // [warps][32] survivors of the step, in order
     {
         CallState s = *st;
-        if (s.obin_overflow || call_aborts(s, p.use_zbuffer, p.rgb888)) return;
+        if (s.obin_overflow || call_aborts(s, p.use_zbuffer, RGB888)) return;
     }
     const uint32_t tile = blockIdx.x;
     const uint32_t n = tile_count[tile];
@@ -1134,41 +1126,89 @@ k_fill_ordered(const SurfRec* __restrict__ recs, BinHead* __restrict__ bins, con
     Pixel px{0, 0.0f};
     if (valid) { px.rgba = fb_rgba[y * p.width + x]; px.z = fb_z[y * p.width + x]; }
     const Pixel px0 = px;
+    uint8_t* my_sidx = s_sidx + warp * 32;
+    const bool early_z = p.use_zbuffer && !p.xray_mode;                                // :1553-1560 / :1313-1320
 
-    for (uint32_t base = 0; base < n; base += FILL_CHUNK) {
-        uint32_t cnt = min((uint32_t)FILL_CHUNK, n - base);
-        __syncthreads();
-        {   // stage cnt records: 8 threads x 16 B per record
-            uint32_t rec_i = threadIdx.x >> 3, part = threadIdx.x & 7;
-            if (rec_i < cnt) {
-                uint32_t f = sorted[base + rec_i].face & 0x3FFFFFFFu;
-                reinterpret_cast<uint4*>(&s_rec[rec_i])[part] = reinterpret_cast<const uint4*>(&recs[f])[part];
+    auto stage = [&](uint32_t c) {                                                     // step c -> ring slot c % ORD_RING
+        uint32_t e = c * ORD_CHUNK + (threadIdx.x >> 3);
+        if (e < n) {
+            uint32_t f = sorted[e].face & 0x3FFFFFFFu;
+            cp_async16(reinterpret_cast<uint4*>(&s_rec[(c % ORD_RING) * ORD_CHUNK + (threadIdx.x >> 3)]) + (threadIdx.x & 7),
+                       reinterpret_cast<const uint4*>(&recs[f]) + (threadIdx.x & 7));
+        }
+        cp_async_commit();
+    };
+    stage(0);
+    stage(1);
+    const uint32_t nchunks = (n + ORD_CHUNK - 1) / ORD_CHUNK;
+    for (uint32_t c = 0; c < nchunks; ++c) {
+        cp_async_wait<1>();
+        __syncthreads();                                   // step c has landed for everybody; slot (c+2) % 3 is free again
+        stage(c + 2);
+        const SurfRec* crec = s_rec + (c % ORD_RING) * ORD_CHUNK;
+        // ---- filter: lane = one staged surface vs this warp's 8x4 block ----
+        bool cand = false;
+        if (c * ORD_CHUNK + lane < n && bx0 < p.width && by0 < p.height) {
+            const SurfRec& r = crec[lane];
+            uint32_t min_x = r.bbox_x & 0xFFFF, max_x = r.bbox_x >> 16, min_y = r.bbox_y & 0xFFFF, max_y = r.bbox_y >> 16;
+            cand = !(max_x <= bx0 || min_x >= bx0 + 8 || max_y <= by0 || min_y >= by0 + 4);
+            if (cand && (r.flags & SF_FAST_EDGE)) {        // exact corner test, as in k_fill_opaque
+                float dx0 = (float)(max(bx0, min_x) - min_x), dx1 = (float)(min(bx0 + 8, max_x) - 1 - min_x);
+                float dy0 = (float)(max(by0, min_y) - min_y), dy1 = (float)(min(by0 + 4, max_y) - 1 - min_y);
+                float r0 = r.w0s + dy0 * r.b0, r1 = r.w0s + dy1 * r.b0, q0 = r.w1s + dy0 * r.b1, q1 = r.w1s + dy1 * r.b1;
+                float ax0 = dx0 * r.a0, ax1 = dx1 * r.a0, cx0 = dx0 * r.a1, cx1 = dx1 * r.a1;
+                float x00 = (r0 + ax0) * r.inv_area, x01 = (r0 + ax1) * r.inv_area, x10 = (r1 + ax0) * r.inv_area, x11 = (r1 + ax1) * r.inv_area;
+                float y00 = (q0 + cx0) * r.inv_area, y01 = (q0 + cx1) * r.inv_area, y10 = (q1 + cx0) * r.inv_area, y11 = (q1 + cx1) * r.inv_area;
+                float xmax = fmaxf(fmaxf(x00, x01), fmaxf(x10, x11)), xmin = fminf(fminf(x00, x01), fminf(x10, x11));
+                float ymax = fmaxf(fmaxf(y00, y01), fmaxf(y10, y11)), ymin = fminf(fminf(y00, y01), fminf(y10, y11));
+                const float ERR = -0.0001f;
+                if (xmax < ERR || ymax < ERR || (1.0f - xmin - ymin) < ERR) cand = false;
             }
         }
-        __syncthreads();
-        for (uint32_t i = 0; i < cnt; ++i) {
-            const SurfRec& r = s_rec[i];
-            uint32_t min_x = r.bbox_x & 0xFFFF, max_x = r.bbox_x >> 16, min_y = r.bbox_y & 0xFFFF, max_y = r.bbox_y >> 16;
-            // warp-uniform reject of surfaces that miss this warp's 8x4 block
-            if (max_x <= bx0 || min_x >= bx0 + 8 || max_y <= by0 || min_y >= by0 + 4) continue;
-            if (!(valid && x >= min_x && x < max_x && y >= min_y && y < max_y)) continue;
-            float bc_x, bc_y, bc_z;
-            if (!inside_test(r, x, y, bc_x, bc_y, bc_z)) continue;
-            float inv_z = bc_x * r.iz1 + bc_y * r.iz2 + bc_z * r.iz3;              // :1549
-            float z = 1.0f / inv_z;
-            if (p.use_zbuffer && !p.xray_mode) { if (z >= px.z) continue; }         // :1553-1560
-            uint32_t o_r, o_g, o_b;
-            if (p.rgb888) {
-                uint32_t blend;
-                if (!shade888(r, x, y, bc_x, bc_y, bc_z, inv_z, tex, reinterpret_cast<const uint32_t*>(texels), p, o_r, o_g, o_b, blend)) continue;
-                write_ordered888(r, px, z, o_r, o_g, o_b, blend, p);
-            } else {
-                bool semi;
-                if (!shade(r, x, y, bc_x, bc_y, bc_z, inv_z, tex, texels, p, o_r, o_g, o_b, semi)) continue;
-                write_ordered(r, px, z, o_r, o_g, o_b, semi, p);
+        const uint32_t mask = __ballot_sync(0xFFFFFFFFu, cand);
+        if (mask == 0) continue;
+        const uint32_t cnt = __popc(mask);
+        __syncwarp();
+        if (cand) my_sidx[__popc(mask & ((1u << lane) - 1))] = (uint8_t)lane;          // ascending = draw order
+        __syncwarp();
+        // ---- survivors in order, ORD_GROUP at a time ----
+        for (uint32_t j0 = 0; j0 < cnt; j0 += ORD_GROUP) {
+            bool in[ORD_GROUP]; float fbx[ORD_GROUP], fby[ORD_GROUP], fz[ORD_GROUP]; uint32_t ftex[ORD_GROUP];
+            #pragma unroll
+            for (int k = 0; k < ORD_GROUP; ++k) {          // everything that does not depend on the running colour / depth
+                in[k] = false; fbx[k] = fby[k] = fz[k] = 0.0f; ftex[k] = 0;
+                if (j0 + k >= cnt) continue;
+                const SurfRec& r = crec[my_sidx[j0 + k]];
+                uint32_t min_x = r.bbox_x & 0xFFFF, max_x = r.bbox_x >> 16, min_y = r.bbox_y & 0xFFFF, max_y = r.bbox_y >> 16;
+                if (!(valid && x >= min_x && x < max_x && y >= min_y && y < max_y)) continue;
+                float bc_x, bc_y, bc_z;
+                if (!inside_test(r, x, y, bc_x, bc_y, bc_z)) continue;
+                float inv_z = bc_x * r.iz1 + bc_y * r.iz2 + bc_z * r.iz3;              // :1549
+                float z = 1.0f / inv_z;
+                if (early_z && z >= px.z) continue;        // px.z only ever decreases, so a reject now is a reject later
+                in[k] = true; fbx[k] = bc_x; fby[k] = bc_y; fz[k] = z;
+                ftex[k] = sample_texel<RGB888>(r, bc_x, bc_y, bc_z, inv_z, tex, texels, p);
+            }
+            #pragma unroll
+            for (int k = 0; k < ORD_GROUP; ++k) {          // the fold over the fragments, in draw order
+                if (!in[k]) continue;
+                if (early_z && fz[k] >= px.z) continue;                                // the reference's early test, at its time
+                const SurfRec& r = crec[my_sidx[j0 + k]];
+                const float bc_x = fbx[k], bc_y = fby[k], bc_z = 1.0f - bc_x - bc_y;   // same expression as inside_test
+                uint32_t o_r, o_g, o_b;
+                if (RGB888) {
+                    uint32_t blend;
+                    if (!shade_color888(r, x, y, bc_x, bc_y, bc_z, ftex[k], p, o_r, o_g, o_b, blend)) continue;
+                    write_ordered888(r, px, fz[k], o_r, o_g, o_b, blend, p);
+                } else {
+                    bool semi;
+                    if (!shade_color(r, x, y, bc_x, bc_y, bc_z, ftex[k], p, o_r, o_g, o_b, semi)) continue;
+                    write_ordered(r, px, fz[k], o_r, o_g, o_b, semi, p);
+                }
             }
         }
     }
+    cp_async_wait<0>();
     if (valid) {
         if (px.rgba != px0.rgba) fb_rgba[y * p.width + x] = px.rgba;
         if (__float_as_uint(px.z) != __float_as_uint(px0.z)) fb_z[y * p.width + x] = px.z;
@@ -1487,10 +1527,13 @@ void launch_fill_ordered(const LaunchCtx& L, const SurfRec* recs, BinHead* obins
     uint32_t ntiles = p.tiles_x * p.tiles_y;
     if (ntiles == 0 || p.nf == 0) return;
     static bool attr_set = false;
-    const int smem = ORD_SORT_MAX * (int)sizeof(BinHead);
-    if (!attr_set) { cudaFuncSetAttribute(k_fill_ordered, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
-    k_fill_ordered<<<ntiles, FILL_THREADS, smem, L.stream>>>(recs, obins, otile_count, tex, texels, fb_rgba, fb_z, st, p, obin_cap);
-    ++*L.launches;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_fill_ordered<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ORD_SMEM);
+        cudaFuncSetAttribute(k_fill_ordered<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ORD_SMEM);
+        attr_set = true;
+    }
+    launch_k(L, p.rgb888 ? k_fill_ordered<true> : k_fill_ordered<false>, ntiles, FILL_THREADS, ORD_SMEM, false,
+             recs, obins, otile_count, tex, static_cast<const void*>(texels), fb_rgba, fb_z, st, p, obin_cap);
 }
 
 void launch_wire(const LaunchCtx& L, const WireTri* wire, uint32_t kind, uint32_t color, bool depth_test,
