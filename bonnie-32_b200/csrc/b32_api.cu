@@ -110,6 +110,7 @@ struct b32_ctx {
     uint32_t* tile_count = nullptr;    // current set's tile counters
     DevBuf<uint32_t> otile_count;
     DevBuf<BinHead> bins, heads, obins;
+    DevBuf<BinHead> bins_sorted;       // walk-order copies of bins larger than k_fill_opaque's shared-memory capacity
     uint32_t obin_cap_hint = 0;
     DevBuf<WireTri> wire;
     uint32_t bin_cap_hint = 0;
@@ -352,7 +353,7 @@ int launch_frame(b32_ctx* ctx, const LaunchCtx& L, const FrameArgs& a, cudaEvent
                  ctx->tile_count, wire_on ? ctx->wire.p : nullptr, ctx->state, a.zero_next, ctx->state_stride, p);
     if (ev_fill) CK(cudaEventRecord(ev_fill, L.stream));
     if (!p.wire_front)
-        launch_fill_opaque(L, ctx->recs.p, ctx->bins.p, ctx->tile_count, a.texdesc, a.texels, a.texmask,
+        launch_fill_opaque(L, ctx->recs.p, ctx->bins.p, ctx->tile_count, ctx->bins_sorted.p, a.texdesc, a.texels, a.texmask,
                            ctx->fb_rgba.p, ctx->fb_z.p, ctx->state, ctx->sticky, p);
     return B32_OK;
 }
@@ -445,6 +446,7 @@ int render_device(b32_ctx* ctx, const b32_vertex* d_verts, uint32_t nv, const b3
         p.bin_cap = pick_bin_cap(ctx, nf, ntiles, !wait);
         p.async_call = wait ? 0 : 1;
         CK(ctx->bins.reserve((size_t)ntiles * p.bin_cap));
+        if (p.bin_cap > OP_SORT_MAX_ENTRIES) CK(ctx->bins_sorted.reserve((size_t)ntiles * p.bin_cap));   // else no bin can need it
         ctx->last_params = p;
         if (p.wire_back || p.wire_front) CK(ctx->wire.reserve(nf));
         // take the set the previous call's k_setup zeroed; this call's k_setup zeroes the other one
@@ -541,7 +543,7 @@ void b32_ctx_destroy(b32_ctx* ctx) {
     ctx->fb_rgba.release(); ctx->fb_z.release(); ctx->texels.release(); ctx->texmask.release(); ctx->texdesc.release();
     ctx->texels8.release(); ctx->tex8mask.release(); ctx->tex8desc.release(); ctx->verts.release(); ctx->faces.release();
     ctx->tv.release(); ctx->recs.release(); ctx->keys.release(); ctx->state_ring.release(); ctx->otile_count.release();
-    ctx->bins.release(); ctx->heads.release(); ctx->obins.release(); ctx->wire.release();
+    ctx->bins.release(); ctx->bins_sorted.release(); ctx->heads.release(); ctx->obins.release(); ctx->wire.release();
     ctx->lights.release(); ctx->dbg.release();
     for (FrameGraph& g : ctx->fgs) g.destroy();
     if (ctx->sticky) cudaFree(ctx->sticky);

@@ -17,6 +17,7 @@ constexpr int TILE_W = 16;            // screen tile owned by one CTA of k_fill
 constexpr int TILE_H = 16;
 constexpr int FILL_THREADS = TILE_W * TILE_H;
 constexpr float NEAR_PLANE = 0.1f;    // math.rs:155
+constexpr int OP_SORT_MAX_ENTRIES = 1024;  // k_fill_opaque orders a tile's bin in shared memory up to this many entries, in a global scratch beyond
 constexpr int OP_MASK_SMEM_WORDS = 2048;   // k_fill_opaque keeps the "texel writes" mask in shared memory up to 65536 texels (8 KB)
 
 // ---- per-vertex output of k_transform (render.rs:2321-2360) ------------------------------------

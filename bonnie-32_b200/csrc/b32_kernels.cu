@@ -605,10 +605,10 @@ __device__ __forceinline__ bool shade888(const SurfRec& r, uint32_t x, uint32_t 
 // warp per 4x4 pixel block; a pixel is owned by TWO lanes (lane and lane+16) that evaluate different
 // surfaces at the same time and merge their winners — the winner rule is associative, so the merge is
 // exact.
-//   1. the tile's bin (<= OP_SORT_MAX entries) is copied into shared memory in walk-key order with
-//      one counting-sort pass: painter's mode = nearest (last drawn) first, z-buffer mode = smallest
-//      depth lower bound first.  The order is an efficiency device only: the per-pixel winner rule is
-//      exact for ANY order, ties and all, so larger bins are simply walked unordered from global memory.
+//   1. the tile's bin is copied in walk-key order with one counting-sort pass — into shared memory up to
+//      OP_SORT_MAX entries, into a global scratch beyond: painter's mode = nearest (last drawn) first, z-buffer
+//      mode = smallest depth lower bound first.  The order is an efficiency device only: the per-pixel winner
+//      rule is exact for ANY order, ties and all.
 //   2. the CTA streams the surface records of the walk order through a 3-deep shared-memory ring,
 //      OP_CHUNK records per step, one 16-byte cp.async per thread: the loads of steps c+1 and c+2 are in
 //      flight while the warps work on step c, so no warp ever waits for an L2 round trip of its own.
@@ -640,7 +640,7 @@ static_assert(OP_PIECES >= 1 && OP_PIECES * OP_THREADS == OP_CHUNK * 8, "OP_THRE
 constexpr int OP_BUCKETS = OP_THREADS < 256 ? OP_THREADS : 256;       // key buckets of the counting sort (one scan thread each)
 constexpr int OP_BUCKET_BITS = OP_BUCKETS == 256 ? 8 : (OP_BUCKETS == 128 ? 7 : 6);
 constexpr int OP_RING = 3;                   // ring depth: steps c, c+1, c+2
-constexpr int OP_SORT_MAX = 1024;            // bin entries orderable in shared memory (16 KB of heads)
+constexpr int OP_SORT_MAX = OP_SORT_MAX_ENTRIES;   // bin entries orderable in shared memory (16 KB of heads)
 constexpr int OP_TEX_SMEM = 256;             // texture descriptors cached in shared memory
 constexpr size_t OP_SMEM = (size_t)OP_SORT_MAX * sizeof(BinHead) + (size_t)OP_RING * OP_CHUNK * sizeof(SurfRec) +
                            (size_t)OP_TEX_SMEM * sizeof(TexDev) + (size_t)OP_MASK_SMEM_WORDS * 4 +
@@ -682,6 +682,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 template <bool RGB888>
 __global__ void __launch_bounds__(OP_THREADS, B32_OP_MINB)
 k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins, const uint32_t* __restrict__ tile_count,
+              BinHead* __restrict__ sorted_scratch,
               const TexDev* __restrict__ tex, const uint16_t* __restrict__ texels, const uint32_t* __restrict__ texmask,
               uint32_t* __restrict__ fb_rgba, float* __restrict__ fb_z, const CallState* __restrict__ st,
               uint32_t* __restrict__ sticky, CallParams p) {
@@ -739,20 +740,32 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
     uint32_t st_t0 = gtime(), st_batches = 0, st_surv = 0, st_inside = 0, st_shaded = 0;
 #endif
 
-    // ---- 1. copy the bin to shared memory ordered by walk key, descending: one counting-sort pass into
-    //         256 key buckets (within a bucket the order is arbitrary; the early-out uses bucket bounds)
-    const bool sorted = n <= OP_SORT_MAX;
+    // ---- 1. copy the bin in walk-key order, descending: one counting-sort pass into OP_BUCKETS key buckets (within a
+    //         bucket the order is arbitrary; the early-out uses bucket bounds).  Bins of up to OP_SORT_MAX entries are
+    //         ordered into shared memory, larger ones into this tile's slice of a global scratch (three streamed passes
+    //         over the bin: key range, histogram, scatter), so the early-out also works for very crowded tiles.
+    const bool in_smem = n <= OP_SORT_MAX;
+    BinHead* gwalk = sorted_scratch + (size_t)tile * p.bin_cap;
+    auto walk = [&](uint32_t i) -> BinHead { return in_smem ? s_sh[i] : gwalk[i]; };    // uniform branch: LDS or LDG
     uint32_t kmin = 0, shift = 0;
-    if (sorted) {
-        constexpr int KPT = OP_SORT_MAX / OP_THREADS;              // entries per thread
+    {
+        // a bin that fits shared memory is read once into registers; a larger one is streamed from L2 in each pass
+        constexpr int KPT = OP_SORT_MAX / OP_THREADS;
         BinHead hh[KPT];
-        uint32_t lo = 0xFFFFFFFFu, hi = 0;
-        #pragma unroll
-        for (int q = 0; q < KPT; ++q) {
-            uint32_t i = q * OP_THREADS + threadIdx.x;
-            if (i < n) hh[q] = bin[i]; else hh[q] = BinHead{0, 0, 0xFFFFFFFFu, 0};
-            if (hh[q].key != 0xFFFFFFFFu) { lo = min(lo, hh[q].key); hi = max(hi, hh[q].key); }   // 0xFFFFFFFF = "never cull": bucket 0
+        if (in_smem) {
+            #pragma unroll
+            for (int q = 0; q < KPT; ++q) { uint32_t i = q * OP_THREADS + threadIdx.x; if (i < n) hh[q] = bin[i]; }
         }
+        auto for_each_entry = [&](auto f) {
+            if (in_smem) {
+                #pragma unroll
+                for (int q = 0; q < KPT; ++q) { if (q * OP_THREADS + threadIdx.x < n) f(hh[q]); }
+            } else {
+                for (uint32_t i = threadIdx.x; i < n; i += OP_THREADS) f(bin[i]);
+            }
+        };
+        uint32_t lo = 0xFFFFFFFFu, hi = 0;
+        for_each_entry([&](const BinHead& h) { if (h.key != 0xFFFFFFFFu) { lo = min(lo, h.key); hi = max(hi, h.key); } });   // 0xFFFFFFFF = "never cull": bucket 0
         if (threadIdx.x < OP_BUCKETS) s_hist[threadIdx.x] = 0;
         if (threadIdx.x == 0) { s_minmax[0] = 0xFFFFFFFFu; s_minmax[1] = 0; }
         for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, o)); hi = max(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, o)); }
@@ -764,11 +777,8 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
         if (kmin > kmax) { kmin = 0; kmax = 0; }
         uint32_t range = kmax - kmin;
         shift = range >= OP_BUCKETS ? (32 - __clz(range)) - OP_BUCKET_BITS : 0;         // (range >> shift) <= OP_BUCKETS - 1
-        #pragma unroll
-        for (int q = 0; q < KPT; ++q) {
-            uint32_t i = q * OP_THREADS + threadIdx.x;
-            if (i < n) atomicAdd(&s_hist[hh[q].key == 0xFFFFFFFFu ? 0 : (OP_BUCKETS - 1) - ((hh[q].key - kmin) >> shift)], 1u);
-        }
+        auto bucket = [&](uint32_t k) { return k == 0xFFFFFFFFu ? 0u : (uint32_t)(OP_BUCKETS - 1) - ((k - kmin) >> shift); };
+        for_each_entry([&](const BinHead& h) { atomicAdd(&s_hist[bucket(h.key)], 1u); });
         __syncthreads();
         uint32_t v = 0, xs = 0;                              // exclusive scan of the bucket counts (threads 0..OP_BUCKETS-1)
         if (threadIdx.x < OP_BUCKETS) {
@@ -783,13 +793,9 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
             s_hist[threadIdx.x] = pre + xs - v;
         }
         __syncthreads();
-        #pragma unroll
-        for (int q = 0; q < KPT; ++q) {
-            uint32_t i = q * OP_THREADS + threadIdx.x;
-            if (i < n) s_sh[atomicAdd(&s_hist[hh[q].key == 0xFFFFFFFFu ? 0 : (OP_BUCKETS - 1) - ((hh[q].key - kmin) >> shift)], 1u)] = hh[q];
-        }
+        for_each_entry([&](const BinHead& h) { uint32_t pos = atomicAdd(&s_hist[bucket(h.key)], 1u); if (in_smem) s_sh[pos] = h; else gwalk[pos] = h; });
     }
-    __syncthreads();                                      // s_sh, s_tex and the mbarrier are ready
+    __syncthreads();                                      // the walk order (shared or global), s_tex and the mbarrier are ready
 
     // ---- 2. the record ring: step c -> slot c % OP_RING; thread t moves piece (t & 7) of entry (t >> 3)
     auto stage = [&](uint32_t c) {
@@ -798,7 +804,7 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
             uint32_t piece = q * OP_THREADS + threadIdx.x;
             uint32_t e = c * OP_CHUNK + (piece >> 3);
             if (e < n) {
-                uint32_t f = sorted ? s_sh[e].face : bin[e].face;
+                uint32_t f = in_smem ? s_sh[e].face : gwalk[e].face;
                 cp_async16(reinterpret_cast<uint4*>(&s_rec[(c % OP_RING) * OP_CHUNK + (piece >> 3)]) + (piece & 7),
                            reinterpret_cast<const uint4*>(&recs[f]) + (piece & 7));
             }
@@ -857,8 +863,8 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
             // `open` pixels are those some entry of this batch or a later one could still change; only their
             // bounding box [ox0,ox1) x [oy0,oy1) needs to be met by a surface's bbox.
             uint32_t ox0 = bx0, ox1 = bx0 + OP_BW, oy0 = by0, oy1 = by0 + OP_BH;
-            if (sorted) {
-                uint32_t k0 = s_sh[base].key;
+            {
+                uint32_t k0 = in_smem ? s_sh[base].key : gwalk[base].key;
                 if (k0 != 0xFFFFFFFFu) {
                     // upper bound of every key still to come = top of k0's bucket
                     uint64_t ub64 = (uint64_t)kmin + (((uint64_t)((k0 - kmin) >> shift) + 1) << shift) - 1;
@@ -882,7 +888,7 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
             BinHead h{0, 0, 0, 0};
             bool cand = false;
             if (base + lane < n) {
-                h = sorted ? s_sh[base + lane] : bin[base + lane];
+                h = walk(base + lane);
                 uint32_t min_x = h.bbox_x & 0xFFFF, max_x = h.bbox_x >> 16, min_y = h.bbox_y & 0xFFFF, max_y = h.bbox_y >> 16;
                 cand = !(max_x <= ox0 || min_x >= ox1 || max_y <= oy0 || min_y >= oy1);
                 if (!p.use_zbuffer) cand = cand && h.key >= wkey;
@@ -1505,7 +1511,7 @@ void launch_bin(const LaunchCtx& L, const BinHead* heads, const uint64_t* keys, 
     launch_k(L, k_bin_opaque, grid, BIN_THREADS, smem, after_setup, heads, keys, recs, bins, tile_count, st, p, bin_cap, ordered);
 }
 
-void launch_fill_opaque(const LaunchCtx& L, const SurfRec* recs, const BinHead* bins, const uint32_t* tile_count,
+void launch_fill_opaque(const LaunchCtx& L, const SurfRec* recs, const BinHead* bins, const uint32_t* tile_count, BinHead* sorted_scratch,
                         const TexDev* tex, const uint16_t* texels, const uint32_t* texmask, uint32_t* fb_rgba, float* fb_z,
                         const CallState* st, uint32_t* sticky, const CallParams& p) {
     uint32_t ntiles = p.tiles_x * p.tiles_y;
@@ -1518,7 +1524,7 @@ void launch_fill_opaque(const LaunchCtx& L, const SurfRec* recs, const BinHead* 
     }
     // launched right behind k_bin_opaque except in x-ray mode (no pass-1 binning: then it is an ordinary launch)
     launch_k(L, p.rgb888 ? k_fill_opaque<true> : k_fill_opaque<false>, ntiles * OP_SPLIT, OP_THREADS, OP_SMEM, !(p.xray_mode && !p.rgb888),
-             recs, bins, tile_count, tex, texels, texmask, fb_rgba, fb_z, st, sticky, p);
+             recs, bins, tile_count, sorted_scratch, tex, texels, texmask, fb_rgba, fb_z, st, sticky, p);
 }
 
 void launch_fill_ordered(const LaunchCtx& L, const SurfRec* recs, BinHead* obins, const uint32_t* otile_count,

@@ -37,7 +37,8 @@ void launch_setup(const LaunchCtx& L, const b32_vertex* verts, const b32_face* f
 // ordered = false: scatter heads[] (pass 1); true: scatter the draw-order entries rebuilt from keys[] + recs[] (pass 2 / x-ray)
 void launch_bin(const LaunchCtx& L, const BinHead* heads, const uint64_t* keys, const SurfRec* recs, BinHead* bins, uint32_t* tile_count,
                 CallState* st, const CallParams& p, uint32_t bin_cap, bool ordered, bool after_setup);
-void launch_fill_opaque(const LaunchCtx& L, const SurfRec* recs, const BinHead* bins, const uint32_t* tile_count,
+// sorted_scratch: one bin-sized slice per tile for bins too large to order in shared memory (same layout as bins)
+void launch_fill_opaque(const LaunchCtx& L, const SurfRec* recs, const BinHead* bins, const uint32_t* tile_count, BinHead* sorted_scratch,
                         const TexDev* tex, const uint16_t* texels, const uint32_t* texmask, uint32_t* fb_rgba, float* fb_z,
                         const CallState* st, uint32_t* sticky, const CallParams& p);
 // ordered pass (pass 2 / x-ray): bins of draw-order keys, sorted per tile, replayed in order
