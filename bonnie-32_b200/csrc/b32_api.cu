@@ -148,6 +148,8 @@ int cuda_fail(b32_ctx* c, cudaError_t e, const char* what) {
     return fail(c, B32_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
 #define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return cuda_fail(ctx, _e, #call); } while (0)
+// A host thread may hold contexts on several GPUs: every entry point first selects its context's device.
+#define USE_DEVICE(ctx) do { if ((ctx) && cudaSetDevice((ctx)->device) != cudaSuccess) return cuda_fail((ctx), cudaGetLastError(), "cudaSetDevice"); } while (0)
 
 constexpr uint32_t STATE_WORDS = 16;    // CallState padded to 64 bytes; the tile counters follow
 static_assert(sizeof(CallState) <= STATE_WORDS * 4, "CallState must fit its slot");
@@ -523,6 +525,7 @@ int b32_ctx_create(int device, b32_ctx** out) {
     cudaError_t e;
     if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e, "cudaSetDevice");
     if ((e = cudaGetDeviceProperties(&ctx->prop, device)) != cudaSuccess) return bail(e, "cudaGetDeviceProperties");
+    if ((e = (cudaError_t)init_kernel_attributes()) != cudaSuccess) return bail(e, "cudaFuncSetAttribute");
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     for (auto& ev : ctx->ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaMalloc(&ctx->sticky, sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
@@ -575,6 +578,7 @@ static int collect_async(b32_ctx* ctx) {
 }
 
 int b32_sync(b32_ctx* ctx) {
+    USE_DEVICE(ctx);
     if (!ctx) return B32_ERR_INVALID;
     int rc = collect_async(ctx);
     CK(cudaStreamSynchronize(ctx->stream));
@@ -583,6 +587,7 @@ int b32_sync(b32_ctx* ctx) {
 }
 
 int b32_fb_resize(b32_ctx* ctx, uint32_t width, uint32_t height) {
+    USE_DEVICE(ctx);
     if (!ctx) return B32_ERR_INVALID;
     if (width == ctx->width && height == ctx->height) return B32_OK;          // render.rs:28
     if (width > 65535 || height > 65535) return fail(ctx, B32_ERR_UNSUPPORTED, "framebuffer dimension > 65535");
@@ -596,6 +601,7 @@ int b32_fb_resize(b32_ctx* ctx, uint32_t width, uint32_t height) {
 }
 
 int b32_fb_clear(b32_ctx* ctx, uint8_t r, uint8_t g, uint8_t b, uint8_t a) {
+    USE_DEVICE(ctx);
     if (!ctx) return B32_ERR_INVALID;
     uint32_t c = (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16) | ((uint32_t)a << 24);
     launch_fb_clear(ctx->L(), ctx->fb_rgba.p, ctx->fb_z.p, ctx->width * ctx->height, c);
@@ -604,6 +610,7 @@ int b32_fb_clear(b32_ctx* ctx, uint8_t r, uint8_t g, uint8_t b, uint8_t a) {
 }
 
 int b32_fb_upload(b32_ctx* ctx, const uint8_t* rgba, const float* z) {
+    USE_DEVICE(ctx);
     if (!ctx || !rgba) return B32_ERR_INVALID;
     size_t n = (size_t)ctx->width * ctx->height;
     int rc = h2d(ctx, ctx->fb_rgba.p, rgba, n * 4); if (rc) return rc;
@@ -613,6 +620,7 @@ int b32_fb_upload(b32_ctx* ctx, const uint8_t* rgba, const float* z) {
 }
 
 int b32_fb_download(b32_ctx* ctx, uint8_t* rgba, float* z) {
+    USE_DEVICE(ctx);
     if (!ctx) return B32_ERR_INVALID;
     size_t n = (size_t)ctx->width * ctx->height;
     if (rgba) CK(cudaMemcpyAsync(rgba, ctx->fb_rgba.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -629,6 +637,7 @@ int b32_fb_size(const b32_ctx* ctx, uint32_t* width, uint32_t* height) {
 }
 
 int b32_textures_set(b32_ctx* ctx, const b32_tex_desc* descs, uint32_t n) {
+    USE_DEVICE(ctx);
     if (!ctx || (n && !descs)) return B32_ERR_INVALID;
     if (n > 0xFFFF) return fail(ctx, B32_ERR_UNSUPPORTED, "more than 65535 textures (face.flags carries a 16-bit texture id)");
     CK(cudaStreamSynchronize(ctx->stream));
@@ -684,6 +693,7 @@ int b32_textures_set(b32_ctx* ctx, const b32_tex_desc* descs, uint32_t n) {
 }
 
 int b32_textures_set_rgb888(b32_ctx* ctx, const b32_tex8_desc* descs, uint32_t n) {
+    USE_DEVICE(ctx);
     if (!ctx || (n && !descs)) return B32_ERR_INVALID;
     if (n > 0xFFFF) return fail(ctx, B32_ERR_UNSUPPORTED, "more than 65535 textures (face.flags carries a 16-bit texture id)");
     CK(cudaStreamSynchronize(ctx->stream));
@@ -718,6 +728,7 @@ int b32_textures_set_rgb888(b32_ctx* ctx, const b32_tex8_desc* descs, uint32_t n
 
 int b32_render_mesh(b32_ctx* ctx, const b32_vertex* vertices, uint32_t nv, const b32_face* faces, uint32_t nf,
                     const b32_camera* camera, const b32_settings* settings, b32_timings* timings) {
+    USE_DEVICE(ctx);
     if (!ctx) return B32_ERR_INVALID;
     if ((nv && !vertices) || (nf && !faces)) return fail(ctx, B32_ERR_INVALID, "vertices/faces is NULL");
     CK(ctx->verts.reserve(std::max<uint32_t>(nv, 1)));
@@ -728,12 +739,14 @@ int b32_render_mesh(b32_ctx* ctx, const b32_vertex* vertices, uint32_t nv, const
 }
 
 int b32_render_mesh_resident(b32_ctx* ctx, const b32_mesh* mesh, const b32_camera* camera, const b32_settings* settings, b32_timings* timings) {
+    USE_DEVICE(ctx);
     if (!ctx || !mesh) return B32_ERR_INVALID;
     return render_device(ctx, mesh->verts, mesh->nv, mesh->faces, mesh->nf, camera, settings, nullptr, timings, true, true);
 }
 
 int b32_render_mesh_15(b32_ctx* ctx, const b32_vertex* vertices, uint32_t nv, const b32_face* faces, uint32_t nf,
                        const b32_camera* camera, const b32_settings* settings, const b32_fog* fog, b32_timings* timings) {
+    USE_DEVICE(ctx);
     if (!ctx) return B32_ERR_INVALID;
     if ((nv && !vertices) || (nf && !faces)) return fail(ctx, B32_ERR_INVALID, "vertices/faces is NULL");
     CK(ctx->verts.reserve(std::max<uint32_t>(nv, 1)));
@@ -745,6 +758,7 @@ int b32_render_mesh_15(b32_ctx* ctx, const b32_vertex* vertices, uint32_t nv, co
 
 int b32_render_mesh_15_ex(b32_ctx* ctx, const b32_vertex* vertices, uint32_t nv, const b32_face* faces, uint32_t nf,
                           const b32_camera* camera, const b32_settings* settings, const b32_fog* fog, uint32_t flags, b32_timings* timings) {
+    USE_DEVICE(ctx);
     if (!ctx) return B32_ERR_INVALID;
     if (!(flags & B32_RENDER_ASYNC)) return b32_render_mesh_15(ctx, vertices, nv, faces, nf, camera, settings, fog, timings);
     if (!(flags & B32_RENDER_ALL_OPAQUE)) return fail(ctx, B32_ERR_INVALID, "B32_RENDER_ASYNC needs B32_RENDER_ALL_OPAQUE (pass 2 needs a host round trip)");
@@ -764,6 +778,7 @@ int b32_render_mesh_15_ex(b32_ctx* ctx, const b32_vertex* vertices, uint32_t nv,
 
 int b32_frame_15_enqueue(b32_ctx* ctx, const uint8_t* clear_rgba, const b32_mesh* mesh, const b32_camera* camera,
                          const b32_settings* settings, const b32_fog* fog) {
+    USE_DEVICE(ctx);
     if (!ctx || !mesh || !settings) return B32_ERR_INVALID;
     bool may_blend = mesh->has_nonopaque || settings->xray_mode || (settings->backface_cull && settings->backface_wireframe) || settings->wireframe_overlay;
     for (const TexDev& t : ctx->texdesc_h) may_blend = may_blend || t.blend != B32_BLEND_OPAQUE;
@@ -775,6 +790,7 @@ int b32_frame_15_enqueue(b32_ctx* ctx, const uint8_t* clear_rgba, const b32_mesh
 uint64_t b32_graph_launches(const b32_ctx* ctx) { return ctx ? ctx->graph_launches : 0; }
 
 int b32_fb_download_async(b32_ctx* ctx, uint8_t* rgba, float* z) {
+    USE_DEVICE(ctx);
     if (!ctx) return B32_ERR_INVALID;
     size_t n = (size_t)ctx->width * ctx->height;
     if (rgba) CK(cudaMemcpyAsync(rgba, ctx->fb_rgba.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -783,6 +799,7 @@ int b32_fb_download_async(b32_ctx* ctx, uint8_t* rgba, float* z) {
 }
 
 int b32_mesh_upload(b32_ctx* ctx, const b32_vertex* vertices, uint32_t nv, const b32_face* faces, uint32_t nf, b32_mesh** out) {
+    USE_DEVICE(ctx);
     if (!ctx || !out) return B32_ERR_INVALID;
     if ((nv && !vertices) || (nf && !faces)) return fail(ctx, B32_ERR_INVALID, "vertices/faces is NULL");
     b32_mesh* m = new b32_mesh();
@@ -804,6 +821,7 @@ int b32_mesh_upload(b32_ctx* ctx, const b32_vertex* vertices, uint32_t nv, const
 
 void b32_mesh_free(b32_ctx* ctx, b32_mesh* mesh) {
     if (!mesh) return;
+    if (ctx) cudaSetDevice(ctx->device);
     if (ctx) cudaStreamSynchronize(ctx->stream);
     cudaFree(mesh->verts); cudaFree(mesh->faces);
     delete mesh;
@@ -811,11 +829,13 @@ void b32_mesh_free(b32_ctx* ctx, b32_mesh* mesh) {
 
 int b32_render_mesh_15_resident(b32_ctx* ctx, const b32_mesh* mesh, const b32_camera* camera, const b32_settings* settings,
                                 const b32_fog* fog, b32_timings* timings) {
+    USE_DEVICE(ctx);
     if (!ctx || !mesh) return B32_ERR_INVALID;
     return render_device(ctx, mesh->verts, mesh->nv, mesh->faces, mesh->nf, camera, settings, fog, timings, true);
 }
 
 int b32_render_mesh_15_enqueue(b32_ctx* ctx, const b32_mesh* mesh, const b32_camera* camera, const b32_settings* settings, const b32_fog* fog) {
+    USE_DEVICE(ctx);
     if (!ctx || !mesh || !settings) return B32_ERR_INVALID;
     // Pass 1 needs no host round trip.  Pass 2 (any semi-transparent surface) and x-ray mode do, so a
     // mesh/texture set that can produce them is rendered synchronously instead.
@@ -827,6 +847,7 @@ int b32_render_mesh_15_enqueue(b32_ctx* ctx, const b32_mesh* mesh, const b32_cam
 }
 
 int b32_render_skybox_mesh(b32_ctx* ctx, const b32_sky_vertex* vertices, uint32_t nv, const uint32_t* faces, uint32_t nf, const b32_camera* camera) {
+    USE_DEVICE(ctx);
     if (!ctx || !camera) return B32_ERR_INVALID;
     if ((nv && !vertices) || (nf && !faces)) return fail(ctx, B32_ERR_INVALID, "vertices/faces is NULL");
     if (ctx->width == 0 || ctx->height == 0) return fail(ctx, B32_ERR_INVALID, "framebuffer has zero size (call b32_fb_resize)");
@@ -874,6 +895,7 @@ void b32_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int b32_debug_transform(b32_ctx* ctx, const b32_vertex* vertices, uint32_t nv, const b32_camera* camera, const b32_settings* settings,
                         float* out_screen, float* out_cam) {
+    USE_DEVICE(ctx);
     if (!ctx || !camera || !settings || (nv && (!vertices || !out_screen || !out_cam))) return B32_ERR_INVALID;
     if (nv == 0) return B32_OK;
     CallParams p; std::vector<LightDev> lights;
@@ -897,6 +919,7 @@ int b32_debug_kernel_times(b32_ctx* ctx, float* out_ms, uint32_t cap) {
 }
 
 int b32_debug_draw_order(b32_ctx* ctx, uint32_t* out_face_idx, uint32_t cap, uint32_t* n) {
+    USE_DEVICE(ctx);
     // Test hook: the draw order of the last call = stable sort of (pass, depth key) over the drawn faces
     // (render.rs:2522-2542).  Pass 1 is order-free on the device and pass 2 sorts per tile, so the global
     // order only exists here, computed on the host from the device's keys.

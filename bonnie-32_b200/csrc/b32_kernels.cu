@@ -1475,6 +1475,16 @@ static void launch_k(const LaunchCtx& L, void (*kern)(KArgs...), dim3 grid, dim3
     launch_k_impl(L, kern, grid, block, smem, pdl, std::index_sequence_for<KArgs...>{}, std::forward<Args>(args)...);
 }
 
+// Per-device kernel attributes (dynamic shared memory above the 48 KB default); called once per context, on its device.
+int init_kernel_attributes() {
+    cudaError_t e = cudaFuncSetAttribute(k_bin_opaque, cudaFuncAttributeMaxDynamicSharedMemorySize, BIN_MAX_TILES * 8);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fill_opaque<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OP_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fill_opaque<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OP_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fill_ordered<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ORD_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fill_ordered<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ORD_SMEM);
+    return (int)e;
+}
+
 static inline uint32_t grid_for(uint32_t n, uint32_t block, uint32_t sms, uint32_t per_sm = 8) {
     uint32_t g = (n + block - 1) / block;
     uint32_t cap = sms * per_sm;
@@ -1503,8 +1513,6 @@ void launch_bin(const LaunchCtx& L, const BinHead* heads, const uint64_t* keys, 
     if (p.nf == 0) return;
     uint32_t ntiles = p.tiles_x * p.tiles_y;
     size_t smem = ntiles <= (uint32_t)BIN_MAX_TILES ? (size_t)ntiles * 8 : 0;
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k_bin_opaque, cudaFuncAttributeMaxDynamicSharedMemorySize, BIN_MAX_TILES * 8); attr_set = true; }
     uint32_t per_round = BIN_THREADS;
     uint32_t grid = (p.nf + per_round - 1) / per_round;
     if (grid > L.sms * 4) grid = L.sms * 4;
@@ -1516,12 +1524,6 @@ void launch_fill_opaque(const LaunchCtx& L, const SurfRec* recs, const BinHead* 
                         const CallState* st, uint32_t* sticky, const CallParams& p) {
     uint32_t ntiles = p.tiles_x * p.tiles_y;
     if (ntiles == 0 || p.nf == 0) return;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_fill_opaque<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OP_SMEM);
-        cudaFuncSetAttribute(k_fill_opaque<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OP_SMEM);
-        attr_set = true;
-    }
     // launched right behind k_bin_opaque except in x-ray mode (no pass-1 binning: then it is an ordinary launch)
     launch_k(L, p.rgb888 ? k_fill_opaque<true> : k_fill_opaque<false>, ntiles * OP_SPLIT, OP_THREADS, OP_SMEM, !(p.xray_mode && !p.rgb888),
              recs, bins, tile_count, sorted_scratch, tex, texels, texmask, fb_rgba, fb_z, st, sticky, p);
@@ -1532,12 +1534,6 @@ void launch_fill_ordered(const LaunchCtx& L, const SurfRec* recs, BinHead* obins
                          const CallState* st, const CallParams& p, uint32_t obin_cap) {
     uint32_t ntiles = p.tiles_x * p.tiles_y;
     if (ntiles == 0 || p.nf == 0) return;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_fill_ordered<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ORD_SMEM);
-        cudaFuncSetAttribute(k_fill_ordered<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ORD_SMEM);
-        attr_set = true;
-    }
     launch_k(L, p.rgb888 ? k_fill_ordered<true> : k_fill_ordered<false>, ntiles, FILL_THREADS, ORD_SMEM, false,
              recs, obins, otile_count, tex, static_cast<const void*>(texels), fb_rgba, fb_z, st, p, obin_cap);
 }

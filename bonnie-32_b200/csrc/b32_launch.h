@@ -29,6 +29,10 @@ struct LaunchCtx {
     GraphPatch* patch = nullptr;  // non-null: patch graph nodes instead of launching
 };
 
+// cudaFuncSetAttribute for the kernels that need more than 48 KB of dynamic shared memory, on the current device.
+// Returns a cudaError_t value.
+int init_kernel_attributes();
+
 void launch_transform(const LaunchCtx& L, const b32_vertex* verts, TVert* out, float* dbg_cam, const CallParams& p);
 // tv == nullptr: vertices are transformed inside k_setup (fused path). Also bins the pass-1 surfaces.
 void launch_setup(const LaunchCtx& L, const b32_vertex* verts, const b32_face* faces, const TVert* tv, const TexDev* tex,

@@ -529,3 +529,23 @@ def test_fuzz_gpu_equals_oracle(ctx, oracle, rgb888):
         assert_same(sc, got, got_z, tm, want, want_z, otm)
         ok += 1
     assert ok >= 30 and ok + panics == 60
+
+
+def test_two_devices_in_one_process(oracle):
+    """A host thread that holds contexts on two GPUs: every entry point selects its context's device."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sc = scenes.scene_c2(n_tris=400, use_zbuffer=True)
+    want, want_z, otm, rc = oracle.render_scene(sc)
+    ctxs = [pkg.Context(0), pkg.Context(1)]
+    fbs = [pkg.Framebuffer(sc.width, sc.height, c) for c in ctxs]
+    for _ in range(2):                                   # interleaved calls on the two devices
+        for c, fb in zip(ctxs, fbs):
+            fb.clear(sc.clear)
+            tm = pkg.render_mesh_15(fb, sc.vertices, sc.faces, sc.textures, sc.camera, sc.settings)
+        for c, fb in zip(ctxs, fbs):
+            got, got_z = fb.download()
+            assert_same(sc, got, got_z, tm, want, want_z, otm)
+    for c in ctxs:
+        c.close()
