@@ -1,3 +1,5 @@
+"""Per-warp timeline of k_fill_opaque on the C4 frame (GPU box only; needs a -DB32_FILL_STATS build):
+    tools/build_variant.sh stats_lib.so -DB32_FILL_STATS && python tools/fill_stats.py"""
 import sys, ctypes as C
 sys.path.insert(0,'.')
 import __graft_entry__ as g, numpy as np
