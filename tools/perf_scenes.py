@@ -82,6 +82,10 @@ def main():
             run(ctx, f"c3_{lv.name}_{mode}", calls, lv.width, lv.height, lv.clear)
             if mode == "zbuffer":
                 run(ctx, f"c3_{lv.name}_{mode}_640x480", calls, 640, 480, lv.clear)
+                # float projection: no surface has integer edge values, every inside test replays the rounded additions
+                fcalls = [(rc.vertices, rc.faces, lv.camera, lv.settings(rc.ambient, use_fixed_point=False, **kw), rc.fog) for rc in lv.rooms]
+                run(ctx, f"c3_{lv.name}_{mode}_float", fcalls, lv.width, lv.height, lv.clear)
+                run(ctx, f"c3_{lv.name}_{mode}_float_640x480", fcalls, 640, 480, lv.clear)
 
 
 if __name__ == "__main__":
