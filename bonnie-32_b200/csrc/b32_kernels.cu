@@ -344,7 +344,10 @@ __device__ __forceinline__ void for_each_tile(const BinHead& h, bool has, uint32
     }
 }
 
-__global__ void __launch_bounds__(SETUP_THREADS)
+#ifndef B32_SETUP_MINB
+#define B32_SETUP_MINB 6          // <= 80 registers: 6 CTAs per SM = 888 slots, so the 782 CTAs of a 100k-face mesh are one wave
+#endif
+__global__ void __launch_bounds__(SETUP_THREADS, B32_SETUP_MINB)
 k_setup(const b32_vertex* __restrict__ verts, const b32_face* __restrict__ faces, const TVert* __restrict__ tv,
         const TexDev* __restrict__ tex, const LightDev* __restrict__ lights,
         SurfRec* __restrict__ recs, uint64_t* __restrict__ keys,
