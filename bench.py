@@ -258,7 +258,6 @@ def run_b200(args):
     for c in ctxs:
         c.sync()
     barrier()
-    clocks = sampler.stop()
     launches = sum(c.kernel_launches() for c in ctxs) - launches0
     total_ms = max(s0.elapsed_time(e1) for s0 in starts for e1 in ends)       # first start -> last end, device clock
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
@@ -333,6 +332,7 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s, e2e_sync_s = float(t[0].item()), float(t[1].item())
+    clocks = sampler.stop()                  # sampled over all timed regions of this run (value, per-kernel, end to end)
     e2e_value = world * N_TRIS / (e2e_s / args.steps) / 1e6
     got = np.ctypeslib.as_array(C.cast(hps[(args.steps - 1) % N_CTX], C.POINTER(C.c_uint8)), shape=(sc.height, sc.width, 4)).copy()
 
