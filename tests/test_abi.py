@@ -45,6 +45,7 @@ int main(void) {
          sizeof(b32_settings), sizeof(b32_fog), sizeof(b32_timings), sizeof(b32_tex_desc));
   printf("%zu %zu %zu %zu %zu\n", offsetof(b32_vertex, uv), offsetof(b32_vertex, normal), offsetof(b32_vertex, r),
          offsetof(b32_settings, ambient), offsetof(b32_settings, lights));
+  printf("%zu %zu %zu %zu\n", sizeof(b32_tex8_desc), offsetof(b32_tex8_desc, pixels), sizeof(b32_sky_vertex), offsetof(b32_sky_vertex, r));
   return 0; }''')
     exe = tmp_path / "sizes"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(prog)])
@@ -52,7 +53,8 @@ int main(void) {
     sizes = [int(x) for x in out]
     assert sizes[:8] == [36, 16, 48, C.sizeof(abi.Light), C.sizeof(abi.Settings), C.sizeof(abi.Fog), C.sizeof(abi.Timings), C.sizeof(abi.TexDesc)]
     assert abi.VERTEX_DTYPE.itemsize == 36 and abi.FACE_DTYPE.itemsize == 16 and C.sizeof(abi.Camera) == 48
-    assert sizes[8:] == [12, 20, 32, abi.Settings.ambient.offset, abi.Settings.lights.offset]
+    assert sizes[8:13] == [12, 20, 32, abi.Settings.ambient.offset, abi.Settings.lights.offset]
+    assert sizes[13:] == [C.sizeof(abi.Tex8Desc), abi.Tex8Desc.pixels.offset, abi.SKY_VERTEX_DTYPE.itemsize, abi.SKY_VERTEX_DTYPE.fields["rgb"][1]]
     assert abi.VERTEX_DTYPE.fields["uv"][1] == 12 and abi.VERTEX_DTYPE.fields["normal"][1] == 20 and abi.VERTEX_DTYPE.fields["rgba"][1] == 32
 
 
