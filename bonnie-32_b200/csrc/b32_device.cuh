@@ -40,6 +40,20 @@ struct __align__(16) SurfRec {
 };
 static_assert(sizeof(SurfRec) == 128, "SurfRec must be 128 bytes");
 
+// The first 80 bytes of a SurfRec: everything the visibility walk of k_fill_opaque needs (edge functions, bbox, depth,
+// texture coordinates).  Same field names, so the fragment helpers are templates over the record type.  Staged at an
+// 80-byte stride, lane-indexed reads hit 8 different banks (a 128-byte stride puts all 32 lanes on one).
+struct __align__(16) SurfHot {
+    float a0, b0, a1, b1;
+    float w0s, w1s, inv_area;
+    uint32_t flags;
+    uint32_t bbox_x, bbox_y;
+    float iz1, iz2, iz3;
+    float u1, v1, u2, v2, u3, v3;
+    uint32_t vc1;
+};
+static_assert(sizeof(SurfHot) == 80, "SurfHot must be the first 80 bytes of SurfRec");
+
 enum : uint32_t {
     SF_BLEND_MASK   = 0x7,        // blend_mode the fill uses: texture's if textured else face's (:1450-1452)
     SF_BLACK_TR     = 1u << 3,    // Face.black_transparent

@@ -454,7 +454,8 @@ k_bin_opaque(const BinHead* __restrict__ heads, const uint64_t* __restrict__ key
 struct Pixel { uint32_t rgba; float z; };
 
 // Edge functions + barycentrics at pixel (x,y): render.rs:1517-1542, 1706-1712.
-__device__ __forceinline__ bool inside_test(const SurfRec& r, uint32_t x, uint32_t y, float& bc_x, float& bc_y, float& bc_z) {
+template <typename Rec>
+__device__ __forceinline__ bool inside_test(const Rec& r, uint32_t x, uint32_t y, float& bc_x, float& bc_y, float& bc_z) {
     uint32_t min_x = r.bbox_x & 0xFFFF, min_y = r.bbox_y & 0xFFFF;
     float w0, w1;
     if (r.flags & SF_FAST_EDGE) {
@@ -612,9 +613,9 @@ __device__ __forceinline__ bool shade888(const SurfRec& r, uint32_t x, uint32_t 
 //      OP_SORT_MAX entries, into a global scratch beyond: painter's mode = nearest (last drawn) first, z-buffer
 //      mode = smallest depth lower bound first.  The order is an efficiency device only: the per-pixel winner
 //      rule is exact for ANY order, ties and all.
-//   2. the CTA streams the surface records of the walk order through a 3-deep shared-memory ring,
-//      OP_CHUNK records per step, one 16-byte cp.async per thread: the loads of steps c+1 and c+2 are in
-//      flight while the warps work on step c, so no warp ever waits for an L2 round trip of its own.
+//   2. the CTA streams the visibility part (80 of 128 bytes) of the surface records of the walk order through a
+//      3-deep shared-memory ring, OP_CHUNK records per step, in 16-byte cp.async pieces: the loads of steps c+1 and
+//      c+2 are in flight while the warps work on step c, so no warp ever waits for an L2 round trip of its own.
 //   3. every warp filters the step's entries one per lane (bbox vs the block's still-open pixels,
 //      priority / depth bound vs the block's weakest pixel); survivors are evaluated two per half-warp at
 //      a time.  The walk only decides WHO wins each pixel: inside test, depth, and — for black-keyed
@@ -637,15 +638,19 @@ constexpr int OP_BW = OP_DUAL ? 4 : 8, OP_BH = 4;                     // pixel b
 constexpr int OP_WPT = (TILE_W / OP_BW) * (TILE_H / OP_BH);            // warps per 16x16 tile
 constexpr int OP_SPLIT = OP_WPT / OP_WARPS;  // CTAs per tile (256 threads, dual: 2 = half tiles of 16x8 px)
 static_assert(OP_SPLIT >= 1 && OP_SPLIT * OP_WARPS == OP_WPT, "a CTA covers a whole number of block rows of one tile");
-constexpr int OP_CHUNK = OP_THREADS > 256 ? OP_THREADS / 8 : 32;   // surface records staged per step (8 x 16 B each), OP_PIECES per thread
-constexpr int OP_PIECES = OP_CHUNK * 8 / OP_THREADS;
-static_assert(OP_PIECES >= 1 && OP_PIECES * OP_THREADS == OP_CHUNK * 8, "OP_THREADS must divide 256 or be a multiple of it");
+#ifndef B32_OP_CHUNK
+#define B32_OP_CHUNK 128
+#endif
+constexpr int OP_CHUNK = B32_OP_CHUNK;       // surface records (their 80-byte visibility part) staged per step: most warps are done within
+                                             // the first step, so the CTA-wide barrier between steps rarely holds anybody up
+constexpr int OP_REC_PIECES = sizeof(SurfHot) / 16;
+static_assert(OP_CHUNK % 32 == 0 && OP_CHUNK <= 256, "whole 32-entry batches; slots are stored in a byte");
 constexpr int OP_BUCKETS = OP_THREADS < 256 ? OP_THREADS : 256;       // key buckets of the counting sort (one scan thread each)
 constexpr int OP_BUCKET_BITS = OP_BUCKETS == 256 ? 8 : (OP_BUCKETS == 128 ? 7 : 6);
 constexpr int OP_RING = 3;                   // ring depth: steps c, c+1, c+2
 constexpr int OP_SORT_MAX = OP_SORT_MAX_ENTRIES;   // bin entries orderable in shared memory (16 KB of heads)
 constexpr int OP_TEX_SMEM = 256;             // texture descriptors cached in shared memory
-constexpr size_t OP_SMEM = (size_t)OP_SORT_MAX * sizeof(BinHead) + (size_t)OP_RING * OP_CHUNK * sizeof(SurfRec) +
+constexpr size_t OP_SMEM = (size_t)OP_SORT_MAX * sizeof(BinHead) + (size_t)OP_RING * OP_CHUNK * sizeof(SurfHot) +
                            (size_t)OP_TEX_SMEM * sizeof(TexDev) + (size_t)OP_MASK_SMEM_WORDS * 4 +
                            (size_t)OP_WARPS * 32 * sizeof(uint2) + (size_t)OP_WARPS * 32;
 #ifdef B32_FILL_STATS
@@ -690,7 +695,7 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
               uint32_t* __restrict__ fb_rgba, float* __restrict__ fb_z, const CallState* __restrict__ st,
               uint32_t* __restrict__ sticky, CallParams p) {
     extern __shared__ __align__(128) uint8_t op_smem[];
-    SurfRec* s_rec = reinterpret_cast<SurfRec*>(op_smem);                               // [OP_RING][OP_CHUNK] record ring
+    SurfHot* s_rec = reinterpret_cast<SurfHot*>(op_smem);                               // [OP_RING][OP_CHUNK] record ring (visibility part)
     BinHead* s_sh = reinterpret_cast<BinHead*>(s_rec + OP_RING * OP_CHUNK);             // [OP_SORT_MAX] bin in walk order
     TexDev* s_tex = reinterpret_cast<TexDev*>(s_sh + OP_SORT_MAX);                      // [OP_TEX_SMEM]
     uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_tex + OP_TEX_SMEM);                // [OP_MASK_SMEM_WORDS] "texel writes" bits
@@ -800,16 +805,15 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
     }
     __syncthreads();                                      // the walk order (shared or global), s_tex and the mbarrier are ready
 
-    // ---- 2. the record ring: step c -> slot c % OP_RING; thread t moves piece (t & 7) of entry (t >> 3)
+    // ---- 2. the record ring: step c -> slot c % OP_RING; the 16-byte pieces of the step's records are dealt round robin
     auto stage = [&](uint32_t c) {
-        #pragma unroll
-        for (int q = 0; q < OP_PIECES; ++q) {
-            uint32_t piece = q * OP_THREADS + threadIdx.x;
-            uint32_t e = c * OP_CHUNK + (piece >> 3);
+        for (uint32_t piece = threadIdx.x; piece < (uint32_t)(OP_CHUNK * OP_REC_PIECES); piece += OP_THREADS) {
+            uint32_t slot = piece / OP_REC_PIECES, part = piece % OP_REC_PIECES;
+            uint32_t e = c * OP_CHUNK + slot;
             if (e < n) {
                 uint32_t f = in_smem ? s_sh[e].face : gwalk[e].face;
-                cp_async16(reinterpret_cast<uint4*>(&s_rec[(c % OP_RING) * OP_CHUNK + (piece >> 3)]) + (piece & 7),
-                           reinterpret_cast<const uint4*>(&recs[f]) + (piece & 7));
+                cp_async16(reinterpret_cast<uint4*>(&s_rec[(c % OP_RING) * OP_CHUNK + slot]) + part,
+                           reinterpret_cast<const uint4*>(&recs[f]) + part);
             }
         }
         cp_async_commit();
@@ -839,7 +843,7 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
         if (__syncthreads_and(done)) break;               // ... and so have everybody else's; slot (c+2) % 3 is free again
         stage(c + 2);
         if (done) continue;
-        const SurfRec* crec = s_rec + (c % OP_RING) * OP_CHUNK;
+        const SurfHot* crec = s_rec + (c % OP_RING) * OP_CHUNK;
         for (uint32_t sb = 0; sb < (uint32_t)OP_CHUNK; sb += 32) {
             const uint32_t base = c * OP_CHUNK + sb;
             if (base >= n) break;
@@ -902,7 +906,7 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
                     // each barycentric's extreme over the box is at a corner; bc_z = fl(fl(1 - bc_x) - bc_y) is
                     // monotone non-increasing in both.  A surface whose upper bounds fail `>= -0.0001` (:1541)
                     // has no inside pixel in the box.
-                    const SurfRec& r = crec[sb + lane];
+                    const SurfHot& r = crec[sb + lane];
                     if (r.flags & SF_FAST_EDGE) {
                         float dx0 = (float)(max(ox0, min_x) - min_x), dx1 = (float)(min(ox1, max_x) - 1 - min_x);
                         float dy0 = (float)(max(oy0, min_y) - min_y), dy1 = (float)(min(oy1, max_y) - 1 - min_y);
@@ -934,7 +938,7 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
                 for (int k = 0; k < 2; ++k) {
                     uint32_t j = j0 + NSUB * k + sub;
                     if (j >= cnt) continue;
-                    const SurfRec& r = crec[my_sidx[j]];
+                    const SurfHot& r = crec[my_sidx[j]];
                     const uint2 kf = my_surv[j];
                     uint32_t min_x = r.bbox_x & 0xFFFF, max_x = r.bbox_x >> 16, min_y = r.bbox_y & 0xFFFF, max_y = r.bbox_y >> 16;
                     if (!(valid && x >= min_x && x < max_x && y >= min_y && y < max_y)) continue;
