@@ -113,6 +113,7 @@ struct b32_ctx {
     DevBuf<BinHead> bins_sorted;       // walk-order copies of bins larger than k_fill_opaque's shared-memory capacity
     uint32_t obin_cap_hint = 0;
     DevBuf<WireTri> wire;
+    DevBuf<uint32_t> wire_table;       // open-addressing table of the wireframe phase's edge de-duplication
     uint32_t bin_cap_hint = 0;
     std::vector<LightDev> lights_h;
     bool async_pending = false;
@@ -489,9 +490,14 @@ int render_device(b32_ctx* ctx, const b32_vertex* d_verts, uint32_t nv, const b3
     bool need_ordered = all_ordered ? (hs.n_opaque + hs.n_transp) > 0 : (!rgb888 && hs.n_transp > 0);
     if (need_ordered && !p.wire_front) { rc = render_ordered(ctx, p, all_ordered ? hs.n_opaque + hs.n_transp : hs.n_transp); if (rc) return rc; }
     if (p.wire_back || p.wire_front) {          // WIREFRAME phase, render.rs:2574-2635
+        uint32_t tsize = 64;
+        while (tsize < 6ull * nf && tsize < 0x80000000u) tsize <<= 1;             // load factor <= 1/2 with 3 edges per face
+        CK(ctx->wire_table.reserve(tsize));
         CK(cudaEventRecord(ctx->ev[0], st));
-        if (p.wire_back) launch_wire(L, ctx->wire.p, 1, 80u | (80u << 8) | (100u << 16) | 0xFF000000u, true, ctx->fb_rgba.p, ctx->fb_z.p, ctx->state, p);
-        if (p.wire_front) launch_wire(L, ctx->wire.p, 2, 200u | (200u << 8) | (220u << 16) | 0xFF000000u, false, ctx->fb_rgba.p, ctx->fb_z.p, ctx->state, p);
+        if (p.wire_back) launch_wire(L, ctx->wire.p, 1, 80u | (80u << 8) | (100u << 16) | 0xFF000000u, true, ctx->wire_table.p, tsize,
+                                     ctx->fb_rgba.p, ctx->fb_z.p, ctx->state, p);
+        if (p.wire_front) launch_wire(L, ctx->wire.p, 2, 200u | (200u << 8) | (220u << 16) | 0xFF000000u, false, ctx->wire_table.p, tsize,
+                                      ctx->fb_rgba.p, ctx->fb_z.p, ctx->state, p);
         CK(cudaEventRecord(ctx->ev[1], st));
         CK(cudaStreamSynchronize(st));
         CK(cudaGetLastError());
@@ -546,7 +552,7 @@ void b32_ctx_destroy(b32_ctx* ctx) {
     ctx->fb_rgba.release(); ctx->fb_z.release(); ctx->texels.release(); ctx->texmask.release(); ctx->texdesc.release();
     ctx->texels8.release(); ctx->tex8mask.release(); ctx->tex8desc.release(); ctx->verts.release(); ctx->faces.release();
     ctx->tv.release(); ctx->recs.release(); ctx->keys.release(); ctx->state_ring.release(); ctx->otile_count.release();
-    ctx->bins.release(); ctx->bins_sorted.release(); ctx->heads.release(); ctx->obins.release(); ctx->wire.release();
+    ctx->bins.release(); ctx->bins_sorted.release(); ctx->heads.release(); ctx->obins.release(); ctx->wire.release(); ctx->wire_table.release();
     ctx->lights.release(); ctx->dbg.release();
     for (FrameGraph& g : ctx->fgs) g.destroy();
     if (ctx->sticky) cudaFree(ctx->sticky);

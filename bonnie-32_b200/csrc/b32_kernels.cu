@@ -1235,7 +1235,7 @@ k_fill_ordered(const SurfRec* __restrict__ recs, BinHead* __restrict__ bins, con
 // lines does not matter and each unique edge can be walked by its own thread.  What does matter is the
 // reference's de-duplication: edges are compared by their integer end points only and the FIRST
 // occurrence (in face order) keeps its depths (:2589-2591), so edge e is drawn iff no earlier edge of
-// the same kind has the same end points.  The reference does this search in O(n^2) too.
+// the same kind has the same end points.
 struct WireEdge { int32_t x0, y0, x1, y1; float z0, z1; };
 
 __device__ __forceinline__ bool wire_edge(const WireTri& t, uint32_t k, WireEdge& e) {
@@ -1246,9 +1246,43 @@ __device__ __forceinline__ bool wire_edge(const WireTri& t, uint32_t k, WireEdge
     return true;
 }
 
+// The reference keeps the FIRST edge (in face order) of every distinct integer end-point pair with a linear search per
+// edge (`unique_edges.iter().any(..)`, :2589: O(n^2)).  Same set, O(n): an open-addressing table in which every slot only
+// ever holds edges of ONE end-point pair and converges to the smallest edge index of that pair (atomicMin); edge e is
+// drawn iff its pair's slot holds e.  A slot is claimed by compare-and-swap from EMPTY; a later edge either finds its own
+// pair there (atomicMin) or a different one (probe on); nothing is ever removed, so all edges of a pair meet in one slot.
+constexpr uint32_t WIRE_EMPTY = 0xFFFFFFFFu;
+__device__ __forceinline__ uint32_t wire_hash(const WireEdge& e) {
+    uint32_t h = (uint32_t)e.x0 * 0x9E3779B1u ^ (uint32_t)e.y0 * 0x85EBCA77u ^ (uint32_t)e.x1 * 0xC2B2AE3Du ^ (uint32_t)e.y1 * 0x27D4EB2Fu;
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12;
+    return h;
+}
+__device__ __forceinline__ bool wire_same(const WireEdge& a, const WireEdge& b) { return a.x0 == b.x0 && a.y0 == b.y0 && a.x1 == b.x1 && a.y1 == b.y1; }
+
+__global__ void __launch_bounds__(128)
+k_wire_dedup(const WireTri* __restrict__ wire, uint32_t nf, uint32_t kind, uint32_t* __restrict__ table, uint32_t mask) {
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < nf * 3; e += gridDim.x * blockDim.x) {
+        const WireTri& t = wire[e / 3];
+        if (t.kind != kind) continue;
+        WireEdge me;
+        wire_edge(t, e % 3, me);
+        for (uint32_t h = wire_hash(me) & mask;; h = (h + 1) & mask) {
+            uint32_t cur = table[h];
+            if (cur == WIRE_EMPTY) {
+                cur = atomicCAS(&table[h], WIRE_EMPTY, e);
+                if (cur == WIRE_EMPTY) break;                               // claimed for this end-point pair
+            }
+            WireEdge oe;
+            wire_edge(wire[cur / 3], cur % 3, oe);                          // any edge ever stored here has the slot's pair
+            if (wire_same(oe, me)) { atomicMin(&table[h], e); break; }
+        }
+    }
+}
+
 // draw_line_3d (depth_test = true, :768-817) / draw_line (:714-751); colour via set_pixel (:301-310)
 __global__ void __launch_bounds__(128)
 k_wire(const WireTri* __restrict__ wire, uint32_t nf, uint32_t kind, uint32_t color, bool depth_test,
+       const uint32_t* __restrict__ table, uint32_t mask,
        uint32_t* __restrict__ fb_rgba, const float* __restrict__ fb_z, const CallState* __restrict__ st, CallParams p) {
     if (call_aborts(*st, p.use_zbuffer, p.rgb888)) return;
     const int32_t W = (int32_t)p.width, H = (int32_t)p.height;
@@ -1257,15 +1291,14 @@ k_wire(const WireTri* __restrict__ wire, uint32_t nf, uint32_t kind, uint32_t co
         if (t.kind != kind) continue;
         WireEdge me;
         wire_edge(t, e % 3, me);
-        bool dup = false;                                                   // unique_edges.iter().any(...)  (:2589)
-        for (uint32_t j = 0; j < e && !dup; ++j) {
-            const WireTri& o = wire[j / 3];
-            if (o.kind != kind) { j += 2 - (j % 3); continue; }
+        uint32_t first = WIRE_EMPTY;                                        // first occurrence of this end-point pair (:2589)
+        for (uint32_t h = wire_hash(me) & mask;; h = (h + 1) & mask) {
+            uint32_t cur = table[h];
             WireEdge oe;
-            wire_edge(o, j % 3, oe);
-            dup = oe.x0 == me.x0 && oe.y0 == me.y0 && oe.x1 == me.x1 && oe.y1 == me.y1;
+            wire_edge(wire[cur / 3], cur % 3, oe);
+            if (wire_same(oe, me)) { first = cur; break; }
         }
-        if (dup) continue;
+        if (first != e) continue;
         // Bresenham with wrapping i32 arithmetic (release-mode Rust)
         int32_t x0 = me.x0, y0 = me.y0, x1 = me.x1, y1 = me.y1;
         int32_t ddx = (int32_t)((uint32_t)x1 - (uint32_t)x0), ddy = (int32_t)((uint32_t)y1 - (uint32_t)y0);
@@ -1545,11 +1578,13 @@ void launch_fill_ordered(const LaunchCtx& L, const SurfRec* recs, BinHead* obins
              recs, obins, otile_count, tex, static_cast<const void*>(texels), fb_rgba, fb_z, st, p, obin_cap);
 }
 
-void launch_wire(const LaunchCtx& L, const WireTri* wire, uint32_t kind, uint32_t color, bool depth_test,
+void launch_wire(const LaunchCtx& L, const WireTri* wire, uint32_t kind, uint32_t color, bool depth_test, uint32_t* table, uint32_t table_size,
                  uint32_t* fb_rgba, const float* fb_z, const CallState* st, const CallParams& p) {
     if (p.nf == 0) return;
-    k_wire<<<grid_for(p.nf * 3, 128, L.sms, 16), 128, 0, L.stream>>>(wire, p.nf, kind, color, depth_test, fb_rgba, fb_z, st, p);
-    ++*L.launches;
+    cudaMemsetAsync(table, 0xFF, (size_t)table_size * sizeof(uint32_t), L.stream);          // WIRE_EMPTY
+    k_wire_dedup<<<grid_for(p.nf * 3, 128, L.sms, 16), 128, 0, L.stream>>>(wire, p.nf, kind, table, table_size - 1);
+    k_wire<<<grid_for(p.nf * 3, 128, L.sms, 16), 128, 0, L.stream>>>(wire, p.nf, kind, color, depth_test, table, table_size - 1, fb_rgba, fb_z, st, p);
+    *L.launches += 2;
 }
 
 void launch_fb_clear(const LaunchCtx& L, uint32_t* rgba, float* z, uint32_t n, uint32_t color) {

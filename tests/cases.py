@@ -145,6 +145,27 @@ def nan_depth_vertices(scene, oracle):
     raise AssertionError("no face produces a NaN sort key")
 
 
+def grid_mesh_scene(nx=40, ny=30, name="wire_grid_shared_edges", flip=True, **kw):
+    """A wavy quad grid with shared vertices seen from behind (every triangle is a back face): each interior edge occurs
+    in two triangles, and many snap to the same integer end points — the case the first-occurrence de-duplication of the
+    wireframe phase (render.rs:2587-2591) exists for."""
+    xs, ys = np.meshgrid(np.linspace(-6.0, 6.0, nx + 1), np.linspace(-4.5, 4.5, ny + 1))
+    zs = 14.0 + 1.5 * np.sin(xs * 0.9) * np.cos(ys * 1.1)
+    pos = np.stack([xs, ys, zs], axis=-1).reshape(-1, 3)
+    u = scenes.splitmix64_u01(4242, len(pos) * 3).reshape(-1, 3)
+    v = scenes.make_vertices(pos, uv=pos[:, :2] * 0.2, normal=np.tile([0.0, 0.0, -1.0], (len(pos), 1)),
+                             rgba=np.concatenate([64 + np.floor(128 * u), np.zeros((len(pos), 1))], axis=1))
+    idx = []
+    for j in range(ny):
+        for i in range(nx):
+            a, b, c, d = j * (nx + 1) + i, j * (nx + 1) + i + 1, (j + 1) * (nx + 1) + i, (j + 1) * (nx + 1) + i + 1
+            idx += [(a, c, b), (b, c, d)] if flip else [(a, b, c), (b, d, c)]
+    base = scenes.scene_c2(n_tris=8)
+    f = scenes.make_faces(idx, tex_id=0)
+    st = scenes.common_settings(use_zbuffer=True, backface_wireframe=True, **kw)
+    return scenes.Scene(name, v, f, base.textures, Camera(), st)
+
+
 def wireframe_scenes(n_tris=160):
     """Editor wireframe phase (render.rs:2574-2635): back-face edges with depth test, front-face overlay."""
     base = scenes.scene_c2(n_tris=n_tris)
@@ -160,6 +181,8 @@ def wireframe_scenes(n_tris=160):
         _with(base, "wire_backface_nocull_is_off", backface_wireframe=True, backface_cull=False, use_zbuffer=True),
         _with(base, "wire_backface_xray", backface_wireframe=True, xray_mode=True),
         _with(big, "wire_backface_large_world", camera=cam, backface_wireframe=True, use_zbuffer=True),
+        grid_mesh_scene(),
+        grid_mesh_scene(name="wire_grid_overlay_nocull", flip=False, wireframe_overlay=True, backface_cull=False),
     ]
 
 
