@@ -312,6 +312,27 @@ __device__ __forceinline__ void setup_face(uint32_t fi, const b32_vertex* __rest
     keys[fi] = ((uint64_t)cls << 32) | dkey;
 }
 
+// Exact trivial reject of a surface against the pixel box [bx0,bx1) x [by0,by1) (it must overlap the surface's bbox).
+// For SF_FAST_EDGE surfaces the edge values are exact integers, linear in (x, y), and bc = fl(w * inv_area) is monotone
+// in w, so each barycentric's extreme over the box (clipped to the bbox) is at a corner; bc_z = fl(fl(1 - bc_x) - bc_y) is
+// monotone non-increasing in both.  A surface whose upper bounds fail `>= -0.0001` (render.rs:1541) has no inside pixel
+// in the box.  Surfaces without the flag (rounded stepping) are never rejected here.
+template <typename Rec>
+__device__ __forceinline__ bool surface_misses_box(const Rec& r, uint32_t bx0, uint32_t bx1, uint32_t by0, uint32_t by1) {
+    if (!(r.flags & SF_FAST_EDGE)) return false;
+    const uint32_t min_x = r.bbox_x & 0xFFFF, max_x = r.bbox_x >> 16, min_y = r.bbox_y & 0xFFFF, max_y = r.bbox_y >> 16;
+    float dx0 = (float)(max(bx0, min_x) - min_x), dx1 = (float)(min(bx1, max_x) - 1 - min_x);
+    float dy0 = (float)(max(by0, min_y) - min_y), dy1 = (float)(min(by1, max_y) - 1 - min_y);
+    float r0 = r.w0s + dy0 * r.b0, r1 = r.w0s + dy1 * r.b0, q0 = r.w1s + dy0 * r.b1, q1 = r.w1s + dy1 * r.b1;
+    float ax0 = dx0 * r.a0, ax1 = dx1 * r.a0, cx0 = dx0 * r.a1, cx1 = dx1 * r.a1;
+    float x00 = (r0 + ax0) * r.inv_area, x01 = (r0 + ax1) * r.inv_area, x10 = (r1 + ax0) * r.inv_area, x11 = (r1 + ax1) * r.inv_area;
+    float y00 = (q0 + cx0) * r.inv_area, y01 = (q0 + cx1) * r.inv_area, y10 = (q1 + cx0) * r.inv_area, y11 = (q1 + cx1) * r.inv_area;
+    float xmax = fmaxf(fmaxf(x00, x01), fmaxf(x10, x11)), xmin = fminf(fminf(x00, x01), fminf(x10, x11));
+    float ymax = fmaxf(fmaxf(y00, y01), fmaxf(y10, y11)), ymin = fminf(fminf(y00, y01), fminf(y10, y11));
+    const float ERR = -0.0001f;
+    return xmax < ERR || ymax < ERR || (1.0f - xmin - ymin) < ERR;
+}
+
 // ---- tile binning helpers -------------------------------------------------------------------------
 __device__ __forceinline__ void head_tiles(const BinHead& h, uint32_t& tx0, uint32_t& tx1, uint32_t& ty0, uint32_t& ty1) {
     uint32_t min_x = h.bbox_x & 0xFFFF, max_x = h.bbox_x >> 16, min_y = h.bbox_y & 0xFFFF, max_y = h.bbox_y >> 16;
@@ -418,6 +439,8 @@ k_bin_opaque(const BinHead* __restrict__ heads, const uint64_t* __restrict__ key
             }
         }
         const bool has = head.bbox_x != 0;
+        // (binning by bbox only: applying the exact corner reject per (face, tile) here was measured — it doubles this
+        //  kernel's time and the fill, whose per-block filter applies the same test, gains nothing)
         if (aggregate) {
             for_each_tile(head, has, p.tiles_x, [&](uint32_t t, const BinHead&) { atomicAdd(&s_cnt[t], 1u); });     // 1) count per tile
             __syncthreads();
@@ -900,27 +923,7 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
                 cand = !(max_x <= ox0 || min_x >= ox1 || max_y <= oy0 || min_y >= oy1);
                 if (!p.use_zbuffer) cand = cand && h.key >= wkey;
                 else cand = cand && (h.key == 0xFFFFFFFFu || !(__uint_as_float(~h.key) > wz));
-                if (cand) {
-                    // trivial reject against the open box (clipped to the bbox).  For SF_FAST_EDGE surfaces the edge
-                    // values are exact integers, linear in (x, y), and bc = fl(w * inv_area) is monotone in w, so
-                    // each barycentric's extreme over the box is at a corner; bc_z = fl(fl(1 - bc_x) - bc_y) is
-                    // monotone non-increasing in both.  A surface whose upper bounds fail `>= -0.0001` (:1541)
-                    // has no inside pixel in the box.
-                    const SurfHot& r = crec[sb + lane];
-                    if (r.flags & SF_FAST_EDGE) {
-                        float dx0 = (float)(max(ox0, min_x) - min_x), dx1 = (float)(min(ox1, max_x) - 1 - min_x);
-                        float dy0 = (float)(max(oy0, min_y) - min_y), dy1 = (float)(min(oy1, max_y) - 1 - min_y);
-                        float r0 = r.w0s + dy0 * r.b0, r1 = r.w0s + dy1 * r.b0, q0 = r.w1s + dy0 * r.b1, q1 = r.w1s + dy1 * r.b1;
-                        float ax0 = dx0 * r.a0, ax1 = dx1 * r.a0, cx0 = dx0 * r.a1, cx1 = dx1 * r.a1;
-                        float x00 = (r0 + ax0) * r.inv_area, x01 = (r0 + ax1) * r.inv_area, x10 = (r1 + ax0) * r.inv_area, x11 = (r1 + ax1) * r.inv_area;
-                        float y00 = (q0 + cx0) * r.inv_area, y01 = (q0 + cx1) * r.inv_area, y10 = (q1 + cx0) * r.inv_area, y11 = (q1 + cx1) * r.inv_area;
-                        float xmax = fmaxf(fmaxf(x00, x01), fmaxf(x10, x11)), xmin = fminf(fminf(x00, x01), fminf(x10, x11));
-                        float ymax = fmaxf(fmaxf(y00, y01), fmaxf(y10, y11)), ymin = fminf(fminf(y00, y01), fminf(y10, y11));
-                        const float ERR = -0.0001f;
-                        float zub = 1.0f - xmin - ymin;
-                        if (xmax < ERR || ymax < ERR || zub < ERR) cand = false;
-                    }
-                }
+                if (cand && surface_misses_box(crec[sb + lane], ox0, ox1, oy0, oy1)) cand = false;   // exact: see surface_misses_box
             }
             uint32_t mask = __ballot_sync(0xFFFFFFFFu, cand);
             if (mask == 0) continue;
@@ -1165,18 +1168,7 @@ k_fill_ordered(const SurfRec* __restrict__ recs, BinHead* __restrict__ bins, con
             const SurfRec& r = crec[lane];
             uint32_t min_x = r.bbox_x & 0xFFFF, max_x = r.bbox_x >> 16, min_y = r.bbox_y & 0xFFFF, max_y = r.bbox_y >> 16;
             cand = !(max_x <= bx0 || min_x >= bx0 + 8 || max_y <= by0 || min_y >= by0 + 4);
-            if (cand && (r.flags & SF_FAST_EDGE)) {        // exact corner test, as in k_fill_opaque
-                float dx0 = (float)(max(bx0, min_x) - min_x), dx1 = (float)(min(bx0 + 8, max_x) - 1 - min_x);
-                float dy0 = (float)(max(by0, min_y) - min_y), dy1 = (float)(min(by0 + 4, max_y) - 1 - min_y);
-                float r0 = r.w0s + dy0 * r.b0, r1 = r.w0s + dy1 * r.b0, q0 = r.w1s + dy0 * r.b1, q1 = r.w1s + dy1 * r.b1;
-                float ax0 = dx0 * r.a0, ax1 = dx1 * r.a0, cx0 = dx0 * r.a1, cx1 = dx1 * r.a1;
-                float x00 = (r0 + ax0) * r.inv_area, x01 = (r0 + ax1) * r.inv_area, x10 = (r1 + ax0) * r.inv_area, x11 = (r1 + ax1) * r.inv_area;
-                float y00 = (q0 + cx0) * r.inv_area, y01 = (q0 + cx1) * r.inv_area, y10 = (q1 + cx0) * r.inv_area, y11 = (q1 + cx1) * r.inv_area;
-                float xmax = fmaxf(fmaxf(x00, x01), fmaxf(x10, x11)), xmin = fminf(fminf(x00, x01), fminf(x10, x11));
-                float ymax = fmaxf(fmaxf(y00, y01), fmaxf(y10, y11)), ymin = fminf(fminf(y00, y01), fminf(y10, y11));
-                const float ERR = -0.0001f;
-                if (xmax < ERR || ymax < ERR || (1.0f - xmin - ymin) < ERR) cand = false;
-            }
+            if (cand && surface_misses_box(r, bx0, bx0 + 8, by0, by0 + 4)) cand = false;
         }
         const uint32_t mask = __ballot_sync(0xFFFFFFFFu, cand);
         if (mask == 0) continue;
