@@ -677,7 +677,7 @@ constexpr size_t OP_SMEM = (size_t)OP_SORT_MAX * sizeof(BinHead) + (size_t)OP_RI
                            (size_t)OP_TEX_SMEM * sizeof(TexDev) + (size_t)OP_MASK_SMEM_WORDS * 4 +
                            (size_t)OP_WARPS * 32 * sizeof(uint2) + (size_t)OP_WARPS * 32;
 #ifdef B32_FILL_STATS
-__device__ uint32_t g_fill_stats[4096 * 16 * 8];     // [tile][warp][8]: t_start, t_sorted, t_end, batches, survivors, inside, shaded, smid
+__device__ uint32_t g_fill_stats[4096 * 16 * 8];     // [tile][warp][8]: t_start, t_sorted, t_end, batches, t_first_data, t_batch0_end, t_batch1_end, t_loop_end
 __device__ __forceinline__ uint32_t smid() { uint32_t r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t gtime() { uint64_t t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return (uint32_t)t; }
 #endif
@@ -857,13 +857,16 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
 #endif
     if (mask_staged) while (!mbar_try_wait(&s_mbar, 0)) {}
 #ifdef B32_FILL_STATS
-    uint32_t st_tm = gtime(), st_tl = 0;
+    uint32_t st_tl = 0, st_tfirst = 0, st_tb0 = 0, st_tb1 = 0;
 #endif
 
     const uint32_t nchunks = (n + OP_CHUNK - 1) / OP_CHUNK;
     for (uint32_t c = 0; c < nchunks; ++c) {
         cp_async_wait<1>();                               // this thread's pieces of step c have landed ...
         if (__syncthreads_and(done)) break;               // ... and so have everybody else's; slot (c+2) % 3 is free again
+#ifdef B32_FILL_STATS
+        if (c == 0) st_tfirst = gtime();
+#endif
         stage(c + 2);
         if (done) continue;
         const SurfHot* crec = s_rec + (c % OP_RING) * OP_CHUNK;
@@ -871,6 +874,8 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
             const uint32_t base = c * OP_CHUNK + sb;
             if (base >= n) break;
 #ifdef B32_FILL_STATS
+            if (st_batches == 1) st_tb0 = gtime();       // end of batch 0
+            if (st_batches == 2) st_tb1 = gtime();       // end of batch 1
             ++st_batches;
 #endif
             // ---- what the weakest pixel of this block still accepts ----------------------------------------
@@ -1007,7 +1012,7 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
         for (int o = 16; o > 0; o >>= 1) { st_inside += __shfl_xor_sync(0xFFFFFFFFu, st_inside, o); st_shaded += __shfl_xor_sync(0xFFFFFFFFu, st_shaded, o); }
         if (lane == 0 && tile < 4096) {
             uint32_t* o = g_fill_stats + (tile * 16 + wt) * 8;
-            o[0] = st_t0; o[1] = st_t1; o[2] = gtime(); o[3] = st_batches; o[4] = st_surv; o[5] = st_tm; o[6] = st_tl; o[7] = smid();
+            o[0] = st_t0; o[1] = st_t1; o[2] = gtime(); o[3] = st_batches; o[4] = st_tfirst; o[5] = st_tb0; o[6] = st_tb1; o[7] = st_tl;
         }
     }
 #endif
