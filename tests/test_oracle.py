@@ -330,3 +330,11 @@ def test_fuzz_oracle_equals_numpy_model(oracle, rgb888):
         assert np.array_equal(z.view(np.uint32), want_z.view(np.uint32)), sc.name
         ok += 1
     assert ok >= 12
+
+
+def test_math_rs_reference_facts():                     # math.rs:783-797 (the reference's own unit tests of the vector helpers)
+    from bonnie32_b200.raster import _cross
+    a = np.array([[1.0, 2.0, 3.0]], dtype=np.float32)
+    assert abs(float(pymodel.dot3(a, np.array([4.0, 5.0, 6.0], dtype=np.float32))[0]) - 32.0) < 0.001
+    c = _cross(np.array([1.0, 0.0, 0.0], np.float32), np.array([0.0, 1.0, 0.0], np.float32))
+    assert abs(float(c[2]) - 1.0) < 0.001 and c[0] == 0 and c[1] == 0
