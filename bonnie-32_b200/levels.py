@@ -500,3 +500,47 @@ def assemble_level(level_path: str, all_textures: List[PackTexture], compact: bo
         texs = all_textures
     textures = [Texture15(t.width, t.height, t.pixels15) for t in texs]
     return LevelScene(os.path.splitext(os.path.basename(level_path))[0], rooms, textures, orbit_camera(level))
+
+
+class LevelRenderer:
+    """render_scene's room loop (src/scene.rs:180-261) on device-resident geometry.
+
+    The reference regenerates `room.to_render_data_with_textures()` and re-marshals it on every frame
+    (scene.rs:199-203).  Here a room's triangles are uploaded once per level *generation* (bump `generation` when the
+    level is edited; cf. `textures_15_cache_generation`, src/editor/viewport_3d.rs:3459) and every frame only enqueues
+    one frame-graph launch per room — no host round trip until the framebuffer is downloaded.  Rooms whose faces or
+    textures can blend fall back to the blocking call inside `Mesh.frame_enqueue`.
+    """
+
+    def __init__(self, ctx, scene: LevelScene):
+        from .raster import Mesh
+        self.ctx = ctx
+        self.scene = scene
+        self.generation = 0
+        self._uploaded = -1
+        self._meshes: list = []
+        self._Mesh = Mesh
+
+    def _sync_geometry(self):
+        if self._uploaded == self.generation:
+            return
+        for m in self._meshes:
+            m.free()
+        self.ctx.set_textures(self.scene.textures)
+        self._meshes = [self._Mesh(self.ctx, rc.vertices, rc.faces) for rc in self.scene.rooms]
+        self._uploaded = self.generation
+
+    def render(self, fb, camera: Optional[Camera] = None, clear=True, **settings_kw):
+        """fb.clear + one render_mesh_15 per room, enqueued; the caller reads the frame with fb.download()."""
+        self._sync_geometry()
+        cam = camera or self.scene.camera
+        for i, (mesh, rc) in enumerate(zip(self._meshes, self.scene.rooms)):
+            mesh.frame_enqueue(self.scene.clear if (clear and i == 0) else None, cam, self.scene.settings(rc.ambient, **settings_kw), rc.fog)
+        if clear and not self._meshes:
+            fb.clear(self.scene.clear)
+
+    def close(self):
+        for m in self._meshes:
+            m.free()
+        self._meshes = []
+        self._uploaded = -1

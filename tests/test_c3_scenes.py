@@ -63,3 +63,31 @@ def test_gpu_matches_oracle(ctx, oracle, path, mode):
     assert not bad.any(), f"{sc.name}/{mode}: {bad.sum()} pixels differ"
     assert np.array_equal(got_z.view(np.uint32), want_z.view(np.uint32))
     assert hashlib.sha256(got.tobytes()).hexdigest() == HASHES[f"{sc.name}:{mode}"]["rgba_sha256"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", PATHS, ids=[os.path.basename(p)[3:-4] for p in PATHS])
+def test_gpu_level_renderer_cached_geometry(ctx, oracle, path):
+    """levels.LevelRenderer: rooms uploaded once per level generation, every frame enqueued (frame graphs), several
+    frames with a moving camera — each equals the oracle's per-room loop."""
+    from bonnie32_b200 import levels
+    import cases
+    sc = c3.load_scene(path)
+    fb = pkg.Framebuffer(sc.width, sc.height, ctx)
+    lr = levels.LevelRenderer(ctx, sc)
+    for k in range(4):
+        cam = cases._rotated_camera(0.0, 0.0, (0.0, 0.0, 0.0))
+        cam.position = (sc.camera.position + np.float32(k * 37.0) * sc.camera.basis_x).astype(np.float32)
+        cam.basis_x, cam.basis_y, cam.basis_z = sc.camera.basis_x, sc.camera.basis_y, sc.camera.basis_z
+        lr.render(fb, cam)
+        got, got_z = fb.download()
+        moved = type(sc)(sc.name, sc.rooms, sc.textures, cam)
+        want, want_z, drawn = render_oracle(oracle, moved, {})
+        assert np.array_equal(got, want), (sc.name, k)
+        assert np.array_equal(got_z.view(np.uint32), want_z.view(np.uint32)), (sc.name, k)
+    lr.generation += 1                      # an edit: geometry is uploaded again
+    lr.render(fb)
+    got, _ = fb.download()
+    want, _, _ = render_oracle(oracle, sc, {})
+    assert np.array_equal(got, want)
+    lr.close()
