@@ -549,3 +549,20 @@ def test_two_devices_in_one_process(oracle):
             assert_same(sc, got, got_z, tm, want, want_z, otm)
     for c in ctxs:
         c.close()
+
+
+@pytest.mark.parametrize("w,h", [(640, 480), (1024, 768), (1920, 1080)])
+def test_large_framebuffers_all_passes(ctx, oracle, w, h):
+    """Both passes, the wireframe phase and the RGB888 replay at the editor / game framebuffer sizes (src/game/renderer.rs:34-49)."""
+    by = {s.name: s for s in cases.feature_scenes(200)}
+    for name in ("mixed_zbuffer", "mixed_painter", "gouraud_lights"):
+        sc = cases._with(by[name], f"{name}_{w}x{h}", width=w, height=h, backface_wireframe=(name == "mixed_zbuffer"))
+        want, want_z, otm, rc = oracle.render_scene(sc)
+        assert rc == 0
+        got, got_z, tm = render_gpu(ctx, sc)
+        assert_same(sc, got, got_z, tm, want, want_z, otm)
+    m = next(s for s in RGB888 if s.name == "rgb888_mixed_zbuffer")
+    sc = cases._with(m, f"rgb888_mixed_zbuffer_{w}x{h}", width=w, height=h)
+    want, want_z, otm, rc = oracle.render_scene888(sc)
+    got, got_z, tm = render_gpu888(ctx, sc)
+    assert_same(sc, got, got_z, tm, want, want_z, otm)
