@@ -128,6 +128,9 @@ struct b32_ctx {
     uint32_t last_nf = 0;
 
     cudaEvent_t ev[8] = {};
+    cudaEvent_t h2d_ev[2] = {};        // slot-free events of the pinned staging ring
+    bool h2d_pending[2] = {false, false};
+    int h2d_next = 0;
     float kernel_ms[7] = {};
     float emit_ms = 0.0f;
     float wire_ms = 0.0f;
@@ -219,20 +222,19 @@ int h2d(b32_ctx* ctx, void* dst, const void* src, size_t bytes) {
     bool pinned_src = cudaPointerGetAttributes(&a, src) == cudaSuccess && (a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged);
     cudaGetLastError();
     if (pinned_src) { CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream)); return B32_OK; }
-    // two-slot ring: memcpy into slot k overlaps the DMA of slot k^1
+    // two-slot ring: memcpy into slot k overlaps the DMA of slot k^1.  `src` is consumed by the memcpy, so the call does
+    // not wait for the DMA: a slot's event is only waited for when the slot is needed again (by this or a later copy).
     const size_t slot = ctx->pinned_bytes / 2;
-    cudaEvent_t done[2]; CK(cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming));
-    bool used[2] = {false, false};
-    size_t off = 0; int k = 0;
+    size_t off = 0;
     while (off < bytes) {
+        const int k = ctx->h2d_next;
         size_t n = std::min(slot, bytes - off);
-        if (used[k]) CK(cudaEventSynchronize(done[k]));
+        if (ctx->h2d_pending[k]) { CK(cudaEventSynchronize(ctx->h2d_ev[k])); ctx->h2d_pending[k] = false; }
         std::memcpy(ctx->pinned + k * slot, (const uint8_t*)src + off, n);
         CK(cudaMemcpyAsync((uint8_t*)dst + off, ctx->pinned + k * slot, n, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaEventRecord(done[k], ctx->stream)); used[k] = true;
-        off += n; k ^= 1;
+        CK(cudaEventRecord(ctx->h2d_ev[k], ctx->stream)); ctx->h2d_pending[k] = true;
+        off += n; ctx->h2d_next = k ^ 1;
     }
-    for (int i = 0; i < 2; ++i) { if (used[i]) cudaEventSynchronize(done[i]); cudaEventDestroy(done[i]); }
     return B32_OK;
 }
 
@@ -534,6 +536,7 @@ int b32_ctx_create(int device, b32_ctx** out) {
     if ((e = (cudaError_t)init_kernel_attributes()) != cudaSuccess) return bail(e, "cudaFuncSetAttribute");
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     for (auto& ev : ctx->ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    for (auto& ev : ctx->h2d_ev) if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaMalloc(&ctx->sticky, sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMemset(ctx->sticky, 0, sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMemset");
     if ((e = cudaMallocHost(&ctx->state_h, sizeof(CallState))) != cudaSuccess) return bail(e, "cudaMallocHost");
@@ -559,6 +562,7 @@ void b32_ctx_destroy(b32_ctx* ctx) {
     if (ctx->state_h) cudaFreeHost(ctx->state_h);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->h2d_ev) if (ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
