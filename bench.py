@@ -177,6 +177,19 @@ def run_reference(args):
     return 0
 
 
+def bind_to_gpu_numa_node(device_index: int):
+    """Pin this process to the CPUs NVML reports as closest to its GPU (one process per GPU), so that the pinned host
+    buffers of the end-to-end leg are allocated on that socket.  Best effort: returns a note for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return f"cpu affinity = NVML ideal set for GPU {device_index} ({len(os.sched_getaffinity(0))} cpus)"
+    except Exception as e:                        # no NVML / not permitted: run unbound
+        return f"unbound ({type(e).__name__})"
+
+
 # ------------------------------------------------------------------------------------------------
 def run_b200(args):
     import torch
@@ -189,6 +202,7 @@ def run_b200(args):
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)      # before any pinned allocation: H2D then reads socket-local memory
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -376,6 +390,7 @@ def run_b200(args):
                     "sync_call": {"value": world * N_TRIS / e2e_sync_s / 1e6, "ms_per_step": e2e_sync_s * 1e3,
                                   "how": "b32_fb_clear + b32_render_mesh_15 + b32_fb_download, one blocking frame at a time"}},
             "sync_call_ms": float(np.mean(sync_call_ms)),
+            "host_binding": numa,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
