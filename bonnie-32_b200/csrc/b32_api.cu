@@ -351,11 +351,11 @@ struct FrameArgs {
 // ev_setup / ev_fill (nullable) are recorded in front of the two kernel groups (synchronous calls time them).
 int launch_frame(b32_ctx* ctx, const LaunchCtx& L, const FrameArgs& a, cudaEvent_t ev_setup, cudaEvent_t ev_fill) {
     const CallParams& p = a.p;
-    if (a.clear) launch_fb_clear(L, ctx->fb_rgba.p, ctx->fb_z.p, ctx->width * ctx->height, a.clear_color);
     if (ev_setup) CK(cudaEventRecord(ev_setup, L.stream));
     const bool wire_on = p.wire_back || p.wire_front;
     launch_setup(L, a.verts, a.faces, nullptr, a.texdesc, ctx->lights.p, ctx->recs.p, ctx->keys.p, ctx->heads.p, ctx->bins.p,
-                 ctx->tile_count, wire_on ? ctx->wire.p : nullptr, ctx->state, a.zero_next, ctx->state_stride, p);
+                 ctx->tile_count, wire_on ? ctx->wire.p : nullptr, ctx->state, a.zero_next, ctx->state_stride,
+                 ctx->fb_rgba.p, ctx->fb_z.p, a.clear ? ctx->width * ctx->height : 0u, a.clear_color, p);    // the frame's clear rides in k_setup
     if (ev_fill) CK(cudaEventRecord(ev_fill, L.stream));
     if (!p.wire_front)
         launch_fill_opaque(L, ctx->recs.p, ctx->bins.p, ctx->tile_count, ctx->bins_sorted.p, a.texdesc, a.texels, a.texmask,

@@ -373,9 +373,13 @@ k_setup(const b32_vertex* __restrict__ verts, const b32_face* __restrict__ faces
         const TexDev* __restrict__ tex, const LightDev* __restrict__ lights,
         SurfRec* __restrict__ recs, uint64_t* __restrict__ keys,
         BinHead* __restrict__ heads, WireTri* __restrict__ wire, CallState* __restrict__ st,
-        uint32_t* __restrict__ zero_next, uint32_t zero_words, CallParams p) {
+        uint32_t* __restrict__ zero_next, uint32_t zero_words,
+        uint32_t* __restrict__ clear_rgba, float* __restrict__ clear_z, uint32_t clear_n, uint32_t clear_color, CallParams p) {
     __shared__ uint32_t s_cnt[2];
     pdl_launch_dependents();           // k_bin_opaque may be scheduled as SM resources free up; it waits for this grid's completion
+    // Framebuffer::clear of the same frame (render.rs:36-45), folded in: nothing of this kernel reads the framebuffer, and
+    // the previous frame's kernels have completed (this kernel is an ordinary, fully ordered launch)
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < clear_n; i += gridDim.x * blockDim.x) { clear_rgba[i] = clear_color; clear_z[i] = 3.40282347e+38f; }
     // the call after this one finds its CallState + tile counters zeroed (two sets, used alternately)
     if (blockIdx.x == 0) for (uint32_t i = threadIdx.x; i < zero_words; i += blockDim.x) zero_next[i] = 0;
     if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
@@ -1536,11 +1540,12 @@ void launch_transform(const LaunchCtx& L, const b32_vertex* verts, TVert* out, f
 
 void launch_setup(const LaunchCtx& L, const b32_vertex* verts, const b32_face* faces, const TVert* tv, const TexDev* tex,
                   const LightDev* lights, SurfRec* recs, uint64_t* keys, BinHead* heads, BinHead* bins,
-                  uint32_t* tile_count, WireTri* wire, CallState* st, uint32_t* zero_next, uint32_t zero_words, const CallParams& p) {
+                  uint32_t* tile_count, WireTri* wire, CallState* st, uint32_t* zero_next, uint32_t zero_words,
+                  uint32_t* clear_rgba, float* clear_z, uint32_t clear_n, uint32_t clear_color, const CallParams& p) {
     if (p.nf == 0) return;
     const bool pass1 = !((p.xray_mode && !p.rgb888) || p.wire_front);        // wireframe_overlay draws no solid surfaces (:2550)
-    launch_k(L, k_setup, grid_for(p.nf, SETUP_THREADS, L.sms, 16), SETUP_THREADS, 0, false, verts, faces, tv, tex, lights, recs, keys, heads, wire, st,
-             zero_next, zero_words, p);
+    launch_k(L, k_setup, grid_for(std::max(p.nf, clear_n / 4), SETUP_THREADS, L.sms, 16), SETUP_THREADS, 0, false, verts, faces, tv, tex, lights, recs, keys, heads, wire, st,
+             zero_next, zero_words, clear_rgba, clear_z, clear_n, clear_color, p);
     if (!pass1) return;
     launch_bin(L, heads, keys, recs, bins, tile_count, st, p, p.bin_cap, false, true);
 }

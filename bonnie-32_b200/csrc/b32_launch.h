@@ -37,7 +37,9 @@ void launch_transform(const LaunchCtx& L, const b32_vertex* verts, TVert* out, f
 // tv == nullptr: vertices are transformed inside k_setup (fused path). Also bins the pass-1 surfaces.
 void launch_setup(const LaunchCtx& L, const b32_vertex* verts, const b32_face* faces, const TVert* tv, const TexDev* tex,
                   const LightDev* lights, SurfRec* recs, uint64_t* keys, BinHead* heads, BinHead* bins,
-                  uint32_t* tile_count, WireTri* wire, CallState* st, uint32_t* zero_next, uint32_t zero_words, const CallParams& p);
+                  uint32_t* tile_count, WireTri* wire, CallState* st, uint32_t* zero_next, uint32_t zero_words,
+                  uint32_t* clear_rgba, float* clear_z, uint32_t clear_n, uint32_t clear_color, const CallParams& p);
+// clear_n != 0: k_setup first clears the framebuffer (clear_n pixels to clear_color, depth to f32::MAX)
 // ordered = false: scatter heads[] (pass 1); true: scatter the draw-order entries rebuilt from keys[] + recs[] (pass 2 / x-ray)
 void launch_bin(const LaunchCtx& L, const BinHead* heads, const uint64_t* keys, const SurfRec* recs, BinHead* bins, uint32_t* tile_count,
                 CallState* st, const CallParams& p, uint32_t bin_cap, bool ordered, bool after_setup);
