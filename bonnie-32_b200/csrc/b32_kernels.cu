@@ -1,12 +1,15 @@
 // b32_kernels.cu — sm_100a kernels of the BONNIE-32 rasterizer hot path.
 //
-//   k_transform    render.rs:2321-2360 + fixed.rs:362-441   vertex transform + snap (stand-alone form)
-//   k_setup        the same transform fused with render.rs:2373-2513 (cull / surface build / fog),
-//                  :1450-1527 (triangle setup), :1013-1071 (lighting), the sort key (:2527-2532) and
-//                  the screen-tile binning of the opaque pass
-//   k_fill_opaque  render.rs:1530-1713 for pass 1 (opaque surfaces), order-free (see below)
-//   k_bin_* + k_fill_ordered   pass 2 (semi-transparent surfaces, sorted back to front) and x-ray
-//                  mode: strict draw-order emulation
+//   k_setup        render.rs:2321-2360 + fixed.rs:362-441 (vertex transform + snap) fused with render.rs:2373-2513 (cull /
+//                  surface build / fog), :1450-1527 (triangle setup), :1013-1071 (lighting) and the sort key (:2527-2532):
+//                  one face per thread, one 128-byte SurfRec + one 16-byte bin head per drawn face
+//   k_bin_opaque   bin heads -> per-tile bins (any order), block-aggregated atomics; also bins the draw-order keys of pass 2
+//   k_fill_opaque  render.rs:1530-1713 for pass 1 (opaque surfaces), order-free (see below); <true> = render_mesh (RGB888)
+//   k_fill_ordered pass 2 (semi-transparent surfaces, back to front), x-ray mode and RGB888 calls that can blend:
+//                  per-tile sort by the unique draw-order key, then strict in-order replay
+//   k_wire_dedup + k_wire   the wireframe phase (render.rs:2574-2635): first-occurrence edge de-duplication, Bresenham
+//   k_sky_setup + k_sky_fill   Framebuffer::render_skybox step 1 (render.rs:81-139, :242-299)
+//   k_transform    the transform alone (stage-output test hook); k_fb_clear, k_tex_expand, k_tex_mask, k_tex8_*: utilities
 //
 // Pixel-order semantics.  The reference draws surfaces one after the other, so a
 // pixel's final value is a fold over the surfaces covering it, in draw order; pixels are independent.
@@ -19,8 +22,8 @@
 //                        framebuffer's incoming depth wins every tie.
 //     k_fill_opaque walks a tile's surfaces in whatever order the binning produced and keeps the
 //     winner; the result is the reference's, bit for bit, and deterministic.
-//   * Pass 2 blends against the running colour, so it is replayed in exact draw order from lists
-//     that a stable radix sort and a stable tile binning produce.
+//   * Pass 2 blends against the running colour, so it is replayed in exact draw order: every surface carries a
+//     unique 64-bit draw-order key (pass, depth key, face index), sorted per tile inside k_fill_ordered.
 #include <algorithm>
 #include <tuple>
 #include <utility>
