@@ -408,10 +408,13 @@ k_setup(const b32_vertex* __restrict__ verts, const b32_face* __restrict__ faces
 // receives hundreds of surfaces, so the binning is aggregated: a block takes BIN_THREADS consecutive
 // faces, counts them per tile in shared memory, reserves one contiguous slot range per touched tile
 // with ONE global atomic, then hands out slots from shared memory.
-constexpr int BIN_THREADS = 1024;
+#ifndef B32_BIN_THREADS
+#define B32_BIN_THREADS 1024
+#endif
+constexpr int BIN_THREADS = B32_BIN_THREADS;
 constexpr int BIN_MAX_TILES = 16384;            // shared-memory aggregation up to this many tiles (2 x 64 KB: 2560x1440 has 14 400)
 
-__global__ void __launch_bounds__(BIN_THREADS, 2)
+__global__ void __launch_bounds__(BIN_THREADS, 2048 / BIN_THREADS)
 k_bin_opaque(const BinHead* __restrict__ heads, const uint64_t* __restrict__ keys, const SurfRec* __restrict__ recs,
              BinHead* __restrict__ bins, uint32_t* __restrict__ tile_count,
              CallState* __restrict__ st, CallParams p, uint32_t bin_cap, bool ordered) {
