@@ -1301,6 +1301,7 @@ k_wire(const WireTri* __restrict__ wire, uint32_t nf, uint32_t kind, uint32_t co
         uint32_t first = WIRE_EMPTY;                                        // first occurrence of this end-point pair (:2589)
         for (uint32_t h = wire_hash(me) & mask;; h = (h + 1) & mask) {
             uint32_t cur = table[h];
+            if (cur == WIRE_EMPTY) break;                                   // cannot happen (k_wire_dedup inserted every edge): draw nothing
             WireEdge oe;
             wire_edge(wire[cur / 3], cur % 3, oe);
             if (wire_same(oe, me)) { first = cur; break; }
