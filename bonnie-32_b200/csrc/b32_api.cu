@@ -491,6 +491,7 @@ int render_device(b32_ctx* ctx, const b32_vertex* d_verts, uint32_t nv, const b3
     const bool all_ordered = rgb888 ? hs.n_transp > 0 : p.xray_mode != 0;
     bool need_ordered = all_ordered ? (hs.n_opaque + hs.n_transp) > 0 : (!rgb888 && hs.n_transp > 0);
     if (need_ordered && !p.wire_front) { rc = render_ordered(ctx, p, all_ordered ? hs.n_opaque + hs.n_transp : hs.n_transp); if (rc) return rc; }
+    bool wire_too_long = false;
     if (p.wire_back || p.wire_front) {          // WIREFRAME phase, render.rs:2574-2635
         uint32_t tsize = 64;
         while (tsize < 6ull * nf && tsize < 0x80000000u) tsize <<= 1;             // load factor <= 1/2 with 3 edges per face
@@ -501,9 +502,11 @@ int render_device(b32_ctx* ctx, const b32_vertex* d_verts, uint32_t nv, const b3
         if (p.wire_front) launch_wire(L, ctx->wire.p, 2, 200u | (200u << 8) | (220u << 16) | 0xFF000000u, false, ctx->wire_table.p, tsize,
                                       ctx->fb_rgba.p, ctx->fb_z.p, ctx->state, p);
         CK(cudaEventRecord(ctx->ev[1], st));
+        CK(cudaMemcpyAsync(ctx->state_h, ctx->state, sizeof(CallState), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         CK(cudaGetLastError());
         cudaEventElapsedTime(&ctx->wire_ms, ctx->ev[0], ctx->ev[1]);
+        wire_too_long = ctx->state_h->wire_too_long != 0;
     } else ctx->wire_ms = 0.0f;
     if (tm) {
         const float* k = ctx->kernel_ms;
@@ -514,6 +517,8 @@ int render_device(b32_ctx* ctx, const b32_vertex* d_verts, uint32_t nv, const b3
         tm->wireframe_ms = ctx->wire_ms;
         tm->triangles_drawn = hs.n_opaque + hs.n_transp;                            // render.rs:2545
     }
+    if (wire_too_long)
+        return fail(ctx, B32_ERR_UNSUPPORTED, "wireframe phase: an edge longer than 2^24 pixels was not drawn (non-finite or absurd screen coordinates)");
     return B32_OK;
 }
 

@@ -17,6 +17,7 @@ constexpr int TILE_W = 16;            // screen tile owned by one CTA of k_fill
 constexpr int TILE_H = 16;
 constexpr int FILL_THREADS = TILE_W * TILE_H;
 constexpr float NEAR_PLANE = 0.1f;    // math.rs:155
+constexpr uint32_t WIRE_MAX_STEPS = 1u << 24;   // longest Bresenham walk k_wire performs (the reference walks every step, on or off screen)
 constexpr int OP_SORT_MAX_ENTRIES = 1024;  // k_fill_opaque orders a tile's bin in shared memory up to this many entries, in a global scratch beyond
 constexpr int OP_MASK_SMEM_WORDS = 2048;   // k_fill_opaque keeps the "texel writes" mask in shared memory up to 65536 texels (8 KB)
 
@@ -97,7 +98,7 @@ struct CallState {
     uint32_t oob;                         // a face index >= nv was seen
     uint32_t obin_overflow;               // ordered pass: a tile bin exceeded its capacity (fill skipped, host grows + retries)
     uint32_t obin_max;                    // ordered pass: largest tile count seen
-    uint32_t _unused;
+    uint32_t wire_too_long;               // wireframe phase: an edge longer than WIRE_MAX_STEPS was skipped (host reports B32_ERR_UNSUPPORTED)
     uint32_t bin_overflow;                // opaque pass: a tile bin exceeded its capacity (fill skipped, host grows + retries)
     uint32_t bin_max;                     // opaque pass: largest tile count seen
 };

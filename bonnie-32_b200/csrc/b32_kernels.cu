@@ -1290,7 +1290,7 @@ k_wire_dedup(const WireTri* __restrict__ wire, uint32_t nf, uint32_t kind, uint3
 __global__ void __launch_bounds__(128)
 k_wire(const WireTri* __restrict__ wire, uint32_t nf, uint32_t kind, uint32_t color, bool depth_test,
        const uint32_t* __restrict__ table, uint32_t mask,
-       uint32_t* __restrict__ fb_rgba, const float* __restrict__ fb_z, const CallState* __restrict__ st, CallParams p) {
+       uint32_t* __restrict__ fb_rgba, const float* __restrict__ fb_z, CallState* __restrict__ st, CallParams p) {
     if (call_aborts(*st, p.use_zbuffer, p.rgb888)) return;
     const int32_t W = (int32_t)p.width, H = (int32_t)p.height;
     for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < nf * 3; e += gridDim.x * blockDim.x) {
@@ -1316,6 +1316,10 @@ k_wire(const WireTri* __restrict__ wire, uint32_t nf, uint32_t kind, uint32_t co
         int32_t err = (int32_t)((uint32_t)dx + (uint32_t)dy), x = x0, y = y0;
         float total_steps = (float)max(dx, max(-dy, 1));
         float step = 0.0f;
+        // The reference walks every step of the line, on screen or not: end points saturated from non-finite or absurdly
+        // large coordinates mean billions of iterations (seconds of CPU there, a hung SM here).  Such an edge is not
+        // walked; the call reports B32_ERR_UNSUPPORTED.  (4.12 fixed-point projection cannot exceed 2^20 steps.)
+        if ((uint32_t)max(dx, -dy) > WIRE_MAX_STEPS || dx < 0 || dy > 0) { st->wire_too_long = 1; continue; }
         for (;;) {
             if (x >= 0 && x < W && y >= 0 && y < H) {
                 uint32_t idx = (uint32_t)y * p.width + (uint32_t)x;
@@ -1588,7 +1592,7 @@ void launch_fill_ordered(const LaunchCtx& L, const SurfRec* recs, BinHead* obins
 }
 
 void launch_wire(const LaunchCtx& L, const WireTri* wire, uint32_t kind, uint32_t color, bool depth_test, uint32_t* table, uint32_t table_size,
-                 uint32_t* fb_rgba, const float* fb_z, const CallState* st, const CallParams& p) {
+                 uint32_t* fb_rgba, const float* fb_z, CallState* st, const CallParams& p) {
     if (p.nf == 0) return;
     cudaMemsetAsync(table, 0xFF, (size_t)table_size * sizeof(uint32_t), L.stream);          // WIRE_EMPTY
     k_wire_dedup<<<grid_for(p.nf * 3, 128, L.sms, 16), 128, 0, L.stream>>>(wire, p.nf, kind, table, table_size - 1);

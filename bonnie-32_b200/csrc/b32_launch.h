@@ -54,7 +54,7 @@ void launch_fill_ordered(const LaunchCtx& L, const SurfRec* recs, BinHead* obins
 // wireframe phase: kind 1 = back-face edges (depth tested), 2 = front-face overlay edges
 // table: table_size (a power of two >= 6 * nf) words of scratch for the first-occurrence edge de-duplication
 void launch_wire(const LaunchCtx& L, const WireTri* wire, uint32_t kind, uint32_t color, bool depth_test, uint32_t* table, uint32_t table_size,
-                 uint32_t* fb_rgba, const float* fb_z, const CallState* st, const CallParams& p);
+                 uint32_t* fb_rgba, const float* fb_z, CallState* st, const CallParams& p);
 void launch_fb_clear(const LaunchCtx& L, uint32_t* rgba, float* z, uint32_t n, uint32_t color);
 void launch_tex_expand(const LaunchCtx& L, const uint8_t* idx, const uint16_t* clut, uint32_t clut_len, uint32_t format, uint32_t n, uint16_t* out);
 

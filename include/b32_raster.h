@@ -32,7 +32,8 @@ extern "C" {
 #define B32_ERR_OOB_INDEX    2  /* face.v* >= nv: reference panics on slice index              */
 #define B32_ERR_NAN_DEPTH    3  /* NaN sort key: reference `partial_cmp().unwrap()` panics,    */
                                 /* src/rasterizer/render.rs:2531                                */
-#define B32_ERR_UNSUPPORTED  4  /* Spot light (libm acos is not bit-reproducible on device)    */
+#define B32_ERR_UNSUPPORTED  4  /* Spot light (libm acos is not bit-reproducible on device);   */
+                                /* a wireframe edge longer than 2^24 pixels (frame otherwise drawn) */
 #define B32_ERR_CUDA         5  /* a CUDA runtime call failed; see b32_last_error()            */
 #define B32_ERR_NO_DEVICE    6  /* no CUDA device: there is NO CPU fallback                    */
 

@@ -566,3 +566,20 @@ def test_large_framebuffers_all_passes(ctx, oracle, w, h):
     want, want_z, otm, rc = oracle.render_scene888(sc)
     got, got_z, tm = render_gpu888(ctx, sc)
     assert_same(sc, got, got_z, tm, want, want_z, otm)
+
+
+def test_wireframe_absurd_edge_is_reported_not_walked(ctx, oracle):
+    """A back-face edge whose end point saturates to +-2^31 would be billions of Bresenham steps (the reference walks them
+    all): the device skips that edge and the call says so; everything else of the frame equals the oracle without it."""
+    sc = cases.grid_mesh_scene(nx=6, ny=4)
+    sc.settings.use_fixed_point = False                       # float projection: screen coordinates can be anything
+    v = sc.vertices.copy()
+    v["pos"][0] = (-3.0e30, 0.0, 14.0)                         # projects to ~6e31 -> `as i32` saturates; the face stays a back face
+    bad = dataclasses.replace(sc, vertices=v)
+    fb = pkg.Framebuffer(sc.width, sc.height, ctx)
+    fb.clear(sc.clear)
+    with pytest.raises(pkg.B32Error) as e:
+        pkg.render_mesh_15(fb, bad.vertices, bad.faces, bad.textures, bad.camera, bad.settings)
+    assert e.value.code == abi.B32_ERR_UNSUPPORTED
+    got, _ = fb.download()
+    assert ((got[..., :3] == [80, 80, 100]).all(-1)).sum() > 100      # the other edges were drawn
