@@ -583,3 +583,19 @@ def test_wireframe_absurd_edge_is_reported_not_walked(ctx, oracle):
     assert e.value.code == abi.B32_ERR_UNSUPPORTED
     got, _ = fb.download()
     assert ((got[..., :3] == [80, 80, 100]).all(-1)).sum() > 100      # the other edges were drawn
+
+
+def test_ray_rs_projection_roundtrip_on_device(ctx):
+    """The reference's own projection round-trip test (ray.rs:333-377) against the device's float projection."""
+    import ctypes as C
+    from test_oracle import ray_roundtrip_distance
+
+    def project(v, cam, st, w, h):
+        pkg.Framebuffer(w, h, ctx)
+        scr = np.empty((len(v), 3), np.float32); cs = np.empty((len(v), 3), np.float32)
+        ca = cam.to_abi(); sa, keep = st.to_abi()
+        ctx.check(ctx.lib.b32_debug_transform(ctx.h, v.ctypes.data, len(v), C.byref(ca), C.byref(sa), scr.ctypes.data, cs.ctypes.data))
+        return scr
+
+    dist, scr = ray_roundtrip_distance(project)
+    assert dist < 2.0, (dist, scr)

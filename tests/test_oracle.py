@@ -338,3 +338,37 @@ def test_math_rs_reference_facts():                     # math.rs:783-797 (the r
     assert abs(float(pymodel.dot3(a, np.array([4.0, 5.0, 6.0], dtype=np.float32))[0]) - 32.0) < 0.001
     c = _cross(np.array([1.0, 0.0, 0.0], np.float32), np.array([0.0, 1.0, 0.0], np.float32))
     assert abs(float(c[2]) - 1.0) < 0.001 and c[0] == 0 and c[1] == 0
+
+
+def _screen_to_ray(sx, sy, w, h, cam):
+    """ray.rs:46-100, restated for the reference's own projection round-trip test."""
+    vs = (min(w, h) / 2.0) * 0.75
+    us = 5.0 - 1.0
+    ndc_x, ndc_y = (sx - w / 2.0) / vs, (sy - h / 2.0) / vs
+    d = np.array([ndc_x / us, ndc_y / us, 1.0])
+    world = cam.basis_x.astype(np.float64) * d[0] + cam.basis_y.astype(np.float64) * d[1] + cam.basis_z.astype(np.float64) * d[2]
+    world /= np.linalg.norm(world)
+    o_cam = np.array([ndc_x * 5.0 / us, ndc_y * 5.0 / us, 0.0])
+    origin = cam.position.astype(np.float64) + cam.basis_x * o_cam[0] + cam.basis_y * o_cam[1] + cam.basis_z * o_cam[2]
+    return origin, world
+
+
+def ray_roundtrip_distance(project, w=320, h=240):
+    """The reference's test_screen_to_ray_roundtrip (ray.rs:333-377): a world point projected with the rasterizer's float
+    projection and cast back as a ray passes within 2 units of the point.  `project(vertices, camera, settings, w, h)`
+    returns screen positions [n,3]."""
+    from bonnie32_b200.raster import Camera
+    cam = Camera()
+    cam.position = np.array([0.0, 0.0, -100.0], np.float32)
+    cam.update_basis()
+    world_point = np.array([50.0, 30.0, 100.0])
+    v = scenes.make_vertices([tuple(world_point)])
+    scr = project(v, cam, scenes.common_settings(use_fixed_point=False), w, h)
+    origin, direction = _screen_to_ray(float(scr[0, 0]), float(scr[0, 1]), w, h, cam)
+    t = np.dot(world_point - origin, direction)
+    return float(np.linalg.norm(origin + t * direction - world_point)), scr[0]
+
+
+def test_ray_rs_projection_roundtrip(oracle):          # ray.rs:333-377 (tolerance of the reference's own test: 2 units)
+    dist, scr = ray_roundtrip_distance(lambda v, c, s, w, h: oracle.transform(v, c, s, w, h)[0])
+    assert dist < 2.0, (dist, scr)
