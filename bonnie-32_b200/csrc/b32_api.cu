@@ -181,6 +181,8 @@ int fill_params(b32_ctx* ctx, CallParams& p, const b32_camera* cam, const b32_se
     p.half_h = (int32_t)(((uint32_t)((int32_t)ctx->height / 2)) << 12);
     p.nv = nv; p.nf = nf; p.ntex = rgb888 ? ctx->ntex8 : ctx->ntex;
     p.rgb888 = rgb888 ? 1 : 0;
+    static const bool no_scan = std::getenv("B32_NO_HEAD_SCAN") != nullptr;        // experiments: always bin with k_bin_opaque
+    p.scan_heads = (nf <= (uint32_t)OP_SORT_MAX_ENTRIES && !no_scan) ? 1 : 0;
     const uint32_t mask_words = rgb888 ? ctx->tex8mask_words : ctx->texmask_words;
     p.mask_smem_words = mask_words <= (uint32_t)OP_MASK_SMEM_WORDS ? mask_words : 0;
     p.affine_textures = s->affine_textures != 0; p.use_zbuffer = s->use_zbuffer != 0; p.shading = s->shading;
@@ -358,7 +360,7 @@ int launch_frame(b32_ctx* ctx, const LaunchCtx& L, const FrameArgs& a, cudaEvent
                  ctx->fb_rgba.p, ctx->fb_z.p, a.clear ? ctx->width * ctx->height : 0u, a.clear_color, p);    // the frame's clear rides in k_setup
     if (ev_fill) CK(cudaEventRecord(ev_fill, L.stream));
     if (!p.wire_front)
-        launch_fill_opaque(L, ctx->recs.p, ctx->bins.p, ctx->tile_count, ctx->bins_sorted.p, a.texdesc, a.texels, a.texmask,
+        launch_fill_opaque(L, ctx->recs.p, ctx->bins.p, ctx->tile_count, ctx->heads.p, ctx->bins_sorted.p, a.texdesc, a.texels, a.texmask,
                            ctx->fb_rgba.p, ctx->fb_z.p, ctx->state, ctx->sticky, p);
     return B32_OK;
 }

@@ -126,7 +126,9 @@ struct CallParams {
     uint32_t mask_smem_words;                         // words of the "texel writes" mask to stage in shared memory (0: read it from global)
     uint8_t affine_textures, use_zbuffer, shading, backface_cull, dithering, use_fixed_point, xray_mode, ortho;
     uint8_t fog_enabled, fog_r, fog_g, fog_b, fog_blend, async_call, wire_back, wire_front;   // wire_*: render.rs:2576, :2606
-    uint8_t rgb888, _padb[3];                         // 1: render_mesh / rasterize_triangle (render.rs:1971-2259, 1202-1433)
+    uint8_t rgb888;                                   // 1: render_mesh / rasterize_triangle (render.rs:1971-2259, 1202-1433)
+    uint8_t scan_heads;                               // 1: no k_bin_opaque for pass 1; k_fill_opaque scans k_setup's bin heads (nf <= OP_SORT_MAX_ENTRIES)
+    uint8_t _padb[2];
     float ambient, ortho_zoom, ortho_cx, ortho_cy;
     float fog_start, fog_falloff, fog_cull;
 };

@@ -678,6 +678,7 @@ constexpr int OP_CHUNK = B32_OP_CHUNK;       // surface records (their 80-byte v
                                              // the first step, so the CTA-wide barrier between steps rarely holds anybody up
 constexpr int OP_REC_PIECES = sizeof(SurfHot) / 16;
 static_assert(OP_CHUNK % 32 == 0 && OP_CHUNK <= 256, "whole 32-entry batches; slots are stored in a byte");
+static_assert((size_t)3 * OP_CHUNK * sizeof(SurfHot) >= (size_t)OP_SORT_MAX_ENTRIES * sizeof(BinHead), "the ring area doubles as the head-scan buffer");
 constexpr int OP_BUCKETS = OP_THREADS < 256 ? OP_THREADS : 256;       // key buckets of the counting sort (one scan thread each)
 constexpr int OP_BUCKET_BITS = OP_BUCKETS == 256 ? 8 : (OP_BUCKETS == 128 ? 7 : 6);
 constexpr int OP_RING = 3;                   // ring depth: steps c, c+1, c+2
@@ -723,7 +724,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 template <bool RGB888>
 __global__ void __launch_bounds__(OP_THREADS, B32_OP_MINB)
 k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins, const uint32_t* __restrict__ tile_count,
-              BinHead* __restrict__ sorted_scratch,
+              const BinHead* __restrict__ heads, BinHead* __restrict__ sorted_scratch,
               const TexDev* __restrict__ tex, const uint16_t* __restrict__ texels, const uint32_t* __restrict__ texmask,
               uint32_t* __restrict__ fb_rgba, float* __restrict__ fb_z, const CallState* __restrict__ st,
               uint32_t* __restrict__ sticky, CallParams p) {
@@ -745,6 +746,8 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
     if (mask_staged && threadIdx.x == 0) { mbar_init(&s_mbar, 1); bulk_g2s(s_mask, texmask, p.mask_smem_words * 4, &s_mbar); }
     const uint32_t* maskw = mask_staged ? s_mask : texmask;
     const BinHead* bin = bins + (size_t)tile * p.bin_cap;
+    __shared__ uint32_t s_scan_n;
+    if (threadIdx.x == 0) s_scan_n = 0;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t pix = OP_DUAL ? (lane & 15) : lane, sub = OP_DUAL ? (lane >> 4) : 0;
     const uint32_t tx = tile % p.tiles_x, ty = tile / p.tiles_x;
@@ -772,7 +775,28 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
         // x-ray (render_mesh_15) and any framebuffer-reading surface (render_mesh) go through the ordered replay instead
         skip = s.bin_overflow || aborts || (p.xray_mode && !RGB888) || (RGB888 && s.n_transp);
     }
-    const uint32_t n = skip ? 0u : tile_count[tile];
+    uint32_t n;
+    if (p.scan_heads) {
+        // Small meshes (<= OP_SORT_MAX faces) have no binning kernel: this tile picks its surfaces straight out of k_setup's
+        // bin heads (16 B per face, L2-resident) — one kernel launch less on the latency path of a game's per-room calls.
+        // The picks land in the (still unused) ring area and are ordered from there exactly like a bin.
+        BinHead* s_raw = reinterpret_cast<BinHead*>(s_rec);
+        const uint32_t ttx = tile % p.tiles_x, tty = tile / p.tiles_x;
+        __syncthreads();                                   // s_scan_n = 0 is visible
+        if (!skip)
+            for (uint32_t i = threadIdx.x; i < p.nf; i += OP_THREADS) {
+                const BinHead h = heads[i];
+                if (!h.bbox_x) continue;
+                uint32_t tx0, tx1, ty0, ty1;
+                head_tiles(h, tx0, tx1, ty0, ty1);
+                if (ttx >= tx0 && ttx <= tx1 && tty >= ty0 && tty <= ty1) s_raw[atomicAdd(&s_scan_n, 1u)] = h;
+            }
+        __syncthreads();
+        n = s_scan_n;
+        bin = s_raw;
+    } else {
+        n = skip ? 0u : tile_count[tile];
+    }
     if (n == 0) {                                          // nothing to draw here; the mask copy must land before the CTA exits
         if (mask_staged && threadIdx.x == 0) while (!mbar_try_wait(&s_mbar, 0)) {}
         return;
@@ -1557,7 +1581,7 @@ void launch_setup(const LaunchCtx& L, const b32_vertex* verts, const b32_face* f
     const bool pass1 = !((p.xray_mode && !p.rgb888) || p.wire_front);        // wireframe_overlay draws no solid surfaces (:2550)
     launch_k(L, k_setup, grid_for(std::max(p.nf, clear_n / 4), SETUP_THREADS, L.sms, 16), SETUP_THREADS, 0, false, verts, faces, tv, tex, lights, recs, keys, heads, wire, st,
              zero_next, zero_words, clear_rgba, clear_z, clear_n, clear_color, p);
-    if (!pass1) return;
+    if (!pass1 || p.scan_heads) return;                // small meshes: k_fill_opaque picks its tile's surfaces out of `heads` itself
     launch_bin(L, heads, keys, recs, bins, tile_count, st, p, p.bin_cap, false, true);
 }
 
@@ -1572,14 +1596,14 @@ void launch_bin(const LaunchCtx& L, const BinHead* heads, const uint64_t* keys, 
     launch_k(L, k_bin_opaque, grid, BIN_THREADS, smem, after_setup, heads, keys, recs, bins, tile_count, st, p, bin_cap, ordered);
 }
 
-void launch_fill_opaque(const LaunchCtx& L, const SurfRec* recs, const BinHead* bins, const uint32_t* tile_count, BinHead* sorted_scratch,
-                        const TexDev* tex, const uint16_t* texels, const uint32_t* texmask, uint32_t* fb_rgba, float* fb_z,
+void launch_fill_opaque(const LaunchCtx& L, const SurfRec* recs, const BinHead* bins, const uint32_t* tile_count, const BinHead* heads,
+                        BinHead* sorted_scratch, const TexDev* tex, const uint16_t* texels, const uint32_t* texmask, uint32_t* fb_rgba, float* fb_z,
                         const CallState* st, uint32_t* sticky, const CallParams& p) {
     uint32_t ntiles = p.tiles_x * p.tiles_y;
     if (ntiles == 0 || p.nf == 0) return;
     // launched right behind k_bin_opaque except in x-ray mode (no pass-1 binning: then it is an ordinary launch)
     launch_k(L, p.rgb888 ? k_fill_opaque<true> : k_fill_opaque<false>, ntiles * OP_SPLIT, OP_THREADS, OP_SMEM, !(p.xray_mode && !p.rgb888),
-             recs, bins, tile_count, sorted_scratch, tex, texels, texmask, fb_rgba, fb_z, st, sticky, p);
+             recs, bins, tile_count, heads, sorted_scratch, tex, texels, texmask, fb_rgba, fb_z, st, sticky, p);
 }
 
 void launch_fill_ordered(const LaunchCtx& L, const SurfRec* recs, BinHead* obins, const uint32_t* otile_count,

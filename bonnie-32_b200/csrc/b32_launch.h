@@ -44,8 +44,9 @@ void launch_setup(const LaunchCtx& L, const b32_vertex* verts, const b32_face* f
 void launch_bin(const LaunchCtx& L, const BinHead* heads, const uint64_t* keys, const SurfRec* recs, BinHead* bins, uint32_t* tile_count,
                 CallState* st, const CallParams& p, uint32_t bin_cap, bool ordered, bool after_setup);
 // sorted_scratch: one bin-sized slice per tile for bins too large to order in shared memory (same layout as bins)
-void launch_fill_opaque(const LaunchCtx& L, const SurfRec* recs, const BinHead* bins, const uint32_t* tile_count, BinHead* sorted_scratch,
-                        const TexDev* tex, const uint16_t* texels, const uint32_t* texmask, uint32_t* fb_rgba, float* fb_z,
+// heads: k_setup's per-face bin heads, read directly when p.scan_heads (small meshes, no binning kernel)
+void launch_fill_opaque(const LaunchCtx& L, const SurfRec* recs, const BinHead* bins, const uint32_t* tile_count, const BinHead* heads,
+                        BinHead* sorted_scratch, const TexDev* tex, const uint16_t* texels, const uint32_t* texmask, uint32_t* fb_rgba, float* fb_z,
                         const CallState* st, uint32_t* sticky, const CallParams& p);
 // ordered pass (pass 2 / x-ray): bins of draw-order keys, sorted per tile, replayed in order
 void launch_fill_ordered(const LaunchCtx& L, const SurfRec* recs, BinHead* obins, const uint32_t* otile_count,

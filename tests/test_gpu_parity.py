@@ -599,3 +599,22 @@ def test_ray_rs_projection_roundtrip_on_device(ctx):
 
     dist, scr = ray_roundtrip_distance(project)
     assert dist < 2.0, (dist, scr)
+
+
+@pytest.mark.parametrize("zbuf", [True, False])
+def test_sparse_calls_compose_over_existing_depth(ctx, oracle, zbuf):
+    """Many small calls (a few surfaces per tile each) into one framebuffer: every call must honour the colour and depth
+    the earlier ones left (a walk that stops early on a stale bound would not)."""
+    fb = pkg.Framebuffer(320, 240, ctx)
+    clear = scenes.CLEAR_COLOR
+    fb.clear(clear)
+    want = np.empty((240, 320, 4), np.uint8); want_z = np.empty((240, 320), np.float32)
+    want[...] = np.array(list(clear) + [255], np.uint8); want_z[...] = np.finfo(np.float32).max
+    for k in range(8):
+        sc = scenes.scene_c2(n_tris=30 + 10 * k, seed=900 + k, use_zbuffer=zbuf)
+        sc.vertices["pos"][:, :2] *= np.float32(0.4)            # crowd the surfaces into the middle tiles, various depths
+        pkg.render_mesh_15(fb, sc.vertices, sc.faces, sc.textures, sc.camera, sc.settings)
+        rc, _, _ = oracle.render_mesh_15(want, want_z, sc.vertices, sc.faces, sc.textures, sc.camera, sc.settings)
+        assert rc == 0
+    got, got_z = fb.download()
+    assert np.array_equal(got, want) and np.array_equal(got_z.view(np.uint32), want_z.view(np.uint32))
