@@ -288,6 +288,17 @@ int render_ordered(b32_ctx* ctx, const CallParams& p, uint32_t n_ordered) {
     LaunchCtx L = ctx->L();
     cudaStream_t st = ctx->stream;
     const uint32_t ntiles = p.tiles_x * p.tiles_y;
+    if (p.scan_heads) {                 // small meshes: k_fill_ordered builds each tile's draw-order entries itself (no bins, no overflow)
+        CK(cudaEventRecord(ctx->ev[3], st));
+        launch_fill_ordered(L, ctx->recs.p, nullptr, nullptr, ctx->keys.p, p.rgb888 ? ctx->tex8desc.p : ctx->texdesc.p,
+                            p.rgb888 ? reinterpret_cast<const uint16_t*>(ctx->texels8.p) : ctx->texels.p,
+                            ctx->fb_rgba.p, ctx->fb_z.p, ctx->state, p, 0);
+        CK(cudaEventRecord(ctx->ev[4], st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        cudaEventElapsedTime(&ctx->kernel_ms[3], ctx->ev[3], ctx->ev[4]);
+        return B32_OK;
+    }
     for (int attempt = 0;; ++attempt) {
         uint32_t cap = std::max<uint32_t>(ctx->obin_cap_hint, 256);
         cap = std::min<uint32_t>(cap, std::max<uint32_t>(n_ordered, 2));
@@ -297,7 +308,7 @@ int render_ordered(b32_ctx* ctx, const CallParams& p, uint32_t n_ordered) {
         CK(cudaEventRecord(ctx->ev[2], st));
         launch_bin(L, nullptr, ctx->keys.p, ctx->recs.p, ctx->obins.p, ctx->otile_count.p, ctx->state, p, cap2, true, false);
         CK(cudaEventRecord(ctx->ev[3], st));
-        launch_fill_ordered(L, ctx->recs.p, ctx->obins.p, ctx->otile_count.p, p.rgb888 ? ctx->tex8desc.p : ctx->texdesc.p,
+        launch_fill_ordered(L, ctx->recs.p, ctx->obins.p, ctx->otile_count.p, ctx->keys.p, p.rgb888 ? ctx->tex8desc.p : ctx->texdesc.p,
                             p.rgb888 ? reinterpret_cast<const uint16_t*>(ctx->texels8.p) : ctx->texels.p,
                             ctx->fb_rgba.p, ctx->fb_z.p, ctx->state, p, cap2);
         CK(cudaEventRecord(ctx->ev[4], st));

@@ -1117,6 +1117,7 @@ constexpr int ORD_GROUP = 4;         // fragments of one pixel whose texels are 
 constexpr int ORD_SORT_MAX = 2048;   // bin entries sortable in shared memory (32 KB); larger bins are sorted in place in global memory
 constexpr size_t ORD_SMEM = (size_t)ORD_SORT_MAX * sizeof(BinHead) + (size_t)ORD_RING * ORD_CHUNK * sizeof(SurfRec) + (FILL_THREADS / 32) * 32;
 static_assert(FILL_THREADS == ORD_CHUNK * 8, "one 16-byte piece of the staged records per thread");
+static_assert(OP_SORT_MAX_ENTRIES <= ORD_SORT_MAX, "a scanned mesh's draw-order entries fit the shared-memory sort");
 
 __device__ __forceinline__ uint64_t ord_key(const BinHead& h) { return ((uint64_t)h.key << 32) | h.face; }
 
@@ -1146,7 +1147,7 @@ __device__ void bitonic_sort_heads(BinHead* a, uint32_t m) {
 template <bool RGB888>
 __global__ void __launch_bounds__(FILL_THREADS)
 k_fill_ordered(const SurfRec* __restrict__ recs, BinHead* __restrict__ bins, const uint32_t* __restrict__ tile_count,
-               const TexDev* __restrict__ tex, const void* __restrict__ texels,
+               const uint64_t* __restrict__ keys, const TexDev* __restrict__ tex, const void* __restrict__ texels,
                uint32_t* __restrict__ fb_rgba, float* __restrict__ fb_z, const CallState* __restrict__ st, CallParams p, uint32_t bin_cap) {
     extern __shared__ __align__(128) uint8_t ord_smem[];
     SurfRec* s_rec = reinterpret_cast<SurfRec*>(ord_smem);                              // [ORD_RING][ORD_CHUNK]
@@ -1157,13 +1158,42 @@ k_fill_ordered(const SurfRec* __restrict__ recs, BinHead* __restrict__ bins, con
         if (s.obin_overflow || call_aborts(s, p.use_zbuffer, RGB888)) return;
     }
     const uint32_t tile = blockIdx.x;
-    const uint32_t n = tile_count[tile];
+    __shared__ uint32_t s_scan_n;
+    uint32_t n;
+    if (p.scan_heads) {
+        // Small meshes (<= OP_SORT_MAX_ENTRIES faces): no binning kernel — this tile builds its draw-order entries straight
+        // from keys[] + the records' bboxes (the same entries k_bin_opaque(ordered) would have scattered).
+        if (threadIdx.x == 0) s_scan_n = 0;
+        __syncthreads();
+        const uint32_t ttx = tile % p.tiles_x, tty = tile / p.tiles_x;
+        for (uint32_t fi = threadIdx.x; fi < p.nf; fi += blockDim.x) {
+            const uint64_t k64 = keys[fi];
+            const uint32_t cls = (uint32_t)(k64 >> 32);
+            if (!(cls < 2 && (cls == 1 || p.xray_mode || RGB888))) continue;
+            const uint2 bb = *reinterpret_cast<const uint2*>(&recs[fi].bbox_x);               // all zero = empty surface
+            if (!bb.x) continue;
+            BinHead h{bb.x, bb.y, 0, 0};
+            uint32_t tx0, tx1, ty0, ty1;
+            head_tiles(h, tx0, tx1, ty0, ty1);
+            if (!(ttx >= tx0 && ttx <= tx1 && tty >= ty0 && tty <= ty1)) continue;
+            const uint64_t okey = ((uint64_t)(RGB888 ? 0u : cls) << 62) | ((uint64_t)(uint32_t)k64 << 30) | fi;
+            h.key = (uint32_t)(okey >> 32); h.face = (uint32_t)okey;
+            s_sorted[atomicAdd(&s_scan_n, 1u)] = h;
+        }
+        __syncthreads();
+        n = s_scan_n;
+    } else {
+        n = tile_count[tile];
+    }
     if (n == 0) return;
     BinHead* bin = bins + (size_t)tile * bin_cap;
     uint32_t m = 2;
     while (m < n) m <<= 1;                              // bin_cap is a power of two >= n
     BinHead* sorted;
-    if (m <= ORD_SORT_MAX) {
+    if (p.scan_heads) {                                 // n <= nf <= OP_SORT_MAX_ENTRIES <= ORD_SORT_MAX: pad in place
+        for (uint32_t i = n + threadIdx.x; i < m; i += blockDim.x) s_sorted[i] = BinHead{0, 0, 0xFFFFFFFFu, 0xFFFFFFFFu};
+        sorted = s_sorted;
+    } else if (m <= ORD_SORT_MAX) {
         for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) s_sorted[i] = i < n ? bin[i] : BinHead{0, 0, 0xFFFFFFFFu, 0xFFFFFFFFu};
         sorted = s_sorted;
     } else {
@@ -1606,13 +1636,13 @@ void launch_fill_opaque(const LaunchCtx& L, const SurfRec* recs, const BinHead* 
              recs, bins, tile_count, heads, sorted_scratch, tex, texels, texmask, fb_rgba, fb_z, st, sticky, p);
 }
 
-void launch_fill_ordered(const LaunchCtx& L, const SurfRec* recs, BinHead* obins, const uint32_t* otile_count,
+void launch_fill_ordered(const LaunchCtx& L, const SurfRec* recs, BinHead* obins, const uint32_t* otile_count, const uint64_t* keys,
                          const TexDev* tex, const uint16_t* texels, uint32_t* fb_rgba, float* fb_z,
                          const CallState* st, const CallParams& p, uint32_t obin_cap) {
     uint32_t ntiles = p.tiles_x * p.tiles_y;
     if (ntiles == 0 || p.nf == 0) return;
     launch_k(L, p.rgb888 ? k_fill_ordered<true> : k_fill_ordered<false>, ntiles, FILL_THREADS, ORD_SMEM, false,
-             recs, obins, otile_count, tex, static_cast<const void*>(texels), fb_rgba, fb_z, st, p, obin_cap);
+             recs, obins, otile_count, keys, tex, static_cast<const void*>(texels), fb_rgba, fb_z, st, p, obin_cap);
 }
 
 void launch_wire(const LaunchCtx& L, const WireTri* wire, uint32_t kind, uint32_t color, bool depth_test, uint32_t* table, uint32_t table_size,

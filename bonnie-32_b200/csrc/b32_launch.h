@@ -49,7 +49,8 @@ void launch_fill_opaque(const LaunchCtx& L, const SurfRec* recs, const BinHead* 
                         BinHead* sorted_scratch, const TexDev* tex, const uint16_t* texels, const uint32_t* texmask, uint32_t* fb_rgba, float* fb_z,
                         const CallState* st, uint32_t* sticky, const CallParams& p);
 // ordered pass (pass 2 / x-ray): bins of draw-order keys, sorted per tile, replayed in order
-void launch_fill_ordered(const LaunchCtx& L, const SurfRec* recs, BinHead* obins, const uint32_t* otile_count,
+// keys: k_setup's (class | depth key) per face, read directly when p.scan_heads (small meshes, no binning kernel)
+void launch_fill_ordered(const LaunchCtx& L, const SurfRec* recs, BinHead* obins, const uint32_t* otile_count, const uint64_t* keys,
                          const TexDev* tex, const uint16_t* texels, uint32_t* fb_rgba, float* fb_z,
                          const CallState* st, const CallParams& p, uint32_t obin_cap);
 // wireframe phase: kind 1 = back-face edges (depth tested), 2 = front-face overlay edges
