@@ -182,7 +182,8 @@ int fill_params(b32_ctx* ctx, CallParams& p, const b32_camera* cam, const b32_se
     p.nv = nv; p.nf = nf; p.ntex = rgb888 ? ctx->ntex8 : ctx->ntex;
     p.rgb888 = rgb888 ? 1 : 0;
     static const bool no_scan = std::getenv("B32_NO_HEAD_SCAN") != nullptr;        // experiments: always bin with k_bin_opaque
-    p.scan_heads = (nf <= (uint32_t)OP_SORT_MAX_ENTRIES && !no_scan) ? 1 : 0;
+    // every tile reads every bin head in this mode: worth it while nf x tiles stays small (1024 faces up to 640x480)
+    p.scan_heads = (nf <= (uint32_t)OP_SORT_MAX_ENTRIES && (uint64_t)nf * p.tiles_x * p.tiles_y <= 1500000ull && !no_scan) ? 1 : 0;
     const uint32_t mask_words = rgb888 ? ctx->tex8mask_words : ctx->texmask_words;
     p.mask_smem_words = mask_words <= (uint32_t)OP_MASK_SMEM_WORDS ? mask_words : 0;
     p.affine_textures = s->affine_textures != 0; p.use_zbuffer = s->use_zbuffer != 0; p.shading = s->shading;
