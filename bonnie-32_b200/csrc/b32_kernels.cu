@@ -813,7 +813,10 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
     BinHead* gwalk = sorted_scratch + (size_t)tile * p.bin_cap;
     auto walk = [&](uint32_t i) -> BinHead { return in_smem ? s_sh[i] : gwalk[i]; };    // uniform branch: LDS or LDG
     uint32_t kmin = 0, shift = 0;
-    {
+    const bool single_batch = n <= 32;                    // one batch: nothing comes "later", so no order (and no early-out) is needed
+    if (single_batch) {
+        if (threadIdx.x < n) s_sh[threadIdx.x] = bin[threadIdx.x];
+    } else {
         // a bin that fits shared memory is read once into registers; a larger one is streamed from L2 in each pass
         constexpr int KPT = OP_SORT_MAX / OP_THREADS;
         BinHead hh[KPT];
@@ -932,7 +935,7 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
             // `open` pixels are those some entry of this batch or a later one could still change; only their
             // bounding box [ox0,ox1) x [oy0,oy1) needs to be met by a surface's bbox.
             uint32_t ox0 = bx0, ox1 = bx0 + OP_BW, oy0 = by0, oy1 = by0 + OP_BH;
-            {
+            if (!single_batch) {
                 uint32_t k0 = in_smem ? s_sh[base].key : gwalk[base].key;
                 if (k0 != 0xFFFFFFFFu) {
                     // upper bound of every key still to come = top of k0's bucket
