@@ -114,6 +114,8 @@ struct b32_ctx {
     uint32_t obin_cap_hint = 0;
     DevBuf<WireTri> wire;
     DevBuf<uint32_t> wire_table;       // open-addressing table of the wireframe phase's edge de-duplication
+    DevBuf<b32_line> lines;            // overlay lines (b32_draw_lines): the list, then per pixel owner + next, then round flags
+    DevBuf<uint32_t> line_scratch;
     uint32_t bin_cap_hint = 0;
     std::vector<LightDev> lights_h;
     bool async_pending = false;
@@ -575,7 +577,7 @@ void b32_ctx_destroy(b32_ctx* ctx) {
     ctx->texels8.release(); ctx->tex8mask.release(); ctx->tex8desc.release(); ctx->verts.release(); ctx->faces.release();
     ctx->tv.release(); ctx->recs.release(); ctx->keys.release(); ctx->state_ring.release(); ctx->otile_count.release();
     ctx->bins.release(); ctx->bins_sorted.release(); ctx->heads.release(); ctx->obins.release(); ctx->wire.release(); ctx->wire_table.release();
-    ctx->lights.release(); ctx->dbg.release();
+    ctx->lights.release(); ctx->dbg.release(); ctx->lines.release(); ctx->line_scratch.release();
     for (FrameGraph& g : ctx->fgs) g.destroy();
     if (ctx->sticky) cudaFree(ctx->sticky);
     if (ctx->state_h) cudaFreeHost(ctx->state_h);
@@ -634,6 +636,16 @@ int b32_fb_clear(b32_ctx* ctx, uint8_t r, uint8_t g, uint8_t b, uint8_t a) {
     if (!ctx) return B32_ERR_INVALID;
     uint32_t c = (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16) | ((uint32_t)a << 24);
     launch_fb_clear(ctx->L(), ctx->fb_rgba.p, ctx->fb_z.p, ctx->width * ctx->height, c);
+    CK(cudaGetLastError());
+    return B32_OK;
+}
+
+int b32_fb_clear_gradient(b32_ctx* ctx, uint8_t tr, uint8_t tg, uint8_t tb, uint8_t br, uint8_t bg, uint8_t bb, uint8_t a) {
+    USE_DEVICE(ctx);
+    if (!ctx) return B32_ERR_INVALID;
+    uint32_t top = (uint32_t)tr | ((uint32_t)tg << 8) | ((uint32_t)tb << 16) | ((uint32_t)a << 24);
+    uint32_t bottom = (uint32_t)br | ((uint32_t)bg << 8) | ((uint32_t)bb << 16);
+    launch_fb_clear_gradient(ctx->L(), ctx->fb_rgba.p, ctx->fb_z.p, ctx->width, ctx->height, top, bottom);
     CK(cudaGetLastError());
     return B32_OK;
 }
@@ -912,6 +924,58 @@ int b32_render_skybox_mesh(b32_ctx* ctx, const b32_sky_vertex* vertices, uint32_
         if (hs.bin_overflow) return fail(ctx, B32_ERR_CUDA, "tile bin overflow persists");
         break;
     }
+    return B32_OK;
+}
+
+int b32_draw_lines(b32_ctx* ctx, const b32_line* lines, uint32_t n) {
+    USE_DEVICE(ctx);
+    if (!ctx) return B32_ERR_INVALID;
+    if (n && !lines) return fail(ctx, B32_ERR_INVALID, "lines is NULL");
+    if (n == 0 || ctx->width == 0 || ctx->height == 0) return B32_OK;
+    bool any_blended = false;
+    for (uint32_t i = 0; i < n; ++i) {
+        const b32_line& l = lines[i];
+        if (l.kind > B32_LINE_3D_ALPHA || (l.kind == B32_LINE_2D && l.mode > B32_BLEND_ERASE))
+            return fail(ctx, B32_ERR_INVALID, "line " + std::to_string(i) + ": unknown kind or blend mode");
+        const int32_t m = B32_LINE_MAX_COORD;
+        if (l.x0 < -m || l.x0 > m || l.y0 < -m || l.y0 > m || l.x1 < -m || l.x1 > m || l.y1 < -m || l.y1 > m)
+            return fail(ctx, B32_ERR_UNSUPPORTED, "line " + std::to_string(i) + ": coordinate beyond B32_LINE_MAX_COORD");
+        bool overwrites = l.kind == B32_LINE_2D ? (l.mode == B32_BLEND_OPAQUE || l.mode == B32_BLEND_ERASE)
+                                                : (l.kind == B32_LINE_3D || l.kind == B32_LINE_3D_OVERLAY);
+        any_blended |= !overwrites;
+    }
+    constexpr uint32_t N_FLAGS = 32;
+    const size_t px = (size_t)ctx->width * ctx->height;
+    CK(ctx->lines.reserve(n));
+    CK(ctx->line_scratch.reserve(3 * px + n + N_FLAGS));
+    uint32_t* owner = ctx->line_scratch.p;
+    uint32_t* next[2] = {owner + px, owner + 2 * px};
+    uint32_t* wait = owner + 3 * px;
+    uint32_t* flags = wait + n;
+    int rc = h2d(ctx, ctx->lines.p, lines, (size_t)n * sizeof(b32_line)); if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    LaunchCtx L = ctx->L();
+    launch_lines_begin(L, ctx->lines.p, n, owner, next[0], wait, flags, N_FLAGS, ctx->fb_rgba.p, ctx->fb_z.p, ctx->width, ctx->height, any_blended);
+    if (any_blended) {
+        // one blended operation per pixel per round, in list order; batches of rounds run until a batch ends with
+        // nothing waiting (rounds after the last useful one return at once)
+        uint32_t plane = 0;
+        auto round = [&](uint32_t r) {
+            launch_lines_round(L, ctx->lines.p, n, owner, next[plane], next[plane ^ 1], wait, flags, r, ctx->fb_rgba.p, ctx->fb_z.p, ctx->width, ctx->height);
+            plane ^= 1;
+        };
+        round(0);
+        for (uint32_t batch = 3;; batch = std::min(2 * batch + 1, N_FLAGS - 1)) {
+            for (uint32_t r = 1; r <= batch; ++r) round(r);
+            CK(cudaMemcpyAsync(ctx->state_h, flags + batch, 4, cudaMemcpyDeviceToHost, st));    // pinned scratch word
+            CK(cudaStreamSynchronize(st));
+            if (*reinterpret_cast<uint32_t*>(ctx->state_h) == 0) break;
+            CK(cudaMemsetAsync(flags, 0, N_FLAGS * 4, st));
+            CK(cudaMemsetAsync(flags, 1, 4, st));                   // the next batch's round 1 sees "waiting"
+        }
+    }
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
     return B32_OK;
 }
 

@@ -58,6 +58,15 @@ void launch_fill_ordered(const LaunchCtx& L, const SurfRec* recs, BinHead* obins
 void launch_wire(const LaunchCtx& L, const WireTri* wire, uint32_t kind, uint32_t color, bool depth_test, uint32_t* table, uint32_t table_size,
                  uint32_t* fb_rgba, const float* fb_z, CallState* st, const CallParams& p);
 void launch_fb_clear(const LaunchCtx& L, uint32_t* rgba, float* z, uint32_t n, uint32_t color);
+// Framebuffer::clear_gradient; top/bottom = r | g << 8 | b << 16 (| alpha byte << 24 in top)
+void launch_fb_clear_gradient(const LaunchCtx& L, uint32_t* rgba, float* z, uint32_t w, uint32_t h, uint32_t top, uint32_t bottom);
+// overlay lines (b32_overlay.cu): begin = last-overwrite claim + store + first proposals; then one launch per round.
+// owner (= applied): one word per pixel; next: two proposal planes of one word per pixel, used alternately; wait: one
+// word per line; flags[r] != 0 iff blended operations still wait after round r.
+void launch_lines_begin(const LaunchCtx& L, const b32_line* lines, uint32_t n, uint32_t* owner, uint32_t* next, uint32_t* wait, uint32_t* flags,
+                        uint32_t n_flags, uint32_t* fb_rgba, const float* fb_z, uint32_t w, uint32_t h, bool any_blended);
+void launch_lines_round(const LaunchCtx& L, const b32_line* lines, uint32_t n, uint32_t* applied, uint32_t* next_cur, uint32_t* next_nxt,
+                        uint32_t* wait, uint32_t* flags, uint32_t round, uint32_t* fb_rgba, const float* fb_z, uint32_t w, uint32_t h);
 void launch_tex_expand(const LaunchCtx& L, const uint8_t* idx, const uint16_t* clut, uint32_t clut_len, uint32_t format, uint32_t n, uint16_t* out);
 
 // skybox sphere pass (render.rs:81-139, :242-299): setup -> tile binning (k_bin_opaque) -> fill

@@ -319,6 +319,34 @@ class Framebuffer:
     def clear_transparent(self):                    # render.rs:48-56
         self.ctx.check(self.ctx.lib.b32_fb_clear(self.ctx.h, 0, 0, 0, 0))
 
+    def clear_gradient(self, top_color, bottom_color):   # render.rs:60-77
+        a = 0 if (len(top_color) > 3 and top_color[3] == abi.BLEND_ERASE) else 255
+        self.ctx.check(self.ctx.lib.b32_fb_clear_gradient(self.ctx.h, *top_color[:3], *bottom_color[:3], a))
+
+    # ---- overlay lines (render.rs:684-872).  One list = one device pass with the result of the calls made in order;
+    # the single-line methods below are the reference's signatures.
+    def draw_lines(self, lines: np.ndarray):
+        ln = np.ascontiguousarray(lines, dtype=abi.LINE_DTYPE)
+        self.ctx.check(self.ctx.lib.b32_draw_lines(self.ctx.h, ln.ctypes.data, len(ln)))
+
+    def draw_line(self, x0, y0, x1, y1, color):
+        self.draw_lines(make_lines([line_entry(abi.LINE_2D, x0, y0, x1, y1, color)]))
+
+    def draw_line_blended(self, x0, y0, x1, y1, color, mode):
+        self.draw_lines(make_lines([line_entry(abi.LINE_2D, x0, y0, x1, y1, color, mode=mode)]))
+
+    def draw_line_alpha(self, x0, y0, x1, y1, color, alpha):
+        self.draw_lines(make_lines([line_entry(abi.LINE_2D_ALPHA, x0, y0, x1, y1, color, alpha=alpha)]))
+
+    def draw_line_3d(self, x0, y0, z0, x1, y1, z1, color):
+        self.draw_lines(make_lines([line_entry(abi.LINE_3D, x0, y0, x1, y1, color, z0, z1)]))
+
+    def draw_line_3d_overlay(self, x0, y0, z0, x1, y1, z1, color):
+        self.draw_lines(make_lines([line_entry(abi.LINE_3D_OVERLAY, x0, y0, x1, y1, color, z0, z1)]))
+
+    def draw_line_3d_alpha(self, x0, y0, z0, x1, y1, z1, color, alpha):
+        self.draw_lines(make_lines([line_entry(abi.LINE_3D_ALPHA, x0, y0, x1, y1, color, z0, z1, alpha=alpha)]))
+
     def upload(self, pixels: np.ndarray, zbuffer: Optional[np.ndarray] = None):
         px = np.ascontiguousarray(pixels, dtype=np.uint8)
         assert px.size == self.width * self.height * 4
@@ -350,6 +378,16 @@ class Framebuffer:
     @property
     def zbuffer(self) -> np.ndarray:
         return self.download(True)[1]
+
+
+def line_entry(kind, x0, y0, x1, y1, color, z0=0.0, z1=0.0, mode=abi.BLEND_OPAQUE, alpha=255):
+    """One b32_line: `color` = (r, g, b[, blend]) as everywhere in this module."""
+    blend = color[3] if len(color) > 3 else abi.BLEND_OPAQUE
+    return (x0, y0, x1, y1, z0, z1, tuple(color[:3]), blend, kind, mode, alpha, 0)
+
+
+def make_lines(entries) -> np.ndarray:
+    return np.array(list(entries), dtype=abi.LINE_DTYPE)
 
 
 def _check_geometry(vertices, faces):

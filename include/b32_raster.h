@@ -170,6 +170,11 @@ uint64_t    b32_kernel_launches(const b32_ctx* ctx);
 int b32_fb_resize(b32_ctx* ctx, uint32_t width, uint32_t height);
 /* Framebuffer::clear(color): every pixel = (r,g,b,a), zbuffer = f32::MAX (render.rs:36-45). */
 int b32_fb_clear(b32_ctx* ctx, uint8_t r, uint8_t g, uint8_t b, uint8_t a);
+/* Framebuffer::clear_gradient(top, bottom) (render.rs:60-77): row y gets Color::lerp(top, bottom, y/(h-1))
+ * (types.rs:811-820, f32, truncating casts; t = 0 when h == 1), zbuffer = f32::MAX.  a = the alpha byte of
+ * Color::to_bytes for `top` (255, or 0 when top.blend == Erase; lerp keeps top's blend tag). */
+int b32_fb_clear_gradient(b32_ctx* ctx, uint8_t top_r, uint8_t top_g, uint8_t top_b,
+                          uint8_t bottom_r, uint8_t bottom_g, uint8_t bottom_b, uint8_t a);
 /* Host access to Framebuffer.pixels / .zbuffer (host overlays, present). z may be NULL. */
 int b32_fb_upload(b32_ctx* ctx, const uint8_t* rgba, const float* z);
 int b32_fb_download(b32_ctx* ctx, uint8_t* rgba, float* z);
@@ -252,6 +257,31 @@ typedef struct b32_sky_vertex {
  * vertex indices.  Step 2 (render_stars, libm sin/cos) stays on the host. */
 int b32_render_skybox_mesh(b32_ctx* ctx, const b32_sky_vertex* vertices, uint32_t nv,
                            const uint32_t* faces, uint32_t nf, const b32_camera* camera);
+
+/* ---- overlay lines (Framebuffer::draw_line*, render.rs:684-872) --------------------------------------- */
+/* The post-passes the editor and the game draw over a rendered frame (grids, gizmos, wireframes, collision
+ * shapes).  On the host they force a framebuffer download between the render and the present; here a whole
+ * list is drawn on the device, with the result of calling the Framebuffer methods one by one in list order. */
+enum {
+    B32_LINE_2D          = 0,   /* draw_line / draw_line_blended(mode) (:714-751): set_pixel or set_pixel_blended */
+    B32_LINE_2D_ALPHA    = 1,   /* draw_line_alpha (:684-711): set_pixel_alpha (:646-667) */
+    B32_LINE_3D          = 2,   /* draw_line_3d (:756-758): depth test z < zbuffer, set_pixel */
+    B32_LINE_3D_OVERLAY  = 3,   /* draw_line_3d_overlay (:763-765): z <= zbuffer, set_pixel */
+    B32_LINE_3D_ALPHA    = 4    /* draw_line_3d_alpha (:822-872): z * 0.995 <= zbuffer, set_pixel_alpha */
+};
+typedef struct b32_line {
+    int32_t x0, y0, x1, y1;     /* end points, |coordinate| <= B32_LINE_MAX_COORD */
+    float   z0, z1;             /* end-point depths of the 3D kinds (never written to the z-buffer) */
+    uint8_t r, g, b, blend;     /* struct Color (types.rs:721-726); blend only decides to_bytes' alpha (Erase: 0) */
+    uint8_t kind;               /* B32_LINE_* */
+    uint8_t mode;               /* B32_LINE_2D: the BlendMode argument of draw_line_blended (B32_BLEND_OPAQUE = draw_line) */
+    uint8_t alpha;              /* the *_ALPHA kinds */
+    uint8_t _pad;
+} b32_line;
+#define B32_LINE_MAX_COORD (1 << 20)
+/* Blocking.  B32_ERR_INVALID for an unknown kind/mode, B32_ERR_UNSUPPORTED for a coordinate beyond
+ * B32_LINE_MAX_COORD (the reference walks every step of a line, on screen or not). */
+int b32_draw_lines(b32_ctx* ctx, const b32_line* lines, uint32_t n);
 
 /* ---- pinned host memory for callers that want zero-copy DMA of their Vec buffers -------- */
 void* b32_host_alloc(size_t bytes);

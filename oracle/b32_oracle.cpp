@@ -621,6 +621,88 @@ inline void fb_set_pixel_blended(Fb& fb, uint64_t x, uint64_t y, Col c, uint32_t
         fb_put(fb, idx, col_blend(c, fb_back(fb, idx), mode));
     }
 }
+inline void fb_set_pixel_alpha(Fb& fb, uint64_t x, uint64_t y, Col color, uint8_t alpha) {   // render.rs:646-667
+    if (x < fb.width && y < fb.height) {
+        uint64_t idx = (y * fb.width + x) * 4;
+        uint8_t back_r = fb.pixels[idx], back_g = fb.pixels[idx + 1], back_b = fb.pixels[idx + 2];
+        uint16_t a = alpha, inv_a = (uint16_t)(255 - a);
+        fb.pixels[idx]     = (uint8_t)(((uint16_t)color.r * a + (uint16_t)back_r * inv_a) / 255);
+        fb.pixels[idx + 1] = (uint8_t)(((uint16_t)color.g * a + (uint16_t)back_g * inv_a) / 255);
+        fb.pixels[idx + 2] = (uint8_t)(((uint16_t)color.b * a + (uint16_t)back_b * inv_a) / 255);
+        fb.pixels[idx + 3] = 255;
+    }
+}
+// The overlay line family, each restated on its own: draw_line_alpha (render.rs:684-711), draw_line_blended
+// (:719-751), draw_line_3d_impl (:767-817), draw_line_3d_alpha (:822-872)
+void fb_draw_line_alpha(Fb& fb, int32_t x0, int32_t y0, int32_t x1, int32_t y1, Col color, uint8_t alpha) {
+    int32_t dx = std::abs(x1 - x0), dy = -std::abs(y1 - y0);
+    int32_t sx = x0 < x1 ? 1 : -1, sy = y0 < y1 ? 1 : -1;
+    int32_t err = dx + dy, x = x0, y = y0;
+    for (;;) {
+        if (x >= 0 && x < (int32_t)fb.width && y >= 0 && y < (int32_t)fb.height) fb_set_pixel_alpha(fb, (uint64_t)x, (uint64_t)y, color, alpha);
+        if (x == x1 && y == y1) break;
+        int32_t e2 = 2 * err;
+        if (e2 >= dy) { err += dy; x += sx; }
+        if (e2 <= dx) { err += dx; y += sy; }
+    }
+}
+void fb_draw_line_blended(Fb& fb, int32_t x0, int32_t y0, int32_t x1, int32_t y1, Col color, uint32_t mode) {
+    int32_t dx = std::abs(x1 - x0), dy = -std::abs(y1 - y0);
+    int32_t sx = x0 < x1 ? 1 : -1, sy = y0 < y1 ? 1 : -1;
+    int32_t err = dx + dy, x = x0, y = y0;
+    for (;;) {
+        if (x >= 0 && x < (int32_t)fb.width && y >= 0 && y < (int32_t)fb.height) {
+            if (mode == B32_BLEND_OPAQUE) fb_set_pixel(fb, (uint64_t)x, (uint64_t)y, color);
+            else fb_set_pixel_blended(fb, (uint64_t)x, (uint64_t)y, color, mode);
+        }
+        if (x == x1 && y == y1) break;
+        int32_t e2 = 2 * err;
+        if (e2 >= dy) { err += dy; x += sx; }
+        if (e2 <= dx) { err += dx; y += sy; }
+    }
+}
+void fb_draw_line_3d_impl(Fb& fb, int32_t x0, int32_t y0, float z0, int32_t x1, int32_t y1, float z1, Col color, bool allow_equal) {
+    int32_t dx = std::abs(x1 - x0), dy = -std::abs(y1 - y0);
+    int32_t sx = x0 < x1 ? 1 : -1, sy = y0 < y1 ? 1 : -1;
+    int32_t err = dx + dy, x = x0, y = y0;
+    float total_steps = (float)std::max(dx, std::max(-dy, 1));
+    float step = 0.0f;
+    for (;;) {
+        if (x >= 0 && x < (int32_t)fb.width && y >= 0 && y < (int32_t)fb.height) {
+            float t = step / total_steps;
+            float z = z0 + t * (z1 - z0);
+            uint64_t idx = (uint64_t)y * fb.width + (uint64_t)x;
+            bool passes = allow_equal ? z <= fb.zbuffer[idx] : z < fb.zbuffer[idx];
+            if (passes) fb_set_pixel(fb, (uint64_t)x, (uint64_t)y, color);
+        }
+        if (x == x1 && y == y1) break;
+        int32_t e2 = 2 * err;
+        if (e2 >= dy) { err += dy; x += sx; step += 1.0f; }
+        if (e2 <= dx) { err += dx; y += sy; if (e2 < dy) step += 1.0f; }
+    }
+}
+void fb_draw_line_3d_alpha(Fb& fb, int32_t x0, int32_t y0, float z0, int32_t x1, int32_t y1, float z1, Col color, uint8_t alpha) {
+    const float DEPTH_BIAS = 0.995f;
+    float z0_biased = z0 * DEPTH_BIAS, z1_biased = z1 * DEPTH_BIAS;
+    int32_t dx = std::abs(x1 - x0), dy = -std::abs(y1 - y0);
+    int32_t sx = x0 < x1 ? 1 : -1, sy = y0 < y1 ? 1 : -1;
+    int32_t err = dx + dy, x = x0, y = y0;
+    float total_steps = (float)std::max(dx, std::max(-dy, 1));
+    float step = 0.0f;
+    for (;;) {
+        if (x >= 0 && x < (int32_t)fb.width && y >= 0 && y < (int32_t)fb.height) {
+            float t = step / total_steps;
+            float z = z0_biased + t * (z1_biased - z0_biased);
+            uint64_t idx = (uint64_t)y * fb.width + (uint64_t)x;
+            if (z <= fb.zbuffer[idx]) fb_set_pixel_alpha(fb, (uint64_t)x, (uint64_t)y, color, alpha);
+        }
+        if (x == x1 && y == y1) break;
+        int32_t e2 = 2 * err;
+        if (e2 >= dy) { err += dy; x += sx; step += 1.0f; }
+        if (e2 <= dx) { err += dx; y += sy; if (e2 < dy) step += 1.0f; }
+    }
+}
+
 // shared tail of the two editor-alpha writers (render.rs:349-373 / 395-419): PS1 blend, then a float lerp
 inline void editor_alpha_write8(Fb& fb, uint64_t idx, Col c, uint32_t mode, uint8_t editor_alpha) {
     Col back = fb_back(fb, idx);
@@ -1213,6 +1295,41 @@ int b32o_render_skybox_mesh(uint8_t* fb_rgba, uint32_t w, uint32_t h, const b32_
                     fb_rgba[idx + 3] = 255;
                 }
             }
+        }
+    }
+    return B32_OK;
+}
+
+// Framebuffer::clear_gradient, render.rs:60-77; Color::lerp, types.rs:811-820
+void b32o_fb_clear_gradient(uint8_t* rgba, float* z, uint32_t w, uint32_t h, const uint8_t top[3], const uint8_t bottom[3], uint8_t a) {
+    for (uint64_t y = 0; y < h; ++y) {
+        float t = h > 1 ? (float)y / (float)(h - 1) : 0.0f;
+        t = rmin(rmax(t, 0.0f), 1.0f);
+        float inv_t = 1.0f - t;
+        uint8_t r = f2u8((float)top[0] * inv_t + (float)bottom[0] * t);
+        uint8_t g = f2u8((float)top[1] * inv_t + (float)bottom[1] * t);
+        uint8_t b = f2u8((float)top[2] * inv_t + (float)bottom[2] * t);
+        for (uint64_t x = 0; x < w; ++x) {
+            uint64_t idx = (y * w + x) * 4;
+            rgba[idx] = r; rgba[idx + 1] = g; rgba[idx + 2] = b; rgba[idx + 3] = a;
+            z[y * w + x] = 3.40282347e+38f;
+        }
+    }
+}
+
+// A list of overlay lines drawn one after the other: what a caller of Framebuffer::draw_line* does
+int b32o_draw_lines(uint8_t* fb_rgba, float* fb_z, uint32_t w, uint32_t h, const b32_line* lines, uint32_t n) {
+    Fb fb{fb_rgba, fb_z, w, h};
+    for (uint32_t i = 0; i < n; ++i) {
+        const b32_line& l = lines[i];
+        Col c{l.r, l.g, l.b, l.blend};
+        switch (l.kind) {
+            case B32_LINE_2D:         fb_draw_line_blended(fb, l.x0, l.y0, l.x1, l.y1, c, l.mode); break;   // draw_line = mode Opaque (:714-716)
+            case B32_LINE_2D_ALPHA:   fb_draw_line_alpha(fb, l.x0, l.y0, l.x1, l.y1, c, l.alpha); break;
+            case B32_LINE_3D:         fb_draw_line_3d_impl(fb, l.x0, l.y0, l.z0, l.x1, l.y1, l.z1, c, false); break;
+            case B32_LINE_3D_OVERLAY: fb_draw_line_3d_impl(fb, l.x0, l.y0, l.z0, l.x1, l.y1, l.z1, c, true); break;
+            case B32_LINE_3D_ALPHA:   fb_draw_line_3d_alpha(fb, l.x0, l.y0, l.z0, l.x1, l.y1, l.z1, c, l.alpha); break;
+            default: return B32_ERR_INVALID;
         }
     }
     return B32_OK;

@@ -74,6 +74,12 @@ int b32o_render_skybox_mesh(uint8_t* fb_rgba, uint32_t w, uint32_t h,
                             const b32_sky_vertex* vertices, uint32_t nv, const uint32_t* faces, uint32_t nf,
                             const b32_camera* camera);
 
+/* Framebuffer::clear_gradient (render.rs:60-77). */
+void b32o_fb_clear_gradient(uint8_t* rgba, float* z, uint32_t w, uint32_t h,
+                            const uint8_t top[3], const uint8_t bottom[3], uint8_t a);
+/* Framebuffer::draw_line* (render.rs:684-872), one call per list entry, in order. */
+int b32o_draw_lines(uint8_t* fb_rgba, float* fb_z, uint32_t w, uint32_t h, const b32_line* lines, uint32_t n);
+
 #ifdef __cplusplus
 }
 #endif

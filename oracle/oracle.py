@@ -141,6 +141,26 @@ def render_skybox_mesh(fb_rgba, sky_vertices, faces, camera):
                                          C.c_uint32(len(v)), C.c_void_p(f.ctypes.data), C.c_uint32(len(f) // 3), C.byref(cam))
 
 
+def fb_clear_gradient(fb_rgba, fb_z, top, bottom):
+    """Framebuffer::clear_gradient on caller-owned arrays; top/bottom = (r, g, b[, blend])."""
+    abi = _abi()
+    h, w = fb_rgba.shape[:2]
+    a = 0 if (len(top) > 3 and top[3] == abi.BLEND_ERASE) else 255
+    t = (C.c_uint8 * 3)(*top[:3]); b = (C.c_uint8 * 3)(*bottom[:3])
+    lib().b32o_fb_clear_gradient.restype = None
+    lib().b32o_fb_clear_gradient(C.c_void_p(fb_rgba.ctypes.data), C.c_void_p(fb_z.ctypes.data), C.c_uint32(w), C.c_uint32(h), t, b, C.c_uint8(a))
+
+
+def draw_lines(fb_rgba, fb_z, lines):
+    """Framebuffer::draw_line* for every entry of `lines` (abi.LINE_DTYPE), in order."""
+    abi = _abi()
+    h, w = fb_rgba.shape[:2]
+    ln = np.ascontiguousarray(lines, dtype=abi.LINE_DTYPE)
+    lib().b32o_draw_lines.restype = C.c_int
+    return lib().b32o_draw_lines(C.c_void_p(fb_rgba.ctypes.data), C.c_void_p(fb_z.ctypes.data), C.c_uint32(w), C.c_uint32(h),
+                                 C.c_void_p(ln.ctypes.data), C.c_uint32(len(ln)))
+
+
 def transform(vertices, camera, settings, w, h):
     abi = _abi()
     v = np.ascontiguousarray(vertices, dtype=abi.VERTEX_DTYPE)

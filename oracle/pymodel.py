@@ -736,3 +736,74 @@ def fb_clear(w, h, color):
     rgba[...] = np.array(list(color[:3]) + [255], dtype=np.uint8)
     z = np.full((h, w), np.finfo(np.float32).max, dtype=np.float32)
     return rgba, z
+
+
+# ------------------------------------------------------------------------------------------
+# Framebuffer::clear_gradient (render.rs:60-77) and the overlay line family (render.rs:684-872)
+# ------------------------------------------------------------------------------------------
+def fb_clear_gradient(w, h, top, bottom):
+    rgba = np.empty((h, w, 4), dtype=np.uint8)
+    y = np.arange(h, dtype=np.float32)
+    t = y / F(h - 1) if h > 1 else np.zeros(h, dtype=np.float32)          # :64
+    t = np.clip(t, F(0.0), F(1.0))                                         # Color::lerp, types.rs:811-820
+    inv_t = F(1.0) - t
+    for k in range(3):
+        rgba[..., k] = as_u8(F(top[k]) * inv_t + F(bottom[k]) * t)[:, None]
+    rgba[..., 3] = 0 if (len(top) > 3 and top[3] == ERASE) else 255        # lerp keeps self.blend; to_bytes :829-832
+    z = np.full((h, w), np.finfo(np.float32).max, dtype=np.float32)
+    return rgba, z
+
+
+LINE_2D, LINE_2D_ALPHA, LINE_3D, LINE_3D_OVERLAY, LINE_3D_ALPHA = range(5)
+
+
+def _line_points(x0, y0, x1, y1):
+    """The pixel sequence and the `step` counter of the reference's Bresenham loop (:768-817; the 2D variants walk the
+    same points and have no step counter), as integer arrays."""
+    dx, dy = abs(x1 - x0), -abs(y1 - y0)
+    sx, sy = (1 if x0 < x1 else -1), (1 if y0 < y1 else -1)
+    err, x, y, step = dx + dy, x0, y0, 0
+    xs, ys, steps = [], [], []
+    while True:
+        xs.append(x); ys.append(y); steps.append(step)
+        if x == x1 and y == y1:
+            break
+        e2 = 2 * err
+        if e2 >= dy:
+            err += dy; x += sx; step += 1
+        if e2 <= dx:
+            err += dx; y += sy
+            if e2 < dy:
+                step += 1
+    return np.array(xs), np.array(ys), np.array(steps), max(dx, max(-dy, 1))
+
+
+def draw_lines(fb_rgba, fb_z, lines):
+    """lines: records with the fields of abi.LINE_DTYPE; drawn in order into fb_rgba (u8[h,w,4]); fb_z is only read."""
+    h, w = fb_z.shape
+    for l in lines:
+        kind, mode, alpha = int(l["kind"]), int(l["mode"]), int(l["alpha"])
+        xs, ys, steps, total = _line_points(int(l["x0"]), int(l["y0"]), int(l["x1"]), int(l["y1"]))
+        on = (xs >= 0) & (xs < w) & (ys >= 0) & (ys < h)
+        xs, ys, steps = xs[on], ys[on], steps[on]
+        if kind >= LINE_3D:
+            z0, z1 = F(l["z0"]), F(l["z1"])
+            if kind == LINE_3D_ALPHA:
+                z0, z1 = z0 * F(0.995), z1 * F(0.995)                      # DEPTH_BIAS :826-828
+            t = steps.astype(np.float32) / F(total)                        # step counts < 2^24 are exact in f32
+            z = z0 + t * (z1 - z0)
+            zb = fb_z[ys, xs]
+            ok = (z < zb) if kind == LINE_3D else (z <= zb)
+            xs, ys = xs[ok], ys[ok]
+        rgb = np.array(l["rgb"], dtype=np.int64)
+        back = fb_rgba[ys, xs, :3].astype(np.int64)
+        if kind in (LINE_2D_ALPHA, LINE_3D_ALPHA):                         # set_pixel_alpha :646-667
+            out, a = (rgb * alpha + back * (255 - alpha)) // 255, 255
+        elif kind == LINE_2D and mode == ERASE:                            # Color::TRANSPARENT, types.rs:920-923
+            out, a = np.zeros_like(back), 0
+        elif kind == LINE_2D and mode != OPAQUE:                           # set_pixel_blended :313-333
+            out, a = blend888(np.broadcast_to(rgb, back.shape), back, mode), 255
+        else:                                                              # set_pixel :301-310
+            out, a = np.broadcast_to(rgb, back.shape), (0 if int(l["blend"]) == ERASE else 255)
+        fb_rgba[ys, xs, :3] = out.astype(np.uint8)
+        fb_rgba[ys, xs, 3] = a

@@ -174,3 +174,56 @@ pub fn render_mesh(fb: &mut Framebuffer, vertices: &[Vertex], faces: &[Face], te
         timings(&tm)
     })
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Overlay lines: Framebuffer::draw_line* (src/rasterizer/render.rs:684-872) and clear_gradient (:60-77).
+// A caller that keeps the framebuffer on the device between the render and the present collects its overlay
+// lines in a LineList (same method names and arguments as the Framebuffer methods) and flushes it once: the
+// device draws the list with the result of the calls made one after the other.
+// ---------------------------------------------------------------------------------------------------
+#[repr(C)] #[derive(Clone, Copy)]
+pub struct b32_line { x0: i32, y0: i32, x1: i32, y1: i32, z0: f32, z1: f32, r: u8, g: u8, b: u8, blend: u8,
+                      kind: u8, mode: u8, alpha: u8, _pad: u8 }
+extern "C" {
+    fn b32_draw_lines(ctx: *mut b32_ctx, lines: *const b32_line, n: u32) -> c_int;
+    fn b32_fb_clear_gradient(ctx: *mut b32_ctx, tr: u8, tg: u8, tb: u8, br: u8, bg: u8, bb: u8, a: u8) -> c_int;
+}
+
+#[derive(Default)]
+pub struct LineList(Vec<b32_line>);
+
+impl LineList {
+    fn push(&mut self, kind: u8, p: (i32, i32, i32, i32), z: (f32, f32), c: Color, mode: BlendMode, alpha: u8) {
+        self.0.push(b32_line { x0: p.0, y0: p.1, x1: p.2, y1: p.3, z0: z.0, z1: z.1, r: c.r, g: c.g, b: c.b,
+                               blend: blend_u8(c.blend), kind, mode: blend_u8(mode), alpha, _pad: 0 });
+    }
+    pub fn draw_line(&mut self, x0: i32, y0: i32, x1: i32, y1: i32, color: Color) {
+        self.push(0, (x0, y0, x1, y1), (0.0, 0.0), color, BlendMode::Opaque, 255);
+    }
+    pub fn draw_line_blended(&mut self, x0: i32, y0: i32, x1: i32, y1: i32, color: Color, mode: BlendMode) {
+        self.push(0, (x0, y0, x1, y1), (0.0, 0.0), color, mode, 255);
+    }
+    pub fn draw_line_alpha(&mut self, x0: i32, y0: i32, x1: i32, y1: i32, color: Color, alpha: u8) {
+        self.push(1, (x0, y0, x1, y1), (0.0, 0.0), color, BlendMode::Opaque, alpha);
+    }
+    pub fn draw_line_3d(&mut self, x0: i32, y0: i32, z0: f32, x1: i32, y1: i32, z1: f32, color: Color) {
+        self.push(2, (x0, y0, x1, y1), (z0, z1), color, BlendMode::Opaque, 255);
+    }
+    pub fn draw_line_3d_overlay(&mut self, x0: i32, y0: i32, z0: f32, x1: i32, y1: i32, z1: f32, color: Color) {
+        self.push(3, (x0, y0, x1, y1), (z0, z1), color, BlendMode::Opaque, 255);
+    }
+    pub fn draw_line_3d_alpha(&mut self, x0: i32, y0: i32, z0: f32, x1: i32, y1: i32, z1: f32, color: Color, alpha: u8) {
+        self.push(4, (x0, y0, x1, y1), (z0, z1), color, BlendMode::Opaque, alpha);
+    }
+    /// Draws the collected lines over the device framebuffer, in the order they were added, and empties the list.
+    pub fn flush(&mut self) {
+        CTX.with(|&ctx| unsafe { check(ctx, b32_draw_lines(ctx, self.0.as_ptr(), self.0.len() as u32)); });
+        self.0.clear();
+    }
+}
+
+/// Framebuffer::clear_gradient on the device framebuffer.
+pub fn clear_gradient(top: Color, bottom: Color) {
+    let a = if top.blend == BlendMode::Erase { 0 } else { 255 };
+    CTX.with(|&ctx| unsafe { check(ctx, b32_fb_clear_gradient(ctx, top.r, top.g, top.b, bottom.r, bottom.g, bottom.b, a)); });
+}

@@ -293,3 +293,73 @@ def sky_cases():
                                     ("sky_straight_up", 200, 150, -1.5707964, 0.0, (0.0, 0.0, 0.0))]:
         out.append((name, w, h, _rotated_camera(rx, ry, pos)))
     return out
+
+
+# ---- overlay lines (Framebuffer::draw_line*, render.rs:684-872) ---------------------------------------------
+def line_background(w, h, seed):
+    """A framebuffer to draw over: random colours and a z-buffer of a few depth planes with f32::MAX holes, so that
+    3D lines hit `<`, `==` and `>` against it."""
+    rng = np.random.default_rng(seed)
+    rgba = rng.integers(0, 256, size=(h, w, 4), dtype=np.uint8)
+    rgba[..., 3] = 255
+    z = np.full((h, w), np.finfo(np.float32).max, dtype=np.float32)
+    for _ in range(6):
+        x0, x1 = sorted(rng.integers(0, w + 1, 2)); y0, y1 = sorted(rng.integers(0, h + 1, 2))
+        z[y0:y1, x0:x1] = np.float32(rng.choice([4.0, 8.0, 8.0, 12.5, 20.0]))
+    return rgba, z
+
+
+def random_lines(w, h, n, seed, kinds=(0, 1, 2, 3, 4), spread=1.3):
+    """n lines with end points in a box `spread` x the screen (so many leave it), every kind / mode / alpha, depths
+    on and around the planes of line_background."""
+    from bonnie32_b200 import abi
+    rng = np.random.default_rng(seed)
+    ln = np.zeros(n, dtype=abi.LINE_DTYPE)
+    cx, cy = w / 2, h / 2
+    for f, c, e in (("x0", cx, w), ("x1", cx, w), ("y0", cy, h), ("y1", cy, h)):
+        ln[f] = (c + (rng.random(n) - 0.5) * e * spread).astype(np.int32)
+    flat = rng.random(n) < 0.15                       # horizontals, verticals, points
+    ln["y1"][flat] = ln["y0"][flat]
+    vert = rng.random(n) < 0.1
+    ln["x1"][vert] = ln["x0"][vert]
+    ln["z0"] = rng.choice(np.array([2.0, 4.0, 8.0, 8.0, 12.5, 30.0], dtype=np.float32), n)
+    ln["z1"] = np.where(rng.random(n) < 0.5, ln["z0"], rng.choice(np.array([3.0, 8.0, 16.0], dtype=np.float32), n))
+    ln["rgb"] = rng.integers(0, 256, size=(n, 3), dtype=np.uint8)
+    ln["blend"] = rng.choice(np.array([0, 0, 0, 1, 5], dtype=np.uint8), n)
+    ln["kind"] = rng.choice(np.array(kinds, dtype=np.uint8), n)
+    ln["mode"] = rng.integers(0, 6, n).astype(np.uint8)
+    ln["alpha"] = rng.choice(np.array([0, 1, 64, 128, 200, 254, 255], dtype=np.uint8), n)
+    return ln
+
+
+def star_lines(w, h, n, kind, mode=0, alpha=128):
+    """n lines through the screen centre: the deepest stack of operations on one pixel."""
+    from bonnie32_b200 import abi
+    ln = np.zeros(n, dtype=abi.LINE_DTYPE)
+    ang = np.arange(n) * (np.pi / n)
+    r = max(w, h)
+    ln["x0"] = (w // 2 + np.round(np.cos(ang) * r)).astype(np.int32); ln["x1"] = (w // 2 - np.round(np.cos(ang) * r)).astype(np.int32)
+    ln["y0"] = (h // 2 + np.round(np.sin(ang) * r)).astype(np.int32); ln["y1"] = (h // 2 - np.round(np.sin(ang) * r)).astype(np.int32)
+    ln["z0"] = 8.0; ln["z1"] = 8.0
+    ln["rgb"] = (np.arange(n)[:, None] * np.array([37, 91, 13]) % 256).astype(np.uint8)
+    ln["kind"] = kind; ln["mode"] = mode; ln["alpha"] = alpha
+    return ln
+
+
+def line_cases():
+    """(name, width, height, background seed, lines)."""
+    out = [("lines_opaque_2d", 320, 240, 1, random_lines(320, 240, 400, 11, kinds=(0,))),
+           ("lines_3d_strict_and_overlay", 320, 240, 2, random_lines(320, 240, 400, 12, kinds=(2, 3))),
+           ("lines_all_kinds", 320, 240, 3, random_lines(320, 240, 600, 13)),
+           ("lines_all_kinds_dense", 64, 48, 4, random_lines(64, 48, 500, 14, spread=1.1)),
+           ("lines_odd_size", 37, 23, 5, random_lines(37, 23, 200, 15, spread=3.0)),
+           ("lines_640x480", 640, 480, 6, random_lines(640, 480, 1500, 16)),
+           ("lines_star_alpha", 160, 120, 7, star_lines(160, 120, 40, 1)),
+           ("lines_star_average", 160, 120, 8, star_lines(160, 120, 9, 0, mode=1)),
+           ("lines_star_3d_alpha", 160, 120, 9, star_lines(160, 120, 12, 4, alpha=77))]
+    ln = random_lines(96, 64, 300, 17)
+    ln[::7]["kind"] = 0
+    out.append(("lines_far_endpoints", 96, 64, 10, ln))
+    ln = out[-1][4]
+    ln["x1"][::5] = 200000; ln["y0"][::9] = -150000                      # long off-screen runs (still below the coordinate cap)
+    return out

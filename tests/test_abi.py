@@ -46,6 +46,8 @@ int main(void) {
   printf("%zu %zu %zu %zu %zu\n", offsetof(b32_vertex, uv), offsetof(b32_vertex, normal), offsetof(b32_vertex, r),
          offsetof(b32_settings, ambient), offsetof(b32_settings, lights));
   printf("%zu %zu %zu %zu\n", sizeof(b32_tex8_desc), offsetof(b32_tex8_desc, pixels), sizeof(b32_sky_vertex), offsetof(b32_sky_vertex, r));
+  printf("%zu %zu %zu %zu %zu %d\n", sizeof(b32_line), offsetof(b32_line, z0), offsetof(b32_line, r), offsetof(b32_line, kind),
+         offsetof(b32_line, alpha), B32_LINE_MAX_COORD);
   return 0; }''')
     exe = tmp_path / "sizes"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(prog)])
@@ -54,7 +56,9 @@ int main(void) {
     assert sizes[:8] == [36, 16, 48, C.sizeof(abi.Light), C.sizeof(abi.Settings), C.sizeof(abi.Fog), C.sizeof(abi.Timings), C.sizeof(abi.TexDesc)]
     assert abi.VERTEX_DTYPE.itemsize == 36 and abi.FACE_DTYPE.itemsize == 16 and C.sizeof(abi.Camera) == 48
     assert sizes[8:13] == [12, 20, 32, abi.Settings.ambient.offset, abi.Settings.lights.offset]
-    assert sizes[13:] == [C.sizeof(abi.Tex8Desc), abi.Tex8Desc.pixels.offset, abi.SKY_VERTEX_DTYPE.itemsize, abi.SKY_VERTEX_DTYPE.fields["rgb"][1]]
+    F = abi.LINE_DTYPE.fields
+    assert sizes[17:] == [abi.LINE_DTYPE.itemsize, F["z0"][1], F["rgb"][1], F["kind"][1], F["alpha"][1], abi.LINE_MAX_COORD]
+    assert sizes[13:17] == [C.sizeof(abi.Tex8Desc), abi.Tex8Desc.pixels.offset, abi.SKY_VERTEX_DTYPE.itemsize, abi.SKY_VERTEX_DTYPE.fields["rgb"][1]]
     assert abi.VERTEX_DTYPE.fields["uv"][1] == 12 and abi.VERTEX_DTYPE.fields["normal"][1] == 20 and abi.VERTEX_DTYPE.fields["rgba"][1] == 32
 
 

@@ -618,3 +618,127 @@ def test_sparse_calls_compose_over_existing_depth(ctx, oracle, zbuf):
         assert rc == 0
     got, got_z = fb.download()
     assert np.array_equal(got, want) and np.array_equal(got_z.view(np.uint32), want_z.view(np.uint32))
+
+
+# ---- Framebuffer::clear_gradient and the overlay line family (render.rs:60-77, :684-872) ---------------------
+LINES = cases.line_cases()
+
+
+@pytest.mark.parametrize("name,w,h,seed,lines", LINES, ids=lambda v: v if isinstance(v, str) else None)
+def test_draw_lines(ctx, oracle, name, w, h, seed, lines):
+    rgba, z = cases.line_background(w, h, seed)
+    fb = pkg.Framebuffer(w, h, ctx)
+    fb.upload(rgba, z)
+    fb.draw_lines(lines)
+    got, got_z = fb.download()
+    want = rgba.copy()
+    assert oracle.draw_lines(want, z, lines) == 0
+    bad = (got != want).any(-1)
+    assert not bad.any(), f"{name}: {bad.sum()} pixels differ, first at {np.argwhere(bad)[0][::-1]}"
+    assert np.array_equal(got_z.view(np.uint32), z.view(np.uint32))          # lines never write depth
+
+
+def test_draw_lines_one_by_one_equals_one_list(ctx, oracle):
+    """The reference's per-line methods (one device pass each) and one list give the same framebuffer."""
+    from bonnie32_b200 import raster
+    name, w, h, seed, lines = LINES[3]
+    rgba, z = cases.line_background(w, h, seed)
+    fb = pkg.Framebuffer(w, h, ctx)
+    fb.upload(rgba, z)
+    for l in lines[:120]:
+        c = (*l["rgb"].tolist(), int(l["blend"]))
+        a = (int(l["x0"]), int(l["y0"]), int(l["x1"]), int(l["y1"]))
+        k = int(l["kind"])
+        if k == abi.LINE_2D and l["mode"] == abi.BLEND_OPAQUE: fb.draw_line(*a, c)
+        elif k == abi.LINE_2D: fb.draw_line_blended(*a, c, int(l["mode"]))
+        elif k == abi.LINE_2D_ALPHA: fb.draw_line_alpha(*a, c, int(l["alpha"]))
+        elif k == abi.LINE_3D: fb.draw_line_3d(a[0], a[1], float(l["z0"]), a[2], a[3], float(l["z1"]), c)
+        elif k == abi.LINE_3D_OVERLAY: fb.draw_line_3d_overlay(a[0], a[1], float(l["z0"]), a[2], a[3], float(l["z1"]), c)
+        else: fb.draw_line_3d_alpha(a[0], a[1], float(l["z0"]), a[2], a[3], float(l["z1"]), c, int(l["alpha"]))
+    got, _ = fb.download()
+    want = rgba.copy()
+    oracle.draw_lines(want, z, lines[:120])
+    assert np.array_equal(got, want)
+
+
+def test_draw_lines_over_rendered_scene(ctx, oracle):
+    """Editor frame order: render the mesh, then depth-tested overlay lines against ITS z-buffer, no download between."""
+    sc = scenes.scene_c2(n_tris=600, use_zbuffer=True)
+    lines = cases.random_lines(sc.width, sc.height, 500, 99, kinds=(2, 3, 4))
+    lines["z0"] = np.linspace(3.0, 60.0, len(lines), dtype=np.float32); lines["z1"] = lines["z0"][::-1]
+    fb = pkg.Framebuffer(sc.width, sc.height, ctx)
+    fb.clear(sc.clear)
+    pkg.render_mesh_15(fb, sc.vertices, sc.faces, sc.textures, sc.camera, sc.settings)
+    fb.draw_lines(lines)
+    got, got_z = fb.download()
+    want, want_z, _, rc = oracle.render_scene(sc)
+    assert rc == 0 and oracle.draw_lines(want, want_z, lines) == 0
+    assert np.array_equal(got, want) and np.array_equal(got_z.view(np.uint32), want_z.view(np.uint32))
+
+
+def test_draw_lines_errors(ctx):
+    from bonnie32_b200 import raster
+    fb = pkg.Framebuffer(64, 48, ctx)
+    fb.draw_lines(raster.make_lines([]))                                       # empty list: nothing to do
+    bad_kind = raster.make_lines([raster.line_entry(7, 0, 0, 5, 5, (1, 2, 3))])
+    with pytest.raises(pkg.B32Error) as e:
+        fb.draw_lines(bad_kind)
+    assert e.value.code == abi.B32_ERR_INVALID
+    bad_mode = raster.make_lines([raster.line_entry(abi.LINE_2D, 0, 0, 5, 5, (1, 2, 3), mode=9)])
+    with pytest.raises(pkg.B32Error) as e:
+        fb.draw_lines(bad_mode)
+    assert e.value.code == abi.B32_ERR_INVALID
+    far = raster.make_lines([raster.line_entry(abi.LINE_2D, 0, 0, abi.LINE_MAX_COORD + 1, 5, (1, 2, 3))])
+    with pytest.raises(pkg.B32Error) as e:
+        fb.draw_lines(far)
+    assert e.value.code == abi.B32_ERR_UNSUPPORTED
+    before, _ = fb.download()
+    assert not before.any()                                                    # rejected lists draw nothing
+
+
+@pytest.mark.parametrize("w,h,top,bottom", [(320, 240, (10, 20, 200), (250, 128, 0)), (5, 1, (9, 8, 7), (200, 100, 50)),
+                                            (641, 479, (0, 0, 0), (255, 255, 255)), (16, 97, (255, 0, 31, 5), (0, 255, 32))])
+def test_clear_gradient(ctx, oracle, w, h, top, bottom):
+    fb = pkg.Framebuffer(w, h, ctx)
+    fb.upload(np.full((h, w, 4), 9, np.uint8), np.zeros((h, w), np.float32))
+    fb.clear_gradient(top, bottom)
+    got, got_z = fb.download()
+    want = np.empty((h, w, 4), np.uint8); want_z = np.empty((h, w), np.float32)
+    oracle.fb_clear_gradient(want, want_z, top, bottom)
+    assert np.array_equal(got, want) and np.array_equal(got_z.view(np.uint32), want_z.view(np.uint32))
+
+
+@pytest.mark.parametrize("kind", [abi.LINE_2D, abi.LINE_3D, abi.LINE_3D_ALPHA], ids=["2d", "3d", "3d_alpha"])
+def test_draw_lines_every_slope(ctx, oracle, kind):
+    """The device computes pixel k of a line in closed form; the reference walks an error term.  Every (dx, dy) of a
+    41 x 41 neighbourhood, each in its own cell of a large framebuffer, plus the same slopes scaled by 7 and by 1000
+    (64-bit path) through a small window."""
+    R, cell = 20, 44
+    side = (2 * R + 1) * cell
+    ln = np.zeros((2 * R + 1) ** 2, dtype=abi.LINE_DTYPE)
+    dy, dx = np.divmod(np.arange(len(ln)), 2 * R + 1)
+    cx, cy = dx * cell + cell // 2, dy * cell + cell // 2
+    ln["x0"], ln["y0"], ln["x1"], ln["y1"] = cx, cy, cx + dx - R, cy + dy - R
+    ln["z0"], ln["z1"] = 4.0, 12.0
+    ln["rgb"] = (np.arange(len(ln))[:, None] * np.array([7, 13, 29]) % 255 + 1).astype(np.uint8)
+    ln["kind"], ln["alpha"] = kind, 200
+    rgba = np.zeros((side, side, 4), np.uint8); rgba[..., 3] = 255
+    z = np.full((side, side), 8.0, np.float32)
+    for scale, (w, h) in ((1, (side, side)), (7, (side, side)), (1000, (97, 61))):
+        l2 = ln.copy()
+        if scale > 1:
+            l2["x1"] = l2["x0"] + (l2["x1"] - l2["x0"]) * scale; l2["y1"] = l2["y0"] + (l2["y1"] - l2["y0"]) * scale
+        if scale == 1000:
+            l2["x0"] = 48 - (ln["x1"] - ln["x0"]) * 333; l2["y0"] = 30 - (ln["y1"] - ln["y0"]) * 333
+            l2["x1"] = l2["x0"] + (ln["x1"] - ln["x0"]) * scale; l2["y1"] = l2["y0"] + (ln["y1"] - ln["y0"]) * scale
+            l2["kind"] = abi.LINE_2D_ALPHA if kind == abi.LINE_2D else kind       # overlapping: make the order matter
+        bg, bz = rgba[:h, :w].copy(), z[:h, :w].copy()
+        fb = pkg.Framebuffer(w, h, ctx)
+        fb.upload(bg, bz)
+        fb.draw_lines(l2)
+        got, _ = fb.download()
+        want = bg.copy()
+        oracle.draw_lines(want, bz, l2)
+        bad = (got != want).any(-1)
+        assert not bad.any(), f"scale {scale}: {bad.sum()} pixels differ, first at {np.argwhere(bad)[0][::-1]}"
+        assert (want[..., :3] != 0).any()

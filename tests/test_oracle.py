@@ -372,3 +372,46 @@ def ray_roundtrip_distance(project, w=320, h=240):
 def test_ray_rs_projection_roundtrip(oracle):          # ray.rs:333-377 (tolerance of the reference's own test: 2 units)
     dist, scr = ray_roundtrip_distance(lambda v, c, s, w, h: oracle.transform(v, c, s, w, h)[0])
     assert dist < 2.0, (dist, scr)
+
+
+# ---- Framebuffer::clear_gradient and the overlay line family: the two restatements agree -------------------
+LINES = cases.line_cases()
+
+
+@pytest.mark.parametrize("name,w,h,seed,lines", [c for c in LINES if c[1] * c[2] <= 320 * 240 and "far" not in c[0]], ids=lambda v: v if isinstance(v, str) else None)
+def test_lines_oracle_matches_numpy_model(oracle, name, w, h, seed, lines):
+    from oracle import pymodel
+    rgba, z = cases.line_background(w, h, seed)
+    a = rgba.copy(); b = rgba.copy()
+    assert oracle.draw_lines(a, z, lines) == 0
+    pymodel.draw_lines(b, z, lines)
+    assert np.array_equal(a, b), f"{name}: {(a != b).any(-1).sum()} pixels differ"
+    assert not np.array_equal(a, rgba)
+
+
+def test_line_walk_known_points(oracle):
+    """Hand-checked walks of the reference loop (render.rs:719-751): end points included, a point is one pixel, and a
+    shallow line steps its minor axis at the half-way error."""
+    from bonnie32_b200 import abi, raster
+    def drawn(x0, y0, x1, y1):
+        rgba = np.zeros((8, 8, 4), np.uint8); z = np.zeros((8, 8), np.float32)
+        oracle.draw_lines(rgba, z, raster.make_lines([raster.line_entry(abi.LINE_2D, x0, y0, x1, y1, (255, 255, 255))]))
+        ys, xs = np.nonzero(rgba[..., 0])
+        return sorted(zip(xs.tolist(), ys.tolist()))
+    assert drawn(2, 3, 2, 3) == [(2, 3)]
+    assert drawn(0, 0, 3, 3) == [(0, 0), (1, 1), (2, 2), (3, 3)]
+    assert drawn(5, 1, 1, 1) == [(1, 1), (2, 1), (3, 1), (4, 1), (5, 1)]
+    # dx = 4, dy = -1: err 3 -> (e2 = 6: x) 2 -> (e2 = 4: x, and 4 <= dx: y) 5 -> 4 -> 3
+    assert drawn(0, 0, 4, 1) == [(0, 0), (1, 0), (2, 1), (3, 1), (4, 1)]
+    assert drawn(-2, 0, 1, 0) == [(0, 0), (1, 0)]                            # off-screen part is walked, not drawn
+
+
+@pytest.mark.parametrize("w,h,top,bottom", [(320, 240, (10, 20, 200), (250, 128, 0)), (5, 1, (9, 8, 7), (200, 100, 50)),
+                                            (3, 2, (0, 0, 0), (255, 255, 255)), (16, 97, (255, 0, 31, 5), (0, 255, 32))])
+def test_clear_gradient_oracle_matches_numpy_model(oracle, w, h, top, bottom):
+    from oracle import pymodel
+    rgba = np.full((h, w, 4), 7, np.uint8); z = np.zeros((h, w), np.float32)
+    oracle.fb_clear_gradient(rgba, z, top, bottom)
+    want, want_z = pymodel.fb_clear_gradient(w, h, top, bottom)
+    assert np.array_equal(rgba, want) and np.array_equal(z, want_z)
+    assert tuple(rgba[0, 0, :3]) == tuple(top[:3]) and (h == 1 or tuple(rgba[-1, 0, :3]) == tuple(bottom[:3]))
