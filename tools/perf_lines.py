@@ -10,7 +10,7 @@ from oracle import oracle as orc
 import cases
 
 ctx = pkg.Context(0)
-for name, w, h, n, kinds in [("opaque 2D", 640, 480, 2000, (0,)), ("3D strict/overlay", 640, 480, 2000, (2, 3)), ("all kinds", 640, 480, 2000, (0, 1, 2, 3, 4)),
+for name, w, h, n, kinds in [("2D, all blend modes", 640, 480, 2000, (0,)), ("3D strict/overlay", 640, 480, 2000, (2, 3)), ("all kinds", 640, 480, 2000, (0, 1, 2, 3, 4)),
                              ("all kinds", 320, 240, 500, (0, 1, 2, 3, 4)), ("editor grid (3D alpha)", 640, 480, 200, (4,))]:
     lines = cases.random_lines(w, h, n, 5, kinds=kinds)
     rgba, z = cases.line_background(w, h, 3)

@@ -47,5 +47,16 @@ got, _ = fb.download()
 want = np.zeros((h, w, 4), np.uint8); want[..., 3] = 255
 orc.render_skybox_mesh(want, sv, f, cam)
 ok = np.array_equal(got, want); print(name, "OK" if ok else "MISMATCH"); bad += not ok
+# overlay lines (all kinds, blended stacks) and the gradient clear
+for name, w, h, seed, lines in [c for c in cases.line_cases() if c[0] in ("lines_all_kinds_dense", "lines_star_alpha", "lines_far_endpoints")]:
+    rgba, z = cases.line_background(w, h, seed)
+    fb = pkg.Framebuffer(w, h, ctx); fb.upload(rgba, z); fb.draw_lines(lines)
+    got, _ = fb.download()
+    want = rgba.copy(); orc.draw_lines(want, z, lines)
+    ok = np.array_equal(got, want); print(name, "OK" if ok else "MISMATCH"); bad += not ok
+fb = pkg.Framebuffer(61, 47, ctx); fb.clear_gradient((10, 20, 200), (250, 128, 0))
+got, gz = fb.download()
+want = np.empty((47, 61, 4), np.uint8); wz = np.empty((47, 61), np.float32); orc.fb_clear_gradient(want, wz, (10, 20, 200), (250, 128, 0))
+ok = np.array_equal(got, want) and np.array_equal(gz, wz); print("clear_gradient", "OK" if ok else "MISMATCH"); bad += not ok
 print("mismatches:", bad)
 sys.exit(1 if bad else 0)
