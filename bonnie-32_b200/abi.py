@@ -36,6 +36,8 @@ assert VERTEX_DTYPE.itemsize == 36 and FACE_DTYPE.itemsize == 16 and SKY_VERTEX_
 LINE_DTYPE = np.dtype([("x0", "<i4"), ("y0", "<i4"), ("x1", "<i4"), ("y1", "<i4"), ("z0", "<f4"), ("z1", "<f4"),
                        ("rgb", "u1", 3), ("blend", "u1"), ("kind", "u1"), ("mode", "u1"), ("alpha", "u1"), ("_pad", "u1")])
 assert LINE_DTYPE.itemsize == 32
+STAR_DTYPE = np.dtype([("dir", "<f4", 3), ("rgb", "u1", 3), ("_pad", "u1")])                # b32_star
+assert STAR_DTYPE.itemsize == 16
 LINE_2D, LINE_2D_ALPHA, LINE_3D, LINE_3D_OVERLAY, LINE_3D_ALPHA = 0, 1, 2, 3, 4
 LINE_MAX_COORD = 1 << 20
 
@@ -106,6 +108,7 @@ SYMBOLS = {
     "b32_fb_clear": (C.c_int, [_P, C.c_uint8, C.c_uint8, C.c_uint8, C.c_uint8]),
     "b32_fb_clear_gradient": (C.c_int, [_P] + [C.c_uint8] * 7),
     "b32_draw_lines": (C.c_int, [_P, _P, C.c_uint32]),
+    "b32_render_stars": (C.c_int, [_P, _P, C.c_uint32, C.POINTER(Camera), C.c_float]),
     "b32_fb_upload": (C.c_int, [_P, _P, _P]),
     "b32_fb_download": (C.c_int, [_P, _P, _P]),
     "b32_fb_size": (C.c_int, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),

@@ -927,6 +927,28 @@ int b32_render_skybox_mesh(b32_ctx* ctx, const b32_sky_vertex* vertices, uint32_
     return B32_OK;
 }
 
+int b32_render_stars(b32_ctx* ctx, const b32_star* stars, uint32_t n, const b32_camera* camera, float size) {
+    USE_DEVICE(ctx);
+    if (!ctx || !camera) return B32_ERR_INVALID;
+    if (n && !stars) return fail(ctx, B32_ERR_INVALID, "stars is NULL");
+    if (n == 0 || ctx->width == 0 || ctx->height == 0) return B32_OK;
+    b32_settings s{};                     // project(): the float path (render.rs:181)
+    b32_camera cam = *camera;
+    cam.position[0] = cam.position[1] = cam.position[2] = 0.0f;      // directions, not positions (:178)
+    CallParams p; std::vector<LightDev> lights;
+    int rc = fill_params(ctx, p, &cam, &s, nullptr, n, 0, lights); if (rc) return rc;
+    static_assert(sizeof(b32_star) * 2 == sizeof(b32_line), "stars are staged in the line list buffer");
+    CK(ctx->lines.reserve((n + 1) / 2));
+    CK(ctx->line_scratch.reserve((size_t)ctx->width * ctx->height));
+    rc = h2d(ctx, ctx->lines.p, stars, (size_t)n * sizeof(b32_star)); if (rc) return rc;
+    float sz = size != size || size < 1.0f ? 1.0f : size;            // size.max(1.0) as i32 (:202)
+    int32_t isz = sz >= 3.0f ? 3 : (int32_t)sz;
+    launch_stars(ctx->L(), reinterpret_cast<const b32_star*>(ctx->lines.p), n, isz, ctx->line_scratch.p, ctx->fb_rgba.p, p);
+    CK(cudaStreamSynchronize(ctx->stream));                          // the caller's list may be pinned memory still being read
+    CK(cudaGetLastError());
+    return B32_OK;
+}
+
 int b32_draw_lines(b32_ctx* ctx, const b32_line* lines, uint32_t n) {
     USE_DEVICE(ctx);
     if (!ctx) return B32_ERR_INVALID;

@@ -9,6 +9,7 @@
 //                  per-tile sort by the unique draw-order key, then strict in-order replay
 //   k_wire_dedup + k_wire   the wireframe phase (render.rs:2574-2635): first-occurrence edge de-duplication, Bresenham
 //   k_sky_setup + k_sky_fill   Framebuffer::render_skybox step 1 (render.rs:81-139, :242-299)
+//   k_stars_claim + k_stars_write   render_skybox step 2: the star diamonds (render.rs:149-235)
 //   k_transform    the transform alone (stage-output test hook); k_fb_clear, k_tex_expand, k_tex_mask, k_tex8_*: utilities
 //
 // Pixel-order semantics.  The reference draws surfaces one after the other, so a
@@ -1489,6 +1490,45 @@ k_sky_fill(const SkyRec* __restrict__ recs, const BinHead* __restrict__ bins, co
 }
 
 // =================================================================================================
+// star field: Framebuffer::render_skybox step 2 = render_stars + draw_star_diamond (render.rs:149-235)
+// =================================================================================================
+// The host keeps the part that needs libm and the LCG (direction, twinkle brightness -> colour); the device does
+// `dir * 10000.0` -> perspective_transform -> `cam_space.z > 0.1` -> project -> the diamond of up to nine set_pixel
+// calls.  Stars are drawn in order and later ones overwrite earlier ones; a star's own pixels are distinct, so the
+// order is resolved per pixel by the largest star index (atomicMax in `owner`, then the owner stores).
+template <class Visit>
+__device__ __forceinline__ void star_pixels(const b32_star& s, int32_t size, const CallParams& p, Visit visit) {
+    TVert t = transform_vertex(s.dir[0] * 10000.0f, s.dir[1] * 10000.0f, s.dir[2] * 10000.0f, p, nullptr);   // p.cam_pos = 0 (:178)
+    if (!(t.w > 0.1f)) return;                                                       // :180 (NaN: not drawn)
+    const int32_t cx = f2i32(t.x), cy = f2i32(t.y);                                  // `screen.x as i32` (:197)
+    const int32_t W = (int32_t)p.width, H = (int32_t)p.height;
+    auto put = [&](int32_t x, int32_t y, float k) {                                  // set_pixel_safe (:237-241)
+        if (x < 0 || y < 0 || x >= W || y >= H) return;
+        uint32_t r = s.r, g = s.g, b = s.b;
+        if (k != 1.0f) { r = f2u8((float)s.r * k); g = f2u8((float)s.g * k); b = f2u8((float)s.b * k); }   // :211-215, :224-228
+        visit((uint32_t)y * p.width + (uint32_t)x, r | (g << 8) | (b << 16) | 0xFF000000u);
+    };
+    put(cx, cy, 1.0f);
+    if (size >= 2) { put(cx - 1, cy, 0.7f); put(cx + 1, cy, 0.7f); put(cx, cy - 1, 0.7f); put(cx, cy + 1, 0.7f); }
+    if (size >= 3) { put(cx - 2, cy, 0.4f); put(cx + 2, cy, 0.4f); put(cx, cy - 2, 0.4f); put(cx, cy + 2, 0.4f); }
+}
+
+__global__ void __launch_bounds__(128)
+k_stars_claim(const b32_star* __restrict__ stars, uint32_t n, int32_t size, uint32_t* __restrict__ owner, CallParams p) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    star_pixels(stars[i], size, p, [&](uint32_t idx, uint32_t) { atomicMax(&owner[idx], i + 1); });
+}
+
+__global__ void __launch_bounds__(128)
+k_stars_write(const b32_star* __restrict__ stars, uint32_t n, int32_t size, const uint32_t* __restrict__ owner,
+              uint32_t* __restrict__ fb_rgba, CallParams p) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    star_pixels(stars[i], size, p, [&](uint32_t idx, uint32_t v) { if (owner[idx] == i + 1) fb_rgba[idx] = v; });
+}
+
+// =================================================================================================
 // small utility kernels
 // =================================================================================================
 __global__ void k_fb_clear(uint32_t* __restrict__ rgba, float* __restrict__ z, uint32_t n, uint32_t color) {
@@ -1674,6 +1714,14 @@ void launch_sky(const LaunchCtx& L, const b32_sky_vertex* verts, const uint32_t*
     launch_k(L, k_sky_setup, grid_for(p.nf, 128, L.sms, 16), 128, 0, false, verts, faces, recs, heads, st, zero_next, zero_words, p);
     launch_bin(L, heads, nullptr, nullptr, bins, tile_count, st, p, p.bin_cap, false, true);
     launch_k(L, k_sky_fill, p.tiles_x * p.tiles_y, FILL_THREADS, 0, true, recs, bins, tile_count, fb_rgba, st, p);
+}
+
+void launch_stars(const LaunchCtx& L, const b32_star* stars, uint32_t n, int32_t size, uint32_t* owner, uint32_t* fb_rgba, const CallParams& p) {
+    if (n == 0) return;
+    cudaMemsetAsync(owner, 0, (size_t)p.width * p.height * 4, L.stream);
+    k_stars_claim<<<(n + 127) / 128, 128, 0, L.stream>>>(stars, n, size, owner, p);
+    k_stars_write<<<(n + 127) / 128, 128, 0, L.stream>>>(stars, n, size, owner, fb_rgba, p);
+    *L.launches += 2;
 }
 
 void launch_tex_mask(const LaunchCtx& L, const uint16_t* texels, uint32_t n_texels, uint32_t n_words, uint32_t* mask) {

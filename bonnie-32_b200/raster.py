@@ -371,6 +371,13 @@ class Framebuffer:
         cam = camera.to_abi()
         self.ctx.check(self.ctx.lib.b32_render_skybox_mesh(self.ctx.h, v.ctypes.data, len(v), f.ctypes.data, len(f) // 3, C.byref(cam)))
 
+    def render_stars(self, stars: np.ndarray, camera: "Camera", size: float):
+        """Star pass of Framebuffer::render_skybox (render.rs:149-235): `stars` (abi.STAR_DTYPE) holds, per star of the
+        reference's loop, the direction and the brightness-scaled colour the host computed with libm + the LCG."""
+        st = np.ascontiguousarray(stars, dtype=abi.STAR_DTYPE)
+        cam = camera.to_abi()
+        self.ctx.check(self.ctx.lib.b32_render_stars(self.ctx.h, st.ctypes.data, len(st), C.byref(cam), float(size)))
+
     @property
     def pixels(self) -> np.ndarray:
         return self.download(False)[0]

@@ -258,6 +258,19 @@ typedef struct b32_sky_vertex {
 int b32_render_skybox_mesh(b32_ctx* ctx, const b32_sky_vertex* vertices, uint32_t nv,
                            const uint32_t* faces, uint32_t nf, const b32_camera* camera);
 
+/* Step 2 of render_skybox: render_stars + draw_star_diamond (render.rs:149-235).  The host keeps what needs libm and
+ * the LCG: for star i (in the reference's loop order, visible or not) dir = (sin(phi)cos(theta), cos(phi),
+ * sin(phi)sin(theta)) and r, g, b = (stars.color.c as f32 * brightness) as u8.  The device does `dir * 10000.0`,
+ * perspective_transform, the `cam_space.z > 0.1` test, `project`, and the diamond of 1 / 5 / 9 set_pixel calls for
+ * `size.max(1.0) as i32` = 1 / 2 / >= 3, later stars over earlier ones.  (The twinkle phase is only drawn from the
+ * LCG for visible stars, render.rs:186-190, so the host evaluates the same visibility test while it builds the list;
+ * it may pass every star or only the visible ones.) */
+typedef struct b32_star {
+    float   dir[3];
+    uint8_t r, g, b, _pad;
+} b32_star;
+int b32_render_stars(b32_ctx* ctx, const b32_star* stars, uint32_t n, const b32_camera* camera, float size);
+
 /* ---- overlay lines (Framebuffer::draw_line*, render.rs:684-872) --------------------------------------- */
 /* The post-passes the editor and the game draw over a rendered frame (grids, gizmos, wireframes, collision
  * shapes).  On the host they force a framebuffer download between the render and the present; here a whole

@@ -1300,6 +1300,38 @@ int b32o_render_skybox_mesh(uint8_t* fb_rgba, uint32_t w, uint32_t h, const b32_
     return B32_OK;
 }
 
+// render_stars from the star's direction on (render.rs:175-199) + draw_star_diamond (:203-235); the LCG and the libm
+// calls that produce `dir` and the brightness-scaled colour stay with the caller (see b32_star in b32_raster.h)
+int b32o_render_stars(uint8_t* fb_rgba, uint32_t w, uint32_t h, const b32_star* stars, uint32_t n, const b32_camera* camera, float size) {
+    Fb fb{fb_rgba, nullptr, w, h};
+    V3 bx{camera->basis_x[0], camera->basis_x[1], camera->basis_x[2]};
+    V3 by{camera->basis_y[0], camera->basis_y[1], camera->basis_y[2]};
+    V3 bz{camera->basis_z[0], camera->basis_z[1], camera->basis_z[2]};
+    auto set_pixel_safe = [&](int32_t x, int32_t y, Col c) {                         // :237-241
+        if (x >= 0 && y >= 0 && x < (int32_t)fb.width && y < (int32_t)fb.height) fb_set_pixel(fb, (uint64_t)x, (uint64_t)y, c);
+    };
+    for (uint32_t i = 0; i < n; ++i) {
+        const b32_star& st = stars[i];
+        V3 dir{st.dir[0], st.dir[1], st.dir[2]};
+        V3 cam_space = perspective_transform(V3{dir.x * 10000.0f, dir.y * 10000.0f, dir.z * 10000.0f}, bx, by, bz);   // :178
+        if (!(cam_space.z > 0.1f)) continue;                                         // :180
+        V3 screen = project(cam_space, w, h);
+        Col color{st.r, st.g, st.b, B32_BLEND_OPAQUE};                               // Color::new
+        int32_t cx = f2i32(screen.x), cy = f2i32(screen.y);
+        int32_t s = f2i32(rmax(size, 1.0f));                                         // :204
+        set_pixel_safe(cx, cy, color);
+        if (s >= 2) {
+            Col dim{f2u8((float)color.r * 0.7f), f2u8((float)color.g * 0.7f), f2u8((float)color.b * 0.7f), B32_BLEND_OPAQUE};
+            set_pixel_safe(cx - 1, cy, dim); set_pixel_safe(cx + 1, cy, dim); set_pixel_safe(cx, cy - 1, dim); set_pixel_safe(cx, cy + 1, dim);
+        }
+        if (s >= 3) {
+            Col faint{f2u8((float)color.r * 0.4f), f2u8((float)color.g * 0.4f), f2u8((float)color.b * 0.4f), B32_BLEND_OPAQUE};
+            set_pixel_safe(cx - 2, cy, faint); set_pixel_safe(cx + 2, cy, faint); set_pixel_safe(cx, cy - 2, faint); set_pixel_safe(cx, cy + 2, faint);
+        }
+    }
+    return B32_OK;
+}
+
 // Framebuffer::clear_gradient, render.rs:60-77; Color::lerp, types.rs:811-820
 void b32o_fb_clear_gradient(uint8_t* rgba, float* z, uint32_t w, uint32_t h, const uint8_t top[3], const uint8_t bottom[3], uint8_t a) {
     for (uint64_t y = 0; y < h; ++y) {

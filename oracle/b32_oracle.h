@@ -74,6 +74,9 @@ int b32o_render_skybox_mesh(uint8_t* fb_rgba, uint32_t w, uint32_t h,
                             const b32_sky_vertex* vertices, uint32_t nv, const uint32_t* faces, uint32_t nf,
                             const b32_camera* camera);
 
+/* render_stars from the star direction on + draw_star_diamond (render.rs:175-235). */
+int b32o_render_stars(uint8_t* fb_rgba, uint32_t w, uint32_t h, const b32_star* stars, uint32_t n,
+                      const b32_camera* camera, float size);
 /* Framebuffer::clear_gradient (render.rs:60-77). */
 void b32o_fb_clear_gradient(uint8_t* rgba, float* z, uint32_t w, uint32_t h,
                             const uint8_t top[3], const uint8_t bottom[3], uint8_t a);

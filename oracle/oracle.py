@@ -141,6 +141,17 @@ def render_skybox_mesh(fb_rgba, sky_vertices, faces, camera):
                                          C.c_uint32(len(v)), C.c_void_p(f.ctypes.data), C.c_uint32(len(f) // 3), C.byref(cam))
 
 
+def render_stars(fb_rgba, stars, camera, size):
+    """Star pass of Framebuffer::render_skybox into a caller-owned u8[h,w,4] array; stars = abi.STAR_DTYPE records."""
+    abi = _abi()
+    h, w = fb_rgba.shape[:2]
+    st = np.ascontiguousarray(stars, dtype=abi.STAR_DTYPE)
+    cam = camera.to_abi()
+    lib().b32o_render_stars.restype = C.c_int
+    return lib().b32o_render_stars(C.c_void_p(fb_rgba.ctypes.data), C.c_uint32(w), C.c_uint32(h), C.c_void_p(st.ctypes.data),
+                                   C.c_uint32(len(st)), C.byref(cam), C.c_float(size))
+
+
 def fb_clear_gradient(fb_rgba, fb_z, top, bottom):
     """Framebuffer::clear_gradient on caller-owned arrays; top/bottom = (r, g, b[, blend])."""
     abi = _abi()

@@ -807,3 +807,34 @@ def draw_lines(fb_rgba, fb_z, lines):
             out, a = np.broadcast_to(rgb, back.shape), (0 if int(l["blend"]) == ERASE else 255)
         fb_rgba[ys, xs, :3] = out.astype(np.uint8)
         fb_rgba[ys, xs, 3] = a
+
+
+# ------------------------------------------------------------------------------------------
+# Framebuffer::render_skybox step 2 (stars): render.rs:175-235, from the star direction on
+# ------------------------------------------------------------------------------------------
+def render_stars(fb_rgba, stars, camera, size):
+    """stars: records with dir f32[3], rgb u8[3] (abi.STAR_DTYPE), in the reference's loop order."""
+    H, W = fb_rgba.shape[:2]
+    d = np.asarray(stars["dir"], dtype=F).reshape(-1, 3)
+    with np.errstate(all="ignore"):
+        cam_space = perspective_transform(d * F(10000.0), camera)                    # :178
+        vs = (F(min(W, H)) / F(2.0)) * F(0.75)                                       # math.rs:117-136
+        denom = cam_space[:, 2] + F(5.0)
+        tiny = np.abs(denom) < F(0.001)
+        sx = as_i32(np.where(tiny, F(W) / F(2.0), (cam_space[:, 0] * F(4.0)) / denom * vs + (F(W) / F(2.0))))
+        sy = as_i32(np.where(tiny, F(H) / F(2.0), (cam_space[:, 1] * F(4.0)) / denom * vs + (F(H) / F(2.0))))
+    s = int(as_i32(np.array([fmax(F(size), F(1.0))], dtype=F))[0])                   # :204
+    rgb = np.asarray(stars["rgb"], dtype=np.uint8).reshape(-1, 3)
+    rings = [(1.0, [(0, 0)])]
+    if s >= 2:
+        rings.append((0.7, [(-1, 0), (1, 0), (0, -1), (0, 1)]))
+    if s >= 3:
+        rings.append((0.4, [(-2, 0), (2, 0), (0, -2), (0, 2)]))
+    for i in np.nonzero(cam_space[:, 2] > F(0.1))[0]:                                # :180, stars in order
+        for k, offs in rings:
+            c = rgb[i] if k == 1.0 else as_u8(rgb[i].astype(F) * F(k))
+            for ox, oy in offs:
+                x, y = int(sx[i]) + ox, int(sy[i]) + oy
+                if 0 <= x < W and 0 <= y < H:
+                    fb_rgba[y, x, :3] = c
+                    fb_rgba[y, x, 3] = 255

@@ -227,3 +227,41 @@ pub fn clear_gradient(top: Color, bottom: Color) {
     let a = if top.blend == BlendMode::Erase { 0 } else { 255 };
     CTX.with(|&ctx| unsafe { check(ctx, b32_fb_clear_gradient(ctx, top.r, top.g, top.b, bottom.r, bottom.g, bottom.b, a)); });
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Star pass of Framebuffer::render_skybox (src/rasterizer/render.rs:149-199): the LCG and the libm calls stay
+// here, the transform / projection / diamond plotting run on the device.
+// ---------------------------------------------------------------------------------------------------
+#[repr(C)] #[derive(Clone, Copy)]
+pub struct b32_star { dir: [f32; 3], r: u8, g: u8, b: u8, _pad: u8 }
+extern "C" {
+    fn b32_render_stars(ctx: *mut b32_ctx, stars: *const b32_star, n: u32, cam: *const b32_camera, size: f32) -> c_int;
+}
+
+pub fn render_stars(skybox: &crate::world::Skybox, camera: &Camera, time: f32) {
+    use std::f32::consts::PI;
+    let stars = &skybox.stars;
+    let mut rng_seed = stars.seed as u64;
+    let mut next_rand = || -> f32 {
+        rng_seed = rng_seed.wrapping_mul(1103515245).wrapping_add(12345);
+        (rng_seed >> 16) as f32 / 65536.0
+    };
+    let mut list = Vec::with_capacity(stars.count as usize);
+    for _ in 0..stars.count {
+        let theta = next_rand() * 2.0 * PI;
+        let phi = next_rand() * (skybox.horizon * PI);
+        let (y, ring) = (phi.cos(), phi.sin());
+        let dir = Vec3::new(ring * theta.cos(), y, ring * theta.sin());
+        // the twinkle phase is drawn for visible stars only (render.rs:180-190): same test as the device's
+        let cam_z = (dir * 10000.0).dot(camera.basis_z);
+        let mut brightness = 1.0f32;
+        if cam_z > 0.1 && stars.twinkle_speed > 0.0 {
+            let phase = next_rand() * 2.0 * PI;
+            brightness = 0.5 + 0.5 * (time * stars.twinkle_speed + phase).sin();
+        }
+        list.push(b32_star { dir: [dir.x, dir.y, dir.z], r: (stars.color.r as f32 * brightness) as u8,
+                             g: (stars.color.g as f32 * brightness) as u8, b: (stars.color.b as f32 * brightness) as u8, _pad: 0 });
+    }
+    let cam = marshal_camera(camera);
+    CTX.with(|&ctx| unsafe { check(ctx, b32_render_stars(ctx, list.as_ptr(), list.len() as u32, &cam, stars.size)); });
+}

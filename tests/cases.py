@@ -363,3 +363,39 @@ def line_cases():
     ln = out[-1][4]
     ln["x1"][::5] = 200000; ln["y0"][::9] = -150000                      # long off-screen runs (still below the coordinate cap)
     return out
+
+
+# ---- star field (render_stars, render.rs:149-199): the host part that builds the b32_star list ----------------
+def star_list(camera, w, h, time, seed=42, count=300, horizon=0.5, twinkle_speed=1.5, color=(255, 250, 220)):
+    """What a shim computes per star: the LCG draws (theta, phi, and the twinkle phase of VISIBLE stars only), the
+    libm direction, and the brightness-scaled colour.  f32 arithmetic through numpy scalars; sin/cos are libm's
+    cosf/sinf (what Rust's f32::cos/sin call on Linux)."""
+    import ctypes as C
+    from bonnie32_b200 import abi
+    libm = C.CDLL("libm.so.6")
+    libm.cosf.restype = libm.sinf.restype = C.c_float
+    libm.cosf.argtypes = libm.sinf.argtypes = [C.c_float]
+    F = np.float32
+    cosf = lambda v: F(libm.cosf(float(v)))
+    sinf = lambda v: F(libm.sinf(float(v)))
+    PI = F(np.pi)
+    state = [seed & 0xFFFFFFFFFFFFFFFF]
+    def next_rand():
+        state[0] = (state[0] * 1103515245 + 12345) & 0xFFFFFFFFFFFFFFFF
+        return F(state[0] >> 16) / F(65536.0)
+    bx, by, bz = (np.asarray(b, dtype=F) for b in (camera.basis_x, camera.basis_y, camera.basis_z))
+    out = np.zeros(count, dtype=abi.STAR_DTYPE)
+    for i in range(count):
+        theta = next_rand() * F(2.0) * PI
+        phi = next_rand() * (F(horizon) * PI)
+        y = cosf(phi); ring = sinf(phi)
+        d = np.array([ring * cosf(theta), y, ring * sinf(theta)], dtype=F)
+        v = d * F(10000.0)
+        cz = v[0] * bz[0] + v[1] * bz[1] + v[2] * bz[2]
+        brightness = F(1.0)
+        if cz > F(0.1) and twinkle_speed > 0.0:
+            phase = next_rand() * F(2.0) * PI
+            brightness = F(0.5) + F(0.5) * sinf(F(time) * F(twinkle_speed) + phase)
+        out["dir"][i] = d
+        out["rgb"][i] = [min(max(int(F(c) * brightness), 0), 255) for c in color]
+    return out

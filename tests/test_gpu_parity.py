@@ -742,3 +742,42 @@ def test_draw_lines_every_slope(ctx, oracle, kind):
         bad = (got != want).any(-1)
         assert not bad.any(), f"scale {scale}: {bad.sum()} pixels differ, first at {np.argwhere(bad)[0][::-1]}"
         assert (want[..., :3] != 0).any()
+
+
+@pytest.mark.parametrize("size", [1.0, 2.0, 3.0])
+@pytest.mark.parametrize("name,w,h,cam", SKY[:4], ids=[s[0] for s in SKY[:4]])
+def test_render_stars(ctx, oracle, name, w, h, cam, size):
+    stars = cases.star_list(cam, w, h, time=0.75, count=2000 if w > 320 else 400)
+    fb = pkg.Framebuffer(w, h, ctx)
+    fb.clear((3, 4, 5))
+    fb.render_stars(stars, cam, size)
+    got, got_z = fb.download()
+    want = np.zeros((h, w, 4), np.uint8); want[...] = (3, 4, 5, 255)
+    assert oracle.render_stars(want, stars, cam, size) == 0
+    bad = (got != want).any(-1)
+    assert not bad.any(), f"{name}: {bad.sum()} pixels differ"
+    assert (got_z == np.finfo(np.float32).max).all()
+
+
+def test_game_frame_without_downloads(ctx, oracle):
+    """The game's frame (src/game/renderer.rs:91-179 + the debug lines of :1018-1047): clear, skybox sphere, stars,
+    room mesh, depth-tested lines — all on the device, one download at the end."""
+    name, w, h, cam = SKY[1]
+    sv, f = cases.sky_mesh(cam.position)
+    stars = cases.star_list(cam, w, h, time=3.0)
+    sc = scenes.scene_c2(n_tris=500, use_zbuffer=True)
+    lines = cases.random_lines(w, h, 60, 5, kinds=(2,))
+    fb = pkg.Framebuffer(w, h, ctx)
+    fb.clear((0, 0, 0))
+    fb.render_skybox_mesh(sv, f, cam)
+    fb.render_stars(stars, cam, 2.0)
+    pkg.render_mesh_15(fb, sc.vertices, sc.faces, sc.textures, sc.camera, sc.settings)
+    fb.draw_lines(lines)
+    got, got_z = fb.download()
+    want = np.zeros((h, w, 4), np.uint8); want[..., 3] = 255
+    want_z = np.full((h, w), np.finfo(np.float32).max, np.float32)
+    oracle.render_skybox_mesh(want, sv, f, cam)
+    oracle.render_stars(want, stars, cam, 2.0)
+    rc, _, _ = oracle.render_mesh_15(want, want_z, sc.vertices, sc.faces, sc.textures, sc.camera, sc.settings)
+    assert rc == 0 and oracle.draw_lines(want, want_z, lines) == 0
+    assert np.array_equal(got, want) and np.array_equal(got_z.view(np.uint32), want_z.view(np.uint32))

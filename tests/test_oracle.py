@@ -415,3 +415,21 @@ def test_clear_gradient_oracle_matches_numpy_model(oracle, w, h, top, bottom):
     want, want_z = pymodel.fb_clear_gradient(w, h, top, bottom)
     assert np.array_equal(rgba, want) and np.array_equal(z, want_z)
     assert tuple(rgba[0, 0, :3]) == tuple(top[:3]) and (h == 1 or tuple(rgba[-1, 0, :3]) == tuple(bottom[:3]))
+
+
+@pytest.mark.parametrize("size", [0.5, 2.0, 3.7])
+def test_stars_oracle_matches_numpy_model(oracle, size):
+    from oracle import pymodel
+    name, w, h, cam = cases.sky_cases()[1]
+    stars = cases.star_list(cam, w, h, time=1.25)
+    a = np.zeros((h, w, 4), np.uint8); b = a.copy()
+    assert oracle.render_stars(a, stars, cam, size) == 0
+    pymodel.render_stars(b, stars, cam, size)
+    assert np.array_equal(a, b)
+    lit = int((a[..., 3] == 255).sum())
+    assert lit > 5 and (size < 2 or lit > 40)
+    # the list builder is deterministic; directions are unit vectors; twinkle dims some stars
+    again = cases.star_list(cam, w, h, time=1.25)
+    assert stars.tobytes() == again.tobytes()
+    assert np.allclose(np.linalg.norm(stars["dir"], axis=1), 1.0, atol=1e-5)
+    assert len(np.unique(stars["rgb"], axis=0)) > 10
