@@ -4,4 +4,4 @@ set -e
 out=$1; shift
 cd "$(dirname "$0")/.."
 nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false -prec-div=true -prec-sqrt=true -ftz=false \
-  -Xcompiler -fPIC,-O2,-ffp-contract=off -shared -cudart static "$@" -I include -o "$out" bonnie-32_b200/csrc/b32_api.cu bonnie-32_b200/csrc/b32_kernels.cu
+  -Xcompiler -fPIC,-O2,-ffp-contract=off -shared -cudart static "$@" -I include -o "$out" bonnie-32_b200/csrc/*.cu
