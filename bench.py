@@ -455,12 +455,15 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=None,
+                    help="timed steps (default 400 frames for the GPU arm: ~8 ms; 20 for --impl reference, whose step is ~0.2 s)")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--inflight", type=int, default=4, help="frames in flight (contexts/streams) for value and e2e")
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 20 if args.impl == "reference" else 400
     if args.impl == "reference":
         return run_reference(args)
     return run_b200(args)
