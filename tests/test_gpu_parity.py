@@ -781,3 +781,24 @@ def test_game_frame_without_downloads(ctx, oracle):
     rc, _, _ = oracle.render_mesh_15(want, want_z, sc.vertices, sc.faces, sc.textures, sc.camera, sc.settings)
     assert rc == 0 and oracle.draw_lines(want, want_z, lines) == 0
     assert np.array_equal(got, want) and np.array_equal(got_z.view(np.uint32), want_z.view(np.uint32))
+
+
+def test_two_host_threads_two_contexts(oracle):
+    """One context per thread (include/b32_raster.h: a context is not thread-safe, contexts are independent): two host
+    threads render different scenes at the same time, each into its own context."""
+    import threading
+    scs = [scenes.scene_c2(n_tris=800, use_zbuffer=False), cases.feature_scenes(300)[3]]
+    out = [None, None]
+
+    def work(i):
+        c = pkg.Context(0)
+        for _ in range(20):
+            out[i] = render_gpu(c, scs[i])
+        c.close()
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    [t.start() for t in th]; [t.join() for t in th]
+    for i, sc in enumerate(scs):
+        want, want_z, otm, rc = oracle.render_scene(sc)
+        assert rc == 0 and out[i] is not None
+        assert_same(sc, out[i][0], out[i][1], out[i][2], want, want_z, otm)
