@@ -34,3 +34,10 @@ show('final shade + store', t2 - tl)
 show('tile total (start -> last warp end)', t2.max(1) - t0.min(1))
 show('32-entry batches walked per warp', nb)
 print('batches histogram', np.bincount(nb.reshape(-1)))
+# slowest tiles: where does their time go?
+tot = t2.max(1) - t0.min(1)
+order = np.argsort(-tot)[:8]
+print('slowest tiles: tile, total ns, sort ns, max batches, mean batches, loop ns (max warp), shade ns (max warp), start offset')
+for t in order:
+    print(int(t), int(tot[t]), int((t1 - t0)[t].max()), int(nb[t].max()), round(float(nb[t].mean()), 1), int((tl - tf)[t].max()), int((t2 - tl)[t].max()), int(t0[t].min() - base))
+print('corr(total, max batches) =', round(float(np.corrcoef(tot, nb.max(1))[0, 1]), 3), ' corr(total, start offset) =', round(float(np.corrcoef(tot, t0.min(1) - base)[0, 1]), 3))
