@@ -95,6 +95,10 @@ class Tex8Desc(C.Structure):
                 ("pixels", C.c_void_p)]
 
 
+class Placement(C.Structure):            # b32_placement
+    _fields_ = [("facing", C.c_float), ("cos_f", C.c_float), ("sin_f", C.c_float), ("world_pos", C.c_float * 3)]
+
+
 # Every symbol include/b32_raster.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -108,6 +112,8 @@ SYMBOLS = {
     "b32_fb_clear": (C.c_int, [_P, C.c_uint8, C.c_uint8, C.c_uint8, C.c_uint8]),
     "b32_fb_clear_gradient": (C.c_int, [_P] + [C.c_uint8] * 7),
     "b32_draw_lines": (C.c_int, [_P, _P, C.c_uint32]),
+    "b32_render_mesh_placed": (C.c_int, [_P, _P, C.POINTER(Placement), C.POINTER(Camera), C.POINTER(Settings), C.POINTER(Fog),
+                                         C.c_int, C.c_uint32, C.POINTER(Timings)]),
     "b32_render_stars": (C.c_int, [_P, _P, C.c_uint32, C.POINTER(Camera), C.c_float]),
     "b32_fb_upload": (C.c_int, [_P, _P, _P]),
     "b32_fb_download": (C.c_int, [_P, _P, _P]),

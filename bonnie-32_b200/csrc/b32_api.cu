@@ -887,6 +887,31 @@ int b32_render_mesh_15_enqueue(b32_ctx* ctx, const b32_mesh* mesh, const b32_cam
     return render_device(ctx, mesh->verts, mesh->nv, mesh->faces, mesh->nf, camera, settings, fog, nullptr, may_blend || !bins_fit);
 }
 
+int b32_render_mesh_placed(b32_ctx* ctx, const b32_mesh* mesh, const b32_placement* pl, const b32_camera* camera, const b32_settings* settings,
+                           const b32_fog* fog, int rgb888, uint32_t flags, b32_timings* timings) {
+    USE_DEVICE(ctx);
+    if (!ctx || !mesh || !pl || !settings) return B32_ERR_INVALID;
+    // scene.rs:123: has_transform
+    bool has_transform = std::fabs(pl->facing) > 0.0001f || std::fabs(pl->world_pos[0]) > 0.0001f ||
+                         std::fabs(pl->world_pos[1]) > 0.0001f || std::fabs(pl->world_pos[2]) > 0.0001f;
+    const b32_vertex* verts = mesh->verts;
+    if (has_transform && mesh->nv) {
+        // the placed copy lives in the host-call staging buffer: stream order keeps it alive until this call's kernels ran
+        CK(ctx->verts.reserve(mesh->nv));
+        launch_place(ctx->L(), mesh->verts, ctx->verts.p, mesh->nv, pl->cos_f, pl->sin_f, pl->world_pos);
+        verts = ctx->verts.p;
+    }
+    bool wait = !(flags & B32_RENDER_ASYNC);
+    if (!wait) {          // same rule as b32_render_mesh_15_enqueue: only calls that cannot blend stay enqueue-only
+        bool may_blend = rgb888 || mesh->has_nonopaque || settings->xray_mode || (settings->backface_cull && settings->backface_wireframe) || settings->wireframe_overlay;
+        for (const TexDev& t : ctx->texdesc_h) may_blend = may_blend || t.blend != B32_BLEND_OPAQUE;
+        uint32_t ntiles = ((ctx->width + TILE_W - 1) / TILE_W) * ((ctx->height + TILE_H - 1) / TILE_H);
+        wait = may_blend || (size_t)ntiles * mesh->nf * sizeof(BinHead) > ((size_t)4 << 30);
+    }
+    return render_device(ctx, verts, mesh->nv, mesh->faces, mesh->nf, camera, settings, rgb888 ? nullptr : fog,
+                         (flags & B32_RENDER_ASYNC) ? nullptr : timings, wait, rgb888 != 0);
+}
+
 int b32_render_skybox_mesh(b32_ctx* ctx, const b32_sky_vertex* vertices, uint32_t nv, const uint32_t* faces, uint32_t nf, const b32_camera* camera) {
     USE_DEVICE(ctx);
     if (!ctx || !camera) return B32_ERR_INVALID;

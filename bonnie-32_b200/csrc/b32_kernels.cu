@@ -1529,6 +1529,25 @@ k_stars_write(const b32_star* __restrict__ stars, uint32_t n, int32_t size, cons
 }
 
 // =================================================================================================
+// placed asset parts: the per-object vertex transform of render_asset_parts (src/scene.rs:141-160)
+// =================================================================================================
+__global__ void __launch_bounds__(256)
+k_place(const b32_vertex* __restrict__ in, b32_vertex* __restrict__ out, uint32_t nv, float cos_f, float sin_f, float wx, float wy, float wz) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += gridDim.x * blockDim.x) {
+        const float* v = reinterpret_cast<const float*>(in + i);
+        float* o = reinterpret_cast<float*>(out + i);
+        float rx = v[0] * cos_f - v[2] * sin_f;                     // rotate around Y by facing (:143-144)
+        float rz = v[0] * sin_f + v[2] * cos_f;
+        o[0] = rx + wx; o[1] = v[1] + wy; o[2] = rz + wz;           // then translate (:146)
+        o[3] = v[3]; o[4] = v[4];                                   // uv
+        o[5] = v[5] * cos_f - v[7] * sin_f;                         // normal (:148-152)
+        o[6] = v[6];
+        o[7] = v[5] * sin_f + v[7] * cos_f;
+        o[8] = v[8];                                                // colour + blend tag
+    }
+}
+
+// =================================================================================================
 // small utility kernels
 // =================================================================================================
 __global__ void k_fb_clear(uint32_t* __restrict__ rgba, float* __restrict__ z, uint32_t n, uint32_t color) {
@@ -1722,6 +1741,12 @@ void launch_stars(const LaunchCtx& L, const b32_star* stars, uint32_t n, int32_t
     k_stars_claim<<<(n + 127) / 128, 128, 0, L.stream>>>(stars, n, size, owner, p);
     k_stars_write<<<(n + 127) / 128, 128, 0, L.stream>>>(stars, n, size, owner, fb_rgba, p);
     *L.launches += 2;
+}
+
+void launch_place(const LaunchCtx& L, const b32_vertex* in, b32_vertex* out, uint32_t nv, float cos_f, float sin_f, const float* world_pos) {
+    if (nv == 0) return;
+    k_place<<<grid_for(nv, 256, L.sms), 256, 0, L.stream>>>(in, out, nv, cos_f, sin_f, world_pos[0], world_pos[1], world_pos[2]);
+    ++*L.launches;
 }
 
 void launch_tex_mask(const LaunchCtx& L, const uint16_t* texels, uint32_t n_texels, uint32_t n_words, uint32_t* mask) {

@@ -73,6 +73,9 @@ void launch_tex_expand(const LaunchCtx& L, const uint8_t* idx, const uint16_t* c
 void launch_sky(const LaunchCtx& L, const b32_sky_vertex* verts, const uint32_t* faces, SkyRec* recs, BinHead* heads, BinHead* bins,
                 uint32_t* tile_count, uint32_t* fb_rgba, CallState* st, uint32_t* zero_next, uint32_t zero_words, const CallParams& p);
 
+// render_asset_parts' vertex transform (scene.rs:141-160): out = in rotated about Y, translated
+void launch_place(const LaunchCtx& L, const b32_vertex* in, b32_vertex* out, uint32_t nv, float cos_f, float sin_f, const float* world_pos);
+
 // star field (render.rs:149-235): owner = one word per pixel of scratch; p.cam_pos must be zero
 void launch_stars(const LaunchCtx& L, const b32_star* stars, uint32_t n, int32_t size, uint32_t* owner, uint32_t* fb_rgba, const CallParams& p);
 

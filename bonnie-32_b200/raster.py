@@ -387,6 +387,27 @@ class Framebuffer:
         return self.download(True)[1]
 
 
+_LIBM = None
+
+
+def _libm():
+    global _LIBM
+    if _LIBM is None:
+        _LIBM = C.CDLL("libm.so.6")
+        for f in (_LIBM.cosf, _LIBM.sinf):
+            f.restype, f.argtypes = C.c_float, [C.c_float]
+    return _LIBM
+
+
+def libm_cosf(x: float) -> float:
+    """f32::cos as Rust evaluates it on Linux (libm cosf), for host-side values that feed the device."""
+    return float(_libm().cosf(float(x)))
+
+
+def libm_sinf(x: float) -> float:
+    return float(_libm().sinf(float(x)))
+
+
 def line_entry(kind, x0, y0, x1, y1, color, z0=0.0, z1=0.0, mode=abi.BLEND_OPAQUE, alpha=255):
     """One b32_line: `color` = (r, g, b[, blend]) as everywhere in this module."""
     blend = color[3] if len(color) > 3 else abi.BLEND_OPAQUE
@@ -478,6 +499,20 @@ class Mesh:
             col = (C.c_uint8 * 4)(clear[0], clear[1], clear[2], a)
         self.ctx.check(self.ctx.lib.b32_frame_15_enqueue(self.ctx.h, col, self.h, C.byref(cam), C.byref(s),
                                                          C.byref(fg) if fg is not None else None))
+
+    def render_placed(self, camera: Camera, settings: RasterSettings, facing: float, world_pos, fog=None, rgb888=False,
+                      enqueue_only=False):
+        """One part of render_asset_parts (src/scene.rs:109-169): this resident mesh rotated about Y by `facing` and moved
+        to `world_pos` on the device, then render_mesh_15 / render_mesh.  cos/sin are libm's f32 functions, as in Rust."""
+        pl = abi.Placement(facing, libm_cosf(facing), libm_sinf(facing), (C.c_float * 3)(*[float(x) for x in world_pos]))
+        cam = camera.to_abi()
+        s, keep = settings.to_abi()
+        fg = fog_to_abi(fog)
+        tm = abi.Timings()
+        self.ctx.check(self.ctx.lib.b32_render_mesh_placed(self.ctx.h, self.h, C.byref(pl), C.byref(cam), C.byref(s),
+                                                           C.byref(fg) if fg is not None else None, int(rgb888),
+                                                           abi.RENDER_ASYNC if enqueue_only else 0, C.byref(tm)))
+        return None if enqueue_only else tm.as_dict()
 
     def render_rgb888(self, camera: Camera, settings: RasterSettings):
         """render_mesh (RGB888) on the resident geometry; textures come from Context.set_textures_rgb888."""

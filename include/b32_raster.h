@@ -231,6 +231,22 @@ int  b32_frame_15_enqueue(b32_ctx* ctx, const uint8_t* clear_rgba, const b32_mes
 /* Number of frames launched as graphs on this context so far. */
 uint64_t b32_graph_launches(const b32_ctx* ctx);
 
+/* Placed asset parts: render_asset_parts (src/scene.rs:109-169) draws one mesh part per render_mesh* call after
+ * rotating its vertices about Y by the object's `facing` and translating them to `world_pos` on the host, every frame.
+ * Here the part is resident (b32_mesh_upload, once) and the per-object transform runs on the device:
+ *   pos    = (x * cos_f - z * sin_f + wx,  y + wy,  x * sin_f + z * cos_f + wz)
+ *   normal = (nx * cos_f - nz * sin_f,     ny,      nx * sin_f + nz * cos_f)        (scene.rs:141-160)
+ * cos_f / sin_f are the caller's `facing.cos()` / `facing.sin()` (libm stays on the host).  As in the reference the
+ * transform is skipped when |facing| and every |world_pos| component are <= 0.0001.  flags: 0 = blocking with timings,
+ * B32_RENDER_ASYNC = enqueue only (like b32_render_mesh_15_enqueue).  rgb888 != 0 selects render_mesh (fog ignored). */
+typedef struct b32_placement {
+    float facing, cos_f, sin_f;
+    float world_pos[3];
+} b32_placement;
+int  b32_render_mesh_placed(b32_ctx* ctx, const b32_mesh* mesh, const b32_placement* placement,
+                            const b32_camera* camera, const b32_settings* settings, const b32_fog* fog_or_null,
+                            int rgb888, uint32_t flags, b32_timings* timings);
+
 /* ---- the RGB888 sibling (RasterSettings.use_rgb555 == false) ----------------------------- */
 /* `textures: &[Texture]` of render_mesh: a second texture table, independent of b32_textures_set's. */
 int b32_textures_set_rgb888(b32_ctx* ctx, const b32_tex8_desc* descs, uint32_t n);

@@ -1332,6 +1332,28 @@ int b32o_render_stars(uint8_t* fb_rgba, uint32_t w, uint32_t h, const b32_star* 
     return B32_OK;
 }
 
+// render_asset_parts' per-object vertex transform, src/scene.rs:121-160 (cos_f / sin_f = facing.cos() / .sin(), computed
+// by the caller): returns 1 when has_transform (:123) and `out` holds the transformed copy, 0 when the part is drawn as is
+int b32o_place_vertices(const b32_vertex* in, uint32_t nv, float facing, float cos_f, float sin_f, const float world_pos[3], b32_vertex* out) {
+    bool has_transform = std::fabs(facing) > 0.0001f || std::fabs(world_pos[0]) > 0.0001f || std::fabs(world_pos[1]) > 0.0001f ||
+                         std::fabs(world_pos[2]) > 0.0001f;
+    for (uint32_t i = 0; i < nv; ++i) {
+        b32_vertex v = in[i];
+        if (has_transform) {
+            float rx = v.pos[0] * cos_f - v.pos[2] * sin_f;
+            float rz = v.pos[0] * sin_f + v.pos[2] * cos_f;
+            b32_vertex o = v;
+            o.pos[0] = rx + world_pos[0]; o.pos[1] = v.pos[1] + world_pos[1]; o.pos[2] = rz + world_pos[2];
+            o.normal[0] = v.normal[0] * cos_f - v.normal[2] * sin_f;
+            o.normal[1] = v.normal[1];
+            o.normal[2] = v.normal[0] * sin_f + v.normal[2] * cos_f;
+            v = o;
+        }
+        out[i] = v;
+    }
+    return has_transform ? 1 : 0;
+}
+
 // Framebuffer::clear_gradient, render.rs:60-77; Color::lerp, types.rs:811-820
 void b32o_fb_clear_gradient(uint8_t* rgba, float* z, uint32_t w, uint32_t h, const uint8_t top[3], const uint8_t bottom[3], uint8_t a) {
     for (uint64_t y = 0; y < h; ++y) {

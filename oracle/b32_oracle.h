@@ -77,6 +77,9 @@ int b32o_render_skybox_mesh(uint8_t* fb_rgba, uint32_t w, uint32_t h,
 /* render_stars from the star direction on + draw_star_diamond (render.rs:175-235). */
 int b32o_render_stars(uint8_t* fb_rgba, uint32_t w, uint32_t h, const b32_star* stars, uint32_t n,
                       const b32_camera* camera, float size);
+/* render_asset_parts' vertex transform (src/scene.rs:121-160). */
+int b32o_place_vertices(const b32_vertex* in, uint32_t nv, float facing, float cos_f, float sin_f,
+                        const float world_pos[3], b32_vertex* out);
 /* Framebuffer::clear_gradient (render.rs:60-77). */
 void b32o_fb_clear_gradient(uint8_t* rgba, float* z, uint32_t w, uint32_t h,
                             const uint8_t top[3], const uint8_t bottom[3], uint8_t a);

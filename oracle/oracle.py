@@ -152,6 +152,18 @@ def render_stars(fb_rgba, stars, camera, size):
                                    C.c_uint32(len(st)), C.byref(cam), C.c_float(size))
 
 
+def place_vertices(vertices, facing, cos_f, sin_f, world_pos):
+    """render_asset_parts' per-object transform (scene.rs:121-160) of an abi.VERTEX_DTYPE array."""
+    abi = _abi()
+    v = np.ascontiguousarray(vertices, dtype=abi.VERTEX_DTYPE)
+    out = np.empty_like(v)
+    wp = (C.c_float * 3)(*[float(x) for x in world_pos])
+    lib().b32o_place_vertices.restype = C.c_int
+    lib().b32o_place_vertices(C.c_void_p(v.ctypes.data), C.c_uint32(len(v)), C.c_float(facing), C.c_float(cos_f), C.c_float(sin_f), wp,
+                              C.c_void_p(out.ctypes.data))
+    return out
+
+
 def fb_clear_gradient(fb_rgba, fb_z, top, bottom):
     """Framebuffer::clear_gradient on caller-owned arrays; top/bottom = (r, g, b[, blend])."""
     abi = _abi()

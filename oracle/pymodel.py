@@ -838,3 +838,23 @@ def render_stars(fb_rgba, stars, camera, size):
                 if 0 <= x < W and 0 <= y < H:
                     fb_rgba[y, x, :3] = c
                     fb_rgba[y, x, 3] = 255
+
+
+# ------------------------------------------------------------------------------------------
+# render_asset_parts' per-object vertex transform: src/scene.rs:121-160
+# ------------------------------------------------------------------------------------------
+def place_vertices(vertices, facing, cos_f, sin_f, world_pos):
+    """vertices: record array with pos / normal f32[3]; returns the transformed copy (or an unchanged copy when the
+    reference's has_transform is false)."""
+    out = vertices.copy()
+    wp = np.asarray(world_pos, dtype=F)
+    if not (abs(F(facing)) > F(0.0001) or (np.abs(wp) > F(0.0001)).any()):
+        return out
+    c, s = F(cos_f), F(sin_f)
+    p = np.asarray(vertices["pos"], dtype=F); n = np.asarray(vertices["normal"], dtype=F)
+    out["pos"][:, 0] = (p[:, 0] * c - p[:, 2] * s) + wp[0]
+    out["pos"][:, 1] = p[:, 1] + wp[1]
+    out["pos"][:, 2] = (p[:, 0] * s + p[:, 2] * c) + wp[2]
+    out["normal"][:, 0] = n[:, 0] * c - n[:, 2] * s
+    out["normal"][:, 2] = n[:, 0] * s + n[:, 2] * c
+    return out

@@ -265,3 +265,26 @@ pub fn render_stars(skybox: &crate::world::Skybox, camera: &Camera, time: f32) {
     let cam = marshal_camera(camera);
     CTX.with(|&ctx| unsafe { check(ctx, b32_render_stars(ctx, list.as_ptr(), list.len() as u32, &cam, stars.size)); });
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Placed asset parts: render_asset_parts (src/scene.rs:109-169) with the part resident on the device and the
+// per-object rotate-about-Y + translate done there.  `part_mesh` = b32_mesh_upload(part.mesh.to_render_data_textured())
+// cached per asset generation; textures as in render_mesh_15 (the part's atlas + CLUT, indexed formats accepted).
+// ---------------------------------------------------------------------------------------------------
+#[repr(C)] pub struct b32_placement { facing: f32, cos_f: f32, sin_f: f32, world_pos: [f32; 3] }
+extern "C" {
+    fn b32_render_mesh_placed(ctx: *mut b32_ctx, mesh: *const b32_mesh, pl: *const b32_placement, cam: *const b32_camera,
+                              s: *const b32_settings, fog: *const b32_fog, rgb888: c_int, flags: u32, out: *mut b32_timings) -> c_int;
+}
+
+pub unsafe fn render_part_placed(part_mesh: *const b32_mesh, camera: &Camera, render_settings: &RasterSettings, facing: f32,
+                                 world_pos: Vec3, fog: Option<(f32, f32, f32, Color)>) -> RasterTimings {
+    let pl = b32_placement { facing, cos_f: facing.cos(), sin_f: facing.sin(), world_pos: [world_pos.x, world_pos.y, world_pos.z] };
+    let (s, _lights) = marshal_settings(render_settings);
+    let cam = marshal_camera(camera);
+    let fogc = fog.map(|(start, falloff, cull_distance, c)| b32_fog { start, falloff, cull_distance, r: c.r, g: c.g, b: c.b, blend: blend_u8(c.blend) });
+    let mut tm = b32_timings::default();
+    CTX.with(|&ctx| check(ctx, b32_render_mesh_placed(ctx, part_mesh, &pl, &cam, &s, fogc.as_ref().map_or(std::ptr::null(), |f| f as *const _),
+                                                      (!render_settings.use_rgb555) as c_int, 0, &mut tm)));
+    timings(&tm)
+}

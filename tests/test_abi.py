@@ -49,6 +49,7 @@ int main(void) {
   printf("%zu %zu %zu %zu %zu %d\n", sizeof(b32_line), offsetof(b32_line, z0), offsetof(b32_line, r), offsetof(b32_line, kind),
          offsetof(b32_line, alpha), B32_LINE_MAX_COORD);
   printf("%zu %zu\n", sizeof(b32_star), offsetof(b32_star, r));
+  printf("%zu %zu\n", sizeof(b32_placement), offsetof(b32_placement, world_pos));
   return 0; }''')
     exe = tmp_path / "sizes"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(prog)])
@@ -58,7 +59,8 @@ int main(void) {
     assert abi.VERTEX_DTYPE.itemsize == 36 and abi.FACE_DTYPE.itemsize == 16 and C.sizeof(abi.Camera) == 48
     assert sizes[8:13] == [12, 20, 32, abi.Settings.ambient.offset, abi.Settings.lights.offset]
     F = abi.LINE_DTYPE.fields
-    assert sizes[23:] == [abi.STAR_DTYPE.itemsize, abi.STAR_DTYPE.fields["rgb"][1]]
+    assert sizes[23:25] == [abi.STAR_DTYPE.itemsize, abi.STAR_DTYPE.fields["rgb"][1]]
+    assert sizes[25:] == [C.sizeof(abi.Placement), abi.Placement.world_pos.offset]
     assert sizes[17:23] == [abi.LINE_DTYPE.itemsize, F["z0"][1], F["rgb"][1], F["kind"][1], F["alpha"][1], abi.LINE_MAX_COORD]
     assert sizes[13:17] == [C.sizeof(abi.Tex8Desc), abi.Tex8Desc.pixels.offset, abi.SKY_VERTEX_DTYPE.itemsize, abi.SKY_VERTEX_DTYPE.fields["rgb"][1]]
     assert abi.VERTEX_DTYPE.fields["uv"][1] == 12 and abi.VERTEX_DTYPE.fields["normal"][1] == 20 and abi.VERTEX_DTYPE.fields["rgba"][1] == 32

@@ -802,3 +802,52 @@ def test_two_host_threads_two_contexts(oracle):
         want, want_z, otm, rc = oracle.render_scene(sc)
         assert rc == 0 and out[i] is not None
         assert_same(sc, out[i][0], out[i][1], out[i][2], want, want_z, otm)
+
+
+# ---- placed asset parts: render_asset_parts' per-object transform on the device (src/scene.rs:109-169) ----------
+@pytest.mark.parametrize("rgb888", [False, True], ids=["rgb555", "rgb888"])
+def test_render_placed_parts(ctx, oracle, rgb888):
+    """A 'room' call, then the same resident part mesh placed four times (facing / position per object, one of them
+    with no transform), enqueue-only where the call allows it: framebuffer and z-buffer equal the oracle drawing
+    host-transformed copies, as the reference does."""
+    from bonnie32_b200 import raster
+    room = scenes.scene_c2(n_tris=300, use_zbuffer=True)
+    part = cases.rgb888_scenes(120)[0] if rgb888 else cases.feature_scenes(120)[1]
+    settings = dataclasses.replace(part.settings, use_zbuffer=True, backface_cull=False)
+    placements = [(0.0, (0.0, 0.0, 0.0)), (0.7, (1.5, 0.25, 6.0)), (-2.2, (-2.0, -0.5, 12.0)), (3.1, (0.0, 1.0, 3.0))]
+    fb = pkg.Framebuffer(room.width, room.height, ctx)
+    fb.clear(room.clear)
+    want, want_z = orc_fb(room)
+    if rgb888:
+        ctx.set_textures_rgb888(part.textures8)
+    else:
+        pkg.render_mesh_15(fb, room.vertices, room.faces, room.textures, room.camera, room.settings)
+        rc, _, _ = oracle.render_mesh_15(want, want_z, room.vertices, room.faces, room.textures, room.camera, room.settings)
+        assert rc == 0
+        ctx.set_textures(part.textures)
+    mesh = pkg.Mesh(ctx, part.vertices, part.faces)
+    drawn, before = [], want.copy()
+    for k, (facing, pos) in enumerate(placements):
+        tm = mesh.render_placed(room.camera, settings, facing, pos, rgb888=rgb888, enqueue_only=(k % 2 == 1))
+        v = oracle.place_vertices(part.vertices, facing, raster.libm_cosf(facing), raster.libm_sinf(facing), pos)
+        if rgb888:
+            rc, otm, _ = oracle.render_mesh(want, want_z, v, part.faces, part.textures8, room.camera, settings)
+        else:
+            rc, otm, _ = oracle.render_mesh_15(want, want_z, v, part.faces, part.textures, room.camera, settings)
+        assert rc == 0
+        if tm is not None:
+            assert tm["triangles_drawn"] == otm["triangles_drawn"]
+            drawn.append(tm["triangles_drawn"])
+    got, got_z = fb.download()
+    mesh.free()
+    assert sum(drawn) > 0 and (want != before).any(-1).sum() > 500          # the placed parts are on screen
+    bad = (got != want).any(-1)
+    assert not bad.any(), f"{bad.sum()} pixels differ"
+    assert np.array_equal(got_z.view(np.uint32), want_z.view(np.uint32))
+
+
+def orc_fb(sc):
+    rgba = np.empty((sc.height, sc.width, 4), np.uint8)
+    a = 0 if (len(sc.clear) > 3 and sc.clear[3] == abi.BLEND_ERASE) else 255
+    rgba[...] = (*sc.clear[:3], a)
+    return rgba, np.full((sc.height, sc.width), np.finfo(np.float32).max, np.float32)

@@ -433,3 +433,16 @@ def test_stars_oracle_matches_numpy_model(oracle, size):
     assert stars.tobytes() == again.tobytes()
     assert np.allclose(np.linalg.norm(stars["dir"], axis=1), 1.0, atol=1e-5)
     assert len(np.unique(stars["rgb"], axis=0)) > 10
+
+
+@pytest.mark.parametrize("facing,pos", [(0.0, (0, 0, 0)), (0.00005, (0.0001, 0, 0)), (1.1, (0, 0, 0)), (-2.7, (3.5, -1.25, 40.0)), (0.0, (0, 0.5, 0))])
+def test_place_vertices_oracle_matches_numpy_model(oracle, facing, pos):
+    from oracle import pymodel
+    from bonnie32_b200 import raster
+    sc = scenes.scene_c2(n_tris=50)
+    c, s = raster.libm_cosf(facing), raster.libm_sinf(facing)
+    a = oracle.place_vertices(sc.vertices, facing, c, s, pos)
+    b = pymodel.place_vertices(sc.vertices, facing, c, s, pos)
+    assert a.tobytes() == b.tobytes()
+    moved = a.tobytes() != np.ascontiguousarray(sc.vertices).tobytes()
+    assert moved == (abs(facing) > 0.0001 or any(abs(x) > 0.0001 for x in pos))
