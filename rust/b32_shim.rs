@@ -271,7 +271,7 @@ pub fn render_stars(skybox: &crate::world::Skybox, camera: &Camera, time: f32) {
 // per-object rotate-about-Y + translate done there.  `part_mesh` = b32_mesh_upload(part.mesh.to_render_data_textured())
 // cached per asset generation; textures as in render_mesh_15 (the part's atlas + CLUT, indexed formats accepted).
 // ---------------------------------------------------------------------------------------------------
-#[repr(C)] pub struct b32_mesh { _opaque: [u8; 0] }
+pub enum b32_mesh {}
 #[repr(C)] pub struct b32_placement { facing: f32, cos_f: f32, sin_f: f32, world_pos: [f32; 3] }
 extern "C" {
     fn b32_render_mesh_placed(ctx: *mut b32_ctx, mesh: *const b32_mesh, pl: *const b32_placement, cam: *const b32_camera,
