@@ -221,10 +221,11 @@ int fill_params(b32_ctx* ctx, CallParams& p, const b32_camera* cam, const b32_se
 }
 
 // copy a host buffer to the device on the context stream; pageable memory goes through the pinned ring
-int h2d(b32_ctx* ctx, void* dst, const void* src, size_t bytes) {
+// consume = true: `src` may be reused by the caller as soon as this returns, so even pinned sources go through the staging ring
+int h2d(b32_ctx* ctx, void* dst, const void* src, size_t bytes, bool consume = false) {
     if (!bytes) return B32_OK;
     cudaPointerAttributes a{};
-    bool pinned_src = cudaPointerGetAttributes(&a, src) == cudaSuccess && (a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged);
+    bool pinned_src = !consume && cudaPointerGetAttributes(&a, src) == cudaSuccess && (a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged);
     cudaGetLastError();
     if (pinned_src) { CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream)); return B32_OK; }
     // two-slot ring: memcpy into slot k overlaps the DMA of slot k^1.  `src` is consumed by the memcpy, so the call does
@@ -965,11 +966,10 @@ int b32_render_stars(b32_ctx* ctx, const b32_star* stars, uint32_t n, const b32_
     static_assert(sizeof(b32_star) * 2 == sizeof(b32_line), "stars are staged in the line list buffer");
     CK(ctx->lines.reserve((n + 1) / 2));
     CK(ctx->line_scratch.reserve((size_t)ctx->width * ctx->height));
-    rc = h2d(ctx, ctx->lines.p, stars, (size_t)n * sizeof(b32_star)); if (rc) return rc;
+    rc = h2d(ctx, ctx->lines.p, stars, (size_t)n * sizeof(b32_star), true); if (rc) return rc;    // enqueue-only: the list is consumed here
     float sz = size != size || size < 1.0f ? 1.0f : size;            // size.max(1.0) as i32 (:202)
     int32_t isz = sz >= 3.0f ? 3 : (int32_t)sz;
     launch_stars(ctx->L(), reinterpret_cast<const b32_star*>(ctx->lines.p), n, isz, ctx->line_scratch.p, ctx->fb_rgba.p, p);
-    CK(cudaStreamSynchronize(ctx->stream));                          // the caller's list may be pinned memory still being read
     CK(cudaGetLastError());
     return B32_OK;
 }
@@ -999,7 +999,7 @@ int b32_draw_lines(b32_ctx* ctx, const b32_line* lines, uint32_t n) {
     uint32_t* next[2] = {owner + px, owner + 2 * px};
     uint32_t* wait = owner + 3 * px;
     uint32_t* flags = wait + n;
-    int rc = h2d(ctx, ctx->lines.p, lines, (size_t)n * sizeof(b32_line)); if (rc) return rc;
+    int rc = h2d(ctx, ctx->lines.p, lines, (size_t)n * sizeof(b32_line), true); if (rc) return rc;   // the list is consumed here
     cudaStream_t st = ctx->stream;
     LaunchCtx L = ctx->L();
     launch_lines_begin(L, ctx->lines.p, n, owner, next[0], wait, flags, N_FLAGS, ctx->fb_rgba.p, ctx->fb_z.p, ctx->width, ctx->height, any_blended);
@@ -1021,7 +1021,6 @@ int b32_draw_lines(b32_ctx* ctx, const b32_line* lines, uint32_t n) {
             CK(cudaMemsetAsync(flags, 1, 4, st));                   // the next batch's round 1 sees "waiting"
         }
     }
-    CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     return B32_OK;
 }

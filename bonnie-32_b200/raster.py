@@ -363,6 +363,33 @@ class Framebuffer:
         self.ctx.check(self.ctx.lib.b32_fb_download(self.ctx.h, px.ctypes.data, zb.ctypes.data if want_z else None))
         return px, zb
 
+    def download_view(self, want_z: bool = False):
+        """download() into pinned buffers owned by this Framebuffer (direct DMA, no allocation per frame): what a game
+        loop hands to `Texture2D::from_rgba8`.  The returned arrays are views, valid until the next download_view /
+        resize of this object."""
+        n = self.width * self.height
+        if getattr(self, "_pin_n", 0) != n:
+            self._free_pinned()
+            self._pin = self.ctx.lib.b32_host_alloc(n * 8)
+            if not self._pin:
+                raise B32Error(abi.B32_ERR_CUDA, "b32_host_alloc failed")
+            self._pin_n = n
+        self.ctx.check(self.ctx.lib.b32_fb_download(self.ctx.h, self._pin, (self._pin + n * 4) if want_z else None))
+        px = np.ctypeslib.as_array(C.cast(self._pin, C.POINTER(C.c_uint8)), shape=(self.height, self.width, 4))
+        zb = np.ctypeslib.as_array(C.cast(self._pin + n * 4, C.POINTER(C.c_float)), shape=(self.height, self.width)) if want_z else None
+        return px, zb
+
+    def _free_pinned(self):
+        if getattr(self, "_pin", None):
+            self.ctx.lib.b32_host_free(self._pin)
+        self._pin, self._pin_n = None, 0
+
+    def __del__(self):
+        try:
+            self._free_pinned()
+        except Exception:
+            pass
+
     def render_skybox_mesh(self, sky_vertices: np.ndarray, faces: np.ndarray, camera: "Camera"):
         """Sphere pass of Framebuffer::render_skybox (render.rs:81-139): `sky_vertices` (abi.SKY_VERTEX_DTYPE) and
         `faces` (int[nf,3]) are what Skybox::generate_mesh returns; stars stay a host pass."""

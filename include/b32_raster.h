@@ -285,6 +285,7 @@ typedef struct b32_star {
     float   dir[3];
     uint8_t r, g, b, _pad;
 } b32_star;
+/* Enqueued without a wait; the list is consumed before the call returns. */
 int b32_render_stars(b32_ctx* ctx, const b32_star* stars, uint32_t n, const b32_camera* camera, float size);
 
 /* ---- overlay lines (Framebuffer::draw_line*, render.rs:684-872) --------------------------------------- */
@@ -308,7 +309,9 @@ typedef struct b32_line {
     uint8_t _pad;
 } b32_line;
 #define B32_LINE_MAX_COORD (1 << 20)
-/* Blocking.  B32_ERR_INVALID for an unknown kind/mode, B32_ERR_UNSUPPORTED for a coordinate beyond
+/* The list is consumed before the call returns.  Lists of overwriting lines only (draw_line, draw_line_3d,
+ * draw_line_3d_overlay, Erase) are enqueued without a wait; lists with blended lines wait once per batch of rounds.
+ * B32_ERR_INVALID for an unknown kind/mode, B32_ERR_UNSUPPORTED for a coordinate beyond
  * B32_LINE_MAX_COORD (the reference walks every step of a line, on screen or not). */
 int b32_draw_lines(b32_ctx* ctx, const b32_line* lines, uint32_t n);
 

@@ -851,3 +851,16 @@ def orc_fb(sc):
     a = 0 if (len(sc.clear) > 3 and sc.clear[3] == abi.BLEND_ERASE) else 255
     rgba[...] = (*sc.clear[:3], a)
     return rgba, np.full((sc.height, sc.width), np.finfo(np.float32).max, np.float32)
+
+
+def test_download_view_equals_download(ctx):
+    sc = scenes.scene_c2(n_tris=300, use_zbuffer=True)
+    fb = pkg.Framebuffer(sc.width, sc.height, ctx)
+    fb.clear(sc.clear)
+    pkg.render_mesh_15(fb, sc.vertices, sc.faces, sc.textures, sc.camera, sc.settings)
+    a, az = fb.download()
+    b, bz = fb.download_view(want_z=True)
+    assert np.array_equal(a, b) and np.array_equal(az.view(np.uint32), bz.view(np.uint32))
+    fb.resize(64, 48); fb.clear((1, 2, 3))
+    c, _ = fb.download_view()
+    assert c.shape == (48, 64, 4) and (c == (1, 2, 3, 255)).all()
