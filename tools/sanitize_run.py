@@ -58,5 +58,24 @@ fb = pkg.Framebuffer(61, 47, ctx); fb.clear_gradient((10, 20, 200), (250, 128, 0
 got, gz = fb.download()
 want = np.empty((47, 61, 4), np.uint8); wz = np.empty((47, 61), np.float32); orc.fb_clear_gradient(want, wz, (10, 20, 200), (250, 128, 0))
 ok = np.array_equal(got, want) and np.array_equal(gz, wz); print("clear_gradient", "OK" if ok else "MISMATCH"); bad += not ok
+# star pass and a placed part
+name, w, h, cam = cases.sky_cases()[1]
+stars = cases.star_list(cam, w, h, time=0.5)
+fb = pkg.Framebuffer(w, h, ctx); fb.clear((0, 0, 0)); fb.render_stars(stars, cam, 3.0)
+got, _ = fb.download()
+want = np.zeros((h, w, 4), np.uint8); want[..., 3] = 255
+orc.render_stars(want, stars, cam, 3.0)
+ok = np.array_equal(got, want); print("stars", "OK" if ok else "MISMATCH"); bad += not ok
+from bonnie32_b200 import raster
+sc = by["zbuffer_idx8"]
+fb = pkg.Framebuffer(sc.width, sc.height, ctx); fb.clear(sc.clear); ctx.set_textures(sc.textures)
+mesh = pkg.Mesh(ctx, sc.vertices, sc.faces)
+mesh.render_placed(sc.camera, sc.settings, 0.6, (0.5, 0.0, 2.0))
+got, gz = fb.download()
+v = orc.place_vertices(sc.vertices, 0.6, raster.libm_cosf(0.6), raster.libm_sinf(0.6), (0.5, 0.0, 2.0))
+want = np.empty((sc.height, sc.width, 4), np.uint8); want[...] = (*sc.clear[:3], 255)
+wz = np.full((sc.height, sc.width), np.finfo(np.float32).max, np.float32)
+orc.render_mesh_15(want, wz, v, sc.faces, sc.textures, sc.camera, sc.settings)
+ok = np.array_equal(got, want) and np.array_equal(gz.view(np.uint32), wz.view(np.uint32)); print("placed_part", "OK" if ok else "MISMATCH"); bad += not ok
 print("mismatches:", bad)
 sys.exit(1 if bad else 0)
