@@ -927,10 +927,30 @@ int b32_render_skybox_mesh(b32_ctx* ctx, const b32_sky_vertex* vertices, uint32_
     static_assert(sizeof(SkyRec) <= sizeof(SurfRec) && sizeof(b32_sky_vertex) <= sizeof(b32_vertex), "staging reuse");
     CK(ctx->verts.reserve(std::max<uint32_t>(nv, 1)));
     CK(ctx->faces.reserve(std::max<uint32_t>(nf, 1)));      // 3 x u32 per face fits the 16-byte b32_face slots
-    rc = h2d(ctx, ctx->verts.p, vertices, (size_t)nv * sizeof(b32_sky_vertex)); if (rc) return rc;
-    rc = h2d(ctx, ctx->faces.p, faces, (size_t)nf * 12); if (rc) return rc;
     const uint32_t ntiles = p.tiles_x * p.tiles_y;
     cudaStream_t st = ctx->stream;
+    // The usual sky (a few thousand faces): indices are checked here and the bins get worst-case capacity, so nothing
+    // can fail on the device and the pass is only enqueued — no wait, no status read-back.
+    const bool enqueue_only = (size_t)ntiles * nf * sizeof(BinHead) <= ((size_t)256 << 20);
+    if (enqueue_only) {
+        for (uint32_t i = 0; i < nf * 3; ++i)
+            if (faces[i] >= nv) return fail(ctx, B32_ERR_OOB_INDEX, "skybox face vertex index out of range (reference: slice index panic)");
+    }
+    rc = h2d(ctx, ctx->verts.p, vertices, (size_t)nv * sizeof(b32_sky_vertex), enqueue_only); if (rc) return rc;
+    rc = h2d(ctx, ctx->faces.p, faces, (size_t)nf * 12, enqueue_only); if (rc) return rc;
+    if (enqueue_only) {
+        p.bin_cap = nf;
+        CK(ctx->bins.reserve((size_t)ntiles * p.bin_cap));
+        ctx->state_cur ^= 1;
+        ctx->state = reinterpret_cast<CallState*>(ctx->state_ring.p + (size_t)ctx->state_cur * ctx->state_stride);
+        ctx->tile_count = ctx->state_ring.p + (size_t)ctx->state_cur * ctx->state_stride + STATE_WORDS;
+        uint32_t* zero_next = ctx->state_ring.p + (size_t)(ctx->state_cur ^ 1) * ctx->state_stride;
+        launch_sky(ctx->L(), reinterpret_cast<const b32_sky_vertex*>(ctx->verts.p), reinterpret_cast<const uint32_t*>(ctx->faces.p),
+                   reinterpret_cast<SkyRec*>(ctx->recs.p), ctx->heads.p, ctx->bins.p, ctx->tile_count, ctx->fb_rgba.p, ctx->state,
+                   zero_next, ctx->state_stride, p);
+        CK(cudaGetLastError());
+        return B32_OK;
+    }
     for (int attempt = 0;; ++attempt) {
         p.bin_cap = pick_bin_cap(ctx, nf, ntiles, false);
         CK(ctx->bins.reserve((size_t)ntiles * p.bin_cap));

@@ -430,7 +430,7 @@ k_bin_opaque(const BinHead* __restrict__ heads, const uint64_t* __restrict__ key
     __syncthreads();
 
     uint32_t bmax = 0;
-    for (uint32_t base = blockIdx.x * BIN_THREADS; base < p.nf; base += gridDim.x * BIN_THREADS) {
+    for (uint32_t base = blockIdx.x * blockDim.x; base < p.nf; base += gridDim.x * blockDim.x) {
         const uint32_t fi = base + threadIdx.x;
         BinHead head{0, 0, 0, 0};
         if (fi < p.nf) {
@@ -455,9 +455,15 @@ k_bin_opaque(const BinHead* __restrict__ heads, const uint64_t* __restrict__ key
         if (aggregate) {
             for_each_tile(head, has, p.tiles_x, [&](uint32_t t, const BinHead&) { atomicAdd(&s_cnt[t], 1u); });     // 1) count per tile
             __syncthreads();
-            for (uint32_t t = threadIdx.x; t < ntiles; t += blockDim.x) {             // 2) reserve ranges
-                uint32_t c = s_cnt[t];
-                if (c) { uint32_t b = atomicAdd(&tile_count[t], c); s_base[t] = b; s_cnt[t] = 0; bmax = max(bmax, b + c); }
+            for (uint32_t t0 = threadIdx.x; t0 < ntiles; t0 += 4 * blockDim.x) {     // 2) reserve ranges, four atomics in flight
+                uint32_t c[4], b[4];
+                #pragma unroll
+                for (int k = 0; k < 4; ++k) { uint32_t t = t0 + k * blockDim.x; c[k] = t < ntiles ? s_cnt[t] : 0u; }
+                #pragma unroll
+                for (int k = 0; k < 4; ++k) b[k] = c[k] ? atomicAdd(&tile_count[t0 + k * blockDim.x], c[k]) : 0u;
+                #pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (c[k]) { uint32_t t = t0 + k * blockDim.x; s_base[t] = b[k]; s_cnt[t] = 0; bmax = max(bmax, b[k] + c[k]); }
             }
             __syncthreads();
             for_each_tile(head, has, p.tiles_x, [&](uint32_t t, const BinHead& h) {                                 // 3) hand out slots
@@ -1448,6 +1454,7 @@ __global__ void __launch_bounds__(FILL_THREADS)
 k_sky_fill(const SkyRec* __restrict__ recs, const BinHead* __restrict__ bins, const uint32_t* __restrict__ tile_count,
            uint32_t* __restrict__ fb_rgba, const CallState* __restrict__ st, CallParams p) {
     __shared__ BinHead s_head[FILL_THREADS];
+    __shared__ SkyRec s_rec[FILL_THREADS];
     pdl_wait();
     {
         CallState s = *st;
@@ -1461,16 +1468,19 @@ k_sky_fill(const SkyRec* __restrict__ recs, const BinHead* __restrict__ bins, co
     const bool valid = x < p.width && y < p.height;
     const float px = (float)x + 0.5f, py = (float)y + 0.5f;                                      // :270-271
     uint32_t best = 0;                                       // face + 1 of the last face covering this pixel centre
-    for (uint32_t base = 0; base < n; base += FILL_THREADS) {
+    // The bin is walked from its end: slots are handed out roughly in face order, so the last covering face tends to be
+    // met first and everything below it is skipped by its index alone.  Heads and records of a step sit in shared memory.
+    for (uint32_t done = 0; done < n; done += FILL_THREADS) {
+        const uint32_t cnt = min((uint32_t)FILL_THREADS, n - done);
+        const uint32_t base = n - done - cnt;
         __syncthreads();
-        if (base + threadIdx.x < n) s_head[threadIdx.x] = bin[base + threadIdx.x];
+        if (threadIdx.x < cnt) { const BinHead h = bin[base + threadIdx.x]; s_head[threadIdx.x] = h; s_rec[threadIdx.x] = recs[h.face]; }
         __syncthreads();
-        const uint32_t cnt = min((uint32_t)FILL_THREADS, n - base);
-        for (uint32_t i = 0; i < cnt; ++i) {
+        for (uint32_t i = cnt; i-- > 0;) {
             const BinHead h = s_head[i];
             if (h.face + 1 <= best) continue;
             if (!(valid && x >= (h.bbox_x & 0xFFFF) && x < (h.bbox_x >> 16) && y >= (h.bbox_y & 0xFFFF) && y < (h.bbox_y >> 16))) continue;
-            const SkyRec r = recs[h.face];
+            const SkyRec& r = s_rec[i];
             float w0 = ((r.p1y - r.p2y) * (px - r.p2x) + (r.p2x - r.p1x) * (py - r.p2y)) * r.inv_denom;   // :274-276
             float w1 = ((r.p2y - r.p0y) * (px - r.p2x) + (r.p0x - r.p2x) * (py - r.p2y)) * r.inv_denom;
             float w2 = 1.0f - w0 - w1;
@@ -1682,10 +1692,12 @@ void launch_bin(const LaunchCtx& L, const BinHead* heads, const uint64_t* keys, 
     if (p.nf == 0) return;
     uint32_t ntiles = p.tiles_x * p.tiles_y;
     size_t smem = ntiles <= (uint32_t)BIN_MAX_TILES ? (size_t)ntiles * 8 : 0;
-    uint32_t per_round = BIN_THREADS;
+    // Large meshes: BIN_THREADS faces per block keep the global atomics few (one per block and touched tile).  Up to 16k
+    // faces that would leave a handful of blocks walking long serial chains, so they get 128-face blocks instead.
+    uint32_t per_round = p.nf <= 16384u ? 128u : (uint32_t)BIN_THREADS;
     uint32_t grid = (p.nf + per_round - 1) / per_round;
     if (grid > L.sms * 4) grid = L.sms * 4;
-    launch_k(L, k_bin_opaque, grid, BIN_THREADS, smem, after_setup, heads, keys, recs, bins, tile_count, st, p, bin_cap, ordered);
+    launch_k(L, k_bin_opaque, grid, per_round, smem, after_setup, heads, keys, recs, bins, tile_count, st, p, bin_cap, ordered);
 }
 
 void launch_fill_opaque(const LaunchCtx& L, const SurfRec* recs, const BinHead* bins, const uint32_t* tile_count, const BinHead* heads,

@@ -270,7 +270,8 @@ typedef struct b32_sky_vertex {
 /* Step 1 of render_skybox: float transform + `project` of every vertex (behind-camera vertices drop their faces),
  * inward-facing triangles only (signed area < 0), rasterize_skybox_triangle (render.rs:242-299): pixel centres,
  * Gouraud vertex colours, no depth test or write, faces drawn in order (later ones overwrite).  faces = 3*nf
- * vertex indices.  Step 2 (render_stars, libm sin/cos) stays on the host. */
+ * vertex indices.  Step 2 is b32_render_stars.  Skies whose worst-case tile bins fit 256 MB (any realistic one) are
+ * enqueued without a wait; the lists are consumed before the call returns. */
 int b32_render_skybox_mesh(b32_ctx* ctx, const b32_sky_vertex* vertices, uint32_t nv,
                            const uint32_t* faces, uint32_t nf, const b32_camera* camera);
 
