@@ -162,7 +162,10 @@ __device__ __forceinline__ bool is_integral(float x) { return truncf(x) == x; }
 // One thread per face.  `tv` (pre-transformed vertices) may be NULL: then the three vertices are
 // transformed here (no intermediate vertex buffer: each vertex record is read once per use).
 // Pass-1 surfaces also emit a 16-byte BinHead (heads[face]); k_bin_opaque scatters those to tiles.
-constexpr int SETUP_THREADS = 128;
+#ifndef B32_SETUP_THREADS
+#define B32_SETUP_THREADS 128
+#endif
+constexpr int SETUP_THREADS = B32_SETUP_THREADS;
 
 __device__ __forceinline__ void setup_face(uint32_t fi, const b32_vertex* __restrict__ verts, const b32_face* __restrict__ faces,
                                            const TVert* __restrict__ tv, const TexDev* __restrict__ tex,
