@@ -26,6 +26,7 @@
 //   * Pass 2 blends against the running colour, so it is replayed in exact draw order: every surface carries a
 //     unique 64-bit draw-order key (pass, depth key, face index), sorted per tile inside k_fill_ordered.
 #include <algorithm>
+#include <cstdlib>
 #include <tuple>
 #include <utility>
 
@@ -674,29 +675,46 @@ __device__ __forceinline__ bool shade888(const SurfRec& r, uint32_t x, uint32_t 
 #ifndef B32_OP_DUAL
 #define B32_OP_DUAL 1
 #endif
-constexpr int OP_THREADS = B32_OP_THREADS;
-constexpr bool OP_DUAL = B32_OP_DUAL != 0;   // true: a warp owns 4x4 pixels, two lanes per pixel; false: 8x4 pixels, one lane per pixel
-constexpr int OP_WARPS = OP_THREADS / 32;
-constexpr int OP_BW = OP_DUAL ? 4 : 8, OP_BH = 4;                     // pixel block of one warp
-constexpr int OP_WPT = (TILE_W / OP_BW) * (TILE_H / OP_BH);            // warps per 16x16 tile
-constexpr int OP_SPLIT = OP_WPT / OP_WARPS;  // CTAs per tile (256 threads, dual: 2 = half tiles of 16x8 px)
-static_assert(OP_SPLIT >= 1 && OP_SPLIT * OP_WARPS == OP_WPT, "a CTA covers a whole number of block rows of one tile");
 #ifndef B32_OP_CHUNK
 #define B32_OP_CHUNK 128
 #endif
-constexpr int OP_CHUNK = B32_OP_CHUNK;       // surface records (their 80-byte visibility part) staged per step: most warps are done within
-                                             // the first step, so the CTA-wide barrier between steps rarely holds anybody up
-constexpr int OP_REC_PIECES = sizeof(SurfHot) / 16;
-static_assert(OP_CHUNK % 32 == 0 && OP_CHUNK <= 256, "whole 32-entry batches; slots are stored in a byte");
-static_assert((size_t)3 * OP_CHUNK * sizeof(SurfHot) >= (size_t)OP_SORT_MAX_ENTRIES * sizeof(BinHead), "the ring area doubles as the head-scan buffer");
-constexpr int OP_BUCKETS = OP_THREADS < 256 ? OP_THREADS : 256;       // key buckets of the counting sort (one scan thread each)
-constexpr int OP_BUCKET_BITS = OP_BUCKETS == 256 ? 8 : (OP_BUCKETS == 128 ? 7 : 6);
-constexpr int OP_RING = 3;                   // ring depth: steps c, c+1, c+2
-constexpr int OP_SORT_MAX = OP_SORT_MAX_ENTRIES;   // bin entries orderable in shared memory (16 KB of heads)
-constexpr int OP_TEX_SMEM = 256;             // texture descriptors cached in shared memory
-constexpr size_t OP_SMEM = (size_t)OP_SORT_MAX * sizeof(BinHead) + (size_t)OP_RING * OP_CHUNK * sizeof(SurfHot) +
-                           (size_t)OP_TEX_SMEM * sizeof(TexDev) + (size_t)OP_MASK_SMEM_WORDS * 4 +
-                           (size_t)OP_WARPS * 32 * sizeof(uint2) + (size_t)OP_WARPS * 32;
+// The kernel exists in two shapes, picked per call by the number of tiles (launch_fill_opaque):
+//   OpDense  512 threads, a warp owns 4x4 pixels with TWO lanes per pixel (two surfaces in flight per pixel): more
+//            instruction-level parallelism per tile; 3 CTAs per SM = 444 tiles in one wave.  Best while the frame's tiles
+//            fit that wave (320x240 = 300 tiles): C4 24.5 vs 26.6 us.
+//   OpSparse 256 threads, a warp owns 8x4 pixels, one lane per pixel; 5 CTAs per SM = 740 tiles per wave.  Best for
+//            larger framebuffers, where the tiles come in several waves of latency-bound CTAs: sample levels at 640x480
+//            23.1 vs 28.7 us, C4 at 640x480 45.0 vs 49.2 us, at 1920x1080 174 vs 213 us.
+template <int THREADS_, bool DUAL_>
+struct OpCfg {
+    static constexpr int THREADS = THREADS_;
+    static constexpr bool DUAL = DUAL_;          // true: a warp owns 4x4 pixels, two lanes per pixel; false: 8x4 pixels, one lane per pixel
+    static constexpr int WARPS = THREADS / 32;
+    static constexpr int BW = DUAL ? 4 : 8, BH = 4;                      // pixel block of one warp
+    static constexpr int WPT = (TILE_W / BW) * (TILE_H / BH);            // warps per 16x16 tile
+    static constexpr int SPLIT = WPT / WARPS;    // CTAs per tile (256 threads, dual: 2 = half tiles of 16x8 px)
+    static_assert(SPLIT >= 1 && SPLIT * WARPS == WPT, "a CTA covers a whole number of block rows of one tile");
+    static constexpr int CHUNK = B32_OP_CHUNK;   // surface records (their 80-byte visibility part) staged per step: most warps are done within
+                                                 // the first step, so the CTA-wide barrier between steps rarely holds anybody up
+    static constexpr int REC_PIECES = sizeof(SurfHot) / 16;
+    static_assert(CHUNK % 32 == 0 && CHUNK <= 256, "whole 32-entry batches; slots are stored in a byte");
+    static_assert((size_t)3 * CHUNK * sizeof(SurfHot) >= (size_t)OP_SORT_MAX_ENTRIES * sizeof(BinHead), "the ring area doubles as the head-scan buffer");
+    static constexpr int BUCKETS = THREADS < 256 ? THREADS : 256;        // key buckets of the counting sort (one scan thread each)
+    static constexpr int BUCKET_BITS = BUCKETS == 256 ? 8 : (BUCKETS == 128 ? 7 : 6);
+    static constexpr int RING = 3;               // ring depth: steps c, c+1, c+2
+    static constexpr int SORT_MAX = OP_SORT_MAX_ENTRIES;   // bin entries orderable in shared memory (16 KB of heads)
+    static constexpr int TEX_SMEM = 256;         // texture descriptors cached in shared memory
+    static constexpr size_t SMEM = (size_t)SORT_MAX * sizeof(BinHead) + (size_t)RING * CHUNK * sizeof(SurfHot) +
+                                   (size_t)TEX_SMEM * sizeof(TexDev) + (size_t)OP_MASK_SMEM_WORDS * 4 +
+                                   (size_t)WARPS * 32 * sizeof(uint2) + (size_t)WARPS * 32;
+#ifdef B32_OP_MINB
+    static constexpr int MINB = B32_OP_MINB;
+#else
+    static constexpr int MINB = THREADS == 512 ? 3 : 5;   // 512 threads: 3 CTAs per SM (444 slots >= the 300 tiles of a 320x240 frame: one wave)
+#endif
+};
+using OpDense = OpCfg<B32_OP_THREADS, B32_OP_DUAL != 0>;
+using OpSparse = OpCfg<256, false>;
 #ifdef B32_FILL_STATS
 __device__ uint32_t g_fill_stats[4096 * 16 * 8];     // [tile][warp][8]: t_start, t_sorted, t_end, batches, t_first_data, t_batch0_end, t_batch1_end, t_loop_end
 __device__ __forceinline__ uint32_t smid() { uint32_t r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
@@ -727,17 +745,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 
-#ifndef B32_OP_MINB
-#define B32_OP_MINB (OP_THREADS == 512 ? 3 : 5)   // 512 threads: 3 CTAs per SM (444 slots >= the 300 tiles of a 320x240 frame: one wave)
-#endif
-// RGB888 = the render_mesh instantiation (8-bit colour pipeline in step 5; everything else is shared)
-template <bool RGB888>
-__global__ void __launch_bounds__(OP_THREADS, B32_OP_MINB)
+// RGB888 = the render_mesh instantiation (8-bit colour pipeline in step 5; everything else is shared); C = OpDense / OpSparse
+template <bool RGB888, class C>
+__global__ void __launch_bounds__(C::THREADS, C::MINB)
 k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins, const uint32_t* __restrict__ tile_count,
               const BinHead* __restrict__ heads, BinHead* __restrict__ sorted_scratch,
               const TexDev* __restrict__ tex, const uint16_t* __restrict__ texels, const uint32_t* __restrict__ texmask,
               uint32_t* __restrict__ fb_rgba, float* __restrict__ fb_z, const CallState* __restrict__ st,
               uint32_t* __restrict__ sticky, CallParams p) {
+    constexpr int OP_THREADS = C::THREADS, OP_WARPS = C::WARPS, OP_BW = C::BW, OP_BH = C::BH, OP_SPLIT = C::SPLIT;
+    constexpr bool OP_DUAL = C::DUAL;
+    constexpr int OP_CHUNK = C::CHUNK, OP_REC_PIECES = C::REC_PIECES, OP_BUCKETS = C::BUCKETS, OP_BUCKET_BITS = C::BUCKET_BITS;
+    constexpr int OP_RING = C::RING, OP_SORT_MAX = C::SORT_MAX, OP_TEX_SMEM = C::TEX_SMEM;
     extern __shared__ __align__(128) uint8_t op_smem[];
     SurfHot* s_rec = reinterpret_cast<SurfHot*>(op_smem);                               // [OP_RING][OP_CHUNK] record ring (visibility part)
     BinHead* s_sh = reinterpret_cast<BinHead*>(s_rec + OP_RING * OP_CHUNK);             // [OP_SORT_MAX] bin in walk order
@@ -1659,8 +1678,10 @@ static void launch_k(const LaunchCtx& L, void (*kern)(KArgs...), dim3 grid, dim3
 // Per-device kernel attributes (dynamic shared memory above the 48 KB default); called once per context, on its device.
 int init_kernel_attributes() {
     cudaError_t e = cudaFuncSetAttribute(k_bin_opaque, cudaFuncAttributeMaxDynamicSharedMemorySize, BIN_MAX_TILES * 8);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fill_opaque<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OP_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fill_opaque<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OP_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fill_opaque<false, OpDense>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OpDense::SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fill_opaque<true, OpDense>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OpDense::SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fill_opaque<false, OpSparse>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OpSparse::SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fill_opaque<true, OpSparse>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OpSparse::SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fill_ordered<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ORD_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fill_ordered<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ORD_SMEM);
     return (int)e;
@@ -1709,8 +1730,16 @@ void launch_fill_opaque(const LaunchCtx& L, const SurfRec* recs, const BinHead* 
     uint32_t ntiles = p.tiles_x * p.tiles_y;
     if (ntiles == 0 || p.nf == 0) return;
     // launched right behind k_bin_opaque except in x-ray mode (no pass-1 binning: then it is an ordinary launch)
-    launch_k(L, p.rgb888 ? k_fill_opaque<true> : k_fill_opaque<false>, ntiles * OP_SPLIT, OP_THREADS, OP_SMEM, !(p.xray_mode && !p.rgb888),
-             recs, bins, tile_count, heads, sorted_scratch, tex, texels, texmask, fb_rgba, fb_z, st, sticky, p);
+    // more tiles than one wave of the two-lanes-per-pixel shape holds (3 CTAs per SM): the 256-thread shape packs 5 per SM
+    static const bool force_dense = getenv("B32_FILL_DENSE") != nullptr, force_sparse = getenv("B32_FILL_SPARSE") != nullptr;
+    const bool sparse = force_sparse || (!force_dense && ntiles * OpDense::SPLIT > L.sms * (uint32_t)OpDense::MINB);
+    const bool pdl = !(p.xray_mode && !p.rgb888);
+    if (sparse)
+        launch_k(L, p.rgb888 ? k_fill_opaque<true, OpSparse> : k_fill_opaque<false, OpSparse>, ntiles * OpSparse::SPLIT, OpSparse::THREADS, OpSparse::SMEM, pdl,
+                 recs, bins, tile_count, heads, sorted_scratch, tex, texels, texmask, fb_rgba, fb_z, st, sticky, p);
+    else
+        launch_k(L, p.rgb888 ? k_fill_opaque<true, OpDense> : k_fill_opaque<false, OpDense>, ntiles * OpDense::SPLIT, OpDense::THREADS, OpDense::SMEM, pdl,
+                 recs, bins, tile_count, heads, sorted_scratch, tex, texels, texmask, fb_rgba, fb_z, st, sticky, p);
 }
 
 void launch_fill_ordered(const LaunchCtx& L, const SurfRec* recs, BinHead* obins, const uint32_t* otile_count, const uint64_t* keys,
