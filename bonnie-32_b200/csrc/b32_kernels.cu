@@ -680,11 +680,12 @@ __device__ __forceinline__ bool shade888(const SurfRec& r, uint32_t x, uint32_t 
 #endif
 // The kernel exists in two shapes, picked per call by the number of tiles (launch_fill_opaque):
 //   OpDense  512 threads, a warp owns 4x4 pixels with TWO lanes per pixel (two surfaces in flight per pixel): more
-//            instruction-level parallelism per tile; 3 CTAs per SM = 444 tiles in one wave.  Best while the frame's tiles
-//            fit that wave (320x240 = 300 tiles): C4 24.5 vs 26.6 us.
+//            instruction-level parallelism per tile; 3 CTAs per SM = 444 tiles in one wave.  Best for a blocking call
+//            whose tiles fit that wave (320x240 = 300 tiles): C4 24.5 vs 26.6 us.
 //   OpSparse 256 threads, a warp owns 8x4 pixels, one lane per pixel; 5 CTAs per SM = 740 tiles per wave.  Best for
-//            larger framebuffers, where the tiles come in several waves of latency-bound CTAs: sample levels at 640x480
-//            23.1 vs 28.7 us, C4 at 640x480 45.0 vs 49.2 us, at 1920x1080 174 vs 213 us.
+//            larger framebuffers, where the tiles come in several waves of latency-bound CTAs (sample levels at 640x480
+//            23.1 vs 28.7 us, C4 at 640x480 45.0 vs 49.2 us, at 1920x1080 174 vs 213 us), and for enqueued frames that
+//            overlap with their neighbours on the GPU.
 template <int THREADS_, bool DUAL_>
 struct OpCfg {
     static constexpr int THREADS = THREADS_;
@@ -1730,9 +1731,12 @@ void launch_fill_opaque(const LaunchCtx& L, const SurfRec* recs, const BinHead* 
     uint32_t ntiles = p.tiles_x * p.tiles_y;
     if (ntiles == 0 || p.nf == 0) return;
     // launched right behind k_bin_opaque except in x-ray mode (no pass-1 binning: then it is an ordinary launch)
-    // more tiles than one wave of the two-lanes-per-pixel shape holds (3 CTAs per SM): the 256-thread shape packs 5 per SM
+    // The 256-thread shape packs 5 CTAs per SM: it wins when the frame has more tiles than one wave of the two-lanes-per-
+    // pixel shape holds (3 CTAs per SM), and for enqueue-only calls, whose kernels share the SMs with the frames queued
+    // around them (4 frames in flight: 5 561 vs 5 224 Mtri/s).  A blocking call of up to 444 tiles has the GPU to itself:
+    // the two-lane shape finishes it sooner (2 424 vs 2 385 Mtri/s).
     static const bool force_dense = getenv("B32_FILL_DENSE") != nullptr, force_sparse = getenv("B32_FILL_SPARSE") != nullptr;
-    const bool sparse = force_sparse || (!force_dense && ntiles * OpDense::SPLIT > L.sms * (uint32_t)OpDense::MINB);
+    const bool sparse = force_sparse || (!force_dense && (p.async_call || ntiles * OpDense::SPLIT > L.sms * (uint32_t)OpDense::MINB));
     const bool pdl = !(p.xray_mode && !p.rgb888);
     if (sparse)
         launch_k(L, p.rgb888 ? k_fill_opaque<true, OpSparse> : k_fill_opaque<false, OpSparse>, ntiles * OpSparse::SPLIT, OpSparse::THREADS, OpSparse::SMEM, pdl,
