@@ -682,11 +682,11 @@ __device__ __forceinline__ bool shade888(const SurfRec& r, uint32_t x, uint32_t 
 //   OpDense  512 threads, a warp owns 4x4 pixels with TWO lanes per pixel (two surfaces in flight per pixel): more
 //            instruction-level parallelism per tile; 3 CTAs per SM = 444 tiles in one wave.  Best for a blocking call
 //            whose tiles fit that wave (320x240 = 300 tiles): C4 24.5 vs 26.6 us.
-//   OpSparse 256 threads, a warp owns 8x4 pixels, one lane per pixel; 5 CTAs per SM = 740 tiles per wave.  Best for
-//            larger framebuffers, where the tiles come in several waves of latency-bound CTAs (sample levels at 640x480
-//            23.1 vs 28.7 us, C4 at 640x480 45.0 vs 49.2 us, at 1920x1080 174 vs 213 us), and for enqueued frames that
-//            overlap with their neighbours on the GPU.
-template <int THREADS_, bool DUAL_>
+//   OpSparse 256 threads, a warp owns 8x4 pixels, one lane per pixel; ring steps of 96 records keep a CTA at 53 KB of shared
+//            memory: 4 CTAs per SM = 592 tiles per wave.  Best for larger framebuffers, where the tiles come in several
+//            waves of latency-bound CTAs (sample levels at 640x480 20.6 vs 28.7 us, C4 at 640x480 39.9 vs 49.2 us, at
+//            1920x1080 144 vs 213 us), and for enqueued frames that overlap with their neighbours on the GPU.
+template <int THREADS_, bool DUAL_, int CHUNK_, int MINB_>
 struct OpCfg {
     static constexpr int THREADS = THREADS_;
     static constexpr bool DUAL = DUAL_;          // true: a warp owns 4x4 pixels, two lanes per pixel; false: 8x4 pixels, one lane per pixel
@@ -695,7 +695,7 @@ struct OpCfg {
     static constexpr int WPT = (TILE_W / BW) * (TILE_H / BH);            // warps per 16x16 tile
     static constexpr int SPLIT = WPT / WARPS;    // CTAs per tile (256 threads, dual: 2 = half tiles of 16x8 px)
     static_assert(SPLIT >= 1 && SPLIT * WARPS == WPT, "a CTA covers a whole number of block rows of one tile");
-    static constexpr int CHUNK = B32_OP_CHUNK;   // surface records (their 80-byte visibility part) staged per step: most warps are done within
+    static constexpr int CHUNK = CHUNK_;         // surface records (their 80-byte visibility part) staged per step: most warps are done within
                                                  // the first step, so the CTA-wide barrier between steps rarely holds anybody up
     static constexpr int REC_PIECES = sizeof(SurfHot) / 16;
     static_assert(CHUNK % 32 == 0 && CHUNK <= 256, "whole 32-entry batches; slots are stored in a byte");
@@ -708,14 +708,19 @@ struct OpCfg {
     static constexpr size_t SMEM = (size_t)SORT_MAX * sizeof(BinHead) + (size_t)RING * CHUNK * sizeof(SurfHot) +
                                    (size_t)TEX_SMEM * sizeof(TexDev) + (size_t)OP_MASK_SMEM_WORDS * 4 +
                                    (size_t)WARPS * 32 * sizeof(uint2) + (size_t)WARPS * 32;
-#ifdef B32_OP_MINB
-    static constexpr int MINB = B32_OP_MINB;
-#else
-    static constexpr int MINB = THREADS == 512 ? 3 : 5;   // 512 threads: 3 CTAs per SM (444 slots >= the 300 tiles of a 320x240 frame: one wave)
-#endif
+    static constexpr int MINB = MINB_;           // CTAs per SM the register allocation must allow (shared memory permitting)
 };
-using OpDense = OpCfg<B32_OP_THREADS, B32_OP_DUAL != 0>;
-using OpSparse = OpCfg<256, false>;
+#ifndef B32_OP_MINB
+#define B32_OP_MINB (B32_OP_THREADS == 512 ? 3 : 5)   // 512 threads: 3 CTAs per SM (444 slots >= the 300 tiles of a 320x240 frame: one wave)
+#endif
+#ifndef B32_OPS_CHUNK
+#define B32_OPS_CHUNK 96          // 53 KB of shared memory per CTA: 4 CTAs per SM
+#endif
+#ifndef B32_OPS_MINB
+#define B32_OPS_MINB 4
+#endif
+using OpDense = OpCfg<B32_OP_THREADS, B32_OP_DUAL != 0, B32_OP_CHUNK, B32_OP_MINB>;
+using OpSparse = OpCfg<256, false, B32_OPS_CHUNK, B32_OPS_MINB>;
 #ifdef B32_FILL_STATS
 __device__ uint32_t g_fill_stats[4096 * 16 * 8];     // [tile][warp][8]: t_start, t_sorted, t_end, batches, t_first_data, t_batch0_end, t_batch1_end, t_loop_end
 __device__ __forceinline__ uint32_t smid() { uint32_t r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
@@ -1731,7 +1736,7 @@ void launch_fill_opaque(const LaunchCtx& L, const SurfRec* recs, const BinHead* 
     uint32_t ntiles = p.tiles_x * p.tiles_y;
     if (ntiles == 0 || p.nf == 0) return;
     // launched right behind k_bin_opaque except in x-ray mode (no pass-1 binning: then it is an ordinary launch)
-    // The 256-thread shape packs 5 CTAs per SM: it wins when the frame has more tiles than one wave of the two-lanes-per-
+    // The 256-thread shape packs 4 CTAs per SM: it wins when the frame has more tiles than one wave of the two-lanes-per-
     // pixel shape holds (3 CTAs per SM), and for enqueue-only calls, whose kernels share the SMs with the frames queued
     // around them (4 frames in flight: 5 561 vs 5 224 Mtri/s).  A blocking call of up to 444 tiles has the GPU to itself:
     // the two-lane shape finishes it sooner (2 424 vs 2 385 Mtri/s).
