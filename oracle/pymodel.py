@@ -276,7 +276,8 @@ def blend555(f8, b8, mode):                                   # render.rs:1093-1
 def render_mesh_15(fb_rgba, fb_z, vertices, faces, textures, camera, settings, fog=None):
     """fb_rgba u8[h,w,4], fb_z f32[h,w] are updated in place. Returns list of face_idx in draw order."""
     tex_px = [texels_u16(t) for t in textures]
-    surfaces = _build_surfaces(fb_z.shape, vertices, faces, textures, camera, settings, fog, rgb888=False)
+    wire = {"back": [], "front": []}
+    surfaces = _build_surfaces(fb_z.shape, vertices, faces, textures, camera, settings, fog, rgb888=False, wire=wire)
 
     # ---- SORT (render.rs:2518-2545) ----
     opaque = [s for s in surfaces if not s["has_tr"]]
@@ -291,6 +292,7 @@ def render_mesh_15(fb_rgba, fb_z, vertices, faces, textures, camera, settings, f
             _fill(fb_rgba, fb_z, s, textures, tex_px, settings, skip_z_write=False)
         for s in transp:
             _fill(fb_rgba, fb_z, s, textures, tex_px, settings, skip_z_write=True)
+    _wireframe_phase(fb_rgba, fb_z, wire, settings)
     return [s["face_idx"] for s in opaque + transp]
 
 
@@ -305,7 +307,7 @@ def _back_to_front(lst):
     return [lst[i] for i in order]
 
 
-def _build_surfaces(shape, vertices, faces, textures, camera, settings, fog, rgb888):
+def _build_surfaces(shape, vertices, faces, textures, camera, settings, fog, rgb888, wire=None):
     """TRANSFORM + CULL phases shared by render_mesh_15 (render.rs:2313-2516) and render_mesh
     (render.rs:1981-2149; no fog, has_transparency = texture blend or editor alpha)."""
     H, W = shape
@@ -391,6 +393,11 @@ def _build_surfaces(shape, vertices, faces, textures, camera, settings, fog, rgb
             cols = newc
         order = (0, 1, 2)
         sign = F(1.0)
+        if wire is not None:                                                            # :2446-2450, :2509-2511
+            if backface and not settings.xray_mode:
+                wire["back"].append((v1, v2, v3))
+            elif not backface and settings.wireframe_overlay:
+                wire["front"].append((v1, v2, v3))
         if backface:
             if not (not settings.backface_cull or settings.xray_mode):                  # :2453
                 continue
@@ -550,12 +557,14 @@ def _fill(fb_rgba, fb_z, s, textures, tex_px, settings, skip_z_write):
 def render_mesh(fb_rgba, fb_z, vertices, faces, textures, camera, settings):
     tex_px = [np.asarray(t.pixels, dtype=np.uint8).reshape(t.height, t.width, 4).astype(I64) if t.width * t.height
               else np.zeros((t.height, t.width, 4), dtype=I64) for t in textures]
-    surfaces = _build_surfaces(fb_z.shape, vertices, faces, textures, camera, settings, None, rgb888=True)
+    wire = {"back": [], "front": []}
+    surfaces = _build_surfaces(fb_z.shape, vertices, faces, textures, camera, settings, None, rgb888=True, wire=wire)
     if not settings.use_zbuffer:                                   # :2155-2162, one list
         surfaces = _back_to_front(surfaces)
     if not settings.wireframe_overlay:                             # :2172-2181
         for s in surfaces:
             _fill888(fb_rgba, fb_z, s, tex_px, settings)
+    _wireframe_phase(fb_rgba, fb_z, wire, settings)                # :2195-2256, the same phase
     return [s["face_idx"] for s in surfaces]
 
 
@@ -858,3 +867,38 @@ def place_vertices(vertices, facing, cos_f, sin_f, world_pos):
     out["normal"][:, 0] = n[:, 0] * c - n[:, 2] * s
     out["normal"][:, 2] = n[:, 0] * s + n[:, 2] * c
     return out
+
+
+# ------------------------------------------------------------------------------------------
+# wireframe phase of render_mesh_15 / render_mesh: render.rs:2574-2635 (and :2195-2256)
+# ------------------------------------------------------------------------------------------
+_LINE_REC = np.dtype([("x0", "<i4"), ("y0", "<i4"), ("x1", "<i4"), ("y1", "<i4"), ("z0", "<f4"), ("z1", "<f4"),
+                      ("rgb", "u1", 3), ("blend", "u1"), ("kind", "u1"), ("mode", "u1"), ("alpha", "u1"), ("_pad", "u1")])
+
+
+def _unique_edges(tris):
+    """First occurrence of every end-point pair, in order (the reference searches its list linearly; a set of the
+    integer end points keeps the same ones)."""
+    seen, out = set(), []
+    for v1, v2, v3 in tris:
+        for a, b in ((v1, v2), (v2, v3), (v3, v1)):
+            pa = (int(as_i32(np.array([a[0]], dtype=F))[0]), int(as_i32(np.array([a[1]], dtype=F))[0]), F(a[2]))
+            pb = (int(as_i32(np.array([b[0]], dtype=F))[0]), int(as_i32(np.array([b[1]], dtype=F))[0]), F(b[2]))
+            e = (pa, pb) if (pa[0], pa[1]) < (pb[0], pb[1]) else (pb, pa)           # tuple order, as in Rust
+            key = (e[0][0], e[0][1], e[1][0], e[1][1])
+            if key not in seen:
+                seen.add(key)
+                out.append(e)
+    return out
+
+
+def _wireframe_phase(fb_rgba, fb_z, wire, settings):
+    def lines(edges, kind, rgb):
+        ln = np.zeros(len(edges), dtype=_LINE_REC)
+        for i, (a, b) in enumerate(edges):
+            ln[i] = (a[0], a[1], b[0], b[1], a[2], b[2], rgb, OPAQUE, kind, OPAQUE, 255, 0)
+        return ln
+    if settings.backface_cull and settings.backface_wireframe:                      # :2577-2603, draw_line_3d
+        draw_lines(fb_rgba, fb_z, lines(_unique_edges(wire["back"]), LINE_3D, (80, 80, 100)))
+    if settings.wireframe_overlay and wire["front"]:                                # :2606-2633, draw_line
+        draw_lines(fb_rgba, fb_z, lines(_unique_edges(wire["front"]), LINE_2D, (200, 200, 220)))

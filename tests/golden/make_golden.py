@@ -52,8 +52,6 @@ def main_rgb888():
     """hashes_rgb888.json: the RGB888 sibling (render_mesh) on cases.rgb888_scenes(), numpy model."""
     hashes = {}
     for sc in cases.rgb888_scenes():
-        if sc.settings.backface_wireframe or sc.settings.wireframe_overlay:
-            continue                                  # the numpy model does not restate the wireframe phase
         rgba, z = pymodel.fb_clear(sc.width, sc.height, sc.clear)
         order = pymodel.render_mesh(rgba, z, sc.vertices, sc.faces, sc.textures8, sc.camera, sc.settings)
         hashes[sc.name] = digest(rgba, z, order)

@@ -237,8 +237,6 @@ with open(os.path.join(GOLDEN, "hashes_rgb888.json")) as _f:
 def test_rgb888_oracle_equals_numpy_model_and_golden(oracle, sc):
     want, want_z, tm, rc, order = oracle.render_scene888(sc, want_order=True)
     assert rc == 0 and tm["triangles_drawn"] == len(order)
-    if sc.settings.backface_wireframe or sc.settings.wireframe_overlay:
-        return                                        # wireframe phase: C++ oracle only
     rgba, z = pymodel.fb_clear(sc.width, sc.height, sc.clear)
     order2 = pymodel.render_mesh(rgba, z, sc.vertices, sc.faces, sc.textures8, sc.camera, sc.settings)
     assert list(order) == order2
@@ -446,3 +444,19 @@ def test_place_vertices_oracle_matches_numpy_model(oracle, facing, pos):
     assert a.tobytes() == b.tobytes()
     moved = a.tobytes() != np.ascontiguousarray(sc.vertices).tobytes()
     assert moved == (abs(facing) > 0.0001 or any(abs(x) > 0.0001 for x in pos))
+
+
+# ---- wireframe phase (render.rs:2574-2635): both restatements, every wireframe scene ---------------------------
+WIRE = cases.wireframe_scenes()
+
+
+@pytest.mark.parametrize("sc", WIRE, ids=[s.name for s in WIRE])
+def test_wireframe_phase_oracle_equals_numpy_model(oracle, sc):
+    want, want_z, tm, rc, order = oracle.render_scene(sc, want_order=True)
+    assert rc == 0
+    rgba, z = pymodel.fb_clear(sc.width, sc.height, sc.clear)
+    order2 = pymodel.render_mesh_15(rgba, z, sc.vertices, sc.faces, sc.textures, sc.camera, sc.settings, sc.fog)
+    assert list(order) == order2
+    bad = (rgba != want).any(-1)
+    assert not bad.any(), f"{sc.name}: {bad.sum()} pixels differ"
+    assert np.array_equal(z.view(np.uint32), want_z.view(np.uint32))
