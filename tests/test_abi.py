@@ -116,3 +116,33 @@ def test_built_for_sm100a_with_exact_arithmetic_flags():
     if out.returncode != 0:
         pytest.skip("cuobjdump unavailable")
     assert "sm_100a" in out.stdout
+
+
+def test_cpp_mirror_compiles_and_links(tmp_path):
+    """include/b32_raster.hpp (the C++ host mirror) compiles with -Wall -Wextra -Werror against the header and links
+    against the built library: every entry point it wraps exists."""
+    src = tmp_path / "mirror.cpp"
+    src.write_text(r'''
+#include "b32_raster.hpp"
+// instantiate every wrapper without running anything (no GPU here)
+int use(b32::Context& c) {
+    b32::Framebuffer fb(c, 4, 4);
+    const uint8_t a[3] = {1, 2, 3}, b[3] = {4, 5, 6};
+    fb.clear_gradient(a, b);
+    b32_camera cam{}; b32_settings st{};
+    fb.render_skybox_mesh({}, {}, cam); fb.render_stars({}, cam, 2.0f); fb.draw_lines({});
+    std::vector<b32_vertex> v; std::vector<b32_face> f;
+    b32::render_mesh_15(fb, v, f, cam, st); b32::render_mesh(fb, v, f, cam, st);
+    b32::Mesh m(c, v, f);
+    const float wp[3] = {0, 0, 0};
+    m.render_15(cam, st); m.frame_15_enqueue(nullptr, cam, st); m.render_placed(0.5f, 0.87f, 0.48f, wp, cam, st);
+    c.set_textures({}); c.set_textures_rgb888({}); c.sync();
+    return (int)fb.pixels().size() + (int)fb.zbuffer().size();
+}
+int main(int argc, char**) { if (argc > 99) { b32::Context c(0); return use(c); } return 0; }
+''')
+    exe = tmp_path / "mirror"
+    lib_dir = os.path.dirname(abi.LIB_PATH)
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src),
+                           "-L", lib_dir, "-l:" + os.path.basename(abi.LIB_PATH), "-Wl,-rpath," + lib_dir])
+    subprocess.check_call([str(exe)])
