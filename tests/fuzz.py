@@ -45,6 +45,13 @@ def fuzz_scene(seed: int, rgb888: bool = False, n_tris: int = 120):
         dithering=bool(rng.random() < 0.7), wireframe_overlay=False,
         ortho_projection=(float(2 + rng.random() * 10), float(rng.normal()), float(rng.normal())) if rng.random() < 0.15 else None,
         use_rgb555=not rgb888, use_fixed_point=bool(rng.random() < 0.6), xray_mode=bool(rng.random() < 0.15))
+    # wireframe phase (its own generator: the scenes of earlier seeds stay what they were).  Not with non-finite
+    # coordinates: their saturated end points make edges of billions of steps, which the reference walks for minutes and
+    # the device refuses (B32_ERR_UNSUPPORTED; tests/test_gpu_parity.py::test_wireframe_absurd_edge_is_reported_not_walked).
+    rng_w = np.random.default_rng(770000 + seed)
+    if np.isfinite(v["pos"]).all() and rng_w.random() < 0.3:
+        st.backface_wireframe = bool(rng_w.random() < 0.7)
+        st.wireframe_overlay = bool(rng_w.random() < 0.4)
     cam = cases._rotated_camera(float(rng.normal() * 0.3), float(rng.normal() * 0.5), rng.normal(size=3) * np.array([2.0, 2.0, 3.0]))
     w, h = [(320, 240), (200, 150), (333, 77), (64, 64), (640, 480)][int(rng.integers(0, 5))]
     fog = (float(rng.random() * 30), float(rng.choice([0.0, 25.0])), float(20 + rng.random() * 60), tuple(int(x) for x in rng.integers(0, 256, size=3))) \
