@@ -39,6 +39,7 @@ assert LINE_DTYPE.itemsize == 32
 STAR_DTYPE = np.dtype([("dir", "<f4", 3), ("rgb", "u1", 3), ("_pad", "u1")])                # b32_star
 assert STAR_DTYPE.itemsize == 16
 LINE_2D, LINE_2D_ALPHA, LINE_3D, LINE_3D_OVERLAY, LINE_3D_ALPHA = 0, 1, 2, 3, 4
+LINE_CIRCLE, LINE_CIRCLE_ALPHA, LINE_FILLED_RECT, LINE_THICK = 5, 6, 7, 8
 LINE_MAX_COORD = 1 << 20
 
 

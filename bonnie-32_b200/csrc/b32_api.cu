@@ -1002,13 +1002,15 @@ int b32_draw_lines(b32_ctx* ctx, const b32_line* lines, uint32_t n) {
     bool any_blended = false;
     for (uint32_t i = 0; i < n; ++i) {
         const b32_line& l = lines[i];
-        if (l.kind > B32_LINE_3D_ALPHA || (l.kind == B32_LINE_2D && l.mode > B32_BLEND_ERASE))
+        if (l.kind > B32_LINE_THICK || (l.kind == B32_LINE_2D && l.mode > B32_BLEND_ERASE) || (l.kind == B32_LINE_THICK && !(l.z0 == std::trunc(l.z0) && std::fabs(l.z0) < 16777216.0f)))
             return fail(ctx, B32_ERR_INVALID, "line " + std::to_string(i) + ": unknown kind or blend mode");
         const int32_t m = B32_LINE_MAX_COORD;
-        if (l.x0 < -m || l.x0 > m || l.y0 < -m || l.y0 > m || l.x1 < -m || l.x1 > m || l.y1 < -m || l.y1 > m)
-            return fail(ctx, B32_ERR_UNSUPPORTED, "line " + std::to_string(i) + ": coordinate beyond B32_LINE_MAX_COORD");
+        const bool circle = l.kind == B32_LINE_CIRCLE || l.kind == B32_LINE_CIRCLE_ALPHA;
+        if (l.x0 < -m || l.x0 > m || l.y0 < -m || l.y0 > m || (!circle && (l.x1 < -m || l.x1 > m || l.y1 < -m || l.y1 > m)) ||
+            (circle && (l.x1 < -32767 || l.x1 > 32767)))            // radius: dx * dx + dy * dy must stay inside i32 as in the reference
+            return fail(ctx, B32_ERR_UNSUPPORTED, "line " + std::to_string(i) + ": coordinate beyond B32_LINE_MAX_COORD (radius beyond 32767)");
         bool overwrites = l.kind == B32_LINE_2D ? (l.mode == B32_BLEND_OPAQUE || l.mode == B32_BLEND_ERASE)
-                                                : (l.kind == B32_LINE_3D || l.kind == B32_LINE_3D_OVERLAY);
+                                                : (l.kind != B32_LINE_2D_ALPHA && l.kind != B32_LINE_3D_ALPHA && l.kind != B32_LINE_CIRCLE_ALPHA);
         any_blended |= !overwrites;
     }
     constexpr uint32_t N_FLAGS = 32;

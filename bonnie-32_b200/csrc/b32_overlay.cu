@@ -2,8 +2,9 @@
 //
 //   k_fb_clear_gradient   Framebuffer::clear_gradient (render.rs:60-77)
 //   k_lines_*             Framebuffer::draw_line / draw_line_blended / draw_line_alpha / draw_line_3d /
-//                         draw_line_3d_overlay / draw_line_3d_alpha (render.rs:684-872) for a whole list of lines,
-//                         with the result of drawing them one after the other in list order.
+//                         draw_line_3d_overlay / draw_line_3d_alpha (render.rs:684-872) and the filled primitives
+//                         draw_circle / draw_circle_alpha / draw_filled_rect / draw_thick_line (render.rs:631-682,
+//                         :875-972) for a whole list, with the result of drawing them one after the other in list order.
 //
 // Order on the device.  A line never writes the z-buffer, so whether line i touches pixel p (bounds + depth test) is
 // independent of every other line; only the colour at p depends on the order.  Two kinds of pixel operations exist:
@@ -63,7 +64,7 @@ constexpr uint32_t LINE_BLOCK = 128;        // one CTA per line: the walks are c
 
 __device__ __forceinline__ bool line_overwrites(const b32_line& l) {
     if (l.kind == B32_LINE_2D) return l.mode == B32_BLEND_OPAQUE || l.mode == B32_BLEND_ERASE;
-    return l.kind == B32_LINE_3D || l.kind == B32_LINE_3D_OVERLAY;
+    return l.kind != B32_LINE_2D_ALPHA && l.kind != B32_LINE_3D_ALPHA && l.kind != B32_LINE_CIRCLE_ALPHA;
 }
 
 // what an overwriting line stores: Color::to_bytes (types.rs:829-832); set_pixel_blended with mode Erase stores
@@ -111,7 +112,7 @@ __device__ __forceinline__ void walk_line(const b32_line& l, int32_t W, int32_t 
     if (lo < 0) lo = 0;
     if (hi > (int64_t)major) hi = major;
     if (lo > hi) return;
-    const bool depth = l.kind >= B32_LINE_3D;
+    const bool depth = l.kind == B32_LINE_3D || l.kind == B32_LINE_3D_OVERLAY || l.kind == B32_LINE_3D_ALPHA;
     const bool allow_equal = l.kind != B32_LINE_3D;
     float z0 = l.z0, z1 = l.z1;
     if (l.kind == B32_LINE_3D_ALPHA) { z0 = z0 * 0.995f; z1 = z1 * 0.995f; }       // DEPTH_BIAS (:826-828)
@@ -137,6 +138,62 @@ __device__ __forceinline__ void walk_line(const b32_line& l, int32_t W, int32_t 
     }
 }
 
+// The filled primitives: every pixel of the clamped bounding box is one work item.
+//   draw_circle / draw_circle_alpha (render.rs:631-644, :670-682), draw_filled_rect (:954-972), draw_thick_line (:875-938)
+template <class Visit>
+__device__ __forceinline__ void walk_area(const b32_line& l, int32_t W, int32_t H, uint32_t lane, Visit visit) {
+    int32_t bx0, bx1, by0, by1;                         // inclusive, clamped to the screen
+    float cx[4] = {0, 0, 0, 0}, cy[4] = {0, 0, 0, 0};   // thick line: the quad's corners
+    if (l.kind == B32_LINE_CIRCLE || l.kind == B32_LINE_CIRCLE_ALPHA) {
+        const int32_t r = l.x1;
+        by0 = max(l.y0 - r, 0); by1 = min(l.y0 + r, H - 1);
+        bx0 = max(l.x0 - r, 0); bx1 = min(l.x0 + r, W - 1);
+    } else if (l.kind == B32_LINE_FILLED_RECT) {
+        bx0 = max(min(l.x0, l.x1), 0); bx1 = min(max(l.x0, l.x1), W - 1);
+        by0 = max(min(l.y0, l.y1), 0); by1 = min(max(l.y0, l.y1), H - 1);
+    } else {                                            // B32_LINE_THICK with thickness > 1
+        const float dx = (float)(l.x1 - l.x0), dy = (float)(l.y1 - l.y0);
+        const float len = sqrtf(dx * dx + dy * dy);                                  // :884
+        if (len < 0.001f) return;
+        const float half = l.z0 * 0.5f;                                              // thickness as f32 * 0.5
+        const float px = -dy / len * half, py = dx / len * half;
+        const float fx0 = (float)l.x0, fy0 = (float)l.y0, fx1 = (float)l.x1, fy1 = (float)l.y1;
+        cx[0] = fx0 + px; cy[0] = fy0 + py; cx[1] = fx0 - px; cy[1] = fy0 - py;      // :894-899
+        cx[2] = fx1 - px; cy[2] = fy1 - py; cx[3] = fx1 + px; cy[3] = fy1 + py;
+        bx0 = max(f2i32(fminf(fminf(cx[0], cx[1]), fminf(cx[2], cx[3]))), 0);         // :902-911 (`as i32` truncates)
+        bx1 = min(f2i32(fmaxf(fmaxf(cx[0], cx[1]), fmaxf(cx[2], cx[3]))), W - 1);
+        by0 = max(f2i32(fminf(fminf(cy[0], cy[1]), fminf(cy[2], cy[3]))), 0);
+        by1 = min(f2i32(fmaxf(fmaxf(cy[0], cy[1]), fmaxf(cy[2], cy[3]))), H - 1);
+    }
+    if (bx0 > bx1 || by0 > by1) return;
+    const uint32_t bw = (uint32_t)(bx1 - bx0 + 1), n = bw * (uint32_t)(by1 - by0 + 1);
+    for (uint32_t k = lane; k < n; k += LINE_BLOCK) {
+        const int32_t x = bx0 + (int32_t)(k % bw), y = by0 + (int32_t)(k / bw);
+        if (l.kind == B32_LINE_CIRCLE || l.kind == B32_LINE_CIRCLE_ALPHA) {
+            const int32_t dx = x - l.x0, dy = y - l.y0;
+            if (dx * dx + dy * dy > l.x1 * l.x1) continue;                           // :637-639
+        } else if (l.kind == B32_LINE_THICK) {
+            const float ppx = (float)x + 0.5f, ppy = (float)y + 0.5f;                // :924
+            bool inside = true;
+            #pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int j = (i + 1) & 3;
+                const float cross = (cx[j] - cx[i]) * (ppy - cy[i]) - (cy[j] - cy[i]) * (ppx - cx[i]);   // :929
+                if (cross < 0.0f) inside = false;
+            }
+            if (!inside) continue;
+        }
+        visit((uint32_t)y * (uint32_t)W + (uint32_t)x);
+    }
+}
+
+template <class Visit>
+__device__ __forceinline__ void walk_prim(const b32_line& l, int32_t W, int32_t H, const float* __restrict__ fb_z, uint32_t lane, Visit visit) {
+    const bool area = l.kind == B32_LINE_CIRCLE || l.kind == B32_LINE_CIRCLE_ALPHA || l.kind == B32_LINE_FILLED_RECT ||
+                      (l.kind == B32_LINE_THICK && l.z0 > 1.0f);                     // thickness <= 1: draw_line (:876-879)
+    if (area) walk_area(l, W, H, lane, visit);
+    else walk_line(l, W, H, fb_z, lane, visit);
+}
 
 // last overwriting line of every pixel
 __global__ void __launch_bounds__(LINE_BLOCK)
@@ -146,7 +203,7 @@ k_lines_claim(const b32_line* __restrict__ lines, uint32_t n, uint32_t* __restri
     if (i >= n) return;
     const b32_line l = lines[i];
     if (!line_overwrites(l)) return;
-    walk_line(l, W, H, fb_z, lane, [&](uint32_t idx) { atomicMax(&owner[idx], i + 1); });
+    walk_prim(l, W, H, fb_z, lane, [&](uint32_t idx) { atomicMax(&owner[idx], i + 1); });
 }
 
 // overwriting lines: the last one of each pixel stores.  Blended lines: first proposal round.
@@ -158,9 +215,9 @@ k_lines_write(const b32_line* __restrict__ lines, uint32_t n, const uint32_t* __
     const b32_line l = lines[i];
     if (line_overwrites(l)) {
         const uint32_t v = line_store_value(l);
-        walk_line(l, W, H, fb_z, lane, [&](uint32_t idx) { if (owner[idx] == i + 1) fb_rgba[idx] = v; });
+        walk_prim(l, W, H, fb_z, lane, [&](uint32_t idx) { if (owner[idx] == i + 1) fb_rgba[idx] = v; });
     } else {
-        walk_line(l, W, H, fb_z, lane, [&](uint32_t idx) { if (i + 1 > owner[idx]) atomicMin(&next[idx], i + 1); });
+        walk_prim(l, W, H, fb_z, lane, [&](uint32_t idx) { if (i + 1 > owner[idx]) atomicMin(&next[idx], i + 1); });
     }
 }
 
@@ -178,7 +235,7 @@ k_lines_round(const b32_line* __restrict__ lines, uint32_t n, uint32_t* __restri
     const b32_line l = lines[i];
     if (line_overwrites(l)) { if (lane == 0) wait[i] = 0; return; }
     bool waiting = false;
-    walk_line(l, W, H, fb_z, lane, [&](uint32_t idx) {
+    walk_prim(l, W, H, fb_z, lane, [&](uint32_t idx) {
         // a line visits a pixel once (the walk moves in every iteration), so `applied` is never this line's own write;
         // a concurrent applier's index is below every waiting line's, so a stale read decides the same
         if (i + 1 <= applied[idx]) return;

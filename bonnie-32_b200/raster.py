@@ -347,6 +347,21 @@ class Framebuffer:
     def draw_line_3d_alpha(self, x0, y0, z0, x1, y1, z1, color, alpha):
         self.draw_lines(make_lines([line_entry(abi.LINE_3D_ALPHA, x0, y0, x1, y1, color, z0, z1, alpha=alpha)]))
 
+    def draw_circle(self, cx, cy, radius, color):                            # render.rs:631-644
+        self.draw_lines(make_lines([line_entry(abi.LINE_CIRCLE, cx, cy, radius, 0, color)]))
+
+    def draw_circle_alpha(self, cx, cy, radius, color, alpha):               # :670-682
+        self.draw_lines(make_lines([line_entry(abi.LINE_CIRCLE_ALPHA, cx, cy, radius, 0, color, alpha=alpha)]))
+
+    def draw_thick_line(self, x0, y0, x1, y1, thickness, color):             # :875-938
+        self.draw_lines(make_lines([line_entry(abi.LINE_THICK, x0, y0, x1, y1, color, z0=float(thickness))]))
+
+    def draw_rect(self, x0, y0, x1, y1, color):                              # :941-951: four draw_line calls
+        self.draw_lines(make_lines(rect_entries(x0, y0, x1, y1, color)))
+
+    def draw_filled_rect(self, x0, y0, x1, y1, color):                       # :954-972
+        self.draw_lines(make_lines([line_entry(abi.LINE_FILLED_RECT, x0, y0, x1, y1, color)]))
+
     def upload(self, pixels: np.ndarray, zbuffer: Optional[np.ndarray] = None):
         px = np.ascontiguousarray(pixels, dtype=np.uint8)
         assert px.size == self.width * self.height * 4
@@ -439,6 +454,14 @@ def line_entry(kind, x0, y0, x1, y1, color, z0=0.0, z1=0.0, mode=abi.BLEND_OPAQU
     """One b32_line: `color` = (r, g, b[, blend]) as everywhere in this module."""
     blend = color[3] if len(color) > 3 else abi.BLEND_OPAQUE
     return (x0, y0, x1, y1, z0, z1, tuple(color[:3]), blend, kind, mode, alpha, 0)
+
+
+def rect_entries(x0, y0, x1, y1, color):
+    """draw_rect (render.rs:941-951): top, right, bottom, left as B32_LINE_2D entries."""
+    min_x, max_x = (x0, x1) if x0 < x1 else (x1, x0)
+    min_y, max_y = (y0, y1) if y0 < y1 else (y1, y0)
+    return [line_entry(abi.LINE_2D, min_x, min_y, max_x, min_y, color), line_entry(abi.LINE_2D, max_x, min_y, max_x, max_y, color),
+            line_entry(abi.LINE_2D, max_x, max_y, min_x, max_y, color), line_entry(abi.LINE_2D, min_x, max_y, min_x, min_y, color)]
 
 
 def make_lines(entries) -> np.ndarray:

@@ -298,7 +298,13 @@ enum {
     B32_LINE_2D_ALPHA    = 1,   /* draw_line_alpha (:684-711): set_pixel_alpha (:646-667) */
     B32_LINE_3D          = 2,   /* draw_line_3d (:756-758): depth test z < zbuffer, set_pixel */
     B32_LINE_3D_OVERLAY  = 3,   /* draw_line_3d_overlay (:763-765): z <= zbuffer, set_pixel */
-    B32_LINE_3D_ALPHA    = 4    /* draw_line_3d_alpha (:822-872): z * 0.995 <= zbuffer, set_pixel_alpha */
+    B32_LINE_3D_ALPHA    = 4,   /* draw_line_3d_alpha (:822-872): z * 0.995 <= zbuffer, set_pixel_alpha */
+    /* the filled primitives of the same family ride in the same list (and the same ordering): */
+    B32_LINE_CIRCLE       = 5,  /* draw_circle (:631-644): x0, y0 = centre, x1 = radius (|radius| <= 32767); set_pixel */
+    B32_LINE_CIRCLE_ALPHA = 6,  /* draw_circle_alpha (:670-682): the same with set_pixel_alpha */
+    B32_LINE_FILLED_RECT  = 7,  /* draw_filled_rect (:954-972): corners (x0, y0), (x1, y1) inclusive; set_pixel.
+                                   draw_rect (:941-951) is four B32_LINE_2D entries: top, right, bottom, left */
+    B32_LINE_THICK        = 8   /* draw_thick_line (:875-938): z0 = thickness as f32 (an integer); thickness <= 1 is draw_line */
 };
 typedef struct b32_line {
     int32_t x0, y0, x1, y1;     /* end points, |coordinate| <= B32_LINE_MAX_COORD */

@@ -53,7 +53,7 @@ public:
     void render_stars(const std::vector<b32_star>& stars, const b32_camera& cam, float size) {
         c_.check(b32_render_stars(c_.get(), stars.data(), (uint32_t)stars.size(), &cam, size));
     }
-    // draw_line* (:684-872): a list drawn with the result of the calls made in order
+    // draw_line*, draw_circle*, draw_thick_line, draw_filled_rect (:631-972): a list drawn with the result of the calls made in order
     void draw_lines(const std::vector<b32_line>& lines) { c_.check(b32_draw_lines(c_.get(), lines.data(), (uint32_t)lines.size())); }
     void upload(const uint8_t* rgba, const float* z) { c_.check(b32_fb_upload(c_.get(), rgba, z)); }
     std::vector<uint8_t> pixels() { std::vector<uint8_t> p((size_t)width * height * 4); c_.check(b32_fb_download(c_.get(), p.data(), nullptr)); return p; }

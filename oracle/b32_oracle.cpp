@@ -703,6 +703,58 @@ void fb_draw_line_3d_alpha(Fb& fb, int32_t x0, int32_t y0, float z0, int32_t x1,
     }
 }
 
+// The filled primitives of the overlay family: draw_circle (render.rs:631-644), draw_circle_alpha (:670-682),
+// draw_thick_line (:875-938), draw_filled_rect (:954-972)
+void fb_draw_circle(Fb& fb, int32_t cx, int32_t cy, int32_t radius, Col color) {
+    int32_t r_sq = radius * radius;
+    for (int32_t y = std::max(cy - radius, 0); y <= std::min(cy + radius, (int32_t)fb.height - 1); ++y)
+        for (int32_t x = std::max(cx - radius, 0); x <= std::min(cx + radius, (int32_t)fb.width - 1); ++x) {
+            int32_t dx = x - cx, dy = y - cy;
+            if (dx * dx + dy * dy <= r_sq) fb_set_pixel(fb, (uint64_t)x, (uint64_t)y, color);
+        }
+}
+void fb_draw_circle_alpha(Fb& fb, int32_t cx, int32_t cy, int32_t radius, Col color, uint8_t alpha) {
+    int32_t r_sq = radius * radius;
+    for (int32_t y = std::max(cy - radius, 0); y <= std::min(cy + radius, (int32_t)fb.height - 1); ++y)
+        for (int32_t x = std::max(cx - radius, 0); x <= std::min(cx + radius, (int32_t)fb.width - 1); ++x) {
+            int32_t dx = x - cx, dy = y - cy;
+            if (dx * dx + dy * dy <= r_sq) fb_set_pixel_alpha(fb, (uint64_t)x, (uint64_t)y, color, alpha);
+        }
+}
+void fb_draw_filled_rect(Fb& fb, int32_t x0, int32_t y0, int32_t x1, int32_t y1, Col color) {
+    int32_t min_x = x0 < x1 ? x0 : x1, max_x = x0 < x1 ? x1 : x0;
+    int32_t min_y = y0 < y1 ? y0 : y1, max_y = y0 < y1 ? y1 : y0;
+    min_x = std::max(min_x, 0); min_y = std::max(min_y, 0);
+    max_x = std::min(max_x, (int32_t)fb.width - 1); max_y = std::min(max_y, (int32_t)fb.height - 1);
+    for (int32_t y = min_y; y <= max_y; ++y)
+        for (int32_t x = min_x; x <= max_x; ++x) fb_set_pixel(fb, (uint64_t)x, (uint64_t)y, color);
+}
+void fb_draw_thick_line(Fb& fb, int32_t x0, int32_t y0, int32_t x1, int32_t y1, int32_t thickness, Col color) {
+    if (thickness <= 1) { fb_draw_line_blended(fb, x0, y0, x1, y1, color, B32_BLEND_OPAQUE); return; }     // draw_line (:876-879)
+    float dx = (float)(x1 - x0), dy = (float)(y1 - y0);
+    float len = std::sqrt(dx * dx + dy * dy);
+    if (len < 0.001f) return;
+    float half = (float)thickness * 0.5f;
+    float px = -dy / len * half, py = dx / len * half;
+    float c[4][2] = {{(float)x0 + px, (float)y0 + py}, {(float)x0 - px, (float)y0 - py}, {(float)x1 - px, (float)y1 - py}, {(float)x1 + px, (float)y1 + py}};
+    float fminx = INFINITY, fmaxx = -INFINITY, fminy = INFINITY, fmaxy = -INFINITY;
+    for (auto& k : c) { fminx = rmin(fminx, k[0]); fmaxx = rmax(fmaxx, k[0]); fminy = rmin(fminy, k[1]); fmaxy = rmax(fmaxy, k[1]); }
+    int32_t min_x = std::max(f2i32(fminx), 0), max_x = std::min(f2i32(fmaxx), (int32_t)fb.width - 1);
+    int32_t min_y = std::max(f2i32(fminy), 0), max_y = std::min(f2i32(fmaxy), (int32_t)fb.height - 1);
+    if (min_x > max_x || min_y > max_y) return;
+    for (int32_t yy = min_y; yy <= max_y; ++yy)
+        for (int32_t xx = min_x; xx <= max_x; ++xx) {
+            float p0 = (float)xx + 0.5f, p1 = (float)yy + 0.5f;
+            bool inside = true;
+            for (int i = 0; i < 4; ++i) {
+                const float* a = c[i]; const float* b = c[(i + 1) % 4];
+                float cross = (b[0] - a[0]) * (p1 - a[1]) - (b[1] - a[1]) * (p0 - a[0]);
+                if (cross < 0.0f) { inside = false; break; }
+            }
+            if (inside) fb_set_pixel(fb, (uint64_t)xx, (uint64_t)yy, color);
+        }
+}
+
 // shared tail of the two editor-alpha writers (render.rs:349-373 / 395-419): PS1 blend, then a float lerp
 inline void editor_alpha_write8(Fb& fb, uint64_t idx, Col c, uint32_t mode, uint8_t editor_alpha) {
     Col back = fb_back(fb, idx);
@@ -1383,6 +1435,10 @@ int b32o_draw_lines(uint8_t* fb_rgba, float* fb_z, uint32_t w, uint32_t h, const
             case B32_LINE_3D:         fb_draw_line_3d_impl(fb, l.x0, l.y0, l.z0, l.x1, l.y1, l.z1, c, false); break;
             case B32_LINE_3D_OVERLAY: fb_draw_line_3d_impl(fb, l.x0, l.y0, l.z0, l.x1, l.y1, l.z1, c, true); break;
             case B32_LINE_3D_ALPHA:   fb_draw_line_3d_alpha(fb, l.x0, l.y0, l.z0, l.x1, l.y1, l.z1, c, l.alpha); break;
+            case B32_LINE_CIRCLE:       fb_draw_circle(fb, l.x0, l.y0, l.x1, c); break;
+            case B32_LINE_CIRCLE_ALPHA: fb_draw_circle_alpha(fb, l.x0, l.y0, l.x1, c, l.alpha); break;
+            case B32_LINE_FILLED_RECT:  fb_draw_filled_rect(fb, l.x0, l.y0, l.x1, l.y1, c); break;
+            case B32_LINE_THICK:        fb_draw_thick_line(fb, l.x0, l.y0, l.x1, l.y1, f2i32(l.z0), c); break;
             default: return B32_ERR_INVALID;
         }
     }

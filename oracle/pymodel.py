@@ -763,7 +763,49 @@ def fb_clear_gradient(w, h, top, bottom):
     return rgba, z
 
 
-LINE_2D, LINE_2D_ALPHA, LINE_3D, LINE_3D_OVERLAY, LINE_3D_ALPHA = range(5)
+LINE_2D, LINE_2D_ALPHA, LINE_3D, LINE_3D_OVERLAY, LINE_3D_ALPHA, LINE_CIRCLE, LINE_CIRCLE_ALPHA, LINE_FILLED_RECT, LINE_THICK = range(9)
+
+
+def _area_points(l, w, h):
+    """Pixels of the filled primitives (render.rs:631-644, :670-682, :875-938, :954-972) as integer arrays."""
+    kind = int(l["kind"])
+    x0, y0, x1, y1 = int(l["x0"]), int(l["y0"]), int(l["x1"]), int(l["y1"])
+    none = (np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64))
+    if kind in (LINE_CIRCLE, LINE_CIRCLE_ALPHA):
+        r = x1
+        ys = np.arange(max(y0 - r, 0), min(y0 + r, h - 1) + 1); xs = np.arange(max(x0 - r, 0), min(x0 + r, w - 1) + 1)
+        if not len(ys) or not len(xs):
+            return none
+        yy, xx = np.meshgrid(ys, xs, indexing="ij")
+        m = (xx - x0) ** 2 + (yy - y0) ** 2 <= r * r
+        return xx[m], yy[m]
+    if kind == LINE_FILLED_RECT:
+        ys = np.arange(max(min(y0, y1), 0), min(max(y0, y1), h - 1) + 1); xs = np.arange(max(min(x0, x1), 0), min(max(x0, x1), w - 1) + 1)
+        if not len(ys) or not len(xs):
+            return none
+        yy, xx = np.meshgrid(ys, xs, indexing="ij")
+        return xx.reshape(-1), yy.reshape(-1)
+    # draw_thick_line with thickness > 1: a quad around the segment, tested at pixel centres
+    dx, dy = F(x1 - x0), F(y1 - y0)
+    ln = np.sqrt(dx * dx + dy * dy)
+    if ln < F(0.001):
+        return none
+    half = F(l["z0"]) * F(0.5)
+    px, py = -dy / ln * half, dx / ln * half
+    c = [(F(x0) + px, F(y0) + py), (F(x0) - px, F(y0) - py), (F(x1) - px, F(y1) - py), (F(x1) + px, F(y1) + py)]
+    cxs = np.array([k[0] for k in c], dtype=F); cys = np.array([k[1] for k in c], dtype=F)
+    bx0 = max(int(as_i32(cxs.min(keepdims=True))[0]), 0); bx1 = min(int(as_i32(cxs.max(keepdims=True))[0]), w - 1)
+    by0 = max(int(as_i32(cys.min(keepdims=True))[0]), 0); by1 = min(int(as_i32(cys.max(keepdims=True))[0]), h - 1)
+    if bx0 > bx1 or by0 > by1:
+        return none
+    yy, xx = np.meshgrid(np.arange(by0, by1 + 1), np.arange(bx0, bx1 + 1), indexing="ij")
+    p0, p1 = xx.astype(F) + F(0.5), yy.astype(F) + F(0.5)
+    inside = np.ones(xx.shape, dtype=bool)
+    for i in range(4):
+        a, b = c[i], c[(i + 1) % 4]
+        cross = (b[0] - a[0]) * (p1 - a[1]) - (b[1] - a[1]) * (p0 - a[0])
+        inside &= ~(cross < 0)
+    return xx[inside], yy[inside]
 
 
 def _line_points(x0, y0, x1, y1):
@@ -792,10 +834,14 @@ def draw_lines(fb_rgba, fb_z, lines):
     h, w = fb_z.shape
     for l in lines:
         kind, mode, alpha = int(l["kind"]), int(l["mode"]), int(l["alpha"])
-        xs, ys, steps, total = _line_points(int(l["x0"]), int(l["y0"]), int(l["x1"]), int(l["y1"]))
-        on = (xs >= 0) & (xs < w) & (ys >= 0) & (ys < h)
-        xs, ys, steps = xs[on], ys[on], steps[on]
-        if kind >= LINE_3D:
+        if kind in (LINE_CIRCLE, LINE_CIRCLE_ALPHA, LINE_FILLED_RECT) or (kind == LINE_THICK and int(as_i32(np.array([l["z0"]], dtype=F))[0]) > 1):
+            xs, ys = _area_points(l, w, h)
+            steps, total = np.zeros(len(xs), dtype=np.int64), 1
+        else:                                                                      # every line kind; draw_thick_line(thickness <= 1) = draw_line
+            xs, ys, steps, total = _line_points(int(l["x0"]), int(l["y0"]), int(l["x1"]), int(l["y1"]))
+            on = (xs >= 0) & (xs < w) & (ys >= 0) & (ys < h)
+            xs, ys, steps = xs[on], ys[on], steps[on]
+        if kind in (LINE_3D, LINE_3D_OVERLAY, LINE_3D_ALPHA):
             z0, z1 = F(l["z0"]), F(l["z1"])
             if kind == LINE_3D_ALPHA:
                 z0, z1 = z0 * F(0.995), z1 * F(0.995)                      # DEPTH_BIAS :826-828
@@ -806,7 +852,7 @@ def draw_lines(fb_rgba, fb_z, lines):
             xs, ys = xs[ok], ys[ok]
         rgb = np.array(l["rgb"], dtype=np.int64)
         back = fb_rgba[ys, xs, :3].astype(np.int64)
-        if kind in (LINE_2D_ALPHA, LINE_3D_ALPHA):                         # set_pixel_alpha :646-667
+        if kind in (LINE_2D_ALPHA, LINE_3D_ALPHA, LINE_CIRCLE_ALPHA):      # set_pixel_alpha :646-667
             out, a = (rgb * alpha + back * (255 - alpha)) // 255, 255
         elif kind == LINE_2D and mode == ERASE:                            # Color::TRANSPARENT, types.rs:920-923
             out, a = np.zeros_like(back), 0

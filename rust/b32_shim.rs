@@ -215,6 +215,26 @@ impl LineList {
     pub fn draw_line_3d_alpha(&mut self, x0: i32, y0: i32, z0: f32, x1: i32, y1: i32, z1: f32, color: Color, alpha: u8) {
         self.push(4, (x0, y0, x1, y1), (z0, z1), color, BlendMode::Opaque, alpha);
     }
+    pub fn draw_circle(&mut self, cx: i32, cy: i32, radius: i32, color: Color) {
+        self.push(5, (cx, cy, radius, 0), (0.0, 0.0), color, BlendMode::Opaque, 255);
+    }
+    pub fn draw_circle_alpha(&mut self, cx: i32, cy: i32, radius: i32, color: Color, alpha: u8) {
+        self.push(6, (cx, cy, radius, 0), (0.0, 0.0), color, BlendMode::Opaque, alpha);
+    }
+    pub fn draw_filled_rect(&mut self, x0: i32, y0: i32, x1: i32, y1: i32, color: Color) {
+        self.push(7, (x0, y0, x1, y1), (0.0, 0.0), color, BlendMode::Opaque, 255);
+    }
+    pub fn draw_thick_line(&mut self, x0: i32, y0: i32, x1: i32, y1: i32, thickness: i32, color: Color) {
+        self.push(8, (x0, y0, x1, y1), (thickness as f32, 0.0), color, BlendMode::Opaque, 255);
+    }
+    pub fn draw_rect(&mut self, x0: i32, y0: i32, x1: i32, y1: i32, color: Color) {      // render.rs:941-951
+        let (min_x, max_x) = if x0 < x1 { (x0, x1) } else { (x1, x0) };
+        let (min_y, max_y) = if y0 < y1 { (y0, y1) } else { (y1, y0) };
+        self.draw_line(min_x, min_y, max_x, min_y, color);
+        self.draw_line(max_x, min_y, max_x, max_y, color);
+        self.draw_line(max_x, max_y, min_x, max_y, color);
+        self.draw_line(min_x, max_y, min_x, min_y, color);
+    }
     /// Draws the collected lines over the device framebuffer, in the order they were added, and empties the list.
     pub fn flush(&mut self) {
         CTX.with(|&ctx| unsafe { check(ctx, b32_draw_lines(ctx, self.0.as_ptr(), self.0.len() as u32)); });

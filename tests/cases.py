@@ -399,3 +399,31 @@ def star_list(camera, w, h, time, seed=42, count=300, horizon=0.5, twinkle_speed
         out["dir"][i] = d
         out["rgb"][i] = [min(max(int(F(c) * brightness), 0), 255) for c in color]
     return out
+
+
+def random_prims(w, h, n, seed):
+    """A list mixing the five line kinds with circles, alpha circles, filled rectangles and thick lines."""
+    from bonnie32_b200 import abi
+    rng = np.random.default_rng(seed)
+    ln = random_lines(w, h, n, seed + 1)
+    kind = rng.integers(0, 9, n).astype(np.uint8)
+    ln["kind"] = kind
+    circ = (kind == abi.LINE_CIRCLE) | (kind == abi.LINE_CIRCLE_ALPHA)
+    ln["x1"][circ] = rng.choice(np.array([-3, 0, 1, 2, 5, 9, 17, 40, 300], dtype=np.int32), int(circ.sum()))      # radius
+    ln["y1"][circ] = 0
+    thick = kind == abi.LINE_THICK
+    ln["z0"][thick] = rng.choice(np.array([-2, 0, 1, 2, 3, 4, 7, 16], dtype=np.float32), int(thick.sum()))          # thickness
+    short = thick & (rng.random(n) < 0.2)                                       # zero-length thick lines draw nothing
+    ln["x1"][short] = ln["x0"][short]; ln["y1"][short] = ln["y0"][short]
+    big = (kind == abi.LINE_FILLED_RECT) & (rng.random(n) < 0.5)                # keep half of the rectangles small
+    for f in ("x1", "y1"):
+        ln[f][(kind == abi.LINE_FILLED_RECT) & ~big] = ln[f.replace("1", "0")][(kind == abi.LINE_FILLED_RECT) & ~big] + rng.integers(-12, 13, int(((kind == abi.LINE_FILLED_RECT) & ~big).sum()))
+    return ln
+
+
+def prim_cases():
+    """(name, width, height, background seed, list)."""
+    return [("prims_320x240", 320, 240, 21, random_prims(320, 240, 300, 31)),
+            ("prims_dense_64x48", 64, 48, 22, random_prims(64, 48, 250, 32)),
+            ("prims_odd_size", 37, 23, 23, random_prims(37, 23, 150, 33)),
+            ("prims_640x480", 640, 480, 24, random_prims(640, 480, 400, 34))]

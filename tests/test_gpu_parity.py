@@ -864,3 +864,50 @@ def test_download_view_equals_download(ctx):
     fb.resize(64, 48); fb.clear((1, 2, 3))
     c, _ = fb.download_view()
     assert c.shape == (48, 64, 4) and (c == (1, 2, 3, 255)).all()
+
+
+# ---- filled primitives of the overlay family: draw_circle(_alpha), draw_filled_rect, draw_thick_line, draw_rect ----------
+PRIMS = cases.prim_cases()
+
+
+@pytest.mark.parametrize("name,w,h,seed,lines", PRIMS, ids=lambda v: v if isinstance(v, str) else None)
+def test_draw_prims(ctx, oracle, name, w, h, seed, lines):
+    rgba, z = cases.line_background(w, h, seed)
+    fb = pkg.Framebuffer(w, h, ctx)
+    fb.upload(rgba, z)
+    fb.draw_lines(lines)
+    got, got_z = fb.download()
+    want = rgba.copy()
+    assert oracle.draw_lines(want, z, lines) == 0
+    bad = (got != want).any(-1)
+    assert not bad.any(), f"{name}: {bad.sum()} pixels differ, first at {np.argwhere(bad)[0][::-1]}"
+    assert np.array_equal(got_z.view(np.uint32), z.view(np.uint32))
+
+
+def test_draw_prims_reference_methods(ctx, oracle):
+    """The Framebuffer methods with the reference's names and arguments, one device pass each."""
+    from bonnie32_b200 import raster
+    w, h = 96, 72
+    rgba, z = cases.line_background(w, h, 5)
+    fb = pkg.Framebuffer(w, h, ctx)
+    fb.upload(rgba, z)
+    fb.draw_filled_rect(70, 60, 10, 20, (10, 200, 30))
+    fb.draw_circle(30, 30, 12, (250, 10, 10))
+    fb.draw_circle_alpha(50, 40, 20, (0, 0, 255), 100)
+    fb.draw_thick_line(5, 65, 90, 8, 5, (255, 255, 0))
+    fb.draw_thick_line(90, 65, 5, 30, 1, (0, 255, 255))
+    fb.draw_rect(3, 3, 92, 68, (255, 255, 255))
+    got, _ = fb.download()
+    entries = [raster.line_entry(abi.LINE_FILLED_RECT, 70, 60, 10, 20, (10, 200, 30)), raster.line_entry(abi.LINE_CIRCLE, 30, 30, 12, 0, (250, 10, 10)),
+               raster.line_entry(abi.LINE_CIRCLE_ALPHA, 50, 40, 20, 0, (0, 0, 255), alpha=100),
+               raster.line_entry(abi.LINE_THICK, 5, 65, 90, 8, (255, 255, 0), z0=5.0), raster.line_entry(abi.LINE_THICK, 90, 65, 5, 30, (0, 255, 255), z0=1.0)]
+    entries += raster.rect_entries(3, 3, 92, 68, (255, 255, 255))
+    want = rgba.copy()
+    assert oracle.draw_lines(want, z, raster.make_lines(entries)) == 0
+    assert np.array_equal(got, want)
+    for bad, code in ((raster.line_entry(abi.LINE_CIRCLE, 5, 5, 40000, 0, (1, 2, 3)), abi.B32_ERR_UNSUPPORTED),
+                      (raster.line_entry(abi.LINE_THICK, 0, 0, 9, 9, (1, 2, 3), z0=2.5), abi.B32_ERR_INVALID),
+                      (raster.line_entry(9, 0, 0, 9, 9, (1, 2, 3)), abi.B32_ERR_INVALID)):
+        with pytest.raises(pkg.B32Error) as e:
+            fb.draw_lines(raster.make_lines([bad]))
+        assert e.value.code == code

@@ -460,3 +460,41 @@ def test_wireframe_phase_oracle_equals_numpy_model(oracle, sc):
     bad = (rgba != want).any(-1)
     assert not bad.any(), f"{sc.name}: {bad.sum()} pixels differ"
     assert np.array_equal(z.view(np.uint32), want_z.view(np.uint32))
+
+
+# ---- filled primitives of the overlay family (draw_circle, draw_circle_alpha, draw_filled_rect, draw_thick_line, draw_rect) ----
+PRIMS = cases.prim_cases()
+
+
+@pytest.mark.parametrize("name,w,h,seed,lines", PRIMS[:3], ids=lambda v: v if isinstance(v, str) else None)
+def test_prims_oracle_matches_numpy_model(oracle, name, w, h, seed, lines):
+    rgba, z = cases.line_background(w, h, seed)
+    a = rgba.copy(); b = rgba.copy()
+    assert oracle.draw_lines(a, z, lines) == 0
+    pymodel.draw_lines(b, z, lines)
+    bad = (a != b).any(-1)
+    assert not bad.any(), f"{name}: {bad.sum()} pixels differ, first at {np.argwhere(bad)[0][::-1]}"
+    assert len({int(k) for k in lines["kind"]}) == 9
+
+
+def test_prims_known_shapes(oracle):
+    """Hand-checked shapes: a radius-1 circle is a plus, radius 0 one pixel, a negative radius nothing; a filled rectangle is
+    inclusive of both corners; draw_rect is its outline; a thick horizontal line of thickness 2 covers the two rows whose
+    centres lie inside the quad."""
+    from bonnie32_b200 import raster
+    def drawn(entries):
+        rgba = np.zeros((12, 12, 4), np.uint8); z = np.zeros((12, 12), np.float32)
+        assert oracle.draw_lines(rgba, z, raster.make_lines(entries)) == 0
+        ys, xs = np.nonzero(rgba[..., 0])
+        return sorted(zip(xs.tolist(), ys.tolist()))
+    c = (255, 255, 255)
+    assert drawn([raster.line_entry(abi.LINE_CIRCLE, 5, 5, 1, 0, c)]) == [(4, 5), (5, 4), (5, 5), (5, 6), (6, 5)]
+    assert drawn([raster.line_entry(abi.LINE_CIRCLE, 5, 5, 0, 0, c)]) == [(5, 5)]
+    assert drawn([raster.line_entry(abi.LINE_CIRCLE, 5, 5, -1, 0, c)]) == []
+    assert drawn([raster.line_entry(abi.LINE_FILLED_RECT, 3, 2, 1, 3, c)]) == [(1, 2), (1, 3), (2, 2), (2, 3), (3, 2), (3, 3)]
+    outline = drawn(raster.rect_entries(2, 2, 5, 4, c))
+    assert outline == sorted({(x, y) for x in range(2, 6) for y in range(2, 5)} - {(3, 3), (4, 3)})
+    # thickness 2 around y = 5: the quad spans y in [4, 6]; pixel centres y + 0.5 inside for rows 4 and 5; x from 2 to 7
+    assert drawn([raster.line_entry(abi.LINE_THICK, 2, 5, 8, 5, c, z0=2.0)]) == sorted((x, y) for x in range(2, 8) for y in (4, 5))
+    assert drawn([raster.line_entry(abi.LINE_THICK, 2, 5, 8, 5, c, z0=1.0)]) == [(x, 5) for x in range(2, 9)]      # thickness 1 = draw_line
+    assert drawn([raster.line_entry(abi.LINE_THICK, 4, 4, 4, 4, c, z0=5.0)]) == []                                   # zero length
