@@ -680,7 +680,7 @@ def test_draw_lines_errors(ctx):
     from bonnie32_b200 import raster
     fb = pkg.Framebuffer(64, 48, ctx)
     fb.draw_lines(raster.make_lines([]))                                       # empty list: nothing to do
-    bad_kind = raster.make_lines([raster.line_entry(7, 0, 0, 5, 5, (1, 2, 3))])
+    bad_kind = raster.make_lines([raster.line_entry(17, 0, 0, 5, 5, (1, 2, 3))])
     with pytest.raises(pkg.B32Error) as e:
         fb.draw_lines(bad_kind)
     assert e.value.code == abi.B32_ERR_INVALID
