@@ -77,5 +77,12 @@ want = np.empty((sc.height, sc.width, 4), np.uint8); want[...] = (*sc.clear[:3],
 wz = np.full((sc.height, sc.width), np.finfo(np.float32).max, np.float32)
 orc.render_mesh_15(want, wz, v, sc.faces, sc.textures, sc.camera, sc.settings)
 ok = np.array_equal(got, want) and np.array_equal(gz.view(np.uint32), wz.view(np.uint32)); print("placed_part", "OK" if ok else "MISMATCH"); bad += not ok
+# filled overlay primitives
+name, w, h, seed, lines = cases.prim_cases()[1]
+rgba, z = cases.line_background(w, h, seed)
+fb = pkg.Framebuffer(w, h, ctx); fb.upload(rgba, z); fb.draw_lines(lines)
+got, _ = fb.download()
+want = rgba.copy(); orc.draw_lines(want, z, lines)
+ok = np.array_equal(got, want); print(name, "OK" if ok else "MISMATCH"); bad += not ok
 print("mismatches:", bad)
 sys.exit(1 if bad else 0)
