@@ -137,6 +137,34 @@ int32_t fx_div_unr(int32_t self, int32_t divisor) {                             
     return result_negative ? -clamped : clamped;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Compatibility switches — used ONLY to pin this restatement against the reference's own compiled
+// code, /root/reference/docs/bonnie-32.wasm (crate version string 0.1.8; the source tree is 0.1.11).
+// The binary predates four source changes; each switch turns ONE of them back so that the rest of
+// the restatement can be compared bit for bit with reference-executed results (oracle/wasm/,
+// tests/golden/ref_wasm/).  Default 0 = the 0.1.11 source.  Evidence for every
+// item is the decompiled function (oracle/wasm/wasmdecomp.py), quoted in oracle/wasm/DRIFT.md.
+enum : uint32_t {
+    COMPAT_DIV_EXACT       = 1,  // project_to_screen: `((c*4) << 12) / denom`, clamped to +-2^27 and `& !7`,
+                                 //   instead of 0.1.11's div_unr (fixed.rs:178-230 did not exist yet)
+    COMPAT_ALWAYS_DITHER   = 2,  // rasterize_triangle_15: dither iff settings.dithering (no needs_dither rule,
+                                 //   render.rs:1487-1492 is newer)
+    COMPAT_RGBA_SHL3       = 4,  // Color15::r8/g8/b8 = v << 3 (0.1.11: (v<<3)|(v>>2), types.rs:138-152)
+    COMPAT_TRANSP_TEX_ONLY = 8,  // has_transparency: texture present => its blend != Opaque decides alone;
+                                 //   no texture => face blend decides (0.1.11: either, render.rs:2403-2415)
+};
+uint32_t g_compat = 0;
+
+// 0.1.8 projection divide, from the decompiled project_fixed:
+//   q = (((n << 2) as i64) << 12) / denom;  q = max(q, -134217728); q = min(q, 134213632); q &= -8
+inline int32_t fx_div_exact_018(int32_t scaled_num, int32_t denom) {
+    int64_t q = ((int64_t)scaled_num << 12) / (int64_t)denom;
+    int32_t r = (int32_t)(uint32_t)(uint64_t)q;          // i32.wrap_i64
+    r = r > -134217728 ? r : -134217728;
+    r = r < 134213632 ? r : 134213632;
+    return r & -8;
+}
+
 struct FxV3 { int32_t x, y, z; };
 inline FxV3 fx_from_vec3(V3 v) { return FxV3{fx_from_f32(v.x), fx_from_f32(v.y), fx_from_f32(v.z)}; } // :291-297
 inline int32_t fx_dot(FxV3 a, FxV3 b) {                                         // fixed.rs:311-313
@@ -160,8 +188,15 @@ inline void project_to_screen(FxV3 cam, uint32_t width, uint32_t height, int32_t
     // i32::abs in a release build wraps for i32::MIN (stays negative => "< 256" holds)
     int32_t adenom = denom < 0 ? (int32_t)((uint32_t)0 - (uint32_t)denom) : denom;
     if (adenom < 256) { *sx = fx_floor(half_w); *sy = fx_floor(half_h); *depth = cam.z; return; }
-    int32_t proj_x = fx_div_unr(fx_mul(cam.x, scl), denom);
-    int32_t proj_y = fx_div_unr(fx_mul(cam.y, scl), denom);
+    int32_t proj_x, proj_y;
+    if (g_compat & COMPAT_DIV_EXACT) {
+        // the binary computes `cam << 2` (wrapping) where 0.1.11 has cam * from_f32(4.0)
+        proj_x = fx_div_exact_018((int32_t)((uint32_t)cam.x << 2), denom);
+        proj_y = fx_div_exact_018((int32_t)((uint32_t)cam.y << 2), denom);
+    } else {
+        proj_x = fx_div_unr(fx_mul(cam.x, scl), denom);
+        proj_y = fx_div_unr(fx_mul(cam.y, scl), denom);
+    }
     int32_t screen_x = fx_add(fx_mul(proj_x, viewport_scale), half_w);
     int32_t screen_y = fx_add(fx_mul(proj_y, viewport_scale), half_h);
     *sx = fx_floor(screen_x); *sy = fx_floor(screen_y); *depth = cam.z;
@@ -315,10 +350,12 @@ inline void fb_set_pixel(Fb& fb, uint64_t x, uint64_t y, Col c) {       // rende
         fb.pixels[idx + 3] = c.blend == B32_BLEND_ERASE ? 0 : 255;
     }
 }
+// Color15::r8/g8/b8, types.rs:138-152
+inline uint8_t c15_ch8(uint8_t v5) { return (g_compat & COMPAT_RGBA_SHL3) ? (uint8_t)(v5 << 3) : expand_5_to_8(v5); }
 // Color15::to_rgba, types.rs:220-226
 inline void c15_to_rgba(uint16_t c, uint8_t out[4]) {
     if (c == 0x0000) { out[0] = out[1] = out[2] = out[3] = 0; return; }
-    out[0] = expand_5_to_8(c15_r5(c)); out[1] = expand_5_to_8(c15_g5(c)); out[2] = expand_5_to_8(c15_b5(c)); out[3] = 255;
+    out[0] = c15_ch8(c15_r5(c)); out[1] = c15_ch8(c15_g5(c)); out[2] = c15_ch8(c15_b5(c)); out[3] = 255;
 }
 inline void fb_set_pixel_15(Fb& fb, uint64_t x, uint64_t y, uint16_t c) {           // render.rs:445-454
     if (x < fb.width && y < fb.height) {
@@ -332,7 +369,7 @@ inline void fb_set_pixel_blended_15(Fb& fb, uint64_t x, uint64_t y, uint16_t c, 
         uint8_t br = fb.pixels[idx], bg = fb.pixels[idx + 1], bb = fb.pixels[idx + 2];
         uint8_t o[3];
         if (c & 0x8000) blend_rgb555(expand_5_to_8(c15_r5(c)), expand_5_to_8(c15_g5(c)), expand_5_to_8(c15_b5(c)), br, bg, bb, mode, o);
-        else { o[0] = expand_5_to_8(c15_r5(c)); o[1] = expand_5_to_8(c15_g5(c)); o[2] = expand_5_to_8(c15_b5(c)); }
+        else { o[0] = c15_ch8(c15_r5(c)); o[1] = c15_ch8(c15_g5(c)); o[2] = c15_ch8(c15_b5(c)); }
         fb.pixels[idx] = o[0]; fb.pixels[idx + 1] = o[1]; fb.pixels[idx + 2] = o[2]; fb.pixels[idx + 3] = 255;
     }
 }
@@ -340,9 +377,9 @@ inline void fb_set_pixel_xray_15(Fb& fb, uint64_t x, uint64_t y, uint16_t c) {  
     if (x < fb.width && y < fb.height) {
         uint64_t idx = (y * fb.width + x) * 4;
         uint8_t br = fb.pixels[idx], bg = fb.pixels[idx + 1], bb = fb.pixels[idx + 2];
-        fb.pixels[idx]     = (uint8_t)(((uint16_t)expand_5_to_8(c15_r5(c)) + br) / 2);
-        fb.pixels[idx + 1] = (uint8_t)(((uint16_t)expand_5_to_8(c15_g5(c)) + bg) / 2);
-        fb.pixels[idx + 2] = (uint8_t)(((uint16_t)expand_5_to_8(c15_b5(c)) + bb) / 2);
+        fb.pixels[idx]     = (uint8_t)(((uint16_t)c15_ch8(c15_r5(c)) + br) / 2);
+        fb.pixels[idx + 1] = (uint8_t)(((uint16_t)c15_ch8(c15_g5(c)) + bg) / 2);
+        fb.pixels[idx + 2] = (uint8_t)(((uint16_t)c15_ch8(c15_b5(c)) + bb) / 2);
         fb.pixels[idx + 3] = 255;
     }
 }
@@ -450,6 +487,7 @@ void rasterize_triangle_15(Fb& fb, const Surface& surface, const Tex15* texture,
     }
     bool needs_dither = settings.dithering && (gouraud || texture != nullptr ||               // :1487-1492
                                                !col_eq(surface.vc1, surface.vc2) || !col_eq(surface.vc2, surface.vc3));
+    if (g_compat & COMPAT_ALWAYS_DITHER) needs_dither = settings.dithering;
 
     V3 v1 = surface.v1, v2 = surface.v2, v3 = surface.v3;
     float area = (v2.y - v3.y) * (v1.x - v3.x) + (v3.x - v2.x) * (v1.y - v3.y);              // :1500
@@ -996,6 +1034,8 @@ inline Col vcol(const b32_vertex& v) { return Col{v.r, v.g, v.b, v.blend}; }
 // =============================================================================================
 extern "C" {
 
+void b32o_set_compat(uint32_t flags) { g_compat = flags; }
+uint32_t b32o_get_compat(void) { return g_compat; }
 uint8_t b32o_unr_table(uint32_t i) { return UNR.t[i < 257 ? i : 256]; }
 int32_t b32o_fixed_from_f32(float f) { return fx_from_f32(f); }
 int32_t b32o_fixed_mul(int32_t a, int32_t b) { return fx_mul(a, b); }
@@ -1087,6 +1127,8 @@ int b32o_render_mesh_15(uint8_t* fb_rgba, float* fb_z, uint32_t w, uint32_t h,
         if (tex && tex->blend_mode != B32_BLEND_OPAQUE) has_transparency = true;
         else if (face_blend != B32_BLEND_OPAQUE) has_transparency = true;
         else has_transparency = editor_alpha < 255;
+        if (g_compat & COMPAT_TRANSP_TEX_ONLY)
+            has_transparency = tex ? tex->blend_mode != B32_BLEND_OPAQUE : face_blend != B32_BLEND_OPAQUE;
 
         double fog_t0 = now_s();
         Col vc1, vc2, vc3;                                                               // :2419-2443

@@ -22,6 +22,12 @@
 extern "C" {
 #endif
 
+/* Compatibility switches (bit mask, default 0 = the 0.1.11 source): turn back, one by one, the four source
+ * changes that separate /root/reference/docs/bonnie-32.wasm (0.1.8) from the source tree, so the restatement
+ * can be compared bit for bit with the reference's own compiled code.  See b32_oracle.cpp COMPAT_*. */
+void     b32o_set_compat(uint32_t flags);
+uint32_t b32o_get_compat(void);
+
 /* fixed.rs */
 uint8_t b32o_unr_table(uint32_t i);                               /* fixed.rs:20-31   */
 int32_t b32o_fixed_from_f32(float f);                             /* fixed.rs:125-127 */
