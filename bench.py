@@ -141,50 +141,58 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def _oracle_worker_init(n_gpus):
-    global _W_PKG, _W_ORC, _W_SCENES, _W_NG
-    _W_PKG = entry.load_package()
+def _oracle_worker(idx, n_gpus, n_rounds, go, done, out):
+    """One pinned worker = one frame slot: builds its scene BEFORE the first round, then renders it once per round."""
+    pkg = entry.load_package()
     from oracle import oracle as orc
-    _W_ORC = orc
-    _W_SCENES = {}
-    _W_NG = n_gpus
-
-
-def _oracle_worker_frame(rank):
-    sc = _W_SCENES.get(rank)
-    if sc is None:
-        sc = _W_SCENES[rank] = frame_scene(_W_PKG, _W_NG, rank)
-    t = time.perf_counter()
-    rgba, z, tm, rc = _W_ORC.render_scene(sc)
-    assert rc == 0
-    return time.perf_counter() - t, tm["triangles_drawn"]
+    sc = frame_scene(pkg, n_gpus, idx % n_gpus)
+    orc.render_scene(sc)                                     # page everything in
+    done.wait()                                              # ready
+    for r in range(n_rounds):
+        go.wait()
+        t = time.perf_counter()
+        rgba, z, tm, rc = orc.render_scene(sc)
+        assert rc == 0
+        out[idx] = time.perf_counter() - t
+        done.wait()
 
 
 def time_oracle(n_gpus: int, steps: int, warmup: int, cores: int = 1):
     """Frames of the same workload through the CPU oracle, one thread per frame (the reference renders a frame on one
-    thread).  A step renders `cores` frames side by side, one process per core (frame i = the frame of rank i % n_gpus).
+    thread).  A step renders `cores` frames side by side, one pinned process per frame slot (slot i always renders the frame
+    of rank i % n_gpus, built before any timing), so the figure does not depend on how frames meet workers.
     Returns (seconds for `steps` steps, cores, frames per step)."""
     import multiprocessing as mp
     entry.build_oracle()
     cores = max(1, min(cores, os.cpu_count() or 1))
-    frames = [i % n_gpus for i in range(cores)]
     if cores == 1:
-        _oracle_worker_init(n_gpus)
-        for _ in range(warmup):
-            _oracle_worker_frame(0)
+        pkg = entry.load_package()
+        from oracle import oracle as orc
+        sc = frame_scene(pkg, n_gpus, 0)
+        for _ in range(max(warmup, 1)):
+            orc.render_scene(sc)
         t0 = time.perf_counter()
         for _ in range(steps):
-            _oracle_worker_frame(0)
-        dt = time.perf_counter() - t0
-    else:
-        with mp.get_context("fork").Pool(cores, initializer=_oracle_worker_init, initargs=(n_gpus,)) as pool:
-            for _ in range(warmup):
-                pool.map(_oracle_worker_frame, frames, chunksize=1)
-            t0 = time.perf_counter()
-            for _ in range(steps):
-                pool.map(_oracle_worker_frame, frames, chunksize=1)
-            dt = time.perf_counter() - t0
-    return dt, cores, len(frames)
+            rgba, z, tm, rc = orc.render_scene(sc)
+            assert rc == 0
+        return time.perf_counter() - t0, 1, 1
+    ctx = mp.get_context("fork")
+    go, done = ctx.Barrier(cores + 1), ctx.Barrier(cores + 1)
+    out = ctx.Array("d", cores)
+    procs = [ctx.Process(target=_oracle_worker, args=(i, n_gpus, warmup + steps, go, done, out), daemon=True) for i in range(cores)]
+    for p_ in procs:
+        p_.start()
+    done.wait()                                              # every worker has built and rendered its scene once
+    dt = 0.0
+    for r in range(warmup + steps):
+        t0 = time.perf_counter()
+        go.wait()
+        done.wait()
+        if r >= warmup:
+            dt += time.perf_counter() - t0
+    for p_ in procs:
+        p_.join(timeout=5)
+    return dt, cores, cores
 
 
 def run_reference(args):
@@ -203,7 +211,8 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32+i32/i64 fixed-point", "data": "synthetic", "config": workload_config(args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                         "note": "Rust reference not executable here (no rustc); CPU figure is the line-by-line C++ restatement in oracle/"},
+                         "note": "the Rust reference is not buildable here (no rustc); the CPU figure is the line-by-line C++ restatement in oracle/, "
+                                 "pinned bit for bit against the reference's own wasm build (tests/test_ref_wasm.py)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "frames_per_s": fps / (dt / args.steps),
     }
@@ -308,6 +317,7 @@ def run_b200(args):
     barrier()
     launches = sum(c.kernel_launches() for c in ctxs) - launches0
     total_ms = max(s0.elapsed_time(e1) for s0 in starts for e1 in ends)       # first start -> last end, device clock
+    own_total_ms = total_ms
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)            # max over ranks; NCCL only gathers timing
@@ -315,7 +325,25 @@ def run_b200(args):
     ms_per_step = total_ms / args.steps
     value = world * N_TRIS / (ms_per_step * 1e-3) / 1e6
 
-    # ---- per-kernel device times and the synchronous call (what one render_mesh_15 caller sees) ---------
+    # ---- per-kernel device times IN THE REGIME OF THE TIMED LOOP: the same frames, the same N_CTX streams in flight, launched
+    #      plainly with CUDA events (on each context's own stream) in front of k_setup, in front of the fill and behind it.
+    #      Enqueued frames run the fill's 256-thread shape (OpSparse), as in the value loop.
+    n_prof = min(args.steps, 120)
+    per = max(1, (n_prof + N_CTX - 1) // N_CTX)
+    for c in ctxs:
+        c.check(lib.b32_debug_timing_ring(c.h, per))
+    barrier()
+    for k in range(per * N_CTX):
+        step_enqueue(k)
+    setup_ms, fill_ms = [], []
+    buf_a, buf_b = (C.c_float * per)(), (C.c_float * per)()
+    for c in ctxs:
+        n = lib.b32_debug_timing_read(c.h, buf_a, buf_b, per)
+        setup_ms += list(buf_a[:n]); fill_ms += list(buf_b[:n])
+        c.check(lib.b32_debug_timing_ring(c.h, 0))
+    kern_inflight = {"k_setup": float(np.mean(setup_ms)), "k_fill_opaque": float(np.mean(fill_ms))}
+
+    # ---- the synchronous call (what one blocking render_mesh_15 caller sees), L2 evicted before each call ------------
     kern = np.zeros(16)
     phase = {"transform_ms": 0.0, "cull_ms": 0.0, "sort_ms": 0.0, "draw_ms": 0.0}
     n_sync = min(args.steps, 20)
@@ -336,25 +364,59 @@ def run_b200(args):
     kern /= n_sync
 
     # ---- end to end through the host-buffer ABI: pinned host inputs, H2D + render + D2H every step -------
-    nvb, nfb = sc.vertices.nbytes, sc.faces.nbytes
-    hv = lib.b32_host_alloc(nvb); hf = lib.b32_host_alloc(nfb)
+    # The bytes a marshalling shim sends for this mesh: normals dropped (shading None reads none), faces implicit (an
+    # unindexed soup): b32_render_mesh_15_ex(B32_VTX_NO_NORMAL | B32_FACES_IMPLICIT).  The full 36 + 16 byte records are
+    # timed beside it (`full_format`).
+    shading_none = sc.settings.shading == abi.SHADE_NONE
+    cv, cf, cflags = abi.compact_buffers(sc.vertices, sc.faces, shading_none)
+    host = {}
+    for name, v_, f_, fl in (("compact", cv, cf, cflags), ("full", sc.vertices, sc.faces, 0)):
+        hv_ = lib.b32_host_alloc(v_.nbytes); hf_ = lib.b32_host_alloc(f_.nbytes)
+        C.memmove(hv_, v_.ctypes.data, v_.nbytes); C.memmove(hf_, f_.ctypes.data, f_.nbytes)
+        host[name] = (hv_, hf_, fl, v_.nbytes + f_.nbytes)
     hps = [lib.b32_host_alloc(sc.width * sc.height * 4) for _ in ctxs]
     hp = hps[0]
-    C.memmove(hv, sc.vertices.ctypes.data, nvb); C.memmove(hf, sc.faces.ctypes.data, nfb)
-    FLAGS = abi.RENDER_ASYNC | abi.RENDER_ALL_OPAQUE
+    nv_, nf_ = len(sc.vertices), len(sc.faces)
 
     def step_e2e_sync():
+        hv_, hf_, fl, _ = host["compact"]
         ctx.check(lib.b32_fb_clear(ctx.h, r, g, b, 255))
-        ctx.check(lib.b32_render_mesh_15(ctx.h, hv, len(sc.vertices), hf, len(sc.faces), C.byref(cam), C.byref(st), None, C.byref(tm)))
+        ctx.check(lib.b32_render_mesh_15_ex(ctx.h, hv_, nv_, hf_, nf_, C.byref(cam), C.byref(st), None, fl, C.byref(tm)))
         ctx.check(lib.b32_fb_download(ctx.h, hp, None))
 
-    def step_e2e(k):
+    def make_step_e2e(fmt):
+        hv_, hf_, fl, _ = host[fmt]
+        flags = fl | abi.RENDER_ASYNC | abi.RENDER_ALL_OPAQUE
+
+        def step(k):
+            i = k % N_CTX
+            c = ctxs[i]
+            c.sync()                                         # frame k - N_CTX (its framebuffer is in hps[i]) is complete
+            c.check(lib.b32_fb_clear(c.h, r, g, b, 255))
+            c.check(lib.b32_render_mesh_15_ex(c.h, hv_, nv_, hf_, nf_, C.byref(cam), C.byref(st), None, flags, None))
+            c.check(lib.b32_fb_download_async(c.h, hps[i], None))
+        return step
+
+    def step_game(k):                                        # SURVEY 8d "second figure": resident geometry, per-frame camera, framebuffer D2H
         i = k % N_CTX
         c = ctxs[i]
-        c.sync()                                             # frame k - N_CTX (its framebuffer is in hps[i]) is complete
-        c.check(lib.b32_fb_clear(c.h, r, g, b, 255))
-        c.check(lib.b32_render_mesh_15_ex(c.h, hv, len(sc.vertices), hf, len(sc.faces), C.byref(cam), C.byref(st), None, FLAGS, None))
+        c.sync()
+        c.check(lib.b32_frame_15_enqueue(c.h, clear4, meshes[k % N_COPIES].h, C.byref(cam), C.byref(st), None))
         c.check(lib.b32_fb_download_async(c.h, hps[i], None))
+
+    def timed_loop(step, n):
+        for k in range(max(args.warmup, 3) * N_CTX):
+            step(k)
+        for c in ctxs:
+            c.sync()
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(n):
+            step(k)
+        for c in ctxs:
+            c.sync()
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0
 
     for _ in range(max(args.warmup, 3)):
         step_e2e_sync()
@@ -364,25 +426,21 @@ def run_b200(args):
         step_e2e_sync()
     torch.cuda.synchronize()
     e2e_sync_s = (time.perf_counter() - t0) / n_sync
-    for k in range(max(args.warmup, 3) * N_CTX):
-        step_e2e(k)
-    for c in ctxs:
-        c.sync()
-    barrier()
-    t0 = time.perf_counter()
-    for k in range(args.steps):
-        step_e2e(k)
-    for c in ctxs:
-        c.sync()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s, e2e_sync_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s, e2e_sync_s = float(t[0].item()), float(t[1].item())
-    clocks = sampler.stop()                  # sampled over all timed regions of this run (value, per-kernel, end to end)
-    e2e_value = world * N_TRIS / (e2e_s / args.steps) / 1e6
+    e2e_full_s = timed_loop(make_step_e2e("full"), args.steps)
+    game_s = timed_loop(step_game, args.steps)
+    e2e_s = timed_loop(make_step_e2e("compact"), args.steps)          # last: its final frame is the one hashed below
     got = np.ctypeslib.as_array(C.cast(hps[(args.steps - 1) % N_CTX], C.POINTER(C.c_uint8)), shape=(sc.height, sc.width, 4)).copy()
+    clocks = sampler.stop()                  # sampled over all timed regions of this run (value, per-kernel, end to end)
+    # every rank's own numbers (the headline is the MAX over ranks = the slowest link)
+    mine = torch.tensor([e2e_s, e2e_sync_s, e2e_full_s, game_s, own_total_ms * 1e-3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        allr = torch.stack(allr).cpu().numpy()
+    else:
+        allr = mine.cpu().numpy()[None, :]
+    e2e_s, e2e_sync_s, e2e_full_s, game_s = (float(allr[:, j].max()) for j in range(4))
+    e2e_value = world * N_TRIS / (e2e_s / args.steps) / 1e6
 
     # ---- parity of the frame just timed, against the committed golden hash -------------------------
     import hashlib
@@ -392,6 +450,10 @@ def run_b200(args):
         parity = hashes[sc.name]["rgba_sha256"] == hashlib.sha256(got.tobytes()).hexdigest()
     except Exception:
         pass
+    if world > 1:                             # every rank's frame is checked, not only rank 0's
+        ok = torch.tensor([1 if parity else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        parity = bool(ok.item())
 
     if rank == 0:
         peaks = {}
@@ -400,48 +462,78 @@ def run_b200(args):
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        names = ["k_setup+k_bin_opaque", "k_fill_opaque", "pass2:k_bin", "pass2:k_fill_ordered"]
-        kavg = {n: float(kern[i]) for i, n in enumerate(names)}
-        dom = max(kavg, key=kavg.get)
+        dom = max(kern_inflight, key=kern_inflight.get)
         alg_bytes = sc.algorithmic_bytes
-        ach = alg_bytes / (kavg[dom] * 1e-3) / 1e9 if kavg[dom] > 0 else None
-        traffic = None                      # dram__bytes_read+write of that kernel from the committed ncu --set full capture
+        ach = alg_bytes / (kern_inflight[dom] * 1e-3) / 1e9
+        # static facts of the dominant kernel from the committed `ncu --set full` capture of this round (profiles/README.md):
+        # DRAM bytes per launch with the caches left alone (steady state) and flushed (ncu's default), warp instructions
+        prof = {}
         try:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_kernels.json")))
-            traffic = prof[dom.split("+")[0]]["dram_bytes"]
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_kernels.json")))
         except Exception:
             pass
+        pk = prof.get(dom, {})
+        inst_frame = sum(v.get("warp_instructions", 0) for v in prof.values() if isinstance(v, dict)) or None
+        sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+        n_sched = 4 * 148
+        h2d = host["compact"][3]
+        d2h = sc.width * sc.height * 4
+        nfr = args.steps
+        per_rank = [{"rank": i, "e2e_ms_per_step": float(allr[i, 0]) * 1e3 / nfr, "e2e_h2d_gbs": h2d * nfr / float(allr[i, 0]) / 1e9,
+                     "e2e_full_format_ms_per_step": float(allr[i, 2]) * 1e3 / nfr, "value_ms_per_step": float(allr[i, 4]) * 1e3 / nfr}
+                    for i in range(world)]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32+i32/i64 fixed-point", "data": "synthetic", "config": workload_config(world),
             "frames_per_s": world / (ms_per_step * 1e-3), "triangles_drawn": int(drawn), "bit_exact_vs_golden": parity,
             "inflight": N_CTX,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nvb + nfb, "d2h_bytes_per_step": sc.width * sc.height * 4,
-                    "ms_per_step": e2e_s * 1e3 / args.steps, "frames_per_s": world / (e2e_s / args.steps),
-                    "how": f"b32_render_mesh_15_ex(ASYNC) + b32_fb_download_async from/to pinned host memory, {N_CTX} frames in flight "
-                           "(one context each), wall clock",
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_s * 1e3 / nfr, "frames_per_s": world / (e2e_s / nfr),
+                    "h2d_gbs_per_gpu": h2d * nfr / e2e_s / 1e9,
+                    "how": f"b32_render_mesh_15_ex(ASYNC | VTX_NO_NORMAL | FACES_IMPLICIT) + b32_fb_download_async from/to pinned host memory, "
+                           f"{N_CTX} frames in flight (one context each), wall clock; the shim's compact marshalling: 24-byte vertices "
+                           "(shading None reads no normals) and one flags word per face (unindexed soup)",
+                    "full_format": {"value": world * N_TRIS / (e2e_full_s / nfr) / 1e6, "ms_per_step": e2e_full_s * 1e3 / nfr,
+                                    "h2d_bytes_per_step": host["full"][3], "how": "same with 36-byte b32_vertex + 16-byte b32_face records"},
+                    "resident_geometry": {"value": world * N_TRIS / (game_s / nfr) / 1e6, "ms_per_step": game_s * 1e3 / nfr,
+                                          "h2d_bytes_per_step": 48 + 64, "d2h_bytes_per_step": d2h,
+                                          "how": "SURVEY 8d second figure (a game loop): resident mesh, per-frame camera + settings, "
+                                                 "b32_frame_15_enqueue + b32_fb_download_async, wall clock"},
                     "sync_call": {"value": world * N_TRIS / e2e_sync_s / 1e6, "ms_per_step": e2e_sync_s * 1e3,
-                                  "how": "b32_fb_clear + b32_render_mesh_15 + b32_fb_download, one blocking frame at a time"}},
+                                  "how": "b32_fb_clear + b32_render_mesh_15_ex(compact) + b32_fb_download, one blocking frame at a time"},
+                    "per_rank": per_rank},
             "sync_call_ms": float(np.mean(sync_call_ms)),
             "host_binding": numa,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": (ach / peak) if ach else None, "traffic": traffic,
+                         "frac": ach / peak, "traffic": pk.get("dram_bytes_steady"),
+                         "traffic_cache_flushed": pk.get("dram_bytes_flushed"),
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                         "kernel_ms": kavg, "phase_ms": {k: v / n_sync for k, v in phase.items()},
-                         "whole_frame_frac": alg_bytes / (ms_per_step * 1e-3) / 1e9 / peak},
+                         "kernel_ms": kern_inflight,
+                         "kernel_ms_how": f"CUDA events on each context's stream around the kernels of {len(setup_ms)} enqueued frames, {N_CTX} "
+                                          "frames in flight as in the timed loop (plain launches instead of graph replays); fill shape OpSparse "
+                                          "(256 threads, one lane per pixel)",
+                         "kernel_ms_blocking_call": {"k_setup": float(kern[0]), "k_fill_opaque": float(kern[1]),
+                                                     "how": "one blocking call at a time, L2 evicted before it; fill shape OpDense (512 threads)"},
+                         "phase_ms": {k: v / n_sync for k, v in phase.items()},
+                         "whole_frame_frac": alg_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
+                         "issue_frac": (inst_frame / (n_sched * sm_hz * ms_per_step * 1e-3)) if inst_frame else None,
+                         "issue_frac_how": "warp instructions per frame (smsp__inst_executed.sum of k_setup + k_fill_opaque, committed ncu capture) "
+                                           "/ (592 schedulers x SM clock x ms_per_step): the path is issue-bound, not HBM-bound"},
         }
         if world == 1 and not args.no_cpu:
             n_cpu = 20
             dt, cores, _ = time_oracle(1, n_cpu, 2, cores=1)
             line["cpu_baseline"] = {"value": N_TRIS / (dt / n_cpu) / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{n_cpu} full 100k-triangle frames of the same scene, single thread, oracle -O3",
-                                    "note": "Rust reference not executable here (no rustc); C++ restatement in oracle/"}
+                                    "note": "the Rust reference is not buildable here (no rustc); the C++ restatement in oracle/ is pinned bit for bit "
+                                            "against the reference's own wasm build (tests/test_ref_wasm.py)"}
         print(json.dumps(line))
-    lib.b32_host_free(hv); lib.b32_host_free(hf)
+    for hv_, hf_, _, _ in host.values():
+        lib.b32_host_free(hv_); lib.b32_host_free(hf_)
     for h_ in hps:
         lib.b32_host_free(h_)
     for m_ in meshes:

@@ -25,13 +25,28 @@ SHADE_NONE, SHADE_FLAT, SHADE_GOURAUD = range(3)
 LIGHT_DIRECTIONAL, LIGHT_POINT, LIGHT_SPOT = range(3)
 TEX_RGB555, TEX_IDX8, TEX_IDX4 = range(3)
 FACE_TEX_NONE = 0xFFFF
-RENDER_ASYNC, RENDER_ALL_OPAQUE = 1, 2
+RENDER_ASYNC, RENDER_ALL_OPAQUE, VTX_NO_NORMAL, FACES_IMPLICIT = 1, 2, 4, 8
 
 # ---- POD records as numpy dtypes (b32_vertex 36 B, b32_face 16 B) ---------------------------
 VERTEX_DTYPE = np.dtype([("pos", "<f4", 3), ("uv", "<f4", 2), ("normal", "<f4", 3), ("rgba", "u1", 4)])
 FACE_DTYPE = np.dtype([("v", "<u4", 3), ("flags", "<u4")])
 SKY_VERTEX_DTYPE = np.dtype([("pos", "<f4", 3), ("rgb", "u1", 3), ("_pad", "u1")])     # b32_sky_vertex
-assert VERTEX_DTYPE.itemsize == 36 and FACE_DTYPE.itemsize == 16 and SKY_VERTEX_DTYPE.itemsize == 16
+VERTEX_NN_DTYPE = np.dtype([("pos", "<f4", 3), ("uv", "<f4", 2), ("rgba", "u1", 4)])                            # b32_vertex_nn
+assert VERTEX_DTYPE.itemsize == 36 and FACE_DTYPE.itemsize == 16 and SKY_VERTEX_DTYPE.itemsize == 16 and VERTEX_NN_DTYPE.itemsize == 24
+
+
+def compact_buffers(vertices, faces, shading_none):
+    """What a marshalling shim sends through b32_render_mesh_15_ex for this mesh: (vertex array, face array, flags).
+    Normals are dropped when nothing reads them; an unindexed soup sends only its flags words."""
+    flags = 0
+    v, f = vertices, faces
+    if shading_none:
+        nn = np.empty(len(vertices), VERTEX_NN_DTYPE)
+        nn["pos"], nn["uv"], nn["rgba"] = vertices["pos"], vertices["uv"], vertices["rgba"]
+        v, flags = nn, flags | VTX_NO_NORMAL
+    if len(faces) * 3 <= len(vertices) and np.array_equal(faces["v"].reshape(-1), np.arange(len(faces) * 3, dtype=np.uint32)):
+        f, flags = np.ascontiguousarray(faces["flags"], dtype=np.uint32), flags | FACES_IMPLICIT
+    return np.ascontiguousarray(v), np.ascontiguousarray(f), flags
 # b32_line (overlay lines, Framebuffer::draw_line*)
 LINE_DTYPE = np.dtype([("x0", "<i4"), ("y0", "<i4"), ("x1", "<i4"), ("y1", "<i4"), ("z0", "<f4"), ("z1", "<f4"),
                        ("rgb", "u1", 3), ("blend", "u1"), ("kind", "u1"), ("mode", "u1"), ("alpha", "u1"), ("_pad", "u1")])
@@ -141,6 +156,8 @@ SYMBOLS = {
     "b32_debug_transform": (C.c_int, [_P, _P, C.c_uint32, C.POINTER(Camera), C.POINTER(Settings), _P, _P]),
     "b32_debug_draw_order": (C.c_int, [_P, _P, C.c_uint32, C.POINTER(C.c_uint32)]),
     "b32_debug_kernel_times": (C.c_int, [_P, C.POINTER(C.c_float), C.c_uint32]),
+    "b32_debug_timing_ring": (C.c_int, [_P, C.c_uint32]),
+    "b32_debug_timing_read": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_uint32]),
 }
 
 _lib = None

@@ -22,14 +22,15 @@ template <typename T>
 struct DevBuf {
     T* p = nullptr;
     size_t cap = 0;     // elements
-    cudaError_t reserve(size_t n, bool keep = false, cudaStream_t s = 0) {
+    // Growing discards the contents.  Enqueued work of any stream may still read the old buffer: wait for the whole
+    // device before it is freed (growth is rare; steady state never gets here).
+    cudaError_t reserve(size_t n) {
         if (n <= cap) return cudaSuccess;
         size_t ncap = std::max(n, cap + cap / 2);
         T* q = nullptr;
         cudaError_t e = cudaMalloc(&q, ncap * sizeof(T));
         if (e != cudaSuccess) return e;
-        if (keep && p && cap) cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, s);
-        if (p) { cudaStreamSynchronize(s); cudaFree(p); }
+        if (p) { cudaDeviceSynchronize(); cudaFree(p); }
         p = q; cap = ncap;
         return cudaSuccess;
     }
@@ -49,10 +50,10 @@ struct b32_mesh {
 struct FrameKey {
     const void* verts = nullptr; const void* faces = nullptr;
     uint32_t nv = 0, nf = 0, width = 0, height = 0;
-    uint8_t rgb888 = 0, pass1 = 0, clear = 0, valid = 0;
+    uint8_t rgb888 = 0, pass1 = 0, clear = 0, valid = 0, ordered = 0;
     bool operator==(const FrameKey& o) const {
         return verts == o.verts && faces == o.faces && nv == o.nv && nf == o.nf && width == o.width && height == o.height &&
-               rgb888 == o.rgb888 && pass1 == o.pass1 && clear == o.clear && valid == o.valid;
+               rgb888 == o.rgb888 && pass1 == o.pass1 && clear == o.clear && valid == o.valid && ordered == o.ordered;
     }
 };
 struct FrameGraph {
@@ -107,16 +108,15 @@ struct b32_ctx {
     DevBuf<uint32_t> state_ring;
     uint32_t state_stride = 0;         // words per set
     int state_cur = 0;
-    uint32_t* tile_count = nullptr;    // current set's tile counters
-    DevBuf<uint32_t> otile_count;
-    DevBuf<BinHead> bins, heads, obins;
-    DevBuf<BinHead> bins_sorted;       // walk-order copies of bins larger than k_fill_opaque's shared-memory capacity
-    uint32_t obin_cap_hint = 0;
+    uint32_t* tile_count = nullptr;    // current set's counters: ordered-pass entries per mask tile
+    DevBuf<uint4> masks;               // tile masks [mask tile][face group] (binning without bins, b32_device.cuh)
+    DevBuf<BinHead> heads, obins;      // per-face heads; obins: scratch slices of the ordered pass's crowded tiles
+    uint32_t obin_cap = 0;             // entries per tile slice of obins (a power of two; 0 = none allocated)
+    uint32_t obin_tiles = 0;           // ... allocated for this many tiles
     DevBuf<WireTri> wire;
     DevBuf<uint32_t> wire_table;       // open-addressing table of the wireframe phase's edge de-duplication
     DevBuf<b32_line> lines;            // overlay lines (b32_draw_lines): the list, then per pixel owner + next, then round flags
     DevBuf<uint32_t> line_scratch;
-    uint32_t bin_cap_hint = 0;
     std::vector<LightDev> lights_h;
     bool async_pending = false;
     CallParams last_params{};
@@ -143,6 +143,10 @@ struct b32_ctx {
     FrameKey fg_seen[N_FRAME_GRAPHS];  // topologies seen once, not captured yet
     int fg_next = 0, fg_seen_next = 0;
     uint64_t graph_launches = 0, graph_captures = 0;
+
+    // measurement aid (b32_debug_timing_ring): enqueued frames are launched plainly with events around their kernel groups
+    std::vector<cudaEvent_t> tring;    // 3 events per slot: before k_setup, before the fill(s), after
+    uint32_t tring_n = 0, tring_count = 0;
 
     LaunchCtx L() { return LaunchCtx{stream, (uint32_t)prop.multiProcessorCount, &launches, nullptr}; }
 };
@@ -183,9 +187,14 @@ int fill_params(b32_ctx* ctx, CallParams& p, const b32_camera* cam, const b32_se
     p.half_h = (int32_t)(((uint32_t)((int32_t)ctx->height / 2)) << 12);
     p.nv = nv; p.nf = nf; p.ntex = rgb888 ? ctx->ntex8 : ctx->ntex;
     p.rgb888 = rgb888 ? 1 : 0;
-    static const bool no_scan = std::getenv("B32_NO_HEAD_SCAN") != nullptr;        // experiments: always bin with k_bin_opaque
-    // every tile reads every bin head in this mode: worth it while nf x tiles stays small (1024 faces up to 640x480)
-    p.scan_heads = (nf <= (uint32_t)OP_SORT_MAX_ENTRIES && (uint64_t)nf * p.tiles_x * p.tiles_y <= 1500000ull && !no_scan) ? 1 : 0;
+    p.vwords = 9;
+    // tile-mask geometry: coarser mask tiles for frames / meshes whose table would be too large (b32_device.cuh)
+    p.n_groups = (nf + SETUP_GROUP - 1) / SETUP_GROUP;
+    for (p.mshift = 0;; ++p.mshift) {
+        p.mtiles_x = (p.tiles_x + (1u << p.mshift) - 1) >> p.mshift; p.mtiles_y = (p.tiles_y + (1u << p.mshift) - 1) >> p.mshift;
+        const uint64_t n_mt = (uint64_t)p.mtiles_x * p.mtiles_y;
+        if ((n_mt <= MASK_TILES_MAX && n_mt * std::max<uint32_t>(p.n_groups, 1) * sizeof(uint4) <= MASK_BYTES_MAX) || n_mt <= 1) break;
+    }
     const uint32_t mask_words = rgb888 ? ctx->tex8mask_words : ctx->texmask_words;
     p.mask_smem_words = mask_words <= (uint32_t)OP_MASK_SMEM_WORDS ? mask_words : 0;
     p.affine_textures = s->affine_textures != 0; p.use_zbuffer = s->use_zbuffer != 0; p.shading = s->shading;
@@ -244,13 +253,13 @@ int h2d(b32_ctx* ctx, void* dst, const void* src, size_t bytes, bool consume = f
     return B32_OK;
 }
 
-int ensure_work(b32_ctx* ctx, uint32_t nv, uint32_t nf) {
-    uint32_t m = std::max<uint32_t>(nf, 1);
+int ensure_work(b32_ctx* ctx, const CallParams& p) {
+    uint32_t m = std::max<uint32_t>(p.nf, 1);
     CK(ctx->recs.reserve(m));
     CK(ctx->keys.reserve(m));
     CK(ctx->heads.reserve(m));
-    uint32_t ntiles = ((ctx->width + TILE_W - 1) / TILE_W) * ((ctx->height + TILE_H - 1) / TILE_H);
-    CK(ctx->otile_count.reserve(std::max<uint32_t>(ntiles, 1)));
+    CK(ctx->masks.reserve(std::max<size_t>((size_t)p.mtiles_x * p.mtiles_y * p.n_groups, 1)));
+    uint32_t ntiles = p.tiles_x * p.tiles_y;
     uint32_t need = STATE_WORDS + ((std::max<uint32_t>(ntiles, 1) + 3u) & ~3u);
     if (need > ctx->state_stride) {
         CK(cudaStreamSynchronize(ctx->stream));
@@ -265,11 +274,9 @@ int ensure_work(b32_ctx* ctx, uint32_t nv, uint32_t nf) {
     return B32_OK;
 }
 
-// capacity (entries) of one tile bin of the opaque pass; a surface adds at most one entry per tile
-uint32_t pick_bin_cap(b32_ctx* ctx, uint32_t nf, uint32_t ntiles, bool worst_case) {
-    uint32_t cap = worst_case ? nf : std::max<uint32_t>(ctx->bin_cap_hint, std::max<uint32_t>(1024, (uint32_t)(16ull * nf / std::max<uint32_t>(ntiles, 1))));
-    cap = std::min<uint32_t>(cap, std::max<uint32_t>(nf, 1));
-    return (cap + 31u) & ~31u;
+// the scratch slices of the ordered pass: `cap` entries (a power of two) for each of the frame's tiles
+uint32_t ordered_scratch_cap(const b32_ctx* ctx, uint32_t ntiles) {
+    return (ctx->obin_cap && ctx->obin_tiles >= ntiles) ? ctx->obin_cap : 0u;
 }
 
 int upload_lights(b32_ctx* ctx, const std::vector<LightDev>& lights) {
@@ -285,50 +292,25 @@ int upload_lights(b32_ctx* ctx, const std::vector<LightDev>& lights) {
     return B32_OK;
 }
 
-// Pass 2 (semi-transparent surfaces, back to front) and x-ray mode: strict draw-order replay.
-// The surfaces' draw-order keys were written by k_setup; bin them per tile (any order), then every
-// tile sorts its bin by key and replays it (k_fill_ordered).
-int render_ordered(b32_ctx* ctx, const CallParams& p, uint32_t n_ordered) {
+// Pass 2 (semi-transparent surfaces, back to front) and x-ray mode: strict draw-order replay (k_fill_ordered).
+// obin_max = the largest number of ordered entries k_setup counted in one mask tile: tiles with more than fit shared
+// memory sort in a slice of a global scratch, sized here (so the pass never has to be redone).
+int render_ordered(b32_ctx* ctx, const CallParams& p, uint32_t obin_max) {
     LaunchCtx L = ctx->L();
     cudaStream_t st = ctx->stream;
     const uint32_t ntiles = p.tiles_x * p.tiles_y;
-    if (p.scan_heads) {                 // small meshes: k_fill_ordered builds each tile's draw-order entries itself (no bins, no overflow)
-        CK(cudaEventRecord(ctx->ev[3], st));
-        launch_fill_ordered(L, ctx->recs.p, nullptr, nullptr, ctx->keys.p, p.rgb888 ? ctx->tex8desc.p : ctx->texdesc.p,
-                            p.rgb888 ? reinterpret_cast<const uint16_t*>(ctx->texels8.p) : ctx->texels.p,
-                            ctx->fb_rgba.p, ctx->fb_z.p, ctx->state, p, 0);
-        CK(cudaEventRecord(ctx->ev[4], st));
-        CK(cudaStreamSynchronize(st));
-        CK(cudaGetLastError());
-        cudaEventElapsedTime(&ctx->kernel_ms[3], ctx->ev[3], ctx->ev[4]);
-        return B32_OK;
-    }
-    for (int attempt = 0;; ++attempt) {
-        uint32_t cap = std::max<uint32_t>(ctx->obin_cap_hint, 256);
-        cap = std::min<uint32_t>(cap, std::max<uint32_t>(n_ordered, 2));
-        uint32_t cap2 = 2; while (cap2 < cap) cap2 <<= 1;                 // power of two: the tile sort pads in place
+    if (obin_max > (uint32_t)ORD_SORT_MAX && obin_max > ordered_scratch_cap(ctx, ntiles)) {
+        uint32_t cap2 = 2; while (cap2 < obin_max) cap2 <<= 1;               // power of two: the tile sort pads in place
         CK(ctx->obins.reserve((size_t)ntiles * cap2));
-        CK(cudaMemsetAsync(ctx->otile_count.p, 0, ntiles * sizeof(uint32_t), st));
-        CK(cudaEventRecord(ctx->ev[2], st));
-        launch_bin(L, nullptr, ctx->keys.p, ctx->recs.p, ctx->obins.p, ctx->otile_count.p, ctx->state, p, cap2, true, false);
-        CK(cudaEventRecord(ctx->ev[3], st));
-        launch_fill_ordered(L, ctx->recs.p, ctx->obins.p, ctx->otile_count.p, ctx->keys.p, p.rgb888 ? ctx->tex8desc.p : ctx->texdesc.p,
-                            p.rgb888 ? reinterpret_cast<const uint16_t*>(ctx->texels8.p) : ctx->texels.p,
-                            ctx->fb_rgba.p, ctx->fb_z.p, ctx->state, p, cap2);
-        CK(cudaEventRecord(ctx->ev[4], st));
-        CK(cudaMemcpyAsync(ctx->state_h, ctx->state, sizeof(CallState), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        CK(cudaGetLastError());
-        CallState hs = *ctx->state_h;
-        if (hs.obin_overflow && attempt < 4) {      // a tile bin was too small: the fill was skipped; grow and redo
-            ctx->obin_cap_hint = hs.obin_max;
-            CK(cudaMemsetAsync(&ctx->state->obin_overflow, 0, 2 * sizeof(uint32_t), st));
-            continue;
-        }
-        if (hs.obin_overflow) return fail(ctx, B32_ERR_CUDA, "ordered tile bin overflow persists");
-        break;
+        ctx->obin_cap = cap2; ctx->obin_tiles = ntiles;
     }
-    cudaEventElapsedTime(&ctx->kernel_ms[2], ctx->ev[2], ctx->ev[3]);
+    CK(cudaEventRecord(ctx->ev[3], st));
+    launch_fill_ordered(L, ctx->recs.p, ctx->masks.p, ctx->obins.p, ctx->keys.p, p.rgb888 ? ctx->tex8desc.p : ctx->texdesc.p,
+                        p.rgb888 ? reinterpret_cast<const uint16_t*>(ctx->texels8.p) : ctx->texels.p,
+                        ctx->fb_rgba.p, ctx->fb_z.p, ctx->state, ctx->sticky, p, ordered_scratch_cap(ctx, ntiles));
+    CK(cudaEventRecord(ctx->ev[4], st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
     cudaEventElapsedTime(&ctx->kernel_ms[3], ctx->ev[3], ctx->ev[4]);
     return B32_OK;
 }
@@ -366,17 +348,24 @@ struct FrameArgs {
 // The kernels of one frame on L: Framebuffer::clear (optional), TRANSFORM + CULL + setup + binning, DRAW pass 1.
 // L decides how: direct launches, launches into a capturing stream, or patches of an instantiated graph's nodes.
 // ev_setup / ev_fill (nullable) are recorded in front of the two kernel groups (synchronous calls time them).
-int launch_frame(b32_ctx* ctx, const LaunchCtx& L, const FrameArgs& a, cudaEvent_t ev_setup, cudaEvent_t ev_fill) {
+int launch_frame(b32_ctx* ctx, const LaunchCtx& L, const FrameArgs& a, cudaEvent_t ev_setup, cudaEvent_t ev_fill, cudaEvent_t ev_end = nullptr) {
     const CallParams& p = a.p;
     if (ev_setup) CK(cudaEventRecord(ev_setup, L.stream));
     const bool wire_on = p.wire_back || p.wire_front;
-    launch_setup(L, a.verts, a.faces, nullptr, a.texdesc, ctx->lights.p, ctx->recs.p, ctx->keys.p, ctx->heads.p, ctx->bins.p,
+    launch_setup(L, a.verts, a.faces, nullptr, a.texdesc, ctx->lights.p, ctx->recs.p, ctx->keys.p, ctx->heads.p, ctx->masks.p,
                  ctx->tile_count, wire_on ? ctx->wire.p : nullptr, ctx->state, a.zero_next, ctx->state_stride,
                  ctx->fb_rgba.p, ctx->fb_z.p, a.clear ? ctx->width * ctx->height : 0u, a.clear_color, p);    // the frame's clear rides in k_setup
     if (ev_fill) CK(cudaEventRecord(ev_fill, L.stream));
-    if (!p.wire_front)
-        launch_fill_opaque(L, ctx->recs.p, ctx->bins.p, ctx->tile_count, ctx->heads.p, ctx->bins_sorted.p, a.texdesc, a.texels, a.texmask,
-                           ctx->fb_rgba.p, ctx->fb_z.p, ctx->state, ctx->sticky, p);
+    if (!p.wire_front) {
+        const bool pass1 = !(p.xray_mode && !p.rgb888);     // x-ray: every surface goes through the ordered replay
+        if (pass1)
+            launch_fill_opaque(L, ctx->recs.p, ctx->masks.p, ctx->heads.p, a.texdesc, a.texels, a.texmask,
+                               ctx->fb_rgba.p, ctx->fb_z.p, ctx->state, ctx->sticky, p);
+        if (p.enq_ordered)                                  // enqueue-only frames that may hold pass-2 surfaces: no host round trip
+            launch_fill_ordered(L, ctx->recs.p, ctx->masks.p, ctx->obins.p, ctx->keys.p, a.texdesc, a.texels,
+                                ctx->fb_rgba.p, ctx->fb_z.p, ctx->state, ctx->sticky, p, ordered_scratch_cap(ctx, p.tiles_x * p.tiles_y));
+    }
+    if (ev_end) CK(cudaEventRecord(ev_end, L.stream));
     return B32_OK;
 }
 
@@ -411,6 +400,11 @@ int enqueue_frame(b32_ctx* ctx, const FrameArgs& a, const FrameKey& key) {
     FrameGraph* fg = nullptr;
     Submit mode = pick_submit_mode(ctx, key, fg);
     ctx->async_pending = true;
+    if (ctx->tring_n) {                                    // measurement: plain launches, timed per kernel group
+        cudaEvent_t* e = &ctx->tring[(size_t)(ctx->tring_count % ctx->tring_n) * 3];
+        ++ctx->tring_count;
+        return launch_frame(ctx, L, a, e[0], e[1], e[2]);
+    }
     if (mode == Submit::CAPTURE) {
         if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
             launch_frame(ctx, L, a, nullptr, nullptr);
@@ -430,11 +424,12 @@ int enqueue_frame(b32_ctx* ctx, const FrameArgs& a, const FrameKey& key) {
 
 // One render_mesh_15 / render_mesh (render.rs:2302-2572 / :1971-2259) on device-resident geometry.
 //   wait=true : returns when the frame is in the framebuffer; fills *tm.
-//   wait=false: only enqueues pass 1 (no host round trip); the caller guarantees there is no pass 2.
+//   wait=false: only enqueues (no host round trip).  all_opaque = the caller promises there is no pass 2: the ordered
+//               replay is not even launched; otherwise it is enqueued behind pass 1 and exits at once when it has nothing to do.
 // clear_rgba (nullable): Framebuffer::clear first, as part of the same frame.
 int render_device(b32_ctx* ctx, const b32_vertex* d_verts, uint32_t nv, const b32_face* d_faces, uint32_t nf,
                   const b32_camera* cam, const b32_settings* s, const b32_fog* fog, b32_timings* tm, bool wait, bool rgb888 = false,
-                  const uint8_t* clear_rgba = nullptr) {
+                  const uint8_t* clear_rgba = nullptr, bool all_opaque = false, uint32_t vwords = 9, bool faces_implicit = false) {
     if (!cam || !s) return fail(ctx, B32_ERR_INVALID, "camera/settings is NULL");
     if (ctx->width == 0 || ctx->height == 0) return fail(ctx, B32_ERR_INVALID, "framebuffer has zero size (call b32_fb_resize)");
     FrameArgs a{};
@@ -442,6 +437,7 @@ int render_device(b32_ctx* ctx, const b32_vertex* d_verts, uint32_t nv, const b3
     std::vector<LightDev> lights;
     int rc = fill_params(ctx, p, cam, s, fog, nv, nf, lights, rgb888);
     if (rc != B32_OK) return rc;
+    p.vwords = (uint8_t)vwords; p.faces_implicit = faces_implicit ? 1 : 0;
     if (tm) std::memset(tm, 0, sizeof(*tm));
     a.verts = d_verts; a.faces = d_faces;
     a.texdesc = rgb888 ? ctx->tex8desc.p : ctx->texdesc.p;
@@ -458,45 +454,35 @@ int render_device(b32_ctx* ctx, const b32_vertex* d_verts, uint32_t nv, const b3
         return B32_OK;
     }
 
-    const uint32_t ntiles = p.tiles_x * p.tiles_y;
-    rc = ensure_work(ctx, nv, nf); if (rc) return rc;
+    rc = ensure_work(ctx, p); if (rc) return rc;
     rc = upload_lights(ctx, lights); if (rc) return rc;
     LaunchCtx L = ctx->L();
     cudaStream_t st = ctx->stream;
     CallState hs{};
-    for (int attempt = 0;; ++attempt) {
-        p.bin_cap = pick_bin_cap(ctx, nf, ntiles, !wait);
-        p.async_call = wait ? 0 : 1;
-        CK(ctx->bins.reserve((size_t)ntiles * p.bin_cap));
-        if (p.bin_cap > OP_SORT_MAX_ENTRIES) CK(ctx->bins_sorted.reserve((size_t)ntiles * p.bin_cap));   // else no bin can need it
-        ctx->last_params = p;
-        if (p.wire_back || p.wire_front) CK(ctx->wire.reserve(nf));
-        // take the set the previous call's k_setup zeroed; this call's k_setup zeroes the other one
-        // (nothing between here and the launch can fail, so the two sets never get out of step)
-        ctx->state_cur ^= 1;
-        ctx->state = reinterpret_cast<CallState*>(ctx->state_ring.p + (size_t)ctx->state_cur * ctx->state_stride);
-        ctx->tile_count = ctx->state_ring.p + (size_t)ctx->state_cur * ctx->state_stride + STATE_WORDS;
-        a.zero_next = ctx->state_ring.p + (size_t)(ctx->state_cur ^ 1) * ctx->state_stride;
-        if (!wait) {
-            FrameKey key;
-            key.verts = d_verts; key.faces = d_faces; key.nv = nv; key.nf = nf; key.width = ctx->width; key.height = ctx->height;
-            key.rgb888 = rgb888; key.pass1 = !((p.xray_mode && !rgb888) || p.wire_front); key.clear = a.clear; key.valid = 1;
-            return enqueue_frame(ctx, a, key);
-        }
-        rc = launch_frame(ctx, L, a, ctx->ev[0], ctx->ev[1]); if (rc) return rc;
-        CK(cudaEventRecord(ctx->ev[2], st));
-        CK(cudaMemcpyAsync(ctx->state_h, ctx->state, sizeof(CallState), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        CK(cudaGetLastError());
-        hs = *ctx->state_h;
-        if (hs.oob) return fail(ctx, B32_ERR_OOB_INDEX, "face vertex index out of range (reference: slice index panic)");
-        if (hs.bin_overflow && attempt < 4) {       // a tile bin was too small: nothing was drawn; grow and redo
-            ctx->bin_cap_hint = hs.bin_max + hs.bin_max / 4;
-            continue;
-        }
-        if (hs.bin_overflow) return fail(ctx, B32_ERR_CUDA, "tile bin overflow persists");
-        break;
+    p.async_call = wait ? 0 : 1;
+    p.enq_ordered = (!wait && !all_opaque) ? 1 : 0;
+    ctx->last_params = p;
+    if (p.wire_back || p.wire_front) CK(ctx->wire.reserve(nf));
+    // take the set the previous call's k_setup zeroed; this call's k_setup zeroes the other one
+    // (nothing between here and the launch can fail, so the two sets never get out of step)
+    ctx->state_cur ^= 1;
+    ctx->state = reinterpret_cast<CallState*>(ctx->state_ring.p + (size_t)ctx->state_cur * ctx->state_stride);
+    ctx->tile_count = ctx->state_ring.p + (size_t)ctx->state_cur * ctx->state_stride + STATE_WORDS;
+    a.zero_next = ctx->state_ring.p + (size_t)(ctx->state_cur ^ 1) * ctx->state_stride;
+    if (!wait) {
+        FrameKey key;
+        key.verts = d_verts; key.faces = d_faces; key.nv = nv; key.nf = nf; key.width = ctx->width; key.height = ctx->height;
+        key.rgb888 = rgb888; key.pass1 = !((p.xray_mode && !rgb888) || p.wire_front); key.clear = a.clear; key.valid = 1;
+        key.ordered = p.enq_ordered;
+        return enqueue_frame(ctx, a, key);
     }
+    rc = launch_frame(ctx, L, a, ctx->ev[0], ctx->ev[1]); if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev[2], st));
+    CK(cudaMemcpyAsync(ctx->state_h, ctx->state, sizeof(CallState), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    hs = *ctx->state_h;
+    if (hs.oob) return fail(ctx, B32_ERR_OOB_INDEX, "face vertex index out of range (reference: slice index panic)");
     {   // the reference panics on a NaN key in a sorted slice of length >= 2 (render.rs:2531; RGB888: one list, :2161)
         bool nan_abort = rgb888 ? (!p.use_zbuffer && hs.nan_opaque && hs.n_opaque + hs.n_transp >= 2)
                                 : (hs.nan_transp && hs.n_transp >= 2) || (!p.use_zbuffer && hs.nan_opaque && hs.n_opaque >= 2);
@@ -507,7 +493,7 @@ int render_device(b32_ctx* ctx, const b32_vertex* d_verts, uint32_t nv, const b3
     // RGB888: one surface that may read the framebuffer sends the whole list through the ordered replay (pass 1 was skipped)
     const bool all_ordered = rgb888 ? hs.n_transp > 0 : p.xray_mode != 0;
     bool need_ordered = all_ordered ? (hs.n_opaque + hs.n_transp) > 0 : (!rgb888 && hs.n_transp > 0);
-    if (need_ordered && !p.wire_front) { rc = render_ordered(ctx, p, all_ordered ? hs.n_opaque + hs.n_transp : hs.n_transp); if (rc) return rc; }
+    if (need_ordered && !p.wire_front) { rc = render_ordered(ctx, p, hs.obin_max); if (rc) return rc; }
     bool wire_too_long = false;
     if (p.wire_back || p.wire_front) {          // WIREFRAME phase, render.rs:2574-2635
         uint32_t tsize = 64;
@@ -576,10 +562,11 @@ void b32_ctx_destroy(b32_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     ctx->fb_rgba.release(); ctx->fb_z.release(); ctx->texels.release(); ctx->texmask.release(); ctx->texdesc.release();
     ctx->texels8.release(); ctx->tex8mask.release(); ctx->tex8desc.release(); ctx->verts.release(); ctx->faces.release();
-    ctx->tv.release(); ctx->recs.release(); ctx->keys.release(); ctx->state_ring.release(); ctx->otile_count.release();
-    ctx->bins.release(); ctx->bins_sorted.release(); ctx->heads.release(); ctx->obins.release(); ctx->wire.release(); ctx->wire_table.release();
+    ctx->tv.release(); ctx->recs.release(); ctx->keys.release(); ctx->state_ring.release(); ctx->masks.release();
+    ctx->heads.release(); ctx->obins.release(); ctx->wire.release(); ctx->wire_table.release();
     ctx->lights.release(); ctx->dbg.release(); ctx->lines.release(); ctx->line_scratch.release();
     for (FrameGraph& g : ctx->fgs) g.destroy();
+    for (cudaEvent_t e : ctx->tring) cudaEventDestroy(e);
     if (ctx->sticky) cudaFree(ctx->sticky);
     if (ctx->state_h) cudaFreeHost(ctx->state_h);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -606,7 +593,8 @@ static int collect_async(b32_ctx* ctx) {
     if (sticky & 1u) return fail(ctx, B32_ERR_OOB_INDEX, "an enqueued call had a face vertex index out of range");
     if (sticky & 2u) return fail(ctx, B32_ERR_NAN_DEPTH, "an enqueued call had a NaN depth key in a sorted pass");
     if (sticky & 8u) return fail(ctx, B32_ERR_INVALID, "an enqueued call had semi-transparent surfaces (pass 2 was not drawn): B32_RENDER_ALL_OPAQUE was wrong");
-    return fail(ctx, B32_ERR_CUDA, "an enqueued call overflowed its tile bins");
+    return fail(ctx, B32_ERR_UNSUPPORTED, "an enqueued call had a tile with more semi-transparent surfaces than fit shared memory (pass 2 was not drawn): "
+                                          "make one blocking call with this mesh first (it sizes the scratch)");
 }
 
 int b32_sync(b32_ctx* ctx) {
@@ -773,7 +761,7 @@ int b32_render_mesh(b32_ctx* ctx, const b32_vertex* vertices, uint32_t nv, const
     USE_DEVICE(ctx);
     if (!ctx) return B32_ERR_INVALID;
     if ((nv && !vertices) || (nf && !faces)) return fail(ctx, B32_ERR_INVALID, "vertices/faces is NULL");
-    CK(ctx->verts.reserve(std::max<uint32_t>(nv, 1)));
+    CK(ctx->verts.reserve((size_t)std::max<uint32_t>(nv, 1) + 1));      // + 1: k_setup's staged window may overrun by < 16 bytes
     CK(ctx->faces.reserve(std::max<uint32_t>(nf, 1)));
     int rc = h2d(ctx, ctx->verts.p, vertices, (size_t)nv * sizeof(b32_vertex)); if (rc) return rc;
     rc = h2d(ctx, ctx->faces.p, faces, (size_t)nf * sizeof(b32_face)); if (rc) return rc;
@@ -791,42 +779,47 @@ int b32_render_mesh_15(b32_ctx* ctx, const b32_vertex* vertices, uint32_t nv, co
     USE_DEVICE(ctx);
     if (!ctx) return B32_ERR_INVALID;
     if ((nv && !vertices) || (nf && !faces)) return fail(ctx, B32_ERR_INVALID, "vertices/faces is NULL");
-    CK(ctx->verts.reserve(std::max<uint32_t>(nv, 1)));
+    CK(ctx->verts.reserve((size_t)std::max<uint32_t>(nv, 1) + 1));      // + 1: k_setup's staged window may overrun by < 16 bytes
     CK(ctx->faces.reserve(std::max<uint32_t>(nf, 1)));
     int rc = h2d(ctx, ctx->verts.p, vertices, (size_t)nv * sizeof(b32_vertex)); if (rc) return rc;
     rc = h2d(ctx, ctx->faces.p, faces, (size_t)nf * sizeof(b32_face)); if (rc) return rc;
     return render_device(ctx, ctx->verts.p, nv, ctx->faces.p, nf, camera, settings, fog, timings, true);
 }
 
-int b32_render_mesh_15_ex(b32_ctx* ctx, const b32_vertex* vertices, uint32_t nv, const b32_face* faces, uint32_t nf,
+int b32_render_mesh_15_ex(b32_ctx* ctx, const void* vertices, uint32_t nv, const void* faces, uint32_t nf,
                           const b32_camera* camera, const b32_settings* settings, const b32_fog* fog, uint32_t flags, b32_timings* timings) {
     USE_DEVICE(ctx);
     if (!ctx) return B32_ERR_INVALID;
-    if (!(flags & B32_RENDER_ASYNC)) return b32_render_mesh_15(ctx, vertices, nv, faces, nf, camera, settings, fog, timings);
-    if (!(flags & B32_RENDER_ALL_OPAQUE)) return fail(ctx, B32_ERR_INVALID, "B32_RENDER_ASYNC needs B32_RENDER_ALL_OPAQUE (pass 2 needs a host round trip)");
     if ((nv && !vertices) || (nf && !faces) || !settings) return fail(ctx, B32_ERR_INVALID, "vertices/faces/settings is NULL");
-    if (settings->xray_mode) return fail(ctx, B32_ERR_INVALID, "x-ray mode cannot be enqueued");
-    if ((settings->backface_cull && settings->backface_wireframe) || settings->wireframe_overlay)
-        return fail(ctx, B32_ERR_INVALID, "the wireframe phase cannot be enqueued");
-    for (const TexDev& t : ctx->texdesc_h) if (t.blend != B32_BLEND_OPAQUE) return fail(ctx, B32_ERR_INVALID, "a bound texture has a blend mode: cannot be enqueued");
-    uint32_t ntiles = ((ctx->width + TILE_W - 1) / TILE_W) * ((ctx->height + TILE_H - 1) / TILE_H);
-    if ((size_t)ntiles * nf * sizeof(BinHead) > ((size_t)4 << 30)) return fail(ctx, B32_ERR_UNSUPPORTED, "mesh too large to enqueue without a host round trip");
-    CK(ctx->verts.reserve(std::max<uint32_t>(nv, 1)));
-    CK(ctx->faces.reserve(std::max<uint32_t>(nf, 1)));
-    int rc = h2d(ctx, ctx->verts.p, vertices, (size_t)nv * sizeof(b32_vertex)); if (rc) return rc;
-    rc = h2d(ctx, ctx->faces.p, faces, (size_t)nf * sizeof(b32_face)); if (rc) return rc;
-    return render_device(ctx, ctx->verts.p, nv, ctx->faces.p, nf, camera, settings, fog, nullptr, false);
+    const bool async = (flags & B32_RENDER_ASYNC) != 0, no_normal = (flags & B32_VTX_NO_NORMAL) != 0, implicit = (flags & B32_FACES_IMPLICIT) != 0;
+    if (no_normal && settings->shading != B32_SHADE_NONE) return fail(ctx, B32_ERR_INVALID, "B32_VTX_NO_NORMAL needs settings.shading == None");
+    if (implicit && (uint64_t)nv < 3ull * nf) return fail(ctx, B32_ERR_OOB_INDEX, "B32_FACES_IMPLICIT: fewer than 3 * nf vertices");
+    const bool wire = (settings->backface_cull && settings->backface_wireframe) || settings->wireframe_overlay;
+    if (async && wire) return fail(ctx, B32_ERR_INVALID, "the wireframe phase cannot be enqueued");
+    bool all_opaque = async && (flags & B32_RENDER_ALL_OPAQUE) != 0;
+    if (all_opaque) {          // the promise is checked where that is free: settings and bound textures
+        if (settings->xray_mode) return fail(ctx, B32_ERR_INVALID, "B32_RENDER_ALL_OPAQUE with x-ray mode");
+        for (const TexDev& t : ctx->texdesc_h) if (t.blend != B32_BLEND_OPAQUE) return fail(ctx, B32_ERR_INVALID, "B32_RENDER_ALL_OPAQUE with a bound texture that has a blend mode");
+    }
+    const size_t vbytes = no_normal ? sizeof(b32_vertex_nn) : sizeof(b32_vertex), fbytes = implicit ? sizeof(uint32_t) : sizeof(b32_face);
+    // staging buffers are sized in b32_vertex / b32_face units; + 1 vertex: k_setup's staged window may overrun by < 16 bytes
+    CK(ctx->verts.reserve(((size_t)nv * vbytes + sizeof(b32_vertex) - 1) / sizeof(b32_vertex) + 1));
+    CK(ctx->faces.reserve(std::max<size_t>(((size_t)nf * fbytes + sizeof(b32_face) - 1) / sizeof(b32_face), 1)));
+    int rc = h2d(ctx, ctx->verts.p, vertices, (size_t)nv * vbytes); if (rc) return rc;
+    rc = h2d(ctx, ctx->faces.p, faces, (size_t)nf * fbytes); if (rc) return rc;
+    return render_device(ctx, ctx->verts.p, nv, ctx->faces.p, nf, camera, settings, fog, async ? nullptr : timings, !async, false, nullptr, all_opaque,
+                         no_normal ? 6 : 9, implicit);
 }
 
 int b32_frame_15_enqueue(b32_ctx* ctx, const uint8_t* clear_rgba, const b32_mesh* mesh, const b32_camera* camera,
                          const b32_settings* settings, const b32_fog* fog) {
     USE_DEVICE(ctx);
     if (!ctx || !mesh || !settings) return B32_ERR_INVALID;
-    bool may_blend = mesh->has_nonopaque || settings->xray_mode || (settings->backface_cull && settings->backface_wireframe) || settings->wireframe_overlay;
+    // only the wireframe phase needs the host (status read-back between its kernels): such a frame is rendered synchronously
+    bool wire = (settings->backface_cull && settings->backface_wireframe) || settings->wireframe_overlay;
+    bool may_blend = mesh->has_nonopaque || settings->xray_mode;
     for (const TexDev& t : ctx->texdesc_h) may_blend = may_blend || t.blend != B32_BLEND_OPAQUE;
-    uint32_t ntiles = ((ctx->width + TILE_W - 1) / TILE_W) * ((ctx->height + TILE_H - 1) / TILE_H);
-    bool bins_fit = (size_t)ntiles * mesh->nf * sizeof(BinHead) <= ((size_t)4 << 30);
-    return render_device(ctx, mesh->verts, mesh->nv, mesh->faces, mesh->nf, camera, settings, fog, nullptr, may_blend || !bins_fit, false, clear_rgba);
+    return render_device(ctx, mesh->verts, mesh->nv, mesh->faces, mesh->nf, camera, settings, fog, nullptr, wire, false, clear_rgba, !may_blend);
 }
 
 uint64_t b32_graph_launches(const b32_ctx* ctx) { return ctx ? ctx->graph_launches : 0; }
@@ -850,7 +843,7 @@ int b32_mesh_upload(b32_ctx* ctx, const b32_vertex* vertices, uint32_t nv, const
         uint32_t fl = faces[i].flags;
         if (((fl >> 16) & 7u) != B32_BLEND_OPAQUE || (fl >> 24) != 255u) { m->has_nonopaque = true; break; }
     }
-    cudaError_t e = cudaMalloc(&m->verts, std::max<size_t>((size_t)nv * sizeof(b32_vertex), 16));
+    cudaError_t e = cudaMalloc(&m->verts, (size_t)nv * sizeof(b32_vertex) + 16);      // + 16: k_setup's staged window may overrun by < 16 bytes
     if (e == cudaSuccess) e = cudaMalloc(&m->faces, std::max<size_t>((size_t)nf * sizeof(b32_face), 16));
     if (e != cudaSuccess) { if (m->verts) cudaFree(m->verts); delete m; return cuda_fail(ctx, e, "cudaMalloc(mesh)"); }
     int rc = h2d(ctx, m->verts, vertices, (size_t)nv * sizeof(b32_vertex));
@@ -879,13 +872,12 @@ int b32_render_mesh_15_resident(b32_ctx* ctx, const b32_mesh* mesh, const b32_ca
 int b32_render_mesh_15_enqueue(b32_ctx* ctx, const b32_mesh* mesh, const b32_camera* camera, const b32_settings* settings, const b32_fog* fog) {
     USE_DEVICE(ctx);
     if (!ctx || !mesh || !settings) return B32_ERR_INVALID;
-    // Pass 1 needs no host round trip.  Pass 2 (any semi-transparent surface) and x-ray mode do, so a
-    // mesh/texture set that can produce them is rendered synchronously instead.
-    bool may_blend = mesh->has_nonopaque || settings->xray_mode || (settings->backface_cull && settings->backface_wireframe) || settings->wireframe_overlay;
+    // Neither pass needs a host round trip: a mesh / texture set that can produce pass-2 surfaces (or x-ray mode) has the
+    // ordered replay enqueued behind pass 1.  Only the wireframe phase is rendered synchronously.
+    bool wire = (settings->backface_cull && settings->backface_wireframe) || settings->wireframe_overlay;
+    bool may_blend = mesh->has_nonopaque || settings->xray_mode;
     for (const TexDev& t : ctx->texdesc_h) may_blend = may_blend || t.blend != B32_BLEND_OPAQUE;
-    uint32_t ntiles = ((ctx->width + TILE_W - 1) / TILE_W) * ((ctx->height + TILE_H - 1) / TILE_H);
-    bool bins_fit = (size_t)ntiles * mesh->nf * sizeof(BinHead) <= ((size_t)4 << 30);   // worst-case bins (no overflow possible)
-    return render_device(ctx, mesh->verts, mesh->nv, mesh->faces, mesh->nf, camera, settings, fog, nullptr, may_blend || !bins_fit);
+    return render_device(ctx, mesh->verts, mesh->nv, mesh->faces, mesh->nf, camera, settings, fog, nullptr, wire, false, nullptr, !may_blend);
 }
 
 int b32_render_mesh_placed(b32_ctx* ctx, const b32_mesh* mesh, const b32_placement* pl, const b32_camera* camera, const b32_settings* settings,
@@ -898,19 +890,20 @@ int b32_render_mesh_placed(b32_ctx* ctx, const b32_mesh* mesh, const b32_placeme
     const b32_vertex* verts = mesh->verts;
     if (has_transform && mesh->nv) {
         // the placed copy lives in the host-call staging buffer: stream order keeps it alive until this call's kernels ran
-        CK(ctx->verts.reserve(mesh->nv));
+        CK(ctx->verts.reserve((size_t)mesh->nv + 1));
         launch_place(ctx->L(), mesh->verts, ctx->verts.p, mesh->nv, pl->cos_f, pl->sin_f, pl->world_pos);
         verts = ctx->verts.p;
     }
     bool wait = !(flags & B32_RENDER_ASYNC);
-    if (!wait) {          // same rule as b32_render_mesh_15_enqueue: only calls that cannot blend stay enqueue-only
-        bool may_blend = rgb888 || mesh->has_nonopaque || settings->xray_mode || (settings->backface_cull && settings->backface_wireframe) || settings->wireframe_overlay;
+    bool all_opaque = false;
+    if (!wait) {          // same rule as b32_render_mesh_15_enqueue
+        wait = (settings->backface_cull && settings->backface_wireframe) || settings->wireframe_overlay;
+        bool may_blend = rgb888 || mesh->has_nonopaque || settings->xray_mode;
         for (const TexDev& t : ctx->texdesc_h) may_blend = may_blend || t.blend != B32_BLEND_OPAQUE;
-        uint32_t ntiles = ((ctx->width + TILE_W - 1) / TILE_W) * ((ctx->height + TILE_H - 1) / TILE_H);
-        wait = may_blend || (size_t)ntiles * mesh->nf * sizeof(BinHead) > ((size_t)4 << 30);
+        all_opaque = !may_blend;
     }
     return render_device(ctx, verts, mesh->nv, mesh->faces, mesh->nf, camera, settings, rgb888 ? nullptr : fog,
-                         (flags & B32_RENDER_ASYNC) ? nullptr : timings, wait, rgb888 != 0);
+                         (flags & B32_RENDER_ASYNC) ? nullptr : timings, wait, rgb888 != 0, nullptr, all_opaque);
 }
 
 int b32_render_skybox_mesh(b32_ctx* ctx, const b32_sky_vertex* vertices, uint32_t nv, const uint32_t* faces, uint32_t nf, const b32_camera* camera) {
@@ -922,54 +915,34 @@ int b32_render_skybox_mesh(b32_ctx* ctx, const b32_sky_vertex* vertices, uint32_
     b32_settings s{};                     // project(): the float path, no ortho (render.rs:89, :107)
     CallParams p; std::vector<LightDev> lights;
     int rc = fill_params(ctx, p, camera, &s, nullptr, nv, nf, lights); if (rc) return rc;
-    rc = ensure_work(ctx, nv, nf); if (rc) return rc;
+    rc = ensure_work(ctx, p); if (rc) return rc;
     // the sky mesh reuses the mesh staging and record buffers (a SkyRec is smaller than a SurfRec)
     static_assert(sizeof(SkyRec) <= sizeof(SurfRec) && sizeof(b32_sky_vertex) <= sizeof(b32_vertex), "staging reuse");
-    CK(ctx->verts.reserve(std::max<uint32_t>(nv, 1)));
+    CK(ctx->verts.reserve((size_t)std::max<uint32_t>(nv, 1) + 1));      // + 1: k_setup's staged window may overrun by < 16 bytes
     CK(ctx->faces.reserve(std::max<uint32_t>(nf, 1)));      // 3 x u32 per face fits the 16-byte b32_face slots
-    const uint32_t ntiles = p.tiles_x * p.tiles_y;
     cudaStream_t st = ctx->stream;
-    // The usual sky (a few thousand faces): indices are checked here and the bins get worst-case capacity, so nothing
-    // can fail on the device and the pass is only enqueued — no wait, no status read-back.
-    const bool enqueue_only = (size_t)ntiles * nf * sizeof(BinHead) <= ((size_t)256 << 20);
+    // The usual sky (a few thousand faces): indices are checked here, so nothing can fail on the device and the pass is
+    // only enqueued — no wait, no status read-back.  Larger ones are checked on the device and waited for.
+    const bool enqueue_only = nf <= 65536;
     if (enqueue_only) {
         for (uint32_t i = 0; i < nf * 3; ++i)
             if (faces[i] >= nv) return fail(ctx, B32_ERR_OOB_INDEX, "skybox face vertex index out of range (reference: slice index panic)");
     }
     rc = h2d(ctx, ctx->verts.p, vertices, (size_t)nv * sizeof(b32_sky_vertex), enqueue_only); if (rc) return rc;
     rc = h2d(ctx, ctx->faces.p, faces, (size_t)nf * 12, enqueue_only); if (rc) return rc;
-    if (enqueue_only) {
-        p.bin_cap = nf;
-        CK(ctx->bins.reserve((size_t)ntiles * p.bin_cap));
-        ctx->state_cur ^= 1;
-        ctx->state = reinterpret_cast<CallState*>(ctx->state_ring.p + (size_t)ctx->state_cur * ctx->state_stride);
-        ctx->tile_count = ctx->state_ring.p + (size_t)ctx->state_cur * ctx->state_stride + STATE_WORDS;
-        uint32_t* zero_next = ctx->state_ring.p + (size_t)(ctx->state_cur ^ 1) * ctx->state_stride;
-        launch_sky(ctx->L(), reinterpret_cast<const b32_sky_vertex*>(ctx->verts.p), reinterpret_cast<const uint32_t*>(ctx->faces.p),
-                   reinterpret_cast<SkyRec*>(ctx->recs.p), ctx->heads.p, ctx->bins.p, ctx->tile_count, ctx->fb_rgba.p, ctx->state,
-                   zero_next, ctx->state_stride, p);
-        CK(cudaGetLastError());
-        return B32_OK;
-    }
-    for (int attempt = 0;; ++attempt) {
-        p.bin_cap = pick_bin_cap(ctx, nf, ntiles, false);
-        CK(ctx->bins.reserve((size_t)ntiles * p.bin_cap));
-        ctx->state_cur ^= 1;
-        ctx->state = reinterpret_cast<CallState*>(ctx->state_ring.p + (size_t)ctx->state_cur * ctx->state_stride);
-        ctx->tile_count = ctx->state_ring.p + (size_t)ctx->state_cur * ctx->state_stride + STATE_WORDS;
-        uint32_t* zero_next = ctx->state_ring.p + (size_t)(ctx->state_cur ^ 1) * ctx->state_stride;
-        launch_sky(ctx->L(), reinterpret_cast<const b32_sky_vertex*>(ctx->verts.p), reinterpret_cast<const uint32_t*>(ctx->faces.p),
-                   reinterpret_cast<SkyRec*>(ctx->recs.p), ctx->heads.p, ctx->bins.p, ctx->tile_count, ctx->fb_rgba.p, ctx->state,
-                   zero_next, ctx->state_stride, p);
-        CK(cudaMemcpyAsync(ctx->state_h, ctx->state, sizeof(CallState), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        CK(cudaGetLastError());
-        CallState hs = *ctx->state_h;
-        if (hs.oob) return fail(ctx, B32_ERR_OOB_INDEX, "skybox face vertex index out of range (reference: slice index panic)");
-        if (hs.bin_overflow && attempt < 4) { ctx->bin_cap_hint = hs.bin_max + hs.bin_max / 4; continue; }
-        if (hs.bin_overflow) return fail(ctx, B32_ERR_CUDA, "tile bin overflow persists");
-        break;
-    }
+    ctx->state_cur ^= 1;
+    ctx->state = reinterpret_cast<CallState*>(ctx->state_ring.p + (size_t)ctx->state_cur * ctx->state_stride);
+    ctx->tile_count = ctx->state_ring.p + (size_t)ctx->state_cur * ctx->state_stride + STATE_WORDS;
+    uint32_t* zero_next = ctx->state_ring.p + (size_t)(ctx->state_cur ^ 1) * ctx->state_stride;
+    launch_sky(ctx->L(), reinterpret_cast<const b32_sky_vertex*>(ctx->verts.p), reinterpret_cast<const uint32_t*>(ctx->faces.p),
+               reinterpret_cast<SkyRec*>(ctx->recs.p), ctx->heads.p, ctx->masks.p, ctx->fb_rgba.p, ctx->state,
+               zero_next, ctx->state_stride, p);
+    CK(cudaGetLastError());
+    if (enqueue_only) return B32_OK;
+    CK(cudaMemcpyAsync(ctx->state_h, ctx->state, sizeof(CallState), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    if (ctx->state_h->oob) return fail(ctx, B32_ERR_OOB_INDEX, "skybox face vertex index out of range (reference: slice index panic)");
     return B32_OK;
 }
 
@@ -1070,6 +1043,31 @@ int b32_debug_transform(b32_ctx* ctx, const b32_vertex* vertices, uint32_t nv, c
     CK(cudaStreamSynchronize(ctx->stream));
     for (uint32_t i = 0; i < nv; ++i) { out_screen[i * 3] = tv[i].x; out_screen[i * 3 + 1] = tv[i].y; out_screen[i * 3 + 2] = tv[i].z; }
     return B32_OK;
+}
+
+// Measurement aid: with n > 0 the next enqueued frames of this context are launched plainly (no CUDA graph) with events in
+// front of k_setup, in front of the fill kernel(s) and behind them, n frames deep; n = 0 switches it off.
+int b32_debug_timing_ring(b32_ctx* ctx, uint32_t n) {
+    USE_DEVICE(ctx);
+    if (!ctx) return B32_ERR_INVALID;
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (cudaEvent_t e : ctx->tring) cudaEventDestroy(e);
+    ctx->tring.clear(); ctx->tring_n = 0; ctx->tring_count = 0;
+    for (uint32_t i = 0; i < 3 * n; ++i) { cudaEvent_t e; CK(cudaEventCreate(&e)); ctx->tring.push_back(e); }
+    ctx->tring_n = n;
+    return B32_OK;
+}
+// Device times of the timed frames (after a sync): setup_ms[i], fill_ms[i] for the last min(frames, n) frames. Returns their number.
+int b32_debug_timing_read(b32_ctx* ctx, float* setup_ms, float* fill_ms, uint32_t cap) {
+    if (!ctx || !ctx->tring_n) return 0;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    uint32_t n = std::min<uint32_t>(std::min<uint32_t>(ctx->tring_count, ctx->tring_n), cap);
+    for (uint32_t i = 0; i < n; ++i) {
+        cudaEvent_t* e = &ctx->tring[(size_t)i * 3];
+        if (cudaEventElapsedTime(&setup_ms[i], e[0], e[1]) != cudaSuccess || cudaEventElapsedTime(&fill_ms[i], e[1], e[2]) != cudaSuccess) { cudaGetLastError(); return (int)i; }
+    }
+    return (int)n;
 }
 
 int b32_debug_kernel_times(b32_ctx* ctx, float* out_ms, uint32_t cap) {

@@ -18,7 +18,10 @@ constexpr int TILE_H = 16;
 constexpr int FILL_THREADS = TILE_W * TILE_H;
 constexpr float NEAR_PLANE = 0.1f;    // math.rs:155
 constexpr uint32_t WIRE_MAX_STEPS = 1u << 24;   // longest Bresenham walk k_wire performs (the reference walks every step, on or off screen)
-constexpr int OP_SORT_MAX_ENTRIES = 1024;  // k_fill_opaque orders a tile's bin in shared memory up to this many entries, in a global scratch beyond
+constexpr int OP_SORT_MAX_ENTRIES = 1024;  // k_fill_opaque orders a tile's candidates in shared memory this many at a time (a window)
+constexpr int ORD_SORT_MAX = 2048;         // draw-order entries k_fill_ordered sorts in shared memory (32 KB); tiles with more use a slice of a global scratch
+constexpr int SETUP_GROUP = 128;           // faces per k_setup CTA pass = bits of one tile-mask entry (uint4)
+constexpr uint32_t MASK_TILES_MAX = 2048;  // mask tiles per frame (k_setup keeps one uint4 per mask tile in shared memory: 32 KB)
 constexpr int OP_MASK_SMEM_WORDS = 2048;   // k_fill_opaque keeps the "texel writes" mask in shared memory up to 65536 texels (8 KB)
 
 // ---- per-vertex output of k_transform (render.rs:2321-2360) ------------------------------------
@@ -64,7 +67,15 @@ enum : uint32_t {
     SF_TRANSPARENT  = 1u << 7,    // has_transparency: drawn in pass 2 with skip_z_write (:2561-2569)
 };
 
-// 16-byte bin entry of the unordered (opaque) pass: what a warp needs to reject a surface without
+// Binning without bins.  k_setup handles SETUP_GROUP consecutive faces per CTA pass ("group") and writes, for every
+// mask tile of the screen, ONE uint4 = 128 bits: bit i set iff face group*128 + i is drawn and its bounding box touches the
+// tile.  Layout masks[mask_tile][group].  A fill CTA reads its tile's row (n_groups x 16 contiguous bytes), and the set
+// bits ARE its surface list, in face order — no atomics, no per-tile capacity, no overflow, deterministic.  A mask tile is
+// (16 << mshift) pixels square: mshift grows with the frame so that the row count stays <= MASK_TILES_MAX and the
+// table <= MASK_BYTES_MAX; with mshift > 0 a fill CTA drops the candidates whose bounding box misses its own 16x16 tile.
+constexpr size_t MASK_BYTES_MAX = (size_t)64 << 20;
+
+// 16-byte per-face record next to the SurfRec: what a warp needs to reject a surface without
 // touching its 128-byte record.
 struct __align__(16) BinHead {
     uint32_t bbox_x, bbox_y;              // as in SurfRec
@@ -96,11 +107,10 @@ struct CallState {
     uint32_t n_opaque, n_transp;          // drawn surfaces per pass
     uint32_t nan_opaque, nan_transp;      // a NaN sort key was seen in the pass
     uint32_t oob;                         // a face index >= nv was seen
-    uint32_t obin_overflow;               // ordered pass: a tile bin exceeded its capacity (fill skipped, host grows + retries)
-    uint32_t obin_max;                    // ordered pass: largest tile count seen
+    uint32_t obin_overflow;               // ordered pass: a tile has more draw-order entries than its scratch slice (tile skipped, host grows + retries)
+    uint32_t obin_max;                    // ordered pass: largest such count seen
     uint32_t wire_too_long;               // wireframe phase: an edge longer than WIRE_MAX_STEPS was skipped (host reports B32_ERR_UNSUPPORTED)
-    uint32_t bin_overflow;                // opaque pass: a tile bin exceeded its capacity (fill skipped, host grows + retries)
-    uint32_t bin_max;                     // opaque pass: largest tile count seen
+    uint32_t _unused0, _unused1;
 };
 
 // The reference panics (and draws nothing) on an out-of-range vertex index, or when a NaN key is
@@ -122,13 +132,15 @@ struct CallParams {
     int32_t viewport_scale, half_w, half_h;           // fixed.rs:398-400
     uint32_t width, height, tiles_x, tiles_y;
     uint32_t nv, nf, ntex, n_lights;
-    uint32_t bin_cap;                                 // capacity (entries) of one tile bin of the opaque pass
+    uint32_t n_groups;                                // ceil(nf / SETUP_GROUP): entries per row of the tile-mask table
+    uint32_t mshift, mtiles_x, mtiles_y;              // mask tile = (16 << mshift) px square; mask tiles per row / column
     uint32_t mask_smem_words;                         // words of the "texel writes" mask to stage in shared memory (0: read it from global)
     uint8_t affine_textures, use_zbuffer, shading, backface_cull, dithering, use_fixed_point, xray_mode, ortho;
     uint8_t fog_enabled, fog_r, fog_g, fog_b, fog_blend, async_call, wire_back, wire_front;   // wire_*: render.rs:2576, :2606
     uint8_t rgb888;                                   // 1: render_mesh / rasterize_triangle (render.rs:1971-2259, 1202-1433)
-    uint8_t scan_heads;                               // 1: no k_bin_opaque for pass 1; k_fill_opaque scans k_setup's bin heads (nf <= OP_SORT_MAX_ENTRIES)
-    uint8_t _padb[2];
+    uint8_t enq_ordered;                              // 1: the ordered pass is enqueued behind pass 1 without a host round trip (k_fill_ordered exits early when it has nothing to do)
+    uint8_t vwords;                                   // words per vertex record: 9 (b32_vertex) or 6 (b32_vertex_nn: no normal; only with shading None)
+    uint8_t faces_implicit;                           // 1: `faces` holds one flags word per face; face i uses vertices 3i, 3i+1, 3i+2
     float ambient, ortho_zoom, ortho_cx, ortho_cy;
     float fog_start, fog_falloff, fog_cull;
 };
@@ -159,22 +171,24 @@ __device__ __forceinline__ uint32_t unr_entry(uint32_t i) {
     return v > 0 ? (uint32_t)v : 0u;
 }
 
-// UNR reciprocal of a non-zero divisor (fixed.rs:183-205): returns nr2 and the final shift.
-__device__ __forceinline__ void unr_recip(int32_t divisor, uint64_t* nr2, uint32_t* shift) {
+// UNR reciprocal of a non-zero divisor (fixed.rs:183-205): returns nr2 and the final shift.  Every intermediate of the
+// reference's u64 arithmetic fits 32 bits (d16 <= 0xFFFF, u <= 0x200: d16 * u < 2^25; nr1 < 2^18: nr1 * u < 2^27), so
+// 32-bit arithmetic gives the same values.
+__device__ __forceinline__ void unr_recip(int32_t divisor, uint32_t* nr2, uint32_t* shift) {
     uint32_t den = divisor < 0 ? 0u - (uint32_t)divisor : (uint32_t)divisor;
     uint32_t z = __clz(den);
-    uint64_t d16 = ((uint64_t)den << z) >> 16;                    // 0x8000..0xFFFF
-    uint32_t idx = min((uint32_t)((d16 - 0x7FC0ull) >> 7), 256u);
-    uint64_t u = (uint64_t)unr_entry(idx) + 0x101;
-    uint64_t nr1 = (0x2000080ull - d16 * u) >> 8;
-    *nr2 = (0x80ull + nr1 * u) >> 8;
+    uint32_t d16 = (den << z) >> 16;                              // 0x8000..0xFFFF
+    uint32_t idx = min((d16 - 0x7FC0u) >> 7, 256u);
+    uint32_t u = unr_entry(idx) + 0x101u;
+    uint32_t nr1 = (0x2000080u - d16 * u) >> 8;
+    *nr2 = (0x80u + nr1 * u) >> 8;
     *shift = 36u - z;
 }
-// fixed.rs:207-230 given the reciprocal
-__device__ __forceinline__ int32_t unr_apply(int32_t num, int32_t divisor, uint64_t nr2, uint32_t shift) {
+// fixed.rs:207-230 given the reciprocal: |num| * nr2 is one 32x32 -> 64-bit multiply
+__device__ __forceinline__ int32_t unr_apply(int32_t num, int32_t divisor, uint32_t nr2, uint32_t shift) {
     bool neg = (num < 0) != (divisor < 0);
-    uint64_t n = num < 0 ? (uint64_t)(0u - (uint32_t)num) : (uint64_t)(uint32_t)num;
-    uint64_t raw = n * nr2;
+    uint32_t n = num < 0 ? 0u - (uint32_t)num : (uint32_t)num;
+    uint64_t raw = (uint64_t)n * nr2;
     uint64_t mag = (raw + (1ull << (shift - 1))) >> shift;       // shift in 5..36
     int32_t c = (int32_t)min((unsigned long long)mag, 0x7FFFFFFFull);
     return neg ? -c : c;

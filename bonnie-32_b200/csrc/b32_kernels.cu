@@ -70,7 +70,7 @@ __device__ __forceinline__ TVert transform_vertex(float px, float py, float pz, 
         if (adenom < 256) {                              // fixed.rs:406-408
             isx = p.half_w >> 12; isy = p.half_h >> 12;
         } else {
-            uint64_t nr2; uint32_t shift;
+            uint32_t nr2, shift;
             unr_recip(denom, &nr2, &shift);              // one reciprocal serves x and y
             int32_t proj_x = unr_apply(fx_mul(fcx, scale), denom, nr2, shift);
             int32_t proj_y = unr_apply(fx_mul(fcy, scale), denom, nr2, shift);
@@ -103,6 +103,30 @@ k_transform(const b32_vertex* __restrict__ verts, TVert* __restrict__ out, float
         out[i] = t;
         if (dbg_cam) { dbg_cam[i * 3] = cxy[0]; dbg_cam[i * 3 + 1] = cxy[1]; dbg_cam[i * 3 + 2] = t.w; }
     }
+}
+
+// ---- asynchronous copies ----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
 }
 
 // =================================================================================================
@@ -168,16 +192,17 @@ __device__ __forceinline__ bool is_integral(float x) { return truncf(x) == x; }
 #endif
 constexpr int SETUP_THREADS = B32_SETUP_THREADS;
 
-__device__ __forceinline__ void setup_face(uint32_t fi, const b32_vertex* __restrict__ verts, const b32_face* __restrict__ faces,
+template <bool STAGED>
+__device__ __forceinline__ void setup_face(uint32_t fi, const uint4& fc, const float* __restrict__ gverts, const float* __restrict__ s_vert, uint32_t lo,
                                            const TVert* __restrict__ tv, const TexDev* __restrict__ tex,
                                            const LightDev* __restrict__ lights,
                                            SurfRec* __restrict__ recs, uint64_t* __restrict__ keys,
                                            CallState* __restrict__ st, const CallParams& p,
                                            uint32_t& n_op, uint32_t& n_tr, BinHead& head, bool& binned,
+                                           bool& marked, uint32_t& mbx, uint32_t& mby,
                                            WireTri* __restrict__ wire) {
     binned = false;
     if (wire) wire[fi].kind = 0;
-    uint4 fc = *reinterpret_cast<const uint4*>(faces + fi);
     uint32_t cls = 2;                 // 0 opaque pass, 1 transparent pass, 2 not drawn
     uint32_t dkey = 0;
     do {
@@ -188,9 +213,12 @@ __device__ __forceinline__ void setup_face(uint32_t fi, const b32_vertex* __rest
         uint32_t tex_blend = 0;
         if (textured) tex_blend = tex[tex_id].blend;
 
-        const float* v0 = reinterpret_cast<const float*>(verts + fc.x);
-        const float* v1 = reinterpret_cast<const float*>(verts + fc.y);
-        const float* v2 = reinterpret_cast<const float*>(verts + fc.z);
+        // vertex records of p.vwords words (9 = b32_vertex, 6 = b32_vertex_nn without the normal); staged groups read them
+        // from the shared-memory window [lo, lo + SETUP_WIN)
+        const uint32_t vw = p.vwords, cw = vw - 1;                             // the colour is the last word
+        const float* v0 = STAGED ? s_vert + (fc.x - lo) * vw : gverts + (size_t)fc.x * vw;
+        const float* v1 = STAGED ? s_vert + (fc.y - lo) * vw : gverts + (size_t)fc.y * vw;
+        const float* v2 = STAGED ? s_vert + (fc.z - lo) * vw : gverts + (size_t)fc.z * vw;
         TVert t1, t2, t3;
         if (tv) { t1 = tv[fc.x]; t2 = tv[fc.y]; t3 = tv[fc.z]; }
         else {
@@ -224,7 +252,7 @@ __device__ __forceinline__ void setup_face(uint32_t fi, const b32_vertex* __rest
         const float* va = v0;
         const float* vb = backface ? v2 : v1;
         const float* vc = backface ? v1 : v2;
-        uint32_t c1 = reinterpret_cast<const uint32_t*>(va)[8], c2 = reinterpret_cast<const uint32_t*>(vb)[8], c3 = reinterpret_cast<const uint32_t*>(vc)[8];
+        uint32_t c1 = reinterpret_cast<const uint32_t*>(va)[cw], c2 = reinterpret_cast<const uint32_t*>(vb)[cw], c3 = reinterpret_cast<const uint32_t*>(vc)[cw];
         if (p.fog_enabled) {                                                  // :2427-2436 (cam z of the same vertex)
             c1 = fog_color(c1, s1.w, p); c2 = fog_color(c2, s2.w, p); c3 = fog_color(c3, s3.w, p);
         }
@@ -314,8 +342,10 @@ __device__ __forceinline__ void setup_face(uint32_t fi, const b32_vertex* __rest
             head = BinHead{r.bbox_x, r.bbox_y, hkey, fi};
             binned = true;
         }
-        // pass-2 surfaces (and every surface in x-ray mode) are replayed in draw order: k_bin_opaque(ordered)
-        // rebuilds their bin entry from keys[fi] (pass, depth key) and this record's bbox.
+        // every drawn, non-empty surface is marked in the tile masks: pass 1 reads the candidates whose head is set; pass 2
+        // and x-ray mode (k_fill_ordered) those whose keys[] class says so, and rebuilds their draw-order key from
+        // keys[fi] (pass, depth key) and this record's bbox.
+        if (!empty) { marked = true; mbx = r.bbox_x; mby = r.bbox_y; }
     } while (0);
     keys[fi] = ((uint64_t)cls << 32) | dkey;
 }
@@ -341,62 +371,199 @@ __device__ __forceinline__ bool surface_misses_box(const Rec& r, uint32_t bx0, u
     return xmax < ERR || ymax < ERR || (1.0f - xmin - ymin) < ERR;
 }
 
-// ---- tile binning helpers -------------------------------------------------------------------------
-__device__ __forceinline__ void head_tiles(const BinHead& h, uint32_t& tx0, uint32_t& tx1, uint32_t& ty0, uint32_t& ty1) {
-    uint32_t min_x = h.bbox_x & 0xFFFF, max_x = h.bbox_x >> 16, min_y = h.bbox_y & 0xFFFF, max_y = h.bbox_y >> 16;
-    tx0 = min_x / TILE_W; tx1 = (max_x - 1) / TILE_W; ty0 = min_y / TILE_H; ty1 = (max_y - 1) / TILE_H;
+// ---- tile masks (see b32_device.cuh: "Binning without bins") ----------------------------------------
+__device__ __forceinline__ void bbox_mtiles(uint32_t bbox_x, uint32_t bbox_y, uint32_t shift, uint32_t& tx0, uint32_t& tx1, uint32_t& ty0, uint32_t& ty1) {
+    uint32_t min_x = bbox_x & 0xFFFF, max_x = bbox_x >> 16, min_y = bbox_y & 0xFFFF, max_y = bbox_y >> 16;
+    tx0 = min_x >> shift; tx1 = (max_x - 1) >> shift; ty0 = min_y >> shift; ty1 = (max_y - 1) >> shift;
 }
 
-// f(tile, head) for every screen tile the bounding box of each lane's head touches.  Must be called by all 32
-// lanes of a warp (has = this lane holds a head).  A head that touches few tiles is walked by its own lane; one
-// that touches many (a wall close to the camera covers hundreds of tiles) is walked by the whole warp, 32 tiles
-// at a time, so no lane ever runs a long serial loop while the other 31 wait.
+// f(mask tile, owner thread) for every mask tile the bounding box of each lane's head touches.  Must be called by all
+// 32 lanes of a warp (has = this lane holds a head).  A head that touches few tiles is walked by its own lane; one that
+// touches many (a wall close to the camera covers hundreds of tiles) is walked by the whole warp, 32 tiles at a time,
+// so no lane ever runs a long serial loop while the other 31 wait.
 constexpr uint32_t COOP_TILES = 16;
 template <typename F>
-__device__ __forceinline__ void for_each_tile(const BinHead& h, bool has, uint32_t tiles_x, F f) {
+__device__ __forceinline__ void for_each_mtile(uint32_t bbox_x, uint32_t bbox_y, bool has, uint32_t pix_shift, uint32_t mtiles_x, F f) {
     const uint32_t lane = threadIdx.x & 31;
     uint32_t tx0 = 0, tx1 = 0, ty0 = 0, ty1 = 0, nt = 0;
-    if (has) { head_tiles(h, tx0, tx1, ty0, ty1); nt = (tx1 - tx0 + 1) * (ty1 - ty0 + 1); }
+    if (has) { bbox_mtiles(bbox_x, bbox_y, pix_shift, tx0, tx1, ty0, ty1); nt = (tx1 - tx0 + 1) * (ty1 - ty0 + 1); }
     const bool big = nt > COOP_TILES;
     if (has && !big)
         for (uint32_t ty = ty0; ty <= ty1; ++ty)
-            for (uint32_t tx = tx0; tx <= tx1; ++tx) f(ty * tiles_x + tx, h);
+            for (uint32_t tx = tx0; tx <= tx1; ++tx) f(ty * mtiles_x + tx, threadIdx.x);
     uint32_t bigmask = __ballot_sync(0xFFFFFFFFu, big);
     while (bigmask) {
         const int src = __ffs(bigmask) - 1;
         bigmask &= bigmask - 1;
-        BinHead hb{__shfl_sync(0xFFFFFFFFu, h.bbox_x, src), __shfl_sync(0xFFFFFFFFu, h.bbox_y, src),
-                   __shfl_sync(0xFFFFFFFFu, h.key, src), __shfl_sync(0xFFFFFFFFu, h.face, src)};
         const uint32_t bx0 = __shfl_sync(0xFFFFFFFFu, tx0, src), by0 = __shfl_sync(0xFFFFFFFFu, ty0, src);
         const uint32_t bw = __shfl_sync(0xFFFFFFFFu, tx1, src) - bx0 + 1, total = __shfl_sync(0xFFFFFFFFu, nt, src);
-        for (uint32_t i = lane; i < total; i += 32) f((by0 + i / bw) * tiles_x + bx0 + i % bw, hb);
+        for (uint32_t i = lane; i < total; i += 32) f((by0 + i / bw) * mtiles_x + bx0 + i % bw, (threadIdx.x & ~31u) + (uint32_t)src);
     }
+}
+
+// One group's tile masks: zero, mark (every thread of the CTA calls mark with its own face's bounding box), flush to
+// masks[mask tile][group].  blockDim.x == SETUP_GROUP.
+__device__ __forceinline__ void masks_zero(uint4* s_mask, uint32_t n_mtiles) {
+    for (uint32_t i = threadIdx.x; i < n_mtiles; i += blockDim.x) s_mask[i] = make_uint4(0, 0, 0, 0);
+}
+__device__ __forceinline__ void masks_mark(uint4* s_mask, uint32_t bbox_x, uint32_t bbox_y, bool has, const CallParams& p) {
+    uint32_t* w = reinterpret_cast<uint32_t*>(s_mask);
+    for_each_mtile(bbox_x, bbox_y, has, 4u + p.mshift, p.mtiles_x, [&](uint32_t t, uint32_t owner) { atomicOr(&w[t * 4 + (owner >> 5)], 1u << (owner & 31)); });
+}
+// ord = which faces of the group are replayed by the ordered pass (pass 2 / x-ray / RGB888): their number per mask tile is
+// accumulated in ocount[] and its maximum in st->obin_max, so that k_fill_ordered knows BEFORE any tile draws whether every
+// tile's draw-order entries fit (shared memory, or its slice of the scratch).  Ordinary frames have none: no atomics.
+__device__ __forceinline__ void masks_flush(const uint4* s_mask, uint4* __restrict__ masks, uint32_t n_mtiles, uint32_t group, const CallParams& p,
+                                            uint4 ord, uint32_t* __restrict__ ocount, CallState* __restrict__ st) {
+    const bool any_ord = (ord.x | ord.y | ord.z | ord.w) != 0;
+    for (uint32_t t = threadIdx.x; t < n_mtiles; t += blockDim.x) {
+        const uint4 m = s_mask[t];
+        masks[(size_t)t * p.n_groups + group] = m;
+        if (any_ord) {
+            const uint32_t c = __popc(m.x & ord.x) + __popc(m.y & ord.y) + __popc(m.z & ord.z) + __popc(m.w & ord.w);
+            if (c) atomicMax(&st->obin_max, atomicAdd(&ocount[t], c) + c);
+        }
+    }
+}
+
+// ---- a fill CTA's surface list out of its mask row ----------------------------------------------------
+// Thread t owns the groups [g0, g1) of the row (contiguous, so the list comes out in face order).  cand_scan counts the
+// set bits (block-wide exclusive scan); cand_expand writes the face indices of the candidates with list position in
+// [w0, w0 + wn) to out[position - w0].  Both contain barriers: every thread of the CTA must call them.
+struct CandScan { uint32_t g0, g1, base, total; };
+__device__ __forceinline__ uint32_t popc128(const uint4& m) { return __popc(m.x) + __popc(m.y) + __popc(m.z) + __popc(m.w); }
+
+template <int THREADS>
+__device__ __forceinline__ CandScan cand_scan(const uint4* __restrict__ mrow, uint32_t n_groups, uint32_t* s_wsum /* [THREADS / 32] */) {
+    const uint32_t k = (n_groups + THREADS - 1) / THREADS;
+    CandScan cs;
+    cs.g0 = min(threadIdx.x * k, n_groups); cs.g1 = min(cs.g0 + k, n_groups);
+    uint32_t cnt = 0;
+    for (uint32_t g = cs.g0; g < cs.g1; ++g) cnt += popc128(mrow[g]);
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t xs = cnt;
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, xs, o); if (lane >= (uint32_t)o) xs += t; }
+    __syncthreads();                                   // s_wsum may still be read by an earlier use
+    if (lane == 31) s_wsum[warp] = xs;
+    __syncthreads();
+    uint32_t pre = 0, total = 0;
+    for (uint32_t w = 0; w < (uint32_t)(THREADS / 32); ++w) { uint32_t v = s_wsum[w]; if (w < warp) pre += v; total += v; }
+    cs.base = pre + xs - cnt;
+    cs.total = total;
+    return cs;
+}
+
+__device__ __forceinline__ void cand_expand(const uint4* __restrict__ mrow, const CandScan& cs, uint32_t w0, uint32_t wn, uint32_t* out) {
+    uint32_t idx = cs.base;
+    for (uint32_t g = cs.g0; g < cs.g1 && idx < w0 + wn; ++g) {
+        const uint4 m = mrow[g];
+        const uint32_t c = popc128(m);
+        if (idx + c <= w0) { idx += c; continue; }
+        const uint32_t words[4] = {m.x, m.y, m.z, m.w};
+        #pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t bits = words[q];
+            while (bits) {
+                const uint32_t b = __ffs(bits) - 1;
+                bits &= bits - 1;
+                if (idx >= w0 && idx < w0 + wn) out[idx - w0] = g * SETUP_GROUP + q * 32 + b;
+                ++idx;
+            }
+        }
+    }
+    __syncthreads();
 }
 
 #ifndef B32_SETUP_MINB
 #define B32_SETUP_MINB 6          // <= 80 registers: 6 CTAs per SM = 888 slots, so the 782 CTAs of a 100k-face mesh are one wave
 #endif
+constexpr int SETUP_WIN = 3 * SETUP_THREADS;            // vertices staged per group when its indices fit a window this wide
+constexpr size_t SETUP_STAGE_BYTES = (size_t)SETUP_WIN * sizeof(b32_vertex) + 32;
+static_assert(SETUP_THREADS == SETUP_GROUP && SETUP_GROUP == 128, "one face per thread and group; a mask entry is one uint4");
+
+// Dynamic shared memory: [n_mtiles] uint4 tile masks, then the staged vertex window.
+// Vertex staging: when the three indices of all faces of the group lie in a window of SETUP_WIN vertices (always for an
+// unindexed triangle soup, usually for level geometry), the window is copied with coalesced 16-byte cp.async pieces and
+// the threads read their 27 floats from shared memory at a 27-word stride (conflict-free); otherwise they gather from
+// global memory.  Every vertex buffer of the library is padded by 16 bytes so that the last piece may overrun the window.
+template <bool STAGED>
+__device__ __forceinline__ void setup_group(uint32_t group, const b32_vertex* __restrict__ verts, const uint4& fc, const float* __restrict__ s_vert,
+                                            uint32_t lo, const TVert* __restrict__ tv, const TexDev* __restrict__ tex, const LightDev* __restrict__ lights,
+                                            SurfRec* __restrict__ recs, uint64_t* __restrict__ keys, BinHead* __restrict__ heads, uint4* s_mask,
+                                            WireTri* __restrict__ wire, CallState* __restrict__ st, const CallParams& p, uint32_t& n_op, uint32_t& n_tr,
+                                            uint32_t* s_ord) {
+    const uint32_t fi = group * SETUP_GROUP + threadIdx.x;
+    BinHead head{0, 0, 0, fi};                               // bbox 0 = not drawn in pass 1
+    bool binned = false, marked = false;
+    uint32_t mbx = 0, mby = 0;
+    if (fi < p.nf) {
+        setup_face<STAGED>(fi, fc, reinterpret_cast<const float*>(verts), s_vert, lo, tv, tex, lights, recs, keys, st, p, n_op, n_tr, head, binned, marked, mbx, mby, wire);
+        heads[fi] = head;
+    }
+    masks_mark(s_mask, mbx, mby, marked, p);
+    // marked and not a pass-1 entry = replayed by the ordered pass; RGB888: any marked surface may be (one list)
+    const uint32_t ob = __ballot_sync(0xFFFFFFFFu, marked && (!binned || p.rgb888));
+    if ((threadIdx.x & 31) == 0) s_ord[threadIdx.x >> 5] = ob;
+}
+
 __global__ void __launch_bounds__(SETUP_THREADS, B32_SETUP_MINB)
 k_setup(const b32_vertex* __restrict__ verts, const b32_face* __restrict__ faces, const TVert* __restrict__ tv,
         const TexDev* __restrict__ tex, const LightDev* __restrict__ lights,
         SurfRec* __restrict__ recs, uint64_t* __restrict__ keys,
-        BinHead* __restrict__ heads, WireTri* __restrict__ wire, CallState* __restrict__ st,
+        BinHead* __restrict__ heads, uint4* __restrict__ masks, uint32_t* __restrict__ ocount, WireTri* __restrict__ wire, CallState* __restrict__ st,
         uint32_t* __restrict__ zero_next, uint32_t zero_words,
         uint32_t* __restrict__ clear_rgba, float* __restrict__ clear_z, uint32_t clear_n, uint32_t clear_color, CallParams p) {
+    extern __shared__ __align__(16) uint8_t su_smem[];
     __shared__ uint32_t s_cnt[2];
-    pdl_launch_dependents();           // k_bin_opaque may be scheduled as SM resources free up; it waits for this grid's completion
+    __shared__ uint32_t s_lohi[2];
+    __shared__ uint32_t s_ord[SETUP_THREADS / 32];
+    const uint32_t n_mtiles = p.mtiles_x * p.mtiles_y;
+    uint4* s_mask = reinterpret_cast<uint4*>(su_smem);
+    uint8_t* s_stage = su_smem + (size_t)n_mtiles * sizeof(uint4);
+    pdl_launch_dependents();           // the fill may be scheduled as SM resources free up; it waits for this grid's completion
     // Framebuffer::clear of the same frame (render.rs:36-45), folded in: nothing of this kernel reads the framebuffer, and
     // the previous frame's kernels have completed (this kernel is an ordinary, fully ordered launch)
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < clear_n; i += gridDim.x * blockDim.x) { clear_rgba[i] = clear_color; clear_z[i] = 3.40282347e+38f; }
-    // the call after this one finds its CallState + tile counters zeroed (two sets, used alternately)
+    // the call after this one finds its CallState zeroed (two sets, used alternately)
     if (blockIdx.x == 0) for (uint32_t i = threadIdx.x; i < zero_words; i += blockDim.x) zero_next[i] = 0;
     if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
     uint32_t n_op = 0, n_tr = 0;
-    for (uint32_t fi = blockIdx.x * blockDim.x + threadIdx.x; fi < p.nf; fi += gridDim.x * blockDim.x) {
-        BinHead head{0, 0, 0, fi};                               // bbox 0 = not binned
-        bool binned;
-        setup_face(fi, verts, faces, tv, tex, lights, recs, keys, st, p, n_op, n_tr, head, binned, wire);
-        heads[fi] = head;
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t group = blockIdx.x; group < p.n_groups; group += gridDim.x) {
+        const uint32_t fi = group * SETUP_GROUP + threadIdx.x;
+        masks_zero(s_mask, n_mtiles);
+        if (threadIdx.x == 0) { s_lohi[0] = 0xFFFFFFFFu; s_lohi[1] = 0; }
+        uint4 fc = make_uint4(0, 0, 0, 0);
+        uint32_t lo = 0xFFFFFFFFu, hi = 0;
+        if (fi < p.nf) {
+            // implicit faces: an unindexed triangle soup sends only the flags word; face i = vertices 3i, 3i+1, 3i+2
+            if (p.faces_implicit) fc = make_uint4(3u * fi, 3u * fi + 1u, 3u * fi + 2u, reinterpret_cast<const uint32_t*>(faces)[fi]);
+            else fc = *reinterpret_cast<const uint4*>(faces + fi);
+            lo = min(fc.x, min(fc.y, fc.z)); hi = max(fc.x, max(fc.y, fc.z));
+        }
+        lo = __reduce_min_sync(0xFFFFFFFFu, lo); hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+        __syncthreads();                                   // masks zeroed, s_lohi initialised (and the previous group's flush is done)
+        if (lane == 0) { atomicMin(&s_lohi[0], lo); atomicMax(&s_lohi[1], hi); }
+        __syncthreads();
+        lo = s_lohi[0]; hi = s_lohi[1];
+        const bool staged = tv == nullptr && hi >= lo && hi - lo < (uint32_t)SETUP_WIN && hi < p.nv;
+        if (staged) {
+            const uint8_t* base = reinterpret_cast<const uint8_t*>(verts);
+            const size_t vbytes = (size_t)p.vwords * 4;
+            const size_t b0 = (size_t)lo * vbytes, a0 = b0 & ~(size_t)15, b1 = (size_t)(hi + 1) * vbytes;
+            const uint32_t n16 = (uint32_t)((b1 - a0 + 15) >> 4);
+            for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) cp_async16(s_stage + (size_t)i * 16, base + a0 + (size_t)i * 16);
+            cp_async_commit();
+            cp_async_wait<0>();
+            __syncthreads();
+            const float* s_vert = reinterpret_cast<const float*>(s_stage + (b0 - a0));
+            setup_group<true>(group, verts, fc, s_vert, lo, tv, tex, lights, recs, keys, heads, s_mask, wire, st, p, n_op, n_tr, s_ord);
+        } else {
+            setup_group<false>(group, verts, fc, nullptr, 0, tv, tex, lights, recs, keys, heads, s_mask, wire, st, p, n_op, n_tr, s_ord);
+        }
+        __syncthreads();
+        masks_flush(s_mask, masks, n_mtiles, group, p, make_uint4(s_ord[0], s_ord[1], s_ord[2], s_ord[3]), ocount, st);
+        __syncthreads();                                   // the masks are reused by the next group of a persistent CTA
     }
     // one pair of global atomics per block
     for (int o = 16; o > 0; o >>= 1) { n_op += __shfl_xor_sync(0xFFFFFFFFu, n_op, o); n_tr += __shfl_xor_sync(0xFFFFFFFFu, n_tr, o); }
@@ -404,92 +571,6 @@ k_setup(const b32_vertex* __restrict__ verts, const b32_face* __restrict__ faces
     if ((threadIdx.x & 31) == 0) { if (n_op) atomicAdd(&s_cnt[0], n_op); if (n_tr) atomicAdd(&s_cnt[1], n_tr); }
     __syncthreads();
     if (threadIdx.x == 0) { if (s_cnt[0]) atomicAdd(&st->n_opaque, s_cnt[0]); if (s_cnt[1]) atomicAdd(&st->n_transp, s_cnt[1]); }
-}
-
-// =================================================================================================
-// k_bin_opaque — scatter pass-1 surfaces into per-tile bins (any order)
-// =================================================================================================
-// Same-address global atomics from different warps are serviced one by one in the L2, and a hot tile
-// receives hundreds of surfaces, so the binning is aggregated: a block takes BIN_THREADS consecutive
-// faces, counts them per tile in shared memory, reserves one contiguous slot range per touched tile
-// with ONE global atomic, then hands out slots from shared memory.
-#ifndef B32_BIN_THREADS
-#define B32_BIN_THREADS 1024
-#endif
-constexpr int BIN_THREADS = B32_BIN_THREADS;
-constexpr int BIN_MAX_TILES = 16384;            // shared-memory aggregation up to this many tiles (2 x 64 KB: 2560x1440 has 14 400)
-
-__global__ void __launch_bounds__(BIN_THREADS, 2048 / BIN_THREADS)
-k_bin_opaque(const BinHead* __restrict__ heads, const uint64_t* __restrict__ keys, const SurfRec* __restrict__ recs,
-             BinHead* __restrict__ bins, uint32_t* __restrict__ tile_count,
-             CallState* __restrict__ st, CallParams p, uint32_t bin_cap, bool ordered) {
-    extern __shared__ uint32_t s_tiles[];            // [ntiles] counts/cursors, [ntiles] bases (when ntiles <= BIN_MAX_TILES)
-    const uint32_t ntiles = p.tiles_x * p.tiles_y;
-    const bool aggregate = ntiles <= BIN_MAX_TILES;
-    uint32_t* s_cnt = s_tiles;
-    uint32_t* s_base = s_tiles + ntiles;
-    if (aggregate) for (uint32_t i = threadIdx.x; i < ntiles; i += blockDim.x) s_cnt[i] = 0;
-    pdl_wait();                        // k_setup has completed: heads / keys / recs / counters are visible
-    pdl_launch_dependents();           // k_fill_opaque may start its prologue
-    __syncthreads();
-
-    uint32_t bmax = 0;
-    for (uint32_t base = blockIdx.x * blockDim.x; base < p.nf; base += gridDim.x * blockDim.x) {
-        const uint32_t fi = base + threadIdx.x;
-        BinHead head{0, 0, 0, 0};
-        if (fi < p.nf) {
-            if (!ordered) head = heads[fi];
-            else {
-                // draw-order entry of a pass-2 surface (or of any surface in x-ray mode): the unique 64-bit key
-                // (pass:2 | depth key:32 | face:30) = opaque list first (sorted only in painter's mode), then the
-                // transparent list, ties by face index = stable sort (render.rs:2522-2542)
-                // (RGB888: one list, so every drawn surface and no pass bit)
-                uint64_t k64 = keys[fi];
-                uint32_t cls = (uint32_t)(k64 >> 32);
-                if (cls < 2 && (cls == 1 || p.xray_mode || p.rgb888)) {
-                    uint2 bb = *reinterpret_cast<const uint2*>(&recs[fi].bbox_x);      // all zero = empty surface
-                    uint64_t okey = ((uint64_t)(p.rgb888 ? 0u : cls) << 62) | ((uint64_t)(uint32_t)k64 << 30) | fi;
-                    if (bb.x) head = BinHead{bb.x, bb.y, (uint32_t)(okey >> 32), (uint32_t)okey};
-                }
-            }
-        }
-        const bool has = head.bbox_x != 0;
-        // (binning by bbox only: applying the exact corner reject per (face, tile) here was measured — it doubles this
-        //  kernel's time and the fill, whose per-block filter applies the same test, gains nothing)
-        if (aggregate) {
-            for_each_tile(head, has, p.tiles_x, [&](uint32_t t, const BinHead&) { atomicAdd(&s_cnt[t], 1u); });     // 1) count per tile
-            __syncthreads();
-            for (uint32_t t0 = threadIdx.x; t0 < ntiles; t0 += 4 * blockDim.x) {     // 2) reserve ranges, four atomics in flight
-                uint32_t c[4], b[4];
-                #pragma unroll
-                for (int k = 0; k < 4; ++k) { uint32_t t = t0 + k * blockDim.x; c[k] = t < ntiles ? s_cnt[t] : 0u; }
-                #pragma unroll
-                for (int k = 0; k < 4; ++k) b[k] = c[k] ? atomicAdd(&tile_count[t0 + k * blockDim.x], c[k]) : 0u;
-                #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (c[k]) { uint32_t t = t0 + k * blockDim.x; s_base[t] = b[k]; s_cnt[t] = 0; bmax = max(bmax, b[k] + c[k]); }
-            }
-            __syncthreads();
-            for_each_tile(head, has, p.tiles_x, [&](uint32_t t, const BinHead& h) {                                 // 3) hand out slots
-                uint32_t slot = s_base[t] + atomicAdd(&s_cnt[t], 1u);
-                if (slot < bin_cap) bins[(size_t)t * bin_cap + slot] = h;
-            });
-            __syncthreads();
-            for (uint32_t t = threadIdx.x; t < ntiles; t += blockDim.x) s_cnt[t] = 0;
-            __syncthreads();
-        } else {
-            for_each_tile(head, has, p.tiles_x, [&](uint32_t t, const BinHead& h) {
-                uint32_t slot = atomicAdd(&tile_count[t], 1u);
-                if (slot < bin_cap) bins[(size_t)t * bin_cap + slot] = h;
-                bmax = max(bmax, slot + 1);
-            });
-        }
-    }
-    for (int o = 16; o > 0; o >>= 1) bmax = max(bmax, __shfl_xor_sync(0xFFFFFFFFu, bmax, o));
-    if ((threadIdx.x & 31) == 0 && bmax) {
-        if (ordered) { atomicMax(&st->obin_max, bmax); if (bmax > bin_cap) st->obin_overflow = 1; }
-        else { atomicMax(&st->bin_max, bmax); if (bmax > bin_cap) st->bin_overflow = 1; }
-    }
 }
 
 // =================================================================================================
@@ -727,35 +808,10 @@ __device__ __forceinline__ uint32_t smid() { uint32_t r; asm volatile("mov.u32 %
 __device__ __forceinline__ uint32_t gtime() { uint64_t t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return (uint32_t)t; }
 #endif
 
-// ---- asynchronous copies ----------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
-// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
-
 // RGB888 = the render_mesh instantiation (8-bit colour pipeline in step 5; everything else is shared); C = OpDense / OpSparse
 template <bool RGB888, class C>
 __global__ void __launch_bounds__(C::THREADS, C::MINB)
-k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins, const uint32_t* __restrict__ tile_count,
-              const BinHead* __restrict__ heads, BinHead* __restrict__ sorted_scratch,
+k_fill_opaque(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks, const BinHead* __restrict__ heads,
               const TexDev* __restrict__ tex, const uint16_t* __restrict__ texels, const uint32_t* __restrict__ texmask,
               uint32_t* __restrict__ fb_rgba, float* __restrict__ fb_z, const CallState* __restrict__ st,
               uint32_t* __restrict__ sticky, CallParams p) {
@@ -765,158 +821,104 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
     constexpr int OP_RING = C::RING, OP_SORT_MAX = C::SORT_MAX, OP_TEX_SMEM = C::TEX_SMEM;
     extern __shared__ __align__(128) uint8_t op_smem[];
     SurfHot* s_rec = reinterpret_cast<SurfHot*>(op_smem);                               // [OP_RING][OP_CHUNK] record ring (visibility part)
-    BinHead* s_sh = reinterpret_cast<BinHead*>(s_rec + OP_RING * OP_CHUNK);             // [OP_SORT_MAX] bin in walk order
+    BinHead* s_sh = reinterpret_cast<BinHead*>(s_rec + OP_RING * OP_CHUNK);             // [OP_SORT_MAX] the window's heads in walk order
     TexDev* s_tex = reinterpret_cast<TexDev*>(s_sh + OP_SORT_MAX);                      // [OP_TEX_SMEM]
     uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_tex + OP_TEX_SMEM);                // [OP_MASK_SMEM_WORDS] "texel writes" bits
     uint2* s_surv = reinterpret_cast<uint2*>(s_mask + OP_MASK_SMEM_WORDS);              // [OP_WARPS][32] survivors: (key, face)
     uint8_t* s_sidx = reinterpret_cast<uint8_t*>(s_surv + OP_WARPS * 32);               // [OP_WARPS][32] ... and their slot in the ring step
+    uint32_t* s_cand = reinterpret_cast<uint32_t*>(s_rec);                              // [OP_SORT_MAX] face indices of the window (the ring is idle then)
     __shared__ uint32_t s_hist[OP_BUCKETS];
-    __shared__ uint32_t s_wsum[OP_BUCKETS / 32];
+    __shared__ uint32_t s_wsum[OP_THREADS / 32];
     __shared__ uint32_t s_minmax[2];
+    __shared__ uint32_t s_nsmall, s_nraw;
+    __shared__ uint32_t s_tile_weak;       // what the tile's weakest pixel still accepts after the windows done so far (see the window loop)
     __shared__ __align__(8) uint64_t s_mbar;
-    // ---- prologue: nothing here reads what k_setup / k_bin_opaque write, so it runs while they finish -----
+    if (threadIdx.x == 0) s_nraw = 0;
+    // ---- prologue: nothing here reads what k_setup writes (the framebuffer included: the frame's clear may ride in
+    //      k_setup), so it runs while k_setup finishes ----------------------------------------------------------------
     const uint32_t tile = blockIdx.x / OP_SPLIT, half = blockIdx.x % OP_SPLIT;
-    // the "texel writes" mask of the whole texel pool travels by TMA while the bin is sorted
+    // the "texel writes" mask of the whole texel pool travels by TMA while the candidates are collected
     const bool mask_staged = p.mask_smem_words != 0;
     if (mask_staged && threadIdx.x == 0) { mbar_init(&s_mbar, 1); bulk_g2s(s_mask, texmask, p.mask_smem_words * 4, &s_mbar); }
     const uint32_t* maskw = mask_staged ? s_mask : texmask;
-    const BinHead* bin = bins + (size_t)tile * p.bin_cap;
-    __shared__ uint32_t s_scan_n;
-    if (threadIdx.x == 0) s_scan_n = 0;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t pix = OP_DUAL ? (lane & 15) : lane, sub = OP_DUAL ? (lane >> 4) : 0;
     const uint32_t tx = tile % p.tiles_x, ty = tile / p.tiles_x;
-    // thread -> pixel: each warp owns a 4x4 block of its half tile; lanes l and l+16 share a pixel
+    // thread -> pixel: each warp owns a block of its (half) tile; dual: lanes l and l+16 share a pixel
     constexpr uint32_t BPR = TILE_W / OP_BW;               // warp blocks per tile row
     const uint32_t wt = half * OP_WARPS + warp;            // this warp's block within the tile
     const uint32_t bx0 = tx * TILE_W + (wt % BPR) * OP_BW, by0 = ty * TILE_H + (wt / BPR) * OP_BH;
     const uint32_t x = bx0 + (pix % OP_BW), y = by0 + (pix / OP_BW);
     const bool valid = x < p.width && y < p.height;
-    // the pixel's framebuffer content (written by earlier stream work, complete before k_setup started)
-    Pixel px{0, 0.0f};
-    if (valid) { px.rgba = fb_rgba[y * p.width + x]; px.z = fb_z[y * p.width + x]; }
     const bool tex_cached = p.ntex <= OP_TEX_SMEM;
     if (tex_cached) for (uint32_t i = threadIdx.x; i < p.ntex; i += OP_THREADS) s_tex[i] = tex[i];
     const TexDev* texd = tex_cached ? s_tex : tex;
-    pdl_wait();                                            // k_bin_opaque (and k_setup before it) have completed
+    pdl_wait();                                            // k_setup has completed: records, heads, masks, counters, cleared framebuffer
+    pdl_launch_dependents();                               // an enqueued ordered pass may be scheduled behind this grid (it waits for its completion)
+    // the pixel's framebuffer content
+    Pixel px{0, 0.0f};
+    if (valid) { px.rgba = fb_rgba[y * p.width + x]; px.z = fb_z[y * p.width + x]; }
     bool skip;
     {
         CallState s = *st;
         bool aborts = call_aborts(s, p.use_zbuffer, RGB888);
         if (p.async_call && blockIdx.x == 0 && threadIdx.x == 0) {                                // enqueue-only callers
-            if (aborts || s.bin_overflow) atomicOr(sticky, s.oob ? 1u : (aborts ? 2u : 4u));
-            else if (s.n_transp) atomicOr(sticky, 8u);                                           // pass 2 exists but was not enqueued
+            if (aborts) atomicOr(sticky, s.oob ? 1u : 2u);
+            else if (s.n_transp && !p.enq_ordered) atomicOr(sticky, 8u);                         // pass 2 exists but was not enqueued
         }
         // x-ray (render_mesh_15) and any framebuffer-reading surface (render_mesh) go through the ordered replay instead
-        skip = s.bin_overflow || aborts || (p.xray_mode && !RGB888) || (RGB888 && s.n_transp);
+        skip = aborts || (p.xray_mode && !RGB888) || (RGB888 && s.n_transp);
     }
-    uint32_t n;
-    if (p.scan_heads) {
-        // Small meshes (<= OP_SORT_MAX faces) have no binning kernel: this tile picks its surfaces straight out of k_setup's
-        // bin heads (16 B per face, L2-resident) — one kernel launch less on the latency path of a game's per-room calls.
-        // The picks land in the (still unused) ring area and are ordered from there exactly like a bin.
-        BinHead* s_raw = reinterpret_cast<BinHead*>(s_rec);
-        const uint32_t ttx = tile % p.tiles_x, tty = tile / p.tiles_x;
-        __syncthreads();                                   // s_scan_n = 0 is visible
-        if (!skip)
-            for (uint32_t i = threadIdx.x; i < p.nf; i += OP_THREADS) {
-                const BinHead h = heads[i];
-                if (!h.bbox_x) continue;
-                uint32_t tx0, tx1, ty0, ty1;
-                head_tiles(h, tx0, tx1, ty0, ty1);
-                if (ttx >= tx0 && ttx <= tx1 && tty >= ty0 && tty <= ty1) s_raw[atomicAdd(&s_scan_n, 1u)] = h;
+    // ---- 0. this tile's candidates: the set bits of its mask row (see b32_device.cuh) ------------------------------
+    // Usual case (the row fits OP_KREG masks per thread and the tile has at most OP_SORT_MAX candidates): every thread takes
+    // the groups tid, tid + THREADS, ..., reserves room for its set bits with one shared-memory atomic and writes the face
+    // indices — any order will do, the list is ordered by walk key next.  Otherwise: cand_scan / cand_expand, a window at a time.
+    const uint32_t mtile = (ty >> p.mshift) * p.mtiles_x + (tx >> p.mshift);
+    const uint4* mrow = masks + (size_t)mtile * p.n_groups;
+    constexpr int OP_KREG = 4;
+    const bool fast = !skip && p.n_groups <= (uint32_t)(OP_KREG * OP_THREADS);
+    uint32_t n_cand = 0;
+    bool fast_ok = false;
+    __syncthreads();                                       // s_nraw = 0 is visible
+    if (fast) {
+        uint4 m[OP_KREG];
+        uint32_t cnt = 0;
+        #pragma unroll
+        for (int j = 0; j < OP_KREG; ++j) {
+            const uint32_t g = j * OP_THREADS + threadIdx.x;
+            m[j] = g < p.n_groups ? mrow[g] : make_uint4(0, 0, 0, 0);
+            cnt += popc128(m[j]);
+        }
+        uint32_t pos = cnt ? atomicAdd(&s_nraw, cnt) : 0u;
+        if (pos + cnt <= (uint32_t)OP_SORT_MAX) {
+            #pragma unroll
+            for (int j = 0; j < OP_KREG; ++j) {
+                const uint32_t f0 = (j * OP_THREADS + threadIdx.x) * SETUP_GROUP;
+                const uint32_t words[4] = {m[j].x, m[j].y, m[j].z, m[j].w};
+                #pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t bits = words[q];
+                    while (bits) { const uint32_t b = __ffs(bits) - 1; bits &= bits - 1; s_cand[pos++] = f0 + q * 32 + b; }
+                }
             }
+        }
         __syncthreads();
-        n = s_scan_n;
-        bin = s_raw;
-    } else {
-        n = skip ? 0u : tile_count[tile];
+        n_cand = s_nraw;
+        fast_ok = n_cand <= (uint32_t)OP_SORT_MAX;
     }
-    if (n == 0) {                                          // nothing to draw here; the mask copy must land before the CTA exits
+    CandScan cs{0, 0, 0, 0};
+    if (!fast_ok) {
+        cs = cand_scan<OP_THREADS>(mrow, skip ? 0u : p.n_groups, s_wsum);
+        n_cand = cs.total;
+    }
+    if (n_cand == 0) {                                     // nothing to draw here; the mask copy must land before the CTA exits
         if (mask_staged && threadIdx.x == 0) while (!mbar_try_wait(&s_mbar, 0)) {}
         return;
     }
 #ifdef B32_FILL_STATS
     uint32_t st_t0 = gtime(), st_batches = 0, st_surv = 0, st_inside = 0, st_shaded = 0;
+    uint32_t st_t1 = 0, st_tl = 0, st_tfirst = 0, st_tb0 = 0, st_tb1 = 0;
 #endif
-
-    // ---- 1. copy the bin in walk-key order, descending: one counting-sort pass into OP_BUCKETS key buckets (within a
-    //         bucket the order is arbitrary; the early-out uses bucket bounds).  Bins of up to OP_SORT_MAX entries are
-    //         ordered into shared memory, larger ones into this tile's slice of a global scratch (three streamed passes
-    //         over the bin: key range, histogram, scatter), so the early-out also works for very crowded tiles.
-    const bool in_smem = n <= OP_SORT_MAX;
-    BinHead* gwalk = sorted_scratch + (size_t)tile * p.bin_cap;
-    auto walk = [&](uint32_t i) -> BinHead { return in_smem ? s_sh[i] : gwalk[i]; };    // uniform branch: LDS or LDG
-    uint32_t kmin = 0, shift = 0;
-    const bool single_batch = n <= 32;                    // one batch: nothing comes "later", so no order (and no early-out) is needed
-    if (single_batch) {
-        if (threadIdx.x < n) s_sh[threadIdx.x] = bin[threadIdx.x];
-    } else {
-        // a bin that fits shared memory is read once into registers; a larger one is streamed from L2 in each pass
-        constexpr int KPT = OP_SORT_MAX / OP_THREADS;
-        BinHead hh[KPT];
-        if (in_smem) {
-            #pragma unroll
-            for (int q = 0; q < KPT; ++q) { uint32_t i = q * OP_THREADS + threadIdx.x; if (i < n) hh[q] = bin[i]; }
-        }
-        auto for_each_entry = [&](auto f) {
-            if (in_smem) {
-                #pragma unroll
-                for (int q = 0; q < KPT; ++q) { if (q * OP_THREADS + threadIdx.x < n) f(hh[q]); }
-            } else {
-                for (uint32_t i = threadIdx.x; i < n; i += OP_THREADS) f(bin[i]);
-            }
-        };
-        uint32_t lo = 0xFFFFFFFFu, hi = 0;
-        for_each_entry([&](const BinHead& h) { if (h.key != 0xFFFFFFFFu) { lo = min(lo, h.key); hi = max(hi, h.key); } });   // 0xFFFFFFFF = "never cull": bucket 0
-        if (threadIdx.x < OP_BUCKETS) s_hist[threadIdx.x] = 0;
-        if (threadIdx.x == 0) { s_minmax[0] = 0xFFFFFFFFu; s_minmax[1] = 0; }
-        for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, o)); hi = max(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, o)); }
-        __syncthreads();
-        if (lane == 0) { atomicMin(&s_minmax[0], lo); atomicMax(&s_minmax[1], hi); }
-        __syncthreads();
-        kmin = s_minmax[0];
-        uint32_t kmax = s_minmax[1];
-        if (kmin > kmax) { kmin = 0; kmax = 0; }
-        uint32_t range = kmax - kmin;
-        shift = range >= OP_BUCKETS ? (32 - __clz(range)) - OP_BUCKET_BITS : 0;         // (range >> shift) <= OP_BUCKETS - 1
-        auto bucket = [&](uint32_t k) { return k == 0xFFFFFFFFu ? 0u : (uint32_t)(OP_BUCKETS - 1) - ((k - kmin) >> shift); };
-        for_each_entry([&](const BinHead& h) { atomicAdd(&s_hist[bucket(h.key)], 1u); });
-        __syncthreads();
-        uint32_t v = 0, xs = 0;                              // exclusive scan of the bucket counts (threads 0..OP_BUCKETS-1)
-        if (threadIdx.x < OP_BUCKETS) {
-            v = s_hist[threadIdx.x]; xs = v;
-            for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, xs, o); if (lane >= (uint32_t)o) xs += t; }
-            if (lane == 31) s_wsum[warp] = xs;
-        }
-        __syncthreads();
-        if (threadIdx.x < OP_BUCKETS) {
-            uint32_t pre = 0;
-            for (uint32_t w = 0; w < warp; ++w) pre += s_wsum[w];
-            s_hist[threadIdx.x] = pre + xs - v;
-        }
-        __syncthreads();
-        for_each_entry([&](const BinHead& h) { uint32_t pos = atomicAdd(&s_hist[bucket(h.key)], 1u); if (in_smem) s_sh[pos] = h; else gwalk[pos] = h; });
-    }
-    __syncthreads();                                      // the walk order (shared or global), s_tex and the mbarrier are ready
-
-    // ---- 2. the record ring: step c -> slot c % OP_RING; the 16-byte pieces of the step's records are dealt round robin
-    auto stage = [&](uint32_t c) {
-        for (uint32_t piece = threadIdx.x; piece < (uint32_t)(OP_CHUNK * OP_REC_PIECES); piece += OP_THREADS) {
-            uint32_t slot = piece / OP_REC_PIECES, part = piece % OP_REC_PIECES;
-            uint32_t e = c * OP_CHUNK + slot;
-            if (e < n) {
-                uint32_t f = in_smem ? s_sh[e].face : gwalk[e].face;
-                cp_async16(reinterpret_cast<uint4*>(&s_rec[(c % OP_RING) * OP_CHUNK + slot]) + part,
-                           reinterpret_cast<const uint4*>(&recs[f]) + part);
-            }
-        }
-        cp_async_commit();
-    };
-    stage(0);
-    stage(1);
-
-    bool done = bx0 >= p.width || by0 >= p.height;        // whole warp off-screen
     const Pixel px0 = px;
     // painter's: best = (key << 32 | face) + 1 of the winner so far (0 = framebuffer content)
     // z-buffer : best_face = face + 1 of the winner so far (0 = framebuffer content), its depth in px.z
@@ -924,139 +926,253 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const BinHead* __restrict__ bins
     uint32_t best_face = 0;
     uint2* my_surv = s_surv + warp * 32;
     uint8_t* my_sidx = s_sidx + warp * 32;
-#ifdef B32_FILL_STATS
-    uint32_t st_t1 = gtime();
-#endif
-    if (mask_staged) while (!mbar_try_wait(&s_mbar, 0)) {}
-#ifdef B32_FILL_STATS
-    uint32_t st_tl = 0, st_tfirst = 0, st_tb0 = 0, st_tb1 = 0;
-#endif
+    const bool offscreen = bx0 >= p.width || by0 >= p.height;      // whole warp off-screen
+    const uint32_t tpx0 = tx * TILE_W, tpy0 = ty * TILE_H;
+    bool mask_waited = !mask_staged;
 
-    const uint32_t nchunks = (n + OP_CHUNK - 1) / OP_CHUNK;
-    for (uint32_t c = 0; c < nchunks; ++c) {
-        cp_async_wait<1>();                               // this thread's pieces of step c have landed ...
-        if (__syncthreads_and(done)) break;               // ... and so have everybody else's; slot (c+2) % 3 is free again
-#ifdef B32_FILL_STATS
-        if (c == 0) st_tfirst = gtime();
-#endif
-        stage(c + 2);
-        if (done) continue;
-        const SurfHot* crec = s_rec + (c % OP_RING) * OP_CHUNK;
-        for (uint32_t sb = 0; sb < (uint32_t)OP_CHUNK; sb += 32) {
-            const uint32_t base = c * OP_CHUNK + sb;
-            if (base >= n) break;
-#ifdef B32_FILL_STATS
-            if (st_batches == 1) st_tb0 = gtime();       // end of batch 0
-            if (st_batches == 2) st_tb1 = gtime();       // end of batch 1
-            ++st_batches;
-#endif
-            // ---- what the weakest pixel of this block still accepts ----------------------------------------
-            // painter's: wkey = smallest winner KEY in the block (0 while some pixel has no winner); z-buffer: wz =
-            // largest depth in the block.  One warp reduction (REDUX) each; both halves hold the same merged state.
-            uint32_t wkey = 0;
-            float wz = 0.0f;
+    // The candidates are taken OP_SORT_MAX at a time (a "window"; almost always there is one).  The winner rule is
+    // order-free, so windows need no order among themselves: each is ordered by walk key on its own (an efficiency
+    // device for the early-out), and the winners carry over.
+    // From the second window on, a candidate that cannot beat the tile's weakest pixel is dropped before it is ordered:
+    // painter's: tile_weak = smallest winner key in the tile (0 while a pixel has no winner): keys below it lose everywhere;
+    // z-buffer : tile_weak = ~bits(largest depth in the tile): a surface whose depth lower bound is behind it loses everywhere.
+    uint32_t tile_weak = 0;
+    for (uint32_t w0 = 0; w0 < n_cand; w0 += OP_SORT_MAX) {
+        const uint32_t wn = min((uint32_t)OP_SORT_MAX, n_cand - w0);
+        if (w0) {
+            cp_async_wait<0>();
+            if (threadIdx.x == 0) s_tile_weak = 0xFFFFFFFFu;
+            __syncthreads();                               // the previous window's ring traffic is over: its area is reused
+            uint32_t wk;
             if (!p.use_zbuffer) {
-                bool allw = __all_sync(0xFFFFFFFFu, best != 0);                          // invalid lanes carry ~0
-                wkey = allw ? __reduce_min_sync(0xFFFFFFFFu, (uint32_t)((best - 1) >> 32)) : 0u;
+                bool allw = __all_sync(0xFFFFFFFFu, best != 0);                              // invalid lanes carry ~0
+                wk = allw ? __reduce_min_sync(0xFFFFFFFFu, (uint32_t)((best - 1) >> 32)) : 0u;
+                if (offscreen) wk = 0xFFFFFFFFu;
             } else {
-                // order-preserving image of the depth (NaN never occurs in px.z: only `z < px.z` winners are stored)
-                uint32_t zb = __float_as_uint(valid ? px.z : -INFINITY);
-                zb ^= (zb >> 31) ? 0xFFFFFFFFu : 0x80000000u;
-                zb = __reduce_max_sync(0xFFFFFFFFu, zb);
-                zb ^= (zb >> 31) ? 0x80000000u : 0xFFFFFFFFu;
-                wz = __uint_as_float(zb);
+                // ~bits of the largest depth (depths >= 0 here or the bound is not used): smaller = farther, as the walk keys
+                float zmax = valid ? px.z : 0.0f;
+                uint32_t zb = (zmax >= 0.0f) ? ~__float_as_uint(zmax) : 0u;                  // negative / NaN depths: no bound
+                if (!valid) zb = 0xFFFFFFFFu;
+                wk = __reduce_min_sync(0xFFFFFFFFu, zb);
             }
-            // ---- 4. early out: entries are in descending key-bucket order ------------------------------------
-            // `open` pixels are those some entry of this batch or a later one could still change; only their
-            // bounding box [ox0,ox1) x [oy0,oy1) needs to be met by a surface's bbox.
-            uint32_t ox0 = bx0, ox1 = bx0 + OP_BW, oy0 = by0, oy1 = by0 + OP_BH;
-            if (!single_batch) {
-                uint32_t k0 = in_smem ? s_sh[base].key : gwalk[base].key;
-                if (k0 != 0xFFFFFFFFu) {
-                    // upper bound of every key still to come = top of k0's bucket
-                    uint64_t ub64 = (uint64_t)kmin + (((uint64_t)((k0 - kmin) >> shift) + 1) << shift) - 1;
-                    uint32_t ub = ub64 > 0xFFFFFFFEull ? 0xFFFFFFFEu : (uint32_t)ub64;
-                    if (!p.use_zbuffer) { if (ub < wkey) { done = true; break; } }    // every later surface was drawn before every winner
-                    else if (__uint_as_float(~ub) > wz) { done = true; break; }   // every later surface is behind every pixel
-                    bool open = valid && (!p.use_zbuffer ? (best == 0 || (uint32_t)((best - 1) >> 32) <= ub)
-                                                         : !(__uint_as_float(~ub) > px.z));
-                    uint32_t om = __ballot_sync(0xFFFFFFFFu, open);                // bit q = pixel q (row-major in the block) is open
-                    if (OP_DUAL) om &= 0xFFFFu;
-                    if (om == 0) { done = true; break; }
-                    constexpr uint32_t RM = (1u << OP_BW) - 1;                      // one block row of `om`
-                    uint32_t cols = (om | (om >> OP_BW) | (om >> (2 * OP_BW)) | (om >> (3 * OP_BW))) & RM;
-                    uint32_t rows = ((om & RM) ? 1u : 0u) | ((om & (RM << OP_BW)) ? 2u : 0u) | ((om & (RM << (2 * OP_BW))) ? 4u : 0u) |
-                                    ((om & (RM << (3 * OP_BW))) ? 8u : 0u);
-                    ox0 = bx0 + (__ffs(cols) - 1); ox1 = bx0 + (32 - __clz(cols));
-                    oy0 = by0 + (__ffs(rows) - 1); oy1 = by0 + (32 - __clz(rows));
-                }
+            if (lane == 0) atomicMin(&s_tile_weak, wk);
+            __syncthreads();
+            tile_weak = s_tile_weak;
+            if (tile_weak == 0xFFFFFFFFu) tile_weak = 0;   // no on-screen pixel at all
+        }
+        if (!fast_ok) cand_expand(mrow, cs, w0, wn, s_cand);
+        // ---- 1. gather the window's heads (one 16-byte record per face, L2-resident) into registers; drop the candidates
+        //         that are not pass-1 surfaces (head bbox 0: pass 2) or, with coarse mask tiles, miss this 16x16 tile
+        constexpr int KPT = OP_SORT_MAX / OP_THREADS;
+        BinHead hh[KPT];
+        uint32_t n = 0;
+        #pragma unroll
+        for (int q = 0; q < KPT; ++q) {
+            const uint32_t i = q * OP_THREADS + threadIdx.x;
+            bool ok = false;
+            if (i < wn) {
+                hh[q] = heads[s_cand[i]];
+                const uint32_t min_x = hh[q].bbox_x & 0xFFFF, max_x = hh[q].bbox_x >> 16, min_y = hh[q].bbox_y & 0xFFFF, max_y = hh[q].bbox_y >> 16;
+                ok = hh[q].bbox_x != 0 && !(max_x <= tpx0 || min_x >= tpx0 + TILE_W || max_y <= tpy0 || min_y >= tpy0 + TILE_H);
+                // (z-buffer: key 0xFFFFFFFF = "no bound claimed" always passes; equal bounds pass: ties are resolved per pixel)
+                ok = ok && hh[q].key >= tile_weak;
             }
-            // ---- 3a. filter 32 bin entries, one per lane ------------------------------------------------------
-            BinHead h{0, 0, 0, 0};
-            bool cand = false;
-            if (base + lane < n) {
-                h = walk(base + lane);
-                uint32_t min_x = h.bbox_x & 0xFFFF, max_x = h.bbox_x >> 16, min_y = h.bbox_y & 0xFFFF, max_y = h.bbox_y >> 16;
-                cand = !(max_x <= ox0 || min_x >= ox1 || max_y <= oy0 || min_y >= oy1);
-                if (!p.use_zbuffer) cand = cand && h.key >= wkey;
-                else cand = cand && (h.key == 0xFFFFFFFFu || !(__uint_as_float(~h.key) > wz));
-                if (cand && surface_misses_box(crec[sb + lane], ox0, ox1, oy0, oy1)) cand = false;   // exact: see surface_misses_box
+            if (!ok) hh[q].bbox_x = 0;
+            n += __syncthreads_count(ok);                  // (also orders the s_cand reads before the ring's writes)
+        }
+        if (n == 0) continue;
+        auto for_each_entry = [&](auto f) {
+            #pragma unroll
+            for (int q = 0; q < KPT; ++q) { if (hh[q].bbox_x) f(hh[q]); }
+        };
+        // ---- 1b. walk-key order, descending: one counting-sort pass into OP_BUCKETS key buckets (within a bucket the
+        //          order is arbitrary; the early-out uses bucket bounds)
+        uint32_t kmin = 0, shift = 0;
+        const bool single_batch = n <= 32;                // one batch: nothing comes "later", so no order (and no early-out) is needed
+        if (single_batch) {
+            if (threadIdx.x == 0) s_nsmall = 0;
+            __syncthreads();
+            for_each_entry([&](const BinHead& h) { s_sh[atomicAdd(&s_nsmall, 1u)] = h; });
+        } else {
+            uint32_t lo = 0xFFFFFFFFu, hi = 0;
+            for_each_entry([&](const BinHead& h) { if (h.key != 0xFFFFFFFFu) { lo = min(lo, h.key); hi = max(hi, h.key); } });   // 0xFFFFFFFF = "never cull": bucket 0
+            if (threadIdx.x < OP_BUCKETS) s_hist[threadIdx.x] = 0;
+            if (threadIdx.x == 0) { s_minmax[0] = 0xFFFFFFFFu; s_minmax[1] = 0; }
+            lo = __reduce_min_sync(0xFFFFFFFFu, lo); hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+            __syncthreads();
+            if (lane == 0) { atomicMin(&s_minmax[0], lo); atomicMax(&s_minmax[1], hi); }
+            __syncthreads();
+            kmin = s_minmax[0];
+            uint32_t kmax = s_minmax[1];
+            if (kmin > kmax) { kmin = 0; kmax = 0; }
+            uint32_t range = kmax - kmin;
+            shift = range >= OP_BUCKETS ? (32 - __clz(range)) - OP_BUCKET_BITS : 0;         // (range >> shift) <= OP_BUCKETS - 1
+            auto bucket = [&](uint32_t k) { return k == 0xFFFFFFFFu ? 0u : (uint32_t)(OP_BUCKETS - 1) - ((k - kmin) >> shift); };
+            for_each_entry([&](const BinHead& h) { atomicAdd(&s_hist[bucket(h.key)], 1u); });
+            __syncthreads();
+            uint32_t v = 0, xs = 0;                              // exclusive scan of the bucket counts (threads 0..OP_BUCKETS-1)
+            if (threadIdx.x < OP_BUCKETS) {
+                v = s_hist[threadIdx.x]; xs = v;
+                for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, xs, o); if (lane >= (uint32_t)o) xs += t; }
+                if (lane == 31) s_wsum[warp] = xs;
             }
-            uint32_t mask = __ballot_sync(0xFFFFFFFFu, cand);
-            if (mask == 0) continue;
-            uint32_t cnt = __popc(mask);
+            __syncthreads();
+            if (threadIdx.x < OP_BUCKETS) {
+                uint32_t pre = 0;
+                for (uint32_t w = 0; w < warp; ++w) pre += s_wsum[w];
+                s_hist[threadIdx.x] = pre + xs - v;
+            }
+            __syncthreads();
+            for_each_entry([&](const BinHead& h) { s_sh[atomicAdd(&s_hist[bucket(h.key)], 1u)] = h; });
+        }
+        __syncthreads();                                      // the walk order, s_tex and the mbarrier are ready
+
+        // ---- 2. the record ring: step c -> slot c % OP_RING; the 16-byte pieces of the step's records are dealt round robin
+        auto stage = [&](uint32_t c) {
+            for (uint32_t piece = threadIdx.x; piece < (uint32_t)(OP_CHUNK * OP_REC_PIECES); piece += OP_THREADS) {
+                uint32_t slot = piece / OP_REC_PIECES, part = piece % OP_REC_PIECES;
+                uint32_t e = c * OP_CHUNK + slot;
+                if (e < n)
+                    cp_async16(reinterpret_cast<uint4*>(&s_rec[(c % OP_RING) * OP_CHUNK + slot]) + part,
+                               reinterpret_cast<const uint4*>(&recs[s_sh[e].face]) + part);
+            }
+            cp_async_commit();
+        };
+        stage(0);
+        stage(1);
 #ifdef B32_FILL_STATS
-            st_surv += cnt;
+        if (!w0) st_t1 = gtime();
 #endif
-            __syncwarp();
-            if (cand) { uint32_t pos = __popc(mask & ((1u << lane) - 1)); my_surv[pos] = make_uint2(h.key, h.face); my_sidx[pos] = (uint8_t)(sb + lane); }
-            __syncwarp();
-            // ---- 3b. survivors, two at a time per pixel lane (dual: each half-warp takes every other one) -----------
-            constexpr uint32_t NSUB = OP_DUAL ? 2 : 1;
-            for (uint32_t j0 = 0; j0 < cnt; j0 += 2 * NSUB) {
-                #pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    uint32_t j = j0 + NSUB * k + sub;
-                    if (j >= cnt) continue;
-                    const SurfHot& r = crec[my_sidx[j]];
-                    const uint2 kf = my_surv[j];
-                    uint32_t min_x = r.bbox_x & 0xFFFF, max_x = r.bbox_x >> 16, min_y = r.bbox_y & 0xFFFF, max_y = r.bbox_y >> 16;
-                    if (!(valid && x >= min_x && x < max_x && y >= min_y && y < max_y)) continue;
-                    uint32_t c_face = kf.y + 1;
-                    uint64_t c_prio = (((uint64_t)kf.x << 32) | kf.y) + 1;
-                    if (!p.use_zbuffer && c_prio <= best) continue;               // drawn earlier than the current winner
-                    float bc_x, bc_y, bc_z;
-                    if (!inside_test(r, x, y, bc_x, bc_y, bc_z)) continue;
-                    float inv_z = 0.0f, c_z = 0.0f;
-                    if (p.use_zbuffer || !p.affine_textures) inv_z = bc_x * r.iz1 + bc_y * r.iz2 + bc_z * r.iz3;   // :1549
-                    if (p.use_zbuffer) {
-                        // lexicographic (z, face) minimum == sequential `z < zbuffer` in face order (:1553-1560, :1684)
-                        c_z = 1.0f / inv_z;
-                        if (!(c_z < px.z || (c_z == px.z && c_face < best_face))) continue;
-                    }
+        if (!mask_waited) { while (!mbar_try_wait(&s_mbar, 0)) {} mask_waited = true; }
+
+        bool done = offscreen;
+        const uint32_t nchunks = (n + OP_CHUNK - 1) / OP_CHUNK;
+        for (uint32_t c = 0; c < nchunks; ++c) {
+            cp_async_wait<1>();                               // this thread's pieces of step c have landed ...
+            if (__syncthreads_and(done)) break;               // ... and so have everybody else's; slot (c+2) % 3 is free again
 #ifdef B32_FILL_STATS
-                    ++st_inside;
+            if (c == 0 && !w0) st_tfirst = gtime();
 #endif
-                    // black-keyed textured surface: the texel decides whether this fragment writes (:1591-1607)
-                    if ((r.flags & (SF_TEXTURED | SF_BLACK_TR)) == (SF_TEXTURED | SF_BLACK_TR)) {
-                        uint32_t ti = texel_index(r, bc_x, bc_y, bc_z, inv_z, texd[r.flags >> 16], p);
-                        if (ti == TEXEL_NONE || !((maskw[ti >> 5] >> (ti & 31)) & 1u)) continue;    // transparent key / black-keyed texel
-                    }
-                    if (!p.use_zbuffer) best = c_prio;
-                    else { px.z = c_z; best_face = c_face; }
+            stage(c + 2);
+            if (done) continue;
+            const SurfHot* crec = s_rec + (c % OP_RING) * OP_CHUNK;
+            for (uint32_t sb = 0; sb < (uint32_t)OP_CHUNK; sb += 32) {
+                const uint32_t base = c * OP_CHUNK + sb;
+                if (base >= n) break;
+#ifdef B32_FILL_STATS
+                if (st_batches == 1) st_tb0 = gtime();       // end of batch 0
+                if (st_batches == 2) st_tb1 = gtime();       // end of batch 1
+                ++st_batches;
+#endif
+                // ---- what the weakest pixel of this block still accepts ----------------------------------------
+                // painter's: wkey = smallest winner KEY in the block (0 while some pixel has no winner); z-buffer: wz =
+                // largest depth in the block.  One warp reduction (REDUX) each; both halves hold the same merged state.
+                uint32_t wkey = 0;
+                float wz = 0.0f;
+                if (!p.use_zbuffer) {
+                    bool allw = __all_sync(0xFFFFFFFFu, best != 0);                          // invalid lanes carry ~0
+                    wkey = allw ? __reduce_min_sync(0xFFFFFFFFu, (uint32_t)((best - 1) >> 32)) : 0u;
+                } else {
+                    // order-preserving image of the depth (NaN never occurs in px.z: only `z < px.z` winners are stored)
+                    uint32_t zb = __float_as_uint(valid ? px.z : -INFINITY);
+                    zb ^= (zb >> 31) ? 0xFFFFFFFFu : 0x80000000u;
+                    zb = __reduce_max_sync(0xFFFFFFFFu, zb);
+                    zb ^= (zb >> 31) ? 0x80000000u : 0xFFFFFFFFu;
+                    wz = __uint_as_float(zb);
                 }
-            }
-            if (OP_DUAL) {   // merge the two half-warps' winners for each pixel (exact: max / lexicographic min are associative)
-                uint64_t ob = __shfl_xor_sync(0xFFFFFFFFu, best, 16);
-                float oz = __shfl_xor_sync(0xFFFFFFFFu, px.z, 16);
-                uint32_t of = __shfl_xor_sync(0xFFFFFFFFu, best_face, 16);
-                // z-buffer: lexicographic (z, face+1) minimum, 0 = framebuffer content wins ties; painter's: max priority
-                bool take = p.use_zbuffer ? (oz < px.z || (oz == px.z && of < best_face)) : (ob > best);
-                if (take) { best = ob; px.z = oz; best_face = of; }
+                // ---- 4. early out: entries are in descending key-bucket order ------------------------------------
+                // `open` pixels are those some entry of this batch or a later one could still change; only their
+                // bounding box [ox0,ox1) x [oy0,oy1) needs to be met by a surface's bbox.
+                uint32_t ox0 = bx0, ox1 = bx0 + OP_BW, oy0 = by0, oy1 = by0 + OP_BH;
+                if (!single_batch) {
+                    uint32_t k0 = s_sh[base].key;
+                    if (k0 != 0xFFFFFFFFu) {
+                        // upper bound of every key still to come = top of k0's bucket
+                        uint64_t ub64 = (uint64_t)kmin + (((uint64_t)((k0 - kmin) >> shift) + 1) << shift) - 1;
+                        uint32_t ub = ub64 > 0xFFFFFFFEull ? 0xFFFFFFFEu : (uint32_t)ub64;
+                        if (!p.use_zbuffer) { if (ub < wkey) { done = true; break; } }    // every later surface was drawn before every winner
+                        else if (__uint_as_float(~ub) > wz) { done = true; break; }   // every later surface is behind every pixel
+                        bool open = valid && (!p.use_zbuffer ? (best == 0 || (uint32_t)((best - 1) >> 32) <= ub)
+                                                             : !(__uint_as_float(~ub) > px.z));
+                        uint32_t om = __ballot_sync(0xFFFFFFFFu, open);                // bit q = pixel q (row-major in the block) is open
+                        if (OP_DUAL) om &= 0xFFFFu;
+                        if (om == 0) { done = true; break; }
+                        constexpr uint32_t RM = (1u << OP_BW) - 1;                      // one block row of `om`
+                        uint32_t cols = (om | (om >> OP_BW) | (om >> (2 * OP_BW)) | (om >> (3 * OP_BW))) & RM;
+                        uint32_t rows = ((om & RM) ? 1u : 0u) | ((om & (RM << OP_BW)) ? 2u : 0u) | ((om & (RM << (2 * OP_BW))) ? 4u : 0u) |
+                                        ((om & (RM << (3 * OP_BW))) ? 8u : 0u);
+                        ox0 = bx0 + (__ffs(cols) - 1); ox1 = bx0 + (32 - __clz(cols));
+                        oy0 = by0 + (__ffs(rows) - 1); oy1 = by0 + (32 - __clz(rows));
+                    }
+                }
+                // ---- 3a. filter 32 entries, one per lane ------------------------------------------------------
+                BinHead h{0, 0, 0, 0};
+                bool cand = false;
+                if (base + lane < n) {
+                    h = s_sh[base + lane];
+                    uint32_t min_x = h.bbox_x & 0xFFFF, max_x = h.bbox_x >> 16, min_y = h.bbox_y & 0xFFFF, max_y = h.bbox_y >> 16;
+                    cand = !(max_x <= ox0 || min_x >= ox1 || max_y <= oy0 || min_y >= oy1);
+                    if (!p.use_zbuffer) cand = cand && h.key >= wkey;
+                    else cand = cand && (h.key == 0xFFFFFFFFu || !(__uint_as_float(~h.key) > wz));
+                    if (cand && surface_misses_box(crec[sb + lane], ox0, ox1, oy0, oy1)) cand = false;   // exact: see surface_misses_box
+                }
+                uint32_t mask = __ballot_sync(0xFFFFFFFFu, cand);
+                if (mask == 0) continue;
+                uint32_t cnt = __popc(mask);
+#ifdef B32_FILL_STATS
+                st_surv += cnt;
+#endif
+                __syncwarp();
+                if (cand) { uint32_t pos = __popc(mask & ((1u << lane) - 1)); my_surv[pos] = make_uint2(h.key, h.face); my_sidx[pos] = (uint8_t)(sb + lane); }
+                __syncwarp();
+                // ---- 3b. survivors, two at a time per pixel lane (dual: each half-warp takes every other one) -----------
+                constexpr uint32_t NSUB = OP_DUAL ? 2 : 1;
+                for (uint32_t j0 = 0; j0 < cnt; j0 += 2 * NSUB) {
+                    #pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        uint32_t j = j0 + NSUB * k + sub;
+                        if (j >= cnt) continue;
+                        const SurfHot& r = crec[my_sidx[j]];
+                        const uint2 kf = my_surv[j];
+                        uint32_t min_x = r.bbox_x & 0xFFFF, max_x = r.bbox_x >> 16, min_y = r.bbox_y & 0xFFFF, max_y = r.bbox_y >> 16;
+                        if (!(valid && x >= min_x && x < max_x && y >= min_y && y < max_y)) continue;
+                        uint32_t c_face = kf.y + 1;
+                        uint64_t c_prio = (((uint64_t)kf.x << 32) | kf.y) + 1;
+                        if (!p.use_zbuffer && c_prio <= best) continue;               // drawn earlier than the current winner
+                        float bc_x, bc_y, bc_z;
+                        if (!inside_test(r, x, y, bc_x, bc_y, bc_z)) continue;
+                        float inv_z = 0.0f, c_z = 0.0f;
+                        if (p.use_zbuffer || !p.affine_textures) inv_z = bc_x * r.iz1 + bc_y * r.iz2 + bc_z * r.iz3;   // :1549
+                        if (p.use_zbuffer) {
+                            // lexicographic (z, face) minimum == sequential `z < zbuffer` in face order (:1553-1560, :1684)
+                            c_z = 1.0f / inv_z;
+                            if (!(c_z < px.z || (c_z == px.z && c_face < best_face))) continue;
+                        }
+#ifdef B32_FILL_STATS
+                        ++st_inside;
+#endif
+                        // black-keyed textured surface: the texel decides whether this fragment writes (:1591-1607)
+                        if ((r.flags & (SF_TEXTURED | SF_BLACK_TR)) == (SF_TEXTURED | SF_BLACK_TR)) {
+                            uint32_t ti = texel_index(r, bc_x, bc_y, bc_z, inv_z, texd[r.flags >> 16], p);
+                            if (ti == TEXEL_NONE || !((maskw[ti >> 5] >> (ti & 31)) & 1u)) continue;    // transparent key / black-keyed texel
+                        }
+                        if (!p.use_zbuffer) best = c_prio;
+                        else { px.z = c_z; best_face = c_face; }
+                    }
+                }
+                if (OP_DUAL) {   // merge the two half-warps' winners for each pixel (exact: max / lexicographic min are associative)
+                    uint64_t ob = __shfl_xor_sync(0xFFFFFFFFu, best, 16);
+                    float oz = __shfl_xor_sync(0xFFFFFFFFu, px.z, 16);
+                    uint32_t of = __shfl_xor_sync(0xFFFFFFFFu, best_face, 16);
+                    // z-buffer: lexicographic (z, face+1) minimum, 0 = framebuffer content wins ties; painter's: max priority
+                    bool take = p.use_zbuffer ? (oz < px.z || (oz == px.z && of < best_face)) : (ob > best);
+                    if (take) { best = ob; px.z = oz; best_face = of; }
+                }
             }
         }
     }
     cp_async_wait<0>();
+    if (!mask_waited) { while (!mbar_try_wait(&s_mbar, 0)) {} }       // the bulk copy must land before the CTA exits
 #ifdef B32_FILL_STATS
     st_tl = gtime();
 #endif
@@ -1152,10 +1268,8 @@ __device__ __forceinline__ void write_ordered888(const SurfRec& r, Pixel& px, fl
 constexpr int ORD_CHUNK = 32;        // surfaces staged in shared memory per step (32 x 128 B = 4 KB), one 16-byte piece per thread
 constexpr int ORD_RING = 3;          // steps c, c+1, c+2 in flight
 constexpr int ORD_GROUP = 4;         // fragments of one pixel whose texels are requested together
-constexpr int ORD_SORT_MAX = 2048;   // bin entries sortable in shared memory (32 KB); larger bins are sorted in place in global memory
 constexpr size_t ORD_SMEM = (size_t)ORD_SORT_MAX * sizeof(BinHead) + (size_t)ORD_RING * ORD_CHUNK * sizeof(SurfRec) + (FILL_THREADS / 32) * 32;
 static_assert(FILL_THREADS == ORD_CHUNK * 8, "one 16-byte piece of the staged records per thread");
-static_assert(OP_SORT_MAX_ENTRIES <= ORD_SORT_MAX, "a scanned mesh's draw-order entries fit the shared-memory sort");
 
 __device__ __forceinline__ uint64_t ord_key(const BinHead& h) { return ((uint64_t)h.key << 32) | h.face; }
 
@@ -1184,59 +1298,78 @@ __device__ void bitonic_sort_heads(BinHead* a, uint32_t m) {
 // on the pixel's running colour), and only then are its fragments shaded and written one after the other.
 template <bool RGB888>
 __global__ void __launch_bounds__(FILL_THREADS)
-k_fill_ordered(const SurfRec* __restrict__ recs, BinHead* __restrict__ bins, const uint32_t* __restrict__ tile_count,
+k_fill_ordered(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks, BinHead* __restrict__ scratch,
                const uint64_t* __restrict__ keys, const TexDev* __restrict__ tex, const void* __restrict__ texels,
-               uint32_t* __restrict__ fb_rgba, float* __restrict__ fb_z, const CallState* __restrict__ st, CallParams p, uint32_t bin_cap) {
+               uint32_t* __restrict__ fb_rgba, float* __restrict__ fb_z, CallState* __restrict__ st, uint32_t* __restrict__ sticky,
+               CallParams p, uint32_t scratch_cap) {
     extern __shared__ __align__(128) uint8_t ord_smem[];
     SurfRec* s_rec = reinterpret_cast<SurfRec*>(ord_smem);                              // [ORD_RING][ORD_CHUNK]
     BinHead* s_sorted = reinterpret_cast<BinHead*>(s_rec + ORD_RING * ORD_CHUNK);       // [ORD_SORT_MAX]
     uint8_t* s_sidx = reinterpret_cast<uint8_t*>(s_sorted + ORD_SORT_MAX);              // [warps][32] survivors of the step, in order
+    uint32_t* s_cand = reinterpret_cast<uint32_t*>(s_rec);                              // [ORD_SORT_MAX] face indices of a window (the ring is idle then)
+    __shared__ uint32_t s_wsum[FILL_THREADS / 32];
+    __shared__ uint32_t s_n;
+    if (p.enq_ordered) pdl_wait();                      // enqueued right behind pass 1: k_fill_opaque (and k_setup before it) have completed
+    const bool all_ordered = RGB888 ? true : p.xray_mode != 0;      // every drawn surface is replayed (RGB888: this kernel only runs when some surface may blend)
     {
         CallState s = *st;
-        if (s.obin_overflow || call_aborts(s, p.use_zbuffer, RGB888)) return;
+        if (call_aborts(s, p.use_zbuffer, RGB888)) return;
+        const uint32_t n_ordered = all_ordered ? s.n_opaque + s.n_transp : s.n_transp;
+        if (n_ordered == 0 || (RGB888 && s.n_transp == 0)) return;                      // nothing to replay (the usual case of an enqueued frame)
+        // k_setup counted the ordered entries per mask tile: a tile with more than fit shared memory needs a slice of the
+        // global scratch; if that is too small NO tile draws (the host grows it and redoes the pass; enqueue-only callers get an error)
+        if (s.obin_max > (uint32_t)ORD_SORT_MAX && s.obin_max > scratch_cap) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) { st->obin_overflow = 1; if (p.async_call) atomicOr(sticky, 16u); }
+            return;
+        }
     }
     const uint32_t tile = blockIdx.x;
-    __shared__ uint32_t s_scan_n;
-    uint32_t n;
-    if (p.scan_heads) {
-        // Small meshes (<= OP_SORT_MAX_ENTRIES faces): no binning kernel — this tile builds its draw-order entries straight
-        // from keys[] + the records' bboxes (the same entries k_bin_opaque(ordered) would have scattered).
-        if (threadIdx.x == 0) s_scan_n = 0;
-        __syncthreads();
-        const uint32_t ttx = tile % p.tiles_x, tty = tile / p.tiles_x;
-        for (uint32_t fi = threadIdx.x; fi < p.nf; fi += blockDim.x) {
+    const uint32_t ttx = tile % p.tiles_x, tty = tile / p.tiles_x;
+    const uint32_t mtile = (tty >> p.mshift) * p.mtiles_x + (ttx >> p.mshift);
+    const uint4* mrow = masks + (size_t)mtile * p.n_groups;
+    CandScan cs = cand_scan<FILL_THREADS>(mrow, p.n_groups, s_wsum);
+    if (cs.total == 0) return;
+    // ---- this tile's draw-order entries: the candidates that are in the ordered pass and touch the tile.  The unique
+    //      64-bit key (pass:2 | depth key:32 | face:30) = opaque list first (sorted only in painter's mode), then the
+    //      transparent list, ties by face index = stable sort (render.rs:2522-2542); RGB888: one list, no pass bit.
+    const bool in_smem_build = cs.total <= (uint32_t)ORD_SORT_MAX;
+    BinHead* gslice = scratch + (size_t)tile * scratch_cap;
+    if (threadIdx.x == 0) s_n = 0;
+    for (uint32_t w0 = 0; w0 < cs.total; w0 += ORD_SORT_MAX) {
+        const uint32_t wn = min((uint32_t)ORD_SORT_MAX, cs.total - w0);
+        cand_expand(mrow, cs, w0, wn, s_cand);           // (its barrier also publishes s_n = 0)
+        for (uint32_t i = threadIdx.x; i < wn; i += blockDim.x) {
+            const uint32_t fi = s_cand[i];
             const uint64_t k64 = keys[fi];
             const uint32_t cls = (uint32_t)(k64 >> 32);
-            if (!(cls < 2 && (cls == 1 || p.xray_mode || RGB888))) continue;
+            if (!(cls < 2 && (cls == 1 || all_ordered))) continue;
             const uint2 bb = *reinterpret_cast<const uint2*>(&recs[fi].bbox_x);               // all zero = empty surface
             if (!bb.x) continue;
             BinHead h{bb.x, bb.y, 0, 0};
             uint32_t tx0, tx1, ty0, ty1;
-            head_tiles(h, tx0, tx1, ty0, ty1);
+            bbox_mtiles(bb.x, bb.y, 4u, tx0, tx1, ty0, ty1);
             if (!(ttx >= tx0 && ttx <= tx1 && tty >= ty0 && tty <= ty1)) continue;
             const uint64_t okey = ((uint64_t)(RGB888 ? 0u : cls) << 62) | ((uint64_t)(uint32_t)k64 << 30) | fi;
             h.key = (uint32_t)(okey >> 32); h.face = (uint32_t)okey;
-            s_sorted[atomicAdd(&s_scan_n, 1u)] = h;
+            const uint32_t pos = atomicAdd(&s_n, 1u);
+            if (in_smem_build) s_sorted[pos] = h; else if (pos < scratch_cap) gslice[pos] = h;
         }
         __syncthreads();
-        n = s_scan_n;
-    } else {
-        n = tile_count[tile];
     }
+    const uint32_t n = s_n;
     if (n == 0) return;
-    BinHead* bin = bins + (size_t)tile * bin_cap;
     uint32_t m = 2;
-    while (m < n) m <<= 1;                              // bin_cap is a power of two >= n
+    while (m < n) m <<= 1;                              // scratch_cap is a power of two >= n whenever the scratch is used
     BinHead* sorted;
-    if (p.scan_heads) {                                 // n <= nf <= OP_SORT_MAX_ENTRIES <= ORD_SORT_MAX: pad in place
+    if (in_smem_build) {
         for (uint32_t i = n + threadIdx.x; i < m; i += blockDim.x) s_sorted[i] = BinHead{0, 0, 0xFFFFFFFFu, 0xFFFFFFFFu};
         sorted = s_sorted;
-    } else if (m <= ORD_SORT_MAX) {
-        for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) s_sorted[i] = i < n ? bin[i] : BinHead{0, 0, 0xFFFFFFFFu, 0xFFFFFFFFu};
+    } else if (m <= (uint32_t)ORD_SORT_MAX) {
+        for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) s_sorted[i] = i < n ? gslice[i] : BinHead{0, 0, 0xFFFFFFFFu, 0xFFFFFFFFu};
         sorted = s_sorted;
     } else {
-        for (uint32_t i = n + threadIdx.x; i < m; i += blockDim.x) bin[i] = BinHead{0, 0, 0xFFFFFFFFu, 0xFFFFFFFFu};
-        sorted = bin;
+        for (uint32_t i = n + threadIdx.x; i < m; i += blockDim.x) gslice[i] = BinHead{0, 0, 0xFFFFFFFFu, 0xFFFFFFFFu};
+        sorted = gslice;
     }
     __syncthreads();
     bitonic_sort_heads(sorted, m);
@@ -1438,14 +1571,20 @@ k_wire(const WireTri* __restrict__ wire, uint32_t nf, uint32_t kind, uint32_t co
 // of the LAST face covering its centre: order-free like pass 1, with the face index as priority.  k_sky_setup
 // projects + culls one face per thread and emits a bin head (walked into the tile bins by k_bin_opaque);
 // k_sky_fill gives each pixel of a tile to one thread.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(SETUP_GROUP)
 k_sky_setup(const b32_sky_vertex* __restrict__ verts, const uint32_t* __restrict__ faces, SkyRec* __restrict__ recs,
-            BinHead* __restrict__ heads, CallState* __restrict__ st, uint32_t* __restrict__ zero_next, uint32_t zero_words, CallParams p) {
+            BinHead* __restrict__ heads, uint4* __restrict__ masks, CallState* __restrict__ st, uint32_t* __restrict__ zero_next, uint32_t zero_words, CallParams p) {
+    extern __shared__ __align__(16) uint8_t su_smem[];
+    uint4* s_mask = reinterpret_cast<uint4*>(su_smem);
+    const uint32_t n_mtiles = p.mtiles_x * p.mtiles_y;
     pdl_launch_dependents();
     if (blockIdx.x == 0) for (uint32_t i = threadIdx.x; i < zero_words; i += blockDim.x) zero_next[i] = 0;
-    for (uint32_t fi = blockIdx.x * blockDim.x + threadIdx.x; fi < p.nf; fi += gridDim.x * blockDim.x) {
+    for (uint32_t group = blockIdx.x; group < p.n_groups; group += gridDim.x) {
+        const uint32_t fi = group * SETUP_GROUP + threadIdx.x;
+        masks_zero(s_mask, n_mtiles);
+        __syncthreads();
         BinHead head{0, 0, 0, fi};
-        do {
+        if (fi < p.nf) do {
             uint32_t i0 = faces[fi * 3], i1 = faces[fi * 3 + 1], i2 = faces[fi * 3 + 2];
             if (i0 >= p.nv || i1 >= p.nv || i2 >= p.nv) { st->oob = 1; break; }
             const b32_sky_vertex a = verts[i0], b = verts[i1], c = verts[i2];
@@ -1472,37 +1611,42 @@ k_sky_setup(const b32_sky_vertex* __restrict__ verts, const uint32_t* __restrict
             r.c0 = a.r | (a.g << 8) | (a.b << 16); r.c1 = b.r | (b.g << 8) | (b.b << 16); r.c2 = c.r | (c.g << 8) | (c.b << 16);
             r._pad0 = r._pad1 = 0;
             recs[fi] = r;
-            head = BinHead{min_x | ((max_x + 1) << 16), min_y | ((max_y + 1) << 16), 0u, fi};   // exclusive max, as the mesh bins
+            head = BinHead{min_x | ((max_x + 1) << 16), min_y | ((max_y + 1) << 16), 0u, fi};   // exclusive max, as the mesh heads
         } while (0);
-        heads[fi] = head;
+        if (fi < p.nf) heads[fi] = head;
+        masks_mark(s_mask, head.bbox_x, head.bbox_y, head.bbox_x != 0, p);
+        __syncthreads();
+        masks_flush(s_mask, masks, n_mtiles, group, p, make_uint4(0, 0, 0, 0), nullptr, st);
+        __syncthreads();
     }
 }
 
 __global__ void __launch_bounds__(FILL_THREADS)
-k_sky_fill(const SkyRec* __restrict__ recs, const BinHead* __restrict__ bins, const uint32_t* __restrict__ tile_count,
+k_sky_fill(const SkyRec* __restrict__ recs, const uint4* __restrict__ masks, const BinHead* __restrict__ heads,
            uint32_t* __restrict__ fb_rgba, const CallState* __restrict__ st, CallParams p) {
     __shared__ BinHead s_head[FILL_THREADS];
     __shared__ SkyRec s_rec[FILL_THREADS];
+    __shared__ uint32_t s_cand[FILL_THREADS];
+    __shared__ uint32_t s_wsum[FILL_THREADS / 32];
     pdl_wait();
-    {
-        CallState s = *st;
-        if (s.oob || s.bin_overflow) return;
-    }
+    if (st->oob) return;
     const uint32_t tile = blockIdx.x;
-    const uint32_t n = tile_count[tile];
-    if (n == 0) return;
-    const BinHead* bin = bins + (size_t)tile * p.bin_cap;
-    const uint32_t x = (tile % p.tiles_x) * TILE_W + (threadIdx.x % TILE_W), y = (tile / p.tiles_x) * TILE_H + (threadIdx.x / TILE_W);
+    const uint32_t ttx = tile % p.tiles_x, tty = tile / p.tiles_x;
+    const uint4* mrow = masks + (size_t)((tty >> p.mshift) * p.mtiles_x + (ttx >> p.mshift)) * p.n_groups;
+    CandScan cs = cand_scan<FILL_THREADS>(mrow, p.n_groups, s_wsum);
+    if (cs.total == 0) return;
+    const uint32_t x = ttx * TILE_W + (threadIdx.x % TILE_W), y = tty * TILE_H + (threadIdx.x / TILE_W);
     const bool valid = x < p.width && y < p.height;
     const float px = (float)x + 0.5f, py = (float)y + 0.5f;                                      // :270-271
     uint32_t best = 0;                                       // face + 1 of the last face covering this pixel centre
-    // The bin is walked from its end: slots are handed out roughly in face order, so the last covering face tends to be
+    // The candidates come in face order; they are walked from the end, FILL_THREADS at a time: the last covering face is
     // met first and everything below it is skipped by its index alone.  Heads and records of a step sit in shared memory.
-    for (uint32_t done = 0; done < n; done += FILL_THREADS) {
-        const uint32_t cnt = min((uint32_t)FILL_THREADS, n - done);
-        const uint32_t base = n - done - cnt;
+    for (uint32_t rem = cs.total; rem > 0;) {
+        const uint32_t cnt = min((uint32_t)FILL_THREADS, rem);
+        rem -= cnt;
         __syncthreads();
-        if (threadIdx.x < cnt) { const BinHead h = bin[base + threadIdx.x]; s_head[threadIdx.x] = h; s_rec[threadIdx.x] = recs[h.face]; }
+        cand_expand(mrow, cs, rem, cnt, s_cand);
+        if (threadIdx.x < cnt) { const BinHead h = heads[s_cand[threadIdx.x]]; s_head[threadIdx.x] = h; s_rec[threadIdx.x] = recs[h.face]; }
         __syncthreads();
         for (uint32_t i = cnt; i-- > 0;) {
             const BinHead h = s_head[i];
@@ -1683,8 +1827,7 @@ static void launch_k(const LaunchCtx& L, void (*kern)(KArgs...), dim3 grid, dim3
 
 // Per-device kernel attributes (dynamic shared memory above the 48 KB default); called once per context, on its device.
 int init_kernel_attributes() {
-    cudaError_t e = cudaFuncSetAttribute(k_bin_opaque, cudaFuncAttributeMaxDynamicSharedMemorySize, BIN_MAX_TILES * 8);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fill_opaque<false, OpDense>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OpDense::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(k_fill_opaque<false, OpDense>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OpDense::SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fill_opaque<true, OpDense>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OpDense::SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fill_opaque<false, OpSparse>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OpSparse::SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fill_opaque<true, OpSparse>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OpSparse::SMEM);
@@ -1706,58 +1849,40 @@ void launch_transform(const LaunchCtx& L, const b32_vertex* verts, TVert* out, f
 }
 
 void launch_setup(const LaunchCtx& L, const b32_vertex* verts, const b32_face* faces, const TVert* tv, const TexDev* tex,
-                  const LightDev* lights, SurfRec* recs, uint64_t* keys, BinHead* heads, BinHead* bins,
-                  uint32_t* tile_count, WireTri* wire, CallState* st, uint32_t* zero_next, uint32_t zero_words,
+                  const LightDev* lights, SurfRec* recs, uint64_t* keys, BinHead* heads, uint4* masks, uint32_t* ocount,
+                  WireTri* wire, CallState* st, uint32_t* zero_next, uint32_t zero_words,
                   uint32_t* clear_rgba, float* clear_z, uint32_t clear_n, uint32_t clear_color, const CallParams& p) {
     if (p.nf == 0) return;
-    const bool pass1 = !((p.xray_mode && !p.rgb888) || p.wire_front);        // wireframe_overlay draws no solid surfaces (:2550)
-    launch_k(L, k_setup, grid_for(std::max(p.nf, clear_n / 4), SETUP_THREADS, L.sms, 16), SETUP_THREADS, 0, false, verts, faces, tv, tex, lights, recs, keys, heads, wire, st,
-             zero_next, zero_words, clear_rgba, clear_z, clear_n, clear_color, p);
-    if (!pass1 || p.scan_heads) return;                // small meshes: k_fill_opaque picks its tile's surfaces out of `heads` itself
-    launch_bin(L, heads, keys, recs, bins, tile_count, st, p, p.bin_cap, false, true);
+    const size_t smem = (size_t)p.mtiles_x * p.mtiles_y * sizeof(uint4) + SETUP_STAGE_BYTES;
+    launch_k(L, k_setup, grid_for(std::max(p.nf, clear_n / 4), SETUP_THREADS, L.sms, 16), SETUP_THREADS, smem, false, verts, faces, tv, tex, lights, recs, keys, heads,
+             masks, ocount, wire, st, zero_next, zero_words, clear_rgba, clear_z, clear_n, clear_color, p);
 }
 
-void launch_bin(const LaunchCtx& L, const BinHead* heads, const uint64_t* keys, const SurfRec* recs, BinHead* bins, uint32_t* tile_count,
-                CallState* st, const CallParams& p, uint32_t bin_cap, bool ordered, bool after_setup) {
-    if (p.nf == 0) return;
-    uint32_t ntiles = p.tiles_x * p.tiles_y;
-    size_t smem = ntiles <= (uint32_t)BIN_MAX_TILES ? (size_t)ntiles * 8 : 0;
-    // Large meshes: BIN_THREADS faces per block keep the global atomics few (one per block and touched tile).  Up to 16k
-    // faces that would leave a handful of blocks walking long serial chains, so they get 128-face blocks instead.
-    uint32_t per_round = p.nf <= 16384u ? 128u : (uint32_t)BIN_THREADS;
-    uint32_t grid = (p.nf + per_round - 1) / per_round;
-    if (grid > L.sms * 4) grid = L.sms * 4;
-    launch_k(L, k_bin_opaque, grid, per_round, smem, after_setup, heads, keys, recs, bins, tile_count, st, p, bin_cap, ordered);
-}
-
-void launch_fill_opaque(const LaunchCtx& L, const SurfRec* recs, const BinHead* bins, const uint32_t* tile_count, const BinHead* heads,
-                        BinHead* sorted_scratch, const TexDev* tex, const uint16_t* texels, const uint32_t* texmask, uint32_t* fb_rgba, float* fb_z,
+void launch_fill_opaque(const LaunchCtx& L, const SurfRec* recs, const uint4* masks, const BinHead* heads,
+                        const TexDev* tex, const uint16_t* texels, const uint32_t* texmask, uint32_t* fb_rgba, float* fb_z,
                         const CallState* st, uint32_t* sticky, const CallParams& p) {
     uint32_t ntiles = p.tiles_x * p.tiles_y;
     if (ntiles == 0 || p.nf == 0) return;
-    // launched right behind k_bin_opaque except in x-ray mode (no pass-1 binning: then it is an ordinary launch)
     // The 256-thread shape packs 4 CTAs per SM: it wins when the frame has more tiles than one wave of the two-lanes-per-
     // pixel shape holds (3 CTAs per SM), and for enqueue-only calls, whose kernels share the SMs with the frames queued
-    // around them (4 frames in flight: 5 561 vs 5 224 Mtri/s).  A blocking call of up to 444 tiles has the GPU to itself:
-    // the two-lane shape finishes it sooner (2 424 vs 2 385 Mtri/s).
+    // around them.  A blocking call of up to 444 tiles has the GPU to itself: the two-lane shape finishes it sooner.
     static const bool force_dense = getenv("B32_FILL_DENSE") != nullptr, force_sparse = getenv("B32_FILL_SPARSE") != nullptr;
     const bool sparse = force_sparse || (!force_dense && (p.async_call || ntiles * OpDense::SPLIT > L.sms * (uint32_t)OpDense::MINB));
-    const bool pdl = !(p.xray_mode && !p.rgb888);
     if (sparse)
-        launch_k(L, p.rgb888 ? k_fill_opaque<true, OpSparse> : k_fill_opaque<false, OpSparse>, ntiles * OpSparse::SPLIT, OpSparse::THREADS, OpSparse::SMEM, pdl,
-                 recs, bins, tile_count, heads, sorted_scratch, tex, texels, texmask, fb_rgba, fb_z, st, sticky, p);
+        launch_k(L, p.rgb888 ? k_fill_opaque<true, OpSparse> : k_fill_opaque<false, OpSparse>, ntiles * OpSparse::SPLIT, OpSparse::THREADS, OpSparse::SMEM, true,
+                 recs, masks, heads, tex, texels, texmask, fb_rgba, fb_z, st, sticky, p);
     else
-        launch_k(L, p.rgb888 ? k_fill_opaque<true, OpDense> : k_fill_opaque<false, OpDense>, ntiles * OpDense::SPLIT, OpDense::THREADS, OpDense::SMEM, pdl,
-                 recs, bins, tile_count, heads, sorted_scratch, tex, texels, texmask, fb_rgba, fb_z, st, sticky, p);
+        launch_k(L, p.rgb888 ? k_fill_opaque<true, OpDense> : k_fill_opaque<false, OpDense>, ntiles * OpDense::SPLIT, OpDense::THREADS, OpDense::SMEM, true,
+                 recs, masks, heads, tex, texels, texmask, fb_rgba, fb_z, st, sticky, p);
 }
 
-void launch_fill_ordered(const LaunchCtx& L, const SurfRec* recs, BinHead* obins, const uint32_t* otile_count, const uint64_t* keys,
+void launch_fill_ordered(const LaunchCtx& L, const SurfRec* recs, const uint4* masks, BinHead* scratch, const uint64_t* keys,
                          const TexDev* tex, const uint16_t* texels, uint32_t* fb_rgba, float* fb_z,
-                         const CallState* st, const CallParams& p, uint32_t obin_cap) {
+                         CallState* st, uint32_t* sticky, const CallParams& p, uint32_t scratch_cap) {
     uint32_t ntiles = p.tiles_x * p.tiles_y;
     if (ntiles == 0 || p.nf == 0) return;
-    launch_k(L, p.rgb888 ? k_fill_ordered<true> : k_fill_ordered<false>, ntiles, FILL_THREADS, ORD_SMEM, false,
-             recs, obins, otile_count, keys, tex, static_cast<const void*>(texels), fb_rgba, fb_z, st, p, obin_cap);
+    launch_k(L, p.rgb888 ? k_fill_ordered<true> : k_fill_ordered<false>, ntiles, FILL_THREADS, ORD_SMEM, p.enq_ordered != 0,
+             recs, masks, scratch, keys, tex, static_cast<const void*>(texels), fb_rgba, fb_z, st, sticky, p, scratch_cap);
 }
 
 void launch_wire(const LaunchCtx& L, const WireTri* wire, uint32_t kind, uint32_t color, bool depth_test, uint32_t* table, uint32_t table_size,
@@ -1780,12 +1905,12 @@ void launch_tex_expand(const LaunchCtx& L, const uint8_t* idx, const uint16_t* c
     ++*L.launches;
 }
 
-void launch_sky(const LaunchCtx& L, const b32_sky_vertex* verts, const uint32_t* faces, SkyRec* recs, BinHead* heads, BinHead* bins,
-                uint32_t* tile_count, uint32_t* fb_rgba, CallState* st, uint32_t* zero_next, uint32_t zero_words, const CallParams& p) {
+void launch_sky(const LaunchCtx& L, const b32_sky_vertex* verts, const uint32_t* faces, SkyRec* recs, BinHead* heads, uint4* masks,
+                uint32_t* fb_rgba, CallState* st, uint32_t* zero_next, uint32_t zero_words, const CallParams& p) {
     if (p.nf == 0) return;
-    launch_k(L, k_sky_setup, grid_for(p.nf, 128, L.sms, 16), 128, 0, false, verts, faces, recs, heads, st, zero_next, zero_words, p);
-    launch_bin(L, heads, nullptr, nullptr, bins, tile_count, st, p, p.bin_cap, false, true);
-    launch_k(L, k_sky_fill, p.tiles_x * p.tiles_y, FILL_THREADS, 0, true, recs, bins, tile_count, fb_rgba, st, p);
+    const size_t smem = (size_t)p.mtiles_x * p.mtiles_y * sizeof(uint4);
+    launch_k(L, k_sky_setup, grid_for(p.nf, SETUP_GROUP, L.sms, 16), SETUP_GROUP, smem, false, verts, faces, recs, heads, masks, st, zero_next, zero_words, p);
+    launch_k(L, k_sky_fill, p.tiles_x * p.tiles_y, FILL_THREADS, 0, true, recs, masks, heads, fb_rgba, st, p);
 }
 
 void launch_stars(const LaunchCtx& L, const b32_star* stars, uint32_t n, int32_t size, uint32_t* owner, uint32_t* fb_rgba, const CallParams& p) {

@@ -10,7 +10,7 @@
 
 namespace b32 {
 
-// An instantiated CUDA graph of one enqueued frame (k_fb_clear, k_setup, k_bin_opaque, k_fill_opaque) whose
+// An instantiated CUDA graph of one enqueued frame (k_setup, k_fill_opaque[, k_fill_ordered]) whose
 // kernel nodes are re-parameterised in place: when LaunchCtx.patch is set, the frame kernels' launchers write
 // their arguments into the graph's nodes instead of launching, and the caller launches the graph once.
 struct GraphPatch {
@@ -34,25 +34,23 @@ struct LaunchCtx {
 int init_kernel_attributes();
 
 void launch_transform(const LaunchCtx& L, const b32_vertex* verts, TVert* out, float* dbg_cam, const CallParams& p);
-// tv == nullptr: vertices are transformed inside k_setup (fused path). Also bins the pass-1 surfaces.
-void launch_setup(const LaunchCtx& L, const b32_vertex* verts, const b32_face* faces, const TVert* tv, const TexDev* tex,
-                  const LightDev* lights, SurfRec* recs, uint64_t* keys, BinHead* heads, BinHead* bins,
-                  uint32_t* tile_count, WireTri* wire, CallState* st, uint32_t* zero_next, uint32_t zero_words,
-                  uint32_t* clear_rgba, float* clear_z, uint32_t clear_n, uint32_t clear_color, const CallParams& p);
+// tv == nullptr: vertices are transformed inside k_setup (fused path).  Also writes the tile masks (binning without bins,
+// b32_device.cuh) and counts the ordered pass's entries per mask tile in ocount[] / CallState.obin_max.
 // clear_n != 0: k_setup first clears the framebuffer (clear_n pixels to clear_color, depth to f32::MAX)
-// ordered = false: scatter heads[] (pass 1); true: scatter the draw-order entries rebuilt from keys[] + recs[] (pass 2 / x-ray)
-void launch_bin(const LaunchCtx& L, const BinHead* heads, const uint64_t* keys, const SurfRec* recs, BinHead* bins, uint32_t* tile_count,
-                CallState* st, const CallParams& p, uint32_t bin_cap, bool ordered, bool after_setup);
-// sorted_scratch: one bin-sized slice per tile for bins too large to order in shared memory (same layout as bins)
-// heads: k_setup's per-face bin heads, read directly when p.scan_heads (small meshes, no binning kernel)
-void launch_fill_opaque(const LaunchCtx& L, const SurfRec* recs, const BinHead* bins, const uint32_t* tile_count, const BinHead* heads,
-                        BinHead* sorted_scratch, const TexDev* tex, const uint16_t* texels, const uint32_t* texmask, uint32_t* fb_rgba, float* fb_z,
+void launch_setup(const LaunchCtx& L, const b32_vertex* verts, const b32_face* faces, const TVert* tv, const TexDev* tex,
+                  const LightDev* lights, SurfRec* recs, uint64_t* keys, BinHead* heads, uint4* masks, uint32_t* ocount,
+                  WireTri* wire, CallState* st, uint32_t* zero_next, uint32_t zero_words,
+                  uint32_t* clear_rgba, float* clear_z, uint32_t clear_n, uint32_t clear_color, const CallParams& p);
+// pass 1: every tile reads its surface list out of its mask row and k_setup's per-face heads
+void launch_fill_opaque(const LaunchCtx& L, const SurfRec* recs, const uint4* masks, const BinHead* heads,
+                        const TexDev* tex, const uint16_t* texels, const uint32_t* texmask, uint32_t* fb_rgba, float* fb_z,
                         const CallState* st, uint32_t* sticky, const CallParams& p);
-// ordered pass (pass 2 / x-ray): bins of draw-order keys, sorted per tile, replayed in order
-// keys: k_setup's (class | depth key) per face, read directly when p.scan_heads (small meshes, no binning kernel)
-void launch_fill_ordered(const LaunchCtx& L, const SurfRec* recs, BinHead* obins, const uint32_t* otile_count, const uint64_t* keys,
+// ordered pass (pass 2 / x-ray): every tile builds its draw-order entries from its mask row + keys[], sorts them and replays
+// them in order.  scratch: scratch_cap (a power of two, or 0) entries per tile for tiles with more entries than fit shared memory.
+// p.enq_ordered: launched right behind pass 1 without a host round trip (exits at once when there is nothing to replay).
+void launch_fill_ordered(const LaunchCtx& L, const SurfRec* recs, const uint4* masks, BinHead* scratch, const uint64_t* keys,
                          const TexDev* tex, const uint16_t* texels, uint32_t* fb_rgba, float* fb_z,
-                         const CallState* st, const CallParams& p, uint32_t obin_cap);
+                         CallState* st, uint32_t* sticky, const CallParams& p, uint32_t scratch_cap);
 // wireframe phase: kind 1 = back-face edges (depth tested), 2 = front-face overlay edges
 // table: table_size (a power of two >= 6 * nf) words of scratch for the first-occurrence edge de-duplication
 void launch_wire(const LaunchCtx& L, const WireTri* wire, uint32_t kind, uint32_t color, bool depth_test, uint32_t* table, uint32_t table_size,
@@ -69,9 +67,9 @@ void launch_lines_round(const LaunchCtx& L, const b32_line* lines, uint32_t n, u
                         uint32_t* wait, uint32_t* flags, uint32_t round, uint32_t* fb_rgba, const float* fb_z, uint32_t w, uint32_t h);
 void launch_tex_expand(const LaunchCtx& L, const uint8_t* idx, const uint16_t* clut, uint32_t clut_len, uint32_t format, uint32_t n, uint16_t* out);
 
-// skybox sphere pass (render.rs:81-139, :242-299): setup -> tile binning (k_bin_opaque) -> fill
-void launch_sky(const LaunchCtx& L, const b32_sky_vertex* verts, const uint32_t* faces, SkyRec* recs, BinHead* heads, BinHead* bins,
-                uint32_t* tile_count, uint32_t* fb_rgba, CallState* st, uint32_t* zero_next, uint32_t zero_words, const CallParams& p);
+// skybox sphere pass (render.rs:81-139, :242-299): setup (+ tile masks) -> fill
+void launch_sky(const LaunchCtx& L, const b32_sky_vertex* verts, const uint32_t* faces, SkyRec* recs, BinHead* heads, uint4* masks,
+                uint32_t* fb_rgba, CallState* st, uint32_t* zero_next, uint32_t zero_words, const CallParams& p);
 
 // render_asset_parts' vertex transform (scene.rs:141-160): out = in rotated about Y, translated
 void launch_place(const LaunchCtx& L, const b32_vertex* in, b32_vertex* out, uint32_t nv, float cos_f, float sin_f, const float* world_pos);

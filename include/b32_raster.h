@@ -195,15 +195,34 @@ int b32_render_mesh_15(b32_ctx* ctx,
 
 /* Same call with control flags.  B32_RENDER_ASYNC: copy + render are only enqueued on the context's
  * stream (the host buffers must stay valid and unchanged until b32_sync / b32_fb_download returns);
- * no timings; errors surface at b32_sync / b32_fb_download.  Only pass 1 can be enqueued, so the caller
- * must also assert B32_RENDER_ALL_OPAQUE: no face has blend_mode != Opaque or editor_alpha < 255, no
- * bound texture has blend_mode != Opaque, and x-ray mode is off (a marshalling shim knows this for
- * free); the device checks the assertion and reports B32_ERR_INVALID at the next sync if it was wrong. */
+ * no timings; errors surface at b32_sync / b32_fb_download.  Both passes of render_mesh_15 are enqueued
+ * (render.rs:2551-2569): the semi-transparent pass decides on the device whether it has anything to do.
+ * B32_RENDER_ALL_OPAQUE (optional) is the caller's promise that there is no second pass — no face has
+ * blend_mode != Opaque or editor_alpha < 255, no bound texture has blend_mode != Opaque, x-ray mode is
+ * off (a marshalling shim knows this for free) — which saves its launch; the device checks the promise
+ * and reports B32_ERR_INVALID at the next sync if it was wrong.  The wireframe phase cannot be enqueued.
+ * One limit: a screen tile holding more than 2048 semi-transparent surfaces needs scratch memory that
+ * only a blocking call sizes; an enqueued call that meets such a tile before any blocking call did
+ * reports B32_ERR_UNSUPPORTED at the next sync (pass 2 was not drawn). */
 #define B32_RENDER_ASYNC       1u
 #define B32_RENDER_ALL_OPAQUE  2u
+/* Compact marshalling for the host-buffer path (the bytes that cross PCIe every call; results are identical):
+ * B32_VTX_NO_NORMAL   `vertices` points to b32_vertex_nn records (24 bytes: no normal).  Legal only with
+ *                     settings.shading == None — the normals are read by nothing else (render.rs:1466-1483);
+ *                     otherwise B32_ERR_INVALID.
+ * B32_FACES_IMPLICIT  `faces` points to nf uint32_t flags words (the `flags` of b32_face); face i uses vertices
+ *                     3i, 3i+1, 3i+2 (an unindexed triangle soup); nv >= 3 * nf, else B32_ERR_OOB_INDEX.
+ * A marshalling shim picks them for free while it converts `&[Vertex]` / `&[Face]`: 36 + 16/3 -> 24 + 4/3 bytes per vertex. */
+#define B32_VTX_NO_NORMAL      4u
+#define B32_FACES_IMPLICIT     8u
+typedef struct b32_vertex_nn {
+    float   pos[3];
+    float   uv[2];
+    uint8_t r, g, b, blend;
+} b32_vertex_nn;
 int b32_render_mesh_15_ex(b32_ctx* ctx,
-                          const b32_vertex* vertices, uint32_t nv,
-                          const b32_face* faces, uint32_t nf,
+                          const void* vertices, uint32_t nv,      /* b32_vertex[nv], or b32_vertex_nn[nv] */
+                          const void* faces, uint32_t nf,         /* b32_face[nf], or uint32_t flags[nf] */
                           const b32_camera* camera, const b32_settings* settings,
                           const b32_fog* fog_or_null, uint32_t flags, b32_timings* timings);
 /* Enqueue the framebuffer read-back (pinned destination recommended); complete after b32_sync. */
@@ -217,7 +236,8 @@ void b32_mesh_free(b32_ctx* ctx, b32_mesh* mesh);
 int  b32_render_mesh_15_resident(b32_ctx* ctx, const b32_mesh* mesh,
                                  const b32_camera* camera, const b32_settings* settings,
                                  const b32_fog* fog_or_null, b32_timings* timings);
-/* Same, but only enqueues (no wait, no timings); errors surface at b32_sync/b32_fb_download. */
+/* Same, but only enqueues (no wait, no timings); errors surface at b32_sync/b32_fb_download.  Both passes
+ * are enqueued; only a call with the wireframe phase on is rendered synchronously instead. */
 int  b32_render_mesh_15_enqueue(b32_ctx* ctx, const b32_mesh* mesh,
                                 const b32_camera* camera, const b32_settings* settings,
                                 const b32_fog* fog_or_null);
@@ -337,10 +357,16 @@ int b32_debug_transform(b32_ctx* ctx, const b32_vertex* vertices, uint32_t nv,
 int b32_debug_draw_order(b32_ctx* ctx, uint32_t* out_face_idx, uint32_t cap, uint32_t* n);
 
 /* Device time (ms, CUDA events on the context stream) of each kernel group of the last synchronous
- * render call: [0] k_setup + k_bin_opaque (transform + cull + setup + binning) [1] k_fill_opaque (pass 1),
- * and for pass 2 / x-ray: [2] binning of the draw-order keys [3] k_fill_ordered (per-tile sort + replay).
+ * render call: [0] k_setup (transform + cull + setup + tile masks) [1] k_fill_opaque (pass 1),
+ * [2] unused (0) [3] k_fill_ordered (pass 2 / x-ray: per-tile sort + replay).
  * Returns the number of values written (<= cap). */
 int b32_debug_kernel_times(b32_ctx* ctx, float* out_ms, uint32_t cap);
+/* Measurement aid for enqueued frames (bench.py's per-kernel times in the regime of its timed loop): with n > 0 the
+ * context's next enqueued frames are launched plainly (no CUDA graph) with events in front of k_setup, in front of the
+ * fill kernel(s) and behind them, n frames deep; n = 0 switches it off.  b32_debug_timing_read (syncs) returns the
+ * number of frames read; setup_ms[i] / fill_ms[i] are their device times. */
+int b32_debug_timing_ring(b32_ctx* ctx, uint32_t n);
+int b32_debug_timing_read(b32_ctx* ctx, float* setup_ms, float* fill_ms, uint32_t cap);
 
 #ifdef __cplusplus
 }

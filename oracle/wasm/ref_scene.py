@@ -110,6 +110,19 @@ class RefRasterizer:
             recs += struct.pack('<IIIIIIIII', len(px), pp, len(px), 1, nm, 1, t.width, t.height, int(t.blend_mode))
         return self._put(recs) if recs else DANGLING
 
+    def _textures8(self, textures):
+        """RGB888 `Texture` (same 36-byte layout as Texture15); a texel is a `Color` {blend@0, r@1, g@2, b@3}."""
+        recs = b''
+        for t in textures:
+            px = np.ascontiguousarray(t.pixels, np.uint8).reshape(-1, 4)          # host order r, g, b, blend
+            w = np.empty_like(px)
+            w[:, 0] = px[:, 3]
+            w[:, 1:4] = px[:, 0:3]
+            pp = self._put(w, 1)
+            nm = self._put(b'T')
+            recs += struct.pack('<IIIIIIIII', len(px), pp, len(px), 1, nm, 1, t.width, t.height, int(t.blend_mode))
+        return self._put(recs) if recs else DANGLING
+
     # ---- calls -------------------------------------------------------------------------------------
     def new_framebuffer(self, width, height, rgba=None, z=None):
         w = self.w
@@ -166,6 +179,35 @@ class RefRasterizer:
         for p, n, a in reversed(self._allocs):
             w.free(p, n, a)
         return drawn
+
+    def render_mesh(self, fb, vertices, faces, textures8, camera, settings):
+        """The RGB888 sibling (render.rs:1971-2259).  0.1.8 has neither Face.blend_mode nor editor_alpha here either."""
+        w = self.w
+        self._allocs = []
+        rec, blend, alpha = self._faces(faces)
+        assert (alpha == 255).all(), 'editor_alpha is not in the 0.1.8 binary'
+        vp = self._put(self._vertices(vertices))
+        fp = self._put(rec)
+        tp = self._textures8(textures8)
+        cp = self._camera(camera)
+        sp = self._settings(settings)
+        tim = self._put(b'\0' * 32, 8)
+        w.call('render11render_mesh17', tim, fb, vp, len(vertices), fp, len(faces), tp, len(textures8), cp, sp)
+        drawn = struct.unpack('<I', w.read(tim + 24, 4))[0]
+        for p, n, a in reversed(self._allocs):
+            w.free(p, n, a)
+        return drawn
+
+    def render_scene888(self, scene):
+        r, g, b = scene.clear[:3]
+        rgba = np.empty((scene.height, scene.width, 4), np.uint8)
+        rgba[:] = (r, g, b, 255)
+        z = np.full((scene.height, scene.width), np.finfo(np.float32).max, np.float32)
+        fb = self.new_framebuffer(scene.width, scene.height, rgba, z)
+        drawn = self.render_mesh(fb, scene.vertices, scene.faces, scene.textures8, scene.camera, scene.settings)
+        out = self.read_framebuffer(fb)
+        self.free_framebuffer(fb)
+        return out[0], out[1], drawn
 
     def render_scene(self, scene, expand=lambda t: t):
         """Clear to scene.clear + render_mesh_15.  Returns (rgba, z, triangles_drawn)."""

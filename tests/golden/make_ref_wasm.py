@@ -31,9 +31,9 @@ OUT = os.path.join(ROOT, "tests", "golden", "ref_wasm")
 KEEP_FRAMES = {"c1_single_triangle", "c1_single_triangle_float", "c2_1000_tris_64x64_idx8", "mixed_zbuffer", "gouraud_lights"}
 
 
-def run(R, sc):
+def run(R, sc, rgb888=False):
     try:
-        rgba, z, drawn = R.render_scene(sc, scenes.expand_texture)
+        rgba, z, drawn = R.render_scene888(sc) if rgb888 else R.render_scene(sc, scenes.expand_texture)
     except WasmTrap as e:
         return {"inputs": refbin_cases.inputs_digest(sc), "trap": str(e)}, None
     a, b = refbin_cases.frame_digest(rgba, z)
@@ -57,6 +57,15 @@ def main():
             frames[sc.name + "/rgba"], frames[sc.name + "/z"] = fr
         print(f"{sc.name:48s} {time.time() - t:6.2f}s {rec.get('drawn', rec.get('trap'))}", flush=True)
     json.dump(res, open(path, "w"), indent=1, sort_keys=True)
+    # the RGB888 sibling
+    path8 = os.path.join(OUT, "render_mesh.json")
+    res8 = {"scenes": {}, "wasm_sha256": res["wasm_sha256"], "wasm": res["wasm"]}
+    for sc in refbin_cases.small_scenes888():
+        t = time.time()
+        rec, fr = run(RefRasterizer(), sc, rgb888=True)
+        res8["scenes"][sc.name] = rec
+        print(f"{sc.name:48s} {time.time() - t:6.2f}s {rec.get('drawn', rec.get('trap'))}", flush=True)
+    json.dump(res8, open(path8, "w"), indent=1, sort_keys=True)
     if frames:
         np.savez_compressed(os.path.join(OUT, "frames.npz"), **frames)
 

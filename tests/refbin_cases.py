@@ -51,6 +51,16 @@ def small_scenes():
     return res
 
 
+def small_scenes888():
+    """The RGB888 sibling `render_mesh` (render.rs:1971-2259): feature scenes + fuzz."""
+    out = list(cases.rgb888_scenes())
+    for seed in range(40):
+        sc = fuzz.fuzz_scene(seed, rgb888=True)
+        if not has_spot_light(sc):
+            out.append(sc)
+    return [strip_editor_alpha(s) for s in out]
+
+
 def big_scenes():
     out = [scenes.scene_c4(), cases._with(scenes.scene_c4(), "c4_100000_zbuffer", use_zbuffer=True),
            cases._with(scenes.scene_c4(), "c4_100000_float_nodither", use_fixed_point=False, dithering=False)]
@@ -63,6 +73,9 @@ def inputs_digest(sc):
     h = hashlib.sha256()
     h.update(np.ascontiguousarray(sc.vertices).tobytes())
     h.update(np.ascontiguousarray(sc.faces).tobytes())
+    for t in (sc.textures8 or []):
+        h.update(np.asarray([t.width, t.height, int(t.blend_mode)], np.uint32).tobytes())
+        h.update(np.ascontiguousarray(t.pixels, dtype=np.uint8).tobytes())
     for t in sc.textures:
         e = scenes.expand_texture(t)
         h.update(np.asarray([e.width, e.height, int(e.blend_mode)], np.uint32).tobytes())

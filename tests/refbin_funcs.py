@@ -1,0 +1,59 @@
+"""Inputs of the direct function-level fixtures of the reference binary (tests/golden/make_ref_wasm_funcs.py writes the
+outputs; tests/test_ref_wasm.py replays the inputs through the oracle).  Deterministic (SplitMix64 / fixed lists)."""
+import numpy as np
+
+from bonnie32_b200 import scenes
+from bonnie32_b200.raster import Light
+import cases
+
+SIZES = [(320, 240), (640, 480), (333, 77)]
+
+
+def cameras():
+    return [cases._rotated_camera(rx, ry, pos) for rx, ry, pos in
+            [(0.0, 0.0, (0, 0, 0)), (0.3, 0.7, (10.0, -20.0, 300.0)), (-0.2, 2.4, (-30.0, 15.0, 900.0)), (1.2, -3.0, (0.5, 0.25, -4.0)),
+             (0.01, 0.02, (1e-3, -1e-3, 1e-4)), (-1.5, 0.0, (1000.0, 2000.0, -3000.0)), (0.7, 5.5, (-7.0, 3.0, 2.0)), (3.1, 3.1, (100000.0, 0.0, 0.0))]]
+
+
+def project_inputs(n=24000):
+    u = scenes.splitmix64_u01(0xF1ED0001, n * 5).reshape(n, 5)
+    scale = np.choose((u[:, 3] * 6).astype(int), [1.0, 10.0, 100.0, 3000.0, 0.01, 600000.0])
+    world = ((2.0 * u[:, :3] - 1.0) * scale[:, None]).astype(np.float32)
+    cam_idx = (u[:, 4] * 8).astype(np.int32) % 8
+    size_idx = (u[:, 3] * 977).astype(np.int32) % 3
+    # adversarial rows: non-finite, denormal, exactly on / next to the |denom| < 256 early-out (camera 0: denom = z + 5)
+    special = np.array([[np.nan, 0, 1], [0, np.inf, 1], [1, 2, -np.inf], [1e-42, -1e-42, 1e-40], [3.4e38, -3.4e38, 3.4e38],
+                        [1, 1, -5.0], [1, 1, -5.0 + 255.0 / 4096.0], [1, 1, -5.0 + 256.0 / 4096.0], [1, 1, -5.0 - 255.0 / 4096.0],
+                        [1, 1, -5.0 - 256.0 / 4096.0], [524287.9, -524288.0, 524287.0], [524288.0, 524288.5, -524289.0],
+                        [0.5 / 4096, 1.5 / 4096, 2.5 / 4096], [-0.5 / 4096, -1.5 / 4096, -2.5 / 4096]], np.float32)
+    world[:len(special)] = special
+    cam_idx[:len(special)] = 0
+    return world, cam_idx, size_idx
+
+
+def light_sets():
+    off = Light.point((0.0, 0.0, 10.0), 50.0, 2.0)
+    off.enabled = False
+    return [
+        [],
+        [Light.directional((-1.0, -1.0, -1.0), 0.7)],
+        [Light.directional((0.3, -2.0, 0.5), 1.4), Light.point_colored((0.5, 0.5, 4.0), 30.0, 1.5, 1.0, 0.5, 0.25), Light.point((-3.0, 2.0, 20.0), 25.0, 0.9), off],
+        [Light.point((0.0, 0.0, 0.0), 0.0, 1.0), Light.point((1.0, 2.0, 3.0), 1e-3, 5.0), Light.point_colored((5.0, 5.0, 5.0), 1e6, 100.0, 0.1, 0.9, 0.5)],
+        [Light.directional((0.0, 0.0, 0.0), 1.0), Light.directional((1e-20, 0.0, 0.0), 2.0)],
+        [Light.point((1.0, 2.0, 3.0), 10.0, -1.0), Light.directional((0.0, 1.0, 0.0), -0.5)],
+    ]
+
+
+def shade_inputs(n=6000):
+    u = scenes.splitmix64_u01(0xF1ED0002, n * 8).reshape(n, 8)
+    normal = (2.0 * u[:, :3] - 1.0).astype(np.float32)
+    pos = ((2.0 * u[:, 3:6] - 1.0) * 30.0).astype(np.float32)
+    set_idx = (u[:, 6] * 6).astype(np.int32) % 6
+    ambient = (u[:, 7] * 1.2).astype(np.float32)
+    # a few exact hits: position == light position (dist < 0.001), zero normal, NaN normal
+    pos[0] = (1.0, 2.0, 3.0); set_idx[0] = 3
+    pos[1] = (0.5, 0.5, 4.0); set_idx[1] = 2
+    normal[2] = 0.0
+    normal[3] = (np.nan, 0.0, 1.0)
+    pos[4] = (np.inf, 0.0, 0.0)
+    return normal, pos, set_idx, ambient

@@ -62,6 +62,26 @@ def test_oracle_matches_reference_binary_100k(compat_oracle, name):
     _check(compat_oracle, sc)
 
 
+FIX8 = json.load(open(os.path.join(HERE, "golden", "ref_wasm", "render_mesh.json")))
+SMALL8 = {s.name: s for s in refbin_cases.small_scenes888()}
+
+
+@pytest.mark.parametrize("name", sorted(SMALL8))
+def test_oracle_render_mesh_rgb888_matches_reference_binary(compat_oracle, name):
+    """The RGB888 sibling `render_mesh` -> `rasterize_triangle` (render.rs:1971-2259, :1202-1433) of the binary."""
+    sc = SMALL8[name]
+    rec = FIX8["scenes"][name]
+    assert rec["inputs"] == refbin_cases.inputs_digest(sc), "scene generator changed: regenerate the fixture"
+    rgba, z, tm, rc = compat_oracle.render_scene888(sc)
+    if "trap" in rec:
+        assert rc != 0
+        return
+    assert rc == 0 and tm["triangles_drawn"] == rec["drawn"]
+    a, b = refbin_cases.frame_digest(rgba, z)
+    assert a == rec["rgba"], "framebuffer differs from the reference binary"
+    assert b == rec["z"], "z-buffer differs from the reference binary"
+
+
 def test_full_frames_kept_for_debugging(compat_oracle):
     fr = np.load(os.path.join(HERE, "golden", "ref_wasm", "frames.npz"))
     for name in ("c1_single_triangle", "c2_1000_tris_64x64_idx8", "gouraud_lights", "mixed_zbuffer"):
@@ -72,3 +92,54 @@ def test_full_frames_kept_for_debugging(compat_oracle):
 
 def test_compat_switches_are_off_by_default(oracle):
     assert oracle.lib().b32o_get_compat() == 0
+
+
+# ---- direct calls of named functions of the binary ------------------------------------------------------------------
+def test_project_fixed_matches_reference_binary(compat_oracle):
+    """fixed::project_fixed (fixed.rs:424-441) on 24 000 vertices x 8 cameras x 3 sizes, incl. non-finite / huge / denormal
+    inputs and the |denom| < 256 early-out.  (The binary's divide is exact, 0.1.11's is div_unr: COMPAT_DIV_EXACT.)"""
+    import ctypes as C
+    import refbin_funcs
+    fx = np.load(os.path.join(HERE, "golden", "ref_wasm", "functions.npz"))
+    world, cam_idx, size_idx = refbin_funcs.project_inputs()
+    cams = [c.to_abi() for c in refbin_funcs.cameras()]
+    lib = compat_oracle.lib()
+    sx, sy, d = C.c_int32(), C.c_int32(), C.c_float()
+    got = np.empty((len(world), 2), np.int32); gd = np.empty(len(world), np.float32)
+    for i in range(len(world)):
+        wv = (C.c_float * 3)(*[float(x) for x in world[i]])
+        w, h = refbin_funcs.SIZES[size_idx[i]]
+        lib.b32o_project_fixed(wv, C.byref(cams[cam_idx[i]]), C.c_uint32(w), C.c_uint32(h), C.byref(sx), C.byref(sy), C.byref(d))
+        got[i] = (sx.value, sy.value); gd[i] = d.value
+    assert np.array_equal(got[:, 0], fx["project_sx"]) and np.array_equal(got[:, 1], fx["project_sy"])
+    assert np.array_equal(gd.view(np.uint32), fx["project_depth"].view(np.uint32))
+    # the early-out rows really took the early-out: centre of the framebuffer
+    for row, early in ((5, True), (6, True), (7, False), (8, True), (9, False)):
+        w, h = refbin_funcs.SIZES[size_idx[row]]
+        assert (tuple(got[row]) == (w // 2, h // 2)) == early, row
+
+
+def test_shade_multi_light_color_matches_reference_binary(oracle):
+    """render::shade_multi_light_color (render.rs:1013-1071): Directional + Point lights, colours, disabled lights, zero
+    radius, dist < 0.001, zero / NaN normals — 6 000 evaluations, bit for bit (no compat switch involved)."""
+    import ctypes as C
+    from bonnie32_b200 import abi
+    import refbin_funcs
+    fx = np.load(os.path.join(HERE, "golden", "ref_wasm", "functions.npz"))
+    normal, pos, set_idx, ambient = refbin_funcs.shade_inputs()
+    sets = []
+    for ls in refbin_funcs.light_sets():
+        arr = (abi.Light * max(1, len(ls)))()
+        for k, l in enumerate(ls):
+            arr[k] = l.to_abi()
+        sets.append((arr, len(ls)))
+    lib = oracle.lib()
+    out = (C.c_float * 3)()
+    got = np.empty((len(normal), 3), np.float32)
+    for i in range(len(normal)):
+        n = (C.c_float * 3)(*[float(x) for x in normal[i]]); p = (C.c_float * 3)(*[float(x) for x in pos[i]])
+        arr, cnt = sets[set_idx[i]]
+        lib.b32o_shade_multi_light(n, p, arr, C.c_uint32(cnt), C.c_float(float(ambient[i])), out)
+        got[i] = out[:]
+    same = (got.view(np.uint32) == fx["shade"].view(np.uint32)) | (np.isnan(got) & np.isnan(fx["shade"]))
+    assert same.all(), np.argwhere(~same)[:5]
