@@ -99,3 +99,12 @@ def inputs_digest(sc):
 def frame_digest(rgba, z):
     return (hashlib.sha256(np.ascontiguousarray(rgba, np.uint8).tobytes()).hexdigest(),
             hashlib.sha256(np.ascontiguousarray(z, "<f4").tobytes()).hexdigest())
+
+
+def geometry_digest(pos, uv, normal, rgba, face_v, black_transparent, with_uv=True):
+    """sha256 of a room's triangles without the texture ids (they depend on the resolver, not on the geometry code).
+    with_uv=False also leaves the UVs out (their scale is 32 / texture width, a resolver result)."""
+    h = hashlib.sha256()
+    for a, dt in ((pos, "<f4"), (uv if with_uv else np.zeros(0), "<f4"), (normal, "<f4"), (rgba, np.uint8), (face_v, "<u4"), (black_transparent, np.uint8)):
+        h.update(np.ascontiguousarray(a, dtype=dt).tobytes())
+    return h.hexdigest()

@@ -143,3 +143,25 @@ def test_shade_multi_light_color_matches_reference_binary(oracle):
         got[i] = out[:]
     same = (got.view(np.uint32) == fx["shade"].view(np.uint32)) | (np.isnan(got) & np.isnan(fx["shade"]))
     assert same.all(), np.argwhere(~same)[:5]
+
+
+def test_sample_level_geometry_matches_reference_binary():
+    """The C3 fixtures' room triangles (tests/golden/c3_*.npz, produced by bonnie-32_b200/levels.py from the reference's
+    level files) against the reference binary's own `load_level_from_str` + `Room::add_*_to_render_data`
+    (src/world/geometry.rs:2839-3352): positions, UVs, normals, colours, indices, black_transparent, bit for bit.
+    Texture ids depend on the resolver and are left out of the digest; so are the UVs of rooms that use textures which are
+    not 64 texels wide (the UV scale is 32 / texture width, and the binary was driven with a resolver that misses)."""
+    import c3
+    fix = json.load(open(os.path.join(HERE, "golden", "ref_wasm", "levels.json")))["levels"]
+    paths = c3.scene_paths()
+    assert len(paths) == 6
+    for p in paths:
+        sc = c3.load_scene(p)
+        all64 = all(t.width == 64 for t in sc.textures)
+        want = fix[sc.name]
+        assert len(want) == len(sc.rooms)
+        for rc, w in zip(sc.rooms, want):
+            assert len(rc.vertices) == w["vertices"] and len(rc.faces) == w["faces"]
+            d = refbin_cases.geometry_digest(rc.vertices["pos"], rc.vertices["uv"], rc.vertices["normal"], rc.vertices["rgba"], rc.faces["v"],
+                                             ((rc.faces["flags"] >> 19) & 1).astype(np.uint8), with_uv=all64)
+            assert d == w["sha256" if all64 else "sha256_no_uv"], sc.name

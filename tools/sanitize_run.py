@@ -84,5 +84,42 @@ fb = pkg.Framebuffer(w, h, ctx); fb.upload(rgba, z); fb.draw_lines(lines)
 got, _ = fb.download()
 want = rgba.copy(); orc.draw_lines(want, z, lines)
 ok = np.array_equal(got, want); print(name, "OK" if ok else "MISMATCH"); bad += not ok
+# round 2: both passes enqueued (graph replay), compact marshalling, coarse mask tiles, several candidate windows per tile
+import ctypes as C
+from bonnie32_b200 import abi
+sc = by["mixed_zbuffer"]
+fb = pkg.Framebuffer(sc.width, sc.height, ctx); ctx.set_textures(sc.textures)
+mesh = pkg.Mesh(ctx, sc.vertices, sc.faces)
+for _ in range(4):
+    mesh.frame_enqueue(sc.clear, sc.camera, sc.settings)
+got, gz = fb.download()
+want, wz, _, rc = orc.render_scene(sc)
+ok = np.array_equal(got, want) and np.array_equal(gz.view(np.uint32), wz.view(np.uint32)); print("mixed_enqueued_pass2", "OK" if ok else "MISMATCH"); bad += not ok
+sc = scenes.scene_c4(n_tris=2000)
+v, f, flags = abi.compact_buffers(sc.vertices, sc.faces, True)
+fb = pkg.Framebuffer(sc.width, sc.height, ctx); fb.clear(sc.clear); ctx.set_textures(sc.textures)
+cam = sc.camera.to_abi(); st, keep = sc.settings.to_abi()
+ctx.check(ctx.lib.b32_render_mesh_15_ex(ctx.h, v.ctypes.data, len(v), f.ctypes.data, len(f), C.byref(cam), C.byref(st), None, flags, None))
+got, gz = fb.download()
+want, wz, _, rc = orc.render_scene(sc)
+ok = np.array_equal(got, want) and np.array_equal(gz.view(np.uint32), wz.view(np.uint32)); print("compact_marshalling", "OK" if ok else "MISMATCH"); bad += not ok
+sc = cases._with(by["mixed_zbuffer"], "mixed_1920x1080", width=1920, height=1080)
+fb = pkg.Framebuffer(sc.width, sc.height, ctx); fb.clear(sc.clear)
+pkg.render_mesh_15(fb, sc.vertices, sc.faces, sc.textures, sc.camera, sc.settings, sc.fog)
+got, gz = fb.download()
+want, wz, _, rc = orc.render_scene(sc)
+ok = np.array_equal(got, want) and np.array_equal(gz.view(np.uint32), wz.view(np.uint32)); print("coarse_mask_tiles_1080p", "OK" if ok else "MISMATCH"); bad += not ok
+n = 2600                                                    # > 2 windows of 1 024 candidates in the centre tiles; > 2 048 ordered entries
+u = scenes.splitmix64_u01(5150, n * 9).reshape(n, 3, 3)
+pos = np.empty((n, 3, 3)); pos[..., 0] = (u[..., 0] - 0.5) * 0.9; pos[..., 1] = (u[..., 1] - 0.5) * 0.9; pos[..., 2] = 10.0 + 30.0 * u[..., 2]
+vv = scenes.make_vertices(pos.reshape(-1, 3), uv=u[..., :2].reshape(-1, 2), rgba=np.concatenate([np.floor(u * 255).reshape(-1, 3), np.zeros((n * 3, 1))], axis=1))
+ff = scenes.make_faces(np.arange(n * 3).reshape(n, 3), tex_id=abi.FACE_TEX_NONE)
+for xray in (False, True):
+    sc = scenes.Scene("crowded", vv, ff, [], pkg.Camera(), scenes.common_settings(use_zbuffer=True, backface_cull=False, xray_mode=xray))
+    fb = pkg.Framebuffer(sc.width, sc.height, ctx); fb.clear(sc.clear)
+    pkg.render_mesh_15(fb, sc.vertices, sc.faces, sc.textures, sc.camera, sc.settings, sc.fog)
+    got, gz = fb.download()
+    want, wz, _, rc = orc.render_scene(sc)
+    ok = np.array_equal(got, want) and np.array_equal(gz.view(np.uint32), wz.view(np.uint32)); print("crowded_tile_xray" if xray else "crowded_tile_windows", "OK" if ok else "MISMATCH"); bad += not ok
 print("mismatches:", bad)
 sys.exit(1 if bad else 0)
