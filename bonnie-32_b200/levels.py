@@ -13,10 +13,13 @@ Mirrors, in Python, the parts of the reference that turn a level file into the a
   * per-room ambient + fog, one call per room     src/scene.rs:180-261, 263-276
   * camera from the level's saved orbit           src/editor/state.rs:1129-1145
 
-All float arithmetic is done in numpy float32 in the reference's operation order.  Placed asset
-meshes (`render_assets`) and lights collected from assets are not assembled (the asset library is
-not part of the path); with no asset lights `render_scene` passes an empty light list, so rooms are
-lit by their ambient term only.
+  * placed asset meshes and asset lights          src/scene.rs:32-107 (collect_scene_lights), :109-169 (render_asset_parts),
+        :219-259 (the object loop of render_scene); AssetInstance::world_position geometry.rs:2353-2364;
+        EditableMesh::to_render_data_textured + EditFace::triangulate src/modeler/mesh_editor.rs:1623-1653, :99-112;
+        resolve_part_texture scene.rs:73-101, IndexedAtlas::to_texture15 mesh_editor.rs:669-682, checkerboard_clut :201-211
+
+All float arithmetic is done in numpy float32 in the reference's operation order.  The room triangles are pinned bit
+for bit against the reference's own compiled geometry code (tests/test_ref_wasm.py::test_sample_level_geometry_...).
 """
 from __future__ import annotations
 
@@ -449,6 +452,19 @@ class RoomCall:
 
 
 @dataclass
+class PartCall:
+    """The arguments of one render_asset_parts iteration (scene.rs:131-168): one visible mesh part of a placed asset.
+    vertices are LOCAL (the per-object rotation about Y by `facing` + translation to `world_pos` is part of the call)."""
+    vertices: np.ndarray
+    faces: np.ndarray             # texture ids already point into LevelScene.textures
+    facing: float
+    world_pos: tuple
+    double_sided: bool
+    ambient: float
+    fog: Optional[tuple]
+
+
+@dataclass
 class LevelScene:
     name: str
     rooms: List[RoomCall]
@@ -457,17 +473,179 @@ class LevelScene:
     width: int = 320
     height: int = 240
     clear: tuple = (20, 22, 28)
+    parts: List[PartCall] = field(default_factory=list)      # placed asset parts, drawn after all rooms (scene.rs:219-259)
+    lights: list = field(default_factory=list)               # collect_scene_lights (scene.rs:32-70)
 
     def settings(self, ambient: float, **kw) -> RasterSettings:
-        """RasterSettings::default() with backface_wireframe off; render_scene replaces lights (none
-        collected without the asset library) and ambient (room.ambient)."""
-        s = RasterSettings(backface_wireframe=False, lights=[], ambient=ambient)
+        """RasterSettings::default() with backface_wireframe off; render_scene replaces lights (the point lights of
+        placed assets) and ambient (room.ambient)."""
+        s = RasterSettings(backface_wireframe=False, lights=list(self.lights), ambient=ambient)
         for k, v in kw.items():
             setattr(s, k, v)
         return s
 
+    def part_settings(self, pc: "PartCall", **kw) -> RasterSettings:
+        """render_asset_parts' per-part settings (scene.rs:138-143): double-sided parts are not culled."""
+        s = self.settings(pc.ambient, **kw)
+        s.backface_cull = (not pc.double_sided) and s.backface_cull
+        s.backface_wireframe = (not pc.double_sided) and s.backface_wireframe
+        return s
 
-def assemble_level(level_path: str, all_textures: List[PackTexture], compact: bool = True) -> LevelScene:
+
+# ------------------------------------------------------------------------------------------------
+# placed assets (src/scene.rs:32-169)
+# ------------------------------------------------------------------------------------------------
+def load_ron_dir(path: str) -> list:
+    """Every brotli-compressed (or plain) .ron file of a directory, parsed, in sorted order."""
+    out = []
+    if not path or not os.path.isdir(path):
+        return out
+    for fn in sorted(os.listdir(path)):
+        if not fn.endswith(".ron"):
+            continue
+        raw = open(os.path.join(path, fn), "rb").read()
+        try:
+            txt = brotli_decompress(raw).decode("utf-8")
+        except ValueError:
+            txt = raw.decode("utf-8")
+        out.append(parse_ron(txt))
+    return out
+
+
+def _variant(c, name):
+    return isinstance(c, dict) and c.get("__variant__") == name
+
+
+def object_world_position(obj: dict, room: dict):
+    """AssetInstance::world_position, geometry.rs:2353-2364 (the floor's average height is NOT offset by room.position.y
+    there: restated as it is)."""
+    pos = room["position"]
+    half = SECTOR_SIZE * F(0.5)
+    bx = F(pos["x"]) + F(obj["sector_x"]) * SECTOR_SIZE + half
+    bz = F(pos["z"]) + F(obj["sector_z"]) * SECTOR_SIZE + half
+    by = F(pos["y"])
+    cols = room["sectors"]
+    sx, sz = int(obj["sector_x"]), int(obj["sector_z"])
+    if sx < len(cols) and sz < len(cols[sx]) and cols[sx][sz] is not None and cols[sx][sz].get("floor") is not None:
+        h = [F(x) for x in cols[sx][sz]["floor"]["heights"]]
+        by = (h[0] + h[1] + h[2] + h[3]) / F(4.0)                                      # HorizontalFace::avg_height :1262
+    return (bx, by + F(obj.get("height", 0.0)), bz)
+
+
+def collect_scene_lights(level: dict, assets: Dict[int, dict]) -> list:
+    """scene.rs:32-70: the first Light component of every enabled placed asset, with per-instance overrides."""
+    from .raster import Light
+    out = []
+    for room in level["rooms"]:
+        for obj in room.get("objects", []) or []:
+            if not obj.get("enabled", True):
+                continue
+            asset = assets.get(int(obj.get("asset_id", 0)))
+            if asset is None:
+                continue
+            for comp in asset.get("components", []):
+                if not _variant(comp, "Light"):
+                    continue
+                c = comp["value"]
+                ov = (obj.get("overrides") or {}).get("light") or {}
+                pick = lambda k: ov[k] if ov.get(k) is not None else c[k]
+                color, intensity, radius, offset = pick("color"), pick("intensity"), pick("radius"), pick("offset")
+                bp = object_world_position(obj, room)
+                lp = (bp[0] + F(offset[0]), bp[1] + F(offset[1]), bp[2] + F(offset[2]))
+                r, g, b = (F(int(color[k])) / F(255.0) for k in range(3))
+                out.append(Light.point_colored(lp, float(F(radius)), float(F(intensity)), r, g, b))
+                break
+    return out
+
+
+def _clut_lookup(palette, idx):
+    """Clut::lookup, types.rs:390-397: out-of-range index -> 0x0000."""
+    pal = np.zeros(256, np.uint16)
+    pal[: min(len(palette), 256)] = np.asarray(palette[:256], np.uint16)
+    valid = np.asarray(idx, np.int64) < len(palette)
+    return np.where(valid, pal[np.asarray(idx, np.int64) & 0xFF], 0).astype(np.uint16)
+
+
+def part_texture15(part: dict, user_textures: Dict[int, dict]) -> Texture15:
+    """resolve_part_texture (scene.rs:73-101) + IndexedAtlas::to_texture15 (mesh_editor.rs:669-682)."""
+    ref = part.get("texture_ref")
+    if _variant(ref, "Id"):
+        v = ref["value"]
+        tid = int(v[0] if isinstance(v, tuple) else v)
+        tex = user_textures.get(tid)
+        if tex is not None:
+            px = _clut_lookup(tex["palette"], tex["indices"])
+            return Texture15(int(tex["width"]), int(tex["height"]), px)
+    atlas = part.get("atlas") or {}
+    w, h, idx = int(atlas.get("width", 0)), int(atlas.get("height", 0)), atlas.get("indices", [])
+    checker = [(v << 10) | (v << 5) | v for v in (2 * i for i in range(16))]             # checkerboard_clut, mesh_editor.rs:201-211
+    return Texture15(w, h, _clut_lookup(checker, idx) if len(idx) else np.zeros(0, np.uint16))
+
+
+def part_render_data(part: dict, tex_index: int):
+    """EditableMesh::to_render_data_textured (mesh_editor.rs:1623-1653): vertices as they are; n-gon faces as a fan from
+    their first vertex (EditFace::triangulate :99-112); texture_id = the face's or Some(0) = the part's atlas, which is
+    texture `tex_index` of the scene's table here (the reference passes a one-element table; other ids are out of range
+    there = untextured)."""
+    mesh = part["mesh"]
+    mv = mesh["vertices"]
+    v = np.zeros(len(mv), dtype=abi.VERTEX_DTYPE)
+    blends = {"Opaque": 0, "Average": 1, "Add": 2, "Subtract": 3, "AddQuarter": 4, "Erase": 5}
+    for i, e in enumerate(mv):
+        v["pos"][i] = (F(e["pos"]["x"]), F(e["pos"]["y"]), F(e["pos"]["z"]))
+        v["uv"][i] = (F(e["uv"]["x"]), F(e["uv"]["y"]))
+        v["normal"][i] = (F(e["normal"]["x"]), F(e["normal"]["y"]), F(e["normal"]["z"]))
+        c = e.get("color") or {"r": 128, "g": 128, "b": 128, "blend": "Opaque"}
+        v["rgba"][i] = (int(c["r"]), int(c["g"]), int(c["b"]), blends.get(c.get("blend", "Opaque"), 0))
+    tris, flags = [], []
+    for f in mesh["faces"]:
+        ids = [int(x) for x in f["vertices"]]
+        n = len(ids)
+        if n < 3:
+            continue
+        fan = [(ids[0], ids[1], ids[2])] if n == 3 else [(ids[0], ids[i], ids[i + 1]) for i in range(1, n - 1)]
+        tid = f.get("texture_id")
+        tid = tex_index if tid is None or int(tid) == 0 else abi.FACE_TEX_NONE
+        fl = abi.face_flags(tid, blends.get(f.get("blend_mode", "Opaque"), 0), bool(f.get("black_transparent", True)), 255)
+        for t in fan:
+            tris.append(t)
+            flags.append(fl)
+    faces = np.zeros(len(tris), dtype=abi.FACE_DTYPE)
+    if tris:
+        faces["v"] = np.asarray(tris, np.uint32)
+        faces["flags"] = np.asarray(flags, np.uint32)
+    return v, faces
+
+
+def assemble_parts(level: dict, assets: Dict[int, dict], user_textures: Dict[int, dict], first_tex: int):
+    """The object loop of render_scene (scene.rs:219-259) -> [PartCall], [their textures]."""
+    parts, texs = [], []
+    for room in level["rooms"]:
+        fog = build_room_fog(room)
+        for obj in room.get("objects", []) or []:
+            if not obj.get("enabled", True):
+                continue
+            asset = assets.get(int(obj.get("asset_id", 0)))
+            if asset is None:
+                continue
+            mesh = next((c["value"] for c in asset.get("components", []) if _variant(c, "Mesh")), None)
+            if mesh is None:
+                continue
+            wp = object_world_position(obj, room)
+            for part in mesh.get("parts", []):
+                if not part.get("visible", True):
+                    continue
+                v, f = part_render_data(part, first_tex + len(texs))
+                if len(v) == 0:
+                    continue
+                texs.append(part_texture15(part, user_textures))
+                parts.append(PartCall(v, f, float(F(obj.get("facing", 0.0))), tuple(float(x) for x in wp), bool(part.get("double_sided", False)),
+                                      float(F(room.get("ambient", 0.5))), fog))
+    return parts, texs
+
+
+def assemble_level(level_path: str, all_textures: List[PackTexture], compact: bool = True, assets_dir: Optional[str] = None,
+                   user_textures_dir: Optional[str] = None) -> LevelScene:
     """Level file -> per-room render_mesh_15 arguments, with the game tab's resolver
     (src/game/renderer.rs:104-112): invalid ref -> (0, 64); first texture whose name matches; miss -> None
     -> (0, 64) in the geometry code.  compact=True renumbers the textures actually used (ids are only
@@ -499,7 +677,16 @@ def assemble_level(level_path: str, all_textures: List[PackTexture], compact: bo
     else:
         texs = all_textures
     textures = [Texture15(t.width, t.height, t.pixels15) for t in texs]
-    return LevelScene(os.path.splitext(os.path.basename(level_path))[0], rooms, textures, orbit_camera(level))
+    # legacy objects (no asset_id) are dropped on load, as Level::load does (geometry.rs:2304-2306 "filtered out on load")
+    for room in level["rooms"]:
+        room["objects"] = [o for o in (room.get("objects") or []) if int(o.get("asset_id", 0)) != 0]
+    assets = {int(a["id"]): a for a in load_ron_dir(assets_dir)}
+    utex = {int(t["id"]): t for t in load_ron_dir(user_textures_dir)}
+    parts, part_texs = assemble_parts(level, assets, utex, len(textures))
+    scene = LevelScene(os.path.splitext(os.path.basename(level_path))[0], rooms, textures + part_texs, orbit_camera(level))
+    scene.parts = parts
+    scene.lights = collect_scene_lights(level, assets)
+    return scene
 
 
 class LevelRenderer:
@@ -508,8 +695,8 @@ class LevelRenderer:
     The reference regenerates `room.to_render_data_with_textures()` and re-marshals it on every frame
     (scene.rs:199-203).  Here a room's triangles are uploaded once per level *generation* (bump `generation` when the
     level is edited; cf. `textures_15_cache_generation`, src/editor/viewport_3d.rs:3459) and every frame only enqueues
-    one frame-graph launch per room — no host round trip until the framebuffer is downloaded.  Rooms whose faces or
-    textures can blend fall back to the blocking call inside `Mesh.frame_enqueue`.
+    one frame-graph launch per room (both passes: rooms with water / glass stay enqueued too) and one enqueued placed
+    render per asset part — no host round trip until the framebuffer is downloaded.
     """
 
     def __init__(self, ctx, scene: LevelScene):
@@ -519,15 +706,17 @@ class LevelRenderer:
         self.generation = 0
         self._uploaded = -1
         self._meshes: list = []
+        self._parts: list = []
         self._Mesh = Mesh
 
     def _sync_geometry(self):
         if self._uploaded == self.generation:
             return
-        for m in self._meshes:
+        for m in self._meshes + self._parts:
             m.free()
         self.ctx.set_textures(self.scene.textures)
         self._meshes = [self._Mesh(self.ctx, rc.vertices, rc.faces) for rc in self.scene.rooms]
+        self._parts = [self._Mesh(self.ctx, pc.vertices, pc.faces) for pc in self.scene.parts]
         self._uploaded = self.generation
 
     def render(self, fb, camera: Optional[Camera] = None, clear=True, **settings_kw):
@@ -538,9 +727,13 @@ class LevelRenderer:
             mesh.frame_enqueue(self.scene.clear if (clear and i == 0) else None, cam, self.scene.settings(rc.ambient, **settings_kw), rc.fog)
         if clear and not self._meshes:
             fb.clear(self.scene.clear)
+        # placed asset parts (scene.rs:219-259): resident, transformed per object on the device, enqueued behind the rooms
+        for mesh, pc in zip(self._parts, self.scene.parts):
+            mesh.render_placed(cam, self.scene.part_settings(pc, **settings_kw), pc.facing, pc.world_pos, pc.fog, enqueue_only=True)
 
     def close(self):
-        for m in self._meshes:
+        for m in self._meshes + self._parts:
             m.free()
+        self._parts = []
         self._meshes = []
         self._uploaded = -1

@@ -22,6 +22,15 @@ def save_scene(sc, path):
         d[f"m{i}"] = np.array([rc.ambient, 1.0 if fog else 0.0] + (list(fog[:3]) + list(fog[3]) if fog else [0.0] * 6), dtype=np.float64)
     for i, t in enumerate(sc.textures):
         d[f"t{i}"] = np.asarray(t.pixels, dtype=np.uint16).reshape(t.height, t.width)
+    # placed asset parts (scene.rs:219-259) and the point lights collected from placed assets (scene.rs:32-70)
+    d["n_parts"] = np.int64(len(sc.parts))
+    for i, pc in enumerate(sc.parts):
+        d[f"pv{i}"] = pc.vertices.view(np.uint8)
+        d[f"pf{i}"] = pc.faces.view(np.uint8)
+        fog = pc.fog
+        d[f"pm{i}"] = np.array([pc.facing, *pc.world_pos, 1.0 if pc.double_sided else 0.0, pc.ambient, 1.0 if fog else 0.0]
+                               + (list(fog[:3]) + list(fog[3]) if fog else [0.0] * 6), dtype=np.float64)
+    d["lights"] = np.array([[*l.position, l.radius, l.intensity, *l.color] for l in sc.lights], dtype=np.float64).reshape(-1, 8)
     np.savez_compressed(path, **d)
 
 
@@ -40,7 +49,18 @@ def load_scene(path):
         a = z[f"t{i}"]
         texs.append(Texture15(a.shape[1], a.shape[0], a.reshape(-1).copy()))
     name = os.path.basename(path)[3:-4]
-    return levels.LevelScene(name, rooms, texs, cam)
+    sc = levels.LevelScene(name, rooms, texs, cam)
+    for i in range(int(z["n_parts"]) if "n_parts" in z else 0):
+        m = z[f"pm{i}"]
+        fog = (float(m[7]), float(m[8]), float(m[9]), (int(m[10]), int(m[11]), int(m[12]))) if m[6] else None
+        sc.parts.append(levels.PartCall(z[f"pv{i}"].view(abi.VERTEX_DTYPE).copy(), z[f"pf{i}"].view(abi.FACE_DTYPE).copy(), float(np.float32(m[0])),
+                                        tuple(float(np.float32(x)) for x in m[1:4]), bool(m[4]), float(np.float32(m[5])), fog))
+    from bonnie32_b200.raster import Light
+    for row in (z["lights"] if "lights" in z else []):
+        l = Light.point(np.asarray(row[0:3], np.float32), float(np.float32(row[3])), float(np.float32(row[4])))
+        l.color = tuple(int(x) for x in row[5:8])
+        sc.lights.append(l)
+    return sc
 
 
 def scene_paths():

@@ -267,9 +267,13 @@ def test_crowded_tile(ctx, oracle):
     f2 = f.copy()
     f2["flags"][::2] = abi.face_flags(abi.FACE_TEX_NONE, abi.BLEND_AVERAGE, True, 200)
     f2["flags"][1::4] = abi.face_flags(abi.FACE_TEX_NONE, abi.BLEND_ADD, False, 255)
-    for faces_, xray in ((f, False), (f2, False), (f2, True)):
+    # third variant: every triangle at the same depth = one walk key for thousands of surfaces (pass 1's depth-ordered
+    # windows meet a single over-full key bucket and take it in face order)
+    v3 = v.copy()
+    v3["pos"][:, 2] = np.float32(20.0)
+    for faces_, xray, verts_ in ((f, False, v), (f2, False, v), (f2, True, v), (f, False, v3)):
         for zbuf in (False, True):
-            sc = scenes.Scene("crowded_tile", v, faces_, [], pkg.Camera(),
+            sc = scenes.Scene("crowded_tile", verts_, faces_, [], pkg.Camera(),
                               scenes.common_settings(use_zbuffer=zbuf, backface_cull=False, xray_mode=xray))
             want, want_z, otm, rc = oracle.render_scene(sc)
             ctx2 = pkg.Context(0)                     # fresh context: no scratch allocated yet
