@@ -473,7 +473,7 @@ def run_b200(args):
         except Exception:
             pass
         pk = prof.get(dom, {})
-        inst_frame = sum(v.get("warp_instructions", 0) for v in prof.values() if isinstance(v, dict)) or None
+        inst_frame = sum(prof.get(k, {}).get("warp_instructions", 0) for k in ("k_setup", "k_fill_opaque")) or None
         sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
         n_sched = 4 * 148
         h2d = host["compact"][3]

@@ -111,6 +111,7 @@ struct b32_ctx {
     uint32_t* tile_count = nullptr;    // current set's counters: ordered-pass entries per mask tile
     DevBuf<uint4> masks;               // tile masks [mask tile][face group] (binning without bins, b32_device.cuh)
     DevBuf<BinHead> heads, obins;      // per-face heads; obins: scratch slices of the ordered pass's crowded tiles
+    DevBuf<BinHead> crowd;             // pass 1: scratch for tiles with more candidates than one window (allocated for large meshes only)
     uint32_t obin_cap = 0;             // entries per tile slice of obins (a power of two; 0 = none allocated)
     uint32_t obin_tiles = 0;           // ... allocated for this many tiles
     DevBuf<WireTri> wire;
@@ -259,6 +260,10 @@ int ensure_work(b32_ctx* ctx, const CallParams& p) {
     CK(ctx->keys.reserve(m));
     CK(ctx->heads.reserve(m));
     CK(ctx->masks.reserve(std::max<size_t>((size_t)p.mtiles_x * p.mtiles_y * p.n_groups, 1)));
+    // A tile is crowded when more than OP_SORT_MAX_ENTRIES of the mesh's faces touch it, so only meshes well beyond that can
+    // have any: they get 5 head-sized slots of scratch per face (a face's bounding box touches ~4 tiles; a slot = one head, or four face indices), capped at 256 MB.  A tile that
+    // finds the scratch exhausted walks its windows in face order instead (same result, later early-out).
+    if (p.nf > 4u * OP_SORT_MAX_ENTRIES) CK(ctx->crowd.reserve(std::min<size_t>((size_t)p.nf * 5, (size_t)16 << 20)));
     uint32_t ntiles = p.tiles_x * p.tiles_y;
     uint32_t need = STATE_WORDS + ((std::max<uint32_t>(ntiles, 1) + 3u) & ~3u);
     if (need > ctx->state_stride) {
@@ -360,7 +365,7 @@ int launch_frame(b32_ctx* ctx, const LaunchCtx& L, const FrameArgs& a, cudaEvent
         const bool pass1 = !(p.xray_mode && !p.rgb888);     // x-ray: every surface goes through the ordered replay
         if (pass1)
             launch_fill_opaque(L, ctx->recs.p, ctx->masks.p, ctx->heads.p, a.texdesc, a.texels, a.texmask,
-                               ctx->fb_rgba.p, ctx->fb_z.p, ctx->state, ctx->sticky, p);
+                               ctx->fb_rgba.p, ctx->fb_z.p, ctx->state, ctx->sticky, ctx->crowd.p, (uint32_t)std::min<size_t>(ctx->crowd.cap, 0xFFFFFFFFu), p);
         if (p.enq_ordered)                                  // enqueue-only frames that may hold pass-2 surfaces: no host round trip
             launch_fill_ordered(L, ctx->recs.p, ctx->masks.p, ctx->obins.p, ctx->keys.p, a.texdesc, a.texels,
                                 ctx->fb_rgba.p, ctx->fb_z.p, ctx->state, ctx->sticky, p, ordered_scratch_cap(ctx, p.tiles_x * p.tiles_y));
@@ -563,7 +568,7 @@ void b32_ctx_destroy(b32_ctx* ctx) {
     ctx->fb_rgba.release(); ctx->fb_z.release(); ctx->texels.release(); ctx->texmask.release(); ctx->texdesc.release();
     ctx->texels8.release(); ctx->tex8mask.release(); ctx->tex8desc.release(); ctx->verts.release(); ctx->faces.release();
     ctx->tv.release(); ctx->recs.release(); ctx->keys.release(); ctx->state_ring.release(); ctx->masks.release();
-    ctx->heads.release(); ctx->obins.release(); ctx->wire.release(); ctx->wire_table.release();
+    ctx->heads.release(); ctx->obins.release(); ctx->crowd.release(); ctx->wire.release(); ctx->wire_table.release();
     ctx->lights.release(); ctx->dbg.release(); ctx->lines.release(); ctx->line_scratch.release();
     for (FrameGraph& g : ctx->fgs) g.destroy();
     for (cudaEvent_t e : ctx->tring) cudaEventDestroy(e);

@@ -110,7 +110,8 @@ struct CallState {
     uint32_t obin_overflow;               // ordered pass: a tile has more draw-order entries than its scratch slice (tile skipped, host grows + retries)
     uint32_t obin_max;                    // ordered pass: largest such count seen
     uint32_t wire_too_long;               // wireframe phase: an edge longer than WIRE_MAX_STEPS was skipped (host reports B32_ERR_UNSUPPORTED)
-    uint32_t _unused0, _unused1;
+    uint32_t crowd_used;                  // pass 1: entries of the crowded-tile scratch handed out so far (one atomic per crowded tile)
+    uint32_t _unused1;
 };
 
 // The reference panics (and draws nothing) on an out-of-range vertex index, or when a NaN key is

@@ -455,19 +455,25 @@ __device__ __forceinline__ CandScan cand_scan(const uint4* __restrict__ mrow, ui
 
 __device__ __forceinline__ void cand_expand(const uint4* __restrict__ mrow, const CandScan& cs, uint32_t w0, uint32_t wn, uint32_t* out) {
     uint32_t idx = cs.base;
-    for (uint32_t g = cs.g0; g < cs.g1 && idx < w0 + wn; ++g) {
-        const uint4 m = mrow[g];
-        const uint32_t c = popc128(m);
-        if (idx + c <= w0) { idx += c; continue; }
-        const uint32_t words[4] = {m.x, m.y, m.z, m.w};
+    for (uint32_t g = cs.g0; g < cs.g1 && idx < w0 + wn; g += 4) {           // mask loads four at a time: one L2 latency per batch
+        uint4 m[4];
         #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            uint32_t bits = words[q];
-            while (bits) {
-                const uint32_t b = __ffs(bits) - 1;
-                bits &= bits - 1;
-                if (idx >= w0 && idx < w0 + wn) out[idx - w0] = g * SETUP_GROUP + q * 32 + b;
-                ++idx;
+        for (int j = 0; j < 4; ++j) m[j] = g + j < cs.g1 ? mrow[g + j] : make_uint4(0, 0, 0, 0);
+        #pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t c = popc128(m[j]);
+            if (c == 0) continue;
+            if (idx + c <= w0 || idx >= w0 + wn) { idx += c; continue; }
+            const uint32_t words[4] = {m[j].x, m[j].y, m[j].z, m[j].w};
+            #pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint32_t bits = words[q];
+                while (bits) {
+                    const uint32_t b = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    if (idx >= w0 && idx < w0 + wn) out[idx - w0] = (g + j) * SETUP_GROUP + q * 32 + b;
+                    ++idx;
+                }
             }
         }
     }
@@ -780,7 +786,7 @@ struct OpCfg {
                                                  // the first step, so the CTA-wide barrier between steps rarely holds anybody up
     static constexpr int REC_PIECES = sizeof(SurfHot) / 16;
     static_assert(CHUNK % 32 == 0 && CHUNK <= 256, "whole 32-entry batches; slots are stored in a byte");
-    static_assert((size_t)3 * CHUNK * sizeof(SurfHot) >= (size_t)OP_SORT_MAX_ENTRIES * sizeof(BinHead), "the ring area doubles as the head-scan buffer");
+    static_assert((size_t)3 * CHUNK * sizeof(SurfHot) >= (size_t)OP_SORT_MAX_ENTRIES * (sizeof(BinHead) + 4), "the ring area doubles as the candidate list + the heads of a depth window");
     static constexpr int BUCKETS = THREADS < 256 ? THREADS : 256;        // key buckets of the counting sort (one scan thread each)
     static constexpr int BUCKET_BITS = BUCKETS == 256 ? 8 : (BUCKETS == 128 ? 7 : 6);
     static constexpr int RING = 3;               // ring depth: steps c, c+1, c+2
@@ -808,13 +814,146 @@ __device__ __forceinline__ uint32_t smid() { uint32_t r; asm volatile("mov.u32 %
 __device__ __forceinline__ uint32_t gtime() { uint64_t t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return (uint32_t)t; }
 #endif
 
+// ---- crowded tiles: depth-ordered windows out of a scratch slice ----------------------------------------------------
+// A tile with more candidates than one window holds (a million-triangle mesh puts thousands of surfaces behind every
+// tile) reserves a slice of a global scratch with ONE atomic, writes the heads of all its pass-1 candidates there (one
+// pass over its mask row), histograms their walk keys into `buckets` key buckets, and then takes its windows in DEPTH
+// order — the nearest few buckets first — so that the early-out of one window holds for every later one and the tile
+// stops as soon as every pixel is settled, usually after its first window.  A single bucket that holds more than a
+// window (many equal keys) is taken in slice order, a window at a time, without that carry-over.  If the scratch is
+// exhausted the tile falls back to windows in face order.  All state lives in shared memory; these functions are
+// deliberately not inlined (they run for a handful of tiles of unusual frames and must not cost the usual tile anything).
+struct CrowdShared {
+    uint32_t n_valid, kmin, shift, b_next, over_b, over_i, item[4], ncol, lo, hi;
+};
+
+// slot for every lane with `take` set: one shared-memory atomic per warp (all 32 lanes must call)
+__device__ __forceinline__ uint32_t warp_append(bool take, uint32_t* counter) {
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, take), lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == 0 && m) base = atomicAdd(counter, (uint32_t)__popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    return base + __popc(m & ((1u << lane) - 1));
+}
+
+__device__ __forceinline__ uint32_t crowd_bucket(uint32_t k, uint32_t kmin, uint32_t shift, uint32_t buckets) {
+    return k == 0xFFFFFFFFu ? 0u : (buckets - 1) - ((k - kmin) >> shift);
+}
+
+// pass 1: every candidate's head -> slice[] (those that are pass-1 surfaces touching this tile), key range, histogram.
+// The face indices of all candidates are written once to ids[] (= the tail of the tile's scratch slice), in face order,
+// with the mask loads batched four at a time; the heads are then gathered with coalesced index reads.
+__device__ __noinline__ void crowd_prepare(const uint4* __restrict__ mrow, const CandScan cs, uint32_t n_cand, const BinHead* __restrict__ heads,
+                                           uint32_t tpx0, uint32_t tpy0, BinHead* __restrict__ slice, uint32_t* __restrict__ ids,
+                                           uint32_t* s_ghist, uint32_t buckets, uint32_t bucket_bits, CrowdShared* cr) {
+    if (threadIdx.x == 0) { cr->ncol = 0; cr->lo = 0xFFFFFFFFu; cr->hi = 0; cr->b_next = 0; cr->over_b = 0xFFFFFFFFu; cr->over_i = 0; }
+    for (uint32_t i = threadIdx.x; i < buckets; i += blockDim.x) s_ghist[i] = 0;
+    uint32_t idx = cs.base;
+    for (uint32_t g = cs.g0; g < cs.g1; g += 4) {
+        uint4 m[4];
+        #pragma unroll
+        for (int j = 0; j < 4; ++j) m[j] = g + j < cs.g1 ? mrow[g + j] : make_uint4(0, 0, 0, 0);
+        #pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if ((m[j].x | m[j].y | m[j].z | m[j].w) == 0) continue;
+            const uint32_t words[4] = {m[j].x, m[j].y, m[j].z, m[j].w};
+            #pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint32_t bits = words[q];
+                while (bits) { const uint32_t bb = __ffs(bits) - 1; bits &= bits - 1; ids[idx++] = (g + j) * SETUP_GROUP + q * 32 + bb; }
+            }
+        }
+    }
+    __syncthreads();                                       // ids[] written by this block: visible to it after the barrier
+    uint32_t lo = 0xFFFFFFFFu, hi = 0;
+    for (uint32_t w0 = threadIdx.x & ~31u; w0 < n_cand; w0 += 4 * blockDim.x) {       // warp-uniform trip count
+        BinHead h[4];
+        #pragma unroll
+        for (int j = 0; j < 4; ++j) { const uint32_t i = w0 + (threadIdx.x & 31) + j * blockDim.x; if (i < n_cand) h[j] = heads[ids[i]]; else h[j].bbox_x = 0; }
+        #pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t min_x = h[j].bbox_x & 0xFFFF, max_x = h[j].bbox_x >> 16, min_y = h[j].bbox_y & 0xFFFF, max_y = h[j].bbox_y >> 16;
+            const bool ok = !(h[j].bbox_x == 0 || max_x <= tpx0 || min_x >= tpx0 + TILE_W || max_y <= tpy0 || min_y >= tpy0 + TILE_H);
+            const uint32_t pos = warp_append(ok, &cr->ncol);
+            if (ok) {
+                slice[pos] = h[j];
+                if (h[j].key != 0xFFFFFFFFu) { lo = min(lo, h[j].key); hi = max(hi, h[j].key); }
+            }
+        }
+    }
+    lo = __reduce_min_sync(0xFFFFFFFFu, lo); hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+    if ((threadIdx.x & 31) == 0) { atomicMin(&cr->lo, lo); atomicMax(&cr->hi, hi); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t kmin = cr->lo, kmax = cr->hi;
+        if (kmin > kmax) { kmin = 0; kmax = 0; }
+        const uint32_t range = kmax - kmin;
+        cr->kmin = kmin;
+        cr->shift = range >= buckets ? (32 - __clz(range)) - bucket_bits : 0;
+        cr->n_valid = cr->ncol;
+    }
+    __syncthreads();
+    const uint32_t nv = cr->n_valid, kmin = cr->kmin, shift = cr->shift;
+    for (uint32_t i = threadIdx.x; i < nv; i += blockDim.x) atomicAdd(&s_ghist[crowd_bucket(slice[i].key, kmin, shift, buckets)], 1u);   // (this thread block wrote slice[]: visible after the barrier)
+    __syncthreads();
+}
+
+// the next depth window: its heads -> s_tmp[0..n).  Returns n; 0xFFFFFFFF = no window left.  *carry = the window is one
+// of the depth sequence (its early-outs hold for every later window).
+__device__ __noinline__ uint32_t crowd_next_window(const BinHead* __restrict__ slice, uint32_t tile_weak, uint32_t* s_ghist, uint32_t buckets,
+                                                   uint32_t win, BinHead* s_tmp, CrowdShared* cr, bool* carry) {
+    __syncthreads();                                       // the previous window's readers of cr->item are through
+    if (threadIdx.x == 0) {
+        cr->ncol = 0;
+        if (cr->over_b != 0xFFFFFFFFu) {                   // an over-full bucket, the next `win` slice entries
+            cr->item[0] = cr->over_b; cr->item[1] = cr->over_b + 1; cr->item[2] = cr->over_i; cr->item[3] = min(cr->over_i + win, cr->n_valid);
+            cr->over_i += win;
+            if (cr->over_i >= cr->n_valid) cr->over_b = 0xFFFFFFFFu;
+        } else {
+            uint32_t b = cr->b_next;
+            while (b < buckets && s_ghist[b] == 0) ++b;
+            if (b >= buckets) { cr->item[0] = 0xFFFFFFFFu; }
+            else if (s_ghist[b] > win) {                   // over-full: this call takes its first `win` slice entries
+                cr->item[0] = b; cr->item[1] = b + 1; cr->item[2] = 0; cr->item[3] = min(win, cr->n_valid);
+                cr->b_next = b + 1;
+                if (win < cr->n_valid) { cr->over_b = b; cr->over_i = win; }
+            } else {
+                uint32_t sum = 0, first = b;
+                while (b < buckets && sum + s_ghist[b] <= win) sum += s_ghist[b++];
+                cr->item[0] = first; cr->item[1] = b; cr->item[2] = 0; cr->item[3] = cr->n_valid;
+                cr->b_next = b;
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t b0 = cr->item[0], b1 = cr->item[1], i0 = cr->item[2], i1 = cr->item[3];
+    if (b0 == 0xFFFFFFFFu) return 0xFFFFFFFFu;
+    *carry = (i0 == 0 && i1 == cr->n_valid && cr->over_b == 0xFFFFFFFFu);
+    const uint32_t kmin = cr->kmin, shift = cr->shift;
+    for (uint32_t w = i0 + (threadIdx.x & ~31u); w < i1; w += blockDim.x) {             // warp-uniform trip count
+        const uint32_t i = w + (threadIdx.x & 31);
+        BinHead h{0, 0, 0, 0};
+        bool take = false;
+        if (i < i1) {
+            h = slice[i];
+            const uint32_t b = crowd_bucket(h.key, kmin, shift, buckets);
+            // (z-buffer: key 0xFFFFFFFF = "no bound claimed" always passes; equal bounds pass: ties are resolved per pixel)
+            take = b >= b0 && b < b1 && h.key >= tile_weak;
+        }
+        const uint32_t pos = warp_append(take, &cr->ncol);
+        if (take && pos < win) s_tmp[pos] = h;
+    }
+    __syncthreads();
+    return min(cr->ncol, win);
+}
+
 // RGB888 = the render_mesh instantiation (8-bit colour pipeline in step 5; everything else is shared); C = OpDense / OpSparse
 template <bool RGB888, class C>
 __global__ void __launch_bounds__(C::THREADS, C::MINB)
 k_fill_opaque(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks, const BinHead* __restrict__ heads,
               const TexDev* __restrict__ tex, const uint16_t* __restrict__ texels, const uint32_t* __restrict__ texmask,
-              uint32_t* __restrict__ fb_rgba, float* __restrict__ fb_z, const CallState* __restrict__ st,
-              uint32_t* __restrict__ sticky, CallParams p) {
+              uint32_t* __restrict__ fb_rgba, float* __restrict__ fb_z, CallState* __restrict__ st,
+              uint32_t* __restrict__ sticky, BinHead* __restrict__ crowd, uint32_t crowd_cap, CallParams p) {
     constexpr int OP_THREADS = C::THREADS, OP_WARPS = C::WARPS, OP_BW = C::BW, OP_BH = C::BH, OP_SPLIT = C::SPLIT;
     constexpr bool OP_DUAL = C::DUAL;
     constexpr int OP_CHUNK = C::CHUNK, OP_REC_PIECES = C::REC_PIECES, OP_BUCKETS = C::BUCKETS, OP_BUCKET_BITS = C::BUCKET_BITS;
@@ -832,6 +971,9 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks,
     __shared__ uint32_t s_minmax[2];
     __shared__ uint32_t s_nsmall, s_nraw;
     __shared__ uint32_t s_tile_weak;       // what the tile's weakest pixel still accepts after the windows done so far (see the window loop)
+    __shared__ uint32_t s_ghist[OP_BUCKETS];   // crowded tiles: histogram of all candidates' walk keys
+    __shared__ CrowdShared s_crowd;
+    __shared__ uint32_t s_slice;
     __shared__ __align__(8) uint64_t s_mbar;
     if (threadIdx.x == 0) s_nraw = 0;
     // ---- prologue: nothing here reads what k_setup writes (the framebuffer included: the frame's clear may ride in
@@ -893,6 +1035,7 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks,
         if (pos + cnt <= (uint32_t)OP_SORT_MAX) {
             #pragma unroll
             for (int j = 0; j < OP_KREG; ++j) {
+                if ((m[j].x | m[j].y | m[j].z | m[j].w) == 0) continue;       // most (tile, group) pairs are empty
                 const uint32_t f0 = (j * OP_THREADS + threadIdx.x) * SETUP_GROUP;
                 const uint32_t words[4] = {m[j].x, m[j].y, m[j].z, m[j].w};
                 #pragma unroll
@@ -937,9 +1080,25 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks,
     // painter's: tile_weak = smallest winner key in the tile (0 while a pixel has no winner): keys below it lose everywhere;
     // z-buffer : tile_weak = ~bits(largest depth in the tile): a surface whose depth lower bound is behind it loses everywhere.
     uint32_t tile_weak = 0;
-    for (uint32_t w0 = 0; w0 < n_cand; w0 += OP_SORT_MAX) {
-        const uint32_t wn = min((uint32_t)OP_SORT_MAX, n_cand - w0);
-        if (w0) {
+    // crowded tile: a slice of the global scratch for its heads (see crowd_prepare); none left = windows in face order
+    BinHead* slice = nullptr;
+    const uint32_t slice_len = n_cand + (n_cand + 3) / 4;          // n_cand heads, then n_cand face indices (4 per head-sized slot)
+    if (n_cand > (uint32_t)OP_SORT_MAX) {
+        if (threadIdx.x == 0) {
+            uint32_t base = crowd_cap >= slice_len ? atomicAdd(&st->crowd_used, slice_len) : 0xFFFFFFFFu;
+            s_slice = (base != 0xFFFFFFFFu && (uint64_t)base + slice_len <= crowd_cap) ? base : 0xFFFFFFFFu;
+        }
+        __syncthreads();
+        if (s_slice != 0xFFFFFFFFu) slice = crowd + s_slice;
+    }
+    BinHead* s_tmp = reinterpret_cast<BinHead*>(s_cand + OP_SORT_MAX);         // [OP_SORT_MAX] a depth window's heads (the ring is idle then)
+    if (slice) crowd_prepare(mrow, cs, n_cand, heads, tpx0, tpy0, slice, reinterpret_cast<uint32_t*>(slice + n_cand), s_ghist, OP_BUCKETS, OP_BUCKET_BITS, &s_crowd);
+    bool gdone = offscreen;                                // depth-ordered windows: this warp's early-out, carried from window to window
+    for (uint32_t win = 0;; ++win) {
+        const uint32_t w0 = win * OP_SORT_MAX;
+        if (!slice && w0 >= n_cand) break;
+        const uint32_t wn = slice ? 0u : min((uint32_t)OP_SORT_MAX, n_cand - w0);
+        if (win) {
             cp_async_wait<0>();
             if (threadIdx.x == 0) s_tile_weak = 0xFFFFFFFFu;
             __syncthreads();                               // the previous window's ring traffic is over: its area is reused
@@ -960,25 +1119,37 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks,
             tile_weak = s_tile_weak;
             if (tile_weak == 0xFFFFFFFFu) tile_weak = 0;   // no on-screen pixel at all
         }
-        if (!fast_ok) cand_expand(mrow, cs, w0, wn, s_cand);
-        // ---- 1. gather the window's heads (one 16-byte record per face, L2-resident) into registers; drop the candidates
-        //         that are not pass-1 surfaces (head bbox 0: pass 2) or, with coarse mask tiles, miss this 16x16 tile
+        // ---- 1. the window's heads (one 16-byte record per face, L2-resident) in registers; dropped: candidates that are not
+        //         pass-1 surfaces (head bbox 0: pass 2) or, with coarse mask tiles, miss this 16x16 tile
         constexpr int KPT = OP_SORT_MAX / OP_THREADS;
         BinHead hh[KPT];
         uint32_t n = 0;
-        #pragma unroll
-        for (int q = 0; q < KPT; ++q) {
-            const uint32_t i = q * OP_THREADS + threadIdx.x;
-            bool ok = false;
-            if (i < wn) {
-                hh[q] = heads[s_cand[i]];
-                const uint32_t min_x = hh[q].bbox_x & 0xFFFF, max_x = hh[q].bbox_x >> 16, min_y = hh[q].bbox_y & 0xFFFF, max_y = hh[q].bbox_y >> 16;
-                ok = hh[q].bbox_x != 0 && !(max_x <= tpx0 || min_x >= tpx0 + TILE_W || max_y <= tpy0 || min_y >= tpy0 + TILE_H);
-                // (z-buffer: key 0xFFFFFFFF = "no bound claimed" always passes; equal bounds pass: ties are resolved per pixel)
-                ok = ok && hh[q].key >= tile_weak;
+        bool carry = false;
+        if (slice) {
+            n = crowd_next_window(slice, tile_weak, s_ghist, OP_BUCKETS, OP_SORT_MAX, s_tmp, &s_crowd, &carry);
+            if (n == 0xFFFFFFFFu) break;
+            #pragma unroll
+            for (int q = 0; q < KPT; ++q) {
+                const uint32_t i = q * OP_THREADS + threadIdx.x;
+                if (i < n) hh[q] = s_tmp[i]; else hh[q].bbox_x = 0;
             }
-            if (!ok) hh[q].bbox_x = 0;
-            n += __syncthreads_count(ok);                  // (also orders the s_cand reads before the ring's writes)
+            __syncthreads();                               // s_tmp has been read: the ring may be written
+        } else {
+            if (!fast_ok) cand_expand(mrow, cs, w0, wn, s_cand);
+            #pragma unroll
+            for (int q = 0; q < KPT; ++q) {
+                const uint32_t i = q * OP_THREADS + threadIdx.x;
+                bool ok = false;
+                if (i < wn) {
+                    hh[q] = heads[s_cand[i]];
+                    const uint32_t min_x = hh[q].bbox_x & 0xFFFF, max_x = hh[q].bbox_x >> 16, min_y = hh[q].bbox_y & 0xFFFF, max_y = hh[q].bbox_y >> 16;
+                    ok = hh[q].bbox_x != 0 && !(max_x <= tpx0 || min_x >= tpx0 + TILE_W || max_y <= tpy0 || min_y >= tpy0 + TILE_H);
+                    // (z-buffer: key 0xFFFFFFFF = "no bound claimed" always passes; equal bounds pass: ties are resolved per pixel)
+                    ok = ok && hh[q].key >= tile_weak;
+                }
+                if (!ok) hh[q].bbox_x = 0;
+                n += __syncthreads_count(ok);              // (also orders the s_cand reads before the ring's writes)
+            }
         }
         if (n == 0) continue;
         auto for_each_entry = [&](auto f) {
@@ -1041,17 +1212,17 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks,
         stage(0);
         stage(1);
 #ifdef B32_FILL_STATS
-        if (!w0) st_t1 = gtime();
+        if (!win) st_t1 = gtime();
 #endif
         if (!mask_waited) { while (!mbar_try_wait(&s_mbar, 0)) {} mask_waited = true; }
 
-        bool done = offscreen;
+        bool done = carry ? gdone : offscreen;             // (carry: depth-ordered windows — an early-out holds for every later window)
         const uint32_t nchunks = (n + OP_CHUNK - 1) / OP_CHUNK;
         for (uint32_t c = 0; c < nchunks; ++c) {
             cp_async_wait<1>();                               // this thread's pieces of step c have landed ...
             if (__syncthreads_and(done)) break;               // ... and so have everybody else's; slot (c+2) % 3 is free again
 #ifdef B32_FILL_STATS
-            if (c == 0 && !w0) st_tfirst = gtime();
+            if (c == 0 && !win) st_tfirst = gtime();
 #endif
             stage(c + 2);
             if (done) continue;
@@ -1169,6 +1340,10 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks,
                     if (take) { best = ob; px.z = oz; best_face = of; }
                 }
             }
+        }
+        if (carry) {                                          // every warp settled: the farther windows cannot change anything
+            gdone = done;
+            if (__syncthreads_and(gdone)) break;
         }
     }
     cp_async_wait<0>();
@@ -1860,7 +2035,7 @@ void launch_setup(const LaunchCtx& L, const b32_vertex* verts, const b32_face* f
 
 void launch_fill_opaque(const LaunchCtx& L, const SurfRec* recs, const uint4* masks, const BinHead* heads,
                         const TexDev* tex, const uint16_t* texels, const uint32_t* texmask, uint32_t* fb_rgba, float* fb_z,
-                        const CallState* st, uint32_t* sticky, const CallParams& p) {
+                        CallState* st, uint32_t* sticky, BinHead* crowd, uint32_t crowd_cap, const CallParams& p) {
     uint32_t ntiles = p.tiles_x * p.tiles_y;
     if (ntiles == 0 || p.nf == 0) return;
     // The 256-thread shape packs 4 CTAs per SM: it wins when the frame has more tiles than one wave of the two-lanes-per-
@@ -1870,10 +2045,10 @@ void launch_fill_opaque(const LaunchCtx& L, const SurfRec* recs, const uint4* ma
     const bool sparse = force_sparse || (!force_dense && (p.async_call || ntiles * OpDense::SPLIT > L.sms * (uint32_t)OpDense::MINB));
     if (sparse)
         launch_k(L, p.rgb888 ? k_fill_opaque<true, OpSparse> : k_fill_opaque<false, OpSparse>, ntiles * OpSparse::SPLIT, OpSparse::THREADS, OpSparse::SMEM, true,
-                 recs, masks, heads, tex, texels, texmask, fb_rgba, fb_z, st, sticky, p);
+                 recs, masks, heads, tex, texels, texmask, fb_rgba, fb_z, st, sticky, crowd, crowd_cap, p);
     else
         launch_k(L, p.rgb888 ? k_fill_opaque<true, OpDense> : k_fill_opaque<false, OpDense>, ntiles * OpDense::SPLIT, OpDense::THREADS, OpDense::SMEM, true,
-                 recs, masks, heads, tex, texels, texmask, fb_rgba, fb_z, st, sticky, p);
+                 recs, masks, heads, tex, texels, texmask, fb_rgba, fb_z, st, sticky, crowd, crowd_cap, p);
 }
 
 void launch_fill_ordered(const LaunchCtx& L, const SurfRec* recs, const uint4* masks, BinHead* scratch, const uint64_t* keys,

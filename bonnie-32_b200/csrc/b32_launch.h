@@ -41,10 +41,12 @@ void launch_setup(const LaunchCtx& L, const b32_vertex* verts, const b32_face* f
                   const LightDev* lights, SurfRec* recs, uint64_t* keys, BinHead* heads, uint4* masks, uint32_t* ocount,
                   WireTri* wire, CallState* st, uint32_t* zero_next, uint32_t zero_words,
                   uint32_t* clear_rgba, float* clear_z, uint32_t clear_n, uint32_t clear_color, const CallParams& p);
-// pass 1: every tile reads its surface list out of its mask row and k_setup's per-face heads
+// pass 1: every tile reads its surface list out of its mask row and k_setup's per-face heads.  crowd: crowd_cap heads of
+// scratch for tiles with more candidates than one window holds (they order their walk by depth through a slice of it;
+// without one they take their windows in face order)
 void launch_fill_opaque(const LaunchCtx& L, const SurfRec* recs, const uint4* masks, const BinHead* heads,
                         const TexDev* tex, const uint16_t* texels, const uint32_t* texmask, uint32_t* fb_rgba, float* fb_z,
-                        const CallState* st, uint32_t* sticky, const CallParams& p);
+                        CallState* st, uint32_t* sticky, BinHead* crowd, uint32_t crowd_cap, const CallParams& p);
 // ordered pass (pass 2 / x-ray): every tile builds its draw-order entries from its mask row + keys[], sorts them and replays
 // them in order.  scratch: scratch_cap (a power of two, or 0) entries per tile for tiles with more entries than fit shared memory.
 // p.enq_ordered: launched right behind pass 1 without a host round trip (exits at once when there is nothing to replay).

@@ -41,6 +41,8 @@ extern "C" {
     fn b32_fb_upload(ctx: *mut b32_ctx, rgba: *const u8, z: *const f32) -> c_int;
     fn b32_fb_download(ctx: *mut b32_ctx, rgba: *mut u8, z: *mut f32) -> c_int;
     fn b32_textures_set(ctx: *mut b32_ctx, descs: *const b32_tex_desc, n: u32) -> c_int;
+    fn b32_render_mesh_15_ex(ctx: *mut b32_ctx, v: *const c_void, nv: u32, f: *const c_void, nf: u32, cam: *const b32_camera,
+                             s: *const b32_settings, fog: *const b32_fog, flags: u32, tm: *mut b32_timings) -> c_int;
     fn b32_render_mesh_15(ctx: *mut b32_ctx, v: *const b32_vertex, nv: u32, f: *const b32_face, nf: u32,
                           cam: *const b32_camera, s: *const b32_settings, fog: *const b32_fog,
                           out: *mut b32_timings) -> c_int;
@@ -65,17 +67,52 @@ fn check(ctx: *mut b32_ctx, rc: c_int) {
     }
 }
 
+#[repr(C)] #[derive(Clone, Copy)]
+pub struct b32_vertex_nn { pos: [f32; 3], uv: [f32; 2], r: u8, g: u8, b: u8, blend: u8 }
+const B32_VTX_NO_NORMAL: u32 = 4;
+const B32_FACES_IMPLICIT: u32 = 8;
+
+fn face_flags(f: &Face) -> u32 {
+    let tex = match f.texture_id { Some(id) if id < 0xFFFF => id as u32, _ => 0xFFFF };
+    tex | ((blend_u8(f.blend_mode) as u32) << 16) | ((f.black_transparent as u32) << 19) | ((f.editor_alpha as u32) << 24)
+}
+
+/// The bytes that cross PCIe, in the most compact layout the call allows (include/b32_raster.h, B32_VTX_NO_NORMAL /
+/// B32_FACES_IMPLICIT): normals are only read when the settings shade (render.rs:1466-1483), and an unindexed triangle
+/// soup (face i = vertices 3i, 3i+1, 3i+2) needs no index buffer.  Both are decided while the slices are converted
+/// anyway; the rendered bytes are identical.  Returns (vertex bytes, face bytes, flags).
+fn marshal_compact(vertices: &[Vertex], faces: &[Face], settings: &RasterSettings) -> (Vec<u8>, Vec<u8>, u32) {
+    let mut flags = 0u32;
+    let as_bytes = |p: *const u8, n: usize| unsafe { std::slice::from_raw_parts(p, n) }.to_vec();
+    let vb = if settings.shading == ShadingMode::None {
+        flags |= B32_VTX_NO_NORMAL;
+        let v: Vec<b32_vertex_nn> = vertices.iter().map(|v| b32_vertex_nn {
+            pos: [v.pos.x, v.pos.y, v.pos.z], uv: [v.uv.x, v.uv.y], r: v.color.r, g: v.color.g, b: v.color.b, blend: blend_u8(v.color.blend) }).collect();
+        as_bytes(v.as_ptr() as *const u8, v.len() * 24)
+    } else {
+        let (v, _) = marshal_geometry(vertices, &[]);
+        as_bytes(v.as_ptr() as *const u8, v.len() * 36)
+    };
+    let soup = vertices.len() >= 3 * faces.len() && faces.iter().enumerate().all(|(i, f)| f.v0 == 3 * i && f.v1 == 3 * i + 1 && f.v2 == 3 * i + 2);
+    let fbytes = if soup {
+        flags |= B32_FACES_IMPLICIT;
+        let f: Vec<u32> = faces.iter().map(face_flags).collect();
+        as_bytes(f.as_ptr() as *const u8, f.len() * 4)
+    } else {
+        let (_, f) = marshal_geometry(&[], faces);
+        as_bytes(f.as_ptr() as *const u8, f.len() * 16)
+    };
+    (vb, fbytes, flags)
+}
+
 // --- marshal &[Vertex] / &[Face] into the 36 B / 16 B POD records (include/b32_raster.h) ---
 fn marshal_geometry(vertices: &[Vertex], faces: &[Face]) -> (Vec<b32_vertex>, Vec<b32_face>) {
     let v = vertices.iter().map(|v| b32_vertex {
         pos: [v.pos.x, v.pos.y, v.pos.z], uv: [v.uv.x, v.uv.y], normal: [v.normal.x, v.normal.y, v.normal.z],
         r: v.color.r, g: v.color.g, b: v.color.b, blend: blend_u8(v.color.blend) }).collect();
-    let f = faces.iter().map(|f| {
-        let tex = match f.texture_id { Some(id) if id < 0xFFFF => id as u32, _ => 0xFFFF };
-        b32_face { v0: f.v0.min(u32::MAX as usize) as u32, v1: f.v1.min(u32::MAX as usize) as u32,
-                   v2: f.v2.min(u32::MAX as usize) as u32,
-                   flags: tex | ((blend_u8(f.blend_mode) as u32) << 16) | ((f.black_transparent as u32) << 19)
-                          | ((f.editor_alpha as u32) << 24) } }).collect();
+    let f = faces.iter().map(|f| b32_face {
+        v0: f.v0.min(u32::MAX as usize) as u32, v1: f.v1.min(u32::MAX as usize) as u32,
+        v2: f.v2.min(u32::MAX as usize) as u32, flags: face_flags(f) }).collect();
     (v, f)
 }
 
@@ -116,7 +153,7 @@ fn timings(tm: &b32_timings) -> RasterTimings {
 pub fn render_mesh_15(fb: &mut Framebuffer, vertices: &[Vertex], faces: &[Face], textures: &[Texture15],
                       camera: &Camera, settings: &RasterSettings, fog: Option<(f32, f32, f32, Color)>) -> RasterTimings {
     CTX.with(|&ctx| unsafe {
-        let (v, f) = marshal_geometry(vertices, faces);
+        let (v, f, layout) = marshal_compact(vertices, faces, settings);
         // --- textures: re-upload only when the slice changed (cf. textures_15_cache_generation) ---
         let key = (textures.as_ptr() as usize, textures.len());
         if TEX_GEN.with(|g| g.replace(key)) != key {
@@ -132,8 +169,8 @@ pub fn render_mesh_15(fb: &mut Framebuffer, vertices: &[Vertex], faces: &[Face],
         check(ctx, b32_fb_resize(ctx, fb.width as u32, fb.height as u32));
         check(ctx, b32_fb_upload(ctx, fb.pixels.as_ptr(), fb.zbuffer.as_ptr()));
         let mut tm = b32_timings::default();
-        check(ctx, b32_render_mesh_15(ctx, v.as_ptr(), v.len() as u32, f.as_ptr(), f.len() as u32, &cam, &s,
-                                      fogc.as_ref().map_or(std::ptr::null(), |f| f as *const _), &mut tm));
+        check(ctx, b32_render_mesh_15_ex(ctx, v.as_ptr() as *const c_void, vertices.len() as u32, f.as_ptr() as *const c_void, faces.len() as u32,
+                                         &cam, &s, fogc.as_ref().map_or(std::ptr::null(), |f| f as *const _), layout, &mut tm));
         check(ctx, b32_fb_download(ctx, fb.pixels.as_mut_ptr(), fb.zbuffer.as_mut_ptr()));
         timings(&tm)
     })
