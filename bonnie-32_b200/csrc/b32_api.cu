@@ -126,6 +126,9 @@ struct b32_ctx {
     CallState* state = nullptr;        // device: current set's CallState
     uint32_t* sticky = nullptr;        // device: error bits of enqueue-only calls
     CallState* state_h = nullptr;      // pinned host
+    HostStatus* hstat = nullptr;       // pinned + mapped: what a blocking call's kernels publish (b32_device.cuh)
+    HostStatus* hstat_dev = nullptr;   // ... its device address
+    uint32_t host_seq = 0;
     uint8_t* pinned = nullptr;         // pinned staging ring for pageable host buffers
     size_t pinned_bytes = 0;
     uint32_t last_nf = 0;
@@ -302,22 +305,41 @@ int upload_lights(b32_ctx* ctx, const std::vector<LightDev>& lights) {
 // memory sort in a slice of a global scratch, sized here (so the pass never has to be redone).
 int render_ordered(b32_ctx* ctx, const CallParams& p, uint32_t obin_max) {
     LaunchCtx L = ctx->L();
-    cudaStream_t st = ctx->stream;
     const uint32_t ntiles = p.tiles_x * p.tiles_y;
     if (obin_max > (uint32_t)ORD_SORT_MAX && obin_max > ordered_scratch_cap(ctx, ntiles)) {
         uint32_t cap2 = 2; while (cap2 < obin_max) cap2 <<= 1;               // power of two: the tile sort pads in place
         CK(ctx->obins.reserve((size_t)ntiles * cap2));
         ctx->obin_cap = cap2; ctx->obin_tiles = ntiles;
     }
-    CK(cudaEventRecord(ctx->ev[3], st));
     launch_fill_ordered(L, ctx->recs.p, ctx->masks.p, ctx->obins.p, ctx->keys.p, p.rgb888 ? ctx->tex8desc.p : ctx->texdesc.p,
                         p.rgb888 ? reinterpret_cast<const uint16_t*>(ctx->texels8.p) : ctx->texels.p,
                         ctx->fb_rgba.p, ctx->fb_z.p, ctx->state, ctx->sticky, p, ordered_scratch_cap(ctx, ntiles));
-    CK(cudaEventRecord(ctx->ev[4], st));
-    CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
-    cudaEventElapsedTime(&ctx->kernel_ms[3], ctx->ev[3], ctx->ev[4]);
     return B32_OK;
+}
+
+// Spin until the kernel's last CTA has published `seq` in the mapped status block (b32_device.cuh, HostStatus).
+// Every few thousand polls the stream is queried: a failed launch / kernel must not hang the caller.
+int wait_stamp(b32_ctx* ctx, int k, uint32_t seq) {
+    const uint32_t* flag = &ctx->hstat->stamp[k].seq;
+    for (uint32_t spins = 1;; ++spins) {
+        if (__atomic_load_n(flag, __ATOMIC_ACQUIRE) == seq) return B32_OK;
+        if ((spins & 0x3FFF) == 0) {
+            cudaError_t e = cudaStreamQuery(ctx->stream);
+            if (e == cudaSuccess) {                               // the stream drained: the flag is there, or the kernel never ran
+                if (__atomic_load_n(flag, __ATOMIC_ACQUIRE) == seq) return B32_OK;
+                return fail(ctx, B32_ERR_CUDA, "a frame kernel finished without reporting (launch failed?)");
+            }
+            if (e != cudaErrorNotReady) { cudaGetLastError(); return fail(ctx, B32_ERR_CUDA, cudaGetErrorString(e)); }
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+}
+static float stamp_ms(const b32_ctx* ctx, int k) {
+    const KernelStamp& t = ctx->hstat->stamp[k];
+    return t.t1 > t.t0 ? (float)((double)(t.t1 - t.t0) * 1e-6) : 0.0f;
 }
 
 // Turn the frame just captured on the context's stream into an executable graph and remember its kernel nodes.
@@ -481,24 +503,32 @@ int render_device(b32_ctx* ctx, const b32_vertex* d_verts, uint32_t nv, const b3
         key.ordered = p.enq_ordered;
         return enqueue_frame(ctx, a, key);
     }
-    rc = launch_frame(ctx, L, a, ctx->ev[0], ctx->ev[1]); if (rc) return rc;
-    CK(cudaEventRecord(ctx->ev[2], st));
-    CK(cudaMemcpyAsync(ctx->state_h, ctx->state, sizeof(CallState), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    // Blocking call: no events, no copy back.  The kernels report in host-mapped memory (HostStatus): k_setup's last CTA
+    // the counters — the host reads them while pass 1 runs and launches the ordered pass behind it if there is one — and
+    // every kernel its start / end times.
+    const uint32_t seq = ++ctx->host_seq;
+    p.host = ctx->hstat_dev; p.host_seq = seq;
+    ctx->last_params = p;
+    for (KernelStamp& t : ctx->hstat->stamp) { t.t0 = 0; t.t1 = 0; }
+    rc = launch_frame(ctx, L, a, nullptr, nullptr); if (rc) return rc;
     CK(cudaGetLastError());
-    hs = *ctx->state_h;
+    rc = wait_stamp(ctx, HS_SETUP, seq); if (rc) return rc;
+    hs = ctx->hstat->state;
     if (hs.oob) return fail(ctx, B32_ERR_OOB_INDEX, "face vertex index out of range (reference: slice index panic)");
     {   // the reference panics on a NaN key in a sorted slice of length >= 2 (render.rs:2531; RGB888: one list, :2161)
         bool nan_abort = rgb888 ? (!p.use_zbuffer && hs.nan_opaque && hs.n_opaque + hs.n_transp >= 2)
                                 : (hs.nan_transp && hs.n_transp >= 2) || (!p.use_zbuffer && hs.nan_opaque && hs.n_opaque >= 2);
         if (nan_abort) return fail(ctx, B32_ERR_NAN_DEPTH, "NaN depth key in a sorted pass (reference: partial_cmp().unwrap() panic, render.rs:2531)");
     }
-    cudaEventElapsedTime(&ctx->kernel_ms[0], ctx->ev[0], ctx->ev[1]);
-    cudaEventElapsedTime(&ctx->kernel_ms[1], ctx->ev[1], ctx->ev[2]);
     // RGB888: one surface that may read the framebuffer sends the whole list through the ordered replay (pass 1 was skipped)
     const bool all_ordered = rgb888 ? hs.n_transp > 0 : p.xray_mode != 0;
-    bool need_ordered = all_ordered ? (hs.n_opaque + hs.n_transp) > 0 : (!rgb888 && hs.n_transp > 0);
-    if (need_ordered && !p.wire_front) { rc = render_ordered(ctx, p, hs.obin_max); if (rc) return rc; }
+    const bool pass1 = !p.wire_front && !(p.xray_mode && !rgb888);
+    const bool need_ordered = !p.wire_front && (all_ordered ? (hs.n_opaque + hs.n_transp) > 0 : (!rgb888 && hs.n_transp > 0));
+    if (need_ordered) { rc = render_ordered(ctx, p, hs.obin_max); if (rc) return rc; }
+    if (need_ordered || pass1) { rc = wait_stamp(ctx, need_ordered ? HS_ORDERED : HS_FILL, seq); if (rc) return rc; }
+    ctx->kernel_ms[0] = stamp_ms(ctx, HS_SETUP);
+    ctx->kernel_ms[1] = pass1 ? stamp_ms(ctx, HS_FILL) : 0.0f;
+    ctx->kernel_ms[3] = need_ordered ? stamp_ms(ctx, HS_ORDERED) : 0.0f;
     bool wire_too_long = false;
     if (p.wire_back || p.wire_front) {          // WIREFRAME phase, render.rs:2574-2635
         uint32_t tsize = 64;
@@ -553,6 +583,9 @@ int b32_ctx_create(int device, b32_ctx** out) {
     if ((e = cudaMalloc(&ctx->sticky, sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMemset(ctx->sticky, 0, sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMemset");
     if ((e = cudaMallocHost(&ctx->state_h, sizeof(CallState))) != cudaSuccess) return bail(e, "cudaMallocHost");
+    if ((e = cudaHostAlloc(&ctx->hstat, sizeof(HostStatus), cudaHostAllocMapped)) != cudaSuccess) return bail(e, "cudaHostAlloc");
+    std::memset(ctx->hstat, 0, sizeof(HostStatus));
+    if ((e = cudaHostGetDevicePointer(&ctx->hstat_dev, ctx->hstat, 0)) != cudaSuccess) return bail(e, "cudaHostGetDevicePointer");
     ctx->pinned_bytes = 8u << 20;
     if ((e = cudaMallocHost(&ctx->pinned, ctx->pinned_bytes)) != cudaSuccess) return bail(e, "cudaMallocHost");
     ctx->texdesc.reserve(1); ctx->texels.reserve(1); ctx->texmask.reserve(4); ctx->lights.reserve(1);
@@ -574,6 +607,7 @@ void b32_ctx_destroy(b32_ctx* ctx) {
     for (cudaEvent_t e : ctx->tring) cudaEventDestroy(e);
     if (ctx->sticky) cudaFree(ctx->sticky);
     if (ctx->state_h) cudaFreeHost(ctx->state_h);
+    if (ctx->hstat) cudaFreeHost(ctx->hstat);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->h2d_ev) if (ev) cudaEventDestroy(ev);

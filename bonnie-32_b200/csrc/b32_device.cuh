@@ -111,7 +111,23 @@ struct CallState {
     uint32_t obin_max;                    // ordered pass: largest such count seen
     uint32_t wire_too_long;               // wireframe phase: an edge longer than WIRE_MAX_STEPS was skipped (host reports B32_ERR_UNSUPPORTED)
     uint32_t crowd_used;                  // pass 1: entries of the crowded-tile scratch handed out so far (one atomic per crowded tile)
-    uint32_t _unused1;
+    uint32_t done[3];                     // blocking calls: CTAs of k_setup / k_fill_opaque / k_fill_ordered that have finished (HostStatus)
+};
+
+// Blocking calls (the reference's calling convention: render_mesh_15 returns timings and the drawn count) do not copy
+// the CallState back and do not bracket the kernels with events: each kernel's last CTA publishes the kernel's end time
+// — k_setup's also the counters — in host-mapped memory, and the host spins on `seq`.  That keeps the programmatic launch
+// chain intact, saves the copy engine's round trip, and lets the host launch the ordered pass while pass 1 still runs.
+enum { HS_SETUP = 0, HS_FILL = 1, HS_ORDERED = 2 };
+struct KernelStamp {
+    unsigned long long t0, t1;            // %globaltimer (ns): first CTA past its wait for the previous kernel, last CTA done
+    uint32_t seq;                         // = CallParams.host_seq once t1 (and the state) are valid
+    uint32_t _pad;
+};
+struct HostStatus {
+    CallState state;                      // as k_setup left it
+    uint32_t _pad[3];
+    KernelStamp stamp[3];
 };
 
 // The reference panics (and draws nothing) on an out-of-range vertex index, or when a NaN key is
@@ -144,6 +160,8 @@ struct CallParams {
     uint8_t faces_implicit;                           // 1: `faces` holds one flags word per face; face i uses vertices 3i, 3i+1, 3i+2
     float ambient, ortho_zoom, ortho_cx, ortho_cy;
     float fog_start, fog_falloff, fog_cull;
+    uint32_t host_seq;                                // blocking calls: the value the kernels publish in HostStatus when done
+    HostStatus* host;                                 // null for enqueue-only calls
 };
 
 // ---- Rust scalar semantics -------------------------------------------------------------------

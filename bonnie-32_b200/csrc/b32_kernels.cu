@@ -42,6 +42,32 @@ namespace b32 {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// ---- HostStatus (b32_device.cuh): what a blocking call's kernels tell the host without a copy ----
+__device__ __forceinline__ unsigned long long gtime64() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ void host_stamp_start(const CallParams& p, int k) {
+    if (p.host && blockIdx.x == 0 && threadIdx.x == 0) p.host->stamp[k].t0 = gtime64();
+}
+// Called by every thread of the CTA on each of the kernel's ways out.  The last CTA to arrive publishes.
+__device__ __forceinline__ void host_signal_done(const CallParams& p, CallState* st, int k) {
+    if (!p.host) return;
+    __threadfence();                                       // this thread's writes (counters, flags) before the CTA's arrival
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    if (blockIdx.x == 0) __threadfence_system();           // t0 reaches the host before seq can
+    if (atomicAdd(&st->done[k], 1u) != gridDim.x - 1) return;
+    __threadfence();
+    HostStatus* h = p.host;
+    if (k == HS_SETUP) {
+        const volatile uint32_t* src = reinterpret_cast<const volatile uint32_t*>(st);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&h->state);
+        #pragma unroll
+        for (int i = 0; i < (int)(sizeof(CallState) / 4); ++i) dst[i] = src[i];
+    }
+    h->stamp[k].t1 = gtime64();
+    __threadfence_system();
+    *reinterpret_cast<volatile uint32_t*>(&h->stamp[k].seq) = p.host_seq;
+}
+
 // =================================================================================================
 // vertex transform + snap (render.rs:2321-2360)
 // =================================================================================================
@@ -527,6 +553,7 @@ k_setup(const b32_vertex* __restrict__ verts, const b32_face* __restrict__ faces
     uint4* s_mask = reinterpret_cast<uint4*>(su_smem);
     uint8_t* s_stage = su_smem + (size_t)n_mtiles * sizeof(uint4);
     pdl_launch_dependents();           // the fill may be scheduled as SM resources free up; it waits for this grid's completion
+    host_stamp_start(p, HS_SETUP);
     // Framebuffer::clear of the same frame (render.rs:36-45), folded in: nothing of this kernel reads the framebuffer, and
     // the previous frame's kernels have completed (this kernel is an ordinary, fully ordered launch)
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < clear_n; i += gridDim.x * blockDim.x) { clear_rgba[i] = clear_color; clear_z[i] = 3.40282347e+38f; }
@@ -577,6 +604,7 @@ k_setup(const b32_vertex* __restrict__ verts, const b32_face* __restrict__ faces
     if ((threadIdx.x & 31) == 0) { if (n_op) atomicAdd(&s_cnt[0], n_op); if (n_tr) atomicAdd(&s_cnt[1], n_tr); }
     __syncthreads();
     if (threadIdx.x == 0) { if (s_cnt[0]) atomicAdd(&st->n_opaque, s_cnt[0]); if (s_cnt[1]) atomicAdd(&st->n_transp, s_cnt[1]); }
+    host_signal_done(p, st, HS_SETUP);
 }
 
 // =================================================================================================
@@ -597,9 +625,21 @@ __device__ __forceinline__ bool inside_test(const Rec& r, uint32_t x, uint32_t y
         w1 = r.w1s + dy * r.b1 + dx * r.a1;
     } else {
         // replay the reference's rounded additions: (y-min_y) row steps, then (x-min_x) pixel steps
+        // (two independent dependent-add chains: unrolled so that the adds, not the loop control, fill the issue slots)
         w0 = r.w0s; w1 = r.w1s;
-        for (uint32_t i = min_y; i < y; ++i) { w0 = __fadd_rn(w0, r.b0); w1 = __fadd_rn(w1, r.b1); }
-        for (uint32_t i = min_x; i < x; ++i) { w0 = __fadd_rn(w0, r.a0); w1 = __fadd_rn(w1, r.a1); }
+        const float b0 = r.b0, b1 = r.b1, a0 = r.a0, a1 = r.a1;
+        uint32_t n = y > min_y ? y - min_y : 0u;
+        for (; n >= 8; n -= 8) {
+            #pragma unroll
+            for (int k = 0; k < 8; ++k) { w0 = __fadd_rn(w0, b0); w1 = __fadd_rn(w1, b1); }
+        }
+        for (; n; --n) { w0 = __fadd_rn(w0, b0); w1 = __fadd_rn(w1, b1); }
+        n = x > min_x ? x - min_x : 0u;
+        for (; n >= 8; n -= 8) {
+            #pragma unroll
+            for (int k = 0; k < 8; ++k) { w0 = __fadd_rn(w0, a0); w1 = __fadd_rn(w1, a1); }
+        }
+        for (; n; --n) { w0 = __fadd_rn(w0, a0); w1 = __fadd_rn(w1, a1); }
     }
     bc_x = w0 * r.inv_area;
     bc_y = w1 * r.inv_area;
@@ -997,6 +1037,7 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks,
     const TexDev* texd = tex_cached ? s_tex : tex;
     pdl_wait();                                            // k_setup has completed: records, heads, masks, counters, cleared framebuffer
     pdl_launch_dependents();                               // an enqueued ordered pass may be scheduled behind this grid (it waits for its completion)
+    host_stamp_start(p, HS_FILL);
     // the pixel's framebuffer content
     Pixel px{0, 0.0f};
     if (valid) { px.rgba = fb_rgba[y * p.width + x]; px.z = fb_z[y * p.width + x]; }
@@ -1056,6 +1097,7 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks,
     }
     if (n_cand == 0) {                                     // nothing to draw here; the mask copy must land before the CTA exits
         if (mask_staged && threadIdx.x == 0) while (!mbar_try_wait(&s_mbar, 0)) {}
+        host_signal_done(p, st, HS_FILL);
         return;
     }
 #ifdef B32_FILL_STATS
@@ -1370,6 +1412,7 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks,
         if (px.rgba != px0.rgba) fb_rgba[y * p.width + x] = px.rgba;
         if (__float_as_uint(px.z) != __float_as_uint(px0.z)) fb_z[y * p.width + x] = px.z;
     }
+    host_signal_done(p, st, HS_FILL);
 #ifdef B32_FILL_STATS
     {
         for (int o = 16; o > 0; o >>= 1) { st_inside += __shfl_xor_sync(0xFFFFFFFFu, st_inside, o); st_shaded += __shfl_xor_sync(0xFFFFFFFFu, st_shaded, o); }
@@ -1442,7 +1485,10 @@ __device__ __forceinline__ void write_ordered888(const SurfRec& r, Pixel& px, fl
 
 constexpr int ORD_CHUNK = 32;        // surfaces staged in shared memory per step (32 x 128 B = 4 KB), one 16-byte piece per thread
 constexpr int ORD_RING = 3;          // steps c, c+1, c+2 in flight
-constexpr int ORD_GROUP = 4;         // fragments of one pixel whose texels are requested together
+#ifndef B32_ORD_GROUP
+#define B32_ORD_GROUP 2
+#endif
+constexpr int ORD_GROUP = B32_ORD_GROUP;   // fragments of one pixel whose texels are requested together
 constexpr size_t ORD_SMEM = (size_t)ORD_SORT_MAX * sizeof(BinHead) + (size_t)ORD_RING * ORD_CHUNK * sizeof(SurfRec) + (FILL_THREADS / 32) * 32;
 static_assert(FILL_THREADS == ORD_CHUNK * 8, "one 16-byte piece of the staged records per thread");
 
@@ -1468,9 +1514,9 @@ __device__ void bitonic_sort_heads(BinHead* a, uint32_t m) {
 // draw-order key; the records stream through a 3-deep cp.async ring in that order; every pixel replays the surfaces
 // covering it one after the other, applying the reference's z-test / blend / write rules (render.rs:1664-1702 and, for
 // RGB888, :1392-1424) to a colour + depth held in registers.  Per step each lane first filters one of the 32 staged
-// surfaces against the warp's block (bbox, exact corner trivial reject); the survivors are then taken in order,
-// ORD_GROUP at a time: the inside tests, depths and texel requests of a group are issued together (they do not depend
-// on the pixel's running colour), and only then are its fragments shaded and written one after the other.
+// surfaces against the warp's block (bbox, exact corner trivial reject); every pixel then marks which survivors cover
+// it (one bit each) and folds its own fragments in draw order — the order only matters per pixel, so the lanes of a
+// warp shade different surfaces side by side.
 template <bool RGB888>
 __global__ void __launch_bounds__(FILL_THREADS)
 k_fill_ordered(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks, BinHead* __restrict__ scratch,
@@ -1485,25 +1531,28 @@ k_fill_ordered(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks
     __shared__ uint32_t s_wsum[FILL_THREADS / 32];
     __shared__ uint32_t s_n;
     if (p.enq_ordered) pdl_wait();                      // enqueued right behind pass 1: k_fill_opaque (and k_setup before it) have completed
+    host_stamp_start(p, HS_ORDERED);
     const bool all_ordered = RGB888 ? true : p.xray_mode != 0;      // every drawn surface is replayed (RGB888: this kernel only runs when some surface may blend)
     {
         CallState s = *st;
-        if (call_aborts(s, p.use_zbuffer, RGB888)) return;
+        bool nothing = call_aborts(s, p.use_zbuffer, RGB888);
         const uint32_t n_ordered = all_ordered ? s.n_opaque + s.n_transp : s.n_transp;
-        if (n_ordered == 0 || (RGB888 && s.n_transp == 0)) return;                      // nothing to replay (the usual case of an enqueued frame)
+        nothing = nothing || n_ordered == 0 || (RGB888 && s.n_transp == 0);             // nothing to replay (the usual case of an enqueued frame)
         // k_setup counted the ordered entries per mask tile: a tile with more than fit shared memory needs a slice of the
-        // global scratch; if that is too small NO tile draws (the host grows it and redoes the pass; enqueue-only callers get an error)
-        if (s.obin_max > (uint32_t)ORD_SORT_MAX && s.obin_max > scratch_cap) {
+        // global scratch; if that is too small NO tile draws (a blocking call sizes it before it launches this kernel;
+        // enqueue-only callers get an error)
+        if (!nothing && s.obin_max > (uint32_t)ORD_SORT_MAX && s.obin_max > scratch_cap) {
             if (blockIdx.x == 0 && threadIdx.x == 0) { st->obin_overflow = 1; if (p.async_call) atomicOr(sticky, 16u); }
-            return;
+            nothing = true;
         }
+        if (nothing) { host_signal_done(p, st, HS_ORDERED); return; }
     }
     const uint32_t tile = blockIdx.x;
     const uint32_t ttx = tile % p.tiles_x, tty = tile / p.tiles_x;
     const uint32_t mtile = (tty >> p.mshift) * p.mtiles_x + (ttx >> p.mshift);
     const uint4* mrow = masks + (size_t)mtile * p.n_groups;
     CandScan cs = cand_scan<FILL_THREADS>(mrow, p.n_groups, s_wsum);
-    if (cs.total == 0) return;
+    if (cs.total == 0) { host_signal_done(p, st, HS_ORDERED); return; }
     // ---- this tile's draw-order entries: the candidates that are in the ordered pass and touch the tile.  The unique
     //      64-bit key (pass:2 | depth key:32 | face:30) = opaque list first (sorted only in painter's mode), then the
     //      transparent list, ties by face index = stable sort (render.rs:2522-2542); RGB888: one list, no pass bit.
@@ -1532,7 +1581,7 @@ k_fill_ordered(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks
         __syncthreads();
     }
     const uint32_t n = s_n;
-    if (n == 0) return;
+    if (n == 0) { host_signal_done(p, st, HS_ORDERED); return; }
     uint32_t m = 2;
     while (m < n) m <<= 1;                              // scratch_cap is a power of two >= n whenever the scratch is used
     BinHead* sorted;
@@ -1591,18 +1640,31 @@ k_fill_ordered(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks
         __syncwarp();
         if (cand) my_sidx[__popc(mask & ((1u << lane) - 1))] = (uint8_t)lane;          // ascending = draw order
         __syncwarp();
-        // ---- survivors in order, ORD_GROUP at a time ----
-        for (uint32_t j0 = 0; j0 < cnt; j0 += ORD_GROUP) {
-            bool in[ORD_GROUP]; float fbx[ORD_GROUP], fby[ORD_GROUP], fz[ORD_GROUP]; uint32_t ftex[ORD_GROUP];
+        // ---- A. which of the step's survivors cover this pixel: the inside tests, in lockstep (nothing here depends on the
+        //         pixel's running colour / depth).  Surfaces on the replayed-additions edge path are only bbox-tested here.
+        uint32_t cov = 0;
+        for (uint32_t j = 0; j < cnt; ++j) {
+            const SurfRec& r = crec[my_sidx[j]];
+            uint32_t min_x = r.bbox_x & 0xFFFF, max_x = r.bbox_x >> 16, min_y = r.bbox_y & 0xFFFF, max_y = r.bbox_y >> 16;
+            if (!(valid && x >= min_x && x < max_x && y >= min_y && y < max_y)) continue;
+            float bc_x, bc_y, bc_z;
+            if (!(r.flags & SF_FAST_EDGE) || inside_test(r, x, y, bc_x, bc_y, bc_z)) cov |= 1u << j;
+        }
+        // ---- B. every pixel folds ITS fragments in draw order, ORD_GROUP at a time: lanes work on different surfaces in
+        //         the same instruction (a small triangle covers a quarter of the block: walking the survivors in lockstep
+        //         left three lanes in four idle through the shading).  The inside tests, depths and texel requests of a
+        //         group are issued together; only then are its fragments shaded and written one after the other.
+        while (cov) {
+            bool in[ORD_GROUP]; float fbx[ORD_GROUP], fby[ORD_GROUP], fz[ORD_GROUP]; uint32_t ftex[ORD_GROUP], fidx[ORD_GROUP];
             #pragma unroll
-            for (int k = 0; k < ORD_GROUP; ++k) {          // everything that does not depend on the running colour / depth
-                in[k] = false; fbx[k] = fby[k] = fz[k] = 0.0f; ftex[k] = 0;
-                if (j0 + k >= cnt) continue;
-                const SurfRec& r = crec[my_sidx[j0 + k]];
-                uint32_t min_x = r.bbox_x & 0xFFFF, max_x = r.bbox_x >> 16, min_y = r.bbox_y & 0xFFFF, max_y = r.bbox_y >> 16;
-                if (!(valid && x >= min_x && x < max_x && y >= min_y && y < max_y)) continue;
+            for (int k = 0; k < ORD_GROUP; ++k) {
+                in[k] = false; fbx[k] = fby[k] = fz[k] = 0.0f; ftex[k] = 0; fidx[k] = 0;
+                if (!cov) continue;
+                const uint32_t j = __ffs(cov) - 1; cov &= cov - 1;
+                fidx[k] = my_sidx[j];
+                const SurfRec& r = crec[fidx[k]];
                 float bc_x, bc_y, bc_z;
-                if (!inside_test(r, x, y, bc_x, bc_y, bc_z)) continue;
+                if (!inside_test(r, x, y, bc_x, bc_y, bc_z)) continue;                  // (only the slow edge path can still fail)
                 float inv_z = bc_x * r.iz1 + bc_y * r.iz2 + bc_z * r.iz3;              // :1549
                 float z = 1.0f / inv_z;
                 if (early_z && z >= px.z) continue;        // px.z only ever decreases, so a reject now is a reject later
@@ -1613,7 +1675,7 @@ k_fill_ordered(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks
             for (int k = 0; k < ORD_GROUP; ++k) {          // the fold over the fragments, in draw order
                 if (!in[k]) continue;
                 if (early_z && fz[k] >= px.z) continue;                                // the reference's early test, at its time
-                const SurfRec& r = crec[my_sidx[j0 + k]];
+                const SurfRec& r = crec[fidx[k]];
                 const float bc_x = fbx[k], bc_y = fby[k], bc_z = 1.0f - bc_x - bc_y;   // same expression as inside_test
                 uint32_t o_r, o_g, o_b;
                 if (RGB888) {
@@ -1633,6 +1695,7 @@ k_fill_ordered(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks
         if (px.rgba != px0.rgba) fb_rgba[y * p.width + x] = px.rgba;
         if (__float_as_uint(px.z) != __float_as_uint(px0.z)) fb_z[y * p.width + x] = px.z;
     }
+    host_signal_done(p, st, HS_ORDERED);
 }
 
 // =================================================================================================
