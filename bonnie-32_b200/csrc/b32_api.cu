@@ -265,7 +265,7 @@ int ensure_work(b32_ctx* ctx, const CallParams& p) {
     CK(ctx->masks.reserve(std::max<size_t>((size_t)p.mtiles_x * p.mtiles_y * p.n_groups, 1)));
     // A tile is crowded when more than OP_SORT_MAX_ENTRIES of the mesh's faces touch it, so only meshes well beyond that can
     // have any: they get 5 head-sized slots of scratch per face (a face's bounding box touches ~4 tiles; a slot = one head, or four face indices), capped at 256 MB.  A tile that
-    // finds the scratch exhausted walks its windows in face order instead (same result, later early-out).
+    // finds the scratch exhausted walks its windows in list order instead (same result, later early-out).
     if (p.nf > 4u * OP_SORT_MAX_ENTRIES) CK(ctx->crowd.reserve(std::min<size_t>((size_t)p.nf * 5, (size_t)16 << 20)));
     uint32_t ntiles = p.tiles_x * p.tiles_y;
     uint32_t need = STATE_WORDS + ((std::max<uint32_t>(ntiles, 1) + 3u) & ~3u);
@@ -514,6 +514,7 @@ int render_device(b32_ctx* ctx, const b32_vertex* d_verts, uint32_t nv, const b3
     CK(cudaGetLastError());
     rc = wait_stamp(ctx, HS_SETUP, seq); if (rc) return rc;
     hs = ctx->hstat->state;
+    if (hs.oob == 2) return fail(ctx, B32_ERR_INVALID, "face blend mode out of range (not a BlendMode)");
     if (hs.oob) return fail(ctx, B32_ERR_OOB_INDEX, "face vertex index out of range (reference: slice index panic)");
     {   // the reference panics on a NaN key in a sorted slice of length >= 2 (render.rs:2531; RGB888: one list, :2161)
         bool nan_abort = rgb888 ? (!p.use_zbuffer && hs.nan_opaque && hs.n_opaque + hs.n_transp >= 2)
@@ -629,6 +630,7 @@ static int collect_async(b32_ctx* ctx) {
     sticky = *reinterpret_cast<uint32_t*>(ctx->state_h);
     if (!sticky) return B32_OK;
     CK(cudaMemsetAsync(ctx->sticky, 0, sizeof(uint32_t), ctx->stream));
+    if (sticky & 32u) return fail(ctx, B32_ERR_INVALID, "an enqueued call had a face whose blend mode is not a BlendMode");
     if (sticky & 1u) return fail(ctx, B32_ERR_OOB_INDEX, "an enqueued call had a face vertex index out of range");
     if (sticky & 2u) return fail(ctx, B32_ERR_NAN_DEPTH, "an enqueued call had a NaN depth key in a sorted pass");
     if (sticky & 8u) return fail(ctx, B32_ERR_INVALID, "an enqueued call had semi-transparent surfaces (pass 2 was not drawn): B32_RENDER_ALL_OPAQUE was wrong");

@@ -70,7 +70,7 @@ enum : uint32_t {
 // Binning without bins.  k_setup handles SETUP_GROUP consecutive faces per CTA pass ("group") and writes, for every
 // mask tile of the screen, ONE uint4 = 128 bits: bit i set iff face group*128 + i is drawn and its bounding box touches the
 // tile.  Layout masks[mask_tile][group].  A fill CTA reads its tile's row (n_groups x 16 contiguous bytes), and the set
-// bits ARE its surface list, in face order — no atomics, no per-tile capacity, no overflow, deterministic.  A mask tile is
+// bits ARE its surface list — no atomics, no per-tile capacity, no overflow, deterministic.  A mask tile is
 // (16 << mshift) pixels square: mshift grows with the frame so that the row count stays <= MASK_TILES_MAX and the
 // table <= MASK_BYTES_MAX; with mshift > 0 a fill CTA drops the candidates whose bounding box misses its own 16x16 tile.
 constexpr size_t MASK_BYTES_MAX = (size_t)64 << 20;

@@ -234,6 +234,7 @@ __device__ __forceinline__ void setup_face(uint32_t fi, const uint4& fc, const f
     do {
         if (fc.x >= p.nv || fc.y >= p.nv || fc.z >= p.nv) { st->oob = 1; break; }
         uint32_t tex_id = fc.w & 0xFFFFu, face_blend = (fc.w >> 16) & 7u, editor_alpha = fc.w >> 24;
+        if (face_blend > B32_BLEND_ERASE) { st->oob = 2; break; }             // not a BlendMode (types.rs): the call draws nothing, B32_ERR_INVALID
         bool black_tr = (fc.w >> 19) & 1u;
         bool textured = tex_id != B32_FACE_TEX_NONE && tex_id < p.ntex;
         uint32_t tex_blend = 0;
@@ -453,19 +454,21 @@ __device__ __forceinline__ void masks_flush(const uint4* s_mask, uint4* __restri
 }
 
 // ---- a fill CTA's surface list out of its mask row ----------------------------------------------------
-// Thread t owns the groups [g0, g1) of the row (contiguous, so the list comes out in face order).  cand_scan counts the
-// set bits (block-wide exclusive scan); cand_expand writes the face indices of the candidates with list position in
-// [w0, w0 + wn) to out[position - w0].  Both contain barriers: every thread of the CTA must call them.
-struct CandScan { uint32_t g0, g1, base, total; };
+// Thread t owns the groups t, t + THREADS, t + 2 THREADS, ... of the row (a warp reads 512 contiguous bytes per load),
+// and its candidates take consecutive list positions: the list is a fixed enumeration of the set bits, not in face order
+// (no user needs one: pass 1 is order-free, the ordered pass sorts by key, the skybox compares face indices).
+// cand_scan counts the set bits (block-wide exclusive scan); cand_expand writes the face indices of the candidates
+// with list position in [w0, w0 + wn) to out[position - w0].  Both contain barriers: every thread of the CTA must call them.
+struct CandScan { uint32_t n_groups, stride, base, total; };
 __device__ __forceinline__ uint32_t popc128(const uint4& m) { return __popc(m.x) + __popc(m.y) + __popc(m.z) + __popc(m.w); }
 
 template <int THREADS>
 __device__ __forceinline__ CandScan cand_scan(const uint4* __restrict__ mrow, uint32_t n_groups, uint32_t* s_wsum /* [THREADS / 32] */) {
-    const uint32_t k = (n_groups + THREADS - 1) / THREADS;
     CandScan cs;
-    cs.g0 = min(threadIdx.x * k, n_groups); cs.g1 = min(cs.g0 + k, n_groups);
+    cs.n_groups = n_groups; cs.stride = THREADS;
     uint32_t cnt = 0;
-    for (uint32_t g = cs.g0; g < cs.g1; ++g) cnt += popc128(mrow[g]);
+    #pragma unroll 4
+    for (uint32_t g = threadIdx.x; g < n_groups; g += THREADS) cnt += popc128(mrow[g]);
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t xs = cnt;
     for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, xs, o); if (lane >= (uint32_t)o) xs += t; }
@@ -481,10 +484,10 @@ __device__ __forceinline__ CandScan cand_scan(const uint4* __restrict__ mrow, ui
 
 __device__ __forceinline__ void cand_expand(const uint4* __restrict__ mrow, const CandScan& cs, uint32_t w0, uint32_t wn, uint32_t* out) {
     uint32_t idx = cs.base;
-    for (uint32_t g = cs.g0; g < cs.g1 && idx < w0 + wn; g += 4) {           // mask loads four at a time: one L2 latency per batch
+    for (uint32_t g = threadIdx.x; g < cs.n_groups && idx < w0 + wn; g += 4 * cs.stride) {      // mask loads four at a time: one L2 latency per batch
         uint4 m[4];
         #pragma unroll
-        for (int j = 0; j < 4; ++j) m[j] = g + j < cs.g1 ? mrow[g + j] : make_uint4(0, 0, 0, 0);
+        for (int j = 0; j < 4; ++j) m[j] = g + j * cs.stride < cs.n_groups ? mrow[g + j * cs.stride] : make_uint4(0, 0, 0, 0);
         #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const uint32_t c = popc128(m[j]);
@@ -497,7 +500,7 @@ __device__ __forceinline__ void cand_expand(const uint4* __restrict__ mrow, cons
                 while (bits) {
                     const uint32_t b = __ffs(bits) - 1;
                     bits &= bits - 1;
-                    if (idx >= w0 && idx < w0 + wn) out[idx - w0] = (g + j) * SETUP_GROUP + q * 32 + b;
+                    if (idx >= w0 && idx < w0 + wn) out[idx - w0] = (g + j * cs.stride) * SETUP_GROUP + q * 32 + b;
                     ++idx;
                 }
             }
@@ -861,7 +864,7 @@ __device__ __forceinline__ uint32_t gtime() { uint64_t t; asm volatile("mov.u64 
 // order — the nearest few buckets first — so that the early-out of one window holds for every later one and the tile
 // stops as soon as every pixel is settled, usually after its first window.  A single bucket that holds more than a
 // window (many equal keys) is taken in slice order, a window at a time, without that carry-over.  If the scratch is
-// exhausted the tile falls back to windows in face order.  All state lives in shared memory; these functions are
+// exhausted the tile falls back to windows in list order.  All state lives in shared memory; these functions are
 // deliberately not inlined (they run for a handful of tiles of unusual frames and must not cost the usual tile anything).
 struct CrowdShared {
     uint32_t n_valid, kmin, shift, b_next, over_b, over_i, item[4], ncol, lo, hi;
@@ -881,7 +884,7 @@ __device__ __forceinline__ uint32_t crowd_bucket(uint32_t k, uint32_t kmin, uint
 }
 
 // pass 1: every candidate's head -> slice[] (those that are pass-1 surfaces touching this tile), key range, histogram.
-// The face indices of all candidates are written once to ids[] (= the tail of the tile's scratch slice), in face order,
+// The face indices of all candidates are written once to ids[] (= the tail of the tile's scratch slice),
 // with the mask loads batched four at a time; the heads are then gathered with coalesced index reads.
 __device__ __noinline__ void crowd_prepare(const uint4* __restrict__ mrow, const CandScan cs, uint32_t n_cand, const BinHead* __restrict__ heads,
                                            uint32_t tpx0, uint32_t tpy0, BinHead* __restrict__ slice, uint32_t* __restrict__ ids,
@@ -889,10 +892,10 @@ __device__ __noinline__ void crowd_prepare(const uint4* __restrict__ mrow, const
     if (threadIdx.x == 0) { cr->ncol = 0; cr->lo = 0xFFFFFFFFu; cr->hi = 0; cr->b_next = 0; cr->over_b = 0xFFFFFFFFu; cr->over_i = 0; }
     for (uint32_t i = threadIdx.x; i < buckets; i += blockDim.x) s_ghist[i] = 0;
     uint32_t idx = cs.base;
-    for (uint32_t g = cs.g0; g < cs.g1; g += 4) {
+    for (uint32_t g = threadIdx.x; g < cs.n_groups; g += 4 * cs.stride) {
         uint4 m[4];
         #pragma unroll
-        for (int j = 0; j < 4; ++j) m[j] = g + j < cs.g1 ? mrow[g + j] : make_uint4(0, 0, 0, 0);
+        for (int j = 0; j < 4; ++j) m[j] = g + j * cs.stride < cs.n_groups ? mrow[g + j * cs.stride] : make_uint4(0, 0, 0, 0);
         #pragma unroll
         for (int j = 0; j < 4; ++j) {
             if ((m[j].x | m[j].y | m[j].z | m[j].w) == 0) continue;
@@ -900,7 +903,7 @@ __device__ __noinline__ void crowd_prepare(const uint4* __restrict__ mrow, const
             #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 uint32_t bits = words[q];
-                while (bits) { const uint32_t bb = __ffs(bits) - 1; bits &= bits - 1; ids[idx++] = (g + j) * SETUP_GROUP + q * 32 + bb; }
+                while (bits) { const uint32_t bb = __ffs(bits) - 1; bits &= bits - 1; ids[idx++] = (g + j * cs.stride) * SETUP_GROUP + q * 32 + bb; }
             }
         }
     }
@@ -1046,7 +1049,7 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks,
         CallState s = *st;
         bool aborts = call_aborts(s, p.use_zbuffer, RGB888);
         if (p.async_call && blockIdx.x == 0 && threadIdx.x == 0) {                                // enqueue-only callers
-            if (aborts) atomicOr(sticky, s.oob ? 1u : 2u);
+            if (aborts) atomicOr(sticky, s.oob == 2 ? 32u : s.oob ? 1u : 2u);
             else if (s.n_transp && !p.enq_ordered) atomicOr(sticky, 8u);                         // pass 2 exists but was not enqueued
         }
         // x-ray (render_mesh_15) and any framebuffer-reading surface (render_mesh) go through the ordered replay instead
@@ -1122,7 +1125,7 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks,
     // painter's: tile_weak = smallest winner key in the tile (0 while a pixel has no winner): keys below it lose everywhere;
     // z-buffer : tile_weak = ~bits(largest depth in the tile): a surface whose depth lower bound is behind it loses everywhere.
     uint32_t tile_weak = 0;
-    // crowded tile: a slice of the global scratch for its heads (see crowd_prepare); none left = windows in face order
+    // crowded tile: a slice of the global scratch for its heads (see crowd_prepare); none left = windows in list order
     BinHead* slice = nullptr;
     const uint32_t slice_len = n_cand + (n_cand + 3) / 4;          // n_cand heads, then n_cand face indices (4 per head-sized slot)
     if (n_cand > (uint32_t)OP_SORT_MAX) {
@@ -1135,6 +1138,9 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks,
     }
     BinHead* s_tmp = reinterpret_cast<BinHead*>(s_cand + OP_SORT_MAX);         // [OP_SORT_MAX] a depth window's heads (the ring is idle then)
     if (slice) crowd_prepare(mrow, cs, n_cand, heads, tpx0, tpy0, slice, reinterpret_cast<uint32_t*>(slice + n_cand), s_ghist, OP_BUCKETS, OP_BUCKET_BITS, &s_crowd);
+#ifdef B32_FILL_STATS
+    uint32_t st_tprep = gtime(), st_twin = 0;
+#endif
     bool gdone = offscreen;                                // depth-ordered windows: this warp's early-out, carried from window to window
     for (uint32_t win = 0;; ++win) {
         const uint32_t w0 = win * OP_SORT_MAX;
@@ -1169,6 +1175,9 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks,
         bool carry = false;
         if (slice) {
             n = crowd_next_window(slice, tile_weak, s_ghist, OP_BUCKETS, OP_SORT_MAX, s_tmp, &s_crowd, &carry);
+#ifdef B32_FILL_STATS
+            if (!win) st_twin = gtime();
+#endif
             if (n == 0xFFFFFFFFu) break;
             #pragma unroll
             for (int q = 0; q < KPT; ++q) {
@@ -1419,6 +1428,7 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks,
         if (lane == 0 && tile < 4096) {
             uint32_t* o = g_fill_stats + (tile * 16 + wt) * 8;
             o[0] = st_t0; o[1] = st_t1; o[2] = gtime(); o[3] = st_batches; o[4] = st_tfirst; o[5] = st_tb0; o[6] = st_tb1; o[7] = st_tl;
+            if (slice) { o[5] = st_tprep; o[6] = st_twin; }        // crowded tiles: end of crowd_prepare / of the first crowd_next_window
         }
     }
 #endif
@@ -1483,14 +1493,18 @@ __device__ __forceinline__ void write_ordered888(const SurfRec& r, Pixel& px, fl
     px.rgba = o_r | (o_g << 8) | (o_b << 16) | 0xFF000000u;
 }
 
-constexpr int ORD_CHUNK = 32;        // surfaces staged in shared memory per step (32 x 128 B = 4 KB), one 16-byte piece per thread
+#ifndef B32_ORD_SUB
+#define B32_ORD_SUB 2
+#endif
+constexpr int ORD_SUB = B32_ORD_SUB; // a step (one CTA barrier) = ORD_SUB batches of 32 surfaces: fewer barriers, and the warps' loads even out over a step
+constexpr int ORD_CHUNK = 32 * ORD_SUB;   // surfaces staged in shared memory per step (128 B each), ORD_SUB 16-byte pieces per thread
 constexpr int ORD_RING = 3;          // steps c, c+1, c+2 in flight
 #ifndef B32_ORD_GROUP
 #define B32_ORD_GROUP 2
 #endif
 constexpr int ORD_GROUP = B32_ORD_GROUP;   // fragments of one pixel whose texels are requested together
 constexpr size_t ORD_SMEM = (size_t)ORD_SORT_MAX * sizeof(BinHead) + (size_t)ORD_RING * ORD_CHUNK * sizeof(SurfRec) + (FILL_THREADS / 32) * 32;
-static_assert(FILL_THREADS == ORD_CHUNK * 8, "one 16-byte piece of the staged records per thread");
+static_assert(FILL_THREADS == 32 * 8, "one 16-byte piece of a batch's staged records per thread");
 
 __device__ __forceinline__ uint64_t ord_key(const BinHead& h) { return ((uint64_t)h.key << 32) | h.face; }
 
@@ -1610,11 +1624,14 @@ k_fill_ordered(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks
     const bool early_z = p.use_zbuffer && !p.xray_mode;                                // :1553-1560 / :1313-1320
 
     auto stage = [&](uint32_t c) {                                                     // step c -> ring slot c % ORD_RING
-        uint32_t e = c * ORD_CHUNK + (threadIdx.x >> 3);
-        if (e < n) {
-            uint32_t f = sorted[e].face & 0x3FFFFFFFu;
-            cp_async16(reinterpret_cast<uint4*>(&s_rec[(c % ORD_RING) * ORD_CHUNK + (threadIdx.x >> 3)]) + (threadIdx.x & 7),
-                       reinterpret_cast<const uint4*>(&recs[f]) + (threadIdx.x & 7));
+        #pragma unroll
+        for (int sb = 0; sb < ORD_SUB; ++sb) {
+            uint32_t slot = sb * 32 + (threadIdx.x >> 3), e = c * ORD_CHUNK + slot;
+            if (e < n) {
+                uint32_t f = sorted[e].face & 0x3FFFFFFFu;
+                cp_async16(reinterpret_cast<uint4*>(&s_rec[(c % ORD_RING) * ORD_CHUNK + slot]) + (threadIdx.x & 7),
+                           reinterpret_cast<const uint4*>(&recs[f]) + (threadIdx.x & 7));
+            }
         }
         cp_async_commit();
     };
@@ -1625,10 +1642,11 @@ k_fill_ordered(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks
         cp_async_wait<1>();
         __syncthreads();                                   // step c has landed for everybody; slot (c+2) % 3 is free again
         stage(c + 2);
-        const SurfRec* crec = s_rec + (c % ORD_RING) * ORD_CHUNK;
+        for (uint32_t sb = 0; sb < (uint32_t)ORD_SUB && c * ORD_CHUNK + sb * 32 < n; ++sb) {
+        const SurfRec* crec = s_rec + (c % ORD_RING) * ORD_CHUNK + sb * 32;
         // ---- filter: lane = one staged surface vs this warp's 8x4 block ----
         bool cand = false;
-        if (c * ORD_CHUNK + lane < n && bx0 < p.width && by0 < p.height) {
+        if (c * ORD_CHUNK + sb * 32 + lane < n && bx0 < p.width && by0 < p.height) {
             const SurfRec& r = crec[lane];
             uint32_t min_x = r.bbox_x & 0xFFFF, max_x = r.bbox_x >> 16, min_y = r.bbox_y & 0xFFFF, max_y = r.bbox_y >> 16;
             cand = !(max_x <= bx0 || min_x >= bx0 + 8 || max_y <= by0 || min_y >= by0 + 4);
@@ -1689,6 +1707,7 @@ k_fill_ordered(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks
                 }
             }
         }
+        }   // batch
     }
     cp_async_wait<0>();
     if (valid) {
@@ -1877,8 +1896,8 @@ k_sky_fill(const SkyRec* __restrict__ recs, const uint4* __restrict__ masks, con
     const bool valid = x < p.width && y < p.height;
     const float px = (float)x + 0.5f, py = (float)y + 0.5f;                                      // :270-271
     uint32_t best = 0;                                       // face + 1 of the last face covering this pixel centre
-    // The candidates come in face order; they are walked from the end, FILL_THREADS at a time: the last covering face is
-    // met first and everything below it is skipped by its index alone.  Heads and records of a step sit in shared memory.
+    // The candidates are walked FILL_THREADS at a time; a face below the best one so far is skipped by its index alone.
+    // Heads and records of a step sit in shared memory.
     for (uint32_t rem = cs.total; rem > 0;) {
         const uint32_t cnt = min((uint32_t)FILL_THREADS, rem);
         rem -= cnt;

@@ -63,7 +63,8 @@ typedef struct b32_vertex {
 } b32_vertex;
 
 /* struct Face, src/rasterizer/types.rs:984-1002.  16 bytes.
- * flags: bits 0-15 texture_id (0xFFFF = None), bits 16-18 blend_mode, bit 19 black_transparent,
+ * flags: bits 0-15 texture_id (0xFFFF = None), bits 16-18 blend_mode (a B32_BLEND_* value: 6 and 7 are not a
+ *        BlendMode, the call draws nothing and returns B32_ERR_INVALID), bit 19 black_transparent,
  *        bits 24-31 editor_alpha. */
 typedef struct b32_face {
     uint32_t v0, v1, v2;

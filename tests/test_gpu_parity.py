@@ -166,6 +166,12 @@ def test_error_codes(ctx, oracle):
         pkg.render_mesh_15(fb, sc.vertices, f, sc.textures, sc.camera, sc.settings)
     assert e.value.code == abi.B32_ERR_OOB_INDEX
     assert np.array_equal(fb.download()[0], before)
+    # a face whose blend bits are not a BlendMode (types.rs: 0..=5): B32_ERR_INVALID, framebuffer untouched
+    f = sc.faces.copy(); f["flags"][3] = abi.face_flags(0, 6, False, 255)
+    with pytest.raises(pkg.B32Error) as e:
+        pkg.render_mesh_15(fb, sc.vertices, f, sc.textures, sc.camera, sc.settings)
+    assert e.value.code == abi.B32_ERR_INVALID
+    assert np.array_equal(fb.download()[0], before)
     # NaN depth in a sorted pass: reference unwrap() panics -> B32_ERR_NAN_DEPTH
     v = cases.nan_depth_vertices(sc, oracle)
     with pytest.raises(pkg.B32Error) as e:
@@ -246,6 +252,14 @@ def test_enqueue_only_errors_surface_at_sync(ctx):
     with pytest.raises(pkg.B32Error) as e:
         ctx.sync()
     assert e.value.code == abi.B32_ERR_OOB_INDEX
+    assert np.array_equal(fb.download()[0], before)
+    mesh.free()
+    f = sc.faces.copy(); f["flags"][3] = abi.face_flags(0, 7, False, 255)        # not a BlendMode
+    mesh = pkg.Mesh(ctx, sc.vertices, f)
+    mesh.render(sc.camera, sc.settings, None, enqueue_only=True)
+    with pytest.raises(pkg.B32Error) as e:
+        ctx.sync()
+    assert e.value.code == abi.B32_ERR_INVALID
     assert np.array_equal(fb.download()[0], before)
     mesh.free()
 

@@ -24,6 +24,9 @@ def show(name, a):
 print('kernel span', t2.max() - base, 'ns')
 show('candidates done after first CTA start', t0.min(1) - base)
 show('first window ready (candidates -> walk order)', (t1 - t0).max(1))
+show('  crowd_prepare', (tb0 - t0).max(1))
+show('  first crowd_next_window', (tb1 - tb0).max(1))
+show('  window sort', (t1 - tb1).max(1))
 show('first step landed', (tf - t1).max(1))
 show('loop (first data -> last window end)', (tl - tf).max(1))
 show('final shade', (t2 - tl).max(1))

@@ -16,8 +16,13 @@ import c3, cases
 from bonnie32_b200 import scenes, abi
 
 
+ONLY = sys.argv[1:]          # optional name filters: run only the scenes whose name contains one of them
+
+
 def run(ctx, name, sc_list, w, h, clear, reps=20):
     """sc_list: list of (vertices, faces, camera, settings, fog) calls composing one frame."""
+    if ONLY and not any(o in name for o in ONLY):
+        return
     fb = pkg.Framebuffer(w, h, ctx)
     meshes = [pkg.Mesh(ctx, v, f) for v, f, *_ in sc_list]
     times = np.zeros(4); wall = []
