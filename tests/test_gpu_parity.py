@@ -285,10 +285,12 @@ def test_crowded_tile(ctx, oracle):
     # windows meet a single over-full key bucket and take it in face order)
     v3 = v.copy()
     v3["pos"][:, 2] = np.float32(20.0)
-    for faces_, xray, verts_ in ((f, False, v), (f2, False, v), (f2, True, v), (f, False, v3)):
+    # last variant: a 1920x1080 framebuffer = coarse mask tiles (a fill tile's candidates include its neighbours' surfaces)
+    for faces_, xray, verts_, size in ((f, False, v, (320, 240)), (f2, False, v, (320, 240)), (f2, True, v, (320, 240)),
+                                       (f, False, v3, (320, 240)), (f2, False, v, (1920, 1080))):
         for zbuf in (False, True):
             sc = scenes.Scene("crowded_tile", verts_, faces_, [], pkg.Camera(),
-                              scenes.common_settings(use_zbuffer=zbuf, backface_cull=False, xray_mode=xray))
+                              scenes.common_settings(use_zbuffer=zbuf, backface_cull=False, xray_mode=xray), width=size[0], height=size[1])
             want, want_z, otm, rc = oracle.render_scene(sc)
             ctx2 = pkg.Context(0)                     # fresh context: no scratch allocated yet
             got, got_z, tm = render_gpu(ctx2, sc)

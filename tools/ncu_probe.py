@@ -28,4 +28,7 @@ if what in ("all", "ordered"):
     run(t); run(x)
 if what == "all":
     run(scenes.scene_c1(), n=3); run(scenes.scene_c2(), n=3)
+if what in ("all", "bigtri"):
     run(cases.big_triangle_scene(), 1920, 1080, n=2)
+if what == "1m":
+    run(scenes.scene_c4(n_tris=1_000_000), n=2)
