@@ -50,10 +50,9 @@ __device__ __forceinline__ void host_stamp_start(const CallParams& p, int k) {
 // Called by every thread of the CTA on each of the kernel's ways out.  The last CTA to arrive publishes.
 __device__ __forceinline__ void host_signal_done(const CallParams& p, CallState* st, int k) {
     if (!p.host) return;
-    __threadfence();                                       // this thread's writes (counters, flags) before the CTA's arrival
-    __syncthreads();
-    if (threadIdx.x != 0) return;
-    if (blockIdx.x == 0) __threadfence_system();           // t0 reaches the host before seq can
+    __syncthreads();                                       // the CTA's writes (counters, flags) happen before thread 0's fence,
+    if (threadIdx.x != 0) return;                          // which is cumulative: one fence orders them before the arrival
+    if (blockIdx.x == 0) __threadfence_system(); else __threadfence();     // (block 0: t0 reaches the host before seq can)
     if (atomicAdd(&st->done[k], 1u) != gridDim.x - 1) return;
     __threadfence();
     HostStatus* h = p.host;

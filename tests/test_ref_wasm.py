@@ -165,3 +165,20 @@ def test_sample_level_geometry_matches_reference_binary():
             d = refbin_cases.geometry_digest(rc.vertices["pos"], rc.vertices["uv"], rc.vertices["normal"], rc.vertices["rgba"], rc.faces["v"],
                                              ((rc.faces["flags"] >> 19) & 1).astype(np.uint8), with_uv=all64)
             assert d == w["sha256" if all64 else "sha256_no_uv"], sc.name
+
+
+@pytest.mark.parametrize("name,w,h,seed,n", __import__("refbin_prims").CASES, ids=lambda v: v if isinstance(v, str) else None)
+def test_overlay_primitives_match_reference_binary(oracle, name, w, h, seed, n):
+    """b32o_draw_lines vs the binary's own Framebuffer::draw_line_3d_impl / draw_circle / draw_thick_line, called once per
+    primitive in list order (tests/golden/make_ref_wasm_prims.py).  No compat switch is involved (RGB888 writers)."""
+    import hashlib
+    import json
+    import refbin_prims
+    fix = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ref_wasm", "prims.json")))["cases"][name]
+    rgba, z = refbin_prims.background(w, h, seed)
+    lines = refbin_prims.primitives(w, h, seed, n)
+    assert hashlib.sha256(rgba.tobytes() + z.tobytes() + lines.tobytes()).hexdigest() == fix["inputs"]
+    z0 = z.copy()
+    assert oracle.draw_lines(rgba, z, lines) == 0
+    assert np.array_equal(z.view(np.uint32), z0.view(np.uint32))
+    assert hashlib.sha256(rgba.tobytes()).hexdigest() == fix["rgba"], "pixels differ from the reference binary"
