@@ -365,8 +365,9 @@ def run_b200(args):
 
     # ---- end to end through the host-buffer ABI: pinned host inputs, H2D + render + D2H every step -------
     # The bytes a marshalling shim sends for this mesh: normals dropped (shading None reads none), faces implicit (an
-    # unindexed soup): b32_render_mesh_15_ex(B32_VTX_NO_NORMAL | B32_FACES_IMPLICIT).  The full 36 + 16 byte records are
-    # timed beside it (`full_format`).
+    # unindexed soup) and uniform (one texture, one blend mode: a single flags word):
+    # b32_render_mesh_15_ex(B32_VTX_NO_NORMAL | B32_FACES_UNIFORM).  The full 36 + 16 byte records are timed beside it
+    # (`full_format`).
     shading_none = sc.settings.shading == abi.SHADE_NONE
     cv, cf, cflags = abi.compact_buffers(sc.vertices, sc.faces, shading_none)
     host = {}
@@ -491,9 +492,11 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s * 1e3 / nfr, "frames_per_s": world / (e2e_s / nfr),
                     "h2d_gbs_per_gpu": h2d * nfr / e2e_s / 1e9,
-                    "how": f"b32_render_mesh_15_ex(ASYNC | VTX_NO_NORMAL | FACES_IMPLICIT) + b32_fb_download_async from/to pinned host memory, "
-                           f"{N_CTX} frames in flight (one context each), wall clock; the shim's compact marshalling: 24-byte vertices "
-                           "(shading None reads no normals) and one flags word per face (unindexed soup)",
+                    "how": "b32_render_mesh_15_ex(ASYNC | " + " | ".join(n for n, bit in (("VTX_NO_NORMAL", abi.VTX_NO_NORMAL), ("FACES_IMPLICIT", abi.FACES_IMPLICIT),
+                                                                                            ("FACES_UNIFORM", abi.FACES_UNIFORM)) if cflags & bit)
+                           + f") + b32_fb_download_async from/to pinned host memory, {N_CTX} frames in flight (one context each), wall clock; "
+                           "the shim's compact marshalling: 24-byte vertices (shading None reads no normals), no index buffer (unindexed soup) "
+                           "and one flags word for the whole mesh (every face has the same texture and blend mode)",
                     "full_format": {"value": world * N_TRIS / (e2e_full_s / nfr) / 1e6, "ms_per_step": e2e_full_s * 1e3 / nfr,
                                     "h2d_bytes_per_step": host["full"][3], "how": "same with 36-byte b32_vertex + 16-byte b32_face records"},
                     "resident_geometry": {"value": world * N_TRIS / (game_s / nfr) / 1e6, "ms_per_step": game_s * 1e3 / nfr,

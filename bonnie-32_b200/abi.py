@@ -25,7 +25,7 @@ SHADE_NONE, SHADE_FLAT, SHADE_GOURAUD = range(3)
 LIGHT_DIRECTIONAL, LIGHT_POINT, LIGHT_SPOT = range(3)
 TEX_RGB555, TEX_IDX8, TEX_IDX4 = range(3)
 FACE_TEX_NONE = 0xFFFF
-RENDER_ASYNC, RENDER_ALL_OPAQUE, VTX_NO_NORMAL, FACES_IMPLICIT = 1, 2, 4, 8
+RENDER_ASYNC, RENDER_ALL_OPAQUE, VTX_NO_NORMAL, FACES_IMPLICIT, FACES_UNIFORM = 1, 2, 4, 8, 16
 
 # ---- POD records as numpy dtypes (b32_vertex 36 B, b32_face 16 B) ---------------------------
 VERTEX_DTYPE = np.dtype([("pos", "<f4", 3), ("uv", "<f4", 2), ("normal", "<f4", 3), ("rgba", "u1", 4)])
@@ -37,7 +37,8 @@ assert VERTEX_DTYPE.itemsize == 36 and FACE_DTYPE.itemsize == 16 and SKY_VERTEX_
 
 def compact_buffers(vertices, faces, shading_none):
     """What a marshalling shim sends through b32_render_mesh_15_ex for this mesh: (vertex array, face array, flags).
-    Normals are dropped when nothing reads them; an unindexed soup sends only its flags words."""
+    Normals are dropped when nothing reads them; an unindexed soup sends only its flags words — or, when they are all
+    equal (one texture, one blend mode), a single word that travels with the kernel parameters."""
     flags = 0
     v, f = vertices, faces
     if shading_none:
@@ -46,6 +47,8 @@ def compact_buffers(vertices, faces, shading_none):
         v, flags = nn, flags | VTX_NO_NORMAL
     if len(faces) * 3 <= len(vertices) and np.array_equal(faces["v"].reshape(-1), np.arange(len(faces) * 3, dtype=np.uint32)):
         f, flags = np.ascontiguousarray(faces["flags"], dtype=np.uint32), flags | FACES_IMPLICIT
+        if len(f) and (f == f[0]).all():
+            f, flags = f[:1].copy(), (flags & ~FACES_IMPLICIT) | FACES_UNIFORM
     return np.ascontiguousarray(v), np.ascontiguousarray(f), flags
 # b32_line (overlay lines, Framebuffer::draw_line*)
 LINE_DTYPE = np.dtype([("x0", "<i4"), ("y0", "<i4"), ("x1", "<i4"), ("y1", "<i4"), ("z0", "<f4"), ("z1", "<f4"),

@@ -456,7 +456,7 @@ int enqueue_frame(b32_ctx* ctx, const FrameArgs& a, const FrameKey& key) {
 // clear_rgba (nullable): Framebuffer::clear first, as part of the same frame.
 int render_device(b32_ctx* ctx, const b32_vertex* d_verts, uint32_t nv, const b32_face* d_faces, uint32_t nf,
                   const b32_camera* cam, const b32_settings* s, const b32_fog* fog, b32_timings* tm, bool wait, bool rgb888 = false,
-                  const uint8_t* clear_rgba = nullptr, bool all_opaque = false, uint32_t vwords = 9, bool faces_implicit = false) {
+                  const uint8_t* clear_rgba = nullptr, bool all_opaque = false, uint32_t vwords = 9, uint32_t faces_implicit = 0, uint32_t uniform_flags = 0) {
     if (!cam || !s) return fail(ctx, B32_ERR_INVALID, "camera/settings is NULL");
     if (ctx->width == 0 || ctx->height == 0) return fail(ctx, B32_ERR_INVALID, "framebuffer has zero size (call b32_fb_resize)");
     FrameArgs a{};
@@ -464,7 +464,7 @@ int render_device(b32_ctx* ctx, const b32_vertex* d_verts, uint32_t nv, const b3
     std::vector<LightDev> lights;
     int rc = fill_params(ctx, p, cam, s, fog, nv, nf, lights, rgb888);
     if (rc != B32_OK) return rc;
-    p.vwords = (uint8_t)vwords; p.faces_implicit = faces_implicit ? 1 : 0;
+    p.vwords = (uint8_t)vwords; p.faces_implicit = (uint8_t)faces_implicit; p.uniform_flags = uniform_flags;
     if (tm) std::memset(tm, 0, sizeof(*tm));
     a.verts = d_verts; a.faces = d_faces;
     a.texdesc = rgb888 ? ctx->tex8desc.p : ctx->texdesc.p;
@@ -832,9 +832,10 @@ int b32_render_mesh_15_ex(b32_ctx* ctx, const void* vertices, uint32_t nv, const
     USE_DEVICE(ctx);
     if (!ctx) return B32_ERR_INVALID;
     if ((nv && !vertices) || (nf && !faces) || !settings) return fail(ctx, B32_ERR_INVALID, "vertices/faces/settings is NULL");
-    const bool async = (flags & B32_RENDER_ASYNC) != 0, no_normal = (flags & B32_VTX_NO_NORMAL) != 0, implicit = (flags & B32_FACES_IMPLICIT) != 0;
+    const bool async = (flags & B32_RENDER_ASYNC) != 0, no_normal = (flags & B32_VTX_NO_NORMAL) != 0;
+    const bool uniform = (flags & B32_FACES_UNIFORM) != 0, implicit = uniform || (flags & B32_FACES_IMPLICIT) != 0;
     if (no_normal && settings->shading != B32_SHADE_NONE) return fail(ctx, B32_ERR_INVALID, "B32_VTX_NO_NORMAL needs settings.shading == None");
-    if (implicit && (uint64_t)nv < 3ull * nf) return fail(ctx, B32_ERR_OOB_INDEX, "B32_FACES_IMPLICIT: fewer than 3 * nf vertices");
+    if (implicit && (uint64_t)nv < 3ull * nf) return fail(ctx, B32_ERR_OOB_INDEX, "B32_FACES_IMPLICIT / B32_FACES_UNIFORM: fewer than 3 * nf vertices");
     const bool wire = (settings->backface_cull && settings->backface_wireframe) || settings->wireframe_overlay;
     if (async && wire) return fail(ctx, B32_ERR_INVALID, "the wireframe phase cannot be enqueued");
     bool all_opaque = async && (flags & B32_RENDER_ALL_OPAQUE) != 0;
@@ -845,11 +846,16 @@ int b32_render_mesh_15_ex(b32_ctx* ctx, const void* vertices, uint32_t nv, const
     const size_t vbytes = no_normal ? sizeof(b32_vertex_nn) : sizeof(b32_vertex), fbytes = implicit ? sizeof(uint32_t) : sizeof(b32_face);
     // staging buffers are sized in b32_vertex / b32_face units; + 1 vertex: k_setup's staged window may overrun by < 16 bytes
     CK(ctx->verts.reserve(((size_t)nv * vbytes + sizeof(b32_vertex) - 1) / sizeof(b32_vertex) + 1));
-    CK(ctx->faces.reserve(std::max<size_t>(((size_t)nf * fbytes + sizeof(b32_face) - 1) / sizeof(b32_face), 1)));
     int rc = h2d(ctx, ctx->verts.p, vertices, (size_t)nv * vbytes); if (rc) return rc;
-    rc = h2d(ctx, ctx->faces.p, faces, (size_t)nf * fbytes); if (rc) return rc;
-    return render_device(ctx, ctx->verts.p, nv, ctx->faces.p, nf, camera, settings, fog, async ? nullptr : timings, !async, false, nullptr, all_opaque,
-                         no_normal ? 6 : 9, implicit);
+    uint32_t uniform_flags = 0;
+    if (uniform) {             // the one flags word travels with the kernel parameters: no face buffer, no copy
+        uniform_flags = *static_cast<const uint32_t*>(faces);
+    } else {
+        CK(ctx->faces.reserve(std::max<size_t>(((size_t)nf * fbytes + sizeof(b32_face) - 1) / sizeof(b32_face), 1)));
+        rc = h2d(ctx, ctx->faces.p, faces, (size_t)nf * fbytes); if (rc) return rc;
+    }
+    return render_device(ctx, ctx->verts.p, nv, uniform ? nullptr : ctx->faces.p, nf, camera, settings, fog, async ? nullptr : timings, !async, false, nullptr, all_opaque,
+                         no_normal ? 6 : 9, uniform ? 2u : implicit ? 1u : 0u, uniform_flags);
 }
 
 int b32_frame_15_enqueue(b32_ctx* ctx, const uint8_t* clear_rgba, const b32_mesh* mesh, const b32_camera* camera,

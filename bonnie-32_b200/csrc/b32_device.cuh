@@ -157,9 +157,10 @@ struct CallParams {
     uint8_t rgb888;                                   // 1: render_mesh / rasterize_triangle (render.rs:1971-2259, 1202-1433)
     uint8_t enq_ordered;                              // 1: the ordered pass is enqueued behind pass 1 without a host round trip (k_fill_ordered exits early when it has nothing to do)
     uint8_t vwords;                                   // words per vertex record: 9 (b32_vertex) or 6 (b32_vertex_nn: no normal; only with shading None)
-    uint8_t faces_implicit;                           // 1: `faces` holds one flags word per face; face i uses vertices 3i, 3i+1, 3i+2
+    uint8_t faces_implicit;                           // 1: `faces` holds one flags word per face; face i uses vertices 3i, 3i+1, 3i+2.  2: no face buffer at all, every face has `uniform_flags`
     float ambient, ortho_zoom, ortho_cx, ortho_cy;
     float fog_start, fog_falloff, fog_cull;
+    uint32_t uniform_flags;                           // faces_implicit == 2: the flags word of every face
     uint32_t host_seq;                                // blocking calls: the value the kernels publish in HostStatus when done
     HostStatus* host;                                 // null for enqueue-only calls
 };

@@ -28,6 +28,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <tuple>
+#include <type_traits>
 #include <utility>
 
 #include "b32_device.cuh"
@@ -572,7 +573,7 @@ k_setup(const b32_vertex* __restrict__ verts, const b32_face* __restrict__ faces
         uint32_t lo = 0xFFFFFFFFu, hi = 0;
         if (fi < p.nf) {
             // implicit faces: an unindexed triangle soup sends only the flags word; face i = vertices 3i, 3i+1, 3i+2
-            if (p.faces_implicit) fc = make_uint4(3u * fi, 3u * fi + 1u, 3u * fi + 2u, reinterpret_cast<const uint32_t*>(faces)[fi]);
+            if (p.faces_implicit) fc = make_uint4(3u * fi, 3u * fi + 1u, 3u * fi + 2u, p.faces_implicit == 2 ? p.uniform_flags : reinterpret_cast<const uint32_t*>(faces)[fi]);
             else fc = *reinterpret_cast<const uint4*>(faces + fi);
             lo = min(fc.x, min(fc.y, fc.z)); hi = max(fc.x, max(fc.y, fc.z));
         }
@@ -1127,6 +1128,7 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks,
     // crowded tile: a slice of the global scratch for its heads (see crowd_prepare); none left = windows in list order
     BinHead* slice = nullptr;
     const uint32_t slice_len = n_cand + (n_cand + 3) / 4;          // n_cand heads, then n_cand face indices (4 per head-sized slot)
+#ifndef B32_NO_CROWD
     if (n_cand > (uint32_t)OP_SORT_MAX) {
         if (threadIdx.x == 0) {
             uint32_t base = crowd_cap >= slice_len ? atomicAdd(&st->crowd_used, slice_len) : 0xFFFFFFFFu;
@@ -1135,17 +1137,21 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks,
         __syncthreads();
         if (s_slice != 0xFFFFFFFFu) slice = crowd + s_slice;
     }
+#endif
     BinHead* s_tmp = reinterpret_cast<BinHead*>(s_cand + OP_SORT_MAX);         // [OP_SORT_MAX] a depth window's heads (the ring is idle then)
     if (slice) crowd_prepare(mrow, cs, n_cand, heads, tpx0, tpy0, slice, reinterpret_cast<uint32_t*>(slice + n_cand), s_ghist, OP_BUCKETS, OP_BUCKET_BITS, &s_crowd);
 #ifdef B32_FILL_STATS
     uint32_t st_tprep = gtime(), st_twin = 0;
 #endif
     bool gdone = offscreen;                                // depth-ordered windows: this warp's early-out, carried from window to window
-    for (uint32_t win = 0;; ++win) {
+    // One window.  MULTI = false_type is the usual tile (one window, no scratch slice, nothing carried over): the same body
+    // with everything that only several windows need compiled out.  Returns false when no further window is needed.
+    auto run_window = [&](auto multi_tag, const uint32_t win) -> bool {
+        constexpr bool MULTI = decltype(multi_tag)::value;
         const uint32_t w0 = win * OP_SORT_MAX;
-        if (!slice && w0 >= n_cand) break;
-        const uint32_t wn = slice ? 0u : min((uint32_t)OP_SORT_MAX, n_cand - w0);
-        if (win) {
+        if (!(MULTI && slice) && w0 >= n_cand) return false;
+        const uint32_t wn = (MULTI && slice) ? 0u : min((uint32_t)OP_SORT_MAX, n_cand - w0);
+        if (MULTI && win) {
             cp_async_wait<0>();
             if (threadIdx.x == 0) s_tile_weak = 0xFFFFFFFFu;
             __syncthreads();                               // the previous window's ring traffic is over: its area is reused
@@ -1172,12 +1178,12 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks,
         BinHead hh[KPT];
         uint32_t n = 0;
         bool carry = false;
-        if (slice) {
+        if (MULTI && slice) {
             n = crowd_next_window(slice, tile_weak, s_ghist, OP_BUCKETS, OP_SORT_MAX, s_tmp, &s_crowd, &carry);
 #ifdef B32_FILL_STATS
             if (!win) st_twin = gtime();
 #endif
-            if (n == 0xFFFFFFFFu) break;
+            if (n == 0xFFFFFFFFu) return false;
             #pragma unroll
             for (int q = 0; q < KPT; ++q) {
                 const uint32_t i = q * OP_THREADS + threadIdx.x;
@@ -1195,13 +1201,13 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks,
                     const uint32_t min_x = hh[q].bbox_x & 0xFFFF, max_x = hh[q].bbox_x >> 16, min_y = hh[q].bbox_y & 0xFFFF, max_y = hh[q].bbox_y >> 16;
                     ok = hh[q].bbox_x != 0 && !(max_x <= tpx0 || min_x >= tpx0 + TILE_W || max_y <= tpy0 || min_y >= tpy0 + TILE_H);
                     // (z-buffer: key 0xFFFFFFFF = "no bound claimed" always passes; equal bounds pass: ties are resolved per pixel)
-                    ok = ok && hh[q].key >= tile_weak;
+                    if (MULTI) ok = ok && hh[q].key >= tile_weak;
                 }
                 if (!ok) hh[q].bbox_x = 0;
                 n += __syncthreads_count(ok);              // (also orders the s_cand reads before the ring's writes)
             }
         }
-        if (n == 0) continue;
+        if (n == 0) return true;
         auto for_each_entry = [&](auto f) {
             #pragma unroll
             for (int q = 0; q < KPT; ++q) { if (hh[q].bbox_x) f(hh[q]); }
@@ -1391,11 +1397,14 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks,
                 }
             }
         }
-        if (carry) {                                          // every warp settled: the farther windows cannot change anything
+        if (MULTI && carry) {                                          // every warp settled: the farther windows cannot change anything
             gdone = done;
-            if (__syncthreads_and(gdone)) break;
+            if (__syncthreads_and(gdone)) return false;
         }
-    }
+        return true;
+    };
+    if (n_cand <= (uint32_t)OP_SORT_MAX) run_window(std::false_type{}, 0u);
+    else for (uint32_t win = 0; run_window(std::true_type{}, win); ++win) {}
     cp_async_wait<0>();
     if (!mask_waited) { while (!mbar_try_wait(&s_mbar, 0)) {} }       // the bulk copy must land before the CTA exits
 #ifdef B32_FILL_STATS

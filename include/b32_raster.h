@@ -213,9 +213,13 @@ int b32_render_mesh_15(b32_ctx* ctx,
  *                     otherwise B32_ERR_INVALID.
  * B32_FACES_IMPLICIT  `faces` points to nf uint32_t flags words (the `flags` of b32_face); face i uses vertices
  *                     3i, 3i+1, 3i+2 (an unindexed triangle soup); nv >= 3 * nf, else B32_ERR_OOB_INDEX.
- * A marshalling shim picks them for free while it converts `&[Vertex]` / `&[Face]`: 36 + 16/3 -> 24 + 4/3 bytes per vertex. */
+ * B32_FACES_UNIFORM   an unindexed soup (as above) whose faces all carry the same flags word — one texture, one blend
+ *                     mode, the usual case of a room or asset part: `faces` points to that ONE uint32_t; it travels with
+ *                     the kernel parameters, no face buffer is copied at all.
+ * A marshalling shim picks them for free while it converts `&[Vertex]` / `&[Face]`: 36 + 16/3 -> 24 + 4/3 (or 24) bytes per vertex. */
 #define B32_VTX_NO_NORMAL      4u
 #define B32_FACES_IMPLICIT     8u
+#define B32_FACES_UNIFORM      16u
 typedef struct b32_vertex_nn {
     float   pos[3];
     float   uv[2];
@@ -223,7 +227,7 @@ typedef struct b32_vertex_nn {
 } b32_vertex_nn;
 int b32_render_mesh_15_ex(b32_ctx* ctx,
                           const void* vertices, uint32_t nv,      /* b32_vertex[nv], or b32_vertex_nn[nv] */
-                          const void* faces, uint32_t nf,         /* b32_face[nf], or uint32_t flags[nf] */
+                          const void* faces, uint32_t nf,         /* b32_face[nf], uint32_t flags[nf], or one uint32_t */
                           const b32_camera* camera, const b32_settings* settings,
                           const b32_fog* fog_or_null, uint32_t flags, b32_timings* timings);
 /* Enqueue the framebuffer read-back (pinned destination recommended); complete after b32_sync. */

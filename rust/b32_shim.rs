@@ -71,6 +71,7 @@ fn check(ctx: *mut b32_ctx, rc: c_int) {
 pub struct b32_vertex_nn { pos: [f32; 3], uv: [f32; 2], r: u8, g: u8, b: u8, blend: u8 }
 const B32_VTX_NO_NORMAL: u32 = 4;
 const B32_FACES_IMPLICIT: u32 = 8;
+const B32_FACES_UNIFORM: u32 = 16;
 
 fn face_flags(f: &Face) -> u32 {
     let tex = match f.texture_id { Some(id) if id < 0xFFFF => id as u32, _ => 0xFFFF };
@@ -79,8 +80,9 @@ fn face_flags(f: &Face) -> u32 {
 
 /// The bytes that cross PCIe, in the most compact layout the call allows (include/b32_raster.h, B32_VTX_NO_NORMAL /
 /// B32_FACES_IMPLICIT): normals are only read when the settings shade (render.rs:1466-1483), and an unindexed triangle
-/// soup (face i = vertices 3i, 3i+1, 3i+2) needs no index buffer.  Both are decided while the slices are converted
-/// anyway; the rendered bytes are identical.  Returns (vertex bytes, face bytes, flags).
+/// soup (face i = vertices 3i, 3i+1, 3i+2) needs no index buffer — and when all its faces carry the same flags word
+/// (one texture, one blend mode: the usual room or asset part) that one word is all that is sent.  All of it is decided
+/// while the slices are converted anyway; the rendered bytes are identical.  Returns (vertex bytes, face bytes, flags).
 fn marshal_compact(vertices: &[Vertex], faces: &[Face], settings: &RasterSettings) -> (Vec<u8>, Vec<u8>, u32) {
     let mut flags = 0u32;
     let as_bytes = |p: *const u8, n: usize| unsafe { std::slice::from_raw_parts(p, n) }.to_vec();
@@ -95,9 +97,14 @@ fn marshal_compact(vertices: &[Vertex], faces: &[Face], settings: &RasterSetting
     };
     let soup = vertices.len() >= 3 * faces.len() && faces.iter().enumerate().all(|(i, f)| f.v0 == 3 * i && f.v1 == 3 * i + 1 && f.v2 == 3 * i + 2);
     let fbytes = if soup {
-        flags |= B32_FACES_IMPLICIT;
         let f: Vec<u32> = faces.iter().map(face_flags).collect();
-        as_bytes(f.as_ptr() as *const u8, f.len() * 4)
+        if !f.is_empty() && f.iter().all(|&w| w == f[0]) {
+            flags |= B32_FACES_UNIFORM;
+            as_bytes(f.as_ptr() as *const u8, 4)
+        } else {
+            flags |= B32_FACES_IMPLICIT;
+            as_bytes(f.as_ptr() as *const u8, f.len() * 4)
+        }
     } else {
         let (_, f) = marshal_geometry(&[], faces);
         as_bytes(f.as_ptr() as *const u8, f.len() * 16)

@@ -1082,7 +1082,7 @@ def test_gpu_against_reference_binary_directly(ctx, name):
 
 
 def test_compact_marshalling_variants(ctx, oracle):
-    """b32_render_mesh_15_ex with B32_VTX_NO_NORMAL / B32_FACES_IMPLICIT: fewer bytes across PCIe, same framebuffer.
+    """b32_render_mesh_15_ex with B32_VTX_NO_NORMAL / B32_FACES_IMPLICIT / B32_FACES_UNIFORM: fewer bytes across PCIe, same framebuffer.
     Blocking and enqueued; C4-style soup (both flags), an indexed mesh (no-normal only), lit scenes (implicit only)."""
     import ctypes as C
     lib = ctx.lib
@@ -1094,24 +1094,33 @@ def test_compact_marshalling_variants(ctx, oracle):
         want, want_z, otm, rc = oracle.render_scene(sc)
         assert rc == 0
         v, f, flags = abi.compact_buffers(sc.vertices, sc.faces, sc.settings.shading == abi.SHADE_NONE)
-        assert flags == expect, sc.name
+        uniform = bool(expect & abi.FACES_IMPLICIT) and bool((sc.faces["flags"] == sc.faces["flags"][0]).all())
+        assert flags == ((expect & ~abi.FACES_IMPLICIT) | abi.FACES_UNIFORM if uniform else expect), sc.name
+        assert len(f) == (1 if uniform else len(sc.faces))
+        layouts = [(f, flags)]
+        if uniform:                                            # the same soup with one flags word per face
+            layouts.append((np.ascontiguousarray(sc.faces["flags"]), (flags & ~abi.FACES_UNIFORM) | abi.FACES_IMPLICIT))
         fb = pkg.Framebuffer(sc.width, sc.height, ctx)
         ctx.set_textures(sc.textures)
         cam = sc.camera.to_abi(); st, keep = sc.settings.to_abi()
         fog = pkg.raster.fog_to_abi(sc.fog)
-        for asyn in (0, abi.RENDER_ASYNC):
-            fb.clear(sc.clear)
-            tm = abi.Timings()
-            ctx.check(lib.b32_render_mesh_15_ex(ctx.h, v.ctypes.data, len(v), f.ctypes.data, len(f), C.byref(cam), C.byref(st),
-                                                C.byref(fog) if fog is not None else None, flags | asyn, C.byref(tm)))
-            got, got_z = fb.download()
-            assert np.array_equal(got, want), (sc.name, asyn)
-            assert np.array_equal(got_z.view(np.uint32), want_z.view(np.uint32)), (sc.name, asyn)
-            if not asyn:
-                assert tm.triangles_drawn == otm["triangles_drawn"]
+        for f_, flags_ in layouts:
+            for asyn in (0, abi.RENDER_ASYNC):
+                fb.clear(sc.clear)
+                tm = abi.Timings()
+                ctx.check(lib.b32_render_mesh_15_ex(ctx.h, v.ctypes.data, len(v), f_.ctypes.data, len(sc.faces), C.byref(cam), C.byref(st),
+                                                    C.byref(fog) if fog is not None else None, flags_ | asyn, C.byref(tm)))
+                got, got_z = fb.download()
+                assert np.array_equal(got, want), (sc.name, asyn, flags_)
+                assert np.array_equal(got_z.view(np.uint32), want_z.view(np.uint32)), (sc.name, asyn, flags_)
+                if not asyn:
+                    assert tm.triangles_drawn == otm["triangles_drawn"]
     # the promise is checked
     sc = by["gouraud_lights"]
     v, f, flags = abi.compact_buffers(sc.vertices, sc.faces, True)
     cam = sc.camera.to_abi(); st, keep = sc.settings.to_abi()
-    assert lib.b32_render_mesh_15_ex(ctx.h, v.ctypes.data, len(v), f.ctypes.data, len(f), C.byref(cam), C.byref(st), None, flags, None) == abi.B32_ERR_INVALID
-    assert lib.b32_render_mesh_15_ex(ctx.h, v.ctypes.data, len(v) - 1, f.ctypes.data, len(f), C.byref(cam), C.byref(st), None, abi.FACES_IMPLICIT, None) == abi.B32_ERR_OOB_INDEX
+    nf = len(sc.faces)
+    assert lib.b32_render_mesh_15_ex(ctx.h, v.ctypes.data, len(v), f.ctypes.data, nf, C.byref(cam), C.byref(st), None, flags, None) == abi.B32_ERR_INVALID
+    fl = np.ascontiguousarray(sc.faces["flags"])
+    assert lib.b32_render_mesh_15_ex(ctx.h, v.ctypes.data, len(v) - 1, fl.ctypes.data, nf, C.byref(cam), C.byref(st), None, abi.FACES_IMPLICIT, None) == abi.B32_ERR_OOB_INDEX
+    assert lib.b32_render_mesh_15_ex(ctx.h, v.ctypes.data, len(v) - 1, fl.ctypes.data, nf, C.byref(cam), C.byref(st), None, abi.FACES_UNIFORM, None) == abi.B32_ERR_OOB_INDEX
