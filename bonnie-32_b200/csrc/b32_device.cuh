@@ -184,12 +184,20 @@ __device__ __forceinline__ int32_t fx_mul(int32_t a, int32_t b) { return (int32_
 __device__ __forceinline__ int32_t fx_add(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
 __device__ __forceinline__ int32_t fx_sub(int32_t a, int32_t b) { return (int32_t)((uint32_t)a - (uint32_t)b); }
 
-// UNR_TABLE[i] (fixed.rs:18-31), computed instead of looked up: one u32 division is cheaper here than a
-// per-block table load + barrier in front of every thread's first global load.
-__device__ __forceinline__ uint32_t unr_entry(uint32_t i) {
-    int32_t v = (int32_t)((0x40000u / (i + 0x100u) + 1u) >> 1) - 0x101;
-    return v > 0 ? (uint32_t)v : 0u;
-}
+// UNR_TABLE[i] (fixed.rs:18-31): 257 bytes built at compile time from the reference's formula and read through the
+// read-only path (neighbouring lanes hit the same three cache lines); a per-thread u32 division cost ~20 instructions
+// per projected vertex.
+struct UnrTable {
+    uint8_t v[260];
+    constexpr UnrTable() : v() {
+        for (uint32_t i = 0; i <= 0x100u; ++i) {
+            int32_t e = (int32_t)((0x40000u / (i + 0x100u) + 1u) >> 1) - 0x101;
+            v[i] = (uint8_t)(e > 0 ? e : 0);
+        }
+    }
+};
+__device__ constexpr UnrTable g_unr_table{};
+__device__ __forceinline__ uint32_t unr_entry(uint32_t i) { return __ldg(&g_unr_table.v[i]); }
 
 // UNR reciprocal of a non-zero divisor (fixed.rs:183-205): returns nr2 and the final shift.  Every intermediate of the
 // reference's u64 arithmetic fits 32 bits (d16 <= 0xFFFF, u <= 0x200: d16 * u < 2^25; nr1 < 2^18: nr1 * u < 2^27), so
