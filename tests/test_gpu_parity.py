@@ -1124,3 +1124,24 @@ def test_compact_marshalling_variants(ctx, oracle):
     fl = np.ascontiguousarray(sc.faces["flags"])
     assert lib.b32_render_mesh_15_ex(ctx.h, v.ctypes.data, len(v) - 1, fl.ctypes.data, nf, C.byref(cam), C.byref(st), None, abi.FACES_IMPLICIT, None) == abi.B32_ERR_OOB_INDEX
     assert lib.b32_render_mesh_15_ex(ctx.h, v.ctypes.data, len(v) - 1, fl.ctypes.data, nf, C.byref(cam), C.byref(st), None, abi.FACES_UNIFORM, None) == abi.B32_ERR_OOB_INDEX
+
+
+def test_skybox_against_reference_binary_directly(ctx):
+    """b32_render_skybox_mesh + b32_render_stars vs the frames the reference's own compiled Framebuffer::render_skybox
+    produced (tests/golden/ref_wasm/skybox.*: mesh and star list as the binary built them), with no oracle in between."""
+    import hashlib, json, os
+    here = os.path.dirname(__file__)
+    meta = json.load(open(os.path.join(here, "golden", "ref_wasm", "skybox.json")))["cases"]
+    arr = np.load(os.path.join(here, "golden", "ref_wasm", "skybox.npz"))
+    for key, m in sorted(meta.items()):
+        cam = cases._rotated_camera(m["camera"][0], m["camera"][1], m["camera"][2])
+        fb = pkg.Framebuffer(m["width"], m["height"], ctx)
+        fb.upload(np.zeros((m["height"], m["width"], 4), np.uint8), np.full((m["height"], m["width"]), np.finfo(np.float32).max, np.float32))
+        fb.render_skybox_mesh(arr[key + "_verts"], arr[key + "_faces"], cam)
+        if m["n_stars"]:
+            fb.render_stars(arr[key + "_stars"], cam, m["star_size"])
+        got, _ = fb.download()
+        if key + "_frame" in arr:
+            bad = (arr[key + "_frame"] != got).any(-1)
+            assert not bad.any(), (key, int(bad.sum()), np.argwhere(bad)[0][::-1])
+        assert hashlib.sha256(got.tobytes()).hexdigest() == m["rgba"], key

@@ -182,3 +182,30 @@ def test_overlay_primitives_match_reference_binary(oracle, name, w, h, seed, n):
     assert oracle.draw_lines(rgba, z, lines) == 0
     assert np.array_equal(z.view(np.uint32), z0.view(np.uint32))
     assert hashlib.sha256(rgba.tobytes()).hexdigest() == fix["rgba"], "pixels differ from the reference binary"
+
+
+def _skybox_fixture():
+    here = os.path.dirname(__file__)
+    meta = json.load(open(os.path.join(here, "golden", "ref_wasm", "skybox.json")))["cases"]
+    return meta, np.load(os.path.join(here, "golden", "ref_wasm", "skybox.npz"))
+
+
+@pytest.mark.parametrize("key", sorted(_skybox_fixture()[0]))
+def test_skybox_passes_match_reference_binary(oracle, key):
+    """b32o_render_skybox_mesh + b32o_render_stars vs the binary's own Framebuffer::render_skybox (render.rs:81-299) on the
+    sphere mesh / star list the binary built for that frame (tests/golden/make_ref_wasm_skybox.py).  No compat switch."""
+    import hashlib
+    import cases
+    meta, arr = _skybox_fixture()
+    m = meta[key]
+    cam = cases._rotated_camera(m["camera"][0], m["camera"][1], m["camera"][2])
+    fb = np.zeros((m["height"], m["width"], 4), np.uint8)                       # Framebuffer::new
+    assert oracle.render_skybox_mesh(fb, arr[key + "_verts"], arr[key + "_faces"], cam) == 0
+    if m["n_stars"]:
+        before = fb.copy()
+        assert oracle.render_stars(fb, arr[key + "_stars"], cam, m["star_size"]) == 0
+        assert (fb != before).any(), "the star pass drew nothing: the fixture does not exercise it"
+    if key + "_frame" in arr:
+        bad = (arr[key + "_frame"] != fb).any(-1)
+        assert not bad.any(), f"{bad.sum()} pixels differ from the reference binary, first at {np.argwhere(bad)[0][::-1]}"
+    assert hashlib.sha256(fb.tobytes()).hexdigest() == m["rgba"], "frame differs from the reference binary"
