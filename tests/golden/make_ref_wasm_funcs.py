@@ -72,6 +72,24 @@ def main():
         w.call('shade_multi_light_color', out, npn, npp, lp, ln, float(ambient[i]))
         shade[i] = np.frombuffer(w.read(out, 12), np.float32)
     res["shade"] = shade
+    # ---- Framebuffer::set_pixel_blended_15(fb, x, y, color15, mode) (render.rs:475-501): one pixel per input, back colour preloaded
+    c15, back, mode = refbin_funcs.blend_inputs()
+    n = len(c15)
+    fb = w.alloc(32, 4)
+    w.call('Framebuffer3new', fb, n, 1)
+    pix_ptr = struct.unpack('<I', w.read(fb + 4, 4))[0]
+    px = np.zeros((n, 4), np.uint8); px[:, :3] = back; px[:, 3] = 77
+    w.write(pix_ptr, px)
+    for i in range(n):
+        w.call('set_pixel_blended_15', fb, i, 0, int(c15[i]), int(mode[i]))
+    res["blend15"] = np.frombuffer(w.read(pix_ptr, n * 4), np.uint8).reshape(n, 4).copy()
+    # ---- Framebuffer::clear(fb, color) (render.rs:36-45)
+    clears = []
+    for word in (0x1C161400, 0xFF000005, 0x01020302, 0x00000000):          # blend @0, r @1, g @2, b @3
+        w.call('Framebuffer5clear', fb, word)
+        zp = struct.unpack('<I', w.read(fb + 16, 4))[0]
+        clears.append(np.concatenate([np.frombuffer(w.read(pix_ptr, 8), np.uint8), np.frombuffer(w.read(zp, 8), np.uint8)]))
+    res["clear"] = np.stack(clears)
     np.savez_compressed(OUT, **res)
     print("wrote", OUT, {k: v.shape for k, v in res.items()})
 

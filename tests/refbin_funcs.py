@@ -57,3 +57,15 @@ def shade_inputs(n=6000):
     normal[3] = (np.nan, 0.0, 1.0)
     pos[4] = (np.inf, 0.0, 0.0)
     return normal, pos, set_idx, ambient
+
+
+def blend_inputs(n=30000):
+    """(color15 incl. bit 15, back r/g/b, blend mode) for Framebuffer::set_pixel_blended_15."""
+    u = scenes.splitmix64_u01(0xF1ED0003, n * 5).reshape(n, 5)
+    c15 = np.floor(u[:, 0] * 65536.0).astype(np.uint16)
+    back = np.floor(u[:, 1:4] * 256.0).astype(np.uint8)
+    mode = (np.floor(u[:, 4] * 6.0).astype(np.uint8)) % 6
+    # a few corners: saturating add, clamping subtract, black front / back
+    c15[:6] = [0xFFFF, 0x8000, 0x8001, 0xFC00, 0x83FF, 0x0000]
+    back[:6] = [[255, 255, 255], [0, 0, 0], [7, 8, 248], [255, 0, 128], [16, 31, 249], [1, 2, 3]]
+    return c15, back, mode

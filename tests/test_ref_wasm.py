@@ -209,3 +209,42 @@ def test_skybox_passes_match_reference_binary(oracle, key):
         bad = (arr[key + "_frame"] != fb).any(-1)
         assert not bad.any(), f"{bad.sum()} pixels differ from the reference binary, first at {np.argwhere(bad)[0][::-1]}"
     assert hashlib.sha256(fb.tobytes()).hexdigest() == m["rgba"], "frame differs from the reference binary"
+
+
+def test_set_pixel_blended_15_matches_reference_binary(oracle):
+    """blend_rgb555 (render.rs:1093-1145) through the binary's Framebuffer::set_pixel_blended_15: 30 000 (Color15, back
+    pixel, BlendMode) triples, all six modes.  What survives in the binary under this name is the blend tail only: its
+    callers have already decided that the texel blends, so bit 15 is not looked at and the br_table's default arm
+    (mode Opaque, never passed in practice) is Average (DRIFT.md item 7).  Its Color15::r8() is `v << 3` (item 3).  What
+    this pins is the arithmetic of every blend mode on arbitrary back pixels, incl. the `>> 3` of a non-multiple-of-8 back."""
+    import ctypes as C
+    import refbin_funcs
+    fx = np.load(os.path.join(HERE, "golden", "ref_wasm", "functions.npz"))["blend15"]
+    c15, back, mode = refbin_funcs.blend_inputs()
+    lib = oracle.lib()
+    out = (C.c_uint8 * 3)()
+    got = np.empty((len(c15), 4), np.uint8)
+    for i in range(len(c15)):
+        c = int(c15[i])
+        f8 = [((c >> 10) & 31) << 3, ((c >> 5) & 31) << 3, (c & 31) << 3]              # the binary's r8 / g8 / b8
+        eff = int(mode[i]) if mode[i] != 0 else 1                                      # the br_table's default arm
+        if eff:
+            lib.b32o_blend_rgb555(C.c_uint8(f8[0]), C.c_uint8(f8[1]), C.c_uint8(f8[2]), C.c_uint8(int(back[i, 0])), C.c_uint8(int(back[i, 1])),
+                                  C.c_uint8(int(back[i, 2])), C.c_uint32(eff), out)
+            got[i, :3] = out[:]
+        else:
+            got[i, :3] = f8
+        got[i, 3] = 255
+    bad = (got != fx).any(1)
+    assert not bad.any(), (int(bad.sum()), np.argwhere(bad)[:3].ravel(), got[bad][:3], fx[bad][:3])
+
+
+def test_framebuffer_clear_matches_reference_binary(oracle):
+    """Framebuffer::clear (render.rs:36-45): colour bytes (alpha 0 only for an Erase-blend colour) and depth f32::MAX."""
+    from bonnie32_b200 import abi
+    fx = np.load(os.path.join(HERE, "golden", "ref_wasm", "functions.npz"))["clear"]
+    for row, word in zip(fx, (0x1C161400, 0xFF000005, 0x01020302, 0x00000000)):
+        blend, r, g, b = word & 255, (word >> 8) & 255, (word >> 16) & 255, (word >> 24) & 255
+        rgba = np.zeros((1, 2, 4), np.uint8); z = np.zeros((1, 2), np.float32)
+        oracle.lib().b32o_fb_clear(rgba.ctypes.data, z.ctypes.data, 2, 1, r, g, b, 0 if blend == abi.BLEND_ERASE else 255)
+        assert np.array_equal(rgba.reshape(-1), row[:8]) and np.array_equal(z.view(np.uint8).reshape(-1), row[8:])
