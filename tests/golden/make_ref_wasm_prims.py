@@ -60,6 +60,24 @@ def main():
         out["cases"][name] = {"inputs": hashlib.sha256(rgba.tobytes() + z.tobytes() + lines.tobytes()).hexdigest(),
                               "rgba": hashlib.sha256(got.tobytes()).hexdigest(), "pixels_changed": changed}
         print(name, changed, "pixels changed")
+    # ---- draw_line through draw::draw_3d_line_clipped(fb, &camera, &p0, &p1, color)
+    from bonnie32_b200.raster import Camera
+    out["clipped"] = {}
+    for name, w, h, seed, n in refbin_prims.CLIPPED:
+        rgba, z = refbin_prims.background(w, h, seed)
+        p0, p1, rgb, ends = refbin_prims.clipped_segments(w, h, seed, n)
+        fb = ref.new_framebuffer(w, h, rgba, z)
+        ref._allocs = []
+        cam = ref._camera(Camera())
+        a, b = ref.w.alloc(12, 4), ref.w.alloc(12, 4)
+        for i in range(n):
+            ref.w.write(a, p0[i].tobytes()); ref.w.write(b, p1[i].tobytes())
+            ref.w.call("draw_3d_line_clipped", fb, cam, a, b, (int(rgb[i, 0]) << 8) | (int(rgb[i, 1]) << 16) | (int(rgb[i, 2]) << 24))
+        got, _ = ref.read_framebuffer(fb)
+        ref.free_framebuffer(fb)
+        out["clipped"][name] = {"inputs": hashlib.sha256(rgba.tobytes() + p0.tobytes() + p1.tobytes() + rgb.tobytes()).hexdigest(),
+                                "rgba": hashlib.sha256(got.tobytes()).hexdigest(), "pixels_changed": int((got != rgba).any(-1).sum())}
+        print(name, out["clipped"][name]["pixels_changed"], "pixels changed")
     json.dump(out, open(OUT, "w"), indent=1)
 
 

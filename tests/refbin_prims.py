@@ -44,3 +44,35 @@ def primitives(w, h, seed, n):
 
 def background(w, h, seed):
     return cases.line_background(w, h, seed)
+
+
+# ---- plain draw_line (render.rs:715-751) through draw::draw_3d_line_clipped (draw.rs:12-66), the one caller that survives
+# as a separate function: world-space segments in front of an identity camera at the origin.
+CLIPPED = [("lines_320x240", 320, 240, 7201, 300), ("lines_97x61", 97, 61, 7202, 200)]
+
+
+def clipped_segments(w, h, seed, n):
+    """(p0[n,3], p1[n,3], rgb[n,3]) in world space, and the integer end points world_to_screen (math.rs:503-534) gives them
+    with the default camera at the origin — Camera::new's basis is x = (-1, 0, 0), y = (0, -1, 0), z = (0, 0, 1)
+    (camera.rs:76-91), so cam_x = -x, cam_y = -y, cam_z = z exactly — every operation in f32, in the reference's order."""
+    rng = np.random.default_rng(seed)
+    f32 = np.float32
+    z = (1.0 + 99.0 * rng.random((n, 2))).astype(f32)
+    span = 1.6                                             # end points up to 60 % outside the screen
+    vs = f32(f32(min(w, h)) / f32(2.0)) * f32(0.75)
+    xy = ((rng.random((n, 2, 2)) - 0.5) * span).astype(f32)
+    p = np.zeros((n, 2, 3), f32)
+    for k in range(2):
+        denom = z[:, k] + f32(5.0)
+        p[:, k, 0] = xy[:, k, 0] * f32(w) * denom / (f32(4.0) * vs)      # roughly on-screen x = (xy + 0.5) * w
+        p[:, k, 1] = xy[:, k, 1] * f32(h) * denom / (f32(4.0) * vs)
+        p[:, k, 2] = z[:, k]
+    ends = np.zeros((n, 2, 2), np.int32)
+    for k in range(2):
+        denom = p[:, k, 2] + f32(5.0)
+        sx = (-p[:, k, 0] * f32(4.0) / denom) * vs + f32(f32(w) / f32(2.0))
+        sy = (-p[:, k, 1] * f32(4.0) / denom) * vs + f32(f32(h) / f32(2.0))
+        ends[:, k, 0] = np.trunc(sx).astype(np.int32)                    # `as i32`
+        ends[:, k, 1] = np.trunc(sy).astype(np.int32)
+    rgb = rng.integers(0, 256, (n, 3), dtype=np.uint8)
+    return p[:, 0].copy(), p[:, 1].copy(), rgb, ends

@@ -248,3 +248,25 @@ def test_framebuffer_clear_matches_reference_binary(oracle):
         rgba = np.zeros((1, 2, 4), np.uint8); z = np.zeros((1, 2), np.float32)
         oracle.lib().b32o_fb_clear(rgba.ctypes.data, z.ctypes.data, 2, 1, r, g, b, 0 if blend == abi.BLEND_ERASE else 255)
         assert np.array_equal(rgba.reshape(-1), row[:8]) and np.array_equal(z.view(np.uint8).reshape(-1), row[8:])
+
+
+@pytest.mark.parametrize("name,w,h,seed,n", __import__("refbin_prims").CLIPPED, ids=lambda v: v if isinstance(v, str) else None)
+def test_plain_draw_line_matches_reference_binary(oracle, name, w, h, seed, n):
+    """Framebuffer::draw_line (render.rs:715-751, B32_LINE_2D) through the one caller the binary keeps as a function,
+    draw::draw_3d_line_clipped (draw.rs:12-66): world-space segments in front of an identity camera; the end points the
+    oracle is given come from a f32 restatement of world_to_screen (math.rs:503-534) in tests/refbin_prims.py."""
+    import hashlib
+    import json
+    import refbin_prims
+    from bonnie32_b200 import abi
+    fix = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ref_wasm", "prims.json")))["clipped"][name]
+    rgba, z = refbin_prims.background(w, h, seed)
+    p0, p1, rgb, ends = refbin_prims.clipped_segments(w, h, seed, n)
+    assert hashlib.sha256(rgba.tobytes() + p0.tobytes() + p1.tobytes() + rgb.tobytes()).hexdigest() == fix["inputs"]
+    lines = np.zeros(n, dtype=abi.LINE_DTYPE)
+    lines["kind"] = abi.LINE_2D
+    lines["mode"] = abi.BLEND_OPAQUE
+    lines["x0"], lines["y0"], lines["x1"], lines["y1"] = ends[:, 0, 0], ends[:, 0, 1], ends[:, 1, 0], ends[:, 1, 1]
+    lines["rgb"] = rgb
+    assert oracle.draw_lines(rgba, z, lines) == 0
+    assert hashlib.sha256(rgba.tobytes()).hexdigest() == fix["rgba"], "pixels differ from the reference binary"
