@@ -555,7 +555,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--inflight", type=int, default=6, help="frames in flight (contexts/streams) for value and e2e")
+    ap.add_argument("--inflight", type=int, default=4, help="frames in flight (contexts/streams) for value and e2e")
     args = ap.parse_args()
     if args.steps is None:
         args.steps = 20 if args.impl == "reference" else 400

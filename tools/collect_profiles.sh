@@ -3,7 +3,7 @@
 set -e
 cd "$(dirname "$0")/.."
 o=gpurun_out
-cp $o/r02_bench.json $o/r02_bench_reference.json $o/r02_launches.csv $o/r02_launches_inflight6.csv $o/r02_perf_scenes.txt \
+cp $o/r02_bench.json $o/r02_bench_reference.json $o/r02_launches.csv $o/r02_launches_inflight4.csv $o/r02_perf_scenes.txt \
    $o/r02_fill_stats.txt $o/r02_fill_stats_1m.txt $o/r02_perf_game.txt profiles/
 cp $o/r02_sanitizer.txt profiles/r02_compute_sanitizer.txt
 cp $o/r02_pytest.log profiles/r02_pytest_gpu.txt
