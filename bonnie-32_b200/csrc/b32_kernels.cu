@@ -602,7 +602,7 @@ k_setup(const b32_vertex* __restrict__ verts, const b32_face* __restrict__ faces
         __syncthreads();                                   // the masks are reused by the next group of a persistent CTA
     }
     // one pair of global atomics per block
-    for (int o = 16; o > 0; o >>= 1) { n_op += __shfl_xor_sync(0xFFFFFFFFu, n_op, o); n_tr += __shfl_xor_sync(0xFFFFFFFFu, n_tr, o); }
+    n_op = __reduce_add_sync(0xFFFFFFFFu, n_op); n_tr = __reduce_add_sync(0xFFFFFFFFu, n_tr);      // REDUX: one instruction each
     __syncthreads();
     if ((threadIdx.x & 31) == 0) { if (n_op) atomicAdd(&s_cnt[0], n_op); if (n_tr) atomicAdd(&s_cnt[1], n_tr); }
     __syncthreads();
