@@ -153,6 +153,8 @@ SYMBOLS = {
     "b32_render_mesh_resident": (C.c_int, [_P, _P, C.POINTER(Camera), C.POINTER(Settings), C.POINTER(Timings)]),
     "b32_frame_15_enqueue": (C.c_int, [_P, _P, _P, C.POINTER(Camera), C.POINTER(Settings), C.POINTER(Fog)]),
     "b32_graph_launches": (C.c_uint64, [_P]),
+    "b32_ctx_frame_timings": (C.c_int, [_P, C.c_int]),
+    "b32_frame_timings": (C.c_int, [_P, C.POINTER(Timings)]),
     "b32_render_skybox_mesh": (C.c_int, [_P, _P, C.c_uint32, _P, C.c_uint32, C.POINTER(Camera)]),
     "b32_host_alloc": (_P, [C.c_size_t]),
     "b32_host_free": (None, [_P]),

@@ -128,6 +128,12 @@ struct b32_ctx {
     CallState* state_h = nullptr;      // pinned host
     HostStatus* hstat = nullptr;       // pinned + mapped: what a blocking call's kernels publish (b32_device.cuh)
     HostStatus* hstat_dev = nullptr;   // ... its device address
+    // opt-in (b32_ctx_frame_timings): enqueued frames report the same way, into a ring of status blocks
+    static constexpr uint32_t N_FRAME_STATUS = 8;
+    HostStatus* fstat = nullptr; HostStatus* fstat_dev = nullptr;
+    struct FrameSlot { uint32_t seq = 0; uint8_t last = 0, pass1 = 0, ordered = 0; } fslot[N_FRAME_STATUS];
+    uint32_t fslot_next = 0;
+    bool frame_timings = false;
     uint32_t host_seq = 0;
     uint8_t* pinned = nullptr;         // pinned staging ring for pageable host buffers
     size_t pinned_bytes = 0;
@@ -501,6 +507,14 @@ int render_device(b32_ctx* ctx, const b32_vertex* d_verts, uint32_t nv, const b3
         key.verts = d_verts; key.faces = d_faces; key.nv = nv; key.nf = nf; key.width = ctx->width; key.height = ctx->height;
         key.rgb888 = rgb888; key.pass1 = !((p.xray_mode && !rgb888) || p.wire_front); key.clear = a.clear; key.valid = 1;
         key.ordered = p.enq_ordered;
+        if (ctx->frame_timings) {                          // the frame's kernels publish counters + times (b32_frame_timings reads them)
+            const uint32_t slot = ctx->fslot_next++ % b32_ctx::N_FRAME_STATUS;
+            b32_ctx::FrameSlot& fs = ctx->fslot[slot];
+            fs.seq = ++ctx->host_seq; fs.pass1 = key.pass1; fs.ordered = p.enq_ordered && !p.wire_front;
+            fs.last = fs.ordered ? HS_ORDERED : fs.pass1 ? HS_FILL : HS_SETUP;
+            p.host = ctx->fstat_dev + slot; p.host_seq = fs.seq;
+            ctx->last_params = p;
+        }
         return enqueue_frame(ctx, a, key);
     }
     // Blocking call: no events, no copy back.  The kernels report in host-mapped memory (HostStatus): k_setup's last CTA
@@ -609,6 +623,7 @@ void b32_ctx_destroy(b32_ctx* ctx) {
     if (ctx->sticky) cudaFree(ctx->sticky);
     if (ctx->state_h) cudaFreeHost(ctx->state_h);
     if (ctx->hstat) cudaFreeHost(ctx->hstat);
+    if (ctx->fstat) cudaFreeHost(ctx->fstat);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->h2d_ev) if (ev) cudaEventDestroy(ev);
@@ -870,6 +885,37 @@ int b32_frame_15_enqueue(b32_ctx* ctx, const uint8_t* clear_rgba, const b32_mesh
 }
 
 uint64_t b32_graph_launches(const b32_ctx* ctx) { return ctx ? ctx->graph_launches : 0; }
+
+int b32_ctx_frame_timings(b32_ctx* ctx, int enable) {
+    USE_DEVICE(ctx);
+    if (!ctx) return B32_ERR_INVALID;
+    if (enable && !ctx->fstat) {
+        CK(cudaHostAlloc(&ctx->fstat, sizeof(HostStatus) * b32_ctx::N_FRAME_STATUS, cudaHostAllocMapped));
+        std::memset(ctx->fstat, 0, sizeof(HostStatus) * b32_ctx::N_FRAME_STATUS);
+        CK(cudaHostGetDevicePointer(&ctx->fstat_dev, ctx->fstat, 0));
+    }
+    ctx->frame_timings = enable != 0;
+    return B32_OK;
+}
+
+int b32_frame_timings(b32_ctx* ctx, b32_timings* out) {
+    if (!ctx || !out) return B32_ERR_INVALID;
+    std::memset(out, 0, sizeof(*out));
+    if (!ctx->fstat) return fail(ctx, B32_ERR_INVALID, "b32_ctx_frame_timings was not enabled");
+    // newest first: the most recent enqueued frame whose last kernel has reported
+    for (uint32_t back = 1; back <= b32_ctx::N_FRAME_STATUS && back <= ctx->fslot_next; ++back) {
+        const uint32_t slot = (ctx->fslot_next - back) % b32_ctx::N_FRAME_STATUS;
+        const b32_ctx::FrameSlot& fs = ctx->fslot[slot];
+        const HostStatus& h = ctx->fstat[slot];
+        if (!fs.seq || __atomic_load_n(&h.stamp[fs.last].seq, __ATOMIC_ACQUIRE) != fs.seq) continue;
+        auto ms = [&](int k) { const KernelStamp& t = h.stamp[k]; return (t.seq == fs.seq && t.t1 > t.t0) ? (float)((double)(t.t1 - t.t0) * 1e-6) : 0.0f; };
+        out->cull_ms = ms(HS_SETUP);                        // transform + cull + setup are one kernel (see b32_timings)
+        out->draw_ms = (fs.pass1 ? ms(HS_FILL) : 0.0f) + (fs.ordered ? ms(HS_ORDERED) : 0.0f);
+        out->triangles_drawn = h.state.n_opaque + h.state.n_transp;
+        return B32_OK;
+    }
+    return B32_OK;                                          // nothing has finished yet: zeros
+}
 
 int b32_fb_download_async(b32_ctx* ctx, uint8_t* rgba, float* z) {
     USE_DEVICE(ctx);

@@ -255,6 +255,13 @@ int  b32_frame_15_enqueue(b32_ctx* ctx, const uint8_t* clear_rgba, const b32_mes
                           const b32_camera* camera, const b32_settings* settings, const b32_fog* fog_or_null);
 /* Number of frames launched as graphs on this context so far. */
 uint64_t b32_graph_launches(const b32_ctx* ctx);
+/* RasterTimings for frames that were only enqueued (the debug overlay of src/game/renderer.rs:735-980 wants them every
+ * frame, and an enqueue has nothing to return yet).  Opt-in per context, because the frame's kernels then publish
+ * their counters and %globaltimer stamps in host-mapped memory (one atomic per CTA).  b32_frame_timings never blocks: it
+ * fills `out` from the most recent enqueued frame that has finished (all zeros while none has).  cull_ms = the fused
+ * transform + cull + setup kernel, draw_ms = pass 1 + pass 2, triangles_drawn exact; the other fields stay 0. */
+int b32_ctx_frame_timings(b32_ctx* ctx, int enable);
+int b32_frame_timings(b32_ctx* ctx, b32_timings* out);
 
 /* Placed asset parts: render_asset_parts (src/scene.rs:109-169) draws one mesh part per render_mesh* call after
  * rotating its vertices about Y by the object's `facing` and translating them to `world_pos` on the host, every frame.

@@ -1145,3 +1145,34 @@ def test_skybox_against_reference_binary_directly(ctx):
             bad = (arr[key + "_frame"] != got).any(-1)
             assert not bad.any(), (key, int(bad.sum()), np.argwhere(bad)[0][::-1])
         assert hashlib.sha256(got.tobytes()).hexdigest() == m["rgba"], key
+
+
+def test_frame_timings_of_enqueued_frames(oracle):
+    """b32_ctx_frame_timings / b32_frame_timings: RasterTimings (types.rs:1499-1514) for frames that were only enqueued —
+    exact triangles_drawn, kernel times from the device's own clock, no effect on the pixels, never blocks."""
+    import ctypes as C
+    c = pkg.Context(0)
+    try:
+        lib = c.lib
+        tm = abi.Timings()
+        assert lib.b32_frame_timings(c.h, C.byref(tm)) == abi.B32_ERR_INVALID         # not enabled yet
+        c.check(lib.b32_ctx_frame_timings(c.h, 1))
+        c.check(lib.b32_frame_timings(c.h, C.byref(tm)))
+        assert tm.triangles_drawn == 0 and tm.draw_ms == 0.0                       # nothing has finished
+        by = {s.name: s for s in cases.feature_scenes(400)}
+        for sc in (scenes.scene_c2(n_tris=700), by["mixed_zbuffer"], by["xray"]):
+            want, want_z, otm, rc = oracle.render_scene(sc)
+            fb = pkg.Framebuffer(sc.width, sc.height, c)
+            c.set_textures(sc.textures)
+            mesh = pkg.Mesh(c, sc.vertices, sc.faces)
+            for _ in range(4):                                                    # plain launches, then graph replays
+                mesh.frame_enqueue(sc.clear, sc.camera, sc.settings, sc.fog)
+            got, got_z = fb.download()
+            assert np.array_equal(got, want) and np.array_equal(got_z.view(np.uint32), want_z.view(np.uint32)), sc.name
+            c.check(lib.b32_frame_timings(c.h, C.byref(tm)))
+            assert tm.triangles_drawn == otm["triangles_drawn"], sc.name
+            assert 0.0 < tm.cull_ms < 5.0 and 0.0 < tm.draw_ms < 50.0, (sc.name, tm.cull_ms, tm.draw_ms)
+            mesh.free()
+        c.check(lib.b32_ctx_frame_timings(c.h, 0))
+    finally:
+        c.close()
