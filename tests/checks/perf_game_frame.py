@@ -1,9 +1,9 @@
-"""The game's frame (src/game/renderer.rs:91-179: clear, skybox sphere + stars, the level's rooms, debug lines, read-back
+"""TEST INFRASTRUCTURE (uses the oracle as the checker; lives under tests/ for that reason).  The game's frame (src/game/renderer.rs:91-179: clear, skybox sphere + stars, the level's rooms, debug lines, read-back
 for present) on the sample levels at the game's 640x480: device path (wall clock, one download per frame) against the CPU
 oracle doing the same calls on one core.  GPU box only; fixtures from tests/golden (no reference tree needed)."""
 import os, sys, time
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import __graft_entry__ as entry
 pkg = entry.load_package()

@@ -1,7 +1,7 @@
-"""Time b32_draw_lines against the CPU oracle on the test line lists (blocking call, pageable host list)."""
+"""TEST INFRASTRUCTURE (uses the oracle as the checker; lives under tests/ for that reason).  Time b32_draw_lines against the CPU oracle on the test line lists (blocking call, pageable host list)."""
 import os, sys, time
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import __graft_entry__ as entry
 pkg = entry.load_package()

@@ -1,4 +1,4 @@
-"""Small end-to-end run for compute-sanitizer (GPU box): every kernel of the library on small scenes, checked vs the oracle."""
+"""TEST INFRASTRUCTURE (uses the oracle as the checker; lives under tests/ for that reason).  Small end-to-end run for compute-sanitizer (GPU box): every kernel of the library on small scenes, checked vs the oracle."""
 import sys
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 import numpy as np
