@@ -105,6 +105,25 @@ def test_product_never_imports_the_oracle():
     assert not bad, bad
 
 
+def test_only_tests_smoke_and_bench_touch_the_oracle():
+    """Outside oracle/ itself, only tests/, __graft_entry__ (build + smoke) and bench.py (its CPU legs) may import or load
+    anything of the oracle: the measurement tools and the Rust shim must not."""
+    bad = []
+    for base in ("tools", "rust"):
+        for dp, _, files in os.walk(os.path.join(ROOT, base)):
+            for fn in files:
+                txt = open(os.path.join(dp, fn), errors="ignore").read()
+                if re.search(r"from oracle|import oracle|libb32oracle|b32o_|pymodel", txt):
+                    bad.append(os.path.join(dp, fn))
+    assert not bad, bad
+    # bench.py: the oracle is loaded inside time_oracle / _oracle_worker only (cpu_baseline and --impl reference)
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    for m in re.finditer(r"from oracle import|import oracle", src):
+        head = src[:m.start()]
+        fn = re.findall(r"^def (\w+)", head, flags=re.M)[-1]
+        assert fn in ("time_oracle", "_oracle_worker", "_oracle_worker_init"), fn
+
+
 def test_built_for_sm100a_with_exact_arithmetic_flags():
     """The cubin targets sm_100a and is compiled without FMA contraction / with IEEE div+sqrt, no FTZ.
     (FFMA still appears in SASS inside the correctly-rounded division sequences, so the flags — and
