@@ -99,10 +99,22 @@ sc = scenes.scene_c4(n_tris=2000)
 v, f, flags = abi.compact_buffers(sc.vertices, sc.faces, True)
 fb = pkg.Framebuffer(sc.width, sc.height, ctx); fb.clear(sc.clear); ctx.set_textures(sc.textures)
 cam = sc.camera.to_abi(); st, keep = sc.settings.to_abi()
-ctx.check(ctx.lib.b32_render_mesh_15_ex(ctx.h, v.ctypes.data, len(v), f.ctypes.data, len(f), C.byref(cam), C.byref(st), None, flags, None))
-got, gz = fb.download()
 want, wz, _, rc = orc.render_scene(sc)
-ok = np.array_equal(got, want) and np.array_equal(gz.view(np.uint32), wz.view(np.uint32)); print("compact_marshalling", "OK" if ok else "MISMATCH"); bad += not ok
+fl = np.ascontiguousarray(sc.faces["flags"])
+for name, f_, flags_ in (("compact_marshalling_uniform", f, flags), ("compact_marshalling_implicit", fl, (flags & ~abi.FACES_UNIFORM) | abi.FACES_IMPLICIT)):
+    fb.clear(sc.clear)
+    ctx.check(ctx.lib.b32_render_mesh_15_ex(ctx.h, v.ctypes.data, len(v), f_.ctypes.data, len(sc.faces), C.byref(cam), C.byref(st), None, flags_, None))
+    got, gz = fb.download()
+    ok = np.array_equal(got, want) and np.array_equal(gz.view(np.uint32), wz.view(np.uint32)); print(name, "OK" if ok else "MISMATCH"); bad += not ok
+# enqueued frames that publish their timings (host-mapped status ring)
+ctx.check(ctx.lib.b32_ctx_frame_timings(ctx.h, 1))
+mesh = pkg.Mesh(ctx, sc.vertices, sc.faces)
+for _ in range(4):
+    mesh.frame_enqueue(sc.clear, sc.camera, sc.settings)
+got, gz = fb.download()
+tmx = abi.Timings(); ctx.check(ctx.lib.b32_frame_timings(ctx.h, C.byref(tmx)))
+ok = np.array_equal(got, want) and tmx.triangles_drawn > 0 and tmx.draw_ms > 0; print("frame_timings_enqueued", "OK" if ok else "MISMATCH"); bad += not ok
+ctx.check(ctx.lib.b32_ctx_frame_timings(ctx.h, 0))
 sc = cases._with(by["mixed_zbuffer"], "mixed_1920x1080", width=1920, height=1080)
 fb = pkg.Framebuffer(sc.width, sc.height, ctx); fb.clear(sc.clear)
 pkg.render_mesh_15(fb, sc.vertices, sc.faces, sc.textures, sc.camera, sc.settings, sc.fog)

@@ -12,5 +12,5 @@ build/call_overhead >> gpurun_out/r02_perf_scenes.txt 2>&1
 python tools/fill_stats.py > gpurun_out/r02_fill_stats.txt 2>&1
 python tools/fill_stats_1m.py > gpurun_out/r02_fill_stats_1m.txt 2>&1
 python tests/checks/perf_game_frame.py > gpurun_out/r02_perf_game.txt 2>&1
-for t in memcheck racecheck synccheck; do echo "== $t" >> gpurun_out/r02_sanitizer.txt; timeout 900 compute-sanitizer --tool $t python tests/checks/sanitize_run.py 2>&1 | tail -60 >> gpurun_out/r02_sanitizer.txt; done
+bash tools/sanitize.sh
 cat gpurun_out/r02_pytest.log; tail -3 gpurun_out/r02_bench.err
