@@ -72,6 +72,24 @@ def test_face_flags_packing():
     assert int(abi.face_flags()) == 0xFFFF | (1 << 19) | (255 << 24)
 
 
+def test_compact_marshalling_choice():
+    """What a shim sends through b32_render_mesh_15_ex (abi.compact_buffers = rust/b32_shim.rs marshal_compact): normals are
+    dropped only when nothing shades; an unindexed soup sends no indices; one flags word when all faces share it."""
+    from bonnie32_b200 import scenes
+    sc = scenes.scene_c4(n_tris=500)
+    v, f, flags = abi.compact_buffers(sc.vertices, sc.faces, True)
+    assert flags == abi.VTX_NO_NORMAL | abi.FACES_UNIFORM and v.dtype == abi.VERTEX_NN_DTYPE and f.shape == (1,) and f.dtype == np.uint32
+    assert v.nbytes + f.nbytes == 500 * 3 * 24 + 4 and np.array_equal(v["pos"], sc.vertices["pos"]) and f[0] == sc.faces["flags"][0]
+    v, f, flags = abi.compact_buffers(sc.vertices, sc.faces, False)          # something shades: the normals travel
+    assert flags == abi.FACES_UNIFORM and v.dtype == abi.VERTEX_DTYPE
+    f2 = sc.faces.copy(); f2["flags"][7] = abi.face_flags(0, abi.BLEND_ADD, True, 255)
+    v, f, flags = abi.compact_buffers(sc.vertices, f2, True)                 # mixed flags: one word per face
+    assert flags == abi.VTX_NO_NORMAL | abi.FACES_IMPLICIT and f.shape == (500,) and np.array_equal(f, f2["flags"])
+    f3 = sc.faces.copy(); f3["v"][3] = f3["v"][3][::-1]
+    v, f, flags = abi.compact_buffers(sc.vertices, f3, True)                 # not a soup in order: the full face records
+    assert flags == abi.VTX_NO_NORMAL and f.dtype == abi.FACE_DTYPE and len(f) == 500
+
+
 def test_no_cpu_fallback_without_gpu():
     """Without a CUDA device context creation fails loudly; nothing renders on the CPU."""
     import torch
