@@ -152,6 +152,22 @@ fn marshal_camera(camera: &Camera) -> b32_camera {
         basis_z: [camera.basis_z.x, camera.basis_z.y, camera.basis_z.z] }
 }
 
+/// `RasterTimings` of the most recent finished frame that was only ENQUEUED (`b32_frame_15_enqueue`, the resident /
+/// placed calls with `B32_RENDER_ASYNC`): what the game's debug overlay shows (src/game/renderer.rs:735-980).  Never
+/// blocks; all zeros until a frame has finished.  Call `enable_frame_timings(true)` once first.
+pub fn enable_frame_timings(on: bool) {
+    extern "C" { fn b32_ctx_frame_timings(ctx: *mut b32_ctx, enable: c_int) -> c_int; }
+    CTX.with(|&ctx| unsafe { check(ctx, b32_ctx_frame_timings(ctx, on as c_int)) })
+}
+pub fn frame_timings() -> RasterTimings {
+    extern "C" { fn b32_frame_timings(ctx: *mut b32_ctx, out: *mut b32_timings) -> c_int; }
+    CTX.with(|&ctx| unsafe {
+        let mut tm = b32_timings::default();
+        check(ctx, b32_frame_timings(ctx, &mut tm));
+        timings(&tm)
+    })
+}
+
 fn timings(tm: &b32_timings) -> RasterTimings {
     RasterTimings { transform_ms: tm.transform_ms, fog_ms: tm.fog_ms, cull_ms: tm.cull_ms, sort_ms: tm.sort_ms,
                     draw_ms: tm.draw_ms, wireframe_ms: tm.wireframe_ms, triangles_drawn: tm.triangles_drawn }
