@@ -78,49 +78,87 @@ fn face_flags(f: &Face) -> u32 {
     tex | ((blend_u8(f.blend_mode) as u32) << 16) | ((f.black_transparent as u32) << 19) | ((f.editor_alpha as u32) << 24)
 }
 
-/// The bytes that cross PCIe, in the most compact layout the call allows (include/b32_raster.h, B32_VTX_NO_NORMAL /
-/// B32_FACES_IMPLICIT): normals are only read when the settings shade (render.rs:1466-1483), and an unindexed triangle
-/// soup (face i = vertices 3i, 3i+1, 3i+2) needs no index buffer — and when all its faces carry the same flags word
-/// (one texture, one blend mode: the usual room or asset part) that one word is all that is sent.  All of it is decided
-/// while the slices are converted anyway; the rendered bytes are identical.  Returns (vertex bytes, face bytes, flags).
-fn marshal_compact(vertices: &[Vertex], faces: &[Face], settings: &RasterSettings) -> (Vec<u8>, Vec<u8>, u32) {
-    let mut flags = 0u32;
-    let as_bytes = |p: *const u8, n: usize| unsafe { std::slice::from_raw_parts(p, n) }.to_vec();
-    let vb = if settings.shading == ShadingMode::None {
-        flags |= B32_VTX_NO_NORMAL;
-        let v: Vec<b32_vertex_nn> = vertices.iter().map(|v| b32_vertex_nn {
-            pos: [v.pos.x, v.pos.y, v.pos.z], uv: [v.uv.x, v.uv.y], r: v.color.r, g: v.color.g, b: v.color.b, blend: blend_u8(v.color.blend) }).collect();
-        as_bytes(v.as_ptr() as *const u8, v.len() * 24)
-    } else {
-        let (v, _) = marshal_geometry(vertices, &[]);
-        as_bytes(v.as_ptr() as *const u8, v.len() * 36)
-    };
-    let soup = vertices.len() >= 3 * faces.len() && faces.iter().enumerate().all(|(i, f)| f.v0 == 3 * i && f.v1 == 3 * i + 1 && f.v2 == 3 * i + 2);
-    let fbytes = if soup {
-        let f: Vec<u32> = faces.iter().map(face_flags).collect();
-        if !f.is_empty() && f.iter().all(|&w| w == f[0]) {
-            flags |= B32_FACES_UNIFORM;
-            as_bytes(f.as_ptr() as *const u8, 4)
-        } else {
-            flags |= B32_FACES_IMPLICIT;
-            as_bytes(f.as_ptr() as *const u8, f.len() * 4)
+/// A pinned (page-locked) staging buffer that only grows: the marshalling below writes straight into it, so the
+/// upload is one DMA from where the bytes already are (b32_host_alloc, include/b32_raster.h) instead of a second copy
+/// through the library's staging ring.
+struct Pinned { ptr: *mut u8, cap: usize }
+impl Pinned {
+    const fn new() -> Self { Pinned { ptr: std::ptr::null_mut(), cap: 0 } }
+    fn reserve(&mut self, bytes: usize) -> *mut u8 {
+        extern "C" { fn b32_host_alloc(bytes: usize) -> *mut c_void; fn b32_host_free(p: *mut c_void); }
+        if bytes > self.cap {
+            unsafe {
+                if !self.ptr.is_null() { b32_host_free(self.ptr as *mut c_void); }
+                self.cap = bytes.next_power_of_two().max(1 << 16);
+                self.ptr = b32_host_alloc(self.cap) as *mut u8;
+                assert!(!self.ptr.is_null(), "b32_host_alloc failed");
+            }
         }
-    } else {
-        let (_, f) = marshal_geometry(&[], faces);
-        as_bytes(f.as_ptr() as *const u8, f.len() * 16)
-    };
-    (vb, fbytes, flags)
+        self.ptr
+    }
+}
+thread_local! {
+    static STAGE_V: std::cell::RefCell<Pinned> = std::cell::RefCell::new(Pinned::new());
+    static STAGE_F: std::cell::RefCell<Pinned> = std::cell::RefCell::new(Pinned::new());
+}
+
+/// The bytes that cross PCIe, in the most compact layout the call allows (include/b32_raster.h, B32_VTX_NO_NORMAL /
+/// B32_FACES_IMPLICIT / B32_FACES_UNIFORM): normals are only read when the settings shade (render.rs:1466-1483), an
+/// unindexed triangle soup (face i = vertices 3i, 3i+1, 3i+2) needs no index buffer, and when all its faces carry the
+/// same flags word (one texture, one blend mode: the usual room or asset part) that one word is all that is sent.  All
+/// of it is decided while the slices are converted anyway, and written once, into pinned memory; the rendered bytes are
+/// identical.  Returns (vertex bytes, face bytes, flags); the pointers stay valid until the next call on this thread.
+fn marshal_compact(vertices: &[Vertex], faces: &[Face], settings: &RasterSettings) -> (*const c_void, *const c_void, u32) {
+    let mut flags = 0u32;
+    let vp = STAGE_V.with(|st| {
+        let mut st = st.borrow_mut();
+        if settings.shading == ShadingMode::None {
+            flags |= B32_VTX_NO_NORMAL;
+            let out = st.reserve(vertices.len() * 24) as *mut b32_vertex_nn;
+            for (i, v) in vertices.iter().enumerate() {
+                unsafe { out.add(i).write(b32_vertex_nn { pos: [v.pos.x, v.pos.y, v.pos.z], uv: [v.uv.x, v.uv.y],
+                                                            r: v.color.r, g: v.color.g, b: v.color.b, blend: blend_u8(v.color.blend) }); }
+            }
+            out as *const c_void
+        } else {
+            let out = st.reserve(vertices.len() * 36) as *mut b32_vertex;
+            for (i, v) in vertices.iter().enumerate() { unsafe { out.add(i).write(vertex_record(v)); } }
+            out as *const c_void
+        }
+    });
+    let soup = vertices.len() >= 3 * faces.len() && faces.iter().enumerate().all(|(i, f)| f.v0 == 3 * i && f.v1 == 3 * i + 1 && f.v2 == 3 * i + 2);
+    let fp = STAGE_F.with(|st| {
+        let mut st = st.borrow_mut();
+        if soup {
+            let out = st.reserve(faces.len().max(1) * 4) as *mut u32;
+            let mut uniform = !faces.is_empty();
+            for (i, f) in faces.iter().enumerate() {
+                let w = face_flags(f);
+                unsafe { out.add(i).write(w); uniform = uniform && w == *out; }
+            }
+            flags |= if uniform { B32_FACES_UNIFORM } else { B32_FACES_IMPLICIT };
+            out as *const c_void
+        } else {
+            let out = st.reserve(faces.len().max(1) * 16) as *mut b32_face;
+            for (i, f) in faces.iter().enumerate() { unsafe { out.add(i).write(face_record(f)); } }
+            out as *const c_void
+        }
+    });
+    (vp, fp, flags)
+}
+
+fn vertex_record(v: &Vertex) -> b32_vertex {
+    b32_vertex { pos: [v.pos.x, v.pos.y, v.pos.z], uv: [v.uv.x, v.uv.y], normal: [v.normal.x, v.normal.y, v.normal.z],
+                 r: v.color.r, g: v.color.g, b: v.color.b, blend: blend_u8(v.color.blend) }
+}
+fn face_record(f: &Face) -> b32_face {
+    b32_face { v0: f.v0.min(u32::MAX as usize) as u32, v1: f.v1.min(u32::MAX as usize) as u32,
+               v2: f.v2.min(u32::MAX as usize) as u32, flags: face_flags(f) }
 }
 
 // --- marshal &[Vertex] / &[Face] into the 36 B / 16 B POD records (include/b32_raster.h) ---
 fn marshal_geometry(vertices: &[Vertex], faces: &[Face]) -> (Vec<b32_vertex>, Vec<b32_face>) {
-    let v = vertices.iter().map(|v| b32_vertex {
-        pos: [v.pos.x, v.pos.y, v.pos.z], uv: [v.uv.x, v.uv.y], normal: [v.normal.x, v.normal.y, v.normal.z],
-        r: v.color.r, g: v.color.g, b: v.color.b, blend: blend_u8(v.color.blend) }).collect();
-    let f = faces.iter().map(|f| b32_face {
-        v0: f.v0.min(u32::MAX as usize) as u32, v1: f.v1.min(u32::MAX as usize) as u32,
-        v2: f.v2.min(u32::MAX as usize) as u32, flags: face_flags(f) }).collect();
-    (v, f)
+    (vertices.iter().map(vertex_record).collect(), faces.iter().map(face_record).collect())
 }
 
 /// The returned Vec owns the lights `b32_settings.lights` points at: keep it alive across the call.
@@ -192,7 +230,7 @@ pub fn render_mesh_15(fb: &mut Framebuffer, vertices: &[Vertex], faces: &[Face],
         check(ctx, b32_fb_resize(ctx, fb.width as u32, fb.height as u32));
         check(ctx, b32_fb_upload(ctx, fb.pixels.as_ptr(), fb.zbuffer.as_ptr()));
         let mut tm = b32_timings::default();
-        check(ctx, b32_render_mesh_15_ex(ctx, v.as_ptr() as *const c_void, vertices.len() as u32, f.as_ptr() as *const c_void, faces.len() as u32,
+        check(ctx, b32_render_mesh_15_ex(ctx, v, vertices.len() as u32, f, faces.len() as u32,
                                          &cam, &s, fogc.as_ref().map_or(std::ptr::null(), |f| f as *const _), layout, &mut tm));
         check(ctx, b32_fb_download(ctx, fb.pixels.as_mut_ptr(), fb.zbuffer.as_mut_ptr()));
         timings(&tm)
