@@ -1682,6 +1682,7 @@ k_fill_ordered(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks
         //         group are issued together; only then are its fragments shaded and written one after the other.
         while (cov) {
             bool in[ORD_GROUP]; float fbx[ORD_GROUP], fby[ORD_GROUP], fz[ORD_GROUP]; uint32_t ftex[ORD_GROUP], fidx[ORD_GROUP];
+            bool nan_before = false;                       // an earlier fragment of this group has a NaN depth (see below)
             #pragma unroll
             for (int k = 0; k < ORD_GROUP; ++k) {
                 in[k] = false; fbx[k] = fby[k] = fz[k] = 0.0f; ftex[k] = 0; fidx[k] = 0;
@@ -1693,7 +1694,13 @@ k_fill_ordered(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks
                 if (!inside_test(r, x, y, bc_x, bc_y, bc_z)) continue;                  // (only the slow edge path can still fail)
                 float inv_z = bc_x * r.iz1 + bc_y * r.iz2 + bc_z * r.iz3;              // :1549
                 float z = 1.0f / inv_z;
-                if (early_z && z >= px.z) continue;        // px.z only ever decreases, so a reject now is a reject later
+                // A reject against the depth the pixel has NOW is a reject at the fragment's own time as long as the depth only
+                // decreases until then.  The one way it can rise is through a NaN: render_mesh's editor-alpha writer stores a
+                // NaN depth (`z >= zbuffer` is false, render.rs:393) and the next such fragment replaces it with any finite
+                // one.  A NaN depth can only come from a fragment whose own depth is NaN: after one of those in this group
+                // nothing is rejected early (the fold below applies the reference's test at its time).
+                if (early_z && !nan_before && z >= px.z) continue;
+                nan_before = nan_before || z != z;
                 in[k] = true; fbx[k] = bc_x; fby[k] = bc_y; fz[k] = z;
                 ftex[k] = sample_texel<RGB888>(r, bc_x, bc_y, bc_z, inv_z, tex, texels, p);
             }
