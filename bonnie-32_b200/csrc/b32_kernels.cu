@@ -1234,7 +1234,12 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks,
             if (kmin > kmax) { kmin = 0; kmax = 0; }
             uint32_t range = kmax - kmin;
             shift = range >= OP_BUCKETS ? (32 - __clz(range)) - OP_BUCKET_BITS : 0;         // (range >> shift) <= OP_BUCKETS - 1
-            auto bucket = [&](uint32_t k) { return k == 0xFFFFFFFFu ? 0u : (uint32_t)(OP_BUCKETS - 1) - ((k - kmin) >> shift); };
+            // Bucket 0 belongs to the "never cull" keys ALONE: within a bucket the order is arbitrary, and the early-out
+            // below takes the top of the current entry's bucket as the bound of everything still to come — a never-cull
+            // entry behind a bounded one of the same bucket would be skipped by a bound that does not hold for it.  (Found
+            // by the extended fuzz: ortho + z-buffer scenes, where both kinds of key occur, differed from run to run.)
+            // The two highest key quanta therefore share bucket 1.
+            auto bucket = [&](uint32_t k) { return k == 0xFFFFFFFFu ? 0u : (uint32_t)(OP_BUCKETS - 1) - min((k - kmin) >> shift, (uint32_t)(OP_BUCKETS - 2)); };
             for_each_entry([&](const BinHead& h) { atomicAdd(&s_hist[bucket(h.key)], 1u); });
             __syncthreads();
             uint32_t v = 0, xs = 0;                              // exclusive scan of the bucket counts (threads 0..OP_BUCKETS-1)
@@ -1315,7 +1320,9 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks,
                     uint32_t k0 = s_sh[base].key;
                     if (k0 != 0xFFFFFFFFu) {
                         // upper bound of every key still to come = top of k0's bucket
-                        uint64_t ub64 = (uint64_t)kmin + (((uint64_t)((k0 - kmin) >> shift) + 1) << shift) - 1;
+                        uint64_t q0 = (k0 - kmin) >> shift;
+                        if (q0 >= (uint64_t)(OP_BUCKETS - 2)) q0 = OP_BUCKETS - 1;          // bucket 1 holds the two highest quanta
+                        uint64_t ub64 = (uint64_t)kmin + ((q0 + 1) << shift) - 1;
                         uint32_t ub = ub64 > 0xFFFFFFFEull ? 0xFFFFFFFEu : (uint32_t)ub64;
                         if (!p.use_zbuffer) { if (ub < wkey) { done = true; break; } }    // every later surface was drawn before every winner
                         else if (__uint_as_float(~ub) > wz) { done = true; break; }   // every later surface is behind every pixel

@@ -49,3 +49,16 @@ if bad.any() or badz.any():
     for k in f["v"]:
         v = sc.vertices[k]; print("   v", k, v["pos"], v["uv"], v["normal"], v["rgba"])
     print("lights", [(int(l.type), l.position, l.direction, l.radius, l.intensity, l.color, l.enabled) for l in s.lights], "ambient", s.ambient)
+
+# ---- the same frame enqueued (sparse fill shape, folded clear, ordered pass behind pass 1) ------------------------------
+if not rgb888:
+    mesh = pkg.Mesh(ctx, sc.vertices, sc.faces)
+    ctx.set_textures(sc.textures)
+    for _ in range(3):
+        mesh.frame_enqueue(sc.clear, sc.camera, sc.settings, sc.fog)
+    g2, gz2 = fb.download()
+    b2 = (g2 != want).any(-1); bz2 = (gz2.view(np.uint32) != want_z.view(np.uint32)) & ~(np.isnan(gz2) & np.isnan(want_z))
+    print("ENQUEUED: pixels differ", int(b2.sum()), "z differ", int(bz2.sum()))
+    ys, xs = np.nonzero(b2 | bz2)
+    for y, x in list(zip(ys, xs))[:8]:
+        print("  ", (x, y), "got", g2[y, x], gz2[y, x], "want", want[y, x], want_z[y, x])

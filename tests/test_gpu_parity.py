@@ -579,6 +579,29 @@ def test_fuzz_regressions_nan_depth_in_render_mesh(ctx, oracle, seed, n_tris):
     assert_same(sc, got, got_z, tm, want, want_z, otm)
 
 
+@pytest.mark.parametrize("seed", [115649, 109344])
+def test_fuzz_regression_never_cull_keys_walk_first(ctx, oracle, seed):
+    """Found by tests/checks/fuzz_extended.py (40 000 scenes): ortho + z-buffer frames, where some surfaces claim no depth
+    bound (walk key 0xFFFFFFFF) and others do, differed from run to run in about every second run — a no-bound surface that
+    shared the top key bucket with bounded ones could land behind them and be skipped by their bound.  Repeated, because
+    the order inside a bucket comes from shared-memory atomics."""
+    sc = fuzz.fuzz_scene(seed, False, n_tris=1500)
+    want, want_z, otm, rc = oracle.render_scene(sc)
+    assert rc == 0
+    fb = pkg.Framebuffer(sc.width, sc.height, ctx)
+    ctx.set_textures(sc.textures)
+    mesh = pkg.Mesh(ctx, sc.vertices, sc.faces)
+    for rep in range(10):
+        fb.clear(sc.clear)
+        tm = mesh.render(sc.camera, sc.settings, sc.fog)
+        got, got_z = fb.download()
+        assert_same(sc, got, got_z, tm, want, want_z, otm)
+        mesh.frame_enqueue(sc.clear, sc.camera, sc.settings, sc.fog)
+        got, got_z = fb.download()
+        assert_same(sc, got, got_z, tm, want, want_z, otm)
+    mesh.free()
+
+
 def test_two_devices_in_one_process(oracle):
     """A host thread that holds contexts on two GPUs: every entry point selects its context's device."""
     import torch
