@@ -1585,7 +1585,9 @@ k_fill_ordered(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks
     // ---- this tile's draw-order entries: the candidates that are in the ordered pass and touch the tile.  The unique
     //      64-bit key (pass:2 | depth key:32 | face:30) = opaque list first (sorted only in painter's mode), then the
     //      transparent list, ties by face index = stable sort (render.rs:2522-2542); RGB888: one list, no pass bit.
-    const bool in_smem_build = cs.total <= (uint32_t)ORD_SORT_MAX;
+    // The entries are collected in shared memory AND (when the tile has a slice of the scratch) in global memory: how many
+    // of the tile's candidates are ordered entries is only known afterwards; k_setup's count per mask tile (obin_max, checked
+    // above) guarantees a slice of at least that many whenever more than ORD_SORT_MAX can occur.
     BinHead* gslice = scratch + (size_t)tile * scratch_cap;
     if (threadIdx.x == 0) s_n = 0;
     for (uint32_t w0 = 0; w0 < cs.total; w0 += ORD_SORT_MAX) {
@@ -1605,7 +1607,8 @@ k_fill_ordered(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks
             const uint64_t okey = ((uint64_t)(RGB888 ? 0u : cls) << 62) | ((uint64_t)(uint32_t)k64 << 30) | fi;
             h.key = (uint32_t)(okey >> 32); h.face = (uint32_t)okey;
             const uint32_t pos = atomicAdd(&s_n, 1u);
-            if (in_smem_build) s_sorted[pos] = h; else if (pos < scratch_cap) gslice[pos] = h;
+            if (pos < (uint32_t)ORD_SORT_MAX) s_sorted[pos] = h;
+            if (pos < scratch_cap) gslice[pos] = h;
         }
         __syncthreads();
     }
@@ -1614,11 +1617,8 @@ k_fill_ordered(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks
     uint32_t m = 2;
     while (m < n) m <<= 1;                              // scratch_cap is a power of two >= n whenever the scratch is used
     BinHead* sorted;
-    if (in_smem_build) {
+    if (m <= (uint32_t)ORD_SORT_MAX) {
         for (uint32_t i = n + threadIdx.x; i < m; i += blockDim.x) s_sorted[i] = BinHead{0, 0, 0xFFFFFFFFu, 0xFFFFFFFFu};
-        sorted = s_sorted;
-    } else if (m <= (uint32_t)ORD_SORT_MAX) {
-        for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) s_sorted[i] = i < n ? gslice[i] : BinHead{0, 0, 0xFFFFFFFFu, 0xFFFFFFFFu};
         sorted = s_sorted;
     } else {
         for (uint32_t i = n + threadIdx.x; i < m; i += blockDim.x) gslice[i] = BinHead{0, 0, 0xFFFFFFFFu, 0xFFFFFFFFu};

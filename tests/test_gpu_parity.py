@@ -288,9 +288,13 @@ def test_crowded_tile(ctx, oracle):
     # windows meet a single over-full key bucket and take it in face order)
     v3 = v.copy()
     v3["pos"][:, 2] = np.float32(20.0)
+    # fourth variant: thousands of candidates in the tile but only a few hundred of them semi-transparent: the ordered pass
+    # meets a crowded mask row whose ordered entries fit shared memory, and no scratch exists (found by tests/checks/fuzz_big.py)
+    f4 = f.copy()
+    f4["flags"][::10] = abi.face_flags(abi.FACE_TEX_NONE, abi.BLEND_AVERAGE, True, 255)
     # last variant: a 1920x1080 framebuffer = coarse mask tiles (a fill tile's candidates include its neighbours' surfaces)
     for faces_, xray, verts_, size in ((f, False, v, (320, 240)), (f2, False, v, (320, 240)), (f2, True, v, (320, 240)),
-                                       (f, False, v3, (320, 240)), (f2, False, v, (1920, 1080))):
+                                       (f, False, v3, (320, 240)), (f4, False, v, (320, 240)), (f2, False, v, (1920, 1080))):
         for zbuf in (False, True):
             sc = scenes.Scene("crowded_tile", verts_, faces_, [], pkg.Camera(),
                               scenes.common_settings(use_zbuffer=zbuf, backface_cull=False, xray_mode=xray), width=size[0], height=size[1])
