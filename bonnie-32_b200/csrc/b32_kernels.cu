@@ -1565,6 +1565,8 @@ k_fill_ordered(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks
     {
         CallState s = *st;
         bool nothing = call_aborts(s, p.use_zbuffer, RGB888);
+        // enqueue-only callers learn of the reference's panics at the next sync; in x-ray mode this is the frame's only fill kernel
+        if (nothing && p.async_call && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(sticky, s.oob == 2 ? 32u : s.oob ? 1u : 2u);
         const uint32_t n_ordered = all_ordered ? s.n_opaque + s.n_transp : s.n_transp;
         nothing = nothing || n_ordered == 0 || (RGB888 && s.n_transp == 0);             // nothing to replay (the usual case of an enqueued frame)
         // k_setup counted the ordered entries per mask tile: a tile with more than fit shared memory needs a slice of the

@@ -33,11 +33,13 @@ for seed in range(first, first + n):
         code = lib.b32_render_mesh_15_ex(ctx.h, v_.ctypes.data, len(v_), f_.ctypes.data, len(sc.faces), C.byref(cam), C.byref(st),
                                          C.byref(fog) if fog is not None else None, flags | asyn, None)
         try:
-            got, got_z = fb.download()
+            ctx.sync()                                      # errors of an enqueue-only call surface here
         except pkg.B32Error as e:
             code = code or e.code
+        got, got_z = fb.download()
         if rc != 0 or code != 0:
-            if code != rc: print("MISMATCH (error code)", seed, asyn, code, rc); bad += 1
+            clear_px = np.array(list(sc.clear[:3]) + [255], np.uint8)
+            if code != rc or not (got == clear_px).all(): print("MISMATCH (error path)", seed, asyn, code, rc); bad += 1
             panics += 1
             continue
         zs = ((got_z.view(np.uint32) == want_z.view(np.uint32)) | (np.isnan(got_z) & np.isnan(want_z))).all()

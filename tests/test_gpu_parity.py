@@ -257,6 +257,18 @@ def test_enqueue_only_errors_surface_at_sync(ctx):
     assert e.value.code == abi.B32_ERR_OOB_INDEX
     assert np.array_equal(fb.download()[0], before)
     mesh.free()
+    # x-ray mode has no pass-1 kernel: the ordered replay reports the reference's panic (found by tests/checks/fuzz_compact.py)
+    import cases as _cases
+    from oracle import oracle as _orc
+    xs = scenes.common_settings(xray_mode=True)
+    vnan = _cases.nan_depth_vertices(dataclasses.replace(sc, settings=xs), _orc)
+    mesh = pkg.Mesh(ctx, vnan, sc.faces)
+    mesh.render(sc.camera, xs, None, enqueue_only=True)
+    with pytest.raises(pkg.B32Error) as e:
+        ctx.sync()
+    assert e.value.code == abi.B32_ERR_NAN_DEPTH
+    assert np.array_equal(fb.download()[0], before)
+    mesh.free()
     f = sc.faces.copy(); f["flags"][3] = abi.face_flags(0, 7, False, 255)        # not a BlendMode
     mesh = pkg.Mesh(ctx, sc.vertices, f)
     mesh.render(sc.camera, sc.settings, None, enqueue_only=True)
