@@ -1,7 +1,8 @@
 """TEST INFRASTRUCTURE (uses the oracle as the checker).  Fuzz of the shapes the ordinary fuzz does not reach: thousands of
 triangles in small framebuffers (crowded tiles: the scratch-slice path, over-full key buckets, the ordered pass's global sort)
 and in 1280x720 / 1920x1080 ones (coarse mask tiles), both colour paths, blocking and (RGB555) enqueued.
-usage (GPU box): python tests/checks/fuzz_big.py [n_scenes] [first_seed]"""
+usage (GPU box): python tests/checks/fuzz_big.py [n_scenes] [first_seed] [triangle counts, e.g. 1500,3000,4000]
+(counts of at most 4 096 get no crowded-tile scratch: their crowded tiles take the windows-in-list-order route)"""
 import dataclasses, os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -13,11 +14,12 @@ import fuzz
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 first = int(sys.argv[2]) if len(sys.argv) > 2 else 700000
+counts = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [4500, 6000, 12000]
 t0 = time.time(); bad = ok = panics = 0
 for seed in range(first, first + n):
     rng = np.random.default_rng(seed ^ 0xB16)
     rgb888 = bool(rng.random() < 0.35)
-    nt = int(rng.choice([4500, 6000, 12000]))
+    nt = int(rng.choice(counts))
     w, h = [(64, 64), (200, 150), (320, 240), (1280, 720), (1920, 1080)][int(rng.integers(0, 5))]
     sc = dataclasses.replace(fuzz.fuzz_scene(seed, rgb888, n_tris=nt), width=w, height=h)
     sc.settings.backface_wireframe = False; sc.settings.wireframe_overlay = False
@@ -57,6 +59,6 @@ for seed in range(first, first + n):
         ok += 1
     finally:
         ctx.close()
-print(f"seeds {first}..{first + n - 1}: {ok} identical frames, {panics} reference panics, 4 500 - 12 000 triangles, 64x64 .. 1920x1080")
+print(f"seeds {first}..{first + n - 1}: {ok} identical frames, {panics} reference panics, triangle counts {counts}, 64x64 .. 1920x1080")
 print(f"mismatches: {bad}   ({time.time() - t0:.0f} s)")
 sys.exit(1 if bad else 0)
