@@ -50,10 +50,10 @@ struct b32_mesh {
 struct FrameKey {
     const void* verts = nullptr; const void* faces = nullptr;
     uint32_t nv = 0, nf = 0, width = 0, height = 0;
-    uint8_t rgb888 = 0, pass1 = 0, clear = 0, valid = 0, ordered = 0;
+    uint8_t rgb888 = 0, pass1 = 0, clear = 0, valid = 0, ordered = 0, spot = 0;
     bool operator==(const FrameKey& o) const {
         return verts == o.verts && faces == o.faces && nv == o.nv && nf == o.nf && width == o.width && height == o.height &&
-               rgb888 == o.rgb888 && pass1 == o.pass1 && clear == o.clear && valid == o.valid && ordered == o.ordered;
+               rgb888 == o.rgb888 && pass1 == o.pass1 && clear == o.clear && valid == o.valid && ordered == o.ordered && spot == o.spot;
     }
 };
 struct FrameGraph {
@@ -223,16 +223,13 @@ int fill_params(b32_ctx* ctx, CallParams& p, const b32_camera* cam, const b32_se
     for (uint32_t i = 0; i < s->n_lights; ++i) {
         const b32_light& l = s->lights[i];
         if (l.type > B32_LIGHT_SPOT) return fail(ctx, B32_ERR_INVALID, "light type out of range");
-        // Spot lights use libm acos (render.rs:1047), not bit-reproducible on the device.  The app never
-        // constructs them (scene.rs:62 only makes point lights); only enabled lights matter (:1018).
-        if (l.type == B32_LIGHT_SPOT && l.enabled && s->shading != B32_SHADE_NONE)
-            return fail(ctx, B32_ERR_UNSUPPORTED, "enabled Spot light: libm acos is not reproducible on the device");
         LightDev d{};
         d.type = l.type; d.px = l.position[0]; d.py = l.position[1]; d.pz = l.position[2];
         d.dx = l.direction[0]; d.dy = l.direction[1]; d.dz = l.direction[2];
         d.radius = l.radius; d.angle = l.angle; d.intensity = l.intensity;
         d.cr = (float)l.r / 255.0f; d.cg = (float)l.g / 255.0f; d.cb = (float)l.b / 255.0f;   // render.rs:1062-1064
-        d.enabled = l.enabled && l.type != B32_LIGHT_SPOT;
+        d.enabled = l.enabled;
+        if (l.type == B32_LIGHT_SPOT && l.enabled && s->shading != B32_SHADE_NONE) p.has_spot = 1;
         lights.push_back(d);
     }
     p.n_lights = (uint32_t)lights.size();
@@ -506,7 +503,7 @@ int render_device(b32_ctx* ctx, const b32_vertex* d_verts, uint32_t nv, const b3
         FrameKey key;
         key.verts = d_verts; key.faces = d_faces; key.nv = nv; key.nf = nf; key.width = ctx->width; key.height = ctx->height;
         key.rgb888 = rgb888; key.pass1 = !((p.xray_mode && !rgb888) || p.wire_front); key.clear = a.clear; key.valid = 1;
-        key.ordered = p.enq_ordered;
+        key.ordered = p.enq_ordered; key.spot = p.has_spot;
         if (ctx->frame_timings) {                          // the frame's kernels publish counters + times (b32_frame_timings reads them)
             const uint32_t slot = ctx->fslot_next++ % b32_ctx::N_FRAME_STATUS;
             b32_ctx::FrameSlot& fs = ctx->fslot[slot];

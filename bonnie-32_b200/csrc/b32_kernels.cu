@@ -166,7 +166,45 @@ __device__ __forceinline__ V3 normalize3(V3 a) {                      // math.rs
     return V3{a.x / l, a.y / l, a.z / l};
 }
 
-// render.rs:1013-1071 (Directional + Point; Spot is rejected on the host with B32_ERR_UNSUPPORTED)
+// f32::acos as the reference's shipped wasm build computes it (compiler_builtins' libm `acosf`, a port of musl's
+// e_acosf.c; render.rs:1047 calls it): plain f32 operators, one rounding each (the library is compiled with
+// -fmad=false; sqrtf / division are the IEEE ones).
+__device__ __forceinline__ float acosf_rpoly(float z) {
+    float p = z * (0.16666586697101593f + z * (-0.04274342209100723f + z * -0.008656363002955914f));
+    float q = z * -0.7066296339035034f + 1.0f;
+    return p / q;
+}
+__device__ __forceinline__ float ref_acosf(float x) {
+    const float pio2_hi = 1.570796251296997f, pio2_lo = 7.549789415861596e-08f;
+    uint32_t hx = __float_as_uint(x), ix = hx & 0x7fffffffu;
+    if (ix >= 0x3f800000u) {
+        if (ix == 0x3f800000u) return (hx >> 31) ? 3.141592502593994f : 0.0f;
+        return 0.0f / (x - x);
+    }
+    if (ix < 0x3f000000u) {
+        if (ix <= 0x32800000u) return pio2_hi;
+        return pio2_hi - (x - (pio2_lo - x * acosf_rpoly(x * x)));
+    }
+    if (hx >> 31) {
+        float z = (1.0f + x) * 0.5f;
+        float s = sqrtf(z);
+        float w = acosf_rpoly(z) * s - pio2_lo;
+        float t = pio2_hi - (s + w);
+        return t + t;
+    }
+    float z = (1.0f - x) * 0.5f;
+    float s = sqrtf(z);
+    float df = __uint_as_float(__float_as_uint(s) & 0xfffff000u);
+    float c = (z - df * df) / (s + df);
+    float w = acosf_rpoly(z) * s + c;
+    float t = df + w;
+    return t + t;
+}
+
+// render.rs:1013-1071 (Directional, Point, Spot).  SPOT = false compiles the kernel the usual scenes run (the app only
+// constructs point lights, scene.rs:62): the acos path costs registers in k_setup, so calls with an enabled Spot light
+// run a second instantiation.
+template <bool SPOT>
 __device__ void shade_multi_light_color(V3 n, V3 wp, const LightDev* __restrict__ lights, uint32_t nl, float ambient, float* out) {
     float tr = ambient, tg = ambient, tb = ambient;
     for (uint32_t i = 0; i < nl; ++i) {
@@ -183,9 +221,23 @@ __device__ void shade_multi_light_color(V3 n, V3 wp, const LightDev* __restrict_
             if (dist > L.radius || dist < 0.001f) {
                 contribution = 0.0f;
             } else {
-                float att = 1.0f - (dist / L.radius);
-                float ndl = fmaxf(dot3(n, normalize3(to_light)), 0.0f);
-                contribution = ndl * L.intensity * att * att;
+                V3 tl = normalize3(to_light);
+                float edge = 1.0f;
+                bool lit = true;
+                if (SPOT && L.type == B32_LIGHT_SPOT) {                           // render.rs:1045-1053
+                    V3 neg{tl.x * -1.0f, tl.y * -1.0f, tl.z * -1.0f};
+                    float spot_angle = ref_acosf(dot3(neg, V3{L.dx, L.dy, L.dz}));
+                    lit = !(spot_angle > L.angle);
+                    edge = 1.0f - (spot_angle / L.angle);
+                }
+                if (!lit) {
+                    contribution = 0.0f;
+                } else {
+                    float att = 1.0f - (dist / L.radius);
+                    float ndl = fmaxf(dot3(n, tl), 0.0f);
+                    contribution = ndl * L.intensity * att * att;
+                    if (SPOT && L.type == B32_LIGHT_SPOT) contribution = contribution * edge;
+                }
             }
         }
         tr += contribution * L.cr; tg += contribution * L.cg; tb += contribution * L.cb;
@@ -218,7 +270,7 @@ __device__ __forceinline__ bool is_integral(float x) { return truncf(x) == x; }
 #endif
 constexpr int SETUP_THREADS = B32_SETUP_THREADS;
 
-template <bool STAGED>
+template <bool STAGED, bool SPOT>
 __device__ __forceinline__ void setup_face(uint32_t fi, const uint4& fc, const float* __restrict__ gverts, const float* __restrict__ s_vert, uint32_t lo,
                                            const TVert* __restrict__ tv, const TexDev* __restrict__ tex,
                                            const LightDev* __restrict__ lights,
@@ -332,11 +384,11 @@ __device__ __forceinline__ void setup_face(uint32_t fi, const uint4& fc, const f
                 const float third = 1.0f / 3.0f;
                 V3 c{((w1.x + w2.x) + w3.x) * third, ((w1.y + w2.y) + w3.y) * third, ((w1.z + w2.z) + w3.z) * third};
                 V3 n = normalize3(V3{((n1.x + n2.x) + n3.x) * third, ((n1.y + n2.y) + n3.y) * third, ((n1.z + n2.z) + n3.z) * third});
-                shade_multi_light_color(n, c, lights, p.n_lights, p.ambient, r.sh);
+                shade_multi_light_color<SPOT>(n, c, lights, p.n_lights, p.ambient, r.sh);
             } else {                                                                    // :1475-1483
-                shade_multi_light_color(n1, w1, lights, p.n_lights, p.ambient, r.sh);
-                shade_multi_light_color(n2, w2, lights, p.n_lights, p.ambient, r.sh + 3);
-                shade_multi_light_color(n3, w3, lights, p.n_lights, p.ambient, r.sh + 6);
+                shade_multi_light_color<SPOT>(n1, w1, lights, p.n_lights, p.ambient, r.sh);
+                shade_multi_light_color<SPOT>(n2, w2, lights, p.n_lights, p.ambient, r.sh + 3);
+                shade_multi_light_color<SPOT>(n3, w3, lights, p.n_lights, p.ambient, r.sh + 6);
             }
         }
         r.flags = flags;
@@ -521,7 +573,7 @@ static_assert(SETUP_THREADS == SETUP_GROUP && SETUP_GROUP == 128, "one face per 
 // unindexed triangle soup, usually for level geometry), the window is copied with coalesced 16-byte cp.async pieces and
 // the threads read their 27 floats from shared memory at a 27-word stride (conflict-free); otherwise they gather from
 // global memory.  Every vertex buffer of the library is padded by 16 bytes so that the last piece may overrun the window.
-template <bool STAGED>
+template <bool STAGED, bool SPOT>
 __device__ __forceinline__ void setup_group(uint32_t group, const b32_vertex* __restrict__ verts, const uint4& fc, const float* __restrict__ s_vert,
                                             uint32_t lo, const TVert* __restrict__ tv, const TexDev* __restrict__ tex, const LightDev* __restrict__ lights,
                                             SurfRec* __restrict__ recs, uint64_t* __restrict__ keys, BinHead* __restrict__ heads, uint4* s_mask,
@@ -532,7 +584,7 @@ __device__ __forceinline__ void setup_group(uint32_t group, const b32_vertex* __
     bool binned = false, marked = false;
     uint32_t mbx = 0, mby = 0;
     if (fi < p.nf) {
-        setup_face<STAGED>(fi, fc, reinterpret_cast<const float*>(verts), s_vert, lo, tv, tex, lights, recs, keys, st, p, n_op, n_tr, head, binned, marked, mbx, mby, wire);
+        setup_face<STAGED, SPOT>(fi, fc, reinterpret_cast<const float*>(verts), s_vert, lo, tv, tex, lights, recs, keys, st, p, n_op, n_tr, head, binned, marked, mbx, mby, wire);
         heads[fi] = head;
     }
     masks_mark(s_mask, mbx, mby, marked, p);
@@ -541,6 +593,7 @@ __device__ __forceinline__ void setup_group(uint32_t group, const b32_vertex* __
     if ((threadIdx.x & 31) == 0) s_ord[threadIdx.x >> 5] = ob;
 }
 
+template <bool SPOT>
 __global__ void __launch_bounds__(SETUP_THREADS, B32_SETUP_MINB)
 k_setup(const b32_vertex* __restrict__ verts, const b32_face* __restrict__ faces, const TVert* __restrict__ tv,
         const TexDev* __restrict__ tex, const LightDev* __restrict__ lights,
@@ -593,9 +646,9 @@ k_setup(const b32_vertex* __restrict__ verts, const b32_face* __restrict__ faces
             cp_async_wait<0>();
             __syncthreads();
             const float* s_vert = reinterpret_cast<const float*>(s_stage + (b0 - a0));
-            setup_group<true>(group, verts, fc, s_vert, lo, tv, tex, lights, recs, keys, heads, s_mask, wire, st, p, n_op, n_tr, s_ord);
+            setup_group<true, SPOT>(group, verts, fc, s_vert, lo, tv, tex, lights, recs, keys, heads, s_mask, wire, st, p, n_op, n_tr, s_ord);
         } else {
-            setup_group<false>(group, verts, fc, nullptr, 0, tv, tex, lights, recs, keys, heads, s_mask, wire, st, p, n_op, n_tr, s_ord);
+            setup_group<false, SPOT>(group, verts, fc, nullptr, 0, tv, tex, lights, recs, keys, heads, s_mask, wire, st, p, n_op, n_tr, s_ord);
         }
         __syncthreads();
         masks_flush(s_mask, masks, n_mtiles, group, p, make_uint4(s_ord[0], s_ord[1], s_ord[2], s_ord[3]), ocount, st);
@@ -2135,7 +2188,7 @@ void launch_setup(const LaunchCtx& L, const b32_vertex* verts, const b32_face* f
                   uint32_t* clear_rgba, float* clear_z, uint32_t clear_n, uint32_t clear_color, const CallParams& p) {
     if (p.nf == 0) return;
     const size_t smem = (size_t)p.mtiles_x * p.mtiles_y * sizeof(uint4) + SETUP_STAGE_BYTES;
-    launch_k(L, k_setup, grid_for(std::max(p.nf, clear_n / 4), SETUP_THREADS, L.sms, 16), SETUP_THREADS, smem, false, verts, faces, tv, tex, lights, recs, keys, heads,
+    launch_k(L, p.has_spot ? k_setup<true> : k_setup<false>, grid_for(std::max(p.nf, clear_n / 4), SETUP_THREADS, L.sms, 16), SETUP_THREADS, smem, false, verts, faces, tv, tex, lights, recs, keys, heads,
              masks, ocount, wire, st, zero_next, zero_words, clear_rgba, clear_z, clear_n, clear_color, p);
 }
 

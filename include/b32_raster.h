@@ -32,8 +32,9 @@ extern "C" {
 #define B32_ERR_OOB_INDEX    2  /* face.v* >= nv: reference panics on slice index              */
 #define B32_ERR_NAN_DEPTH    3  /* NaN sort key: reference `partial_cmp().unwrap()` panics,    */
                                 /* src/rasterizer/render.rs:2531                                */
-#define B32_ERR_UNSUPPORTED  4  /* Spot light (libm acos is not bit-reproducible on device);   */
-                                /* a wireframe edge longer than 2^24 pixels (frame otherwise drawn) */
+#define B32_ERR_UNSUPPORTED  4  /* a size beyond what the device layout holds (framebuffer side  */
+                                /* > 65535, > 65535 textures, ...); a wireframe edge longer than */
+                                /* 2^24 pixels (frame otherwise drawn)                          */
 #define B32_ERR_CUDA         5  /* a CUDA runtime call failed; see b32_last_error()            */
 #define B32_ERR_NO_DEVICE    6  /* no CUDA device: there is NO CPU fallback                    */
 
@@ -91,7 +92,8 @@ typedef struct b32_light {
     float    position[3];    /* Point, Spot                                   */
     float    direction[3];   /* Directional, Spot                             */
     float    radius;         /* Point, Spot                                   */
-    float    angle;          /* Spot                                          */
+    float    angle;          /* Spot: cone half-angle in radians; `acos` of render.rs:1047   */
+                             /* is the libm `acosf` of the reference's shipped wasm build    */
     float    intensity;
     uint8_t  r, g, b;        /* Light.color                                   */
     uint8_t  enabled;

@@ -263,6 +263,48 @@ inline uint16_t tex_sample(const Tex15& t, float u, float v) {
 struct Col { uint8_t r, g, b, blend; };   // types.rs:719-726
 inline bool col_eq(Col a, Col b) { return a.r == b.r && a.g == b.g && a.b == b.b && a.blend == b.blend; }
 
+// f32::acos of the reference's shipped build.  Rust lowers `f32::acos` to the `acosf` symbol: on wasm32 that is
+// compiler_builtins' `libm` crate (a port of musl / FreeBSD e_acosf.c), on native targets the platform libm (which may
+// differ in the last ulp).  This restates the function as it stands in the reference's own binary
+// (docs/bonnie-32.wasm, `compiler_builtins::math::partial_availability::acosf`, func 2057; disassembly checked op by
+// op) and is pinned against it on 400 000 inputs (tests/test_ref_wasm.py::test_acosf_matches_reference_binary).
+// Every operator rounds once (-ffp-contract=off); the binary drops musl's `+ 0x1p-120f` terms (they do not change the
+// rounded result).
+inline float acosf_rpoly(float z) {
+    float p = z * (0.16666586697101593f + z * (-0.04274342209100723f + z * -0.008656363002955914f));
+    float q = z * -0.7066296339035034f + 1.0f;
+    return p / q;
+}
+float ref_acosf(float x) {
+    const float pio2_hi = 1.570796251296997f;        // 0x3fc90fda
+    const float pio2_lo = 7.549789415861596e-08f;    // 0x33a22168
+    uint32_t hx; std::memcpy(&hx, &x, 4);
+    uint32_t ix = hx & 0x7fffffffu;
+    if (ix >= 0x3f800000u) {                         // |x| >= 1 or NaN
+        if (ix == 0x3f800000u) return (hx >> 31) ? 3.141592502593994f : 0.0f;
+        return 0.0f / (x - x);
+    }
+    if (ix < 0x3f000000u) {                          // |x| < 0.5
+        if (ix <= 0x32800000u) return pio2_hi;       // |x| < 2^-26
+        return pio2_hi - (x - (pio2_lo - x * acosf_rpoly(x * x)));
+    }
+    if (hx >> 31) {                                  // x < -0.5
+        float z = (1.0f + x) * 0.5f;
+        float s = std::sqrt(z);
+        float w = acosf_rpoly(z) * s - pio2_lo;
+        float t = pio2_hi - (s + w);
+        return t + t;
+    }
+    float z = (1.0f - x) * 0.5f;                     // x > 0.5
+    float s = std::sqrt(z);
+    uint32_t sb; std::memcpy(&sb, &s, 4); sb &= 0xfffff000u;
+    float df; std::memcpy(&df, &sb, 4);
+    float c = (z - df * df) / (s + df);
+    float w = acosf_rpoly(z) * s + c;
+    float t = df + w;
+    return t + t;
+}
+
 // render.rs:1013-1071
 void shade_multi_light_color(V3 normal, V3 world_pos, const b32_light* lights, uint32_t n, float ambient, float out[3]) {
     float total_r = ambient, total_g = ambient, total_b = ambient;
@@ -284,7 +326,7 @@ void shade_multi_light_color(V3 normal, V3 world_pos, const b32_light* lights, u
                 float n_dot_l = rmax(dot(normal, normalize(to_light)), 0.0f);
                 contribution = n_dot_l * L.intensity * attenuation * attenuation;
             }
-        } else {  // Spot (render.rs:1040-1058); acos is libm — host oracle only
+        } else {  // Spot (render.rs:1040-1058); acos = ref_acosf above
             V3 to_light = sub(mk3(L.position), world_pos);
             float dist = len(to_light);
             if (dist > L.radius || dist < 0.001f) {
@@ -292,7 +334,7 @@ void shade_multi_light_color(V3 normal, V3 world_pos, const b32_light* lights, u
             } else {
                 V3 to_surface = normalize(to_light);
                 V3 neg = scale(to_surface, -1.0f);
-                float spot_angle = std::acos(dot(neg, mk3(L.direction)));
+                float spot_angle = ref_acosf(dot(neg, mk3(L.direction)));
                 if (spot_angle > L.angle) {
                     contribution = 0.0f;
                 } else {
@@ -1056,6 +1098,10 @@ uint16_t b32o_texture_sample(const b32_tex_desc* tex, float u, float v) {
 void b32o_shade_multi_light(const float normal[3], const float world_pos[3], const b32_light* lights, uint32_t n_lights,
                             float ambient, float out_rgb[3]) {
     shade_multi_light_color(mk3(normal), mk3(world_pos), lights, n_lights, ambient, out_rgb);
+}
+
+void b32o_acosf(const float* x, float* out, uint32_t n) {
+    for (uint32_t i = 0; i < n; ++i) out[i] = ref_acosf(x[i]);
 }
 
 void b32o_fb_clear(uint8_t* rgba, float* z, uint32_t w, uint32_t h, uint8_t r, uint8_t g, uint8_t b, uint8_t a) {

@@ -45,6 +45,7 @@ uint16_t b32o_texture_sample(const b32_tex_desc* tex, float u, float v); /* type
 void b32o_shade_multi_light(const float normal[3], const float world_pos[3],
                             const b32_light* lights, uint32_t n_lights, float ambient,
                             float out_rgb[3]);                    /* render.rs:1013-1071 */
+void b32o_acosf(const float* x, float* out, uint32_t n);   /* f32::acos of the reference's wasm build (compiler_builtins libm acosf), render.rs:1047 */
 
 /* Framebuffer::clear, render.rs:36-45 */
 void b32o_fb_clear(uint8_t* rgba, float* z, uint32_t w, uint32_t h,

@@ -182,6 +182,43 @@ def perspective_transform(v, cam):                            # math.rs:103-109
 # ------------------------------------------------------------------------------------------
 # lighting, render.rs:1013-1071 (scalar; called 1-3 times per triangle)
 # ------------------------------------------------------------------------------------------
+def _acosf_rpoly(z):
+    p = F(z * F(F(0.16666586697101593) + F(z * F(F(-0.04274342209100723) + F(z * F(-0.008656363002955914))))))
+    q = F(F(z * F(-0.7066296339035034)) + F(1.0))
+    return F(p / q)
+
+
+def ref_acosf(x):
+    """f32::acos as the reference's wasm build computes it: compiler_builtins' libm `acosf` (port of musl e_acosf.c),
+    docs/bonnie-32.wasm func 2057; called at render.rs:1047.  Scalar, one rounding per operator."""
+    x = F(x)
+    pio2_hi, pio2_lo = F(1.570796251296997), F(7.549789415861596e-08)
+    hx = int(np.asarray(x, dtype=F).view(np.uint32))
+    ix = hx & 0x7FFFFFFF
+    with np.errstate(invalid="ignore", divide="ignore"):
+        if ix >= 0x3F800000:
+            if ix == 0x3F800000:
+                return F(3.141592502593994) if hx >> 31 else F(0.0)
+            return F(F(0.0) / F(x - x))
+        if ix < 0x3F000000:
+            if ix <= 0x32800000:
+                return pio2_hi
+            return F(pio2_hi - F(x - F(pio2_lo - F(x * _acosf_rpoly(F(x * x))))))
+        if hx >> 31:
+            z = F(F(F(1.0) + x) * F(0.5))
+            s = F(np.sqrt(z))
+            w = F(F(_acosf_rpoly(z) * s) - pio2_lo)
+            t = F(pio2_hi - F(s + w))
+            return F(t + t)
+        z = F(F(F(1.0) - x) * F(0.5))
+        s = F(np.sqrt(z))
+        df = (np.asarray(s, dtype=F).view(np.uint32) & np.uint32(0xFFFFF000)).view(F)[()]
+        c = F(F(z - F(df * df)) / F(s + df))
+        w = F(F(_acosf_rpoly(z) * s) + c)
+        t = F(df + w)
+        return F(t + t)
+
+
 def shade_multi_light_color(normal, world_pos, lights, ambient):
     normal = np.asarray(normal, dtype=F); world_pos = np.asarray(world_pos, dtype=F)
     tot = [F(ambient), F(ambient), F(ambient)]
@@ -201,8 +238,21 @@ def shade_multi_light_color(normal, world_pos, lights, ambient):
                 att = F(1.0) - (dist / F(L.radius))
                 n_dot_l = fmax(dot3(normal, normalize3(to_light)), F(0.0))
                 contribution = F(F(F(n_dot_l * F(L.intensity)) * att) * att)
-        else:
-            raise NotImplementedError("Spot lights use libm acos (not modelled)")
+        else:                                                    # Spot, render.rs:1038-1059
+            to_light = np.asarray(L.position, dtype=F) - world_pos
+            dist = np.sqrt(dot3(to_light, to_light))
+            if dist > F(L.radius) or dist < F(0.001):
+                contribution = F(0.0)
+            else:
+                to_surface = normalize3(to_light)
+                spot_angle = ref_acosf(dot3(to_surface * F(-1.0), np.asarray(L.direction, dtype=F)))
+                if spot_angle > F(L.angle):
+                    contribution = F(0.0)
+                else:
+                    att = F(1.0) - (dist / F(L.radius))
+                    edge = F(1.0) - (spot_angle / F(L.angle))
+                    n_dot_l = fmax(dot3(normal, to_surface), F(0.0))
+                    contribution = F(F(F(F(n_dot_l * F(L.intensity)) * att) * att) * edge)
         lr, lg, lb = (F(c) / F(255.0) for c in L.color)
         tot[0] = F(tot[0] + F(contribution * lr))
         tot[1] = F(tot[1] + F(contribution * lg))

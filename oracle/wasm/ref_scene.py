@@ -15,7 +15,7 @@ calling the binary's own constructors `Framebuffer::new`, `RasterSettings::game`
   RasterSettings (44B) ortho Option{tag@0,zoom@4,cx@8,cy@12}  lights Vec{cap,ptr,len}@16  ambient@28
                        affine@32 zbuffer@33 cull@34 bf_wire@35 lowres@36 dither@37 stretch@38 wire_overlay@39
                        rgb555@40 fixed@41 xray@42 shading@43
-  Light (60 B)         type tag@0 (0 Directional{dir@4}, 1 Point{pos@4,radius@16}, 2 Spot)  name String@36
+  Light (60 B)         type tag@0 (0 Directional{dir@4}, 1 Point{pos@4,radius@16}, 2 Spot{pos@4,dir@16,angle@28,radius@32})  name String@36
                        color{blend@48,r@49,g@50,b@51}  intensity@52  enabled@56
   fog Option<(f32,f32,f32,Color)> (16 B, by pointer)  start@0 falloff@4 cull@8 color{blend@12 (6 = None),r,g,b}
   RasterTimings (32 B) six f32 + triangles_drawn u32 @24
@@ -80,8 +80,11 @@ class RefRasterizer:
             elif tag == 1:
                 payload[0:3] = [float(x) for x in l.position]
                 payload[3] = float(l.radius)
-            else:
-                raise NotImplementedError('spot light layout not recovered')
+            else:                     # Spot{position@4, direction@16, angle@28, radius@32}: read off shade_multi_light_color's loads
+                payload[0:3] = [float(x) for x in l.position]
+                payload[3:6] = [float(x) for x in l.direction]
+                payload[6] = float(l.angle)
+                payload[7] = float(l.radius)
             lights += struct.pack('<I8f', tag, *payload) + struct.pack('<III', 1, name, 1) \
                 + bytes([0, l.color[0], l.color[1], l.color[2]]) + struct.pack('<f', l.intensity) \
                 + bytes([1 if l.enabled else 0, 0, 0, 0])

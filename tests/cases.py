@@ -247,6 +247,70 @@ def rgb888_scenes(n_tris=160):
     return out
 
 
+def spot_lights():
+    """Spot lights (render.rs:1038-1059) over the C2 volume: a torch at the camera, a coloured one from the side with a
+    wide cone, a narrow one whose direction is not normalised (|dot| > 1 at the axis: acos = NaN, which the reference
+    lets through its `spot_angle > angle` test), one with a zero cone, one disabled."""
+    torch = Light.spot((0.0, 0.0, 0.0), (0.0, 0.0, 1.0), 0.6, 70.0, 1.8)
+    side = Light.spot((-30.0, 10.0, 30.0), (0.8, -0.2, 0.1), 1.3, 80.0, 2.5)
+    side.color = (255, 120, 40)
+    unnorm = Light.spot((5.0, -20.0, 10.0), (-0.2, 1.1, 1.3), 2.0, 90.0, 0.7)
+    unnorm.direction = np.asarray((-0.2, 1.1, 1.3), dtype=np.float32)          # Light::spot normalises; the field is public
+    zero_cone = Light.spot((0.0, 0.0, 5.0), (0.0, 0.0, 1.0), 0.0, 50.0, 3.0)
+    off = Light.spot((0.0, 0.0, 0.0), (0.0, 0.0, 1.0), 3.0, 500.0, 9.0)
+    off.enabled = False
+    return [torch, side, unnorm, zero_cone, off]
+
+
+def spot_scenes(n_tris=160):
+    """Scenes lit by Spot lights, alone and mixed with Directional / Point ones: Gouraud and flat, painter's and z-buffer,
+    both colour depths, no-cull (flipped normals), a mixed-blend mesh.  Kept apart from feature_scenes() so that the
+    fixtures made from that list stay what they are."""
+    import fuzz
+    out = []
+    base = scenes.scene_c2(n_tris=n_tris)
+    g = copy.copy(base)
+    g.vertices = base.vertices.copy()
+    un = scenes.splitmix64_u01(79, len(g.vertices) * 3).reshape(-1, 3)
+    g.vertices["normal"] = (2.0 * un - 1.0).astype(np.float32)
+    sp = spot_lights()
+    mixed = [Light.directional((-1.0, -1.0, -1.0), 0.4), sp[0], Light.point_colored((0.5, 0.5, 4.0), 30.0, 1.5, 1.0, 0.5, 0.25), sp[1], sp[4]]
+    out.append(_with(g, "spot_gouraud_torch", shading=abi.SHADE_GOURAUD, lights=[sp[0]], ambient=0.15, use_zbuffer=True))
+    out.append(_with(g, "spot_gouraud_all", shading=abi.SHADE_GOURAUD, lights=sp, ambient=0.1))
+    out.append(_with(g, "spot_flat_all", shading=abi.SHADE_FLAT, lights=sp, ambient=0.2, use_zbuffer=True))
+    out.append(_with(g, "spot_gouraud_mixed_nocull", shading=abi.SHADE_GOURAUD, lights=mixed, ambient=0.25, backface_cull=False, use_zbuffer=True))
+    out.append(_with(g, "spot_flat_mixed_float_nodither", shading=abi.SHADE_FLAT, lights=mixed, ambient=0.0, use_fixed_point=False, dithering=False))
+    out.append(_with(g, "spot_shading_none_is_ignored", shading=abi.SHADE_NONE, lights=sp, ambient=0.3))
+    m = copy.copy(g)
+    m.textures = [_rng_texture(11, 64, 64, semi_fraction=0.5), _rng_texture(12, 32, 64, blend=abi.BLEND_AVERAGE, semi_fraction=0.5),
+                  _rng_texture(13, 16, 8, blend=abi.BLEND_ADD, semi_fraction=0.9, zero_fraction=0.3)]
+    m.faces = _mixed_faces(base, 99)
+    out.append(_with(m, "spot_mixed_blend_gouraud", shading=abi.SHADE_GOURAUD, lights=mixed, ambient=0.3, use_zbuffer=True))
+    for seed in (3, 5, 8, 11, 17, 23, 30, 36, 41, 52):                     # fuzz scenes, their own lights replaced
+        sc = fuzz.fuzz_scene(seed)
+        rng = np.random.default_rng(880000 + seed)
+        ls = list(sc.settings.lights)
+        for _ in range(int(rng.integers(1, 4))):
+            l = Light.spot(rng.normal(size=3) * 8 + np.array([0, 0, 10.0]), rng.normal(size=3),
+                           float(rng.random() * 2.5), float(10 + rng.random() * 80), float(rng.random() * 3))
+            if rng.random() < 0.3:
+                l.direction = (l.direction * np.float32(1.0 + rng.random() * 1e-6)).astype(np.float32)   # a hair over unit length
+            l.color = tuple(int(x) for x in rng.integers(0, 256, size=3))
+            ls.insert(int(rng.integers(0, len(ls) + 1)), l)
+        out.append(_with(sc, f"spot_fuzz_{seed}", lights=ls, shading=int(abi.SHADE_GOURAUD if seed % 2 else abi.SHADE_FLAT)))
+    return out
+
+
+def spot_scenes888(n_tris=160):
+    """The same lights through the RGB888 sibling `render_mesh`."""
+    by = {s.name: s for s in rgb888_scenes(n_tris)}
+    sp = spot_lights()
+    mixed = [Light.point((-3.0, 2.0, 20.0), 25.0, 2.9), sp[1], sp[0], sp[3]]
+    return [_with(by["rgb888_gouraud_lights"], "rgb888_spot_gouraud", lights=sp, ambient=0.2),
+            _with(by["rgb888_flat_lights"], "rgb888_spot_flat_mixed", lights=mixed, ambient=0.1, use_zbuffer=True),
+            _with(by["rgb888_mixed_gouraud"], "rgb888_spot_mixed_blend", lights=mixed, ambient=0.3)]
+
+
 # ---- skybox sphere pass (Framebuffer::render_skybox step 1, render.rs:81-139) ------------------------------
 def sky_mesh(center, seed=5, h_segments=48, v_segments=32, radius=10000.0, n_mountains=40):
     """A mesh shaped like Skybox::generate_mesh's (src/world/geometry.rs:529-): a vertex-coloured sphere around `center`

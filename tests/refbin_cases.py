@@ -61,6 +61,14 @@ def small_scenes888():
     return [strip_editor_alpha(s) for s in out]
 
 
+def spot_scenes():
+    return [strip_editor_alpha(s) for s in cases.spot_scenes()]
+
+
+def spot_scenes888():
+    return [strip_editor_alpha(s) for s in cases.spot_scenes888()]
+
+
 def big_scenes():
     out = [scenes.scene_c4(), cases._with(scenes.scene_c4(), "c4_100000_zbuffer", use_zbuffer=True),
            cases._with(scenes.scene_c4(), "c4_100000_float_nodither", use_fixed_point=False, dithering=False)]
@@ -91,6 +99,8 @@ def inputs_digest(sc):
     for l in s.lights:
         h.update(repr((int(l.type), [float(np.float32(x)) for x in l.position], [float(np.float32(x)) for x in l.direction],
                        float(np.float32(l.radius)), float(np.float32(l.intensity)), tuple(int(x) for x in l.color), bool(l.enabled))).encode())
+        if int(l.type) == abi.LIGHT_SPOT:                     # the cone angle only exists for Spot lights (older digests stay valid)
+            h.update(repr(float(np.float32(l.angle))).encode())
     h.update(repr((None if sc.fog is None else (float(np.float32(sc.fog[0])), float(np.float32(sc.fog[1])), float(np.float32(sc.fog[2])),
                                                 tuple(int(x) for x in sc.fog[3][:3])), sc.width, sc.height, tuple(sc.clear[:3]))).encode())
     return h.hexdigest()

@@ -69,3 +69,57 @@ def blend_inputs(n=30000):
     c15[:6] = [0xFFFF, 0x8000, 0x8001, 0xFC00, 0x83FF, 0x0000]
     back[:6] = [[255, 255, 255], [0, 0, 0], [7, 8, 248], [255, 0, 128], [16, 31, 249], [1, 2, 3]]
     return c15, back, mode
+
+
+def acosf_inputs(n=400000):
+    """Arguments for the binary's `acosf` (compiler_builtins libm): uniform over [-1.0001, 1.0001], denser towards 0 and
+    towards +-1 / +-0.5 (the branch boundaries), every float within 64 ulps of the boundaries, and the specials."""
+    u = scenes.splitmix64_u01(0xF1ED0004, n * 2).reshape(n, 2)
+    x = (2.0002 * u[:, 0] - 1.0001)
+    k = (u[:, 1] * 5).astype(int)
+    x = np.where(k == 1, x ** 5, x)                                    # near 0 (down to the 2^-26 early-out)
+    x = np.where(k == 2, np.sign(x) * (1.0 - np.abs(x) ** 6 * 1e-3), x)    # just inside +-1
+    x = np.where(k == 3, np.sign(x) * (0.5 + x ** 7 * 1e-3), x)        # around +-0.5
+    x = x.astype(np.float32)
+    near = []
+    for b in (0.0, 0.5, 1.0, 2.0 ** -26, 2.0 ** -27, 1e-38, 0.70710678):
+        bits = int(np.float32(b).view(np.uint32))
+        w = np.arange(max(bits - 64, 0), bits + 65, dtype=np.uint32)
+        near += [w, w | np.uint32(0x80000000)]
+    special = np.array([np.nan, np.inf, -np.inf, 2.0, -2.0, 3.4e38, -3.4e38, 1e-45, -1e-45, 1.0000001, -1.0000001], np.float32)
+    return np.concatenate([x, np.concatenate(near).view(np.float32), special])
+
+
+def spot_light_sets():
+    import cases
+    sp = cases.spot_lights()
+    neg_angle = Light.spot((1.0, 2.0, 3.0), (0.0, 1.0, 0.0), -0.5, 40.0, 1.0)
+    wide = Light.spot((0.0, 0.0, 0.0), (1.0, 0.0, 0.0), 3.2, 100.0, 1.0)              # cone wider than pi: everything inside the radius
+    zero_dir = Light.spot((2.0, 2.0, 2.0), (0.0, 0.0, 0.0), 1.0, 60.0, 2.0)           # normalize(0) = 0: acos(0) = pi/2 > 1.0
+    zero_dir2 = Light.spot((2.0, 2.0, 2.0), (0.0, 0.0, 0.0), 1.6, 60.0, 2.0)
+    tiny_r = Light.spot((1.0, 2.0, 3.0), (0.0, 0.0, 1.0), 1.0, 1e-3, 5.0)
+    return [
+        [sp[0]],
+        sp,
+        [Light.directional((0.3, -2.0, 0.5), 1.4), sp[1], Light.point((-3.0, 2.0, 20.0), 25.0, 0.9), sp[2], sp[4]],
+        [neg_angle, wide, zero_dir, zero_dir2],
+        [tiny_r, sp[3], wide],
+        [sp[2]],
+    ]
+
+
+def spot_shade_inputs(n=8000):
+    u = scenes.splitmix64_u01(0xF1ED0005, n * 8).reshape(n, 8)
+    normal = (2.0 * u[:, :3] - 1.0).astype(np.float32)
+    pos = ((2.0 * u[:, 3:6] - 1.0) * 40.0).astype(np.float32)
+    set_idx = (u[:, 6] * 6).astype(np.int32) % 6
+    ambient = (u[:, 7] * 1.2).astype(np.float32)
+    # on the axis of the torch (dot = -1 exactly, and a hair beyond with the un-normalised light), at a light's position
+    pos[0] = (0.0, 0.0, 10.0); set_idx[0] = 0
+    pos[1] = (0.0, 0.0, -10.0); set_idx[1] = 0
+    pos[2] = (1.0, 2.0, 3.0); set_idx[2] = 3
+    pos[3] = (5.0 - 0.2 * 7, -20.0 + 1.1 * 7, 10.0 + 1.3 * 7); set_idx[3] = 5
+    normal[4] = 0.0
+    normal[5] = (np.nan, 0.0, 1.0)
+    pos[6] = (np.inf, 0.0, 0.0)
+    return normal, pos, set_idx, ambient

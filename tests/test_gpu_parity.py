@@ -189,11 +189,12 @@ def test_error_codes(ctx, oracle):
     assert rc == 0
     got, got_z, tm = render_gpu(ctx, s2)
     assert_same(s2, got, got_z, tm, want, want_z, otm)
-    # spot light is unsupported on the device
-    s3 = copy.copy(sc); s3.settings = scenes.common_settings(shading=abi.SHADE_GOURAUD, lights=[pkg.Light.spot((0, 0, 0), (0, 0, 1), 0.5, 10.0, 1.0)])
+    # a light type beyond Spot is not a LightType
+    bad = pkg.Light.spot((0, 0, 0), (0, 0, 1), 0.5, 10.0, 1.0); bad.type = 3
+    s3 = copy.copy(sc); s3.settings = scenes.common_settings(shading=abi.SHADE_GOURAUD, lights=[bad])
     with pytest.raises(pkg.B32Error) as e:
         pkg.render_mesh_15(fb, sc.vertices, sc.faces, sc.textures, sc.camera, s3.settings)
-    assert e.value.code == abi.B32_ERR_UNSUPPORTED
+    assert e.value.code == abi.B32_ERR_INVALID
 
 
 def test_empty_inputs(ctx):
@@ -1233,3 +1234,65 @@ def test_frame_timings_of_enqueued_frames(oracle):
         c.check(lib.b32_ctx_frame_timings(c.h, 0))
     finally:
         c.close()
+
+
+# ---- Spot lights (render.rs:1038-1059; acos = the shipped build's libm acosf, k_setup<true>) -------------------------------
+SPOT15 = cases.spot_scenes()
+SPOT888 = cases.spot_scenes888()
+
+
+@pytest.mark.parametrize("sc", SPOT15 + SPOT888, ids=[s.name for s in SPOT15 + SPOT888])
+def test_spot_light_scene(ctx, oracle, sc):
+    rgb888 = not sc.settings.use_rgb555
+    want, want_z, otm, rc = (oracle.render_scene888 if rgb888 else oracle.render_scene)(sc)
+    assert rc == 0
+    got, got_z, tm = (render_gpu888 if rgb888 else render_gpu)(ctx, sc)
+    assert_same(sc, got, got_z, tm, want, want_z, otm)
+
+
+def test_spot_lights_at_scale_blocking_and_enqueued(ctx, oracle):
+    """30 000 Gouraud-lit triangles under the five spot lights: host buffers, resident mesh, and enqueued frames that
+    alternate between a Spot and a Point light list (the two k_setup instantiations under one frame topology)."""
+    sc = scenes.scene_c4(n_tris=30000)
+    un = scenes.splitmix64_u01(91, len(sc.vertices) * 3).reshape(-1, 3)
+    sc.vertices = sc.vertices.copy()
+    sc.vertices["normal"] = (2.0 * un - 1.0).astype(np.float32)
+    spot = cases._with(sc, "c4_30000_spot", shading=abi.SHADE_GOURAUD, lights=cases.spot_lights(), ambient=0.1)
+    point = cases._with(sc, "c4_30000_point", shading=abi.SHADE_GOURAUD, lights=[pkg.Light.point((0.0, 0.0, 0.0), 70.0, 1.8)], ambient=0.1)
+    wants = {}
+    for s in (spot, point):
+        want, want_z, otm, rc = oracle.render_scene(s)
+        assert rc == 0
+        wants[s.name] = (want, want_z, otm)
+        for resident in (False, True):
+            got, got_z, tm = render_gpu(ctx, s, resident=resident)
+            assert_same(s, got, got_z, tm, want, want_z, otm)
+    assert not np.array_equal(wants[spot.name][0], wants[point.name][0])
+    fb = pkg.Framebuffer(sc.width, sc.height, ctx)
+    ctx.set_textures(sc.textures)
+    mesh = pkg.Mesh(ctx, sc.vertices, sc.faces)
+    for k in range(8):
+        s = spot if k % 2 == 0 else point
+        mesh.frame_enqueue(sc.clear, s.camera, s.settings, s.fog)
+        got, got_z = fb.download()                         # syncs; frames 3.. are graph launches
+        assert np.array_equal(got, wants[s.name][0]), (k, s.name)
+        assert np.array_equal(got_z.view(np.uint32), wants[s.name][1].view(np.uint32)), (k, s.name)
+    mesh.free()
+
+
+def test_spot_lights_against_reference_binary_directly(ctx):
+    """CUDA vs the reference's own compiled code with no oracle in between: flat shading under Directional + Spot + Point
+    lights, float projection, no dither, opaque faces (the conditions of test_gpu_against_reference_binary_directly)."""
+    import hashlib, json, os
+    import refbin_cases
+    here = os.path.dirname(__file__)
+    name = "spot_flat_mixed_float_nodither"
+    fix = json.load(open(os.path.join(here, "golden", "ref_wasm", "spot.json")))["scenes"][name]
+    frame = np.load(os.path.join(here, "golden", "ref_wasm", "spot.npz"))["frame/" + name]
+    sc = {s.name: s for s in refbin_cases.spot_scenes()}[name]
+    assert fix["inputs"] == refbin_cases.inputs_digest(sc)
+    got, got_z, tm = render_gpu(ctx, sc)
+    assert tm["triangles_drawn"] == fix["drawn"]
+    assert hashlib.sha256(np.ascontiguousarray(got_z, "<f4").tobytes()).hexdigest() == fix["z"], "z-buffer differs from the reference binary"
+    assert hashlib.sha256(frame.tobytes()).hexdigest() == fix["rgba"]
+    assert np.array_equal(got, _expand_shl3(frame, sc.clear)), "framebuffer differs from the reference binary (after 5->8-bit re-expansion)"

@@ -270,3 +270,87 @@ def test_plain_draw_line_matches_reference_binary(oracle, name, w, h, seed, n):
     lines["rgb"] = rgb
     assert oracle.draw_lines(rgba, z, lines) == 0
     assert hashlib.sha256(rgba.tobytes()).hexdigest() == fix["rgba"], "pixels differ from the reference binary"
+
+
+# ---- Spot lights (render.rs:1038-1059): f32::acos of the shipped build, the lighting function, whole frames ---------------
+SPOT = json.load(open(os.path.join(HERE, "golden", "ref_wasm", "spot.json")))
+SPOT15 = {s.name: s for s in refbin_cases.spot_scenes()}
+SPOT888 = {s.name: s for s in refbin_cases.spot_scenes888()}
+
+
+def test_acosf_matches_reference_binary(oracle):
+    """`f32::acos` (render.rs:1047) is the `acosf` symbol: compiler_builtins' libm port in the reference's own wasm build.
+    The oracle's restatement against that function on 400 000+ arguments (every branch, every float within 64 ulps of the
+    branch boundaries, NaN / out-of-domain inputs), bit for bit; the numpy model on a sample."""
+    import ctypes as C
+    import refbin_funcs
+    from oracle import pymodel
+    x = refbin_funcs.acosf_inputs()
+    want = np.load(os.path.join(HERE, "golden", "ref_wasm", "spot.npz"))["acosf"]
+    assert len(want) == len(x)
+    got = np.empty_like(x)
+    oracle.lib().b32o_acosf(x.ctypes.data_as(C.c_void_p), got.ctypes.data_as(C.c_void_p), C.c_uint32(len(x)))
+    same = (got.view(np.uint32) == want.view(np.uint32)) | (np.isnan(got) & np.isnan(want))
+    assert same.all(), (x[~same][:5], got[~same][:5], want[~same][:5])
+    err = np.abs(got[np.isfinite(got)].astype(np.float64) - np.arccos(x[np.isfinite(got)].astype(np.float64)))
+    assert err.max() < 2.5e-7                                  # and it is an arc cosine
+    idx = np.concatenate([np.arange(0, 400000, 97), np.arange(400000, len(x))])
+    py = np.array([pymodel.ref_acosf(v) for v in x[idx]], np.float32)
+    same = (py.view(np.uint32) == want[idx].view(np.uint32)) | (np.isnan(py) & np.isnan(want[idx]))
+    assert same.all(), x[idx][~same][:5]
+
+
+def test_shade_multi_light_color_spot_matches_reference_binary(oracle):
+    """shade_multi_light_color with Spot lights in the list (cone test, edge falloff, zero / un-normalised directions whose
+    acos is NaN, cones wider than pi, negative angles, disabled lights) — 8 000 evaluations of the binary, bit for bit; the
+    numpy model on every 8th."""
+    import ctypes as C
+    from bonnie32_b200 import abi
+    from oracle import pymodel
+    import refbin_funcs
+    want = np.load(os.path.join(HERE, "golden", "ref_wasm", "spot.npz"))["shade"]
+    normal, pos, set_idx, ambient = refbin_funcs.spot_shade_inputs()
+    light_sets = refbin_funcs.spot_light_sets()
+    sets = []
+    for ls in light_sets:
+        arr = (abi.Light * max(1, len(ls)))()
+        for k, l in enumerate(ls):
+            arr[k] = l.to_abi()
+        sets.append((arr, len(ls)))
+    lib = oracle.lib()
+    out = (C.c_float * 3)()
+    got = np.empty((len(normal), 3), np.float32)
+    for i in range(len(normal)):
+        n = (C.c_float * 3)(*[float(v) for v in normal[i]]); p = (C.c_float * 3)(*[float(v) for v in pos[i]])
+        arr, cnt = sets[set_idx[i]]
+        lib.b32o_shade_multi_light(n, p, arr, C.c_uint32(cnt), C.c_float(float(ambient[i])), out)
+        got[i] = out[:]
+    same = (got.view(np.uint32) == want.view(np.uint32)) | (np.isnan(got) & np.isnan(want))
+    assert same.all(), np.argwhere(~same)[:5]
+    assert (want != want[:, :1]).any()                 # coloured contributions are in there (a NaN total leaves as 1.0: f32::min)
+    with np.errstate(all="ignore"):
+        for i in range(0, len(normal), 8):
+            py = np.asarray(pymodel.shade_multi_light_color(normal[i], pos[i], light_sets[set_idx[i]], ambient[i]), np.float32)
+            ok = (py.view(np.uint32) == want[i].view(np.uint32)) | (np.isnan(py) & np.isnan(want[i]))
+            assert ok.all(), i
+
+
+def test_spot_fixture_covers_every_scene():
+    assert set(SPOT["scenes"]) == set(SPOT15) | set(SPOT888)
+
+
+@pytest.mark.parametrize("name", sorted(SPOT15) + sorted(SPOT888))
+def test_oracle_spot_scenes_match_reference_binary(compat_oracle, name):
+    """Whole frames lit by Spot lights through the binary's render_mesh_15 / render_mesh: framebuffer and z-buffer."""
+    rgb888 = name in SPOT888
+    sc = (SPOT888 if rgb888 else SPOT15)[name]
+    rec = SPOT["scenes"][name]
+    assert rec["inputs"] == refbin_cases.inputs_digest(sc), "scene generator changed: regenerate the fixture"
+    rgba, z, tm, rc = compat_oracle.render_scene888(sc) if rgb888 else compat_oracle.render_scene(sc)
+    if "trap" in rec:
+        assert rc != 0
+        return
+    assert rc == 0 and tm["triangles_drawn"] == rec["drawn"]
+    a, b = refbin_cases.frame_digest(rgba, z)
+    assert a == rec["rgba"], "framebuffer differs from the reference binary"
+    assert b == rec["z"], "z-buffer differs from the reference binary"
