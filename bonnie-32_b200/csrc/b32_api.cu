@@ -260,11 +260,15 @@ int h2d(b32_ctx* ctx, void* dst, const void* src, size_t bytes, bool consume = f
     return B32_OK;
 }
 
+// Experiment switch: the vertex transform as its own kernel (one vertex per thread) in front of k_setup.
+static bool split_transform() { static const bool on = std::getenv("B32_SPLIT_TRANSFORM") != nullptr; return on; }
+
 int ensure_work(b32_ctx* ctx, const CallParams& p) {
     uint32_t m = std::max<uint32_t>(p.nf, 1);
     CK(ctx->recs.reserve(m));
     CK(ctx->keys.reserve(m));
     CK(ctx->heads.reserve(m));
+    if (split_transform()) CK(ctx->tv.reserve(std::max<uint32_t>(p.nv, 1)));
     CK(ctx->masks.reserve(std::max<size_t>((size_t)p.mtiles_x * p.mtiles_y * p.n_groups, 1)));
     // A tile is crowded when more than OP_SORT_MAX_ENTRIES of the mesh's faces touch it, so only meshes well beyond that can
     // have any: they get 5 head-sized slots of scratch per face (a face's bounding box touches ~4 tiles; a slot = one head, or four face indices), capped at 256 MB.  A tile that
@@ -382,7 +386,9 @@ int launch_frame(b32_ctx* ctx, const LaunchCtx& L, const FrameArgs& a, cudaEvent
     const CallParams& p = a.p;
     if (ev_setup) CK(cudaEventRecord(ev_setup, L.stream));
     const bool wire_on = p.wire_back || p.wire_front;
-    launch_setup(L, a.verts, a.faces, nullptr, a.texdesc, ctx->lights.p, ctx->recs.p, ctx->keys.p, ctx->heads.p, ctx->masks.p,
+    const TVert* tv = nullptr;
+    if (split_transform() && p.nf) { launch_transform(L, a.verts, ctx->tv.p, nullptr, p); tv = ctx->tv.p; }
+    launch_setup(L, a.verts, a.faces, tv, a.texdesc, ctx->lights.p, ctx->recs.p, ctx->keys.p, ctx->heads.p, ctx->masks.p,
                  ctx->tile_count, wire_on ? ctx->wire.p : nullptr, ctx->state, a.zero_next, ctx->state_stride,
                  ctx->fb_rgba.p, ctx->fb_z.p, a.clear ? ctx->width * ctx->height : 0u, a.clear_color, p);    // the frame's clear rides in k_setup
     if (ev_fill) CK(cudaEventRecord(ev_fill, L.stream));

@@ -122,8 +122,10 @@ __device__ __forceinline__ TVert transform_vertex(float px, float py, float pz, 
 
 __global__ void __launch_bounds__(256)
 k_transform(const b32_vertex* __restrict__ verts, TVert* __restrict__ out, float* __restrict__ dbg_cam, CallParams p) {
+    pdl_launch_dependents();           // split front end (B32_SPLIT_TRANSFORM): k_setup is scheduled behind this grid and waits for its completion
+    const uint32_t vw = p.vwords ? p.vwords : 9u;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < p.nv; i += gridDim.x * blockDim.x) {
-        const float* vp = reinterpret_cast<const float*>(verts + i);
+        const float* vp = reinterpret_cast<const float*>(verts) + (size_t)i * vw;
         float cxy[2];
         TVert t = transform_vertex(vp[0], vp[1], vp[2], p, cxy);
         out[i] = t;
@@ -618,6 +620,7 @@ k_setup(const b32_vertex* __restrict__ verts, const b32_face* __restrict__ faces
     if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
     uint32_t n_op = 0, n_tr = 0;
     const uint32_t lane = threadIdx.x & 31;
+    if (tv) pdl_wait();                // split front end: k_transform (an ordinary, fully ordered launch) has completed
     for (uint32_t group = blockIdx.x; group < p.n_groups; group += gridDim.x) {
         const uint32_t fi = group * SETUP_GROUP + threadIdx.x;
         masks_zero(s_mask, n_mtiles);
@@ -2178,8 +2181,7 @@ static inline uint32_t grid_for(uint32_t n, uint32_t block, uint32_t sms, uint32
 
 void launch_transform(const LaunchCtx& L, const b32_vertex* verts, TVert* out, float* dbg_cam, const CallParams& p) {
     if (p.nv == 0) return;
-    k_transform<<<grid_for(p.nv, 256, L.sms), 256, 0, L.stream>>>(verts, out, dbg_cam, p);
-    ++*L.launches;
+    launch_k(L, k_transform, grid_for(p.nv, 256, L.sms), 256, 0, false, verts, out, dbg_cam, p);
 }
 
 void launch_setup(const LaunchCtx& L, const b32_vertex* verts, const b32_face* faces, const TVert* tv, const TexDev* tex,
@@ -2188,7 +2190,7 @@ void launch_setup(const LaunchCtx& L, const b32_vertex* verts, const b32_face* f
                   uint32_t* clear_rgba, float* clear_z, uint32_t clear_n, uint32_t clear_color, const CallParams& p) {
     if (p.nf == 0) return;
     const size_t smem = (size_t)p.mtiles_x * p.mtiles_y * sizeof(uint4) + SETUP_STAGE_BYTES;
-    launch_k(L, p.has_spot ? k_setup<true> : k_setup<false>, grid_for(std::max(p.nf, clear_n / 4), SETUP_THREADS, L.sms, 16), SETUP_THREADS, smem, false, verts, faces, tv, tex, lights, recs, keys, heads,
+    launch_k(L, p.has_spot ? k_setup<true> : k_setup<false>, grid_for(std::max(p.nf, clear_n / 4), SETUP_THREADS, L.sms, 16), SETUP_THREADS, smem, tv != nullptr, verts, faces, tv, tex, lights, recs, keys, heads,
              masks, ocount, wire, st, zero_next, zero_words, clear_rgba, clear_z, clear_n, clear_color, p);
 }
 
