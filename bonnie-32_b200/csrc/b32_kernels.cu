@@ -53,9 +53,6 @@ __device__ __forceinline__ void host_signal_done(const CallParams& p, CallState*
     if (!p.host) return;
     __syncthreads();                                       // the CTA's writes (counters, flags) happen before thread 0's fence,
     if (threadIdx.x != 0) return;                          // which is cumulative: one fence orders them before the arrival
-#ifdef B32_EXP_SETUP_NOFENCE        // timing experiment only (NOT correct): what the per-CTA fence of k_setup costs a blocking call
-    if (k != HS_SETUP)
-#endif
     if (blockIdx.x == 0) __threadfence_system(); else __threadfence();     // (block 0: t0 reaches the host before seq can)
     if (atomicAdd(&st->done[k], 1u) != gridDim.x - 1) return;
     __threadfence();
