@@ -649,11 +649,44 @@ def test_large_framebuffers_all_passes(ctx, oracle, w, h):
         assert rc == 0
         got, got_z, tm = render_gpu(ctx, sc)
         assert_same(sc, got, got_z, tm, want, want_z, otm)
+        if not sc.settings.backface_wireframe:                 # the same frame enqueued (clear folded in, both passes, graph replay)
+            fb = pkg.Framebuffer(w, h, ctx)
+            ctx.set_textures(sc.textures)
+            mesh = pkg.Mesh(ctx, sc.vertices, sc.faces)
+            for _ in range(3):
+                mesh.frame_enqueue(sc.clear, sc.camera, sc.settings, sc.fog)
+            got, got_z = fb.download()
+            mesh.free()
+            assert np.array_equal(got, want) and np.array_equal(got_z.view(np.uint32), want_z.view(np.uint32)), (sc.name, "enqueued")
     m = next(s for s in RGB888 if s.name == "rgb888_mixed_zbuffer")
     sc = cases._with(m, f"rgb888_mixed_zbuffer_{w}x{h}", width=w, height=h)
     want, want_z, otm, rc = oracle.render_scene888(sc)
     got, got_z, tm = render_gpu888(ctx, sc)
     assert_same(sc, got, got_z, tm, want, want_z, otm)
+
+
+def test_enqueued_c4_at_1080p_stays_small(oracle):
+    """An enqueued 100k-triangle frame at 1920x1080 (8 160 fill tiles): round 1's worst-case bins needed 26 GB per context
+    here; the tile masks need a few MB.  Device memory taken by a fresh context for this frame stays below 200 MB (the
+    framebuffer, the resident mesh and the work buffers together), and the frame equals the oracle."""
+    import torch
+    sc = cases._with(scenes.scene_c4(), "c4_1080p", width=1920, height=1080)
+    want, want_z, otm, rc = oracle.render_scene(sc)
+    assert rc == 0
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info(0)
+    c = pkg.Context(0)
+    fb = pkg.Framebuffer(sc.width, sc.height, c)
+    c.set_textures(sc.textures)
+    mesh = pkg.Mesh(c, sc.vertices, sc.faces)
+    for _ in range(3):
+        mesh.frame_enqueue(sc.clear, sc.camera, sc.settings, sc.fog)
+    got, got_z = fb.download()
+    free1, _ = torch.cuda.mem_get_info(0)
+    mesh.free()
+    c.close()
+    assert np.array_equal(got, want) and np.array_equal(got_z.view(np.uint32), want_z.view(np.uint32))
+    assert free0 - free1 < 200 << 20, f"{(free0 - free1) >> 20} MB taken"
 
 
 def test_wireframe_absurd_edge_is_reported_not_walked(ctx, oracle):
