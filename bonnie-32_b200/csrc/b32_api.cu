@@ -50,10 +50,10 @@ struct b32_mesh {
 struct FrameKey {
     const void* verts = nullptr; const void* faces = nullptr;
     uint32_t nv = 0, nf = 0, width = 0, height = 0;
-    uint8_t rgb888 = 0, pass1 = 0, clear = 0, valid = 0, ordered = 0, spot = 0;
+    uint8_t rgb888 = 0, pass1 = 0, clear = 0, valid = 0, ordered = 0, spot = 0, prefix = 0;
     bool operator==(const FrameKey& o) const {
         return verts == o.verts && faces == o.faces && nv == o.nv && nf == o.nf && width == o.width && height == o.height &&
-               rgb888 == o.rgb888 && pass1 == o.pass1 && clear == o.clear && valid == o.valid && ordered == o.ordered && spot == o.spot;
+               rgb888 == o.rgb888 && pass1 == o.pass1 && clear == o.clear && valid == o.valid && ordered == o.ordered && spot == o.spot && prefix == o.prefix;
     }
 };
 struct FrameGraph {
@@ -509,7 +509,7 @@ int render_device(b32_ctx* ctx, const b32_vertex* d_verts, uint32_t nv, const b3
         FrameKey key;
         key.verts = d_verts; key.faces = d_faces; key.nv = nv; key.nf = nf; key.width = ctx->width; key.height = ctx->height;
         key.rgb888 = rgb888; key.pass1 = !((p.xray_mode && !rgb888) || p.wire_front); key.clear = a.clear; key.valid = 1;
-        key.ordered = p.enq_ordered; key.spot = p.has_spot;
+        key.ordered = p.enq_ordered; key.spot = p.has_spot; key.prefix = fill_uses_edge_prefix(p);
         if (ctx->frame_timings) {                          // the frame's kernels publish counters + times (b32_frame_timings reads them)
             const uint32_t slot = ctx->fslot_next++ % b32_ctx::N_FRAME_STATUS;
             b32_ctx::FrameSlot& fs = ctx->fslot[slot];

@@ -166,6 +166,10 @@ struct CallParams {
     HostStatus* host;                                 // null for enqueue-only calls
 };
 
+// Calls whose surfaces cannot have exact-integer edge values (float or ortho projection: SF_FAST_EDGE is never set) run the
+// pass-1 fill with the shared edge prefix (k_fill_opaque<.., PRE = true>); also part of an enqueued frame's graph key.
+inline bool fill_uses_edge_prefix(const CallParams& p) { return !p.use_fixed_point || p.ortho; }
+
 // ---- Rust scalar semantics -------------------------------------------------------------------
 // `f as i32` / `f as u32-ish`: cvt.rzi saturates and maps NaN to 0, exactly like Rust's `as`.
 __device__ __forceinline__ int32_t f2i32(float f) { return __float2int_rz(f); }

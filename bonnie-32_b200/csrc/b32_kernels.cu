@@ -452,6 +452,35 @@ __device__ __forceinline__ bool surface_misses_box(const Rec& r, uint32_t bx0, u
     return xmax < ERR || ymax < ERR || (1.0f - xmin - ymin) < ERR;
 }
 
+// The same question for a surface WITHOUT SF_FAST_EDGE (its edge values are the reference's chain of rounded additions,
+// not a closed form): a conservative answer.  Let L(dx, dy) = w_start + dy * b + dx * a in real arithmetic.  Each of the
+// n = dx + dy chain steps rounds once (relative error <= 2^-24 of a partial sum, and every partial sum is bounded by
+// M = |w_start| + dy_max |b| + dx_max |a| up to (1 + 2^-24)^n), so |chain - L| <= n 2^-23 M; the float evaluation of L at a
+// corner is within 4 * 2^-24 M.  E = (n + 8) 2^-22 M covers both twice over.  L is linear, so its extremes over the box are
+// at the corners; bc = fl(chain * inv_area) adds one more rounding, covered by the slack term.  The surface is rejected
+// only when an upper bound of a barycentric over the whole box is below the inside threshold (render.rs:1541): every
+// pixel of the box then fails the exact test, so dropping the surface cannot change the frame.  Non-finite values make
+// every comparison false: no reject.  tests/test_edge_reject.py holds the numpy mirror, checked against brute-force chains.
+template <typename Rec>
+__device__ __forceinline__ bool stepped_surface_misses_box(const Rec& r, uint32_t bx0, uint32_t bx1, uint32_t by0, uint32_t by1) {
+    const uint32_t min_x = r.bbox_x & 0xFFFF, max_x = r.bbox_x >> 16, min_y = r.bbox_y & 0xFFFF, max_y = r.bbox_y >> 16;
+    const uint32_t ix0 = max(bx0, min_x) - min_x, ix1 = min(bx1, max_x) - 1 - min_x, iy0 = max(by0, min_y) - min_y, iy1 = min(by1, max_y) - 1 - min_y;
+    const float dx0 = (float)ix0, dx1 = (float)ix1, dy0 = (float)iy0, dy1 = (float)iy1;
+    const float r0 = r.w0s + dy0 * r.b0, r1 = r.w0s + dy1 * r.b0, q0 = r.w1s + dy0 * r.b1, q1 = r.w1s + dy1 * r.b1;
+    const float ax0 = dx0 * r.a0, ax1 = dx1 * r.a0, cx0 = dx0 * r.a1, cx1 = dx1 * r.a1;
+    const float x00 = (r0 + ax0) * r.inv_area, x01 = (r0 + ax1) * r.inv_area, x10 = (r1 + ax0) * r.inv_area, x11 = (r1 + ax1) * r.inv_area;
+    const float y00 = (q0 + cx0) * r.inv_area, y01 = (q0 + cx1) * r.inv_area, y10 = (q1 + cx0) * r.inv_area, y11 = (q1 + cx1) * r.inv_area;
+    const float xmax = fmaxf(fmaxf(x00, x01), fmaxf(x10, x11)), xmin = fminf(fminf(x00, x01), fminf(x10, x11));
+    const float ymax = fmaxf(fmaxf(y00, y01), fmaxf(y10, y11)), ymin = fminf(fminf(y00, y01), fminf(y10, y11));
+    const float steps = (float)(ix1 + iy1 + 8u) * 2.384185791015625e-07f;                                  // (n + 8) 2^-22
+    const float ia = fabsf(r.inv_area);
+    const float ex = steps * (fabsf(r.w0s) + dy1 * fabsf(r.b0) + dx1 * fabsf(r.a0)) * ia;
+    const float ey = steps * (fabsf(r.w1s) + dy1 * fabsf(r.b1) + dx1 * fabsf(r.a1)) * ia;
+    const float slack = 9.5367431640625e-07f * (1.0f + fabsf(xmax) + fabsf(xmin) + fabsf(ymax) + fabsf(ymin));   // 2^-20 (...)
+    const float ERR = -0.0001f;
+    return xmax + ex + slack < ERR || ymax + ey + slack < ERR || (1.0f - xmin - ymin) + ex + ey + 3.0f * slack < ERR;
+}
+
 // ---- tile masks (see b32_device.cuh: "Binning without bins") ----------------------------------------
 __device__ __forceinline__ void bbox_mtiles(uint32_t bbox_x, uint32_t bbox_y, uint32_t shift, uint32_t& tx0, uint32_t& tx1, uint32_t& ty0, uint32_t& ty1) {
     uint32_t min_x = bbox_x & 0xFFFF, max_x = bbox_x >> 16, min_y = bbox_y & 0xFFFF, max_y = bbox_y >> 16;
@@ -705,6 +734,35 @@ __device__ __forceinline__ bool inside_test(const Rec& r, uint32_t x, uint32_t y
     bc_z = 1.0f - bc_x - bc_y;
     const float ERR = -0.0001f;
     return bc_x >= ERR && bc_y >= ERR && bc_z >= ERR;                              // :1541-1542
+}
+
+// n rounded additions of (s0, s1) to (w0, w1): the reference's incremental edge stepping (render.rs:1706-1712), unrolled
+__device__ __forceinline__ void edge_steps(float& w0, float& w1, float s0, float s1, uint32_t n) {
+    for (; n >= 8; n -= 8) {
+        #pragma unroll
+        for (int k = 0; k < 8; ++k) { w0 = __fadd_rn(w0, s0); w1 = __fadd_rn(w1, s1); }
+    }
+    for (; n; --n) { w0 = __fadd_rn(w0, s0); w1 = __fadd_rn(w1, s1); }
+}
+
+// inside_test for a pixel of a warp's block when the edge values of the block's row start (column max(bx0, min_x), this
+// pixel's row) are already known (pw0, pw1: see k_fill_opaque, "shared edge prefix"): the same rounded additions as
+// inside_test replays, minus the prefix the pixels of a block row have in common.  At most BW - 1 steps are left.
+template <int BW, typename Rec>
+__device__ __forceinline__ bool inside_test_prefix(const Rec& r, uint32_t x, uint32_t y, float pw0, float pw1, uint32_t bx0,
+                                                   float& bc_x, float& bc_y, float& bc_z) {
+    if (r.flags & SF_FAST_EDGE) return inside_test(r, x, y, bc_x, bc_y, bc_z);
+    const uint32_t min_x = r.bbox_x & 0xFFFF;
+    const uint32_t n = x - max(bx0, min_x);                 // the caller's bounding-box test guarantees x >= min_x (and x >= bx0)
+    float w0 = pw0, w1 = pw1;
+    const float a0 = r.a0, a1 = r.a1;
+    #pragma unroll
+    for (int k = 0; k < BW - 1; ++k) if ((uint32_t)k < n) { w0 = __fadd_rn(w0, a0); w1 = __fadd_rn(w1, a1); }
+    bc_x = w0 * r.inv_area;
+    bc_y = w1 * r.inv_area;
+    bc_z = 1.0f - bc_x - bc_y;
+    const float ERR = -0.0001f;
+    return bc_x >= ERR && bc_y >= ERR && bc_z >= ERR;
 }
 
 // texel of the surface at barycentric (bc): render.rs:1563-1586, types.rs:671-681.  Returns its index
@@ -1046,8 +1104,12 @@ __device__ __noinline__ uint32_t crowd_next_window(const BinHead* __restrict__ s
     return min(cr->ncol, win);
 }
 
-// RGB888 = the render_mesh instantiation (8-bit colour pipeline in step 5; everything else is shared); C = OpDense / OpSparse
-template <bool RGB888, class C>
+// RGB888 = the render_mesh instantiation (8-bit colour pipeline in step 5; everything else is shared); C = OpDense / OpSparse.
+// PRE = shared edge prefix: calls whose surfaces replay the reference's rounded edge additions (float / ortho projection:
+// no SF_FAST_EDGE) compute, per 8 survivors, the edge values at the start of each of the block's 4 rows ONCE — one
+// (survivor, row) pair per lane, 32 chains side by side — and every pixel only adds its last < BW steps, instead of every
+// lane replaying the whole O(bbox width + height) chain of every survivor.  Same additions in the same order: bit-exact.
+template <bool RGB888, class C, bool PRE>
 __global__ void __launch_bounds__(C::THREADS, C::MINB)
 k_fill_opaque(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks, const BinHead* __restrict__ heads,
               const TexDev* __restrict__ tex, const uint16_t* __restrict__ texels, const uint32_t* __restrict__ texmask,
@@ -1405,6 +1467,7 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks,
                     if (!p.use_zbuffer) cand = cand && h.key >= wkey;
                     else cand = cand && (h.key == 0xFFFFFFFFu || !(__uint_as_float(~h.key) > wz));
                     if (cand && surface_misses_box(crec[sb + lane], ox0, ox1, oy0, oy1)) cand = false;   // exact: see surface_misses_box
+                    if (PRE && cand && !(crec[sb + lane].flags & SF_FAST_EDGE) && stepped_surface_misses_box(crec[sb + lane], ox0, ox1, oy0, oy1)) cand = false;
                 }
                 uint32_t mask = __ballot_sync(0xFFFFFFFFu, cand);
                 if (mask == 0) continue;
@@ -1417,11 +1480,33 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks,
                 __syncwarp();
                 // ---- 3b. survivors, two at a time per pixel lane (dual: each half-warp takes every other one) -----------
                 constexpr uint32_t NSUB = OP_DUAL ? 2 : 1;
-                for (uint32_t j0 = 0; j0 < cnt; j0 += 2 * NSUB) {
+                constexpr uint32_t JB = PRE ? 8u : 32u;                // survivors per shared-prefix round (4 rows x 8 = 32 lanes)
+                for (uint32_t jb = 0; jb < cnt; jb += JB) {
+                const uint32_t jend = PRE ? min(cnt, jb + JB) : cnt;
+                float pw0 = 0.0f, pw1 = 0.0f;
+                if (PRE) {                                              // lane -> (survivor jb + lane / 4, block row lane % 4)
+                    const uint32_t sj = jb + (lane >> 2), yr = by0 + (lane & 3u);
+                    if (sj < jend) {
+                        const SurfHot& r = crec[my_sidx[sj]];
+                        const uint32_t min_x = r.bbox_x & 0xFFFF, min_y = r.bbox_y & 0xFFFF, max_y = r.bbox_y >> 16;
+                        if (!(r.flags & SF_FAST_EDGE) && yr >= min_y && yr < max_y) {
+                            pw0 = r.w0s; pw1 = r.w1s;
+                            edge_steps(pw0, pw1, r.b0, r.b1, yr - min_y);                       // row steps first (:1706-1712) ...
+                            edge_steps(pw0, pw1, r.a0, r.a1, bx0 > min_x ? bx0 - min_x : 0u);   // ... then along the row to the block
+                        }
+                    }
+                    __syncwarp();
+                }
+                for (uint32_t j0 = jb; j0 < jend; j0 += 2 * NSUB) {
                     #pragma unroll
                     for (int k = 0; k < 2; ++k) {
                         uint32_t j = j0 + NSUB * k + sub;
-                        if (j >= cnt) continue;
+                        float sw0 = 0.0f, sw1 = 0.0f;
+                        if (PRE) {                                      // every lane takes part (no lane has left the loop)
+                            const uint32_t src = ((min(j, jend - 1) - jb) << 2) | (pix / OP_BW);
+                            sw0 = __shfl_sync(0xFFFFFFFFu, pw0, src); sw1 = __shfl_sync(0xFFFFFFFFu, pw1, src);
+                        }
+                        if (j >= jend) continue;
                         const SurfHot& r = crec[my_sidx[j]];
                         const uint2 kf = my_surv[j];
                         uint32_t min_x = r.bbox_x & 0xFFFF, max_x = r.bbox_x >> 16, min_y = r.bbox_y & 0xFFFF, max_y = r.bbox_y >> 16;
@@ -1430,7 +1515,7 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks,
                         uint64_t c_prio = (((uint64_t)kf.x << 32) | kf.y) + 1;
                         if (!p.use_zbuffer && c_prio <= best) continue;               // drawn earlier than the current winner
                         float bc_x, bc_y, bc_z;
-                        if (!inside_test(r, x, y, bc_x, bc_y, bc_z)) continue;
+                        if (!(PRE ? inside_test_prefix<OP_BW>(r, x, y, sw0, sw1, bx0, bc_x, bc_y, bc_z) : inside_test(r, x, y, bc_x, bc_y, bc_z))) continue;
                         float inv_z = 0.0f, c_z = 0.0f;
                         if (p.use_zbuffer || !p.affine_textures) inv_z = bc_x * r.iz1 + bc_y * r.iz2 + bc_z * r.iz3;   // :1549
                         if (p.use_zbuffer) {
@@ -1449,6 +1534,7 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks,
                         if (!p.use_zbuffer) best = c_prio;
                         else { px.z = c_z; best_face = c_face; }
                     }
+                }
                 }
                 if (OP_DUAL) {   // merge the two half-warps' winners for each pixel (exact: max / lexicographic min are associative)
                     uint64_t ob = __shfl_xor_sync(0xFFFFFFFFu, best, 16);
@@ -2164,10 +2250,12 @@ static void launch_k(const LaunchCtx& L, void (*kern)(KArgs...), dim3 grid, dim3
 
 // Per-device kernel attributes (dynamic shared memory above the 48 KB default); called once per context, on its device.
 int init_kernel_attributes() {
-    cudaError_t e = cudaFuncSetAttribute(k_fill_opaque<false, OpDense>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OpDense::SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fill_opaque<true, OpDense>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OpDense::SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fill_opaque<false, OpSparse>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OpSparse::SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fill_opaque<true, OpSparse>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OpSparse::SMEM);
+    cudaError_t e = cudaSuccess;
+    auto smem_attr = [&](auto kern, size_t bytes) { if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); };
+    smem_attr(k_fill_opaque<false, OpDense, false>, OpDense::SMEM);  smem_attr(k_fill_opaque<true, OpDense, false>, OpDense::SMEM);
+    smem_attr(k_fill_opaque<false, OpDense, true>, OpDense::SMEM);   smem_attr(k_fill_opaque<true, OpDense, true>, OpDense::SMEM);
+    smem_attr(k_fill_opaque<false, OpSparse, false>, OpSparse::SMEM); smem_attr(k_fill_opaque<true, OpSparse, false>, OpSparse::SMEM);
+    smem_attr(k_fill_opaque<false, OpSparse, true>, OpSparse::SMEM);  smem_attr(k_fill_opaque<true, OpSparse, true>, OpSparse::SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fill_ordered<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ORD_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fill_ordered<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ORD_SMEM);
     return (int)e;
@@ -2204,12 +2292,22 @@ void launch_fill_opaque(const LaunchCtx& L, const SurfRec* recs, const uint4* ma
     // around them.  A blocking call of up to 444 tiles has the GPU to itself: the two-lane shape finishes it sooner.
     static const bool force_dense = getenv("B32_FILL_DENSE") != nullptr, force_sparse = getenv("B32_FILL_SPARSE") != nullptr;
     const bool sparse = force_sparse || (!force_dense && (p.async_call || ntiles * OpDense::SPLIT > L.sms * (uint32_t)OpDense::MINB));
-    if (sparse)
-        launch_k(L, p.rgb888 ? k_fill_opaque<true, OpSparse> : k_fill_opaque<false, OpSparse>, ntiles * OpSparse::SPLIT, OpSparse::THREADS, OpSparse::SMEM, true,
-                 recs, masks, heads, tex, texels, texmask, fb_rgba, fb_z, st, sticky, crowd, crowd_cap, p);
-    else
-        launch_k(L, p.rgb888 ? k_fill_opaque<true, OpDense> : k_fill_opaque<false, OpDense>, ntiles * OpDense::SPLIT, OpDense::THREADS, OpDense::SMEM, true,
-                 recs, masks, heads, tex, texels, texmask, fb_rgba, fb_z, st, sticky, crowd, crowd_cap, p);
+    // Float / ortho projection: no surface has integer edge values, all of them replay the reference's rounded additions:
+    // the shared-edge-prefix instantiation (see k_fill_opaque).  Fixed-point calls keep the per-pixel replay for the few
+    // surfaces that leave the exact-integer range (far off-screen vertices).
+    static const bool no_prefix = getenv("B32_NO_EDGE_PREFIX") != nullptr;
+    const bool pre = fill_uses_edge_prefix(p) && !no_prefix;
+    using Kern = void (*)(const SurfRec*, const uint4*, const BinHead*, const TexDev*, const uint16_t*, const uint32_t*, uint32_t*, float*,
+                          CallState*, uint32_t*, BinHead*, uint32_t, CallParams);
+    Kern k;
+    if (sparse) k = p.rgb888 ? (pre ? k_fill_opaque<true, OpSparse, true> : k_fill_opaque<true, OpSparse, false>)
+                             : (pre ? k_fill_opaque<false, OpSparse, true> : k_fill_opaque<false, OpSparse, false>);
+    else        k = p.rgb888 ? (pre ? k_fill_opaque<true, OpDense, true> : k_fill_opaque<true, OpDense, false>)
+                             : (pre ? k_fill_opaque<false, OpDense, true> : k_fill_opaque<false, OpDense, false>);
+    if (sparse) launch_k(L, k, ntiles * OpSparse::SPLIT, OpSparse::THREADS, OpSparse::SMEM, true,
+                         recs, masks, heads, tex, texels, texmask, fb_rgba, fb_z, st, sticky, crowd, crowd_cap, p);
+    else        launch_k(L, k, ntiles * OpDense::SPLIT, OpDense::THREADS, OpDense::SMEM, true,
+                         recs, masks, heads, tex, texels, texmask, fb_rgba, fb_z, st, sticky, crowd, crowd_cap, p);
 }
 
 void launch_fill_ordered(const LaunchCtx& L, const SurfRec* recs, const uint4* masks, BinHead* scratch, const uint64_t* keys,
