@@ -162,6 +162,7 @@ SYMBOLS = {
     "b32_debug_draw_order": (C.c_int, [_P, _P, C.c_uint32, C.POINTER(C.c_uint32)]),
     "b32_debug_kernel_times": (C.c_int, [_P, C.POINTER(C.c_float), C.c_uint32]),
     "b32_debug_timing_ring": (C.c_int, [_P, C.c_uint32]),
+    "b32_debug_prefix_hint": (C.c_int, [_P]),
     "b32_debug_timing_read": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_uint32]),
 }
 

@@ -120,6 +120,9 @@ struct b32_ctx {
     DevBuf<uint32_t> line_scratch;
     std::vector<LightDev> lights_h;
     bool async_pending = false;
+    // the last call whose counters the host saw (a blocking call, or an enqueued frame read by b32_frame_timings) drew
+    // large surfaces with stepped edge values in fixed-point mode: the next calls run the shared-prefix fill (k_fill_opaque<.., PRE>)
+    bool prefix_hint = false;
     CallParams last_params{};
     DevBuf<LightDev> lights;
     DevBuf<float> dbg;
@@ -131,7 +134,7 @@ struct b32_ctx {
     // opt-in (b32_ctx_frame_timings): enqueued frames report the same way, into a ring of status blocks
     static constexpr uint32_t N_FRAME_STATUS = 8;
     HostStatus* fstat = nullptr; HostStatus* fstat_dev = nullptr;
-    struct FrameSlot { uint32_t seq = 0; uint8_t last = 0, pass1 = 0, ordered = 0; } fslot[N_FRAME_STATUS];
+    struct FrameSlot { uint32_t seq = 0; uint8_t last = 0, pass1 = 0, ordered = 0, counts_stepped = 0; } fslot[N_FRAME_STATUS];
     uint32_t fslot_next = 0;
     bool frame_timings = false;
     uint32_t host_seq = 0;
@@ -233,6 +236,7 @@ int fill_params(b32_ctx* ctx, CallParams& p, const b32_camera* cam, const b32_se
         lights.push_back(d);
     }
     p.n_lights = (uint32_t)lights.size();
+    p.prefer_prefix = ctx->prefix_hint ? 1 : 0;
     return B32_OK;
 }
 
@@ -509,11 +513,11 @@ int render_device(b32_ctx* ctx, const b32_vertex* d_verts, uint32_t nv, const b3
         FrameKey key;
         key.verts = d_verts; key.faces = d_faces; key.nv = nv; key.nf = nf; key.width = ctx->width; key.height = ctx->height;
         key.rgb888 = rgb888; key.pass1 = !((p.xray_mode && !rgb888) || p.wire_front); key.clear = a.clear; key.valid = 1;
-        key.ordered = p.enq_ordered; key.spot = p.has_spot; key.prefix = fill_uses_edge_prefix(p);
+        key.ordered = p.enq_ordered; key.spot = p.has_spot; key.prefix = fill_uses_edge_prefix(p) || p.prefer_prefix;
         if (ctx->frame_timings) {                          // the frame's kernels publish counters + times (b32_frame_timings reads them)
             const uint32_t slot = ctx->fslot_next++ % b32_ctx::N_FRAME_STATUS;
             b32_ctx::FrameSlot& fs = ctx->fslot[slot];
-            fs.seq = ++ctx->host_seq; fs.pass1 = key.pass1; fs.ordered = p.enq_ordered && !p.wire_front;
+            fs.seq = ++ctx->host_seq; fs.pass1 = key.pass1; fs.ordered = p.enq_ordered && !p.wire_front; fs.counts_stepped = !fill_uses_edge_prefix(p);
             fs.last = fs.ordered ? HS_ORDERED : fs.pass1 ? HS_FILL : HS_SETUP;
             p.host = ctx->fstat_dev + slot; p.host_seq = fs.seq;
             ctx->last_params = p;
@@ -531,6 +535,7 @@ int render_device(b32_ctx* ctx, const b32_vertex* d_verts, uint32_t nv, const b3
     CK(cudaGetLastError());
     rc = wait_stamp(ctx, HS_SETUP, seq); if (rc) return rc;
     hs = ctx->hstat->state;
+    if (!fill_uses_edge_prefix(p)) ctx->prefix_hint = hs.n_big_stepped >= 2;
     if (hs.oob == 2) return fail(ctx, B32_ERR_INVALID, "face blend mode out of range (not a BlendMode)");
     if (hs.oob) return fail(ctx, B32_ERR_OOB_INDEX, "face vertex index out of range (reference: slice index panic)");
     {   // the reference panics on a NaN key in a sorted slice of length >= 2 (render.rs:2531; RGB888: one list, :2161)
@@ -915,6 +920,7 @@ int b32_frame_timings(b32_ctx* ctx, b32_timings* out) {
         out->cull_ms = ms(HS_SETUP);                        // transform + cull + setup are one kernel (see b32_timings)
         out->draw_ms = (fs.pass1 ? ms(HS_FILL) : 0.0f) + (fs.ordered ? ms(HS_ORDERED) : 0.0f);
         out->triangles_drawn = h.state.n_opaque + h.state.n_transp;
+        if (fs.counts_stepped) ctx->prefix_hint = h.state.n_big_stepped >= 2;
         return B32_OK;
     }
     return B32_OK;                                          // nothing has finished yet: zeros
@@ -1153,6 +1159,7 @@ int b32_debug_timing_ring(b32_ctx* ctx, uint32_t n) {
     ctx->tring_n = n;
     return B32_OK;
 }
+int b32_debug_prefix_hint(b32_ctx* ctx) { return ctx ? (ctx->prefix_hint ? 1 : 0) : -1; }
 // Device times of the timed frames (after a sync): setup_ms[i], fill_ms[i] for the last min(frames, n) frames. Returns their number.
 int b32_debug_timing_read(b32_ctx* ctx, float* setup_ms, float* fill_ms, uint32_t cap) {
     if (!ctx || !ctx->tring_n) return 0;

@@ -111,6 +111,7 @@ struct CallState {
     uint32_t obin_max;                    // ordered pass: largest such count seen
     uint32_t wire_too_long;               // wireframe phase: an edge longer than WIRE_MAX_STEPS was skipped (host reports B32_ERR_UNSUPPORTED)
     uint32_t crowd_used;                  // pass 1: entries of the crowded-tile scratch handed out so far (one atomic per crowded tile)
+    uint32_t n_big_stepped;               // pass-1 surfaces covering >= 1/64 of the framebuffer whose edge values are stepped (no SF_FAST_EDGE) in a fixed-point call
     uint32_t done[3];                     // blocking calls: CTAs of k_setup / k_fill_opaque / k_fill_ordered that have finished (HostStatus)
 };
 
@@ -160,6 +161,7 @@ struct CallParams {
     uint8_t faces_implicit;                           // 1: `faces` holds one flags word per face; face i uses vertices 3i, 3i+1, 3i+2.  2: no face buffer at all, every face has `uniform_flags`
     float ambient, ortho_zoom, ortho_cx, ortho_cy;
     float fog_start, fog_falloff, fog_cull;
+    uint8_t prefer_prefix;                            // host's hint from the previous call on this context: large stepped surfaces were seen, run the shared-prefix fill
     uint8_t has_spot;                                 // an enabled Spot light is in the list and shading is on: k_setup<true> (the acos path) runs
     uint32_t uniform_flags;                           // faces_implicit == 2: the flags word of every face
     uint32_t host_seq;                                // blocking calls: the value the kernels publish in HostStatus when done
@@ -168,7 +170,7 @@ struct CallParams {
 
 // Calls whose surfaces cannot have exact-integer edge values (float or ortho projection: SF_FAST_EDGE is never set) run the
 // pass-1 fill with the shared edge prefix (k_fill_opaque<.., PRE = true>); also part of an enqueued frame's graph key.
-inline bool fill_uses_edge_prefix(const CallParams& p) { return !p.use_fixed_point || p.ortho; }
+__host__ __device__ inline bool fill_uses_edge_prefix(const CallParams& p) { return !p.use_fixed_point || p.ortho; }
 
 // ---- Rust scalar semantics -------------------------------------------------------------------
 // `f as i32` / `f as u32-ish`: cvt.rzi saturates and maps NaN to 0, exactly like Rust's `as`.

@@ -370,6 +370,12 @@ __device__ __forceinline__ void setup_face(uint32_t fi, const uint4& fc, const f
             bool ints = is_integral(r.a0) && is_integral(r.b0) && is_integral(r.a1) && is_integral(r.b1) &&
                         is_integral(r.w0s) && is_integral(r.w1s);
             if (ints && m0 < 8388608.0f && m1 < 8388608.0f) flags |= SF_FAST_EDGE;
+            else if (!empty && !fill_uses_edge_prefix(p) && (max_x - min_x) * (max_y - min_y) * 64u >= p.width * p.height) {
+                // a fixed-point call's large surface with stepped edge values (far off-screen vertices): counted for the host's
+                // choice of the fill instantiation of the NEXT call (CallState.n_big_stepped); one atomic per warp that gets here
+                const uint32_t am = __activemask();
+                if ((threadIdx.x & 31u) == (uint32_t)(__ffs(am) - 1)) atomicAdd(&st->n_big_stepped, __popc(am));
+            }
         }
         r.iz1 = 1.0f / s1.z; r.iz2 = 1.0f / s2.z; r.iz3 = 1.0f / s3.z;                  // :1546-1548
         r.u1 = va[3]; r.v1 = va[4]; r.u2 = vb[3]; r.v2 = vb[4]; r.u3 = vc[3]; r.v3 = vc[4];
@@ -2294,9 +2300,10 @@ void launch_fill_opaque(const LaunchCtx& L, const SurfRec* recs, const uint4* ma
     const bool sparse = force_sparse || (!force_dense && (p.async_call || ntiles * OpDense::SPLIT > L.sms * (uint32_t)OpDense::MINB));
     // Float / ortho projection: no surface has integer edge values, all of them replay the reference's rounded additions:
     // the shared-edge-prefix instantiation (see k_fill_opaque).  Fixed-point calls keep the per-pixel replay for the few
-    // surfaces that leave the exact-integer range (far off-screen vertices).
-    static const bool no_prefix = getenv("B32_NO_EDGE_PREFIX") != nullptr;
-    const bool pre = fill_uses_edge_prefix(p) && !no_prefix;
+    // surfaces that leave the exact-integer range (far off-screen vertices) — unless the previous call on this context
+    // counted large ones (CallState.n_big_stepped -> CallParams.prefer_prefix): a camera next to a wall stays there.
+    static const bool no_prefix = getenv("B32_NO_EDGE_PREFIX") != nullptr, force_prefix = getenv("B32_FORCE_EDGE_PREFIX") != nullptr;
+    const bool pre = (fill_uses_edge_prefix(p) || p.prefer_prefix || force_prefix) && !no_prefix;
     using Kern = void (*)(const SurfRec*, const uint4*, const BinHead*, const TexDev*, const uint16_t*, const uint32_t*, uint32_t*, float*,
                           CallState*, uint32_t*, BinHead*, uint32_t, CallParams);
     Kern k;
