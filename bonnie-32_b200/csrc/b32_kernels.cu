@@ -1236,6 +1236,7 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks,
     // z-buffer : best_face = face + 1 of the winner so far (0 = framebuffer content), its depth in px.z
     uint64_t best = valid ? 0ull : ~0ull;
     uint32_t best_face = 0;
+    float win_bx = 0.0f, win_by = 0.0f;                    // PRE: the winner's barycentrics as the walk computed them (step 5 then needs no second replay of its chain)
     uint2* my_surv = s_surv + warp * 32;
     uint8_t* my_sidx = s_sidx + warp * 32;
     const bool offscreen = bx0 >= p.width || by0 >= p.height;      // whole warp off-screen
@@ -1539,6 +1540,7 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks,
                         }
                         if (!p.use_zbuffer) best = c_prio;
                         else { px.z = c_z; best_face = c_face; }
+                        if (PRE) { win_bx = bc_x; win_by = bc_y; }
                     }
                 }
                 }
@@ -1548,6 +1550,10 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks,
                     uint32_t of = __shfl_xor_sync(0xFFFFFFFFu, best_face, 16);
                     // z-buffer: lexicographic (z, face+1) minimum, 0 = framebuffer content wins ties; painter's: max priority
                     bool take = p.use_zbuffer ? (oz < px.z || (oz == px.z && of < best_face)) : (ob > best);
+                    if (PRE) {
+                        const float obx = __shfl_xor_sync(0xFFFFFFFFu, win_bx, 16), oby = __shfl_xor_sync(0xFFFFFFFFu, win_by, 16);
+                        if (take) { win_bx = obx; win_by = oby; }
+                    }
                     if (take) { best = ob; px.z = oz; best_face = of; }
                 }
             }
@@ -1571,7 +1577,8 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks,
         if (winner) {
             const SurfRec& r = recs[winner - 1];
             float bc_x, bc_y, bc_z;
-            inside_test(r, x, y, bc_x, bc_y, bc_z);                        // same arithmetic as in the walk
+            if (PRE) { bc_x = win_bx; bc_y = win_by; bc_z = 1.0f - bc_x - bc_y; }      // the walk's own values (:1536-1538)
+            else inside_test(r, x, y, bc_x, bc_y, bc_z);                   // same arithmetic as in the walk
             float inv_z = bc_x * r.iz1 + bc_y * r.iz2 + bc_z * r.iz3;      // :1549
             uint32_t o_r, o_g, o_b, o_blend; bool semi;
             bool wrote = RGB888 ? shade888(r, x, y, bc_x, bc_y, bc_z, inv_z, texd, reinterpret_cast<const uint32_t*>(texels), p, o_r, o_g, o_b, o_blend)
