@@ -14,7 +14,7 @@ def load(rep):
     res = {}
     for r in rows[2:]:
         name = r[ix["Kernel Name"]]
-        key = "k_setup" if name.startswith("k_setup") else ("k_fill_opaque_dense" if "OpCfg<512" in name else "k_fill_opaque")
+        key = "k_setup" if "k_setup" in name.split("(")[0] else ("k_fill_opaque_dense" if "OpCfg<512" in name else "k_fill_opaque")
         f = lambda m: float(r[ix[m]].replace(",", "")) if m in ix and r[ix[m]] not in ("", "n/a") else None
         scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         rd = f("dram__bytes_read.sum") * scale[rows[1][ix["dram__bytes_read.sum"]]]
