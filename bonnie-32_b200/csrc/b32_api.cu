@@ -120,9 +120,18 @@ struct b32_ctx {
     DevBuf<uint32_t> line_scratch;
     std::vector<LightDev> lights_h;
     bool async_pending = false;
-    // the last call whose counters the host saw (a blocking call, or an enqueued frame read by b32_frame_timings) drew
-    // large surfaces with stepped edge values in fixed-point mode: the next calls run the shared-prefix fill (k_fill_opaque<.., PRE>)
+    // One of the last PREFIX_HINT_CALLS calls on this context drew large surfaces with stepped edge values in fixed-point
+    // mode (k_setup stored its call number in the mapped word behind hstat): the next calls run the shared-prefix fill
+    // (k_fill_opaque<.., PRE>).  Blocking and enqueue-only callers alike: nobody waits for the word.
+    static constexpr uint32_t PREFIX_HINT_CALLS = 8;
     bool prefix_hint = false;
+    uint32_t call_seq = 0;
+    uint32_t* stepped_seq = nullptr;   // host view of the mapped word
+    uint32_t* stepped_seq_dev = nullptr;
+    bool next_prefix_hint() const {
+        const uint32_t seen = __atomic_load_n(stepped_seq, __ATOMIC_RELAXED);
+        return seen != 0 && (call_seq + 1 - seen) <= PREFIX_HINT_CALLS;
+    }
     CallParams last_params{};
     DevBuf<LightDev> lights;
     DevBuf<float> dbg;
@@ -134,7 +143,7 @@ struct b32_ctx {
     // opt-in (b32_ctx_frame_timings): enqueued frames report the same way, into a ring of status blocks
     static constexpr uint32_t N_FRAME_STATUS = 8;
     HostStatus* fstat = nullptr; HostStatus* fstat_dev = nullptr;
-    struct FrameSlot { uint32_t seq = 0; uint8_t last = 0, pass1 = 0, ordered = 0, counts_stepped = 0; } fslot[N_FRAME_STATUS];
+    struct FrameSlot { uint32_t seq = 0; uint8_t last = 0, pass1 = 0, ordered = 0; } fslot[N_FRAME_STATUS];
     uint32_t fslot_next = 0;
     bool frame_timings = false;
     uint32_t host_seq = 0;
@@ -236,6 +245,8 @@ int fill_params(b32_ctx* ctx, CallParams& p, const b32_camera* cam, const b32_se
         lights.push_back(d);
     }
     p.n_lights = (uint32_t)lights.size();
+    ctx->prefix_hint = ctx->next_prefix_hint();
+    p.call_seq = ++ctx->call_seq; p.stepped_seq_host = ctx->stepped_seq_dev;
     p.prefer_prefix = ctx->prefix_hint ? 1 : 0;
     return B32_OK;
 }
@@ -517,7 +528,7 @@ int render_device(b32_ctx* ctx, const b32_vertex* d_verts, uint32_t nv, const b3
         if (ctx->frame_timings) {                          // the frame's kernels publish counters + times (b32_frame_timings reads them)
             const uint32_t slot = ctx->fslot_next++ % b32_ctx::N_FRAME_STATUS;
             b32_ctx::FrameSlot& fs = ctx->fslot[slot];
-            fs.seq = ++ctx->host_seq; fs.pass1 = key.pass1; fs.ordered = p.enq_ordered && !p.wire_front; fs.counts_stepped = !fill_uses_edge_prefix(p);
+            fs.seq = ++ctx->host_seq; fs.pass1 = key.pass1; fs.ordered = p.enq_ordered && !p.wire_front;
             fs.last = fs.ordered ? HS_ORDERED : fs.pass1 ? HS_FILL : HS_SETUP;
             p.host = ctx->fstat_dev + slot; p.host_seq = fs.seq;
             ctx->last_params = p;
@@ -535,7 +546,6 @@ int render_device(b32_ctx* ctx, const b32_vertex* d_verts, uint32_t nv, const b3
     CK(cudaGetLastError());
     rc = wait_stamp(ctx, HS_SETUP, seq); if (rc) return rc;
     hs = ctx->hstat->state;
-    if (!fill_uses_edge_prefix(p)) ctx->prefix_hint = hs.n_big_stepped >= 2;
     if (hs.oob == 2) return fail(ctx, B32_ERR_INVALID, "face blend mode out of range (not a BlendMode)");
     if (hs.oob) return fail(ctx, B32_ERR_OOB_INDEX, "face vertex index out of range (reference: slice index panic)");
     {   // the reference panics on a NaN key in a sorted slice of length >= 2 (render.rs:2531; RGB888: one list, :2161)
@@ -606,9 +616,11 @@ int b32_ctx_create(int device, b32_ctx** out) {
     if ((e = cudaMalloc(&ctx->sticky, sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMemset(ctx->sticky, 0, sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMemset");
     if ((e = cudaMallocHost(&ctx->state_h, sizeof(CallState))) != cudaSuccess) return bail(e, "cudaMallocHost");
-    if ((e = cudaHostAlloc(&ctx->hstat, sizeof(HostStatus), cudaHostAllocMapped)) != cudaSuccess) return bail(e, "cudaHostAlloc");
-    std::memset(ctx->hstat, 0, sizeof(HostStatus));
+    if ((e = cudaHostAlloc(&ctx->hstat, sizeof(HostStatus) + 64, cudaHostAllocMapped)) != cudaSuccess) return bail(e, "cudaHostAlloc");
+    std::memset(ctx->hstat, 0, sizeof(HostStatus) + 64);
     if ((e = cudaHostGetDevicePointer(&ctx->hstat_dev, ctx->hstat, 0)) != cudaSuccess) return bail(e, "cudaHostGetDevicePointer");
+    ctx->stepped_seq = reinterpret_cast<uint32_t*>(ctx->hstat + 1);               // the word behind the status block
+    ctx->stepped_seq_dev = reinterpret_cast<uint32_t*>(ctx->hstat_dev + 1);
     ctx->pinned_bytes = 8u << 20;
     if ((e = cudaMallocHost(&ctx->pinned, ctx->pinned_bytes)) != cudaSuccess) return bail(e, "cudaMallocHost");
     ctx->texdesc.reserve(1); ctx->texels.reserve(1); ctx->texmask.reserve(4); ctx->lights.reserve(1);
@@ -920,7 +932,6 @@ int b32_frame_timings(b32_ctx* ctx, b32_timings* out) {
         out->cull_ms = ms(HS_SETUP);                        // transform + cull + setup are one kernel (see b32_timings)
         out->draw_ms = (fs.pass1 ? ms(HS_FILL) : 0.0f) + (fs.ordered ? ms(HS_ORDERED) : 0.0f);
         out->triangles_drawn = h.state.n_opaque + h.state.n_transp;
-        if (fs.counts_stepped) ctx->prefix_hint = h.state.n_big_stepped >= 2;
         return B32_OK;
     }
     return B32_OK;                                          // nothing has finished yet: zeros
@@ -1159,7 +1170,7 @@ int b32_debug_timing_ring(b32_ctx* ctx, uint32_t n) {
     ctx->tring_n = n;
     return B32_OK;
 }
-int b32_debug_prefix_hint(b32_ctx* ctx) { return ctx ? (ctx->prefix_hint ? 1 : 0) : -1; }
+int b32_debug_prefix_hint(b32_ctx* ctx) { return ctx ? (ctx->next_prefix_hint() ? 1 : 0) : -1; }
 // Device times of the timed frames (after a sync): setup_ms[i], fill_ms[i] for the last min(frames, n) frames. Returns their number.
 int b32_debug_timing_read(b32_ctx* ctx, float* setup_ms, float* fill_ms, uint32_t cap) {
     if (!ctx || !ctx->tring_n) return 0;

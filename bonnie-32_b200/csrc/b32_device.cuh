@@ -161,9 +161,11 @@ struct CallParams {
     uint8_t faces_implicit;                           // 1: `faces` holds one flags word per face; face i uses vertices 3i, 3i+1, 3i+2.  2: no face buffer at all, every face has `uniform_flags`
     float ambient, ortho_zoom, ortho_cx, ortho_cy;
     float fog_start, fog_falloff, fog_cull;
-    uint8_t prefer_prefix;                            // host's hint from the previous call on this context: large stepped surfaces were seen, run the shared-prefix fill
+    uint8_t prefer_prefix;                            // host's hint: one of the last calls on this context drew large stepped surfaces, run the shared-prefix fill
     uint8_t has_spot;                                 // an enabled Spot light is in the list and shading is on: k_setup<true> (the acos path) runs
     uint32_t uniform_flags;                           // faces_implicit == 2: the flags word of every face
+    uint32_t call_seq;                                // this context's call counter; the first large stepped surface of a fixed-point call stores it in *stepped_seq_host
+    uint32_t* stepped_seq_host;                       // host-mapped word (never null)
     uint32_t host_seq;                                // blocking calls: the value the kernels publish in HostStatus when done
     HostStatus* host;                                 // null for enqueue-only calls
 };

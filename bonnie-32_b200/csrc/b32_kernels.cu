@@ -371,8 +371,8 @@ __device__ __forceinline__ void setup_face(uint32_t fi, const uint4& fc, const f
                         is_integral(r.w0s) && is_integral(r.w1s);
             if (ints && m0 < 8388608.0f && m1 < 8388608.0f) flags |= SF_FAST_EDGE;
             else if (!empty && !fill_uses_edge_prefix(p) && (max_x - min_x) * (max_y - min_y) * 64u >= p.width * p.height) {
-                // a fixed-point call's large surface with stepped edge values (far off-screen vertices): counted for the host's
-                // choice of the fill instantiation of the NEXT call (CallState.n_big_stepped); one atomic per warp that gets here
+                // a fixed-point call's large surface with stepped edge values (far off-screen vertices): counted (one atomic per
+                // warp that gets here); the fill kernel tells the host, which picks the fill instantiation of the NEXT calls by it
                 const uint32_t am = __activemask();
                 if ((threadIdx.x & 31u) == (uint32_t)(__ffs(am) - 1)) atomicAdd(&st->n_big_stepped, __popc(am));
             }
@@ -1176,6 +1176,9 @@ k_fill_opaque(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks,
             if (aborts) atomicOr(sticky, s.oob == 2 ? 32u : s.oob ? 1u : 2u);
             else if (s.n_transp && !p.enq_ordered) atomicOr(sticky, 8u);                         // pass 2 exists but was not enqueued
         }
+        // large stepped surfaces in a fixed-point call (k_setup counted them): one 4-byte store into host-mapped memory, from
+        // which the host picks the fill instantiation of this context's next calls (see launch_fill_opaque)
+        if (blockIdx.x == 0 && threadIdx.x == 0 && s.n_big_stepped) *reinterpret_cast<volatile uint32_t*>(p.stepped_seq_host) = p.call_seq;
         // x-ray (render_mesh_15) and any framebuffer-reading surface (render_mesh) go through the ordered replay instead
         skip = aborts || (p.xray_mode && !RGB888) || (RGB888 && s.n_transp);
     }

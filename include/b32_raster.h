@@ -380,8 +380,8 @@ int b32_debug_kernel_times(b32_ctx* ctx, float* out_ms, uint32_t cap);
  * fill kernel(s) and behind them, n frames deep; n = 0 switches it off.  b32_debug_timing_read (syncs) returns the
  * number of frames read; setup_ms[i] / fill_ms[i] are their device times. */
 int b32_debug_timing_ring(b32_ctx* ctx, uint32_t n);
-/* 1 when the next fixed-point call on this context will run the shared-edge-prefix fill because the last call whose
- * counters the host saw drew large surfaces with stepped (non-integer-exact) edge values; 0 otherwise; < 0 on error. */
+/* 1 when the next fixed-point call on this context will run the shared-edge-prefix fill because one of its last 8 calls
+ * (as far as the device has got) drew a large surface with stepped (non-integer-exact) edge values; 0 otherwise; < 0 on error. */
 int b32_debug_prefix_hint(b32_ctx* ctx);
 int b32_debug_timing_read(b32_ctx* ctx, float* setup_ms, float* fill_ms, uint32_t cap);
 

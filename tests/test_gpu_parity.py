@@ -76,32 +76,37 @@ def test_big_triangles_slow_edge_path(ctx, oracle):
 
 @pytest.mark.parametrize("size", [(320, 240), (1920, 1080)])
 def test_stepped_surfaces_switch_the_fill_to_the_shared_edge_prefix(ctx, oracle, size):
-    """Fixed-point calls whose large surfaces leave the exact-integer range (far off-screen vertices): the first call counts
-    them (CallState.n_big_stepped), the following calls on the context run k_fill_opaque<.., PRE> (shared edge prefix +
-    conservative box reject) — blocking, resident and enqueued — and an ordinary scene switches back.  Every frame equals
-    the oracle, whichever instantiation drew it."""
+    """Fixed-point calls whose large surfaces leave the exact-integer range (far off-screen vertices): k_setup tells the
+    host through a mapped word, and the next calls on the context — blocking, resident or enqueue-only — run
+    k_fill_opaque<.., PRE> (shared edge prefix + conservative box reject) until 8 calls have gone by without such a
+    surface.  Every frame equals the oracle, whichever instantiation drew it."""
     big = cases._with(cases.big_triangle_scene(), "big_triangles", width=size[0], height=size[1])
     plain = cases._with(scenes.scene_c2(n_tris=300), "plain", width=size[0], height=size[1])
     want_big = oracle.render_scene(big)
     want_plain = oracle.render_scene(plain)
     assert want_big[3] == 0 and want_plain[3] == 0
-    got, got_z, tm = render_gpu(ctx, plain)
-    assert ctx.lib.b32_debug_prefix_hint(ctx.h) == 0
+    hint = lambda: ctx.lib.b32_debug_prefix_hint(ctx.h)
+    for _ in range(9):                                      # whatever earlier tests left behind has aged out after 8 calls
+        got, got_z, tm = render_gpu(ctx, plain)
+    assert_same(plain, got, got_z, tm, *want_plain[:3])
+    assert hint() == 0
     for k in range(3):                                      # call 0 per-pixel replay, calls 1.. the shared prefix
         got, got_z, tm = render_gpu(ctx, big, resident=(k == 2))
         assert_same(big, got, got_z, tm, *want_big[:3])
-        assert ctx.lib.b32_debug_prefix_hint(ctx.h) == 1
+        assert hint() == 1
     fb = pkg.Framebuffer(big.width, big.height, ctx)
     ctx.set_textures(big.textures)
     mesh = pkg.Mesh(ctx, big.vertices, big.faces)
-    for _ in range(3):                                      # enqueued (third frame: graph replay), hint still on
+    for _ in range(12):                                     # enqueue-only frames keep the hint alive by themselves
         mesh.frame_enqueue(big.clear, big.camera, big.settings, big.fog)
     got, got_z = fb.download()
     mesh.free()
     assert np.array_equal(got, want_big[0]) and np.array_equal(got_z.view(np.uint32), want_big[1].view(np.uint32))
-    got, got_z, tm = render_gpu(ctx, plain)                 # drawn by the PRE instantiation (the hint was on when it was launched) ...
-    assert_same(plain, got, got_z, tm, *want_plain[:3])
-    assert ctx.lib.b32_debug_prefix_hint(ctx.h) == 0        # ... and its counters switch the hint off
+    assert hint() == 1
+    for k in range(9):                                      # ordinary scenes: drawn by the PRE instantiation while the hint lasts, ...
+        got, got_z, tm = render_gpu(ctx, plain)
+        assert_same(plain, got, got_z, tm, *want_plain[:3])
+        assert hint() == (1 if k < 7 else 0), k             # ... which is 8 calls
     got, got_z, tm = render_gpu(ctx, plain)
     assert_same(plain, got, got_z, tm, *want_plain[:3])
 
