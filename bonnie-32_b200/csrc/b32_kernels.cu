@@ -1677,6 +1677,9 @@ constexpr int ORD_RING = 3;          // steps c, c+1, c+2 in flight
 #endif
 constexpr int ORD_GROUP = B32_ORD_GROUP;   // fragments of one pixel whose texels are requested together
 constexpr size_t ORD_SMEM = (size_t)ORD_SORT_MAX * sizeof(BinHead) + (size_t)ORD_RING * ORD_CHUNK * sizeof(SurfRec) + (FILL_THREADS / 32) * 32;
+// PRE instantiations (shared edge prefix, see k_fill_opaque): the edge values of every (survivor, block row) of a batch, per warp
+constexpr size_t ORD_SMEM_PRE = ORD_SMEM + (size_t)(FILL_THREADS / 32) * 32 * 4 * sizeof(float2);
+static_assert(ORD_SMEM % 8 == 0, "the prefix table behind it holds float2");
 static_assert(FILL_THREADS == 32 * 8, "one 16-byte piece of a batch's staged records per thread");
 
 __device__ __forceinline__ uint64_t ord_key(const BinHead& h) { return ((uint64_t)h.key << 32) | h.face; }
@@ -1704,7 +1707,10 @@ __device__ void bitonic_sort_heads(BinHead* a, uint32_t m) {
 // surfaces against the warp's block (bbox, exact corner trivial reject); every pixel then marks which survivors cover
 // it (one bit each) and folds its own fragments in draw order — the order only matters per pixel, so the lanes of a
 // warp shade different surfaces side by side.
-template <bool RGB888>
+// PRE (float / ortho calls, or the stepped-surface hint): surfaces whose edge values are the reference's rounded additions
+// get their chains replayed once per (survivor, block row) — 32 chains side by side, into a per-warp table — instead of once
+// per covered fragment per pixel; phase A then tests them exactly (not just by bounding box) and phase B adds < 8 steps.
+template <bool RGB888, bool PRE>
 __global__ void __launch_bounds__(FILL_THREADS)
 k_fill_ordered(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks, BinHead* __restrict__ scratch,
                const uint64_t* __restrict__ keys, const TexDev* __restrict__ tex, const void* __restrict__ texels,
@@ -1714,6 +1720,7 @@ k_fill_ordered(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks
     SurfRec* s_rec = reinterpret_cast<SurfRec*>(ord_smem);                              // [ORD_RING][ORD_CHUNK]
     BinHead* s_sorted = reinterpret_cast<BinHead*>(s_rec + ORD_RING * ORD_CHUNK);       // [ORD_SORT_MAX]
     uint8_t* s_sidx = reinterpret_cast<uint8_t*>(s_sorted + ORD_SORT_MAX);              // [warps][32] survivors of the step, in order
+    float2* s_pre = reinterpret_cast<float2*>(ord_smem + ORD_SMEM);                     // PRE: [warps][32 survivors][4 block rows] (w0, w1) at the row's first column
     uint32_t* s_cand = reinterpret_cast<uint32_t*>(s_rec);                              // [ORD_SORT_MAX] face indices of a window (the ring is idle then)
     __shared__ uint32_t s_wsum[FILL_THREADS / 32];
     __shared__ uint32_t s_n;
@@ -1835,13 +1842,33 @@ k_fill_ordered(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks
         __syncwarp();
         // ---- A. which of the step's survivors cover this pixel: the inside tests, in lockstep (nothing here depends on the
         //         pixel's running colour / depth).  Surfaces on the replayed-additions edge path are only bbox-tested here.
+        float2* my_pre = s_pre + (size_t)(threadIdx.x >> 5) * 32 * 4;
+        if (PRE) {                                             // lane -> (survivor jb + lane / 4, block row lane % 4)
+            for (uint32_t jb = 0; jb < cnt; jb += 8) {
+                const uint32_t sj = jb + (lane >> 2), yr = by0 + (lane & 3u);
+                if (sj < cnt) {
+                    const SurfRec& r = crec[my_sidx[sj]];
+                    const uint32_t min_x = r.bbox_x & 0xFFFF, min_y = r.bbox_y & 0xFFFF, max_y = r.bbox_y >> 16;
+                    if (!(r.flags & SF_FAST_EDGE) && yr >= min_y && yr < max_y) {
+                        float w0 = r.w0s, w1 = r.w1s;
+                        edge_steps(w0, w1, r.b0, r.b1, yr - min_y);                        // row steps first (:1706-1712) ...
+                        edge_steps(w0, w1, r.a0, r.a1, bx0 > min_x ? bx0 - min_x : 0u);    // ... then along the row to the block
+                        my_pre[sj * 4 + (lane & 3u)] = make_float2(w0, w1);
+                    }
+                }
+            }
+            __syncwarp();
+        }
         uint32_t cov = 0;
         for (uint32_t j = 0; j < cnt; ++j) {
             const SurfRec& r = crec[my_sidx[j]];
             uint32_t min_x = r.bbox_x & 0xFFFF, max_x = r.bbox_x >> 16, min_y = r.bbox_y & 0xFFFF, max_y = r.bbox_y >> 16;
             if (!(valid && x >= min_x && x < max_x && y >= min_y && y < max_y)) continue;
             float bc_x, bc_y, bc_z;
-            if (!(r.flags & SF_FAST_EDGE) || inside_test(r, x, y, bc_x, bc_y, bc_z)) cov |= 1u << j;
+            if (PRE) {
+                const float2 pw = my_pre[j * 4 + (y - by0)];
+                if (inside_test_prefix<8>(r, x, y, pw.x, pw.y, bx0, bc_x, bc_y, bc_z)) cov |= 1u << j;
+            } else if (!(r.flags & SF_FAST_EDGE) || inside_test(r, x, y, bc_x, bc_y, bc_z)) cov |= 1u << j;
         }
         // ---- B. every pixel folds ITS fragments in draw order, ORD_GROUP at a time: lanes work on different surfaces in
         //         the same instruction (a small triangle covers a quarter of the block: walking the survivors in lockstep
@@ -1858,7 +1885,10 @@ k_fill_ordered(const SurfRec* __restrict__ recs, const uint4* __restrict__ masks
                 fidx[k] = my_sidx[j];
                 const SurfRec& r = crec[fidx[k]];
                 float bc_x, bc_y, bc_z;
-                if (!inside_test(r, x, y, bc_x, bc_y, bc_z)) continue;                  // (only the slow edge path can still fail)
+                if (PRE) {
+                    const float2 pw = my_pre[j * 4 + (y - by0)];
+                    if (!inside_test_prefix<8>(r, x, y, pw.x, pw.y, bx0, bc_x, bc_y, bc_z)) continue;      // (cannot fail: phase A tested it)
+                } else if (!inside_test(r, x, y, bc_x, bc_y, bc_z)) continue;           // (only the slow edge path can still fail)
                 float inv_z = bc_x * r.iz1 + bc_y * r.iz2 + bc_z * r.iz3;              // :1549
                 float z = 1.0f / inv_z;
                 // A reject against the depth the pixel has NOW is a reject at the fragment's own time as long as the depth only
@@ -2272,8 +2302,8 @@ int init_kernel_attributes() {
     smem_attr(k_fill_opaque<false, OpDense, true>, OpDense::SMEM);   smem_attr(k_fill_opaque<true, OpDense, true>, OpDense::SMEM);
     smem_attr(k_fill_opaque<false, OpSparse, false>, OpSparse::SMEM); smem_attr(k_fill_opaque<true, OpSparse, false>, OpSparse::SMEM);
     smem_attr(k_fill_opaque<false, OpSparse, true>, OpSparse::SMEM);  smem_attr(k_fill_opaque<true, OpSparse, true>, OpSparse::SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fill_ordered<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ORD_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fill_ordered<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ORD_SMEM);
+    smem_attr(k_fill_ordered<false, false>, ORD_SMEM); smem_attr(k_fill_ordered<true, false>, ORD_SMEM);
+    smem_attr(k_fill_ordered<false, true>, ORD_SMEM_PRE); smem_attr(k_fill_ordered<true, true>, ORD_SMEM_PRE);
     return (int)e;
 }
 
@@ -2332,7 +2362,10 @@ void launch_fill_ordered(const LaunchCtx& L, const SurfRec* recs, const uint4* m
                          CallState* st, uint32_t* sticky, const CallParams& p, uint32_t scratch_cap) {
     uint32_t ntiles = p.tiles_x * p.tiles_y;
     if (ntiles == 0 || p.nf == 0) return;
-    launch_k(L, p.rgb888 ? k_fill_ordered<true> : k_fill_ordered<false>, ntiles, FILL_THREADS, ORD_SMEM, p.enq_ordered != 0,
+    static const bool no_prefix = getenv("B32_NO_EDGE_PREFIX") != nullptr;
+    const bool pre = (fill_uses_edge_prefix(p) || p.prefer_prefix) && !no_prefix;
+    launch_k(L, p.rgb888 ? (pre ? k_fill_ordered<true, true> : k_fill_ordered<true, false>) : (pre ? k_fill_ordered<false, true> : k_fill_ordered<false, false>),
+             ntiles, FILL_THREADS, pre ? ORD_SMEM_PRE : ORD_SMEM, p.enq_ordered != 0,
              recs, masks, scratch, keys, tex, static_cast<const void*>(texels), fb_rgba, fb_z, st, sticky, p, scratch_cap);
 }
 

@@ -30,6 +30,15 @@ for sc in cases.wireframe_scenes(60)[:2] + [s for s in cases.rgb888_scenes(100) 
     got, gz = fb.download()
     ok = rc == 0 and np.array_equal(got, want) and np.array_equal(gz.view(np.uint32), wz.view(np.uint32))
     print(sc.name, "OK" if ok else "MISMATCH"); bad += not ok
+# float projection with semi-transparent surfaces and x-ray: the shared-edge-prefix instantiations of both fill kernels
+for name in ("mixed_zbuffer", "xray"):
+    sc = cases._with(by[name], name + "_float", use_fixed_point=False)
+    fb = pkg.Framebuffer(sc.width, sc.height, ctx); fb.clear(sc.clear)
+    pkg.render_mesh_15(fb, sc.vertices, sc.faces, sc.textures, sc.camera, sc.settings, sc.fog)
+    got, gz = fb.download()
+    want, wz, _, rc = orc.render_scene(sc)
+    ok = rc == 0 and np.array_equal(got, want) and np.array_equal(gz.view(np.uint32), wz.view(np.uint32))
+    print(sc.name, "OK" if ok else "MISMATCH"); bad += not ok
 # Spot lights: the k_setup<true> instantiation (acos path, the one kernel with a stack frame)
 for sc in [s for s in cases.spot_scenes(100) if s.name in ("spot_gouraud_all", "spot_flat_mixed_float_nodither", "spot_mixed_blend_gouraud")]:
     fb = pkg.Framebuffer(sc.width, sc.height, ctx); fb.clear(sc.clear)
