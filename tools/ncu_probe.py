@@ -30,5 +30,9 @@ if what == "all":
     run(scenes.scene_c1(), n=3); run(scenes.scene_c2(), n=3)
 if what in ("all", "bigtri"):
     run(cases.big_triangle_scene(), 1920, 1080, n=2)
+if what == "float":         # float-projection level-like scene: every surface stepped -> the PRE instantiations
+    f = cases._with(cases.feature_scenes(1000)[0], "c2_float", use_fixed_point=False, width=640, height=480)
+    run(f, 640, 480, n=2)
+    run(cases.big_triangle_scene(), 1920, 1080, n=3)     # fixed point: call 1 per-pixel replay, calls 2, 3 the shared prefix
 if what == "1m":
     run(scenes.scene_c4(n_tris=1_000_000), n=2)
