@@ -159,6 +159,24 @@ def test_oracle_equals_numpy_model_and_golden(oracle, sc):
     assert _digest(want, want_z, order) == HASHES[sc.name]
 
 
+SPOT_SMALL = [s for s in cases.spot_scenes() if s.name in ("spot_gouraud_all", "spot_flat_all", "spot_gouraud_mixed_nocull", "spot_mixed_blend_gouraud")]
+
+
+@pytest.mark.parametrize("sc", SPOT_SMALL, ids=[s.name for s in SPOT_SMALL])
+def test_oracle_equals_numpy_model_spot_lights(oracle, sc):
+    """Spot lights (render.rs:1038-1059) through both restatements: the C++ oracle and the numpy model (its own ref_acosf)
+    draw the same frame; the binary's frames pin both (tests/test_ref_wasm.py)."""
+    want, want_z, tm, rc, order = oracle.render_scene(sc, want_order=True)
+    assert rc == 0
+    rgba, z = pymodel.fb_clear(sc.width, sc.height, sc.clear)
+    order2 = pymodel.render_mesh_15(rgba, z, sc.vertices, sc.faces, sc.textures, sc.camera, sc.settings, sc.fog)
+    assert list(order) == order2
+    assert np.array_equal(rgba, want)
+    assert np.array_equal(z.view(np.uint32), want_z.view(np.uint32))
+    lit, _, _, _ = oracle.render_scene(cases._with(sc, sc.name + "_unlit", lights=[]))
+    assert not np.array_equal(lit, want)                   # the lights do reach the frame
+
+
 def test_scenes_exercise_their_feature(oracle):
     """Guards against vacuous parity: the feature scenes must really hit the code they name."""
     by = {s.name: s for s in cases.feature_scenes()}
